@@ -1,0 +1,110 @@
+/* orbx_types.h — plain-old-data types that cross the orbx C ABI.
+ *
+ * Every struct here is the flat ("SoA / CSR") form of an object the reference keeps as C++ containers; the
+ * reference type each one replaces is cited beside it (paths relative to the reference checkout).
+ * No C++ types, no torch types: a maintainer can bind these from C, C++, ctypes or cffi.
+ */
+#ifndef ORBX_TYPES_H_
+#define ORBX_TYPES_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cv::KeyPoint, 28 bytes, standard layout {Point2f pt; float size, angle, response; int octave, class_id;}.
+ * `std::vector<cv::KeyPoint>::data()` can be reinterpret_cast to orbx_kp* (include/Frame.h:254-255). */
+typedef struct orbx_kp {
+  float x, y;
+  float size;
+  float angle;    /* degrees, [0,360) */
+  float response; /* FAST corner score (src/ORBextractor.cc:810-815) */
+  int32_t octave;
+  int32_t class_id; /* always -1 */
+} orbx_kp;
+
+#define ORBX_DESC_BYTES 32 /* one row of the N x 32 CV_8U descriptor cv::Mat (include/Frame.h:268) */
+
+#define ORBX_GRID_COLS 64 /* FRAME_GRID_COLS include/Frame.h:42 */
+#define ORBX_GRID_ROWS 48 /* FRAME_GRID_ROWS include/Frame.h:41 */
+
+/* Frame::mGrid[64][48] (include/Frame.h:279) as CSR. Cell id = col * 48 + row (mGrid[col][row]); items inside a
+ * cell are ascending keypoint indices, the order Frame::AssignFeaturesToGrid produces (src/Frame.cc:520-547). */
+typedef struct orbx_grid {
+  const int32_t* cell_offsets; /* [64*48 + 1] */
+  const int32_t* cell_items;   /* [cell_offsets[64*48]] */
+  float min_x, min_y;          /* Frame::mnMinX, mnMinY */
+  float inv_w, inv_h;          /* Frame::mfGridElementWidthInv / HeightInv */
+} orbx_grid;
+
+/* The part of a Frame that the guided searches read (Nleft == -1, i.e. pinhole mono / stereo / RGB-D):
+ * mvKeysUn, mDescriptors, mvuRight, mGrid, mvScaleFactors (include/Frame.h:254-279). */
+typedef struct orbx_frame_view {
+  int32_t n;
+  const orbx_kp* kps;   /* mvKeysUn */
+  const uint8_t* desc;  /* n x 32 */
+  const float* u_right; /* mvuRight or NULL (monocular) */
+  /* per keypoint: 1 if mvpMapPoints[i] != NULL && mvpMapPoints[i]->Observations() > 0 (src/ORBmatcher.cc:92-93) */
+  const uint8_t* occupied;
+  orbx_grid grid;
+  const float* scale_factors; /* mvScaleFactors[n_levels] */
+  int32_t n_levels;
+} orbx_frame_view;
+
+/* Local-map points as flattened by the shim from MapPoint tracking scratch (include/MapPoint.h:172-180), already
+ * filtered through Frame::isInFrustum (src/Frame.cc:632-699). One entry per element of vpMapPoints. */
+typedef struct orbx_mappoints {
+  int32_t m;
+  const uint8_t* track_in_view; /* mbTrackInView && !isBad() */
+  const float* proj_x;          /* mTrackProjX */
+  const float* proj_y;          /* mTrackProjY */
+  const float* proj_xr;         /* mTrackProjXR */
+  const int32_t* level;         /* mnTrackScaleLevel */
+  const float* view_cos;        /* mTrackViewCos */
+  const float* depth;           /* mTrackDepth */
+  const uint8_t* has_obs;       /* Observations() > 0: a keypoint that receives this point blocks later ones */
+  const uint8_t* desc;          /* m x 32, MapPoint::GetDescriptor() */
+} orbx_mappoints;
+
+/* Points of the last frame / a keyframe already projected into the current frame by the caller (the SE3 product and
+ * camera projection stay on the host so Eigen's evaluation order is untouched): src/ORBmatcher.cc:1617-1660,
+ * 1826-1853. One entry per candidate point that survived the caller-side tests. */
+typedef struct orbx_projected {
+  int32_t m;
+  const float* u;          /* projected column */
+  const float* v;          /* projected row */
+  const float* u_right;    /* u - bf * invz, used only when the frame has stereo (NULL otherwise) */
+  const float* radius;     /* th * scale[level] */
+  const int32_t* min_level;
+  const int32_t* max_level;
+  const float* angle;      /* orientation of the source keypoint, degrees */
+  const uint8_t* has_obs;  /* does the point block the keypoint it is written to (see orbx_search_by_projection_frame) */
+  const uint8_t* desc;     /* m x 32 */
+} orbx_projected;
+
+/* DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>, Thirdparty/DBoW2/DBoW2/FeatureVector.h) as CSR. */
+typedef struct orbx_featvec {
+  int32_t n_nodes;
+  const uint32_t* node_ids; /* ascending */
+  const int32_t* offsets;   /* [n_nodes + 1] */
+  const uint32_t* indices;  /* keypoint indices, per node in insertion order */
+} orbx_featvec;
+
+/* KeyFrame view for SearchForTriangulation (pinhole, NLeft == -1): include/KeyFrame.h:384-401. */
+typedef struct orbx_keyframe_view {
+  int32_t n;
+  const orbx_kp* kps;           /* mvKeysUn */
+  const uint8_t* desc;          /* n x 32 */
+  const float* u_right;         /* mvuRight (values < 0 = monocular point) or NULL */
+  const uint8_t* has_mappoint;  /* GetMapPoint(i) != NULL */
+  orbx_featvec featvec;
+  const float* scale_factors;   /* mvScaleFactors */
+  const float* level_sigma2;    /* mvLevelSigma2 */
+  int32_t n_levels;
+} orbx_keyframe_view;
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_TYPES_H_ */

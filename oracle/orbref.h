@@ -1,0 +1,97 @@
+/* orbref.h — CPU ORACLE for the ORB front-end hot path. TEST INFRASTRUCTURE ONLY.
+ *
+ * A serial-order restatement of the reference's CPU algorithm (hellovuong/ORB_SLAM3_FAST @ 6255e16), used by
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs as the checker and as the
+ * timed CPU baseline. Nothing under orb_slam3_fast_b200/ may include, link or load this library.
+ *
+ * PINNING STATUS
+ *   - The reference has no tests, golden vectors or fixtures for this path, and it cannot be compiled
+ *     here (needs OpenCV C++ headers/libs, TBB, Eigen, Sophus, Pangolin; none installed, no network) — so there is
+ *     no oracle/_ref and the ORCHESTRATION parity (ORBextractor.cc / ORBmatcher.cc / Frame.cc logic) is UNPINNED by
+ *     the reference's own tests.
+ *   - The third-party arithmetic the reference calls (OpenCV resize / GaussianBlur / FAST / copyMakeBorder /
+ *     fastAtan2 / BFMatcher, glibc cosf/sinf, libstdc++ std::sort) IS pinned: tests/test_oracle_primitives.py checks
+ *     every primitive below byte-for-byte against the real OpenCV 4.13.0 kernels through cv2, and
+ *     tests/test_oracle_pipeline.py checks the whole extractor against an independent Python pipeline that drives the
+ *     real cv2 kernels (oracle/cv2_pipeline.py), from which tests/golden/ is frozen.
+ *
+ * Build: oracle/Makefile (g++ -O2, no -march=native, -ffp-contract=off: the reference is built without FMA,
+ * CMakeLists.txt:13-18).
+ */
+#ifndef ORBREF_H_
+#define ORBREF_H_
+
+#include "../include/orbx_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- OpenCV / glibc primitives (restated; pinned to cv2 4.13.0 in tests) ---- */
+void orbref_resize_linear(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+void orbref_gauss7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride);
+void orbref_border101(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int border);
+/* cv::FAST(img, kps, threshold, nonmaxSuppression=true), TYPE_9_16. Returns the count; fills up to cap entries. */
+int orbref_fast9(const uint8_t* img, int w, int h, int stride, int threshold, int* xs, int* ys, int* scores, int cap);
+float orbref_fast_atan2(float y, float x);
+int orbref_cv_round(float v);
+/* libstdc++ std::sort on (key0, key1) pairs with the reference's compareNodes ordering (src/ORBextractor.cc:542-555);
+ * writes the resulting permutation (perm[i] = original index of the element now at position i). */
+void orbref_std_sort_perm(const int* key0, const int* key1, int n, int* perm);
+
+/* ---- ORBextractor (src/ORBextractor.cc, serial path) ---- */
+typedef struct orbref_extractor orbref_extractor;
+orbref_extractor* orbref_extractor_create(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th);
+void orbref_extractor_destroy(orbref_extractor* ex);
+/* tables: each array has nlevels entries (umax has 16). Any pointer may be NULL. */
+void orbref_extractor_tables(const orbref_extractor* ex, float* scale, float* inv_scale, float* sigma2,
+                             float* inv_sigma2, int* features_per_level, int* umax);
+/* operator(): returns 0, or -1 on empty image, or -2 if cap is too small. *mono_index = the reference's return. */
+int orbref_extract(orbref_extractor* ex, const uint8_t* img, int w, int h, int stride, int lap0, int lap1,
+                   orbx_kp* kps, uint8_t* desc, int cap, int* n_out, int* mono_index);
+/* intermediates of the last orbref_extract call (for stage-by-stage parity tests) */
+int orbref_level_dims(const orbref_extractor* ex, int level, int* w, int* h);
+const uint8_t* orbref_level_image(const orbref_extractor* ex, int level, int* stride);    /* ROI of the bordered buffer */
+const uint8_t* orbref_level_bordered(const orbref_extractor* ex, int level, int* stride); /* (w+38) x (h+38) */
+const uint8_t* orbref_level_blurred(const orbref_extractor* ex, int level, int* stride);
+int orbref_level_candidates(const orbref_extractor* ex, int level, orbx_kp* out, int cap); /* before the quadtree */
+int orbref_level_keypoints(const orbref_extractor* ex, int level, orbx_kp* out, int cap);  /* after, with angle */
+
+/* ---- matching ---- */
+int orbref_descriptor_distance(const uint8_t* a, const uint8_t* b); /* src/ORBmatcher.cc:1959-1973 */
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) (src/Frame.cc:1293): per query the two train rows minimising
+ * (distance, trainIdx). idx = -1 / dist = -1 when the train set has fewer rows. */
+void orbref_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx1, int32_t* d1, int32_t* idx2,
+                 int32_t* d2);
+/* Frame::ComputeStereoMatches (src/Frame.cc:921-1084). Reads the raw pyramids of the two extractors' last extract.
+ * best_dist_out (optional) receives the SAD of accepted matches (or -1). Returns the number of surviving matches. */
+int orbref_stereo_match(const orbref_extractor* left, const orbref_extractor* right, const orbx_kp* kps_l,
+                        const uint8_t* desc_l, int n_l, const orbx_kp* kps_r, const uint8_t* desc_r, int n_r,
+                        float mbf, float mb, float* u_right, float* depth);
+/* Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:520-547,833-844). offsets[64*48+1], items[n]. */
+void orbref_build_grid(const orbx_kp* kps, int n, float min_x, float min_y, float inv_w, float inv_h,
+                       int32_t* offsets, int32_t* items);
+/* Frame::GetFeaturesInArea (src/Frame.cc:765-831), Nleft == -1. Returns the count written to out (cap >= n). */
+int orbref_features_in_area(const orbx_frame_view* f, float x, float y, float r, int min_level, int max_level,
+                            int32_t* out);
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints), serial MapPoint
+ * order (src/ORBmatcher.cc:42-221), Nleft == -1. assign[n]: index of the MapPoint written to each keypoint or -1
+ * (keypoints that were already occupied stay -1). Returns nmatches. */
+int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoints* mps, float th, float nnratio,
+                                    int far_points, float th_far, int32_t* assign);
+/* ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / (Frame&, KeyFrame*, set, th, ORBdist) after the
+ * caller-side projection (src/ORBmatcher.cc:1594-1806, 1808-1918). block_any != 0 selects the keyframe variant's
+ * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
+int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
+                                      int check_orientation, int32_t* assign);
+/* ORBmatcher::SearchForTriangulation, pinhole mono/stereo keyframes (src/ORBmatcher.cc:886-1106 +
+ * src/CameraModels/Pinhole.cpp:122-149). F12 = K1^-T [t12]x R12 K2^-1 computed by the caller (row-major 3x3);
+ * ep = projection of camera centre 1 into image 2. matches12[kf1->n] = idx2 or -1. Returns nmatches. */
+int orbref_search_for_triangulation(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, const float* F12,
+                                    float ep_x, float ep_y, int only_stereo, int coarse, int check_orientation,
+                                    int32_t* matches12);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

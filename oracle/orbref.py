@@ -1,0 +1,360 @@
+"""ctypes binding of the CPU oracle (oracle/liborbref.so). TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module; the
+product package (orb_slam3_fast_b200/) never does. See oracle/orbref.h for what each entry point restates.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborbref.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+GRID_COLS, GRID_ROWS = 64, 48
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in ("orbref.cpp", "orbref_mt.cpp", "orbref.h")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+class Grid(C.Structure):
+    _fields_ = [("cell_offsets", C.c_void_p), ("cell_items", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("inv_w", C.c_float), ("inv_h", C.c_float)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p),
+                ("occupied", C.c_void_p), ("grid", Grid), ("scale_factors", C.c_void_p), ("n_levels", C.c_int32)]
+
+
+class MapPoints(C.Structure):
+    _fields_ = [("m", C.c_int32), ("track_in_view", C.c_void_p), ("proj_x", C.c_void_p), ("proj_y", C.c_void_p),
+                ("proj_xr", C.c_void_p), ("level", C.c_void_p), ("view_cos", C.c_void_p), ("depth", C.c_void_p),
+                ("has_obs", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class Projected(C.Structure):
+    _fields_ = [("m", C.c_int32), ("u", C.c_void_p), ("v", C.c_void_p), ("u_right", C.c_void_p),
+                ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p), ("angle", C.c_void_p),
+                ("has_obs", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("indices", C.c_void_p)]
+
+
+class KeyFrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p),
+                ("has_mappoint", C.c_void_p), ("featvec", FeatVec), ("scale_factors", C.c_void_p),
+                ("level_sigma2", C.c_void_p), ("n_levels", C.c_int32)]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Holder:
+    """Keeps numpy arrays alive next to the ctypes struct that points into them."""
+
+    def __init__(self, struct, keep):
+        self.struct = struct
+        self.keep = keep
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def make_grid(offsets, items, min_x, min_y, inv_w, inv_h):
+    offsets = _c(offsets, np.int32)
+    items = _c(items, np.int32)
+    g = Grid(_ptr(offsets), _ptr(items), float(min_x), float(min_y), float(inv_w), float(inv_h))
+    return g, (offsets, items)
+
+
+def make_frame_view(kps, desc, u_right, occupied, grid, grid_keep, scale_factors):
+    kps = _c(kps, KP_DTYPE)
+    desc = _c(desc, np.uint8)
+    u_right = None if u_right is None else _c(u_right, np.float32)
+    occupied = _c(occupied, np.uint8)
+    sf = _c(scale_factors, np.float32)
+    fv = FrameView(len(kps), _ptr(kps), _ptr(desc), _ptr(u_right), _ptr(occupied), grid, _ptr(sf), len(sf))
+    return Holder(fv, (kps, desc, u_right, occupied, grid_keep, sf))
+
+
+def make_mappoints(track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth, has_obs, desc):
+    arrs = (_c(track_in_view, np.uint8), _c(proj_x, np.float32), _c(proj_y, np.float32), _c(proj_xr, np.float32),
+            _c(level, np.int32), _c(view_cos, np.float32), _c(depth, np.float32), _c(has_obs, np.uint8),
+            _c(desc, np.uint8))
+    return Holder(MapPoints(len(arrs[0]), *[_ptr(a) for a in arrs]), arrs)
+
+
+def make_projected(u, v, u_right, radius, min_level, max_level, angle, has_obs, desc):
+    arrs = (_c(u, np.float32), _c(v, np.float32), None if u_right is None else _c(u_right, np.float32),
+            _c(radius, np.float32), _c(min_level, np.int32), _c(max_level, np.int32), _c(angle, np.float32),
+            _c(has_obs, np.uint8), _c(desc, np.uint8))
+    return Holder(Projected(len(arrs[0]), *[_ptr(a) for a in arrs]), arrs)
+
+
+def make_keyframe_view(kps, desc, u_right, has_mappoint, node_ids, offsets, indices, scale_factors, level_sigma2):
+    kps = _c(kps, KP_DTYPE)
+    desc = _c(desc, np.uint8)
+    u_right = None if u_right is None else _c(u_right, np.float32)
+    hm = _c(has_mappoint, np.uint8)
+    node_ids = _c(node_ids, np.uint32)
+    offsets = _c(offsets, np.int32)
+    indices = _c(indices, np.uint32)
+    sf = _c(scale_factors, np.float32)
+    s2 = _c(level_sigma2, np.float32)
+    fv = FeatVec(len(node_ids), _ptr(node_ids), _ptr(offsets), _ptr(indices))
+    kv = KeyFrameView(len(kps), _ptr(kps), _ptr(desc), _ptr(u_right), _ptr(hm), fv, _ptr(sf), _ptr(s2), len(sf))
+    return Holder(kv, (kps, desc, u_right, hm, node_ids, offsets, indices, sf, s2))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.orbref_resize_linear.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci]
+        L.orbref_gauss7.argtypes = [vp, ci, ci, ci, vp, ci]
+        L.orbref_border101.argtypes = [vp, ci, ci, ci, vp, ci, ci]
+        L.orbref_fast9.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, ci]
+        L.orbref_fast_atan2.argtypes = [cf, cf]
+        L.orbref_fast_atan2.restype = cf
+        L.orbref_cv_round.argtypes = [cf]
+        L.orbref_std_sort_perm.argtypes = [vp, vp, ci, vp]
+        L.orbref_extractor_create.argtypes = [ci, cf, ci, ci, ci]
+        L.orbref_extractor_create.restype = vp
+        L.orbref_extractor_destroy.argtypes = [vp]
+        L.orbref_extractor_tables.argtypes = [vp] * 7
+        L.orbref_extract.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, vp, vp]
+        L.orbref_level_dims.argtypes = [vp, ci, vp, vp]
+        for f in (L.orbref_level_image, L.orbref_level_bordered, L.orbref_level_blurred):
+            f.argtypes = [vp, ci, vp]
+            f.restype = vp
+        L.orbref_level_candidates.argtypes = [vp, ci, vp, ci]
+        L.orbref_level_keypoints.argtypes = [vp, ci, vp, ci]
+        L.orbref_descriptor_distance.argtypes = [vp, vp]
+        L.orbref_knn2.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp]
+        L.orbref_stereo_match.argtypes = [vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
+        L.orbref_build_grid.argtypes = [vp, ci, cf, cf, cf, cf, vp, vp]
+        L.orbref_features_in_area.argtypes = [vp, cf, cf, cf, ci, ci, vp]
+        L.orbref_search_by_projection_map.argtypes = [vp, vp, cf, cf, ci, cf, vp]
+        L.orbref_search_by_projection_frame.argtypes = [vp, vp, ci, ci, vp]
+        L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
+        L.orbref_extract_many.argtypes = [vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]
+        L.orbref_stereo_many.argtypes = [vp, vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, cf, cf, ci, vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+# ---- primitives -------------------------------------------------------------------------------------------------
+def resize_linear(src, dw, dh):
+    src = _c(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orbref_resize_linear(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dw, dh, dw)
+    return dst
+
+
+def gauss7(src):
+    src = _c(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orbref_gauss7(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dst.strides[0])
+    return dst
+
+
+def border101(src, border):
+    src = _c(src, np.uint8)
+    dst = np.empty((src.shape[0] + 2 * border, src.shape[1] + 2 * border), np.uint8)
+    lib().orbref_border101(_ptr(src), src.shape[1], src.shape[0], src.strides[0], _ptr(dst), dst.strides[0], border)
+    return dst
+
+
+def fast9(img, threshold):
+    img = _c(img, np.uint8)
+    cap = img.size
+    xs, ys, sc = (np.empty(cap, np.int32) for _ in range(3))
+    n = lib().orbref_fast9(_ptr(img), img.shape[1], img.shape[0], img.strides[0], threshold, _ptr(xs), _ptr(ys),
+                           _ptr(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def fast_atan2(y, x):
+    return lib().orbref_fast_atan2(float(y), float(x))
+
+
+def std_sort_perm(key0, key1):
+    key0 = _c(key0, np.int32)
+    key1 = _c(key1, np.int32)
+    perm = np.empty(len(key0), np.int32)
+    lib().orbref_std_sort_perm(_ptr(key0), _ptr(key1), len(key0), _ptr(perm))
+    return perm
+
+
+# ---- extractor --------------------------------------------------------------------------------------------------
+class Extractor:
+    """Mirror of ORB_SLAM3::ORBextractor (include/ORBextractor.h:48-120) over the oracle."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = lib().orbref_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.scale = np.empty(nlevels, np.float32)
+        self.inv_scale = np.empty(nlevels, np.float32)
+        self.sigma2 = np.empty(nlevels, np.float32)
+        self.inv_sigma2 = np.empty(nlevels, np.float32)
+        self.features_per_level = np.empty(nlevels, np.int32)
+        self.umax = np.empty(16, np.int32)
+        lib().orbref_extractor_tables(self._h, _ptr(self.scale), _ptr(self.inv_scale), _ptr(self.sigma2),
+                                      _ptr(self.inv_sigma2), _ptr(self.features_per_level), _ptr(self.umax))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orbref_extractor_destroy(self._h)
+            self._h = None
+
+    def __call__(self, img, lapping=(0, 0)):
+        """Returns (mono_index, keypoints[KP_DTYPE], descriptors[n,32]); mono_index = -1 on empty input."""
+        if img is None or img.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        img = _c(img, np.uint8)
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n, mono = C.c_int(0), C.c_int(0)
+        rc = lib().orbref_extract(self._h, _ptr(img), img.shape[1], img.shape[0], img.strides[0], lapping[0],
+                                  lapping[1], _ptr(kps), _ptr(desc), cap, C.byref(n), C.byref(mono))
+        if rc != 0:
+            raise RuntimeError("orbref_extract rc=%d n=%d" % (rc, n.value))
+        return mono.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level_dims(self, level):
+        w, h = C.c_int(0), C.c_int(0)
+        lib().orbref_level_dims(self._h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def _view(self, fn, level, w, h):
+        st = C.c_int(0)
+        p = fn(self._h, level, C.byref(st))
+        if not p:
+            return None
+        buf = (C.c_uint8 * (st.value * (h - 1) + w)).from_address(p)
+        return np.lib.stride_tricks.as_strided(np.frombuffer(buf, np.uint8), (h, w), (st.value, 1)).copy()
+
+    def level_image(self, level):
+        w, h = self.level_dims(level)
+        return self._view(lib().orbref_level_image, level, w, h)
+
+    def level_bordered(self, level):
+        w, h = self.level_dims(level)
+        return self._view(lib().orbref_level_bordered, level, w + 38, h + 38)
+
+    def level_blurred(self, level):
+        w, h = self.level_dims(level)
+        return self._view(lib().orbref_level_blurred, level, w, h)
+
+    def _kps(self, fn, level):
+        n = fn(self._h, level, None, 0)
+        out = np.zeros(max(n, 1), KP_DTYPE)
+        fn(self._h, level, _ptr(out), n)
+        return out[:n]
+
+    def level_candidates(self, level):
+        return self._kps(lib().orbref_level_candidates, level)
+
+    def level_keypoints(self, level):
+        return self._kps(lib().orbref_level_keypoints, level)
+
+
+# ---- matching ---------------------------------------------------------------------------------------------------
+def descriptor_distance(a, b):
+    a = _c(a, np.uint8)
+    b = _c(b, np.uint8)
+    return lib().orbref_descriptor_distance(_ptr(a), _ptr(b))
+
+
+def knn2(q, t):
+    q = _c(q, np.uint8).reshape(-1, 32)
+    t = _c(t, np.uint8).reshape(-1, 32)
+    out = [np.empty(len(q), np.int32) for _ in range(4)]
+    lib().orbref_knn2(_ptr(q), len(q), _ptr(t), len(t), *[_ptr(o) for o in out])
+    return tuple(out)  # idx1, d1, idx2, d2
+
+
+def stereo_match(ex_l, ex_r, kps_l, desc_l, kps_r, desc_r, mbf, mb):
+    kps_l, kps_r = _c(kps_l, KP_DTYPE), _c(kps_r, KP_DTYPE)
+    desc_l, desc_r = _c(desc_l, np.uint8), _c(desc_r, np.uint8)
+    ur = np.empty(len(kps_l), np.float32)
+    dp = np.empty(len(kps_l), np.float32)
+    n = lib().orbref_stereo_match(ex_l._h, ex_r._h, _ptr(kps_l), _ptr(desc_l), len(kps_l), _ptr(kps_r), _ptr(desc_r),
+                                  len(kps_r), mbf, mb, _ptr(ur), _ptr(dp))
+    return n, ur, dp
+
+
+def build_grid(kps, min_x, min_y, inv_w, inv_h):
+    kps = _c(kps, KP_DTYPE)
+    off = np.empty(GRID_COLS * GRID_ROWS + 1, np.int32)
+    items = np.empty(max(len(kps), 1), np.int32)
+    lib().orbref_build_grid(_ptr(kps), len(kps), min_x, min_y, inv_w, inv_h, _ptr(off), _ptr(items))
+    return off, items[:off[-1]].copy()
+
+
+def features_in_area(fv, x, y, r, min_level, max_level):
+    out = np.empty(max(fv.struct.n, 1), np.int32)
+    n = lib().orbref_features_in_area(fv.ref(), x, y, r, min_level, max_level, _ptr(out))
+    return out[:n].copy()
+
+
+def search_by_projection_map(fv, mps, th, nnratio, far_points=False, th_far=0.0):
+    assign = np.empty(max(fv.struct.n, 1), np.int32)
+    n = lib().orbref_search_by_projection_map(fv.ref(), mps.ref(), th, nnratio, int(far_points), th_far, _ptr(assign))
+    return n, assign[:fv.struct.n]
+
+
+def search_by_projection_frame(fv, pts, max_dist=100, check_orientation=True):
+    assign = np.empty(max(fv.struct.n, 1), np.int32)
+    n = lib().orbref_search_by_projection_frame(fv.ref(), pts.ref(), max_dist, int(check_orientation), _ptr(assign))
+    return n, assign[:fv.struct.n]
+
+
+def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False, check_orientation=True):
+    F12 = _c(F12, np.float32).reshape(9)
+    m = np.empty(max(kf1.struct.n, 1), np.int32)
+    n = lib().orbref_search_for_triangulation(kf1.ref(), kf2.ref(), _ptr(F12), float(ep[0]), float(ep[1]),
+                                              int(only_stereo), int(coarse), int(check_orientation), _ptr(m))
+    return n, m[:kf1.struct.n]
+
+
+def extract_many(imgs, nfeatures, scale_factor, nlevels, ini_th, min_th, lapping, threads):
+    imgs = _c(imgs, np.uint8)
+    n, h, w = imgs.shape
+    counts = np.zeros(n, np.int32)
+    cap = nfeatures + 8 * nlevels + 64
+    lib().orbref_extract_many(_ptr(imgs), n, w, h, w * h, nfeatures, scale_factor, nlevels, ini_th, min_th,
+                              lapping[0], lapping[1], threads, None, None, cap, _ptr(counts))
+    return counts
+
+
+def stereo_many(imgs_l, imgs_r, nfeatures, scale_factor, nlevels, ini_th, min_th, mbf, mb, threads):
+    imgs_l, imgs_r = _c(imgs_l, np.uint8), _c(imgs_r, np.uint8)
+    n, h, w = imgs_l.shape
+    cl, cr, mt = (np.zeros(n, np.int32) for _ in range(3))
+    lib().orbref_stereo_many(_ptr(imgs_l), _ptr(imgs_r), n, w, h, w * h, nfeatures, scale_factor, nlevels, ini_th,
+                             min_th, mbf, mb, threads, _ptr(cl), _ptr(cr), _ptr(mt))
+    return cl, cr, mt

@@ -1,0 +1,137 @@
+"""Seeded synthetic inputs for the ORB front-end (SURVEY.md §8d "Synthetic images"). numpy only, deterministic.
+
+There is no network for EuRoC / TUM-VI, so tests and bench.py use these generators; `data: "synthetic"` in the
+bench line refers to them.
+"""
+import numpy as np
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def _bilinear_up(a, h, w):
+    gh, gw = a.shape
+    ys = np.linspace(0, gh - 1, h)
+    xs = np.linspace(0, gw - 1, w)
+    y0 = np.minimum(ys.astype(np.int64), gh - 2)
+    x0 = np.minimum(xs.astype(np.int64), gw - 2)
+    fy = (ys - y0)[:, None]
+    fx = (xs - x0)[None, :]
+    a00 = a[y0][:, x0]
+    a01 = a[y0][:, x0 + 1]
+    a10 = a[y0 + 1][:, x0]
+    a11 = a[y0 + 1][:, x0 + 1]
+    return (a00 * (1 - fx) + a01 * fx) * (1 - fy) + (a10 * (1 - fx) + a11 * fx) * fy
+
+
+def scene(h, w, seed=0, n_rect=150):
+    """5-octave value noise + random rectangles, normalised to 0..255: ~7-10 k FAST candidates at 640x480."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w), np.float64)
+    for cell, amp in ((4, 60), (8, 40), (16, 30), (32, 20), (64, 10)):
+        g = rng.random((h // cell + 3, w // cell + 3))
+        img += amp * _bilinear_up(g, h, w)
+    for _ in range(n_rect):
+        rw, rh = rng.integers(8, 80, 2)
+        x, y = rng.integers(0, w - 8), rng.integers(0, h - 8)
+        img[y:y + rh, x:x + rw] += rng.uniform(-60, 60)
+    img -= img.min()
+    img *= 255.0 / max(img.max(), 1e-9)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def _box_blur(img, k):
+    out = img.astype(np.float64)
+    for axis in (0, 1):
+        acc = np.zeros_like(out)
+        for d in range(-k, k + 1):
+            acc += np.roll(out, d, axis=axis)
+        out = acc / (2 * k + 1)
+    return out
+
+
+def noise_blur(h, w, seed=0):
+    rng = np.random.default_rng(seed)
+    img = _box_blur(rng.integers(0, 256, (h, w)).astype(np.float64), 1)
+    img = (img - img.min()) * (255.0 / (img.max() - img.min()))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def uniform_noise(h, w, seed=0):
+    return np.random.default_rng(seed).integers(0, 256, (h, w), dtype=np.uint8)
+
+
+def constant(h, w, value=127):
+    return np.full((h, w), value, np.uint8)
+
+
+def low_contrast(h, w, seed=0, amplitude=12):
+    """Amplitude <= 15 around mid-grey: no pixel passes iniThFAST=20, so every cell takes the minThFAST retry."""
+    img = scene(h, w, seed).astype(np.float64)
+    return np.clip(np.rint(128 + (img - 128) * (amplitude / 128.0)), 0, 255).astype(np.uint8)
+
+
+KINDS = {"scene": scene, "noise_blur": noise_blur, "uniform_noise": uniform_noise}
+
+
+def make(kind, h, w, seed=0):
+    return KINDS[kind](h, w, seed)
+
+
+def stereo_pair(h, w, seed=0, d_min=2, d_max=60, kind="scene"):
+    """Left image + right image = left shifted left by a per-row-band constant disparity (so true matches exist).
+
+    Returns (left, right, disparity_per_row)."""
+    rng = np.random.default_rng(seed + 7919)
+    wide = make(kind, h, w + d_max + 1, seed)
+    left = np.ascontiguousarray(wide[:, :w])
+    disp = np.empty(h, np.int64)
+    y = 0
+    while y < h:
+        band = int(rng.integers(24, 64))
+        disp[y:y + band] = int(rng.integers(d_min, d_max + 1))
+        y += band
+    right = np.empty_like(left)
+    cols = np.arange(w)
+    for r in range(h):
+        right[r] = wide[r, cols + disp[r]]
+    return left, right, disp
+
+
+def descriptors(n, seed=0, prototypes=0):
+    """i.i.d. uniform 256-bit descriptors; prototypes > 0 draws rows from that many prototypes (tie-heavy)."""
+    rng = np.random.default_rng(seed)
+    if prototypes:
+        protos = rng.integers(0, 256, (prototypes, 32), dtype=np.uint8)
+        return np.ascontiguousarray(protos[rng.integers(0, prototypes, n)])
+    return rng.integers(0, 256, (n, 32), dtype=np.uint8)
+
+
+def flip_bits(desc, k, rng):
+    """Copy of desc (n,32) with k[i] random bit flips in row i."""
+    out = desc.copy()
+    for i in range(len(out)):
+        bits = rng.choice(256, size=int(k[i]), replace=False)
+        for b in bits:
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out
+
+
+def local_map(kps, desc, m, w, h, n_levels, seed=0, bf=47.9):
+    """Config 4: m synthetic local-map points against one frame. Returns a dict of SoA arrays in
+    the orbx_mappoints layout. Half of the points are anchored on real keypoints (projection jittered, descriptor =
+    the keypoint's with 0..80 flipped bits), the rest are uniform over the image."""
+    rng = np.random.default_rng(seed + 104729)
+    n = len(kps)
+    src = rng.integers(0, n, m)
+    anchored = rng.random(m) < 0.5
+    px = np.where(anchored, kps["x"][src] + rng.normal(0, 1.5, m), rng.uniform(0, w, m)).astype(np.float32)
+    py = np.where(anchored, kps["y"][src] + rng.normal(0, 1.5, m), rng.uniform(0, h, m)).astype(np.float32)
+    level = np.where(anchored, np.clip(kps["octave"][src] + rng.integers(0, 2, m), 0, n_levels - 1),
+                     rng.integers(0, n_levels, m)).astype(np.int32)
+    depth = rng.uniform(0.5, 20.0, m).astype(np.float32)
+    d = flip_bits(desc[src], rng.integers(0, 81, m), rng)
+    return dict(track_in_view=(rng.random(m) < 0.95).astype(np.uint8), proj_x=px, proj_y=py,
+                proj_xr=(px - np.float32(bf) / depth).astype(np.float32), level=level,
+                view_cos=rng.uniform(0.5, 1.0, m).astype(np.float32), depth=depth,
+                has_obs=(rng.random(m) < 0.9).astype(np.uint8), desc=d)
