@@ -1,0 +1,228 @@
+// k_fast.cu — the FAST stage of ORBextractor::ComputeKeyPointsOctTree (src/ORBextractor.cc:886-960 serial twin,
+// :759-846 TBB) including the arithmetic of cv::FAST(TYPE_9_16, nonmaxSuppression = true) that it calls per cell
+// (:923-955 / :810-826).
+//
+// What the reference does per ~35x35 cell: cv::FAST at iniThFAST; if that yields nothing, again at minThFAST; the
+// surviving corners (pixel row-major) are appended to the level's candidate list, cells in row-major order.
+// OpenCV's cornerScore is the largest t for which the pixel is still a corner, which has the closed form
+//     m = max( v - min_arcs max_{k in arc} p_k ,  max_arcs min_{k in arc} p_k - v ),   score = m - 1,
+// over the 16 arcs of 9 consecutive ring pixels, and "corner at threshold T" <=> m > T. So one threshold-free pass
+// gives everything both thresholds need (verified against cv2).
+//
+// Mapping: ONE WARP PER CELL. The cell's (wCell+6)x(hCell+6) raw window is staged in shared memory widened to
+// 16 bit, so that a lane scores 4 horizontally adjacent pixels as two u16x2 SIMD pairs with the native
+// VIMNMX3.U16x2 (3-input packed min/max): window-of-9 max = max3 of max3's, 40 packed ops per pair and ring
+// polarity. Non-max suppression and the iniTh -> minTh retry run on a byte score map in shared memory, emission is
+// ballot-ordered so the candidate order equals the serial reference. Integer-ALU bound, not HBM bound.
+#include "orbx_kernels.cuh"
+#include "orbx_quadtree.h"
+
+namespace orbx {
+
+constexpr int kFastWarps = 4;
+
+struct FastSmemLayout {
+  int tp;         // u16 row pitch of the raw tile (multiple of 4)
+  int sp;         // byte row pitch of the score map (multiple of 4)
+  int raw_bytes;  // per warp
+  int score_bytes;
+  int per_warp;
+};
+
+static FastSmemLayout fast_layout(const Plan& P) {
+  int wc = 0, hc = 0;
+  for (int l = 0; l < P.nlevels; l++) {
+    if (P.lv[l].wCell > wc) wc = P.lv[l].wCell;
+    if (P.lv[l].hCell > hc) hc = P.lv[l].hCell;
+  }
+  FastSmemLayout L;
+  L.tp = round_up(wc + 12, 4);
+  L.sp = round_up(wc + 8, 4);
+  L.raw_bytes = round_up(L.tp * (hc + 6) * 2, 16);
+  L.score_bytes = round_up(L.sp * (hc + 2), 16);
+  L.per_warp = L.raw_bytes + L.score_bytes;
+  return L;
+}
+
+size_t fast_smem_bytes(const Plan& P) { return (size_t)fast_layout(P).per_warp * kFastWarps; }
+
+// ring pixel pair for the two pixels whose u16 columns are O, O+1 inside the 10-column window W (5 words)
+template <int O>
+__device__ __forceinline__ uint32_t pair_at(const uint32_t (&W)[5]) {
+  if constexpr ((O & 1) == 0) return W[O / 2];
+  else return __byte_perm(W[(O - 1) / 2], W[(O + 1) / 2], 0x5432);
+}
+
+__device__ __forceinline__ void arc_minmax(const uint32_t (&v)[16], uint32_t& rhi, uint32_t& rlo) {
+  uint32_t a[16], b[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    a[k] = __vimax3_u16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+    b[k] = __vimin3_u16x2(v[k], v[(k + 1) & 15], v[(k + 2) & 15]);
+  }
+  uint32_t hi = 0xffffffffu, lo = 0u;
+#pragma unroll
+  for (int s = 0; s < 16; s += 2) {
+    const uint32_t m0 = __vimax3_u16x2(a[s], a[(s + 3) & 15], a[(s + 6) & 15]);
+    const uint32_t m1 = __vimax3_u16x2(a[s + 1], a[(s + 4) & 15], a[(s + 7) & 15]);
+    hi = __vimin3_u16x2(hi, m0, m1);
+    const uint32_t n0 = __vimin3_u16x2(b[s], b[(s + 3) & 15], b[(s + 6) & 15]);
+    const uint32_t n1 = __vimin3_u16x2(b[s + 1], b[(s + 4) & 15], b[(s + 7) & 15]);
+    lo = __vimax3_u16x2(lo, n0, n1);
+  }
+  rhi = hi;
+  rlo = lo;
+}
+
+// FAST "m" of the two pixels packed in c (u16x2) -> two byte scores (m - 1 if m > tlow else 0)
+__device__ __forceinline__ uint32_t score_pair(uint32_t c, uint32_t rhi, uint32_t rlo, int tlow) {
+  const int c0 = (int)(c & 0xffff), c1 = (int)(c >> 16);
+  const int m0 = max(c0 - (int)(rhi & 0xffff), (int)(rlo & 0xffff) - c0);
+  const int m1 = max(c1 - (int)(rhi >> 16), (int)(rlo >> 16) - c1);
+  const uint32_t s0 = m0 > tlow ? (uint32_t)(m0 - 1) : 0u;
+  const uint32_t s1 = m1 > tlow ? (uint32_t)(m1 - 1) : 0u;
+  return s0 | (s1 << 8);
+}
+
+__global__ void __launch_bounds__(kFastWarps * 32)
+k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int ini_th, int min_th, int tp, int sp,
+       int raw_bytes, int per_warp) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * kFastWarps + warp;
+  const int f = blockIdx.y;
+  if (cell >= P.cells_per_frame) return;
+  int l = 0;
+  while (l + 1 < P.nlevels && P.lv[l + 1].cell_base <= cell) l++;
+  const LevelPlan& L = P.lv[l];
+  const int ci = cell - L.cell_base;
+  const int i = ci / L.nCols, j = ci - i * L.nCols;
+  int32_t* count_out = ws.cell_count + (int64_t)f * P.cells_per_frame + cell;
+  uint32_t* slot = ws.slots + (int64_t)f * P.slots_per_frame + L.slot_base + (int64_t)ci * L.slot_cap;
+
+  // cell window (:909-921): [iniX, maxX) x [iniY, maxY) in level coordinates
+  const int iniX = kMinBorder + j * L.wCell, iniY = kMinBorder + i * L.hCell;
+  int maxX = iniX + L.wCell + 6, maxY = iniY + L.hCell + 6;
+  if (maxX > L.maxBX) maxX = L.maxBX;
+  if (maxY > L.maxBY) maxY = L.maxBY;
+  const int tw = maxX - iniX, th = maxY - iniY;
+  const int iw = tw - 6, ih = th - 6;  // pixels cv::FAST evaluates: a 3-px rim is skipped
+  if (iniY >= L.maxBY - 3 || iniX >= L.maxBX - 6 || iw <= 0 || ih <= 0) {
+    if (lane == 0) *count_out = 0;
+    return;
+  }
+
+  uint16_t* raw = reinterpret_cast<uint16_t*>(smem + (size_t)warp * per_warp);
+  uint8_t* score = smem + (size_t)warp * per_warp + raw_bytes;
+
+  // ---- stage the raw window, widened to u16; columns >= tw are zero ----
+  int pitch;
+  const uint8_t* img = raw_level(P, fs, l, f, &pitch);
+  const uint8_t* src = img + (int64_t)iniY * pitch + iniX;
+  for (int r = 0; r < th; r++) {
+    const uint8_t* srow = src + (int64_t)r * pitch;
+    for (int c = lane; c < tp; c += 32) raw[r * tp + c] = c < tw ? (uint16_t)srow[c] : (uint16_t)0;
+  }
+  // ---- clear the score map (1-row / 4-column zero frame around the interior) ----
+  {
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(score);
+    const int words = sp * (ih + 2) / 4;
+    for (int k = lane; k < words; k += 32) s32[k] = 0u;
+  }
+  __syncwarp();
+
+  // ---- threshold-free score of every interior pixel, 4 pixels per lane step ----
+  const int tlow = ini_th < min_th ? ini_th : min_th;
+  const int gpr = (iw + 3) >> 2;
+  const int ngroups = gpr * ih;
+  const float inv_gpr = 1.0f / (float)gpr;
+  for (int G = lane; G < ngroups; G += 32) {
+    const int r = (int)(((float)G + 0.5f) * inv_gpr);
+    const int g = G - r * gpr;
+    // rows r .. r+6 of the tile are dy = -3 .. 3 around interior row r; u16 columns 4g .. 4g+9
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
+    const int rp = tp >> 1;  // words per tile row
+    uint32_t Wm3[5], Wm2[5], Wm1[5], W0[5], Wp1[5], Wp2[5], Wp3[5];
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+      Wm3[c] = base[0 * rp + c];
+      Wm2[c] = base[1 * rp + c];
+      Wm1[c] = base[2 * rp + c];
+      W0[c] = base[3 * rp + c];
+      Wp1[c] = base[4 * rp + c];
+      Wp2[c] = base[5 * rp + c];
+      Wp3[c] = base[6 * rp + c];
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      // ring k = 0..15: (dx, dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+      uint32_t v[16];
+      uint32_t c;
+      if (half == 0) {
+        v[0] = pair_at<3>(Wp3);  v[1] = pair_at<4>(Wp3);  v[2] = pair_at<5>(Wp2);  v[3] = pair_at<6>(Wp1);
+        v[4] = pair_at<6>(W0);   v[5] = pair_at<6>(Wm1);  v[6] = pair_at<5>(Wm2);  v[7] = pair_at<4>(Wm3);
+        v[8] = pair_at<3>(Wm3);  v[9] = pair_at<2>(Wm3);  v[10] = pair_at<1>(Wm2); v[11] = pair_at<0>(Wm1);
+        v[12] = pair_at<0>(W0);  v[13] = pair_at<0>(Wp1); v[14] = pair_at<1>(Wp2); v[15] = pair_at<2>(Wp3);
+        c = pair_at<3>(W0);
+      } else {
+        v[0] = pair_at<5>(Wp3);  v[1] = pair_at<6>(Wp3);  v[2] = pair_at<7>(Wp2);  v[3] = pair_at<8>(Wp1);
+        v[4] = pair_at<8>(W0);   v[5] = pair_at<8>(Wm1);  v[6] = pair_at<7>(Wm2);  v[7] = pair_at<6>(Wm3);
+        v[8] = pair_at<5>(Wm3);  v[9] = pair_at<4>(Wm3);  v[10] = pair_at<3>(Wm2); v[11] = pair_at<2>(Wm1);
+        v[12] = pair_at<2>(W0);  v[13] = pair_at<2>(Wp1); v[14] = pair_at<3>(Wp2); v[15] = pair_at<4>(Wp3);
+        c = pair_at<5>(W0);
+      }
+      uint32_t rhi, rlo;
+      arc_minmax(v, rhi, rlo);
+      out |= score_pair(c, rhi, rlo, tlow) << (16 * half);
+    }
+    // pixels beyond the interior width (last group of a row) must not score
+    const int valid = iw - 4 * g;  // >= 1
+    if (valid < 4) out &= (1u << (8 * valid)) - 1u;
+    *reinterpret_cast<uint32_t*>(score + (r + 1) * sp + 4 + 4 * g) = out;
+  }
+  __syncwarp();
+
+  // ---- per-cell threshold, 3x3 non-max suppression inside the cell interior, ordered emission ----
+  const int npx = iw * ih;
+  const float inv_iw = 1.0f / (float)iw;
+  const int x_off = iniX + 3 - kMinBorder, y_off = iniY + 3 - kMinBorder;  // candidate coords are minBorder-relative
+  int total = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int T = pass == 0 ? ini_th : min_th;
+    total = 0;
+    for (int base = 0; base < npx; base += 32) {
+      const int idx = base + lane;
+      bool keep = false;
+      int s = 0, x = 0, y = 0;
+      if (idx < npx) {
+        y = (int)(((float)idx + 0.5f) * inv_iw);
+        x = idx - y * iw;
+        const uint8_t* sc = score + (y + 1) * sp + 4 + x;
+        s = sc[0];
+        if (s >= T && s > 0) {  // corner at T  <=>  m > T  <=>  score >= T
+          // a neighbour counts with its score if it is a corner at T, else 0 (OpenCV keeps 0 in its score rows)
+          auto eff = [&](int o) { const int n = sc[o]; return n >= T ? n : 0; };
+          keep = s > eff(-1) && s > eff(1) && s > eff(-sp - 1) && s > eff(-sp) && s > eff(-sp + 1) &&
+                 s > eff(sp - 1) && s > eff(sp) && s > eff(sp + 1);
+        }
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      if (keep) slot[total + __popc(mask & ((1u << lane) - 1u))] = cand_pack(x + x_off, y + y_off, s);
+      total += __popc(mask);
+    }
+    if (total > 0) break;  // :946 — retry with minThFAST only when the cell came back empty
+  }
+  if (lane == 0) *count_out = total;
+}
+
+void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_th, int min_th, int frames,
+                 cudaStream_t st) {
+  const FastSmemLayout L = fast_layout(P);
+  const size_t smem = (size_t)L.per_warp * kFastWarps;
+  cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+  dim3 grid((P.cells_per_frame + kFastWarps - 1) / kFastWarps, frames);
+  k_fast<<<grid, kFastWarps * 32, smem, st>>>(P, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes, L.per_warp);
+}
+
+}  // namespace orbx

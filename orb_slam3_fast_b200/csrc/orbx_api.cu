@@ -1,0 +1,499 @@
+// orbx_api.cu — the extern "C" extractor ABI declared in include/orbx.h: handle, device memory, streams, launch order.
+// No result is ever computed on the host: a missing device or a CUDA error is reported as ORBX_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+#include "orbx_kernels.cuh"
+#include "orbx_quadtree.h"
+
+using namespace orbx;
+
+namespace {
+const int8_t kPatternHost[256 * 4] = {
+#include "orb_pattern.inc"
+};
+thread_local std::string g_create_error;
+enum { kStages = 6 };
+}  // namespace
+
+struct orbx_extractor {
+  int device = 0;
+  int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0, max_batch = 1;
+  float scale_factor = 1.2f;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  // geometry-dependent state (rebuilt when the image size changes)
+  bool planned = false;
+  Plan plan;
+  int64_t slab_fstride = 0;
+  int in_pitch = 0;
+  int64_t in_fstride = 0;
+  uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr;
+  ResizeTab* d_tab = nullptr;
+  WorkSet ws{};
+  int8_t* d_pattern = nullptr;
+  // outputs of the host-facing calls
+  int out_cap = 0;
+  orbx_kp* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int32_t *d_n = nullptr, *d_mono = nullptr, *d_status = nullptr;
+  // last call (for downloads / stereo)
+  FrameSet last_fs{};
+  int last_frames = 0;
+  // profiling
+  bool profile = false;
+  cudaEvent_t ev[kStages + 1] = {};
+  float prof_ms[kStages] = {};
+  int prof_launches[kStages] = {};
+};
+
+namespace {
+
+int fail(orbx_extractor* ex, int code, const std::string& msg) {
+  if (ex) ex->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define ORBX_CUDA(ex, call)                                                                              \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      return fail(ex, ORBX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+  } while (0)
+
+void free_plan_buffers(orbx_extractor* ex) {
+  cudaFree(ex->d_in);
+  cudaFree(ex->d_pyr);
+  cudaFree(ex->d_blur);
+  cudaFree(ex->d_tab);
+  cudaFree(ex->ws.slots);
+  cudaFree(ex->ws.cell_count);
+  cudaFree(ex->ws.cand);
+  cudaFree(ex->ws.lab);
+  cudaFree(ex->ws.lvl_kp);
+  cudaFree(ex->ws.lvl_n);
+  cudaFree(ex->ws.lvl_c);
+  cudaFree(ex->ws.dst);
+  ex->d_in = ex->d_pyr = ex->d_blur = nullptr;
+  ex->d_tab = nullptr;
+  ex->ws = WorkSet{};
+  ex->planned = false;
+}
+
+void free_out_buffers(orbx_extractor* ex) {
+  cudaFree(ex->d_kps);
+  cudaFree(ex->d_desc);
+  cudaFree(ex->d_n);
+  cudaFree(ex->d_mono);
+  cudaFree(ex->d_status);
+  ex->d_kps = nullptr;
+  ex->d_desc = nullptr;
+  ex->d_n = ex->d_mono = ex->d_status = nullptr;
+  ex->out_cap = 0;
+}
+
+int ensure_plan(orbx_extractor* ex, int w, int h) {
+  if (ex->planned && ex->plan.w == w && ex->plan.h == h) return ORBX_OK;
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  if (ex->planned) {
+    ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+    free_plan_buffers(ex);
+  }
+  Plan P;
+  const int rc = make_plan(w, h, ex->nfeatures, ex->scale_factor, ex->nlevels, &P);
+  if (rc == -2) return fail(ex, ORBX_E_SIZE, "image too small for the pyramid depth (a level has no 35-px cell)");
+  if (rc == -3) return fail(ex, ORBX_E_SIZE, "image larger than 4096 px");
+  if (rc != 0) return fail(ex, ORBX_E_ARG, "bad extractor parameters");
+  for (int l = 0; l < P.nlevels; l++)
+    if ((int64_t)P.lv[l].nCols * P.lv[l].nRows * P.lv[l].slot_cap >= (1 << 20))
+      return fail(ex, ORBX_E_SIZE, "level too large: more than 2^20 candidate slots");
+  ex->plan = P;
+  const int B = ex->max_batch;
+  ex->slab_fstride = (P.pyr_bytes_per_frame + 255) / 256 * 256;
+  ex->in_pitch = round_up(w, 64);
+  ex->in_fstride = (int64_t)ex->in_pitch * h;
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_in, (size_t)ex->in_fstride * B));
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_pyr, (size_t)ex->slab_fstride * B));
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_blur, (size_t)ex->slab_fstride * B));
+  ORBX_CUDA(ex, cudaMemsetAsync(ex->d_in, 0, (size_t)ex->in_fstride * B, ex->stream));
+  // resize tables
+  std::vector<ResizeTab> tab(std::max(P.tab_entries, 1));
+  {
+    std::vector<int16_t> ofs, c0, c1;
+    for (int l = 1; l < P.nlevels; l++) {
+      const LevelPlan &D = P.lv[l], &S = P.lv[l - 1];
+      for (int axis = 0; axis < 2; axis++) {
+        const int ds = axis ? D.h : D.w, ss = axis ? S.h : S.w;
+        ofs.resize(ds);
+        c0.resize(ds);
+        c1.resize(ds);
+        axis_table(ss, ds, axis == 0, ofs.data(), c0.data(), c1.data());
+        ResizeTab* t = tab.data() + (axis ? D.ytab_off : D.xtab_off);
+        for (int d = 0; d < ds; d++) t[d] = ResizeTab{ofs[d], c0[d], c1[d], 0};
+      }
+    }
+  }
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_tab, tab.size() * sizeof(ResizeTab)));
+  ORBX_CUDA(ex, cudaMemcpyAsync(ex->d_tab, tab.data(), tab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice,
+                                ex->stream));
+  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));  // `tab` goes out of scope
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.slots, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.cand, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lab, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.cell_count, (size_t)P.cells_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lvl_kp, (size_t)P.kps_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.dst, (size_t)P.kps_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lvl_n, (size_t)P.nlevels * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lvl_c, (size_t)P.nlevels * B * 4));
+  ex->planned = true;
+  ex->last_frames = 0;
+  return ORBX_OK;
+}
+
+int ensure_out(orbx_extractor* ex, int cap) {
+  if (ex->out_cap >= cap && ex->d_kps) return ORBX_OK;
+  free_out_buffers(ex);
+  const int B = ex->max_batch;
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_kps, (size_t)cap * B * sizeof(orbx_kp)));
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_desc, (size_t)cap * B * ORBX_DESC_BYTES));
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_n, (size_t)B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_mono, (size_t)B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&ex->d_status, (size_t)B * 4));
+  ex->out_cap = cap;
+  return ORBX_OK;
+}
+
+// The whole extractor for `frames` frames whose level 0 is described by fs.{lvl0,pitch0,fstride0}.
+int run_pipeline(orbx_extractor* ex, FrameSet fs, int frames, int lap0, int lap1, const OutSet& out,
+                 cudaStream_t st) {
+  const Plan& P = ex->plan;
+  fs.pyr = ex->d_pyr;
+  fs.blur = ex->d_blur;
+  fs.slab_fstride = ex->slab_fstride;
+  const bool prof = ex->profile;
+  int stage = 0;
+  auto mark = [&]() {
+    if (prof) cudaEventRecord(ex->ev[stage], st);
+    stage++;
+  };
+  mark();
+  launch_pyramid(P, fs, ex->d_tab, frames, st);
+  mark();
+  launch_fast(P, fs, ex->ws, ex->ini_th, ex->min_th, frames, st);
+  mark();
+  launch_quadtree(P, ex->ws, frames, st);
+  mark();
+  launch_blur(P, fs, frames, st);
+  mark();
+  launch_assemble(P, ex->ws, out, lap0, lap1, frames, st);
+  mark();
+  launch_describe(P, fs, ex->ws, out, ex->d_pattern, frames, st);
+  mark();
+  ORBX_CUDA(ex, cudaGetLastError());
+  if (prof) {
+    ORBX_CUDA(ex, cudaEventSynchronize(ex->ev[kStages]));
+    for (int s = 0; s < kStages; s++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ex->ev[s], ex->ev[s + 1]);
+      ex->prof_ms[s] += ms;
+      ex->prof_launches[s] += 1;
+    }
+  }
+  ex->last_fs = fs;
+  ex->last_frames = frames;
+  return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float scale_factor, int nlevels,
+                          int ini_th_fast, int min_th_fast, int max_batch) {
+  if (!out) return fail(nullptr, ORBX_E_ARG, "out == NULL");
+  *out = nullptr;
+  if (nfeatures < 1 || nlevels < 1 || nlevels > kMaxLevels || !(scale_factor > 1.0f) || max_batch < 1 ||
+      ini_th_fast < 0 || ini_th_fast > 255 || min_th_fast < 0 || min_th_fast > 255)
+    return fail(nullptr, ORBX_E_ARG, "bad extractor parameters");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, ORBX_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, ORBX_E_ARG, "bad device ordinal");
+  orbx_extractor* ex = new orbx_extractor;
+  ex->device = device;
+  ex->nfeatures = nfeatures;
+  ex->scale_factor = scale_factor;
+  ex->nlevels = nlevels;
+  ex->ini_th = ini_th_fast;
+  ex->min_th = min_th_fast;
+  ex->max_batch = max_batch;
+  auto bail = [&](const char* what, cudaError_t ce) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    orbx_extractor_destroy(ex);
+    return ORBX_E_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail("cudaStreamCreate", e);
+  if ((e = cudaMalloc(&ex->d_pattern, sizeof(kPatternHost))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaMemcpy(ex->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail("cudaMemcpy", e);
+  for (auto& ev : ex->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  *out = ex;
+  return ORBX_OK;
+}
+
+void orbx_extractor_destroy(orbx_extractor* ex) {
+  if (!ex) return;
+  cudaSetDevice(ex->device);
+  if (ex->stream) cudaStreamSynchronize(ex->stream);
+  free_plan_buffers(ex);
+  free_out_buffers(ex);
+  cudaFree(ex->d_pattern);
+  for (auto& ev : ex->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ex->stream) cudaStreamDestroy(ex->stream);
+  delete ex;
+}
+
+const char* orbx_last_error(const orbx_extractor* ex) { return ex ? ex->err.c_str() : g_create_error.c_str(); }
+
+int orbx_extractor_levels(const orbx_extractor* ex) { return ex ? ex->nlevels : ORBX_E_ARG; }
+
+int orbx_extractor_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                          int32_t* features_per_level) {
+  if (!ex) return ORBX_E_ARG;
+  Plan P;  // the tables do not depend on the image size; use a size every level count accepts
+  if (make_plan(4096, 4096, ex->nfeatures, ex->scale_factor, ex->nlevels, &P) != 0) return ORBX_E_ARG;
+  for (int l = 0; l < ex->nlevels; l++) {
+    if (scale) scale[l] = P.lv[l].scale;
+    if (inv_scale) inv_scale[l] = P.lv[l].inv_scale;
+    if (sigma2) sigma2[l] = P.lv[l].sigma2;
+    if (inv_sigma2) inv_sigma2[l] = P.lv[l].inv_sigma2;
+    if (features_per_level) features_per_level[l] = P.lv[l].quota;
+  }
+  return ORBX_OK;
+}
+
+int orbx_extractor_capacity(const orbx_extractor* ex) {
+  if (!ex) return ORBX_E_ARG;
+  // every level may overshoot its quota by 3 (or return the 4*nIni nodes of the first split when the quota is tiny)
+  return ex->nfeatures + 16 * ex->nlevels;
+}
+
+int orbx_extract_batch_device(orbx_extractor* ex, int n_frames, const uint8_t* d_images, int width, int height,
+                              int stride, int64_t frame_stride, int lap0, int lap1, orbx_kp* d_kps, uint8_t* d_desc,
+                              int cap, int32_t* d_n, int32_t* d_mono_index, int32_t* d_status, void* cuda_stream) {
+  if (!ex) return ORBX_E_ARG;
+  if (!d_images || width <= 0 || height <= 0 || n_frames <= 0) return fail(ex, ORBX_E_EMPTY, "empty image");
+  if (n_frames > ex->max_batch) return fail(ex, ORBX_E_ARG, "n_frames > max_batch");
+  if (stride < width || !d_kps || !d_desc || !d_n || !d_mono_index || !d_status || cap < 1)
+    return fail(ex, ORBX_E_ARG, "bad argument");
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  int rc = ensure_plan(ex, width, height);
+  if (rc) return rc;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->stream;
+  FrameSet fs{};
+  fs.lvl0 = d_images;
+  fs.pitch0 = stride;
+  fs.fstride0 = frame_stride;
+  OutSet out{d_kps, d_desc, d_n, d_mono_index, d_status, cap};
+  return run_pipeline(ex, fs, n_frames, lap0, lap1, out, st);
+}
+
+int orbx_extract_batch(orbx_extractor* ex, int n_frames, const uint8_t* images, int width, int height, int stride,
+                       int64_t frame_stride, int lap0, int lap1, orbx_kp* kps, uint8_t* desc, int cap,
+                       int32_t* n_out, int32_t* mono_index) {
+  if (!ex) return ORBX_E_ARG;
+  if (!images || width <= 0 || height <= 0 || n_frames <= 0) return fail(ex, ORBX_E_EMPTY, "empty image");
+  if (stride < width || !kps || !desc || !n_out || cap < 1) return fail(ex, ORBX_E_ARG, "bad argument");
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  int rc = ensure_plan(ex, width, height);
+  if (rc) return rc;
+  rc = ensure_out(ex, cap);
+  if (rc) return rc;
+  cudaStream_t st = ex->stream;
+  std::vector<int32_t> status(ex->max_batch), mono(ex->max_batch);
+  int first_err = ORBX_OK;
+  for (int f0 = 0; f0 < n_frames; f0 += ex->max_batch) {
+    const int nb = std::min(ex->max_batch, n_frames - f0);
+    const uint8_t* src = images + (int64_t)f0 * frame_stride;
+    if (frame_stride == (int64_t)stride * height) {
+      ORBX_CUDA(ex, cudaMemcpy2DAsync(ex->d_in, ex->in_pitch, src, stride, width, (size_t)height * nb,
+                                      cudaMemcpyHostToDevice, st));
+    } else {
+      for (int f = 0; f < nb; f++)
+        ORBX_CUDA(ex, cudaMemcpy2DAsync(ex->d_in + f * ex->in_fstride, ex->in_pitch, src + f * frame_stride, stride,
+                                        width, height, cudaMemcpyHostToDevice, st));
+    }
+    FrameSet fs{};
+    fs.lvl0 = ex->d_in;
+    fs.pitch0 = ex->in_pitch;
+    fs.fstride0 = ex->in_fstride;
+    OutSet out{ex->d_kps, ex->d_desc, ex->d_n, ex->d_mono, ex->d_status, ex->out_cap};
+    rc = run_pipeline(ex, fs, nb, lap0, lap1, out, st);
+    if (rc) return rc;
+    ORBX_CUDA(ex, cudaMemcpyAsync(n_out + f0, ex->d_n, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(ex, cudaMemcpyAsync(mono.data(), ex->d_mono, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(ex, cudaMemcpyAsync(status.data(), ex->d_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    // rows: device arrays are [nb][out_cap], the caller's are [n_frames][cap]
+    ORBX_CUDA(ex, cudaMemcpy2DAsync(kps + (int64_t)f0 * cap, (size_t)cap * sizeof(orbx_kp), ex->d_kps,
+                                    (size_t)ex->out_cap * sizeof(orbx_kp), (size_t)cap * sizeof(orbx_kp), nb,
+                                    cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(ex, cudaMemcpy2DAsync(desc + (int64_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES,
+                                    ex->d_desc, (size_t)ex->out_cap * ORBX_DESC_BYTES,
+                                    (size_t)cap * ORBX_DESC_BYTES, nb, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(ex, cudaStreamSynchronize(st));
+    for (int f = 0; f < nb; f++) {
+      if (mono_index) mono_index[f0 + f] = mono[f];
+      if ((status[f] != 0 || n_out[f0 + f] > cap) && first_err == ORBX_OK) first_err = ORBX_E_CAPACITY;
+    }
+  }
+  if (first_err) return fail(ex, first_err, "output capacity too small for at least one frame");
+  return ORBX_OK;
+}
+
+int orbx_extract(orbx_extractor* ex, const uint8_t* image, int width, int height, int stride, int lap0, int lap1,
+                 orbx_kp* kps, uint8_t* desc, int cap, int32_t* n_out, int32_t* mono_index) {
+  int32_t n = 0, mono = 0;
+  const int rc = orbx_extract_batch(ex, 1, image, width, height, stride, (int64_t)stride * height, lap0, lap1, kps,
+                                    desc, cap, &n, &mono);
+  if (n_out) *n_out = n;
+  if (mono_index) *mono_index = mono;
+  return rc;
+}
+
+int orbx_level_size(const orbx_extractor* ex, int level, int* width, int* height) {
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels) return ORBX_E_ARG;
+  if (width) *width = ex->plan.lv[level].w;
+  if (height) *height = ex->plan.lv[level].h;
+  return ORBX_OK;
+}
+
+int orbx_debug_level(orbx_extractor* ex, int frame, int level, int which, uint8_t* dst, int dst_stride) {
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames || !dst)
+    return ORBX_E_ARG;
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  const LevelPlan& L = ex->plan.lv[level];
+  const FrameSet& fs = ex->last_fs;
+  const uint8_t* src;
+  int pitch;
+  if (which == 1) {
+    src = fs.blur + (int64_t)frame * fs.slab_fstride + L.img_off;
+    pitch = L.pitch;
+  } else if (level == 0) {
+    src = fs.lvl0 + (int64_t)frame * fs.fstride0;
+    pitch = fs.pitch0;
+  } else {
+    src = fs.pyr + (int64_t)frame * fs.slab_fstride + L.img_off;
+    pitch = L.pitch;
+  }
+  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+  ORBX_CUDA(ex, cudaMemcpy2D(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+  return ORBX_OK;
+}
+
+int orbx_download_pyramid(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride) {
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || !dst) return ORBX_E_ARG;
+  const LevelPlan& L = ex->plan.lv[level];
+  if (dst_stride < L.w + 2 * kEdge) return fail(ex, ORBX_E_ARG, "dst_stride < w + 38");
+  // interior first, then the reflect-101 frame is a pure copy of interior pixels (cv::copyMakeBorder, :1129-1143)
+  uint8_t* roi = dst + (size_t)kEdge * dst_stride + kEdge;
+  int rc = orbx_debug_level(ex, frame, level, 0, roi, dst_stride);
+  if (rc) return rc;
+  for (int y = 0; y < L.h; y++) {
+    uint8_t* row = roi + (size_t)y * dst_stride;
+    for (int x = 1; x <= kEdge; x++) {
+      row[-x] = row[reflect101(-x, L.w)];
+      row[L.w - 1 + x] = row[reflect101(L.w - 1 + x, L.w)];
+    }
+  }
+  for (int y = 1; y <= kEdge; y++) {
+    memcpy(dst + (size_t)(kEdge - y) * dst_stride, dst + (size_t)(kEdge + reflect101(-y, L.h)) * dst_stride,
+           L.w + 2 * kEdge);
+    memcpy(dst + (size_t)(kEdge + L.h - 1 + y) * dst_stride,
+           dst + (size_t)(kEdge + reflect101(L.h - 1 + y, L.h)) * dst_stride, L.w + 2 * kEdge);
+  }
+  return ORBX_OK;
+}
+
+static void unpack_kp(uint32_t cw, int add, int level, float size, orbx_kp* k) {
+  k->x = (float)(cand_x(cw) + add);
+  k->y = (float)(cand_y(cw) + add);
+  k->size = size;
+  k->angle = -1.f;
+  k->response = (float)cand_s(cw);
+  k->octave = level;
+  k->class_id = -1;
+}
+
+int orbx_debug_candidates(orbx_extractor* ex, int frame, int level, orbx_kp* out, int cap) {
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames)
+    return ORBX_E_ARG;
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+  const Plan& P = ex->plan;
+  int32_t C = 0;
+  ORBX_CUDA(ex, cudaMemcpy(&C, ex->ws.lvl_c + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+  const int n = std::min(C, cap);
+  std::vector<uint32_t> buf(std::max(n, 1));
+  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->ws.cand + (int64_t)frame * P.slots_per_frame + P.lv[level].slot_base,
+                           (size_t)n * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n && out; i++) unpack_kp(buf[i], 0, 0, 7.f, out + i);
+  return C;
+}
+
+int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp* out, int cap) {
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames)
+    return ORBX_E_ARG;
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+  const Plan& P = ex->plan;
+  int32_t C = 0;
+  ORBX_CUDA(ex, cudaMemcpy(&C, ex->ws.lvl_n + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+  const int n = std::min(C, cap);
+  std::vector<uint32_t> buf(std::max(n, 1));
+  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->ws.lvl_kp + (int64_t)frame * P.kps_per_frame + P.lv[level].kp_base,
+                           (size_t)n * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n && out; i++) unpack_kp(buf[i], kMinBorder, level, (float)P.lv[level].patch, out + i);
+  return C;
+}
+
+int orbx_profile_enable(orbx_extractor* ex, int on) {
+  if (!ex) return ORBX_E_ARG;
+  ex->profile = on != 0;
+  return ORBX_OK;
+}
+
+int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int reset) {
+  if (!ex) return ORBX_E_ARG;
+  for (int s = 0; s < kStages; s++) {
+    if (ms) ms[s] = ex->prof_ms[s];
+    if (launches) launches[s] = ex->prof_launches[s];
+    if (reset) {
+      ex->prof_ms[s] = 0;
+      ex->prof_launches[s] = 0;
+    }
+  }
+  return ORBX_OK;
+}
+
+void* orbx_host_alloc(int64_t bytes) {
+  void* p = nullptr;
+  if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void orbx_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Parity of the CUDA extractor (through the C ABI) with the CPU oracle, stage by stage and end to end.
+
+Bar (BASELINE.json north_star): bit-exact keypoint coordinates / octave / descriptors; angle and response within 1e-4
+(they are in fact compared bit-exactly here, the tolerance is only the documented bar).
+"""
+import numpy as np
+import pytest
+
+from orb_slam3_fast_b200 import ORBextractor, OrbxError, synth
+from oracle import orbref
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL = 1e-4
+
+
+def _compare_frame(ex_ref, kps, desc, mono, img, lap, tag):
+    mono_r, kps_r, desc_r = ex_ref(img, lap)
+    assert len(kps) == len(kps_r), "%s: keypoint count %d vs oracle %d" % (tag, len(kps), len(kps_r))
+    assert mono == mono_r, "%s: monoIndex %d vs %d" % (tag, mono, mono_r)
+    for fld in ("x", "y", "size", "octave", "class_id", "response"):
+        bad = np.nonzero(kps[fld] != kps_r[fld])[0]
+        assert len(bad) == 0, "%s: field %s differs at %s" % (tag, fld, bad[:10])
+    da = np.abs(kps["angle"] - kps_r["angle"])
+    assert (da <= ANGLE_TOL).all(), "%s: angle differs by up to %g" % (tag, da.max())
+    assert (kps["angle"] == kps_r["angle"]).all(), "%s: angle not bit-exact (max diff %g)" % (tag, da.max())
+    bad = np.nonzero((desc != desc_r).any(axis=1))[0]
+    assert len(bad) == 0, "%s: %d descriptors differ, first rows %s" % (tag, len(bad), bad[:10])
+
+
+def _stage_check(ex, ex_ref, tag):
+    for l in range(ex.nlevels):
+        assert ex.level_size(l) == ex_ref.level_dims(l), "%s: level %d size" % (tag, l)
+        raw, raw_r = ex.debug_level(l), ex_ref.level_image(l)
+        assert np.array_equal(raw, raw_r), "%s: pyramid level %d differs in %d px" % (tag, l, (raw != raw_r).sum())
+    for l in range(ex.nlevels):
+        c, c_r = ex.debug_candidates(l), ex_ref.level_candidates(l)
+        assert len(c) == len(c_r), "%s: level %d candidates %d vs %d" % (tag, l, len(c), len(c_r))
+        for fld in ("x", "y", "response"):
+            assert np.array_equal(c[fld], c_r[fld]), "%s: level %d candidate %s" % (tag, l, fld)
+    for l in range(ex.nlevels):
+        k, k_r = ex.debug_level_keypoints(l), ex_ref.level_keypoints(l)
+        assert len(k) == len(k_r), "%s: level %d quadtree count %d vs %d" % (tag, l, len(k), len(k_r))
+        for fld in ("x", "y", "response", "size", "octave"):
+            assert np.array_equal(k[fld], k_r[fld]), "%s: level %d quadtree %s" % (tag, l, fld)
+    for l in range(ex.nlevels):
+        b_r = ex_ref.level_blurred(l)
+        if b_r is None:
+            continue
+        b = ex.debug_level(l, blurred=True)
+        assert np.array_equal(b, b_r), "%s: blurred level %d differs in %d px" % (tag, l, (b != b_r).sum())
+
+
+CASES = [
+    ("scene", 480, 640, 1000, (0, 0)),
+    ("scene", 480, 640, 1000, (0, 1000)),   # monocular lapping: everything written from the back
+    ("scene", 480, 752, 1200, (0, 0)),
+    ("noise_blur", 480, 640, 1000, (0, 0)),
+    ("uniform_noise", 480, 640, 1000, (0, 0)),
+    ("scene", 720, 1280, 2000, (0, 1000)),
+    ("scene", 241, 241, 500, (0, 0)),        # minimum size for 8 levels
+    ("scene", 300, 900, 300, (100, 500)),    # 3 root nodes, partial lapping
+]
+
+
+@pytest.mark.parametrize("kind,h,w,nf,lap", CASES)
+def test_extract_matches_oracle(gpu, kind, h, w, nf, lap):
+    img = synth.make(kind, h, w, seed=3)
+    ex = ORBextractor(nf)
+    ex_ref = orbref.Extractor(nf)
+    mono, kps, desc = ex(img, lap)
+    tag = "%s %dx%d nf=%d" % (kind, w, h, nf)
+    mono_r, kps_r, desc_r = ex_ref(img, lap)
+    _stage_check(ex, ex_ref, tag)
+    _compare_frame(ex_ref, kps, desc, mono, img, lap, tag)
+
+
+def test_low_contrast_uses_min_threshold(gpu):
+    img = synth.low_contrast(480, 640, seed=1)
+    ex, ex_ref = ORBextractor(1000), orbref.Extractor(1000)
+    mono, kps, desc = ex(img)
+    ex_ref(img, (0, 0))
+    _stage_check(ex, ex_ref, "low_contrast")
+    _compare_frame(ex_ref, kps, desc, mono, img, (0, 0), "low_contrast")
+
+
+def test_constant_image_gives_no_keypoints(gpu):
+    ex = ORBextractor(1000)
+    mono, kps, desc = ex(synth.constant(480, 640))
+    assert mono == 0 and len(kps) == 0 and desc.shape == (0, 32)
+
+
+def test_empty_image_returns_minus_one(gpu):
+    ex = ORBextractor(1000)
+    mono, kps, desc = ex(np.empty((0, 0), np.uint8))
+    assert mono == -1 and len(kps) == 0
+
+
+def test_too_small_image_is_an_error(gpu):
+    ex = ORBextractor(1000)
+    with pytest.raises(OrbxError) as e:
+        ex(synth.scene(100, 100, 0))
+    assert e.value.code == -5
+
+
+def test_strided_input_and_size_change(gpu):
+    big = synth.scene(500, 700, seed=5)
+    view = big[10:490, 20:660]  # non-contiguous rows
+    ex, ex_ref = ORBextractor(1000), orbref.Extractor(1000)
+    mono, kps, desc = ex(view)
+    _compare_frame(ex_ref, kps, desc, mono, np.ascontiguousarray(view), (0, 0), "strided")
+    img2 = synth.scene(480, 752, seed=6)  # same handle, new geometry
+    mono, kps, desc = ex(img2)
+    _compare_frame(ex_ref, kps, desc, mono, img2, (0, 0), "resized")
+
+
+def test_batch_matches_single_and_oracle(gpu):
+    imgs = np.stack([synth.make(k, 480, 640, s) for s, k in enumerate(["scene", "noise_blur", "scene", "uniform_noise",
+                                                                        "scene"])])
+    ex = ORBextractor(1000, max_batch=3)  # 5 frames through groups of 3 + 2
+    ex_ref = orbref.Extractor(1000)
+    n, mono, kps, desc = ex.extract_batch(imgs, (0, 0))
+    for f in range(len(imgs)):
+        _compare_frame(ex_ref, kps[f, :n[f]], desc[f, :n[f]], mono[f], imgs[f], (0, 0), "batch frame %d" % f)
+
+
+def test_host_pyramid_mirror_has_reference_border(gpu):
+    img = synth.scene(480, 640, seed=9)
+    ex, ex_ref = ORBextractor(1000), orbref.Extractor(1000)
+    ex(img)
+    ex_ref(img, (0, 0))
+    for l in (0, 3, 7):
+        assert np.array_equal(ex.image_pyramid_bordered(l), ex_ref.level_bordered(l)), "level %d" % l
+
+
+def test_other_parameters(gpu):
+    img = synth.scene(480, 640, seed=11)
+    for nf, sf, nl, it, mt in ((500, 1.2, 4, 20, 7), (1500, 1.1, 8, 15, 5), (5000, 1.2, 8, 20, 7), (300, 1.5, 3, 30, 10)):
+        ex = ORBextractor(nf, sf, nl, it, mt)
+        ex_ref = orbref.Extractor(nf, sf, nl, it, mt)
+        assert np.array_equal(ex.mnFeaturesPerLevel, ex_ref.features_per_level)
+        assert np.array_equal(ex.GetScaleFactors(), ex_ref.scale)
+        mono, kps, desc = ex(img)
+        _compare_frame(ex_ref, kps, desc, mono, img, (0, 0), "params %s" % ((nf, sf, nl, it, mt),))
