@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the ORB front-end hot path on B200 (driver contract: see the task statement / DESIGN.md).
+
+Workload (BASELINE.json configs[1]): EuRoC-shaped 752x480 rectified stereo pairs, 1200 features per eye, 8 levels,
+scale 1.2, FAST 20/7: ORBextractor::operator() for both eyes + Frame::ComputeStereoMatches. One "step" = one batch of
+`--pairs` independent pairs per GPU (frames are independent: weak scaling, no data-path collective; the only
+collective is the gather of the per-pair result counts). A stereo pair counts as 2 frames (2 ORBextractor calls).
+
+  value  device-resident: images already in HBM, results left in HBM, CUDA events on the launching stream.
+  e2e    the same batch through the host-facing C ABI call orbm_stereo_frames_batch (pinned host buffers in and out,
+         H2D / D2H inside the timed region).
+  --impl reference: the CPU oracle port of the reference (oracle/liborbref.so) on all host cores, same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 752, 480, 1200, 8, 1.2, 20, 7
+FX, BASELINE_M = 435.2, 0.11  # EuRoC-like rectified focal length / baseline
+MBF, MB = float(np.float32(FX * BASELINE_M)), float(np.float32(BASELINE_M))
+METRIC = "frames/sec ORB extract+match (752x480 stereo pairs, 1200 feat/eye, extract + ComputeStereoMatches)"
+WORKLOAD = "configs[1]: EuRoC-shaped 752x480 stereo pair, 1200 features/eye, extract + ComputeStereoMatches"
+KERNELS_PER_EXTRACT = (NLEVELS - 1) + 1 + 1 + NLEVELS + 1 + 1  # resize x7, fast, quadtree, blur x8, assemble, describe
+KERNELS_PER_STEP = 2 * KERNELS_PER_EXTRACT + 2                 # + stereo match + stereo median
+
+
+def make_pairs(n_distinct, seed0):
+    from orb_slam3_fast_b200 import synth
+    L, R = [], []
+    for s in range(n_distinct):
+        l, r, _ = synth.stereo_pair(H, W, seed0 + s)
+        L.append(l)
+        R.append(r)
+    return np.stack(L), np.stack(R)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(n_pairs, threads, seed0=1000):
+    """Times the oracle port (extract x2 + ComputeStereoMatches per pair) on `threads` host threads."""
+    from oracle import orbref
+    L, R = make_pairs(min(n_pairs, 8), seed0)
+    reps = (n_pairs + len(L) - 1) // len(L)
+    L = np.ascontiguousarray(np.tile(L, (reps, 1, 1))[:n_pairs])
+    R = np.ascontiguousarray(np.tile(R, (reps, 1, 1))[:n_pairs])
+    orbref.lib()
+    t0 = time.perf_counter()
+    orbref.stereo_many(L, R, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, MBF, MB, threads)
+    dt = time.perf_counter() - t0
+    return 2.0 * n_pairs / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # bounded sample: calibrate on one pair per core, then size each step to ~4 s of wall time
+    fps1, dt1 = cpu_reference_run(cores, cores)
+    per_step = max(cores, int(4.0 / max(dt1, 1e-3) * cores))
+    per_step = min(per_step, 4096)
+    for _ in range(args.warmup):
+        cpu_reference_run(per_step, cores)
+    total = 0.0  # only the oracle calls are timed, not the synthetic image generation
+    for _ in range(args.steps):
+        total += cpu_reference_run(per_step, cores)[1]
+    fps = 2.0 * per_step * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_step": per_step, "frames_per_step": 2 * per_step,
+                       "note": "CPU oracle port of the reference's serial path, pair-parallel over all host threads; "
+                               "the reference itself needs OpenCV/TBB/Eigen C++ and cannot be built here"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": "%d stereo pairs per step x %d steps" % (per_step, args.steps)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="orbx")
+    ap.add_argument("--pairs", type=int, default=256, help="stereo pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs tiled into a batch")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from orb_slam3_fast_b200 import ORBextractor, ORBmatcher
+    from orb_slam3_fast_b200.lib import KP_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = args.pairs
+    exl = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=P)
+    exr = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=P)
+    mt = ORBmatcher(0.6, True, device=local)
+    cap = exl.capacity
+
+    # ---- synthetic data: `distinct` seeded pairs per rank, tiled to a batch; two rotating batches in HBM ----
+    Ld, Rd = make_pairs(args.distinct, 100 * rank)
+    reps = (P + args.distinct - 1) // args.distinct
+    n_rot = 2
+    hostL = [np.ascontiguousarray(np.tile(np.roll(Ld, k, axis=0), (reps, 1, 1))[:P]) for k in range(n_rot)]
+    hostR = [np.ascontiguousarray(np.tile(np.roll(Rd, k, axis=0), (reps, 1, 1))[:P]) for k in range(n_rot)]
+    devL = [torch.from_numpy(a).to(dev) for a in hostL]
+    devR = [torch.from_numpy(a).to(dev) for a in hostR]
+
+    def dev_out():
+        return dict(kps=torch.empty((P, cap, 7), dtype=torch.int32, device=dev),
+                    desc=torch.empty((P, cap, 32), dtype=torch.uint8, device=dev),
+                    n=torch.empty(P, dtype=torch.int32, device=dev), mono=torch.empty(P, dtype=torch.int32, device=dev),
+                    status=torch.empty(P, dtype=torch.int32, device=dev))
+    oL, oR = dev_out(), dev_out()
+    d_ur = torch.empty((P, cap), dtype=torch.float32, device=dev)
+    d_dp = torch.empty((P, cap), dtype=torch.float32, device=dev)
+    d_nm = torch.empty(P, dtype=torch.int32, device=dev)
+    gathered = torch.empty((world, 3, P), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step_device(k):
+        st = torch.cuda.current_stream().cuda_stream
+        for ex, imgs, o in ((exl, devL[k % n_rot], oL), (exr, devR[k % n_rot], oR)):
+            ex.extract_batch_device(imgs.data_ptr(), P, W, H, W, W * H, (0, 0), o["kps"].data_ptr(),
+                                    o["desc"].data_ptr(), cap, o["n"].data_ptr(), o["mono"].data_ptr(),
+                                    o["status"].data_ptr(), st)
+        mt.ComputeStereoMatches_device(exl, exr, P, oL["kps"].data_ptr(), oL["desc"].data_ptr(), oL["n"].data_ptr(),
+                                       oR["kps"].data_ptr(), oR["desc"].data_ptr(), oR["n"].data_ptr(), cap, MBF, MB,
+                                       d_ur.data_ptr(), d_dp.data_ptr(), d_nm.data_ptr(), st)
+        if world > 1:  # the trivial result gather: per-pair counts of every rank
+            dist.all_gather_into_tensor(gathered, torch.stack((oL["n"], oR["n"], d_nm)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity gate on this configuration before any timing (rank 0, 2 pairs, CPU oracle as the checker) ----
+    parity = "skipped"
+    if rank == 0:
+        from oracle import orbref
+        out = mt.StereoFramesBatch(exl, exr, hostL[0][:2], hostR[0][:2], MBF, MB)
+        rl, rr = orbref.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH), orbref.Extractor(NFEAT, SCALE, NLEVELS,
+                                                                                           INI_TH, MIN_TH)
+        for i in range(2):
+            _, kl, dl = rl(hostL[0][i], (0, 0))
+            _, kr, dr = rr(hostR[0][i], (0, 0))
+            nm, ur, dp = orbref.stereo_match(rl, rr, kl, dl, kr, dr, MBF, MB)
+            nl, nr = int(out["n_l"][i]), int(out["n_r"][i])
+            ok = (nl == len(kl) and nr == len(kr) and np.array_equal(out["kps_l"][i, :nl], kl) and
+                  np.array_equal(out["desc_l"][i, :nl], dl) and np.array_equal(out["desc_r"][i, :nr], dr) and
+                  int(out["n_matched"][i]) == nm and np.array_equal(out["u_right"][i, :nl], ur) and
+                  np.array_equal(out["depth"][i, :nl], dp))
+            if not ok:
+                raise SystemExit("bench.py: parity check against the oracle FAILED on pair %d — not timing" % i)
+        parity = "bit-exact vs oracle on 2 pairs (keypoints, descriptors, uRight, depth)"
+
+    # ---- device-resident timing ----
+    for k in range(args.warmup):
+        step_device(k)
+    barrier()
+    exl.profile(True)
+    exr.profile(True)
+    exl.profile_read(True)
+    exr.profile_read(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        step_device(k)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    stage_ms_l, stage_cnt = exl.profile_read(True)
+    stage_ms_r, _ = exr.profile_read(True)
+    exl.profile(False)
+    exr.profile(False)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    frames_per_step = 2 * P * world
+    value = frames_per_step * args.steps / (ms * 1e-3)
+    status_ok = bool((oL["status"] == 0).all().item() and (oR["status"] == 0).all().item())
+    n_keypoints = float(oL["n"].float().mean().item())
+    matched = float(d_nm.float().mean().item())
+
+    # ---- roofline of the dominant kernel (stage times from CUDA events on the launching stream, timed region) ----
+    stage_ms = {k: stage_ms_l[k] + stage_ms_r[k] for k in stage_ms_l}
+    launches = stage_cnt["fast"] * 2  # one k_fast launch per extract call
+    dom = max(stage_ms, key=stage_ms.get)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # candidates per frame (C) from a few frames of the last batch
+    C = 0
+    for f in range(4):
+        C += sum(exl._check(exl._L.orbx_debug_candidates(exl._h, f, l, None, 0)) for l in range(NLEVELS))
+    C /= 4.0
+    sumP = sum(exl.level_size(l)[0] * exl.level_size(l)[1] for l in range(NLEVELS))
+    P0 = W * H
+    Nk = n_keypoints
+    alg_bytes_per_frame = {
+        "pyramid": P0 + sumP, "fast": sumP + 8 * C, "blur": 2 * sumP, "describe": (749 + 1849 + 32 + 28) * Nk,
+        "quadtree": 8 * C + 4 * Nk, "assemble": 8 * Nk}
+    dur_ms = stage_ms[dom] / max(stage_cnt[dom] * 2, 1)   # per extract call (one batch of P frames)
+    achieved = alg_bytes_per_frame[dom] * P / (dur_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "ms_per_launch_group": dur_ms, "algorithmic_bytes_per_frame": alg_bytes_per_frame[dom],
+                "frames_per_launch": P,
+                "note": "FAST / quadtree are integer-ALU / latency bound, not HBM bound (SURVEY.md §8d); the HBM "
+                        "fraction is reported as the contract asks, the ALU analysis is in DESIGN.md",
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+
+    # ---- end to end through the host-facing ABI (pinned buffers; H2D + D2H inside the timed region) ----
+    def pinned(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        tbuf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        arr = tbuf.numpy()[:nbytes].view(dtype).reshape(shape)
+        pinned.keep.append(tbuf)
+        return arr
+    pinned.keep = []
+    pinL = [pinned(a.shape, np.uint8) for a in hostL]
+    pinR = [pinned(a.shape, np.uint8) for a in hostR]
+    for k in range(n_rot):
+        pinL[k][...] = hostL[k]
+        pinR[k][...] = hostR[k]
+    # the fused call pipelines groups of max_batch pairs over two lanes: use smaller groups than the resident batch
+    G = max(8, P // 8)
+    exl2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
+    exr2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
+    outs = ORBmatcher.alloc_stereo_outputs(P, cap, empty=pinned)
+    e2e_steps = args.e2e_steps or args.steps
+    for k in range(max(3, args.warmup // 2)):
+        mt.StereoFramesBatch(exl2, exr2, pinL[k % n_rot], pinR[k % n_rot], MBF, MB, outs)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        mt.StereoFramesBatch(exl2, exr2, pinL[k % n_rot], pinR[k % n_rot], MBF, MB, outs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    e2e_val = frames_per_step * e2e_steps / dt
+    h2d = 2 * P * W * H
+    d2h = P * (2 * cap * (KP_DTYPE.itemsize + 32) + 2 * cap * 4 + 3 * 4 * 3)
+    e2e = {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "orbm_stereo_frames_batch (host buffers, pinned)", "ms_per_step": 1e3 * dt / e2e_steps,
+           "group_pairs": G, "timer": "host wall clock around the synchronous ABI calls, max over ranks"}
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N = 1 only ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _, dt1 = cpu_reference_run(cores, cores)
+        n_pairs = int(min(max(cores, 15.0 / max(dt1, 1e-3) * cores), 8192))
+        fps, dtc = cpu_reference_run(n_pairs, cores)
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "%d stereo pairs (752x480, 1200 feat/eye), oracle port pair-parallel on %d threads, %.1f s"
+                         % (n_pairs, cores, dtc)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "frames_per_step": frames_per_step,
+                           "frame_definition": "one ORBextractor call (a stereo pair = 2 frames)",
+                           "distinct_synthetic_pairs_per_rank": args.distinct,
+                           "l2": "per-step working set (%d frames x ~5.5 MB of pyramid/blur/candidate scratch) far "
+                                 "exceeds the 126 MB L2; two input batches alternate" % (2 * P),
+                           "keypoints_per_frame": n_keypoints, "candidates_per_frame": C,
+                           "stereo_matches_per_pair": matched, "all_frames_within_capacity": status_ok,
+                           "parity": parity, "parallelism": "frames sharded over GPUs, no data-path collective"},
+                "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": clk, "e2e": e2e, "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

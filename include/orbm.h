@@ -1,0 +1,104 @@
+/* orbm.h — C ABI of the Hamming searches of the ORB front-end (liborbx.so).
+ *
+ * Replaces, behind unchanged C++ signatures (shim/), the data-parallel part of ORB_SLAM3::ORBmatcher
+ * (include/ORBmatcher.h:38-133), Frame::ComputeStereoMatches (src/Frame.cc:921-1084) and the brute-force
+ * cv::BFMatcher::knnMatch call of Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1293). The C++ shim flattens the
+ * reference's pointer graph (MapPoint*, KeyFrame*, DBoW2::FeatureVector) into the SoA / CSR views of orbx_types.h and
+ * scatters the results back.
+ *
+ * Conventions as in orbx.h. A matcher context owns a CUDA stream and grow-only device scratch; ORBmatcher objects are
+ * per-call temporaries used concurrently from the Tracking / LocalMapping / LoopClosing threads
+ * (src/Tracking.cc:2784, src/LocalMapping.cc:435), so keep one context per thread.
+ */
+#ifndef ORBM_H_
+#define ORBM_H_
+
+#include <stdint.h>
+
+#include "orbx.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBM_TH_LOW 50        /* ORBmatcher::TH_LOW       src/ORBmatcher.cc:36 */
+#define ORBM_TH_HIGH 100      /* ORBmatcher::TH_HIGH      src/ORBmatcher.cc:35 */
+#define ORBM_HISTO_LENGTH 30  /* ORBmatcher::HISTO_LENGTH src/ORBmatcher.cc:37 */
+
+typedef struct orbm_matcher orbm_matcher;
+
+int orbm_create(orbm_matcher** out, int device);
+void orbm_destroy(orbm_matcher* m);
+const char* orbm_last_error(const orbm_matcher* m);
+
+/* static int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) (src/ORBmatcher.cc:1959-1973) for
+ * n pairs at once: a[n][32], b[n][32] -> dist[n] (host buffers). The single-pair form is an inline popcount in the
+ * shim header; a device launch per pair would be absurd. */
+int orbm_descriptor_distance_batch(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
+
+/* cv::BFMatcher(cv::NORM_HAMMING).knnMatch(query, train, matches, 2) (src/Frame.cc:1293): for every query row the two
+ * train rows minimising (distance, trainIdx). idx = -1 and dist = -1 where the train set has fewer than 1 / 2 rows.
+ * Host buffers: q[nq][32], t[nt][32], outputs [nq]. */
+int orbm_knn2(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx1, int32_t* d1,
+              int32_t* idx2, int32_t* d2);
+/* Same with every pointer in device memory; enqueued on cuda_stream (NULL = the context's stream), not synchronised. */
+int orbm_knn2_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_idx1,
+                     int32_t* d_d1, int32_t* d_idx2, int32_t* d_d2, void* cuda_stream);
+
+/* void Frame::ComputeStereoMatches() (src/Frame.cc:921-1084). `left` / `right` are the extractors whose LAST call
+ * produced the pyramids of this pair (mpORBextractorLeft/Right->mvImagePyramid, :927,1011,1029); `frame` selects the
+ * frame of that call. kps / desc are mvKeys, mDescriptors, mvKeysRight, mDescriptorsRight (host). mbf, mb as in Frame.
+ * Outputs (host): u_right[n_l] = mvuRight, depth[n_l] = mvDepth (-1 = no match); *n_matched = surviving matches.
+ * Where the reference would index out of range (empty match list at :1073, windows outside the level) the pair is
+ * simply left unmatched. */
+int orbm_stereo_match(orbm_matcher* m, const orbx_extractor* left, const orbx_extractor* right, int frame,
+                      const orbx_kp* kps_l, const uint8_t* desc_l, int n_l, const orbx_kp* kps_r,
+                      const uint8_t* desc_r, int n_r, float mbf, float mb, float* u_right, float* depth,
+                      int32_t* n_matched);
+/* Batched, device-resident: pair p uses frame p of both extractors' last call and rows [p][cap] of the keypoint /
+ * descriptor arrays with counts d_n_l[p], d_n_r[p] (exactly what orbx_extract_batch_device wrote). Outputs
+ * d_u_right[p][cap], d_depth[p][cap], d_n_matched[p]. Enqueued on cuda_stream, not synchronised. */
+int orbm_stereo_match_batch_device(orbm_matcher* m, const orbx_extractor* left, const orbx_extractor* right,
+                                   int n_pairs, const orbx_kp* d_kps_l, const uint8_t* d_desc_l, const int32_t* d_n_l,
+                                   const orbx_kp* d_kps_r, const uint8_t* d_desc_r, const int32_t* d_n_r, int cap,
+                                   float mbf, float mb, float* d_u_right, float* d_depth, int32_t* d_n_matched,
+                                   void* cuda_stream);
+
+/* The hot path of the stereo Frame constructor (src/Frame.cc:149-279) for n_pairs independent rectified pairs, host
+ * buffers in and out: both ORBextractor::operator() calls with vLappingArea = {0, 0} (:200-203) and
+ * ComputeStereoMatches (:223). Pairs are cut into groups of max_batch and pipelined over the extractors' two lanes:
+ * the H2D copy of group i+1 and the D2H copy of group i-1 overlap the kernels of group i (use orbx_host_alloc memory).
+ * Outputs: kps / desc [n_pairs][cap] per eye with counts n_l / n_r, u_right / depth [n_pairs][cap], n_matched. */
+int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                             const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                             int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
+                             int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
+                             float* depth, int32_t* n_matched);
+
+/* int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th,
+ * const bool bFarPoints, const float thFarPoints) (include/ORBmatcher.h:49-51, src/ORBmatcher.cc:42-221), serial
+ * MapPoint order, Nleft == -1. mfNNratio is the matcher's constructor argument (include/ORBmatcher.h:38).
+ * assign[f->n] (host): index of the MapPoint written to F.mvpMapPoints[i], or -1. *nmatches = the return value. */
+int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, const orbx_mappoints* mps, float th,
+                                  float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches);
+
+/* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
+ * (src/ORBmatcher.cc:1594-1806) and (Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (:1808-1918), after the
+ * caller-side SE3 projection (orbx_projected). max_dist = TH_HIGH or ORBdist; check_orientation = mbCheckOrientation.
+ * assign[f->n] (host): index into `pts` or -1. */
+int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
+                                    int max_dist, int check_orientation, int32_t* assign, int32_t* nmatches);
+
+/* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
+ * const bool bOnlyStereo, const bool bCoarse) (src/ORBmatcher.cc:886-1106), pinhole keyframes. F12 (row-major 3x3)
+ * and the epipole (ep_x, ep_y) are computed by the shim exactly as the reference does (:893-911,
+ * src/CameraModels/Pinhole.cpp:122-149). matches12[kf1->n] (host) = index in kf2 or -1; the shim turns it into
+ * vMatchedPairs in ascending idx1 order (:1097-1103). */
+int orbm_search_for_triangulation(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2,
+                                  const float* F12, float ep_x, float ep_y, int only_stereo, int coarse,
+                                  int check_orientation, int32_t* matches12, int32_t* nmatches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBM_H_ */

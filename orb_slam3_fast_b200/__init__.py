@@ -5,3 +5,5 @@ in liborbx.so (hand-written CUDA). There is no CPU fallback.
 """
 from .lib import KP_DTYPE, OrbxError, build  # noqa: F401
 from .extractor import ORBextractor  # noqa: F401
+from .matcher import ORBmatcher  # noqa: F401
+from . import views  # noqa: F401

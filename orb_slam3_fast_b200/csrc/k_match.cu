@@ -1,0 +1,308 @@
+// k_match.cu — Hamming-search kernels behind include/orbm.h.
+//   k_knn2 / k_knn2_merge        cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2)                     src/Frame.cc:1293
+//   k_desc_dist                  ORBmatcher::DescriptorDistance                                  src/ORBmatcher.cc:1959-1973
+//   k_stereo_match / _median     Frame::ComputeStereoMatches                                     src/Frame.cc:921-1084
+// All integer / bitwise work: descriptors are held in registers as 8 x u32, distances are __popc(a ^ b); warp-level
+// argmin keeps the reference's tie rules (first minimal element in visiting order wins because it compares with <).
+#include "orbx_match.cuh"
+
+namespace orbx {
+
+__device__ __forceinline__ void load_desc(const uint8_t* p, uint32_t (&d)[8]) {
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+  d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+__device__ __forceinline__ int hamming(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  int d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// knn2: thread = one query (descriptor in registers); the train set streams through shared memory in tiles that every
+// thread reads at the same address (broadcast). blockIdx.y splits the train set so that small query sets still fill
+// the chip; partial (d1, i1, d2, i2) are merged in split order, which keeps "lower trainIdx wins ties".
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kKnnThreads = 128;
+constexpr int kKnnTile = 256;  // train rows per shared-memory tile (8 KB)
+
+__device__ __forceinline__ void top2_push(int d, int j, int& b1, int& i1, int& b2, int& i2) {
+  if (d < b1) {
+    b2 = b1; i2 = i1; b1 = d; i1 = j;
+  } else if (d < b2) {
+    b2 = d; i2 = j;
+  }
+}
+
+__global__ void __launch_bounds__(kKnnThreads)
+k_knn2(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ t, int nt, int rows_per_split,
+       int4* __restrict__ partial) {
+  __shared__ uint4 tile[kKnnTile * 2];
+  const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
+  const int t0 = blockIdx.y * rows_per_split;
+  const int t1 = min(nt, t0 + rows_per_split);
+  uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (qi < nq) load_desc(q + (size_t)qi * 32, a);
+  int b1 = 0x7fffffff, b2 = 0x7fffffff, i1 = -1, i2 = -1;
+  for (int base = t0; base < t1; base += kKnnTile) {
+    const int rows = min(kKnnTile, t1 - base);
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(t + (size_t)base * 32);
+    for (int k = threadIdx.x; k < rows * 2; k += kKnnThreads) tile[k] = src[k];
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < rows; r++) {
+      const uint4 u = tile[2 * r], v = tile[2 * r + 1];
+      const int d = __popc(a[0] ^ u.x) + __popc(a[1] ^ u.y) + __popc(a[2] ^ u.z) + __popc(a[3] ^ u.w) +
+                    __popc(a[4] ^ v.x) + __popc(a[5] ^ v.y) + __popc(a[6] ^ v.z) + __popc(a[7] ^ v.w);
+      top2_push(d, base + r, b1, i1, b2, i2);
+    }
+  }
+  if (qi < nq) partial[(size_t)blockIdx.y * nq + qi] = make_int4(b1, i1, b2, i2);
+}
+
+__global__ void k_knn2_merge(const int4* __restrict__ partial, int nq, int splits, int32_t* idx1, int32_t* d1,
+                             int32_t* idx2, int32_t* d2) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  int b1 = 0x7fffffff, b2 = 0x7fffffff, i1 = -1, i2 = -1;
+  for (int s = 0; s < splits; s++) {
+    const int4 p = partial[(size_t)s * nq + qi];
+    if (p.y >= 0) top2_push(p.x, p.y, b1, i1, b2, i2);
+    if (p.w >= 0) top2_push(p.z, p.w, b1, i1, b2, i2);
+  }
+  idx1[qi] = i1;
+  d1[qi] = i1 < 0 ? -1 : b1;
+  idx2[qi] = i2;
+  d2[qi] = i2 < 0 ? -1 : b2;
+}
+
+int knn2_splits(int nq, int nt) {
+  const int qblocks = (nq + kKnnThreads - 1) / kKnnThreads;
+  int splits = (4 * 148 + qblocks - 1) / qblocks;  // aim at >= 4 CTAs per SM
+  const int max_splits = (nt + kKnnTile - 1) / kKnnTile;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int4* partial, int splits, int32_t* idx1,
+                 int32_t* d1, int32_t* idx2, int32_t* d2, cudaStream_t st) {
+  if (nq <= 0) return;
+  int rows = (nt + splits - 1) / splits;
+  rows = (rows + kKnnTile - 1) / kKnnTile * kKnnTile;
+  if (rows < kKnnTile) rows = kKnnTile;
+  dim3 grid((nq + kKnnThreads - 1) / kKnnThreads, splits);
+  k_knn2<<<grid, kKnnThreads, 0, st>>>(q, nq, t, nt, rows, partial);
+  k_knn2_merge<<<(nq + 255) / 256, 256, 0, st>>>(partial, nq, splits, idx1, d1, idx2, d2);
+}
+
+__global__ void k_desc_dist(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int n, int32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x[8], y[8];
+  load_desc(a + (size_t)i * 32, x);
+  load_desc(b + (size_t)i * 32, y);
+  out[i] = hamming(x, y);
+}
+
+void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, cudaStream_t st) {
+  if (n > 0) k_desc_dist<<<(n + 255) / 256, 256, 0, st>>>(a, b, n, out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ComputeStereoMatches. One warp per left keypoint:
+//  1. the reference's row table (right keypoints listed under every row of y +- 2*scale, :939-949) is replaced by
+//     testing that membership directly for all right keypoints, 32 per step; candidates are visited in ascending iR,
+//     the table's order, and the warp argmin breaks ties towards the lower iR (the reference's strict <, :993);
+//  2. 11x11 SAD over 11 shifts on the raw pyramid level of the left keypoint's octave (:1005-1040): lanes own pixels,
+//     11 running sums each, then 11 warp reductions;
+//  3. parabola fit in non-fused FP32 (:1045-1052), disparity / depth (:1055-1067).
+// A second kernel (one CTA per pair) finds the median SAD and removes matches >= 1.5 * 1.4 * median (:1072-1083).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStereoWarps = 4;
+
+__global__ void __launch_bounds__(kStereoWarps * 32)
+k_stereo_match(const StereoArgs A) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int iL = blockIdx.x * kStereoWarps + warp;
+  const int pair = blockIdx.y;
+  const int nL = A.n_l ? A.n_l[pair] : A.n_l_host, nR = A.n_r ? A.n_r[pair] : A.n_r_host;
+  if (iL >= nL || iL >= A.cap) return;
+  const orbx_kp* kpsL = A.kps_l + (size_t)pair * A.cap;
+  const orbx_kp* kpsR = A.kps_r + (size_t)pair * A.cap;
+  const uint8_t* descL = A.desc_l + (size_t)pair * A.cap * 32;
+  const uint8_t* descR = A.desc_r + (size_t)pair * A.cap * 32;
+  float* u_right = A.u_right + (size_t)pair * A.cap;
+  float* depth = A.depth + (size_t)pair * A.cap;
+  int32_t* sad = A.sad + (size_t)pair * A.cap;
+  const int fL = A.frame0 + pair;
+
+  const orbx_kp kpL = kpsL[iL];
+  const int levelL = kpL.octave;
+  const float vL = kpL.y, uL = kpL.x;
+  float out_u = -1.0f, out_d = -1.0f;
+  int out_sad = -1;
+  const int nRows = A.left.h[0];
+  const float minD = 0.0f, maxD = fdiv(A.mbf, A.mb);
+  const float minU = fsub(uL, maxD), maxU = fsub(uL, minD);
+  const int row = (int)vL;  // vRowIndices[vL]: float -> size_t                             :966
+  bool ok = row >= 0 && row < nRows && !(maxU < 0) && levelL >= 0 && levelL < A.nlevels;
+  int bestDist = ORBM_TH_HIGH_I, bestIdxR = 0;
+  if (ok) {
+    uint32_t dl[8];
+    load_desc(descL + (size_t)iL * 32, dl);
+    int bd = 0x7fffffff, bi = 0x7fffffff;
+    for (int base = 0; base < nR; base += 32) {
+      const int iR = base + lane;
+      int d = 0x7fffffff;
+      if (iR < nR) {
+        const orbx_kp kpR = kpsR[iR];
+        const int oR = kpR.octave;
+        if (!(kpR.y == 0.0f && kpR.x == 0.0f) && oR >= 0 && oR < A.nlevels) {
+          const float r = fmul(2.0f, A.scale[oR]);
+          const int maxr = (int)ceilf(fadd(kpR.y, r));
+          const int minr = (int)floorf(fsub(kpR.y, r));
+          if (row >= minr && row <= maxr && !(oR < levelL - 1 || oR > levelL + 1) && kpR.x >= minU &&
+              kpR.x <= maxU) {
+            uint32_t dr[8];
+            load_desc(descR + (size_t)iR * 32, dr);
+            d = hamming(dl, dr);
+          }
+        }
+      }
+      // keep the lexicographic minimum of (dist, iR) per lane; lanes visit ascending iR so < suffices
+      if (d < bd) { bd = d; bi = iR; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (bd < bestDist) { bestDist = bd; bestIdxR = bi; }
+  }
+  if (ok && bestDist < (ORBM_TH_HIGH_I + ORBM_TH_LOW_I) / 2) {  // thOrbDist                   :925,1001
+    const float uR0 = kpsR[bestIdxR].x;
+    const float sfac = A.inv_scale[levelL];
+    const float scaleduL = roundf(fmul(kpL.x, sfac)), scaledvL = roundf(fmul(kpL.y, sfac));
+    const float scaleduR0 = roundf(fmul(uR0, sfac));
+    const int w = 5, L = 5;
+    const float iniu = fsub(fadd(scaleduR0, (float)L), (float)w);
+    const float endu = fadd(fadd(fadd(scaleduR0, (float)L), (float)w), 1.0f);
+    const int colsR = A.right.w[levelL];
+    bool inb = !(iniu < 0 || endu >= (float)colsR);
+    const int yl = (int)fsub(scaledvL, (float)w), xl = (int)fsub(scaleduL, (float)w);
+    const int xr0 = (int)fsub(scaleduR0, (float)w);  // inc = 0
+    // the reference's cv::Mat ranges throw outside the level; such keypoints cannot come from the extractor
+    inb = inb && yl >= 0 && yl + 2 * w < A.left.h[levelL] && yl + 2 * w < A.right.h[levelL] && xl >= 0 &&
+          xl + 2 * w < A.left.w[levelL] && xr0 - L >= 0 && xr0 + L + 2 * w < colsR;
+    if (inb) {
+      const uint8_t* IL = A.left.base[levelL] + (int64_t)fL * A.left.fstride[levelL];
+      const uint8_t* IR = A.right.base[levelL] + (int64_t)fL * A.right.fstride[levelL];
+      const int pl = A.left.pitch[levelL], pr = A.right.pitch[levelL];
+      int acc[11];
+#pragma unroll
+      for (int k = 0; k < 11; k++) acc[k] = 0;
+      for (int p = lane; p < 121; p += 32) {
+        const int yy = p / 11, xx = p - yy * 11;
+        const int a = IL[(int64_t)(yl + yy) * pl + xl + xx];
+        const uint8_t* rrow = IR + (int64_t)(yl + yy) * pr + xr0 + xx - L;
+#pragma unroll
+        for (int k = 0; k < 11; k++) acc[k] += abs(a - (int)rrow[k]);
+      }
+      float dists[11];
+      int bestSad = 0x7fffffff, bestinc = 0;
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const int s = __reduce_add_sync(0xffffffffu, acc[k]);
+        dists[k] = (float)s;          // cv::norm(IL, IR, NORM_L1) -> float               :1033
+        if (s < bestSad) { bestSad = s; bestinc = k - L; }
+      }
+      if (!(bestinc == -L || bestinc == L)) {
+        float dist1 = 0, dist2 = 0, dist3 = 0;
+#pragma unroll
+        for (int k = 1; k < 10; k++)
+          if (k == bestinc + L) { dist1 = dists[k - 1]; dist2 = dists[k]; dist3 = dists[k + 1]; }
+        const float deltaR = fdiv(fsub(dist1, dist3), fmul(2.0f, fsub(fadd(dist1, dist3), fmul(2.0f, dist2))));
+        if (!(deltaR < -1 || deltaR > 1)) {
+          float bestuR = fmul(A.scale[levelL], fadd(fadd(scaleduR0, (float)bestinc), deltaR));
+          float disparity = fsub(uL, bestuR);
+          if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0) {
+              disparity = 0.01f;
+              bestuR = (float)dsub((double)uL, 0.01);  // float - double literal          :1061
+            }
+            out_d = fdiv(A.mbf, disparity);
+            out_u = bestuR;
+            out_sad = bestSad;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+    u_right[iL] = out_u;
+    depth[iL] = out_d;
+    sad[iL] = out_sad;
+  }
+}
+
+// median of the accepted SADs (= element size/2 of the sorted (dist, iL) vector) by rank counting, then the cut
+__global__ void __launch_bounds__(256) k_stereo_median(const StereoArgs A) {
+  extern __shared__ int32_t sh[];
+  __shared__ int s_m, s_median, s_kept;
+  const int pair = blockIdx.x;
+  const int nL = min(A.n_l ? A.n_l[pair] : A.n_l_host, A.cap);
+  float* u_right = A.u_right + (size_t)pair * A.cap;
+  float* depth = A.depth + (size_t)pair * A.cap;
+  const int32_t* sad = A.sad + (size_t)pair * A.cap;
+  if (threadIdx.x == 0) { s_m = 0; s_median = -1; s_kept = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+    const int v = sad[i];
+    sh[i] = v;
+    if (v >= 0) atomicAdd(&s_m, 1);
+  }
+  __syncthreads();
+  const int m = s_m;
+  if (m == 0) {  // the reference reads vDistIdx[0] of an empty vector here (UB); defined as "no matches"
+    if (threadIdx.x == 0) A.n_matched[pair] = 0;
+    return;
+  }
+  const int target = m / 2;
+  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+    const int v = sh[i];
+    if (v < 0) continue;
+    int rank = 0;
+    for (int j = 0; j < nL; j++) {
+      const int u = sh[j];
+      rank += (u >= 0) && (u < v || (u == v && j < i));
+    }
+    if (rank == target) s_median = v;
+  }
+  __syncthreads();
+  const float median = (float)s_median;
+  const float thDist = fmul(0x1.0cccccp+1f, median);  // 1.5f * 1.4f folded to float, then * median   :1074
+  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+    const int v = sh[i];
+    if (v < 0) continue;
+    if ((float)v < thDist) atomicAdd(&s_kept, 1);
+    else { u_right[i] = -1.0f; depth[i] = -1.0f; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) A.n_matched[pair] = s_kept;
+}
+
+void launch_stereo(const StereoArgs& A, int n_pairs, int max_rows, cudaStream_t st) {
+  if (n_pairs <= 0 || max_rows <= 0) return;
+  dim3 grid((max_rows + kStereoWarps - 1) / kStereoWarps, n_pairs);
+  k_stereo_match<<<grid, kStereoWarps * 32, 0, st>>>(A);
+  const size_t smem = (size_t)max_rows * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_median, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_stereo_median<<<n_pairs, 256, smem, st>>>(A);
+}
+
+}  // namespace orbx

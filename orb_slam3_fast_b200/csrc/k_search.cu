@@ -1,0 +1,484 @@
+// k_search.cu — the guided Hamming searches of ORBmatcher behind include/orbm.h:
+//   SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   src/ORBmatcher.cc:42-221
+//   SearchByProjection(Frame&, const Frame&, th, bMono) / (Frame&, KeyFrame*, set, ...)  :1594-1806, :1808-1918
+//   SearchForTriangulation(KeyFrame*, KeyFrame*, ...)                                    :886-1106
+// with Frame::GetFeaturesInArea (src/Frame.cc:765-831) on the 64x48 grid as a CSR.
+//
+// Structure of the projection searches:
+//   count / fill   one warp per projected point: lanes own the grid cells of the search window, so the candidate list
+//                  comes out in the reference's order (ix outer, iy inner, ascending keypoint index inside a cell) from
+//                  a prefix sum; the filling pass also computes the Hamming distances and the unconstrained best /
+//                  second best per point.
+//   resolve        the reference assigns points greedily in vector order and a keypoint taken by an earlier point is
+//                  skipped by later ones (:92-93, :130). One warp replays that order: a point whose two best
+//                  candidates are both still free keeps its precomputed result (2 shared-memory reads); otherwise the
+//                  warp rescans that point's candidate list against the occupancy map.
+#include "orbx_match.cuh"
+
+namespace orbx {
+
+__device__ __forceinline__ void load_desc8(const uint8_t* p, uint32_t (&d)[8]) {
+  const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+  d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ int hamming8(const uint32_t (&a)[8], const uint8_t* p) {
+  uint32_t b[8];
+  load_desc8(p, b);
+  int d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+  return d;
+}
+
+struct Window {
+  int x0, x1, y0, y1;  // inclusive cell range; x1 < x0 = empty
+};
+
+// Frame::GetFeaturesInArea cell range (src/Frame.cc:777-801)
+__device__ __forceinline__ Window cell_window(const DevFrame& F, float x, float y, float r) {
+  Window w;
+  const int C = ORBX_GRID_COLS, R = ORBX_GRID_ROWS;
+  w.x0 = max(0, (int)floorf(fmul(fsub(fsub(x, F.min_x), r), F.inv_w)));
+  w.x1 = min(C - 1, (int)ceilf(fmul(fadd(fsub(x, F.min_x), r), F.inv_w)));
+  w.y0 = max(0, (int)floorf(fmul(fsub(fsub(y, F.min_y), r), F.inv_h)));
+  w.y1 = min(R - 1, (int)ceilf(fmul(fadd(fsub(y, F.min_y), r), F.inv_h)));
+  if (w.x0 >= C || w.x1 < 0 || w.y0 >= R || w.y1 < 0) w.x1 = w.x0 - 1;
+  return w;
+}
+
+// all per-candidate tests of the search loops that do not depend on earlier assignments
+__device__ __forceinline__ bool cand_ok(const DevFrame& F, int idx, float x, float y, float r, int minLevel,
+                                        int maxLevel, bool has_ur, float ur) {
+  const orbx_kp kp = F.kps[idx];
+  const bool check = (minLevel > 0) || (maxLevel >= 0);  // :803
+  if (check) {
+    if (kp.octave < minLevel) return false;
+    if (maxLevel >= 0 && kp.octave > maxLevel) return false;
+  }
+  if (!(fabsf(fsub(kp.x, x)) < r && fabsf(fsub(kp.y, y)) < r)) return false;  // :823-826
+  if (F.occupied[idx]) return false;                                           // ORBmatcher.cc:92-93 (static part)
+  if (has_ur && F.u_right[idx] > 0) {                                          // :95-98
+    const float er = fabsf(fsub(ur, F.u_right[idx]));
+    if (er > r) return false;
+  }
+  return true;
+}
+
+constexpr int kSearchWarps = 4;
+
+struct Top2 {
+  int d1, p1, d2, p2;  // lexicographic (dist, position) minimum and runner-up; p = -1 when absent
+};
+__device__ __forceinline__ void top2_insert(Top2& t, int d, int p) {
+  if (p < 0) return;
+  if (t.p1 < 0 || d < t.d1 || (d == t.d1 && p < t.p1)) {
+    t.d2 = t.d1; t.p2 = t.p1; t.d1 = d; t.p1 = p;
+  } else if (t.p2 < 0 || d < t.d2 || (d == t.d2 && p < t.p2)) {
+    t.d2 = d; t.p2 = p;
+  }
+}
+__device__ __forceinline__ Top2 top2_warp(Top2 t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int d1 = __shfl_xor_sync(0xffffffffu, t.d1, o), p1 = __shfl_xor_sync(0xffffffffu, t.p1, o);
+    const int d2 = __shfl_xor_sync(0xffffffffu, t.d2, o), p2 = __shfl_xor_sync(0xffffffffu, t.p2, o);
+    top2_insert(t, d1, p1);
+    top2_insert(t, d2, p2);
+  }
+  return t;
+}
+
+// FILL = false: counts[i] = number of candidates of point i.
+// FILL = true : candidates written at counts[i] (exclusive offsets) + unconstrained top-2 record per point.
+template <bool FILL>
+__global__ void __launch_bounds__(kSearchWarps * 32)
+k_search_enum(const DevFrame F, const DevQueries Q, int32_t* counts, int32_t* cand_idx, int32_t* cand_dist,
+              int4* pre) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kSearchWarps + warp;
+  if (i >= Q.m) return;
+  int total = 0;
+  Top2 best{0, -1, 0, -1};
+  if (!Q.active || Q.active[i]) {
+    const float x = Q.u[i], y = Q.v[i], r = Q.radius[i];
+    const int minL = Q.min_level[i], maxL = Q.max_level[i];
+    const bool has_ur = Q.u_right != nullptr && F.u_right != nullptr;
+    const float ur = has_ur ? Q.u_right[i] : 0.f;
+    const Window w = cell_window(F, x, y, r);
+    const int ny = w.y1 - w.y0 + 1;
+    const int ncell = w.x1 < w.x0 ? 0 : (w.x1 - w.x0 + 1) * ny;
+    uint32_t dq[8];
+    int out_base = 0;
+    if (FILL) {
+      load_desc8(Q.desc + (size_t)i * 32, dq);
+      out_base = counts[i];
+    }
+    for (int cb = 0; cb < ncell; cb += 32) {
+      const int c = cb + lane;
+      int j0 = 0, j1 = 0;
+      if (c < ncell) {
+        const int ix = w.x0 + c / ny, iy = w.y0 + c % ny;  // ix outer, iy inner
+        const int cell = ix * ORBX_GRID_ROWS + iy;
+        j0 = F.cell_offsets[cell];
+        j1 = F.cell_offsets[cell + 1];
+      }
+      int n = 0;
+      for (int j = j0; j < j1; j++) n += cand_ok(F, F.cell_items[j], x, y, r, minL, maxL, has_ur, ur) ? 1 : 0;
+      int inc = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+      }
+      if (FILL) {
+        int pos = total + inc - n;
+        for (int j = j0; j < j1; j++) {
+          const int idx = F.cell_items[j];
+          if (!cand_ok(F, idx, x, y, r, minL, maxL, has_ur, ur)) continue;
+          const int dist = hamming8(dq, F.desc + (size_t)idx * 32);
+          cand_idx[out_base + pos] = idx;
+          cand_dist[out_base + pos] = dist | (F.kps[idx].octave << 16);
+          top2_insert(best, dist, pos);
+          pos++;
+        }
+      }
+      total += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  if (!FILL) {
+    if (lane == 0) counts[i] = total;
+  } else {
+    best = top2_warp(best);
+    if (lane == 0) pre[i] = make_int4(best.d1, best.p1, best.d2, best.p2);
+  }
+}
+
+void launch_search_count(const DevFrame& F, const DevQueries& Q, int32_t* counts, cudaStream_t st) {
+  if (Q.m <= 0) return;
+  k_search_enum<false><<<(Q.m + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, st>>>(F, Q, counts, nullptr,
+                                                                                                nullptr, nullptr);
+}
+
+// exclusive scan of counts[0..m) in place, counts[m] = total, *total_out = total (single CTA; m is ~10^4)
+__global__ void __launch_bounds__(1024) k_scan(int32_t* counts, int m, int32_t* total_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < m ? counts[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int s = warp_sums[lane];
+      int sinc = s;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, sinc, d);
+        if (lane >= d) sinc += t;
+      }
+      warp_sums[lane] = sinc - s;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    if (i < m) counts[i] = carry + warp_sums[warp] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_sums[warp] + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[m] = carry_s;
+    *total_out = carry_s;
+  }
+}
+
+void launch_scan(int32_t* counts, int m, int32_t* total_out, cudaStream_t st) {
+  k_scan<<<1, 1024, 0, st>>>(counts, m, total_out);
+}
+
+void launch_search_fill(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, cudaStream_t st) {
+  if (Q.m <= 0) return;
+  k_search_enum<true><<<(Q.m + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, st>>>(
+      F, Q, S.counts, S.cand_idx, S.cand_dist, S.pre);
+}
+
+// ---- ORBmatcher::ComputeThreeMaxima (src/ORBmatcher.cc:1920-1955) on bin sizes ----
+__device__ void three_maxima(const int* histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  ind1 = ind2 = ind3 = -1;
+  for (int i = 0; i < L; i++) {
+    const int s = histo[i];
+    if (s > max1) {
+      max3 = max2; max2 = max1; max1 = s;
+      ind3 = ind2; ind2 = ind1; ind1 = i;
+    } else if (s > max2) {
+      max3 = max2; max2 = s;
+      ind3 = ind2; ind2 = i;
+    } else if (s > max3) {
+      max3 = s;
+      ind3 = i;
+    }
+  }
+  if ((float)max2 < fmul(0.1f, (float)max1)) {
+    ind2 = -1;
+    ind3 = -1;
+  } else if ((float)max3 < fmul(0.1f, (float)max1)) {
+    ind3 = -1;
+  }
+}
+
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+  const float factor = 1.0f / kHistoLength;
+  float rot = fsub(a1, a2);
+  if (rot < 0.0f) rot = fadd(rot, 360.0f);
+  int bin = (int)roundf(fmul(rot, factor));
+  if (bin == kHistoLength) bin = 0;
+  return bin;
+}
+
+__global__ void __launch_bounds__(32)
+k_search_resolve(const DevFrame F, const DevQueries Q, const SearchScratch S, const ResolveArgs R) {
+  extern __shared__ uint8_t occ[];  // [n] then (aligned) int histo[32]
+  const int lane = threadIdx.x;
+  const int n = F.n;
+  int* histo = reinterpret_cast<int*>(occ + ((n + 15) / 16) * 16);
+  for (int k = lane; k < n; k += 32) {
+    occ[k] = F.occupied[k];
+    R.assign[k] = -1;
+  }
+  histo[lane] = 0;
+  __syncwarp();
+  const int32_t* offsets = S.counts;
+  const bool rot = R.mode == 1 && R.check_orientation;
+  int nmatches = 0, nevents = 0;
+  for (int base = 0; base < Q.m; base += 32) {
+    // ---- every lane prefetches one point's precomputed record (hides the global-memory latency) ----
+    const int i = base + lane;
+    int off = 0, cnt = 0, hobs = 0, k1 = -1, k2 = -1, l1 = -1, l2 = -1;
+    int4 p = make_int4(0, -1, 0, -1);
+    float ang_q = 0.f, ang_k1 = 0.f;
+    if (i < Q.m) {
+      off = offsets[i];
+      cnt = offsets[i + 1] - off;
+      p = S.pre[i];
+      hobs = R.has_obs[i];
+      if (cnt > 0 && p.y >= 0) {
+        k1 = S.cand_idx[off + p.y];
+        l1 = S.cand_dist[off + p.y] >> 16;
+      }
+      if (cnt > 0 && p.w >= 0) {
+        k2 = S.cand_idx[off + p.w];
+        l2 = S.cand_dist[off + p.w] >> 16;
+      }
+      if (rot) {
+        ang_q = R.angle[i];
+        if (k1 >= 0) ang_k1 = F.kps[k1].angle;
+      }
+    }
+    const int lim = min(32, Q.m - base);
+    for (int j = 0; j < lim; j++) {
+      const int cj = __shfl_sync(0xffffffffu, cnt, j);
+      if (cj == 0) continue;
+      int dirty = 0;
+      if (lane == j) dirty = (k1 >= 0 && occ[k1]) || (k2 >= 0 && occ[k2]);
+      dirty = __shfl_sync(0xffffffffu, dirty, j);
+      int bestDist, bestDist2, bestIdx, bestLevel, bestLevel2;
+      float ang_k;
+      if (!dirty) {
+        // both precomputed best candidates are still free: the filtered search would find the same two
+        bestDist = __shfl_sync(0xffffffffu, p.x, j);
+        bestDist2 = __shfl_sync(0xffffffffu, p.z, j);
+        bestIdx = __shfl_sync(0xffffffffu, k1, j);
+        bestLevel = __shfl_sync(0xffffffffu, l1, j);
+        bestLevel2 = __shfl_sync(0xffffffffu, l2, j);
+        ang_k = __shfl_sync(0xffffffffu, ang_k1, j);
+        if (__shfl_sync(0xffffffffu, k2, j) < 0) bestDist2 = 256;
+      } else {
+        const int oj = __shfl_sync(0xffffffffu, off, j);
+        Top2 t{0, -1, 0, -1};
+        for (int c = lane; c < cj; c += 32)
+          if (!occ[S.cand_idx[oj + c]]) top2_insert(t, S.cand_dist[oj + c] & 0xffff, c);
+        t = top2_warp(t);
+        if (t.p1 < 0) continue;  // every candidate already taken
+        bestDist = t.d1;
+        bestIdx = S.cand_idx[oj + t.p1];
+        bestLevel = S.cand_dist[oj + t.p1] >> 16;
+        bestDist2 = t.p2 >= 0 ? t.d2 : 256;
+        bestLevel2 = t.p2 >= 0 ? (S.cand_dist[oj + t.p2] >> 16) : -1;
+        ang_k = rot ? F.kps[bestIdx].angle : 0.f;
+      }
+      bool accept;
+      if (R.mode == 0)
+        accept = bestDist <= ORBM_TH_HIGH_I &&
+                 !(bestLevel == bestLevel2 && (float)bestDist > fmul(R.nnratio, (float)bestDist2));  // :124-129
+      else
+        accept = bestDist <= R.max_dist;  // :1699 / :1897
+      if (!accept) continue;
+      const int ho = __shfl_sync(0xffffffffu, hobs, j);
+      const float aq = __shfl_sync(0xffffffffu, ang_q, j);
+      if (lane == 0) {
+        R.assign[bestIdx] = base + j;   // F.mvpMapPoints[bestIdx] = pMP                :130
+        occ[bestIdx] = (uint8_t)ho;     // a point with observations blocks the keypoint :92-93
+        if (rot) {
+          const int bin = rot_bin(aq, ang_k);
+          R.events[2 * nevents] = bestIdx;
+          R.events[2 * nevents + 1] = bin;
+          histo[bin]++;
+        }
+      }
+      nevents++;
+      nmatches++;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  if (rot) {
+    int ind1, ind2, ind3;
+    three_maxima(histo, kHistoLength, ind1, ind2, ind3);  // every lane computes the same
+    int removed = 0;
+    for (int e = lane; e < nevents; e += 32) {
+      const int bin = R.events[2 * e + 1];
+      if (bin != ind1 && bin != ind2 && bin != ind3) {
+        R.assign[R.events[2 * e]] = -1;  // :1795-1800
+        removed++;
+      }
+    }
+    removed = __reduce_add_sync(0xffffffffu, removed);
+    nmatches -= removed;
+  }
+  if (lane == 0) *R.nmatches = nmatches;
+}
+
+void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, const ResolveArgs& R,
+                           cudaStream_t st) {
+  const size_t smem = ((size_t)(F.n + 15) / 16) * 16 + 32 * sizeof(int);
+  cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+  k_search_resolve<<<1, 32, smem, st>>>(F, Q, S, R);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SearchForTriangulation. Rows of the result are independent (vbMatched2 is never written in the reference), so:
+//   k_tri_nodes   node a of kf1 -> position of the same vocabulary node in kf2 (binary search; both lists ascend)
+//   k_tri_match   one thread per shared node replays the reference's double loop for its features
+//   k_tri_rot     rotation-consistency histogram + count (one CTA)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_tri_nodes(const TriArgs A) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.k1.n_nodes) return;
+  const uint32_t id = A.k1.node_ids[a];
+  int lo = 0, hi = A.k2.n_nodes - 1, found = -1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint32_t v = A.k2.node_ids[mid];
+    if (v == id) { found = mid; break; }
+    if (v < id) lo = mid + 1;
+    else hi = mid - 1;
+  }
+  A.node_match[a] = found;
+}
+
+__global__ void k_tri_match(const TriArgs A) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.k1.n_nodes) return;
+  const int b = A.node_match[a];
+  if (b < 0) return;
+  const DevKeyFrame &K1 = A.k1, &K2 = A.k2;
+  for (int p1 = K1.offsets[a]; p1 < K1.offsets[a + 1]; p1++) {
+    const int idx1 = (int)K1.indices[p1];
+    if (K1.has_mappoint[idx1]) continue;                                   // :953-956
+    const bool bStereo1 = K1.u_right && K1.u_right[idx1] >= 0;             // :958-960
+    if (A.only_stereo && !bStereo1) continue;
+    const orbx_kp kp1 = K1.kps[idx1];
+    uint32_t d1[8];
+    load_desc8(K1.desc + (size_t)idx1 * 32, d1);
+    int bestDist = ORBM_TH_LOW_I, bestIdx2 = -1;
+    for (int p2 = K2.offsets[b]; p2 < K2.offsets[b + 1]; p2++) {
+      const int idx2 = (int)K2.indices[p2];
+      if (K2.has_mappoint[idx2]) continue;                                 // :977-980
+      const bool bStereo2 = K2.u_right && K2.u_right[idx2] >= 0;
+      if (A.only_stereo && !bStereo2) continue;
+      const int dist = hamming8(d1, K2.desc + (size_t)idx2 * 32);
+      if (dist > ORBM_TH_LOW_I || dist > bestDist) continue;               // :988
+      const orbx_kp kp2 = K2.kps[idx2];
+      if (!bStereo1 && !bStereo2) {                                        // :996-1003 (pinhole pair)
+        const float distex = fsub(A.ep_x, kp2.x), distey = fsub(A.ep_y, kp2.y);
+        if (fadd(fmul(distex, distex), fmul(distey, distey)) < fmul(100.f, K2.scale_factors[kp2.octave])) continue;
+      }
+      bool ok = A.coarse != 0;
+      if (!ok) {  // Pinhole::epipolarConstrain, src/CameraModels/Pinhole.cpp:136-148
+        const float* F = A.F12;
+        const float ea = fadd(fadd(fmul(kp1.x, F[0]), fmul(kp1.y, F[3])), F[6]);
+        const float eb = fadd(fadd(fmul(kp1.x, F[1]), fmul(kp1.y, F[4])), F[7]);
+        const float ec = fadd(fadd(fmul(kp1.x, F[2]), fmul(kp1.y, F[5])), F[8]);
+        const float num = fadd(fadd(fmul(ea, kp2.x), fmul(eb, kp2.y)), ec);
+        const float den = fadd(fmul(ea, ea), fmul(eb, eb));
+        if (den != 0) {
+          const float dsqr = fdiv(fmul(num, num), den);
+          ok = (double)dsqr < dmul(3.84, (double)K2.level_sigma2[kp2.octave]);
+        }
+      }
+      if (ok) {
+        bestIdx2 = idx2;
+        bestDist = dist;
+      }
+    }
+    if (bestIdx2 >= 0) A.matches12[idx1] = bestIdx2;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tri_rot(const TriArgs A) {
+  __shared__ int histo[32];
+  __shared__ int s_count, s_removed;
+  if (threadIdx.x < 32) histo[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_count = 0; s_removed = 0; }
+  __syncthreads();
+  const int n = A.k1.n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int j = A.matches12[i];
+    if (j < 0) continue;
+    atomicAdd(&s_count, 1);
+    if (A.check_orientation) atomicAdd(&histo[rot_bin(A.k1.kps[i].angle, A.k2.kps[j].angle)], 1);
+  }
+  __syncthreads();
+  if (A.check_orientation) {
+    int ind1, ind2, ind3;
+    three_maxima(histo, kHistoLength, ind1, ind2, ind3);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int j = A.matches12[i];
+      if (j < 0) continue;
+      const int bin = rot_bin(A.k1.kps[i].angle, A.k2.kps[j].angle);
+      if (bin != ind1 && bin != ind2 && bin != ind3) {
+        A.matches12[i] = -1;
+        atomicAdd(&s_removed, 1);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *A.nmatches = s_count - s_removed;
+}
+
+__global__ void k_fill_i32(int32_t* p, int n, int32_t v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+void launch_triangulation(const TriArgs& A, cudaStream_t st) {
+  if (A.k1.n > 0) k_fill_i32<<<(A.k1.n + 255) / 256, 256, 0, st>>>(A.matches12, A.k1.n, -1);
+  if (A.k1.n_nodes > 0) {
+    k_tri_nodes<<<(A.k1.n_nodes + 127) / 128, 128, 0, st>>>(A);
+    k_tri_match<<<(A.k1.n_nodes + 63) / 64, 64, 0, st>>>(A);
+  }
+  k_tri_rot<<<1, 256, 0, st>>>(A);
+}
+
+}  // namespace orbx

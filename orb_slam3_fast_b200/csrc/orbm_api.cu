@@ -1,0 +1,580 @@
+// orbm_api.cu — the extern "C" matcher ABI declared in include/orbm.h: uploads the flat views, launches the kernels
+// of k_match.cu / k_search.cu on the context's stream, downloads the results. No result is computed on the host.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/orbm.h"
+#include "orbx_handle.h"
+#include "orbx_match.cuh"
+
+using namespace orbx;
+
+namespace {
+thread_local std::string g_m_create_error;
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max(bytes, (size_t)4096) * 5 / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+enum { kBufs = 40 };
+}  // namespace
+
+struct orbm_matcher {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  DevBuf buf[kBufs];
+  int next_buf = 0;
+  // per-lane device outputs of orbm_stereo_frames_batch: u_right, depth, sad [B][cap], n_matched [B] (+ pinned copy)
+  DevBuf lane_buf[kLanes][4];
+  int32_t* lane_h_nm[kLanes] = {};
+  int lane_h_cap[kLanes] = {};
+};
+
+namespace {
+
+int mfail(orbm_matcher* m, int code, const std::string& msg) {
+  if (m) m->err = msg;
+  else g_m_create_error = msg;
+  return code;
+}
+
+#define ORBM_CUDA(m, call)                                                                \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return mfail(m, ORBX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+  } while (0)
+
+// One call = a sequence of scratch allocations in fixed order; buffers are reused across calls by position.
+struct Arena {
+  orbm_matcher* m;
+  cudaError_t err = cudaSuccess;
+  explicit Arena(orbm_matcher* mm) : m(mm) { m->next_buf = 0; }
+  template <typename T>
+  T* alloc(size_t count) {
+    if (m->next_buf >= kBufs) {
+      err = cudaErrorMemoryAllocation;
+      return nullptr;
+    }
+    DevBuf& b = m->buf[m->next_buf++];
+    cudaError_t e = b.reserve(std::max(count, (size_t)1) * sizeof(T));
+    if (e != cudaSuccess) err = e;
+    return reinterpret_cast<T*>(b.p);
+  }
+  template <typename T>
+  T* upload(const T* host, size_t count) {
+    T* d = alloc<T>(count);
+    if (d && host && count) {
+      cudaError_t e = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, m->stream);
+      if (e != cudaSuccess) err = e;
+    }
+    return d;
+  }
+};
+
+void pyr_view(const orbx_extractor* ex, PyrView* v, int ln = -1) {
+  memset(v, 0, sizeof(*v));
+  const Plan& P = ex->plan;
+  const FrameSet& fs = ex->lane[ln < 0 ? ex->last_lane : ln].last_fs;
+  for (int l = 0; l < P.nlevels; l++) {
+    if (l == 0) {
+      v->base[l] = fs.lvl0;
+      v->pitch[l] = fs.pitch0;
+      v->fstride[l] = fs.fstride0;
+    } else {
+      v->base[l] = fs.pyr + P.lv[l].img_off;
+      v->pitch[l] = P.lv[l].pitch;
+      v->fstride[l] = fs.slab_fstride;
+    }
+    v->w[l] = P.lv[l].w;
+    v->h[l] = P.lv[l].h;
+  }
+}
+
+int stereo_args_common(orbm_matcher* m, const orbx_extractor* left, const orbx_extractor* right, StereoArgs* A,
+                       int ln = -1) {
+  if (!left || !right || !left->planned || !right->planned || left->lane[left->last_lane].last_frames < 1 || right->lane[right->last_lane].last_frames < 1)
+    return mfail(m, ORBX_E_ARG, "stereo match needs both extractors to have run");
+  if (left->device != m->device || right->device != m->device)
+    return mfail(m, ORBX_E_ARG, "extractors and matcher must live on the same device");
+  if (left->nlevels != right->nlevels) return mfail(m, ORBX_E_ARG, "level count mismatch");
+  memset(A, 0, sizeof(*A));
+  pyr_view(left, &A->left, ln);
+  pyr_view(right, &A->right, ln);
+  A->nlevels = left->nlevels;
+  for (int l = 0; l < left->nlevels; l++) {
+    A->scale[l] = left->plan.lv[l].scale;
+    A->inv_scale[l] = left->plan.lv[l].inv_scale;
+  }
+  return ORBX_OK;
+}
+
+DevFrame upload_frame(Arena& ar, const orbx_frame_view* f) {
+  DevFrame F{};
+  const int cells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
+  F.n = f->n;
+  F.n_levels = f->n_levels;
+  F.kps = ar.upload(f->kps, f->n);
+  F.desc = ar.upload(f->desc, (size_t)f->n * 32);
+  F.u_right = f->u_right ? ar.upload(f->u_right, f->n) : (ar.alloc<float>(1), nullptr);
+  F.occupied = ar.upload(f->occupied, f->n);
+  F.cell_offsets = ar.upload(f->grid.cell_offsets, cells + 1);
+  F.cell_items = ar.upload(f->grid.cell_items, (size_t)f->grid.cell_offsets[cells]);
+  F.min_x = f->grid.min_x;
+  F.min_y = f->grid.min_y;
+  F.inv_w = f->grid.inv_w;
+  F.inv_h = f->grid.inv_h;
+  F.scale_factors = ar.upload(f->scale_factors, f->n_levels);
+  return F;
+}
+
+// count -> scan -> (size scratch) -> fill -> resolve, then the results come back
+int run_search(orbm_matcher* m, Arena& ar, const DevFrame& F, const DevQueries& Q, ResolveArgs R, int n,
+               int32_t* assign, int32_t* nmatches) {
+  cudaStream_t st = m->stream;
+  SearchScratch S{};
+  S.counts = ar.alloc<int32_t>((size_t)Q.m + 1);
+  S.pre = ar.alloc<int4>(Q.m);
+  int32_t* d_total = ar.alloc<int32_t>(1);
+  R.assign = ar.alloc<int32_t>(n);
+  R.nmatches = ar.alloc<int32_t>(1);
+  R.events = ar.alloc<int32_t>(2 * (size_t)Q.m);
+  R.occ = nullptr;
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  int32_t total = 0;
+  if (Q.m > 0) {
+    launch_search_count(F, Q, S.counts, st);
+    launch_scan(S.counts, Q.m, d_total, st);
+    ORBM_CUDA(m, cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
+    ORBM_CUDA(m, cudaStreamSynchronize(st));
+  } else {
+    ORBM_CUDA(m, cudaMemsetAsync(S.counts, 0, 4, st));
+  }
+  S.cand_idx = ar.alloc<int32_t>(total);
+  S.cand_dist = ar.alloc<int32_t>(total);
+  S.cap_total = total;
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_search_fill(F, Q, S, st);
+  launch_search_resolve(F, Q, S, R, st);
+  ORBM_CUDA(m, cudaGetLastError());
+  if (n > 0) ORBM_CUDA(m, cudaMemcpyAsync(assign, R.assign, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  int32_t nm = 0;
+  ORBM_CUDA(m, cudaMemcpyAsync(&nm, R.nmatches, 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaStreamSynchronize(st));
+  if (nmatches) *nmatches = nm;
+  return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbm_create(orbm_matcher** out, int device) {
+  if (!out) return mfail(nullptr, ORBX_E_ARG, "out == NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return mfail(nullptr, ORBX_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return mfail(nullptr, ORBX_E_ARG, "bad device ordinal");
+  orbm_matcher* m = new orbm_matcher;
+  m->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_m_create_error = cudaGetErrorString(e);
+    delete m;
+    return ORBX_E_CUDA;
+  }
+  *out = m;
+  return ORBX_OK;
+}
+
+void orbm_destroy(orbm_matcher* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  for (auto& b : m->buf) b.release();
+  for (auto& lb : m->lane_buf)
+    for (auto& b : lb) b.release();
+  for (auto& h : m->lane_h_nm)
+    if (h) cudaFreeHost(h);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+const char* orbm_last_error(const orbm_matcher* m) { return m ? m->err.c_str() : g_m_create_error.c_str(); }
+
+int orbm_descriptor_distance_batch(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist) {
+  if (!m || n < 0 || (n > 0 && (!a || !b || !dist))) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (n == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const uint8_t* da = ar.upload(a, (size_t)n * 32);
+  const uint8_t* db = ar.upload(b, (size_t)n * 32);
+  int32_t* dd = ar.alloc<int32_t>(n);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_desc_dist(da, db, n, dd, m->stream);
+  ORBM_CUDA(m, cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  return ORBX_OK;
+}
+
+int orbm_knn2_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_idx1,
+                     int32_t* d_d1, int32_t* d_idx2, int32_t* d_d2, void* cuda_stream) {
+  if (!m || nq < 0 || nt < 0) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nq == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m->stream;
+  const int splits = knn2_splits(nq, nt);
+  // the partial buffer is the LAST arena slot so that host-API uploads (slots 0..) are not disturbed
+  DevBuf& pb = m->buf[kBufs - 1];
+  cudaError_t e = pb.reserve((size_t)splits * nq * sizeof(int4));
+  if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+  launch_knn2(d_q, nq, d_t, nt, reinterpret_cast<int4*>(pb.p), splits, d_idx1, d_d1, d_idx2, d_d2, st);
+  ORBM_CUDA(m, cudaGetLastError());
+  return ORBX_OK;
+}
+
+int orbm_knn2(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx1, int32_t* d1,
+              int32_t* idx2, int32_t* d2) {
+  if (!m || nq < 0 || nt < 0 || (nq > 0 && (!q || !idx1 || !d1 || !idx2 || !d2)) || (nt > 0 && !t))
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nq == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const uint8_t* dq = ar.upload(q, (size_t)nq * 32);
+  const uint8_t* dt = ar.upload(t, (size_t)nt * 32);
+  int32_t* out = ar.alloc<int32_t>((size_t)nq * 4);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  int rc = orbm_knn2_device(m, dq, nq, dt, nt, out, out + nq, out + 2 * (size_t)nq, out + 3 * (size_t)nq, nullptr);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  ORBM_CUDA(m, cudaMemcpyAsync(idx1, out, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaMemcpyAsync(d1, out + nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaMemcpyAsync(idx2, out + 2 * (size_t)nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaMemcpyAsync(d2, out + 3 * (size_t)nq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaStreamSynchronize(st));
+  return ORBX_OK;
+}
+
+int orbm_stereo_match_batch_device(orbm_matcher* m, const orbx_extractor* left, const orbx_extractor* right,
+                                   int n_pairs, const orbx_kp* d_kps_l, const uint8_t* d_desc_l, const int32_t* d_n_l,
+                                   const orbx_kp* d_kps_r, const uint8_t* d_desc_r, const int32_t* d_n_r, int cap,
+                                   float mbf, float mb, float* d_u_right, float* d_depth, int32_t* d_n_matched,
+                                   void* cuda_stream) {
+  if (!m || n_pairs < 1 || cap < 1 || !d_kps_l || !d_desc_l || !d_n_l || !d_kps_r || !d_desc_r || !d_n_r ||
+      !d_u_right || !d_depth || !d_n_matched)
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  StereoArgs A;
+  int rc = stereo_args_common(m, left, right, &A);
+  if (rc) return rc;
+  if (n_pairs > left->lane[left->last_lane].last_frames || n_pairs > right->lane[right->last_lane].last_frames)
+    return mfail(m, ORBX_E_ARG, "n_pairs exceeds the frames of the extractors' last call");
+  DevBuf& sb = m->buf[kBufs - 2];
+  cudaError_t e = sb.reserve((size_t)n_pairs * cap * 4);
+  if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+  A.frame0 = 0;
+  A.kps_l = d_kps_l; A.kps_r = d_kps_r; A.desc_l = d_desc_l; A.desc_r = d_desc_r;
+  A.n_l = d_n_l; A.n_r = d_n_r; A.cap = cap; A.mbf = mbf; A.mb = mb;
+  A.u_right = d_u_right; A.depth = d_depth; A.sad = reinterpret_cast<int32_t*>(sb.p); A.n_matched = d_n_matched;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m->stream;
+  launch_stereo(A, n_pairs, cap, st);
+  ORBM_CUDA(m, cudaGetLastError());
+  return ORBX_OK;
+}
+
+int orbm_stereo_match(orbm_matcher* m, const orbx_extractor* left, const orbx_extractor* right, int frame,
+                      const orbx_kp* kps_l, const uint8_t* desc_l, int n_l, const orbx_kp* kps_r,
+                      const uint8_t* desc_r, int n_r, float mbf, float mb, float* u_right, float* depth,
+                      int32_t* n_matched) {
+  if (!m || n_l < 0 || n_r < 0 || (n_l > 0 && (!kps_l || !desc_l || !u_right || !depth)) ||
+      (n_r > 0 && (!kps_r || !desc_r)))
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (n_matched) *n_matched = 0;
+  if (n_l == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  StereoArgs A;
+  int rc = stereo_args_common(m, left, right, &A);
+  if (rc) return rc;
+  if (frame < 0 || frame >= left->lane[left->last_lane].last_frames || frame >= right->lane[right->last_lane].last_frames)
+    return mfail(m, ORBX_E_ARG, "frame out of range");
+  // the extractors ran on their own streams
+  ORBM_CUDA(m, cudaStreamSynchronize(left->lane[left->last_lane].stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(right->lane[right->last_lane].stream));
+  Arena ar(m);
+  A.frame0 = frame;
+  A.kps_l = ar.upload(kps_l, n_l);
+  A.desc_l = ar.upload(desc_l, (size_t)n_l * 32);
+  A.kps_r = ar.upload(kps_r, n_r);  // n_r == 0: a 1-element dummy is allocated, the count gates every read
+  A.desc_r = ar.upload(desc_r, (size_t)n_r * 32);
+  A.n_l = nullptr; A.n_r = nullptr; A.n_l_host = n_l; A.n_r_host = n_r;
+  A.cap = std::max(n_l, n_r);
+  A.mbf = mbf; A.mb = mb;
+  A.u_right = ar.alloc<float>(n_l);
+  A.depth = ar.alloc<float>(n_l);
+  A.sad = ar.alloc<int32_t>(n_l);
+  A.n_matched = ar.alloc<int32_t>(1);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_stereo(A, 1, n_l, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  int32_t nm = 0;
+  ORBM_CUDA(m, cudaMemcpyAsync(u_right, A.u_right, (size_t)n_l * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(depth, A.depth, (size_t)n_l * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(&nm, A.n_matched, 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  if (n_matched) *n_matched = nm;
+  return ORBX_OK;
+}
+
+int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                             const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                             int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
+                             int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
+                             float* depth, int32_t* n_matched) {
+  if (!m || !left || !right || left == right) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (!imgs_l || !imgs_r || width <= 0 || height <= 0 || n_pairs <= 0) return mfail(m, ORBX_E_EMPTY, "empty image");
+  if (stride < width || cap < 1 || !kps_l || !desc_l || !n_l || !kps_r || !desc_r || !n_r || !u_right || !depth ||
+      !n_matched)
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (left->device != m->device || right->device != m->device || left->max_batch != right->max_batch ||
+      left->nlevels != right->nlevels)
+    return mfail(m, ORBX_E_ARG, "extractors must share device, max_batch and level count with the matcher");
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  int rc;
+  for (orbx_extractor* ex : {left, right}) {
+    if ((rc = api_ensure_plan(ex, width, height)) != 0 || (rc = api_ensure_out(ex, cap)) != 0)
+      return mfail(m, rc, orbx_last_error(ex));
+  }
+  const int B = left->max_batch;
+  for (int ln = 0; ln < kLanes; ln++) {
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < 3 && e == cudaSuccess; k++) e = m->lane_buf[ln][k].reserve((size_t)B * cap * 4);
+    if (e == cudaSuccess) e = m->lane_buf[ln][3].reserve((size_t)B * 4);
+    if (e == cudaSuccess && m->lane_h_cap[ln] < B) {
+      if (m->lane_h_nm[ln]) cudaFreeHost(m->lane_h_nm[ln]);
+      m->lane_h_nm[ln] = nullptr;
+      e = cudaHostAlloc(&m->lane_h_nm[ln], (size_t)B * 4, cudaHostAllocDefault);
+      m->lane_h_cap[ln] = e == cudaSuccess ? B : 0;
+    }
+    if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+  }
+  int first_err = ORBX_OK;
+  int pending_f0[kLanes], pending_nb[kLanes];
+  for (int i = 0; i < kLanes; i++) pending_nb[i] = 0;
+  auto retire = [&](int ln) -> int {
+    if (pending_nb[ln] == 0) return ORBX_OK;
+    ORBM_CUDA(m, cudaEventSynchronize(left->lane[ln].done));
+    for (int f = 0; f < pending_nb[ln]; f++) {
+      const int g = pending_f0[ln] + f;
+      n_l[g] = left->lane[ln].h_small[f];
+      n_r[g] = right->lane[ln].h_small[f];
+      n_matched[g] = m->lane_h_nm[ln][f];
+      const bool bad = left->lane[ln].h_small[2 * B + f] != 0 || right->lane[ln].h_small[2 * B + f] != 0 ||
+                       n_l[g] > cap || n_r[g] > cap;
+      if (bad && first_err == ORBX_OK) first_err = ORBX_E_CAPACITY;
+    }
+    pending_nb[ln] = 0;
+    return ORBX_OK;
+  };
+  int group = 0;
+  for (int f0 = 0; f0 < n_pairs; f0 += B, group++) {
+    const int nb = std::min(B, n_pairs - f0);
+    const int ln = group % kLanes;
+    if ((rc = retire(ln)) != 0) return rc;
+    cudaStream_t st = left->lane[ln].stream;
+    // both extractor calls of the stereo Frame constructor (vLapping = {0, 0}, src/Frame.cc:200-203) ...
+    if ((rc = api_upload_and_run(left, ln, imgs_l + (int64_t)f0 * frame_stride, nb, width, height, stride,
+                                 frame_stride, 0, 0, st)) != 0)
+      return mfail(m, rc, orbx_last_error(left));
+    if ((rc = api_upload_and_run(right, ln, imgs_r + (int64_t)f0 * frame_stride, nb, width, height, stride,
+                                 frame_stride, 0, 0, st)) != 0)
+      return mfail(m, rc, orbx_last_error(right));
+    // ... and ComputeStereoMatches (:223) on the outputs still resident in the lanes
+    StereoArgs A;
+    if ((rc = stereo_args_common(m, left, right, &A, ln)) != 0) return rc;
+    const OrbxLane &LL = left->lane[ln], &RL = right->lane[ln];
+    const int dcap = LL.out_cap;
+    if (RL.out_cap != dcap) return mfail(m, ORBX_E_ARG, "extractor output capacities differ");
+    A.frame0 = 0;
+    A.kps_l = LL.d_kps; A.desc_l = LL.d_desc; A.n_l = LL.d_n;
+    A.kps_r = RL.d_kps; A.desc_r = RL.d_desc; A.n_r = RL.d_n;
+    A.cap = dcap; A.mbf = mbf; A.mb = mb;
+    // the lane buffers were sized for `cap` rows per pair; rows are addressed with the device capacity
+    for (int k = 0; k < 3; k++) {
+      cudaError_t e = m->lane_buf[ln][k].reserve((size_t)B * dcap * 4);
+      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+    }
+    A.u_right = reinterpret_cast<float*>(m->lane_buf[ln][0].p);
+    A.depth = reinterpret_cast<float*>(m->lane_buf[ln][1].p);
+    A.sad = reinterpret_cast<int32_t*>(m->lane_buf[ln][2].p);
+    A.n_matched = reinterpret_cast<int32_t*>(m->lane_buf[ln][3].p);
+    launch_stereo(A, nb, dcap, st);
+    ORBM_CUDA(m, cudaGetLastError());
+    if ((rc = api_download(left, ln, nb, kps_l + (int64_t)f0 * cap, desc_l + (int64_t)f0 * cap * 32, cap, st)) != 0)
+      return mfail(m, rc, orbx_last_error(left));
+    if ((rc = api_download(right, ln, nb, kps_r + (int64_t)f0 * cap, desc_r + (int64_t)f0 * cap * 32, cap, st)) != 0)
+      return mfail(m, rc, orbx_last_error(right));
+    const int rows = std::min(cap, dcap);
+    ORBM_CUDA(m, cudaMemcpy2DAsync(u_right + (int64_t)f0 * cap, (size_t)cap * 4, A.u_right, (size_t)dcap * 4,
+                                   (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
+    ORBM_CUDA(m, cudaMemcpy2DAsync(depth + (int64_t)f0 * cap, (size_t)cap * 4, A.depth, (size_t)dcap * 4,
+                                   (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
+    ORBM_CUDA(m, cudaMemcpyAsync(m->lane_h_nm[ln], A.n_matched, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    ORBM_CUDA(m, cudaEventRecord(left->lane[ln].done, st));
+    pending_f0[ln] = f0;
+    pending_nb[ln] = nb;
+  }
+  for (int ln = 0; ln < kLanes; ln++)
+    if ((rc = retire(ln)) != 0) return rc;
+  if (first_err) return mfail(m, first_err, "output capacity too small for at least one frame");
+  return ORBX_OK;
+}
+
+int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, const orbx_mappoints* mps, float th,
+                                  float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
+  if (!m || !f || !mps || f->n < 0 || mps->m < 0 || (f->n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int M = mps->m;
+  // per-point query set-up = the scalar prologue of the reference loop (:55-74): which points take part, the search
+  // radius r = RadiusByViewingCos(viewCos) * th * scale[level] (:65-67, :223-228) and the level window [L-1, L].
+  std::vector<uint8_t> active(std::max(M, 1));
+  std::vector<float> radius(std::max(M, 1));
+  std::vector<int32_t> minl(std::max(M, 1)), maxl(std::max(M, 1));
+  const bool bFactor = th != 1.0;
+  for (int i = 0; i < M; i++) {
+    bool on = mps->track_in_view[i] != 0;
+    if (on && far_points && mps->depth[i] > th_far) on = false;
+    const int level = mps->level[i];
+    if (on && (level < 0 || level >= f->n_levels)) on = false;
+    active[i] = on;
+    float r = ((double)mps->view_cos[i] > 0.998) ? 2.5f : 4.0f;
+    if (bFactor) r *= th;
+    radius[i] = on ? r * f->scale_factors[level] : 0.f;
+    minl[i] = level - 1;
+    maxl[i] = level;
+  }
+  Arena ar(m);
+  const DevFrame F = upload_frame(ar, f);
+  DevQueries Q{};
+  Q.m = M;
+  Q.active = ar.upload(active.data(), M);
+  Q.u = ar.upload(mps->proj_x, M);
+  Q.v = ar.upload(mps->proj_y, M);
+  Q.radius = ar.upload(radius.data(), M);
+  Q.min_level = ar.upload(minl.data(), M);
+  Q.max_level = ar.upload(maxl.data(), M);
+  Q.u_right = f->u_right ? ar.upload(mps->proj_xr, M) : (ar.alloc<float>(1), nullptr);
+  Q.desc = ar.upload(mps->desc, (size_t)M * 32);
+  ResolveArgs R{};
+  R.mode = 0;
+  R.nnratio = nnratio;
+  R.max_dist = ORBM_TH_HIGH_I;
+  R.check_orientation = 0;
+  R.has_obs = ar.upload(mps->has_obs, M);
+  R.angle = nullptr;
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  return run_search(m, ar, F, Q, R, f->n, assign, nmatches);
+}
+
+int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
+                                    int max_dist, int check_orientation, int32_t* assign, int32_t* nmatches) {
+  if (!m || !f || !pts || f->n < 0 || pts->m < 0 || (f->n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int M = pts->m;
+  Arena ar(m);
+  const DevFrame F = upload_frame(ar, f);
+  DevQueries Q{};
+  Q.m = M;
+  Q.active = nullptr;
+  Q.u = ar.upload(pts->u, M);
+  Q.v = ar.upload(pts->v, M);
+  Q.radius = ar.upload(pts->radius, M);
+  Q.min_level = ar.upload(pts->min_level, M);
+  Q.max_level = ar.upload(pts->max_level, M);
+  Q.u_right = (f->u_right && pts->u_right) ? ar.upload(pts->u_right, M) : (ar.alloc<float>(1), nullptr);
+  Q.desc = ar.upload(pts->desc, (size_t)M * 32);
+  ResolveArgs R{};
+  R.mode = 1;
+  R.nnratio = 0.f;
+  R.max_dist = max_dist;
+  R.check_orientation = check_orientation;
+  R.has_obs = ar.upload(pts->has_obs, M);
+  R.angle = ar.upload(pts->angle, M);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  return run_search(m, ar, F, Q, R, f->n, assign, nmatches);
+}
+
+static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {
+  DevKeyFrame K{};
+  K.n = k->n;
+  K.n_levels = k->n_levels;
+  K.kps = ar.upload(k->kps, k->n);
+  K.desc = ar.upload(k->desc, (size_t)k->n * 32);
+  K.u_right = k->u_right ? ar.upload(k->u_right, k->n) : (ar.alloc<float>(1), nullptr);
+  K.has_mappoint = ar.upload(k->has_mappoint, k->n);
+  K.n_nodes = k->featvec.n_nodes;
+  K.node_ids = ar.upload(k->featvec.node_ids, K.n_nodes);
+  K.offsets = ar.upload(k->featvec.offsets, (size_t)K.n_nodes + 1);
+  K.indices = ar.upload(k->featvec.indices, K.n_nodes > 0 ? (size_t)k->featvec.offsets[K.n_nodes] : 0);
+  K.scale_factors = ar.upload(k->scale_factors, k->n_levels);
+  K.level_sigma2 = ar.upload(k->level_sigma2, k->n_levels);
+  return K;
+}
+
+int orbm_search_for_triangulation(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2,
+                                  const float* F12, float ep_x, float ep_y, int only_stereo, int coarse,
+                                  int check_orientation, int32_t* matches12, int32_t* nmatches) {
+  if (!m || !kf1 || !kf2 || !F12 || kf1->n < 0 || kf2->n < 0 || (kf1->n > 0 && !matches12))
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  TriArgs A{};
+  A.k1 = upload_keyframe(ar, kf1);
+  A.k2 = upload_keyframe(ar, kf2);
+  memcpy(A.F12, F12, sizeof(A.F12));
+  A.ep_x = ep_x;
+  A.ep_y = ep_y;
+  A.only_stereo = only_stereo;
+  A.coarse = coarse;
+  A.check_orientation = check_orientation;
+  A.matches12 = ar.alloc<int32_t>(kf1->n);
+  A.nmatches = ar.alloc<int32_t>(1);
+  A.node_match = ar.alloc<int32_t>(A.k1.n_nodes);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_triangulation(A, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  int32_t nm = 0;
+  if (kf1->n > 0)
+    ORBM_CUDA(m, cudaMemcpyAsync(matches12, A.matches12, (size_t)kf1->n * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(&nm, A.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  if (nmatches) *nmatches = nm;
+  return ORBX_OK;
+}
+
+}  // extern "C"

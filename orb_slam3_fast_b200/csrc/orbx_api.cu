@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/orbx.h"
+#include "orbx_handle.h"
 #include "orbx_kernels.cuh"
 #include "orbx_quadtree.h"
 
@@ -19,110 +20,169 @@ const int8_t kPatternHost[256 * 4] = {
 #include "orb_pattern.inc"
 };
 thread_local std::string g_create_error;
-enum { kStages = 6 };
-}  // namespace
-
-struct orbx_extractor {
-  int device = 0;
-  int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0, max_batch = 1;
-  float scale_factor = 1.2f;
-  std::string err;
-  cudaStream_t stream = nullptr;
-  // geometry-dependent state (rebuilt when the image size changes)
-  bool planned = false;
-  Plan plan;
-  int64_t slab_fstride = 0;
-  int in_pitch = 0;
-  int64_t in_fstride = 0;
-  uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr;
-  ResizeTab* d_tab = nullptr;
-  WorkSet ws{};
-  int8_t* d_pattern = nullptr;
-  // outputs of the host-facing calls
-  int out_cap = 0;
-  orbx_kp* d_kps = nullptr;
-  uint8_t* d_desc = nullptr;
-  int32_t *d_n = nullptr, *d_mono = nullptr, *d_status = nullptr;
-  // last call (for downloads / stereo)
-  FrameSet last_fs{};
-  int last_frames = 0;
-  // profiling
-  bool profile = false;
-  cudaEvent_t ev[kStages + 1] = {};
-  float prof_ms[kStages] = {};
-  int prof_launches[kStages] = {};
-};
-
-namespace {
-
-int fail(orbx_extractor* ex, int code, const std::string& msg) {
-  if (ex) ex->err = msg;
-  else g_create_error = msg;
-  return code;
-}
 
 #define ORBX_CUDA(ex, call)                                                                              \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
     if (e_ != cudaSuccess)                                                                               \
-      return fail(ex, ORBX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+      return api_fail(ex, ORBX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));               \
   } while (0)
 
 void free_plan_buffers(orbx_extractor* ex) {
-  cudaFree(ex->d_in);
-  cudaFree(ex->d_pyr);
-  cudaFree(ex->d_blur);
+  for (OrbxLane& L : ex->lane) {
+    cudaFree(L.d_in);
+    cudaFree(L.d_pyr);
+    cudaFree(L.d_blur);
+    cudaFree(L.ws.slots);
+    cudaFree(L.ws.cell_count);
+    cudaFree(L.ws.cand);
+    cudaFree(L.ws.lab);
+    cudaFree(L.ws.lvl_kp);
+    cudaFree(L.ws.lvl_n);
+    cudaFree(L.ws.lvl_c);
+    cudaFree(L.ws.dst);
+    L.d_in = L.d_pyr = L.d_blur = nullptr;
+    L.ws = WorkSet{};
+    L.last_frames = 0;
+  }
   cudaFree(ex->d_tab);
-  cudaFree(ex->ws.slots);
-  cudaFree(ex->ws.cell_count);
-  cudaFree(ex->ws.cand);
-  cudaFree(ex->ws.lab);
-  cudaFree(ex->ws.lvl_kp);
-  cudaFree(ex->ws.lvl_n);
-  cudaFree(ex->ws.lvl_c);
-  cudaFree(ex->ws.dst);
-  ex->d_in = ex->d_pyr = ex->d_blur = nullptr;
   ex->d_tab = nullptr;
-  ex->ws = WorkSet{};
   ex->planned = false;
 }
 
 void free_out_buffers(orbx_extractor* ex) {
-  cudaFree(ex->d_kps);
-  cudaFree(ex->d_desc);
-  cudaFree(ex->d_n);
-  cudaFree(ex->d_mono);
-  cudaFree(ex->d_status);
-  ex->d_kps = nullptr;
-  ex->d_desc = nullptr;
-  ex->d_n = ex->d_mono = ex->d_status = nullptr;
-  ex->out_cap = 0;
+  for (OrbxLane& L : ex->lane) {
+    cudaFree(L.d_kps);
+    cudaFree(L.d_desc);
+    cudaFree(L.d_n);
+    cudaFree(L.d_mono);
+    cudaFree(L.d_status);
+    L.d_kps = nullptr;
+    L.d_desc = nullptr;
+    L.d_n = L.d_mono = L.d_status = nullptr;
+    L.out_cap = 0;
+  }
 }
 
-int ensure_plan(orbx_extractor* ex, int w, int h) {
+int sync_all_lanes(orbx_extractor* ex) {
+  for (OrbxLane& L : ex->lane)
+    if (L.stream) ORBX_CUDA(ex, cudaStreamSynchronize(L.stream));
+  return ORBX_OK;
+}
+
+// scratch of one lane; lanes beyond the first are only materialised when a call needs them
+int alloc_lane(orbx_extractor* ex, OrbxLane& L) {
+  if (L.d_pyr) return ORBX_OK;
+  const Plan& P = ex->plan;
+  const size_t B = ex->max_batch;
+  ORBX_CUDA(ex, cudaMalloc(&L.d_in, (size_t)ex->in_fstride * B));
+  ORBX_CUDA(ex, cudaMalloc(&L.d_pyr, (size_t)ex->slab_fstride * B));
+  ORBX_CUDA(ex, cudaMalloc(&L.d_blur, (size_t)ex->slab_fstride * B));
+  ORBX_CUDA(ex, cudaMemsetAsync(L.d_in, 0, (size_t)ex->in_fstride * B, L.stream));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.slots, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.cand, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.lab, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.cell_count, (size_t)P.cells_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_kp, (size_t)P.kps_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.dst, (size_t)P.kps_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_n, (size_t)P.nlevels * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_c, (size_t)P.nlevels * B * 4));
+  return ORBX_OK;
+}
+
+int alloc_lane_out(orbx_extractor* ex, OrbxLane& L, int cap) {
+  if (L.out_cap >= cap && L.d_kps) return ORBX_OK;
+  ORBX_CUDA(ex, cudaStreamSynchronize(L.stream));
+  cudaFree(L.d_kps);
+  cudaFree(L.d_desc);
+  cudaFree(L.d_n);
+  cudaFree(L.d_mono);
+  cudaFree(L.d_status);
+  L.d_kps = nullptr;
+  const size_t B = ex->max_batch;
+  ORBX_CUDA(ex, cudaMalloc(&L.d_kps, (size_t)cap * B * sizeof(orbx_kp)));
+  ORBX_CUDA(ex, cudaMalloc(&L.d_desc, (size_t)cap * B * ORBX_DESC_BYTES));
+  ORBX_CUDA(ex, cudaMalloc(&L.d_n, B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.d_mono, B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.d_status, B * 4));
+  L.out_cap = cap;
+  return ORBX_OK;
+}
+
+// The whole extractor for `frames` frames whose level 0 is described by fs.{lvl0,pitch0,fstride0}, on lane ln.
+int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, int lap1, const OutSet& out,
+                 cudaStream_t st) {
+  const Plan& P = ex->plan;
+  OrbxLane& L = ex->lane[ln];
+  int rc = alloc_lane(ex, L);
+  if (rc) return rc;
+  fs.pyr = L.d_pyr;
+  fs.blur = L.d_blur;
+  fs.slab_fstride = ex->slab_fstride;
+  bool prof = ex->profile;
+  if (prof) {  // take kStages + 1 events from the pool
+    while (ex->prof_events.size() < ex->prof_used + kStages + 1) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { prof = false; break; }
+      ex->prof_events.push_back(e);
+    }
+  }
+  int stage = 0;
+  auto mark = [&]() {
+    if (prof) cudaEventRecord(ex->prof_events[ex->prof_used + stage], st);
+    stage++;
+  };
+  mark();
+  launch_pyramid(P, fs, ex->d_tab, frames, st);
+  mark();
+  launch_fast(P, fs, L.ws, ex->ini_th, ex->min_th, frames, st);
+  mark();
+  launch_quadtree(P, L.ws, frames, st);
+  mark();
+  launch_blur(P, fs, frames, st);
+  mark();
+  launch_assemble(P, L.ws, out, lap0, lap1, frames, st);
+  mark();
+  launch_describe(P, fs, L.ws, out, ex->d_pattern, frames, st);
+  mark();
+  ORBX_CUDA(ex, cudaGetLastError());
+  if (prof) ex->prof_used += kStages + 1;
+  L.last_fs = fs;
+  L.last_frames = frames;
+  ex->last_lane = ln;
+  return ORBX_OK;
+}
+
+}  // namespace
+
+namespace orbx {
+
+int api_fail(orbx_extractor* ex, int code, const std::string& msg) {
+  if (ex) ex->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+int api_ensure_plan(orbx_extractor* ex, int w, int h) {
   if (ex->planned && ex->plan.w == w && ex->plan.h == h) return ORBX_OK;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   if (ex->planned) {
-    ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+    int rc = sync_all_lanes(ex);
+    if (rc) return rc;
     free_plan_buffers(ex);
   }
   Plan P;
   const int rc = make_plan(w, h, ex->nfeatures, ex->scale_factor, ex->nlevels, &P);
-  if (rc == -2) return fail(ex, ORBX_E_SIZE, "image too small for the pyramid depth (a level has no 35-px cell)");
-  if (rc == -3) return fail(ex, ORBX_E_SIZE, "image larger than 4096 px");
-  if (rc != 0) return fail(ex, ORBX_E_ARG, "bad extractor parameters");
+  if (rc == -2) return api_fail(ex, ORBX_E_SIZE, "image too small for the pyramid depth (a level has no 35-px cell)");
+  if (rc == -3) return api_fail(ex, ORBX_E_SIZE, "image larger than 4096 px");
+  if (rc != 0) return api_fail(ex, ORBX_E_ARG, "bad extractor parameters");
   for (int l = 0; l < P.nlevels; l++)
     if ((int64_t)P.lv[l].nCols * P.lv[l].nRows * P.lv[l].slot_cap >= (1 << 20))
-      return fail(ex, ORBX_E_SIZE, "level too large: more than 2^20 candidate slots");
+      return api_fail(ex, ORBX_E_SIZE, "level too large: more than 2^20 candidate slots");
   ex->plan = P;
-  const int B = ex->max_batch;
   ex->slab_fstride = (P.pyr_bytes_per_frame + 255) / 256 * 256;
   ex->in_pitch = round_up(w, 64);
   ex->in_fstride = (int64_t)ex->in_pitch * h;
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_in, (size_t)ex->in_fstride * B));
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_pyr, (size_t)ex->slab_fstride * B));
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_blur, (size_t)ex->slab_fstride * B));
-  ORBX_CUDA(ex, cudaMemsetAsync(ex->d_in, 0, (size_t)ex->in_fstride * B, ex->stream));
   // resize tables
   std::vector<ResizeTab> tab(std::max(P.tab_entries, 1));
   {
@@ -141,92 +201,71 @@ int ensure_plan(orbx_extractor* ex, int w, int h) {
     }
   }
   ORBX_CUDA(ex, cudaMalloc(&ex->d_tab, tab.size() * sizeof(ResizeTab)));
-  ORBX_CUDA(ex, cudaMemcpyAsync(ex->d_tab, tab.data(), tab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice,
-                                ex->stream));
-  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));  // `tab` goes out of scope
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.slots, (size_t)P.slots_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.cand, (size_t)P.slots_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lab, (size_t)P.slots_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.cell_count, (size_t)P.cells_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lvl_kp, (size_t)P.kps_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.dst, (size_t)P.kps_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lvl_n, (size_t)P.nlevels * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->ws.lvl_c, (size_t)P.nlevels * B * 4));
+  ORBX_CUDA(ex, cudaMemcpy(ex->d_tab, tab.data(), tab.size() * sizeof(ResizeTab), cudaMemcpyHostToDevice));
   ex->planned = true;
-  ex->last_frames = 0;
   return ORBX_OK;
 }
 
-int ensure_out(orbx_extractor* ex, int cap) {
-  if (ex->out_cap >= cap && ex->d_kps) return ORBX_OK;
-  free_out_buffers(ex);
-  const int B = ex->max_batch;
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_kps, (size_t)cap * B * sizeof(orbx_kp)));
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_desc, (size_t)cap * B * ORBX_DESC_BYTES));
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_n, (size_t)B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_mono, (size_t)B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&ex->d_status, (size_t)B * 4));
-  ex->out_cap = cap;
-  return ORBX_OK;
-}
-
-// The whole extractor for `frames` frames whose level 0 is described by fs.{lvl0,pitch0,fstride0}.
-int run_pipeline(orbx_extractor* ex, FrameSet fs, int frames, int lap0, int lap1, const OutSet& out,
-                 cudaStream_t st) {
-  const Plan& P = ex->plan;
-  fs.pyr = ex->d_pyr;
-  fs.blur = ex->d_blur;
-  fs.slab_fstride = ex->slab_fstride;
-  const bool prof = ex->profile;
-  int stage = 0;
-  auto mark = [&]() {
-    if (prof) cudaEventRecord(ex->ev[stage], st);
-    stage++;
-  };
-  mark();
-  launch_pyramid(P, fs, ex->d_tab, frames, st);
-  mark();
-  launch_fast(P, fs, ex->ws, ex->ini_th, ex->min_th, frames, st);
-  mark();
-  launch_quadtree(P, ex->ws, frames, st);
-  mark();
-  launch_blur(P, fs, frames, st);
-  mark();
-  launch_assemble(P, ex->ws, out, lap0, lap1, frames, st);
-  mark();
-  launch_describe(P, fs, ex->ws, out, ex->d_pattern, frames, st);
-  mark();
-  ORBX_CUDA(ex, cudaGetLastError());
-  if (prof) {
-    ORBX_CUDA(ex, cudaEventSynchronize(ex->ev[kStages]));
-    for (int s = 0; s < kStages; s++) {
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ex->ev[s], ex->ev[s + 1]);
-      ex->prof_ms[s] += ms;
-      ex->prof_launches[s] += 1;
-    }
+int api_ensure_out(orbx_extractor* ex, int cap) {
+  for (OrbxLane& L : ex->lane) {
+    int rc = alloc_lane_out(ex, L, cap);
+    if (rc) return rc;
   }
-  ex->last_fs = fs;
-  ex->last_frames = frames;
   return ORBX_OK;
 }
 
-}  // namespace
+int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, int width, int height, int stride,
+                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st) {
+  OrbxLane& L = ex->lane[ln];
+  int rc = alloc_lane(ex, L);
+  if (rc) return rc;
+  if (frame_stride == (int64_t)stride * height) {
+    ORBX_CUDA(ex, cudaMemcpy2DAsync(L.d_in, ex->in_pitch, src, stride, width, (size_t)height * nb,
+                                    cudaMemcpyHostToDevice, st));
+  } else {
+    for (int f = 0; f < nb; f++)
+      ORBX_CUDA(ex, cudaMemcpy2DAsync(L.d_in + f * ex->in_fstride, ex->in_pitch, src + f * frame_stride, stride,
+                                      width, height, cudaMemcpyHostToDevice, st));
+  }
+  FrameSet fs{};
+  fs.lvl0 = L.d_in;
+  fs.pitch0 = ex->in_pitch;
+  fs.fstride0 = ex->in_fstride;
+  OutSet out{L.d_kps, L.d_desc, L.d_n, L.d_mono, L.d_status, L.out_cap};
+  return run_pipeline(ex, ln, fs, nb, lap0, lap1, out, st);
+}
+
+int api_download(orbx_extractor* ex, int ln, int nb, orbx_kp* kps, uint8_t* desc, int cap, cudaStream_t st) {
+  OrbxLane& L = ex->lane[ln];
+  const int B = ex->max_batch;
+  ORBX_CUDA(ex, cudaMemcpyAsync(L.h_small, L.d_n, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(ex, cudaMemcpyAsync(L.h_small + B, L.d_mono, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(ex, cudaMemcpyAsync(L.h_small + 2 * B, L.d_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+  // rows: device arrays are [nb][out_cap], the caller's are [..][cap]
+  const int rows = std::min(cap, L.out_cap);
+  ORBX_CUDA(ex, cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_kp), L.d_kps, (size_t)L.out_cap * sizeof(orbx_kp),
+                                  (size_t)rows * sizeof(orbx_kp), nb, cudaMemcpyDeviceToHost, st));
+  ORBX_CUDA(ex, cudaMemcpy2DAsync(desc, (size_t)cap * ORBX_DESC_BYTES, L.d_desc, (size_t)L.out_cap * ORBX_DESC_BYTES,
+                                  (size_t)rows * ORBX_DESC_BYTES, nb, cudaMemcpyDeviceToHost, st));
+  return ORBX_OK;
+}
+
+}  // namespace orbx
 
 extern "C" {
 
 int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float scale_factor, int nlevels,
                           int ini_th_fast, int min_th_fast, int max_batch) {
-  if (!out) return fail(nullptr, ORBX_E_ARG, "out == NULL");
+  if (!out) return api_fail(nullptr, ORBX_E_ARG, "out == NULL");
   *out = nullptr;
   if (nfeatures < 1 || nlevels < 1 || nlevels > kMaxLevels || !(scale_factor > 1.0f) || max_batch < 1 ||
       ini_th_fast < 0 || ini_th_fast > 255 || min_th_fast < 0 || min_th_fast > 255)
-    return fail(nullptr, ORBX_E_ARG, "bad extractor parameters");
+    return api_fail(nullptr, ORBX_E_ARG, "bad extractor parameters");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
-    return fail(nullptr, ORBX_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
-  if (device < 0 || device >= ndev) return fail(nullptr, ORBX_E_ARG, "bad device ordinal");
+    return api_fail(nullptr, ORBX_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return api_fail(nullptr, ORBX_E_ARG, "bad device ordinal");
   orbx_extractor* ex = new orbx_extractor;
   ex->device = device;
   ex->nfeatures = nfeatures;
@@ -241,13 +280,17 @@ int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float
     return ORBX_E_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-  if ((e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking)) != cudaSuccess)
-    return bail("cudaStreamCreate", e);
+  for (OrbxLane& L : ex->lane) {
+    if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess)
+      return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
+      return bail("cudaEventCreate", e);
+    if ((e = cudaHostAlloc(&L.h_small, (size_t)3 * max_batch * 4, cudaHostAllocDefault)) != cudaSuccess)
+      return bail("cudaHostAlloc", e);
+  }
   if ((e = cudaMalloc(&ex->d_pattern, sizeof(kPatternHost))) != cudaSuccess) return bail("cudaMalloc", e);
   if ((e = cudaMemcpy(ex->d_pattern, kPatternHost, sizeof(kPatternHost), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy", e);
-  for (auto& ev : ex->ev)
-    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   *out = ex;
   return ORBX_OK;
 }
@@ -255,13 +298,17 @@ int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float
 void orbx_extractor_destroy(orbx_extractor* ex) {
   if (!ex) return;
   cudaSetDevice(ex->device);
-  if (ex->stream) cudaStreamSynchronize(ex->stream);
+  for (OrbxLane& L : ex->lane)
+    if (L.stream) cudaStreamSynchronize(L.stream);
   free_plan_buffers(ex);
   free_out_buffers(ex);
   cudaFree(ex->d_pattern);
-  for (auto& ev : ex->ev)
-    if (ev) cudaEventDestroy(ev);
-  if (ex->stream) cudaStreamDestroy(ex->stream);
+  for (auto& ev : ex->prof_events) cudaEventDestroy(ev);
+  for (OrbxLane& L : ex->lane) {
+    if (L.h_small) cudaFreeHost(L.h_small);
+    if (L.done) cudaEventDestroy(L.done);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
   delete ex;
 }
 
@@ -294,71 +341,69 @@ int orbx_extract_batch_device(orbx_extractor* ex, int n_frames, const uint8_t* d
                               int stride, int64_t frame_stride, int lap0, int lap1, orbx_kp* d_kps, uint8_t* d_desc,
                               int cap, int32_t* d_n, int32_t* d_mono_index, int32_t* d_status, void* cuda_stream) {
   if (!ex) return ORBX_E_ARG;
-  if (!d_images || width <= 0 || height <= 0 || n_frames <= 0) return fail(ex, ORBX_E_EMPTY, "empty image");
-  if (n_frames > ex->max_batch) return fail(ex, ORBX_E_ARG, "n_frames > max_batch");
+  if (!d_images || width <= 0 || height <= 0 || n_frames <= 0) return api_fail(ex, ORBX_E_EMPTY, "empty image");
+  if (n_frames > ex->max_batch) return api_fail(ex, ORBX_E_ARG, "n_frames > max_batch");
   if (stride < width || !d_kps || !d_desc || !d_n || !d_mono_index || !d_status || cap < 1)
-    return fail(ex, ORBX_E_ARG, "bad argument");
+    return api_fail(ex, ORBX_E_ARG, "bad argument");
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
-  int rc = ensure_plan(ex, width, height);
+  int rc = api_ensure_plan(ex, width, height);
   if (rc) return rc;
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->stream;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->lane[0].stream;
   FrameSet fs{};
   fs.lvl0 = d_images;
   fs.pitch0 = stride;
   fs.fstride0 = frame_stride;
   OutSet out{d_kps, d_desc, d_n, d_mono_index, d_status, cap};
-  return run_pipeline(ex, fs, n_frames, lap0, lap1, out, st);
+  return run_pipeline(ex, 0, fs, n_frames, lap0, lap1, out, st);
 }
 
 int orbx_extract_batch(orbx_extractor* ex, int n_frames, const uint8_t* images, int width, int height, int stride,
                        int64_t frame_stride, int lap0, int lap1, orbx_kp* kps, uint8_t* desc, int cap,
                        int32_t* n_out, int32_t* mono_index) {
   if (!ex) return ORBX_E_ARG;
-  if (!images || width <= 0 || height <= 0 || n_frames <= 0) return fail(ex, ORBX_E_EMPTY, "empty image");
-  if (stride < width || !kps || !desc || !n_out || cap < 1) return fail(ex, ORBX_E_ARG, "bad argument");
+  if (!images || width <= 0 || height <= 0 || n_frames <= 0) return api_fail(ex, ORBX_E_EMPTY, "empty image");
+  if (stride < width || !kps || !desc || !n_out || cap < 1) return api_fail(ex, ORBX_E_ARG, "bad argument");
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
-  int rc = ensure_plan(ex, width, height);
+  int rc = api_ensure_plan(ex, width, height);
   if (rc) return rc;
-  rc = ensure_out(ex, cap);
+  rc = api_ensure_out(ex, cap);
   if (rc) return rc;
-  cudaStream_t st = ex->stream;
-  std::vector<int32_t> status(ex->max_batch), mono(ex->max_batch);
+  const int B = ex->max_batch;
   int first_err = ORBX_OK;
-  for (int f0 = 0; f0 < n_frames; f0 += ex->max_batch) {
-    const int nb = std::min(ex->max_batch, n_frames - f0);
-    const uint8_t* src = images + (int64_t)f0 * frame_stride;
-    if (frame_stride == (int64_t)stride * height) {
-      ORBX_CUDA(ex, cudaMemcpy2DAsync(ex->d_in, ex->in_pitch, src, stride, width, (size_t)height * nb,
-                                      cudaMemcpyHostToDevice, st));
-    } else {
-      for (int f = 0; f < nb; f++)
-        ORBX_CUDA(ex, cudaMemcpy2DAsync(ex->d_in + f * ex->in_fstride, ex->in_pitch, src + f * frame_stride, stride,
-                                        width, height, cudaMemcpyHostToDevice, st));
+  int pending_f0[kLanes], pending_nb[kLanes];
+  for (int i = 0; i < kLanes; i++) pending_nb[i] = 0;
+  // collect the small per-frame results of the group a lane finished
+  auto retire = [&](int ln) -> int {
+    if (pending_nb[ln] == 0) return ORBX_OK;
+    OrbxLane& L = ex->lane[ln];
+    ORBX_CUDA(ex, cudaEventSynchronize(L.done));
+    for (int f = 0; f < pending_nb[ln]; f++) {
+      const int g = pending_f0[ln] + f;
+      n_out[g] = L.h_small[f];
+      if (mono_index) mono_index[g] = L.h_small[B + f];
+      if ((L.h_small[2 * B + f] != 0 || n_out[g] > cap) && first_err == ORBX_OK) first_err = ORBX_E_CAPACITY;
     }
-    FrameSet fs{};
-    fs.lvl0 = ex->d_in;
-    fs.pitch0 = ex->in_pitch;
-    fs.fstride0 = ex->in_fstride;
-    OutSet out{ex->d_kps, ex->d_desc, ex->d_n, ex->d_mono, ex->d_status, ex->out_cap};
-    rc = run_pipeline(ex, fs, nb, lap0, lap1, out, st);
+    pending_nb[ln] = 0;
+    return ORBX_OK;
+  };
+  int group = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += B, group++) {
+    const int nb = std::min(B, n_frames - f0);
+    const int ln = group % kLanes;
+    OrbxLane& L = ex->lane[ln];
+    if ((rc = retire(ln)) != 0) return rc;
+    rc = api_upload_and_run(ex, ln, images + (int64_t)f0 * frame_stride, nb, width, height, stride, frame_stride,
+                            lap0, lap1, L.stream);
     if (rc) return rc;
-    ORBX_CUDA(ex, cudaMemcpyAsync(n_out + f0, ex->d_n, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(ex, cudaMemcpyAsync(mono.data(), ex->d_mono, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(ex, cudaMemcpyAsync(status.data(), ex->d_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-    // rows: device arrays are [nb][out_cap], the caller's are [n_frames][cap]
-    ORBX_CUDA(ex, cudaMemcpy2DAsync(kps + (int64_t)f0 * cap, (size_t)cap * sizeof(orbx_kp), ex->d_kps,
-                                    (size_t)ex->out_cap * sizeof(orbx_kp), (size_t)cap * sizeof(orbx_kp), nb,
-                                    cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(ex, cudaMemcpy2DAsync(desc + (int64_t)f0 * cap * ORBX_DESC_BYTES, (size_t)cap * ORBX_DESC_BYTES,
-                                    ex->d_desc, (size_t)ex->out_cap * ORBX_DESC_BYTES,
-                                    (size_t)cap * ORBX_DESC_BYTES, nb, cudaMemcpyDeviceToHost, st));
-    ORBX_CUDA(ex, cudaStreamSynchronize(st));
-    for (int f = 0; f < nb; f++) {
-      if (mono_index) mono_index[f0 + f] = mono[f];
-      if ((status[f] != 0 || n_out[f0 + f] > cap) && first_err == ORBX_OK) first_err = ORBX_E_CAPACITY;
-    }
+    rc = api_download(ex, ln, nb, kps + (int64_t)f0 * cap, desc + (int64_t)f0 * cap * ORBX_DESC_BYTES, cap, L.stream);
+    if (rc) return rc;
+    ORBX_CUDA(ex, cudaEventRecord(L.done, L.stream));
+    pending_f0[ln] = f0;
+    pending_nb[ln] = nb;
   }
-  if (first_err) return fail(ex, first_err, "output capacity too small for at least one frame");
+  for (int ln = 0; ln < kLanes; ln++)
+    if ((rc = retire(ln)) != 0) return rc;
+  if (first_err) return api_fail(ex, first_err, "output capacity too small for at least one frame");
   return ORBX_OK;
 }
 
@@ -380,11 +425,11 @@ int orbx_level_size(const orbx_extractor* ex, int level, int* width, int* height
 }
 
 int orbx_debug_level(orbx_extractor* ex, int frame, int level, int which, uint8_t* dst, int dst_stride) {
-  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames || !dst)
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lane[ex->last_lane].last_frames || !dst)
     return ORBX_E_ARG;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   const LevelPlan& L = ex->plan.lv[level];
-  const FrameSet& fs = ex->last_fs;
+  const FrameSet& fs = ex->lane[ex->last_lane].last_fs;
   const uint8_t* src;
   int pitch;
   if (which == 1) {
@@ -397,7 +442,7 @@ int orbx_debug_level(orbx_extractor* ex, int frame, int level, int which, uint8_
     src = fs.pyr + (int64_t)frame * fs.slab_fstride + L.img_off;
     pitch = L.pitch;
   }
-  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+  ORBX_CUDA(ex, cudaDeviceSynchronize());
   ORBX_CUDA(ex, cudaMemcpy2D(dst, dst_stride, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
   return ORBX_OK;
 }
@@ -405,7 +450,7 @@ int orbx_debug_level(orbx_extractor* ex, int frame, int level, int which, uint8_
 int orbx_download_pyramid(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride) {
   if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || !dst) return ORBX_E_ARG;
   const LevelPlan& L = ex->plan.lv[level];
-  if (dst_stride < L.w + 2 * kEdge) return fail(ex, ORBX_E_ARG, "dst_stride < w + 38");
+  if (dst_stride < L.w + 2 * kEdge) return api_fail(ex, ORBX_E_ARG, "dst_stride < w + 38");
   // interior first, then the reflect-101 frame is a pure copy of interior pixels (cv::copyMakeBorder, :1129-1143)
   uint8_t* roi = dst + (size_t)kEdge * dst_stride + kEdge;
   int rc = orbx_debug_level(ex, frame, level, 0, roi, dst_stride);
@@ -437,32 +482,32 @@ static void unpack_kp(uint32_t cw, int add, int level, float size, orbx_kp* k) {
 }
 
 int orbx_debug_candidates(orbx_extractor* ex, int frame, int level, orbx_kp* out, int cap) {
-  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames)
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lane[ex->last_lane].last_frames)
     return ORBX_E_ARG;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
-  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+  ORBX_CUDA(ex, cudaDeviceSynchronize());
   const Plan& P = ex->plan;
   int32_t C = 0;
-  ORBX_CUDA(ex, cudaMemcpy(&C, ex->ws.lvl_c + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(ex, cudaMemcpy(&C, ex->lane[ex->last_lane].ws.lvl_c + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
   const int n = std::min(C, cap);
   std::vector<uint32_t> buf(std::max(n, 1));
-  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->ws.cand + (int64_t)frame * P.slots_per_frame + P.lv[level].slot_base,
+  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->lane[ex->last_lane].ws.cand + (int64_t)frame * P.slots_per_frame + P.lv[level].slot_base,
                            (size_t)n * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n && out; i++) unpack_kp(buf[i], 0, 0, 7.f, out + i);
   return C;
 }
 
 int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp* out, int cap) {
-  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_frames)
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lane[ex->last_lane].last_frames)
     return ORBX_E_ARG;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
-  ORBX_CUDA(ex, cudaStreamSynchronize(ex->stream));
+  ORBX_CUDA(ex, cudaDeviceSynchronize());
   const Plan& P = ex->plan;
   int32_t C = 0;
-  ORBX_CUDA(ex, cudaMemcpy(&C, ex->ws.lvl_n + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(ex, cudaMemcpy(&C, ex->lane[ex->last_lane].ws.lvl_n + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
   const int n = std::min(C, cap);
   std::vector<uint32_t> buf(std::max(n, 1));
-  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->ws.lvl_kp + (int64_t)frame * P.kps_per_frame + P.lv[level].kp_base,
+  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->lane[ex->last_lane].ws.lvl_kp + (int64_t)frame * P.kps_per_frame + P.lv[level].kp_base,
                            (size_t)n * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n && out; i++) unpack_kp(buf[i], kMinBorder, level, (float)P.lv[level].patch, out + i);
   return C;
@@ -476,6 +521,17 @@ int orbx_profile_enable(orbx_extractor* ex, int on) {
 
 int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int reset) {
   if (!ex) return ORBX_E_ARG;
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  for (size_t r = 0; r + kStages < ex->prof_used; r += kStages + 1) {
+    ORBX_CUDA(ex, cudaEventSynchronize(ex->prof_events[r + kStages]));
+    for (int s = 0; s < kStages; s++) {
+      float t = 0;
+      ORBX_CUDA(ex, cudaEventElapsedTime(&t, ex->prof_events[r + s], ex->prof_events[r + s + 1]));
+      ex->prof_ms[s] += t;
+      ex->prof_launches[s] += 1;
+    }
+  }
+  ex->prof_used = 0;
   for (int s = 0; s < kStages; s++) {
     if (ms) ms[s] = ex->prof_ms[s];
     if (launches) launches[s] = ex->prof_launches[s];

@@ -1,0 +1,70 @@
+// orbx_handle.h — the extractor handle, shared by the extractor ABI (orbx_api.cu) and the matcher ABI (orbm_api.cu:
+// Frame::ComputeStereoMatches reads both extractors' pyramids, src/Frame.cc:927,1011,1029).
+//
+// A handle owns kLanes independent copies of the per-batch device state ("lanes"), each with its own stream. The
+// host-facing batched calls cut the frames into groups of max_batch and alternate lanes, so the H2D copy of group
+// i+1 and the D2H copy of group i-1 overlap the kernels of group i.
+#ifndef ORBX_HANDLE_H_
+#define ORBX_HANDLE_H_
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "orbx_kernels.cuh"
+
+enum { kStages = 6, kLanes = 2 };
+
+struct OrbxLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  // geometry-dependent device state
+  uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr;
+  orbx::WorkSet ws{};
+  // device outputs of the host-facing calls, [max_batch][out_cap]
+  int out_cap = 0;
+  orbx_kp* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int32_t *d_n = nullptr, *d_mono = nullptr, *d_status = nullptr;
+  int32_t* h_small = nullptr;  // pinned [3][max_batch]: n, mono, status
+  // what the lane holds since its last run (for downloads / stereo matching)
+  orbx::FrameSet last_fs{};
+  int last_frames = 0;
+};
+
+struct orbx_extractor {
+  int device = 0;
+  int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0, max_batch = 1;
+  float scale_factor = 1.2f;
+  std::string err;
+  bool planned = false;
+  orbx::Plan plan;
+  int64_t slab_fstride = 0;
+  int in_pitch = 0;
+  int64_t in_fstride = 0;
+  orbx::ResizeTab* d_tab = nullptr;
+  int8_t* d_pattern = nullptr;
+  OrbxLane lane[kLanes];
+  int last_lane = 0;  // lane of the most recent run: "frame f of the last call" lives there
+  // profiling: event records around every stage, resolved lazily by orbx_profile_read (no sync inside a run)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;  // pool, kStages + 1 per recorded run
+  size_t prof_used = 0;                  // events recorded since the last read
+  float prof_ms[kStages] = {};
+  int prof_launches[kStages] = {};
+};
+
+namespace orbx {
+// internal entry points of orbx_api.cu used by the matcher's fused stereo call
+int api_fail(orbx_extractor* ex, int code, const std::string& msg);
+int api_ensure_plan(orbx_extractor* ex, int w, int h);
+int api_ensure_out(orbx_extractor* ex, int cap);
+// H2D of nb frames into lane `ln` and the whole extractor on stream st; results stay in the lane's device outputs
+int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, int width, int height, int stride,
+                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st);
+// D2H of the lane's outputs of nb frames into rows [0, nb) of the caller's arrays (counts go to the pinned h_small)
+int api_download(orbx_extractor* ex, int ln, int nb, orbx_kp* kps, uint8_t* desc, int cap, cudaStream_t st);
+}  // namespace orbx
+
+#endif

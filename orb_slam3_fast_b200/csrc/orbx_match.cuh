@@ -1,0 +1,125 @@
+// orbx_match.cuh — internal launch interface of the matcher kernels (k_match.cu, k_search.cu) used by orbm_api.cu.
+#ifndef ORBX_MATCH_CUH_
+#define ORBX_MATCH_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbx_types.h"
+#include "orbx_math.h"
+
+namespace orbx {
+
+constexpr int ORBM_TH_HIGH_I = 100;  // ORBmatcher::TH_HIGH   src/ORBmatcher.cc:35
+constexpr int ORBM_TH_LOW_I = 50;    // ORBmatcher::TH_LOW    src/ORBmatcher.cc:36
+constexpr int kHistoLength = 30;     // HISTO_LENGTH          src/ORBmatcher.cc:37
+
+// raw pyramid of one extractor's last call (border-less levels)
+struct PyrView {
+  const uint8_t* base[kMaxLevels];
+  int64_t fstride[kMaxLevels];
+  int pitch[kMaxLevels];
+  int w[kMaxLevels];
+  int h[kMaxLevels];
+};
+
+struct StereoArgs {
+  PyrView left, right;
+  float scale[kMaxLevels], inv_scale[kMaxLevels];  // Frame::mvScaleFactors / mvInvScaleFactors (left extractor)
+  int nlevels;
+  int frame0;                     // pair p reads frame frame0 + p of both pyramids
+  const orbx_kp *kps_l, *kps_r;   // [pairs][cap]
+  const uint8_t *desc_l, *desc_r; // [pairs][cap][32]
+  const int32_t *n_l, *n_r;       // [pairs] device counts, or NULL -> n_l_host / n_r_host
+  int n_l_host, n_r_host;
+  int cap;
+  float mbf, mb;
+  float *u_right, *depth;         // [pairs][cap]
+  int32_t* sad;                   // [pairs][cap] scratch: accepted SAD or -1
+  int32_t* n_matched;             // [pairs]
+};
+
+int knn2_splits(int nq, int nt);
+void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int4* partial, int splits, int32_t* idx1,
+                 int32_t* d1, int32_t* idx2, int32_t* d2, cudaStream_t st);
+void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, cudaStream_t st);
+void launch_stereo(const StereoArgs& A, int n_pairs, int max_rows, cudaStream_t st);
+
+// ---- guided searches (k_search.cu) ----
+// Device copies of the orbx_frame_view / orbx_mappoints / orbx_projected / orbx_keyframe_view arrays.
+struct DevFrame {
+  int n, n_levels;
+  const orbx_kp* kps;
+  const uint8_t* desc;
+  const float* u_right;      // or NULL
+  const uint8_t* occupied;
+  const int32_t* cell_offsets;
+  const int32_t* cell_items;
+  float min_x, min_y, inv_w, inv_h;
+  const float* scale_factors;
+};
+
+// One search query per projected point: centre, window half-size, level window, optional stereo gate, descriptor.
+struct DevQueries {
+  int m;
+  const uint8_t* active;     // or NULL = all
+  const float *u, *v, *radius;
+  const int32_t *min_level, *max_level;
+  const float* u_right;      // or NULL
+  const uint8_t* desc;
+};
+
+struct SearchScratch {
+  int32_t* counts;    // [m + 1] candidates per query, then exclusive offsets
+  int32_t* cand_idx;  // [total]
+  int32_t* cand_dist; // [total] dist | octave << 16
+  int4* pre;          // [m] unconstrained best / second best: (d1, pos1, d2, pos2), pos = -1 when absent
+  int64_t cap_total;
+};
+
+void launch_search_count(const DevFrame& F, const DevQueries& Q, int32_t* counts, cudaStream_t st);
+void launch_scan(int32_t* counts, int m, int32_t* total_out, cudaStream_t st);
+void launch_search_fill(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, cudaStream_t st);
+// mode 0: SearchByProjection(Frame&, vector<MapPoint*>) — ratio test with levels; mode 1: best only + rotation check
+struct ResolveArgs {
+  int mode;
+  float nnratio;
+  int max_dist;
+  int check_orientation;
+  const uint8_t* has_obs;   // [m]
+  const float* angle;       // [m] (mode 1)
+  int32_t* assign;          // [n]
+  int32_t* nmatches;        // [1]
+  uint8_t* occ;             // [n] scratch, initialised from DevFrame::occupied
+  int32_t* events;          // [2 * m] scratch (mode 1): accepted (idx, bin)
+};
+void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, const ResolveArgs& R,
+                           cudaStream_t st);
+
+struct DevKeyFrame {
+  int n, n_levels;
+  const orbx_kp* kps;
+  const uint8_t* desc;
+  const float* u_right;        // or NULL
+  const uint8_t* has_mappoint;
+  int n_nodes;
+  const uint32_t* node_ids;
+  const int32_t* offsets;
+  const uint32_t* indices;
+  const float* scale_factors;
+  const float* level_sigma2;
+};
+struct TriArgs {
+  DevKeyFrame k1, k2;
+  float F12[9];
+  float ep_x, ep_y;
+  int only_stereo, coarse, check_orientation;
+  int32_t* matches12;  // [k1.n]
+  int32_t* nmatches;   // [1]
+  int32_t* node_match; // [k1.n_nodes] scratch: index of the same node id in k2 or -1
+};
+void launch_triangulation(const TriArgs& A, cudaStream_t st);
+
+}  // namespace orbx
+
+#endif

@@ -1,0 +1,157 @@
+"""Host-side mirror of ORB_SLAM3::ORBmatcher (include/ORBmatcher.h:38-133) and of the two Frame methods on the hot
+path (ComputeStereoMatches, the knnMatch of ComputeStereoFishEyeMatches) over the orbm C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _l
+from .lib import KP_DTYPE, OrbxError
+
+TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30  # src/ORBmatcher.cc:35-37
+
+
+def _bind(L):
+    if getattr(L, "_orbm_bound", False):
+        return
+    vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+    L.orbm_create.argtypes = [C.POINTER(vp), ci]
+    L.orbm_destroy.argtypes = [vp]
+    L.orbm_destroy.restype = None
+    L.orbm_last_error.argtypes = [vp]
+    L.orbm_last_error.restype = C.c_char_p
+    L.orbm_descriptor_distance_batch.argtypes = [vp, vp, vp, ci, vp]
+    L.orbm_knn2.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp]
+    L.orbm_knn2_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp]
+    L.orbm_stereo_match.argtypes = [vp, vp, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp, vp]
+    L.orbm_stereo_match_batch_device.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, cf, cf, vp, vp, vp, vp]
+    L.orbm_stereo_frames_batch.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.c_int64, cf, cf, vp, vp, vp, vp, vp, vp,
+                                           ci, vp, vp, vp]
+    L.orbm_search_by_projection_map.argtypes = [vp, vp, vp, cf, cf, ci, cf, vp, vp]
+    L.orbm_search_by_projection_frame.argtypes = [vp, vp, vp, ci, ci, vp, vp]
+    L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
+    L._orbm_bound = True
+
+
+class ORBmatcher:
+    """ORBmatcher(nnratio = 0.6, checkOri = true) (include/ORBmatcher.h:38)."""
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self._L = _l.lib()
+        _bind(self._L)
+        h = C.c_void_p()
+        rc = self._L.orbm_create(C.byref(h), device)
+        if rc != 0:
+            raise OrbxError(rc, self._L.orbm_last_error(None).decode())
+        self._h = h
+        self.mfNNratio, self.mbCheckOrientation = float(nnratio), bool(checkOri)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orbm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise OrbxError(rc, self._L.orbm_last_error(self._h).decode())
+        return rc
+
+    # static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) — src/ORBmatcher.cc:1959-1973
+    def DescriptorDistanceBatch(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.empty(len(a), np.int32)
+        self._check(self._L.orbm_descriptor_distance_batch(self._h, _l.ptr(a), _l.ptr(b), len(a), _l.ptr(out)))
+        return out
+
+    # cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, matches, 2) — src/Frame.cc:1293
+    def knnMatch2(self, q, t):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)
+        out = [np.empty(len(q), np.int32) for _ in range(4)]
+        self._check(self._L.orbm_knn2(self._h, _l.ptr(q), len(q), _l.ptr(t), len(t), *[_l.ptr(o) for o in out]))
+        return tuple(out)  # idx1, d1, idx2, d2
+
+    def knnMatch2_device(self, d_q, nq, d_t, nt, d_idx1, d_d1, d_idx2, d_d2, stream=0):
+        self._check(self._L.orbm_knn2_device(self._h, C.c_void_p(d_q), nq, C.c_void_p(d_t), nt, C.c_void_p(d_idx1),
+                                             C.c_void_p(d_d1), C.c_void_p(d_idx2), C.c_void_p(d_d2),
+                                             C.c_void_p(stream) if stream else None))
+
+    # void Frame::ComputeStereoMatches() — src/Frame.cc:921-1084
+    def ComputeStereoMatches(self, ex_left, ex_right, kps_l, desc_l, kps_r, desc_r, mbf, mb, frame=0):
+        kps_l, kps_r = np.ascontiguousarray(kps_l, KP_DTYPE), np.ascontiguousarray(kps_r, KP_DTYPE)
+        desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+        ur = np.empty(len(kps_l), np.float32)
+        dp = np.empty(len(kps_l), np.float32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_stereo_match(self._h, ex_left._h, ex_right._h, frame, _l.ptr(kps_l), _l.ptr(desc_l),
+                                              len(kps_l), _l.ptr(kps_r), _l.ptr(desc_r), len(kps_r), mbf, mb,
+                                              _l.ptr(ur), _l.ptr(dp), C.byref(nm)))
+        return nm.value, ur, dp
+
+    def ComputeStereoMatches_device(self, ex_left, ex_right, n_pairs, d_kps_l, d_desc_l, d_n_l, d_kps_r, d_desc_r,
+                                    d_n_r, cap, mbf, mb, d_u_right, d_depth, d_n_matched, stream=0):
+        vp = C.c_void_p
+        self._check(self._L.orbm_stereo_match_batch_device(self._h, ex_left._h, ex_right._h, n_pairs, vp(d_kps_l),
+                                                           vp(d_desc_l), vp(d_n_l), vp(d_kps_r), vp(d_desc_r),
+                                                           vp(d_n_r), cap, mbf, mb, vp(d_u_right), vp(d_depth),
+                                                           vp(d_n_matched), vp(stream) if stream else None))
+
+    # Frame::Frame(stereo) hot path, batched, host buffers: extract x2 + ComputeStereoMatches — src/Frame.cc:149-279
+    @staticmethod
+    def alloc_stereo_outputs(n_pairs, cap, empty=np.empty):
+        """Output arrays of StereoFramesBatch; pass an `empty` that returns pinned memory for asynchronous copies."""
+        return dict(kps_l=empty((n_pairs, cap), KP_DTYPE), desc_l=empty((n_pairs, cap, 32), np.uint8),
+                    n_l=empty((n_pairs,), np.int32), kps_r=empty((n_pairs, cap), KP_DTYPE),
+                    desc_r=empty((n_pairs, cap, 32), np.uint8), n_r=empty((n_pairs,), np.int32),
+                    u_right=empty((n_pairs, cap), np.float32), depth=empty((n_pairs, cap), np.float32),
+                    n_matched=empty((n_pairs,), np.int32))
+
+    def StereoFramesBatch(self, ex_left, ex_right, imgs_l, imgs_r, mbf, mb, out=None):
+        """imgs_l / imgs_r: uint8 [n, h, w] host arrays (row stride may exceed w). Returns the dict of outputs."""
+        assert imgs_l.shape == imgs_r.shape and imgs_l.strides == imgs_r.strides and imgs_l.strides[2] == 1
+        n, h, w = imgs_l.shape
+        cap = ex_left.capacity
+        if out is None:
+            out = self.alloc_stereo_outputs(n, cap)
+        self._check(self._L.orbm_stereo_frames_batch(
+            self._h, ex_left._h, ex_right._h, n, _l.ptr(imgs_l), _l.ptr(imgs_r), w, h, imgs_l.strides[1],
+            imgs_l.strides[0], mbf, mb, _l.ptr(out["kps_l"]), _l.ptr(out["desc_l"]), _l.ptr(out["n_l"]),
+            _l.ptr(out["kps_r"]), _l.ptr(out["desc_r"]), _l.ptr(out["n_r"]), cap, _l.ptr(out["u_right"]),
+            _l.ptr(out["depth"]), _l.ptr(out["n_matched"])))
+        return out
+
+    # int SearchByProjection(Frame& F, const vector<MapPoint*>&, th, bFarPoints, thFarPoints) — src/ORBmatcher.cc:42
+    def SearchByProjection(self, frame_view, mappoints, th=3.0, bFarPoints=False, thFarPoints=50.0):
+        n = frame_view.struct.n
+        assign = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_by_projection_map(self._h, frame_view.ref(), mappoints.ref(), th,
+                                                          self.mfNNratio, int(bFarPoints), thFarPoints,
+                                                          _l.ptr(assign), C.byref(nm)))
+        return nm.value, assign[:n]
+
+    # int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) — :1594; KeyFrame form — :1808
+    def SearchByProjectionProjected(self, frame_view, projected, max_dist=TH_HIGH):
+        n = frame_view.struct.n
+        assign = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_by_projection_frame(self._h, frame_view.ref(), projected.ref(), max_dist,
+                                                            int(self.mbCheckOrientation), _l.ptr(assign),
+                                                            C.byref(nm)))
+        return nm.value, assign[:n]
+
+    # int SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse) — :886
+    def SearchForTriangulation(self, kf1, kf2, F12, ep, bOnlyStereo=False, bCoarse=False):
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(9)
+        n = kf1.struct.n
+        m12 = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_for_triangulation(self._h, kf1.ref(), kf2.ref(), _l.ptr(F12), float(ep[0]),
+                                                          float(ep[1]), int(bOnlyStereo), int(bCoarse),
+                                                          int(self.mbCheckOrientation), _l.ptr(m12), C.byref(nm)))
+        m12 = m12[:n]
+        pairs = [(i, int(j)) for i, j in enumerate(m12) if j >= 0]  # vMatchedPairs, ascending idx1 (:1097-1103)
+        return nm.value, m12, pairs

@@ -135,3 +135,39 @@ def local_map(kps, desc, m, w, h, n_levels, seed=0, bf=47.9):
                 proj_xr=(px - np.float32(bf) / depth).astype(np.float32), level=level,
                 view_cos=rng.uniform(0.5, 1.0, m).astype(np.float32), depth=depth,
                 has_obs=(rng.random(m) < 0.9).astype(np.uint8), desc=d)
+
+
+def projected_points(kps, desc, m, w, h, n_levels, scale_factors, seed=0, bf=47.9, th=7.0, stereo=True):
+    """Points of a 'last frame' projected into the current one (input of SearchByProjection(Frame&, const Frame&)):
+    most are real keypoints jittered by a small motion, the rest uniform. Returns a dict in the orbx_projected layout."""
+    rng = np.random.default_rng(seed + 15485863)
+    n = len(kps)
+    src = rng.integers(0, n, m)
+    anchored = rng.random(m) < 0.8
+    u = np.where(anchored, kps["x"][src] + rng.normal(0, 2.0, m), rng.uniform(0, w, m)).astype(np.float32)
+    v = np.where(anchored, kps["y"][src] + rng.normal(0, 2.0, m), rng.uniform(0, h, m)).astype(np.float32)
+    octave = np.where(anchored, kps["octave"][src], rng.integers(0, n_levels, m)).astype(np.int32)
+    mode = rng.integers(0, 3, m)  # forward / backward / neither, src/ORBmatcher.cc:1671-1680
+    min_level = np.where(mode == 0, octave, np.where(mode == 1, 0, octave - 1)).astype(np.int32)
+    max_level = np.where(mode == 0, -1, np.where(mode == 1, octave, octave + 1)).astype(np.int32)
+    radius = (np.float32(th) * np.asarray(scale_factors, np.float32)[octave]).astype(np.float32)
+    depth = rng.uniform(0.5, 20.0, m).astype(np.float32)
+    d = flip_bits(desc[src], rng.integers(0, 70, m), rng)
+    angle = np.where(anchored, kps["angle"][src] + rng.normal(0, 8.0, m), rng.uniform(0, 360, m)) % 360.0
+    return dict(u=u, v=v, u_right=(u - np.float32(bf) / depth).astype(np.float32) if stereo else None, radius=radius,
+                min_level=min_level, max_level=max_level, angle=angle.astype(np.float32),
+                has_obs=(rng.random(m) < 0.9).astype(np.uint8), desc=d)
+
+
+def feature_vector(n, n_nodes, seed=0):
+    """A DBoW2::FeatureVector as CSR: every feature index 0..n-1 falls in exactly one of n_nodes vocabulary nodes
+    (ids ascending, sparse), indices inside a node ascending (the order DBoW2 appends them in)."""
+    rng = np.random.default_rng(seed + 32452843)
+    ids_all = np.sort(rng.choice(10 * n_nodes, n_nodes, replace=False)).astype(np.uint32)
+    node_of = rng.integers(0, n_nodes, n)
+    order = np.argsort(node_of, kind="stable")
+    counts = np.bincount(node_of, minlength=n_nodes)
+    keep = counts > 0
+    offsets = np.zeros(keep.sum() + 1, np.int32)
+    offsets[1:] = np.cumsum(counts[keep])
+    return ids_all[keep], offsets, order.astype(np.uint32), node_of

@@ -1,0 +1,117 @@
+"""ctypes mirrors of the flat views in include/orbx_types.h (what the C++ shim builds from Frame / MapPoint / KeyFrame).
+
+Each `make_*` returns a Holder that keeps the numpy arrays alive next to the struct that points into them.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .lib import KP_DTYPE
+
+GRID_COLS, GRID_ROWS = 64, 48  # FRAME_GRID_COLS / FRAME_GRID_ROWS, include/Frame.h:41-42
+
+
+class Grid(C.Structure):
+    _fields_ = [("cell_offsets", C.c_void_p), ("cell_items", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("inv_w", C.c_float), ("inv_h", C.c_float)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p),
+                ("occupied", C.c_void_p), ("grid", Grid), ("scale_factors", C.c_void_p), ("n_levels", C.c_int32)]
+
+
+class MapPoints(C.Structure):
+    _fields_ = [("m", C.c_int32), ("track_in_view", C.c_void_p), ("proj_x", C.c_void_p), ("proj_y", C.c_void_p),
+                ("proj_xr", C.c_void_p), ("level", C.c_void_p), ("view_cos", C.c_void_p), ("depth", C.c_void_p),
+                ("has_obs", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class Projected(C.Structure):
+    _fields_ = [("m", C.c_int32), ("u", C.c_void_p), ("v", C.c_void_p), ("u_right", C.c_void_p),
+                ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p), ("angle", C.c_void_p),
+                ("has_obs", C.c_void_p), ("desc", C.c_void_p)]
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("indices", C.c_void_p)]
+
+
+class KeyFrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kps", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p),
+                ("has_mappoint", C.c_void_p), ("featvec", FeatVec), ("scale_factors", C.c_void_p),
+                ("level_sigma2", C.c_void_p), ("n_levels", C.c_int32)]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Holder:
+    def __init__(self, struct, keep):
+        self.struct, self.keep = struct, keep
+
+    def ref(self):
+        return C.byref(self.struct)
+
+
+def assign_features_to_grid(kps, min_x, min_y, inv_w, inv_h):
+    """Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:520-547, 833-844) as a CSR — host-side, like in the
+    reference, where the grid is built by the Frame constructor (the caller of the hot path)."""
+    px = np.round((kps["x"].astype(np.float32) - np.float32(min_x)) * np.float32(inv_w))
+    py = np.round((kps["y"].astype(np.float32) - np.float32(min_y)) * np.float32(inv_h))
+    # np.round is half-to-even, C round() is half-away-from-zero: fix the exact .5 cases
+    fx = (kps["x"].astype(np.float32) - np.float32(min_x)) * np.float32(inv_w)
+    fy = (kps["y"].astype(np.float32) - np.float32(min_y)) * np.float32(inv_h)
+    px = np.where(np.abs(fx - np.trunc(fx)) == 0.5, np.trunc(fx) + np.sign(fx), px).astype(np.int64)
+    py = np.where(np.abs(fy - np.trunc(fy)) == 0.5, np.trunc(fy) + np.sign(fy), py).astype(np.int64)
+    ok = (px >= 0) & (px < GRID_COLS) & (py >= 0) & (py < GRID_ROWS)
+    cell = np.where(ok, px * GRID_ROWS + py, GRID_COLS * GRID_ROWS)
+    order = np.argsort(cell, kind="stable")
+    counts = np.bincount(cell, minlength=GRID_COLS * GRID_ROWS + 1)[:GRID_COLS * GRID_ROWS]
+    offsets = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+    offsets[1:] = np.cumsum(counts)
+    items = order[:offsets[-1]].astype(np.int32)
+    return offsets, items
+
+
+def make_frame_view(kps, desc, u_right, occupied, offsets, items, min_x, min_y, inv_w, inv_h, scale_factors):
+    kps = _c(kps, KP_DTYPE)
+    desc = _c(desc, np.uint8)
+    u_right = None if u_right is None else _c(u_right, np.float32)
+    occupied = _c(occupied, np.uint8)
+    offsets, items = _c(offsets, np.int32), _c(items, np.int32)
+    sf = _c(scale_factors, np.float32)
+    g = Grid(_p(offsets), _p(items), float(min_x), float(min_y), float(inv_w), float(inv_h))
+    fv = FrameView(len(kps), _p(kps), _p(desc), _p(u_right), _p(occupied), g, _p(sf), len(sf))
+    return Holder(fv, (kps, desc, u_right, occupied, offsets, items, sf))
+
+
+def make_mappoints(track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth, has_obs, desc):
+    arrs = (_c(track_in_view, np.uint8), _c(proj_x, np.float32), _c(proj_y, np.float32), _c(proj_xr, np.float32),
+            _c(level, np.int32), _c(view_cos, np.float32), _c(depth, np.float32), _c(has_obs, np.uint8),
+            _c(desc, np.uint8))
+    return Holder(MapPoints(len(arrs[0]), *[_p(a) for a in arrs]), arrs)
+
+
+def make_projected(u, v, u_right, radius, min_level, max_level, angle, has_obs, desc):
+    arrs = (_c(u, np.float32), _c(v, np.float32), None if u_right is None else _c(u_right, np.float32),
+            _c(radius, np.float32), _c(min_level, np.int32), _c(max_level, np.int32), _c(angle, np.float32),
+            _c(has_obs, np.uint8), _c(desc, np.uint8))
+    return Holder(Projected(len(arrs[0]), *[_p(a) for a in arrs]), arrs)
+
+
+def make_keyframe_view(kps, desc, u_right, has_mappoint, node_ids, offsets, indices, scale_factors, level_sigma2):
+    kps = _c(kps, KP_DTYPE)
+    desc = _c(desc, np.uint8)
+    u_right = None if u_right is None else _c(u_right, np.float32)
+    hm = _c(has_mappoint, np.uint8)
+    node_ids, offsets, indices = _c(node_ids, np.uint32), _c(offsets, np.int32), _c(indices, np.uint32)
+    sf, s2 = _c(scale_factors, np.float32), _c(level_sigma2, np.float32)
+    fv = FeatVec(len(node_ids), _p(node_ids), _p(offsets), _p(indices))
+    kv = KeyFrameView(len(kps), _p(kps), _p(desc), _p(u_right), _p(hm), fv, _p(sf), _p(s2), len(sf))
+    return Holder(kv, (kps, desc, u_right, hm, node_ids, offsets, indices, sf, s2))

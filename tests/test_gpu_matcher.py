@@ -1,0 +1,179 @@
+"""Parity of the CUDA Hamming searches (through the orbm C ABI) with the CPU oracle. Integer outputs bit-exact;
+float outputs (uRight, depth) compared bit-exactly as well (the documented bar is 1e-4)."""
+import numpy as np
+import pytest
+
+from orb_slam3_fast_b200 import ORBextractor, ORBmatcher, synth, views
+from oracle import orbref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def matcher(gpu):
+    return ORBmatcher(0.8, True)
+
+
+def test_descriptor_distance(matcher):
+    a, b = synth.descriptors(5000, 1), synth.descriptors(5000, 2)
+    b[:10] = a[:10]
+    d = matcher.DescriptorDistanceBatch(a, b)
+    ref = np.array([orbref.descriptor_distance(a[i], b[i]) for i in range(len(a))])
+    assert np.array_equal(d, ref)
+
+
+@pytest.mark.parametrize("nq,nt,proto", [(1000, 1000, 0), (3000, 3000, 0), (1000, 1000, 64), (257, 5000, 16),
+                                         (5000, 129, 0), (33, 2, 0), (10, 1, 0), (7, 0, 0), (10000, 10000, 0)])
+def test_knn2_matches_oracle(matcher, nq, nt, proto):
+    q, t = synth.descriptors(nq, 3, proto), synth.descriptors(nt, 4, proto)
+    got = matcher.knnMatch2(q, t)
+    ref = orbref.knn2(q, t) if nt > 0 else tuple(np.full(nq, -1, np.int32) for _ in range(4))
+    for g, r, name in zip(got, ref, ("idx1", "d1", "idx2", "d2")):
+        assert np.array_equal(g, r), "%s differs at %s" % (name, np.nonzero(g != r)[0][:10])
+
+
+def test_knn2_agrees_with_cv2_bfmatcher(matcher):
+    cv2 = pytest.importorskip("cv2")
+    q, t = synth.descriptors(800, 5, 32), synth.descriptors(900, 6, 32)  # tie-heavy
+    idx1, d1, idx2, d2 = matcher.knnMatch2(q, t)
+    mm = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)
+    assert [m[0].trainIdx for m in mm] == idx1.tolist() and [m[1].trainIdx for m in mm] == idx2.tolist()
+    assert [int(m[0].distance) for m in mm] == d1.tolist() and [int(m[1].distance) for m in mm] == d2.tolist()
+
+
+def _stereo_case(w, h, nf, seed, kind="scene"):
+    left, right, _ = synth.stereo_pair(h, w, seed, kind=kind)
+    exl, exr = ORBextractor(nf), ORBextractor(nf)
+    rl, rr = orbref.Extractor(nf), orbref.Extractor(nf)
+    _, kl, dl = exl(left)
+    _, kr, dr = exr(right)
+    _, kl_r, dl_r = rl(left, (0, 0))
+    _, kr_r, dr_r = rr(right, (0, 0))
+    assert np.array_equal(kl, kl_r) and np.array_equal(kr, kr_r) and np.array_equal(dl, dl_r)
+    return (exl, exr, rl, rr), (kl, dl, kr, dr)
+
+
+@pytest.mark.parametrize("w,h,nf,seed", [(752, 480, 1200, 0), (640, 480, 1000, 1), (1280, 720, 2000, 2)])
+def test_stereo_matches_oracle(matcher, w, h, nf, seed):
+    (exl, exr, rl, rr), (kl, dl, kr, dr) = _stereo_case(w, h, nf, seed)
+    fx = 435.2
+    mbf, mb = np.float32(fx * 0.11), np.float32(0.11)
+    n, ur, dp = matcher.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, float(mbf), float(mb))
+    n_r, ur_r, dp_r = orbref.stereo_match(rl, rr, kl, dl, kr, dr, float(mbf), float(mb))
+    assert n_r > 50, "degenerate test: oracle found only %d matches" % n_r
+    assert n == n_r
+    assert np.array_equal(ur, ur_r), "uRight differs at %s" % np.nonzero(ur != ur_r)[0][:10]
+    assert np.array_equal(dp, dp_r)
+
+
+def test_stereo_no_matches_is_defined(matcher):
+    exl, exr = ORBextractor(1000), ORBextractor(1000)
+    _, kl, dl = exl(synth.scene(480, 640, 1))
+    _, kr, dr = exr(synth.scene(480, 640, 99))  # unrelated image
+    n, ur, dp = matcher.ComputeStereoMatches(exl, exr, kl, dl, kr[:0], dr[:0], 40.0, 0.1)
+    assert n == 0 and (ur == -1).all() and (dp == -1).all()
+
+
+def _frame_views(kps, desc, w, h, scale, u_right, occupied):
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    off, items = views.assign_features_to_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    fv = views.make_frame_view(kps, desc, u_right, occupied, off, items, 0.0, 0.0, inv_w, inv_h, scale)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    fr = orbref.make_frame_view(kps, desc, u_right, occupied, g, keep, scale)
+    return fv, fr
+
+
+@pytest.mark.parametrize("m,th,stereo,seed", [(10000, 1.0, True, 0), (3000, 3.0, False, 1), (2000, 15.0, True, 2)])
+def test_search_by_projection_map(matcher, m, th, stereo, seed):
+    w, h = 640, 480
+    ex = ORBextractor(1200)
+    _, kps, desc = ex(synth.scene(h, w, seed))
+    rng = np.random.default_rng(seed)
+    ur = np.where(rng.random(len(kps)) < 0.7, kps["x"] - rng.uniform(1, 40, len(kps)), -1).astype(np.float32)
+    occ = (rng.random(len(kps)) < 0.1).astype(np.uint8)
+    fv, fr = _frame_views(kps, desc, w, h, ex.GetScaleFactors(), ur if stereo else None, occ)
+    mp = synth.local_map(kps, desc, m, w, h, 8, seed)
+    n, assign = matcher.SearchByProjection(fv, views.make_mappoints(**mp), th, True, 15.0)
+    n_r, assign_r = orbref.search_by_projection_map(fr, orbref.make_mappoints(**mp), th, 0.8, True, 15.0)
+    assert n_r > 100
+    assert n == n_r
+    assert np.array_equal(assign, assign_r), "assign differs at %s" % np.nonzero(assign != assign_r)[0][:10]
+
+
+@pytest.mark.parametrize("m,th,stereo,check,seed", [(1200, 7.0, True, True, 0), (1200, 15.0, False, True, 1),
+                                                    (4000, 7.0, True, False, 2)])
+def test_search_by_projection_frame(gpu, m, th, stereo, check, seed):
+    w, h = 752, 480
+    ex = ORBextractor(1200)
+    _, kps, desc = ex(synth.scene(h, w, seed))
+    rng = np.random.default_rng(seed)
+    ur = np.where(rng.random(len(kps)) < 0.7, kps["x"] - rng.uniform(1, 40, len(kps)), -1).astype(np.float32)
+    occ = np.zeros(len(kps), np.uint8)
+    fv, fr = _frame_views(kps, desc, w, h, ex.GetScaleFactors(), ur if stereo else None, occ)
+    pts = synth.projected_points(kps, desc, m, w, h, 8, ex.GetScaleFactors(), seed, th=th, stereo=stereo)
+    mt = ORBmatcher(0.9, check)
+    n, assign = mt.SearchByProjectionProjected(fv, views.make_projected(**pts), 100)
+    n_r, assign_r = orbref.search_by_projection_frame(fr, orbref.make_projected(**pts), 100, check)
+    assert n_r > 100
+    assert n == n_r
+    assert np.array_equal(assign, assign_r)
+
+
+@pytest.mark.parametrize("only_stereo,coarse,check,seed", [(False, False, True, 0), (True, False, True, 1),
+                                                           (False, True, False, 2)])
+def test_search_for_triangulation(gpu, only_stereo, coarse, check, seed):
+    w, h = 752, 480
+    left, right, _ = synth.stereo_pair(h, w, seed, d_min=5, d_max=30)
+    e1, e2 = ORBextractor(1500), ORBextractor(1500)
+    _, k1, d1 = e1(left)
+    _, k2, d2 = e2(right)
+    rng = np.random.default_rng(seed)
+    # vocabulary nodes: make corresponding features (similar descriptors) likely to share a node by hashing 10 bits
+    def featvec(desc):
+        node_of = (desc[:, 0].astype(np.int64) >> 3) * 32 + (desc[:, 1].astype(np.int64) >> 3)
+        ids, inv = np.unique(node_of, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        offsets = np.zeros(len(ids) + 1, np.int32)
+        offsets[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+        return ids.astype(np.uint32), offsets, order.astype(np.uint32)
+    sf, s2 = e1.GetScaleFactors(), e1.GetScaleSigmaSquares()
+    args = []
+    for k, d in ((k1, d1), (k2, d2)):
+        ids, off, idx = featvec(d)
+        ur = np.where(rng.random(len(k)) < 0.5, k["x"] - 10, -1).astype(np.float32)
+        hm = (rng.random(len(k)) < 0.2).astype(np.uint8)
+        args.append((k, d, ur, hm, ids, off, idx, sf, s2))
+    # pure horizontal translation: F = [t]x up to scale => epipolar lines are image rows
+    F12 = np.array([[0, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)
+    ep = (1e6, 240.0)
+    mt = ORBmatcher(0.6, check)
+    n, m12, pairs = mt.SearchForTriangulation(views.make_keyframe_view(*args[0]), views.make_keyframe_view(*args[1]),
+                                              F12, ep, only_stereo, coarse)
+    n_r, m12_r = orbref.search_for_triangulation(orbref.make_keyframe_view(*args[0]),
+                                                 orbref.make_keyframe_view(*args[1]), F12, ep, only_stereo, coarse,
+                                                 check)
+    assert n_r > 20, "degenerate test: %d" % n_r
+    assert n == n_r and np.array_equal(m12, m12_r)
+    assert len(pairs) == n
+
+
+def test_stereo_frames_batch_matches_per_pair_oracle(matcher):
+    """Fused host-facing batch (extract x2 + ComputeStereoMatches, pipelined over lanes) == oracle pair by pair."""
+    w, h, nf = 752, 480, 1200
+    pairs = [synth.stereo_pair(h, w, s) for s in range(5)]
+    L = np.stack([p[0] for p in pairs])
+    R = np.stack([p[1] for p in pairs])
+    exl, exr = ORBextractor(nf, max_batch=2), ORBextractor(nf, max_batch=2)  # 5 pairs -> groups 2 + 2 + 1
+    mbf, mb = float(np.float32(435.2 * 0.11)), float(np.float32(0.11))
+    out = matcher.StereoFramesBatch(exl, exr, L, R, mbf, mb)
+    rl, rr = orbref.Extractor(nf), orbref.Extractor(nf)
+    for i in range(len(pairs)):
+        _, kl, dl = rl(L[i], (0, 0))
+        _, kr, dr = rr(R[i], (0, 0))
+        n_r, ur_r, dp_r = orbref.stereo_match(rl, rr, kl, dl, kr, dr, mbf, mb)
+        nl, nr = out["n_l"][i], out["n_r"][i]
+        assert nl == len(kl) and nr == len(kr)
+        assert np.array_equal(out["kps_l"][i, :nl], kl) and np.array_equal(out["desc_l"][i, :nl], dl)
+        assert np.array_equal(out["kps_r"][i, :nr], kr) and np.array_equal(out["desc_r"][i, :nr], dr)
+        assert out["n_matched"][i] == n_r
+        assert np.array_equal(out["u_right"][i, :nl], ur_r) and np.array_equal(out["depth"][i, :nl], dp_r)
