@@ -184,8 +184,14 @@ def main():
     d_nm = torch.empty(P, dtype=torch.int32, device=dev)
     gathered = torch.empty((world, 3, P), dtype=torch.int32, device=dev) if world > 1 else None
 
+    # a non-default torch stream: its handle is what the C ABI launches on, so torch.cuda.Event brackets the work
+    # (the legacy default stream's handle is 0, which the ABI reads as "use the extractor's own stream")
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    assert work_stream.cuda_stream != 0
+
     def step_device(k):
-        st = torch.cuda.current_stream().cuda_stream
+        st = work_stream.cuda_stream
         for ex, imgs, o in ((exl, devL[k % n_rot], oL), (exr, devR[k % n_rot], oR)):
             ex.extract_batch_device(imgs.data_ptr(), P, W, H, W, W * H, (0, 0), o["kps"].data_ptr(),
                                     o["desc"].data_ptr(), cap, o["n"].data_ptr(), o["mono"].data_ptr(),

@@ -11,67 +11,99 @@ namespace orbx {
 
 // ---------------------------------------------------------------------------------------------------------------
 // 7x7 Gaussian, Q0.8 taps {18,34,48,56,48,34,18} on both axes, 16-bit row sums, one rounding: (sum + 32768) >> 16.
-// Block = 32x8 threads, output tile 128 x 16; the 22 needed rows of horizontal sums are kept in shared memory.
+// Streaming design without shared memory: a thread owns 4 adjacent columns and walks down a strip of kBlurRows output
+// rows. Per source row it reads the 3 aligned words x-4 .. x+7, forms the 4 horizontal sums with packed u16x2
+// arithmetic (two pixels per IMAD; the sums stay below 65536 so the halves never carry into each other) and pushes them
+// into a 7-deep register window; once the window is full every new row yields one 32-bit store of 4 output pixels.
+// The row loop is fully unrolled so the window is pure register renaming. Reflect-101 happens in the address (rows)
+// or in a byte-wise slow path taken only by the lanes that touch the left / right image edge (columns).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 128, kBlurTH = 16;
+constexpr int kBlurRows = 32;
+constexpr int kBlurThreads = 128;
 
-__device__ __forceinline__ int hsum7(int a, int b, int c, int d, int e, int f, int g) {
-  return 18 * (a + g) + 34 * (b + f) + 48 * (c + e) + 56 * d;
+// [b(i), 0, b(i+1), 0] for two adjacent bytes of the 12-byte window (w0 w1 w2); I is compile-time
+template <int I>
+__device__ __forceinline__ uint32_t bpair(uint32_t w0, uint32_t w1, uint32_t w2) {
+  constexpr int word = I >> 2, off = I & 3;
+  const uint32_t wa = word == 0 ? w0 : (word == 1 ? w1 : w2);
+  if constexpr (off < 3) {
+    return __byte_perm(wa, 0u, off | (4 << 4) | ((off + 1) << 8) | (4 << 12));
+  } else {
+    const uint32_t wb = word == 0 ? w1 : w2;
+    const uint32_t t = __byte_perm(wa, wb, 0x0043);  // byte 3 of wa, byte 0 of wb
+    return __byte_perm(t, 0u, 0x4140);
+  }
 }
 
-__global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ Plan P, const FrameSet fs, int l) {
-  __shared__ uint16_t H[kBlurTH + 6][kBlurTW];
+__global__ void __launch_bounds__(kBlurThreads) k_blur7(const __grid_constant__ Plan P, const FrameSet fs, int l) {
   const LevelPlan& L = P.lv[l];
   const int f = blockIdx.z;
-  const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x = 4 * (blockIdx.x * kBlurThreads + threadIdx.x);
+  const int y0 = blockIdx.y * kBlurRows;
+  const int w = L.w, h = L.h;
+  if (x >= w) return;
   int pitch;
   const uint8_t* src = raw_level(P, fs, l, f, &pitch);
-  const int w = L.w, h = L.h;
-  const int x = x0 + 4 * tx;
-  for (int rr = ty; rr < kBlurTH + 6; rr += 8) {
-    const int y = reflect101(y0 - 3 + rr, h);
-    const uint8_t* row = src + (int64_t)y * pitch;
-    uint8_t b[10];
-    if (x >= 4 && x + 7 < w && ((reinterpret_cast<uintptr_t>(row) & 3) == 0)) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + x - 4);
-      const uint32_t w0 = r32[0], w1 = r32[1], w2 = r32[2];
-      b[0] = (w0 >> 8) & 0xff; b[1] = (w0 >> 16) & 0xff; b[2] = w0 >> 24;
-      b[3] = w1 & 0xff; b[4] = (w1 >> 8) & 0xff; b[5] = (w1 >> 16) & 0xff; b[6] = w1 >> 24;
-      b[7] = w2 & 0xff; b[8] = (w2 >> 8) & 0xff; b[9] = (w2 >> 16) & 0xff;
-    } else {
-#pragma unroll
-      for (int k = 0; k < 10; k++) {
-        const int xx = x - 3 + k;
-        b[k] = xx < w + 3 ? row[reflect101(xx, w)] : 0;  // columns past w+2 only feed outputs past w
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      H[rr][4 * tx + k] = (uint16_t)hsum7(b[k], b[k + 1], b[k + 2], b[k + 3], b[k + 4], b[k + 5], b[k + 6]);
-  }
-  __syncthreads();
   uint8_t* dst = blur_level(P, fs, l, f);
-  for (int r = ty; r < kBlurTH; r += 8) {
-    const int y = y0 + r;
-    if (y >= h || x >= L.pitch) continue;
-    uint32_t packed = 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
+  const bool fast = aligned && x >= 4 && x + 8 <= w;
+  int win[7][4];  // horizontal sums of the last 7 source rows
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int c = 4 * tx + k;
-      const uint32_t acc = 32768u + 18u * (H[r][c] + H[r + 6][c]) + 34u * (H[r + 1][c] + H[r + 5][c]) +
-                           48u * (H[r + 2][c] + H[r + 4][c]) + 56u * H[r + 3][c];
-      packed |= (acc >> 16) << (8 * k);
+  for (int r = 0; r < kBlurRows + 6; r++) {
+    const int yo = y0 + r - 6;  // output row completed by this source row
+    if (yo >= h) break;
+    const int ys = reflect101(y0 - 3 + r, h);
+    const uint8_t* row = src + (int64_t)ys * pitch;
+    uint32_t w0, w1, w2;
+    if (fast) {
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + x - 4);
+      w0 = r32[0];
+      w1 = r32[1];
+      w2 = r32[2];
+    } else {
+      // bytes x-4 .. x+7 with reflect-101 columns; columns beyond w+2 only feed outputs beyond w
+      uint32_t b[12];
+#pragma unroll
+      for (int k = 0; k < 12; k++) {
+        const int xx = x - 4 + k;
+        b[k] = (xx >= -3 && xx < w + 3) ? row[reflect101(xx, w)] : 0;
+      }
+      w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+      w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
     }
-    *reinterpret_cast<uint32_t*>(dst + (int64_t)y * L.pitch + x) = packed;
+    // window byte i = column x - 4 + i; output pixel k reads bytes k+1 .. k+7
+    const uint32_t o0 = bpair<1>(w0, w1, w2), e1 = bpair<2>(w0, w1, w2), o1 = bpair<3>(w0, w1, w2);
+    const uint32_t e2 = bpair<4>(w0, w1, w2), o2 = bpair<5>(w0, w1, w2), e3 = bpair<6>(w0, w1, w2);
+    const uint32_t o3 = bpair<7>(w0, w1, w2), e4 = bpair<8>(w0, w1, w2), o4 = bpair<9>(w0, w1, w2);
+    const uint32_t h01 = 18u * (o0 + o3) + 34u * (e1 + e3) + 48u * (o1 + o2) + 56u * e2;  // pixels 0, 1
+    const uint32_t h23 = 18u * (o1 + o4) + 34u * (e2 + e4) + 48u * (o2 + o3) + 56u * e3;  // pixels 2, 3
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) win[j][k] = win[j + 1][k];
+    win[6][0] = (int)(h01 & 0xffff);
+    win[6][1] = (int)(h01 >> 16);
+    win[6][2] = (int)(h23 & 0xffff);
+    win[6][3] = (int)(h23 >> 16);
+    if (r >= 6) {
+      uint32_t packed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t acc = 32768u + 18u * (uint32_t)(win[0][k] + win[6][k]) + 34u * (uint32_t)(win[1][k] + win[5][k]) +
+                             48u * (uint32_t)(win[2][k] + win[4][k]) + 56u * (uint32_t)win[3][k];
+        packed |= (acc >> 16) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t*>(dst + (int64_t)yo * L.pitch + x) = packed;
+    }
   }
 }
 
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st) {
   for (int l = 0; l < P.nlevels; l++) {
     const LevelPlan& L = P.lv[l];
-    dim3 grid((L.w + kBlurTW - 1) / kBlurTW, (L.h + kBlurTH - 1) / kBlurTH, frames);
-    k_blur7<<<grid, dim3(32, 8), 0, st>>>(P, fs, l);
+    dim3 grid(((L.w + 3) / 4 + kBlurThreads - 1) / kBlurThreads, (L.h + kBlurRows - 1) / kBlurRows, frames);
+    k_blur7<<<grid, kBlurThreads, 0, st>>>(P, fs, l);
   }
 }
 

@@ -115,13 +115,34 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   uint16_t* raw = reinterpret_cast<uint16_t*>(smem + (size_t)warp * per_warp);
   uint8_t* score = smem + (size_t)warp * per_warp + raw_bytes;
 
-  // ---- stage the raw window, widened to u16; columns >= tw are zero ----
+  // ---- stage the raw window, widened to u16; columns >= tw are zero. A lane step produces 4 tile columns from the
+  //      two aligned global words that hold them (funnel shift by the row's byte misalignment), one 8-byte store ----
   int pitch;
   const uint8_t* img = raw_level(P, fs, l, f, &pitch);
   const uint8_t* src = img + (int64_t)iniY * pitch + iniX;
-  for (int r = 0; r < th; r++) {
-    const uint8_t* srow = src + (int64_t)r * pitch;
-    for (int c = lane; c < tp; c += 32) raw[r * tp + c] = c < tw ? (uint16_t)srow[c] : (uint16_t)0;
+  {
+    const int groups = tp >> 2;
+    const float inv_groups = 1.0f / (float)groups;
+    const int nsteps = groups * th;
+    for (int idx = lane; idx < nsteps; idx += 32) {
+      const int r = (int)(((float)idx + 0.5f) * inv_groups);
+      const int j = idx - r * groups;
+      const int valid = tw - 4 * j;  // tile columns 4j .. 4j+3 that exist
+      uint32_t v = 0;
+      if (valid > 0) {
+        const uint8_t* p = src + (int64_t)r * pitch + 4 * j;
+        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(p - sh);
+        const uint32_t lo = a[0];
+        const uint32_t hi = sh ? a[1] : 0u;  // stays inside the image row: the window ends >= 16 px before it
+        v = __funnelshift_r(lo, hi, 8 * sh);
+        if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+      }
+      uint2 o;
+      o.x = __byte_perm(v, 0u, 0x4140);  // [b0, 0, b1, 0]
+      o.y = __byte_perm(v, 0u, 0x4342);  // [b2, 0, b3, 0]
+      *reinterpret_cast<uint2*>(raw + r * tp + 4 * j) = o;
+    }
   }
   // ---- clear the score map (1-row / 4-column zero frame around the interior) ----
   {

@@ -436,11 +436,18 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
       return mfail(m, rc, orbx_last_error(left));
     if ((rc = api_download(right, ln, nb, kps_r + (int64_t)f0 * cap, desc_r + (int64_t)f0 * cap * 32, cap, st)) != 0)
       return mfail(m, rc, orbx_last_error(right));
-    const int rows = std::min(cap, dcap);
-    ORBM_CUDA(m, cudaMemcpy2DAsync(u_right + (int64_t)f0 * cap, (size_t)cap * 4, A.u_right, (size_t)dcap * 4,
-                                   (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
-    ORBM_CUDA(m, cudaMemcpy2DAsync(depth + (int64_t)f0 * cap, (size_t)cap * 4, A.depth, (size_t)dcap * 4,
-                                   (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
+    if (cap == dcap) {
+      ORBM_CUDA(m, cudaMemcpyAsync(u_right + (int64_t)f0 * cap, A.u_right, (size_t)nb * cap * 4,
+                                   cudaMemcpyDeviceToHost, st));
+      ORBM_CUDA(m, cudaMemcpyAsync(depth + (int64_t)f0 * cap, A.depth, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost,
+                                   st));
+    } else {
+      const int rows = std::min(cap, dcap);
+      ORBM_CUDA(m, cudaMemcpy2DAsync(u_right + (int64_t)f0 * cap, (size_t)cap * 4, A.u_right, (size_t)dcap * 4,
+                                     (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
+      ORBM_CUDA(m, cudaMemcpy2DAsync(depth + (int64_t)f0 * cap, (size_t)cap * 4, A.depth, (size_t)dcap * 4,
+                                     (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
+    }
     ORBM_CUDA(m, cudaMemcpyAsync(m->lane_h_nm[ln], A.n_matched, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
     ORBM_CUDA(m, cudaEventRecord(left->lane[ln].done, st));
     pending_f0[ln] = f0;

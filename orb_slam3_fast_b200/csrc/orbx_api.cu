@@ -219,18 +219,21 @@ int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, i
   OrbxLane& L = ex->lane[ln];
   int rc = alloc_lane(ex, L);
   if (rc) return rc;
-  if (frame_stride == (int64_t)stride * height) {
-    ORBX_CUDA(ex, cudaMemcpy2DAsync(L.d_in, ex->in_pitch, src, stride, width, (size_t)height * nb,
-                                    cudaMemcpyHostToDevice, st));
+  FrameSet fs{};
+  fs.lvl0 = L.d_in;
+  if (frame_stride == (int64_t)stride * height && stride <= ex->in_pitch) {
+    // densely packed frames: ONE contiguous copy, level 0 keeps the caller's pitch (a 2-D copy of 752-byte rows runs at
+    // a fraction of the PCIe rate)
+    ORBX_CUDA(ex, cudaMemcpyAsync(L.d_in, src, (size_t)frame_stride * nb, cudaMemcpyHostToDevice, st));
+    fs.pitch0 = stride;
+    fs.fstride0 = frame_stride;
   } else {
     for (int f = 0; f < nb; f++)
       ORBX_CUDA(ex, cudaMemcpy2DAsync(L.d_in + f * ex->in_fstride, ex->in_pitch, src + f * frame_stride, stride,
                                       width, height, cudaMemcpyHostToDevice, st));
+    fs.pitch0 = ex->in_pitch;
+    fs.fstride0 = ex->in_fstride;
   }
-  FrameSet fs{};
-  fs.lvl0 = L.d_in;
-  fs.pitch0 = ex->in_pitch;
-  fs.fstride0 = ex->in_fstride;
   OutSet out{L.d_kps, L.d_desc, L.d_n, L.d_mono, L.d_status, L.out_cap};
   return run_pipeline(ex, ln, fs, nb, lap0, lap1, out, st);
 }
@@ -242,11 +245,17 @@ int api_download(orbx_extractor* ex, int ln, int nb, orbx_kp* kps, uint8_t* desc
   ORBX_CUDA(ex, cudaMemcpyAsync(L.h_small + B, L.d_mono, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
   ORBX_CUDA(ex, cudaMemcpyAsync(L.h_small + 2 * B, L.d_status, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
   // rows: device arrays are [nb][out_cap], the caller's are [..][cap]
-  const int rows = std::min(cap, L.out_cap);
-  ORBX_CUDA(ex, cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_kp), L.d_kps, (size_t)L.out_cap * sizeof(orbx_kp),
-                                  (size_t)rows * sizeof(orbx_kp), nb, cudaMemcpyDeviceToHost, st));
-  ORBX_CUDA(ex, cudaMemcpy2DAsync(desc, (size_t)cap * ORBX_DESC_BYTES, L.d_desc, (size_t)L.out_cap * ORBX_DESC_BYTES,
-                                  (size_t)rows * ORBX_DESC_BYTES, nb, cudaMemcpyDeviceToHost, st));
+  if (cap == L.out_cap) {
+    ORBX_CUDA(ex, cudaMemcpyAsync(kps, L.d_kps, (size_t)nb * cap * sizeof(orbx_kp), cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(ex, cudaMemcpyAsync(desc, L.d_desc, (size_t)nb * cap * ORBX_DESC_BYTES, cudaMemcpyDeviceToHost, st));
+  } else {
+    const int rows = std::min(cap, L.out_cap);
+    ORBX_CUDA(ex, cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(orbx_kp), L.d_kps, (size_t)L.out_cap * sizeof(orbx_kp),
+                                    (size_t)rows * sizeof(orbx_kp), nb, cudaMemcpyDeviceToHost, st));
+    ORBX_CUDA(ex, cudaMemcpy2DAsync(desc, (size_t)cap * ORBX_DESC_BYTES, L.d_desc,
+                                    (size_t)L.out_cap * ORBX_DESC_BYTES, (size_t)rows * ORBX_DESC_BYTES, nb,
+                                    cudaMemcpyDeviceToHost, st));
+  }
   return ORBX_OK;
 }
 

@@ -298,22 +298,37 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
       ORBX_LANES(p, S) child_nxt[p] = 0;
     }
     ORBX_WSYNC();
-    // ---- one sweep over the candidates: move to the new node, then histogram / argmax ----
-    ORBX_LANES(c, C) {
-      const uint32_t l = T.lab[c];
-      const int p = (int)(l & 0xffff);
-      const int np = T.committed[p] ? T.childpos[4 * p + (int)(l >> 16)] : T.newpos[p];
-      uint32_t nl = (uint32_t)np;
-      const uint32_t cw = T.cand[c];
-      if (finish) {
-        const uint32_t v = ((uint32_t)cand_s(cw) << 24) | (0xffffffu - (uint32_t)c);
-        ORBX_ATOMIC_MAX((unsigned int*)&child_nxt[np], v);
-      } else if (split_nxt[np]) {
-        const int q = quadrant_of(cw, T.box[nxt][np]);
-        nl |= (uint32_t)q << 16;
-        ORBX_ATOMIC_ADD(&child_nxt[4 * np + q], 1);
+    // ---- one sweep over the candidates: move to the new node, then histogram / argmax. The loads of 4 lane steps
+    //      are issued before any of them is used (memory-level parallelism: a lone warp cannot hide L2 latency) ----
+    for (int c0 = ORBX_LANE(); c0 < C; c0 += 4 * ORBX_NLANES) {
+      uint32_t lv[4], cv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = c0 + u * ORBX_NLANES;
+        if (c < C) {
+          lv[u] = T.lab[c];
+          cv[u] = T.cand[c];
+        }
       }
-      T.lab[c] = nl;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = c0 + u * ORBX_NLANES;
+        if (c >= C) continue;
+        const uint32_t l = lv[u];
+        const int p = (int)(l & 0xffff);
+        const int np = T.committed[p] ? T.childpos[4 * p + (int)(l >> 16)] : T.newpos[p];
+        uint32_t nl = (uint32_t)np;
+        const uint32_t cw = cv[u];
+        if (finish) {
+          const uint32_t v = ((uint32_t)cand_s(cw) << 24) | (0xffffffu - (uint32_t)c);
+          ORBX_ATOMIC_MAX((unsigned int*)&child_nxt[np], v);
+        } else if (split_nxt[np]) {
+          const int q = quadrant_of(cw, T.box[nxt][np]);
+          nl |= (uint32_t)q << 16;
+          ORBX_ATOMIC_ADD(&child_nxt[4 * np + q], 1);
+        }
+        T.lab[c] = nl;
+      }
     }
     ORBX_WSYNC();
     phase2 = next_phase2;
