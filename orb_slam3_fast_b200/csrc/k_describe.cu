@@ -48,18 +48,19 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur7(const __grid_constant__ 
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
   const bool fast = aligned && x >= 4 && x + 8 <= w;
   int win[7][4];  // horizontal sums of the last 7 source rows
-#pragma unroll
-  for (int r = 0; r < kBlurRows + 6; r++) {
-    const int yo = y0 + r - 6;  // output row completed by this source row
-    if (yo >= h) break;
+  // the 3 words of row r are requested kBlurAhead iterations before they are used (the loop is fully unrolled, so the
+  // queue is register renaming): without this every row pays a full DRAM round trip between load and use
+  constexpr int kBlurAhead = 4;
+  uint32_t q[kBlurAhead][3];
+  auto fetch = [&](int r, uint32_t (&o)[3]) {
+    if (y0 + r - 6 >= h) return;  // this source row completes no output row
     const int ys = reflect101(y0 - 3 + r, h);
     const uint8_t* row = src + (int64_t)ys * pitch;
-    uint32_t w0, w1, w2;
     if (fast) {
       const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + x - 4);
-      w0 = r32[0];
-      w1 = r32[1];
-      w2 = r32[2];
+      o[0] = __ldg(r32);
+      o[1] = __ldg(r32 + 1);
+      o[2] = __ldg(r32 + 2);
     } else {
       // bytes x-4 .. x+7 with reflect-101 columns; columns beyond w+2 only feed outputs beyond w
       uint32_t b[12];
@@ -68,10 +69,19 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur7(const __grid_constant__ 
         const int xx = x - 4 + k;
         b[k] = (xx >= -3 && xx < w + 3) ? row[reflect101(xx, w)] : 0;
       }
-      w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-      w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-      w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
+      o[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      o[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+      o[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
     }
+  };
+#pragma unroll
+  for (int r = 0; r < kBlurAhead; r++) fetch(r, q[r]);
+#pragma unroll
+  for (int r = 0; r < kBlurRows + 6; r++) {
+    const int yo = y0 + r - 6;  // output row completed by this source row
+    if (yo >= h) break;
+    const uint32_t w0 = q[r % kBlurAhead][0], w1 = q[r % kBlurAhead][1], w2 = q[r % kBlurAhead][2];
+    if (r + kBlurAhead < kBlurRows + 6) fetch(r + kBlurAhead, q[r % kBlurAhead]);
     // window byte i = column x - 4 + i; output pixel k reads bytes k+1 .. k+7
     const uint32_t o0 = bpair<1>(w0, w1, w2), e1 = bpair<2>(w0, w1, w2), o1 = bpair<3>(w0, w1, w2);
     const uint32_t e2 = bpair<4>(w0, w1, w2), o2 = bpair<5>(w0, w1, w2), e3 = bpair<6>(w0, w1, w2);

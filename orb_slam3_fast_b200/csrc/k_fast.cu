@@ -205,32 +205,48 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   __syncwarp();
 
   // ---- per-cell threshold, 3x3 non-max suppression inside the cell interior, ordered emission ----
-  const int npx = iw * ih;
-  const float inv_iw = 1.0f / (float)iw;
+  // A lane step looks at one 4-pixel score word (most are 0). Lane order = group order = pixel row-major, so the
+  // candidate order of the serial reference falls out of two ballots: no two kept pixels are adjacent, hence a group
+  // of 4 consecutive pixels keeps at most 2.
   const int x_off = iniX + 3 - kMinBorder, y_off = iniY + 3 - kMinBorder;  // candidate coords are minBorder-relative
+  const unsigned lt = (1u << lane) - 1u;
   int total = 0;
   for (int pass = 0; pass < 2; pass++) {
     const int T = pass == 0 ? ini_th : min_th;
     total = 0;
-    for (int base = 0; base < npx; base += 32) {
-      const int idx = base + lane;
-      bool keep = false;
-      int s = 0, x = 0, y = 0;
-      if (idx < npx) {
-        y = (int)(((float)idx + 0.5f) * inv_iw);
-        x = idx - y * iw;
-        const uint8_t* sc = score + (y + 1) * sp + 4 + x;
-        s = sc[0];
-        if (s >= T && s > 0) {  // corner at T  <=>  m > T  <=>  score >= T
-          // a neighbour counts with its score if it is a corner at T, else 0 (OpenCV keeps 0 in its score rows)
-          auto eff = [&](int o) { const int n = sc[o]; return n >= T ? n : 0; };
-          keep = s > eff(-1) && s > eff(1) && s > eff(-sp - 1) && s > eff(-sp) && s > eff(-sp + 1) &&
-                 s > eff(sp - 1) && s > eff(sp) && s > eff(sp + 1);
+    for (int base = 0; base < ngroups; base += 32) {
+      const int G = base + lane;
+      uint32_t word = 0;
+      int r = 0, g = 0;
+      if (G < ngroups) {
+        r = (int)(((float)G + 0.5f) * inv_gpr);
+        g = G - r * gpr;
+        word = *reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g);
+      }
+      unsigned keepmask = 0;
+      if (word) {
+        const uint8_t* sc0 = score + (r + 1) * sp + 4 + 4 * g;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int sv = (int)((word >> (8 * k)) & 0xff);
+          if (sv >= T && sv > 0) {  // corner at T  <=>  m > T  <=>  score >= T
+            const uint8_t* sc = sc0 + k;
+            // a neighbour counts with its score if it is a corner at T, else 0 (OpenCV keeps 0 in its score rows)
+            auto eff = [&](int o) { const int n = sc[o]; return n >= T ? n : 0; };
+            const bool keep = sv > eff(-1) && sv > eff(1) && sv > eff(-sp - 1) && sv > eff(-sp) && sv > eff(-sp + 1) &&
+                              sv > eff(sp - 1) && sv > eff(sp) && sv > eff(sp + 1);
+            keepmask |= (unsigned)keep << k;
+          }
         }
       }
-      const unsigned mask = __ballot_sync(0xffffffffu, keep);
-      if (keep) slot[total + __popc(mask & ((1u << lane) - 1u))] = cand_pack(x + x_off, y + y_off, s);
-      total += __popc(mask);
+      const int c = __popc(keepmask);
+      const unsigned b0 = __ballot_sync(0xffffffffu, c >= 1), b1 = __ballot_sync(0xffffffffu, c >= 2);
+      int pos = total + __popc(b0 & lt) + __popc(b1 & lt);
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if ((keepmask >> k) & 1u)
+          slot[pos++] = cand_pack(4 * g + k + x_off, r + y_off, (int)((word >> (8 * k)) & 0xff));
+      total += __popc(b0) + __popc(b1);
     }
     if (total > 0) break;  // :946 — retry with minThFAST only when the cell came back empty
   }

@@ -120,33 +120,44 @@ int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, 
   fs.blur = L.d_blur;
   fs.slab_fstride = ex->slab_fstride;
   bool prof = ex->profile;
-  if (prof) {  // take kStages + 1 events from the pool
-    while (ex->prof_events.size() < ex->prof_used + kStages + 1) {
+  if (prof) {  // take 2 * kStages events from the pool: (start, end) of every stage
+    while (ex->prof_events.size() < ex->prof_used + 2 * kStages) {
       cudaEvent_t e;
       if (cudaEventCreate(&e) != cudaSuccess) { prof = false; break; }
       ex->prof_events.push_back(e);
     }
   }
-  int stage = 0;
-  auto mark = [&]() {
-    if (prof) cudaEventRecord(ex->prof_events[ex->prof_used + stage], st);
-    stage++;
+  auto begin = [&](int stage, cudaStream_t s) {
+    if (prof) cudaEventRecord(ex->prof_events[ex->prof_used + 2 * stage], s);
   };
-  mark();
+  auto end = [&](int stage, cudaStream_t s) {
+    if (prof) cudaEventRecord(ex->prof_events[ex->prof_used + 2 * stage + 1], s);
+  };
+  begin(0, st);
   launch_pyramid(P, fs, ex->d_tab, frames, st);
-  mark();
+  end(0, st);
+  // fork: the blur (a streaming kernel) overlaps FAST (ALU bound) and the quadtree (latency bound)
+  ORBX_CUDA(ex, cudaEventRecord(L.fork, st));
+  ORBX_CUDA(ex, cudaStreamWaitEvent(L.side, L.fork, 0));
+  begin(3, L.side);
+  launch_blur(P, fs, frames, L.side);
+  end(3, L.side);
+  ORBX_CUDA(ex, cudaEventRecord(L.join, L.side));
+  begin(1, st);
   launch_fast(P, fs, L.ws, ex->ini_th, ex->min_th, frames, st);
-  mark();
+  end(1, st);
+  begin(2, st);
   launch_quadtree(P, L.ws, frames, st);
-  mark();
-  launch_blur(P, fs, frames, st);
-  mark();
+  end(2, st);
+  begin(4, st);
   launch_assemble(P, L.ws, out, lap0, lap1, frames, st);
-  mark();
+  end(4, st);
+  ORBX_CUDA(ex, cudaStreamWaitEvent(st, L.join, 0));
+  begin(5, st);
   launch_describe(P, fs, L.ws, out, ex->d_pattern, frames, st);
-  mark();
+  end(5, st);
   ORBX_CUDA(ex, cudaGetLastError());
-  if (prof) ex->prof_used += kStages + 1;
+  if (prof) ex->prof_used += 2 * kStages;
   L.last_fs = fs;
   L.last_frames = frames;
   ex->last_lane = ln;
@@ -292,7 +303,11 @@ int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float
   for (OrbxLane& L : ex->lane) {
     if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess)
       return bail("cudaStreamCreate", e);
-    if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
+    if ((e = cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking)) != cudaSuccess)
+      return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming)) != cudaSuccess)
       return bail("cudaEventCreate", e);
     if ((e = cudaHostAlloc(&L.h_small, (size_t)3 * max_batch * 4, cudaHostAllocDefault)) != cudaSuccess)
       return bail("cudaHostAlloc", e);
@@ -316,6 +331,9 @@ void orbx_extractor_destroy(orbx_extractor* ex) {
   for (OrbxLane& L : ex->lane) {
     if (L.h_small) cudaFreeHost(L.h_small);
     if (L.done) cudaEventDestroy(L.done);
+    if (L.fork) cudaEventDestroy(L.fork);
+    if (L.join) cudaEventDestroy(L.join);
+    if (L.side) cudaStreamDestroy(L.side);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete ex;
@@ -531,11 +549,11 @@ int orbx_profile_enable(orbx_extractor* ex, int on) {
 int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int reset) {
   if (!ex) return ORBX_E_ARG;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
-  for (size_t r = 0; r + kStages < ex->prof_used; r += kStages + 1) {
-    ORBX_CUDA(ex, cudaEventSynchronize(ex->prof_events[r + kStages]));
+  for (size_t r = 0; r + 2 * kStages <= ex->prof_used; r += 2 * kStages) {
     for (int s = 0; s < kStages; s++) {
       float t = 0;
-      ORBX_CUDA(ex, cudaEventElapsedTime(&t, ex->prof_events[r + s], ex->prof_events[r + s + 1]));
+      ORBX_CUDA(ex, cudaEventSynchronize(ex->prof_events[r + 2 * s + 1]));
+      ORBX_CUDA(ex, cudaEventElapsedTime(&t, ex->prof_events[r + 2 * s], ex->prof_events[r + 2 * s + 1]));
       ex->prof_ms[s] += t;
       ex->prof_launches[s] += 1;
     }

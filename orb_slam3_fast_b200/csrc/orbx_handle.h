@@ -18,7 +18,8 @@ enum { kStages = 6, kLanes = 2 };
 
 struct OrbxLane {
   cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaStream_t side = nullptr;   // the blur runs here, concurrently with FAST + quadtree (both only need the pyramid)
+  cudaEvent_t done = nullptr, fork = nullptr, join = nullptr;
   // geometry-dependent device state
   uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr;
   orbx::WorkSet ws{};
@@ -49,7 +50,7 @@ struct orbx_extractor {
   int last_lane = 0;  // lane of the most recent run: "frame f of the last call" lives there
   // profiling: event records around every stage, resolved lazily by orbx_profile_read (no sync inside a run)
   bool profile = false;
-  std::vector<cudaEvent_t> prof_events;  // pool, kStages + 1 per recorded run
+  std::vector<cudaEvent_t> prof_events;  // pool, 2 * kStages per recorded run: (start, end) of every stage
   size_t prof_used = 0;                  // events recorded since the last read
   float prof_ms[kStages] = {};
   int prof_launches[kStages] = {};
