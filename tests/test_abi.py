@@ -1,0 +1,88 @@
+"""The C-ABI shared library without a GPU: it loads, exports every symbol include/*.h declares, mirrors the reference's
+error behaviour at the boundary, and FAILS LOUDLY (ORBX_E_CUDA) instead of computing anything on the host."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+INCLUDE = os.path.join(ROOT, "include")
+
+
+def declared_symbols():
+    names = []
+    for hdr in ("orbx.h", "orbm.h"):
+        txt = open(os.path.join(INCLUDE, hdr)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names += re.findall(r"\b(orb[xm]_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_headers_declare_the_expected_surface():
+    names = declared_symbols()
+    for must in ("orbx_extractor_create", "orbx_extract", "orbx_extract_batch", "orbx_extract_batch_device",
+                 "orbx_download_pyramid", "orbx_extractor_tables", "orbm_knn2", "orbm_stereo_match",
+                 "orbm_stereo_frames_batch", "orbm_search_by_projection_map", "orbm_search_by_projection_frame",
+                 "orbm_search_for_triangulation", "orbm_descriptor_distance_batch"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from orb_slam3_fast_b200 import lib
+    L = lib.lib()
+    missing = [n for n in declared_symbols() if not hasattr(L, n)]
+    assert not missing, "declared in include/*.h but not exported by liborbx.so: %s" % missing
+
+
+def test_headers_compile_as_plain_c(tmp_path):
+    src = tmp_path / "abi.c"
+    src.write_text('#include "orbx.h"\n#include "orbm.h"\n'
+                   "int main(void) { orbx_kp k; orbx_frame_view f; (void)k; (void)f; "
+                   "return sizeof(orbx_kp) == 28 ? 0 : 1; }\n")
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", INCLUDE, str(src), "-o", str(exe)])
+    assert subprocess.call([str(exe)]) == 0   # cv::KeyPoint is 28 bytes (include/Frame.h:254)
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from orb_slam3_fast_b200 import ORBextractor, ORBmatcher, OrbxError
+    with pytest.raises(OrbxError) as e:
+        ORBextractor(1000)
+    assert e.value.code == -4 and "CUDA" in str(e.value)
+    with pytest.raises(OrbxError) as e:
+        ORBmatcher()
+    assert e.value.code == -4
+
+
+def test_argument_errors_are_codes_not_crashes():
+    from orb_slam3_fast_b200 import lib
+    L = lib.lib()
+    h = C.c_void_p()
+    assert L.orbx_extractor_create(None, 0, 1000, C.c_float(1.2), 8, 20, 7, 1) == -3
+    assert L.orbx_extractor_create(C.byref(h), 0, 0, C.c_float(1.2), 8, 20, 7, 1) == -3       # nfeatures < 1
+    assert L.orbx_extractor_create(C.byref(h), 0, 1000, C.c_float(1.0), 8, 20, 7, 1) == -3    # scale <= 1
+    assert L.orbx_extractor_create(C.byref(h), 0, 1000, C.c_float(1.2), 99, 20, 7, 1) == -3   # too many levels
+    assert h.value is None
+    assert L.orbx_extractor_levels(None) == -3
+    assert L.orbx_extract(None, None, 0, 0, 0, 0, 0, None, None, 0, None, None) == -3
+    assert L.orbx_last_error(None) is not None
+    L.orbx_extractor_destroy(None)   # no-op
+    assert L.orbx_host_alloc(0) is None
+
+
+def test_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "orb_slam3_fast_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inc")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "orbref" not in txt and "oracle/" not in txt and "from oracle" not in txt, \
+                    "%s references the oracle" % os.path.join(dirpath, f)
+    out = subprocess.check_output(["ldd", os.path.join(pkg, "liborbx.so")], text=True)
+    assert "orbref" not in out
