@@ -11,91 +11,131 @@ namespace orbx {
 
 // ---------------------------------------------------------------------------------------------------------------
 // 7x7 Gaussian, Q0.8 taps {18,34,48,56,48,34,18} on both axes, 16-bit row sums, one rounding: (sum + 32768) >> 16.
-// Streaming design without shared memory: a thread owns 4 adjacent columns and walks down a strip of kBlurRows output
-// rows. Per source row it reads the 3 aligned words x-4 .. x+7, forms the 4 horizontal sums with packed u16x2
-// arithmetic (two pixels per IMAD; the sums stay below 65536 so the halves never carry into each other) and pushes them
-// into a 7-deep register window; once the window is full every new row yields one 32-bit store of 4 output pixels.
-// The row loop is fully unrolled so the window is pure register renaming. Reflect-101 happens in the address (rows)
-// or in a byte-wise slow path taken only by the lanes that touch the left / right image edge (columns).
+//
+// ONE launch covers every level of every frame. The unit of work is a warp task = (level, 128-column strip,
+// kBlurRows-row strip); a lane owns 4 adjacent columns and walks down the strip. Streaming, no shared memory:
+//  * per source row a lane reads the 3 aligned words that hold columns x-4 .. x+7. The 4 horizontal sums are 8 DP4A
+//    (4 taps each, the 8th coefficient is 0) on byte groups cut out of the window with 6 funnel shifts;
+//  * the sums go into a 7-deep register window (the row loop is fully unrolled, so the window is register renaming);
+//    once it is full every new source row yields one 32-bit store of 4 output pixels;
+//  * the words of row r are requested kBlurAhead iterations before they are used;
+//  * reflect-101 costs nothing in the common case: rows are reflected in the address (warp uniform); the one or two
+//    lanes of a row that touch the left / right image edge patch their window with three PRMTs whose selectors are
+//    computed once per task — no byte loads, no divergent slow path (the first version of this kernel spent 2/3 of
+//    its time in edge warps).
+// Level 0 is read in place from the caller's buffer: when its base or pitch is not word aligned the strip falls back
+// to byte loads for its window (same kernel, `aligned` false).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBlurRows = 32;
-constexpr int kBlurThreads = 128;
+constexpr int kBlurWarps = 4;
+constexpr int kBlurAhead = 4;
 
-// [b(i), 0, b(i+1), 0] for two adjacent bytes of the 12-byte window (w0 w1 w2); I is compile-time
-template <int I>
-__device__ __forceinline__ uint32_t bpair(uint32_t w0, uint32_t w1, uint32_t w2) {
-  constexpr int word = I >> 2, off = I & 3;
-  const uint32_t wa = word == 0 ? w0 : (word == 1 ? w1 : w2);
-  if constexpr (off < 3) {
-    return __byte_perm(wa, 0u, off | (4 << 4) | ((off + 1) << 8) | (4 << 12));
-  } else {
-    const uint32_t wb = word == 0 ? w1 : w2;
-    const uint32_t t = __byte_perm(wa, wb, 0x0043);  // byte 3 of wa, byte 0 of wb
-    return __byte_perm(t, 0u, 0x4140);
+__device__ __forceinline__ int blur_strips_x(int w) { return (w + 127) >> 7; }
+__device__ __forceinline__ int blur_strips_y(int h) { return (h + kBlurRows - 1) / kBlurRows; }
+
+__global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant__ Plan P, const FrameSet fs) {
+  const int lane = threadIdx.x & 31;
+  int t = blockIdx.x * kBlurWarps + (threadIdx.x >> 5);
+  const int f = blockIdx.y;
+  int l = 0;
+  for (;; l++) {
+    if (l == P.nlevels) return;
+    const int n = blur_strips_x(P.lv[l].w) * blur_strips_y(P.lv[l].h);
+    if (t < n) break;
+    t -= n;
   }
-}
-
-__global__ void __launch_bounds__(kBlurThreads) k_blur7(const __grid_constant__ Plan P, const FrameSet fs, int l) {
   const LevelPlan& L = P.lv[l];
-  const int f = blockIdx.z;
-  const int x = 4 * (blockIdx.x * kBlurThreads + threadIdx.x);
-  const int y0 = blockIdx.y * kBlurRows;
   const int w = L.w, h = L.h;
+  const int sx = blur_strips_x(w);
+  const int ty = t / sx, tx = t - ty * sx;
+  const int x = 4 * (tx * 32 + lane);
+  const int y0 = ty * kBlurRows;
   if (x >= w) return;
   int pitch;
   const uint8_t* src = raw_level(P, fs, l, f, &pitch);
   uint8_t* dst = blur_level(P, fs, l, f);
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
-  const bool fast = aligned && x >= 4 && x + 8 <= w;
-  int win[7][4];  // horizontal sums of the last 7 source rows
-  // the 3 words of row r are requested kBlurAhead iterations before they are used (the loop is fully unrolled, so the
-  // queue is register renaming): without this every row pays a full DRAM round trip between load and use
-  constexpr int kBlurAhead = 4;
+
+  // ---- edge patch: window byte i holds column x - 4 + i; columns outside [0, w) take their reflect-101 source, which
+  //      always lies inside the two neighbouring words of the same window ----
+  const bool ld0 = x >= 4, ld2 = x + 8 <= pitch;  // words that exist (word 1 always does)
+  const bool edge = x < 4 || x + 8 > w;
+  uint32_t sel[3] = {0x3210u, 0x7654u, 0x7654u};
+  bool hi[3] = {false, false, true};  // operands of the PRMT: (w0, w1) or (w1, w2)
+  if (edge) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      int j[4], lo = 12, top = -1;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int c = x - 4 + 4 * k + b;
+        j[b] = -1;                                   // don't care
+        if (c >= -3 && c <= w + 2) {
+          j[b] = reflect101(c, w) - (x - 4);
+          lo = min(lo, j[b]);
+          top = max(top, j[b]);
+        }
+      }
+      const bool up = top >= 8;                      // then every source is >= 4 (checked for every w in tests)
+      const int base = up ? 4 : 0;
+      uint32_t s_ = 0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) s_ |= (uint32_t)((j[b] < 0 ? (lo < 12 ? lo : 4 * k + b) : j[b]) - base) << (4 * b);
+      sel[k] = top < 0 ? (k == 0 ? 0x3210u : 0x7654u) : s_;
+      hi[k] = top < 0 ? k == 2 : up;
+    }
+  }
+
+  int win[7][4];
   uint32_t q[kBlurAhead][3];
   auto fetch = [&](int r, uint32_t (&o)[3]) {
     if (y0 + r - 6 >= h) return;  // this source row completes no output row
     const int ys = reflect101(y0 - 3 + r, h);
     const uint8_t* row = src + (int64_t)ys * pitch;
-    if (fast) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + x - 4);
-      o[0] = __ldg(r32);
-      o[1] = __ldg(r32 + 1);
-      o[2] = __ldg(r32 + 2);
+    if (aligned) {
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + x);
+      o[0] = ld0 ? __ldg(r32 - 1) : 0u;
+      o[1] = __ldg(r32);
+      o[2] = ld2 ? __ldg(r32 + 1) : 0u;
     } else {
-      // bytes x-4 .. x+7 with reflect-101 columns; columns beyond w+2 only feed outputs beyond w
       uint32_t b[12];
 #pragma unroll
       for (int k = 0; k < 12; k++) {
         const int xx = x - 4 + k;
-        b[k] = (xx >= -3 && xx < w + 3) ? row[reflect101(xx, w)] : 0;
+        b[k] = (xx >= 0 && xx < w) ? row[xx] : 0;
       }
       o[0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
       o[1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
       o[2] = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
     }
   };
+  constexpr uint32_t kTapsA = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+  constexpr uint32_t kTapsB = 48u | (34u << 8) | (18u << 16);
 #pragma unroll
   for (int r = 0; r < kBlurAhead; r++) fetch(r, q[r]);
 #pragma unroll
   for (int r = 0; r < kBlurRows + 6; r++) {
     const int yo = y0 + r - 6;  // output row completed by this source row
     if (yo >= h) break;
-    const uint32_t w0 = q[r % kBlurAhead][0], w1 = q[r % kBlurAhead][1], w2 = q[r % kBlurAhead][2];
+    uint32_t w0 = q[r % kBlurAhead][0], w1 = q[r % kBlurAhead][1], w2 = q[r % kBlurAhead][2];
     if (r + kBlurAhead < kBlurRows + 6) fetch(r + kBlurAhead, q[r % kBlurAhead]);
-    // window byte i = column x - 4 + i; output pixel k reads bytes k+1 .. k+7
-    const uint32_t o0 = bpair<1>(w0, w1, w2), e1 = bpair<2>(w0, w1, w2), o1 = bpair<3>(w0, w1, w2);
-    const uint32_t e2 = bpair<4>(w0, w1, w2), o2 = bpair<5>(w0, w1, w2), e3 = bpair<6>(w0, w1, w2);
-    const uint32_t o3 = bpair<7>(w0, w1, w2), e4 = bpair<8>(w0, w1, w2), o4 = bpair<9>(w0, w1, w2);
-    const uint32_t h01 = 18u * (o0 + o3) + 34u * (e1 + e3) + 48u * (o1 + o2) + 56u * e2;  // pixels 0, 1
-    const uint32_t h23 = 18u * (o1 + o4) + 34u * (e2 + e4) + 48u * (o2 + o3) + 56u * e3;  // pixels 2, 3
+    if (edge) {
+      const uint32_t n0 = __byte_perm(hi[0] ? w1 : w0, hi[0] ? w2 : w1, sel[0]);
+      const uint32_t n1 = __byte_perm(hi[1] ? w1 : w0, hi[1] ? w2 : w1, sel[1]);
+      const uint32_t n2 = __byte_perm(hi[2] ? w1 : w0, hi[2] ? w2 : w1, sel[2]);
+      w0 = n0;
+      w1 = n1;
+      w2 = n2;
+    }
 #pragma unroll
     for (int j = 0; j < 6; j++)
 #pragma unroll
       for (int k = 0; k < 4; k++) win[j][k] = win[j + 1][k];
-    win[6][0] = (int)(h01 & 0xffff);
-    win[6][1] = (int)(h01 >> 16);
-    win[6][2] = (int)(h23 & 0xffff);
-    win[6][3] = (int)(h23 >> 16);
+    // output pixel k reads window bytes k+1 .. k+7: group A = bytes k+1..k+4, group B = bytes k+5..k+8 (tap 8 = 0)
+    win[6][0] = (int)__dp4a(__funnelshift_r(w0, w1, 8), kTapsA, __dp4a(__funnelshift_r(w1, w2, 8), kTapsB, 0u));
+    win[6][1] = (int)__dp4a(__funnelshift_r(w0, w1, 16), kTapsA, __dp4a(__funnelshift_r(w1, w2, 16), kTapsB, 0u));
+    win[6][2] = (int)__dp4a(__funnelshift_r(w0, w1, 24), kTapsA, __dp4a(__funnelshift_r(w1, w2, 24), kTapsB, 0u));
+    win[6][3] = (int)__dp4a(w1, kTapsA, __dp4a(w2, kTapsB, 0u));
     if (r >= 6) {
       uint32_t packed = 0;
 #pragma unroll
@@ -110,11 +150,10 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur7(const __grid_constant__ 
 }
 
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st) {
-  for (int l = 0; l < P.nlevels; l++) {
-    const LevelPlan& L = P.lv[l];
-    dim3 grid(((L.w + 3) / 4 + kBlurThreads - 1) / kBlurThreads, (L.h + kBlurRows - 1) / kBlurRows, frames);
-    k_blur7<<<grid, kBlurThreads, 0, st>>>(P, fs, l);
-  }
+  int tasks = 0;
+  for (int l = 0; l < P.nlevels; l++) tasks += ((P.lv[l].w + 127) / 128) * ((P.lv[l].h + kBlurRows - 1) / kBlurRows);
+  dim3 grid((tasks + kBlurWarps - 1) / kBlurWarps, frames);
+  k_blur7<<<grid, kBlurWarps * 32, 0, st>>>(P, fs);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
