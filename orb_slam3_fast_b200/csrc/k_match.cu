@@ -114,24 +114,36 @@ void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// ComputeStereoMatches. One warp per left keypoint:
-//  1. the reference's row table (right keypoints listed under every row of y +- 2*scale, :939-949) is replaced by
-//     testing that membership directly for all right keypoints, 32 per step; candidates are visited in ascending iR,
-//     the table's order, and the warp argmin breaks ties towards the lower iR (the reference's strict <, :993);
-//  2. 11x11 SAD over 11 shifts on the raw pyramid level of the left keypoint's octave (:1005-1040): lanes own pixels,
+// ComputeStereoMatches. One CTA per (pair, band of kBandRows image rows):
+//  1. the reference's row table (right keypoints listed under every row of y +- 2*scale, :939-949) becomes a per-band
+//     list in shared memory: the CTA filters the right keypoints whose row span touches its band (a keypoint spans
+//     <= ~16 rows, so it lands in 1-2 bands), and the left keypoints whose row int(vL) lies in the band;
+//  2. one warp per left keypoint of the band: exact row / octave / u-range test against the band list, 32 candidates
+//     per step, Hamming distance of the survivors, lexicographic (distance, iR) argmin — the reference visits the row's
+//     candidates in ascending iR with a strict < (:993), i.e. exactly that minimum, so list order is irrelevant;
+//  3. 11x11 SAD over 11 shifts on the raw pyramid level of the left keypoint's octave (:1005-1040): lanes own pixels,
 //     11 running sums each, then 11 warp reductions;
-//  3. parabola fit in non-fused FP32 (:1045-1052), disparity / depth (:1055-1067).
-// A second kernel (one CTA per pair) finds the median SAD and removes matches >= 1.5 * 1.4 * median (:1072-1083).
+//  4. parabola fit in non-fused FP32 (:1045-1052), disparity / depth (:1055-1067).
+// The first version let every left keypoint scan all right keypoints (1200 x 1200 tests per pair); the band lists cut
+// that ~7x. A second kernel (one CTA per pair) finds the median SAD by a two-level histogram select and removes
+// matches >= 1.5 * 1.4 * median (:1072-1083).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kStereoWarps = 4;
+constexpr int kBandRows = 16;
+
+struct BandEntry {
+  int32_t rows;  // minr | maxr << 16
+  float x;
+  int32_t idx;   // iR | octave << 16
+};
 
 __global__ void __launch_bounds__(kStereoWarps * 32)
 k_stereo_match(const StereoArgs A) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ int s_nr, s_nl;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int iL = blockIdx.x * kStereoWarps + warp;
-  const int pair = blockIdx.y;
-  const int nL = A.n_l ? A.n_l[pair] : A.n_l_host, nR = A.n_r ? A.n_r[pair] : A.n_r_host;
-  if (iL >= nL || iL >= A.cap) return;
+  const int band = blockIdx.x, pair = blockIdx.y;
+  const int nL = min(A.n_l ? A.n_l[pair] : A.n_l_host, A.cap), nR = min(A.n_r ? A.n_r[pair] : A.n_r_host, A.cap);
   const orbx_kp* kpsL = A.kps_l + (size_t)pair * A.cap;
   const orbx_kp* kpsR = A.kps_r + (size_t)pair * A.cap;
   const uint8_t* descL = A.desc_l + (size_t)pair * A.cap * 32;
@@ -140,169 +152,239 @@ k_stereo_match(const StereoArgs A) {
   float* depth = A.depth + (size_t)pair * A.cap;
   int32_t* sad = A.sad + (size_t)pair * A.cap;
   const int fL = A.frame0 + pair;
-
-  const orbx_kp kpL = kpsL[iL];
-  const int levelL = kpL.octave;
-  const float vL = kpL.y, uL = kpL.x;
-  float out_u = -1.0f, out_d = -1.0f;
-  int out_sad = -1;
+  BandEntry* rlist = reinterpret_cast<BandEntry*>(smem_raw);
+  uint16_t* llist = reinterpret_cast<uint16_t*>(smem_raw + (size_t)A.cap * sizeof(BandEntry));
   const int nRows = A.left.h[0];
+  const int band_lo = band * kBandRows, band_hi = band_lo + kBandRows - 1;
   const float minD = 0.0f, maxD = fdiv(A.mbf, A.mb);
-  const float minU = fsub(uL, maxD), maxU = fsub(uL, minD);
-  const int row = (int)vL;  // vRowIndices[vL]: float -> size_t                             :966
-  bool ok = row >= 0 && row < nRows && !(maxU < 0) && levelL >= 0 && levelL < A.nlevels;
-  int bestDist = ORBM_TH_HIGH_I, bestIdxR = 0;
-  if (ok) {
-    uint32_t dl[8];
-    load_desc(descL + (size_t)iL * 32, dl);
-    int bd = 0x7fffffff, bi = 0x7fffffff;
-    for (int base = 0; base < nR; base += 32) {
-      const int iR = base + lane;
-      int d = 0x7fffffff;
-      if (iR < nR) {
-        const orbx_kp kpR = kpsR[iR];
-        const int oR = kpR.octave;
-        if (!(kpR.y == 0.0f && kpR.x == 0.0f) && oR >= 0 && oR < A.nlevels) {
-          const float r = fmul(2.0f, A.scale[oR]);
-          const int maxr = (int)ceilf(fadd(kpR.y, r));
-          const int minr = (int)floorf(fsub(kpR.y, r));
-          if (row >= minr && row <= maxr && !(oR < levelL - 1 || oR > levelL + 1) && kpR.x >= minU &&
-              kpR.x <= maxU) {
+  if (threadIdx.x == 0) { s_nr = 0; s_nl = 0; }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  // ---- right keypoints whose rows [floor(y - r), ceil(y + r)] touch the band (:939-949) ----
+  for (int base = 0; base < nR; base += kStereoWarps * 32) {
+    const int iR = base + threadIdx.x;
+    bool take = false;
+    BandEntry e{};
+    if (iR < nR) {
+      const orbx_kp kpR = kpsR[iR];
+      const int oR = kpR.octave;
+      if (!(kpR.y == 0.0f && kpR.x == 0.0f) && oR >= 0 && oR < A.nlevels) {  // (0,0) skip: src/Frame.cc:943
+        const float r = fmul(2.0f, A.scale[oR]);
+        const int maxr = (int)ceilf(fadd(kpR.y, r));
+        const int minr = (int)floorf(fsub(kpR.y, r));
+        take = maxr >= band_lo && minr <= band_hi;
+        e.rows = (minr & 0xffff) | (maxr << 16);
+        e.x = kpR.x;
+        e.idx = iR | (oR << 16);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    int pos = 0;
+    if (lane == 0 && m) pos = atomicAdd(&s_nr, __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (take) rlist[pos + __popc(m & lt)] = e;
+  }
+  // ---- left keypoints of the band; the ones the reference skips (:966-972) are answered here with -1 ----
+  for (int base = 0; base < nL; base += kStereoWarps * 32) {
+    const int iL = base + threadIdx.x;
+    bool take = false;
+    if (iL < nL) {
+      const orbx_kp kpL = kpsL[iL];
+      const int row = (int)kpL.y;  // vRowIndices[vL]: float -> size_t                     :966
+      const bool row_ok = row >= 0 && row < nRows;
+      if ((row_ok ? row / kBandRows : 0) == band) {
+        const float maxU = fsub(kpL.x, minD);
+        take = row_ok && !(maxU < 0) && kpL.octave >= 0 && kpL.octave < A.nlevels;
+        if (!take) {
+          u_right[iL] = -1.0f;
+          depth[iL] = -1.0f;
+          sad[iL] = -1;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    int pos = 0;
+    if (lane == 0 && m) pos = atomicAdd(&s_nl, __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (take) llist[pos + __popc(m & lt)] = (uint16_t)iL;
+  }
+  __syncthreads();
+  const int nBR = s_nr, nBL = s_nl;
+
+  for (int li = warp; li < nBL; li += kStereoWarps) {
+    const int iL = llist[li];
+    const orbx_kp kpL = kpsL[iL];
+    const int levelL = kpL.octave;
+    const float vL = kpL.y, uL = kpL.x;
+    float out_u = -1.0f, out_d = -1.0f;
+    int out_sad = -1;
+    const float minU = fsub(uL, maxD), maxU = fsub(uL, minD);
+    const int row = (int)vL;
+    int bestDist = ORBM_TH_HIGH_I, bestIdxR = 0;
+    {
+      uint32_t dl[8];
+      load_desc(descL + (size_t)iL * 32, dl);
+      int bd = 0x7fffffff, bi = 0x7fffffff;
+      for (int base = 0; base < nBR; base += 32) {
+        const int k = base + lane;
+        if (k < nBR) {
+          const BandEntry e = rlist[k];
+          const int minr = (int)(int16_t)(e.rows & 0xffff), maxr = e.rows >> 16;
+          const int oR = e.idx >> 16, iR = e.idx & 0xffff;
+          if (row >= minr && row <= maxr && !(oR < levelL - 1 || oR > levelL + 1) && e.x >= minU && e.x <= maxU) {
             uint32_t dr[8];
             load_desc(descR + (size_t)iR * 32, dr);
-            d = hamming(dl, dr);
+            const int d = hamming(dl, dr);
+            if (d < bd || (d == bd && iR < bi)) { bd = d; bi = iR; }
           }
         }
       }
-      // keep the lexicographic minimum of (dist, iR) per lane; lanes visit ascending iR so < suffices
-      if (d < bd) { bd = d; bi = iR; }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-    }
-    if (bd < bestDist) { bestDist = bd; bestIdxR = bi; }
-  }
-  if (ok && bestDist < (ORBM_TH_HIGH_I + ORBM_TH_LOW_I) / 2) {  // thOrbDist                   :925,1001
-    const float uR0 = kpsR[bestIdxR].x;
-    const float sfac = A.inv_scale[levelL];
-    const float scaleduL = roundf(fmul(kpL.x, sfac)), scaledvL = roundf(fmul(kpL.y, sfac));
-    const float scaleduR0 = roundf(fmul(uR0, sfac));
-    const int w = 5, L = 5;
-    const float iniu = fsub(fadd(scaleduR0, (float)L), (float)w);
-    const float endu = fadd(fadd(fadd(scaleduR0, (float)L), (float)w), 1.0f);
-    const int colsR = A.right.w[levelL];
-    bool inb = !(iniu < 0 || endu >= (float)colsR);
-    const int yl = (int)fsub(scaledvL, (float)w), xl = (int)fsub(scaleduL, (float)w);
-    const int xr0 = (int)fsub(scaleduR0, (float)w);  // inc = 0
-    // the reference's cv::Mat ranges throw outside the level; such keypoints cannot come from the extractor
-    inb = inb && yl >= 0 && yl + 2 * w < A.left.h[levelL] && yl + 2 * w < A.right.h[levelL] && xl >= 0 &&
-          xl + 2 * w < A.left.w[levelL] && xr0 - L >= 0 && xr0 + L + 2 * w < colsR;
-    if (inb) {
-      const uint8_t* IL = A.left.base[levelL] + (int64_t)fL * A.left.fstride[levelL];
-      const uint8_t* IR = A.right.base[levelL] + (int64_t)fL * A.right.fstride[levelL];
-      const int pl = A.left.pitch[levelL], pr = A.right.pitch[levelL];
-      int acc[11];
-#pragma unroll
-      for (int k = 0; k < 11; k++) acc[k] = 0;
-      for (int p = lane; p < 121; p += 32) {
-        const int yy = p / 11, xx = p - yy * 11;
-        const int a = IL[(int64_t)(yl + yy) * pl + xl + xx];
-        const uint8_t* rrow = IR + (int64_t)(yl + yy) * pr + xr0 + xx - L;
-#pragma unroll
-        for (int k = 0; k < 11; k++) acc[k] += abs(a - (int)rrow[k]);
+      for (int o = 16; o > 0; o >>= 1) {
+        const int od = __shfl_xor_sync(0xffffffffu, bd, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
       }
-      float dists[11];
-      int bestSad = 0x7fffffff, bestinc = 0;
+      if (bd < bestDist) { bestDist = bd; bestIdxR = bi; }
+    }
+    if (bestDist < (ORBM_TH_HIGH_I + ORBM_TH_LOW_I) / 2) {  // thOrbDist                       :925,1001
+      const float uR0 = kpsR[bestIdxR].x;
+      const float sfac = A.inv_scale[levelL];
+      const float scaleduL = roundf(fmul(kpL.x, sfac)), scaledvL = roundf(fmul(kpL.y, sfac));
+      const float scaleduR0 = roundf(fmul(uR0, sfac));
+      const int w = 5, L = 5;
+      const float iniu = fsub(fadd(scaleduR0, (float)L), (float)w);
+      const float endu = fadd(fadd(fadd(scaleduR0, (float)L), (float)w), 1.0f);
+      const int colsR = A.right.w[levelL];
+      bool inb = !(iniu < 0 || endu >= (float)colsR);
+      const int yl = (int)fsub(scaledvL, (float)w), xl = (int)fsub(scaleduL, (float)w);
+      const int xr0 = (int)fsub(scaleduR0, (float)w);  // inc = 0
+      // the reference's cv::Mat ranges throw outside the level; such keypoints cannot come from the extractor
+      inb = inb && yl >= 0 && yl + 2 * w < A.left.h[levelL] && yl + 2 * w < A.right.h[levelL] && xl >= 0 &&
+            xl + 2 * w < A.left.w[levelL] && xr0 - L >= 0 && xr0 + L + 2 * w < colsR;
+      if (inb) {
+        const uint8_t* IL = A.left.base[levelL] + (int64_t)fL * A.left.fstride[levelL];
+        const uint8_t* IR = A.right.base[levelL] + (int64_t)fL * A.right.fstride[levelL];
+        const int pl = A.left.pitch[levelL], pr = A.right.pitch[levelL];
+        int acc[11];
 #pragma unroll
-      for (int k = 0; k < 11; k++) {
-        const int s = __reduce_add_sync(0xffffffffu, acc[k]);
-        dists[k] = (float)s;          // cv::norm(IL, IR, NORM_L1) -> float               :1033
-        if (s < bestSad) { bestSad = s; bestinc = k - L; }
-      }
-      if (!(bestinc == -L || bestinc == L)) {
-        float dist1 = 0, dist2 = 0, dist3 = 0;
+        for (int k = 0; k < 11; k++) acc[k] = 0;
+        for (int p = lane; p < 121; p += 32) {
+          const int yy = p / 11, xx = p - yy * 11;
+          const int a = IL[(int64_t)(yl + yy) * pl + xl + xx];
+          const uint8_t* rrow = IR + (int64_t)(yl + yy) * pr + xr0 + xx - L;
 #pragma unroll
-        for (int k = 1; k < 10; k++)
-          if (k == bestinc + L) { dist1 = dists[k - 1]; dist2 = dists[k]; dist3 = dists[k + 1]; }
-        const float deltaR = fdiv(fsub(dist1, dist3), fmul(2.0f, fsub(fadd(dist1, dist3), fmul(2.0f, dist2))));
-        if (!(deltaR < -1 || deltaR > 1)) {
-          float bestuR = fmul(A.scale[levelL], fadd(fadd(scaleduR0, (float)bestinc), deltaR));
-          float disparity = fsub(uL, bestuR);
-          if (disparity >= minD && disparity < maxD) {
-            if (disparity <= 0) {
-              disparity = 0.01f;
-              bestuR = (float)dsub((double)uL, 0.01);  // float - double literal          :1061
+          for (int k = 0; k < 11; k++) acc[k] += abs(a - (int)rrow[k]);
+        }
+        float dists[11];
+        int bestSad = 0x7fffffff, bestinc = 0;
+#pragma unroll
+        for (int k = 0; k < 11; k++) {
+          const int s = __reduce_add_sync(0xffffffffu, acc[k]);
+          dists[k] = (float)s;          // cv::norm(IL, IR, NORM_L1) -> float               :1033
+          if (s < bestSad) { bestSad = s; bestinc = k - L; }
+        }
+        if (!(bestinc == -L || bestinc == L)) {
+          float dist1 = 0, dist2 = 0, dist3 = 0;
+#pragma unroll
+          for (int k = 1; k < 10; k++)
+            if (k == bestinc + L) { dist1 = dists[k - 1]; dist2 = dists[k]; dist3 = dists[k + 1]; }
+          const float deltaR = fdiv(fsub(dist1, dist3), fmul(2.0f, fsub(fadd(dist1, dist3), fmul(2.0f, dist2))));
+          if (!(deltaR < -1 || deltaR > 1)) {
+            float bestuR = fmul(A.scale[levelL], fadd(fadd(scaleduR0, (float)bestinc), deltaR));
+            float disparity = fsub(uL, bestuR);
+            if (disparity >= minD && disparity < maxD) {
+              if (disparity <= 0) {
+                disparity = 0.01f;
+                bestuR = (float)dsub((double)uL, 0.01);  // float - double literal          :1061
+              }
+              out_d = fdiv(A.mbf, disparity);
+              out_u = bestuR;
+              out_sad = bestSad;
             }
-            out_d = fdiv(A.mbf, disparity);
-            out_u = bestuR;
-            out_sad = bestSad;
           }
         }
       }
     }
-  }
-  if (lane == 0) {
-    u_right[iL] = out_u;
-    depth[iL] = out_d;
-    sad[iL] = out_sad;
+    if (lane == 0) {
+      u_right[iL] = out_u;
+      depth[iL] = out_d;
+      sad[iL] = out_sad;
+    }
   }
 }
 
-// median of the accepted SADs (= element size/2 of the sorted (dist, iL) vector) by rank counting, then the cut
+// median of the accepted SADs = value of element size/2 of the sorted (dist, iL) vector (:1072-1074) = the
+// (m/2)-th smallest SAD; a SAD is < 2^15 (121 * 255), so a two-level histogram select finds it in O(n).
 __global__ void __launch_bounds__(256) k_stereo_median(const StereoArgs A) {
-  extern __shared__ int32_t sh[];
-  __shared__ int s_m, s_median, s_kept;
+  __shared__ int hist[256];
+  __shared__ int s_m, s_bin, s_rank, s_median, s_kept;
   const int pair = blockIdx.x;
   const int nL = min(A.n_l ? A.n_l[pair] : A.n_l_host, A.cap);
   float* u_right = A.u_right + (size_t)pair * A.cap;
   float* depth = A.depth + (size_t)pair * A.cap;
   const int32_t* sad = A.sad + (size_t)pair * A.cap;
-  if (threadIdx.x == 0) { s_m = 0; s_median = -1; s_kept = 0; }
+  hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_m = 0; s_kept = 0; s_median = -1; }
   __syncthreads();
-  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
+  int cnt = 0;
+  for (int i = threadIdx.x; i < nL; i += 256) {
     const int v = sad[i];
-    sh[i] = v;
-    if (v >= 0) atomicAdd(&s_m, 1);
+    if (v >= 0) {
+      atomicAdd(&hist[(v >> 7) & 255], 1);
+      cnt++;
+    }
   }
+  if (cnt) atomicAdd(&s_m, cnt);
   __syncthreads();
   const int m = s_m;
   if (m == 0) {  // the reference reads vDistIdx[0] of an empty vector here (UB); defined as "no matches"
     if (threadIdx.x == 0) A.n_matched[pair] = 0;
     return;
   }
-  const int target = m / 2;
-  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
-    const int v = sh[i];
-    if (v < 0) continue;
-    int rank = 0;
-    for (int j = 0; j < nL; j++) {
-      const int u = sh[j];
-      rank += (u >= 0) && (u < v || (u == v && j < i));
-    }
-    if (rank == target) s_median = v;
+  if (threadIdx.x == 0) {
+    int rank = m / 2, b = 0;
+    while (rank >= hist[b]) rank -= hist[b++];
+    s_bin = b;
+    s_rank = rank;
+  }
+  __syncthreads();
+  const int bin = s_bin;
+  __syncthreads();
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nL; i += 256) {
+    const int v = sad[i];
+    if (v >= 0 && ((v >> 7) & 255) == bin) atomicAdd(&hist[v & 127], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int rank = s_rank, b = 0;
+    while (rank >= hist[b]) rank -= hist[b++];
+    s_median = (bin << 7) | b;
   }
   __syncthreads();
   const float median = (float)s_median;
   const float thDist = fmul(0x1.0cccccp+1f, median);  // 1.5f * 1.4f folded to float, then * median   :1074
-  for (int i = threadIdx.x; i < nL; i += blockDim.x) {
-    const int v = sh[i];
+  int kept = 0;
+  for (int i = threadIdx.x; i < nL; i += 256) {
+    const int v = sad[i];
     if (v < 0) continue;
-    if ((float)v < thDist) atomicAdd(&s_kept, 1);
+    if ((float)v < thDist) kept++;
     else { u_right[i] = -1.0f; depth[i] = -1.0f; }
   }
+  if (kept) atomicAdd(&s_kept, kept);
   __syncthreads();
   if (threadIdx.x == 0) A.n_matched[pair] = s_kept;
 }
 
 void launch_stereo(const StereoArgs& A, int n_pairs, int max_rows, cudaStream_t st) {
   if (n_pairs <= 0 || max_rows <= 0) return;
-  dim3 grid((max_rows + kStereoWarps - 1) / kStereoWarps, n_pairs);
-  k_stereo_match<<<grid, kStereoWarps * 32, 0, st>>>(A);
-  const size_t smem = (size_t)max_rows * 4;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_median, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_stereo_median<<<n_pairs, 256, smem, st>>>(A);
+  const int bands = (A.left.h[0] + kBandRows - 1) / kBandRows;
+  const size_t smem = (size_t)A.cap * (sizeof(BandEntry) + sizeof(uint16_t));
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(bands, n_pairs);
+  k_stereo_match<<<grid, kStereoWarps * 32, smem, st>>>(A);
+  k_stereo_median<<<n_pairs, 256, 0, st>>>(A);
 }
 
 }  // namespace orbx

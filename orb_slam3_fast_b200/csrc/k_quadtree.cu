@@ -57,27 +57,40 @@ __global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P,
   uint32_t* cand = ws.cand + (int64_t)f * P.slots_per_frame + L.slot_base;
   uint32_t* lab = ws.lab + (int64_t)f * P.slots_per_frame + L.slot_base;
 
-  // ---- compact the cell slots in cell order ----
+  // ---- compact the cell slots in cell order: exclusive scan of the cell counts (chunks of kCellChunk cells), then a
+  //      flat gather — output o belongs to the last cell whose prefix is <= o (binary search in shared memory). Every
+  //      lane step is independent, 4 are in flight per lane: the first version copied cell after cell and paid one L2
+  //      round trip per cell (240 dependent trips at level 0) ----
+  // the prefix array borrows the tree's node arrays (box / cnt / child), which are not live yet
+  int* pref = reinterpret_cast<int*>(smem + S.off_box0);
+  const int kCellChunk = (int)((S.off_newpos - S.off_box0) / 4) - 1;
   const int ncell = L.nCols * L.nRows;
   int C = 0;
-  for (int base = 0; base < ncell; base += 32) {
-    const int ci = base + lane;
-    const int n = ci < ncell ? counts[ci] : 0;
-    int inc = n;
+  for (int cb = 0; cb < ncell; cb += kCellChunk) {
+    const int nc = min(kCellChunk, ncell - cb);
+    for (int i = lane; i < nc; i += 32) pref[i] = counts[cb + i];
+    __syncwarp();
+    const int total = excl_scan(pref, nc);
+    auto locate = [&](int o) {
+      int lo = 0, hi = nc - 1;  // largest i with pref[i] <= o
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (pref[mid] <= o) lo = mid;
+        else hi = mid - 1;
+      }
+      return slots + (int64_t)(cb + lo) * L.slot_cap + (o - pref[lo]);
+    };
+    for (int o0 = lane; o0 < total; o0 += 4 * 32) {
+      uint32_t v[4];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
+      for (int u = 0; u < 4; u++)
+        if (o0 + 32 * u < total) v[u] = *locate(o0 + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (o0 + 32 * u < total) cand[C + o0 + 32 * u] = v[u];
     }
-    const int off = C + inc - n;
-    const int lim = min(32, ncell - base);
-    for (int t = 0; t < lim; t++) {
-      const int nt = __shfl_sync(0xffffffffu, n, t);
-      const int ot = __shfl_sync(0xffffffffu, off, t);
-      const uint32_t* s = slots + (int64_t)(base + t) * L.slot_cap;
-      for (int k = lane; k < nt; k += 32) cand[ot + k] = s[k];
-    }
-    C += __shfl_sync(0xffffffffu, inc, 31);
+    C += total;
+    __syncwarp();
   }
   __syncwarp();
   if (lane == 0) ws.lvl_c[f * P.nlevels + l] = C;
