@@ -30,7 +30,7 @@ FX, BASELINE_M = 435.2, 0.11  # EuRoC-like rectified focal length / baseline (SU
 MBF, MB = float(np.float32(FX * BASELINE_M)), float(np.float32(BASELINE_M))
 METRIC = "frames/sec ORB extract+match (752x480 stereo pairs, 1200 feat/eye, extract + ComputeStereoMatches)"
 WORKLOAD = "configs[1]: EuRoC-shaped 752x480 stereo pair, 1200 features/eye, extract + ComputeStereoMatches"
-KERNELS_PER_EXTRACT = (NLEVELS - 1) + 1 + 1 + NLEVELS + 1 + 1  # resize x7, fast, quadtree, blur x8, assemble, describe
+KERNELS_PER_EXTRACT = (NLEVELS - 1) + 1 + 1 + 1 + 1  # resize x7, fast, quadtree, blur, describe
 KERNELS_PER_STEP = 2 * KERNELS_PER_EXTRACT + 2                 # + stereo match + stereo median
 
 
@@ -283,7 +283,7 @@ def main():
     Nk = n_keypoints
     alg_bytes_per_frame = {
         "pyramid": P0 + sumP, "fast": sumP + 8 * C, "blur": 2 * sumP, "describe": (749 + 1849 + 32 + 28) * Nk,
-        "quadtree": 8 * C + 4 * Nk, "assemble": 8 * Nk}
+        "quadtree": 8 * C + 4 * Nk}
     dur_ms = stage_ms[dom] / max(stage_cnt[dom] * 2, 1)   # per extract call (one batch of P frames)
     achieved = alg_bytes_per_frame[dom] * P / (dur_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -87,7 +87,7 @@ int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp
 
 /* Per-stage device time of the calls since the last reset, measured with CUDA events on the handle's stream when
  * profiling is enabled (adds event records between kernels; leave it off for throughput runs).
- * Stages: 0 pyramid, 1 fast, 2 quadtree, 3 blur, 4 assemble, 5 describe. ms[6] accumulates, launches[6] counts. */
+ * Stages: 0 pyramid, 1 fast, 2 quadtree, 3 blur, 4 describe. ms[5] accumulates, launches[5] counts. */
 int orbx_profile_enable(orbx_extractor* ex, int on);
 int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int reset);
 

@@ -1,9 +1,9 @@
 // k_describe.cu — everything after the quadtree in ORBextractor::operator() (src/ORBextractor.cc:1059-1105):
 //   k_blur7     cv::GaussianBlur(level, 7x7, sigma 2, REFLECT_101) (:1074-1076), OpenCV's fixed-point path
-//   k_assemble  output row of every keypoint: levels ascending, "mono" rows from the front, rows whose scaled x lies in
-//               the lapping area from the back (:1083-1101)
 //   k_describe  IC_Angle (:75-99, :471-488) on the raw level + computeOrbDescriptor (:102-147) on the blurred level,
-//               one warp per keypoint, writing the final cv::KeyPoint record and descriptor row
+//               one warp per keypoint, writing the final cv::KeyPoint record and descriptor row at its output row:
+//               levels ascending, "mono" rows from the front, rows whose scaled x lies in the lapping area from the
+//               back (:1083-1101) — the per-level ranks come from k_quadtree, the level offsets are summed here
 #include "orbx_kernels.cuh"
 #include "orbx_quadtree.h"
 
@@ -157,53 +157,6 @@ void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Output rows. One warp per frame; ballot prefix sums keep the encounter order the serial reference has.
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_assemble(const __grid_constant__ Plan P, const WorkSet ws, const OutSet out,
-                                                 int lap0, int lap1) {
-  const int f = blockIdx.x, lane = threadIdx.x;
-  int total = 0;
-  for (int l = 0; l < P.nlevels; l++) total += ws.lvl_n[f * P.nlevels + l];
-  const bool fits = total <= out.cap;
-  int mono = 0, stereo = total - 1;
-  const float flap0 = (float)lap0, flap1 = (float)lap1;
-  for (int l = 0; l < P.nlevels; l++) {
-    const LevelPlan& L = P.lv[l];
-    const int n = ws.lvl_n[f * P.nlevels + l];
-    const uint32_t* kp = ws.lvl_kp + (int64_t)f * P.kps_per_frame + L.kp_base;
-    int32_t* dst = ws.dst + (int64_t)f * P.kps_per_frame + L.kp_base;
-    for (int base = 0; base < n; base += 32) {
-      const int p = base + lane;
-      bool is_st = false, valid = p < n;
-      if (valid) {
-        float x = (float)(cand_x(kp[p]) + kMinBorder);
-        if (l != 0) x = fmul(x, L.scale);           // keypoint->pt *= scale          :1086
-        is_st = x >= flap0 && x <= flap1;           // inclusive lapping test          :1088-1089
-      }
-      const unsigned m_st = __ballot_sync(0xffffffffu, valid && is_st);
-      const unsigned m_mo = __ballot_sync(0xffffffffu, valid && !is_st);
-      const unsigned lt = (1u << lane) - 1u;
-      if (valid) {
-        const int d = is_st ? stereo - __popc(m_st & lt) : mono + __popc(m_mo & lt);
-        dst[p] = fits ? d : -1;
-      }
-      stereo -= __popc(m_st);
-      mono += __popc(m_mo);
-    }
-  }
-  if (lane == 0) {
-    out.n[f] = total;
-    out.mono[f] = mono;  // the reference's return value (monoIndex, :1105)
-    out.status[f] = fits ? 0 : -2;
-  }
-}
-
-void launch_assemble(const Plan& P, const WorkSet& ws, const OutSet& out, int lap0, int lap1, int frames,
-                     cudaStream_t st) {
-  k_assemble<<<frames, 32, 0, st>>>(P, ws, out, lap0, lap1);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Orientation + descriptor, one warp per keypoint.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kDescWarps = 4;
@@ -219,9 +172,31 @@ k_describe(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, 
   while (l + 1 < P.nlevels && P.lv[l + 1].kp_base <= e) l++;
   const LevelPlan& L = P.lv[l];
   const int p = e - L.kp_base;
-  if (p >= ws.lvl_n[f * P.nlevels + l]) return;
-  const int dst = ws.dst[(int64_t)f * P.kps_per_frame + e];
-  if (dst < 0) return;
+  // ---- output row (:1083-1101): monoIndex counts up from 0, stereoIndex down from N - 1, levels ascending ----
+  int total = 0, st_total = 0, mono_before = 0, st_before = 0, n_here = 0;
+  {
+    const int32_t* ln = ws.lvl_n + f * P.nlevels;
+    const int32_t* ls = ws.lvl_st + f * P.nlevels;
+    for (int k = 0; k < P.nlevels; k++) {
+      const int n = ln[k], s = ls[k];
+      total += n;
+      st_total += s;
+      if (k < l) {
+        mono_before += n - s;
+        st_before += s;
+      }
+      if (k == l) n_here = n;
+    }
+  }
+  const bool fits = total <= out.cap;
+  if (e == 0 && lane == 0) {
+    out.n[f] = total;
+    out.mono[f] = total - st_total;  // the reference's return value (monoIndex, :1105)
+    out.status[f] = fits ? 0 : -2;
+  }
+  if (p >= n_here || !fits) return;
+  const int rk = ws.dst[(int64_t)f * P.kps_per_frame + e];
+  const int dst = (rk & 0x40000000) ? total - 1 - (st_before + (rk & 0x3fffffff)) : mono_before + rk;
   const uint32_t cw = ws.lvl_kp[(int64_t)f * P.kps_per_frame + e];
   const int X = cand_x(cw) + kMinBorder, Y = cand_y(cw) + kMinBorder;  // :867-868
 

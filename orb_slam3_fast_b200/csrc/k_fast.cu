@@ -116,32 +116,52 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   uint8_t* score = smem + (size_t)warp * per_warp + raw_bytes;
 
   // ---- stage the raw window, widened to u16; columns >= tw are zero. A lane step produces 4 tile columns from the
-  //      two aligned global words that hold them (funnel shift by the row's byte misalignment), one 8-byte store ----
+  //      two aligned global words that hold them (funnel shift by the row's byte misalignment), one 8-byte store.
+  //      The (row, group) walk is incremental (no division) and 4 lane steps are in flight at once: the loads of a
+  //      batch are all issued before the first conversion, otherwise every step pays a full L2 / HBM round trip ----
   int pitch;
   const uint8_t* img = raw_level(P, fs, l, f, &pitch);
   const uint8_t* src = img + (int64_t)iniY * pitch + iniX;
   {
     const int groups = tp >> 2;
-    const float inv_groups = 1.0f / (float)groups;
-    const int nsteps = groups * th;
-    for (int idx = lane; idx < nsteps; idx += 32) {
-      const int r = (int)(((float)idx + 0.5f) * inv_groups);
-      const int j = idx - r * groups;
-      const int valid = tw - 4 * j;  // tile columns 4j .. 4j+3 that exist
-      uint32_t v = 0;
-      if (valid > 0) {
-        const uint8_t* p = src + (int64_t)r * pitch + 4 * j;
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
-        const uint32_t* a = reinterpret_cast<const uint32_t*>(p - sh);
-        const uint32_t lo = a[0];
-        const uint32_t hi = sh ? a[1] : 0u;  // stays inside the image row: the window ends >= 16 px before it
-        v = __funnelshift_r(lo, hi, 8 * sh);
-        if (valid < 4) v &= (1u << (8 * valid)) - 1u;
+    const int q32 = 32 / groups, m32 = 32 - q32 * groups;
+    int r = lane / groups, j = lane - r * groups;
+    constexpr int kStageBatch = 4;
+    while (r < th) {
+      uint32_t lo[kStageBatch], hi[kStageBatch], sh[kStageBatch];
+      int rr[kStageBatch], jj[kStageBatch], valid[kStageBatch];
+#pragma unroll
+      for (int u = 0; u < kStageBatch; u++) {
+        rr[u] = r;
+        jj[u] = j;
+        valid[u] = r < th ? tw - 4 * j : 0;  // tile columns 4j .. 4j+3 that exist
+        lo[u] = hi[u] = sh[u] = 0;
+        if (valid[u] > 0) {
+          const uint8_t* p = src + (int64_t)r * pitch + 4 * j;
+          sh[u] = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3);
+          const uint32_t* a = reinterpret_cast<const uint32_t*>(p - sh[u]);
+          lo[u] = __ldg(a);
+          if (sh[u]) hi[u] = __ldg(a + 1);  // stays inside the image row: the window ends >= 16 px before it
+        }
+        j += m32;
+        r += q32;
+        if (j >= groups) {
+          j -= groups;
+          r++;
+        }
       }
-      uint2 o;
-      o.x = __byte_perm(v, 0u, 0x4140);  // [b0, 0, b1, 0]
-      o.y = __byte_perm(v, 0u, 0x4342);  // [b2, 0, b3, 0]
-      *reinterpret_cast<uint2*>(raw + r * tp + 4 * j) = o;
+#pragma unroll
+      for (int u = 0; u < kStageBatch; u++) {
+        if (rr[u] < th) {
+          uint32_t v = __funnelshift_r(lo[u], hi[u], 8 * sh[u]);
+          if (valid[u] <= 0) v = 0;
+          else if (valid[u] < 4) v &= (1u << (8 * valid[u])) - 1u;
+          uint2 o;
+          o.x = __byte_perm(v, 0u, 0x4140);  // [b0, 0, b1, 0]
+          o.y = __byte_perm(v, 0u, 0x4342);  // [b2, 0, b3, 0]
+          *reinterpret_cast<uint2*>(raw + rr[u] * tp + 4 * jj[u]) = o;
+        }
+      }
     }
   }
   // ---- clear the score map (1-row / 4-column zero frame around the interior) ----
@@ -204,10 +224,46 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   }
   __syncwarp();
 
-  // ---- per-cell threshold, 3x3 non-max suppression inside the cell interior, ordered emission ----
-  // A lane step looks at one 4-pixel score word (most are 0). Lane order = group order = pixel row-major, so the
-  // candidate order of the serial reference falls out of two ballots: no two kept pixels are adjacent, hence a group
-  // of 4 consecutive pixels keeps at most 2.
+  // ---- 3x3 non-max suppression inside the cell interior, threshold independent. OpenCV keeps a corner at threshold
+  //      T iff its score beats the scores of its 8 neighbours that are corners at T; for a pixel that is itself a
+  //      corner at T (score >= T) a neighbour below T can never beat it, so "beats all 8 raw scores" is the same test
+  //      and is computed ONCE for both thresholds. Four pixels per lane step, branch free: the bytes of the three
+  //      score rows are split into u16x2 lanes (even / odd pixels), neighbour maxima are VIMNMX3, the comparison is a
+  //      biased subtraction. The result word (score where the pixel is a strict local maximum, else 0) goes into the
+  //      raw tile's shared memory, which is dead by now. ----
+  uint32_t* wmap = reinterpret_cast<uint32_t*>(raw);
+  for (int G = lane; G < ngroups; G += 32) {
+    const int r = (int)(((float)G + 0.5f) * inv_gpr);
+    const int g = G - r * gpr;
+    const uint32_t* mid = reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g);
+    const int rw = sp >> 2;
+    // per row: A = (p-1, p1), B = (p0, p2), Cc = (p1, p3), D = (p2, p4) as u16x2
+    uint32_t A[3], B[3], Cc[3], D[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint32_t* rowp = mid + (k - 1) * rw;
+      const uint32_t wl = rowp[-1], wc = rowp[0], wr = rowp[1];
+      A[k] = __byte_perm(wl, wc, 0x0503) & 0x00ff00ffu;
+      B[k] = __byte_perm(wc, 0u, 0x4240);
+      Cc[k] = __byte_perm(wc, 0u, 0x4341);
+      D[k] = __byte_perm(wc, wr, 0x0402) & 0x00ff00ffu;
+    }
+    uint32_t ne = __vimax3_u16x2(__vimax3_u16x2(A[0], B[0], Cc[0]), __vimax3_u16x2(A[2], B[2], Cc[2]), A[1]);
+    ne = __vimax3_u16x2(ne, Cc[1], Cc[1]);                       // neighbours of the even pixels (p0, p2)
+    uint32_t no = __vimax3_u16x2(__vimax3_u16x2(B[0], Cc[0], D[0]), __vimax3_u16x2(B[2], Cc[2], D[2]), B[1]);
+    no = __vimax3_u16x2(no, D[1], D[1]);                         // neighbours of the odd pixels (p1, p3)
+    // lane = 0x8000 + neighbour max - self: bit 15 set <=> some neighbour >= self <=> not a strict local maximum
+    const uint32_t te = ((ne | 0x80008000u) - B[1]) & 0x80008000u;
+    const uint32_t to = ((no | 0x80008000u) - Cc[1]) & 0x80008000u;
+    const uint32_t ke = B[1] & ~((te >> 15) * 0xffu);
+    const uint32_t ko = Cc[1] & ~((to >> 15) * 0xffu);
+    wmap[G] = __byte_perm(ke, ko, 0x6240);                       // bytes p0 p1 p2 p3
+  }
+  __syncwarp();
+
+  // ---- per-cell threshold and ordered emission. Lane order = group order = pixel row-major, so the candidate order
+  //      of the serial reference falls out of two ballots: no two kept pixels are adjacent, hence a group of 4
+  //      consecutive pixels keeps at most 2. ----
   const int x_off = iniX + 3 - kMinBorder, y_off = iniY + 3 - kMinBorder;  // candidate coords are minBorder-relative
   const unsigned lt = (1u << lane) - 1u;
   int total = 0;
@@ -216,36 +272,24 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
     total = 0;
     for (int base = 0; base < ngroups; base += 32) {
       const int G = base + lane;
-      uint32_t word = 0;
-      int r = 0, g = 0;
-      if (G < ngroups) {
-        r = (int)(((float)G + 0.5f) * inv_gpr);
-        g = G - r * gpr;
-        word = *reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g);
-      }
+      const uint32_t word = G < ngroups ? wmap[G] : 0u;
       unsigned keepmask = 0;
-      if (word) {
-        const uint8_t* sc0 = score + (r + 1) * sp + 4 + 4 * g;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int sv = (int)((word >> (8 * k)) & 0xff);
-          if (sv >= T && sv > 0) {  // corner at T  <=>  m > T  <=>  score >= T
-            const uint8_t* sc = sc0 + k;
-            // a neighbour counts with its score if it is a corner at T, else 0 (OpenCV keeps 0 in its score rows)
-            auto eff = [&](int o) { const int n = sc[o]; return n >= T ? n : 0; };
-            const bool keep = sv > eff(-1) && sv > eff(1) && sv > eff(-sp - 1) && sv > eff(-sp) && sv > eff(-sp + 1) &&
-                              sv > eff(sp - 1) && sv > eff(sp) && sv > eff(sp + 1);
-            keepmask |= (unsigned)keep << k;
-          }
-        }
+      for (int k = 0; k < 4; k++) {
+        const int sv = (int)((word >> (8 * k)) & 0xff);
+        keepmask |= (unsigned)(sv >= T && sv > 0) << k;  // corner at T  <=>  m > T  <=>  score >= T
       }
       const int c = __popc(keepmask);
       const unsigned b0 = __ballot_sync(0xffffffffu, c >= 1), b1 = __ballot_sync(0xffffffffu, c >= 2);
-      int pos = total + __popc(b0 & lt) + __popc(b1 & lt);
+      if (keepmask) {
+        const int r = (int)(((float)G + 0.5f) * inv_gpr);
+        const int g = G - r * gpr;
+        int pos = total + __popc(b0 & lt) + __popc(b1 & lt);
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-        if ((keepmask >> k) & 1u)
-          slot[pos++] = cand_pack(4 * g + k + x_off, r + y_off, (int)((word >> (8 * k)) & 0xff));
+        for (int k = 0; k < 4; k++)
+          if ((keepmask >> k) & 1u)
+            slot[pos++] = cand_pack(4 * g + k + x_off, r + y_off, (int)((word >> (8 * k)) & 0xff));
+      }
       total += __popc(b0) + __popc(b1);
     }
     if (total > 0) break;  // :946 — retry with minThFAST only when the cell came back empty

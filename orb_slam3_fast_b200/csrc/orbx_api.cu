@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,6 +41,8 @@ void free_plan_buffers(orbx_extractor* ex) {
     cudaFree(L.ws.lvl_kp);
     cudaFree(L.ws.lvl_n);
     cudaFree(L.ws.lvl_c);
+    cudaFree(L.ws.lvl_st);
+    cudaFree(L.ws.qt_prof);
     cudaFree(L.ws.dst);
     L.d_in = L.d_pyr = L.d_blur = nullptr;
     L.ws = WorkSet{};
@@ -81,12 +84,16 @@ int alloc_lane(orbx_extractor* ex, OrbxLane& L) {
   ORBX_CUDA(ex, cudaMemsetAsync(L.d_in, 0, (size_t)ex->in_fstride * B, L.stream));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.slots, (size_t)P.slots_per_frame * B * 4));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.cand, (size_t)P.slots_per_frame * B * 4));
-  ORBX_CUDA(ex, cudaMalloc(&L.ws.lab, (size_t)P.slots_per_frame * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.lab, (size_t)P.slots_per_frame * B * 2));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.cell_count, (size_t)P.cells_per_frame * B * 4));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_kp, (size_t)P.kps_per_frame * B * 4));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.dst, (size_t)P.kps_per_frame * B * 4));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_n, (size_t)P.nlevels * B * 4));
   ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_c, (size_t)P.nlevels * B * 4));
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.lvl_st, (size_t)P.nlevels * B * 4));
+#ifdef ORBX_QT_PROF
+  ORBX_CUDA(ex, cudaMalloc(&L.ws.qt_prof, (size_t)P.nlevels * B * 16 * 8));
+#endif
   return ORBX_OK;
 }
 
@@ -133,29 +140,24 @@ int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, 
   auto end = [&](int stage, cudaStream_t s) {
     if (prof) cudaEventRecord(ex->prof_events[ex->prof_used + 2 * stage + 1], s);
   };
+  // One stream, stages back to back. (Forking the blur onto a second stream so that it overlaps FAST + quadtree was
+  // measured SLOWER on B200: 7.01 vs 6.78 ms per 512-frame step — the blur's CTAs crowd out the latency-bound
+  // quadtree warps and slow FAST, and nothing is gained because every stage already fills the chip.)
   begin(0, st);
   launch_pyramid(P, fs, ex->d_tab, frames, st);
   end(0, st);
-  // fork: the blur (a streaming kernel) overlaps FAST (ALU bound) and the quadtree (latency bound)
-  ORBX_CUDA(ex, cudaEventRecord(L.fork, st));
-  ORBX_CUDA(ex, cudaStreamWaitEvent(L.side, L.fork, 0));
-  begin(3, L.side);
-  launch_blur(P, fs, frames, L.side);
-  end(3, L.side);
-  ORBX_CUDA(ex, cudaEventRecord(L.join, L.side));
+  begin(3, st);
+  launch_blur(P, fs, frames, st);
+  end(3, st);
   begin(1, st);
   launch_fast(P, fs, L.ws, ex->ini_th, ex->min_th, frames, st);
   end(1, st);
   begin(2, st);
-  launch_quadtree(P, L.ws, frames, st);
+  launch_quadtree(P, L.ws, lap0, lap1, frames, st);
   end(2, st);
   begin(4, st);
-  launch_assemble(P, L.ws, out, lap0, lap1, frames, st);
-  end(4, st);
-  ORBX_CUDA(ex, cudaStreamWaitEvent(st, L.join, 0));
-  begin(5, st);
   launch_describe(P, fs, L.ws, out, ex->d_pattern, frames, st);
-  end(5, st);
+  end(4, st);
   ORBX_CUDA(ex, cudaGetLastError());
   if (prof) ex->prof_used += 2 * kStages;
   L.last_fs = fs;
@@ -303,11 +305,7 @@ int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float
   for (OrbxLane& L : ex->lane) {
     if ((e = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking)) != cudaSuccess)
       return bail("cudaStreamCreate", e);
-    if ((e = cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking)) != cudaSuccess)
-      return bail("cudaStreamCreate", e);
-    if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&L.fork, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming)) != cudaSuccess)
+    if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
       return bail("cudaEventCreate", e);
     if ((e = cudaHostAlloc(&L.h_small, (size_t)3 * max_batch * 4, cudaHostAllocDefault)) != cudaSuccess)
       return bail("cudaHostAlloc", e);
@@ -331,9 +329,6 @@ void orbx_extractor_destroy(orbx_extractor* ex) {
   for (OrbxLane& L : ex->lane) {
     if (L.h_small) cudaFreeHost(L.h_small);
     if (L.done) cudaEventDestroy(L.done);
-    if (L.fork) cudaEventDestroy(L.fork);
-    if (L.join) cudaEventDestroy(L.join);
-    if (L.side) cudaStreamDestroy(L.side);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete ex;
@@ -513,14 +508,22 @@ int orbx_debug_candidates(orbx_extractor* ex, int frame, int level, orbx_kp* out
     return ORBX_E_ARG;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   ORBX_CUDA(ex, cudaDeviceSynchronize());
+  // the candidates of a level in the order the reference appends them (:905-958) = the per-cell slots written by
+  // k_fast, cells in row-major order (pure data movement: the quadtree kernel builds the same array in shared memory)
   const Plan& P = ex->plan;
-  int32_t C = 0;
-  ORBX_CUDA(ex, cudaMemcpy(&C, ex->lane[ex->last_lane].ws.lvl_c + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
-  const int n = std::min(C, cap);
-  std::vector<uint32_t> buf(std::max(n, 1));
-  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->lane[ex->last_lane].ws.cand + (int64_t)frame * P.slots_per_frame + P.lv[level].slot_base,
-                           (size_t)n * 4, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < n && out; i++) unpack_kp(buf[i], 0, 0, 7.f, out + i);
+  const LevelPlan& L = P.lv[level];
+  const OrbxLane& ln = ex->lane[ex->last_lane];
+  const int ncell = L.nCols * L.nRows;
+  std::vector<int32_t> cnt(ncell);
+  std::vector<uint32_t> slots((size_t)ncell * L.slot_cap);
+  ORBX_CUDA(ex, cudaMemcpy(cnt.data(), ln.ws.cell_count + (int64_t)frame * P.cells_per_frame + L.cell_base,
+                           (size_t)ncell * 4, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(ex, cudaMemcpy(slots.data(), ln.ws.slots + (int64_t)frame * P.slots_per_frame + L.slot_base,
+                           slots.size() * 4, cudaMemcpyDeviceToHost));
+  int C = 0;
+  for (int c = 0; c < ncell; c++)
+    for (int k = 0; k < cnt[c]; k++, C++)
+      if (out && C < cap) unpack_kp(slots[(size_t)c * L.slot_cap + k], 0, 0, 7.f, out + C);
   return C;
 }
 
@@ -538,6 +541,19 @@ int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp
                            (size_t)n * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n && out; i++) unpack_kp(buf[i], kMinBorder, level, (float)P.lv[level].patch, out + i);
   return C;
+}
+
+// Cycle accounting of k_quadtree for (frame, level) of the last call: out[16] (see orbx_quadtree.h). Only in builds
+// with -DORBX_QT_PROF; otherwise ORBX_E_ARG. Development aid, not part of the public header.
+int orbx_debug_qt_profile(orbx_extractor* ex, int frame, int level, long long* out) {
+  if (!ex || !ex->planned || !out) return ORBX_E_ARG;
+  const OrbxLane& ln = ex->lane[ex->last_lane];
+  if (!ln.ws.qt_prof || frame < 0 || frame >= ln.last_frames || level < 0 || level >= ex->nlevels) return ORBX_E_ARG;
+  ORBX_CUDA(ex, cudaSetDevice(ex->device));
+  ORBX_CUDA(ex, cudaDeviceSynchronize());
+  ORBX_CUDA(ex, cudaMemcpy(out, ln.ws.qt_prof + ((int64_t)frame * ex->nlevels + level) * 16, 16 * 8,
+                           cudaMemcpyDeviceToHost));
+  return ORBX_OK;
 }
 
 int orbx_profile_enable(orbx_extractor* ex, int on) {

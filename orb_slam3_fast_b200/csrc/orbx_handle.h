@@ -14,12 +14,11 @@
 
 #include "orbx_kernels.cuh"
 
-enum { kStages = 6, kLanes = 2 };
+enum { kStages = 5, kLanes = 2 };
 
 struct OrbxLane {
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;   // the blur runs here, concurrently with FAST + quadtree (both only need the pyramid)
-  cudaEvent_t done = nullptr, fork = nullptr, join = nullptr;
+  cudaEvent_t done = nullptr;
   // geometry-dependent device state
   uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr;
   orbx::WorkSet ws{};

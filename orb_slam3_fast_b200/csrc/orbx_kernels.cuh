@@ -39,11 +39,14 @@ struct WorkSet {
   uint32_t* slots;        // [frames][slots_per_frame]   FAST candidates per cell, packed x|y|score
   int32_t* cell_count;    // [frames][cells_per_frame]
   uint32_t* cand;         // [frames][slots_per_frame]   per-level compacted candidates (quadtree order)
-  uint32_t* lab;          // [frames][slots_per_frame]   quadtree labels
+  uint16_t* lab;          // [frames][slots_per_frame]   quadtree labels (levels whose candidates do not fit in smem)
   uint32_t* lvl_kp;       // [frames][kps_per_frame]     selected keypoints per level, packed x|y|score (ROI-16)
   int32_t* lvl_n;         // [frames][nlevels]           count per level
   int32_t* lvl_c;         // [frames][nlevels]           candidate count per level (diagnostics)
-  int32_t* dst;           // [frames][kps_per_frame]     output row of every level keypoint
+  int32_t* lvl_st;        // [frames][nlevels]           keypoints of the level inside the lapping area ("stereo")
+  long long* qt_prof;     // [frames][nlevels][16]       cycle accounting of k_quadtree (ORBX_QT_PROF builds), or null
+  int32_t* dst;           // [frames][kps_per_frame]     rank among the level's mono keypoints, or 1<<30 | rank among
+                          //                             its stereo keypoints
 };
 
 struct OutSet {
@@ -62,10 +65,8 @@ struct ResizeTab {  // one entry per destination row / column
 void launch_pyramid(const Plan& P, const FrameSet& fs, const ResizeTab* tab, int frames, cudaStream_t st);
 void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_th, int min_th, int frames,
                  cudaStream_t st);
-void launch_quadtree(const Plan& P, const WorkSet& ws, int frames, cudaStream_t st);
+void launch_quadtree(const Plan& P, const WorkSet& ws, int lap0, int lap1, int frames, cudaStream_t st);
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st);
-void launch_assemble(const Plan& P, const WorkSet& ws, const OutSet& out, int lap0, int lap1, int frames,
-                     cudaStream_t st);
 void launch_describe(const Plan& P, const FrameSet& fs, const WorkSet& ws, const OutSet& out, const int8_t* pattern,
                      int frames, cudaStream_t st);
 size_t fast_smem_bytes(const Plan& P);

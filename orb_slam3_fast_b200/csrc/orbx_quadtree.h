@@ -8,12 +8,17 @@
 //    argmax(response, -candidate index), which needs no ordering at all.
 //  * The std::list is an array that is rebuilt once per round. In both phases of the reference the list after a
 //    round is   reverse(children in creation order) ++ (old list without the split parents, order kept)
-//    because children are push_front'ed (:621-672, :697-722) and parents erased in place. Positions are prefix sums.
-//  * Phase 2 (:678-735) needs the permutation libstdc++'s std::sort produces for nodes that tie on (size, UL.x); lane 0
-//    runs the emulation from orbx_math.h, then walks from the back until the list holds >= N nodes (:729).
+//    because children are push_front'ed (:621-672, :697-722) and parents erased in place. Positions are prefix sums
+//    (ballot ranks / one blocked warp scan per round).
+//  * Phase 2 (:678-735) needs the permutation libstdc++'s std::sort produces for nodes that tie on (size, UL.x).
+//    std_sort_emulate_warp below reproduces it with the whole warp: every Hoare partition of the introsort is two
+//    ordered compactions (the stop positions of the two scanning pointers) + one round of pairwise swaps, and the
+//    final insertion sort is a stable rank inside a +-15 window. Lane 0 then walks from the back until the list holds
+//    >= N nodes (:729).
 //
-// The same source runs on the CPU (tests/hostcheck.cpp) with one "lane": ORBX_LANES loops cover every index, scans are
-// serial. That is how the algorithm is checked against the oracle without a GPU.
+// The same source runs on the CPU (tests/hostcheck.cpp) with one "lane": ORBX_LANES loops cover every index, ballots
+// degenerate to serial counters. That is how the algorithm is checked against the oracle (and the sort against the
+// real std::sort) without a GPU.
 #ifndef ORBX_QUADTREE_H_
 #define ORBX_QUADTREE_H_
 
@@ -42,6 +47,203 @@ ORBX_HD int cand_x(uint32_t c) { return (int)(c & 0xfff); }
 ORBX_HD int cand_y(uint32_t c) { return (int)((c >> 12) & 0xfff); }
 ORBX_HD int cand_s(uint32_t c) { return (int)(c >> 24); }
 
+// Optional cycle accounting (build with -DORBX_QT_PROF): lane 0 adds the cycles since the previous mark to a category.
+#if defined(ORBX_QT_PROF) && defined(__CUDA_ARCH__)
+#define ORBX_QT_MARK(T, cat)                                \
+  do {                                                      \
+    if (ORBX_LANE() == 0 && (T).prof) {                     \
+      const long long now_ = clock64();                     \
+      (T).prof[cat] += now_ - (T).prof_prev;                \
+      (T).prof_prev = now_;                                 \
+    }                                                       \
+  } while (0)
+#else
+#define ORBX_QT_MARK(T, cat) (void)0
+#endif
+enum { kQtInit = 2, kQtSelect = 3, kQtSort = 4, kQtWalk = 5, kQtChildren = 6, kQtPrep = 7, kQtSweep = 8, kQtRounds = 10,
+       kQtRounds2 = 11, kQtProfSlots = 16 };
+
+// ---- warp primitives with a serial twin ---------------------------------------------------------------------------
+// Indices i in [0, n) with pred(i), ascending, are written to out[0..count); returns count. If rank_of is not null,
+// rank_of[i] receives the rank of every selected i (others untouched).
+template <class Pred>
+ORBX_HD int warp_compact(int n, uint16_t* out, Pred pred) {
+#if defined(__CUDA_ARCH__)
+  const int lane = ORBX_LANE();
+  const unsigned lt = (1u << lane) - 1u;
+  int base = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int i = b + lane;
+    const bool f = i < n && pred(i);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (f) out[base + __popc(m & lt)] = (uint16_t)i;
+    base += __popc(m);
+  }
+  __syncwarp();
+  return base;
+#else
+  int c = 0;
+  for (int i = 0; i < n; i++)
+    if (pred(i)) out[c++] = (uint16_t)i;
+  return c;
+#endif
+}
+
+template <class Pred>
+ORBX_HD int warp_count(int n, Pred pred) {
+#if defined(__CUDA_ARCH__)
+  int c = 0;
+  for (int b = 0; b < n; b += 32) {
+    const int i = b + ORBX_LANE();
+    c += __popc(__ballot_sync(0xffffffffu, i < n && pred(i)));
+  }
+  return c;
+#else
+  int c = 0;
+  for (int i = 0; i < n; i++) c += pred(i) ? 1 : 0;
+  return c;
+#endif
+}
+
+// exclusive prefix sum of a[0..n) in place, returns the total. Device: every lane owns a contiguous block of `per`
+// elements (per odd: conflict-free shared-memory strides), one shuffle scan over the 32 block sums.
+ORBX_HD int excl_scan(int* a, int n) {
+#if defined(__CUDA_ARCH__)
+  const int lane = ORBX_LANE();
+  const int per = ((n + 31) >> 5) | 1;
+  const int b0 = lane * per;
+  int sum = 0;
+  for (int k = 0; k < per; k++) sum += (b0 + k < n) ? a[b0 + k] : 0;
+  int inc = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, inc, 31);
+  int run = inc - sum;
+  for (int k = 0; k < per; k++) {
+    if (b0 + k < n) {
+      const int v = a[b0 + k];
+      a[b0 + k] = run;
+      run += v;
+    }
+  }
+  __syncwarp();
+  return total;
+#else
+  int s = 0;
+  for (int i = 0; i < n; i++) {
+    const int v = a[i];
+    a[i] = s;
+    s += v;
+  }
+  return s;
+#endif
+}
+
+// ---- libstdc++ std::sort, warp-cooperative ------------------------------------------------------------------------
+// Produces exactly the permutation of std_sort_emulate (orbx_math.h), i.e. of std::sort in bits/stl_algo.h.
+//  * __unguarded_partition(first + 1, last, pivot = first): the left pointer stops at the elements with !(a < pivot),
+//    the right pointer at the elements with !(pivot < a). Until the pointers cross, both only look at positions that
+//    no swap has touched yet, so the k-th left stop i_k / right stop j_k are the k-th such positions of the ORIGINAL
+//    segment counted from the left / right. Pairs are swapped while i_k < j_k (K pairs, a prefix because i grows and
+//    j shrinks). The returned cut is the left pointer's next stop: the next original stop i_K or the position j_{K-1}
+//    that has just received an element >= pivot, whichever comes first.
+//  * The ranges left by __introsort_loop are <= 16 long (or heap-sorted), and every element of a range is <= every
+//    element of the ranges to its right; __final_insertion_sort is a stable insertion sort, so the final index of
+//    element i is  #{j : key_j < key_i  or  (key_j == key_i and j < i)}  and only j in [i - 15, i + 15] can differ
+//    from "j < i".
+struct SortScratch {
+  uint16_t* lidx;  // [n]
+  uint16_t* ridx;  // [n]
+  SortElem* tmp;   // [n]
+};
+
+ORBX_HD int ss_partition_warp(SortElem* a, int lo, int hi, const SortScratch& W) {
+  const uint32_t p = a[lo].key;
+  const int m = hi - lo - 1;  // partitioned range: lo + 1 .. hi - 1
+  const int nL = warp_compact(m, W.lidx, [&](int t) { return !(a[lo + 1 + t].key < p); });
+  const int nR = warp_compact(m, W.ridx, [&](int t) { return !(p < a[hi - 1 - t].key); });
+  const int nmin = nL < nR ? nL : nR;
+  const int K = warp_count(nmin, [&](int k) { return lo + 1 + (int)W.lidx[k] < hi - 1 - (int)W.ridx[k]; });
+  int cut = hi;
+  if (K < nL) cut = lo + 1 + (int)W.lidx[K];
+  if (K >= 1) {
+    const int j = hi - 1 - (int)W.ridx[K - 1];
+    if (j < cut) cut = j;
+  }
+  ORBX_WSYNC();
+  ORBX_LANES(k, K) se_swap(a[lo + 1 + (int)W.lidx[k]], a[hi - 1 - (int)W.ridx[k]]);
+  ORBX_WSYNC();
+  return cut;
+}
+
+ORBX_HD void ss_move_median_to_first_warp(SortElem* a, int result, int ia, int ib, int ic) {
+  const uint32_t ka = a[ia].key, kb = a[ib].key, kc = a[ic].key;
+  int pick;
+  if (ka < kb) pick = kb < kc ? ib : (ka < kc ? ic : ia);
+  else pick = ka < kc ? ia : (kb < kc ? ic : ib);
+  ORBX_WSYNC();
+  if (ORBX_LANE() == 0) se_swap(a[result], a[pick]);
+  ORBX_WSYNC();
+}
+
+ORBX_HD void std_sort_emulate_warp(SortElem* a, int n, const SortScratch& W) {
+  if (n <= 1) return;
+  int lg = 0;
+  for (int t = n; t > 1; t >>= 1) lg++;
+  int stack[3 * 48];  // (first, last, depth); at most one entry per partition level of the current path
+  int sp = 0;
+  stack[sp++] = 0;
+  stack[sp++] = n;
+  stack[sp++] = 2 * lg;
+  while (sp > 0) {
+    int depth = stack[--sp];
+    int last = stack[--sp];
+    int first = stack[--sp];
+    while (last - first > 16) {
+      if (depth == 0) {
+        ORBX_WSYNC();
+        if (ORBX_LANE() == 0) {
+          ORBX_SORT_HEAP_HOOK;
+          ss_heap_sort(a + first, last - first);
+        }
+        ORBX_WSYNC();
+        break;
+      }
+      --depth;
+      ss_move_median_to_first_warp(a, first, first + 1, first + (last - first) / 2, last - 1);
+      const int cut = ss_partition_warp(a, first, last, W);
+      // the original recurses into [cut, last) and loops on [first, cut); the ranges are disjoint, the order of
+      // processing does not change the result. Push the larger one so the stack stays logarithmic.
+      if (last - cut > cut - first) {
+        stack[sp++] = cut; stack[sp++] = last; stack[sp++] = depth;
+        last = cut;
+      } else {
+        stack[sp++] = first; stack[sp++] = cut; stack[sp++] = depth;
+        first = cut;
+      }
+    }
+  }
+  ORBX_WSYNC();
+  // __final_insertion_sort == stable sort of ranges that are already ordered among themselves
+  ORBX_LANES(i, n) {
+    const SortElem e = a[i];
+    const int jlo = i - 15 > 0 ? i - 15 : 0, jhi = i + 15 < n - 1 ? i + 15 : n - 1;
+    int r = jlo;
+    for (int j = jlo; j <= jhi; j++) {
+      const uint32_t kj = a[j].key;
+      r += (kj < e.key || (kj == e.key && j < i)) ? 1 : 0;
+    }
+    W.tmp[r] = e;
+  }
+  ORBX_WSYNC();
+  ORBX_LANES(i, n) a[i] = W.tmp[i];
+  ORBX_WSYNC();
+}
+
+// ---- the tree -----------------------------------------------------------------------------------------------------
 struct QBox {
   int16_t ulx, urx, uly, bry;
 };
@@ -53,49 +255,23 @@ struct QTree {
   int* cnt[2];         // keys per node
   int* child[2];       // [cap * 4] histogram of the splittable nodes' candidates over the 4 quadrants
   uint16_t* newpos;    // old position -> new position (survivors)
-  uint16_t* childpos;  // [cap * 4] old position, quadrant -> new position (split parents)
+  uint16_t* childpos;  // [cap * 4] old position, quadrant -> new position (split parents); sort scratch in between
   uint8_t* committed;  // old position was split this round
   uint8_t* splittable; // [2][cap] node takes part in the next round's histogram
   uint16_t* pending[2];// positions of the nodes the next phase-2 round may split, in creation order
   SortElem* sortbuf;
-  uint16_t* rank2pos;  // creation rank -> old position of the parent (phase 2), [cap]
+  uint16_t* rank2pos;  // creation rank -> old position of the parent, [cap]
   int* scan;           // [cap + 1] scratch for prefix sums
   int* vars;           // [8] warp-uniform scalars written by lane 0
-  // candidates (global memory on the device)
+  // candidates: shared memory when they fit, else global memory
   const uint32_t* cand;
-  uint32_t* lab;       // per candidate: node position | quadrant << 16
+  uint16_t* lab;       // per candidate: node position | quadrant << 14
   int C;
+  long long* prof;     // [kQtProfSlots] or null (ORBX_QT_PROF builds)
+  long long prof_prev;
 };
 
-// exclusive prefix sum of a[0..n) in place, returns the total (warp-cooperative on the device)
-ORBX_HD int excl_scan(int* a, int n) {
-#if defined(__CUDA_ARCH__)
-  const int lane = ORBX_LANE();
-  int carry = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
-    const int v = i < n ? a[i] : 0;
-    int inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
-    }
-    if (i < n) a[i] = carry + inc - v;
-    carry += __shfl_sync(0xffffffffu, inc, 31);
-  }
-  __syncwarp();
-  return carry;
-#else
-  int s = 0;
-  for (int i = 0; i < n; i++) {
-    const int v = a[i];
-    a[i] = s;
-    s += v;
-  }
-  return s;
-#endif
-}
+constexpr int kLabPosMask = 0x3fff;  // cap < 16384
 
 ORBX_HD int quadrant_of(uint32_t c, const QBox& b) {
   const int mx = b.ulx + ((b.urx - b.ulx + 1) >> 1);  // UL.x + ceil((UR.x - UL.x) / 2)   :494
@@ -113,6 +289,9 @@ ORBX_HD QBox child_box(const QBox& b, int q) {
   c.bry = (int16_t)((q & 2) ? b.bry : my);
   return c;
 }
+
+ORBX_HD int nonempty4(const int* h) { return (h[0] > 0) + (h[1] > 0) + (h[2] > 0) + (h[3] > 0); }
+ORBX_HD int multi4(const int* h) { return (h[0] > 1) + (h[1] > 1) + (h[2] > 1) + (h[3] > 1); }
 
 // Runs the whole culling for one level. Returns the number of selected keypoints; out[i] = candidate index of the
 // i-th keypoint in list order (front to back). `width`, `height` = maxBorder - minBorder of the level.
@@ -133,28 +312,21 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
   ORBX_WSYNC();
   ORBX_LANES(c, C) {
     const int r = (int)fdiv((float)cand_x(T.cand[c]), hX);
-    T.lab[c] = (uint32_t)r;
+    T.lab[c] = (uint16_t)r;
     ORBX_ATOMIC_ADD(&T.cnt[1][r], 1);
   }
   ORBX_WSYNC();
-  ORBX_LANES(i, nIni) T.scan[i] = T.cnt[1][i] > 0 ? 1 : 0;
-  ORBX_WSYNC();
-  int S = excl_scan(T.scan, nIni);
-  ORBX_LANES(i, nIni) {
-    if (T.cnt[1][i] > 0) {
-      const int p = T.scan[i];
-      T.box[0][p] = T.box[1][i];
-      T.cnt[0][p] = T.cnt[1][i];
-      T.newpos[i] = (uint16_t)p;
-    }
-  }
-  ORBX_WSYNC();
-  ORBX_LANES(i, S) {
-    T.splittable[i] = T.cnt[0][i] > 1;
-    T.child[0][4 * i + 0] = 0;
-    T.child[0][4 * i + 1] = 0;
-    T.child[0][4 * i + 2] = 0;
-    T.child[0][4 * i + 3] = 0;
+  int S = warp_compact(nIni, T.rank2pos, [&](int i) { return T.cnt[1][i] > 0; });
+  ORBX_LANES(p, S) {
+    const int i = T.rank2pos[p];
+    T.box[0][p] = T.box[1][i];
+    T.cnt[0][p] = T.cnt[1][i];
+    T.newpos[i] = (uint16_t)p;
+    T.splittable[p] = T.cnt[1][i] > 1;
+    T.child[0][4 * p + 0] = 0;
+    T.child[0][4 * p + 1] = 0;
+    T.child[0][4 * p + 2] = 0;
+    T.child[0][4 * p + 3] = 0;
   }
   ORBX_WSYNC();
   ORBX_LANES(c, C) {
@@ -162,12 +334,13 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     uint32_t l = (uint32_t)p;
     if (T.splittable[p]) {
       const int q = quadrant_of(T.cand[c], T.box[0][p]);
-      l |= (uint32_t)q << 16;
+      l |= (uint32_t)q << 14;
       ORBX_ATOMIC_ADD(&T.child[0][4 * p + q], 1);
     }
-    T.lab[c] = l;
+    T.lab[c] = (uint16_t)l;
   }
   ORBX_WSYNC();
+  ORBX_QT_MARK(T, kQtInit);
 
   bool phase2 = false;
   int n_pending = 0;  // entries of T.pending[cur]
@@ -180,39 +353,39 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     const uint8_t* split_cur = T.splittable + cur * T.cap;
     uint8_t* split_nxt = T.splittable + nxt * T.cap;
     const int prevS = S;
-    int K = 0;         // children created this round
-    int n_parents = 0; // parents split this round
+    int n_parents = 0;  // parents split this round; T.rank2pos[r] = position of the r-th created parent
     // ---- choose the parents and their creation order ----
     if (!phase2) {
       // phase 1 (:610-672): every non-leaf node, in list order
-      ORBX_LANES(p, S) {
-        T.committed[p] = split_cur[p];
-        T.scan[p] = split_cur[p] ? 1 : 0;
-      }
+      n_parents = warp_compact(S, T.rank2pos, [&](int p) { return split_cur[p] != 0; });
+      ORBX_LANES(p, S) T.committed[p] = split_cur[p];
       ORBX_WSYNC();
-      n_parents = excl_scan(T.scan, S);
-      ORBX_LANES(p, S) if (T.committed[p]) T.rank2pos[T.scan[p]] = (uint16_t)p;
-      ORBX_WSYNC();
+      ORBX_QT_MARK(T, kQtSelect);
     } else {
       // phase 2 (:679-735): sort the pending nodes by (size, UL.x) with std::sort, walk from the back, stop at N
+      const uint16_t* pend = T.pending[cur];
       ORBX_LANES(p, S) T.committed[p] = 0;
+      ORBX_LANES(i, n_pending) {
+        const int p = pend[i];
+        SortElem e;
+        e.key = ((uint32_t)cnt[p] << 12) | (uint32_t)(uint16_t)box[p].ulx;
+        e.id = (uint32_t)p;
+        T.sortbuf[i] = e;
+      }
       ORBX_WSYNC();
+      SortScratch W;
+      W.lidx = T.childpos;
+      W.ridx = T.childpos + T.cap;
+      W.tmp = reinterpret_cast<SortElem*>(T.box[nxt]);  // sizeof(SortElem) == sizeof(QBox); not live until below
+      std_sort_emulate_warp(T.sortbuf, n_pending, W);
+      ORBX_QT_MARK(T, kQtSort);
       if (ORBX_LANE() == 0) {
-        const uint16_t* pend = T.pending[cur];
-        for (int i = 0; i < n_pending; i++) {
-          const int p = pend[i];
-          T.sortbuf[i].key = ((uint32_t)cnt[p] << 12) | (uint32_t)(uint16_t)box[p].ulx;
-          T.sortbuf[i].id = (uint32_t)p;
-        }
-        int stack[kSortStack];
-        std_sort_emulate(T.sortbuf, n_pending, stack);
         int size = S, t = 0;
         for (int j = n_pending - 1; j >= 0; j--) {
           const int p = (int)T.sortbuf[j].id;
-          const int ne = (child[4 * p] > 0) + (child[4 * p + 1] > 0) + (child[4 * p + 2] > 0) + (child[4 * p + 3] > 0);
           T.committed[p] = 1;
           T.rank2pos[t++] = (uint16_t)p;
-          size += ne - 1;
+          size += nonempty4(child + 4 * p) - 1;
           if (size >= N) break;
         }
         T.vars[0] = t;
@@ -220,19 +393,25 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
       ORBX_WSYNC();
       n_parents = T.vars[0];
       ORBX_WSYNC();
+      ORBX_QT_MARK(T, kQtWalk);
+#if defined(ORBX_QT_PROF) && defined(__CUDA_ARCH__)
+      if (ORBX_LANE() == 0 && T.prof) T.prof[kQtRounds2] += 1;
+#endif
     }
-    // ---- children positions: creation rank r -> first child index; list = reverse(children) ++ survivors ----
+    // ---- children: creation rank r -> first child index (low half) and first pending index (high half) ----
     ORBX_LANES(r, n_parents) {
-      const int p = T.rank2pos[r];
-      T.scan[r] = (child[4 * p] > 0) + (child[4 * p + 1] > 0) + (child[4 * p + 2] > 0) + (child[4 * p + 3] > 0);
+      const int* h = child + 4 * (int)T.rank2pos[r];
+      T.scan[r] = nonempty4(h) | (multi4(h) << 16);
     }
     ORBX_WSYNC();
-    K = excl_scan(T.scan, n_parents);
-    // children boxes / counts, written at their final position; remember who may be split next
+    const int tot = excl_scan(T.scan, n_parents);
+    const int K = tot & 0xffff, n_expand = tot >> 16;
+    // children boxes / counts at their final position (list = reverse(children) ++ survivors); the ones with more than
+    // one key form the pending list of the next phase-2 round, in creation order (:636-665, :700-720)
     int* child_nxt = T.child[nxt];
     ORBX_LANES(r, n_parents) {
       const int p = T.rank2pos[r];
-      int k = T.scan[r];
+      int k = T.scan[r] & 0xffff, e = T.scan[r] >> 16;
       const QBox pb = box[p];
       for (int q = 0; q < 4; q++) {
         const int n = child[4 * p + q];
@@ -241,39 +420,47 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
           T.box[nxt][pos] = child_box(pb, q);
           T.cnt[nxt][pos] = n;
           T.childpos[4 * p + q] = (uint16_t)pos;
+          if (n > 1) T.pending[nxt][e++] = (uint16_t)pos;
           k++;
         }
       }
     }
-    ORBX_WSYNC();
     // survivors keep their relative order behind the children
-    ORBX_LANES(p, S) T.scan[p] = T.committed[p] ? 0 : 1;
-    ORBX_WSYNC();
-    const int n_surv = excl_scan(T.scan, S);
-    ORBX_LANES(p, S) {
-      if (!T.committed[p]) {
-        const int pos = K + T.scan[p];
-        T.box[nxt][pos] = box[p];
-        T.cnt[nxt][pos] = cnt[p];
-        T.newpos[p] = (uint16_t)pos;
+#if defined(__CUDA_ARCH__)
+    {
+      const int lane = ORBX_LANE();
+      const unsigned lt = (1u << lane) - 1u;
+      int base = K;
+      for (int b = 0; b < S; b += 32) {
+        const int p = b + lane;
+        const bool f = p < S && !T.committed[p];
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) {
+          const int pos = base + __popc(m & lt);
+          T.box[nxt][pos] = box[p];
+          T.cnt[nxt][pos] = cnt[p];
+          T.newpos[p] = (uint16_t)pos;
+        }
+        base += __popc(m);
       }
+      S = base;
     }
-    ORBX_WSYNC();
-    S = K + n_surv;
-    // pending list of the next phase-2 round = children with > 1 keys, in creation order (:636-665, :700-720)
-    ORBX_LANES(r, n_parents) {
-      const int p = T.rank2pos[r];
-      T.scan[r] = (child[4 * p] > 1) + (child[4 * p + 1] > 1) + (child[4 * p + 2] > 1) + (child[4 * p + 3] > 1);
+#else
+    {
+      int base = K;
+      for (int p = 0; p < S; p++) {
+        if (!T.committed[p]) {
+          T.box[nxt][base] = box[p];
+          T.cnt[nxt][base] = cnt[p];
+          T.newpos[p] = (uint16_t)base;
+          base++;
+        }
+      }
+      S = base;
     }
+#endif
     ORBX_WSYNC();
-    const int n_expand = excl_scan(T.scan, n_parents);
-    ORBX_LANES(r, n_parents) {
-      const int p = T.rank2pos[r];
-      int k = T.scan[r];
-      for (int q = 0; q < 4; q++)
-        if (child[4 * p + q] > 1) T.pending[nxt][k++] = T.childpos[4 * p + q];
-    }
-    ORBX_WSYNC();
+    ORBX_QT_MARK(T, kQtChildren);
     // ---- termination (:676-678, :731-733) ----
     bool next_phase2 = phase2;
     if (S >= N || S == prevS) finish = true;
@@ -298,8 +485,9 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
       ORBX_LANES(p, S) child_nxt[p] = 0;
     }
     ORBX_WSYNC();
+    ORBX_QT_MARK(T, kQtPrep);
     // ---- one sweep over the candidates: move to the new node, then histogram / argmax. The loads of 4 lane steps
-    //      are issued before any of them is used (memory-level parallelism: a lone warp cannot hide L2 latency) ----
+    //      are issued before any of them is used ----
     for (int c0 = ORBX_LANE(); c0 < C; c0 += 4 * ORBX_NLANES) {
       uint32_t lv[4], cv[4];
 #pragma unroll
@@ -315,8 +503,8 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
         const int c = c0 + u * ORBX_NLANES;
         if (c >= C) continue;
         const uint32_t l = lv[u];
-        const int p = (int)(l & 0xffff);
-        const int np = T.committed[p] ? T.childpos[4 * p + (int)(l >> 16)] : T.newpos[p];
+        const int p = (int)(l & kLabPosMask);
+        const int np = T.committed[p] ? T.childpos[4 * p + (int)(l >> 14)] : T.newpos[p];
         uint32_t nl = (uint32_t)np;
         const uint32_t cw = cv[u];
         if (finish) {
@@ -324,13 +512,17 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
           ORBX_ATOMIC_MAX((unsigned int*)&child_nxt[np], v);
         } else if (split_nxt[np]) {
           const int q = quadrant_of(cw, T.box[nxt][np]);
-          nl |= (uint32_t)q << 16;
+          nl |= (uint32_t)q << 14;
           ORBX_ATOMIC_ADD(&child_nxt[4 * np + q], 1);
         }
-        T.lab[c] = nl;
+        T.lab[c] = (uint16_t)nl;
       }
     }
     ORBX_WSYNC();
+    ORBX_QT_MARK(T, kQtSweep);
+#if defined(ORBX_QT_PROF) && defined(__CUDA_ARCH__)
+    if (ORBX_LANE() == 0 && T.prof) T.prof[kQtRounds] += 1;
+#endif
     phase2 = next_phase2;
     n_pending = n_expand;
     cur = nxt;

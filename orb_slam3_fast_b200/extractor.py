@@ -11,7 +11,7 @@ import numpy as np
 from . import lib as _l
 from .lib import KP_DTYPE, OrbxError
 
-STAGES = ("pyramid", "fast", "quadtree", "blur", "assemble", "describe")
+STAGES = ("pyramid", "fast", "quadtree", "blur", "describe")
 
 
 class ORBextractor:
@@ -144,7 +144,7 @@ class ORBextractor:
         self._check(self._L.orbx_profile_enable(self._h, 1 if on else 0))
 
     def profile_read(self, reset=True):
-        ms = np.zeros(6, np.float32)
-        cnt = np.zeros(6, np.int32)
+        ms = np.zeros(len(STAGES), np.float32)
+        cnt = np.zeros(len(STAGES), np.int32)
         self._check(self._L.orbx_profile_read(self._h, _l.ptr(ms), _l.ptr(cnt), 1 if reset else 0))
         return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, cnt.tolist()))

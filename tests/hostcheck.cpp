@@ -27,6 +27,18 @@ void hc_std_sort_perm(const int* key0, const int* key1, int n, int* perm) {
   orbx::std_sort_emulate(a.data(), n, stack);
   for (int i = 0; i < n; i++) perm[i] = (int)a[i].id;
 }
+// the warp-cooperative std::sort emulation (one "lane" on the CPU): same interface
+void hc_std_sort_perm_warp(const int* key0, const int* key1, int n, int* perm) {
+  std::vector<orbx::SortElem> a(n > 0 ? n : 1), tmp(n > 0 ? n : 1);
+  std::vector<uint16_t> li(n > 0 ? n : 1), ri(n > 0 ? n : 1);
+  for (int i = 0; i < n; i++) {
+    a[i].key = ((uint32_t)key0[i] << 12) | (uint32_t)key1[i];
+    a[i].id = (uint32_t)i;
+  }
+  orbx::SortScratch W{li.data(), ri.data(), tmp.data()};
+  orbx::std_sort_emulate_warp(a.data(), n, W);
+  for (int i = 0; i < n; i++) perm[i] = (int)a[i].id;
+}
 // counts mismatches of sincosf_glibc vs glibc over all floats with bit patterns in [lo, hi)
 long hc_sincosf_sweep(uint32_t lo, uint32_t hi) {
   long bad = 0;
@@ -56,7 +68,7 @@ int hc_quadtree(const uint32_t* cand, int C, int width, int height, int nIni, fl
   std::vector<uint16_t> newpos(cap), childpos(cap * 4), pend0(cap), pend1(cap), rank2pos(cap);
   std::vector<uint8_t> committed(cap), splittable(2 * cap);
   std::vector<SortElem> sortbuf(cap);
-  std::vector<uint32_t> lab(C > 0 ? C : 1);
+  std::vector<uint16_t> lab(C > 0 ? C : 1);
   QTree T;
   T.cap = cap;
   T.box[0] = box0.data(); T.box[1] = box1.data();

@@ -24,6 +24,7 @@ def hc():
     L.hc_sincosf.argtypes = [C.c_float, C.c_void_p, C.c_void_p]
     L.hc_cv_round.argtypes = [C.c_float]
     L.hc_std_sort_perm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.hc_std_sort_perm_warp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.hc_sincosf_sweep.argtypes = [C.c_uint32, C.c_uint32]
     L.hc_sincosf_sweep.restype = C.c_long
     L.hc_heap_calls.restype = C.c_long
@@ -75,7 +76,9 @@ def test_cv_round_ties_to_even(hc):
         assert hc.hc_cv_round(v) == r
 
 
-def test_std_sort_emulation_reproduces_libstdcxx_permutation(hc):
+@pytest.mark.parametrize("which", ["serial", "warp"])
+def test_std_sort_emulation_reproduces_libstdcxx_permutation(hc, which):
+    sort = hc.hc_std_sort_perm if which == "serial" else hc.hc_std_sort_perm_warp
     # DistributeOctTree sorts (size, UL.x) pairs with std::sort (src/ORBextractor.cc:686); ties are common and the
     # permutation libstdc++'s introsort leaves them in decides which node is split last (SURVEY.md §7 hard part 1)
     rng = np.random.default_rng(5)
@@ -84,15 +87,24 @@ def test_std_sort_emulation_reproduces_libstdcxx_permutation(hc):
             k0 = rng.integers(2, 2 + max(2, n // 8), n).astype(np.int32)
             k1 = (rng.integers(0, 16, n) * 37).astype(np.int32)
             got = np.empty(n, np.int32)
-            hc.hc_std_sort_perm(_p(k0), _p(k1), n, _p(got))
+            sort(_p(k0), _p(k1), n, _p(got))
             ref = orbref.std_sort_perm(k0, k1)  # the real std::sort, compiled into the oracle
             assert np.array_equal(got, ref), (n, rep)
+    # fully random keys, all-equal keys, two-valued keys, sorted and reversed inputs
+    for n in (17, 33, 64, 129, 300, 777, 2048):
+        for k0 in (rng.integers(0, 1 << 18, n), np.zeros(n), rng.integers(0, 2, n), np.arange(n), np.arange(n)[::-1],
+                   np.repeat(np.arange((n + 4) // 5), 5)[:n]):
+            k0 = np.ascontiguousarray(k0, np.int32)
+            k1 = np.zeros(n, np.int32)
+            got = np.empty(n, np.int32)
+            sort(_p(k0), _p(k1), n, _p(got))
+            assert np.array_equal(got, orbref.std_sort_perm(k0, k1)), n
     # adversarial inputs that push introsort into its heapsort fallback must take that path too
     n = 2000
     k0 = np.arange(n, dtype=np.int32)[::-1].copy()
     k1 = np.zeros(n, np.int32)
     got = np.empty(n, np.int32)
-    hc.hc_std_sort_perm(_p(k0), _p(k1), n, _p(got))
+    sort(_p(k0), _p(k1), n, _p(got))
     assert np.array_equal(got, orbref.std_sort_perm(k0, k1))
 
 
