@@ -33,6 +33,7 @@ constexpr int kBlurAhead = 4;
 __device__ __forceinline__ int blur_strips_x(int w) { return (w + 127) >> 7; }
 __device__ __forceinline__ int blur_strips_y(int h) { return (h + kBlurRows - 1) / kBlurRows; }
 
+template <bool kAligned>
 __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant__ Plan P, const FrameSet fs) {
   const int lane = threadIdx.x & 31;
   int t = blockIdx.x * kBlurWarps + (threadIdx.x >> 5);
@@ -54,7 +55,6 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
   int pitch;
   const uint8_t* src = raw_level(P, fs, l, f, &pitch);
   uint8_t* dst = blur_level(P, fs, l, f);
-  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)pitch) & 3) == 0;
 
   // ---- edge patch: window byte i holds column x - 4 + i; columns outside [0, w) take their reflect-101 source, which
   //      always lies inside the two neighbouring words of the same window ----
@@ -88,12 +88,16 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
 
   int win[7][4];
   uint32_t q[kBlurAhead][3];
+  // source rows past the bottom reflection range only feed output rows >= h, which are never stored: clamp them so
+  // that the row loop needs no early exit (the unrolled loop stays branch free)
+  const uint8_t* srcx = src + x;
+  const int h2 = 2 * h - 2;
   auto fetch = [&](int r, uint32_t (&o)[3]) {
-    if (y0 + r - 6 >= h) return;  // this source row completes no output row
-    const int ys = reflect101(y0 - 3 + r, h);
+    const int v = abs(min(y0 - 3 + r, h + 2));
+    const int ys = min(v, h2 - v);  // reflect-101 of a row in [-3, h + 2], branch free
     const uint8_t* row = src + (int64_t)ys * pitch;
-    if (aligned) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + x);
+    if (kAligned) {
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(srcx + (int64_t)ys * pitch);
       o[0] = ld0 ? __ldg(r32 - 1) : 0u;
       o[1] = __ldg(r32);
       o[2] = ld2 ? __ldg(r32 + 1) : 0u;
@@ -111,12 +115,13 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
   };
   constexpr uint32_t kTapsA = 18u | (34u << 8) | (48u << 16) | (56u << 24);
   constexpr uint32_t kTapsB = 48u | (34u << 8) | (18u << 16);
+  const int dpitch = L.pitch;
+  uint8_t* dptr = dst + (int64_t)y0 * dpitch + x;  // output row y0 + r - 6 is completed by source row r
+  int rows_left = h - y0;
 #pragma unroll
   for (int r = 0; r < kBlurAhead; r++) fetch(r, q[r]);
 #pragma unroll
   for (int r = 0; r < kBlurRows + 6; r++) {
-    const int yo = y0 + r - 6;  // output row completed by this source row
-    if (yo >= h) break;
     uint32_t w0 = q[r % kBlurAhead][0], w1 = q[r % kBlurAhead][1], w2 = q[r % kBlurAhead][2];
     if (r + kBlurAhead < kBlurRows + 6) fetch(r + kBlurAhead, q[r % kBlurAhead]);
     if (edge) {
@@ -131,20 +136,22 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
     for (int j = 0; j < 6; j++)
 #pragma unroll
       for (int k = 0; k < 4; k++) win[j][k] = win[j + 1][k];
-    // output pixel k reads window bytes k+1 .. k+7: group A = bytes k+1..k+4, group B = bytes k+5..k+8 (tap 8 = 0)
-    win[6][0] = (int)__dp4a(__funnelshift_r(w0, w1, 8), kTapsA, __dp4a(__funnelshift_r(w1, w2, 8), kTapsB, 0u));
-    win[6][1] = (int)__dp4a(__funnelshift_r(w0, w1, 16), kTapsA, __dp4a(__funnelshift_r(w1, w2, 16), kTapsB, 0u));
-    win[6][2] = (int)__dp4a(__funnelshift_r(w0, w1, 24), kTapsA, __dp4a(__funnelshift_r(w1, w2, 24), kTapsB, 0u));
-    win[6][3] = (int)__dp4a(w1, kTapsA, __dp4a(w2, kTapsB, 0u));
+    // output pixel k reads window bytes k+1 .. k+7: group A = bytes k+1..k+4, group B = bytes k+5..k+8 (tap 8 = 0).
+    // Every row sum starts at 128: the vertical taps add up to 256, so the 7 rows carry the +32768 of the final rounding
+    win[6][0] = (int)__dp4a(__funnelshift_r(w0, w1, 8), kTapsA, __dp4a(__funnelshift_r(w1, w2, 8), kTapsB, 128u));
+    win[6][1] = (int)__dp4a(__funnelshift_r(w0, w1, 16), kTapsA, __dp4a(__funnelshift_r(w1, w2, 16), kTapsB, 128u));
+    win[6][2] = (int)__dp4a(__funnelshift_r(w0, w1, 24), kTapsA, __dp4a(__funnelshift_r(w1, w2, 24), kTapsB, 128u));
+    win[6][3] = (int)__dp4a(w1, kTapsA, __dp4a(w2, kTapsB, 128u));
     if (r >= 6) {
-      uint32_t packed = 0;
+      uint32_t acc[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t acc = 32768u + 18u * (uint32_t)(win[0][k] + win[6][k]) + 34u * (uint32_t)(win[1][k] + win[5][k]) +
-                             48u * (uint32_t)(win[2][k] + win[4][k]) + 56u * (uint32_t)win[3][k];
-        packed |= (acc >> 16) << (8 * k);
-      }
-      *reinterpret_cast<uint32_t*>(dst + (int64_t)yo * L.pitch + x) = packed;
+      for (int k = 0; k < 4; k++)
+        acc[k] = 18u * (uint32_t)(win[0][k] + win[6][k]) + 34u * (uint32_t)(win[1][k] + win[5][k]) +
+                 48u * (uint32_t)(win[2][k] + win[4][k]) + 56u * (uint32_t)win[3][k];
+      // byte 2 of every accumulator = (sum + 32768) >> 16
+      const uint32_t packed = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+      if (r - 6 < rows_left) *reinterpret_cast<uint32_t*>(dptr) = packed;
+      dptr += dpitch;
     }
   }
 }
@@ -153,7 +160,10 @@ void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st)
   int tasks = 0;
   for (int l = 0; l < P.nlevels; l++) tasks += ((P.lv[l].w + 127) / 128) * ((P.lv[l].h + kBlurRows - 1) / kBlurRows);
   dim3 grid((tasks + kBlurWarps - 1) / kBlurWarps, frames);
-  k_blur7<<<grid, kBlurWarps * 32, 0, st>>>(P, fs);
+  // levels >= 1 are owned buffers (256-byte aligned, pitch multiple of 64); level 0 is the caller's
+  const bool aligned = ((reinterpret_cast<uintptr_t>(fs.lvl0) | (uintptr_t)fs.pitch0 | (uintptr_t)fs.fstride0) & 3) == 0;
+  if (aligned) k_blur7<true><<<grid, kBlurWarps * 32, 0, st>>>(P, fs);
+  else k_blur7<false><<<grid, kBlurWarps * 32, 0, st>>>(P, fs);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
