@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs tiled into a batch")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-group", type=int, default=0, help="pairs per pipelined group of the host-facing call")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -308,7 +309,7 @@ def main():
         pinL[k][...] = hostL[k]
         pinR[k][...] = hostR[k]
     # the fused call pipelines groups of max_batch pairs over two lanes: use smaller groups than the resident batch
-    G = max(8, P // 8)
+    G = args.e2e_group or max(8, P // 8)
     exl2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
     exr2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
     outs = ORBmatcher.alloc_stereo_outputs(P, cap, empty=pinned)

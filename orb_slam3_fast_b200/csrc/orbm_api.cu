@@ -403,14 +403,21 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
     const int nb = std::min(B, n_pairs - f0);
     const int ln = group % kLanes;
     if ((rc = retire(ln)) != 0) return rc;
-    cudaStream_t st = left->lane[ln].stream;
-    // both extractor calls of the stereo Frame constructor (vLapping = {0, 0}, src/Frame.cc:200-203) ...
+    // The two eyes run on their own streams, like the two std::threads of the reference's stereo constructor
+    // (src/Frame.cc:200-203): the latency-bound stages of one eye (quadtree, small pyramid levels) overlap the
+    // ALU-bound stages of the other, and with kLanes groups in flight the copy engines stay busy too.
+    cudaStream_t st = left->lane[ln].stream, sr = right->lane[ln].stream;
     if ((rc = api_upload_and_run(left, ln, imgs_l + (int64_t)f0 * frame_stride, nb, width, height, stride,
                                  frame_stride, 0, 0, st)) != 0)
       return mfail(m, rc, orbx_last_error(left));
     if ((rc = api_upload_and_run(right, ln, imgs_r + (int64_t)f0 * frame_stride, nb, width, height, stride,
-                                 frame_stride, 0, 0, st)) != 0)
+                                 frame_stride, 0, 0, sr)) != 0)
       return mfail(m, rc, orbx_last_error(right));
+    // the right eye's descriptors can go home while the stereo matcher runs
+    if ((rc = api_download(right, ln, nb, kps_r + (int64_t)f0 * cap, desc_r + (int64_t)f0 * cap * 32, cap, sr)) != 0)
+      return mfail(m, rc, orbx_last_error(right));
+    ORBM_CUDA(m, cudaEventRecord(right->lane[ln].done, sr));
+    ORBM_CUDA(m, cudaStreamWaitEvent(st, right->lane[ln].done, 0));
     // ... and ComputeStereoMatches (:223) on the outputs still resident in the lanes
     StereoArgs A;
     if ((rc = stereo_args_common(m, left, right, &A, ln)) != 0) return rc;
@@ -434,8 +441,6 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
     ORBM_CUDA(m, cudaGetLastError());
     if ((rc = api_download(left, ln, nb, kps_l + (int64_t)f0 * cap, desc_l + (int64_t)f0 * cap * 32, cap, st)) != 0)
       return mfail(m, rc, orbx_last_error(left));
-    if ((rc = api_download(right, ln, nb, kps_r + (int64_t)f0 * cap, desc_r + (int64_t)f0 * cap * 32, cap, st)) != 0)
-      return mfail(m, rc, orbx_last_error(right));
     if (cap == dcap) {
       ORBM_CUDA(m, cudaMemcpyAsync(u_right + (int64_t)f0 * cap, A.u_right, (size_t)nb * cap * 4,
                                    cudaMemcpyDeviceToHost, st));

@@ -2,8 +2,8 @@
 // Frame::ComputeStereoMatches reads both extractors' pyramids, src/Frame.cc:927,1011,1029).
 //
 // A handle owns kLanes independent copies of the per-batch device state ("lanes"), each with its own stream. The
-// host-facing batched calls cut the frames into groups of max_batch and alternate lanes, so the H2D copy of group
-// i+1 and the D2H copy of group i-1 overlap the kernels of group i.
+// host-facing batched calls cut the frames into groups of max_batch and rotate through the lanes, so the H2D copy of
+// group i+1 and the D2H copy of group i-1 overlap the kernels of group i.
 #ifndef ORBX_HANDLE_H_
 #define ORBX_HANDLE_H_
 
@@ -14,7 +14,7 @@
 
 #include "orbx_kernels.cuh"
 
-enum { kStages = 5, kLanes = 2 };
+enum { kStages = 5, kLanes = 3 };
 
 struct OrbxLane {
   cudaStream_t stream = nullptr;
