@@ -1,0 +1,184 @@
+// shim/ORBmatcher_orbx.cc — bodies of the three ORBmatcher searches on the hot path, forwarding to the orbm C ABI.
+//
+// COMPILES ONLY INSIDE THE REFERENCE TREE (needs include/ORBmatcher.h, Frame.h, KeyFrame.h, MapPoint.h and their
+// OpenCV / Eigen / Sophus / DBoW2 dependencies). Replace the bodies of
+//   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   src/ORBmatcher.cc:42-221
+//   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)                                 :1594-1806
+//   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse)   :886-1106
+// with the ones below (pinhole rigs, Nleft == -1; keep the reference's code for the KannalaBrandt8 branches).
+// The shim's only job is flattening the pointer graph into the SoA / CSR views of include/orbx_types.h and scattering
+// the answers back; every float that decides a match is computed by the reference's own expressions on the host
+// (projection, radius) or by the device with the same non-fused FP32 operations.
+#include "ORBmatcher.h"
+#include "orbm.h"
+
+namespace ORB_SLAM3 {
+
+namespace {
+orbm_matcher* ThreadMatcher() {  // ORBmatcher objects are per-call temporaries on three threads: one context per thread
+  thread_local orbm_matcher* m = nullptr;
+  if (!m && orbm_create(&m, 0) != ORBX_OK) throw std::runtime_error(orbm_last_error(nullptr));
+  return m;
+}
+
+// Frame::mGrid[64][48] (std::vector<size_t> per cell, include/Frame.h:279) -> CSR; cell id = col * 48 + row
+struct GridCSR {
+  std::vector<int32_t> offsets, items;
+  explicit GridCSR(const Frame& F) : offsets(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0) {
+    for (int c = 0; c < FRAME_GRID_COLS; c++)
+      for (int r = 0; r < FRAME_GRID_ROWS; r++) {
+        offsets[c * FRAME_GRID_ROWS + r + 1] = offsets[c * FRAME_GRID_ROWS + r] + (int32_t)F.mGrid[c][r].size();
+        for (size_t i : F.mGrid[c][r]) items.push_back((int32_t)i);
+      }
+  }
+};
+
+struct FrameFlat {
+  GridCSR grid;
+  std::vector<uint8_t> occupied;
+  orbx_frame_view v;
+  explicit FrameFlat(const Frame& F) : grid(F), occupied(F.N) {
+    for (int i = 0; i < F.N; i++)  // the skip rule of :92-93
+      occupied[i] = F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0;
+    v.n = F.N;
+    v.kps = reinterpret_cast<const orbx_kp*>(F.mvKeysUn.data());
+    v.desc = F.mDescriptors.data;
+    v.u_right = F.mvuRight.empty() ? nullptr : F.mvuRight.data();
+    v.occupied = occupied.data();
+    v.grid = orbx_grid{grid.offsets.data(), grid.items.data(), Frame::mnMinX, Frame::mnMinY,
+                       Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    v.scale_factors = F.mvScaleFactors.data();
+    v.n_levels = (int32_t)F.mvScaleFactors.size();
+  }
+};
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th,
+                                   const bool bFarPoints, const float thFarPoints) {
+  const int M = (int)vpMapPoints.size();
+  std::vector<uint8_t> in_view(M), has_obs(M), desc((size_t)M * 32);
+  std::vector<float> px(M), py(M), pxr(M), vcos(M), depth(M);
+  std::vector<int32_t> level(M);
+  for (int i = 0; i < M; i++) {  // MapPoint tracking scratch, include/MapPoint.h:172-180
+    MapPoint* p = vpMapPoints[i];
+    in_view[i] = p->mbTrackInView && !p->isBad();
+    px[i] = p->mTrackProjX; py[i] = p->mTrackProjY; pxr[i] = p->mTrackProjXR;
+    level[i] = p->mnTrackScaleLevel; vcos[i] = p->mTrackViewCos; depth[i] = p->mTrackDepth;
+    has_obs[i] = p->Observations() > 0;
+    if (in_view[i]) memcpy(&desc[(size_t)i * 32], p->GetDescriptor().data, 32);
+  }
+  FrameFlat ff(F);
+  orbx_mappoints mp{M, in_view.data(), px.data(), py.data(), pxr.data(), level.data(), vcos.data(), depth.data(),
+                    has_obs.data(), desc.data()};
+  std::vector<int32_t> assign(F.N, -1);
+  int32_t nmatches = 0;
+  if (orbm_search_by_projection_map(ThreadMatcher(), &ff.v, &mp, th, mfNNratio, bFarPoints, thFarPoints, assign.data(),
+                                    &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+  for (int i = 0; i < F.N; i++)
+    if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assign[i]];  // :130
+  return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+  // caller-side projection, exactly the reference's expressions (:1607-1690): Tcw, forward / backward, x3Dc, uv, level
+  // window and radius are computed here on the host with Sophus / Eigen; only points that pass those tests are sent
+  const Sophus::SE3f Tcw = CurrentFrame.GetPose();
+  const Eigen::Vector3f twc = Tcw.inverse().translation();
+  const Sophus::SE3f Tlw = LastFrame.GetPose();
+  const Eigen::Vector3f tlc = Tlw * twc;
+  const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
+  const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
+  std::vector<float> u, v, ur, radius, angle;
+  std::vector<int32_t> lo, hi, src;
+  std::vector<uint8_t> has_obs, desc;
+  for (int i = 0; i < LastFrame.N; i++) {
+    MapPoint* pMP = LastFrame.mvpMapPoints[i];
+    if (!pMP || LastFrame.mvbOutlier[i]) continue;
+    const Eigen::Vector3f x3Dc = Tcw * pMP->GetWorldPos();
+    const float invzc = 1.0 / x3Dc(2);
+    if (invzc < 0) continue;
+    const Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+    if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+    if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+    const int nLastOctave = LastFrame.mvKeys[i].octave;
+    u.push_back(uv(0)); v.push_back(uv(1));
+    ur.push_back(uv(0) - CurrentFrame.mbf * invzc);
+    radius.push_back(th * CurrentFrame.mvScaleFactors[nLastOctave]);
+    lo.push_back(bForward ? nLastOctave : (bBackward ? 0 : nLastOctave - 1));
+    hi.push_back(bForward ? -1 : (bBackward ? nLastOctave : nLastOctave + 1));
+    angle.push_back(LastFrame.mvKeysUn[i].angle);
+    has_obs.push_back(1);
+    desc.insert(desc.end(), pMP->GetDescriptor().data, pMP->GetDescriptor().data + 32);
+    src.push_back(i);
+  }
+  FrameFlat ff(CurrentFrame);
+  orbx_projected pts{(int32_t)u.size(), u.data(), v.data(), CurrentFrame.mvuRight.empty() ? nullptr : ur.data(),
+                     radius.data(), lo.data(), hi.data(), angle.data(), has_obs.data(), desc.data()};
+  std::vector<int32_t> assign(CurrentFrame.N, -1);
+  int32_t nmatches = 0;
+  if (orbm_search_by_projection_frame(ThreadMatcher(), &ff.v, &pts, TH_HIGH, mbCheckOrientation, assign.data(),
+                                      &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+  for (int i = 0; i < CurrentFrame.N; i++)
+    if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[src[assign[i]]];
+  return nmatches;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2,
+                                       std::vector<std::pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo,
+                                       const bool bCoarse) {
+  // epipole and F12 exactly as the reference computes them (:893-911, src/CameraModels/Pinhole.cpp:122-149)
+  const Sophus::SE3f T1w = pKF1->GetPose(), T2w = pKF2->GetPose(), Tw2 = pKF2->GetPoseInverse();
+  const Eigen::Vector3f C2 = T2w * pKF1->GetCameraCenter();
+  const Eigen::Vector2f ep = pKF2->mpCamera->project(C2);
+  const Sophus::SE3f T12 = T1w * Tw2;
+  const Eigen::Matrix3f R12 = T12.rotationMatrix();
+  const Eigen::Vector3f t12 = T12.translation();
+  Eigen::Matrix3f t12x;
+  t12x << 0, -t12(2), t12(1), t12(2), 0, -t12(0), -t12(1), t12(0), 0;
+  const Eigen::Matrix3f K1 = pKF1->mpCamera->toK_(), K2 = pKF2->mpCamera->toK_();
+  const Eigen::Matrix3f F12 = K1.transpose().inverse() * t12x * R12 * K2.inverse();
+  float F[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) F[3 * r + c] = F12(r, c);
+
+  auto flatten = [](KeyFrame* kf, std::vector<uint8_t>& has_mp, std::vector<uint32_t>& ids, std::vector<int32_t>& off,
+                    std::vector<uint32_t>& idx, orbx_keyframe_view* out) {
+    has_mp.resize(kf->N);
+    for (int i = 0; i < kf->N; i++) has_mp[i] = kf->GetMapPoint(i) != nullptr;
+    off.push_back(0);
+    for (const auto& node : kf->mFeatVec) {  // DBoW2::FeatureVector = std::map<NodeId, std::vector<unsigned>>
+      ids.push_back(node.first);
+      idx.insert(idx.end(), node.second.begin(), node.second.end());
+      off.push_back((int32_t)idx.size());
+    }
+    out->n = kf->N;
+    out->kps = reinterpret_cast<const orbx_kp*>(kf->mvKeysUn.data());
+    out->desc = kf->mDescriptors.data;
+    out->u_right = kf->mvuRight.empty() ? nullptr : kf->mvuRight.data();
+    out->has_mappoint = has_mp.data();
+    out->featvec = orbx_featvec{(int32_t)ids.size(), ids.data(), off.data(), idx.data()};
+    out->scale_factors = kf->mvScaleFactors.data();
+    out->level_sigma2 = kf->mvLevelSigma2.data();
+    out->n_levels = (int32_t)kf->mvScaleFactors.size();
+  };
+  std::vector<uint8_t> hm1, hm2;
+  std::vector<uint32_t> ids1, ids2, idx1, idx2;
+  std::vector<int32_t> off1, off2;
+  orbx_keyframe_view v1, v2;
+  flatten(pKF1, hm1, ids1, off1, idx1, &v1);
+  flatten(pKF2, hm2, ids2, off2, idx2, &v2);
+  std::vector<int32_t> m12(pKF1->N, -1);
+  int32_t nmatches = 0;
+  if (orbm_search_for_triangulation(ThreadMatcher(), &v1, &v2, F, ep(0), ep(1), bOnlyStereo, bCoarse,
+                                    mbCheckOrientation, m12.data(), &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+  vMatchedPairs.clear();  // :1097-1103, ascending idx1
+  vMatchedPairs.reserve(nmatches);
+  for (size_t i = 0; i < m12.size(); i++)
+    if (m12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)m12[i]));
+  return nmatches;
+}
+
+}  // namespace ORB_SLAM3
