@@ -5,16 +5,17 @@
 // synthesised only by orbx_download_pyramid for the host mirror of mvImagePyramid.
 //
 // One launch per level (7 dependent steps) over all frames of the batch. Streaming design, no shared memory:
-// a thread owns 4 consecutive destination columns and walks kResizeRows destination rows. Its column taps
-// (offset + the coefficient pair packed for IDP.2A) are loaded once; per source row it reads the 3 aligned words
-// that cover its 4 x 2 source bytes, PRMT-selects each byte pair and forms c0*b0 + c1*b1 with one dp2a. Horizontal
-// results of a source row are kept for the next destination row (consecutive rows share a source row ~80% of the
-// time at scale 1.2). One 32-bit store per 4 pixels.
+// a thread owns 4 consecutive destination columns and a strip of kResizeRows destination rows, and walks the SOURCE rows
+// the strip needs in order. Its column taps (offset + the coefficient pair packed for IDP.2A) are loaded once; per
+// source row it reads the 3 aligned words that cover its 4 x 2 source bytes (requested two rows ahead), PRMT-selects
+// each byte pair and forms c0*b0 + c1*b1 with one dp2a. The previous source row's horizontal results stay in
+// registers; a destination row is emitted when its second source row arrives (at a scale >= 1 every source row
+// completes at most two destination rows). One 32-bit store per 4 pixels.
 #include "orbx_kernels.cuh"
 
 namespace orbx {
 
-constexpr int kResizeRows = 8;
+constexpr int kResizeRows = 16;
 constexpr int kResizeThreads = 128;
 
 __global__ void __launch_bounds__(kResizeThreads)
@@ -28,6 +29,7 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
   int spitch;
   const uint8_t* src = raw_level(P, fs, l - 1, f, &spitch);
   uint8_t* dst = fs.pyr + (int64_t)f * fs.slab_fstride + D.img_off;
+  const int dpitch = D.pitch, sh1 = S.h - 1, sw1 = S.w - 1;
 
   // ---- column taps of the 4 destination pixels ----
   int s[4];
@@ -57,69 +59,69 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
     const int oo = hi[k] ? o - 4 : o;
     sel[k] = (uint32_t)(oo & 7) | ((uint32_t)((oo + 1) & 7) << 4) | 0x4400u;  // bytes 2,3 of the result: don't care
   }
+  const uint8_t* srcb = src + base;
 
-  // horizontal pass of one source row -> 4 ints
-  auto hrow = [&](int sy, int (&h)[4]) {
-    const uint8_t* row = src + (int64_t)sy * spitch;
+  struct Row3 {
+    uint32_t w0, w1, w2;
+  };
+  auto fetch = [&](int sy) {
+    Row3 r{0u, 0u, 0u};
     if (fast) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(row + base);
-      const uint32_t w0 = r32[0], w1 = r32[1], w2 = r32[2];
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(srcb + (int64_t)sy * spitch);
+      r.w0 = __ldg(r32);
+      r.w1 = __ldg(r32 + 1);
+      r.w2 = __ldg(r32 + 2);
+    }
+    return r;
+  };
+  // horizontal pass of one source row -> 4 ints, already >> 4 (the vertical pass only uses them that way)
+  auto hrow = [&](int sy, const Row3& r, int (&h)[4]) {
+    if (fast) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const uint32_t pair = __byte_perm(hi[k] ? w1 : w0, hi[k] ? w2 : w1, sel[k]);
-        h[k] = (int)__dp2a_lo(coef[k], pair, 0u);  // c0 * b0 + c1 * b1
+        const uint32_t pair = __byte_perm(hi[k] ? r.w1 : r.w0, hi[k] ? r.w2 : r.w1, sel[k]);
+        h[k] = (int)__dp2a_lo(coef[k], pair, 0u) >> 4;  // c0 * b0 + c1 * b1
       }
     } else {
+      const uint8_t* row = src + (int64_t)sy * spitch;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        const int s1 = s[k] + 1 < S.w ? s[k] + 1 : S.w - 1;
-        h[k] = (int)row[s[k]] * (int)(coef[k] & 0xffff) + (int)row[s1] * (int)(coef[k] >> 16);
+        const int s1 = s[k] + 1 < sw1 ? s[k] + 1 : sw1;
+        h[k] = ((int)row[s[k]] * (int)(coef[k] & 0xffff) + (int)row[s1] * (int)(coef[k] >> 16)) >> 4;
       }
     }
   };
+  auto clip = [&](int v) { return v < 0 ? 0 : (v > sh1 ? sh1 : v); };  // rows are clipped, the coefficients kept
 
-  // the two most recent source rows (indices are warp-uniform: they depend on y only)
-  int ia = -1, ib = -1;
-  int ha[4] = {0, 0, 0, 0}, hb[4] = {0, 0, 0, 0};
-  for (int r = 0; r < kResizeRows; r++) {
-    const int y = y_begin + r;
-    if (y >= D.h) break;
-    const ResizeTab ty = tab[D.ytab_off + y];
-    int sy0 = ty.ofs, sy1 = ty.ofs + 1;  // rows are clipped, the coefficients kept (resizeGeneric_Invoker)
-    sy0 = sy0 < 0 ? 0 : (sy0 >= S.h ? S.h - 1 : sy0);
-    sy1 = sy1 < 0 ? 0 : (sy1 >= S.h ? S.h - 1 : sy1);
-    const int b0 = ty.c0, b1 = ty.c1;
-    int n0[4], n1[4];
-    if (sy0 == ia) {
+  const int y_end = min(y_begin + kResizeRows, D.h);
+  const ResizeTab* ytab = tab + D.ytab_off;
+  const int s_first = clip(ytab[y_begin].ofs), s_last = clip(ytab[y_end - 1].ofs + 1);
+  Row3 qa = fetch(s_first), qb = fetch(min(s_first + 1, s_last));
+  int y = y_begin;
+  ResizeTab ty = ytab[y];
+  int hp[4] = {0, 0, 0, 0}, hc[4];
+  uint8_t* dptr = dst + (int64_t)y_begin * dpitch + d0;
+  for (int sy = s_first; sy <= s_last; sy++) {
+    const Row3 cur = qa;
+    qa = qb;
+    if (sy + 2 <= s_last) qb = fetch(sy + 2);
+    hrow(sy, cur, hc);
+    while (y < y_end && clip(ty.ofs + 1) == sy) {
+      const bool same = clip(ty.ofs) == sy;  // both taps on this row (clipped at the image bottom / top)
+      const int b0 = ty.c0, b1 = ty.c1;
+      uint32_t v[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) n0[k] = ha[k];
-    } else if (sy0 == ib) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) n0[k] = hb[k];
-    } else {
-      hrow(sy0, n0);
+      for (int k = 0; k < 4; k++) {
+        const int n0 = same ? hc[k] : hp[k];
+        v[k] = (uint32_t)((((b0 * n0) >> 16) + ((b1 * hc[k]) >> 16) + 2) >> 2);  // in [0, 255]: taps sum to 2048
+      }
+      *reinterpret_cast<uint32_t*>(dptr) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+      dptr += dpitch;
+      y++;
+      if (y < y_end) ty = ytab[y];
     }
-    if (sy1 == sy0) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) n1[k] = n0[k];
-    } else if (sy1 == ib) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) n1[k] = hb[k];
-    } else {
-      hrow(sy1, n1);
-    }
-    uint32_t packed = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int v = (((b0 * (n0[k] >> 4)) >> 16) + ((b1 * (n1[k] >> 4)) >> 16) + 2) >> 2;
-      v = v < 0 ? 0 : (v > 255 ? 255 : v);
-      packed |= (uint32_t)v << (8 * k);
-      ha[k] = n0[k];
-      hb[k] = n1[k];
-    }
-    ia = sy0;
-    ib = sy1;
-    *reinterpret_cast<uint32_t*>(dst + (int64_t)y * D.pitch + d0) = packed;
+    for (int k = 0; k < 4; k++) hp[k] = hc[k];
   }
 }
 
