@@ -133,7 +133,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="orbx")
-    ap.add_argument("--pairs", type=int, default=256, help="stereo pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=1024, help="stereo pairs per step per GPU")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs tiled into a batch")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
     ap.add_argument("--no-cpu", action="store_true")
@@ -309,7 +309,7 @@ def main():
         pinL[k][...] = hostL[k]
         pinR[k][...] = hostR[k]
     # the fused call pipelines groups of max_batch pairs over two lanes: use smaller groups than the resident batch
-    G = args.e2e_group or max(8, P // 8)
+    G = args.e2e_group or max(8, min(64, P // 8))
     exl2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
     exr2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
     outs = ORBmatcher.alloc_stereo_outputs(P, cap, empty=pinned)

@@ -178,26 +178,22 @@ k_describe(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, 
   const int e = blockIdx.x * kDescWarps + warp;
   const int f = blockIdx.y;
   if (e >= P.kps_per_frame) return;
-  int l = 0;
-  while (l + 1 < P.nlevels && P.lv[l + 1].kp_base <= e) l++;
+  // level of entry e: the last level whose first entry is <= e (lane k looks at level k)
+  const int l = __popc(__ballot_sync(0xffffffffu, lane < P.nlevels && P.lv[lane < P.nlevels ? lane : 0].kp_base <= e)) - 1;
   const LevelPlan& L = P.lv[l];
   const int p = e - L.kp_base;
-  // ---- output row (:1083-1101): monoIndex counts up from 0, stereoIndex down from N - 1, levels ascending ----
-  int total = 0, st_total = 0, mono_before = 0, st_before = 0, n_here = 0;
-  {
-    const int32_t* ln = ws.lvl_n + f * P.nlevels;
-    const int32_t* ls = ws.lvl_st + f * P.nlevels;
-    for (int k = 0; k < P.nlevels; k++) {
-      const int n = ln[k], s = ls[k];
-      total += n;
-      st_total += s;
-      if (k < l) {
-        mono_before += n - s;
-        st_before += s;
-      }
-      if (k == l) n_here = n;
-    }
+  // ---- output row (:1083-1101): monoIndex counts up from 0, stereoIndex down from N - 1, levels ascending.
+  //      Lane k holds level k's counts; the sums over all levels / the levels below l are warp reductions ----
+  int n_k = 0, s_k = 0;
+  if (lane < P.nlevels) {
+    n_k = ws.lvl_n[f * P.nlevels + lane];
+    s_k = ws.lvl_st[f * P.nlevels + lane];
   }
+  const int total = __reduce_add_sync(0xffffffffu, n_k);
+  const int st_total = __reduce_add_sync(0xffffffffu, s_k);
+  const int mono_before = __reduce_add_sync(0xffffffffu, lane < l ? n_k - s_k : 0);
+  const int st_before = __reduce_add_sync(0xffffffffu, lane < l ? s_k : 0);
+  const int n_here = __shfl_sync(0xffffffffu, n_k, l);
   const bool fits = total <= out.cap;
   if (e == 0 && lane == 0) {
     out.n[f] = total;
@@ -214,19 +210,25 @@ k_describe(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, 
   int pitch;
   const uint8_t* img = raw_level(P, fs, l, f, &pitch);
   const uint8_t* center = img + (int64_t)Y * pitch + X;
+  // lane = column u + 15; a row v takes part where |u| <= umax[|v|]. Since u is fixed per lane, m10 = u * (sum of the
+  // lane's pixels); the row pointer is bumped by the pitch (no per-row multiply) and umax is a compile-time table.
   const int u = lane - kHalfPatch;
   const int au = u < 0 ? -u : u;
   int m10 = 0, m01 = 0;
   if (lane < 31) {
+    constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // :456-468, HALF_PATCH 15
+    const uint8_t* rowp = center - (int64_t)kHalfPatch * pitch + u;
+    int colsum = 0;
 #pragma unroll
     for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-      const int d = P.umax[v < 0 ? -v : v];
-      if (au <= d) {
-        const int val = center[v * pitch + u];
-        m10 += u * val;
+      if (au <= kUmax[v < 0 ? -v : v]) {
+        const int val = *rowp;
+        colsum += val;
         m01 += v * val;
       }
+      rowp += pitch;
     }
+    m10 = u * colsum;
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -239,8 +241,10 @@ k_describe(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, 
   const uint8_t* bimg = blur_level(P, fs, l, f);
   const int bp = L.pitch;
   const uint8_t* bc = bimg + (int64_t)Y * bp + X;
+  // 32 bytes of pattern per lane: 8 tests x (x0, y0, x1, y1) as int8. (A float table was tried: 4x the L1 traffic per
+  // warp made the kernel 40 % slower than converting here.)
   const int4* pat4 = reinterpret_cast<const int4*>(pattern) + lane * 2;
-  const int4 q0 = pat4[0], q1 = pat4[1];
+  const int4 q0 = __ldg(pat4), q1 = __ldg(pat4 + 1);
   const int words[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
   uint32_t byte = 0;
 #pragma unroll

@@ -74,14 +74,12 @@ __device__ __forceinline__ void arc_minmax(const uint32_t (&v)[16], uint32_t& rh
   rlo = lo;
 }
 
-// FAST "m" of the two pixels packed in c (u16x2) -> two byte scores (m - 1 if m > tlow else 0)
-__device__ __forceinline__ uint32_t score_pair(uint32_t c, uint32_t rhi, uint32_t rlo, int tlow) {
-  const int c0 = (int)(c & 0xffff), c1 = (int)(c >> 16);
-  const int m0 = max(c0 - (int)(rhi & 0xffff), (int)(rlo & 0xffff) - c0);
-  const int m1 = max(c1 - (int)(rhi >> 16), (int)(rlo >> 16) - c1);
-  const uint32_t s0 = m0 > tlow ? (uint32_t)(m0 - 1) : 0u;
-  const uint32_t s1 = m1 > tlow ? (uint32_t)(m1 - 1) : 0u;
-  return s0 | (s1 << 8);
+// FAST "m" of the two pixels packed in c (u16x2) -> r = max(m - tlow, 0) per u16 lane (0 <=> not a corner at tlow).
+// All lanes hold values < 256, so a bias of 256 per lane keeps the packed subtractions borrow free.
+__device__ __forceinline__ uint32_t score_pair(uint32_t c, uint32_t rhi, uint32_t rlo, uint32_t k_bias) {
+  const uint32_t t1 = (c | 0x01000100u) - rhi;    // 256 + v - min_arcs max
+  const uint32_t t2 = (rlo | 0x01000100u) - c;    // 256 + max_arcs min - v
+  return __vmaxu2(__vmaxu2(t1, t2), k_bias) - k_bias;  // k_bias = 256 + tlow per lane
 }
 
 __global__ void __launch_bounds__(kFastWarps * 32)
@@ -173,7 +171,10 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   __syncwarp();
 
   // ---- threshold-free score of every interior pixel, 4 pixels per lane step ----
+  // The score map holds r = max(m - tlow, 0): a pixel is a corner at threshold T (m > T) iff r >= T - tlow + 1, its
+  // OpenCV score is m - 1 = r + tlow - 1, and scores of 0 are never kept (cv::FAST compares with a strict >).
   const int tlow = ini_th < min_th ? ini_th : min_th;
+  const uint32_t k_bias = 0x01000100u + (uint32_t)tlow * 0x00010001u;
   const int gpr = (iw + 3) >> 2;
   const int ngroups = gpr * ih;
   const float inv_gpr = 1.0f / (float)gpr;
@@ -194,7 +195,7 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
       Wp2[c] = base[5 * rp + c];
       Wp3[c] = base[6 * rp + c];
     }
-    uint32_t out = 0;
+    uint32_t rr[2];
 #pragma unroll
     for (int half = 0; half < 2; half++) {
       // ring k = 0..15: (dx, dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
@@ -215,8 +216,9 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
       }
       uint32_t rhi, rlo;
       arc_minmax(v, rhi, rlo);
-      out |= score_pair(c, rhi, rlo, tlow) << (16 * half);
+      rr[half] = score_pair(c, rhi, rlo, k_bias);
     }
+    uint32_t out = __byte_perm(rr[0], rr[1], 0x6420);  // low bytes of the 4 lanes = pixels 0..3
     // pixels beyond the interior width (last group of a row) must not score
     const int valid = iw - 4 * g;  // >= 1
     if (valid < 4) out &= (1u << (8 * valid)) - 1u;
@@ -269,6 +271,7 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   int total = 0;
   for (int pass = 0; pass < 2; pass++) {
     const int T = pass == 0 ? ini_th : min_th;
+    const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
     total = 0;
     for (int base = 0; base < ngroups; base += 32) {
       const int G = base + lane;
@@ -277,7 +280,7 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const int sv = (int)((word >> (8 * k)) & 0xff);
-        keepmask |= (unsigned)(sv >= T && sv > 0) << k;  // corner at T  <=>  m > T  <=>  score >= T
+        keepmask |= (unsigned)(sv >= r_min) << k;
       }
       const int c = __popc(keepmask);
       const unsigned b0 = __ballot_sync(0xffffffffu, c >= 1), b1 = __ballot_sync(0xffffffffu, c >= 2);
@@ -288,7 +291,7 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
 #pragma unroll
         for (int k = 0; k < 4; k++)
           if ((keepmask >> k) & 1u)
-            slot[pos++] = cand_pack(4 * g + k + x_off, r + y_off, (int)((word >> (8 * k)) & 0xff));
+            slot[pos++] = cand_pack(4 * g + k + x_off, r + y_off, (int)((word >> (8 * k)) & 0xff) + tlow - 1);
       }
       total += __popc(b0) + __popc(b1);
     }
