@@ -99,6 +99,36 @@ def cpu_reference_run(n_pairs, threads, seed0=1000):
     return 2.0 * n_pairs / dt, dt
 
 
+def opencv_primitives_ms():
+    """Second opinion for the CPU baseline: the three OpenCV kernels the reference spends most of
+    its extraction time in — resize chain, FAST on the 8 whole levels, 7x7 blur — timed through cv2 (OpenCV's SIMD
+    builds) on one 752x480 frame, one thread. A lower bound of the reference's per-frame extraction cost on this host;
+    the oracle port is scalar C++ and slower than that. Returns None when cv2 is missing."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    from orb_slam3_fast_b200 import synth
+    cv2.setNumThreads(1)
+    img = synth.stereo_pair(H, W, 1000)[0]
+    sizes = [(W, H)]
+    for l in range(1, NLEVELS):
+        s = 1.0 / (SCALE ** l)
+        sizes.append((int(round(W * s)), int(round(H * s))))
+    det = cv2.FastFeatureDetector_create(INI_TH, True)
+    best = 1e9
+    for _ in range(5):
+        t0 = time.perf_counter()
+        lv = [img]
+        for l in range(1, NLEVELS):
+            lv.append(cv2.resize(lv[-1], sizes[l], interpolation=cv2.INTER_LINEAR))
+        for a in lv:
+            det.detect(a)
+            cv2.GaussianBlur(a, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+        best = min(best, time.perf_counter() - t0)
+    return 1e3 * best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -123,11 +153,29 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": "%d stereo pairs per step x %d steps" % (per_step, args.steps)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything that is not the result line goes to stderr: libraries (NCCL prints its version banner on stdout)
+    write to fd 1, so fd 1 is pointed at stderr and the JSON line is written to a private duplicate of the real one."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -342,7 +390,11 @@ def main():
         fps, dtc = cpu_reference_run(n_pairs, cores)
         cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "%d stereo pairs (752x480, 1200 feat/eye), oracle port pair-parallel on %d threads, %.1f s"
-                         % (n_pairs, cores, dtc)}
+                         % (n_pairs, cores, dtc),
+               "opencv_simd_primitives_ms_per_frame_1thread": opencv_primitives_ms(),
+               "note": "the port is scalar C++ (the reference itself cannot be built here); the cv2 figure is the time "
+                       "of resize + FAST + blur alone in OpenCV's SIMD build, a lower bound of the reference's "
+                       "per-frame extraction cost on this host"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -358,7 +410,7 @@ def main():
                            "parity": parity, "parallelism": "frames sharded over GPUs, no data-path collective"},
                 "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": clk, "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

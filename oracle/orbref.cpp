@@ -102,21 +102,29 @@ void resize_linear(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst
 // Q0.8 kernel {18,34,48,56,48,34,18}, 16-bit horizontal sums, one rounding at the end. src/ORBextractor.cc:1075-1076.
 // ---------------------------------------------------------------------------------------------------------------
 void gauss7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
-  static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+  // same arithmetic as before (Q0.8 taps, 16-bit row sums, one rounding), arranged so that gcc vectorises both passes:
+  // a reflect-padded copy of each row, then 7 shifted adds; the vertical pass walks 7 row pointers.
   std::vector<uint16_t> H((size_t)w * h);
+  std::vector<uint8_t> pad((size_t)w + 6);
   for (int y = 0; y < h; y++) {
     const uint8_t* S = src + (size_t)y * sstride;
-    for (int x = 0; x < w; x++) {
-      int acc = 0;
-      for (int i = 0; i < 7; i++) acc += k[i] * S[reflect101(x + i - 3, w)];
-      H[(size_t)y * w + x] = (uint16_t)acc;
+    for (int i = 0; i < 3; i++) {
+      pad[i] = S[reflect101(i - 3, w)];
+      pad[(size_t)w + 3 + i] = S[reflect101(w + i, w)];
     }
+    memcpy(pad.data() + 3, S, (size_t)w);
+    const uint8_t* P = pad.data();
+    uint16_t* Hr = H.data() + (size_t)y * w;
+    for (int x = 0; x < w; x++)
+      Hr[x] = (uint16_t)(18 * (P[x] + P[x + 6]) + 34 * (P[x + 1] + P[x + 5]) + 48 * (P[x + 2] + P[x + 4]) + 56 * P[x + 3]);
   }
   for (int y = 0; y < h; y++) {
     uint8_t* D = dst + (size_t)y * dstride;
+    const uint16_t* r[7];
+    for (int j = 0; j < 7; j++) r[j] = H.data() + (size_t)reflect101(y + j - 3, h) * w;
     for (int x = 0; x < w; x++) {
-      uint32_t acc = 32768;
-      for (int j = 0; j < 7; j++) acc += (uint32_t)k[j] * H[(size_t)reflect101(y + j - 3, h) * w + x];
+      const uint32_t acc = 32768u + 18u * ((uint32_t)r[0][x] + r[6][x]) + 34u * ((uint32_t)r[1][x] + r[5][x]) +
+                           48u * ((uint32_t)r[2][x] + r[4][x]) + 56u * (uint32_t)r[3][x];
       D[x] = (uint8_t)(acc >> 16);
     }
   }
@@ -143,17 +151,19 @@ const int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
 const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 
 inline int fast_m(const uint8_t* p, int stride) {
-  int d[16];
+  // max over the 16 arcs of max(min_arc d, min_arc -d): windows of 9 are built from windows of 3
+  int d[16], lo3[16], hi3[16];
   const int v = p[0];
   for (int k = 0; k < 16; k++) d[k] = v - p[kRingDy[k] * stride + kRingDx[k]];
+  for (int k = 0; k < 16; k++) {
+    const int a = d[k], b = d[(k + 1) & 15], c = d[(k + 2) & 15];
+    lo3[k] = std::min(a, std::min(b, c));
+    hi3[k] = std::max(a, std::max(b, c));
+  }
   int best = -256;
   for (int s = 0; s < 16; s++) {
-    int lo = 256, hi = -256;
-    for (int j = 0; j < 9; j++) {
-      int dk = d[(s + j) & 15];
-      lo = std::min(lo, dk);
-      hi = std::max(hi, dk);
-    }
+    const int lo = std::min(lo3[s], std::min(lo3[(s + 3) & 15], lo3[(s + 6) & 15]));
+    const int hi = std::max(hi3[s], std::max(hi3[(s + 3) & 15], hi3[(s + 6) & 15]));
     best = std::max(best, std::max(lo, -hi));
   }
   return best;
@@ -175,18 +185,61 @@ void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std:
   out.clear();
   threshold = std::min(std::max(threshold, 0), 255);
   if (w < 7 || h < 7) return;
-  std::vector<int> score((size_t)w * h, 0);
+  // three score rows are enough for the 3x3 non-max suppression (OpenCV keeps a rolling buffer the same way)
+  std::vector<int> rows((size_t)3 * w, 0);
+  std::vector<uint8_t> pass((size_t)w, 0), tmp((size_t)4 * w);
   int off[16];
   for (int k = 0; k < 16; k++) off[k] = kRingDy[k] * stride + kRingDx[k];
-  for (int y = 3; y < h - 3; y++)
+  const int T = threshold;
+  auto emit_row = [&](int y) {  // NMS of row y: needs the score rows y - 1, y, y + 1
+    const int* up = &rows[(size_t)((y - 1) % 3) * w];
+    const int* c = &rows[(size_t)(y % 3) * w];
+    const int* dn = &rows[(size_t)((y + 1) % 3) * w];
     for (int x = 3; x < w - 3; x++) {
-      const uint8_t* p = img + (size_t)y * stride + x;
-      const int v = p[0], T = threshold;
-      // every arc of 9 ring pixels contains ring pixel 0 or 8, and 4 or 12: cheap rejection before the full test
-      const int d0 = v - p[off[0]], d8 = v - p[off[8]];
-      if (!(d0 > T || d8 > T) && !(d0 < -T || d8 < -T)) continue;
-      const int d4 = v - p[off[4]], d12 = v - p[off[12]];
-      if (!(d4 > T || d12 > T) && !(d4 < -T || d12 < -T)) continue;
+      const int s = c[x];
+      if (s == 0) continue;  // OpenCV keeps scores in a buffer where 0 = "not a corner"; a 0-score corner never wins
+      if (s > c[x - 1] && s > c[x + 1] && s > up[x - 1] && s > up[x] && s > up[x + 1] && s > dn[x - 1] && s > dn[x] &&
+          s > dn[x + 1])
+        out.push_back({x, y, s});
+    }
+  };
+  for (int y = 3; y < h - 3; y++) {
+    const uint8_t* r = img + (size_t)y * stride;
+    int* sc = &rows[(size_t)(y % 3) * w];
+    std::fill(sc, sc + w, 0);
+    // every arc of 9 ring pixels contains one end of each of the 8 diameters (k, k + 8): all 8 diameters must have a
+    // brighter end, or all 8 a darker end. Branch free over the row so that the compiler vectorises it (16 px / op).
+    uint8_t* __restrict__ ps = pass.data();
+    uint8_t* __restrict__ vb = tmp.data();
+    uint8_t* __restrict__ vd = tmp.data() + w;
+    uint8_t* __restrict__ br = tmp.data() + 2 * (size_t)w;
+    uint8_t* __restrict__ dk = tmp.data() + 3 * (size_t)w;
+    const int n = w - 6;
+    {
+      const uint8_t* __restrict__ c = r + 3;
+      for (int i = 0; i < n; i++) {
+        const int v = c[i];
+        vb[i] = (uint8_t)(v + T > 255 ? 255 : v + T);
+        vd[i] = (uint8_t)(v - T < 0 ? 0 : v - T);
+        br[i] = 1;
+        dk[i] = 1;
+      }
+    }
+    for (int k = 0; k < 8; k++) {
+      const uint8_t* __restrict__ qa = r + 3 + off[k];
+      const uint8_t* __restrict__ qb = r + 3 + off[k + 8];
+      for (int i = 0; i < n; i++) {
+        const uint8_t a = qa[i], b = qb[i];
+        const uint8_t hi = a > b ? a : b, lo = a < b ? a : b;
+        br[i] &= (uint8_t)(hi > vb[i]);
+        dk[i] &= (uint8_t)(lo < vd[i]);
+      }
+    }
+    for (int i = 0; i < n; i++) ps[i + 3] = br[i] | dk[i];
+    for (int x = 3; x < w - 3; x++) {
+      if (!ps[x]) continue;
+      const uint8_t* p = r + x;
+      const int v = p[0];
       unsigned ma = 0, mb = 0;
       for (int k = 0; k < 16; k++) {
         int d = v - p[off[k]];
@@ -194,17 +247,19 @@ void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std:
         mb |= (unsigned)(d < -T) << k;
       }
       if (!has_arc9(ma) && !has_arc9(mb)) continue;
-      score[(size_t)y * w + x] = fast_m(p, stride) - 1;  // m > T is guaranteed here
+      sc[x] = fast_m(p, stride) - 1;  // m > T is guaranteed here
     }
-  for (int y = 3; y < h - 3; y++)
-    for (int x = 3; x < w - 3; x++) {
-      int s = score[(size_t)y * w + x];
-      if (s == 0) continue;  // OpenCV keeps scores in a buffer where 0 = "not a corner"; a 0-score corner never wins
-      const int* c = &score[(size_t)y * w + x];
-      if (s > c[-1] && s > c[1] && s > c[-w - 1] && s > c[-w] && s > c[-w + 1] && s > c[w - 1] && s > c[w] &&
-          s > c[w + 1])
-        out.push_back({x, y, s});
-    }
+    if (y >= 5) emit_row(y - 1);  // rows y - 2, y - 1, y are final (row 3's upper neighbour row 2 is all zeros)
+    else if (y == 4) emit_row(3);
+  }
+  // last interior row: its lower neighbour (row h - 3) holds no corners
+  if (h - 4 >= 4) {
+    std::fill(&rows[(size_t)((h - 3) % 3) * w], &rows[(size_t)((h - 3) % 3) * w] + w, 0);
+    emit_row(h - 4);
+  } else if (h - 4 == 3) {
+    std::fill(&rows[(size_t)((h - 3) % 3) * w], &rows[(size_t)((h - 3) % 3) * w] + w, 0);
+    emit_row(3);
+  }
 }
 
 // cv::fastAtan2 — OpenCV core mathfuncs_core.simd.hpp atan_f32 (degrees). Called at src/ORBextractor.cc:98.
