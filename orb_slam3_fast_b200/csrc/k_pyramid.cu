@@ -47,17 +47,17 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
     }
   }
   const int base = s[0] & ~3;
-  // fast path: the 12 bytes [base, base + 12) hold every tap and lie inside the row; rows are word aligned
+  // fast path: the 12 bytes [base, base + 12) hold every tap and lie inside the row; rows are word aligned. The
+  // window is first shifted right by the thread's misalignment s[0] & 3 (two funnel shifts per row), after which all
+  // 8 tap bytes of the 4 pixels sit in 8 consecutive bytes and one PRMT per pixel picks its pair.
   bool fast = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch) & 3) == 0 && base + 12 <= spitch;
+  const uint32_t mis = (uint32_t)(s[0] - base) * 8u;
   uint32_t sel[4];
-  bool hi[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const int o = s[k] - base;  // byte offset of the left tap; the right tap is o + 1 (its weight is 0 when clamped)
-    if (o < 0 || o + 1 > 11) fast = false;
-    hi[k] = o > 6;
-    const int oo = hi[k] ? o - 4 : o;
-    sel[k] = (uint32_t)(oo & 7) | ((uint32_t)((oo + 1) & 7) << 4) | 0x4400u;  // bytes 2,3 of the result: don't care
+    const int o = s[k] - s[0];  // byte offset of the left tap in the shifted window; the right tap is o + 1
+    if (o < 0 || o + 1 > 7) fast = false;
+    sel[k] = (uint32_t)(o & 7) | ((uint32_t)((o + 1) & 7) << 4) | 0x4400u;  // bytes 2,3 of the result: don't care
   }
   const uint8_t* srcb = src + base;
 
@@ -77,11 +77,10 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
   // horizontal pass of one source row -> 4 ints, already >> 4 (the vertical pass only uses them that way)
   auto hrow = [&](int sy, const Row3& r, int (&h)[4]) {
     if (fast) {
+      const uint32_t a0 = __funnelshift_r(r.w0, r.w1, mis), a1 = __funnelshift_r(r.w1, r.w2, mis);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint32_t pair = __byte_perm(hi[k] ? r.w1 : r.w0, hi[k] ? r.w2 : r.w1, sel[k]);
-        h[k] = (int)__dp2a_lo(coef[k], pair, 0u) >> 4;  // c0 * b0 + c1 * b1
-      }
+      for (int k = 0; k < 4; k++)
+        h[k] = (int)__dp2a_lo(coef[k], __byte_perm(a0, a1, sel[k]), 0u) >> 4;  // (c0 * b0 + c1 * b1) >> 4
     } else {
       const uint8_t* row = src + (int64_t)sy * spitch;
 #pragma unroll

@@ -41,6 +41,19 @@ namespace orbx {
 #endif
 #define ORBX_LANES(i, n) for (int i = ORBX_LANE(); i < (n); i += ORBX_NLANES)
 
+// Shared-memory histogram / arg-max updates, predicated. (Warp-aggregating them with __match_any_sync was measured
+// 15 % SLOWER on B200 than letting the hardware serialise same-address shared atomics.)
+#define ORBX_AGG_ADD(base, key, valid)                \
+  do {                                                \
+    if (valid) ORBX_ATOMIC_ADD(&(base)[key], 1);      \
+  } while (0)
+#define ORBX_AGG_MAX(base, key, val, valid)                                  \
+  do {                                                                       \
+    if (valid) ORBX_ATOMIC_MAX((unsigned int*)&(base)[key], (unsigned)(val)); \
+  } while (0)
+// loops whose body contains a warp collective: the same trip count for every lane, `i` may run past n
+#define ORBX_LANES_UNIFORM(i, n) for (int i = ORBX_LANE(); i - ORBX_LANE() < (n); i += ORBX_NLANES)
+
 // candidate word: x:12 | y:12 | score:8 (x, y relative to minBorder, as the reference's vToDistributeKeys)
 ORBX_HD uint32_t cand_pack(int x, int y, int s) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)s << 24); }
 ORBX_HD int cand_x(uint32_t c) { return (int)(c & 0xfff); }
@@ -310,10 +323,11 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     T.cnt[1][i] = 0;
   }
   ORBX_WSYNC();
-  ORBX_LANES(c, C) {
-    const int r = (int)fdiv((float)cand_x(T.cand[c]), hX);
-    T.lab[c] = (uint16_t)r;
-    ORBX_ATOMIC_ADD(&T.cnt[1][r], 1);
+  ORBX_LANES_UNIFORM(c, C) {
+    const bool ok = c < C;
+    const int r = ok ? (int)fdiv((float)cand_x(T.cand[c]), hX) : 0;
+    if (ok) T.lab[c] = (uint16_t)r;
+    ORBX_AGG_ADD(T.cnt[1], r, ok);
   }
   ORBX_WSYNC();
   int S = warp_compact(nIni, T.rank2pos, [&](int i) { return T.cnt[1][i] > 0; });
@@ -329,15 +343,18 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     T.child[0][4 * p + 3] = 0;
   }
   ORBX_WSYNC();
-  ORBX_LANES(c, C) {
-    const int p = T.newpos[T.lab[c]];
+  ORBX_LANES_UNIFORM(c, C) {
+    const bool ok = c < C;
+    const int p = ok ? T.newpos[T.lab[c]] : 0;
     uint32_t l = (uint32_t)p;
-    if (T.splittable[p]) {
-      const int q = quadrant_of(T.cand[c], T.box[0][p]);
+    const bool split = ok && T.splittable[p];
+    int q = 0;
+    if (split) {
+      q = quadrant_of(T.cand[c], T.box[0][p]);
       l |= (uint32_t)q << 14;
-      ORBX_ATOMIC_ADD(&T.child[0][4 * p + q], 1);
     }
-    T.lab[c] = (uint16_t)l;
+    ORBX_AGG_ADD(T.child[0], 4 * p + q, split);
+    if (ok) T.lab[c] = (uint16_t)l;
   }
   ORBX_WSYNC();
   ORBX_QT_MARK(T, kQtInit);
@@ -439,7 +456,7 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
           const int pos = base + __popc(m & lt);
           T.box[nxt][pos] = box[p];
           T.cnt[nxt][pos] = cnt[p];
-          T.newpos[p] = (uint16_t)pos;
+          T.childpos[4 * p + 0] = T.childpos[4 * p + 1] = T.childpos[4 * p + 2] = T.childpos[4 * p + 3] = (uint16_t)pos;
         }
         base += __popc(m);
       }
@@ -452,7 +469,7 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
         if (!T.committed[p]) {
           T.box[nxt][base] = box[p];
           T.cnt[nxt][base] = cnt[p];
-          T.newpos[p] = (uint16_t)base;
+          T.childpos[4 * p + 0] = T.childpos[4 * p + 1] = T.childpos[4 * p + 2] = T.childpos[4 * p + 3] = (uint16_t)base;
           base++;
         }
       }
@@ -474,11 +491,16 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
       } else {
         ORBX_LANES(p, S) split_nxt[p] = T.cnt[nxt][p] > 1;
       }
+      ORBX_WSYNC();
+      // one word per node for the sweep: split point of the nodes that take part in the next histogram
       ORBX_LANES(p, S) {
         child_nxt[4 * p + 0] = 0;
         child_nxt[4 * p + 1] = 0;
         child_nxt[4 * p + 2] = 0;
         child_nxt[4 * p + 3] = 0;
+        const QBox b = T.box[nxt][p];
+        const uint32_t mx = (uint32_t)(b.ulx + ((b.urx - b.ulx + 1) >> 1)), my = (uint32_t)(b.uly + ((b.bry - b.uly + 1) >> 1));
+        T.scan[p] = split_nxt[p] ? (int)(0x80000000u | mx | (my << 12)) : 0;
       }
     } else {
       // final round: child_nxt[p] doubles as "best candidate" accumulator (response << 24 | ~index)
@@ -488,34 +510,41 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     ORBX_QT_MARK(T, kQtPrep);
     // ---- one sweep over the candidates: move to the new node, then histogram / argmax. The loads of 4 lane steps
     //      are issued before any of them is used ----
-    for (int c0 = ORBX_LANE(); c0 < C; c0 += 4 * ORBX_NLANES) {
+    // Stage-wise over 4 lane steps so that the dependent shared-memory loads of different steps overlap:
+    // label -> new position (one table for split parents and survivors) -> node word -> quadrant -> histogram.
+    for (int c0 = 0; c0 < C; c0 += 4 * ORBX_NLANES) {
       uint32_t lv[4], cv[4];
+      int np[4];
+      bool ok[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int c = c0 + u * ORBX_NLANES;
-        if (c < C) {
-          lv[u] = T.lab[c];
-          cv[u] = T.cand[c];
-        }
+        const int c = c0 + u * ORBX_NLANES + ORBX_LANE();
+        ok[u] = c < C;
+        lv[u] = ok[u] ? (uint32_t)T.lab[c] : 0u;
+        cv[u] = ok[u] ? T.cand[c] : 0u;
       }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int c = c0 + u * ORBX_NLANES;
-        if (c >= C) continue;
-        const uint32_t l = lv[u];
-        const int p = (int)(l & kLabPosMask);
-        const int np = T.committed[p] ? T.childpos[4 * p + (int)(l >> 14)] : T.newpos[p];
-        uint32_t nl = (uint32_t)np;
-        const uint32_t cw = cv[u];
-        if (finish) {
-          const uint32_t v = ((uint32_t)cand_s(cw) << 24) | (0xffffffu - (uint32_t)c);
-          ORBX_ATOMIC_MAX((unsigned int*)&child_nxt[np], v);
-        } else if (split_nxt[np]) {
-          const int q = quadrant_of(cw, T.box[nxt][np]);
-          nl |= (uint32_t)q << 14;
-          ORBX_ATOMIC_ADD(&child_nxt[4 * np + q], 1);
+      for (int u = 0; u < 4; u++) np[u] = T.childpos[4 * (int)(lv[u] & kLabPosMask) + (int)(lv[u] >> 14)];
+      if (finish) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int c = c0 + u * ORBX_NLANES + ORBX_LANE();
+          const uint32_t v = ((uint32_t)cand_s(cv[u]) << 24) | (0xffffffu - (uint32_t)c);
+          ORBX_AGG_MAX(child_nxt, np[u], v, ok[u]);
+          if (ok[u]) T.lab[c] = (uint16_t)np[u];
         }
-        T.lab[c] = (uint16_t)nl;
+      } else {
+        uint32_t info[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) info[u] = (uint32_t)T.scan[np[u]];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int c = c0 + u * ORBX_NLANES + ORBX_LANE();
+          const bool split = ok[u] && (info[u] >> 31);
+          const int q = (cand_x(cv[u]) < (int)(info[u] & 0xfff) ? 0 : 1) + (cand_y(cv[u]) < (int)((info[u] >> 12) & 0xfff) ? 0 : 2);
+          ORBX_AGG_ADD(child_nxt, 4 * np[u] + q, split);
+          if (ok[u]) T.lab[c] = (uint16_t)((uint32_t)np[u] | (split ? (uint32_t)q << 14 : 0u));
+        }
       }
     }
     ORBX_WSYNC();
