@@ -50,7 +50,11 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
   // fast path: the 12 bytes [base, base + 12) hold every tap and lie inside the row; rows are word aligned. The
   // window is first shifted right by the thread's misalignment s[0] & 3 (two funnel shifts per row), after which all
   // 8 tap bytes of the 4 pixels sit in 8 consecutive bytes and one PRMT per pixel picks its pair.
-  bool fast = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch) & 3) == 0 && base + 12 <= spitch;
+  // The last thread of a row may find its third word past the row end (level 0 is read with the caller's pitch, which
+  // can equal the width): that word then only holds right-hand taps of weight 0, so it is simply not loaded. (Before
+  // this, that one lane took the byte-load path and its whole warp — one in five — waited for it: 52 % of the stalls.)
+  bool fast = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch) & 3) == 0 && base + 8 <= spitch;
+  const bool ld2 = base + 12 <= spitch;
   const uint32_t mis = (uint32_t)(s[0] - base) * 8u;
   uint32_t sel[4];
 #pragma unroll
@@ -70,7 +74,7 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
       const uint32_t* r32 = reinterpret_cast<const uint32_t*>(srcb + (int64_t)sy * spitch);
       r.w0 = __ldg(r32);
       r.w1 = __ldg(r32 + 1);
-      r.w2 = __ldg(r32 + 2);
+      if (ld2) r.w2 = __ldg(r32 + 2);
     }
     return r;
   };
