@@ -9,24 +9,40 @@
 // over the 16 arcs of 9 consecutive ring pixels, and "corner at threshold T" <=> m > T. So one threshold-free pass
 // gives everything both thresholds need (verified against cv2).
 //
-// Mapping: ONE WARP PER CELL. The cell's (wCell+6)x(hCell+6) raw window is staged in shared memory widened to
-// 16 bit, so that a lane scores 4 horizontally adjacent pixels as two u16x2 SIMD pairs with the native
+// Mapping: ONE WARP PER CELL. The cell's (wCell+6)x(hCell+6) raw window is brought into shared memory by ONE TMA
+// tile copy per warp (cp.async.bulk.tensor.3d on a per-level {x, y, frame} tensor map, completion on the warp's own
+// mbarrier; the box starts at the 16-byte boundary below the window origin, and the level base / pitch / frame stride
+// must be 16-byte multiples — otherwise the kernel's LDG staging variant runs) and widened to 16 bit by a
+// smem -> smem pass, so that a lane scores 4 horizontally adjacent pixels as two u16x2 SIMD pairs with the native
 // VIMNMX3.U16x2 (3-input packed min/max): window-of-9 max = max3 of max3's, 40 packed ops per pair and ring
 // polarity. Non-max suppression and the iniTh -> minTh retry run on a byte score map in shared memory, emission is
 // ballot-ordered so the candidate order equals the serial reference. Integer-ALU bound, not HBM bound.
+#include <cuda.h>  // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
 #include "orbx_kernels.cuh"
 #include "orbx_quadtree.h"
 
 namespace orbx {
 
 constexpr int kFastWarps = 4;
+constexpr int kFastHead = 128;  // bytes in front of the per-warp regions: one mbarrier per warp
+
+// Kernel parameters must stay below 4 KB for the descriptors to be usable from parameter space, so the TMA variant
+// covers up to 8 levels — every configuration the reference ships (Examples/**/*.yaml: ORBextractor.nLevels = 8);
+// more levels take the LDG variant.
+constexpr int kFastMapLevels = 8;
+struct FastMaps {
+  CUtensorMap lv[kFastMapLevels];  // u8 [frames][h][w] view of every raw level; box = (box_w, box_h, 1)
+};
 
 struct FastSmemLayout {
   int tp;         // u16 row pitch of the raw tile (multiple of 4)
   int sp;         // byte row pitch of the score map (multiple of 4)
+  int box_w;      // TMA box: bytes per row (multiple of 16) x rows; the u8 landing zone is reused as the score map
+  int box_h;
   int raw_bytes;  // per warp
   int score_bytes;
-  int per_warp;
+  int per_warp;   // multiple of 128 (TMA destination alignment)
 };
 
 static FastSmemLayout fast_layout(const Plan& P) {
@@ -38,13 +54,17 @@ static FastSmemLayout fast_layout(const Plan& P) {
   FastSmemLayout L;
   L.tp = round_up(wc + 12, 4);
   L.sp = round_up(wc + 8, 4);
-  L.raw_bytes = round_up(L.tp * (hc + 6) * 2, 16);
+  L.box_w = round_up(wc + 6 + 15 + 4, 16);  // 16-byte aligned start + one spare word for the widening pass
+  L.box_h = hc + 6;
+  L.raw_bytes = round_up(L.tp * (hc + 6) * 2, 128);
   L.score_bytes = round_up(L.sp * (hc + 2), 16);
+  if (L.box_w * L.box_h > L.score_bytes) L.score_bytes = L.box_w * L.box_h;
+  L.score_bytes = round_up(L.score_bytes, 128);
   L.per_warp = L.raw_bytes + L.score_bytes;
   return L;
 }
 
-size_t fast_smem_bytes(const Plan& P) { return (size_t)fast_layout(P).per_warp * kFastWarps; }
+size_t fast_smem_bytes(const Plan& P) { return kFastHead + (size_t)fast_layout(P).per_warp * kFastWarps; }
 
 // ring pixel pair for the two pixels whose u16 columns are O, O+1 inside the 10-column window W (5 words)
 template <int O>
@@ -53,6 +73,10 @@ __device__ __forceinline__ uint32_t pair_at(const uint32_t (&W)[5]) {
   else return __byte_perm(W[(O - 1) / 2], W[(O + 1) / 2], 0x5432);
 }
 
+// Measured dead ends (tools/ubench/alu_tput.cu): every VIMNMX form, 2- or 3-input, issues at 64 lanes/clk/SM, so the
+// window-of-3 / window-of-9 scheme below (80 three-input operations per pixel pair) beats a prefix / suffix (van
+// Herk) split of the ring (57 two-input operations per polarity, measured 9 % slower in the kernel); HFMA2.RELU runs
+// on the other pipe at the same rate but shares the issue port (a VIMNMX3 | HFMA2 mix reaches 82 lanes/clk/SM).
 __device__ __forceinline__ void arc_minmax(const uint32_t (&v)[16], uint32_t& rhi, uint32_t& rlo) {
   uint32_t a[16], b[16];
 #pragma unroll
@@ -82,10 +106,13 @@ __device__ __forceinline__ uint32_t score_pair(uint32_t c, uint32_t rhi, uint32_
   return __vmaxu2(__vmaxu2(t1, t2), k_bias) - k_bias;  // k_bias = 256 + tlow per lane
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool kTma>
 __global__ void __launch_bounds__(kFastWarps * 32)
-k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int ini_th, int min_th, int tp, int sp,
-       int raw_bytes, int per_warp) {
-  extern __shared__ __align__(16) uint8_t smem[];
+k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, const FrameSet fs, const WorkSet ws,
+       int ini_th, int min_th, int tp, int sp, int raw_bytes, int per_warp, int box_w, int box_bytes) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x * kFastWarps + warp;
   const int f = blockIdx.y;
@@ -110,8 +137,58 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
     return;
   }
 
-  uint16_t* raw = reinterpret_cast<uint16_t*>(smem + (size_t)warp * per_warp);
-  uint8_t* score = smem + (size_t)warp * per_warp + raw_bytes;
+  uint16_t* raw = reinterpret_cast<uint16_t*>(smem + kFastHead + (size_t)warp * per_warp);
+  uint8_t* score = smem + kFastHead + (size_t)warp * per_warp + raw_bytes;
+
+  if constexpr (kTma) {
+    // ---- one TMA tile copy per warp: box_w x box_h bytes of the level at (iniX & ~15, iniY, f) land in the (not yet
+    //      used) score region; bytes outside the level read as zero. The box must START on a 16-byte boundary of the
+    //      row (measured: an unaligned innermost coordinate raises an illegal-instruction fault, tools/ubench/
+    //      tma_probe.cu), so the box is 15 columns wider than the window and the widening pass below starts at the
+    //      byte offset iniX & 15. It only touches the th x tp window it needs — what lies to the right of the cell
+    //      window are the neighbour cell's pixels, which only ever feed the scores of columns >= iw, and those are
+    //      masked. ----
+    const uint32_t bar = smem_u32(smem + 8 * warp), dst = smem_u32(score);
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(box_bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&maps.lv[l])), "r"(iniX & ~15), "r"(iniY), "r"(f), "r"(bar)
+          : "memory");
+    }
+    __syncwarp();
+    uint32_t ok;
+    do {
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+          : "=r"(ok) : "r"(bar) : "memory");
+    } while (!ok);
+    // widen u8 -> u16: a lane step cuts 4 pixels out of two landing-zone words (one PRMT, the byte offset is a
+    // per-warp constant) and turns them into one 8-byte store
+    const int off = iniX & 15;
+    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(score) + (off >> 2);
+    const uint32_t cut = 0x3210u + 0x1111u * (uint32_t)(off & 3);
+    const int groups = tp >> 2, wpr = box_w >> 2, jmax = wpr - (off >> 2) - 1;  // word j + 1 must exist
+    const int q32 = 32 / groups, m32 = 32 - q32 * groups;
+    int r = lane / groups, j = lane - r * groups;
+    while (r < th) {
+      uint32_t v = 0u;
+      if (j < jmax) v = __byte_perm(t32[r * wpr + j], t32[r * wpr + j + 1], cut);
+      uint2 o;
+      o.x = __byte_perm(v, 0u, 0x4140);  // [b0, 0, b1, 0]
+      o.y = __byte_perm(v, 0u, 0x4342);  // [b2, 0, b3, 0]
+      *reinterpret_cast<uint2*>(raw + r * tp + 4 * j) = o;
+      j += m32;
+      r += q32;
+      if (j >= groups) {
+        j -= groups;
+        r++;
+      }
+    }
+    __syncwarp();  // the landing zone becomes the score map
+  } else {
 
   // ---- stage the raw window, widened to u16; columns >= tw are zero. A lane step produces 4 tile columns from the
   //      two aligned global words that hold them (funnel shift by the row's byte misalignment), one 8-byte store.
@@ -161,6 +238,7 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
         }
       }
     }
+  }
   }
   // ---- clear the score map (1-row / 4-column zero frame around the interior) ----
   {
@@ -300,13 +378,63 @@ k_fast(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, int 
   if (lane == 0) *count_out = total;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Tensor maps of the raw levels of this batch. Returns false when a level cannot be described (base, pitch or frame
+// stride not a 16-byte multiple — only possible for a caller-owned level 0): the LDG staging variant is used then.
+static bool make_fast_maps(const Plan& P, const FrameSet& fs, const FastSmemLayout& L, int frames, FastMaps* M) {
+  const EncodeTiledFn enc = encode_tiled();
+  if (!enc || P.nlevels > kFastMapLevels) return false;
+  for (int l = 0; l < P.nlevels; l++) {
+    const uint8_t* base = l == 0 ? fs.lvl0 : fs.pyr + P.lv[l].img_off;
+    const int64_t pitch = l == 0 ? fs.pitch0 : P.lv[l].pitch;
+    int64_t fstride = l == 0 ? fs.fstride0 : fs.slab_fstride;
+    if (frames == 1) fstride = (pitch * P.lv[l].h + 15) / 16 * 16;  // never applied
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (fstride & 15) || pitch <= 0 || fstride <= 0)
+      return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P.lv[l].w, (cuuint64_t)P.lv[l].h, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {(cuuint32_t)L.box_w, (cuuint32_t)L.box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&M->lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
 void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_th, int min_th, int frames,
                  cudaStream_t st) {
   const FastSmemLayout L = fast_layout(P);
-  const size_t smem = (size_t)L.per_warp * kFastWarps;
-  cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+  const size_t smem = kFastHead + (size_t)L.per_warp * kFastWarps;
+  const int attr = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
   dim3 grid((P.cells_per_frame + kFastWarps - 1) / kFastWarps, frames);
-  k_fast<<<grid, kFastWarps * 32, smem, st>>>(P, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes, L.per_warp);
+  FastMaps M;
+  if (L.box_w <= 256 && L.box_h <= 256 && make_fast_maps(P, fs, L, frames, &M)) {
+    cudaFuncSetAttribute(k_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
+    k_fast<true><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
+                                                      L.per_warp, L.box_w, L.box_w * L.box_h);
+  } else {
+    memset(&M, 0, sizeof(M));
+    cudaFuncSetAttribute(k_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
+    k_fast<false><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
+                                                       L.per_warp, L.box_w, L.box_w * L.box_h);
+  }
 }
 
 }  // namespace orbx

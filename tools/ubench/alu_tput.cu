@@ -30,6 +30,30 @@ __global__ void k(uint32_t* out, int iters) {
         if (OP == 8) a[i] = __vimin3_u16x2(__vimax3_u16x2(a[i], b, c), b, c);
         if (OP == 9) a[i] = __dp4a(a[i], b, c);
         if (OP == 10) a[i] = __vimax3_u16x2(a[i], b, c) * 3u + c;  // VIMNMX3 + IMAD interleaved (two pipes)
+        if (OP == 11) {  // HFMA2.RELU: max(a, b) = relu(a - b) + b costs two of these on the fma pipe
+          __half2 h = __hfma2_relu(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b),
+                                   *reinterpret_cast<__half2*>(&c));
+          a[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        if (OP == 12) {  // independent chains: even registers VIMNMX3 (alu pipe), odd registers HFMA2.RELU (fma pipe)
+          if (i & 1) {
+            __half2 h = __hfma2_relu(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b),
+                                     *reinterpret_cast<__half2*>(&c));
+            a[i] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            a[i] = __vimax3_u16x2(a[i], b, c);
+          }
+        }
+        if (OP == 13) {  // HMNMX2 and VIMNMX3 on independent chains: same pipe or not?
+          if (i & 1) {
+            __half2 h = __hmax2(*reinterpret_cast<__half2*>(&a[i]), *reinterpret_cast<__half2*>(&b));
+            a[i] = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            a[i] = __vimax3_u16x2(a[i], b, c);
+          }
+        }
+        if (OP == 14) a[i] = __viaddmax_u16x2(a[i], b, c);
+        if (OP == 15) a[i] = __vmaxu4(a[i], b);
       }
       b += 0x00010001u;
     }
@@ -75,5 +99,10 @@ int main() {
   run<8>("VIMNMX3 x2 dependent", 2);
   run<9>("IDP.4A", 1);
   run<10>("VIMNMX3 + IMAD (two pipes)", 2);
+  run<11>("HFMA2.RELU", 1);
+  run<12>("VIMNMX3 | HFMA2.RELU independent", 1);
+  run<13>("VIMNMX3 | HMNMX2 independent", 1);
+  run<14>("VIADDMNMX.U16x2", 1);
+  run<15>("vmaxu4 (byte SIMD)", 1);
   return 0;
 }
