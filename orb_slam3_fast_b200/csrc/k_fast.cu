@@ -42,6 +42,7 @@ struct FastSmemLayout {
   int box_h;
   int raw_bytes;  // per warp
   int score_bytes;
+  int list_bytes; // u16 per 4-pixel group: the groups that hold a pixel at or above the pass threshold
   int per_warp;   // multiple of 128 (TMA destination alignment)
 };
 
@@ -60,7 +61,8 @@ static FastSmemLayout fast_layout(const Plan& P) {
   L.score_bytes = round_up(L.sp * (hc + 2), 16);
   if (L.box_w * L.box_h > L.score_bytes) L.score_bytes = L.box_w * L.box_h;
   L.score_bytes = round_up(L.score_bytes, 128);
-  L.per_warp = L.raw_bytes + L.score_bytes;
+  L.list_bytes = round_up(2 * ((wc + 3) / 4) * hc, 128);
+  L.per_warp = L.raw_bytes + L.score_bytes + L.list_bytes;
   return L;
 }
 
@@ -106,12 +108,54 @@ __device__ __forceinline__ uint32_t score_pair(uint32_t c, uint32_t rhi, uint32_
   return __vmaxu2(__vmaxu2(t1, t2), k_bias) - k_bias;  // k_bias = 256 + tlow per lane
 }
 
+// 0x80 in every byte of w that is >= k (1 <= k <= 128; the caller handles larger k byte by byte): the low 7 bits
+// carry into bit 7 exactly when they reach k, and a byte with bit 7 set is >= 128 >= k anyway.
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t w, int k) {
+  if (k <= 128) return (((w & 0x7f7f7f7fu) + (uint32_t)(128 - k) * 0x01010101u) | w) & 0x80808080u;
+  uint32_t m = 0;
+#pragma unroll
+  for (int b = 0; b < 4; b++) m |= (uint32_t)((int)((w >> (8 * b)) & 0xff) >= k) << (8 * b + 7);
+  return m;
+}
+
+// 3x3 non-max suppression of the 4 pixels of group g in interior row r: returns their score bytes where the pixel is
+// a strict maximum of its 8 neighbours' raw scores, else 0. OpenCV keeps a corner at threshold T iff its score beats
+// the scores of its neighbours that are corners at T; for a pixel that is itself a corner at T a neighbour below T can
+// never beat it, so this one word serves every threshold. The bytes of the three score rows are split into u16x2
+// lanes (even / odd pixels), neighbour maxima are VIMNMX3, the comparison is a biased subtraction.
+__device__ __forceinline__ uint32_t nms_word(const uint8_t* score, int sp, int r, int g) {
+  const uint32_t* mid = reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g);
+  const int rw = sp >> 2;
+  // per row: A = (p-1, p1), B = (p0, p2), Cc = (p1, p3), D = (p2, p4) as u16x2
+  uint32_t A[3], B[3], Cc[3], D[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const uint32_t* rowp = mid + (k - 1) * rw;
+    const uint32_t wl = rowp[-1], wc = rowp[0], wr = rowp[1];
+    A[k] = __byte_perm(wl, wc, 0x0503) & 0x00ff00ffu;
+    B[k] = __byte_perm(wc, 0u, 0x4240);
+    Cc[k] = __byte_perm(wc, 0u, 0x4341);
+    D[k] = __byte_perm(wc, wr, 0x0402) & 0x00ff00ffu;
+  }
+  uint32_t ne = __vimax3_u16x2(__vimax3_u16x2(A[0], B[0], Cc[0]), __vimax3_u16x2(A[2], B[2], Cc[2]), A[1]);
+  ne = __vimax3_u16x2(ne, Cc[1], Cc[1]);                       // neighbours of the even pixels (p0, p2)
+  uint32_t no = __vimax3_u16x2(__vimax3_u16x2(B[0], Cc[0], D[0]), __vimax3_u16x2(B[2], Cc[2], D[2]), B[1]);
+  no = __vimax3_u16x2(no, D[1], D[1]);                         // neighbours of the odd pixels (p1, p3)
+  // lane = 0x8000 + neighbour max - self: bit 15 set <=> some neighbour >= self <=> not a strict local maximum
+  const uint32_t te = ((ne | 0x80008000u) - B[1]) & 0x80008000u;
+  const uint32_t to = ((no | 0x80008000u) - Cc[1]) & 0x80008000u;
+  const uint32_t ke = B[1] & ~((te >> 15) * 0xffu);
+  const uint32_t ko = Cc[1] & ~((to >> 15) * 0xffu);
+  return __byte_perm(ke, ko, 0x6240);                          // bytes p0 p1 p2 p3
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool kTma>
 __global__ void __launch_bounds__(kFastWarps * 32)
 k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, const FrameSet fs, const WorkSet ws,
-       int ini_th, int min_th, int tp, int sp, int raw_bytes, int per_warp, int box_w, int box_bytes) {
+       int ini_th, int min_th, int tp, int sp, int raw_bytes, int score_bytes, int per_warp, int box_w,
+       int box_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x * kFastWarps + warp;
@@ -139,6 +183,7 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
 
   uint16_t* raw = reinterpret_cast<uint16_t*>(smem + kFastHead + (size_t)warp * per_warp);
   uint8_t* score = smem + kFastHead + (size_t)warp * per_warp + raw_bytes;
+  uint16_t* list = reinterpret_cast<uint16_t*>(score + score_bytes);
 
   if constexpr (kTma) {
     // ---- one TMA tile copy per warp: box_w x box_h bytes of the level at (iniX & ~15, iniY, f) land in the (not yet
@@ -253,12 +298,21 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
   // OpenCV score is m - 1 = r + tlow - 1, and scores of 0 are never kept (cv::FAST compares with a strict >).
   const int tlow = ini_th < min_th ? ini_th : min_th;
   const uint32_t k_bias = 0x01000100u + (uint32_t)tlow * 0x00010001u;
+  // While the scores are made, the groups that hold a pixel at or above the FIRST pass threshold (iniThFAST) are
+  // listed in pixel order (ballot compaction): only those — a few percent of the cell on natural images — go through
+  // non-max suppression and emission below.
   const int gpr = (iw + 3) >> 2;
   const int ngroups = gpr * ih;
   const float inv_gpr = 1.0f / (float)gpr;
-  for (int G = lane; G < ngroups; G += 32) {
+  const unsigned lt = (1u << lane) - 1u;
+  const int r_min0 = max(max(ini_th - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
+  int n_list = 0;
+  for (int gbase = 0; gbase < ngroups; gbase += 32) {
+    const int G = gbase + lane;
+    bool hit = false;
     const int r = (int)(((float)G + 0.5f) * inv_gpr);
     const int g = G - r * gpr;
+    if (G < ngroups) {
     // rows r .. r+6 of the tile are dy = -3 .. 3 around interior row r; u16 columns 4g .. 4g+9
     const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
     const int rp = tp >> 1;  // words per tile row
@@ -301,79 +355,61 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
     const int valid = iw - 4 * g;  // >= 1
     if (valid < 4) out &= (1u << (8 * valid)) - 1u;
     *reinterpret_cast<uint32_t*>(score + (r + 1) * sp + 4 + 4 * g) = out;
-  }
-  __syncwarp();
-
-  // ---- 3x3 non-max suppression inside the cell interior, threshold independent. OpenCV keeps a corner at threshold
-  //      T iff its score beats the scores of its 8 neighbours that are corners at T; for a pixel that is itself a
-  //      corner at T (score >= T) a neighbour below T can never beat it, so "beats all 8 raw scores" is the same test
-  //      and is computed ONCE for both thresholds. Four pixels per lane step, branch free: the bytes of the three
-  //      score rows are split into u16x2 lanes (even / odd pixels), neighbour maxima are VIMNMX3, the comparison is a
-  //      biased subtraction. The result word (score where the pixel is a strict local maximum, else 0) goes into the
-  //      raw tile's shared memory, which is dead by now. ----
-  uint32_t* wmap = reinterpret_cast<uint32_t*>(raw);
-  for (int G = lane; G < ngroups; G += 32) {
-    const int r = (int)(((float)G + 0.5f) * inv_gpr);
-    const int g = G - r * gpr;
-    const uint32_t* mid = reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g);
-    const int rw = sp >> 2;
-    // per row: A = (p-1, p1), B = (p0, p2), Cc = (p1, p3), D = (p2, p4) as u16x2
-    uint32_t A[3], B[3], Cc[3], D[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const uint32_t* rowp = mid + (k - 1) * rw;
-      const uint32_t wl = rowp[-1], wc = rowp[0], wr = rowp[1];
-      A[k] = __byte_perm(wl, wc, 0x0503) & 0x00ff00ffu;
-      B[k] = __byte_perm(wc, 0u, 0x4240);
-      Cc[k] = __byte_perm(wc, 0u, 0x4341);
-      D[k] = __byte_perm(wc, wr, 0x0402) & 0x00ff00ffu;
+    hit = bytes_ge(out, r_min0) != 0u;
     }
-    uint32_t ne = __vimax3_u16x2(__vimax3_u16x2(A[0], B[0], Cc[0]), __vimax3_u16x2(A[2], B[2], Cc[2]), A[1]);
-    ne = __vimax3_u16x2(ne, Cc[1], Cc[1]);                       // neighbours of the even pixels (p0, p2)
-    uint32_t no = __vimax3_u16x2(__vimax3_u16x2(B[0], Cc[0], D[0]), __vimax3_u16x2(B[2], Cc[2], D[2]), B[1]);
-    no = __vimax3_u16x2(no, D[1], D[1]);                         // neighbours of the odd pixels (p1, p3)
-    // lane = 0x8000 + neighbour max - self: bit 15 set <=> some neighbour >= self <=> not a strict local maximum
-    const uint32_t te = ((ne | 0x80008000u) - B[1]) & 0x80008000u;
-    const uint32_t to = ((no | 0x80008000u) - Cc[1]) & 0x80008000u;
-    const uint32_t ke = B[1] & ~((te >> 15) * 0xffu);
-    const uint32_t ko = Cc[1] & ~((to >> 15) * 0xffu);
-    wmap[G] = __byte_perm(ke, ko, 0x6240);                       // bytes p0 p1 p2 p3
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (hit) list[n_list + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
+    n_list += __popc(bal);
   }
   __syncwarp();
 
-  // ---- per-cell threshold and ordered emission. Lane order = group order = pixel row-major, so the candidate order
-  //      of the serial reference falls out of two ballots: no two kept pixels are adjacent, hence a group of 4
-  //      consecutive pixels keeps at most 2. ----
+  // ---- non-max suppression + per-cell threshold + ordered emission, on the listed groups only. The list is in
+  //      pixel row-major order, so the candidate order of the serial reference falls out of two ballots: no two kept
+  //      pixels are adjacent, hence a group of 4 consecutive pixels keeps at most 2. ----
   const int x_off = iniX + 3 - kMinBorder, y_off = iniY + 3 - kMinBorder;  // candidate coords are minBorder-relative
-  const unsigned lt = (1u << lane) - 1u;
   int total = 0;
   for (int pass = 0; pass < 2; pass++) {
     const int T = pass == 0 ? ini_th : min_th;
-    const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
-    total = 0;
-    for (int base = 0; base < ngroups; base += 32) {
-      const int G = base + lane;
-      const uint32_t word = G < ngroups ? wmap[G] : 0u;
-      unsigned keepmask = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int sv = (int)((word >> (8 * k)) & 0xff);
-        keepmask |= (unsigned)(sv >= r_min) << k;
-      }
-      const int c = __popc(keepmask);
-      const unsigned b0 = __ballot_sync(0xffffffffu, c >= 1), b1 = __ballot_sync(0xffffffffu, c >= 2);
-      if (keepmask) {
+    const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);
+    if (pass == 1) {
+      // :946 — the cell came back empty at iniThFAST: list the groups again at minThFAST, from the score map
+      n_list = 0;
+      for (int gbase = 0; gbase < ngroups; gbase += 32) {
+        const int G = gbase + lane;
         const int r = (int)(((float)G + 0.5f) * inv_gpr);
         const int g = G - r * gpr;
+        const bool hit =
+            G < ngroups && bytes_ge(*reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g), r_min) != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) list[n_list + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
+        n_list += __popc(bal);
+      }
+      __syncwarp();
+    }
+    total = 0;
+    for (int kbase = 0; kbase < n_list; kbase += 32) {
+      const int k = kbase + lane;
+      uint32_t word = 0u, keep = 0u;
+      int r = 0, g = 0;
+      if (k < n_list) {
+        const uint32_t e = list[k];
+        r = (int)(e >> 8);
+        g = (int)(e & 255u);
+        word = nms_word(score, sp, r, g);
+        keep = bytes_ge(word, r_min);
+      }
+      const int c = __popc(keep);
+      const unsigned b0 = __ballot_sync(0xffffffffu, c >= 1), b1 = __ballot_sync(0xffffffffu, c >= 2);
+      if (keep) {
         int pos = total + __popc(b0 & lt) + __popc(b1 & lt);
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-          if ((keepmask >> k) & 1u)
-            slot[pos++] = cand_pack(4 * g + k + x_off, r + y_off, (int)((word >> (8 * k)) & 0xff) + tlow - 1);
+        for (int q = 0; q < 4; q++)
+          if ((keep >> (8 * q + 7)) & 1u)
+            slot[pos++] = cand_pack(4 * g + q + x_off, r + y_off, (int)((word >> (8 * q)) & 0xff) + tlow - 1);
       }
       total += __popc(b0) + __popc(b1);
     }
-    if (total > 0) break;  // :946 — retry with minThFAST only when the cell came back empty
+    if (total > 0 || min_th == ini_th) break;  // :946 — retry with minThFAST only when the cell came back empty
   }
   if (lane == 0) *count_out = total;
 }
@@ -428,12 +464,12 @@ void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_t
   if (L.box_w <= 256 && L.box_h <= 256 && make_fast_maps(P, fs, L, frames, &M)) {
     cudaFuncSetAttribute(k_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     k_fast<true><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
-                                                      L.per_warp, L.box_w, L.box_w * L.box_h);
+                                                      L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h);
   } else {
     memset(&M, 0, sizeof(M));
     cudaFuncSetAttribute(k_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     k_fast<false><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
-                                                       L.per_warp, L.box_w, L.box_w * L.box_h);
+                                                       L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h);
   }
 }
 

@@ -28,3 +28,9 @@ tot = sum(v[1] for v in agg.values()) or 1
 for k, v in agg.items():
     print("%-28s n=%3d %9.1f us %5.1f%%" % (k, v[0], v[1] / 1e3, 100 * v[1] / tot))
 PY
+# optional: PROF=<kernel regex> captures ONE launch with the full set + source counters (read here with ncu -i)
+if [ -n "$PROF" ]; then
+  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$PROF" -s ${PROF_SKIP:-2} -c 1 -f \
+      -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 3 --pairs 64 --no-cpu > gpurun_out/ncu_prof_$TAG.log 2>&1
+  ls -la gpurun_out/prof_$TAG.ncu-rep
+fi
