@@ -293,99 +293,139 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
   }
   __syncwarp();
 
-  // ---- threshold-free score of every interior pixel, 4 pixels per lane step ----
+  // ---- scores, non-max suppression, per-cell threshold, ordered emission ----
   // The score map holds r = max(m - tlow, 0): a pixel is a corner at threshold T (m > T) iff r >= T - tlow + 1, its
   // OpenCV score is m - 1 = r + tlow - 1, and scores of 0 are never kept (cv::FAST compares with a strict >).
+  //
+  // Pass 0 (iniThFAST) does NOT score every pixel. A 9-arc of the 16-ring contains one end of every diameter, so a
+  // corner at threshold T has max(p_k, p_k+8) > v + T on both compass diameters (or min < v - T on both): a 4-point
+  // test that only ~2-7 % of the pixels of a natural image pass at T = 20. The groups of 4 pixels that contain such a
+  // pixel are listed (ballot compaction keeps pixel order), only they get the 16-arc score, and of those only the
+  // groups that reach the threshold go through non-max suppression and emission. Unlisted pixels keep score 0, which
+  // is what a neighbour that is not a corner at T counts as in OpenCV's suppression. If the cell comes back empty
+  // (:946) pass 1 scores every group at minThFAST the dense way.
   const int tlow = ini_th < min_th ? ini_th : min_th;
   const uint32_t k_bias = 0x01000100u + (uint32_t)tlow * 0x00010001u;
-  // While the scores are made, the groups that hold a pixel at or above the FIRST pass threshold (iniThFAST) are
-  // listed in pixel order (ballot compaction): only those — a few percent of the cell on natural images — go through
-  // non-max suppression and emission below.
   const int gpr = (iw + 3) >> 2;
   const int ngroups = gpr * ih;
   const float inv_gpr = 1.0f / (float)gpr;
   const unsigned lt = (1u << lane) - 1u;
-  const int r_min0 = max(max(ini_th - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
-  int n_list = 0;
-  for (int gbase = 0; gbase < ngroups; gbase += 32) {
-    const int G = gbase + lane;
-    bool hit = false;
-    const int r = (int)(((float)G + 0.5f) * inv_gpr);
-    const int g = G - r * gpr;
-    if (G < ngroups) {
-    // rows r .. r+6 of the tile are dy = -3 .. 3 around interior row r; u16 columns 4g .. 4g+9
-    const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
-    const int rp = tp >> 1;  // words per tile row
-    uint32_t Wm3[5], Wm2[5], Wm1[5], W0[5], Wp1[5], Wp2[5], Wp3[5];
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-      Wm3[c] = base[0 * rp + c];
-      Wm2[c] = base[1 * rp + c];
-      Wm1[c] = base[2 * rp + c];
-      W0[c] = base[3 * rp + c];
-      Wp1[c] = base[4 * rp + c];
-      Wp2[c] = base[5 * rp + c];
-      Wp3[c] = base[6 * rp + c];
-    }
-    uint32_t rr[2];
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-      // ring k = 0..15: (dx, dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-      uint32_t v[16];
-      uint32_t c;
-      if (half == 0) {
-        v[0] = pair_at<3>(Wp3);  v[1] = pair_at<4>(Wp3);  v[2] = pair_at<5>(Wp2);  v[3] = pair_at<6>(Wp1);
-        v[4] = pair_at<6>(W0);   v[5] = pair_at<6>(Wm1);  v[6] = pair_at<5>(Wm2);  v[7] = pair_at<4>(Wm3);
-        v[8] = pair_at<3>(Wm3);  v[9] = pair_at<2>(Wm3);  v[10] = pair_at<1>(Wm2); v[11] = pair_at<0>(Wm1);
-        v[12] = pair_at<0>(W0);  v[13] = pair_at<0>(Wp1); v[14] = pair_at<1>(Wp2); v[15] = pair_at<2>(Wp3);
-        c = pair_at<3>(W0);
-      } else {
-        v[0] = pair_at<5>(Wp3);  v[1] = pair_at<6>(Wp3);  v[2] = pair_at<7>(Wp2);  v[3] = pair_at<8>(Wp1);
-        v[4] = pair_at<8>(W0);   v[5] = pair_at<8>(Wm1);  v[6] = pair_at<7>(Wm2);  v[7] = pair_at<6>(Wm3);
-        v[8] = pair_at<5>(Wm3);  v[9] = pair_at<4>(Wm3);  v[10] = pair_at<3>(Wm2); v[11] = pair_at<2>(Wm1);
-        v[12] = pair_at<2>(W0);  v[13] = pair_at<2>(Wp1); v[14] = pair_at<3>(Wp2); v[15] = pair_at<4>(Wp3);
-        c = pair_at<5>(W0);
-      }
-      uint32_t rhi, rlo;
-      arc_minmax(v, rhi, rlo);
-      rr[half] = score_pair(c, rhi, rlo, k_bias);
-    }
-    uint32_t out = __byte_perm(rr[0], rr[1], 0x6420);  // low bytes of the 4 lanes = pixels 0..3
-    // pixels beyond the interior width (last group of a row) must not score
-    const int valid = iw - 4 * g;  // >= 1
-    if (valid < 4) out &= (1u << (8 * valid)) - 1u;
-    *reinterpret_cast<uint32_t*>(score + (r + 1) * sp + 4 + 4 * g) = out;
-    hit = bytes_ge(out, r_min0) != 0u;
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (hit) list[n_list + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
-    n_list += __popc(bal);
-  }
-  __syncwarp();
-
-  // ---- non-max suppression + per-cell threshold + ordered emission, on the listed groups only. The list is in
-  //      pixel row-major order, so the candidate order of the serial reference falls out of two ballots: no two kept
-  //      pixels are adjacent, hence a group of 4 consecutive pixels keeps at most 2. ----
+  const int rp = tp >> 1;  // words per tile row
   const int x_off = iniX + 3 - kMinBorder, y_off = iniY + 3 - kMinBorder;  // candidate coords are minBorder-relative
   int total = 0;
   for (int pass = 0; pass < 2; pass++) {
     const int T = pass == 0 ? ini_th : min_th;
-    const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);
-    if (pass == 1) {
-      // :946 — the cell came back empty at iniThFAST: list the groups again at minThFAST, from the score map
-      n_list = 0;
+    const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
+    int n_score = ngroups;
+    if (pass == 0) {
+      // -- compass pre-test of every group: rows r, r+3, r+6 of the tile are dy = -3, 0, +3 --
+      const uint32_t K = (uint32_t)(T + 1) * 0x00010001u;
+      n_score = 0;
       for (int gbase = 0; gbase < ngroups; gbase += 32) {
         const int G = gbase + lane;
         const int r = (int)(((float)G + 0.5f) * inv_gpr);
         const int g = G - r * gpr;
-        const bool hit =
-            G < ngroups && bytes_ge(*reinterpret_cast<const uint32_t*>(score + (r + 1) * sp + 4 + 4 * g), r_min) != 0u;
+        bool hit = false;
+        if (G < ngroups) {
+          const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
+          uint32_t Wm3[5], W0[5], Wp3[5];
+#pragma unroll
+          for (int c = 0; c < 5; c++) W0[c] = base[3 * rp + c];
+#pragma unroll
+          for (int c = 1; c < 4; c++) {
+            Wm3[c] = base[c];
+            Wp3[c] = base[6 * rp + c];
+          }
+          Wm3[0] = Wm3[4] = Wp3[0] = Wp3[4] = 0u;  // not referenced below
+          uint32_t bits = 0u;
+#pragma unroll
+          for (int half = 0; half < 2; half++) {
+            const uint32_t p0 = half ? pair_at<5>(Wp3) : pair_at<3>(Wp3), p8 = half ? pair_at<5>(Wm3) : pair_at<3>(Wm3);
+            const uint32_t p4 = half ? pair_at<8>(W0) : pair_at<6>(W0), p12 = half ? pair_at<2>(W0) : pair_at<0>(W0);
+            const uint32_t c = half ? pair_at<5>(W0) : pair_at<3>(W0);
+            const uint32_t lo_of_hi = __vminu2(__vmaxu2(p0, p8), __vmaxu2(p4, p12));  // bright: must exceed v + T
+            const uint32_t hi_of_lo = __vmaxu2(__vminu2(p0, p8), __vminu2(p4, p12));  // dark: must be below v - T
+            // lanes stay below 0x8000, so bit 15 of (x | 0x8000) - y says x >= y without borrowing across lanes
+            bits |= ((lo_of_hi | 0x80008000u) - (c + K)) | ((c | 0x80008000u) - (hi_of_lo + K));
+          }
+          hit = (bits & 0x80008000u) != 0u;
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) list[n_list + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
-        n_list += __popc(bal);
+        if (hit) list[n_score + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
+        n_score += __popc(bal);
       }
       __syncwarp();
     }
+
+    // -- 16-arc score of the listed groups (pass 0) or of every group (pass 1), 4 pixels per lane step; the groups
+    //    that reach the pass threshold are listed again, in place (the write index never passes the read index) --
+    int n_list = 0;
+    for (int kbase = 0; kbase < n_score; kbase += 32) {
+      const int k = kbase + lane;
+      int r, g;
+      if (pass == 0) {
+        const uint32_t e = k < n_score ? list[k] : 0u;
+        r = (int)(e >> 8);
+        g = (int)(e & 255u);
+      } else {
+        r = (int)(((float)k + 0.5f) * inv_gpr);
+        g = k - r * gpr;
+      }
+      bool hit = false;
+      if (k < n_score) {
+        // rows r .. r+6 of the tile are dy = -3 .. 3 around interior row r; u16 columns 4g .. 4g+9
+        const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
+        uint32_t Wm3[5], Wm2[5], Wm1[5], W0[5], Wp1[5], Wp2[5], Wp3[5];
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+          Wm3[c] = base[0 * rp + c];
+          Wm2[c] = base[1 * rp + c];
+          Wm1[c] = base[2 * rp + c];
+          W0[c] = base[3 * rp + c];
+          Wp1[c] = base[4 * rp + c];
+          Wp2[c] = base[5 * rp + c];
+          Wp3[c] = base[6 * rp + c];
+        }
+        uint32_t rr[2];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          // ring k = 0..15: (dx, dy) = (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+          uint32_t v[16];
+          uint32_t c;
+          if (half == 0) {
+            v[0] = pair_at<3>(Wp3);  v[1] = pair_at<4>(Wp3);  v[2] = pair_at<5>(Wp2);  v[3] = pair_at<6>(Wp1);
+            v[4] = pair_at<6>(W0);   v[5] = pair_at<6>(Wm1);  v[6] = pair_at<5>(Wm2);  v[7] = pair_at<4>(Wm3);
+            v[8] = pair_at<3>(Wm3);  v[9] = pair_at<2>(Wm3);  v[10] = pair_at<1>(Wm2); v[11] = pair_at<0>(Wm1);
+            v[12] = pair_at<0>(W0);  v[13] = pair_at<0>(Wp1); v[14] = pair_at<1>(Wp2); v[15] = pair_at<2>(Wp3);
+            c = pair_at<3>(W0);
+          } else {
+            v[0] = pair_at<5>(Wp3);  v[1] = pair_at<6>(Wp3);  v[2] = pair_at<7>(Wp2);  v[3] = pair_at<8>(Wp1);
+            v[4] = pair_at<8>(W0);   v[5] = pair_at<8>(Wm1);  v[6] = pair_at<7>(Wm2);  v[7] = pair_at<6>(Wm3);
+            v[8] = pair_at<5>(Wm3);  v[9] = pair_at<4>(Wm3);  v[10] = pair_at<3>(Wm2); v[11] = pair_at<2>(Wm1);
+            v[12] = pair_at<2>(W0);  v[13] = pair_at<2>(Wp1); v[14] = pair_at<3>(Wp2); v[15] = pair_at<4>(Wp3);
+            c = pair_at<5>(W0);
+          }
+          uint32_t rhi, rlo;
+          arc_minmax(v, rhi, rlo);
+          rr[half] = score_pair(c, rhi, rlo, k_bias);
+        }
+        uint32_t out = __byte_perm(rr[0], rr[1], 0x6420);  // low bytes of the 4 lanes = pixels 0..3
+        // pixels beyond the interior width (last group of a row) must not score
+        const int valid = iw - 4 * g;  // >= 1
+        if (valid < 4) out &= (1u << (8 * valid)) - 1u;
+        *reinterpret_cast<uint32_t*>(score + (r + 1) * sp + 4 + 4 * g) = out;
+        hit = bytes_ge(out, r_min) != 0u;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      __syncwarp();
+      if (hit) list[n_list + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
+      n_list += __popc(bal);
+    }
+    __syncwarp();
+
+    // -- non-max suppression + threshold + emission on the listed groups. The list is in pixel row-major order, so
+    //    the candidate order of the serial reference falls out of two ballots: no two kept pixels are adjacent, hence
+    //    a group of 4 consecutive pixels keeps at most 2 --
     total = 0;
     for (int kbase = 0; kbase < n_list; kbase += 32) {
       const int k = kbase + lane;
