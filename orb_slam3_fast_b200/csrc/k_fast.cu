@@ -53,9 +53,12 @@ static FastSmemLayout fast_layout(const Plan& P) {
     if (P.lv[l].hCell > hc) hc = P.lv[l].hCell;
   }
   FastSmemLayout L;
-  L.tp = round_up(wc + 12, 4);
+  L.tp = round_up(wc + 12, 8);   // 16-byte rows: the widening pass stores 8 pixels at a time
   L.sp = round_up(wc + 8, 4);
-  L.box_w = round_up(wc + 6 + 15 + 4, 16);  // 16-byte aligned start + one spare word for the widening pass
+  // 16-byte aligned start (up to 15 columns in front of the window) + the words the widening pass reads for the last
+  // 8-pixel group that holds a window column
+  const int need_px = wc + 6 + 15, need_words = 3 + 2 * ((wc + 5) / 8) + 3;
+  L.box_w = round_up(need_px > 4 * need_words ? need_px : 4 * need_words, 16);
   L.box_h = hc + 6;
   L.raw_bytes = round_up(L.tp * (hc + 6) * 2, 128);
   L.score_bytes = round_up(L.sp * (hc + 2), 16);
@@ -210,21 +213,28 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
           "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
           : "=r"(ok) : "r"(bar) : "memory");
     } while (!ok);
-    // widen u8 -> u16: a lane step cuts 4 pixels out of two landing-zone words (one PRMT, the byte offset is a
-    // per-warp constant) and turns them into one 8-byte store
+    // widen u8 -> u16: a lane step cuts 8 pixels out of three landing-zone words (two PRMTs, the byte offset is a
+    // per-warp constant) and turns them into one 16-byte store. tp is padded to a multiple of 8 for this.
     const int off = iniX & 15;
     const uint32_t* t32 = reinterpret_cast<const uint32_t*>(score) + (off >> 2);
     const uint32_t cut = 0x3210u + 0x1111u * (uint32_t)(off & 3);
-    const int groups = tp >> 2, wpr = box_w >> 2, jmax = wpr - (off >> 2) - 1;  // word j + 1 must exist
+    const int groups = tp >> 3, wpr = box_w >> 2, jmax = wpr - (off >> 2) - 2;  // words 2j .. 2j + 2 must exist
     const int q32 = 32 / groups, m32 = 32 - q32 * groups;
     int r = lane / groups, j = lane - r * groups;
     while (r < th) {
-      uint32_t v = 0u;
-      if (j < jmax) v = __byte_perm(t32[r * wpr + j], t32[r * wpr + j + 1], cut);
-      uint2 o;
-      o.x = __byte_perm(v, 0u, 0x4140);  // [b0, 0, b1, 0]
-      o.y = __byte_perm(v, 0u, 0x4342);  // [b2, 0, b3, 0]
-      *reinterpret_cast<uint2*>(raw + r * tp + 4 * j) = o;
+      uint32_t v0 = 0u, v1 = 0u;
+      if (2 * j < jmax) {
+        const uint32_t* p = t32 + r * wpr + 2 * j;
+        const uint32_t a = p[0], b = p[1], c = p[2];
+        v0 = __byte_perm(a, b, cut);
+        v1 = __byte_perm(b, c, cut);
+      }
+      uint4 o;
+      o.x = __byte_perm(v0, 0u, 0x4140);  // [b0, 0, b1, 0]
+      o.y = __byte_perm(v0, 0u, 0x4342);  // [b2, 0, b3, 0]
+      o.z = __byte_perm(v1, 0u, 0x4140);
+      o.w = __byte_perm(v1, 0u, 0x4342);
+      *reinterpret_cast<uint4*>(raw + r * tp + 8 * j) = o;
       j += m32;
       r += q32;
       if (j >= groups) {
@@ -321,10 +331,10 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
       // -- compass pre-test of every group: rows r, r+3, r+6 of the tile are dy = -3, 0, +3 --
       const uint32_t K = (uint32_t)(T + 1) * 0x00010001u;
       n_score = 0;
+      const int q32 = 32 / gpr, m32 = 32 - q32 * gpr;  // a step of 32 groups = q32 rows + m32 groups
+      int r = lane / gpr, g = lane - r * gpr;
       for (int gbase = 0; gbase < ngroups; gbase += 32) {
         const int G = gbase + lane;
-        const int r = (int)(((float)G + 0.5f) * inv_gpr);
-        const int g = G - r * gpr;
         bool hit = false;
         if (G < ngroups) {
           const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
@@ -353,6 +363,12 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
         if (hit) list[n_score + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
         n_score += __popc(bal);
+        g += m32;
+        r += q32;
+        if (g >= gpr) {
+          g -= gpr;
+          r++;
+        }
       }
       __syncwarp();
     }
