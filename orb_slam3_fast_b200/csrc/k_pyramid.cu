@@ -11,6 +11,8 @@
 // each byte pair and forms c0*b0 + c1*b1 with one dp2a. The second source row's horizontal results stay in registers:
 // the next destination row usually starts on it. One 32-bit store per 4 pixels. (The first version walked the SOURCE
 // rows and emitted destination rows from a while loop: 42 instructions per pixel, issue bound at 1.4 TB/s.)
+#include <cuda.h>  // CUtensorMap types; the encoder comes from cudaGetDriverEntryPoint
+
 #include "orbx_kernels.cuh"
 
 namespace orbx {
@@ -151,11 +153,222 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA variant (the one that normally runs). The LDG kernel above is latency bound in the step (1.4 TB/s with ~16 KB of
+// loads in flight per SM, and removing a quarter of its instructions did not move its in-step time): here a block
+// first pulls the SOURCE rectangle its 256 x 16 destination tile needs into shared memory with cp.async.bulk.tensor
+// (nbox boxes of box_w x box_h bytes side by side, the first one starting at the 16-byte boundary below the first
+// tap — an unaligned innermost coordinate faults, tools/ubench/tma_probe.cu), so ~8 KB per resident block are in
+// flight without costing registers; the arithmetic is the same as above, reading 32-bit words from the tile.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRtColThreads = 64;   // x 4 destination columns = 256 per block
+constexpr int kRtRowGroups = 2;     // x kResizeRows destination rows = 16 per block
+constexpr int kRtCols = kRtColThreads * 4, kRtRows = kRtRowGroups * kResizeRows;
+constexpr int kRtHead = 128;        // mbarrier in front of the tile
+constexpr int kRtMaxBoxes = 4;
+
+struct ResizeMaps {
+  CUtensorMap lv[8];  // u8 [frames][h][w] view of the SOURCE level l - 1 at index l - 1; box = (box_w, box_h, 1)
+};
+
+__global__ void __launch_bounds__(kRtColThreads * kRtRowGroups)
+k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps maps, const FrameSet fs,
+             const ResizeTab* __restrict__ tab, int l, int box_w, int box_h, int nbox) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const LevelPlan& D = P.lv[l];
+  const LevelPlan& S = P.lv[l - 1];
+  const int tx = threadIdx.x % kRtColThreads, tr = threadIdx.x / kRtColThreads;
+  const int dblock = blockIdx.x * kRtCols;  // < D.w: pitch is w rounded up to 64 and the tile is 256 wide
+  const int d0 = dblock + tx * 4;
+  const int yb = blockIdx.y * kRtRows;
+  const int f = blockIdx.z;
+  const ResizeTab* xtab = tab + D.xtab_off;
+  const ResizeTab* ytab = tab + D.ytab_off;
+  const int sh1 = S.h - 1, sw1 = S.w - 1;
+  auto clip = [&](int v) { return v < 0 ? 0 : (v > sh1 ? sh1 : v); };  // rows are clipped, the coefficients kept
+  const int xa = xtab[dblock].ofs & ~15;
+  const int ys0 = clip(ytab[yb].ofs);
+  const int box_bytes = box_w * box_h;
+  const int box_stride = (box_bytes + 127) & ~127;  // TMA destinations are 128-byte aligned
+  uint8_t* tile = smem + kRtHead;
+  {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbox * box_bytes) : "memory");
+      for (int b = 0; b < nbox; b++)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"((uint32_t)__cvta_generic_to_shared(tile + b * box_stride)),
+            "l"(reinterpret_cast<uint64_t>(&maps.lv[l - 1])), "r"(xa + b * box_w), "r"(ys0), "r"(f), "r"(bar)
+            : "memory");
+    }
+    __syncthreads();
+    uint32_t ok;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar) : "memory");
+    } while (!ok);
+  }
+  const int y_begin = yb + tr * kResizeRows;
+  if (d0 >= D.pitch || y_begin >= D.h) return;
+  uint8_t* dst = fs.pyr + (int64_t)f * fs.slab_fstride + D.img_off;
+  const int dpitch = D.pitch;
+
+  // ---- column taps of the 4 destination pixels (as in k_resize) ----
+  int s[4];
+  uint32_t coef[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int d = d0 + k;
+    if (d < D.w) {
+      const ResizeTab t = xtab[d];
+      s[k] = t.ofs;
+      coef[k] = (uint32_t)(uint16_t)t.c0 | ((uint32_t)(uint16_t)t.c1 << 16);
+    } else {
+      s[k] = d0 < D.w ? s[0] : xa;
+      coef[k] = 0;  // padding columns are written as zeros
+    }
+  }
+  const int base = s[0] & ~3;
+  bool fast = true;
+  const uint32_t mis = (uint32_t)(s[0] - base) * 8u;
+  uint32_t sel[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int o = s[k] - s[0];
+    if (o < 0 || o + 1 > 7) fast = false;
+    sel[k] = (uint32_t)(o & 7) | ((uint32_t)((o + 1) & 7) << 4) | 0x4400u;
+  }
+  // tile address of source column c: boxes lie side by side, each box_h rows of box_w bytes
+  auto tcol = [&](int c) {
+    const int rel = c - xa, b = rel / box_w;
+    return tile + b * box_stride + (rel - b * box_w);
+  };
+  const uint8_t* pw[3] = {tcol(base), tcol(base + 4), tcol(base + 8)};  // words never straddle a box (box_w % 16 == 0)
+  const uint8_t* pb[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    pb[2 * k] = tcol(s[k]);
+    pb[2 * k + 1] = tcol(s[k] + 1 < sw1 ? s[k] + 1 : sw1);
+  }
+  auto hrow = [&](int sy, int (&h)[4]) {
+    const int ro = (sy - ys0) * box_w;
+    if (fast) {
+      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pw[0] + ro), w1 = *reinterpret_cast<const uint32_t*>(pw[1] + ro),
+                     w2 = *reinterpret_cast<const uint32_t*>(pw[2] + ro);
+      const uint32_t a0 = __funnelshift_r(w0, w1, mis), a1 = __funnelshift_r(w1, w2, mis);
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        h[k] = (int)__dp2a_lo(coef[k], __byte_perm(a0, a1, sel[k]), 0u) >> 4;  // (c0 * b0 + c1 * b1) >> 4
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        h[k] = ((int)pb[2 * k][ro] * (int)(coef[k] & 0xffff) + (int)pb[2 * k + 1][ro] * (int)(coef[k] >> 16)) >> 4;
+    }
+  };
+  const int y_end = min(y_begin + kResizeRows, D.h);
+  int hp[4] = {0, 0, 0, 0};
+  int prev = -1;
+  uint8_t* dptr = dst + (int64_t)y_begin * dpitch + d0;
+  for (int y = y_begin; y < y_end; y++) {
+    const ResizeTab ty = ytab[y];
+    const int a0 = clip(ty.ofs), a1 = clip(ty.ofs + 1);
+    int h0[4], h1[4];
+    if (a0 == prev) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) h0[k] = hp[k];
+    } else {
+      hrow(a0, h0);
+    }
+    if (a1 == a0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) h1[k] = h0[k];
+    } else {
+      hrow(a1, h1);
+    }
+    const int b0 = ty.c0, b1 = ty.c1;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      v[k] = (uint32_t)((((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2);
+    *reinterpret_cast<uint32_t*>(dptr) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+    dptr += dpitch;
+#pragma unroll
+    for (int k = 0; k < 4; k++) hp[k] = h1[k];
+    prev = a1;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn resize_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+struct ResizeTile {
+  int box_w, box_h, nbox;
+};
+// Source rectangle of a 256 x 16 destination tile, from the tap formula s(d) = floor((d + 0.5) * scale - 0.5).
+static ResizeTile resize_tile(const LevelPlan& S, const LevelPlan& D) {
+  const double sx = (double)S.w / D.w, sy = (double)S.h / D.h;
+  // columns: up to 15 in front (aligned start), the taps of 256 pixels, the right tap, the 12-byte word window
+  const int need_w = 15 + (int)ceil((kRtCols - 1) * sx) + 2 + 12 + 1;
+  const int need_h = (int)ceil((kRtRows - 1) * sy) + 3;
+  ResizeTile t;
+  t.nbox = (need_w + 255) / 256;
+  t.box_w = round_up((need_w + t.nbox - 1) / t.nbox, 16);
+  t.box_h = need_h;
+  return t;
+}
+
 void launch_pyramid(const Plan& P, const FrameSet& fs, const ResizeTab* tab, int frames, cudaStream_t st) {
+  // tensor maps of the source levels 0 .. nlevels - 2; any level that cannot be described sends the whole chain to
+  // the LDG kernel (only a caller-owned level 0 with an odd base / pitch / frame stride can do that)
+  ResizeMaps M;
+  ResizeTile T[kMaxLevels];
+  bool tma = resize_encode_tiled() != nullptr && P.nlevels - 1 <= 8;
+  for (int l = 1; l < P.nlevels && tma; l++) {
+    const LevelPlan& S = P.lv[l - 1];
+    T[l] = resize_tile(S, P.lv[l]);
+    const uint8_t* base = l == 1 ? fs.lvl0 : fs.pyr + S.img_off;
+    const int64_t pitch = l == 1 ? fs.pitch0 : S.pitch;
+    int64_t fstride = l == 1 ? fs.fstride0 : fs.slab_fstride;
+    if (frames == 1) fstride = (pitch * S.h + 15) / 16 * 16;  // never applied
+    if (T[l].nbox > kRtMaxBoxes || T[l].box_h > 256 || kRtHead + T[l].nbox * round_up(T[l].box_w * T[l].box_h, 128) > 48 * 1024 || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) ||
+        (fstride & 15) || pitch <= 0 || fstride <= 0) {
+      tma = false;
+      break;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)S.w, (cuuint64_t)S.h, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {(cuuint32_t)T[l].box_w, (cuuint32_t)T[l].box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (resize_encode_tiled()(&M.lv[l - 1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      tma = false;
+  }
   for (int l = 1; l < P.nlevels; l++) {
     const LevelPlan& D = P.lv[l];
-    dim3 grid((D.pitch / 4 + kResizeThreads - 1) / kResizeThreads, (D.h + kResizeRows - 1) / kResizeRows, frames);
-    k_resize<<<grid, kResizeThreads, 0, st>>>(P, fs, tab, l);
+    if (tma) {
+      const size_t smem = kRtHead + (size_t)T[l].nbox * round_up(T[l].box_w * T[l].box_h, 128);
+      dim3 grid((D.pitch + kRtCols - 1) / kRtCols, (D.h + kRtRows - 1) / kRtRows, frames);
+      k_resize_tma<<<grid, kRtColThreads * kRtRowGroups, smem, st>>>(P, M, fs, tab, l, T[l].box_w, T[l].box_h, T[l].nbox);
+    } else {
+      dim3 grid((D.pitch / 4 + kResizeThreads - 1) / kResizeThreads, (D.h + kResizeRows - 1) / kResizeRows, frames);
+      k_resize<<<grid, kResizeThreads, 0, st>>>(P, fs, tab, l);
+    }
   }
 }
 
