@@ -156,16 +156,17 @@ k_resize(const __grid_constant__ Plan P, const FrameSet fs, const ResizeTab* __r
 // ---------------------------------------------------------------------------------------------------------------
 // TMA variant (the one that normally runs). The LDG kernel above is latency bound in the step (1.4 TB/s with ~16 KB of
 // loads in flight per SM, and removing a quarter of its instructions did not move its in-step time): here a block
-// first pulls the SOURCE rectangle its 256 x 16 destination tile needs into shared memory with cp.async.bulk.tensor
-// (nbox boxes of box_w x box_h bytes side by side, the first one starting at the 16-byte boundary below the first
-// tap — an unaligned innermost coordinate faults, tools/ubench/tma_probe.cu), so ~8 KB per resident block are in
-// flight without costing registers; the arithmetic is the same as above, reading 32-bit words from the tile.
+// first pulls the SOURCE rectangle its 128 x 32 destination tile needs into shared memory with ONE
+// cp.async.bulk.tensor box (box_w x box_h bytes, starting at the 16-byte boundary below the first tap — an unaligned
+// innermost coordinate faults, tools/ubench/tma_probe.cu), so ~8 KB per resident block are in flight without costing
+// registers; the arithmetic is the same as above, reading 32-bit words from the tile. Scale factors whose rectangle
+// is wider than the 256-byte box limit (> ~1.75) take the LDG kernel.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kRtColThreads = 64;   // x 4 destination columns = 256 per block
-constexpr int kRtRowGroups = 2;     // x kResizeRows destination rows = 16 per block
+constexpr int kRtColThreads = 32;   // x 4 destination columns = 128 per block: the source rectangle fits ONE box
+constexpr int kRtRowGroups = 4;     // x kResizeRows destination rows = 32 per block
 constexpr int kRtCols = kRtColThreads * 4, kRtRows = kRtRowGroups * kResizeRows;
 constexpr int kRtHead = 128;        // mbarrier in front of the tile
-constexpr int kRtMaxBoxes = 4;
+constexpr int kRtMaxBoxes = 1;
 
 struct ResizeMaps {
   CUtensorMap lv[8];  // u8 [frames][h][w] view of the SOURCE level l - 1 at index l - 1; box = (box_w, box_h, 1)
@@ -173,12 +174,12 @@ struct ResizeMaps {
 
 __global__ void __launch_bounds__(kRtColThreads * kRtRowGroups)
 k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps maps, const FrameSet fs,
-             const ResizeTab* __restrict__ tab, int l, int box_w, int box_h, int nbox) {
+             const ResizeTab* __restrict__ tab, int l, int box_w, int box_h) {
   extern __shared__ __align__(128) uint8_t smem[];
   const LevelPlan& D = P.lv[l];
   const LevelPlan& S = P.lv[l - 1];
   const int tx = threadIdx.x % kRtColThreads, tr = threadIdx.x / kRtColThreads;
-  const int dblock = blockIdx.x * kRtCols;  // < D.w: pitch is w rounded up to 64 and the tile is 256 wide
+  const int dblock = blockIdx.x * kRtCols;  // < D.w: pitch is w rounded up to 64, the tile width is a multiple of it
   const int d0 = dblock + tx * 4;
   const int yb = blockIdx.y * kRtRows;
   const int f = blockIdx.z;
@@ -188,21 +189,18 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
   auto clip = [&](int v) { return v < 0 ? 0 : (v > sh1 ? sh1 : v); };  // rows are clipped, the coefficients kept
   const int xa = xtab[dblock].ofs & ~15;
   const int ys0 = clip(ytab[yb].ofs);
-  const int box_bytes = box_w * box_h;
-  const int box_stride = (box_bytes + 127) & ~127;  // TMA destinations are 128-byte aligned
-  uint8_t* tile = smem + kRtHead;
+  uint8_t* tile = smem + kRtHead - xa;  // tile[c + row * box_w] = source column c of tile row `row`
   {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem);
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbox * box_bytes) : "memory");
-      for (int b = 0; b < nbox; b++)
-        asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"((uint32_t)__cvta_generic_to_shared(tile + b * box_stride)),
-            "l"(reinterpret_cast<uint64_t>(&maps.lv[l - 1])), "r"(xa + b * box_w), "r"(ys0), "r"(f), "r"(bar)
-            : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(box_w * box_h) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(smem + kRtHead)), "l"(reinterpret_cast<uint64_t>(&maps.lv[l - 1])),
+          "r"(xa), "r"(ys0), "r"(f), "r"(bar)
+          : "memory");
     }
     __syncthreads();
     uint32_t ok;
@@ -241,23 +239,12 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
     if (o < 0 || o + 1 > 7) fast = false;
     sel[k] = (uint32_t)(o & 7) | ((uint32_t)((o + 1) & 7) << 4) | 0x4400u;
   }
-  // tile address of source column c: boxes lie side by side, each box_h rows of box_w bytes
-  auto tcol = [&](int c) {
-    const int rel = c - xa, b = rel / box_w;
-    return tile + b * box_stride + (rel - b * box_w);
-  };
-  const uint8_t* pw[3] = {tcol(base), tcol(base + 4), tcol(base + 8)};  // words never straddle a box (box_w % 16 == 0)
-  const uint8_t* pb[8];
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    pb[2 * k] = tcol(s[k]);
-    pb[2 * k + 1] = tcol(s[k] + 1 < sw1 ? s[k] + 1 : sw1);
-  }
+  const uint8_t* pw = tile + base;
   auto hrow = [&](int sy, int (&h)[4]) {
     const int ro = (sy - ys0) * box_w;
     if (fast) {
-      const uint32_t w0 = *reinterpret_cast<const uint32_t*>(pw[0] + ro), w1 = *reinterpret_cast<const uint32_t*>(pw[1] + ro),
-                     w2 = *reinterpret_cast<const uint32_t*>(pw[2] + ro);
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(pw + ro);
+      const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
       const uint32_t a0 = __funnelshift_r(w0, w1, mis), a1 = __funnelshift_r(w1, w2, mis);
 #pragma unroll
       for (int k = 0; k < 4; k++)
@@ -265,7 +252,8 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
     } else {
 #pragma unroll
       for (int k = 0; k < 4; k++)
-        h[k] = ((int)pb[2 * k][ro] * (int)(coef[k] & 0xffff) + (int)pb[2 * k + 1][ro] * (int)(coef[k] >> 16)) >> 4;
+        h[k] = ((int)tile[ro + s[k]] * (int)(coef[k] & 0xffff) +
+                (int)tile[ro + (s[k] + 1 < sw1 ? s[k] + 1 : sw1)] * (int)(coef[k] >> 16)) >> 4;
     }
   };
   const int y_end = min(y_begin + kResizeRows, D.h);
@@ -319,15 +307,15 @@ static EncodeTiledFn resize_encode_tiled() {
 struct ResizeTile {
   int box_w, box_h, nbox;
 };
-// Source rectangle of a 256 x 16 destination tile, from the tap formula s(d) = floor((d + 0.5) * scale - 0.5).
+// Source rectangle of a kRtCols x kRtRows destination tile, from the tap formula s(d) = floor((d + 0.5) * scale - 0.5).
 static ResizeTile resize_tile(const LevelPlan& S, const LevelPlan& D) {
   const double sx = (double)S.w / D.w, sy = (double)S.h / D.h;
-  // columns: up to 15 in front (aligned start), the taps of 256 pixels, the right tap, the 12-byte word window
+  // columns: up to 15 in front (aligned start), the taps of the tile's pixels, the right tap, the 12-byte word window
   const int need_w = 15 + (int)ceil((kRtCols - 1) * sx) + 2 + 12 + 1;
   const int need_h = (int)ceil((kRtRows - 1) * sy) + 3;
   ResizeTile t;
   t.nbox = (need_w + 255) / 256;
-  t.box_w = round_up((need_w + t.nbox - 1) / t.nbox, 16);
+  t.box_w = round_up(need_w, 16);
   t.box_h = need_h;
   return t;
 }
@@ -345,7 +333,7 @@ void launch_pyramid(const Plan& P, const FrameSet& fs, const ResizeTab* tab, int
     const int64_t pitch = l == 1 ? fs.pitch0 : S.pitch;
     int64_t fstride = l == 1 ? fs.fstride0 : fs.slab_fstride;
     if (frames == 1) fstride = (pitch * S.h + 15) / 16 * 16;  // never applied
-    if (T[l].nbox > kRtMaxBoxes || T[l].box_h > 256 || kRtHead + T[l].nbox * round_up(T[l].box_w * T[l].box_h, 128) > 48 * 1024 || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) ||
+    if (T[l].nbox > kRtMaxBoxes || T[l].box_h > 256 || kRtHead + T[l].box_w * T[l].box_h > 48 * 1024 || (reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) ||
         (fstride & 15) || pitch <= 0 || fstride <= 0) {
       tma = false;
       break;
@@ -362,9 +350,9 @@ void launch_pyramid(const Plan& P, const FrameSet& fs, const ResizeTab* tab, int
   for (int l = 1; l < P.nlevels; l++) {
     const LevelPlan& D = P.lv[l];
     if (tma) {
-      const size_t smem = kRtHead + (size_t)T[l].nbox * round_up(T[l].box_w * T[l].box_h, 128);
+      const size_t smem = kRtHead + (size_t)T[l].box_w * T[l].box_h;
       dim3 grid((D.pitch + kRtCols - 1) / kRtCols, (D.h + kRtRows - 1) / kRtRows, frames);
-      k_resize_tma<<<grid, kRtColThreads * kRtRowGroups, smem, st>>>(P, M, fs, tab, l, T[l].box_w, T[l].box_h, T[l].nbox);
+      k_resize_tma<<<grid, kRtColThreads * kRtRowGroups, smem, st>>>(P, M, fs, tab, l, T[l].box_w, T[l].box_h);
     } else {
       dim3 grid((D.pitch / 4 + kResizeThreads - 1) / kResizeThreads, (D.h + kResizeRows - 1) / kResizeRows, frames);
       k_resize<<<grid, kResizeThreads, 0, st>>>(P, fs, tab, l);
