@@ -4,6 +4,8 @@
 //               one warp per keypoint, writing the final cv::KeyPoint record and descriptor row at its output row:
 //               levels ascending, "mono" rows from the front, rows whose scaled x lies in the lapping area from the
 //               back (:1083-1101) — the per-level ranks come from k_quadtree, the level offsets are summed here
+#include <cuda.h>  // CUtensorMap types; the encoder comes from cudaGetDriverEntryPoint
+
 #include "orbx_kernels.cuh"
 #include "orbx_quadtree.h"
 
@@ -23,18 +25,33 @@ namespace orbx {
 //    lanes of a row that touch the left / right image edge patch their window with three PRMTs whose selectors are
 //    computed once per task — no byte loads, no divergent slow path (the first version of this kernel spent 2/3 of
 //    its time in edge warps).
-// Level 0 is read in place from the caller's buffer: when its base or pitch is not word aligned the strip falls back
-// to byte loads for its window (same kernel, `aligned` false).
+// Where the words come from is the template parameter: kBlurTma (the normal case) — the warp's whole source rectangle
+// (160 x 38 bytes: the strip, a 3-row halo above and below, the aligned words left and right) is brought into shared
+// memory by ONE cp.async.bulk.tensor box per warp before the row loop, so the loop's loads are LDS and the bytes in
+// flight per SM (~6 KB per resident warp) no longer depend on registers (the LDG variant sat at 1.6 TB/s in the step,
+// stalled on its prefetch queue); kBlurLdg — the same loop on aligned global words; kBlurBytes — level 0 read in
+// place from a caller buffer whose base or pitch is not word aligned (byte loads).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBlurRows = 32;
 constexpr int kBlurWarps = 4;
 constexpr int kBlurAhead = 4;
+constexpr int kBlurBytes = 0, kBlurLdg = 1, kBlurTma = 2;
+constexpr int kBlurBoxW = 160, kBlurBoxH = kBlurRows + 6;             // bytes x rows per warp
+constexpr int kBlurTile = (kBlurBoxW * kBlurBoxH + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
+constexpr int kBlurHead = 128;                                        // one mbarrier per warp
+
+struct BlurMaps {
+  CUtensorMap lv[8];  // u8 [frames][h][w] view of every raw level; box = (160, 38, 1)
+};
 
 __device__ __forceinline__ int blur_strips_x(int w) { return (w + 127) >> 7; }
 __device__ __forceinline__ int blur_strips_y(int h) { return (h + kBlurRows - 1) / kBlurRows; }
 
-template <bool kAligned>
-__global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant__ Plan P, const FrameSet fs) {
+template <int kMode>
+__global__ void __launch_bounds__(kBlurWarps * 32)
+k_blur7(const __grid_constant__ Plan P, const __grid_constant__ BlurMaps maps, const FrameSet fs) {
+  constexpr bool kAligned = kMode != kBlurBytes;
+  extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   int t = blockIdx.x * kBlurWarps + (threadIdx.x >> 5);
   const int f = blockIdx.y;
@@ -51,6 +68,31 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
   const int ty = t / sx, tx = t - ty * sx;
   const int x = 4 * (tx * 32 + lane);
   const int y0 = ty * kBlurRows;
+  const uint32_t* tile32 = nullptr;
+  if constexpr (kMode == kBlurTma) {
+    // box origin: 16 bytes left of the strip (the lane's first word is x - 4; the start must be 16-byte aligned) and 3
+    // rows above it; everything outside the level — including negative coordinates — arrives as zeros
+    const int warp = threadIdx.x >> 5;
+    uint8_t* tile = smem + kBlurHead + warp * kBlurTile;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem + 8 * warp);
+    if (lane == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kBlurBoxW * kBlurBoxH) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+          ::"r"((uint32_t)__cvta_generic_to_shared(tile)), "l"(reinterpret_cast<uint64_t>(&maps.lv[l])),
+          "r"(128 * tx - 16), "r"(y0 - 3), "r"(f), "r"(bar)
+          : "memory");
+    }
+    __syncwarp();
+    uint32_t ok;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar) : "memory");
+    } while (!ok);
+    tile32 = reinterpret_cast<const uint32_t*>(tile) + lane + 3;  // word of column x - 4 in tile row 0
+  }
   if (x >= w) return;
   int pitch;
   const uint8_t* src = raw_level(P, fs, l, f, &pitch);
@@ -95,6 +137,13 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
   auto fetch = [&](int r, uint32_t (&o)[3]) {
     const int v = abs(min(y0 - 3 + r, h + 2));
     const int ys = min(v, h2 - v);  // reflect-101 of a row in [-3, h + 2], branch free
+    if constexpr (kMode == kBlurTma) {
+      const uint32_t* r32 = tile32 + (ys - (y0 - 3)) * (kBlurBoxW / 4);
+      o[0] = r32[0];
+      o[1] = r32[1];
+      o[2] = r32[2];
+      return;
+    }
     const uint8_t* row = src + (int64_t)ys * pitch;
     if (kAligned) {
       const uint32_t* r32 = reinterpret_cast<const uint32_t*>(srcx + (int64_t)ys * pitch);
@@ -156,14 +205,58 @@ __global__ void __launch_bounds__(kBlurWarps * 32) k_blur7(const __grid_constant
   }
 }
 
+typedef CUresult (*BlurEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_blur_maps(const Plan& P, const FrameSet& fs, int frames, BlurMaps* M) {
+  static BlurEncodeFn enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<BlurEncodeFn>(p);
+  }();
+  if (!enc || P.nlevels > 8) return false;
+  for (int l = 0; l < P.nlevels; l++) {
+    const uint8_t* base = l == 0 ? fs.lvl0 : fs.pyr + P.lv[l].img_off;
+    const int64_t pitch = l == 0 ? fs.pitch0 : P.lv[l].pitch;
+    int64_t fstride = l == 0 ? fs.fstride0 : fs.slab_fstride;
+    if (frames == 1) fstride = (pitch * P.lv[l].h + 15) / 16 * 16;  // never applied
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (pitch & 15) || (fstride & 15) || pitch <= 0 || fstride <= 0)
+      return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P.lv[l].w, (cuuint64_t)P.lv[l].h, (cuuint64_t)frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {(cuuint32_t)kBlurBoxW, (cuuint32_t)kBlurBoxH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (enc(&M->lv[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st) {
   int tasks = 0;
   for (int l = 0; l < P.nlevels; l++) tasks += ((P.lv[l].w + 127) / 128) * ((P.lv[l].h + kBlurRows - 1) / kBlurRows);
   dim3 grid((tasks + kBlurWarps - 1) / kBlurWarps, frames);
+  BlurMaps M;
+  if (make_blur_maps(P, fs, frames, &M)) {
+    static const bool carve = [] {
+      cudaFuncSetAttribute(k_blur7<kBlurTma>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      return true;
+    }();
+    (void)carve;
+    k_blur7<kBlurTma><<<grid, kBlurWarps * 32, kBlurHead + kBlurWarps * kBlurTile, st>>>(P, M, fs);
+    return;
+  }
+  memset(&M, 0, sizeof(M));
   // levels >= 1 are owned buffers (256-byte aligned, pitch multiple of 64); level 0 is the caller's
   const bool aligned = ((reinterpret_cast<uintptr_t>(fs.lvl0) | (uintptr_t)fs.pitch0 | (uintptr_t)fs.fstride0) & 3) == 0;
-  if (aligned) k_blur7<true><<<grid, kBlurWarps * 32, 0, st>>>(P, fs);
-  else k_blur7<false><<<grid, kBlurWarps * 32, 0, st>>>(P, fs);
+  if (aligned) k_blur7<kBlurLdg><<<grid, kBlurWarps * 32, 0, st>>>(P, M, fs);
+  else k_blur7<kBlurBytes><<<grid, kBlurWarps * 32, 0, st>>>(P, M, fs);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
