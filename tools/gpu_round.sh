@@ -11,17 +11,14 @@ BENCH="python bench.py --steps 2 --warmup 3 --pairs 64 --no-cpu"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 60 --csv \
     --log-file gpurun_out/launches_$TAG.csv $BENCH > gpurun_out/ncu_list_$TAG.log 2>&1
 if [ "$2" = "full" ]; then
-  # one full-set capture per kernel family (ncu replays every kernel ~40x: keep the counts small)
-  timeout 600 ncu --set full --clock-control none --import-source on \
-      -k 'regex:k_fast|k_quadtree|k_describe|k_stereo_match|k_stereo_median|k_blur7' -s 20 -c 6 -f -o /tmp/prof_a_$TAG \
-      $BENCH > gpurun_out/ncu_a_$TAG.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_resize' -s 28 -c 7 -f \
-      -o /tmp/prof_b_$TAG $BENCH > gpurun_out/ncu_b_$TAG.log 2>&1
-  for x in a b; do
-    ncu -i /tmp/prof_${x}_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${x}_${TAG}_raw.csv 2>/dev/null
-    sz=$(stat -c %s /tmp/prof_${x}_$TAG.ncu-rep 2>/dev/null || echo 0)
-    echo "prof_$x size $sz"
-    if [ "$sz" -gt 0 ] && [ "$sz" -lt 30000000 ]; then cp /tmp/prof_${x}_$TAG.ncu-rep gpurun_out/; fi
-  done
+  # one full-set capture of every launch of ONE step (the first 24 launches are the 2-pair parity check): 2 extract
+  # calls x (7 k_resize_tma + k_fast + k_quadtree + k_blur7 + k_describe) + k_stereo_match + k_stereo_median
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k 'regex:k_fast|k_quadtree|k_describe|k_stereo_match|k_stereo_median|k_blur7|k_resize' -s 24 -c 24 -f \
+      -o /tmp/prof_$TAG $BENCH > gpurun_out/ncu_full_$TAG.log 2>&1
+  ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
+  sz=$(stat -c %s /tmp/prof_$TAG.ncu-rep 2>/dev/null || echo 0)
+  echo "prof size $sz"
+  if [ "$sz" -gt 0 ] && [ "$sz" -lt 40000000 ]; then cp /tmp/prof_$TAG.ncu-rep gpurun_out/; fi
 fi
 du -sh gpurun_out
