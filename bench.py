@@ -335,13 +335,28 @@ def main():
         "quadtree": 8 * C + 4 * Nk}
     dur_ms = stage_ms[dom] / max(stage_cnt[dom] * 2, 1)   # per extract call (one batch of P frames)
     achieved = alg_bytes_per_frame[dom] * P / (dur_ms * 1e-3) / 1e9
+    # measured DRAM traffic of that kernel (ncu --set full capture summarised by tools/profile_digest.py), per launch
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["stages"][dom]["dram_bytes_per_frame"] * P
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes_per_frame[dom] * P,
+                "peak_source": peak_src,
                 "ms_per_launch_group": dur_ms, "algorithmic_bytes_per_frame": alg_bytes_per_frame[dom],
                 "frames_per_launch": P,
                 "note": "FAST / quadtree are integer-ALU / latency bound, not HBM bound (SURVEY.md §8d); the HBM "
                         "fraction is reported as the contract asks, the ALU analysis is in DESIGN.md",
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                # the same quotient for every stage: algorithmic GB/s (SURVEY §8d bytes) and its fraction of the peak
+                "stage_gbs": {k: round(alg_bytes_per_frame[k] * frames_per_step / world * args.steps / (v * 1e-3) / 1e9, 1)
+                              for k, v in stage_ms.items() if v > 0 and k in alg_bytes_per_frame},
+                "stage_frac": {k: round(alg_bytes_per_frame[k] * frames_per_step / world * args.steps / (v * 1e-3) / 1e9 / peak, 4)
+                               for k, v in stage_ms.items() if v > 0 and k in alg_bytes_per_frame}}
 
     # ---- end to end through the host-facing ABI (pinned buffers; H2D + D2H inside the timed region) ----
     def pinned(shape, dtype):

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Turns one `ncu --set full` capture of a bench step (tools/gpu_round.sh <tag> full -> gpurun_out/prof_<tag>_raw.csv) into
+the two files that are committed under profiles/:
+
+  profiles/r01_<tag>_ncu_summary.txt   one block per launch (tools/ncu_summary.py) + a per-stage table
+  profiles/traffic.json                measured DRAM bytes per frame and launch time of every stage's kernels;
+                                       bench.py reads it for `roofline.traffic` (per launch, like `achieved`)
+
+Usage: python tools/profile_digest.py <tag> [frames_per_launch=64]
+"""
+import csv
+import io
+import json
+import os
+import sys
+from contextlib import redirect_stdout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import ncu_summary  # noqa: E402
+
+STAGE = {"k_resize": "pyramid", "k_resize_tma": "pyramid", "k_fast": "fast", "k_quadtree": "quadtree", "k_blur7": "blur",
+         "k_describe": "describe", "k_stereo_match": "stereo", "k_stereo_median": "stereo"}
+
+
+def num(v):
+    return float(v.replace(",", ""))
+
+
+def main(tag, frames):
+    raw = os.path.join(ROOT, "gpurun_out", "prof_%s_raw.csv" % tag)
+    rows = list(csv.reader(open(raw)))
+    h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+    hdr, units = rows[h], rows[h + 1]
+    col = {k: hdr.index(k) for k in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum",
+                                     "dram__bytes_write.sum", "Grid Size")}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[col["gpu__time_duration.sum"]]]
+    agg = {}
+    seen_calls = 0
+    for r in rows[h + 2:]:
+        if len(r) != len(hdr):
+            continue
+        name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].replace("orbx::", "")
+        st = STAGE.get(name)
+        if st is None:
+            continue
+        if seen_calls >= 1 and st != "stereo":
+            continue  # one extract call (left eye) is enough; the second repeats it
+        if name == "k_describe":
+            seen_calls += 1  # k_describe is the last kernel of an extract call
+        a = agg.setdefault(st, {"kernel": name, "launches": 0, "time_us": 0.0, "dram_bytes": 0.0})
+        a["launches"] += 1
+        a["time_us"] += num(r[col["gpu__time_duration.sum"]]) * tscale
+        a["dram_bytes"] += num(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]] + \
+            num(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]]
+    out = {"source": "profiles/r01_%s_ncu_summary.txt (ncu --set full, %d frames per launch, cold cache, serialised)" % (tag, frames),
+           "frames_per_launch": frames, "stages": {}}
+    for st, a in agg.items():
+        per = frames if st != "stereo" else frames  # stereo: pairs per launch == frames per eye launch
+        out["stages"][st] = {"kernel": a["kernel"], "launches_per_call": a["launches"], "time_us_per_call": round(a["time_us"], 2),
+                             "dram_bytes_per_frame": round(a["dram_bytes"] / per, 1)}
+    os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        print("# ncu --set full --clock-control none, one bench step at %d pairs per step (tools/gpu_round.sh %s full)" % (frames, tag))
+        print("# per-stage totals of one extract call (+ the stereo kernels of the pair batch):")
+        for st, a in out["stages"].items():
+            print("#   %-9s %-16s launches %d  %8.1f us  DRAM %10.0f B/frame" % (st, a["kernel"], a["launches_per_call"],
+                                                                               a["time_us_per_call"], a["dram_bytes_per_frame"]))
+        ncu_summary.main(raw)
+    open(os.path.join(ROOT, "profiles", "r01_%s_ncu_summary.txt" % tag), "w").write(buf.getvalue())
+    print(json.dumps(out["stages"], indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 64)
