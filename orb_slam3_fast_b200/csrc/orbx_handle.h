@@ -14,7 +14,7 @@
 
 #include "orbx_kernels.cuh"
 
-enum { kStages = 5, kLanes = 3 };
+enum { kStages = 5, kLanes = 4 };
 
 struct OrbxLane {
   cudaStream_t stream = nullptr;
