@@ -82,6 +82,25 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
 int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, const orbx_mappoints* mps, float th,
                                   float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches);
 
+/* void Frame::AssignFeaturesToGrid() with bool Frame::PosInGrid(const cv::KeyPoint&, int&, int&) (include/Frame.h:107,
+ * 263; src/Frame.cc:520-547, 833-844), Nleft == -1: the 64x48 lookup grid of mvKeysUn as CSR (orbx_grid layout: cell
+ * id = col * 48 + row, ascending keypoint indices inside a cell). SURVEY.md §8(f) rank 1 — the step immediately
+ * before SearchByProjection. kps[n] (host) -> cell_offsets[64*48 + 1], cell_items[n] (host; the first
+ * cell_offsets[64*48] entries are used). */
+int orbm_assign_features_to_grid(orbm_matcher* m, const orbx_kp* kps, int n, float min_x, float min_y, float inv_w,
+                                 float inv_h, int32_t* cell_offsets, int32_t* cell_items);
+
+/* orbm_search_by_projection_map on a frame that never left the device: frame `frame` of the extractor's most recent
+ * host-facing call (orbx_extract / orbx_extract_batch; n = the keypoint count that call returned). Keypoints and
+ * descriptors are read from the extractor's device outputs, the lookup grid is built on the device
+ * (Frame::AssignFeaturesToGrid, as above) and mvScaleFactors come from the extractor. Valid for an undistorted camera,
+ * where Frame::UndistortKeyPoints leaves mvKeysUn = mvKeys (src/Frame.cc:562-571). u_right[n] (mvuRight) and
+ * occupied[n] are host arrays and may be NULL (monocular / no keypoint holds a MapPoint yet). */
+int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,
+                                           const float* u_right, const uint8_t* occupied, float min_x, float min_y,
+                                           float inv_w, float inv_h, const orbx_mappoints* mps, float th, float nnratio,
+                                           int far_points, float th_far, int32_t* assign, int32_t* nmatches);
+
 /* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
  * (src/ORBmatcher.cc:1594-1806) and (Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (:1808-1918), after the
  * caller-side SE3 projection (orbx_projected). max_dist = TH_HIGH or ORBdist; check_orientation = mbCheckOrientation.

@@ -245,125 +245,153 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
   return bin;
 }
 
-__global__ void __launch_bounds__(32)
+// The greedy, order-dependent part of the searches (src/ORBmatcher.cc:92-93, :130, :1672-1674): point i may only take a
+// keypoint that no EARLIER accepted point with observations has taken. Restated as a fixed point: let T[k] be the
+// lowest index of an accepted point with observations whose choice is keypoint k; then keypoint k is closed for point
+// i iff it was occupied to begin with or T[k] < i, and point i's decision is a pure function of T. Every round
+// evaluates all points in parallel against the previous round's T and rebuilds T from the decisions; a decision that
+// only depends on lower, already final, decisions is final, so by induction on the index the iteration reaches the
+// serial result — and that is its only fixed point — after at most (longest dependency chain) rounds: 3-8 on the
+// test maps, where the one-warp serial replay this replaces spent 2.1 ms on 10 000 points. One CTA; T lives in shared
+// memory; a point whose two precomputed best candidates are both still open needs no rescan.
+constexpr int kResolveThreads = 1024;
+
+struct Decision {
+  int idx;    // chosen keypoint, or -1
+  float ang;  // its angle (mode 1 with the rotation check)
+};
+
+__device__ __forceinline__ Decision resolve_point(const DevFrame& F, const SearchScratch& S, const ResolveArgs& R, int i,
+                                                  const int* T, const uint8_t* occ0, bool rot) {
+  Decision out{-1, 0.f};
+  const int off = S.counts[i], cnt = S.counts[i + 1] - off;
+  if (cnt == 0) return out;
+  const int4 p = S.pre[i];
+  auto closed = [&](int k) { return occ0[k] || T[k] < i; };
+  const int k1 = p.y >= 0 ? S.cand_idx[off + p.y] : -1, k2 = p.w >= 0 ? S.cand_idx[off + p.w] : -1;
+  int bestDist, bestDist2, bestIdx, bestLevel, bestLevel2;
+  if (!((k1 >= 0 && closed(k1)) || (k2 >= 0 && closed(k2)))) {
+    // both precomputed best candidates are still open: the filtered search would find the same two
+    if (k1 < 0) return out;
+    bestDist = p.x;
+    bestIdx = k1;
+    bestLevel = S.cand_dist[off + p.y] >> 16;
+    bestDist2 = k2 >= 0 ? p.z : 256;
+    bestLevel2 = k2 >= 0 ? (S.cand_dist[off + p.w] >> 16) : -1;
+  } else {
+    Top2 t{0, -1, 0, -1};
+    for (int c = 0; c < cnt; c++)
+      if (!closed(S.cand_idx[off + c])) top2_insert(t, S.cand_dist[off + c] & 0xffff, c);
+    if (t.p1 < 0) return out;  // every candidate already taken
+    bestDist = t.d1;
+    bestIdx = S.cand_idx[off + t.p1];
+    bestLevel = S.cand_dist[off + t.p1] >> 16;
+    bestDist2 = t.p2 >= 0 ? t.d2 : 256;
+    bestLevel2 = t.p2 >= 0 ? (S.cand_dist[off + t.p2] >> 16) : -1;
+  }
+  bool accept;
+  if (R.mode == 0)
+    accept = bestDist <= ORBM_TH_HIGH_I &&
+             !(bestLevel == bestLevel2 && (float)bestDist > fmul(R.nnratio, (float)bestDist2));  // :124-129
+  else
+    accept = bestDist <= R.max_dist;  // :1699 / :1897
+  if (!accept) return out;
+  out.idx = bestIdx;
+  if (rot) out.ang = F.kps[bestIdx].angle;
+  return out;
+}
+
+__global__ void __launch_bounds__(kResolveThreads)
 k_search_resolve(const DevFrame F, const DevQueries Q, const SearchScratch S, const ResolveArgs R) {
-  extern __shared__ uint8_t occ[];  // [n] then (aligned) int histo[32]
-  const int lane = threadIdx.x;
-  const int n = F.n;
-  int* histo = reinterpret_cast<int*>(occ + ((n + 15) / 16) * 16);
-  for (int k = lane; k < n; k += 32) {
-    occ[k] = F.occupied[k];
+  extern __shared__ __align__(16) uint8_t rs_smem[];  // int T[n] | int histo[32] | int flag, count | u8 occ0[n]
+  const int n = F.n, M = Q.m, tid = threadIdx.x;
+  int* T = reinterpret_cast<int*>(rs_smem);
+  int* histo = T + n;
+  int* flag = histo + 32;
+  int* count = flag + 1;
+  uint8_t* occ0 = reinterpret_cast<uint8_t*>(count + 1);
+  const bool rot = R.mode == 1 && R.check_orientation;
+  for (int k = tid; k < n; k += kResolveThreads) {
+    T[k] = 0x7fffffff;
+    occ0[k] = F.occupied[k];
     R.assign[k] = -1;
   }
-  histo[lane] = 0;
-  __syncwarp();
-  const int32_t* offsets = S.counts;
-  const bool rot = R.mode == 1 && R.check_orientation;
-  int nmatches = 0, nevents = 0;
-  for (int base = 0; base < Q.m; base += 32) {
-    // ---- every lane prefetches one point's precomputed record (hides the global-memory latency) ----
-    const int i = base + lane;
-    int off = 0, cnt = 0, hobs = 0, k1 = -1, k2 = -1, l1 = -1, l2 = -1;
-    int4 p = make_int4(0, -1, 0, -1);
-    float ang_q = 0.f, ang_k1 = 0.f;
-    if (i < Q.m) {
-      off = offsets[i];
-      cnt = offsets[i + 1] - off;
-      p = S.pre[i];
-      hobs = R.has_obs[i];
-      if (cnt > 0 && p.y >= 0) {
-        k1 = S.cand_idx[off + p.y];
-        l1 = S.cand_dist[off + p.y] >> 16;
-      }
-      if (cnt > 0 && p.w >= 0) {
-        k2 = S.cand_idx[off + p.w];
-        l2 = S.cand_dist[off + p.w] >> 16;
-      }
-      if (rot) {
-        ang_q = R.angle[i];
-        if (k1 >= 0) ang_k1 = F.kps[k1].angle;
+  for (int i = tid; i < M; i += kResolveThreads) R.dec[i] = -1;
+  if (tid < 32) histo[tid] = 0;
+  if (tid == 0) *count = 0;
+  __syncthreads();
+  for (int round = 0; round <= M; round++) {
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+    bool changed = false;
+    for (int i = tid; i < M; i += kResolveThreads) {
+      const int d = resolve_point(F, S, R, i, T, occ0, false).idx;
+      if (d != R.dec[i]) {
+        R.dec[i] = d;
+        changed = true;
       }
     }
-    const int lim = min(32, Q.m - base);
-    for (int j = 0; j < lim; j++) {
-      const int cj = __shfl_sync(0xffffffffu, cnt, j);
-      if (cj == 0) continue;
-      int dirty = 0;
-      if (lane == j) dirty = (k1 >= 0 && occ[k1]) || (k2 >= 0 && occ[k2]);
-      dirty = __shfl_sync(0xffffffffu, dirty, j);
-      int bestDist, bestDist2, bestIdx, bestLevel, bestLevel2;
-      float ang_k;
-      if (!dirty) {
-        // both precomputed best candidates are still free: the filtered search would find the same two
-        bestDist = __shfl_sync(0xffffffffu, p.x, j);
-        bestDist2 = __shfl_sync(0xffffffffu, p.z, j);
-        bestIdx = __shfl_sync(0xffffffffu, k1, j);
-        bestLevel = __shfl_sync(0xffffffffu, l1, j);
-        bestLevel2 = __shfl_sync(0xffffffffu, l2, j);
-        ang_k = __shfl_sync(0xffffffffu, ang_k1, j);
-        if (__shfl_sync(0xffffffffu, k2, j) < 0) bestDist2 = 256;
-      } else {
-        const int oj = __shfl_sync(0xffffffffu, off, j);
-        Top2 t{0, -1, 0, -1};
-        for (int c = lane; c < cj; c += 32)
-          if (!occ[S.cand_idx[oj + c]]) top2_insert(t, S.cand_dist[oj + c] & 0xffff, c);
-        t = top2_warp(t);
-        if (t.p1 < 0) continue;  // every candidate already taken
-        bestDist = t.d1;
-        bestIdx = S.cand_idx[oj + t.p1];
-        bestLevel = S.cand_dist[oj + t.p1] >> 16;
-        bestDist2 = t.p2 >= 0 ? t.d2 : 256;
-        bestLevel2 = t.p2 >= 0 ? (S.cand_dist[oj + t.p2] >> 16) : -1;
-        ang_k = rot ? F.kps[bestIdx].angle : 0.f;
-      }
-      bool accept;
-      if (R.mode == 0)
-        accept = bestDist <= ORBM_TH_HIGH_I &&
-                 !(bestLevel == bestLevel2 && (float)bestDist > fmul(R.nnratio, (float)bestDist2));  // :124-129
-      else
-        accept = bestDist <= R.max_dist;  // :1699 / :1897
-      if (!accept) continue;
-      const int ho = __shfl_sync(0xffffffffu, hobs, j);
-      const float aq = __shfl_sync(0xffffffffu, ang_q, j);
-      if (lane == 0) {
-        R.assign[bestIdx] = base + j;   // F.mvpMapPoints[bestIdx] = pMP                :130
-        occ[bestIdx] = (uint8_t)ho;     // a point with observations blocks the keypoint :92-93
-        if (rot) {
-          const int bin = rot_bin(aq, ang_k);
-          R.events[2 * nevents] = bestIdx;
-          R.events[2 * nevents + 1] = bin;
-          histo[bin]++;
-        }
-      }
-      nevents++;
-      nmatches++;
-      __syncwarp();
+    if (changed) *flag = 1;
+    __syncthreads();
+    if (*flag == 0) break;  // fixed point: every decision equals the serial one
+    for (int k = tid; k < n; k += kResolveThreads) T[k] = 0x7fffffff;
+    __syncthreads();
+    for (int i = tid; i < M; i += kResolveThreads) {
+      const int d = R.dec[i];
+      if (d >= 0 && R.has_obs[i]) atomicMin(&T[d], i);  // a point with observations blocks the keypoint :92-93
+    }
+    __syncthreads();
+  }
+  // ---- F.mvpMapPoints[bestIdx] = pMP (:130): the LAST accepted point that chose a keypoint stays; nmatches counts
+  //      every acceptance; mode 1 also files every acceptance in the rotation histogram (:1757-1768) ----
+  int mine = 0;
+  for (int i = tid; i < M; i += kResolveThreads) {
+    const int d = R.dec[i];
+    if (d < 0) continue;
+    atomicMax(&R.assign[d], i);
+    mine++;
+    if (rot) {
+      const int bin = rot_bin(R.angle[i], F.kps[d].angle);
+      const int e = atomicAdd(count, 1);
+      R.events[2 * e] = d;
+      R.events[2 * e + 1] = bin;
+      atomicAdd(&histo[bin], 1);
     }
   }
-  __syncwarp();
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  __shared__ int warp_sum[kResolveThreads / 32];
+  if ((tid & 31) == 0) warp_sum[tid >> 5] = mine;
+  __syncthreads();
+  int nmatches = 0;
+  for (int w = 0; w < kResolveThreads / 32; w++) nmatches += warp_sum[w];
   if (rot) {
     int ind1, ind2, ind3;
-    three_maxima(histo, kHistoLength, ind1, ind2, ind3);  // every lane computes the same
+    three_maxima(histo, kHistoLength, ind1, ind2, ind3);  // every thread computes the same
+    const int nevents = *count;
+    __syncthreads();
+    if (tid == 0) *count = 0;
+    __syncthreads();
     int removed = 0;
-    for (int e = lane; e < nevents; e += 32) {
+    for (int e = tid; e < nevents; e += kResolveThreads) {
       const int bin = R.events[2 * e + 1];
       if (bin != ind1 && bin != ind2 && bin != ind3) {
         R.assign[R.events[2 * e]] = -1;  // :1795-1800
         removed++;
       }
     }
-    removed = __reduce_add_sync(0xffffffffu, removed);
-    nmatches -= removed;
+    if (removed) atomicAdd(count, removed);
+    __syncthreads();
+    nmatches -= *count;
   }
-  if (lane == 0) *R.nmatches = nmatches;
+  if (tid == 0) *R.nmatches = nmatches;
 }
 
 void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, const ResolveArgs& R,
                            cudaStream_t st) {
-  const size_t smem = ((size_t)(F.n + 15) / 16) * 16 + 32 * sizeof(int);
+  const size_t smem = (size_t)F.n * 4 + 34 * 4 + ((size_t)F.n + 15) / 16 * 16;
   cudaFuncSetAttribute(k_search_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(smem > 48 * 1024 ? smem : 48 * 1024));
-  k_search_resolve<<<1, 32, smem, st>>>(F, Q, S, R);
+  k_search_resolve<<<1, kResolveThreads, smem, st>>>(F, Q, S, R);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -479,6 +507,79 @@ void launch_triangulation(const TriArgs& A, cudaStream_t st) {
     k_tri_match<<<(A.k1.n_nodes + 63) / 64, 64, 0, st>>>(A);
   }
   k_tri_rot<<<1, 256, 0, st>>>(A);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame::AssignFeaturesToGrid + Frame::PosInGrid (src/Frame.cc:520-547, :833-844), Nleft == -1: the 64x48 lookup grid
+// as CSR, cell id = col * 48 + row, keypoint indices ascending inside a cell (push_back order of the serial loop).
+// One warp per frame: histogram in shared memory, warp scan over the 3072 cells, then the keypoints are placed in
+// index order 32 at a time — lanes that fall into the same cell find each other with match.any and take consecutive
+// slots, which keeps every cell's list ascending.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_cell(const orbx_kp& kp, float min_x, float min_y, float inv_w, float inv_h) {
+  const int px = (int)roundf(fmul(fsub(kp.x, min_x), inv_w));  // round(): half away from zero              :836-837
+  const int py = (int)roundf(fmul(fsub(kp.y, min_y), inv_h));
+  if (px < 0 || px >= ORBX_GRID_COLS || py < 0 || py >= ORBX_GRID_ROWS) return -1;  //                        :840-841
+  return px * ORBX_GRID_ROWS + py;
+}
+
+__global__ void __launch_bounds__(32)
+k_build_grid(const orbx_kp* __restrict__ kps, const int32_t* __restrict__ n_ptr, int n_fixed, int64_t kp_stride,
+             float min_x, float min_y, float inv_w, float inv_h, int32_t* __restrict__ offsets,
+             int32_t* __restrict__ items, int64_t item_stride) {
+  constexpr int kCells = ORBX_GRID_COLS * ORBX_GRID_ROWS, kPerLane = kCells / 32;
+  __shared__ int32_t cur[kCells];
+  const int lane = threadIdx.x, f = blockIdx.x;
+  const int n = n_ptr ? n_ptr[f] : n_fixed;
+  kps += f * kp_stride;
+  offsets += (int64_t)f * (kCells + 1);
+  items += f * item_stride;
+  for (int c = lane; c < kCells; c += 32) cur[c] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int c = grid_cell(kps[i], min_x, min_y, inv_w, inv_h);
+    if (c >= 0) atomicAdd(&cur[c], 1);
+  }
+  __syncwarp();
+  // exclusive scan: lane k owns cells [96k, 96k + 96)
+  int sum = 0;
+  for (int c = 0; c < kPerLane; c++) sum += cur[lane * kPerLane + c];
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  int run = incl - sum;
+  for (int c = 0; c < kPerLane; c++) {
+    const int k = lane * kPerLane + c, cnt = cur[k];
+    offsets[k] = run;
+    cur[k] = run;  // becomes the cell's write cursor
+    run += cnt;
+  }
+  if (lane == 31) offsets[kCells] = run;
+  __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const int c = i < n ? grid_cell(kps[i], min_x, min_y, inv_w, inv_h) : -1;
+    const unsigned same = __match_any_sync(0xffffffffu, c);
+    int pos = 0;
+    if (c >= 0) pos = cur[c];
+    __syncwarp();
+    if (c >= 0) {
+      items[pos + __popc(same & lt)] = i;
+      if ((same & lt) == 0u) cur[c] = pos + __popc(same);  // the group's first lane moves the cursor
+    }
+    __syncwarp();
+  }
+}
+
+void launch_build_grid(const orbx_kp* kps, const int32_t* n_ptr, int n_fixed, int64_t kp_stride, int frames, float min_x,
+                       float min_y, float inv_w, float inv_h, int32_t* offsets, int32_t* items, int64_t item_stride,
+                       cudaStream_t st) {
+  k_build_grid<<<frames, 32, 0, st>>>(kps, n_ptr, n_fixed, kp_stride, min_x, min_y, inv_w, inv_h, offsets, items,
+                                      item_stride);
 }
 
 }  // namespace orbx

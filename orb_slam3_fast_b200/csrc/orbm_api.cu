@@ -163,6 +163,7 @@ int run_search(orbm_matcher* m, Arena& ar, const DevFrame& F, const DevQueries& 
   R.assign = ar.alloc<int32_t>(n);
   R.nmatches = ar.alloc<int32_t>(1);
   R.events = ar.alloc<int32_t>(2 * (size_t)Q.m);
+  R.dec = ar.alloc<int32_t>(Q.m);
   R.occ = nullptr;
   if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   int32_t total = 0;
@@ -497,14 +498,14 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
   return ORBX_OK;
 }
 
-int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, const orbx_mappoints* mps, float th,
-                                  float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
-  if (!m || !f || !mps || f->n < 0 || mps->m < 0 || (f->n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
-  if (nmatches) *nmatches = 0;
-  ORBM_CUDA(m, cudaSetDevice(m->device));
+namespace {
+// The part of SearchByProjection(Frame&, vector<MapPoint*>) that does not depend on where the frame lives: the scalar
+// prologue of the reference loop (:55-74) — which points take part, the search radius
+// r = RadiusByViewingCos(viewCos) * th * scale[level] (:65-67, :223-228), the level window [L-1, L] — then the search.
+int search_map_common(orbm_matcher* m, Arena& ar, const DevFrame& F, const float* scale_factors, int n_levels,
+                      bool has_u_right, const orbx_mappoints* mps, float th, float nnratio, int far_points,
+                      float th_far, int n, int32_t* assign, int32_t* nmatches) {
   const int M = mps->m;
-  // per-point query set-up = the scalar prologue of the reference loop (:55-74): which points take part, the search
-  // radius r = RadiusByViewingCos(viewCos) * th * scale[level] (:65-67, :223-228) and the level window [L-1, L].
   std::vector<uint8_t> active(std::max(M, 1));
   std::vector<float> radius(std::max(M, 1));
   std::vector<int32_t> minl(std::max(M, 1)), maxl(std::max(M, 1));
@@ -513,16 +514,14 @@ int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, con
     bool on = mps->track_in_view[i] != 0;
     if (on && far_points && mps->depth[i] > th_far) on = false;
     const int level = mps->level[i];
-    if (on && (level < 0 || level >= f->n_levels)) on = false;
+    if (on && (level < 0 || level >= n_levels)) on = false;
     active[i] = on;
     float r = ((double)mps->view_cos[i] > 0.998) ? 2.5f : 4.0f;
     if (bFactor) r *= th;
-    radius[i] = on ? r * f->scale_factors[level] : 0.f;
+    radius[i] = on ? r * scale_factors[level] : 0.f;
     minl[i] = level - 1;
     maxl[i] = level;
   }
-  Arena ar(m);
-  const DevFrame F = upload_frame(ar, f);
   DevQueries Q{};
   Q.m = M;
   Q.active = ar.upload(active.data(), M);
@@ -531,7 +530,7 @@ int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, con
   Q.radius = ar.upload(radius.data(), M);
   Q.min_level = ar.upload(minl.data(), M);
   Q.max_level = ar.upload(maxl.data(), M);
-  Q.u_right = f->u_right ? ar.upload(mps->proj_xr, M) : (ar.alloc<float>(1), nullptr);
+  Q.u_right = has_u_right ? ar.upload(mps->proj_xr, M) : (ar.alloc<float>(1), nullptr);
   Q.desc = ar.upload(mps->desc, (size_t)M * 32);
   ResolveArgs R{};
   R.mode = 0;
@@ -541,7 +540,81 @@ int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, con
   R.has_obs = ar.upload(mps->has_obs, M);
   R.angle = nullptr;
   if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
-  return run_search(m, ar, F, Q, R, f->n, assign, nmatches);
+  return run_search(m, ar, F, Q, R, n, assign, nmatches);
+}
+}  // namespace
+
+int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, const orbx_mappoints* mps, float th,
+                                  float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
+  if (!m || !f || !mps || f->n < 0 || mps->m < 0 || (f->n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const DevFrame F = upload_frame(ar, f);
+  return search_map_common(m, ar, F, f->scale_factors, f->n_levels, f->u_right != nullptr, mps, th, nnratio, far_points,
+                           th_far, f->n, assign, nmatches);
+}
+
+int orbm_assign_features_to_grid(orbm_matcher* m, const orbx_kp* kps, int n, float min_x, float min_y, float inv_w,
+                                 float inv_h, int32_t* cell_offsets, int32_t* cell_items) {
+  if (!m || n < 0 || (n > 0 && (!kps || !cell_items)) || !cell_offsets) return mfail(m, ORBX_E_ARG, "bad argument");
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int cells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
+  Arena ar(m);
+  const orbx_kp* d_kps = ar.upload(kps, n);
+  int32_t* d_off = ar.alloc<int32_t>(cells + 1);
+  int32_t* d_items = ar.alloc<int32_t>(n);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_build_grid(d_kps, nullptr, n, 0, 1, min_x, min_y, inv_w, inv_h, d_off, d_items, 0, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  ORBM_CUDA(m, cudaMemcpyAsync(cell_offsets, d_off, (size_t)(cells + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
+  if (n > 0) ORBM_CUDA(m, cudaMemcpyAsync(cell_items, d_items, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  return ORBX_OK;
+}
+
+int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,
+                                           const float* u_right, const uint8_t* occupied, float min_x, float min_y,
+                                           float inv_w, float inv_h, const orbx_mappoints* mps, float th, float nnratio,
+                                           int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
+  if (!m || !ex || !mps || n < 0 || mps->m < 0 || (n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  if (!ex->planned || ex->device != m->device) return mfail(m, ORBX_E_ARG, "extractor has not run on this device");
+  const OrbxLane& L = ex->lane[ex->last_lane];
+  if (frame < 0 || frame >= L.last_frames || !L.d_kps || n > L.out_cap)
+    return mfail(m, ORBX_E_ARG, "frame is not resident in the extractor's last batch");
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int cells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
+  const Plan& P = ex->plan;
+  float sf[kMaxLevels];
+  for (int l = 0; l < P.nlevels; l++) sf[l] = P.lv[l].scale;  // mvScaleFactors (src/ORBextractor.cc:418-425)
+  Arena ar(m);
+  DevFrame F{};
+  F.n = n;
+  F.n_levels = P.nlevels;
+  F.kps = L.d_kps + (int64_t)frame * L.out_cap;  // mvKeysUn == mvKeys for an undistorted camera (src/Frame.cc:562-571)
+  F.desc = L.d_desc + (int64_t)frame * L.out_cap * 32;
+  F.u_right = u_right ? ar.upload(u_right, n) : (ar.alloc<float>(1), nullptr);
+  uint8_t* d_occ = ar.alloc<uint8_t>(n);
+  int32_t* d_off = ar.alloc<int32_t>(cells + 1);
+  int32_t* d_items = ar.alloc<int32_t>(n);
+  F.scale_factors = ar.upload(sf, P.nlevels);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (n > 0) {
+    if (occupied) ORBM_CUDA(m, cudaMemcpyAsync(d_occ, occupied, n, cudaMemcpyHostToDevice, m->stream));
+    else ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, n, m->stream));
+  }
+  launch_build_grid(F.kps, nullptr, n, 0, 1, min_x, min_y, inv_w, inv_h, d_off, d_items, 0, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  F.occupied = d_occ;
+  F.cell_offsets = d_off;
+  F.cell_items = d_items;
+  F.min_x = min_x;
+  F.min_y = min_y;
+  F.inv_w = inv_w;
+  F.inv_h = inv_h;
+  return search_map_common(m, ar, F, sf, P.nlevels, u_right != nullptr, mps, th, nnratio, far_points, th_far, n, assign,
+                           nmatches);
 }
 
 int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,

@@ -92,6 +92,7 @@ struct ResolveArgs {
   int32_t* nmatches;        // [1]
   uint8_t* occ;             // [n] scratch, initialised from DevFrame::occupied
   int32_t* events;          // [2 * m] scratch (mode 1): accepted (idx, bin)
+  int32_t* dec;             // [m] scratch: the keypoint each point takes (-1 = none), iterated to the fixed point
 };
 void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, const ResolveArgs& R,
                            cudaStream_t st);
@@ -119,6 +120,10 @@ struct TriArgs {
   int32_t* node_match; // [k1.n_nodes] scratch: index of the same node id in k2 or -1
 };
 void launch_triangulation(const TriArgs& A, cudaStream_t st);
+// Frame::AssignFeaturesToGrid for `frames` keypoint arrays (kp_stride apart; counts from n_ptr[f] or n_fixed)
+void launch_build_grid(const orbx_kp* kps, const int32_t* n_ptr, int n_fixed, int64_t kp_stride, int frames, float min_x,
+                       float min_y, float inv_w, float inv_h, int32_t* offsets, int32_t* items, int64_t item_stride,
+                       cudaStream_t st);
 
 }  // namespace orbx
 

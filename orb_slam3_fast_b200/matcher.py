@@ -29,6 +29,9 @@ def _bind(L):
                                            ci, vp, vp, vp]
     L.orbm_search_by_projection_map.argtypes = [vp, vp, vp, cf, cf, ci, cf, vp, vp]
     L.orbm_search_by_projection_frame.argtypes = [vp, vp, vp, ci, ci, vp, vp]
+    L.orbm_assign_features_to_grid.argtypes = [vp, vp, ci, cf, cf, cf, cf, vp, vp]
+    L.orbm_search_by_projection_map_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, cf, cf, ci, cf, vp,
+                                                         vp]
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
     L._orbm_bound = True
 
@@ -131,6 +134,29 @@ class ORBmatcher:
         self._check(self._L.orbm_search_by_projection_map(self._h, frame_view.ref(), mappoints.ref(), th,
                                                           self.mfNNratio, int(bFarPoints), thFarPoints,
                                                           _l.ptr(assign), C.byref(nm)))
+        return nm.value, assign[:n]
+
+    # void Frame::AssignFeaturesToGrid() — src/Frame.cc:520-547 (PosInGrid :833-844), on the device
+    def AssignFeaturesToGrid(self, kps, min_x, min_y, inv_w, inv_h):
+        kps = np.ascontiguousarray(kps)
+        off = np.empty(64 * 48 + 1, np.int32)
+        items = np.empty(max(len(kps), 1), np.int32)
+        self._check(self._L.orbm_assign_features_to_grid(self._h, _l.ptr(kps), len(kps), min_x, min_y, inv_w, inv_h,
+                                                         _l.ptr(off), _l.ptr(items)))
+        return off, items[:off[-1]]
+
+    # SearchByProjection(Frame&, vector<MapPoint*>) on frame `frame` of the extractor's last call, still on the device
+    def SearchByProjectionResident(self, extractor, frame, n, mappoints, grid_params, u_right=None, occupied=None, th=3.0,
+                                   bFarPoints=False, thFarPoints=50.0):
+        assign = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        min_x, min_y, inv_w, inv_h = grid_params
+        self._check(self._L.orbm_search_by_projection_map_resident(
+            self._h, extractor._h, frame, n, None if ur is None else _l.ptr(ur), None if oc is None else _l.ptr(oc),
+            min_x, min_y, inv_w, inv_h, mappoints.ref(), th, self.mfNNratio, int(bFarPoints), thFarPoints,
+            _l.ptr(assign), C.byref(nm)))
         return nm.value, assign[:n]
 
     # int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) — :1594; KeyFrame form — :1808

@@ -100,6 +100,54 @@ def test_search_by_projection_map(matcher, m, th, stereo, seed):
     assert np.array_equal(assign, assign_r), "assign differs at %s" % np.nonzero(assign != assign_r)[0][:10]
 
 
+@pytest.mark.parametrize("kind,n_extra,seed", [("scene", 0, 0), ("uniform_noise", 300, 1), ("scene", 50, 2)])
+def test_assign_features_to_grid(matcher, kind, n_extra, seed):
+    # Frame::AssignFeaturesToGrid (src/Frame.cc:520-547): device CSR == oracle == the host mirror, including keypoints
+    # that fall outside the grid (PosInGrid false) and cells holding many keypoints
+    w, h = 640, 480
+    _, kps, _ = ORBextractor(1200)(synth.make(kind, h, w, seed))
+    rng = np.random.default_rng(seed)
+    if n_extra:
+        extra = np.zeros(n_extra, kps.dtype)
+        extra["x"] = rng.uniform(-30, w + 30, n_extra).astype(np.float32)   # some land outside [0, 64) x [0, 48)
+        extra["y"] = rng.uniform(-30, h + 30, n_extra).astype(np.float32)
+        extra[: n_extra // 3] = kps[: n_extra // 3]                          # duplicates: several indices per cell
+        kps = np.concatenate([kps, extra])[rng.permutation(len(kps) + n_extra)]
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    for (mx, my) in ((0.0, 0.0), (-7.5, 3.25)):
+        off, items = matcher.AssignFeaturesToGrid(kps, mx, my, inv_w, inv_h)
+        off_r, items_r = orbref.build_grid(kps, mx, my, inv_w, inv_h)
+        off_h, items_h = views.assign_features_to_grid(kps, mx, my, inv_w, inv_h)
+        assert np.array_equal(off, off_r) and np.array_equal(items, items_r[: off_r[-1]])
+        assert np.array_equal(off, off_h) and np.array_equal(items, items_h[: off_h[-1]])
+    off, items = matcher.AssignFeaturesToGrid(kps[:0], 0.0, 0.0, inv_w, inv_h)
+    assert (off == 0).all() and len(items) == 0
+
+
+@pytest.mark.parametrize("m,th,stereo,seed", [(10000, 1.0, True, 0), (3000, 3.0, False, 1)])
+def test_search_by_projection_resident_frame(matcher, m, th, stereo, seed):
+    # configs[3]: extract, then SearchByProjection against a 10k-point local map without the frame leaving the device
+    w, h = 640, 480
+    ex = ORBextractor(1200, max_batch=4)
+    imgs = np.stack([synth.scene(h, w, seed + k) for k in range(3)])
+    n_all, _, kps_all, desc_all = ex.extract_batch(imgs, (0, 0))
+    f = 1
+    kps, desc = kps_all[f, : n_all[f]], desc_all[f, : n_all[f]]
+    rng = np.random.default_rng(seed)
+    ur = np.where(rng.random(len(kps)) < 0.7, kps["x"] - rng.uniform(1, 40, len(kps)), -1).astype(np.float32)
+    occ = (rng.random(len(kps)) < 0.1).astype(np.uint8)
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    _, fr = _frame_views(kps, desc, w, h, ex.GetScaleFactors(), ur if stereo else None, occ)
+    mp = synth.local_map(kps, desc, m, w, h, 8, seed)
+    n, assign = matcher.SearchByProjectionResident(ex, f, len(kps), views.make_mappoints(**mp), (0.0, 0.0, inv_w, inv_h),
+                                                   ur if stereo else None, occ, th, True, 15.0)
+    n_r, assign_r = orbref.search_by_projection_map(fr, orbref.make_mappoints(**mp), th, 0.8, True, 15.0)
+    assert n_r > 100 and n == n_r
+    assert np.array_equal(assign, assign_r), "assign differs at %s" % np.nonzero(assign != assign_r)[0][:10]
+    with pytest.raises(Exception):
+        matcher.SearchByProjectionResident(ex, 7, len(kps), views.make_mappoints(**mp), (0.0, 0.0, inv_w, inv_h))
+
+
 @pytest.mark.parametrize("m,th,stereo,check,seed", [(1200, 7.0, True, True, 0), (1200, 15.0, False, True, 1),
                                                     (4000, 7.0, True, False, 2)])
 def test_search_by_projection_frame(gpu, m, th, stereo, check, seed):
