@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Per-call timings of the matcher rows of SURVEY.md §8 (a11-a16) on 1 x B200, each next to the CPU oracle, plus
+BASELINE.json configs[4] (the brute-force 256-bit Hamming 2-NN sweep 1k x 1k ... 100k x 100k).
+Parity with the oracle / numpy is asserted before anything is timed. Usage: python tools/bench_matchers.py > out.json
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from orb_slam3_fast_b200 import ORBextractor, ORBmatcher, synth, views  # noqa: E402
+from oracle import orbref  # noqa: E402  (checker + CPU baseline only)
+
+
+def timed(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return 1e3 * (time.perf_counter() - t0) / reps
+
+
+def knn2_sweep(mt):
+    rows = []
+    for n in (1000, 3000, 10000, 30000, 100000):
+        q, t = synth.descriptors(n, 21), synth.descriptors(n, 22)
+        dq, dt = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+        i1 = torch.empty(n, dtype=torch.int32, device="cuda"); d1 = torch.empty_like(i1)
+        i2 = torch.empty_like(i1); d2 = torch.empty_like(i1)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def dev():
+            mt.knnMatch2_device(dq.data_ptr(), n, dt.data_ptr(), n, i1.data_ptr(), d1.data_ptr(), i2.data_ptr(),
+                                d2.data_ptr(), st)
+        for _ in range(2):
+            dev()
+        reps = 20 if n <= 10000 else 3
+        torch.cuda.synchronize()   # the call runs on the matcher's own stream: device-wide syncs bracket the region
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dev()
+        torch.cuda.synchronize()
+        ms = 1e3 * (time.perf_counter() - t0) / reps
+        # spot check against numpy on 16 rows
+        rr = np.random.default_rng(n).integers(0, n, 16)
+        D = np.bitwise_count(q[rr].view(np.uint64)[:, None, :] ^ t.view(np.uint64)[None, :, :]).sum(axis=2)
+        order = np.lexsort((np.broadcast_to(np.arange(n), D.shape), D), axis=1)[:, :2]
+        assert np.array_equal(i1.cpu().numpy()[rr], order[:, 0]) and np.array_equal(i2.cpu().numpy()[rr], order[:, 1])
+        row = {"n": n, "ms_device": ms, "gpairs_per_s": n * n / ms / 1e6,
+               "ms_host_call": timed(lambda: mt.knnMatch2(q, t), 3 if n > 10000 else 10)}
+        if n <= 3000:
+            import cv2
+            bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+            row["ms_cv2_bfmatcher_host_threads"] = timed(lambda: bf.knnMatch(q, t, k=2), 3)
+        rows.append(row)
+    return rows
+
+
+def main():
+    mt = ORBmatcher(0.8)
+    out = {"knn2_sweep_configs4": knn2_sweep(mt)}
+    # ---- a12: Frame::ComputeStereoMatches on one 752x480 pair (per-call, host keypoints in / uRight, depth out) ----
+    w, h = 752, 480
+    left, right, _ = synth.stereo_pair(h, w, 5)
+    exl, exr = ORBextractor(1200), ORBextractor(1200)
+    _, kl, dl = exl(left)
+    _, kr, dr = exr(right)
+    mbf, mb = float(np.float32(435.2 * 0.11)), float(np.float32(0.11))
+    rl, rr_ = orbref.Extractor(1200), orbref.Extractor(1200)
+    rl(left, (0, 0)); rr_(right, (0, 0))
+    nm, u, d = mt.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, mbf, mb)
+    _, u_r, d_r = orbref.stereo_match(rl, rr_, kl, dl, kr, dr, mbf, mb)
+    assert np.array_equal(u, u_r) and np.array_equal(d, d_r)
+    out["stereo_match_one_pair"] = {
+        "ms_gpu_call": timed(lambda: mt.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, mbf, mb), 50),
+        "ms_cpu_oracle": timed(lambda: orbref.stereo_match(rl, rr_, kl, dl, kr, dr, mbf, mb), 10), "matched": int(nm)}
+    # ---- a14: SearchByProjection(Frame&, const Frame&) after the caller-side projection ----
+    ur = np.where(np.random.default_rng(0).random(len(kl)) < 0.7, kl["x"] - 10, -1).astype(np.float32)
+    occ = np.zeros(len(kl), np.uint8)
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    off, items = views.assign_features_to_grid(kl, 0.0, 0.0, inv_w, inv_h)
+    fv = views.make_frame_view(kl, dl, ur, occ, off, items, 0.0, 0.0, inv_w, inv_h, exl.GetScaleFactors())
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    fr = orbref.make_frame_view(kl, dl, ur, occ, g, keep, exl.GetScaleFactors())
+    pts = synth.projected_points(kl, dl, 1200, w, h, 8, exl.GetScaleFactors(), 0, th=7.0, stereo=True)
+    m2 = ORBmatcher(0.9, True)
+    pv, pr = views.make_projected(**pts), orbref.make_projected(**pts)
+    n, a = m2.SearchByProjectionProjected(fv, pv, 100)
+    n_r, a_r = orbref.search_by_projection_frame(fr, pr, 100, True)
+    assert n == n_r and np.array_equal(a, a_r)
+    out["search_by_projection_frame_1200pts"] = {
+        "ms_gpu_call": timed(lambda: m2.SearchByProjectionProjected(fv, pv, 100), 50),
+        "ms_cpu_oracle": timed(lambda: orbref.search_by_projection_frame(fr, pr, 100, True), 20), "matches": int(n)}
+    out["timer"] = "host wall clock around synchronous ABI calls unless the key says device (CUDA events)"
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
