@@ -142,3 +142,40 @@ def test_other_parameters(gpu):
         assert np.array_equal(ex.GetScaleFactors(), ex_ref.scale)
         mono, kps, desc = ex(img)
         _compare_frame(ex_ref, kps, desc, mono, img, (0, 0), "params %s" % ((nf, sf, nl, it, mt),))
+
+
+@pytest.mark.parametrize("base_off,pad", [(0, 0), (0, 16), (0, 4), (0, 3), (1, 0), (4, 8)])
+def test_device_resident_input_every_staging_variant(gpu, base_off, pad):
+    """orbx_extract_batch_device reads level 0 in place from the caller's device buffer. A 16-byte aligned base / pitch
+    / frame stride takes the TMA kernels (k_fast<true>, k_resize_tma, k_blur7<kBlurTma>); anything else must fall back
+    to the LDG kernels (word aligned: k_blur7<kBlurLdg>; odd: byte loads) — all of them bit-exact with the oracle."""
+    import torch
+    from orb_slam3_fast_b200.synth import KP_DTYPE
+    h, w, nf, B = 480, 640, 1000, 3
+    imgs = [synth.scene(h, w, 40 + k) for k in range(B)]
+    pitch = w + pad
+    fstride = pitch * h + (0 if (base_off == 0 and pad % 16 == 0) else 0)
+    buf = torch.zeros(base_off + B * fstride + 64, dtype=torch.uint8, device="cuda")
+    for k, im in enumerate(imgs):
+        view = buf[base_off + k * fstride: base_off + (k + 1) * fstride].view(h, pitch)
+        view[:, :w] = torch.from_numpy(im).cuda()
+        if pad:
+            view[:, w:] = 255 - view[:, :pad]   # the padding is not image data: it must never influence the result
+    ex = ORBextractor(nf, max_batch=B)
+    cap = ex.capacity
+    d_kps = torch.empty((B, cap, 7), dtype=torch.int32, device="cuda")
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.empty(B, dtype=torch.int32, device="cuda")
+    d_mono = torch.empty(B, dtype=torch.int32, device="cuda")
+    d_status = torch.empty(B, dtype=torch.int32, device="cuda")
+    ex.extract_batch_device(buf.data_ptr() + base_off, B, w, h, pitch, fstride, (0, 0), d_kps.data_ptr(),
+                            d_desc.data_ptr(), cap, d_n.data_ptr(), d_mono.data_ptr(), d_status.data_ptr())
+    torch.cuda.synchronize()
+    assert (d_status.cpu().numpy() == 0).all()
+    n = d_n.cpu().numpy()
+    kps = d_kps.cpu().numpy().view(np.uint8).reshape(B, cap, 28).copy().view(KP_DTYPE).reshape(B, cap)
+    desc = d_desc.cpu().numpy()
+    ref = orbref.Extractor(nf)
+    for k in range(B):
+        _compare_frame(ref, kps[k, :n[k]], desc[k, :n[k]], int(d_mono[k].item()), imgs[k], (0, 0),
+                       "device input base+%d pitch+%d frame %d" % (base_off, pad, k))
