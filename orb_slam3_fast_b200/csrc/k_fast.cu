@@ -72,8 +72,8 @@ static FastSmemLayout fast_layout(const Plan& P) {
 size_t fast_smem_bytes(const Plan& P) { return kFastHead + (size_t)fast_layout(P).per_warp * kFastWarps; }
 
 // ring pixel pair for the two pixels whose u16 columns are O, O+1 inside the 10-column window W (5 words)
-template <int O>
-__device__ __forceinline__ uint32_t pair_at(const uint32_t (&W)[5]) {
+template <int O, int N>
+__device__ __forceinline__ uint32_t pair_at(const uint32_t (&W)[N]) {
   if constexpr ((O & 1) == 0) return W[O / 2];
   else return __byte_perm(W[(O - 1) / 2], W[(O + 1) / 2], 0x5432);
 }
@@ -328,45 +328,49 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
     const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
     int n_score = ngroups;
     if (pass == 0) {
-      // -- compass pre-test of every group: rows r, r+3, r+6 of the tile are dy = -3, 0, +3 --
+      // -- compass pre-test, two adjacent groups (8 pixels) per lane step: rows r, r+3, r+6 of the tile are
+      //    dy = -3, 0, +3; the step's tile words come in with 16-byte loads (tile rows and 8-pixel starts are 16-byte
+      //    aligned) --
       const uint32_t K = (uint32_t)(T + 1) * 0x00010001u;
       n_score = 0;
-      const int q32 = 32 / gpr, m32 = 32 - q32 * gpr;  // a step of 32 groups = q32 rows + m32 groups
-      int r = lane / gpr, g = lane - r * gpr;
-      for (int gbase = 0; gbase < ngroups; gbase += 32) {
-        const int G = gbase + lane;
-        bool hit = false;
-        if (G < ngroups) {
-          const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
-          uint32_t Wm3[5], W0[5], Wp3[5];
-#pragma unroll
-          for (int c = 0; c < 5; c++) W0[c] = base[3 * rp + c];
-#pragma unroll
-          for (int c = 1; c < 4; c++) {
-            Wm3[c] = base[c];
-            Wp3[c] = base[6 * rp + c];
+      const int ppr = (gpr + 1) >> 1, npairs = ppr * ih;      // group pairs per row / per cell
+      const int q32 = 32 / ppr, m32 = 32 - q32 * ppr;         // a step of 32 pairs = q32 rows + m32 pairs
+      int r = lane / ppr, g2 = lane - r * ppr;
+      for (int gbase = 0; gbase < npairs; gbase += 32) {
+        bool hitA = false, hitB = false;
+        if (gbase + lane < npairs) {
+          const uint16_t* base = raw + r * tp + 8 * g2;
+          uint32_t Wm3[6], W0[8], Wp3[6];
+          {
+            const uint4 a = *reinterpret_cast<const uint4*>(base), b = *reinterpret_cast<const uint4*>(base + 6 * tp);
+            const uint2 a2 = *reinterpret_cast<const uint2*>(base + 8), b2 = *reinterpret_cast<const uint2*>(base + 6 * tp + 8);
+            const uint4 c = *reinterpret_cast<const uint4*>(base + 3 * tp), c2 = *reinterpret_cast<const uint4*>(base + 3 * tp + 8);
+            Wm3[0] = a.x; Wm3[1] = a.y; Wm3[2] = a.z; Wm3[3] = a.w; Wm3[4] = a2.x; Wm3[5] = a2.y;
+            Wp3[0] = b.x; Wp3[1] = b.y; Wp3[2] = b.z; Wp3[3] = b.w; Wp3[4] = b2.x; Wp3[5] = b2.y;
+            W0[0] = c.x; W0[1] = c.y; W0[2] = c.z; W0[3] = c.w; W0[4] = c2.x; W0[5] = c2.y; W0[6] = c2.z; W0[7] = c2.w;
           }
-          Wm3[0] = Wm3[4] = Wp3[0] = Wp3[4] = 0u;  // not referenced below
-          uint32_t bits = 0u;
-#pragma unroll
-          for (int half = 0; half < 2; half++) {
-            const uint32_t p0 = half ? pair_at<5>(Wp3) : pair_at<3>(Wp3), p8 = half ? pair_at<5>(Wm3) : pair_at<3>(Wm3);
-            const uint32_t p4 = half ? pair_at<8>(W0) : pair_at<6>(W0), p12 = half ? pair_at<2>(W0) : pair_at<0>(W0);
-            const uint32_t c = half ? pair_at<5>(W0) : pair_at<3>(W0);
+          auto test = [&](uint32_t p0, uint32_t p8, uint32_t p4, uint32_t p12, uint32_t c) {
             const uint32_t lo_of_hi = __vminu2(__vmaxu2(p0, p8), __vmaxu2(p4, p12));  // bright: must exceed v + T
             const uint32_t hi_of_lo = __vmaxu2(__vminu2(p0, p8), __vminu2(p4, p12));  // dark: must be below v - T
             // lanes stay below 0x8000, so bit 15 of (x | 0x8000) - y says x >= y without borrowing across lanes
-            bits |= ((lo_of_hi | 0x80008000u) - (c + K)) | ((c | 0x80008000u) - (hi_of_lo + K));
-          }
-          hit = (bits & 0x80008000u) != 0u;
+            return ((lo_of_hi | 0x80008000u) - (c + K)) | ((c | 0x80008000u) - (hi_of_lo + K));
+          };
+          const uint32_t bitsA = test(pair_at<3>(Wp3), pair_at<3>(Wm3), pair_at<6>(W0), pair_at<0>(W0), pair_at<3>(W0)) |
+                                 test(pair_at<5>(Wp3), pair_at<5>(Wm3), pair_at<8>(W0), pair_at<2>(W0), pair_at<5>(W0));
+          const uint32_t bitsB = test(pair_at<7>(Wp3), pair_at<7>(Wm3), pair_at<10>(W0), pair_at<4>(W0), pair_at<7>(W0)) |
+                                 test(pair_at<9>(Wp3), pair_at<9>(Wm3), pair_at<12>(W0), pair_at<6>(W0), pair_at<9>(W0));
+          hitA = (bitsA & 0x80008000u) != 0u;
+          hitB = (bitsB & 0x80008000u) != 0u && 2 * g2 + 1 < gpr;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) list[n_score + __popc(bal & lt)] = (uint16_t)((r << 8) | g);
-        n_score += __popc(bal);
-        g += m32;
+        const unsigned balA = __ballot_sync(0xffffffffu, hitA), balB = __ballot_sync(0xffffffffu, hitB);
+        const int pos = n_score + __popc(balA & lt) + __popc(balB & lt);
+        if (hitA) list[pos] = (uint16_t)((r << 8) | (2 * g2));
+        if (hitB) list[pos + (hitA ? 1 : 0)] = (uint16_t)((r << 8) | (2 * g2 + 1));
+        n_score += __popc(balA) + __popc(balB);
+        g2 += m32;
         r += q32;
-        if (g >= gpr) {
-          g -= gpr;
+        if (g2 >= ppr) {
+          g2 -= ppr;
           r++;
         }
       }
