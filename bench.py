@@ -11,6 +11,8 @@ collective is the gather of the per-pair result counts). A stereo pair counts as
          H2D / D2H inside the timed region).
   --impl reference: the CPU oracle port of the reference (oracle/liborbref.so) on all host cores, same workload.
 """
+import os as _os
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA starts: 2 streams per pipeline lane (see orbx_api.cu)
 import argparse
 import json
 import os

@@ -467,7 +467,8 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
     A.depth = reinterpret_cast<float*>(m->lane_buf[ln][1].p);
     A.sad = reinterpret_cast<int32_t*>(m->lane_buf[ln][2].p);
     A.n_matched = reinterpret_cast<int32_t*>(m->lane_buf[ln][3].p);
-    launch_stereo(A, nb, dcap, st);
+    static const bool skip_kernels = getenv("ORBX_DEBUG_SKIP_KERNELS") != nullptr;  // timing experiment only
+    if (!skip_kernels) launch_stereo(A, nb, dcap, st);
     ORBM_CUDA(m, cudaGetLastError());
     if ((rc = api_download(left, ln, nb, kps_l + (int64_t)f0 * cap, desc_l + (int64_t)f0 * cap * 32, cap, st)) != 0)
       return mfail(m, rc, orbx_last_error(left));

@@ -16,6 +16,12 @@
 
 using namespace orbx;
 
+// The pipelined host-facing calls keep 2 streams per lane busy (8 in all) next to the caller's own; with the default of
+// 8 hardware work queues streams alias and falsely serialise (measured: 109 k -> 115 k frames/s end to end with 32). The
+// variable is only read when the CUDA context is created, so it is set — if the process has not chosen a value — when
+// the library is loaded.
+__attribute__((constructor)) static void orbx_default_connections() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 namespace {
 const int8_t kPatternHost[256 * 4] = {
 #include "orb_pattern.inc"
@@ -143,6 +149,13 @@ int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, 
   // One stream, stages back to back. (Forking the blur onto a second stream so that it overlaps FAST + quadtree was
   // measured SLOWER on B200: 7.01 vs 6.78 ms per 512-frame step — the blur's CTAs crowd out the latency-bound
   // quadtree warps and slow FAST, and nothing is gained because every stage already fills the chip.)
+  static const bool skip_kernels = getenv("ORBX_DEBUG_SKIP_KERNELS") != nullptr;  // timing experiment only
+  if (skip_kernels) {
+    L.last_fs = fs;
+    L.last_frames = frames;
+    ex->last_lane = ln;
+    return ORBX_OK;
+  }
   begin(0, st);
   launch_pyramid(P, fs, ex->d_tab, frames, st);
   end(0, st);
@@ -237,7 +250,11 @@ int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, i
   if (frame_stride == (int64_t)stride * height && stride <= ex->in_pitch) {
     // densely packed frames: ONE contiguous copy, level 0 keeps the caller's pitch (a 2-D copy of 752-byte rows runs at
     // a fraction of the PCIe rate)
-    ORBX_CUDA(ex, cudaMemcpyAsync(L.d_in, src, (size_t)frame_stride * nb, cudaMemcpyHostToDevice, st));
+    // ORBX_DEBUG_SKIP_H2D: timing experiment only (what the pipelined calls cost without the upload); results are then
+    // those of whatever the lane held before
+    static const bool skip_h2d = getenv("ORBX_DEBUG_SKIP_H2D") != nullptr;
+    if (!skip_h2d)
+      ORBX_CUDA(ex, cudaMemcpyAsync(L.d_in, src, (size_t)frame_stride * nb, cudaMemcpyHostToDevice, st));
     fs.pitch0 = stride;
     fs.fstride0 = frame_stride;
   } else {
