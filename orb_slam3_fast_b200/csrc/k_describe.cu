@@ -277,6 +277,9 @@ k_describe(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, 
   const int p = e - L.kp_base;
   // ---- output row (:1083-1101): monoIndex counts up from 0, stereoIndex down from N - 1, levels ascending.
   //      Lane k holds level k's counts; the sums over all levels / the levels below l are warp reductions ----
+  // the entry's own record does not depend on the counts: requested first, so that its latency overlaps theirs
+  const int rk = ws.dst[(int64_t)f * P.kps_per_frame + e];
+  const uint32_t cw = ws.lvl_kp[(int64_t)f * P.kps_per_frame + e];
   int n_k = 0, s_k = 0;
   if (lane < P.nlevels) {
     n_k = ws.lvl_n[f * P.nlevels + lane];
@@ -294,9 +297,7 @@ k_describe(const __grid_constant__ Plan P, const FrameSet fs, const WorkSet ws, 
     out.status[f] = fits ? 0 : -2;
   }
   if (p >= n_here || !fits) return;
-  const int rk = ws.dst[(int64_t)f * P.kps_per_frame + e];
   const int dst = (rk & 0x40000000) ? total - 1 - (st_before + (rk & 0x3fffffff)) : mono_before + rk;
-  const uint32_t cw = ws.lvl_kp[(int64_t)f * P.kps_per_frame + e];
   const int X = cand_x(cw) + kMinBorder, Y = cand_y(cw) + kMinBorder;  // :867-868
 
   // ---- IC_Angle: m10 = sum u*I, m01 = sum v*I over the radius-15 disc; lane = column u + 15 ----
