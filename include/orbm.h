@@ -108,6 +108,14 @@ int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor
 int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
                                     int max_dist, int check_orientation, int32_t* assign, int32_t* nmatches);
 
+/* orbm_search_by_projection_frame on a frame that never left the device (see orbm_search_by_projection_map_resident
+ * for the conditions): SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, ...) right after ExtractORB,
+ * src/Tracking.cc:2811. */
+int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,
+                                             const float* u_right, const uint8_t* occupied, float min_x, float min_y,
+                                             float inv_w, float inv_h, const orbx_projected* pts, int max_dist,
+                                             int check_orientation, int32_t* assign, int32_t* nmatches);
+
 /* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
  * const bool bOnlyStereo, const bool bCoarse) (src/ORBmatcher.cc:886-1106), pinhole keyframes. F12 (row-major 3x3)
  * and the epipole (ep_x, ep_y) are computed by the shim exactly as the reference does (:893-911,

@@ -574,12 +574,12 @@ int orbm_assign_features_to_grid(orbm_matcher* m, const orbx_kp* kps, int n, flo
   return ORBX_OK;
 }
 
-int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,
-                                           const float* u_right, const uint8_t* occupied, float min_x, float min_y,
-                                           float inv_w, float inv_h, const orbx_mappoints* mps, float th, float nnratio,
-                                           int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
-  if (!m || !ex || !mps || n < 0 || mps->m < 0 || (n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
-  if (nmatches) *nmatches = 0;
+namespace {
+// DevFrame of frame `frame` of the extractor's most recent host-facing call: keypoints / descriptors where the
+// extractor left them, mvScaleFactors from its plan, the 64x48 grid built on the device (Frame::AssignFeaturesToGrid).
+int resident_frame(orbm_matcher* m, Arena& ar, const orbx_extractor* ex, int frame, int n, const float* u_right,
+                   const uint8_t* occupied, float min_x, float min_y, float inv_w, float inv_h, DevFrame* out,
+                   float* sf) {
   if (!ex->planned || ex->device != m->device) return mfail(m, ORBX_E_ARG, "extractor has not run on this device");
   const OrbxLane& L = ex->lane[ex->last_lane];
   if (frame < 0 || frame >= L.last_frames || !L.d_kps || n > L.out_cap)
@@ -587,9 +587,7 @@ int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor
   ORBM_CUDA(m, cudaSetDevice(m->device));
   const int cells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
   const Plan& P = ex->plan;
-  float sf[kMaxLevels];
   for (int l = 0; l < P.nlevels; l++) sf[l] = P.lv[l].scale;  // mvScaleFactors (src/ORBextractor.cc:418-425)
-  Arena ar(m);
   DevFrame F{};
   F.n = n;
   F.n_levels = P.nlevels;
@@ -614,18 +612,30 @@ int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor
   F.min_y = min_y;
   F.inv_w = inv_w;
   F.inv_h = inv_h;
-  return search_map_common(m, ar, F, sf, P.nlevels, u_right != nullptr, mps, th, nnratio, far_points, th_far, n, assign,
+  *out = F;
+  return ORBX_OK;
+}
+}  // namespace
+
+int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,
+                                           const float* u_right, const uint8_t* occupied, float min_x, float min_y,
+                                           float inv_w, float inv_h, const orbx_mappoints* mps, float th, float nnratio,
+                                           int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
+  if (!m || !ex || !mps || n < 0 || mps->m < 0 || (n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  Arena ar(m);
+  DevFrame F;
+  float sf[kMaxLevels];
+  int rc = resident_frame(m, ar, ex, frame, n, u_right, occupied, min_x, min_y, inv_w, inv_h, &F, sf);
+  if (rc) return rc;
+  return search_map_common(m, ar, F, sf, F.n_levels, u_right != nullptr, mps, th, nnratio, far_points, th_far, n, assign,
                            nmatches);
 }
 
-int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
-                                    int max_dist, int check_orientation, int32_t* assign, int32_t* nmatches) {
-  if (!m || !f || !pts || f->n < 0 || pts->m < 0 || (f->n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
-  if (nmatches) *nmatches = 0;
-  ORBM_CUDA(m, cudaSetDevice(m->device));
+namespace {
+int search_frame_common(orbm_matcher* m, Arena& ar, const DevFrame& F, bool has_u_right, const orbx_projected* pts,
+                        int max_dist, int check_orientation, int n, int32_t* assign, int32_t* nmatches) {
   const int M = pts->m;
-  Arena ar(m);
-  const DevFrame F = upload_frame(ar, f);
   DevQueries Q{};
   Q.m = M;
   Q.active = nullptr;
@@ -634,7 +644,7 @@ int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, c
   Q.radius = ar.upload(pts->radius, M);
   Q.min_level = ar.upload(pts->min_level, M);
   Q.max_level = ar.upload(pts->max_level, M);
-  Q.u_right = (f->u_right && pts->u_right) ? ar.upload(pts->u_right, M) : (ar.alloc<float>(1), nullptr);
+  Q.u_right = (has_u_right && pts->u_right) ? ar.upload(pts->u_right, M) : (ar.alloc<float>(1), nullptr);
   Q.desc = ar.upload(pts->desc, (size_t)M * 32);
   ResolveArgs R{};
   R.mode = 1;
@@ -644,7 +654,32 @@ int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, c
   R.has_obs = ar.upload(pts->has_obs, M);
   R.angle = ar.upload(pts->angle, M);
   if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
-  return run_search(m, ar, F, Q, R, f->n, assign, nmatches);
+  return run_search(m, ar, F, Q, R, n, assign, nmatches);
+}
+}  // namespace
+
+int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
+                                    int max_dist, int check_orientation, int32_t* assign, int32_t* nmatches) {
+  if (!m || !f || !pts || f->n < 0 || pts->m < 0 || (f->n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const DevFrame F = upload_frame(ar, f);
+  return search_frame_common(m, ar, F, f->u_right != nullptr, pts, max_dist, check_orientation, f->n, assign, nmatches);
+}
+
+int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,
+                                             const float* u_right, const uint8_t* occupied, float min_x, float min_y,
+                                             float inv_w, float inv_h, const orbx_projected* pts, int max_dist,
+                                             int check_orientation, int32_t* assign, int32_t* nmatches) {
+  if (!m || !ex || !pts || n < 0 || pts->m < 0 || (n > 0 && !assign)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  Arena ar(m);
+  DevFrame F;
+  float sf[kMaxLevels];
+  int rc = resident_frame(m, ar, ex, frame, n, u_right, occupied, min_x, min_y, inv_w, inv_h, &F, sf);
+  if (rc) return rc;
+  return search_frame_common(m, ar, F, u_right != nullptr, pts, max_dist, check_orientation, n, assign, nmatches);
 }
 
 static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {

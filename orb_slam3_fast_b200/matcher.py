@@ -32,6 +32,7 @@ def _bind(L):
     L.orbm_assign_features_to_grid.argtypes = [vp, vp, ci, cf, cf, cf, cf, vp, vp]
     L.orbm_search_by_projection_map_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, cf, cf, ci, cf, vp,
                                                          vp]
+    L.orbm_search_by_projection_frame_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, ci, ci, vp, vp]
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
     L._orbm_bound = True
 
@@ -157,6 +158,20 @@ class ORBmatcher:
             self._h, extractor._h, frame, n, None if ur is None else _l.ptr(ur), None if oc is None else _l.ptr(oc),
             min_x, min_y, inv_w, inv_h, mappoints.ref(), th, self.mfNNratio, int(bFarPoints), thFarPoints,
             _l.ptr(assign), C.byref(nm)))
+        return nm.value, assign[:n]
+
+    # SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, ...) on a device-resident current frame
+    def SearchByProjectionProjectedResident(self, extractor, frame, n, projected, grid_params, u_right=None,
+                                            occupied=None, max_dist=TH_HIGH):
+        assign = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        oc = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+        min_x, min_y, inv_w, inv_h = grid_params
+        self._check(self._L.orbm_search_by_projection_frame_resident(
+            self._h, extractor._h, frame, n, None if ur is None else _l.ptr(ur), None if oc is None else _l.ptr(oc),
+            min_x, min_y, inv_w, inv_h, projected.ref(), max_dist, int(self.mbCheckOrientation), _l.ptr(assign),
+            C.byref(nm)))
         return nm.value, assign[:n]
 
     # int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) — :1594; KeyFrame form — :1808

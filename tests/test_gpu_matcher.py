@@ -165,6 +165,11 @@ def test_search_by_projection_frame(gpu, m, th, stereo, check, seed):
     assert n_r > 100
     assert n == n_r
     assert np.array_equal(assign, assign_r)
+    # the same search on the frame as the extractor left it on the device (grid built there too)
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    n2, assign2 = mt.SearchByProjectionProjectedResident(ex, 0, len(kps), views.make_projected(**pts),
+                                                         (0.0, 0.0, inv_w, inv_h), ur if stereo else None, occ, 100)
+    assert n2 == n_r and np.array_equal(assign2, assign_r)
 
 
 @pytest.mark.parametrize("only_stereo,coarse,check,seed", [(False, False, True, 0), (True, False, True, 1),
