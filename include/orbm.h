@@ -36,6 +36,14 @@ const char* orbm_last_error(const orbm_matcher* m);
  * shim header; a device launch per pair would be absurd. */
 int orbm_descriptor_distance_batch(orbm_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist);
 
+/* void MapPoint::ComputeDistinctiveDescriptors() (include/MapPoint.h:84, src/MapPoint.cc:372-441), the arithmetic after
+ * the observed descriptors have been gathered (:407-435), batched over map points: descriptors
+ * of point p are rows [offsets[p], offsets[p + 1]) of desc (host, 32 bytes each). best_idx[p] = position inside the
+ * point's list of the descriptor with the least median Hamming distance to the rest (first one on ties), -1 for an
+ * empty list; the shim then does mDescriptor = vDescriptors[best].clone(). */
+int orbm_distinctive_descriptors(orbm_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                 int32_t* best_idx);
+
 /* cv::BFMatcher(cv::NORM_HAMMING).knnMatch(query, train, matches, 2) (src/Frame.cc:1293): for every query row the two
  * train rows minimising (distance, trainIdx). idx = -1 and dist = -1 where the train set has fewer than 1 / 2 rows.
  * Host buffers: q[nq][32], t[nt][32], outputs [nq]. */

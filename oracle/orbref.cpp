@@ -861,6 +861,32 @@ void orbref_build_grid(const orbx_kp* kps, int n, float min_x, float min_y, floa
   offsets[C * R] = o;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors — src/MapPoint.cc:407-435
+int orbref_distinctive_descriptor(const uint8_t* desc, int n) {
+  if (n <= 0) return -1;
+  const size_t N = (size_t)n;
+  std::vector<float> D(N * N);  // float Distances[N][N], :412
+  for (size_t i = 0; i < N; i++) {
+    D[i * N + i] = 0;
+    for (size_t j = i + 1; j < N; j++) {
+      const int dij = orbref_descriptor_distance(desc + i * 32, desc + j * 32);
+      D[i * N + j] = (float)dij;
+      D[j * N + i] = (float)dij;
+    }
+  }
+  int BestMedian = INT_MAX, BestIdx = 0;
+  for (size_t i = 0; i < N; i++) {
+    std::vector<int> vDists(D.begin() + i * N, D.begin() + (i + 1) * N);  // vector<int>(float*, float*), :427
+    std::sort(vDists.begin(), vDists.end());
+    const int median = vDists[(size_t)(0.5 * (N - 1))];                  // :429
+    if (median < BestMedian) {
+      BestMedian = median;
+      BestIdx = (int)i;
+    }
+  }
+  return BestIdx;
+}
+
 // Frame::GetFeaturesInArea — src/Frame.cc:765-831 (Nleft == -1 branch)
 int orbref_features_in_area(const orbx_frame_view* f, float x, float y, float r, int minLevel, int maxLevel,
                             int32_t* out) {

@@ -63,6 +63,10 @@ int orbref_descriptor_distance(const uint8_t* a, const uint8_t* b); /* src/ORBma
  * (distance, trainIdx). idx = -1 / dist = -1 when the train set has fewer rows. */
 void orbref_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx1, int32_t* d1, int32_t* idx2,
                  int32_t* d2);
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:372-441), the arithmetic after the observations have been
+ * gathered: all-pairs distances of the n descriptors, per row the element [0.5 * (n - 1)] of the sorted row, first row
+ * with the least such median. Returns the index of that descriptor, -1 for n == 0. */
+int orbref_distinctive_descriptor(const uint8_t* desc, int n);
 /* Frame::ComputeStereoMatches (src/Frame.cc:921-1084). Reads the raw pyramids of the two extractors' last extract.
  * best_dist_out (optional) receives the SAD of accepted matches (or -1). Returns the number of surviving matches. */
 int orbref_stereo_match(const orbref_extractor* left, const orbref_extractor* right, const orbx_kp* kps_l,

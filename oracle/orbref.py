@@ -153,6 +153,8 @@ def lib():
         L.orbref_level_keypoints.argtypes = [vp, ci, vp, ci]
         L.orbref_descriptor_distance.argtypes = [vp, vp]
         L.orbref_knn2.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp]
+        L.orbref_distinctive_descriptor.argtypes = [vp, ci]
+        L.orbref_distinctive_descriptor.restype = ci
         L.orbref_stereo_match.argtypes = [vp, vp, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp]
         L.orbref_build_grid.argtypes = [vp, ci, cf, cf, cf, cf, vp, vp]
         L.orbref_features_in_area.argtypes = [vp, cf, cf, cf, ci, ci, vp]
@@ -295,6 +297,12 @@ def knn2(q, t):
     out = [np.empty(len(q), np.int32) for _ in range(4)]
     lib().orbref_knn2(_ptr(q), len(q), _ptr(t), len(t), *[_ptr(o) for o in out])
     return tuple(out)  # idx1, d1, idx2, d2
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors on one point's observed descriptors [n, 32] -> index or -1."""
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    return int(lib().orbref_distinctive_descriptor(_ptr(desc), len(desc)))
 
 
 def stereo_match(ex_l, ex_r, kps_l, desc_l, kps_r, desc_r, mbf, mb):

@@ -141,6 +141,83 @@ void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:407-435), batched over map points: CSR of observed
+// descriptors -> per point the index of the descriptor with the least median distance to the others. One warp per
+// point. For row i the lanes take the columns j = lane, lane + 32, ...; the element [0.5 * (N - 1)] of the sorted row
+// is found without sorting: distances are integers in 0..256, so a 257-bin histogram in shared memory + one warp
+// scan gives the k-th smallest. The first row with the least median wins (the reference compares with <).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDistinctWarps = 4;
+constexpr int kDistinctBins = 288;  // 257 rounded up to 9 bins per lane
+
+__global__ void __launch_bounds__(kDistinctWarps * 32)
+k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ offsets, int n_points,
+              int32_t* __restrict__ best_out) {
+  __shared__ int hist_all[kDistinctWarps][kDistinctBins];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kDistinctWarps + warp;
+  if (p >= n_points) return;
+  int* hist = hist_all[warp];
+  const int o = offsets[p], N = offsets[p + 1] - o;
+  if (N <= 0) {
+    if (lane == 0) best_out[p] = -1;
+    return;
+  }
+  const uint8_t* D = desc + (size_t)o * 32;
+  const int k = (N - 1) >> 1;  // (size_t)(0.5 * (N - 1))                                :429
+  int best_median = 0x7fffffff, best_idx = 0;
+  for (int i = 0; i < N; i++) {
+#pragma unroll
+    for (int b = 0; b < kDistinctBins / 32; b++) hist[lane * (kDistinctBins / 32) + b] = 0;
+    __syncwarp();
+    uint32_t a[8];
+    load_desc(D + (size_t)i * 32, a);
+    for (int j = lane; j < N; j += 32) {
+      uint32_t b[8];
+      load_desc(D + (size_t)j * 32, b);
+      atomicAdd(&hist[hamming(a, b)], 1);
+    }
+    __syncwarp();
+    // k-th smallest (0-based): the first bin whose inclusive prefix count exceeds k
+    int mine = 0;
+#pragma unroll
+    for (int b = 0; b < kDistinctBins / 32; b++) mine += hist[lane * (kDistinctBins / 32) + b];
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > k);
+    const int owner = __ffs(hit) - 1;  // N > k, so some lane reaches it
+    int median = 0;
+    if (lane == owner) {
+      int run = incl - mine;
+      for (int b = 0; b < kDistinctBins / 32; b++) {
+        run += hist[lane * (kDistinctBins / 32) + b];
+        if (run > k) {
+          median = lane * (kDistinctBins / 32) + b;
+          break;
+        }
+      }
+    }
+    median = __shfl_sync(0xffffffffu, median, owner);
+    if (median < best_median) {  //                                                       :431-434
+      best_median = median;
+      best_idx = i;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) best_out[p] = best_idx;
+}
+
+void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best, cudaStream_t st) {
+  if (n_points > 0)
+    k_distinctive<<<(n_points + kDistinctWarps - 1) / kDistinctWarps, kDistinctWarps * 32, 0, st>>>(desc, offsets,
+                                                                                                   n_points, best);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // ComputeStereoMatches. One CTA per (pair, band of kBandRows image rows):
 //  1. the reference's row table (right keypoints listed under every row of y +- 2*scale, :939-949) becomes a per-band
 //     list in shared memory: the CTA filters the right keypoints whose row span touches its band (a keypoint spans

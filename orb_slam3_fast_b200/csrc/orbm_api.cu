@@ -244,6 +244,25 @@ int orbm_descriptor_distance_batch(orbm_matcher* m, const uint8_t* a, const uint
   return ORBX_OK;
 }
 
+int orbm_distinctive_descriptors(orbm_matcher* m, const uint8_t* desc, const int32_t* offsets, int n_points,
+                                 int32_t* best_idx) {
+  if (!m || n_points < 0 || (n_points > 0 && (!offsets || !best_idx))) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (n_points == 0) return ORBX_OK;
+  const int total = offsets[n_points];
+  if (total < 0 || (total > 0 && !desc)) return mfail(m, ORBX_E_ARG, "bad argument");
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const uint8_t* dd = ar.upload(desc, (size_t)total * 32);
+  const int32_t* doff = ar.upload(offsets, (size_t)n_points + 1);
+  int32_t* db = ar.alloc<int32_t>(n_points);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_distinctive(dd, doff, n_points, db, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  ORBM_CUDA(m, cudaMemcpyAsync(best_idx, db, (size_t)n_points * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  return ORBX_OK;
+}
+
 int orbm_knn2_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_idx1,
                      int32_t* d_d1, int32_t* d_idx2, int32_t* d_d2, void* cuda_stream) {
   if (!m || nq < 0 || nt < 0) return mfail(m, ORBX_E_ARG, "bad argument");

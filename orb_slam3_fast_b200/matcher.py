@@ -22,6 +22,7 @@ def _bind(L):
     L.orbm_last_error.restype = C.c_char_p
     L.orbm_descriptor_distance_batch.argtypes = [vp, vp, vp, ci, vp]
     L.orbm_knn2.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp]
+    L.orbm_distinctive_descriptors.argtypes = [vp, vp, vp, ci, vp]
     L.orbm_knn2_device.argtypes = [vp, vp, ci, vp, ci, vp, vp, vp, vp, vp]
     L.orbm_stereo_match.argtypes = [vp, vp, vp, ci, vp, vp, ci, vp, vp, ci, cf, cf, vp, vp, vp]
     L.orbm_stereo_match_batch_device.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, ci, cf, cf, vp, vp, vp, vp]
@@ -71,6 +72,18 @@ class ORBmatcher:
         return out
 
     # cv::BFMatcher(NORM_HAMMING).knnMatch(q, t, matches, 2) — src/Frame.cc:1293
+    # void MapPoint::ComputeDistinctiveDescriptors() — src/MapPoint.cc:372-441, batched: lists[p] = [n_p, 32] arrays
+    def ComputeDistinctiveDescriptors(self, lists):
+        offsets = np.zeros(len(lists) + 1, np.int32)
+        offsets[1:] = np.cumsum([len(x) for x in lists])
+        desc = (np.concatenate([np.asarray(x, np.uint8).reshape(-1, 32) for x in lists]) if len(lists) and offsets[-1]
+                else np.zeros((1, 32), np.uint8))
+        desc = np.ascontiguousarray(desc)
+        best = np.empty(max(len(lists), 1), np.int32)
+        self._check(self._L.orbm_distinctive_descriptors(self._h, _l.ptr(desc), _l.ptr(offsets), len(lists),
+                                                         _l.ptr(best)))
+        return best[:len(lists)]
+
     def knnMatch2(self, q, t):
         q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
         t = np.ascontiguousarray(t, np.uint8).reshape(-1, 32)

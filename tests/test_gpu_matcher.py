@@ -230,3 +230,23 @@ def test_stereo_frames_batch_matches_per_pair_oracle(matcher):
         assert np.array_equal(out["kps_r"][i, :nr], kr) and np.array_equal(out["desc_r"][i, :nr], dr)
         assert out["n_matched"][i] == n_r
         assert np.array_equal(out["u_right"][i, :nl], ur_r) and np.array_equal(out["depth"][i, :nl], dp_r)
+
+
+def test_compute_distinctive_descriptors(matcher):
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:372-441) for a batch of map points: list sizes 0, 1, 2,
+    odd / even, > 32 and > 256 observations, duplicated descriptors (median ties -> the first row wins)."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 2, 3, 4, 7, 8, 31, 32, 33, 64, 100, 300] + list(rng.integers(2, 40, 200))
+    lists = []
+    for n in sizes:
+        base = synth.descriptors(1, int(rng.integers(1 << 30)))[0]
+        d = np.stack([synth.flip_bits(base[None], [int(rng.integers(0, 60))], rng)[0] for _ in range(n)]) if n else \
+            np.zeros((0, 32), np.uint8)
+        if n >= 4:
+            d[n // 2] = d[0]            # exact duplicates
+            d[n - 1] = d[1]
+        lists.append(d)
+    best = matcher.ComputeDistinctiveDescriptors(lists)
+    ref = np.array([orbref.distinctive_descriptor(d) for d in lists], np.int32)
+    assert np.array_equal(best, ref), np.nonzero(best != ref)[0][:10]
+    assert len(matcher.ComputeDistinctiveDescriptors([])) == 0

@@ -140,3 +140,17 @@ def test_descriptor_distance_is_popcount():
         ref = int(np.unpackbits(a[i] ^ b[i]).sum())
         assert orbref.descriptor_distance(a[i], b[i]) == ref
         assert int(cv2.norm(a[i], b[i], cv2.NORM_HAMMING)) == ref
+
+
+def test_distinctive_descriptor_matches_a_numpy_restatement():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:407-435): least median of the sorted distance rows,
+    element [0.5 * (N - 1)], first row on ties."""
+    rng = np.random.default_rng(9)
+    assert orbref.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
+    for n in (1, 2, 3, 4, 5, 8, 9, 33, 64, 150):
+        d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        if n >= 4:
+            d[n // 2] = d[0]
+        D = np.bitwise_count(d.view(np.uint64)[:, None, :] ^ d.view(np.uint64)[None, :, :]).sum(axis=2)
+        med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+        assert orbref.distinctive_descriptor(d) == int(np.argmin(med)), n
