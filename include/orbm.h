@@ -124,6 +124,15 @@ int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extract
                                              float inv_w, float inv_h, const orbx_projected* pts, int max_dist,
                                              int check_orientation, int32_t* assign, int32_t* nmatches);
 
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:66,
+ * src/ORBmatcher.cc:230-404), Nleft == -1. kf->has_mappoint[i] = vpMapPointsKF[i] != NULL &&
+ * !isBad(); `frame` carries F.mvKeys, F.mDescriptors and F.mFeatVec (its has_mappoint is not read; every feature may
+ * appear under one node only, as DBoW2 produces — otherwise ORBX_E_ARG). mfNNratio / mbCheckOrientation are the
+ * matcher's constructor arguments. matches_f[frame->n] (host) = index of the KeyFrame feature whose MapPoint goes to
+ * vpMapPointMatches[i], or -1; *nmatches = the return value. */
+int orbm_search_by_bow(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
+                       int check_orientation, int32_t* matches_f, int32_t* nmatches);
+
 /* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
  * const bool bOnlyStereo, const bool bCoarse) (src/ORBmatcher.cc:886-1106), pinhole keyframes. F12 (row-major 3x3)
  * and the epipole (ep_x, ep_y) are computed by the shim exactly as the reference does (:893-911,

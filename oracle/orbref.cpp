@@ -1042,6 +1042,64 @@ int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_proje
 
 // ORBmatcher::SearchForTriangulation — src/ORBmatcher.cc:886-1106; Pinhole::epipolarConstrain —
 // src/CameraModels/Pinhole.cpp:122-149 (F12 supplied by the caller, row-major).
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — src/ORBmatcher.cc:230-404, Nleft == -1
+int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
+                         int check_orientation, int32_t* matches_f) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  std::vector<int> rotHist[kHisto];
+  for (int i = 0; i < frame->n; i++) matches_f[i] = -1;  // vpMapPointMatches = vector<MapPoint*>(F.N, NULL)  :235
+  const orbx_featvec& vK = kf->featvec;
+  const orbx_featvec& vF = frame->featvec;
+  int a = 0, b = 0;
+  while (a < vK.n_nodes && b < vF.n_nodes) {
+    if (vK.node_ids[a] == vF.node_ids[b]) {
+      for (int pK = vK.offsets[a]; pK < vK.offsets[a + 1]; pK++) {
+        const int realIdxKF = (int)vK.indices[pK];
+        if (!kf->has_mappoint[realIdxKF]) continue;  // !pMP || pMP->isBad()                                  :262-264
+        const uint8_t* dKF = kf->desc + (size_t)realIdxKF * 32;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int pF = vF.offsets[b]; pF < vF.offsets[b + 1]; pF++) {
+          const int realIdxF = (int)vF.indices[pF];
+          if (matches_f[realIdxF] >= 0) continue;  //                                                          :280
+          const int dist = orbref_descriptor_distance(dKF, frame->desc + (size_t)realIdxF * 32);
+          if (dist < bestDist1) {
+            bestDist2 = bestDist1;
+            bestDist1 = dist;
+            bestIdxF = realIdxF;
+          } else if (dist < bestDist2) {
+            bestDist2 = dist;
+          }
+        }
+        if (bestDist1 <= TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {  //                        :319-321
+          matches_f[bestIdxF] = realIdxKF;
+          if (check_orientation)
+            rotHist[rot_bin(kf->kps[realIdxKF].angle, frame->kps[bestIdxF].angle)].push_back(bestIdxF);
+          nmatches++;
+        }
+      }
+      a++;
+      b++;
+    } else if (vK.node_ids[a] < vF.node_ids[b]) {
+      while (a < vK.n_nodes && vK.node_ids[a] < vF.node_ids[b]) a++;  // lower_bound
+    } else {
+      while (b < vF.n_nodes && vF.node_ids[b] < vK.node_ids[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, kHisto, ind1, ind2, ind3);
+    for (int i = 0; i < kHisto; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idxF : rotHist[i]) {
+        matches_f[idxF] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
 int orbref_search_for_triangulation(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, const float* F12,
                                     float ep_x, float ep_y, int only_stereo, int coarse, int check_orientation,
                                     int32_t* matches12) {

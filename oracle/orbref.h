@@ -88,6 +88,12 @@ int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoin
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
 int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                       int check_orientation, int32_t* assign);
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:230-404),
+ * Nleft == -1. kf->has_mappoint[i] = vpMapPointsKF[i] != NULL && !isBad(); `frame` carries F.mvKeys, F.mDescriptors and
+ * F.mFeatVec (has_mappoint unused). matches_f[frame->n] = index of the KeyFrame feature whose MapPoint is written to
+ * vpMapPointMatches[i], or -1. Returns nmatches. */
+int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
+                         int check_orientation, int32_t* matches_f);
 /* ORBmatcher::SearchForTriangulation, pinhole mono/stereo keyframes (src/ORBmatcher.cc:886-1106 +
  * src/CameraModels/Pinhole.cpp:122-149). F12 = K1^-T [t12]x R12 K2^-1 computed by the caller (row-major 3x3);
  * ep = projection of camera centre 1 into image 2. matches12[kf1->n] = idx2 or -1. Returns nmatches. */

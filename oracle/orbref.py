@@ -161,6 +161,7 @@ def lib():
         L.orbref_search_by_projection_map.argtypes = [vp, vp, cf, cf, ci, cf, vp]
         L.orbref_search_by_projection_frame.argtypes = [vp, vp, ci, ci, vp]
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
+        L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_extract_many.argtypes = [vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]
         L.orbref_stereo_many.argtypes = [vp, vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, cf, cf, ci, vp, vp, vp]
         _lib = L
@@ -347,6 +348,12 @@ def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False,
     n = lib().orbref_search_for_triangulation(kf1.ref(), kf2.ref(), _ptr(F12), float(ep[0]), float(ep[1]),
                                               int(only_stereo), int(coarse), int(check_orientation), _ptr(m))
     return n, m[:kf1.struct.n]
+
+
+def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):
+    m = np.empty(max(frame.struct.n, 1), np.int32)
+    n = lib().orbref_search_by_bow(kf.ref(), frame.ref(), float(nnratio), int(check_orientation), _ptr(m))
+    return n, m[:frame.struct.n]
 
 
 def extract_many(imgs, nfeatures, scale_factor, nlevels, ini_th, min_th, lapping, threads):

@@ -510,6 +510,102 @@ void launch_triangulation(const TriArgs& A, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:230-404), Nleft == -1. The only order
+// dependence — a frame feature that already received a MapPoint is skipped (:280) — stays inside one vocabulary node,
+// because DBoW2 files every feature under exactly one node of the FeatureVector (the ABI checks that the frame's
+// lists are disjoint). So: k_bow_nodes pairs the node lists (binary search; both ascend), k_bow_match lets ONE THREAD
+// PER SHARED NODE replay the reference's double loop for its features in order, k_bow_rot applies the rotation
+// histogram (:371-388) and counts.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_bow_nodes(const BowArgs A) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.kf.n_nodes) return;
+  const uint32_t id = A.kf.node_ids[a];
+  int lo = 0, hi = A.fr.n_nodes - 1, found = -1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const uint32_t v = A.fr.node_ids[mid];
+    if (v == id) { found = mid; break; }
+    if (v < id) lo = mid + 1;
+    else hi = mid - 1;
+  }
+  A.node_match[a] = found;
+}
+
+__global__ void k_bow_match(const BowArgs A) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.kf.n_nodes) return;
+  const int b = A.node_match[a];
+  if (b < 0) return;
+  const DevKeyFrame &K = A.kf, &F = A.fr;
+  for (int pK = K.offsets[a]; pK < K.offsets[a + 1]; pK++) {
+    const int idxK = (int)K.indices[pK];
+    if (!K.has_mappoint[idxK]) continue;                                   // :262-264
+    uint32_t dK[8];
+    load_desc8(K.desc + (size_t)idxK * 32, dK);
+    int best1 = 256, best2 = 256, bestF = -1;
+    for (int pF = F.offsets[b]; pF < F.offsets[b + 1]; pF++) {
+      const int idxF = (int)F.indices[pF];
+      if (A.matches_f[idxF] >= 0) continue;                                // :280 (written by this thread only)
+      const int dist = hamming8(dK, F.desc + (size_t)idxF * 32);
+      if (dist < best1) {
+        best2 = best1;
+        best1 = dist;
+        bestF = idxF;
+      } else if (dist < best2) {
+        best2 = dist;
+      }
+    }
+    if (best1 <= ORBM_TH_LOW_I && (float)best1 < fmul(A.nnratio, (float)best2)) A.matches_f[bestF] = idxK;  // :319-322
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bow_rot(const BowArgs A) {
+  __shared__ int histo[32];
+  __shared__ int s_count, s_removed;
+  if (threadIdx.x < 32) histo[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_count = 0; s_removed = 0; }
+  __syncthreads();
+  const int n = A.fr.n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int j = A.matches_f[i];
+    if (j < 0) continue;
+    atomicAdd(&s_count, 1);
+    if (A.check_orientation) atomicAdd(&histo[rot_bin(A.kf.kps[j].angle, A.fr.kps[i].angle)], 1);  // :338-344
+  }
+  __syncthreads();
+  if (A.check_orientation) {
+    int ind1, ind2, ind3;
+    three_maxima(histo, kHistoLength, ind1, ind2, ind3);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int j = A.matches_f[i];
+      if (j < 0) continue;
+      const int bin = rot_bin(A.kf.kps[j].angle, A.fr.kps[i].angle);
+      if (bin != ind1 && bin != ind2 && bin != ind3) {
+        A.matches_f[i] = -1;
+        atomicAdd(&s_removed, 1);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *A.nmatches = s_count - s_removed;
+}
+
+__global__ void k_fill_minus_one(int32_t* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = -1;
+}
+
+void launch_search_by_bow(const BowArgs& A, cudaStream_t st) {
+  if (A.fr.n > 0) k_fill_minus_one<<<(A.fr.n + 255) / 256, 256, 0, st>>>(A.matches_f, A.fr.n);
+  if (A.kf.n_nodes > 0 && A.fr.n_nodes > 0) {
+    k_bow_nodes<<<(A.kf.n_nodes + 127) / 128, 128, 0, st>>>(A);
+    k_bow_match<<<(A.kf.n_nodes + 63) / 64, 64, 0, st>>>(A);
+  }
+  k_bow_rot<<<1, 256, 0, st>>>(A);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Frame::AssignFeaturesToGrid + Frame::PosInGrid (src/Frame.cc:520-547, :833-844), Nleft == -1: the 64x48 lookup grid
 // as CSR, cell id = col * 48 + row, keypoint indices ascending inside a cell (push_back order of the serial loop).
 // One warp per frame: histogram in shared memory, warp scan over the 3072 cells, then the keypoints are placed in

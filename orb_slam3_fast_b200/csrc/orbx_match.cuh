@@ -122,6 +122,16 @@ struct TriArgs {
   int32_t* node_match; // [k1.n_nodes] scratch: index of the same node id in k2 or -1
 };
 void launch_triangulation(const TriArgs& A, cudaStream_t st);
+// SearchByBoW(KeyFrame*, Frame&, ...): kf.has_mappoint = the KeyFrame features that carry a good MapPoint
+struct BowArgs {
+  DevKeyFrame kf, fr;
+  float nnratio;
+  int check_orientation;
+  int32_t* matches_f;   // [fr.n] KeyFrame feature index or -1
+  int32_t* nmatches;    // [1]
+  int32_t* node_match;  // [kf.n_nodes] scratch: index of the same node id in fr or -1
+};
+void launch_search_by_bow(const BowArgs& A, cudaStream_t st);
 // Frame::AssignFeaturesToGrid for `frames` keypoint arrays (kp_stride apart; counts from n_ptr[f] or n_fixed)
 void launch_build_grid(const orbx_kp* kps, const int32_t* n_ptr, int n_fixed, int64_t kp_stride, int frames, float min_x,
                        float min_y, float inv_w, float inv_h, int32_t* offsets, int32_t* items, int64_t item_stride,

@@ -35,6 +35,7 @@ def _bind(L):
                                                          vp]
     L.orbm_search_by_projection_frame_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, ci, ci, vp, vp]
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
+    L.orbm_search_by_bow.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L._orbm_bound = True
 
 
@@ -198,6 +199,15 @@ class ORBmatcher:
         return nm.value, assign[:n]
 
     # int SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse) — :886
+    # int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) — src/ORBmatcher.cc:230
+    def SearchByBoW(self, kf, frame):
+        n = frame.struct.n
+        mf = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_by_bow(self._h, kf.ref(), frame.ref(), self.mfNNratio,
+                                               int(self.mbCheckOrientation), _l.ptr(mf), C.byref(nm)))
+        return nm.value, mf[:n]
+
     def SearchForTriangulation(self, kf1, kf2, F12, ep, bOnlyStereo=False, bCoarse=False):
         F12 = np.ascontiguousarray(F12, np.float32).reshape(9)
         n = kf1.struct.n

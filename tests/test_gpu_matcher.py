@@ -250,3 +250,40 @@ def test_compute_distinctive_descriptors(matcher):
     ref = np.array([orbref.distinctive_descriptor(d) for d in lists], np.int32)
     assert np.array_equal(best, ref), np.nonzero(best != ref)[0][:10]
     assert len(matcher.ComputeDistinctiveDescriptors([])) == 0
+
+
+@pytest.mark.parametrize("nnratio,check,seed", [(0.7, True, 0), (0.9, False, 1), (0.75, True, 2)])
+def test_search_by_bow_keyframe_frame(gpu, nnratio, check, seed):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (src/ORBmatcher.cc:230-404): per shared vocabulary node the
+    KeyFrame features that carry a MapPoint take the best still-free frame feature (ratio test, TH_LOW), then the
+    rotation histogram. Frame = the right image of a stereo pair, so corresponding descriptors are close."""
+    w, h = 752, 480
+    left, right, _ = synth.stereo_pair(h, w, seed, d_min=3, d_max=20)
+    e1, e2 = ORBextractor(1500), ORBextractor(1500)
+    _, k1, d1 = e1(left)
+    _, k2, d2 = e2(right)
+    rng = np.random.default_rng(seed)
+
+    def featvec(desc, bits):
+        # coarse hash of the descriptor = vocabulary node: few nodes (many features per node) stresses the greedy part
+        node_of = (desc[:, 0].astype(np.int64) >> (8 - bits)) * 7 + 3
+        ids, inv = np.unique(node_of, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        offsets = np.zeros(len(ids) + 1, np.int32)
+        offsets[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+        return ids.astype(np.uint32), offsets, order.astype(np.uint32)
+    sf, s2 = e1.GetScaleFactors(), e1.GetScaleSigmaSquares()
+    for bits in (3, 6):
+        views_g, views_r = [], []
+        for k, d in ((k1, d1), (k2, d2)):
+            ids, off, idx = featvec(d, bits)
+            ur = np.full(len(k), -1, np.float32)
+            hm = (rng.random(len(k)) < 0.6).astype(np.uint8)   # KeyFrame features that carry a good MapPoint
+            a = (k, d, ur, hm, ids, off, idx, sf, s2)
+            views_g.append(views.make_keyframe_view(*a))
+            views_r.append(orbref.make_keyframe_view(*a))
+        mt = ORBmatcher(nnratio, check)
+        n, mf = mt.SearchByBoW(views_g[0], views_g[1])
+        n_r, mf_r = orbref.search_by_bow(views_r[0], views_r[1], nnratio, check)
+        assert n_r > 20, "degenerate test: %d matches" % n_r
+        assert n == n_r and np.array_equal(mf, mf_r), np.nonzero(mf != mf_r)[0][:10]
