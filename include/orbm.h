@@ -133,6 +133,12 @@ int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extract
 int orbm_search_by_bow(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
                        int check_orientation, int32_t* matches_f, int32_t* nmatches);
 
+/* int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (include/ORBmatcher.h:67,
+ * src/ORBmatcher.cc:766-884), NLeft == -1. has_mappoint[i] = vpMapPoints[i] != NULL && !isBad() on both sides;
+ * matches12[kf1->n] (host) = index of the KeyFrame-2 feature whose MapPoint goes to vpMatches12[i], or -1. */
+int orbm_search_by_bow_kf(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,
+                          int check_orientation, int32_t* matches12, int32_t* nmatches);
+
 /* int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, vector<pair<size_t,size_t>>& vMatchedPairs,
  * const bool bOnlyStereo, const bool bCoarse) (src/ORBmatcher.cc:886-1106), pinhole keyframes. F12 (row-major 3x3)
  * and the epipole (ep_x, ep_y) are computed by the shim exactly as the reference does (:893-911,

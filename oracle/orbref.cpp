@@ -1100,6 +1100,65 @@ int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view*
   return nmatches;
 }
 
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) — src/ORBmatcher.cc:766-884, NLeft == -1
+int orbref_search_by_bow_kf(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,
+                            int check_orientation, int32_t* matches12) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  std::vector<int> rotHist[kHisto];
+  for (int i = 0; i < kf1->n; i++) matches12[i] = -1;
+  std::vector<bool> vbMatched2(std::max(kf2->n, 1), false);
+  const orbx_featvec& v1 = kf1->featvec;
+  const orbx_featvec& v2 = kf2->featvec;
+  int a = 0, b = 0;
+  while (a < v1.n_nodes && b < v2.n_nodes) {
+    if (v1.node_ids[a] == v2.node_ids[b]) {
+      for (int p1 = v1.offsets[a]; p1 < v1.offsets[a + 1]; p1++) {
+        const int idx1 = (int)v1.indices[p1];
+        if (!kf1->has_mappoint[idx1]) continue;  //                                                           :802-804
+        const uint8_t* d1 = kf1->desc + (size_t)idx1 * 32;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int p2 = v2.offsets[b]; p2 < v2.offsets[b + 1]; p2++) {
+          const int idx2 = (int)v2.indices[p2];
+          if (vbMatched2[idx2] || !kf2->has_mappoint[idx2]) continue;  //                                     :821-823
+          const int dist = orbref_descriptor_distance(d1, kf2->desc + (size_t)idx2 * 32);
+          if (dist < bestDist1) {
+            bestDist2 = bestDist1;
+            bestDist1 = dist;
+            bestIdx2 = idx2;
+          } else if (dist < bestDist2) {
+            bestDist2 = dist;
+          }
+        }
+        if (bestDist1 < TH_LOW && (float)bestDist1 < nnratio * (float)bestDist2) {  //                         :838-840
+          matches12[idx1] = bestIdx2;
+          vbMatched2[bestIdx2] = true;
+          if (check_orientation) rotHist[rot_bin(kf1->kps[idx1].angle, kf2->kps[bestIdx2].angle)].push_back(idx1);
+          nmatches++;
+        }
+      }
+      a++;
+      b++;
+    } else if (v1.node_ids[a] < v2.node_ids[b]) {
+      while (a < v1.n_nodes && v1.node_ids[a] < v2.node_ids[b]) a++;  // lower_bound
+    } else {
+      while (b < v2.n_nodes && v2.node_ids[b] < v1.node_ids[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, kHisto, ind1, ind2, ind3);
+    for (int i = 0; i < kHisto; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) {
+        matches12[idx1] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
 int orbref_search_for_triangulation(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, const float* F12,
                                     float ep_x, float ep_y, int only_stereo, int coarse, int check_orientation,
                                     int32_t* matches12) {

@@ -88,6 +88,11 @@ int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoin
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
 int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                       int check_orientation, int32_t* assign);
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:766-884),
+ * NLeft == -1. has_mappoint[i] = vpMapPoints[i] != NULL && !isBad() on both sides. matches12[kf1->n] = index of the
+ * KeyFrame-2 feature whose MapPoint is written to vpMatches12[i], or -1. Returns nmatches. */
+int orbref_search_by_bow_kf(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,
+                            int check_orientation, int32_t* matches12);
 /* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (src/ORBmatcher.cc:230-404),
  * Nleft == -1. kf->has_mappoint[i] = vpMapPointsKF[i] != NULL && !isBad(); `frame` carries F.mvKeys, F.mDescriptors and
  * F.mFeatVec (has_mappoint unused). matches_f[frame->n] = index of the KeyFrame feature whose MapPoint is written to

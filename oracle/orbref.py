@@ -162,6 +162,7 @@ def lib():
         L.orbref_search_by_projection_frame.argtypes = [vp, vp, ci, ci, vp]
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_extract_many.argtypes = [vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]
         L.orbref_stereo_many.argtypes = [vp, vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, cf, cf, ci, vp, vp, vp]
         _lib = L
@@ -354,6 +355,12 @@ def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):
     m = np.empty(max(frame.struct.n, 1), np.int32)
     n = lib().orbref_search_by_bow(kf.ref(), frame.ref(), float(nnratio), int(check_orientation), _ptr(m))
     return n, m[:frame.struct.n]
+
+
+def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
+    m = np.empty(max(kf1.struct.n, 1), np.int32)
+    n = lib().orbref_search_by_bow_kf(kf1.ref(), kf2.ref(), float(nnratio), int(check_orientation), _ptr(m))
+    return n, m[:kf1.struct.n]
 
 
 def extract_many(imgs, nfeatures, scale_factor, nlevels, ini_th, min_th, lapping, threads):

@@ -540,13 +540,14 @@ __global__ void k_bow_match(const BowArgs A) {
   const DevKeyFrame &K = A.kf, &F = A.fr;
   for (int pK = K.offsets[a]; pK < K.offsets[a + 1]; pK++) {
     const int idxK = (int)K.indices[pK];
-    if (!K.has_mappoint[idxK]) continue;                                   // :262-264
+    if (!K.has_mappoint[idxK]) continue;                                   // :262-264 / :802-804
     uint32_t dK[8];
     load_desc8(K.desc + (size_t)idxK * 32, dK);
     int best1 = 256, best2 = 256, bestF = -1;
     for (int pF = F.offsets[b]; pF < F.offsets[b + 1]; pF++) {
       const int idxF = (int)F.indices[pF];
-      if (A.matches_f[idxF] >= 0) continue;                                // :280 (written by this thread only)
+      // taken earlier — only ever by this thread: :280 / :821
+      if (A.kf_kf ? (A.matched2[idxF] || !F.has_mappoint[idxF]) : (A.matches_f[idxF] >= 0)) continue;
       const int dist = hamming8(dK, F.desc + (size_t)idxF * 32);
       if (dist < best1) {
         best2 = best1;
@@ -556,7 +557,15 @@ __global__ void k_bow_match(const BowArgs A) {
         best2 = dist;
       }
     }
-    if (best1 <= ORBM_TH_LOW_I && (float)best1 < fmul(A.nnratio, (float)best2)) A.matches_f[bestF] = idxK;  // :319-322
+    const bool low = A.kf_kf ? best1 < ORBM_TH_LOW_I : best1 <= ORBM_TH_LOW_I;  // :838 is strict, :319 is not
+    if (low && (float)best1 < fmul(A.nnratio, (float)best2)) {
+      if (A.kf_kf) {
+        A.matches_f[idxK] = bestF;
+        A.matched2[bestF] = 1;
+      } else {
+        A.matches_f[bestF] = idxK;
+      }
+    }
   }
 }
 
@@ -566,12 +575,16 @@ __global__ void __launch_bounds__(256) k_bow_rot(const BowArgs A) {
   if (threadIdx.x < 32) histo[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_count = 0; s_removed = 0; }
   __syncthreads();
-  const int n = A.fr.n;
+  const int n = A.kf_kf ? A.kf.n : A.fr.n;
+  // rot = angle(KeyFrame / KeyFrame-1 feature) - angle(frame / KeyFrame-2 feature)        :338-344 / :845-851
+  auto bin_of = [&](int i, int j) {
+    return A.kf_kf ? rot_bin(A.kf.kps[i].angle, A.fr.kps[j].angle) : rot_bin(A.kf.kps[j].angle, A.fr.kps[i].angle);
+  };
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int j = A.matches_f[i];
     if (j < 0) continue;
     atomicAdd(&s_count, 1);
-    if (A.check_orientation) atomicAdd(&histo[rot_bin(A.kf.kps[j].angle, A.fr.kps[i].angle)], 1);  // :338-344
+    if (A.check_orientation) atomicAdd(&histo[bin_of(i, j)], 1);
   }
   __syncthreads();
   if (A.check_orientation) {
@@ -580,7 +593,7 @@ __global__ void __launch_bounds__(256) k_bow_rot(const BowArgs A) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int j = A.matches_f[i];
       if (j < 0) continue;
-      const int bin = rot_bin(A.kf.kps[j].angle, A.fr.kps[i].angle);
+      const int bin = bin_of(i, j);
       if (bin != ind1 && bin != ind2 && bin != ind3) {
         A.matches_f[i] = -1;
         atomicAdd(&s_removed, 1);
@@ -597,7 +610,9 @@ __global__ void k_fill_minus_one(int32_t* p, int n) {
 }
 
 void launch_search_by_bow(const BowArgs& A, cudaStream_t st) {
-  if (A.fr.n > 0) k_fill_minus_one<<<(A.fr.n + 255) / 256, 256, 0, st>>>(A.matches_f, A.fr.n);
+  const int n_out = A.kf_kf ? A.kf.n : A.fr.n;
+  if (n_out > 0) k_fill_minus_one<<<(n_out + 255) / 256, 256, 0, st>>>(A.matches_f, n_out);
+  if (A.kf_kf && A.fr.n > 0) cudaMemsetAsync(A.matched2, 0, A.fr.n, st);
   if (A.kf.n_nodes > 0 && A.fr.n_nodes > 0) {
     k_bow_nodes<<<(A.kf.n_nodes + 127) / 128, 128, 0, st>>>(A);
     k_bow_match<<<(A.kf.n_nodes + 63) / 64, 64, 0, st>>>(A);

@@ -718,41 +718,60 @@ static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {
   return K;
 }
 
-int orbm_search_by_bow(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
-                       int check_orientation, int32_t* matches_f, int32_t* nmatches) {
-  if (!m || !kf || !frame || kf->n < 0 || frame->n < 0 || (frame->n > 0 && !matches_f))
+namespace {
+// every feature of the second view under at most one node (DBoW2's FeatureVector): what makes the nodes independent
+bool featvec_is_disjoint(const orbx_keyframe_view* k) {
+  const orbx_featvec& v = k->featvec;
+  const int total = v.n_nodes > 0 ? v.offsets[v.n_nodes] : 0;
+  std::vector<uint8_t> seen(std::max(k->n, 1), 0);
+  for (int i = 0; i < total; i++) {
+    const uint32_t idx = v.indices[i];
+    if (idx >= (uint32_t)k->n || seen[idx]) return false;
+    seen[idx] = 1;
+  }
+  return true;
+}
+
+int search_by_bow_common(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* second, float nnratio,
+                         int check_orientation, int kf_kf, int32_t* matches, int32_t* nmatches) {
+  const int n_out = kf_kf ? kf->n : second->n;
+  if (!m || !kf || !second || kf->n < 0 || second->n < 0 || (n_out > 0 && !matches))
     return mfail(m, ORBX_E_ARG, "bad argument");
   if (nmatches) *nmatches = 0;
-  {  // every frame feature under at most one node (DBoW2's FeatureVector): what makes the nodes independent
-    const orbx_featvec& v = frame->featvec;
-    const int total = v.n_nodes > 0 ? v.offsets[v.n_nodes] : 0;
-    std::vector<uint8_t> seen(std::max(frame->n, 1), 0);
-    for (int k = 0; k < total; k++) {
-      const uint32_t idx = v.indices[k];
-      if (idx >= (uint32_t)frame->n || seen[idx]) return mfail(m, ORBX_E_ARG, "frame FeatureVector lists a feature twice");
-      seen[idx] = 1;
-    }
-  }
+  if (!featvec_is_disjoint(second)) return mfail(m, ORBX_E_ARG, "FeatureVector lists a feature twice");
   ORBM_CUDA(m, cudaSetDevice(m->device));
   Arena ar(m);
   BowArgs A{};
   A.kf = upload_keyframe(ar, kf);
-  A.fr = upload_keyframe(ar, frame);
+  A.fr = upload_keyframe(ar, second);
   A.nnratio = nnratio;
   A.check_orientation = check_orientation;
-  A.matches_f = ar.alloc<int32_t>(frame->n);
+  A.kf_kf = kf_kf;
+  A.matches_f = ar.alloc<int32_t>(n_out);
+  A.matched2 = ar.alloc<uint8_t>(second->n);
   A.nmatches = ar.alloc<int32_t>(1);
   A.node_match = ar.alloc<int32_t>(A.kf.n_nodes);
   if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_search_by_bow(A, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   int32_t nm = 0;
-  if (frame->n > 0)
-    ORBM_CUDA(m, cudaMemcpyAsync(matches_f, A.matches_f, (size_t)frame->n * 4, cudaMemcpyDeviceToHost, m->stream));
+  if (n_out > 0)
+    ORBM_CUDA(m, cudaMemcpyAsync(matches, A.matches_f, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
   ORBM_CUDA(m, cudaMemcpyAsync(&nm, A.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
   ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
   if (nmatches) *nmatches = nm;
   return ORBX_OK;
+}
+}  // namespace
+
+int orbm_search_by_bow(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
+                       int check_orientation, int32_t* matches_f, int32_t* nmatches) {
+  return search_by_bow_common(m, kf, frame, nnratio, check_orientation, 0, matches_f, nmatches);
+}
+
+int orbm_search_by_bow_kf(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,
+                          int check_orientation, int32_t* matches12, int32_t* nmatches) {
+  return search_by_bow_common(m, kf1, kf2, nnratio, check_orientation, 1, matches12, nmatches);
 }
 
 int orbm_search_for_triangulation(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2,

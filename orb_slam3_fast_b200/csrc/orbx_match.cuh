@@ -127,7 +127,9 @@ struct BowArgs {
   DevKeyFrame kf, fr;
   float nnratio;
   int check_orientation;
-  int32_t* matches_f;   // [fr.n] KeyFrame feature index or -1
+  int kf_kf;            // 1: the KeyFrame-KeyFrame form (:766-884): matches indexed by kf, fr.has_mappoint read, < TH_LOW
+  int32_t* matches_f;   // [fr.n] KeyFrame feature index or -1 (kf_kf: [kf.n] index into fr or -1)
+  uint8_t* matched2;    // [fr.n] scratch (kf_kf): vbMatched2
   int32_t* nmatches;    // [1]
   int32_t* node_match;  // [kf.n_nodes] scratch: index of the same node id in fr or -1
 };

@@ -36,6 +36,7 @@ def _bind(L):
     L.orbm_search_by_projection_frame_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, ci, ci, vp, vp]
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
     L.orbm_search_by_bow.argtypes = [vp, vp, vp, cf, ci, vp, vp]
+    L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L._orbm_bound = True
 
 
@@ -207,6 +208,15 @@ class ORBmatcher:
         self._check(self._L.orbm_search_by_bow(self._h, kf.ref(), frame.ref(), self.mfNNratio,
                                                int(self.mbCheckOrientation), _l.ptr(mf), C.byref(nm)))
         return nm.value, mf[:n]
+
+    # int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) — src/ORBmatcher.cc:766
+    def SearchByBoWKeyFrames(self, kf1, kf2):
+        n = kf1.struct.n
+        m12 = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_by_bow_kf(self._h, kf1.ref(), kf2.ref(), self.mfNNratio,
+                                                  int(self.mbCheckOrientation), _l.ptr(m12), C.byref(nm)))
+        return nm.value, m12[:n]
 
     def SearchForTriangulation(self, kf1, kf2, F12, ep, bOnlyStereo=False, bCoarse=False):
         F12 = np.ascontiguousarray(F12, np.float32).reshape(9)

@@ -287,3 +287,8 @@ def test_search_by_bow_keyframe_frame(gpu, nnratio, check, seed):
         n_r, mf_r = orbref.search_by_bow(views_r[0], views_r[1], nnratio, check)
         assert n_r > 20, "degenerate test: %d matches" % n_r
         assert n == n_r and np.array_equal(mf, mf_r), np.nonzero(mf != mf_r)[0][:10]
+        # the KeyFrame-KeyFrame form (:766-884): MapPoints required on both sides, strict < TH_LOW, matches by kf1 index
+        n2, m12 = mt.SearchByBoWKeyFrames(views_g[0], views_g[1])
+        n2_r, m12_r = orbref.search_by_bow_kf(views_r[0], views_r[1], nnratio, check)
+        assert n2_r > 10, "degenerate test: %d matches" % n2_r
+        assert n2 == n2_r and np.array_equal(m12, m12_r), np.nonzero(m12 != m12_r)[0][:10]
