@@ -124,6 +124,17 @@ int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extract
                                              float inv_w, float inv_h, const orbx_projected* pts, int max_dist,
                                              int check_orientation, int32_t* assign, int32_t* nmatches);
 
+/* The matching loop of int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th,
+ * const bool bRight) (include/ORBmatcher.h:94, src/ORBmatcher.cc:1108-1275; bRight = false, NLeft == -1) — SURVEY.md
+ * §8(f) rank 3. The shim projects the points that pass :1141-1187 (orbx_projected: u, v, u_right = ur, radius =
+ * th * mvScaleFactors[nPredictedLevel], max_level = nPredictedLevel, desc = GetDescriptor(); min_level, angle, has_obs
+ * are not read); kf carries mvKeysUn, mDescriptors, mvuRight and the KeyFrame's grid; inv_level_sigma2 =
+ * mvInvLevelSigma2[kf->n_levels]. best_idx[m] / best_dist[m] (host): the most similar keypoint that passes the level
+ * window and the chi-square gate (:1194-1257), -1 / 256 when none. The shim then applies bestDist <= TH_LOW and does
+ * the Replace / AddObservation surgery in point order (:1261-1273). */
+int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
+                    const orbx_projected* pts, int32_t* best_idx, int32_t* best_dist);
+
 /* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:66,
  * src/ORBmatcher.cc:230-404), Nleft == -1. kf->has_mappoint[i] = vpMapPointsKF[i] != NULL &&
  * !isBad(); `frame` carries F.mvKeys, F.mDescriptors and F.mFeatVec (its has_mappoint is not read; every feature may

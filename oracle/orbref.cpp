@@ -1100,6 +1100,42 @@ int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view*
   return nmatches;
 }
 
+// ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight) — the matching loop, src/ORBmatcher.cc:1194-1257
+void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2, const orbx_projected* pts,
+                       int32_t* best_idx, int32_t* best_dist) {
+  std::vector<int32_t> idxs(std::max(kf->n, 1));
+  for (int i = 0; i < pts->m; i++) {
+    const float u = pts->u[i], v = pts->v[i], ur = pts->u_right ? pts->u_right[i] : 0.f;
+    const int nPredictedLevel = pts->max_level[i];
+    // KeyFrame::GetFeaturesInArea has no level filter (src/KeyFrame.cc:705-749): minLevel = -1, maxLevel = -1
+    const int nc = orbref_features_in_area(kf, u, v, pts->radius[i], -1, -1, idxs.data());
+    const uint8_t* dMP = pts->desc + (size_t)i * 32;
+    int bestDist = 256, bestIdx = -1;
+    for (int c = 0; c < nc; c++) {
+      const int idx = idxs[c];
+      const orbx_kp& kp = kf->kps[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;  //                          :1221
+      if (kf->u_right && kf->u_right[idx] >= 0) {  // check reprojection error in stereo                       :1223-1233
+        const float ex = u - kp.x, ey = v - kp.y, er = ur - kf->u_right[idx];
+        const float e2 = ex * ex + ey * ey + er * er;
+        if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+      } else {  //                                                                                            :1235-1243
+        const float ex = u - kp.x, ey = v - kp.y;
+        const float e2 = ex * ex + ey * ey;
+        if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+      }
+      const int dist = orbref_descriptor_distance(dMP, kf->desc + (size_t)idx * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx = idx;
+      }
+    }
+    best_idx[i] = bestIdx;
+    best_dist[i] = bestDist;
+  }
+}
+
 // ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) — src/ORBmatcher.cc:766-884, NLeft == -1
 int orbref_search_by_bow_kf(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,
                             int check_orientation, int32_t* matches12) {

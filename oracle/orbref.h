@@ -88,6 +88,15 @@ int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoin
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
 int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                       int check_orientation, int32_t* assign);
+/* The matching part of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight = false)
+ * (src/ORBmatcher.cc:1108-1275), NLeft == -1, after the caller-side projection (:1152-1192): per point
+ * KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:705-749), the level window [L-1, L] (:1221), the chi-square gate on the
+ * reprojection error (7.8 stereo / 5.99 mono, :1223-1244), the most similar keypoint (:1250-1257).
+ * kf: mvKeysUn, mDescriptors, mvuRight, grid of the KeyFrame. pts: u, v, u_right (ur), radius, max_level =
+ * nPredictedLevel (min_level, angle, has_obs unused), desc = MapPoint::GetDescriptor(). best_idx[i] = keypoint or -1,
+ * best_dist[i] = its distance (256 when none); the caller applies bestDist <= TH_LOW and the graph surgery. */
+void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2, const orbx_projected* pts,
+                       int32_t* best_idx, int32_t* best_dist);
 /* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:766-884),
  * NLeft == -1. has_mappoint[i] = vpMapPoints[i] != NULL && !isBad() on both sides. matches12[kf1->n] = index of the
  * KeyFrame-2 feature whose MapPoint is written to vpMatches12[i], or -1. Returns nmatches. */

@@ -163,6 +163,8 @@ def lib():
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_fuse_match.argtypes = [vp, vp, vp, vp, vp]
+        L.orbref_fuse_match.restype = None
         L.orbref_extract_many.argtypes = [vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]
         L.orbref_stereo_many.argtypes = [vp, vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, cf, cf, ci, vp, vp, vp]
         _lib = L
@@ -361,6 +363,14 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
     m = np.empty(max(kf1.struct.n, 1), np.int32)
     n = lib().orbref_search_by_bow_kf(kf1.ref(), kf2.ref(), float(nnratio), int(check_orientation), _ptr(m))
     return n, m[:kf1.struct.n]
+
+
+def fuse_match(kf, inv_level_sigma2, pts):
+    inv = _c(inv_level_sigma2, np.float32)
+    m = pts.struct.m
+    bi, bd = np.empty(max(m, 1), np.int32), np.empty(max(m, 1), np.int32)
+    lib().orbref_fuse_match(kf.ref(), _ptr(inv), pts.ref(), _ptr(bi), _ptr(bd))
+    return bi[:m], bd[:m]
 
 
 def extract_many(imgs, nfeatures, scale_factor, nlevels, ini_th, min_th, lapping, threads):

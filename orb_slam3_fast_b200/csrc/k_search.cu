@@ -510,6 +510,81 @@ void launch_triangulation(const TriArgs& A, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The matching loop of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:1194-1257) after
+// the caller-side projection: points are independent (the MapPoint / KeyFrame graph surgery that follows stays with
+// the caller, in point order). One warp per point: lanes take the cells of KeyFrame::GetFeaturesInArea's window
+// (src/KeyFrame.cc:705-749; ix outer, iy inner) and walk their keypoints; "first keypoint with the least distance"
+// (:1253, strict <) is the minimum of (distance, cell position in the window, position in the cell).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSearchWarps * 32)
+k_fuse_match(const DevFrame F, const DevQueries Q, const float* __restrict__ inv_level_sigma2,
+             int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kSearchWarps + warp;
+  if (i >= Q.m) return;
+  const float x = Q.u[i], y = Q.v[i], r = Q.radius[i];
+  const float ur = Q.u_right ? Q.u_right[i] : 0.f;
+  const int L = Q.max_level[i];
+  const Window w = cell_window(F, x, y, r);
+  const int ny = w.y1 - w.y0 + 1;
+  const int ncell = w.x1 < w.x0 ? 0 : (w.x1 - w.x0 + 1) * ny;
+  uint32_t dq[8];
+  load_desc8(Q.desc + (size_t)i * 32, dq);
+  unsigned long long best = ~0ull;  // dist << 32 | window cell << 16 | position in the cell
+  int bidx = -1;
+  for (int cb = 0; cb < ncell; cb += 32) {
+    const int c = cb + lane;
+    if (c >= ncell) continue;
+    const int ix = w.x0 + c / ny, iy = w.y0 + c % ny;
+    const int cell = ix * ORBX_GRID_ROWS + iy;
+    const int j0 = F.cell_offsets[cell], j1 = F.cell_offsets[cell + 1];
+    for (int j = j0; j < j1; j++) {
+      const int idx = F.cell_items[j];
+      const orbx_kp kp = F.kps[idx];
+      if (!(fabsf(fsub(kp.x, x)) < r && fabsf(fsub(kp.y, y)) < r)) continue;            // KeyFrame.cc:739-743
+      const int lv = kp.octave;
+      if (lv < L - 1 || lv > L) continue;                                              // :1221
+      const float ex = fsub(x, kp.x), ey = fsub(y, kp.y);
+      const float kr = F.u_right ? F.u_right[idx] : -1.f;
+      if (kr >= 0) {                                                                   // :1223-1233
+        const float er = fsub(ur, kr);
+        const float e2 = fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(er, er));
+        if ((double)fmul(e2, inv_level_sigma2[lv]) > 7.8) continue;
+      } else {                                                                         // :1235-1243
+        const float e2 = fadd(fmul(ex, ex), fmul(ey, ey));
+        if ((double)fmul(e2, inv_level_sigma2[lv]) > 5.99) continue;
+      }
+      const int dist = hamming8(dq, F.desc + (size_t)idx * 32);
+      const unsigned long long key = ((unsigned long long)dist << 32) | ((unsigned)c << 16) | (unsigned)(j - j0);
+      if (key < best) {
+        best = key;
+        bidx = idx;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ob < best) {
+      best = ob;
+      bidx = oi;
+    }
+  }
+  if (lane == 0) {
+    best_idx[i] = bidx;
+    best_dist[i] = bidx < 0 ? 256 : (int)(best >> 32);
+  }
+}
+
+void launch_fuse_match(const DevFrame& F, const DevQueries& Q, const float* inv_level_sigma2, int32_t* best_idx,
+                       int32_t* best_dist, cudaStream_t st) {
+  if (Q.m > 0)
+    k_fuse_match<<<(Q.m + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, st>>>(F, Q, inv_level_sigma2, best_idx,
+                                                                                        best_dist);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:230-404), Nleft == -1. The only order
 // dependence — a frame feature that already received a MapPoint is skipped (:280) — stays inside one vocabulary node,
 // because DBoW2 files every feature under exactly one node of the FeatureVector (the ABI checks that the frame's

@@ -718,6 +718,35 @@ static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {
   return K;
 }
 
+int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
+                    const orbx_projected* pts, int32_t* best_idx, int32_t* best_dist) {
+  if (!m || !kf || !pts || !inv_level_sigma2 || kf->n < 0 || pts->m < 0 || (pts->m > 0 && (!best_idx || !best_dist)))
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (pts->m == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int M = pts->m;
+  Arena ar(m);
+  const DevFrame F = upload_frame(ar, kf);
+  DevQueries Q{};
+  Q.m = M;
+  Q.u = ar.upload(pts->u, M);
+  Q.v = ar.upload(pts->v, M);
+  Q.radius = ar.upload(pts->radius, M);
+  Q.max_level = ar.upload(pts->max_level, M);
+  Q.u_right = pts->u_right ? ar.upload(pts->u_right, M) : (ar.alloc<float>(1), nullptr);
+  Q.desc = ar.upload(pts->desc, (size_t)M * 32);
+  const float* d_inv = ar.upload(inv_level_sigma2, kf->n_levels);
+  int32_t* d_bi = ar.alloc<int32_t>(M);
+  int32_t* d_bd = ar.alloc<int32_t>(M);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_fuse_match(F, Q, d_inv, d_bi, d_bd, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  ORBM_CUDA(m, cudaMemcpyAsync(best_idx, d_bi, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(best_dist, d_bd, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  return ORBX_OK;
+}
+
 namespace {
 // every feature of the second view under at most one node (DBoW2's FeatureVector): what makes the nodes independent
 bool featvec_is_disjoint(const orbx_keyframe_view* k) {

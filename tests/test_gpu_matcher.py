@@ -292,3 +292,38 @@ def test_search_by_bow_keyframe_frame(gpu, nnratio, check, seed):
         n2_r, m12_r = orbref.search_by_bow_kf(views_r[0], views_r[1], nnratio, check)
         assert n2_r > 10, "degenerate test: %d matches" % n2_r
         assert n2 == n2_r and np.array_equal(m12, m12_r), np.nonzero(m12 != m12_r)[0][:10]
+
+
+@pytest.mark.parametrize("m,th,stereo,seed", [(3000, 3.0, True, 0), (1500, 2.5, False, 1), (6000, 4.0, True, 2)])
+def test_fuse_match(matcher, m, th, stereo, seed):
+    """The matching loop of ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>, th) (src/ORBmatcher.cc:1194-1257): window
+    from KeyFrame::GetFeaturesInArea, level window [L-1, L], chi-square gate (7.8 stereo / 5.99 mono), best distance
+    with the first keypoint winning ties."""
+    w, h = 752, 480
+    ex = ORBextractor(1200)
+    _, kps, desc = ex(synth.scene(h, w, seed + 20))
+    rng = np.random.default_rng(seed)
+    n = len(kps)
+    ur_kf = np.where(rng.random(n) < 0.6, kps["x"] - rng.uniform(1, 40, n), -1).astype(np.float32) if stereo else None
+    occ = np.zeros(n, np.uint8)
+    fv, fr = _frame_views(kps, desc, w, h, ex.GetScaleFactors(), ur_kf, occ)
+    inv_sigma2 = 1.0 / np.asarray(ex.GetScaleSigmaSquares(), np.float32)
+    # projected MapPoints: most sit within a pixel or two of a keypoint (so that the chi-square gate decides), with the
+    # keypoint's level or a neighbouring one and a descriptor a few bits away; duplicates force distance ties
+    src = rng.integers(0, n, m)
+    near = rng.random(m) < 0.85
+    u = np.where(near, kps["x"][src] + rng.normal(0, 1.2, m), rng.uniform(0, w, m)).astype(np.float32)
+    v = np.where(near, kps["y"][src] + rng.normal(0, 1.2, m), rng.uniform(0, h, m)).astype(np.float32)
+    level = np.clip(kps["octave"][src] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    radius = (np.float32(th) * np.asarray(ex.GetScaleFactors(), np.float32)[level]).astype(np.float32)
+    d = synth.flip_bits(desc[src], rng.integers(0, 60, m), rng)
+    d[::7] = desc[src[::7]]
+    base_ur = ur_kf[src] if stereo else np.zeros(m, np.float32)
+    u_r = np.where(base_ur >= 0, base_ur + rng.normal(0, 1.0, m), u - 5).astype(np.float32)
+    pts = dict(u=u, v=v, u_right=u_r if stereo else None, radius=radius, min_level=level - 1, max_level=level,
+               angle=np.zeros(m, np.float32), has_obs=np.zeros(m, np.uint8), desc=d)
+    bi, bd = matcher.FuseMatch(fv, inv_sigma2, views.make_projected(**pts))
+    bi_r, bd_r = orbref.fuse_match(fr, inv_sigma2, orbref.make_projected(**pts))
+    assert (bi_r >= 0).sum() > m // 4 and ((bi_r < 0) & near).sum() > 0, "degenerate test"
+    assert np.array_equal(bi, bi_r), np.nonzero(bi != bi_r)[0][:10]
+    assert np.array_equal(bd, bd_r)
