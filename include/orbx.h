@@ -91,6 +91,18 @@ int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp
 int orbx_profile_enable(orbx_extractor* ex, int on);
 int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int reset);
 
+/* cv::cvtColor(src, dst, cv::COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit images — what Tracking::GrabImageStereo /
+ * GrabImageRGBD / GrabImageMonocular apply to colour input before the Frame constructor (src/Tracking.cc:1394-1412,
+ * 1500-1513, 1558-1571); SURVEY.md §8(f) rank 4 (image front-end). channels = 3 or 4, rgb != 0 when the first channel
+ * is red (mbRGB). The device form converts n_frames images in place of the caller's buffers on `cuda_stream` (NULL =
+ * the default stream) without synchronising, so a colour batch can feed orbx_extract_batch_device directly; the host
+ * form is synchronous. No handle: errors are return codes only. */
+int orbx_cvt_gray_device(int device, int n_frames, const uint8_t* d_src, int width, int height, int src_stride,
+                         int64_t src_frame_stride, int channels, int rgb, uint8_t* d_dst, int dst_stride,
+                         int64_t dst_frame_stride, void* cuda_stream);
+int orbx_cvt_gray(int device, const uint8_t* src, int width, int height, int src_stride, int channels, int rgb,
+                  uint8_t* dst, int dst_stride);
+
 /* Pinned host memory for the batched calls. */
 void* orbx_host_alloc(int64_t bytes);
 void orbx_host_free(void* p);

@@ -1100,6 +1100,19 @@ int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view*
   return nmatches;
 }
 
+// cv::cvtColor(..., COLOR_*2GRAY), 8-bit (OpenCV imgproc/color_rgb: RGB2Gray<uchar>, 15-bit coefficients)
+void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb, uint8_t* dst, int dstride) {
+  const int BY = 3735, GY = 19235, RY = 9798;
+  for (int y = 0; y < h; y++) {
+    const uint8_t* s = src + (size_t)y * stride;
+    uint8_t* d = dst + (size_t)y * dstride;
+    for (int x = 0; x < w; x++, s += channels) {
+      const int b = rgb ? s[2] : s[0], g = s[1], r = rgb ? s[0] : s[2];
+      d[x] = (uint8_t)((b * BY + g * GY + r * RY + (1 << 14)) >> 15);
+    }
+  }
+}
+
 // ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight) — the matching loop, src/ORBmatcher.cc:1194-1257
 void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2, const orbx_projected* pts,
                        int32_t* best_idx, int32_t* best_dist) {

@@ -88,6 +88,11 @@ int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoin
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
 int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                       int check_orientation, int32_t* assign);
+/* cv::cvtColor(src, dst, COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit images, the conversion Tracking::GrabImage* applies to
+ * colour input (src/Tracking.cc:1394-1412, 1500-1513, 1558-1571): OpenCV's fixed point,
+ * gray = (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15 (pinned to cv2 4.13 in tests/test_oracle_primitives.py).
+ * channels = 3 or 4; rgb != 0 when the first channel is red. */
+void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb, uint8_t* dst, int dstride);
 /* The matching part of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight = false)
  * (src/ORBmatcher.cc:1108-1275), NLeft == -1, after the caller-side projection (:1152-1192): per point
  * KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:705-749), the level window [L-1, L] (:1221), the chi-square gate on the

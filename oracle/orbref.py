@@ -163,6 +163,8 @@ def lib():
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_cvt_gray.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci]
+        L.orbref_cvt_gray.restype = None
         L.orbref_fuse_match.argtypes = [vp, vp, vp, vp, vp]
         L.orbref_fuse_match.restype = None
         L.orbref_extract_many.argtypes = [vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]
@@ -363,6 +365,15 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
     m = np.empty(max(kf1.struct.n, 1), np.int32)
     n = lib().orbref_search_by_bow_kf(kf1.ref(), kf2.ref(), float(nnratio), int(check_orientation), _ptr(m))
     return n, m[:kf1.struct.n]
+
+
+def cvt_gray(img, rgb=False):
+    """cv::cvtColor(img, COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) for an [h, w, 3|4] uint8 image."""
+    img = _c(img, np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orbref_cvt_gray(_ptr(img), w, h, img.strides[0], c, int(rgb), _ptr(out), w)
+    return out
 
 
 def fuse_match(kf, inv_level_sigma2, pts):

@@ -289,6 +289,61 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// cv::cvtColor(..., COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit images (src/Tracking.cc:1394-1412): OpenCV's fixed point
+// gray = (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15. SURVEY.md §8(f) rank 4 (the image front-end). Pure
+// streaming: a thread turns 4 pixels (three or four aligned words) into one output word; the only kernel of the
+// library that is bound by HBM rather than by instruction issue.
+// ---------------------------------------------------------------------------------------------------------------
+template <int kChannels>
+__global__ void __launch_bounds__(256)
+k_cvt_gray(const uint8_t* __restrict__ src, int w, int h, int sstride, int64_t sfstride, uint8_t* __restrict__ dst,
+           int dstride, int64_t dfstride, int rgb, int aligned) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y, f = blockIdx.z;
+  if (x >= w) return;
+  const uint8_t* s = src + f * sfstride + (int64_t)y * sstride + (int64_t)x * kChannels;
+  uint8_t* d = dst + f * dfstride + (int64_t)y * dstride + x;
+  const int c0 = rgb ? 9798 : 3735, c2 = rgb ? 3735 : 9798;  // weight of the first / third channel
+  uint32_t out = 0;
+  if (aligned && x + 4 <= w) {
+    uint32_t px[4];  // per pixel: byte 0 = first channel, byte 1 = green, byte 2 = third channel
+    if (kChannels == 4) {
+      const uint4 q = *reinterpret_cast<const uint4*>(s);
+      px[0] = q.x; px[1] = q.y; px[2] = q.z; px[3] = q.w;
+    } else {
+      const uint32_t a = reinterpret_cast<const uint32_t*>(s)[0], b = reinterpret_cast<const uint32_t*>(s)[1],
+                     c = reinterpret_cast<const uint32_t*>(s)[2];
+      px[0] = a;
+      px[1] = __funnelshift_r(a, b, 24);
+      px[2] = __funnelshift_r(b, c, 16);
+      px[3] = c >> 8;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t v = (px[k] & 0xff) * c0 + ((px[k] >> 8) & 0xff) * 19235u + ((px[k] >> 16) & 0xff) * c2 + 16384u;
+      out |= (v >> 15) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(d) = out;
+  } else {
+    for (int k = 0; k < 4 && x + k < w; k++) {
+      const uint8_t* p = s + k * kChannels;
+      d[k] = (uint8_t)(((uint32_t)p[0] * c0 + (uint32_t)p[1] * 19235u + (uint32_t)p[2] * c2 + 16384u) >> 15);
+    }
+  }
+}
+
+int launch_cvt_gray(const uint8_t* src, int w, int h, int sstride, int64_t sfstride, int channels, int rgb, uint8_t* dst,
+                    int dstride, int64_t dfstride, int frames, cudaStream_t st) {
+  if (channels != 3 && channels != 4) return -1;
+  const int aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)sstride | (uintptr_t)sfstride) & (channels == 4 ? 15 : 3)) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)dstride | (uintptr_t)dfstride) & 3) == 0;
+  dim3 grid(((w + 3) / 4 + 255) / 256, h, frames);
+  if (channels == 3) k_cvt_gray<3><<<grid, 256, 0, st>>>(src, w, h, sstride, sfstride, dst, dstride, dfstride, rgb, aligned);
+  else k_cvt_gray<4><<<grid, 256, 0, st>>>(src, w, h, sstride, sfstride, dst, dstride, dfstride, rgb, aligned);
+  return 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -603,6 +603,40 @@ int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int rese
   return ORBX_OK;
 }
 
+int orbx_cvt_gray_device(int device, int n_frames, const uint8_t* d_src, int width, int height, int src_stride,
+                         int64_t src_frame_stride, int channels, int rgb, uint8_t* d_dst, int dst_stride,
+                         int64_t dst_frame_stride, void* cuda_stream) {
+  if (!d_src || !d_dst || width <= 0 || height <= 0 || n_frames <= 0 || (channels != 3 && channels != 4) ||
+      src_stride < width * channels || dst_stride < width)
+    return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  if (orbx::launch_cvt_gray(d_src, width, height, src_stride, src_frame_stride, channels, rgb, d_dst, dst_stride,
+                            dst_frame_stride, n_frames, (cudaStream_t)cuda_stream) != 0)
+    return ORBX_E_ARG;
+  return cudaGetLastError() == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbx_cvt_gray(int device, const uint8_t* src, int width, int height, int src_stride, int channels, int rgb,
+                  uint8_t* dst, int dst_stride) {
+  if (!src || !dst || width <= 0 || height <= 0 || (channels != 3 && channels != 4) ||
+      src_stride < width * channels || dst_stride < width)
+    return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  uint8_t *d_src = nullptr, *d_dst = nullptr;
+  const size_t sb = (size_t)src_stride * height, db = (size_t)dst_stride * height;
+  int rc = ORBX_E_CUDA;
+  if (cudaMalloc(&d_src, sb) == cudaSuccess && cudaMalloc(&d_dst, db) == cudaSuccess &&
+      cudaMemcpy(d_src, src, sb, cudaMemcpyHostToDevice) == cudaSuccess &&
+      cudaMemset(d_dst, 0, db) == cudaSuccess) {
+    rc = orbx_cvt_gray_device(device, 1, d_src, width, height, src_stride, 0, channels, rgb, d_dst, dst_stride, 0, nullptr);
+    if (rc == ORBX_OK && cudaMemcpy2D(dst, dst_stride, d_dst, dst_stride, width, height, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = ORBX_E_CUDA;
+  }
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  return rc;
+}
+
 void* orbx_host_alloc(int64_t bytes) {
   void* p = nullptr;
   if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

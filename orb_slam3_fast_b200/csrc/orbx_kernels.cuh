@@ -69,6 +69,8 @@ void launch_quadtree(const Plan& P, const WorkSet& ws, int lap0, int lap1, int f
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st);
 void launch_describe(const Plan& P, const FrameSet& fs, const WorkSet& ws, const OutSet& out, const int8_t* pattern,
                      int frames, cudaStream_t st);
+int launch_cvt_gray(const uint8_t* src, int w, int h, int sstride, int64_t sfstride, int channels, int rgb, uint8_t* dst,
+                    int dstride, int64_t dfstride, int frames, cudaStream_t st);
 size_t fast_smem_bytes(const Plan& P);
 size_t quadtree_smem_bytes(const Plan& P);
 

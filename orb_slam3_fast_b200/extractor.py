@@ -148,3 +148,15 @@ class ORBextractor:
         cnt = np.zeros(len(STAGES), np.int32)
         self._check(self._L.orbx_profile_read(self._h, _l.ptr(ms), _l.ptr(cnt), 1 if reset else 0))
         return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, cnt.tolist()))
+
+
+def cvtColorToGray(img, rgb=False, device=0):
+    """cv::cvtColor(img, COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) (src/Tracking.cc:1394-1412) for an [h, w, 3|4] uint8 host image."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h, w), np.uint8)
+    L = _l.lib()
+    rc = L.orbx_cvt_gray(device, _l.ptr(img), w, h, img.strides[0], c, int(rgb), _l.ptr(out), w)
+    if rc != 0:
+        raise OrbxError(rc, "orbx_cvt_gray failed")
+    return out

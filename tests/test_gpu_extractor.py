@@ -179,3 +179,29 @@ def test_device_resident_input_every_staging_variant(gpu, base_off, pad):
     for k in range(B):
         _compare_frame(ref, kps[k, :n[k]], desc[k, :n[k]], int(d_mono[k].item()), imgs[k], (0, 0),
                        "device input base+%d pitch+%d frame %d" % (base_off, pad, k))
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, False), (3, True), (4, False), (4, True)])
+def test_cvt_color_to_gray(gpu, channels, rgb):
+    """cv::cvtColor(..., COLOR_*2GRAY) (src/Tracking.cc:1394-1412) on the device == oracle (== cv2, CPU suite); widths
+    that are not a multiple of 4 and the batched device form on a strided buffer."""
+    import torch
+    from orb_slam3_fast_b200 import cvtColorToGray
+    from orb_slam3_fast_b200 import lib as _lib
+    rng = np.random.default_rng(channels * 2 + int(rgb))
+    for (h, w) in ((480, 752), (33, 101), (5, 3)):
+        img = rng.integers(0, 256, (h, w, channels), dtype=np.uint8)
+        assert np.array_equal(cvtColorToGray(img, rgb), orbref.cvt_gray(img, rgb)), (h, w)
+    # device form: 3 frames, padded rows on both sides, converted straight into an extractor-ready gray batch
+    B, h, w, spad, dpad = 3, 120, 200, 8 * channels, 16
+    imgs = rng.integers(0, 256, (B, h, w + 8, channels), dtype=np.uint8)
+    d_src = torch.from_numpy(imgs).cuda()
+    d_dst = torch.zeros((B, h, w + dpad), dtype=torch.uint8, device="cuda")
+    rc = _lib.lib().orbx_cvt_gray_device(0, B, d_src.data_ptr(), w, h, (w + 8) * channels, h * (w + 8) * channels, channels,
+                                         int(rgb), d_dst.data_ptr(), w + dpad, h * (w + dpad), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    out = d_dst.cpu().numpy()
+    for k in range(B):
+        assert np.array_equal(out[k, :, :w], orbref.cvt_gray(np.ascontiguousarray(imgs[k, :, :w]), rgb))
+    assert (out[:, :, w:] == 0).all()

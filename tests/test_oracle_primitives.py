@@ -154,3 +154,20 @@ def test_distinctive_descriptor_matches_a_numpy_restatement():
         D = np.bitwise_count(d.view(np.uint64)[:, None, :] ^ d.view(np.uint64)[None, :, :]).sum(axis=2)
         med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
         assert orbref.distinctive_descriptor(d) == int(np.argmin(med)), n
+
+
+def test_cvt_gray_matches_cv2():
+    """cv::cvtColor(..., COLOR_*2GRAY) as Tracking::GrabImage* applies it (src/Tracking.cc:1394-1412): the 15-bit fixed
+    point restated in the oracle equals cv2 on every channel order, including odd widths."""
+    rng = np.random.default_rng(3)
+    for (h, w) in ((64, 4096), (37, 101)):
+        px3 = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        px4 = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        assert np.array_equal(orbref.cvt_gray(px3, rgb=False), cv2.cvtColor(px3, cv2.COLOR_BGR2GRAY))
+        assert np.array_equal(orbref.cvt_gray(px3, rgb=True), cv2.cvtColor(px3, cv2.COLOR_RGB2GRAY))
+        assert np.array_equal(orbref.cvt_gray(px4, rgb=False), cv2.cvtColor(px4, cv2.COLOR_BGRA2GRAY))
+        assert np.array_equal(orbref.cvt_gray(px4, rgb=True), cv2.cvtColor(px4, cv2.COLOR_RGBA2GRAY))
+    # every (b, g, r) on a coarse lattice + the extremes
+    v = np.array(sorted(set(list(range(0, 256, 5)) + [1, 2, 253, 254, 255])), np.uint8)
+    grid = np.stack(np.meshgrid(v, v, v, indexing="ij"), axis=-1).reshape(1, -1, 3)
+    assert np.array_equal(orbref.cvt_gray(grid), cv2.cvtColor(grid, cv2.COLOR_BGR2GRAY))
