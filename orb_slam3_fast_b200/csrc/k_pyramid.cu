@@ -295,40 +295,66 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
 // streaming: a thread turns 4 pixels (three or four aligned words) into one output word; the only kernel of the
 // library that is bound by HBM rather than by instruction issue.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kCvtRows = 4;  // rows per thread: their loads are all issued before the first pixel is computed
+
 template <int kChannels>
 __global__ void __launch_bounds__(256)
 k_cvt_gray(const uint8_t* __restrict__ src, int w, int h, int sstride, int64_t sfstride, uint8_t* __restrict__ dst,
            int dstride, int64_t dfstride, int rgb, int aligned) {
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y, f = blockIdx.z;
+  const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+  const int y0 = blockIdx.y * (4 * kCvtRows) + (threadIdx.x >> 6);  // rows y0, y0 + 4, y0 + 8, y0 + 12
+  const int f = blockIdx.z;
   if (x >= w) return;
-  const uint8_t* s = src + f * sfstride + (int64_t)y * sstride + (int64_t)x * kChannels;
-  uint8_t* d = dst + f * dfstride + (int64_t)y * dstride + x;
-  const int c0 = rgb ? 9798 : 3735, c2 = rgb ? 3735 : 9798;  // weight of the first / third channel
-  uint32_t out = 0;
+  const uint8_t* s = src + f * sfstride + (int64_t)x * kChannels;
+  uint8_t* d = dst + f * dfstride + x;
+  const uint32_t c0 = rgb ? 9798u : 3735u, c2 = rgb ? 3735u : 9798u;  // weight of the first / third channel
   if (aligned && x + 4 <= w) {
-    uint32_t px[4];  // per pixel: byte 0 = first channel, byte 1 = green, byte 2 = third channel
-    if (kChannels == 4) {
-      const uint4 q = *reinterpret_cast<const uint4*>(s);
-      px[0] = q.x; px[1] = q.y; px[2] = q.z; px[3] = q.w;
-    } else {
-      const uint32_t a = reinterpret_cast<const uint32_t*>(s)[0], b = reinterpret_cast<const uint32_t*>(s)[1],
-                     c = reinterpret_cast<const uint32_t*>(s)[2];
-      px[0] = a;
-      px[1] = __funnelshift_r(a, b, 24);
-      px[2] = __funnelshift_r(b, c, 16);
-      px[3] = c >> 8;
+    uint32_t raw[kCvtRows][4];
+#pragma unroll
+    for (int k = 0; k < kCvtRows; k++) {
+      const int y = y0 + 4 * k;
+      if (y < h) {
+        const uint8_t* p = s + (int64_t)y * sstride;
+        if (kChannels == 4) {
+          const uint4 q = *reinterpret_cast<const uint4*>(p);
+          raw[k][0] = q.x; raw[k][1] = q.y; raw[k][2] = q.z; raw[k][3] = q.w;
+        } else {
+          raw[k][0] = reinterpret_cast<const uint32_t*>(p)[0];
+          raw[k][1] = reinterpret_cast<const uint32_t*>(p)[1];
+          raw[k][2] = reinterpret_cast<const uint32_t*>(p)[2];
+          raw[k][3] = 0;
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t v = (px[k] & 0xff) * c0 + ((px[k] >> 8) & 0xff) * 19235u + ((px[k] >> 16) & 0xff) * c2 + 16384u;
-      out |= (v >> 15) << (8 * k);
+    for (int k = 0; k < kCvtRows; k++) {
+      const int y = y0 + 4 * k;
+      if (y >= h) continue;
+      uint32_t px[4];  // per pixel: byte 0 = first channel, byte 1 = green, byte 2 = third channel
+      if (kChannels == 4) {
+        px[0] = raw[k][0]; px[1] = raw[k][1]; px[2] = raw[k][2]; px[3] = raw[k][3];
+      } else {
+        px[0] = raw[k][0];
+        px[1] = __funnelshift_r(raw[k][0], raw[k][1], 24);
+        px[2] = __funnelshift_r(raw[k][1], raw[k][2], 16);
+        px[3] = raw[k][2] >> 8;
+      }
+      uint32_t out = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t v = (px[q] & 0xff) * c0 + ((px[q] >> 8) & 0xff) * 19235u + ((px[q] >> 16) & 0xff) * c2 + 16384u;
+        out |= (v >> 15) << (8 * q);
+      }
+      *reinterpret_cast<uint32_t*>(d + (int64_t)y * dstride) = out;
     }
-    *reinterpret_cast<uint32_t*>(d) = out;
   } else {
-    for (int k = 0; k < 4 && x + k < w; k++) {
-      const uint8_t* p = s + k * kChannels;
-      d[k] = (uint8_t)(((uint32_t)p[0] * c0 + (uint32_t)p[1] * 19235u + (uint32_t)p[2] * c2 + 16384u) >> 15);
+    for (int k = 0; k < kCvtRows; k++) {
+      const int y = y0 + 4 * k;
+      if (y >= h) continue;
+      for (int q = 0; q < 4 && x + q < w; q++) {
+        const uint8_t* p = s + (int64_t)y * sstride + q * kChannels;
+        d[(int64_t)y * dstride + q] = (uint8_t)(((uint32_t)p[0] * c0 + (uint32_t)p[1] * 19235u + (uint32_t)p[2] * c2 + 16384u) >> 15);
+      }
     }
   }
 }
@@ -338,7 +364,7 @@ int launch_cvt_gray(const uint8_t* src, int w, int h, int sstride, int64_t sfstr
   if (channels != 3 && channels != 4) return -1;
   const int aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)sstride | (uintptr_t)sfstride) & (channels == 4 ? 15 : 3)) == 0 &&
                       ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)dstride | (uintptr_t)dfstride) & 3) == 0;
-  dim3 grid(((w + 3) / 4 + 255) / 256, h, frames);
+  dim3 grid(((w + 3) / 4 + 63) / 64, (h + 4 * kCvtRows - 1) / (4 * kCvtRows), frames);
   if (channels == 3) k_cvt_gray<3><<<grid, 256, 0, st>>>(src, w, h, sstride, sfstride, dst, dstride, dfstride, rgb, aligned);
   else k_cvt_gray<4><<<grid, 256, 0, st>>>(src, w, h, sstride, sfstride, dst, dstride, dfstride, rgb, aligned);
   return 0;
