@@ -1,0 +1,188 @@
+// shim/ORBmatcher_next_orbx.cc — the SURVEY.md §8(f) "next" rows that are built so far, forwarding to the orbm C ABI:
+//   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)            src/ORBmatcher.cc:230-404
+//   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)         :766-884
+//   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight)         :1108-1275
+//   Frame::AssignFeaturesToGrid()                                             src/Frame.cc:520-547
+//   MapPoint::ComputeDistinctiveDescriptors() for a batch of points           src/MapPoint.cc:372-441
+//
+// COMPILES ONLY INSIDE THE REFERENCE TREE (needs the reference headers and their OpenCV / Eigen / Sophus / DBoW2
+// dependencies); pinhole rigs (Nleft / NLeft == -1, bRight == false) — keep the reference's code for the fisheye
+// branches. As in ORBmatcher_orbx.cc the shim only flattens the pointer graph and scatters the answers back; every
+// float that decides a match comes from the reference's own expressions on the host (projection) or from the device
+// with the same non-fused FP32 operations.
+#include "ORBmatcher.h"
+#include "orbm.h"
+
+namespace ORB_SLAM3 {
+
+namespace {
+orbm_matcher* NextMatcher() {
+  thread_local orbm_matcher* m = nullptr;
+  if (!m && orbm_create(&m, 0) != ORBX_OK) throw std::runtime_error(orbm_last_error(nullptr));
+  return m;
+}
+
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR, plus the per-feature flag the search reads
+struct BowFlat {
+  std::vector<uint8_t> has_mp;
+  std::vector<uint32_t> ids, idx;
+  std::vector<int32_t> off{0};
+  orbx_keyframe_view v;
+  template <class Keys>
+  BowFlat(int N, const Keys& keys, const cv::Mat& desc, const DBoW2::FeatureVector& fv,
+          const std::vector<float>& scale, const std::vector<float>& sigma2) : has_mp(N, 0) {
+    for (const auto& node : fv) {
+      ids.push_back(node.first);
+      idx.insert(idx.end(), node.second.begin(), node.second.end());
+      off.push_back((int32_t)idx.size());
+    }
+    v.n = N;
+    v.kps = reinterpret_cast<const orbx_kp*>(keys.data());
+    v.desc = desc.data;
+    v.u_right = nullptr;
+    v.has_mappoint = has_mp.data();
+    v.featvec = orbx_featvec{(int32_t)ids.size(), ids.data(), off.data(), idx.data()};
+    v.scale_factors = scale.data();
+    v.level_sigma2 = sigma2.data();
+    v.n_levels = (int32_t)scale.size();
+  }
+};
+}  // namespace
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+  const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+  BowFlat kf(pKF->N, pKF->mvKeysUn, pKF->mDescriptors, pKF->mFeatVec, pKF->mvScaleFactors, pKF->mvLevelSigma2);
+  for (int i = 0; i < pKF->N; i++) kf.has_mp[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();  // :262-264
+  BowFlat fr(F.N, F.mvKeys, F.mDescriptors, F.mFeatVec, F.mvScaleFactors, F.mvLevelSigma2);          // angles: F.mvKeys
+  std::vector<int32_t> mf(F.N, -1);
+  int32_t nmatches = 0;
+  if (orbm_search_by_bow(NextMatcher(), &kf.v, &fr.v, mfNNratio, mbCheckOrientation, mf.data(), &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  vpMapPointMatches.assign(F.N, static_cast<MapPoint*>(NULL));  // :235
+  for (int i = 0; i < F.N; i++)
+    if (mf[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[mf[i]];
+  return nmatches;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+  const std::vector<MapPoint*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+  BowFlat k1(pKF1->N, pKF1->mvKeysUn, pKF1->mDescriptors, pKF1->mFeatVec, pKF1->mvScaleFactors, pKF1->mvLevelSigma2);
+  BowFlat k2(pKF2->N, pKF2->mvKeysUn, pKF2->mDescriptors, pKF2->mFeatVec, pKF2->mvScaleFactors, pKF2->mvLevelSigma2);
+  for (int i = 0; i < pKF1->N; i++) k1.has_mp[i] = mp1[i] && !mp1[i]->isBad();  // :802-804
+  for (int i = 0; i < pKF2->N; i++) k2.has_mp[i] = mp2[i] && !mp2[i]->isBad();  // :821-825
+  std::vector<int32_t> m12(pKF1->N, -1);
+  int32_t nmatches = 0;
+  if (orbm_search_by_bow_kf(NextMatcher(), &k1.v, &k2.v, mfNNratio, mbCheckOrientation, m12.data(), &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  vpMatches12.assign(mp1.size(), static_cast<MapPoint*>(NULL));  // :779-780
+  for (int i = 0; i < pKF1->N; i++)
+    if (m12[i] >= 0) vpMatches12[i] = mp2[m12[i]];
+  return nmatches;
+}
+
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bRight) {
+  // (bRight == true: keep the reference body.) Host part = :1141-1192 verbatim: which points take part, uv, ur, level.
+  const Sophus::SE3f Tcw = pKF->GetPose();
+  const Eigen::Vector3f Ow = pKF->GetCameraCenter();
+  const float bf = pKF->mbf;
+  std::vector<int> src;
+  std::vector<float> u, v, ur, radius;
+  std::vector<int32_t> lmin, lmax;
+  std::vector<uint8_t> desc;
+  for (int i = 0; i < (int)vpMapPoints.size(); i++) {
+    MapPoint* pMP = vpMapPoints[i];
+    if (!pMP || pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+    const Eigen::Vector3f p3Dw = pMP->GetWorldPos(), p3Dc = Tcw * p3Dw;
+    if (p3Dc(2) < 0.0f) continue;
+    const float invz = 1 / p3Dc(2);
+    const Eigen::Vector2f uv = pKF->mpCamera->project(p3Dc);
+    if (!pKF->IsInImage(uv(0), uv(1))) continue;
+    const Eigen::Vector3f PO = p3Dw - Ow;
+    const float dist3D = PO.norm();
+    if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+    if (PO.dot(pMP->GetNormal()) < 0.5 * dist3D) continue;
+    const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+    src.push_back(i);
+    u.push_back(uv(0));
+    v.push_back(uv(1));
+    ur.push_back(uv(0) - bf * invz);
+    radius.push_back(th * pKF->mvScaleFactors[nPredictedLevel]);
+    lmin.push_back(nPredictedLevel - 1);
+    lmax.push_back(nPredictedLevel);
+    const cv::Mat d = pMP->GetDescriptor();
+    desc.insert(desc.end(), d.data, d.data + 32);
+  }
+  // KeyFrame view: mvKeysUn, mDescriptors, mvuRight, the KeyFrame's grid (mGrid, same layout as Frame's)
+  std::vector<int32_t> off(pKF->mnGridCols * pKF->mnGridRows + 1, 0), items;
+  for (int c = 0; c < pKF->mnGridCols; c++)
+    for (int r = 0; r < pKF->mnGridRows; r++) {
+      const std::vector<size_t>& cell = pKF->GetGridCell(c, r);  // accessor to add next to mGrid (include/KeyFrame.h)
+      off[c * pKF->mnGridRows + r + 1] = off[c * pKF->mnGridRows + r] + (int32_t)cell.size();
+      for (size_t k : cell) items.push_back((int32_t)k);
+    }
+  std::vector<uint8_t> occupied(pKF->N, 0);
+  orbx_frame_view kv;
+  kv.n = pKF->N;
+  kv.kps = reinterpret_cast<const orbx_kp*>(pKF->mvKeysUn.data());
+  kv.desc = pKF->mDescriptors.data;
+  kv.u_right = pKF->mvuRight.data();
+  kv.occupied = occupied.data();
+  kv.grid = orbx_grid{off.data(), items.data(), (float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv,
+                      pKF->mfGridElementHeightInv};
+  kv.scale_factors = pKF->mvScaleFactors.data();
+  kv.n_levels = (int32_t)pKF->mvScaleFactors.size();
+  std::vector<float> angle(src.size(), 0.f);
+  std::vector<uint8_t> has_obs(src.size(), 0);
+  orbx_projected pts{(int32_t)src.size(), u.data(), v.data(), ur.data(), radius.data(), lmin.data(), lmax.data(),
+                     angle.data(), has_obs.data(), desc.data()};
+  std::vector<int32_t> best_idx(src.size(), -1), best_dist(src.size(), 256);
+  if (orbm_fuse_match(NextMatcher(), &kv, pKF->mvInvLevelSigma2.data(), &pts, best_idx.data(), best_dist.data()) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  int nFused = 0;  // :1261-1273, in point order
+  for (size_t k = 0; k < src.size(); k++) {
+    if (best_dist[k] > TH_LOW) continue;
+    MapPoint* pMP = vpMapPoints[src[k]];
+    if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;  // an earlier Replace may have moved it in (:1141-1147)
+    MapPoint* pMPinKF = pKF->GetMapPoint(best_idx[k]);
+    if (pMPinKF) {
+      if (!pMPinKF->isBad()) {
+        if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+        else pMPinKF->Replace(pMP);
+      }
+    } else {
+      pMP->AddObservation(pKF, best_idx[k]);
+      pKF->AddMapPoint(pMP, best_idx[k]);
+    }
+    nFused++;
+  }
+  return nFused;
+}
+
+// Frame::AssignFeaturesToGrid() (src/Frame.cc:520-547), Nleft == -1
+void AssignFeaturesToGrid_orbx(Frame& F) {
+  std::vector<int32_t> off(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1), items(F.N);
+  if (orbm_assign_features_to_grid(NextMatcher(), reinterpret_cast<const orbx_kp*>(F.mvKeysUn.data()), F.N, Frame::mnMinX,
+                                   Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv,
+                                   off.data(), items.data()) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  for (int c = 0; c < FRAME_GRID_COLS; c++)
+    for (int r = 0; r < FRAME_GRID_ROWS; r++)
+      F.mGrid[c][r].assign(items.begin() + off[c * FRAME_GRID_ROWS + r], items.begin() + off[c * FRAME_GRID_ROWS + r + 1]);
+}
+
+// MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:372-441) for every point LocalMapping touched in one go:
+// lists[p] = the observed descriptors of point p as gathered by :386-405; returns the winning position per point.
+std::vector<int32_t> DistinctiveDescriptors_orbx(const std::vector<std::vector<cv::Mat>>& lists) {
+  std::vector<uint8_t> all;
+  std::vector<int32_t> off{0};
+  for (const auto& l : lists) {
+    for (const cv::Mat& d : l) all.insert(all.end(), d.data, d.data + 32);
+    off.push_back((int32_t)(all.size() / 32));
+  }
+  std::vector<int32_t> best(lists.size(), -1);
+  if (orbm_distinctive_descriptors(NextMatcher(), all.data(), off.data(), (int)lists.size(), best.data()) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  return best;  // mDescriptor = lists[p][best[p]].clone()                                                 :437-440
+}
+
+}  // namespace ORB_SLAM3
