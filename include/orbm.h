@@ -131,9 +131,11 @@ int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extract
  * are not read); kf carries mvKeysUn, mDescriptors, mvuRight and the KeyFrame's grid; inv_level_sigma2 =
  * mvInvLevelSigma2[kf->n_levels]. best_idx[m] / best_dist[m] (host): the most similar keypoint that passes the level
  * window and the chi-square gate (:1194-1257), -1 / 256 when none. The shim then applies bestDist <= TH_LOW and does
- * the Replace / AddObservation surgery in point order (:1261-1273). */
+ * the Replace / AddObservation surgery in point order (:1261-1273). chi2_gate = 1 for this overload; 0 gives the loop
+ * of Fuse(KeyFrame*, Sophus::Sim3f& Scw, const vector<MapPoint*>&, float th, vector<MapPoint*>& vpReplacePoint)
+ * (:1277-1390), which has the same window and level test but no reprojection gate (:1356-1372). */
 int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
-                    const orbx_projected* pts, int32_t* best_idx, int32_t* best_dist);
+                    const orbx_projected* pts, int chi2_gate, int32_t* best_idx, int32_t* best_dist);
 
 /* int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) (include/ORBmatcher.h:66,
  * src/ORBmatcher.cc:230-404), Nleft == -1. kf->has_mappoint[i] = vpMapPointsKF[i] != NULL &&

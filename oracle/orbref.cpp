@@ -1115,7 +1115,7 @@ void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels,
 
 // ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight) — the matching loop, src/ORBmatcher.cc:1194-1257
 void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2, const orbx_projected* pts,
-                       int32_t* best_idx, int32_t* best_dist) {
+                       int chi2_gate, int32_t* best_idx, int32_t* best_dist) {
   std::vector<int32_t> idxs(std::max(kf->n, 1));
   for (int i = 0; i < pts->m; i++) {
     const float u = pts->u[i], v = pts->v[i], ur = pts->u_right ? pts->u_right[i] : 0.f;
@@ -1129,7 +1129,8 @@ void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2,
       const orbx_kp& kp = kf->kps[idx];
       const int kpLevel = kp.octave;
       if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;  //                          :1221
-      if (kf->u_right && kf->u_right[idx] >= 0) {  // check reprojection error in stereo                       :1223-1233
+      if (!chi2_gate) {  // Fuse(KeyFrame*, Sim3f&, ...) has no reprojection gate                               :1363-1367
+      } else if (kf->u_right && kf->u_right[idx] >= 0) {  // check reprojection error in stereo                       :1223-1233
         const float ex = u - kp.x, ey = v - kp.y, er = ur - kf->u_right[idx];
         const float e2 = ex * ex + ey * ey + er * er;
         if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;

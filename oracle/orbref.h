@@ -99,9 +99,10 @@ void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels,
  * reprojection error (7.8 stereo / 5.99 mono, :1223-1244), the most similar keypoint (:1250-1257).
  * kf: mvKeysUn, mDescriptors, mvuRight, grid of the KeyFrame. pts: u, v, u_right (ur), radius, max_level =
  * nPredictedLevel (min_level, angle, has_obs unused), desc = MapPoint::GetDescriptor(). best_idx[i] = keypoint or -1,
- * best_dist[i] = its distance (256 when none); the caller applies bestDist <= TH_LOW and the graph surgery. */
+ * best_dist[i] = its distance (256 when none); the caller applies bestDist <= TH_LOW and the graph surgery.
+ * chi2_gate = 0 gives the loop of Fuse(KeyFrame*, Sophus::Sim3f&, ...) (:1356-1372), which has no such gate. */
 void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2, const orbx_projected* pts,
-                       int32_t* best_idx, int32_t* best_dist);
+                       int chi2_gate, int32_t* best_idx, int32_t* best_dist);
 /* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:766-884),
  * NLeft == -1. has_mappoint[i] = vpMapPoints[i] != NULL && !isBad() on both sides. matches12[kf1->n] = index of the
  * KeyFrame-2 feature whose MapPoint is written to vpMatches12[i], or -1. Returns nmatches. */

@@ -165,7 +165,7 @@ def lib():
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_cvt_gray.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci]
         L.orbref_cvt_gray.restype = None
-        L.orbref_fuse_match.argtypes = [vp, vp, vp, vp, vp]
+        L.orbref_fuse_match.argtypes = [vp, vp, vp, ci, vp, vp]
         L.orbref_fuse_match.restype = None
         L.orbref_extract_many.argtypes = [vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]
         L.orbref_stereo_many.argtypes = [vp, vp, ci, ci, ci, C.c_long, ci, cf, ci, ci, ci, cf, cf, ci, vp, vp, vp]
@@ -376,11 +376,11 @@ def cvt_gray(img, rgb=False):
     return out
 
 
-def fuse_match(kf, inv_level_sigma2, pts):
+def fuse_match(kf, inv_level_sigma2, pts, chi2_gate=True):
     inv = _c(inv_level_sigma2, np.float32)
     m = pts.struct.m
     bi, bd = np.empty(max(m, 1), np.int32), np.empty(max(m, 1), np.int32)
-    lib().orbref_fuse_match(kf.ref(), _ptr(inv), pts.ref(), _ptr(bi), _ptr(bd))
+    lib().orbref_fuse_match(kf.ref(), _ptr(inv), pts.ref(), int(chi2_gate), _ptr(bi), _ptr(bd))
     return bi[:m], bd[:m]
 
 

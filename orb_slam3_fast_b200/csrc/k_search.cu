@@ -517,7 +517,7 @@ void launch_triangulation(const TriArgs& A, cudaStream_t st) {
 // (:1253, strict <) is the minimum of (distance, cell position in the window, position in the cell).
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSearchWarps * 32)
-k_fuse_match(const DevFrame F, const DevQueries Q, const float* __restrict__ inv_level_sigma2,
+k_fuse_match(const DevFrame F, const DevQueries Q, const float* __restrict__ inv_level_sigma2, int chi2_gate,
              int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kSearchWarps + warp;
@@ -546,7 +546,8 @@ k_fuse_match(const DevFrame F, const DevQueries Q, const float* __restrict__ inv
       if (lv < L - 1 || lv > L) continue;                                              // :1221
       const float ex = fsub(x, kp.x), ey = fsub(y, kp.y);
       const float kr = F.u_right ? F.u_right[idx] : -1.f;
-      if (kr >= 0) {                                                                   // :1223-1233
+      if (!chi2_gate) {                                                                // the Sim3 form has none
+      } else if (kr >= 0) {                                                            // :1223-1233
         const float er = fsub(ur, kr);
         const float e2 = fadd(fadd(fmul(ex, ex), fmul(ey, ey)), fmul(er, er));
         if ((double)fmul(e2, inv_level_sigma2[lv]) > 7.8) continue;
@@ -577,11 +578,11 @@ k_fuse_match(const DevFrame F, const DevQueries Q, const float* __restrict__ inv
   }
 }
 
-void launch_fuse_match(const DevFrame& F, const DevQueries& Q, const float* inv_level_sigma2, int32_t* best_idx,
-                       int32_t* best_dist, cudaStream_t st) {
+void launch_fuse_match(const DevFrame& F, const DevQueries& Q, const float* inv_level_sigma2, int chi2_gate,
+                       int32_t* best_idx, int32_t* best_dist, cudaStream_t st) {
   if (Q.m > 0)
-    k_fuse_match<<<(Q.m + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, st>>>(F, Q, inv_level_sigma2, best_idx,
-                                                                                        best_dist);
+    k_fuse_match<<<(Q.m + kSearchWarps - 1) / kSearchWarps, kSearchWarps * 32, 0, st>>>(F, Q, inv_level_sigma2, chi2_gate,
+                                                                                        best_idx, best_dist);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -719,7 +719,7 @@ static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {
 }
 
 int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
-                    const orbx_projected* pts, int32_t* best_idx, int32_t* best_dist) {
+                    const orbx_projected* pts, int chi2_gate, int32_t* best_idx, int32_t* best_dist) {
   if (!m || !kf || !pts || !inv_level_sigma2 || kf->n < 0 || pts->m < 0 || (pts->m > 0 && (!best_idx || !best_dist)))
     return mfail(m, ORBX_E_ARG, "bad argument");
   if (pts->m == 0) return ORBX_OK;
@@ -739,7 +739,7 @@ int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv
   int32_t* d_bi = ar.alloc<int32_t>(M);
   int32_t* d_bd = ar.alloc<int32_t>(M);
   if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
-  launch_fuse_match(F, Q, d_inv, d_bi, d_bd, m->stream);
+  launch_fuse_match(F, Q, d_inv, chi2_gate, d_bi, d_bd, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   ORBM_CUDA(m, cudaMemcpyAsync(best_idx, d_bi, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
   ORBM_CUDA(m, cudaMemcpyAsync(best_dist, d_bd, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));

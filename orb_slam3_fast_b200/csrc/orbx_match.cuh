@@ -135,8 +135,8 @@ struct BowArgs {
 };
 void launch_search_by_bow(const BowArgs& A, cudaStream_t st);
 // The matching loop of ORBmatcher::Fuse: Q.max_level = nPredictedLevel, Q.u_right = ur of the projection
-void launch_fuse_match(const DevFrame& F, const DevQueries& Q, const float* inv_level_sigma2, int32_t* best_idx,
-                       int32_t* best_dist, cudaStream_t st);
+void launch_fuse_match(const DevFrame& F, const DevQueries& Q, const float* inv_level_sigma2, int chi2_gate,
+                       int32_t* best_idx, int32_t* best_dist, cudaStream_t st);
 // Frame::AssignFeaturesToGrid for `frames` keypoint arrays (kp_stride apart; counts from n_ptr[f] or n_fixed)
 void launch_build_grid(const orbx_kp* kps, const int32_t* n_ptr, int n_fixed, int64_t kp_stride, int frames, float min_x,
                        float min_y, float inv_w, float inv_h, int32_t* offsets, int32_t* items, int64_t item_stride,

@@ -36,7 +36,7 @@ def _bind(L):
     L.orbm_search_by_projection_frame_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, ci, ci, vp, vp]
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
     L.orbm_search_by_bow.argtypes = [vp, vp, vp, cf, ci, vp, vp]
-    L.orbm_fuse_match.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.orbm_fuse_match.argtypes = [vp, vp, vp, vp, ci, vp, vp]
     L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L._orbm_bound = True
 
@@ -202,12 +202,12 @@ class ORBmatcher:
 
     # int SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse) — :886
     # the matching loop of int Fuse(KeyFrame* pKF, const vector<MapPoint*>&, th, bRight) — src/ORBmatcher.cc:1194-1257
-    def FuseMatch(self, kf_view, inv_level_sigma2, projected):
+    def FuseMatch(self, kf_view, inv_level_sigma2, projected, chi2_gate=True):
         inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
         m = projected.struct.m
         bi, bd = np.empty(max(m, 1), np.int32), np.empty(max(m, 1), np.int32)
-        self._check(self._L.orbm_fuse_match(self._h, kf_view.ref(), _l.ptr(inv), projected.ref(), _l.ptr(bi),
-                                            _l.ptr(bd)))
+        self._check(self._L.orbm_fuse_match(self._h, kf_view.ref(), _l.ptr(inv), projected.ref(), int(chi2_gate),
+                                            _l.ptr(bi), _l.ptr(bd)))
         return bi[:m], bd[:m]
 
     # int SearchByBoW(KeyFrame* pKF, Frame& F, vector<MapPoint*>& vpMapPointMatches) — src/ORBmatcher.cc:230

@@ -136,7 +136,8 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
   orbx_projected pts{(int32_t)src.size(), u.data(), v.data(), ur.data(), radius.data(), lmin.data(), lmax.data(),
                      angle.data(), has_obs.data(), desc.data()};
   std::vector<int32_t> best_idx(src.size(), -1), best_dist(src.size(), 256);
-  if (orbm_fuse_match(NextMatcher(), &kv, pKF->mvInvLevelSigma2.data(), &pts, best_idx.data(), best_dist.data()) != ORBX_OK)
+  if (orbm_fuse_match(NextMatcher(), &kv, pKF->mvInvLevelSigma2.data(), &pts, /*chi2_gate*/ 1, best_idx.data(),
+                      best_dist.data()) != ORBX_OK)
     throw std::runtime_error(orbm_last_error(NextMatcher()));
   int nFused = 0;  // :1261-1273, in point order
   for (size_t k = 0; k < src.size(); k++) {

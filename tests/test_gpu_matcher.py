@@ -327,3 +327,7 @@ def test_fuse_match(matcher, m, th, stereo, seed):
     assert (bi_r >= 0).sum() > m // 4 and ((bi_r < 0) & near).sum() > 0, "degenerate test"
     assert np.array_equal(bi, bi_r), np.nonzero(bi != bi_r)[0][:10]
     assert np.array_equal(bd, bd_r)
+    # Fuse(KeyFrame*, Sim3f&, ...) (:1277-1390): the same loop without the reprojection gate
+    bi2, bd2 = matcher.FuseMatch(fv, inv_sigma2, views.make_projected(**pts), chi2_gate=False)
+    bi2_r, bd2_r = orbref.fuse_match(fr, inv_sigma2, orbref.make_projected(**pts), chi2_gate=False)
+    assert np.array_equal(bi2, bi2_r) and np.array_equal(bd2, bd2_r) and (bi2_r >= 0).sum() > (bi_r >= 0).sum()
