@@ -63,6 +63,19 @@ class FrameSharder:
         g_k = np.ascontiguousarray(g_k).view(KP_DTYPE).reshape(g_k.shape[:2])
         return g_n, g_m, g_k, g_d
 
+    def gather_knn2(self, n_queries, idx1, d1, idx2, d2):
+        """BASELINE configs[4] on several GPUs: the QUERY rows are sharded, every rank holds the whole
+        train set (100 k x 32 B = 3.2 MB), so the 2-NN of a query never needs another rank. Per-rank results of
+        ORBmatcher.knnMatch2 on rows my_range(n_queries) (numpy or torch int32 [my_rows]) -> the four global arrays
+        (numpy) on every rank. One all_gather of 16 B per query is the only communication."""
+        def t(a):
+            if isinstance(a, np.ndarray):
+                a = torch.from_numpy(np.ascontiguousarray(a))
+            return a.to(self.device)
+        packed = torch.stack([t(idx1), t(d1), t(idx2), t(d2)], dim=1)  # [my_rows, 4]: one collective instead of four
+        g = self._gather_padded(packed, n_queries).cpu().numpy()
+        return g[:, 0].copy(), g[:, 1].copy(), g[:, 2].copy(), g[:, 3].copy()
+
     def gather_counts(self, counts):
         """counts: int32 tensor [k, my_units] on self.device -> [k, n_units_total_padded...] per rank stacked:
         returns a tensor [world, k, m] (m = largest shard). The 'trivial result gather' of bench.py."""

@@ -91,3 +91,37 @@ def test_sharded_extract_gathers_to_the_serial_result(world, n_frames):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert len({s for _, _, s in res}) == 1 and res[0][2] > 0
+
+
+def _knn_worker(rank, world, port, nq, nt, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from orb_slam3_fast_b200 import synth
+        from oracle import orbref
+        qd, td = synth.descriptors(nq, 7, prototypes=16), synth.descriptors(nt, 8, prototypes=16)  # tie heavy
+        sh = sharding.FrameSharder()
+        a, b = sh.my_range(nq)
+        local = orbref.knn2(qd[a:b], td)            # the CPU oracle stands in for the per-rank GPU call
+        g = sh.gather_knn2(nq, *local)
+        ref = orbref.knn2(qd, td)
+        q.put((rank, bool(all(np.array_equal(x, y) for x, y in zip(g, ref)))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq,nt", [(2, 101, 300), (3, 50, 64)])
+def test_sharded_knn2_gathers_to_the_serial_result(world, nq, nt):
+    """configs[4] on several GPUs: queries sharded, train set replicated, one gather of 16 B per query."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_knn_worker, args=(r, world, port, nq, nt, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=90) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res
