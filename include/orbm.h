@@ -124,6 +124,16 @@ int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extract
                                              float inv_w, float inv_h, const orbx_projected* pts, int max_dist,
                                              int check_orientation, int32_t* assign, int32_t* nmatches);
 
+/* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
+ * vector<int>& vnMatches12, int windowSize = 10) (include/ORBmatcher.h:73-77, src/ORBmatcher.cc:618-764) — SURVEY.md
+ * §8(f) rank 3 — in the serial order of its loop (the fork's tbb::parallel_for at :634 races on vnMatches21 /
+ * vMatchedDistance; the serial order is the well-defined semantics, as for the other searches). f1: F1.mvKeysUn and
+ * F1.mDescriptors (its grid is not read); f2: F2 with grid; prev_matched_xy[f1->n][2] = vbPrevMatched.
+ * matches12[f1->n] (host) = vnMatches12; the shim then refreshes vbPrevMatched from it (:758-761). */
+int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, const orbx_frame_view* f2,
+                                   const float* prev_matched_xy, int window_size, float nnratio, int check_orientation,
+                                   int32_t* matches12, int32_t* nmatches);
+
 /* The matching loop of int ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>& vpMapPoints, const float th,
  * const bool bRight) (include/ORBmatcher.h:94, src/ORBmatcher.cc:1108-1275; bRight = false, NLeft == -1) — SURVEY.md
  * §8(f) rank 3. The shim projects the points that pass :1141-1187 (orbx_projected: u, v, u_right = ur, radius =

@@ -1113,6 +1113,65 @@ void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels,
   }
 }
 
+// ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:618-764, serial order of the loop body
+int orbref_search_for_initialization(const orbx_frame_view* f1, const orbx_frame_view* f2, const float* prev_xy,
+                                     int window_size, float nnratio, int check_orientation, int32_t* matches12) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+  std::vector<int> rotHist[kHisto];
+  std::vector<int> vMatchedDistance(std::max(f2->n, 1), INT_MAX), vnMatches21(std::max(f2->n, 1), -1);
+  std::vector<int32_t> idxs(std::max(f2->n, 1));
+  for (int i1 = 0; i1 < f1->n; i1++) {
+    const orbx_kp& kp1 = f1->kps[i1];
+    const int level1 = kp1.octave;
+    if (level1 > 0) continue;  //                                                                             :642
+    const int nc = orbref_features_in_area(f2, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window_size, level1, level1,
+                                           idxs.data());
+    if (nc == 0) continue;
+    const uint8_t* d1 = f1->desc + (size_t)i1 * 32;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    for (int c = 0; c < nc; c++) {
+      const int i2 = idxs[c];
+      const int dist = orbref_descriptor_distance(d1, f2->desc + (size_t)i2 * 32);
+      if (vMatchedDistance[i2] <= dist) continue;  //                                                          :685
+      if (dist < bestDist) {
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestIdx2 = i2;
+      } else if (dist < bestDist2) {
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= TH_LOW) {
+      if (bestDist < (float)bestDist2 * nnratio) {  //                                                         :700
+        if (vnMatches21[bestIdx2] >= 0) {
+          matches12[vnMatches21[bestIdx2]] = -1;
+          nmatches--;
+        }
+        matches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (check_orientation) rotHist[rot_bin(f1->kps[i1].angle, f2->kps[bestIdx2].angle)].push_back(i1);
+      }
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, kHisto, ind1, ind2, ind3);
+    for (int i = 0; i < kHisto; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (matches12[idx1] >= 0) {  //                                                                       :748-751
+          matches12[idx1] = -1;
+          nmatches--;
+        }
+    }
+  }
+  return nmatches;
+}
+
 // ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight) — the matching loop, src/ORBmatcher.cc:1194-1257
 void orbref_fuse_match(const orbx_frame_view* kf, const float* inv_level_sigma2, const orbx_projected* pts,
                        int chi2_gate, int32_t* best_idx, int32_t* best_dist) {

@@ -93,6 +93,12 @@ int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_proje
  * gray = (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15 (pinned to cv2 4.13 in tests/test_oracle_primitives.py).
  * channels = 3 or 4; rgb != 0 when the first channel is red. */
 void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb, uint8_t* dst, int dstride);
+/* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12,
+ * int windowSize) (src/ORBmatcher.cc:618-764), in the SERIAL order of its loop (the fork wraps it in a racy
+ * tbb::parallel_for, :634). f1: mvKeysUn + mDescriptors of F1 (grid unused); f2: F2 with its grid; prev_xy[f1->n][2] =
+ * vbPrevMatched. matches12[f1->n] = vnMatches12. Returns nmatches. (The caller then refreshes vbPrevMatched, :758-761.) */
+int orbref_search_for_initialization(const orbx_frame_view* f1, const orbx_frame_view* f2, const float* prev_xy,
+                                     int window_size, float nnratio, int check_orientation, int32_t* matches12);
 /* The matching part of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight = false)
  * (src/ORBmatcher.cc:1108-1275), NLeft == -1, after the caller-side projection (:1152-1192): per point
  * KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:705-749), the level window [L-1, L] (:1221), the chi-square gate on the

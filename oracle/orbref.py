@@ -163,6 +163,7 @@ def lib():
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_search_for_initialization.argtypes = [vp, vp, vp, ci, cf, ci, vp]
         L.orbref_cvt_gray.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci]
         L.orbref_cvt_gray.restype = None
         L.orbref_fuse_match.argtypes = [vp, vp, vp, ci, vp, vp]
@@ -365,6 +366,14 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
     m = np.empty(max(kf1.struct.n, 1), np.int32)
     n = lib().orbref_search_by_bow_kf(kf1.ref(), kf2.ref(), float(nnratio), int(check_orientation), _ptr(m))
     return n, m[:kf1.struct.n]
+
+
+def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, check_orientation=True):
+    prev = _c(prev_xy, np.float32).reshape(-1, 2)
+    m = np.empty(max(f1.struct.n, 1), np.int32)
+    n = lib().orbref_search_for_initialization(f1.ref(), f2.ref(), _ptr(prev), int(window_size), float(nnratio),
+                                               int(check_orientation), _ptr(m))
+    return n, m[:f1.struct.n]
 
 
 def cvt_gray(img, rgb=False):

@@ -245,6 +245,82 @@ __device__ __forceinline__ int rot_bin(float a1, float a2) {
   return bin;
 }
 
+// SearchForInitialization (src/ORBmatcher.cc:618-764): every F2 keypoint keeps the closest F1 keypoint seen so far, a
+// later F1 keypoint may only take it with a strictly smaller distance (:685) and then evicts the earlier owner
+// (:703-706). The candidate lists are produced in parallel by the same count / scan / fill kernels as the other
+// searches; this replay of the order dependence is one warp walking the F1 keypoints in index order (the monocular
+// initialiser runs a handful of times per session; ~1000 level-0 keypoints).
+__global__ void __launch_bounds__(32)
+k_init_resolve(const DevFrame F2, const DevQueries Q, const SearchScratch S, const InitArgs A) {
+  __shared__ int histo[32];
+  const int lane = threadIdx.x;
+  for (int k = lane; k < A.n2; k += 32) {
+    A.matches21[k] = -1;
+    A.matched_dist[k] = 0x7fffffff;
+  }
+  for (int i = lane; i < Q.m; i += 32) A.matches12[i] = -1;
+  histo[lane] = 0;
+  __syncwarp();
+  int nevents = 0;
+  for (int i1 = 0; i1 < Q.m; i1++) {
+    const int off = S.counts[i1], cnt = S.counts[i1 + 1] - off;
+    if (cnt == 0) continue;  // octave > 0 (:642) or an empty window (:658)
+    Top2 t{0, -1, 0, -1};
+    for (int c = lane; c < cnt; c += 32) {
+      const int dist = S.cand_dist[off + c] & 0xffff;
+      if (A.matched_dist[S.cand_idx[off + c]] <= dist) continue;                       // :685
+      top2_insert(t, dist, c);
+    }
+    t = top2_warp(t);
+    if (t.p1 < 0) continue;
+    const int bestDist = t.d1;
+    const float second = t.p2 >= 0 ? (float)t.d2 : (float)0x7fffffff;                  // bestDist2 = INT_MAX when absent
+    if (!(bestDist <= ORBM_TH_LOW_I && (float)bestDist < fmul(second, A.nnratio))) continue;  // :697-700
+    const int bestIdx2 = S.cand_idx[off + t.p1];
+    if (lane == 0) {
+      const int prev = A.matches21[bestIdx2];
+      if (prev >= 0) A.matches12[prev] = -1;                                            // :703-706
+      A.matches12[i1] = bestIdx2;
+      A.matches21[bestIdx2] = i1;
+      A.matched_dist[bestIdx2] = bestDist;
+      if (A.check_orientation) {
+        const int bin = rot_bin(A.kps1[i1].angle, F2.kps[bestIdx2].angle);              // :724-734
+        A.events[2 * nevents] = i1;
+        A.events[2 * nevents + 1] = bin;
+        histo[bin]++;
+      }
+    }
+    nevents++;
+    __syncwarp();  // lane 0's stores are visible to the whole warp before the next keypoint reads them
+  }
+  __syncwarp();
+  // every eviction took one match away (:705): recount instead of tracking it per step
+  int alive = 0;
+  for (int i = lane; i < Q.m; i += 32) alive += A.matches12[i] >= 0;
+  alive = __reduce_add_sync(0xffffffffu, alive);
+  int nmatches = alive;
+  if (A.check_orientation) {
+    int ind1, ind2, ind3;
+    three_maxima(histo, kHistoLength, ind1, ind2, ind3);
+    int removed = 0;
+    for (int e = lane; e < nevents; e += 32) {
+      const int bin = A.events[2 * e + 1], idx1 = A.events[2 * e];
+      if (bin != ind1 && bin != ind2 && bin != ind3 && A.matches12[idx1] >= 0) {        // :748-751
+        A.matches12[idx1] = -1;
+        removed++;
+      }
+    }
+    removed = __reduce_add_sync(0xffffffffu, removed);
+    nmatches -= removed;
+  }
+  if (lane == 0) *A.nmatches = nmatches;
+}
+
+void launch_init_resolve(const DevFrame& F2, const DevQueries& Q, const SearchScratch& S, const InitArgs& A,
+                         cudaStream_t st) {
+  k_init_resolve<<<1, 32, 0, st>>>(F2, Q, S, A);
+}
+
 // The greedy, order-dependent part of the searches (src/ORBmatcher.cc:92-93, :130, :1672-1674): point i may only take a
 // keypoint that no EARLIER accepted point with observations has taken. Restated as a fixed point: let T[k] be the
 // lowest index of an accepted point with observations whose choice is keypoint k; then keypoint k is closed for point

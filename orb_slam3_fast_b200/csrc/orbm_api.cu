@@ -718,6 +718,77 @@ static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {
   return K;
 }
 
+int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, const orbx_frame_view* f2,
+                                   const float* prev_matched_xy, int window_size, float nnratio, int check_orientation,
+                                   int32_t* matches12, int32_t* nmatches) {
+  if (!m || !f1 || !f2 || f1->n < 0 || f2->n < 0 || (f1->n > 0 && (!matches12 || !prev_matched_xy)))
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  if (f1->n == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int M = f1->n;
+  // per-keypoint query set-up = the scalar prologue of the loop body (:637-656): only level-0 keypoints take part, the
+  // window is centred on vbPrevMatched with half-size windowSize and restricted to level 0
+  std::vector<uint8_t> active(M);
+  std::vector<float> u(M), v(M), radius(M, (float)window_size);
+  std::vector<int32_t> zero(M, 0);
+  for (int i = 0; i < M; i++) {
+    active[i] = f1->kps[i].octave <= 0;
+    u[i] = prev_matched_xy[2 * i];
+    v[i] = prev_matched_xy[2 * i + 1];
+  }
+  std::vector<uint8_t> free2(std::max(f2->n, 1), 0);
+  orbx_frame_view f2v = *f2;
+  f2v.occupied = free2.data();  // the static "occupied" test of the other searches does not exist here
+  f2v.u_right = nullptr;
+  Arena ar(m);
+  const DevFrame F2 = upload_frame(ar, &f2v);
+  DevQueries Q{};
+  Q.m = M;
+  Q.active = ar.upload(active.data(), M);
+  Q.u = ar.upload(u.data(), M);
+  Q.v = ar.upload(v.data(), M);
+  Q.radius = ar.upload(radius.data(), M);
+  Q.min_level = ar.upload(zero.data(), M);
+  Q.max_level = ar.upload(zero.data(), M);
+  Q.u_right = nullptr;
+  Q.desc = ar.upload(f1->desc, (size_t)M * 32);
+  InitArgs A{};
+  A.kps1 = ar.upload(f1->kps, M);
+  A.nnratio = nnratio;
+  A.check_orientation = check_orientation;
+  A.n2 = f2->n;
+  A.matches12 = ar.alloc<int32_t>(M);
+  A.matches21 = ar.alloc<int32_t>(f2->n);
+  A.matched_dist = ar.alloc<int32_t>(f2->n);
+  A.events = ar.alloc<int32_t>(2 * (size_t)M);
+  A.nmatches = ar.alloc<int32_t>(1);
+  SearchScratch S{};
+  S.counts = ar.alloc<int32_t>((size_t)M + 1);
+  S.pre = ar.alloc<int4>(M);
+  int32_t* d_total = ar.alloc<int32_t>(1);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  cudaStream_t st = m->stream;
+  int32_t total = 0;
+  launch_search_count(F2, Q, S.counts, st);
+  launch_scan(S.counts, M, d_total, st);
+  ORBM_CUDA(m, cudaMemcpyAsync(&total, d_total, 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaStreamSynchronize(st));
+  S.cand_idx = ar.alloc<int32_t>(total);
+  S.cand_dist = ar.alloc<int32_t>(total);
+  S.cap_total = total;
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_search_fill(F2, Q, S, st);
+  launch_init_resolve(F2, Q, S, A, st);
+  ORBM_CUDA(m, cudaGetLastError());
+  int32_t nm = 0;
+  ORBM_CUDA(m, cudaMemcpyAsync(matches12, A.matches12, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaMemcpyAsync(&nm, A.nmatches, 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaStreamSynchronize(st));
+  if (nmatches) *nmatches = nm;
+  return ORBX_OK;
+}
+
 int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
                     const orbx_projected* pts, int chi2_gate, int32_t* best_idx, int32_t* best_dist) {
   if (!m || !kf || !pts || !inv_level_sigma2 || kf->n < 0 || pts->m < 0 || (pts->m > 0 && (!best_idx || !best_dist)))

@@ -122,6 +122,20 @@ struct TriArgs {
   int32_t* node_match; // [k1.n_nodes] scratch: index of the same node id in k2 or -1
 };
 void launch_triangulation(const TriArgs& A, cudaStream_t st);
+// SearchForInitialization: serial replay over the candidate lists of run_search (Q = the level-0 keypoints of F1)
+struct InitArgs {
+  const orbx_kp* kps1;      // F1.mvKeysUn
+  float nnratio;
+  int check_orientation;
+  int n2;
+  int32_t* matches12;       // [Q.m]
+  int32_t* matches21;       // [n2] scratch
+  int32_t* matched_dist;    // [n2] scratch
+  int32_t* events;          // [2 * Q.m] scratch
+  int32_t* nmatches;        // [1]
+};
+void launch_init_resolve(const DevFrame& F2, const DevQueries& Q, const SearchScratch& S, const InitArgs& A,
+                         cudaStream_t st);
 // SearchByBoW(KeyFrame*, Frame&, ...): kf.has_mappoint = the KeyFrame features that carry a good MapPoint
 struct BowArgs {
   DevKeyFrame kf, fr;

@@ -37,6 +37,7 @@ def _bind(L):
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
     L.orbm_search_by_bow.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L.orbm_fuse_match.argtypes = [vp, vp, vp, vp, ci, vp, vp]
+    L.orbm_search_for_initialization.argtypes = [vp, vp, vp, vp, ci, cf, ci, vp, vp]
     L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L._orbm_bound = True
 
@@ -201,6 +202,17 @@ class ORBmatcher:
         return nm.value, assign[:n]
 
     # int SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse) — :886
+    # int SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:618
+    def SearchForInitialization(self, f1_view, f2_view, prev_matched_xy, windowSize=10):
+        prev = np.ascontiguousarray(prev_matched_xy, np.float32).reshape(-1, 2)
+        n = f1_view.struct.n
+        m12 = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_for_initialization(self._h, f1_view.ref(), f2_view.ref(), _l.ptr(prev),
+                                                           int(windowSize), self.mfNNratio,
+                                                           int(self.mbCheckOrientation), _l.ptr(m12), C.byref(nm)))
+        return nm.value, m12[:n]
+
     # the matching loop of int Fuse(KeyFrame* pKF, const vector<MapPoint*>&, th, bRight) — src/ORBmatcher.cc:1194-1257
     def FuseMatch(self, kf_view, inv_level_sigma2, projected, chi2_gate=True):
         inv = np.ascontiguousarray(inv_level_sigma2, np.float32)

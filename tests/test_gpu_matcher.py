@@ -331,3 +331,26 @@ def test_fuse_match(matcher, m, th, stereo, seed):
     bi2, bd2 = matcher.FuseMatch(fv, inv_sigma2, views.make_projected(**pts), chi2_gate=False)
     bi2_r, bd2_r = orbref.fuse_match(fr, inv_sigma2, orbref.make_projected(**pts), chi2_gate=False)
     assert np.array_equal(bi2, bi2_r) and np.array_equal(bd2, bd2_r) and (bi2_r >= 0).sum() > (bi_r >= 0).sum()
+
+
+@pytest.mark.parametrize("window,nnratio,check,seed", [(100, 0.9, True, 0), (30, 0.9, False, 1), (100, 0.8, True, 2)])
+def test_search_for_initialization(gpu, window, nnratio, check, seed):
+    """ORBmatcher::SearchForInitialization (src/ORBmatcher.cc:618-764) in the serial order of its loop: level-0
+    keypoints of F1 against the level-0 keypoints of F2 inside a window around vbPrevMatched, the running
+    vMatchedDistance / eviction logic, rotation histogram."""
+    w, h = 640, 480
+    img1 = synth.scene(h, w, seed + 70)
+    img2 = np.roll(img1, (3, -5), axis=(0, 1))                 # a small camera motion
+    e1, e2 = ORBextractor(2000), ORBextractor(2000)           # the initialiser uses 5 x nFeatures
+    _, k1, d1 = e1(img1)
+    _, k2, d2 = e2(img2)
+    occ1, occ2 = np.zeros(len(k1), np.uint8), np.zeros(len(k2), np.uint8)
+    f1, r1 = _frame_views(k1, d1, w, h, e1.GetScaleFactors(), None, occ1)
+    f2, r2 = _frame_views(k2, d2, w, h, e2.GetScaleFactors(), None, occ2)
+    prev = np.stack([k1["x"], k1["y"]], axis=1).astype(np.float32)   # vbPrevMatched starts as F1's keypoints (:2414)
+    mt = ORBmatcher(nnratio, check)
+    n, m12 = mt.SearchForInitialization(f1, f2, prev, window)
+    n_r, m12_r = orbref.search_for_initialization(r1, r2, prev, window, nnratio, check)
+    assert n_r > 50, "degenerate test: %d matches" % n_r
+    assert n == n_r and np.array_equal(m12, m12_r), np.nonzero(m12 != m12_r)[0][:10]
+    assert (m12[k1["octave"] > 0] == -1).all()
