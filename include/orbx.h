@@ -91,6 +91,19 @@ int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp
 int orbx_profile_enable(orbx_extractor* ex, int on);
 int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int reset);
 
+/* cv::remap(src, dst, M1, M2, cv::INTER_LINEAR) for 8-bit single-channel images and CV_32FC1 maps (border constant 0):
+ * the stereo rectification System::TrackStereo applies before the Frame constructor (src/System.cc:286-294; the maps
+ * are built once by cv::initUndistortRectifyMap(..., CV_32F, ...), src/Settings.cc:557-572) — SURVEY.md §8(f) rank 4.
+ * mapx / mapy: [dst_height][dst_width] floats, dense. The device form rectifies n_frames images with the same maps on
+ * `cuda_stream` without synchronising (its output can be handed to orbx_extract_batch_device); the host form is
+ * synchronous. */
+int orbx_remap_linear_device(int device, int n_frames, const uint8_t* d_src, int src_width, int src_height,
+                             int src_stride, int64_t src_frame_stride, const float* d_mapx, const float* d_mapy,
+                             int dst_width, int dst_height, uint8_t* d_dst, int dst_stride, int64_t dst_frame_stride,
+                             void* cuda_stream);
+int orbx_remap_linear(int device, const uint8_t* src, int src_width, int src_height, int src_stride, const float* mapx,
+                      const float* mapy, int dst_width, int dst_height, uint8_t* dst, int dst_stride);
+
 /* cv::cvtColor(src, dst, cv::COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit images — what Tracking::GrabImageStereo /
  * GrabImageRGBD / GrabImageMonocular apply to colour input before the Frame constructor (src/Tracking.cc:1394-1412,
  * 1500-1513, 1558-1571); SURVEY.md §8(f) rank 4 (image front-end). channels = 3 or 4, rgb != 0 when the first channel

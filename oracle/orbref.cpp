@@ -1100,6 +1100,23 @@ int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view*
   return nmatches;
 }
 
+// cv::remap(..., INTER_LINEAR), CV_8UC1 source, CV_32FC1 maps, BORDER_CONSTANT(0) (OpenCV imgproc/imgwarp.cpp:
+// remapBilinear with INTER_BITS = 5, INTER_REMAP_COEF_BITS = 15; the 32 x 32 weight table is exact: w = a * b * 32)
+void orbref_remap_linear(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw,
+                         int dh, uint8_t* dst, int dstride) {
+  auto px = [&](int y, int x) -> int {
+    return (x >= 0 && x < sw && y >= 0 && y < sh) ? src[(size_t)y * sstride + x] : 0;
+  };
+  for (int y = 0; y < dh; y++)
+    for (int x = 0; x < dw; x++) {
+      const int sx = (int)lrintf(mapx[(size_t)y * dw + x] * 32.f), sy = (int)lrintf(mapy[(size_t)y * dw + x] * 32.f);
+      const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+      const int top = (32 - fx) * px(iy, ix) + fx * px(iy, ix + 1);
+      const int bot = (32 - fx) * px(iy + 1, ix) + fx * px(iy + 1, ix + 1);
+      dst[(size_t)y * dstride + x] = (uint8_t)(((32 - fy) * top + fy * bot + 512) >> 10);
+    }
+}
+
 // cv::cvtColor(..., COLOR_*2GRAY), 8-bit (OpenCV imgproc/color_rgb: RGB2Gray<uchar>, 15-bit coefficients)
 void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb, uint8_t* dst, int dstride) {
   const int BY = 3735, GY = 19235, RY = 9798;

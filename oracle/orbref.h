@@ -88,6 +88,12 @@ int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoin
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
 int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                       int check_orientation, int32_t* assign);
+/* cv::remap(src, dst, mapx, mapy, INTER_LINEAR) with CV_32FC1 maps, 8-bit single channel, BORDER_CONSTANT 0 — the stereo
+ * rectification of System::TrackStereo (src/System.cc:293-294; maps from initUndistortRectifyMap(..., CV_32F, ...),
+ * src/Settings.cc:557-572). OpenCV's fixed point: coordinates rounded to 1/32 px (cvRound(map * 32)), the four taps
+ * weighted with 5-bit fractions, (sum + 512) >> 10 (pinned to cv2 4.13 in tests/test_oracle_primitives.py). */
+void orbref_remap_linear(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw,
+                         int dh, uint8_t* dst, int dstride);
 /* cv::cvtColor(src, dst, COLOR_{BGR,RGB,BGRA,RGBA}2GRAY) on 8-bit images, the conversion Tracking::GrabImage* applies to
  * colour input (src/Tracking.cc:1394-1412, 1500-1513, 1558-1571): OpenCV's fixed point,
  * gray = (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15 (pinned to cv2 4.13 in tests/test_oracle_primitives.py).

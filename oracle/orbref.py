@@ -164,6 +164,8 @@ def lib():
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_for_initialization.argtypes = [vp, vp, vp, ci, cf, ci, vp]
+        L.orbref_remap_linear.argtypes = [vp, ci, ci, ci, vp, vp, ci, ci, vp, ci]
+        L.orbref_remap_linear.restype = None
         L.orbref_cvt_gray.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci]
         L.orbref_cvt_gray.restype = None
         L.orbref_fuse_match.argtypes = [vp, vp, vp, ci, vp, vp]
@@ -374,6 +376,17 @@ def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, che
     n = lib().orbref_search_for_initialization(f1.ref(), f2.ref(), _ptr(prev), int(window_size), float(nnratio),
                                                int(check_orientation), _ptr(m))
     return n, m[:f1.struct.n]
+
+
+def remap_linear(img, mapx, mapy):
+    """cv::remap(img, mapx, mapy, INTER_LINEAR) for a uint8 [h, w] image and float32 maps [dh, dw]."""
+    img = _c(img, np.uint8)
+    mapx, mapy = _c(mapx, np.float32), _c(mapy, np.float32)
+    dh, dw = mapx.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().orbref_remap_linear(_ptr(img), img.shape[1], img.shape[0], img.strides[0], _ptr(mapx), _ptr(mapy), dw, dh,
+                              _ptr(out), dw)
+    return out
 
 
 def cvt_gray(img, rgb=False):

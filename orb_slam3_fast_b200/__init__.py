@@ -4,6 +4,6 @@ Python here is the host-side mirror of the reference's C++ class surface over th
 in liborbx.so (hand-written CUDA). There is no CPU fallback.
 """
 from .lib import KP_DTYPE, OrbxError, build  # noqa: F401
-from .extractor import ORBextractor, cvtColorToGray  # noqa: F401
+from .extractor import ORBextractor, cvtColorToGray, remapLinear  # noqa: F401
 from .matcher import ORBmatcher  # noqa: F401
 from . import views  # noqa: F401

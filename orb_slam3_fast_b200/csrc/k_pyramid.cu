@@ -295,6 +295,64 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
 // streaming: a thread turns 4 pixels (three or four aligned words) into one output word; the only kernel of the
 // library that is bound by HBM rather than by instruction issue.
 // ---------------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------
+// cv::remap(src, dst, mapx, mapy, INTER_LINEAR), CV_8UC1 / CV_32FC1 maps / BORDER_CONSTANT 0: the stereo rectification
+// of System::TrackStereo (src/System.cc:293-294). OpenCV's fixed point: coordinates in 1/32 px, exact 5-bit weights,
+// (sum + 512) >> 10. A thread produces 4 neighbouring destination pixels (one float4 of each map, 16 gathered bytes,
+// one output word); the maps are shared by every frame of the batch, so they stay in L2.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_remap_linear(const uint8_t* __restrict__ src, int sw, int sh, int sstride, int64_t sfstride,
+               const float* __restrict__ mapx, const float* __restrict__ mapy, int dw, int dh, uint8_t* __restrict__ dst,
+               int dstride, int64_t dfstride, int vec) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y, f = blockIdx.z;
+  if (x >= dw) return;
+  const uint8_t* s = src + f * sfstride;
+  uint8_t* d = dst + f * dfstride + (int64_t)y * dstride + x;
+  const int64_t mo = (int64_t)y * dw + x;
+  float mx[4], my[4];
+  const int n = min(4, dw - x);
+  if (vec && n == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(mapx + mo), b = *reinterpret_cast<const float4*>(mapy + mo);
+    mx[0] = a.x; mx[1] = a.y; mx[2] = a.z; mx[3] = a.w;
+    my[0] = b.x; my[1] = b.y; my[2] = b.z; my[3] = b.w;
+  } else {
+    for (int k = 0; k < 4; k++) {
+      mx[k] = k < n ? mapx[mo + k] : 0.f;
+      my[k] = k < n ? mapy[mo + k] : 0.f;
+    }
+  }
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int sx = __float2int_rn(fmul(mx[k], 32.f)), sy = __float2int_rn(fmul(my[k], 32.f));  // cvRound(map * 32)
+    const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+    const bool x0 = ix >= 0 && ix < sw, x1 = ix + 1 >= 0 && ix + 1 < sw, y0 = iy >= 0 && iy < sh, y1 = iy + 1 >= 0 && iy + 1 < sh;
+    const uint8_t* r0 = s + (int64_t)iy * sstride + ix;
+    const uint8_t* r1 = r0 + sstride;
+    const int p00 = (x0 && y0) ? r0[0] : 0, p01 = (x1 && y0) ? r0[1] : 0;
+    const int p10 = (x0 && y1) ? r1[0] : 0, p11 = (x1 && y1) ? r1[1] : 0;
+    const int top = (32 - fx) * p00 + fx * p01, bot = (32 - fx) * p10 + fx * p11;
+    out |= (uint32_t)(((32 - fy) * top + fy * bot + 512) >> 10) << (8 * k);
+  }
+  if (vec && n == 4) {
+    *reinterpret_cast<uint32_t*>(d) = out;
+  } else {
+    for (int k = 0; k < n; k++) d[k] = (uint8_t)(out >> (8 * k));
+  }
+}
+
+int launch_remap_linear(const uint8_t* src, int sw, int sh, int sstride, int64_t sfstride, const float* mapx,
+                        const float* mapy, int dw, int dh, uint8_t* dst, int dstride, int64_t dfstride, int frames,
+                        cudaStream_t st) {
+  const int vec = (dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(mapx) | reinterpret_cast<uintptr_t>(mapy)) & 15) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)dstride | (uintptr_t)dfstride) & 3) == 0;
+  dim3 grid(((dw + 3) / 4 + 255) / 256, dh, frames);
+  k_remap_linear<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sfstride, mapx, mapy, dw, dh, dst, dstride, dfstride, vec);
+  return 0;
+}
+
 constexpr int kCvtRows = 4;  // rows per thread: their loads are all issued before the first pixel is computed
 
 template <int kChannels>

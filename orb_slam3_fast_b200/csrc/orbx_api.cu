@@ -603,6 +603,48 @@ int orbx_profile_read(orbx_extractor* ex, float* ms, int32_t* launches, int rese
   return ORBX_OK;
 }
 
+int orbx_remap_linear_device(int device, int n_frames, const uint8_t* d_src, int src_width, int src_height,
+                             int src_stride, int64_t src_frame_stride, const float* d_mapx, const float* d_mapy,
+                             int dst_width, int dst_height, uint8_t* d_dst, int dst_stride, int64_t dst_frame_stride,
+                             void* cuda_stream) {
+  if (!d_src || !d_dst || !d_mapx || !d_mapy || src_width <= 0 || src_height <= 0 || dst_width <= 0 ||
+      dst_height <= 0 || n_frames <= 0 || src_stride < src_width || dst_stride < dst_width)
+    return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  orbx::launch_remap_linear(d_src, src_width, src_height, src_stride, src_frame_stride, d_mapx, d_mapy, dst_width,
+                            dst_height, d_dst, dst_stride, dst_frame_stride, n_frames, (cudaStream_t)cuda_stream);
+  return cudaGetLastError() == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbx_remap_linear(int device, const uint8_t* src, int src_width, int src_height, int src_stride, const float* mapx,
+                      const float* mapy, int dst_width, int dst_height, uint8_t* dst, int dst_stride) {
+  if (!src || !dst || !mapx || !mapy || src_width <= 0 || src_height <= 0 || dst_width <= 0 || dst_height <= 0 ||
+      src_stride < src_width || dst_stride < dst_width)
+    return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  uint8_t *d_src = nullptr, *d_dst = nullptr;
+  float *d_mx = nullptr, *d_my = nullptr;
+  const size_t sb = (size_t)src_stride * src_height, db = (size_t)dst_stride * dst_height,
+               mb = (size_t)dst_width * dst_height * sizeof(float);
+  int rc = ORBX_E_CUDA;
+  if (cudaMalloc(&d_src, sb) == cudaSuccess && cudaMalloc(&d_dst, db) == cudaSuccess &&
+      cudaMalloc(&d_mx, mb) == cudaSuccess && cudaMalloc(&d_my, mb) == cudaSuccess &&
+      cudaMemcpy(d_src, src, sb, cudaMemcpyHostToDevice) == cudaSuccess &&
+      cudaMemcpy(d_mx, mapx, mb, cudaMemcpyHostToDevice) == cudaSuccess &&
+      cudaMemcpy(d_my, mapy, mb, cudaMemcpyHostToDevice) == cudaSuccess) {
+    rc = orbx_remap_linear_device(device, 1, d_src, src_width, src_height, src_stride, 0, d_mx, d_my, dst_width,
+                                  dst_height, d_dst, dst_stride, 0, nullptr);
+    if (rc == ORBX_OK &&
+        cudaMemcpy2D(dst, dst_stride, d_dst, dst_stride, dst_width, dst_height, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = ORBX_E_CUDA;
+  }
+  cudaFree(d_src);
+  cudaFree(d_dst);
+  cudaFree(d_mx);
+  cudaFree(d_my);
+  return rc;
+}
+
 int orbx_cvt_gray_device(int device, int n_frames, const uint8_t* d_src, int width, int height, int src_stride,
                          int64_t src_frame_stride, int channels, int rgb, uint8_t* d_dst, int dst_stride,
                          int64_t dst_frame_stride, void* cuda_stream) {

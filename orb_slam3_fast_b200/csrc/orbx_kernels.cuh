@@ -71,6 +71,9 @@ void launch_describe(const Plan& P, const FrameSet& fs, const WorkSet& ws, const
                      int frames, cudaStream_t st);
 int launch_cvt_gray(const uint8_t* src, int w, int h, int sstride, int64_t sfstride, int channels, int rgb, uint8_t* dst,
                     int dstride, int64_t dfstride, int frames, cudaStream_t st);
+int launch_remap_linear(const uint8_t* src, int sw, int sh, int sstride, int64_t sfstride, const float* mapx,
+                        const float* mapy, int dw, int dh, uint8_t* dst, int dstride, int64_t dfstride, int frames,
+                        cudaStream_t st);
 size_t fast_smem_bytes(const Plan& P);
 size_t quadtree_smem_bytes(const Plan& P);
 

@@ -160,3 +160,16 @@ def cvtColorToGray(img, rgb=False, device=0):
     if rc != 0:
         raise OrbxError(rc, "orbx_cvt_gray failed")
     return out
+
+
+def remapLinear(img, mapx, mapy, device=0):
+    """cv::remap(img, mapx, mapy, INTER_LINEAR) (src/System.cc:293-294) for a uint8 [h, w] host image, float32 maps."""
+    img = np.ascontiguousarray(img, np.uint8)
+    mapx, mapy = np.ascontiguousarray(mapx, np.float32), np.ascontiguousarray(mapy, np.float32)
+    dh, dw = mapx.shape
+    out = np.empty((dh, dw), np.uint8)
+    rc = _l.lib().orbx_remap_linear(device, _l.ptr(img), img.shape[1], img.shape[0], img.strides[0], _l.ptr(mapx),
+                                    _l.ptr(mapy), dw, dh, _l.ptr(out), dw)
+    if rc != 0:
+        raise OrbxError(rc, "orbx_remap_linear failed")
+    return out

@@ -63,6 +63,8 @@ def lib():
     L.orbx_debug_level_keypoints.argtypes = [vp, ci, ci, vp, ci]
     L.orbx_profile_enable.argtypes = [vp, ci]
     L.orbx_profile_read.argtypes = [vp, vp, vp, ci]
+    L.orbx_remap_linear.argtypes = [ci, vp, ci, ci, ci, vp, vp, ci, ci, vp, ci]
+    L.orbx_remap_linear_device.argtypes = [ci, ci, vp, ci, ci, ci, i64, vp, vp, ci, ci, vp, ci, i64, vp]
     L.orbx_cvt_gray.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp, ci]
     L.orbx_cvt_gray_device.argtypes = [ci, ci, vp, ci, ci, ci, i64, ci, ci, vp, ci, i64, vp]
     L.orbx_host_alloc.argtypes = [i64]

@@ -205,3 +205,29 @@ def test_cvt_color_to_gray(gpu, channels, rgb):
     for k in range(B):
         assert np.array_equal(out[k, :, :w], orbref.cvt_gray(np.ascontiguousarray(imgs[k, :, :w]), rgb))
     assert (out[:, :, w:] == 0).all()
+
+
+def test_remap_linear_rectification(gpu):
+    """cv::remap(..., INTER_LINEAR) (src/System.cc:293-294) on the device == oracle (== cv2, CPU suite): host form on two
+    geometries, device form on a batch that shares one pair of maps."""
+    import torch
+    from orb_slam3_fast_b200 import remapLinear
+    from orb_slam3_fast_b200 import lib as _lib
+    from test_oracle_primitives import _rectify_maps
+    rng = np.random.default_rng(12)
+    for (h, w, dh, dw) in ((480, 752, 480, 752), (120, 161, 97, 203)):
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        mapx, mapy = _rectify_maps(h, w, h + w, dh, dw)
+        assert np.array_equal(remapLinear(src, mapx, mapy), orbref.remap_linear(src, mapx, mapy)), (h, w)
+    B, h, w = 3, 240, 320
+    imgs = rng.integers(0, 256, (B, h, w), dtype=np.uint8)
+    mapx, mapy = _rectify_maps(h, w, 5)
+    d_src, d_mx, d_my = torch.from_numpy(imgs).cuda(), torch.from_numpy(mapx).cuda(), torch.from_numpy(mapy).cuda()
+    d_dst = torch.zeros((B, h, w), dtype=torch.uint8, device="cuda")
+    rc = _lib.lib().orbx_remap_linear_device(0, B, d_src.data_ptr(), w, h, w, h * w, d_mx.data_ptr(), d_my.data_ptr(), w, h,
+                                             d_dst.data_ptr(), w, h * w, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    out = d_dst.cpu().numpy()
+    for k in range(B):
+        assert np.array_equal(out[k], orbref.remap_linear(imgs[k], mapx, mapy))

@@ -171,3 +171,25 @@ def test_cvt_gray_matches_cv2():
     v = np.array(sorted(set(list(range(0, 256, 5)) + [1, 2, 253, 254, 255])), np.uint8)
     grid = np.stack(np.meshgrid(v, v, v, indexing="ij"), axis=-1).reshape(1, -1, 3)
     assert np.array_equal(orbref.cvt_gray(grid), cv2.cvtColor(grid, cv2.COLOR_BGR2GRAY))
+
+
+def _rectify_maps(h, w, seed, dh=None, dw=None):
+    """Smooth EuRoC-like rectification maps + sub-pixel noise, reaching outside the source on every side."""
+    rng = np.random.default_rng(seed)
+    dh, dw = dh or h, dw or w
+    ys, xs = np.mgrid[0:dh, 0:dw].astype(np.float32)
+    mapx = (xs * (w / dw) + 3.7 * np.sin(ys / 50.0) + rng.uniform(-0.5, 0.5, (dh, dw)) - 4).astype(np.float32)
+    mapy = (ys * (h / dh) + 2.9 * np.cos(xs / 70.0) + rng.uniform(-0.5, 0.5, (dh, dw)) - 3).astype(np.float32)
+    mapx[:3, :5] = -40.25   # far outside
+    mapy[-2:, -7:] = h + 9.5
+    return mapx, mapy
+
+
+def test_remap_linear_matches_cv2():
+    """cv::remap(..., INTER_LINEAR) with CV_32F maps (src/System.cc:293-294): 1/32-pixel coordinates, exact 5-bit
+    weights, constant-0 border — the oracle's restatement equals cv2 byte for byte."""
+    rng = np.random.default_rng(11)
+    for (h, w, dh, dw) in ((480, 752, 480, 752), (120, 161, 97, 203)):
+        src = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        mapx, mapy = _rectify_maps(h, w, h + w, dh, dw)
+        assert np.array_equal(orbref.remap_linear(src, mapx, mapy), cv2.remap(src, mapx, mapy, cv2.INTER_LINEAR))

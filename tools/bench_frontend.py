@@ -45,6 +45,33 @@ def main():
         gbs = B * h * w * (ch + 1) / (ms * 1e-3) / 1e9
         out["rows"].append({"channels": ch, "ms_per_launch": ms, "algorithmic_gbs": gbs, "frac_of_peak": gbs / peak,
                             "frames_per_s": B / (ms * 1e-3)})
+    # ---- cv::remap rectification (src/System.cc:293-294): 1024 frames, one pair of maps shared by the batch ----
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float32)
+    rng = np.random.default_rng(0)
+    mapx = (xs + 3.7 * np.sin(ys / 50.0) + rng.uniform(-0.5, 0.5, (h, w)) - 4).astype(np.float32)
+    mapy = (ys + 2.9 * np.cos(xs / 70.0) + rng.uniform(-0.5, 0.5, (h, w)) - 3).astype(np.float32)
+    d_mx, d_my = torch.from_numpy(mapx).cuda(), torch.from_numpy(mapy).cuda()
+    src = torch.randint(0, 256, (B, h, w), dtype=torch.uint8, device="cuda")
+    dst = torch.empty((B, h, w), dtype=torch.uint8, device="cuda")
+
+    def run_remap():
+        rc = L.orbx_remap_linear_device(0, B, src.data_ptr(), w, h, w, h * w, d_mx.data_ptr(), d_my.data_ptr(), w, h,
+                                        dst.data_ptr(), w, h * w, st.cuda_stream)
+        assert rc == 0
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            run_remap()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(st)
+        for _ in range(20):
+            run_remap()
+        e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    assert np.array_equal(dst[7].cpu().numpy(), orbref.remap_linear(src[7].cpu().numpy(), mapx, mapy))
+    gbs = B * h * w * 2 / (ms * 1e-3) / 1e9   # 1 byte read + 1 byte written per pixel; the maps stay in L2
+    out["remap_linear"] = {"ms_per_launch": ms, "algorithmic_gbs": gbs, "frac_of_peak": gbs / peak,
+                           "frames_per_s": B / (ms * 1e-3)}
     print(json.dumps(out))
 
 
