@@ -301,19 +301,20 @@ k_resize_tma(const __grid_constant__ Plan P, const __grid_constant__ ResizeMaps 
 // (sum + 512) >> 10. A thread produces 4 neighbouring destination pixels (one float4 of each map, 16 gathered bytes,
 // one output word); the maps are shared by every frame of the batch, so they stay in L2.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kRemapFrames = 4;  // frames per thread: the map values, tap addresses and weights are computed once for them
+
 __global__ void __launch_bounds__(256)
 k_remap_linear(const uint8_t* __restrict__ src, int sw, int sh, int sstride, int64_t sfstride,
                const float* __restrict__ mapx, const float* __restrict__ mapy, int dw, int dh, uint8_t* __restrict__ dst,
-               int dstride, int64_t dfstride, int vec) {
+               int dstride, int64_t dfstride, int vec, int frames) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  const int y = blockIdx.y, f = blockIdx.z;
+  const int y = blockIdx.y, f0 = blockIdx.z * kRemapFrames;
   if (x >= dw) return;
-  const uint8_t* s = src + f * sfstride;
-  uint8_t* d = dst + f * dfstride + (int64_t)y * dstride + x;
   const int64_t mo = (int64_t)y * dw + x;
   float mx[4], my[4];
   const int n = min(4, dw - x);
-  if (vec && n == 4) {
+  const bool wide = vec && n == 4;
+  if (wide) {
     const float4 a = *reinterpret_cast<const float4*>(mapx + mo), b = *reinterpret_cast<const float4*>(mapy + mo);
     mx[0] = a.x; mx[1] = a.y; mx[2] = a.z; mx[3] = a.w;
     my[0] = b.x; my[1] = b.y; my[2] = b.z; my[3] = b.w;
@@ -323,23 +324,37 @@ k_remap_linear(const uint8_t* __restrict__ src, int sw, int sh, int sstride, int
       my[k] = k < n ? mapy[mo + k] : 0.f;
     }
   }
-  uint32_t out = 0;
+  int off[4], fxs[4], fys[4];
+  unsigned ok[4];  // bit 0..3: taps (0,0) (0,1) (1,0) (1,1) inside the source
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int sx = __float2int_rn(fmul(mx[k], 32.f)), sy = __float2int_rn(fmul(my[k], 32.f));  // cvRound(map * 32)
-    const int ix = sx >> 5, iy = sy >> 5, fx = sx & 31, fy = sy & 31;
+    const int ix = sx >> 5, iy = sy >> 5;
+    fxs[k] = sx & 31;
+    fys[k] = sy & 31;
     const bool x0 = ix >= 0 && ix < sw, x1 = ix + 1 >= 0 && ix + 1 < sw, y0 = iy >= 0 && iy < sh, y1 = iy + 1 >= 0 && iy + 1 < sh;
-    const uint8_t* r0 = s + (int64_t)iy * sstride + ix;
-    const uint8_t* r1 = r0 + sstride;
-    const int p00 = (x0 && y0) ? r0[0] : 0, p01 = (x1 && y0) ? r0[1] : 0;
-    const int p10 = (x0 && y1) ? r1[0] : 0, p11 = (x1 && y1) ? r1[1] : 0;
-    const int top = (32 - fx) * p00 + fx * p01, bot = (32 - fx) * p10 + fx * p11;
-    out |= (uint32_t)(((32 - fy) * top + fy * bot + 512) >> 10) << (8 * k);
+    ok[k] = (unsigned)(x0 && y0) | ((unsigned)(x1 && y0) << 1) | ((unsigned)(x0 && y1) << 2) | ((unsigned)(x1 && y1) << 3);
+    // clamp the address of a fully outside tap so that `off` stays a valid int; it is never dereferenced then
+    off[k] = ok[k] ? iy * sstride + ix : 0;
   }
-  if (vec && n == 4) {
-    *reinterpret_cast<uint32_t*>(d) = out;
-  } else {
-    for (int k = 0; k < n; k++) d[k] = (uint8_t)(out >> (8 * k));
+  for (int df = 0; df < kRemapFrames && f0 + df < frames; df++) {
+    const uint8_t* s = src + (f0 + df) * sfstride;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint8_t* r0 = s + off[k];
+      const uint8_t* r1 = r0 + sstride;
+      const int p00 = (ok[k] & 1u) ? r0[0] : 0, p01 = (ok[k] & 2u) ? r0[1] : 0;
+      const int p10 = (ok[k] & 4u) ? r1[0] : 0, p11 = (ok[k] & 8u) ? r1[1] : 0;
+      const int top = (32 - fxs[k]) * p00 + fxs[k] * p01, bot = (32 - fxs[k]) * p10 + fxs[k] * p11;
+      out |= (uint32_t)(((32 - fys[k]) * top + fys[k] * bot + 512) >> 10) << (8 * k);
+    }
+    uint8_t* d = dst + (f0 + df) * dfstride + (int64_t)y * dstride + x;
+    if (wide) {
+      *reinterpret_cast<uint32_t*>(d) = out;
+    } else {
+      for (int k = 0; k < n; k++) d[k] = (uint8_t)(out >> (8 * k));
+    }
   }
 }
 
@@ -348,8 +363,9 @@ int launch_remap_linear(const uint8_t* src, int sw, int sh, int sstride, int64_t
                         cudaStream_t st) {
   const int vec = (dw % 4 == 0) && ((reinterpret_cast<uintptr_t>(mapx) | reinterpret_cast<uintptr_t>(mapy)) & 15) == 0 &&
                   ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)dstride | (uintptr_t)dfstride) & 3) == 0;
-  dim3 grid(((dw + 3) / 4 + 255) / 256, dh, frames);
-  k_remap_linear<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sfstride, mapx, mapy, dw, dh, dst, dstride, dfstride, vec);
+  dim3 grid(((dw + 3) / 4 + 255) / 256, dh, (frames + kRemapFrames - 1) / kRemapFrames);
+  k_remap_linear<<<grid, 256, 0, st>>>(src, sw, sh, sstride, sfstride, mapx, mapy, dw, dh, dst, dstride, dfstride, vec,
+                                       frames);
   return 0;
 }
 
