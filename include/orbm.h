@@ -124,6 +124,18 @@ int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extract
                                              float inv_w, float inv_h, const orbx_projected* pts, int max_dist,
                                              int check_orientation, int32_t* assign, int32_t* nmatches);
 
+/* void Frame::ComputeBoW() / KeyFrame::ComputeBoW() (src/Frame.cc:846-851, src/KeyFrame.cc) — SURVEY.md §8(f) rank 2:
+ * mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4). orbm_set_vocabulary uploads the DBoW2 tree once
+ * (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h: m_nodes, m_L; ORBvoc has 1.1 M nodes = 35 MB of descriptors) and
+ * keeps it on the device; orbm_bow_transform runs the per-feature tree descent of transform(feature, word_id, weight,
+ * &nid, levelsup) (:1218-1262) for n descriptors: word_id[n], weight[n] (the leaf's WordValue), node_id[n] (the node
+ * at level m_L - levelsup, 0 = root). The shim then fills the two std::maps in feature order exactly as :1147-1160 does
+ * (v.addWeight(id, w) when w > 0, fv.addFeature(nid, i)) and normalises (:1198), so every double is summed by the
+ * reference's own code. */
+int orbm_set_vocabulary(orbm_matcher* m, const orbx_vocabulary* voc);
+int orbm_bow_transform(orbm_matcher* m, const uint8_t* desc, int n, int levelsup, uint32_t* word_id, double* weight,
+                       uint32_t* node_id);
+
 /* int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched,
  * vector<int>& vnMatches12, int windowSize = 10) (include/ORBmatcher.h:73-77, src/ORBmatcher.cc:618-764) — SURVEY.md
  * §8(f) rank 3 — in the serial order of its loop (the fork's tbb::parallel_for at :634 races on vnMatches21 /

@@ -91,6 +91,20 @@ typedef struct orbx_featvec {
   const uint32_t* indices;  /* keypoint indices, per node in insertion order */
 } orbx_featvec;
 
+/* The vocabulary tree of DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (Thirdparty/DBoW2/DBoW2/
+ * TemplatedVocabulary.h: m_nodes with children / descriptor / word_id / weight, m_L) flattened node by node; node 0 is
+ * the root. children of node n = children[child_offsets[n] .. child_offsets[n + 1]) in m_nodes[n].children order; a
+ * node without children is a leaf (a word). */
+typedef struct orbx_vocabulary {
+  int32_t n_nodes;
+  int32_t depth;                /* m_L */
+  const int32_t* child_offsets; /* [n_nodes + 1] */
+  const uint32_t* children;
+  const uint8_t* descriptors;   /* n_nodes x 32 (the root's row is not read) */
+  const uint32_t* word_id;      /* per node; meaningful for leaves */
+  const double* weight;         /* per node; WordValue of the leaf */
+} orbx_vocabulary;
+
 /* KeyFrame view for SearchForTriangulation (pinhole, NLeft == -1): include/KeyFrame.h:384-401. */
 typedef struct orbx_keyframe_view {
   int32_t n;

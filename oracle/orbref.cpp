@@ -1130,6 +1130,35 @@ void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels,
   }
 }
 
+// TemplatedVocabulary::transform(const TDescriptor&, WordId&, WordValue&, NodeId*, int) — TemplatedVocabulary.h:1218-1262
+void orbref_bow_transform(const orbx_vocabulary* voc, const uint8_t* desc, int n, int levelsup, uint32_t* word_id,
+                          double* weight, uint32_t* node_id) {
+  const int nid_level = voc->depth - levelsup;
+  for (int i = 0; i < n; i++) {
+    const uint8_t* f = desc + (size_t)i * 32;
+    uint32_t nid = 0, final_id = 0;
+    int current_level = 0;
+    do {
+      ++current_level;
+      const int c0 = voc->child_offsets[final_id], c1 = voc->child_offsets[final_id + 1];
+      final_id = voc->children[c0];
+      double best_d = orbref_descriptor_distance(f, voc->descriptors + (size_t)final_id * 32);
+      for (int c = c0 + 1; c < c1; c++) {
+        const uint32_t id = voc->children[c];
+        const double d = orbref_descriptor_distance(f, voc->descriptors + (size_t)id * 32);
+        if (d < best_d) {
+          best_d = d;
+          final_id = id;
+        }
+      }
+      if (current_level == nid_level) nid = final_id;
+    } while (voc->child_offsets[final_id + 1] > voc->child_offsets[final_id]);  // !isLeaf()
+    word_id[i] = voc->word_id[final_id];
+    weight[i] = voc->weight[final_id];
+    node_id[i] = nid;
+  }
+}
+
 // ORBmatcher::SearchForInitialization — src/ORBmatcher.cc:618-764, serial order of the loop body
 int orbref_search_for_initialization(const orbx_frame_view* f1, const orbx_frame_view* f2, const float* prev_xy,
                                      int window_size, float nnratio, int check_orientation, int32_t* matches12) {

@@ -99,6 +99,12 @@ void orbref_remap_linear(const uint8_t* src, int sw, int sh, int sstride, const 
  * gray = (B * 3735 + G * 19235 + R * 9798 + 16384) >> 15 (pinned to cv2 4.13 in tests/test_oracle_primitives.py).
  * channels = 3 or 4; rgb != 0 when the first channel is red. */
 void orbref_cvt_gray(const uint8_t* src, int w, int h, int stride, int channels, int rgb, uint8_t* dst, int dstride);
+/* The per-feature part of Frame::ComputeBoW (src/Frame.cc:846-851) = TemplatedVocabulary::transform(feature, word_id,
+ * weight, &nid, levelsup) (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1262): descend the tree taking at every
+ * level the FIRST child with the least FORB::distance; nid = the node passed at level m_L - levelsup (0 = root when that
+ * level is <= 0 or never reached). Outputs per feature. */
+void orbref_bow_transform(const orbx_vocabulary* voc, const uint8_t* desc, int n, int levelsup, uint32_t* word_id,
+                          double* weight, uint32_t* node_id);
 /* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<cv::Point2f>& vbPrevMatched, vector<int>& vnMatches12,
  * int windowSize) (src/ORBmatcher.cc:618-764), in the SERIAL order of its loop (the fork wraps it in a racy
  * tbb::parallel_for, :634). f1: mvKeysUn + mDescriptors of F1 (grid unused); f2: F2 with its grid; prev_xy[f1->n][2] =

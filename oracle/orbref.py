@@ -26,6 +26,11 @@ def build(force=False):
     return _SO
 
 
+class Vocabulary(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("depth", C.c_int32), ("child_offsets", C.c_void_p), ("children", C.c_void_p),
+                ("descriptors", C.c_void_p), ("word_id", C.c_void_p), ("weight", C.c_void_p)]
+
+
 class Grid(C.Structure):
     _fields_ = [("cell_offsets", C.c_void_p), ("cell_items", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
                 ("inv_w", C.c_float), ("inv_h", C.c_float)]
@@ -163,6 +168,8 @@ def lib():
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+        L.orbref_bow_transform.restype = None
         L.orbref_search_for_initialization.argtypes = [vp, vp, vp, ci, cf, ci, vp]
         L.orbref_remap_linear.argtypes = [vp, ci, ci, ci, vp, vp, ci, ci, vp, ci]
         L.orbref_remap_linear.restype = None
@@ -368,6 +375,20 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
     m = np.empty(max(kf1.struct.n, 1), np.int32)
     n = lib().orbref_search_by_bow_kf(kf1.ref(), kf2.ref(), float(nnratio), int(check_orientation), _ptr(m))
     return n, m[:kf1.struct.n]
+
+
+def make_vocabulary(depth, child_offsets, children, descriptors, word_id, weight):
+    arrs = (_c(child_offsets, np.int32), _c(children, np.uint32), _c(descriptors, np.uint8), _c(word_id, np.uint32),
+            _c(weight, np.float64))
+    return Holder(Vocabulary(len(arrs[0]) - 1, int(depth), *[_ptr(a) for a in arrs]), arrs)
+
+
+def bow_transform(voc, desc, levelsup=4):
+    desc = _c(desc, np.uint8).reshape(-1, 32)
+    n = len(desc)
+    w, wt, nd = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.float64), np.empty(max(n, 1), np.uint32)
+    lib().orbref_bow_transform(voc.ref(), _ptr(desc), n, int(levelsup), _ptr(w), _ptr(wt), _ptr(nd))
+    return w[:n], wt[:n], nd[:n]
 
 
 def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, check_orientation=True):

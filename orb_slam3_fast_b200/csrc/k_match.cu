@@ -141,6 +141,51 @@ void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The per-feature part of Frame::ComputeBoW (src/Frame.cc:846-851): DBoW2 TemplatedVocabulary::transform(feature,
+// word_id, weight, &nid, levelsup) (TemplatedVocabulary.h:1218-1262). One thread per feature walks the tree: at every
+// level the first child with the least Hamming distance (strict <), the node passed at level m_L - levelsup is kept
+// for the FeatureVector. The 10 children of a node are consecutive rows of the descriptor table, so a level is 20
+// independent 16-byte loads; the whole ORB vocabulary (1.1 M nodes x 32 B) sits in the 126 MB L2.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_bow_transform(const DevVocabulary V, const uint8_t* __restrict__ desc, int n, int levelsup,
+                uint32_t* __restrict__ word_id, double* __restrict__ weight, uint32_t* __restrict__ node_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[8];
+  load_desc(desc + (size_t)i * 32, a);
+  const int nid_level = V.depth - levelsup;
+  uint32_t nid = 0, final_id = 0;
+  int level = 0;
+  int c0 = V.child_offsets[0], c1 = V.child_offsets[1];
+  do {
+    ++level;
+    int best_d = 0x7fffffff;
+    for (int c = c0; c < c1; c++) {
+      const uint32_t id = V.children[c];
+      uint32_t b[8];
+      load_desc(V.descriptors + (size_t)id * 32, b);
+      const int d = hamming(a, b);
+      if (d < best_d) {  // the first child wins ties                                      :1242-1251
+        best_d = d;
+        final_id = id;
+      }
+    }
+    if (level == nid_level) nid = final_id;
+    c0 = V.child_offsets[final_id];
+    c1 = V.child_offsets[final_id + 1];
+  } while (c1 > c0);
+  word_id[i] = V.word_id[final_id];
+  weight[i] = V.weight[final_id];
+  node_id[i] = nid;
+}
+
+void launch_bow_transform(const DevVocabulary& V, const uint8_t* desc, int n, int levelsup, uint32_t* word_id,
+                          double* weight, uint32_t* node_id, cudaStream_t st) {
+  if (n > 0) k_bow_transform<<<(n + 127) / 128, 128, 0, st>>>(V, desc, n, levelsup, word_id, weight, node_id);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:407-435), batched over map points: CSR of observed
 // descriptors -> per point the index of the descriptor with the least median distance to the others. One warp per
 // point. For row i the lanes take the columns j = lane, lane + 32, ...; the element [0.5 * (N - 1)] of the sorted row

@@ -52,6 +52,9 @@ struct orbm_matcher {
   DevBuf lane_buf[kLanes][4];
   int32_t* lane_h_nm[kLanes] = {};
   int lane_h_cap[kLanes] = {};
+  // the vocabulary tree of orbm_set_vocabulary (device resident across calls)
+  DevBuf voc_buf[5];
+  orbx::DevVocabulary voc{};
 };
 
 namespace {
@@ -223,6 +226,7 @@ void orbm_destroy(orbm_matcher* m) {
     for (auto& b : lb) b.release();
   for (auto& h : m->lane_h_nm)
     if (h) cudaFreeHost(h);
+  for (auto& b : m->voc_buf) b.release();
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -716,6 +720,63 @@ static DevKeyFrame upload_keyframe(Arena& ar, const orbx_keyframe_view* k) {
   K.scale_factors = ar.upload(k->scale_factors, k->n_levels);
   K.level_sigma2 = ar.upload(k->level_sigma2, k->n_levels);
   return K;
+}
+
+int orbm_set_vocabulary(orbm_matcher* m, const orbx_vocabulary* voc) {
+  if (!m || !voc || voc->n_nodes < 1 || voc->depth < 0 || !voc->child_offsets || !voc->descriptors || !voc->word_id ||
+      !voc->weight)
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  const int N = voc->n_nodes;
+  const int n_children = voc->child_offsets[N];
+  if (voc->child_offsets[0] != 0 || n_children < 0 || (n_children > 0 && !voc->children) ||
+      voc->child_offsets[1] <= 0)
+    return mfail(m, ORBX_E_ARG, "vocabulary: the root needs children and offsets must start at 0");
+  for (int i = 0; i < N; i++)
+    if (voc->child_offsets[i + 1] < voc->child_offsets[i]) return mfail(m, ORBX_E_ARG, "vocabulary: offsets must ascend");
+  for (int c = 0; c < n_children; c++)
+    if (voc->children[c] == 0 || voc->children[c] >= (uint32_t)N)
+      return mfail(m, ORBX_E_ARG, "vocabulary: child id out of range");
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const size_t bytes[5] = {(size_t)(N + 1) * 4, (size_t)std::max(n_children, 1) * 4, (size_t)N * 32, (size_t)N * 4,
+                           (size_t)N * 8};
+  const void* host[5] = {voc->child_offsets, voc->children, voc->descriptors, voc->word_id, voc->weight};
+  for (int k = 0; k < 5; k++) {
+    cudaError_t e = m->voc_buf[k].reserve(bytes[k]);
+    if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+    if (host[k] && (k != 1 || n_children > 0))
+      ORBM_CUDA(m, cudaMemcpyAsync(m->voc_buf[k].p, host[k], k == 1 ? (size_t)n_children * 4 : bytes[k],
+                                   cudaMemcpyHostToDevice, m->stream));
+  }
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  m->voc.n_nodes = N;
+  m->voc.depth = voc->depth;
+  m->voc.child_offsets = reinterpret_cast<const int32_t*>(m->voc_buf[0].p);
+  m->voc.children = reinterpret_cast<const uint32_t*>(m->voc_buf[1].p);
+  m->voc.descriptors = reinterpret_cast<const uint8_t*>(m->voc_buf[2].p);
+  m->voc.word_id = reinterpret_cast<const uint32_t*>(m->voc_buf[3].p);
+  m->voc.weight = reinterpret_cast<const double*>(m->voc_buf[4].p);
+  return ORBX_OK;
+}
+
+int orbm_bow_transform(orbm_matcher* m, const uint8_t* desc, int n, int levelsup, uint32_t* word_id, double* weight,
+                       uint32_t* node_id) {
+  if (!m || n < 0 || (n > 0 && (!desc || !word_id || !weight || !node_id))) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (m->voc.n_nodes < 1) return mfail(m, ORBX_E_ARG, "no vocabulary: call orbm_set_vocabulary first");
+  if (n == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const uint8_t* dd = ar.upload(desc, (size_t)n * 32);
+  uint32_t* dw = ar.alloc<uint32_t>(n);
+  double* dwt = ar.alloc<double>(n);
+  uint32_t* dn = ar.alloc<uint32_t>(n);
+  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_bow_transform(m->voc, dd, n, levelsup, dw, dwt, dn, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  ORBM_CUDA(m, cudaMemcpyAsync(word_id, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(weight, dwt, (size_t)n * 8, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(node_id, dn, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  return ORBX_OK;
 }
 
 int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, const orbx_frame_view* f2,

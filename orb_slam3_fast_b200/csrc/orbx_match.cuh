@@ -43,6 +43,17 @@ int knn2_splits(int nq, int nt);
 void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int4* partial, int splits, int32_t* idx1,
                  int32_t* d1, int32_t* idx2, int32_t* d2, cudaStream_t st);
 void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, cudaStream_t st);
+// TemplatedVocabulary::transform per feature; the vocabulary arrays are device resident (orbm_vocabulary handle)
+struct DevVocabulary {
+  int n_nodes, depth;
+  const int32_t* child_offsets;
+  const uint32_t* children;
+  const uint8_t* descriptors;
+  const uint32_t* word_id;
+  const double* weight;
+};
+void launch_bow_transform(const DevVocabulary& V, const uint8_t* desc, int n, int levelsup, uint32_t* word_id,
+                          double* weight, uint32_t* node_id, cudaStream_t st);
 // MapPoint::ComputeDistinctiveDescriptors for n_points CSR lists of descriptors
 void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int32_t* best, cudaStream_t st);
 void launch_stereo(const StereoArgs& A, int n_pairs, int max_rows, cudaStream_t st);

@@ -37,6 +37,8 @@ def _bind(L):
     L.orbm_search_for_triangulation.argtypes = [vp, vp, vp, vp, cf, cf, ci, ci, ci, vp, vp]
     L.orbm_search_by_bow.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L.orbm_fuse_match.argtypes = [vp, vp, vp, vp, ci, vp, vp]
+    L.orbm_set_vocabulary.argtypes = [vp, vp]
+    L.orbm_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     L.orbm_search_for_initialization.argtypes = [vp, vp, vp, vp, ci, cf, ci, vp, vp]
     L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L._orbm_bound = True
@@ -202,6 +204,19 @@ class ORBmatcher:
         return nm.value, assign[:n]
 
     # int SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse) — :886
+    # Frame::ComputeBoW — src/Frame.cc:846-851: the vocabulary goes to the device once, then per-feature descents
+    def SetVocabulary(self, voc):
+        self._voc_keep = voc
+        self._check(self._L.orbm_set_vocabulary(self._h, voc.ref()))
+
+    def BowTransform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        w, wt, nd = np.empty(max(n, 1), np.uint32), np.empty(max(n, 1), np.float64), np.empty(max(n, 1), np.uint32)
+        self._check(self._L.orbm_bow_transform(self._h, _l.ptr(desc), n, int(levelsup), _l.ptr(w), _l.ptr(wt),
+                                               _l.ptr(nd)))
+        return w[:n], wt[:n], nd[:n]
+
     # int SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) — src/ORBmatcher.cc:618
     def SearchForInitialization(self, f1_view, f2_view, prev_matched_xy, windowSize=10):
         prev = np.ascontiguousarray(prev_matched_xy, np.float32).reshape(-1, 2)

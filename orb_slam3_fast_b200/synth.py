@@ -171,3 +171,47 @@ def feature_vector(n, n_nodes, seed=0):
     offsets = np.zeros(keep.sum() + 1, np.int32)
     offsets[1:] = np.cumsum(counts[keep])
     return ids_all[keep], offsets, order.astype(np.uint32), node_of
+
+
+def vocabulary(k=10, depth=4, seed=0, ragged=True):
+    """A synthetic DBoW2-style vocabulary tree (k children per node, `depth` levels below the root) in the flat layout of
+    orbx_vocabulary: children descriptors are the parent's with a few dozen bits flipped (so descents are meaningful),
+    some siblings are exact duplicates (distance ties: the first must win), and with `ragged` a few inner nodes have
+    fewer children / become early leaves. Returns a dict in the orbx_vocabulary layout (views.make_vocabulary)."""
+    rng = np.random.default_rng(seed + 424243)
+    desc = [np.zeros(32, np.uint8)]
+    child_lists = [[]]
+    level_of = [0]
+    frontier = [0]
+    for lv in range(1, depth + 1):
+        nxt = []
+        for node in frontier:
+            nc = k
+            if ragged and lv > 1 and rng.random() < 0.08:
+                nc = int(rng.integers(0, k))          # fewer children, possibly none (an early leaf)
+            base = desc[node] if node else rng.integers(0, 256, 32, dtype=np.uint8)
+            for c in range(nc):
+                d = base.copy() if node else rng.integers(0, 256, 32, dtype=np.uint8)
+                for b in rng.choice(256, size=int(rng.integers(8, 48)), replace=False):
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                if c and rng.random() < 0.1:
+                    d = desc[child_lists[node][0]].copy()   # duplicate of the first sibling
+                desc.append(d)
+                child_lists.append([])
+                level_of.append(lv)
+                child_lists[node].append(len(desc) - 1)
+                nxt.append(len(desc) - 1)
+        frontier = nxt
+    n = len(desc)
+    offsets = np.zeros(n + 1, np.int32)
+    children = []
+    for i in range(n):
+        children.extend(child_lists[i])
+        offsets[i + 1] = len(children)
+    is_leaf = np.diff(offsets) == 0
+    word_id = np.zeros(n, np.uint32)
+    word_id[is_leaf] = np.arange(int(is_leaf.sum()), dtype=np.uint32)
+    weight = np.where(is_leaf, rng.uniform(0.0, 9.0, n), 0.0)
+    weight[is_leaf & (rng.random(n) < 0.05)] = 0.0     # "stopped" words (w > 0 fails, TemplatedVocabulary.h:1154)
+    return dict(depth=depth, child_offsets=offsets, children=np.asarray(children, np.uint32),
+                descriptors=np.stack(desc), word_id=word_id, weight=weight.astype(np.float64))

@@ -33,6 +33,11 @@ class Projected(C.Structure):
                 ("has_obs", C.c_void_p), ("desc", C.c_void_p)]
 
 
+class Vocabulary(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("depth", C.c_int32), ("child_offsets", C.c_void_p), ("children", C.c_void_p),
+                ("descriptors", C.c_void_p), ("word_id", C.c_void_p), ("weight", C.c_void_p)]
+
+
 class FeatVec(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("indices", C.c_void_p)]
 
@@ -103,6 +108,31 @@ def make_projected(u, v, u_right, radius, min_level, max_level, angle, has_obs, 
             _c(radius, np.float32), _c(min_level, np.int32), _c(max_level, np.int32), _c(angle, np.float32),
             _c(has_obs, np.uint8), _c(desc, np.uint8))
     return Holder(Projected(len(arrs[0]), *[_p(a) for a in arrs]), arrs)
+
+
+def make_vocabulary(depth, child_offsets, children, descriptors, word_id, weight):
+    """orbx_vocabulary: DBoW2's m_nodes flattened (include/orbx_types.h)."""
+    arrs = (_c(child_offsets, np.int32), _c(children, np.uint32), _c(descriptors, np.uint8), _c(word_id, np.uint32),
+            _c(weight, np.float64))
+    return Holder(Vocabulary(len(arrs[0]) - 1, int(depth), *[_p(a) for a in arrs]), arrs)
+
+
+def assemble_bow(word_id, weight, node_id):
+    """What the shim does with the per-feature answers (TemplatedVocabulary.h:1147-1160, 1198; BowVector.cpp:34-84):
+    BowVector = {word: sum of weights in feature order}, L1-normalised in ascending word order; FeatureVector =
+    {node: feature indices in order}. Plain Python floats are the reference's doubles."""
+    bow, fv = {}, {}
+    for i, (w, wt, nd) in enumerate(zip(word_id.tolist(), weight.tolist(), node_id.tolist())):
+        if wt > 0:
+            bow[w] = bow[w] + wt if w in bow else wt
+            fv.setdefault(nd, []).append(i)
+    norm = 0.0
+    for w in sorted(bow):
+        norm += abs(bow[w])
+    if norm > 0.0:
+        for w in bow:
+            bow[w] /= norm
+    return bow, fv
 
 
 def make_keyframe_view(kps, desc, u_right, has_mappoint, node_ids, offsets, indices, scale_factors, level_sigma2):

@@ -354,3 +354,26 @@ def test_search_for_initialization(gpu, window, nnratio, check, seed):
     assert n_r > 50, "degenerate test: %d matches" % n_r
     assert n == n_r and np.array_equal(m12, m12_r), np.nonzero(m12 != m12_r)[0][:10]
     assert (m12[k1["octave"] > 0] == -1).all()
+
+
+@pytest.mark.parametrize("k,depth,levelsup,seed", [(10, 4, 2, 0), (10, 3, 4, 1), (6, 5, 4, 2)])
+def test_bow_transform(matcher, k, depth, levelsup, seed):
+    """The per-feature part of Frame::ComputeBoW (src/Frame.cc:846-851; DBoW2 TemplatedVocabulary::transform,
+    TemplatedVocabulary.h:1218-1262) on a synthetic vocabulary: word, weight and FeatureVector node of every feature,
+    including distance ties between siblings, ragged nodes and levelsup >= depth (node = root)."""
+    voc = synth.vocabulary(k, depth, seed)
+    rng = np.random.default_rng(seed)
+    n_nodes = len(voc["descriptors"])
+    src = rng.integers(1, n_nodes, 3000)
+    feats = synth.flip_bits(voc["descriptors"][src], rng.integers(0, 40, len(src)), rng)
+    feats[::11] = voc["descriptors"][src[::11]]           # exact copies of node descriptors
+    feats = np.concatenate([feats, synth.descriptors(500, seed + 5)])
+    matcher.SetVocabulary(views.make_vocabulary(**voc))
+    w, wt, nd = matcher.BowTransform(feats, levelsup)
+    w_r, wt_r, nd_r = orbref.bow_transform(orbref.make_vocabulary(**voc), feats, levelsup)
+    assert np.array_equal(w, w_r) and np.array_equal(nd, nd_r) and np.array_equal(wt, wt_r)
+    assert len(np.unique(w_r)) > 50
+    bow, fv = views.assemble_bow(w, wt, nd)
+    assert abs(sum(bow.values()) - 1.0) < 1e-9 and sum(len(x) for x in fv.values()) == int((wt > 0).sum())
+    if depth - levelsup <= 0:
+        assert (nd == 0).all()
