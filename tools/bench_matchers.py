@@ -110,6 +110,63 @@ def main():
         "ms_cpu_oracle": timed(lambda: [orbref.distinctive_descriptor(d) for d in lists], 2),
         "observations": int(sum(len(d) for d in lists)),
         "note": "the GPU figure includes the Python-side concatenation of the 10 000 lists and the H2D / D2H copies"}
+    # ---- §8f rank 2 / 3 rows on one 752x480 stereo pair's features (1500 per image) ----
+    e1, e2 = ORBextractor(1500), ORBextractor(1500)
+    _, k1, d1 = e1(left)
+    _, k2, d2 = e2(right)
+    rngf = np.random.default_rng(4)
+
+    def featvec(desc):
+        node_of = (desc[:, 0].astype(np.int64) >> 2) * 7 + 3      # 64 "vocabulary nodes"
+        ids, inv = np.unique(node_of, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        offsets = np.zeros(len(ids) + 1, np.int32)
+        offsets[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+        return ids.astype(np.uint32), offsets, order.astype(np.uint32)
+    sf, s2 = e1.GetScaleFactors(), e1.GetScaleSigmaSquares()
+    vg, vr = [], []
+    for k, d in ((k1, d1), (k2, d2)):
+        ids, off, idx = featvec(d)
+        a = (k, d, np.full(len(k), -1, np.float32), (rngf.random(len(k)) < 0.6).astype(np.uint8), ids, off, idx, sf, s2)
+        vg.append(views.make_keyframe_view(*a))
+        vr.append(orbref.make_keyframe_view(*a))
+    mb_ = ORBmatcher(0.7, True)
+    n, mf = mb_.SearchByBoW(vg[0], vg[1])
+    n_r, mf_r = orbref.search_by_bow(vr[0], vr[1], 0.7, True)
+    assert n == n_r and np.array_equal(mf, mf_r)
+    out["search_by_bow_kf_frame"] = {"ms_gpu_call": timed(lambda: mb_.SearchByBoW(vg[0], vg[1]), 30),
+                                     "ms_cpu_oracle": timed(lambda: orbref.search_by_bow(vr[0], vr[1], 0.7, True), 10),
+                                     "matches": int(n)}
+    voc = synth.vocabulary(10, 5, 0, ragged=False)              # 111 111 nodes
+    mt.SetVocabulary(views.make_vocabulary(**voc))
+    vref = orbref.make_vocabulary(**voc)
+    w, wt, nd = mt.BowTransform(d1, 4)
+    w_r, wt_r, nd_r = orbref.bow_transform(vref, d1, 4)
+    assert np.array_equal(w, w_r) and np.array_equal(nd, nd_r)
+    out["bow_transform_1500_features_depth5"] = {"ms_gpu_call": timed(lambda: mt.BowTransform(d1, 4), 30),
+                                                 "ms_cpu_oracle": timed(lambda: orbref.bow_transform(vref, d1, 4), 10),
+                                                 "vocabulary_nodes": int(len(voc["descriptors"]))}
+    inv_w2, inv_h2 = np.float32(64) / np.float32(w_img := 752), np.float32(48) / np.float32(480)
+    off2, items2 = views.assign_features_to_grid(k1, 0.0, 0.0, inv_w2, inv_h2)
+    kfv = views.make_frame_view(k1, d1, None, np.zeros(len(k1), np.uint8), off2, items2, 0.0, 0.0, inv_w2, inv_h2, sf)
+    g2, keep2 = orbref.make_grid(off2, items2, 0.0, 0.0, inv_w2, inv_h2)
+    kfr = orbref.make_frame_view(k1, d1, None, np.zeros(len(k1), np.uint8), g2, keep2, sf)
+    mpts = 5000
+    srcp = rngf.integers(0, len(k1), mpts)
+    lev = np.clip(k1["octave"][srcp] + rngf.integers(-1, 2, mpts), 0, 7).astype(np.int32)
+    fp = dict(u=(k1["x"][srcp] + rngf.normal(0, 1.2, mpts)).astype(np.float32),
+              v=(k1["y"][srcp] + rngf.normal(0, 1.2, mpts)).astype(np.float32), u_right=None,
+              radius=(np.float32(3.0) * np.asarray(sf, np.float32)[lev]).astype(np.float32), min_level=lev - 1,
+              max_level=lev, angle=np.zeros(mpts, np.float32), has_obs=np.zeros(mpts, np.uint8),
+              desc=synth.flip_bits(d1[srcp], rngf.integers(0, 60, mpts), rngf))
+    inv_s2 = 1.0 / np.asarray(s2, np.float32)
+    pg, pr2 = views.make_projected(**fp), orbref.make_projected(**fp)
+    bi, bd = mt.FuseMatch(kfv, inv_s2, pg)
+    bi_r, bd_r = orbref.fuse_match(kfr, inv_s2, pr2)
+    assert np.array_equal(bi, bi_r) and np.array_equal(bd, bd_r)
+    out["fuse_match_5000_points"] = {"ms_gpu_call": timed(lambda: mt.FuseMatch(kfv, inv_s2, pg), 30),
+                                     "ms_cpu_oracle": timed(lambda: orbref.fuse_match(kfr, inv_s2, pr2), 10),
+                                     "fused": int((bd_r <= 50).sum())}
     out["timer"] = "host wall clock around synchronous ABI calls unless the key says device (CUDA events)"
     print(json.dumps(out))
 
