@@ -52,6 +52,11 @@ struct orbm_matcher {
   DevBuf lane_buf[kLanes][4];
   int32_t* lane_h_nm[kLanes] = {};
   int lane_h_cap[kLanes] = {};
+  // small host arrays of one call are packed into one pinned block and cross PCIe in ONE copy (a frame / keyframe
+  // view is 8-10 arrays: 20 separate pageable copies cost more than the kernels of a guided search)
+  uint8_t* h_stage = nullptr;
+  uint8_t* d_stage = nullptr;
+  size_t stage_used = 0, stage_flushed = 0;
   // the vocabulary tree of orbm_set_vocabulary (device resident across calls)
   DevBuf voc_buf[5];
   orbx::DevVocabulary voc{};
@@ -73,10 +78,23 @@ int mfail(orbm_matcher* m, int code, const std::string& msg) {
   } while (0)
 
 // One call = a sequence of scratch allocations in fixed order; buffers are reused across calls by position.
+constexpr size_t kStageBytes = 8u << 20, kStageMaxItem = 512u << 10;
+
 struct Arena {
   orbm_matcher* m;
   cudaError_t err = cudaSuccess;
-  explicit Arena(orbm_matcher* mm) : m(mm) { m->next_buf = 0; }
+  explicit Arena(orbm_matcher* mm) : m(mm) {
+    m->next_buf = 0;
+    m->stage_used = m->stage_flushed = 0;
+    if (!m->h_stage) {
+      if (cudaHostAlloc(reinterpret_cast<void**>(&m->h_stage), kStageBytes, cudaHostAllocDefault) != cudaSuccess ||
+          cudaMalloc(reinterpret_cast<void**>(&m->d_stage), kStageBytes) != cudaSuccess) {
+        if (m->h_stage) cudaFreeHost(m->h_stage);
+        m->h_stage = nullptr;  // staging is an optimisation: fall back to one copy per array
+        cudaGetLastError();
+      }
+    }
+  }
   template <typename T>
   T* alloc(size_t count) {
     if (m->next_buf >= kBufs) {
@@ -90,12 +108,30 @@ struct Arena {
   }
   template <typename T>
   T* upload(const T* host, size_t count) {
+    const size_t bytes = count * sizeof(T);
+    if (host && bytes && bytes <= kStageMaxItem && m->h_stage && m->stage_used + bytes <= kStageBytes) {
+      const size_t off = m->stage_used;
+      memcpy(m->h_stage + off, host, bytes);
+      m->stage_used = (off + bytes + 255) & ~(size_t)255;
+      return reinterpret_cast<T*>(m->d_stage + off);
+    }
     T* d = alloc<T>(count);
     if (d && host && count) {
-      cudaError_t e = cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, m->stream);
+      cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream);
       if (e != cudaSuccess) err = e;
     }
     return d;
+  }
+  // Sends what upload() packed since the last call (one H2D copy on the matcher's stream) and reports the first error
+  // of the arena. Every entry point calls it after its last upload and before its first kernel.
+  cudaError_t sync_uploads() {
+    if (m->stage_used > m->stage_flushed) {
+      cudaError_t e = cudaMemcpyAsync(m->d_stage + m->stage_flushed, m->h_stage + m->stage_flushed,
+                                      m->stage_used - m->stage_flushed, cudaMemcpyHostToDevice, m->stream);
+      if (e != cudaSuccess && err == cudaSuccess) err = e;
+      m->stage_flushed = m->stage_used;
+    }
+    return err;
   }
 };
 
@@ -168,7 +204,7 @@ int run_search(orbm_matcher* m, Arena& ar, const DevFrame& F, const DevQueries& 
   R.events = ar.alloc<int32_t>(2 * (size_t)Q.m);
   R.dec = ar.alloc<int32_t>(Q.m);
   R.occ = nullptr;
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   int32_t total = 0;
   if (Q.m > 0) {
     launch_search_count(F, Q, S.counts, st);
@@ -181,7 +217,7 @@ int run_search(orbm_matcher* m, Arena& ar, const DevFrame& F, const DevQueries& 
   S.cand_idx = ar.alloc<int32_t>(total);
   S.cand_dist = ar.alloc<int32_t>(total);
   S.cap_total = total;
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_search_fill(F, Q, S, st);
   launch_search_resolve(F, Q, S, R, st);
   ORBM_CUDA(m, cudaGetLastError());
@@ -227,6 +263,8 @@ void orbm_destroy(orbm_matcher* m) {
   for (auto& h : m->lane_h_nm)
     if (h) cudaFreeHost(h);
   for (auto& b : m->voc_buf) b.release();
+  if (m->h_stage) cudaFreeHost(m->h_stage);
+  if (m->d_stage) cudaFree(m->d_stage);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -241,7 +279,7 @@ int orbm_descriptor_distance_batch(orbm_matcher* m, const uint8_t* a, const uint
   const uint8_t* da = ar.upload(a, (size_t)n * 32);
   const uint8_t* db = ar.upload(b, (size_t)n * 32);
   int32_t* dd = ar.alloc<int32_t>(n);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_desc_dist(da, db, n, dd, m->stream);
   ORBM_CUDA(m, cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
   ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
@@ -259,7 +297,7 @@ int orbm_distinctive_descriptors(orbm_matcher* m, const uint8_t* desc, const int
   const uint8_t* dd = ar.upload(desc, (size_t)total * 32);
   const int32_t* doff = ar.upload(offsets, (size_t)n_points + 1);
   int32_t* db = ar.alloc<int32_t>(n_points);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_distinctive(dd, doff, n_points, db, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   ORBM_CUDA(m, cudaMemcpyAsync(best_idx, db, (size_t)n_points * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -293,7 +331,7 @@ int orbm_knn2(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int n
   const uint8_t* dq = ar.upload(q, (size_t)nq * 32);
   const uint8_t* dt = ar.upload(t, (size_t)nt * 32);
   int32_t* out = ar.alloc<int32_t>((size_t)nq * 4);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   int rc = orbm_knn2_device(m, dq, nq, dt, nt, out, out + nq, out + 2 * (size_t)nq, out + 3 * (size_t)nq, nullptr);
   if (rc) return rc;
   cudaStream_t st = m->stream;
@@ -363,7 +401,7 @@ int orbm_stereo_match(orbm_matcher* m, const orbx_extractor* left, const orbx_ex
   A.depth = ar.alloc<float>(n_l);
   A.sad = ar.alloc<int32_t>(n_l);
   A.n_matched = ar.alloc<int32_t>(1);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_stereo(A, 1, n_l, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   int32_t nm = 0;
@@ -563,7 +601,7 @@ int search_map_common(orbm_matcher* m, Arena& ar, const DevFrame& F, const float
   R.check_orientation = 0;
   R.has_obs = ar.upload(mps->has_obs, M);
   R.angle = nullptr;
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   return run_search(m, ar, F, Q, R, n, assign, nmatches);
 }
 }  // namespace
@@ -588,7 +626,7 @@ int orbm_assign_features_to_grid(orbm_matcher* m, const orbx_kp* kps, int n, flo
   const orbx_kp* d_kps = ar.upload(kps, n);
   int32_t* d_off = ar.alloc<int32_t>(cells + 1);
   int32_t* d_items = ar.alloc<int32_t>(n);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_build_grid(d_kps, nullptr, n, 0, 1, min_x, min_y, inv_w, inv_h, d_off, d_items, 0, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   ORBM_CUDA(m, cudaMemcpyAsync(cell_offsets, d_off, (size_t)(cells + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -621,7 +659,7 @@ int resident_frame(orbm_matcher* m, Arena& ar, const orbx_extractor* ex, int fra
   int32_t* d_off = ar.alloc<int32_t>(cells + 1);
   int32_t* d_items = ar.alloc<int32_t>(n);
   F.scale_factors = ar.upload(sf, P.nlevels);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   if (n > 0) {
     if (occupied) ORBM_CUDA(m, cudaMemcpyAsync(d_occ, occupied, n, cudaMemcpyHostToDevice, m->stream));
     else ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, n, m->stream));
@@ -676,7 +714,7 @@ int search_frame_common(orbm_matcher* m, Arena& ar, const DevFrame& F, bool has_
   R.check_orientation = check_orientation;
   R.has_obs = ar.upload(pts->has_obs, M);
   R.angle = ar.upload(pts->angle, M);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   return run_search(m, ar, F, Q, R, n, assign, nmatches);
 }
 }  // namespace
@@ -769,7 +807,7 @@ int orbm_bow_transform(orbm_matcher* m, const uint8_t* desc, int n, int levelsup
   uint32_t* dw = ar.alloc<uint32_t>(n);
   double* dwt = ar.alloc<double>(n);
   uint32_t* dn = ar.alloc<uint32_t>(n);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_bow_transform(m->voc, dd, n, levelsup, dw, dwt, dn, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   ORBM_CUDA(m, cudaMemcpyAsync(word_id, dw, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -828,7 +866,7 @@ int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, c
   S.counts = ar.alloc<int32_t>((size_t)M + 1);
   S.pre = ar.alloc<int4>(M);
   int32_t* d_total = ar.alloc<int32_t>(1);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   cudaStream_t st = m->stream;
   int32_t total = 0;
   launch_search_count(F2, Q, S.counts, st);
@@ -838,7 +876,7 @@ int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, c
   S.cand_idx = ar.alloc<int32_t>(total);
   S.cand_dist = ar.alloc<int32_t>(total);
   S.cap_total = total;
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_search_fill(F2, Q, S, st);
   launch_init_resolve(F2, Q, S, A, st);
   ORBM_CUDA(m, cudaGetLastError());
@@ -870,7 +908,7 @@ int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv
   const float* d_inv = ar.upload(inv_level_sigma2, kf->n_levels);
   int32_t* d_bi = ar.alloc<int32_t>(M);
   int32_t* d_bd = ar.alloc<int32_t>(M);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_fuse_match(F, Q, d_inv, chi2_gate, d_bi, d_bd, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   ORBM_CUDA(m, cudaMemcpyAsync(best_idx, d_bi, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -912,7 +950,7 @@ int search_by_bow_common(orbm_matcher* m, const orbx_keyframe_view* kf, const or
   A.matched2 = ar.alloc<uint8_t>(second->n);
   A.nmatches = ar.alloc<int32_t>(1);
   A.node_match = ar.alloc<int32_t>(A.kf.n_nodes);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_search_by_bow(A, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   int32_t nm = 0;
@@ -955,7 +993,7 @@ int orbm_search_for_triangulation(orbm_matcher* m, const orbx_keyframe_view* kf1
   A.matches12 = ar.alloc<int32_t>(kf1->n);
   A.nmatches = ar.alloc<int32_t>(1);
   A.node_match = ar.alloc<int32_t>(A.k1.n_nodes);
-  if (ar.err != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
   launch_triangulation(A, m->stream);
   ORBM_CUDA(m, cudaGetLastError());
   int32_t nm = 0;
