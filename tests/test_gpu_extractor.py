@@ -135,7 +135,10 @@ def test_host_pyramid_mirror_has_reference_border(gpu):
 
 def test_other_parameters(gpu):
     img = synth.scene(480, 640, seed=11)
-    for nf, sf, nl, it, mt in ((500, 1.2, 4, 20, 7), (1500, 1.1, 8, 15, 5), (5000, 1.2, 8, 20, 7), (300, 1.5, 3, 30, 10)):
+    # (…, 1.1, 10, …): more than 8 levels -> the LDG kernels (the tensor-map arrays hold 8); (…, 2.0, 3, …): a source
+    # rectangle wider than one TMA box -> the LDG resize
+    for nf, sf, nl, it, mt in ((500, 1.2, 4, 20, 7), (1500, 1.1, 8, 15, 5), (5000, 1.2, 8, 20, 7), (300, 1.5, 3, 30, 10),
+                               (800, 1.1, 10, 20, 7), (300, 2.0, 3, 20, 7)):
         ex = ORBextractor(nf, sf, nl, it, mt)
         ex_ref = orbref.Extractor(nf, sf, nl, it, mt)
         assert np.array_equal(ex.mnFeaturesPerLevel, ex_ref.features_per_level)
