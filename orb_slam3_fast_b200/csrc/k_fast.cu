@@ -331,7 +331,7 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
       // -- compass pre-test, two adjacent groups (8 pixels) per lane step: rows r, r+3, r+6 of the tile are
       //    dy = -3, 0, +3; the step's tile words come in with 16-byte loads (tile rows and 8-pixel starts are 16-byte
       //    aligned) --
-      const uint32_t K = (uint32_t)(T + 1) * 0x00010001u;
+      const uint32_t kb = 0x80008000u - (uint32_t)(min(max(T, 0), 255) + 1) * 0x00010001u;  // x >= y + T + 1 <=> bit 15 of x + kb - y
       n_score = 0;
       const int ppr = (gpr + 1) >> 1, npairs = ppr * ih;      // group pairs per row / per cell
       const int q32 = 32 / ppr, m32 = 32 - q32 * ppr;         // a step of 32 pairs = q32 rows + m32 pairs
@@ -352,8 +352,9 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
           auto test = [&](uint32_t p0, uint32_t p8, uint32_t p4, uint32_t p12, uint32_t c) {
             const uint32_t lo_of_hi = __vminu2(__vmaxu2(p0, p8), __vmaxu2(p4, p12));  // bright: must exceed v + T
             const uint32_t hi_of_lo = __vmaxu2(__vminu2(p0, p8), __vminu2(p4, p12));  // dark: must be below v - T
-            // lanes stay below 0x8000, so bit 15 of (x | 0x8000) - y says x >= y without borrowing across lanes
-            return ((lo_of_hi | 0x80008000u) - (c + K)) | ((c | 0x80008000u) - (hi_of_lo + K));
+            // every lane stays in [0x8000 - 511, 0x8000 + 255], so bit 15 of x + 0x8000 - y says x >= y and nothing is
+            // carried or borrowed across the two lanes; kb = 0x80008000 - K folds the bias and the threshold
+            return (lo_of_hi + kb - c) | (c + kb - hi_of_lo);
           };
           const uint32_t bitsA = test(pair_at<3>(Wp3), pair_at<3>(Wm3), pair_at<6>(W0), pair_at<0>(W0), pair_at<3>(W0)) |
                                  test(pair_at<5>(Wp3), pair_at<5>(Wm3), pair_at<8>(W0), pair_at<2>(W0), pair_at<5>(W0));
