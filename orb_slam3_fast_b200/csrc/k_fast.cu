@@ -397,16 +397,19 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
         // rows r .. r+6 of the tile are dy = -3 .. 3 around interior row r; u16 columns 4g .. 4g+9
         const uint32_t* base = reinterpret_cast<const uint32_t*>(raw + r * tp + 4 * g);
         uint32_t Wm3[5], Wm2[5], Wm1[5], W0[5], Wp1[5], Wp2[5], Wp3[5];
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-          Wm3[c] = base[0 * rp + c];
-          Wm2[c] = base[1 * rp + c];
-          Wm1[c] = base[2 * rp + c];
-          W0[c] = base[3 * rp + c];
-          Wp1[c] = base[4 * rp + c];
-          Wp2[c] = base[5 * rp + c];
-          Wp3[c] = base[6 * rp + c];
-        }
+        // a group starts on an 8-byte boundary of its tile row: two 8-byte loads + one word per row
+        auto load_row = [&](int row, uint32_t (&W)[5]) {
+          const uint2 a = *reinterpret_cast<const uint2*>(base + row * rp), b = *reinterpret_cast<const uint2*>(base + row * rp + 2);
+          W[0] = a.x; W[1] = a.y; W[2] = b.x; W[3] = b.y;
+          W[4] = base[row * rp + 4];
+        };
+        load_row(0, Wm3);
+        load_row(1, Wm2);
+        load_row(2, Wm1);
+        load_row(3, W0);
+        load_row(4, Wp1);
+        load_row(5, Wp2);
+        load_row(6, Wp3);
         uint32_t rr[2];
 #pragma unroll
         for (int half = 0; half < 2; half++) {
