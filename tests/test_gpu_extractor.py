@@ -194,7 +194,12 @@ def test_cvt_color_to_gray(gpu, channels, rgb):
     rng = np.random.default_rng(channels * 2 + int(rgb))
     for (h, w) in ((480, 752), (33, 101), (5, 3)):
         img = rng.integers(0, 256, (h, w, channels), dtype=np.uint8)
-        assert np.array_equal(cvtColorToGray(img, rgb), orbref.cvt_gray(img, rgb)), (h, w)
+        got = cvtColorToGray(img, rgb)
+        assert np.array_equal(got, orbref.cvt_gray(img, rgb)), (h, w)
+        import cv2  # the real OpenCV kernel, directly
+        code = {(3, False): cv2.COLOR_BGR2GRAY, (3, True): cv2.COLOR_RGB2GRAY, (4, False): cv2.COLOR_BGRA2GRAY,
+                (4, True): cv2.COLOR_RGBA2GRAY}[(channels, rgb)]
+        assert np.array_equal(got, cv2.cvtColor(img, code)), (h, w)
     # device form: 3 frames, padded rows on both sides, converted straight into an extractor-ready gray batch
     B, h, w, spad, dpad = 3, 120, 200, 8 * channels, 16
     imgs = rng.integers(0, 256, (B, h, w + 8, channels), dtype=np.uint8)
@@ -221,7 +226,10 @@ def test_remap_linear_rectification(gpu):
     for (h, w, dh, dw) in ((480, 752, 480, 752), (120, 161, 97, 203)):
         src = rng.integers(0, 256, (h, w), dtype=np.uint8)
         mapx, mapy = _rectify_maps(h, w, h + w, dh, dw)
-        assert np.array_equal(remapLinear(src, mapx, mapy), orbref.remap_linear(src, mapx, mapy)), (h, w)
+        got = remapLinear(src, mapx, mapy)
+        assert np.array_equal(got, orbref.remap_linear(src, mapx, mapy)), (h, w)
+        import cv2  # the real OpenCV kernel, directly
+        assert np.array_equal(got, cv2.remap(src, mapx, mapy, cv2.INTER_LINEAR)), (h, w)
     B, h, w = 3, 240, 320
     imgs = rng.integers(0, 256, (B, h, w), dtype=np.uint8)
     mapx, mapy = _rectify_maps(h, w, 5)
