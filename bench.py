@@ -32,8 +32,6 @@ FX, BASELINE_M = 435.2, 0.11  # EuRoC-like rectified focal length / baseline (SU
 MBF, MB = float(np.float32(FX * BASELINE_M)), float(np.float32(BASELINE_M))
 METRIC = "frames/sec ORB extract+match (752x480 stereo pairs, 1200 feat/eye, extract + ComputeStereoMatches)"
 WORKLOAD = "configs[1]: EuRoC-shaped 752x480 stereo pair, 1200 features/eye, extract + ComputeStereoMatches"
-KERNELS_PER_EXTRACT = (NLEVELS - 1) + 1 + 1 + 1 + 1  # resize x7, fast, quadtree, blur, describe
-KERNELS_PER_STEP = 2 * KERNELS_PER_EXTRACT + 2                 # + stereo match + stereo median
 
 
 def make_pairs(n_distinct, seed0):
@@ -425,7 +423,7 @@ def main():
                            "keypoints_per_frame": n_keypoints, "candidates_per_frame": C,
                            "stereo_matches_per_pair": matched, "all_frames_within_capacity": status_ok,
                            "parity": parity, "parallelism": "frames sharded over GPUs, no data-path collective"},
-                "gpu_launches": KERNELS_PER_STEP * args.steps, "clocks": clk, "e2e": e2e, "roofline": roofline,
+                "gpu_launches": (2 * int(exl._L.orbx_kernel_launches(exl._h)) + 2) * args.steps, "clocks": clk, "e2e": e2e, "roofline": roofline,
                 "cpu_baseline": cpu}
         emit(line)
     if world > 1:

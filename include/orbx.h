@@ -116,6 +116,11 @@ int orbx_cvt_gray_device(int device, int n_frames, const uint8_t* d_src, int wid
 int orbx_cvt_gray(int device, const uint8_t* src, int width, int height, int src_stride, int channels, int rgb,
                   uint8_t* dst, int dst_stride);
 
+/* Number of kernels one extract call launches for the geometry the handle is planned for (0 before the first call):
+ * one resize per level >= 1, one or two FAST launches (the small levels' tall cells get their own shared-memory
+ * layout), quadtree, blur, describe. bench.py reports it as gpu_launches. */
+int orbx_kernel_launches(const orbx_extractor* ex);
+
 /* Pinned host memory for the batched calls. */
 void* orbx_host_alloc(int64_t bytes);
 void orbx_host_free(void* p);

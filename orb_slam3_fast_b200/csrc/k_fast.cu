@@ -46,9 +46,10 @@ struct FastSmemLayout {
   int per_warp;   // multiple of 128 (TMA destination alignment)
 };
 
-static FastSmemLayout fast_layout(const Plan& P) {
+// shared-memory layout that fits every cell of levels [l0, l1)
+static FastSmemLayout fast_layout(const Plan& P, int l0, int l1) {
   int wc = 0, hc = 0;
-  for (int l = 0; l < P.nlevels; l++) {
+  for (int l = l0; l < l1; l++) {
     if (P.lv[l].wCell > wc) wc = P.lv[l].wCell;
     if (P.lv[l].hCell > hc) hc = P.lv[l].hCell;
   }
@@ -69,7 +70,7 @@ static FastSmemLayout fast_layout(const Plan& P) {
   return L;
 }
 
-size_t fast_smem_bytes(const Plan& P) { return kFastHead + (size_t)fast_layout(P).per_warp * kFastWarps; }
+size_t fast_smem_bytes(const Plan& P) { return kFastHead + (size_t)fast_layout(P, 0, P.nlevels).per_warp * kFastWarps; }
 
 // ring pixel pair for the two pixels whose u16 columns are O, O+1 inside the 10-column window W (5 words)
 template <int O, int N>
@@ -158,12 +159,12 @@ template <bool kTma>
 __global__ void __launch_bounds__(kFastWarps * 32)
 k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, const FrameSet fs, const WorkSet ws,
        int ini_th, int min_th, int tp, int sp, int raw_bytes, int score_bytes, int per_warp, int box_w,
-       int box_bytes) {
+       int box_bytes, int cell_begin, int cell_end) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cell = blockIdx.x * kFastWarps + warp;
+  const int cell = cell_begin + blockIdx.x * kFastWarps + warp;  // this launch covers the cells [cell_begin, cell_end)
   const int f = blockIdx.y;
-  if (cell >= P.cells_per_frame) return;
+  if (cell >= cell_end) return;
   int l = 0;
   while (l + 1 < P.nlevels && P.lv[l + 1].cell_base <= cell) l++;
   const LevelPlan& L = P.lv[l];
@@ -518,23 +519,59 @@ static bool make_fast_maps(const Plan& P, const FrameSet& fs, const FastSmemLayo
   return true;
 }
 
-void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_th, int min_th, int frames,
-                 cudaStream_t st) {
-  const FastSmemLayout L = fast_layout(P);
+// One launch for the levels [l0, l1) (their cells are consecutive in the per-frame numbering).
+static void launch_fast_levels(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_th, int min_th, int frames,
+                               int l0, int l1, cudaStream_t st) {
+  const FastSmemLayout L = fast_layout(P, l0, l1);
   const size_t smem = kFastHead + (size_t)L.per_warp * kFastWarps;
   const int attr = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
-  dim3 grid((P.cells_per_frame + kFastWarps - 1) / kFastWarps, frames);
+  const int cell_begin = P.lv[l0].cell_base, cell_end = l1 < P.nlevels ? P.lv[l1].cell_base : P.cells_per_frame;
+  dim3 grid((cell_end - cell_begin + kFastWarps - 1) / kFastWarps, frames);
   FastMaps M;
   if (L.box_w <= 256 && L.box_h <= 256 && make_fast_maps(P, fs, L, frames, &M)) {
     cudaFuncSetAttribute(k_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     k_fast<true><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
-                                                      L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h);
+                                                      L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h,
+                                                      cell_begin, cell_end);
   } else {
     memset(&M, 0, sizeof(M));
     cudaFuncSetAttribute(k_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     k_fast<false><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
-                                                       L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h);
+                                                       L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h,
+                                                       cell_begin, cell_end);
   }
+}
+
+// The small levels have a few tall cells (2 cell rows over ~100 pixel rows: hCell 51 where level 0 has 38) that would
+// size the shared memory of EVERY warp. The levels are therefore cut into (at most) two launches at the point that
+// minimises sum(cells / resident blocks per SM): at 752x480 levels 0-3 (86 % of the cells) run with 6 blocks per SM
+// instead of 5.
+static int fast_split_level(const Plan& P) {
+  auto cost = [&](int l0, int l1) {
+    const size_t smem = kFastHead + (size_t)fast_layout(P, l0, l1).per_warp * kFastWarps + 1024;  // + per-block reserve
+    const int blocks = (int)((227u << 10) / smem);
+    const int cells = (l1 < P.nlevels ? P.lv[l1].cell_base : P.cells_per_frame) - P.lv[l0].cell_base;
+    return blocks > 0 ? (double)cells / blocks : 1e30;
+  };
+  int best_k = P.nlevels;
+  double best = cost(0, P.nlevels);
+  for (int k = 1; k < P.nlevels; k++) {
+    const double c = cost(0, k) + cost(k, P.nlevels) + 4.0;  // a second launch must pay for itself
+    if (c < best) {
+      best = c;
+      best_k = k;
+    }
+  }
+  return best_k;
+}
+
+int fast_launch_count(const Plan& P) { return fast_split_level(P) < P.nlevels ? 2 : 1; }
+
+void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_th, int min_th, int frames,
+                 cudaStream_t st) {
+  const int k = fast_split_level(P);
+  launch_fast_levels(P, fs, ws, ini_th, min_th, frames, 0, k, st);
+  if (k < P.nlevels) launch_fast_levels(P, fs, ws, ini_th, min_th, frames, k, P.nlevels, st);
 }
 
 }  // namespace orbx

@@ -679,6 +679,11 @@ int orbx_cvt_gray(int device, const uint8_t* src, int width, int height, int src
   return rc;
 }
 
+int orbx_kernel_launches(const orbx_extractor* ex) {
+  if (!ex || !ex->planned) return 0;
+  return (ex->plan.nlevels - 1) + orbx::fast_launch_count(ex->plan) + 3;  // resize per level, FAST, quadtree, blur, describe
+}
+
 void* orbx_host_alloc(int64_t bytes) {
   void* p = nullptr;
   if (bytes <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;

@@ -75,6 +75,7 @@ int launch_remap_linear(const uint8_t* src, int sw, int sh, int sstride, int64_t
                         const float* mapy, int dw, int dh, uint8_t* dst, int dstride, int64_t dfstride, int frames,
                         cudaStream_t st);
 size_t fast_smem_bytes(const Plan& P);
+int fast_launch_count(const Plan& P);  // k_fast launches per extract call (1, or 2 when the small levels are split off)
 size_t quadtree_smem_bytes(const Plan& P);
 
 }  // namespace orbx

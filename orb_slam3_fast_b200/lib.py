@@ -67,6 +67,7 @@ def lib():
     L.orbx_remap_linear_device.argtypes = [ci, ci, vp, ci, ci, ci, i64, vp, vp, ci, ci, vp, ci, i64, vp]
     L.orbx_cvt_gray.argtypes = [ci, vp, ci, ci, ci, ci, ci, vp, ci]
     L.orbx_cvt_gray_device.argtypes = [ci, ci, vp, ci, ci, ci, i64, ci, ci, vp, ci, i64, vp]
+    L.orbx_kernel_launches.argtypes = [vp]
     L.orbx_host_alloc.argtypes = [i64]
     L.orbx_host_alloc.restype = vp
     L.orbx_host_free.argtypes = [vp]

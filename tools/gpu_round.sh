@@ -11,10 +11,10 @@ BENCH="python bench.py --steps 2 --warmup 3 --pairs 64 --no-cpu"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 60 --csv \
     --log-file gpurun_out/launches_$TAG.csv $BENCH > gpurun_out/ncu_list_$TAG.log 2>&1
 if [ "$2" = "full" ]; then
-  # one full-set capture of every launch of ONE step (the first 24 launches are the 2-pair parity check): 2 extract
-  # calls x (7 k_resize_tma + k_fast + k_quadtree + k_blur7 + k_describe) + k_stereo_match + k_stereo_median
+  # one full-set capture of every launch of ONE step (the first 26 launches are the 2-pair parity check): 2 extract
+  # calls x (7 k_resize_tma + 2 k_fast + k_quadtree + k_blur7 + k_describe) + k_stereo_match + k_stereo_median
   timeout 900 ncu --set full --clock-control none --import-source on \
-      -k 'regex:k_fast|k_quadtree|k_describe|k_stereo_match|k_stereo_median|k_blur7|k_resize' -s 24 -c 24 -f \
+      -k 'regex:k_fast|k_quadtree|k_describe|k_stereo_match|k_stereo_median|k_blur7|k_resize' -s 26 -c 26 -f \
       -o /tmp/prof_$TAG $BENCH > gpurun_out/ncu_full_$TAG.log 2>&1
   ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
   sz=$(stat -c %s /tmp/prof_$TAG.ncu-rep 2>/dev/null || echo 0)
