@@ -1,0 +1,261 @@
+"""Independent cross-checks of the oracle's matcher restatements that have no external pin (DBoW2 / the reference cannot
+be built here): each one is compared with a second, differently written (numpy / pure Python) restatement of the same
+reference lines, plus the invariants the reference's data structures guarantee. CPU only.
+
+  orbref.search_by_bow / search_by_bow_kf     src/ORBmatcher.cc:230-404, 766-884
+  orbref.fuse_match                           src/ORBmatcher.cc:1194-1257 (and the gate-free Sim3 form :1356-1372)
+  orbref.search_for_initialization            src/ORBmatcher.cc:618-764
+  orbref.bow_transform                        Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1262
+  orbref.build_grid                           src/Frame.cc:520-547
+"""
+import numpy as np
+
+from orb_slam3_fast_b200 import synth, views
+from oracle import orbref
+
+
+def _ham(a, b):
+    return int(np.bitwise_count(np.bitwise_xor(a, b)).sum())
+
+
+def _rot_bin(a1, a2):
+    rot = np.float32(a1) - np.float32(a2)
+    if rot < 0.0:
+        rot = np.float32(rot + np.float32(360.0))
+    b = int(np.floor(np.float32(rot * np.float32(1.0 / 30)) + np.float32(0.5)))  # round(): values are >= 0 here
+    return 0 if b == 30 else b
+
+
+def _three_maxima(hist):
+    """ComputeThreeMaxima, src/ORBmatcher.cc:1920-1955."""
+    max1 = max2 = max3 = 0
+    i1 = i2 = i3 = -1
+    for i, h in enumerate(hist):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            i3, i2, i1 = i2, i1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            i3, i2 = i2, i
+        elif s > max3:
+            max3, i3 = s, i
+    if max2 < 0.1 * np.float32(max1):
+        i2 = i3 = -1
+    elif max3 < 0.1 * np.float32(max1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def _keyframes(seed, n=400, n_nodes=12):
+    rng = np.random.default_rng(seed)
+    d1 = synth.descriptors(n, seed)
+    d2 = synth.flip_bits(d1[rng.permutation(n)], rng.integers(0, 70, n), rng)
+    out = []
+    for d in (d1, d2):
+        kps = np.zeros(n, synth.KP_DTYPE)
+        kps["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+        kps["octave"] = rng.integers(0, 8, n)
+        node_of = d[:, 0].astype(np.int64) % n_nodes * 5 + 2
+        ids, inv = np.unique(node_of, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        off = np.zeros(len(ids) + 1, np.int32)
+        off[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+        hm = (rng.random(n) < 0.7).astype(np.uint8)
+        out.append(dict(kps=kps, desc=d, hm=hm, ids=ids.astype(np.uint32), off=off, idx=order.astype(np.uint32)))
+    return out
+
+
+def _view(k):
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    return orbref.make_keyframe_view(k["kps"], k["desc"], None, k["hm"], k["ids"], k["off"], k["idx"], sf, sf * sf)
+
+
+def _bow_python(k1, k2, nnratio, check, kf_kf):
+    """The two SearchByBoW overloads written once more, straight from the reference text."""
+    n_out = len(k1["kps"]) if kf_kf else len(k2["kps"])
+    out = [-1] * n_out
+    matched2 = [False] * len(k2["kps"])
+    hist = [[] for _ in range(30)]
+    nm = 0
+    nodes2 = {int(i): j for j, i in enumerate(k2["ids"])}
+    for a, nid in enumerate(k1["ids"]):
+        b = nodes2.get(int(nid))
+        if b is None:
+            continue
+        for i1 in k1["idx"][k1["off"][a]:k1["off"][a + 1]]:
+            if not k1["hm"][i1]:
+                continue
+            best1, best2, bi = 256, 256, -1
+            for i2 in k2["idx"][k2["off"][b]:k2["off"][b + 1]]:
+                if (kf_kf and (matched2[i2] or not k2["hm"][i2])) or (not kf_kf and out[i2] >= 0):
+                    continue
+                d = _ham(k1["desc"][i1], k2["desc"][i2])
+                if d < best1:
+                    best2, best1, bi = best1, d, int(i2)
+                elif d < best2:
+                    best2 = d
+            low = best1 < 50 if kf_kf else best1 <= 50
+            if low and np.float32(best1) < np.float32(nnratio) * np.float32(best2):
+                if kf_kf:
+                    out[i1] = bi
+                    matched2[bi] = True
+                    key = int(i1)
+                else:
+                    out[bi] = int(i1)
+                    key = bi
+                if check:
+                    hist[_rot_bin(k1["kps"]["angle"][i1], k2["kps"]["angle"][bi])].append(key)
+                nm += 1
+    if check:
+        keep = _three_maxima(hist)
+        for i, h in enumerate(hist):
+            if i in keep:
+                continue
+            for key in h:
+                out[key] = -1
+                nm -= 1
+    return nm, np.asarray(out, np.int32)
+
+
+def test_search_by_bow_equals_a_python_restatement():
+    for seed, nnratio, check in ((0, 0.7, True), (1, 0.9, False), (2, 0.8, True)):
+        k1, k2 = _keyframes(seed)
+        for kf_kf in (False, True):
+            fn = orbref.search_by_bow_kf if kf_kf else orbref.search_by_bow
+            n, m = fn(_view(k1), _view(k2), nnratio, check)
+            n_p, m_p = _bow_python(k1, k2, nnratio, check, kf_kf)
+            assert n == n_p and np.array_equal(m, m_p), (seed, kf_kf)
+            assert n_p > 5
+            taken = m[m >= 0]
+            assert len(np.unique(taken)) == len(taken)      # a feature of the other view is used at most once
+
+
+def test_bow_transform_descends_to_a_leaf_through_the_recorded_node():
+    voc = synth.vocabulary(8, 4, 3)
+    off, ch = voc["child_offsets"], voc["children"]
+    parent = np.zeros(len(voc["descriptors"]), np.int64)
+    for n in range(len(off) - 1):
+        parent[ch[off[n]:off[n + 1]]] = n
+    leaf_of_word = {int(voc["word_id"][n]): n for n in range(len(off) - 1) if off[n + 1] == off[n]}
+    rng = np.random.default_rng(0)
+    feats = synth.flip_bits(voc["descriptors"][rng.integers(1, len(parent), 400)], rng.integers(0, 50, 400), rng)
+    for levelsup in (0, 2, 4, 9):
+        w, wt, nd = orbref.bow_transform(orbref.make_vocabulary(**voc), feats, levelsup)
+        for i in range(len(feats)):
+            leaf = leaf_of_word[int(w[i])]
+            assert wt[i] == voc["weight"][leaf]
+            # greedy descent, re-done in numpy: the first child with the least distance at every level
+            node, path = 0, [0]
+            while off[node + 1] > off[node]:
+                kids = ch[off[node]:off[node + 1]]
+                d = [_ham(feats[i], voc["descriptors"][k]) for k in kids]
+                node = int(kids[int(np.argmin(d))])
+                path.append(node)
+            assert node == leaf
+            lvl = voc["depth"] - levelsup
+            assert nd[i] == (path[lvl] if 0 < lvl < len(path) else 0)
+
+
+def test_fuse_match_equals_a_numpy_restatement():
+    rng = np.random.default_rng(4)
+    n, m, w, h = 600, 900, 640, 480
+    kps = np.zeros(n, synth.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(0, w, n).astype(np.float32), rng.uniform(0, h, n).astype(np.float32)
+    kps["octave"] = rng.integers(0, 8, n)
+    desc = synth.descriptors(n, 4)
+    ur = np.where(rng.random(n) < 0.5, kps["x"] - rng.uniform(1, 30, n), -1).astype(np.float32)
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    fr = orbref.make_frame_view(kps, desc, ur, np.zeros(n, np.uint8), g, keep, sf)
+    src = rng.integers(0, n, m)
+    u = (kps["x"][src] + rng.normal(0, 1.5, m)).astype(np.float32)
+    v = (kps["y"][src] + rng.normal(0, 1.5, m)).astype(np.float32)
+    lev = np.clip(kps["octave"][src] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    radius = (np.float32(3.0) * sf[lev]).astype(np.float32)
+    d = synth.flip_bits(desc[src], rng.integers(0, 50, m), rng)
+    pur = (u - 4).astype(np.float32)
+    pts = orbref.make_projected(u, v, pur, radius, lev - 1, lev, np.zeros(m, np.float32), np.zeros(m, np.uint8), d)
+    inv_s2 = (1.0 / (sf * sf)).astype(np.float32)
+    for gate in (True, False):
+        bi, bd = orbref.fuse_match(fr, inv_s2, pts, gate)
+        for i in range(0, m, 7):
+            best, bidx = 256, -1
+            cx0 = max(0, int(np.floor(np.float32(np.float32(u[i] - radius[i]) * inv_w))))
+            cx1 = min(63, int(np.ceil(np.float32(np.float32(u[i] + radius[i]) * inv_w))))
+            cy0 = max(0, int(np.floor(np.float32(np.float32(v[i] - radius[i]) * inv_h))))
+            cy1 = min(47, int(np.ceil(np.float32(np.float32(v[i] + radius[i]) * inv_h))))
+            for cx in range(cx0, cx1 + 1):
+                for cy in range(cy0, cy1 + 1):
+                    c = cx * 48 + cy
+                    for k in items[off[c]:off[c + 1]]:
+                        if not (abs(np.float32(kps["x"][k] - u[i])) < radius[i] and abs(np.float32(kps["y"][k] - v[i])) < radius[i]):
+                            continue
+                        lv = kps["octave"][k]
+                        if lv < lev[i] - 1 or lv > lev[i]:
+                            continue
+                        ex, ey = np.float32(u[i] - kps["x"][k]), np.float32(v[i] - kps["y"][k])
+                        if gate:
+                            if ur[k] >= 0:
+                                er = np.float32(pur[i] - ur[k])
+                                e2 = np.float32(np.float32(np.float32(ex * ex) + np.float32(ey * ey)) + np.float32(er * er))
+                                if float(np.float32(e2 * inv_s2[lv])) > 7.8:
+                                    continue
+                            else:
+                                e2 = np.float32(np.float32(ex * ex) + np.float32(ey * ey))
+                                if float(np.float32(e2 * inv_s2[lv])) > 5.99:
+                                    continue
+                        dist = _ham(d[i], desc[k])
+                        if dist < best:
+                            best, bidx = dist, int(k)
+            assert bi[i] == bidx and bd[i] == best, (gate, i)
+        assert (bi >= 0).sum() > m // 3
+
+
+def test_search_for_initialization_invariants():
+    rng = np.random.default_rng(6)
+    n, w, h = 500, 640, 480
+    k1 = np.zeros(n, synth.KP_DTYPE)
+    k1["x"], k1["y"] = rng.uniform(20, w - 20, n).astype(np.float32), rng.uniform(20, h - 20, n).astype(np.float32)
+    k1["octave"] = (rng.random(n) < 0.3).astype(np.int32) * rng.integers(1, 8, n)
+    k1["angle"] = rng.uniform(0, 360, n).astype(np.float32)
+    d1 = synth.descriptors(n, 6)
+    perm = rng.permutation(n)
+    k2 = k1[perm].copy()
+    k2["x"] += rng.normal(0, 3, n).astype(np.float32)
+    k2["y"] += rng.normal(0, 3, n).astype(np.float32)
+    d2 = synth.flip_bits(d1[perm], rng.integers(0, 45, n), rng)
+    inv_w, inv_h = np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+
+    def view(k, d):
+        off, items = orbref.build_grid(k, 0.0, 0.0, inv_w, inv_h)
+        g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+        return orbref.make_frame_view(k, d, None, np.zeros(len(k), np.uint8), g, keep, sf)
+    prev = np.stack([k1["x"], k1["y"]], axis=1)
+    nm, m12 = orbref.search_for_initialization(view(k1, d1), view(k2, d2), prev, 30, 0.9, True)
+    matched = np.nonzero(m12 >= 0)[0]
+    assert nm == len(matched) and nm > 50
+    assert (k1["octave"][matched] == 0).all() and (k2["octave"][m12[matched]] == 0).all()   # level 0 on both sides
+    assert len(np.unique(m12[matched])) == len(matched)                                      # vnMatches21 is a map
+    for i in matched:                                                                         # inside the window, TH_LOW
+        j = m12[i]
+        assert abs(k2["x"][j] - prev[i, 0]) < 30 and abs(k2["y"][j] - prev[i, 1]) < 30
+        assert _ham(d1[i], d2[j]) <= 50
+    # without the rotation check nothing is removed afterwards: at least as many matches
+    nm2, _ = orbref.search_for_initialization(view(k1, d1), view(k2, d2), prev, 30, 0.9, False)
+    assert nm2 >= nm
+
+
+def test_build_grid_is_the_host_mirror():
+    rng = np.random.default_rng(8)
+    kps = np.zeros(700, synth.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(-20, 660, 700).astype(np.float32), rng.uniform(-20, 500, 700).astype(np.float32)
+    inv_w, inv_h = np.float32(64) / np.float32(640), np.float32(48) / np.float32(480)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    off_h, items_h = views.assign_features_to_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    assert np.array_equal(off, off_h) and np.array_equal(items, items_h[:off_h[-1]])
+    for c in range(64 * 48):
+        assert (np.diff(items[off[c]:off[c + 1]]) > 0).all()        # push_back order = ascending index
