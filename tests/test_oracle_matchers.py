@@ -259,3 +259,87 @@ def test_build_grid_is_the_host_mirror():
     assert np.array_equal(off, off_h) and np.array_equal(items, items_h[:off_h[-1]])
     for c in range(64 * 48):
         assert (np.diff(items[off[c]:off[c + 1]]) > 0).all()        # push_back order = ascending index
+
+
+def _features_in_area(kps, off, items, x, y, r, min_level, max_level, inv_w, inv_h):
+    """Frame::GetFeaturesInArea (src/Frame.cc:765-831), min corner (0, 0), written from the reference text."""
+    f32 = np.float32
+    x0 = max(0, int(np.floor(f32(f32(x - r) * inv_w))))
+    if x0 >= 64:
+        return []
+    x1 = min(63, int(np.ceil(f32(f32(x + r) * inv_w))))
+    if x1 < 0:
+        return []
+    y0 = max(0, int(np.floor(f32(f32(y - r) * inv_h))))
+    if y0 >= 48:
+        return []
+    y1 = min(47, int(np.ceil(f32(f32(y + r) * inv_h))))
+    if y1 < 0:
+        return []
+    check = min_level > 0 or max_level >= 0
+    out = []
+    for cx in range(x0, x1 + 1):
+        for cy in range(y0, y1 + 1):
+            c = cx * 48 + cy
+            for k in items[off[c]:off[c + 1]]:
+                if check:
+                    if kps["octave"][k] < min_level:
+                        continue
+                    if max_level >= 0 and kps["octave"][k] > max_level:
+                        continue
+                if abs(f32(kps["x"][k] - x)) < r and abs(f32(kps["y"][k] - y)) < r:
+                    out.append(int(k))
+    return out
+
+
+def test_search_by_projection_map_equals_a_python_restatement():
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints), serial MapPoint
+    order (src/ORBmatcher.cc:42-146): the row SURVEY.md §8 calls a13."""
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    n, w, h = 500, 640, 480
+    kps = np.zeros(n, synth.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(0, w, n).astype(f32), rng.uniform(0, h, n).astype(f32)
+    kps["octave"] = rng.integers(0, 8, n)
+    desc = synth.descriptors(n, 3)
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    for stereo, th, nnratio in ((True, 1.0, 0.8), (False, 3.0, 0.8), (True, 5.0, 0.6)):
+        ur = np.where(rng.random(n) < 0.7, kps["x"] - rng.uniform(1, 40, n), -1).astype(f32) if stereo else None
+        occ = (rng.random(n) < 0.1).astype(np.uint8)
+        fr = orbref.make_frame_view(kps, desc, ur, occ, g, keep, sf)
+        mp = synth.local_map(kps, desc, 1500, w, h, 8, int(th * 10))
+        n_o, a_o = orbref.search_by_projection_map(fr, orbref.make_mappoints(**mp), th, nnratio, True, 15.0)
+        # ---- the same loop in Python ----
+        assign = [-1] * n
+        blocked = occ.astype(bool).copy()        # mvpMapPoints[idx] with Observations() > 0
+        nm = 0
+        for i in range(len(mp["proj_x"])):
+            if not mp["track_in_view"][i] or mp["depth"][i] > f32(15.0):
+                continue
+            L = int(mp["level"][i])
+            r = f32(2.5) if float(mp["view_cos"][i]) > 0.998 else f32(4.0)
+            if th != 1.0:
+                r = f32(r * f32(th))
+            rs = f32(r * sf[L])
+            best, best2, bl, bl2, bi = 256, 256, -1, -1, -1
+            for k in _features_in_area(kps, off, items, mp["proj_x"][i], mp["proj_y"][i], rs, L - 1, L, inv_w, inv_h):
+                if blocked[k]:
+                    continue
+                if stereo and ur[k] > 0 and abs(f32(mp["proj_xr"][i] - ur[k])) > rs:
+                    continue
+                d = _ham(mp["desc"][i], desc[k])
+                if d < best:
+                    best2, best, bl2, bl, bi = best, d, bl, int(kps["octave"][k]), k
+                elif d < best2:
+                    bl2, best2 = int(kps["octave"][k]), d
+            if best <= 100:
+                if bl == bl2 and f32(best) > f32(f32(nnratio) * f32(best2)):
+                    continue
+                assign[bi] = i
+                blocked[bi] = bool(mp["has_obs"][i])
+                nm += 1
+        assert nm == n_o and np.array_equal(np.asarray(assign, np.int32), a_o), (stereo, th)
+        assert n_o > 30
