@@ -343,3 +343,95 @@ def test_search_by_projection_map_equals_a_python_restatement():
                 nm += 1
         assert nm == n_o and np.array_equal(np.asarray(assign, np.int32), a_o), (stereo, th)
         assert n_o > 30
+
+
+def _stereo_python(ex_l, ex_r, kl, dl, kr, dr, mbf, mb):
+    """Frame::ComputeStereoMatches, src/Frame.cc:921-1084, written over numpy slices of the oracle's pyramid levels."""
+    import math
+    f32 = np.float32
+    n = len(kl)
+    u_right = np.full(n, -1.0, f32)
+    depth = np.full(n, -1.0, f32)
+    n_rows = ex_l.level_dims(0)[1]
+    sf, inv_sf = ex_l.scale, ex_l.inv_scale
+    pyr_l = [ex_l.level_image(l).astype(np.int32) for l in range(ex_l.nlevels)]
+    pyr_r = [ex_r.level_image(l).astype(np.int32) for l in range(ex_r.nlevels)]
+    # row table: right keypoint iR is a candidate of row y  <=>  floor(y_R - r) <= y <= ceil(y_R + r), in index order
+    r = f32(2.0) * sf[kr["octave"]]
+    lo = np.floor((kr["y"] - r).astype(f32)).astype(np.int64)
+    hi = np.ceil((kr["y"] + r).astype(f32)).astype(np.int64)
+    live = ~((kr["x"] == 0) & (kr["y"] == 0))
+    max_d = f32(f32(mbf) / f32(mb))
+    dist_idx = []
+    for i in range(n):
+        u_l, v_l, lev = f32(kl["x"][i]), f32(kl["y"][i]), int(kl["octave"][i])
+        row = int(v_l)
+        if not 0 <= row < n_rows:
+            continue
+        cand = np.flatnonzero(live & (lo <= row) & (row <= hi))
+        if len(cand) == 0:
+            continue
+        min_u, max_u = f32(u_l - max_d), u_l
+        if max_u < 0:
+            continue
+        ok = cand[(np.abs(kr["octave"][cand].astype(np.int64) - lev) <= 1) & (kr["x"][cand] >= min_u)
+                  & (kr["x"][cand] <= max_u)]
+        if len(ok) == 0:
+            continue
+        d = np.bitwise_count(np.bitwise_xor(dr[ok], dl[i][None, :])).sum(1).astype(np.int64)
+        j = int(np.argmin(d))  # first minimum == the serial strict-< scan
+        if not (d[j] < 100 and d[j] < 75):
+            continue
+        rnd = lambda x: math.floor(float(x) + 0.5)  # std::round for the non-negative values here
+        s = inv_sf[lev]
+        su_l, sv_l, su_r0 = rnd(f32(u_l * s)), rnd(f32(v_l * s)), rnd(f32(f32(kr["x"][ok[j]]) * s))
+        w = L = 5
+        img_l, img_r = pyr_l[lev], pyr_r[lev]
+        if su_r0 + L - w < 0 or su_r0 + L + w + 1 >= img_r.shape[1]:
+            continue
+        patch = img_l[sv_l - w:sv_l + w + 1, su_l - w:su_l + w + 1]
+        sad = np.array([np.abs(patch - img_r[sv_l - w:sv_l + w + 1, su_r0 + inc - w:su_r0 + inc + w + 1]).sum()
+                        for inc in range(-L, L + 1)], np.int64)
+        b = int(np.argmin(sad))
+        if b == 0 or b == 2 * L:
+            continue
+        d1, d2, d3 = f32(sad[b - 1]), f32(sad[b]), f32(sad[b + 1])
+        with np.errstate(all="ignore"):
+            delta = f32(f32(d1 - d3) / f32(f32(2.0) * f32(f32(d1 + d3) - f32(f32(2.0) * d2))))
+            if delta < -1 or delta > 1:
+                continue
+            best_ur = f32(sf[lev] * f32(f32(f32(su_r0) + f32(b - L)) + delta))
+            disparity = f32(u_l - best_ur)
+        if disparity >= 0 and disparity < max_d:
+            if disparity <= 0:
+                disparity = f32(0.01)
+                best_ur = f32(float(u_l) - 0.01)
+            depth[i] = f32(f32(mbf) / disparity)
+            u_right[i] = best_ur
+            dist_idx.append((int(sad[b]), i))
+    if not dist_idx:
+        return 0, u_right, depth
+    dist_idx.sort()
+    th = f32(f32(f32(1.5) * f32(1.4)) * f32(dist_idx[len(dist_idx) // 2][0]))
+    kept = len(dist_idx)
+    for sad_b, i in reversed(dist_idx):
+        if f32(sad_b) < th:
+            break
+        u_right[i] = depth[i] = -1
+        kept -= 1
+    return kept, u_right, depth
+
+
+def test_stereo_match_equals_a_python_restatement():
+    for (w, h, nf, seed, kind) in ((320, 240, 400, 3, "scene"), (400, 300, 600, 8, "scene")):
+        left, right, _ = synth.stereo_pair(h, w, seed, kind=kind)
+        ex_l, ex_r = orbref.Extractor(nf), orbref.Extractor(nf)
+        _, kl, dl = ex_l(left)
+        _, kr, dr = ex_r(right)
+        mbf, mb = 0.8 * w * 0.11, 0.11
+        n_o, ur_o, dp_o = orbref.stereo_match(ex_l, ex_r, kl, dl, kr, dr, float(mbf), float(mb))
+        n_p, ur_p, dp_p = _stereo_python(ex_l, ex_r, kl, dl, kr, dr, mbf, mb)
+        assert n_o > 20, "case must exercise the match path"
+        assert n_p == n_o
+        assert np.array_equal(ur_p.view(np.uint32), ur_o.view(np.uint32))
+        assert np.array_equal(dp_p.view(np.uint32), dp_o.view(np.uint32))
