@@ -435,3 +435,60 @@ def test_stereo_match_equals_a_python_restatement():
         assert n_p == n_o
         assert np.array_equal(ur_p.view(np.uint32), ur_o.view(np.uint32))
         assert np.array_equal(dp_p.view(np.uint32), dp_o.view(np.uint32))
+
+
+def test_search_by_projection_frame_equals_a_python_restatement():
+    """The matching stage of ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)
+    (src/ORBmatcher.cc:1574-1722) over pre-projected points: window by forward / backward / neither level range, the
+    already-matched rule, the uRight gate, strict-< best, rotation-histogram pruning."""
+    f32 = np.float32
+    rng = np.random.default_rng(17)
+    n, w, h = 600, 640, 480
+    kps = np.zeros(n, synth.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(0, w, n).astype(f32), rng.uniform(0, h, n).astype(f32)
+    kps["octave"] = rng.integers(0, 8, n)
+    kps["angle"] = rng.uniform(0, 360, n).astype(f32)
+    desc = synth.descriptors(n, 17)
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    for stereo, th, check, max_dist in ((True, 7.0, True, 100), (False, 15.0, True, 100), (True, 7.0, False, 60)):
+        ur = np.where(rng.random(n) < 0.7, kps["x"] - rng.uniform(1, 40, n), -1).astype(f32) if stereo else None
+        occ = (rng.random(n) < 0.1).astype(np.uint8)
+        fr = orbref.make_frame_view(kps, desc, ur, occ, g, keep, sf)
+        pts = synth.projected_points(kps, desc, 900, w, h, 8, sf, seed=int(th), th=th, stereo=stereo)
+        n_o, a_o = orbref.search_by_projection_frame(fr, orbref.make_projected(**pts), max_dist, check)
+        assign = np.full(n, -1, np.int32)
+        blocked = occ.astype(bool).copy()
+        hist = [[] for _ in range(30)]
+        accepted = 0
+        for i in range(len(pts["u"])):
+            best, bi = 256, -1
+            for k in _features_in_area(kps, off, items, pts["u"][i], pts["v"][i], pts["radius"][i],
+                                       int(pts["min_level"][i]), int(pts["max_level"][i]), inv_w, inv_h):
+                if blocked[k]:
+                    continue
+                if stereo and ur[k] > 0 and abs(f32(pts["u_right"][i] - ur[k])) > pts["radius"][i]:
+                    continue
+                d = _ham(pts["desc"][i], desc[k])
+                if d < best:
+                    best, bi = d, k
+            if best <= max_dist:
+                assign[bi] = i
+                blocked[bi] = bool(pts["has_obs"][i])
+                accepted += 1
+                if check:
+                    hist[_rot_bin(pts["angle"][i], kps["angle"][bi])].append(bi)
+        keep_bins = ()
+        if check:
+            keep_bins = _three_maxima(hist)
+            for b in range(30):
+                if b not in keep_bins:
+                    for k in hist[b]:
+                        assign[k] = -1
+        assert np.array_equal(assign, a_o), (stereo, th, check)
+        # the reference's counter: +1 per accepted point, -1 per pruned histogram entry (an entry whose keypoint was
+        # re-assigned later is still counted once per entry)
+        nm = accepted - (sum(len(hist[b]) for b in range(30) if b not in keep_bins) if check else 0)
+        assert nm == n_o and n_o > 30
