@@ -492,3 +492,90 @@ def test_search_by_projection_frame_equals_a_python_restatement():
         # re-assigned later is still counted once per entry)
         nm = accepted - (sum(len(hist[b]) for b in range(30) if b not in keep_bins) if check else 0)
         assert nm == n_o and n_o > 30
+
+
+def test_search_for_triangulation_equals_a_python_restatement():
+    """ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:886-1103) with Pinhole::epipolarConstrain
+    (src/CameraModels/Pinhole.cpp:122-149) given F12. Written per shared vocabulary node as: the winner for idx1 is the
+    LAST candidate, in node order, that attains the minimum distance among the candidates passing every gate with
+    distance <= TH_LOW -- the closed form of the reference's `dist > bestDist -> continue` running scan."""
+    f32 = np.float32
+    w, h = 640, 400
+    left, right, _ = synth.stereo_pair(h, w, 5, d_min=5, d_max=30)
+    e1, e2 = orbref.Extractor(1200), orbref.Extractor(1200)
+    _, k1, d1 = e1(left)
+    _, k2, d2 = e2(right)
+    rng = np.random.default_rng(5)
+
+    def featvec(desc):
+        node_of = (desc[:, 0].astype(np.int64) >> 4) * 16 + (desc[:, 1].astype(np.int64) >> 4)
+        ids, inv = np.unique(node_of, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        offsets = np.zeros(len(ids) + 1, np.int32)
+        offsets[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+        return ids.astype(np.uint32), offsets, order.astype(np.uint32)
+
+    sf, s2 = e1.scale, e1.sigma2
+    kfs = []
+    for k, d in ((k1, d1), (k2, d2)):
+        ids, off, idx = featvec(d)
+        ur = np.where(rng.random(len(k)) < 0.5, k["x"] - 10, -1).astype(f32)
+        hm = (rng.random(len(k)) < 0.2).astype(np.uint8)
+        kfs.append((k, d, ur, hm, ids, off, idx, sf, s2))
+    # near-horizontal translation with a slight tilt so that every term of the line equation is exercised
+    F12 = np.array([[1e-7, 2e-6, -3e-4], [-2e-6, 1e-7, -1], [4e-4, 1, 2e-2]], f32)
+    for only_stereo, coarse, check, ep in ((False, False, True, (1e6, 200.0)), (True, False, True, (1e6, 200.0)),
+                                           (False, True, False, (320.0, 200.0)), (False, False, False, (100.0, 150.0))):
+        n_o, m_o = orbref.search_for_triangulation(orbref.make_keyframe_view(*kfs[0]),
+                                                   orbref.make_keyframe_view(*kfs[1]), F12, ep, only_stereo, coarse,
+                                                   check)
+        (ka, da, ua, ha, ia, oa, xa, _, _), (kb, db, ub, hb, ib, ob, xb, _, _) = kfs
+        m12 = np.full(len(ka), -1, np.int32)
+        hist = [[] for _ in range(30)]
+        nm = 0
+        Ff = F12.ravel()
+        for node in np.intersect1d(ia, ib):
+            a, b = int(np.searchsorted(ia, node)), int(np.searchsorted(ib, node))
+            c2 = xb[ob[b]:ob[b + 1]].astype(np.int64)
+            c2 = c2[hb[c2] == 0]
+            st2 = ub[c2] >= 0
+            if only_stereo:
+                c2, st2 = c2[st2], st2[st2]
+            for i1 in xa[oa[a]:oa[a + 1]].astype(np.int64):
+                st1 = ua[i1] >= 0
+                if ha[i1] or (only_stereo and not st1) or len(c2) == 0:
+                    continue
+                dist = np.bitwise_count(np.bitwise_xor(db[c2], da[i1][None, :])).sum(1).astype(np.int64)
+                x2, y2 = kb["x"][c2], kb["y"][c2]
+                ok = dist <= 50
+                ex, ey = (f32(ep[0]) - x2).astype(f32), (f32(ep[1]) - y2).astype(f32)
+                near_epipole = (ex * ex + ey * ey).astype(f32) < (f32(100) * sf[kb["octave"][c2]]).astype(f32)
+                ok &= ~(near_epipole & ~st2 & (not st1))
+                if not coarse:
+                    x1, y1 = f32(ka["x"][i1]), f32(ka["y"][i1])
+                    la = f32(f32(f32(x1 * Ff[0]) + f32(y1 * Ff[3])) + Ff[6])
+                    lb = f32(f32(f32(x1 * Ff[1]) + f32(y1 * Ff[4])) + Ff[7])
+                    lc = f32(f32(f32(x1 * Ff[2]) + f32(y1 * Ff[5])) + Ff[8])
+                    num = ((la * x2).astype(f32) + (lb * y2).astype(f32)).astype(f32) + lc
+                    den = f32(f32(la * la) + f32(lb * lb))
+                    if den == 0:
+                        continue
+                    dsqr = ((num * num).astype(f32) / den).astype(f32)
+                    ok &= dsqr.astype(np.float64) < 3.84 * s2[kb["octave"][c2]].astype(np.float64)
+                if not ok.any():
+                    continue
+                best = dist[ok].min()
+                j = int(np.flatnonzero(ok & (dist == best))[-1])
+                m12[i1] = c2[j]
+                nm += 1
+                if check:
+                    hist[_rot_bin(ka["angle"][i1], kb["angle"][c2[j]])].append(int(i1))
+        if check:
+            keep_bins = _three_maxima(hist)
+            for bn in range(30):
+                if bn not in keep_bins:
+                    for i1 in hist[bn]:
+                        m12[i1] = -1
+                        nm -= 1
+        assert n_o > 20, (only_stereo, coarse, n_o)
+        assert nm == n_o and np.array_equal(m12, m_o), (only_stereo, coarse, check)
