@@ -34,3 +34,10 @@ if [ -n "$PROF" ]; then
       -o gpurun_out/prof_$TAG python bench.py --steps 2 --warmup 3 --pairs 64 --no-cpu > gpurun_out/ncu_prof_$TAG.log 2>&1
   ls -la gpurun_out/prof_$TAG.ncu-rep
 fi
+# optional: UBENCH=1 runs the stand-alone prototypes of tools/ubench (self-checking, watchdog-bounded)
+if [ -n "$UBENCH" ]; then
+  for args in "1000 1000" "10000 10000" "100000 100000" "100000 100000 0 0"; do
+    timeout 120 tools/ubench/knn2_tc $args 2>&1 | tail -12
+  done > gpurun_out/knn2_tc_$TAG.log
+  tail -20 gpurun_out/knn2_tc_$TAG.log
+fi
