@@ -1,0 +1,298 @@
+// k_knn2_tc.cu — tensor-core form of cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2) (src/Frame.cc:1293; SURVEY.md §8(f)
+// rank 4) for large query x train sets; k_knn2 in k_match.cu stays the path for small ones.
+//
+// A 256-bit descriptor is expanded once to 256 signed bytes of +-1 (32 B -> 256 B per row); then
+//   dot(a', b') = 256 - 2 * hamming(a, b)      exactly, in int32,
+// i.e. a plain s8 x s8 -> s32 GEMM: tcgen05.mma kind::i8, M = 128 queries x N = 256 train rows x K = 256 per tile,
+// operands K-major in 128B-swizzled shared memory written by TMA, the accumulator double-buffered in TMEM (2 x 256
+// columns) so that the epilogue of tile i overlaps the MMAs of tile i + 1. The epilogue owns one query row per thread
+// (= TMEM lane), reads 32 accumulator columns per tcgen05.ld and keeps the best two as packed
+// (distance << 22 | train row) keys: the same keys, and therefore the same "lower trainIdx wins ties" order, as k_knn2.
+// Train tiles are visited in ascending row order, so a candidate can only enter the best two if its distance is
+// STRICTLY below the current second best: a 32-column chunk is skipped after one 3-input max reduction (half an
+// instruction per value) unless its largest accumulator beats that threshold; the exact insertion runs on ~2 ln(nt)
+// chunks per row. One CTA per SM (160 KB of shared memory, all 512 TMEM columns): warp 0 = TMA producer, warp 1 = MMA
+// issuer, warps 2..5 = epilogue (warp w may touch TMEM lanes 32 (w % 4) .. +31). blockIdx.y splits the train set;
+// the per-split (d1, i1, d2, i2) are merged by k_knn2_merge in split order like the POPC kernel's.
+//
+// Measured (profiles/r01_knn2_tc_prototype.log, the stand-alone form in tools/ubench/knn2_tc.cu): 100k x 100k in
+// 2.20 ms = 4.5 Tpair/s including expansion and merge (POPC kernel: 15.0 ms); 3.66 ms without the chunk filter
+// (epilogue bound); MMA-bound floor at the int8 peak ~1.1 ms.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orbx_match.cuh"
+
+namespace orbx {
+namespace {
+constexpr int kM = 128, kN = 256, kRowBytes = 256, kHalf = 128;  // K = 256 bytes per row = two 128-byte swizzle spans
+constexpr int kABytes = kM * kRowBytes, kBBytes = kN * kRowBytes;
+constexpr int kThreads = 192;
+constexpr int kSmem = kABytes + 2 * kBBytes + 256 + 1024;  // + barriers + alignment slack
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
+}
+// Bounded spin (~seconds): see the trap below.
+__device__ __forceinline__ void bar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  for (uint32_t spins = 0;; spins++) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(sptr(b)), "r"(parity) : "memory");
+    if (ok) return;
+    if (spins > (1u << 24)) {
+      __trap();  // a protocol error must surface as a CUDA error on the caller's stream, never as a hung device
+    }
+  }
+}
+__device__ __forceinline__ void tma_rows(const CUtensorMap* map, void* dst, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(sptr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(sptr(bar)) : "memory");
+}
+// K-major operand in SWIZZLE_128B layout: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO unused (1), version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(const void* p) {
+  const uint64_t a = (sptr(p) & 0x3ffff) >> 4;
+  return a | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 B of bits -> 256 B of +-1 (bit j of byte b -> element 8 b + j; any fixed order works, both sides use the same)
+__global__ void k_expand_pm1(const uint8_t* __restrict__ desc, int n, int8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 32) return;
+  const uint32_t b = desc[i];
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    lo |= (((b >> j) & 1) ? 0x01u : 0xffu) << (8 * j);
+    hi |= (((b >> (4 + j)) & 1) ? 0x01u : 0xffu) << (8 * j);
+  }
+  reinterpret_cast<uint2*>(out)[i] = make_uint2(lo, hi);
+}
+
+template <bool kFilter>
+__global__ void __launch_bounds__(kThreads, 1)
+k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, int nq, int nt,
+          int tiles_per_split, int4* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                       // [2 halves][128 rows][128 B]
+  uint8_t* sB = smem + kABytes;             // [2 stages][2 halves][256 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + 2 * kBBytes);
+  uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = bars + 3, *acc_full = bars + 5, *acc_empty = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kM;
+  const int total_tiles = (nt + kN - 1) / kN;
+  const int tb = blockIdx.y * tiles_per_split;
+  const int ntile = max(0, min(total_tiles, tb + tiles_per_split) - tb);
+
+  if (threadIdx.x == 0) {
+    bar_init(a_full, 1);
+    for (int s = 0; s < 2; s++) {
+      bar_init(b_full + s, 1);
+      bar_init(b_empty + s, 1);
+      bar_init(acc_full + s, 1);
+      bar_init(acc_empty + s, 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sptr(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      bar_expect(a_full, kABytes);
+      tma_rows(&map_q, sA, a_full, 0, q0);
+      tma_rows(&map_q, sA + kM * kHalf, a_full, kHalf, q0);
+      for (int i = 0; i < ntile; i++) {
+        const int s = i & 1;
+        bar_wait(b_empty + s, ((i >> 1) & 1) ^ 1);
+        bar_expect(b_full + s, kBBytes);
+        tma_rows(&map_t, sB + s * kBBytes, b_full + s, 0, (tb + i) * kN);
+        tma_rows(&map_t, sB + s * kBBytes + kN * kHalf, b_full + s, kHalf, (tb + i) * kN);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      bar_wait(a_full, 0);
+      for (int i = 0; i < ntile; i++) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        bar_wait(b_full + s, ph);
+        bar_wait(acc_empty + s, ph ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) {  // 8 x (K = 32 bytes); 4 steps inside each 128-byte swizzle span
+          const uint64_t da = smem_desc(sA + (kk >> 2) * (kM * kHalf) + (kk & 3) * 32);
+          const uint64_t db = smem_desc(sB + s * kBBytes + (kk >> 2) * (kN * kHalf) + (kk & 3) * 32);
+          mma_i8(tmem + s * kN, da, db, kk > 0);
+        }
+        mma_commit(b_empty + s);   // the stage may be refilled once these MMAs have read it
+        mma_commit(acc_full + s);  // ... and the accumulator is complete
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int row = q0 + quad * 32 + lane;
+    uint32_t k1 = 0xffffffffu, k2 = 0xffffffffu;
+    int thr = -100000;  // accumulators above thr have a distance strictly below the current second best
+    for (int i = 0; i < ntile; i++) {
+      const int s = i & 1;
+      bar_wait(acc_full + s, (i >> 1) & 1);
+      tc_fence_after();
+      const int col0 = (tb + i) * kN;
+#pragma unroll 1
+      for (int c = 0; c < kN / 32; c++) {
+        int v[32];
+        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + s * kN + c * 32, v);
+        bool hit = true;
+        if (kFilter) {
+          int mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 31; j += 2) mx = max(mx, max(v[j], v[j + 1]));
+          mx = max(mx, v[31]);
+          hit = mx > thr;
+        }
+        if (hit) {
+          const uint32_t base = (256u << 21) | (uint32_t)(col0 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (col0 + c * 32 + j < nt) {  // rows past the end are TMA zero fill (accumulator 0 = distance 128)
+              const uint32_t key = base + j - ((uint32_t)v[j] << 21);  // ((256 - acc) / 2) << 22 | col
+              k2 = min(k2, max(k1, key));
+              k1 = min(k1, key);
+            }
+          }
+          thr = 256 - 2 * (int)(k2 >> 22);
+        }
+      }
+      tc_fence_before();
+      bar_arrive(acc_empty + s);
+    }
+    if (row < nq) {
+      const int i1 = k1 == 0xffffffffu ? -1 : (int)(k1 & 0x3fffff), i2 = k2 == 0xffffffffu ? -1 : (int)(k2 & 0x3fffff);
+      partial[(size_t)blockIdx.y * nq + row] =
+          make_int4(i1 < 0 ? 0x7fffffff : (int)(k1 >> 22), i1, i2 < 0 ? 0x7fffffff : (int)(k2 >> 22), i2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encoder() {
+  static EncodeTiledFn enc = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return enc;
+}
+
+// rows x 256 signed bytes, box = 128 bytes (one swizzle span) x box_rows; rows past the end read as zero
+bool make_rows_map(CUtensorMap* m, const void* base, int rows, int box_rows) {
+  EncodeTiledFn enc = encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)kRowBytes, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kRowBytes};
+  const cuuint32_t box[2] = {(cuuint32_t)kHalf, (cuuint32_t)box_rows}, es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+// Large enough for the GEMM form to pay for its expansion pass and 128-row query tiles; keys need nt < 2^22 and the
+// expanded train set (256 B per row) is kept to 256 MB of scratch.
+bool knn2_tc_eligible(int nq, int nt) {
+  return nq >= 1024 && nq <= (1 << 24) && nt >= 256 && nt <= (1 << 20) && (long long)nq * nt >= (1ll << 25) && encoder() != nullptr;
+}
+
+size_t knn2_tc_expanded_bytes(int rows) { return (size_t)rows * kRowBytes; }
+
+// Splits of the train set: enough CTAs to fill 148 SMs twice for small query sets, and for large ones the count
+// (<= 8) that leaves the smallest idle tail in the last wave; every split keeps at least 4 tiles.
+int knn2_tc_splits(int nq, int nt, int* tiles_per_split) {
+  const int qblocks = (nq + kM - 1) / kM, total_tiles = (nt + kN - 1) / kN;
+  int smax = (2 * 148 + qblocks - 1) / qblocks;
+  if (smax < 8) smax = 8;
+  if (smax > total_tiles / 4) smax = total_tiles / 4;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= smax; s++) {
+    const int tps = (total_tiles + s - 1) / s;
+    const int ctas = qblocks * ((total_tiles + tps - 1) / tps);
+    const double waves = (double)((ctas + 147) / 148);
+    const double cost = waves * (tps + 1.0);  // +1: the query tile load and the partial write of each CTA
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  const int tps = (total_tiles + best - 1) / best;
+  *tiles_per_split = tps;
+  return (total_tiles + tps - 1) / tps;  // no empty split
+}
+
+cudaError_t launch_knn2_tc(const uint8_t* q, int nq, const uint8_t* t, int nt, int8_t* expanded_q, int8_t* expanded_t,
+                           int4* partial, int splits, int tiles_per_split, cudaStream_t st) {
+  CUtensorMap mq, mt;
+  if (!make_rows_map(&mq, expanded_q, nq, kM) || !make_rows_map(&mt, expanded_t, nt, kN)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(k_knn2_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  if (e != cudaSuccess) return e;
+  k_expand_pm1<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, nq, expanded_q);
+  k_expand_pm1<<<(nt * 32 + 255) / 256, 256, 0, st>>>(t, nt, expanded_t);
+  k_knn2_tc<true><<<dim3((nq + kM - 1) / kM, splits), kThreads, kSmem, st>>>(mq, mt, nq, nt, tiles_per_split, partial);
+  return cudaGetLastError();
+}
+
+}  // namespace orbx

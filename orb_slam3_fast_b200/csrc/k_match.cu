@@ -136,6 +136,11 @@ __global__ void k_desc_dist(const uint8_t* __restrict__ a, const uint8_t* __rest
   out[i] = hamming(x, y);
 }
 
+void launch_knn2_merge(const int4* partial, int nq, int splits, int32_t* idx1, int32_t* d1, int32_t* idx2,
+                       int32_t* d2, cudaStream_t st) {
+  k_knn2_merge<<<(nq + 255) / 256, 256, 0, st>>>(partial, nq, splits, idx1, d1, idx2, d2);
+}
+
 void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, cudaStream_t st) {
   if (n > 0) k_desc_dist<<<(n + 255) / 256, 256, 0, st>>>(a, b, n, out);
 }

@@ -60,9 +60,17 @@ struct orbm_matcher {
   // the vocabulary tree of orbm_set_vocabulary (device resident across calls)
   DevBuf voc_buf[5];
   orbx::DevVocabulary voc{};
+  // +-1 byte expansions of the query / train descriptors for the tensor-core knn2 (256 B per row)
+  DevBuf tc_buf[2];
 };
 
 namespace {
+
+// ORBM_KNN2_TC=0 keeps every knn2 call on the POPC kernel (A/B runs, and the parity test of one path against the other)
+bool knn2_tc_enabled() {
+  const char* v = getenv("ORBM_KNN2_TC");
+  return !(v && v[0] == '0');
+}
 
 int mfail(orbm_matcher* m, int code, const std::string& msg) {
   if (m) m->err = msg;
@@ -263,6 +271,7 @@ void orbm_destroy(orbm_matcher* m) {
   for (auto& h : m->lane_h_nm)
     if (h) cudaFreeHost(h);
   for (auto& b : m->voc_buf) b.release();
+  for (auto& b : m->tc_buf) b.release();
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -311,9 +320,24 @@ int orbm_knn2_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t*
   if (nq == 0) return ORBX_OK;
   ORBM_CUDA(m, cudaSetDevice(m->device));
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m->stream;
-  const int splits = knn2_splits(nq, nt);
   // the partial buffer is the LAST arena slot so that host-API uploads (slots 0..) are not disturbed
   DevBuf& pb = m->buf[kBufs - 1];
+  if (knn2_tc_enabled() && knn2_tc_eligible(nq, nt)) {
+    // large sets: Hamming as an s8 GEMM on the tensor cores (k_knn2_tc.cu); same keys, same merge, same results
+    int tiles_per_split = 0;
+    const int splits = knn2_tc_splits(nq, nt, &tiles_per_split);
+    cudaError_t e = pb.reserve((size_t)splits * nq * sizeof(int4));
+    if (e == cudaSuccess) e = m->tc_buf[0].reserve(knn2_tc_expanded_bytes(nq));
+    if (e == cudaSuccess) e = m->tc_buf[1].reserve(knn2_tc_expanded_bytes(nt));
+    if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+    ORBM_CUDA(m, launch_knn2_tc(d_q, nq, d_t, nt, static_cast<int8_t*>(m->tc_buf[0].p),
+                                static_cast<int8_t*>(m->tc_buf[1].p), reinterpret_cast<int4*>(pb.p), splits,
+                                tiles_per_split, st));
+    launch_knn2_merge(reinterpret_cast<int4*>(pb.p), nq, splits, d_idx1, d_d1, d_idx2, d_d2, st);
+    ORBM_CUDA(m, cudaGetLastError());
+    return ORBX_OK;
+  }
+  const int splits = knn2_splits(nq, nt);
   cudaError_t e = pb.reserve((size_t)splits * nq * sizeof(int4));
   if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
   launch_knn2(d_q, nq, d_t, nt, reinterpret_cast<int4*>(pb.p), splits, d_idx1, d_d1, d_idx2, d_d2, st);

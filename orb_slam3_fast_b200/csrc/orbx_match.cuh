@@ -42,6 +42,14 @@ struct StereoArgs {
 int knn2_splits(int nq, int nt);
 void launch_knn2(const uint8_t* q, int nq, const uint8_t* t, int nt, int4* partial, int splits, int32_t* idx1,
                  int32_t* d1, int32_t* idx2, int32_t* d2, cudaStream_t st);
+void launch_knn2_merge(const int4* partial, int nq, int splits, int32_t* idx1, int32_t* d1, int32_t* idx2,
+                       int32_t* d2, cudaStream_t st);
+// k_knn2_tc.cu: the tcgen05 (s8 GEMM) form for large sets; partial = [splits][nq] like launch_knn2's
+bool knn2_tc_eligible(int nq, int nt);
+size_t knn2_tc_expanded_bytes(int rows);
+int knn2_tc_splits(int nq, int nt, int* tiles_per_split);
+cudaError_t launch_knn2_tc(const uint8_t* q, int nq, const uint8_t* t, int nt, int8_t* expanded_q, int8_t* expanded_t,
+                           int4* partial, int splits, int tiles_per_split, cudaStream_t st);
 void launch_desc_dist(const uint8_t* a, const uint8_t* b, int n, int32_t* out, cudaStream_t st);
 // TemplatedVocabulary::transform per feature; the vocabulary arrays are device resident (orbm_vocabulary handle)
 struct DevVocabulary {

@@ -32,6 +32,22 @@ def test_knn2_matches_oracle(matcher, nq, nt, proto):
         assert np.array_equal(g, r), "%s differs at %s" % (name, np.nonzero(g != r)[0][:10])
 
 
+@pytest.mark.parametrize("nq,nt,proto", [(6000, 6000, 64), (8192, 4097, 16), (20000, 3000, 0), (1024, 32768, 8)])
+def test_knn2_tensor_core_path_equals_popc_path_and_oracle(matcher, monkeypatch, nq, nt, proto):
+    """Sizes above the switch-over run as an s8 GEMM on the tensor cores (k_knn2_tc.cu); ORBM_KNN2_TC=0 keeps the call on
+    the POPC kernel. Both must give the oracle's words, ties (duplicate rows, exact hits) included."""
+    q, t = synth.descriptors(nq, 11, proto), synth.descriptors(nt, 12, proto)
+    q[: min(nq, nt) // 2] = t[: min(nq, nt) // 2]  # exact hits (d = 0), duplicated among the prototypes
+    tc = matcher.knnMatch2(q, t)
+    monkeypatch.setenv("ORBM_KNN2_TC", "0")
+    popc = matcher.knnMatch2(q, t)
+    monkeypatch.delenv("ORBM_KNN2_TC")
+    ref = orbref.knn2(q, t)
+    for a, b, r, name in zip(tc, popc, ref, ("idx1", "d1", "idx2", "d2")):
+        assert np.array_equal(a, r), "tensor-core %s differs at %s" % (name, np.nonzero(a != r)[0][:10])
+        assert np.array_equal(b, r), "POPC %s differs at %s" % (name, np.nonzero(b != r)[0][:10])
+
+
 def test_knn2_agrees_with_cv2_bfmatcher(matcher):
     cv2 = pytest.importorskip("cv2")
     q, t = synth.descriptors(800, 5, 32), synth.descriptors(900, 6, 32)  # tie-heavy
