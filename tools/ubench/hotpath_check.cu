@@ -6,12 +6,13 @@
 //
 //   nvcc -O2 -std=c++17 -o hotpath_check hotpath_check.cu -I../../include -L../../orb_slam3_fast_b200 -lorbx \
 //        -Xlinker -rpath -Xlinker '$ORIGIN/../../orb_slam3_fast_b200'
-//   ./hotpath_check [pairs per step = 1024] [steps = 10] [case file]
+//   ./hotpath_check [pairs per step = 1024] [steps = 10] [e2e steps = steps, 0 = skip] [case file]
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -63,7 +64,8 @@ static int alloc_out(DevOut* o, int P, int cap) {
 
 int main(int argc, char** argv) {
   const int P = argc > 1 ? atoi(argv[1]) : 1024, steps = argc > 2 ? atoi(argv[2]) : 10;
-  std::string path = argc > 3 ? argv[3] : "";
+  const int e2e_steps = argc > 3 ? atoi(argv[3]) : steps;
+  std::string path = argc > 4 ? argv[4] : "";
   if (path.empty()) {
     path = argv[0];
     const size_t s = path.find_last_of('/');
@@ -201,6 +203,66 @@ int main(int argc, char** argv) {
          2.0 * P * steps / (ms * 1e-3));
   printf("stage ms/step: pyramid %.3f fast %.3f quadtree %.3f blur %.3f describe %.3f\n", stage[0] / steps,
          stage[1] / steps, stage[2] / steps, stage[3] / steps, stage[4] / steps);
+
+  // ---- end to end: orbm_stereo_frames_batch, pinned host buffers in and out (bench.py's e2e leg) ----
+  if (e2e_steps > 0) {
+    const int G = P / 8 < 8 ? 8 : (P / 8 > 64 ? 64 : P / 8);
+    orbx_extractor* ex2[2] = {nullptr, nullptr};
+    for (int e = 0; e < 2; e++) OX(nullptr, orbx_extractor_create(&ex2[e], 0, nfeat, 1.2f, 8, 20, 7, G));
+    uint8_t* h_img[2][2];
+    for (int k = 0; k < 2; k++)
+      for (int e = 0; e < 2; e++) {
+        h_img[k][e] = static_cast<uint8_t*>(orbx_host_alloc((int64_t)P * fbytes));
+        if (!h_img[k][e]) return printf("orbx_host_alloc failed\n"), 1;
+        for (int p = 0; p < P; p++)
+          memcpy(h_img[k][e] + (size_t)p * fbytes, imgs[e].data() + (size_t)((p + k) % D) * fbytes, fbytes);
+      }
+    orbx_kp* h_kps[2];
+    uint8_t* h_desc[2];
+    int32_t* h_n[2];
+    for (int e = 0; e < 2; e++) {
+      h_kps[e] = static_cast<orbx_kp*>(orbx_host_alloc((int64_t)P * cap * sizeof(orbx_kp)));
+      h_desc[e] = static_cast<uint8_t*>(orbx_host_alloc((int64_t)P * cap * 32));
+      h_n[e] = static_cast<int32_t*>(orbx_host_alloc((int64_t)P * 4));
+    }
+    float* h_ur = static_cast<float*>(orbx_host_alloc((int64_t)P * cap * 4));
+    float* h_dp = static_cast<float*>(orbx_host_alloc((int64_t)P * cap * 4));
+    int32_t* h_nm = static_cast<int32_t*>(orbx_host_alloc((int64_t)P * 4));
+    auto e2e = [&](int k) -> int {
+      const int rc = orbm_stereo_frames_batch(mt, ex2[0], ex2[1], P, h_img[k & 1][0], h_img[k & 1][1], W, H, W,
+                                              (int64_t)fbytes, mbf, mb, h_kps[0], h_desc[0], h_n[0], h_kps[1], h_desc[1],
+                                              h_n[1], cap, h_ur, h_dp, h_nm);
+      if (rc != 0) return printf("orbm_stereo_frames_batch: rc %d: %s\n", rc, orbm_last_error(mt)), 1;
+      return 0;
+    };
+    for (int k = 0; k < 3; k++)
+      if (e2e(k)) return 1;
+    // the host-facing call must give the oracle's words too (batch 0 = the case's pairs in order)
+    long bad2 = 0;
+    if (e2e(0)) return 1;
+    for (int i = 0; i < nchk; i++) {
+      const Pair& w = want[i];
+      const int nl = w.eye[0].n;
+      bool ok = h_n[0][i] == nl && h_n[1][i] == w.eye[1].n && h_nm[i] == w.n_matched;
+      ok = ok && memcmp(h_kps[0] + (size_t)i * cap, w.eye[0].kps.data(), (size_t)nl * 28) == 0 &&
+           memcmp(h_desc[1] + (size_t)i * cap * 32, w.eye[1].desc.data(), (size_t)w.eye[1].n * 32) == 0 &&
+           memcmp(h_ur + (size_t)i * cap, w.u_right.data(), (size_t)nl * 4) == 0 &&
+           memcmp(h_dp + (size_t)i * cap, w.depth.data(), (size_t)nl * 4) == 0;
+      if (!ok && bad2++ < 8) printf("e2e pair %d differs\n", i);
+    }
+    printf("e2e parity vs oracle: %s\n", bad2 ? "FAILED" : "bit-exact");
+    bad += bad2;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int k = 0; k < e2e_steps; k++)
+      if (e2e(k)) return 1;
+    CK(cudaDeviceSynchronize());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    printf("e2e (host buffers, groups of %d pairs): %.3f ms/step = %.0f frames/s\n", G, 1e3 * dt / e2e_steps,
+           2.0 * P * e2e_steps / dt);
+    for (int e = 0; e < 2; e++) orbx_extractor_destroy(ex2[e]);
+  }
   orbm_destroy(mt);
   for (int e = 0; e < 2; e++) orbx_extractor_destroy(ex[e]);
   return bad ? 2 : 0;
