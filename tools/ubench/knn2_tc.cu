@@ -5,7 +5,7 @@
 //   brute-force kernel, 100k x 100k in 2.20 ms (3.66 ms with the chunk filter off). The kernel now lives in the library
 //   as orb_slam3_fast_b200/csrc/k_knn2_tc.cu; this file stays as the stand-alone bench / bring-up harness:
 //       nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o knn2_tc knn2_tc.cu -lcuda
-//       timeout 120 ./knn2_tc 1000 1000 && timeout 120 ./knn2_tc 100000 100000     # [nq] [nt] [splits] [filter 0|1]
+//       timeout 120 ./knn2_tc 1000 1000 && timeout 120 ./knn2_tc 100000 100000     # [nq] [nt] [splits] [filter 0|1] [loads in flight 1|2|4]
 //
 // Idea. A 256-bit descriptor is expanded once to 256 signed bytes of +-1 (k_expand_pm1, 32 B -> 256 B per row); then
 //   dot(a', b') = 256 - 2 * hamming(a, b)      exactly, in int32,
@@ -81,7 +81,7 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, int (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -90,8 +90,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -109,7 +109,7 @@ __global__ void k_expand_pm1(const uint8_t* __restrict__ desc, int n, int8_t* __
   reinterpret_cast<uint2*>(out)[i] = make_uint2(lo, hi);
 }
 
-template <bool kFilter>
+template <bool kFilter, int kGroups>  // kGroups = 32-column TMEM loads in flight per tcgen05.wait::ld
 __global__ void __launch_bounds__(kThreads, 1)
 k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, int nq, int nt,
           int tiles_per_split, int4* __restrict__ partial) {
@@ -191,28 +191,35 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
       tc_fence_after();
       const int col0 = (tb + i) * kN;
 #pragma unroll 1
-      for (int c = 0; c < kN / 32; c++) {
-        int v[32];
-        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + s * kN + c * 32, v);
-        bool hit = true;
-        if (kFilter) {
-          int mx = v[0];
+      for (int c0 = 0; c0 < kN / 32; c0 += kGroups) {
+        int v[kGroups][32];
 #pragma unroll
-          for (int j = 1; j < 31; j += 2) mx = max(mx, max(v[j], v[j + 1]));
-          mx = max(mx, v[31]);
-          hit = mx > thr;
-        }
-        if (hit) {
-          const uint32_t base = (256u << 21) | (uint32_t)(col0 + c * 32);
+        for (int g = 0; g < kGroups; g++)
+          tmem_ld32_issue(tmem + ((uint32_t)(quad * 32) << 16) + s * kN + (c0 + g) * 32, v[g]);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            if (col0 + c * 32 + j < nt) {  // rows past the end are TMA zero fill (accumulator 0 = distance 128)
-              const uint32_t key = base + j - ((uint32_t)v[j] << 21);  // ((256 - acc) / 2) << 22 | col
-              k2 = min(k2, max(k1, key));
-              k1 = min(k1, key);
-            }
+        for (int g = 0; g < kGroups; g++) {
+          const int c = c0 + g;
+          bool hit = true;
+          if (kFilter) {
+            int mx = v[g][0];
+#pragma unroll
+            for (int j = 1; j < 31; j += 2) mx = max(mx, max(v[g][j], v[g][j + 1]));
+            mx = max(mx, v[g][31]);
+            hit = mx > thr;
           }
-          thr = 256 - 2 * (int)(k2 >> 22);
+          if (hit) {
+            const uint32_t base = (256u << 21) | (uint32_t)(col0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              if (col0 + c * 32 + j < nt) {  // rows past the end are TMA zero fill (accumulator 0 = distance 128)
+                const uint32_t key = base + j - ((uint32_t)v[g][j] << 21);  // ((256 - acc) / 2) << 22 | col
+                k2 = min(k2, max(k1, key));
+                k1 = min(k1, key);
+              }
+            }
+            thr = 256 - 2 * (int)(k2 >> 22);
+          }
         }
       }
       tc_fence_before();
@@ -294,6 +301,7 @@ int main(int argc, char** argv) {
   const int nq = argc > 1 ? atoi(argv[1]) : 10000, nt = argc > 2 ? atoi(argv[2]) : 10000;
   int splits = argc > 3 ? atoi(argv[3]) : 0;
   const bool filter = argc > 4 ? atoi(argv[4]) != 0 : true;
+  const int groups = argc > 5 ? atoi(argv[5]) : 1;  // 1, 2 or 4 TMEM loads in flight
   if (nt >= (1 << 22) || nq < 1 || nt < 1) return printf("sizes out of range\n"), 1;
   const int qblocks = (nq + kM - 1) / kM, total_tiles = (nt + kN - 1) / kN;
   if (splits <= 0) splits = (2 * 148 + qblocks - 1) / qblocks;
@@ -329,7 +337,7 @@ int main(int argc, char** argv) {
   CUtensorMap mq, mt;
   if (!p || !make_map((Enc)p, &mq, eq, nq, kM) || !make_map((Enc)p, &mt, et, nt, kN)) return 1;
 
-  auto kern = filter ? k_knn2_tc<true> : k_knn2_tc<false>;
+  auto kern = !filter ? k_knn2_tc<false, 1> : groups == 4 ? k_knn2_tc<true, 4> : groups == 2 ? k_knn2_tc<true, 2> : k_knn2_tc<true, 1>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   auto run = [&]() {
     k_expand_pm1<<<(nq * 32 + 255) / 256, 256>>>(dq, nq, eq);
@@ -363,7 +371,7 @@ int main(int argc, char** argv) {
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   ms /= reps;
-  printf("knn2_tc %d x %d splits %d filter %d: %.3f ms (expand + mma + merge) = %.1f Gpair/s\n", nq, nt, splits,
-         (int)filter, ms, (double)nq * nt / ms * 1e-6);
+  printf("knn2_tc %d x %d splits %d filter %d groups %d: %.3f ms (expand + mma + merge) = %.1f Gpair/s\n", nq, nt,
+         splits, (int)filter, groups, ms, (double)nq * nt / ms * 1e-6);
   return bad ? 2 : 0;
 }
