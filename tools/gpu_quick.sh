@@ -40,4 +40,10 @@ if [ -n "$UBENCH" ]; then
     timeout 120 tools/ubench/knn2_tc $args 2>&1 | tail -12
   done > gpurun_out/knn2_tc_$TAG.log
   tail -20 gpurun_out/knn2_tc_$TAG.log
+  # loads-in-flight variants of the epilogue, and one full-set capture of the tensor-core kernel (stand-alone binary:
+  # no Python start-up under ncu)
+  for g in 2 4; do timeout 120 tools/ubench/knn2_tc 100000 100000 0 1 $g 2>&1 | tail -2; done >> gpurun_out/knn2_tc_$TAG.log
+  timeout 300 ncu --set full --clock-control none --import-source on -k "regex:k_knn2_tc" -c 1 -f \
+      -o gpurun_out/prof_knn2_tc_$TAG tools/ubench/knn2_tc 100000 100000 > gpurun_out/ncu_knn2_tc_$TAG.log 2>&1
+  ls -la gpurun_out/prof_knn2_tc_$TAG.ncu-rep
 fi
