@@ -579,3 +579,73 @@ def test_search_for_triangulation_equals_a_python_restatement():
                         nm -= 1
         assert n_o > 20, (only_stereo, coarse, n_o)
         assert nm == n_o and np.array_equal(m12, m_o), (only_stereo, coarse, check)
+
+
+def test_search_for_initialization_equals_a_python_restatement():
+    """ORBmatcher::SearchForInitialization, serial order (src/ORBmatcher.cc:618-764): level-0 keypoints only, window via
+    GetFeaturesInArea(level 0..0), candidates already matched at a distance <= dist are skipped, ratio test in float,
+    a re-matched F2 keypoint un-matches its previous F1 partner, rotation-histogram pruning counts only live entries."""
+    f32 = np.float32
+    for seed, window, nnratio, check in ((6, 30, 0.9, True), (7, 60, 0.9, False), (8, 100, 0.7, True)):
+        rng = np.random.default_rng(seed)
+        n, w, h = 500, 640, 480
+        k1 = np.zeros(n, synth.KP_DTYPE)
+        k1["x"], k1["y"] = rng.uniform(20, w - 20, n).astype(f32), rng.uniform(20, h - 20, n).astype(f32)
+        k1["octave"] = (rng.random(n) < 0.3).astype(np.int32) * rng.integers(1, 8, n)
+        k1["angle"] = rng.uniform(0, 360, n).astype(f32)
+        # few prototypes, individually perturbed: several F1 points compete for the same F2 point at different distances
+        d1 = synth.flip_bits(synth.descriptors(n, seed, 40), rng.integers(0, 12, n), rng)
+        perm = rng.permutation(n)
+        k2 = k1[perm].copy()
+        k2["x"] += rng.normal(0, 3, n).astype(f32)
+        k2["y"] += rng.normal(0, 3, n).astype(f32)
+        k2["angle"] = ((k2["angle"] + rng.normal(0, 20, n)) % 360).astype(f32)
+        d2 = synth.flip_bits(d1[perm], rng.integers(0, 30, n), rng)
+        inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+        sf = f32(1.2) ** np.arange(8, dtype=f32)
+        grids = []
+        for k in (k1, k2):
+            off, items = orbref.build_grid(k, 0.0, 0.0, inv_w, inv_h)
+            grids.append((off, items) + orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h))
+        v1 = orbref.make_frame_view(k1, d1, None, np.zeros(n, np.uint8), grids[0][2], grids[0][3], sf)
+        v2 = orbref.make_frame_view(k2, d2, None, np.zeros(n, np.uint8), grids[1][2], grids[1][3], sf)
+        prev = np.stack([k1["x"], k1["y"]], axis=1)
+        n_o, m_o = orbref.search_for_initialization(v1, v2, prev, window, nnratio, check)
+        # ---- the same loop in Python ----
+        big = 2 ** 31 - 1
+        m12, m21, matched_dist = [-1] * n, [-1] * n, [big] * n
+        hist = [[] for _ in range(30)]
+        nm = rematched = 0
+        for i1 in range(n):
+            if k1["octave"][i1] > 0:
+                continue
+            cands = _features_in_area(k2, grids[1][0], grids[1][1], prev[i1, 0], prev[i1, 1], f32(window), 0, 0,
+                                      inv_w, inv_h)
+            best, best2, bi = big, big, -1
+            for i2 in cands:
+                d = _ham(d1[i1], d2[i2])
+                if matched_dist[i2] <= d:
+                    continue
+                if d < best:
+                    best2, best, bi = best, d, i2
+                elif d < best2:
+                    best2 = d
+            if best <= 50 and f32(best) < f32(f32(best2) * f32(nnratio)):
+                if m21[bi] >= 0:
+                    m12[m21[bi]] = -1
+                    nm -= 1
+                    rematched += 1
+                m12[i1], m21[bi], matched_dist[bi] = bi, i1, best
+                nm += 1
+                if check:
+                    hist[_rot_bin(k1["angle"][i1], k2["angle"][bi])].append(i1)
+        if check:
+            keep_bins = _three_maxima(hist)
+            for b in range(30):
+                if b not in keep_bins:
+                    for i1 in hist[b]:
+                        if m12[i1] >= 0:
+                            m12[i1] = -1
+                            nm -= 1
+        assert nm == n_o and np.array_equal(np.asarray(m12, np.int32), m_o), (seed, window, check)
+        assert n_o > 30 and (rematched > 0 or window < 60), "the re-match path must be exercised"
