@@ -54,6 +54,16 @@ def knn2_sweep(mt):
         assert np.array_equal(i1.cpu().numpy()[rr], order[:, 0]) and np.array_equal(i2.cpu().numpy()[rr], order[:, 1])
         row = {"n": n, "ms_device": ms, "gpairs_per_s": n * n / ms / 1e6,
                "ms_host_call": timed(lambda: mt.knnMatch2(q, t), 3 if n > 10000 else 10)}
+        # A/B: the same call with the tensor-core path switched off (every size on the POPC kernel)
+        os.environ["ORBM_KNN2_TC"] = "0"
+        dev()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dev()
+        torch.cuda.synchronize()
+        del os.environ["ORBM_KNN2_TC"]
+        row["ms_device_popc_kernel"] = 1e3 * (time.perf_counter() - t0) / reps
         if n <= 3000:
             import cv2
             bf = cv2.BFMatcher(cv2.NORM_HAMMING)
