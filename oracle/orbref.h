@@ -5,15 +5,24 @@
  * timed CPU baseline. Nothing under orb_slam3_fast_b200/ may include, link or load this library.
  *
  * PINNING STATUS
- *   - The reference has no tests, golden vectors or fixtures for this path, and it cannot be compiled
- *     here (needs OpenCV C++ headers/libs, TBB, Eigen, Sophus, Pangolin; none installed, no network) — so there is
- *     no oracle/_ref and the ORCHESTRATION parity (ORBextractor.cc / ORBmatcher.cc / Frame.cc logic) is UNPINNED by
- *     the reference's own tests.
+ *   - The reference has no tests, golden vectors or fixtures for this path, and its library cannot be
+ *     built here as a whole (OpenCV C++ headers/libs, TBB, Eigen, Sophus, Pangolin: none installed, no network).
+ *   - EXTRACTOR (src/ORBextractor.cc, rows a1-a10): pinned by the reference's OWN source. oracle/Makefile (target `ref`)
+ *     compiles /root/reference/src/ORBextractor.cc where it lies into oracle/_ref/liborbref_src.so against stand-in
+ *     OpenCV / TBB headers (oracle/ref_stubs: types with OpenCV's semantics, TBB run serially, the five image
+ *     primitives forwarded to the cv2-pinned restatements below); tests/test_oracle_vs_reference_source.py requires
+ *     this oracle to equal it bit for bit (constructor tables, 9 image / size / lapping cases, parameter variants,
+ *     degenerate images, and DistributeOctTree called directly on 65 k-candidate levels).
  *   - The third-party arithmetic the reference calls (OpenCV resize / GaussianBlur / FAST / copyMakeBorder /
- *     fastAtan2 / BFMatcher, glibc cosf/sinf, libstdc++ std::sort) IS pinned: tests/test_oracle_primitives.py checks
+ *     fastAtan2 / BFMatcher, glibc cosf/sinf, libstdc++ std::sort) is pinned: tests/test_oracle_primitives.py checks
  *     every primitive below byte-for-byte against the real OpenCV 4.13.0 kernels through cv2, and
  *     tests/test_oracle_pipeline.py checks the whole extractor against an independent Python pipeline that drives the
  *     real cv2 kernels (oracle/cv2_pipeline.py), from which tests/golden/ is frozen.
+ *   - MATCHERS (src/ORBmatcher.cc, Frame::ComputeStereoMatches): their translation units pull in Eigen, Sophus, DBoW2
+ *     and boost through Frame.h / KeyFrame.h / MapPoint.h and cannot be compiled here, so their ORCHESTRATION parity is
+ *     UNPINNED by reference code; every matcher restatement is instead cross-checked against a second, independently
+ *     written Python restatement of the same reference lines (tests/test_oracle_matchers.py), and knn2 against
+ *     cv2.BFMatcher itself.
  *
  * Build: oracle/Makefile (g++ -O2, no -march=native, -ffp-contract=off: the reference is built without FMA,
  * CMakeLists.txt:13-18).

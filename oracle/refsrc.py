@@ -1,0 +1,76 @@
+"""ctypes loader of oracle/_ref/liborbref_src.so: the reference's OWN src/ORBextractor.cc, compiled where it lies under
+/root/reference against the stand-in OpenCV / TBB headers of oracle/ref_stubs (image primitives = the oracle's
+cv2-pinned ones, TBB = serial). TEST INFRASTRUCTURE: it checks the oracle's restatement against the reference code."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from oracle.orbref import KP_DTYPE
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liborbref_src.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(_PATH)
+        L.orbrefsrc_create.restype = C.c_void_p
+        L.orbrefsrc_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orbrefsrc_destroy.argtypes = [C.c_void_p]
+        L.orbrefsrc_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orbrefsrc_extract.restype = C.c_int
+        L.orbrefsrc_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.orbrefsrc_distribute.restype = C.c_int
+        L.orbrefsrc_distribute.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+class ReferenceExtractor:
+    """ORB_SLAM3::ORBextractor of the reference source."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = lib().orbrefsrc_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orbrefsrc_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        f = [np.empty(self.nlevels, np.float32) for _ in range(4)]
+        per_level, umax = np.empty(self.nlevels, np.int32), np.empty(16, np.int32)
+        lib().orbrefsrc_tables(self._h, *[a.ctypes.data for a in f], per_level.ctypes.data, umax.ctypes.data)
+        return f[0], f[1], f[2], f[3], per_level, umax
+
+    def __call__(self, img, lapping=(0, 0)):
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps, desc = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        if img is None or img.size == 0:
+            mono = lib().orbrefsrc_extract(self._h, None, 0, 0, 0, lapping[0], lapping[1], kps.ctypes.data,
+                                           desc.ctypes.data, cap, C.byref(n))
+        else:
+            img = np.ascontiguousarray(img, np.uint8)
+            mono = lib().orbrefsrc_extract(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0],
+                                           lapping[0], lapping[1], kps.ctypes.data, desc.ctypes.data, cap, C.byref(n))
+        if mono == -1000:
+            raise RuntimeError("capacity")
+        return mono, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def distribute(self, kps, min_x, max_x, min_y, max_y, n_want, level):
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        out = np.zeros(len(kps) + 8, KP_DTYPE)
+        n = lib().orbrefsrc_distribute(self._h, kps.ctypes.data, len(kps), min_x, max_x, min_y, max_y, n_want, level,
+                                       out.ctypes.data, len(out))
+        if n < 0:
+            raise RuntimeError("capacity")
+        return out[:n].copy()

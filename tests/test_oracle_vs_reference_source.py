@@ -1,0 +1,84 @@
+"""The oracle against the reference's OWN extractor source. oracle/_ref/liborbref_src.so is /root/reference/src/
+ORBextractor.cc compiled where it lies (oracle/Makefile, target `ref`) against stand-in OpenCV / TBB headers
+(oracle/ref_stubs): types with OpenCV's semantics, TBB executed serially, and the five image primitives
+(resize, GaussianBlur, FAST, copyMakeBorder, fastAtan2) forwarded to the oracle's restatements that
+test_oracle_primitives.py pins byte for byte to the real OpenCV 4.13 kernels. Everything else that runs here is the
+reference's code: the constructor tables, ComputePyramid, the cell loop with the iniTh -> minTh retry,
+DistributeOctTree / DivideNode / the sorted expansion, IC_Angle, computeOrbDescriptor, the mono / stereo assembly of
+operator(). CPU only; skipped where the reference tree was not available at build time."""
+import numpy as np
+import pytest
+
+from orb_slam3_fast_b200 import synth
+from oracle import orbref, refsrc
+
+pytestmark = pytest.mark.skipif(not refsrc.available(), reason="oracle/_ref not built (no /root/reference at build time)")
+
+
+def _same(params, img, lapping):
+    r = refsrc.ReferenceExtractor(*params)
+    o = orbref.Extractor(*params)
+    mono_r, k_r, d_r = r(img, lapping)
+    mono_o, k_o, d_o = o(img, lapping)
+    assert mono_r == mono_o and len(k_r) == len(k_o)
+    assert np.array_equal(k_r, k_o), np.nonzero(k_r != k_o)[0][:5]
+    assert np.array_equal(d_r, d_o)
+    return len(k_r)
+
+
+@pytest.mark.parametrize("params", [(1000, 1.2, 8, 20, 7), (1200, 1.2, 8, 20, 7), (2000, 1.2, 8, 20, 7),
+                                    (500, 1.5, 5, 15, 5), (300, 2.0, 3, 20, 7), (1500, 1.2, 10, 20, 7)])
+def test_constructor_tables(params):
+    """src/ORBextractor.cc:408-469: scale / sigma tables, per-level quotas, umax."""
+    r, o = refsrc.ReferenceExtractor(*params), orbref.Extractor(*params)
+    for a, b in zip(r.tables(), (o.scale, o.inv_scale, o.sigma2, o.inv_sigma2, o.features_per_level, o.umax)):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("kind,w,h,nfeat,lapping,seed", [
+    ("scene", 640, 480, 1000, (0, 0), 0), ("scene", 640, 480, 1000, (0, 1000), 1),   # BASELINE configs[0], both lappings
+    ("scene", 752, 480, 1200, (0, 0), 2), ("noise_blur", 752, 480, 1200, (0, 0), 3),  # configs[1]
+    ("scene", 1280, 720, 2000, (0, 1000), 4),                                         # configs[2]: x > 1000 goes to the front
+    ("uniform_noise", 640, 480, 1000, (0, 0), 5),                                     # 65 k candidates into the quadtree
+    ("low_contrast40", 640, 480, 1000, (0, 0), 6),                                    # minThFAST retry in most cells
+    ("scene", 241, 241, 300, (0, 0), 7), ("scene", 333, 517, 700, (100, 200), 8)])    # minimum size; partial lapping
+def test_extractor_equals_the_reference_source(kind, w, h, nfeat, lapping, seed):
+    img = synth.low_contrast(h, w, seed, 40) if kind == "low_contrast40" else synth.make(kind, h, w, seed)
+    n = _same((nfeat, 1.2, 8, 20, 7), img, lapping)
+    assert n > 0
+
+
+def test_stereo_pair_and_other_parameters():
+    left, right, _ = synth.stereo_pair(480, 752, 11)
+    for img in (left, right):
+        _same((1200, 1.2, 8, 20, 7), img, (0, 0))
+    img = synth.scene(480, 640, 12)
+    _same((800, 1.5, 5, 15, 5), img, (0, 0))
+    _same((600, 2.0, 3, 20, 7), img, (0, 0))
+    _same((1000, 1.2, 8, 20, 20), img, (0, 0))   # iniTh == minTh: the retry is the same call again
+
+
+def test_degenerate_images():
+    assert _same((1000, 1.2, 8, 20, 7), synth.constant(480, 640), (0, 0)) == 0       # N = 0: released descriptors
+    assert _same((1000, 1.2, 8, 20, 7), synth.low_contrast(480, 640, 1, 12), (0, 0)) == 0  # no corner at either threshold
+    r = refsrc.ReferenceExtractor(1000)
+    mono, k, d = r(None)
+    assert mono == -1 and len(k) == 0                                                # :1021, empty image
+    assert orbref.Extractor(1000)(None)[0] == -1
+
+
+def test_quadtree_of_the_reference_source_on_the_oracles_candidates():
+    """DistributeOctTree (:557-757) called directly: fed with the candidate list the oracle built for each level, the
+    reference's quadtree must return the oracle's kept keypoints in the oracle's order."""
+    img = synth.uniform_noise(480, 640, 21)
+    o = orbref.Extractor(1000)
+    o(img, (0, 0))
+    r = refsrc.ReferenceExtractor(1000)
+    for level in range(8):
+        w, h = o.level_dims(level)
+        cands = o.level_candidates(level)                       # minBorder-relative, octave 0, size 7, angle -1
+        kept = r.distribute(cands, 16, w - 16, 16, h - 16, int(o.features_per_level[level]), level)
+        want = o.level_keypoints(level)
+        assert len(kept) == len(want) and len(kept) > 0
+        assert np.array_equal(kept["x"] + 16, want["x"]) and np.array_equal(kept["y"] + 16, want["y"])
+        assert np.array_equal(kept["response"], want["response"])
