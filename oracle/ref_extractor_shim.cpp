@@ -63,7 +63,7 @@ int orbrefsrc_distribute(void* h, const void* kps_in, int n_in, int min_x, int m
                          int level, void* kps_out, int cap) {
   Access* ex = static_cast<Access*>(h);
   std::vector<cv::KeyPoint> in(n_in);
-  if (n_in) memcpy(in.data(), kps_in, (size_t)n_in * sizeof(cv::KeyPoint));
+  if (n_in) memcpy(static_cast<void*>(in.data()), kps_in, (size_t)n_in * sizeof(cv::KeyPoint));
   const std::vector<cv::KeyPoint> out = ex->DistributeOctTree(in, min_x, max_x, min_y, max_y, n_want, level);
   if ((int)out.size() > cap) return -1000;
   if (!out.empty()) memcpy(kps_out, out.data(), out.size() * sizeof(cv::KeyPoint));

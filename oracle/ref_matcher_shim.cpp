@@ -1,0 +1,152 @@
+// C entry points over the reference's own ORB_SLAM3::ORBmatcher (compiled from /root/reference/src/ORBmatcher.cc against
+// the stand-in world of oracle/ref_stubs/matcher_world.h). Same flat views and result conventions as the oracle's
+// functions of the same name (oracle/orbref.h), so a test compares the two outputs directly. TEST INFRASTRUCTURE.
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "ORBmatcher.h"
+
+using namespace ORB_SLAM3;
+
+namespace {
+cv::Mat rows32(const uint8_t* p, int n) { return cv::Mat(n, 32, CV_8UC1, const_cast<uint8_t*>(p), 32); }
+
+std::vector<cv::KeyPoint> keypoints(const orbx_kp* k, int n) {
+  std::vector<cv::KeyPoint> v(n);
+  if (n) memcpy(static_cast<void*>(v.data()), k, (size_t)n * sizeof(cv::KeyPoint));
+  return v;
+}
+
+void fill_common(FeatureHolder& h, const orbx_kp* kps, const uint8_t* desc, const float* u_right, int n,
+                 const float* scale_factors, const float* level_sigma2, int n_levels) {
+  h.N = n;
+  h.Nleft = h.NLeft = -1;
+  h.mvKeys = h.mvKeysUn = keypoints(kps, n);
+  h.mvuRight.assign(n, -1.f);
+  if (u_right) h.mvuRight.assign(u_right, u_right + n);
+  h.mDescriptors = rows32(desc, n);
+  if (scale_factors) h.mvScaleFactors.assign(scale_factors, scale_factors + n_levels);
+  if (level_sigma2) h.mvLevelSigma2.assign(level_sigma2, level_sigma2 + n_levels);
+}
+
+void fill_featvec(DBoW2::FeatureVector& fv, const orbx_featvec& c) {
+  for (int a = 0; a < c.n_nodes; a++)
+    fv[c.node_ids[a]] = std::vector<unsigned int>(c.indices + c.offsets[a], c.indices + c.offsets[a + 1]);
+}
+
+// a KeyFrame whose feature i holds MapPoint &points[i] when has_mappoint[i]
+struct KeyFrameWorld {
+  KeyFrame kf;
+  std::vector<MapPoint> points;
+  GeometricCamera camera;
+  explicit KeyFrameWorld(const orbx_keyframe_view* v) : points(v->n) {
+    fill_common(kf, v->kps, v->desc, v->u_right, v->n, v->scale_factors, v->level_sigma2, v->n_levels);
+    fill_featvec(kf.mFeatVec, v->featvec);
+    kf.mvpMapPoints.assign(v->n, nullptr);
+    for (int i = 0; i < v->n; i++)
+      if (v->has_mappoint && v->has_mappoint[i]) kf.mvpMapPoints[i] = &points[i];
+    kf.mpCamera = &camera;
+  }
+  int index_of(const MapPoint* p) const { return p ? (int)(p - points.data()) : -1; }
+};
+
+struct FrameWorld {
+  Frame f;
+  MapPoint occupied;  // stands for "a MapPoint with observations" on the keypoints flagged occupied
+  GeometricCamera camera;
+  explicit FrameWorld(const orbx_frame_view* v) {
+    fill_common(f, v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
+    f.view = v;
+    occupied.observations = 1;
+    f.mvpMapPoints.assign(v->n, nullptr);
+    for (int i = 0; i < v->n; i++)
+      if (v->occupied && v->occupied[i]) f.mvpMapPoints[i] = &occupied;
+    f.mpCamera = &camera;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int orbrefsrc_descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  return ORBmatcher::DescriptorDistance(rows32(a, 1), rows32(b, 1));
+}
+
+int orbrefsrc_search_by_projection_map(const orbx_frame_view* fv, const orbx_mappoints* mps, float th, float nnratio,
+                                       int far_points, float th_far, int32_t* assign) {
+  FrameWorld W(fv);
+  std::vector<MapPoint> pts(mps->m);
+  std::vector<MapPoint*> ptrs(mps->m);
+  for (int i = 0; i < mps->m; i++) {
+    MapPoint& p = pts[i];
+    p.mbTrackInView = mps->track_in_view[i] != 0;
+    p.mTrackProjX = mps->proj_x[i];
+    p.mTrackProjY = mps->proj_y[i];
+    p.mTrackProjXR = mps->proj_xr ? mps->proj_xr[i] : 0.f;
+    p.mnTrackScaleLevel = mps->level[i];
+    p.mTrackViewCos = mps->view_cos[i];
+    p.mTrackDepth = mps->depth[i];
+    p.observations = mps->has_obs[i] ? 1 : 0;
+    p.descriptor = rows32(mps->desc + (size_t)i * 32, 1);
+    ptrs[i] = &p;
+  }
+  ORBmatcher matcher(nnratio, true);
+  const int n = matcher.SearchByProjection(W.f, ptrs, th, far_points != 0, th_far);
+  for (int i = 0; i < fv->n; i++) {
+    const MapPoint* p = W.f.mvpMapPoints[i];
+    assign[i] = (p && p != &W.occupied) ? (int)(p - pts.data()) : -1;
+  }
+  return n;
+}
+
+int orbrefsrc_search_for_triangulation(const orbx_keyframe_view* v1, const orbx_keyframe_view* v2, const float* F12,
+                                       float ep_x, float ep_y, int only_stereo, int coarse, int check_orientation,
+                                       int32_t* matches12) {
+  KeyFrameWorld A(v1), B(v2);
+  memcpy(A.camera.F12, F12, sizeof(A.camera.F12));
+  // camera centre 1 at (ep_x, ep_y, 0), keyframe 2 at the origin, orthographic stand-in camera: ep = (ep_x, ep_y)
+  A.kf.pose = Sophus::SE3f(Eigen::Matrix3f(), Eigen::Vector3f(-ep_x, -ep_y, 0.f));
+  ORBmatcher matcher(0.6f, check_orientation != 0);
+  std::vector<std::pair<size_t, size_t>> pairs;
+  const int n = matcher.SearchForTriangulation(&A.kf, &B.kf, pairs, only_stereo != 0, coarse != 0);
+  for (int i = 0; i < v1->n; i++) matches12[i] = -1;
+  for (const auto& pr : pairs) matches12[pr.first] = (int32_t)pr.second;
+  return n;
+}
+
+int orbrefsrc_search_by_bow(const orbx_keyframe_view* kfv, const orbx_keyframe_view* frame, float nnratio,
+                            int check_orientation, int32_t* matches_f) {
+  KeyFrameWorld K(kfv);
+  Frame F;
+  fill_common(F, frame->kps, frame->desc, frame->u_right, frame->n, frame->scale_factors, nullptr, frame->n_levels);
+  fill_featvec(F.mFeatVec, frame->featvec);
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> out;
+  const int n = matcher.SearchByBoW(&K.kf, F, out);
+  for (int i = 0; i < frame->n; i++) matches_f[i] = K.index_of(out[i]);
+  return n;
+}
+
+int orbrefsrc_search_by_bow_kf(const orbx_keyframe_view* v1, const orbx_keyframe_view* v2, float nnratio,
+                               int check_orientation, int32_t* matches12) {
+  KeyFrameWorld A(v1), B(v2);
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> out;
+  const int n = matcher.SearchByBoW(&A.kf, &B.kf, out);
+  for (int i = 0; i < v1->n; i++) matches12[i] = B.index_of(out[i]);
+  return n;
+}
+
+int orbrefsrc_search_for_initialization(const orbx_frame_view* f1, const orbx_frame_view* f2, const float* prev_xy,
+                                        int window_size, float nnratio, int check_orientation, int32_t* matches12) {
+  FrameWorld A(f1), B(f2);
+  std::vector<cv::Point2f> prev(f1->n);
+  for (int i = 0; i < f1->n; i++) prev[i] = cv::Point2f(prev_xy[2 * i], prev_xy[2 * i + 1]);
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  std::vector<int> m12;
+  const int n = matcher.SearchForInitialization(A.f, B.f, prev, m12, window_size);
+  for (int i = 0; i < f1->n; i++) matches12[i] = m12[i];
+  return n;
+}
+}

@@ -1,0 +1,229 @@
+// Stand-in world for compiling the reference's src/ORBmatcher.cc where it lies (oracle/Makefile, target `ref`): the
+// headers Frame.h / KeyFrame.h / MapPoint.h pull in Eigen, Sophus, DBoW2's vocabulary, g2o and boost and cannot be used
+// here, so their include guards are pre-defined and the classes below offer exactly the members ORBmatcher.cc touches,
+// as plain data the test shim fills in. The matcher code that runs against them is the reference's own. TEST
+// INFRASTRUCTURE. Geometry types are small value types; the tests drive the projecting overloads with identity poses
+// and an orthographic stand-in camera so that no result depends on how a 3x3 product is associated.
+#ifndef ORBREF_STUB_MATCHER_WORLD_H_
+#define ORBREF_STUB_MATCHER_WORLD_H_
+#define FRAME_H
+#define KEYFRAME_H
+#define MAPPOINT_H
+#define FRAME_GRID_ROWS 48
+#define FRAME_GRID_COLS 64
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+#include <cmath>
+#include <map>
+#include <set>
+#include <tuple>
+#include <vector>
+
+#include <opencv2/opencv.hpp>
+#include <tbb/parallel_for.h>
+
+#include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+
+namespace Eigen {
+struct Vector2f {
+  float v[2];
+  Vector2f() : v{0, 0} {}
+  Vector2f(float a, float b) : v{a, b} {}
+  float operator()(int i) const { return v[i]; }
+  float& operator()(int i) { return v[i]; }
+};
+struct Vector3f {
+  float v[3];
+  Vector3f() : v{0, 0, 0} {}
+  Vector3f(float a, float b, float c) : v{a, b, c} {}
+  float operator()(int i) const { return v[i]; }
+  float& operator()(int i) { return v[i]; }
+  Vector3f operator-(const Vector3f& o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+  Vector3f operator+(const Vector3f& o) const { return Vector3f(v[0] + o.v[0], v[1] + o.v[1], v[2] + o.v[2]); }
+  Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
+  Vector3f operator*(float s) const { return Vector3f(v[0] * s, v[1] * s, v[2] * s); }
+  Vector3f operator-() const { return Vector3f(-v[0], -v[1], -v[2]); }
+  float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+  float norm() const { return std::sqrt(dot(*this)); }
+};
+struct Matrix3f {
+  float m[3][3];
+  Matrix3f() : m{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}} {}
+  float operator()(int i, int j) const { return m[i][j]; }
+  float& operator()(int i, int j) { return m[i][j]; }
+  Vector3f operator*(const Vector3f& p) const {
+    return Vector3f(m[0][0] * p.v[0] + m[0][1] * p.v[1] + m[0][2] * p.v[2],
+                    m[1][0] * p.v[0] + m[1][1] * p.v[1] + m[1][2] * p.v[2],
+                    m[2][0] * p.v[0] + m[2][1] * p.v[1] + m[2][2] * p.v[2]);
+  }
+  Matrix3f operator*(const Matrix3f& o) const {
+    Matrix3f r;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) r.m[i][j] = m[i][0] * o.m[0][j] + m[i][1] * o.m[1][j] + m[i][2] * o.m[2][j];
+    return r;
+  }
+  Matrix3f transpose() const {
+    Matrix3f r;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) r.m[i][j] = m[j][i];
+    return r;
+  }
+};
+}  // namespace Eigen
+
+namespace Sophus {
+struct SE3f {
+  Eigen::Matrix3f R;
+  Eigen::Vector3f t;
+  SE3f() {}
+  SE3f(const Eigen::Matrix3f& R_, const Eigen::Vector3f& t_) : R(R_), t(t_) {}
+  Eigen::Matrix3f rotationMatrix() const { return R; }
+  Eigen::Vector3f translation() const { return t; }
+  SE3f inverse() const { return SE3f(R.transpose(), -(R.transpose() * t)); }
+  Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return R * p + t; }
+  SE3f operator*(const SE3f& o) const { return SE3f(R * o.R, R * o.t + t); }
+};
+template <typename T>
+struct Sim3 {
+  Eigen::Matrix3f R;
+  Eigen::Vector3f t;
+  float s = 1.f;
+  Eigen::Matrix3f rotationMatrix() const { return R; }
+  Eigen::Vector3f translation() const { return t; }
+  float scale() const { return s; }
+  Sim3 inverse() const {
+    Sim3 r;
+    r.R = R.transpose();
+    r.s = 1.f / s;
+    r.t = -((R.transpose() * t) * (1.f / s));
+    return r;
+  }
+  Eigen::Vector3f operator*(const Eigen::Vector3f& p) const { return (R * p) * s + t; }
+};
+typedef Sim3<float> Sim3f;
+}  // namespace Sophus
+
+namespace ORB_SLAM3 {
+class Frame;
+class KeyFrame;
+class MapPoint;
+
+class GeometricCamera {
+ public:
+  virtual ~GeometricCamera() {}
+  // orthographic stand-in: the image point of (x, y, z) is (x, y); see the header comment
+  virtual Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f(p(0), p(1)); }
+  // Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:122-149) with F12 supplied by the test
+  float F12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
+                                 const Eigen::Matrix3f&, const Eigen::Vector3f&, const float, const float unc) {
+    const float a = kp1.pt.x * F12[0] + kp1.pt.y * F12[3] + F12[6];
+    const float b = kp1.pt.x * F12[1] + kp1.pt.y * F12[4] + F12[7];
+    const float c = kp1.pt.x * F12[2] + kp1.pt.y * F12[5] + F12[8];
+    const float num = a * kp2.pt.x + b * kp2.pt.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * unc;
+  }
+};
+
+class MapPoint {
+ public:
+  // what Frame::isInFrustum leaves on the point (include/MapPoint.h:172-180)
+  bool mbTrackInView = false, mbTrackInViewR = false;
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackProjYR = 0, mTrackDepth = 0, mTrackDepthR = 0;
+  int mnTrackScaleLevel = 0, mnTrackScaleLevelR = 0;
+  float mTrackViewCos = 0, mTrackViewCosR = 0;
+  long unsigned int mnLastFrameSeen = 0, mnFuseCandidateForKF = 0;
+  // state behind the accessors
+  bool bad = false;
+  int observations = 0, predicted_level = 0;
+  cv::Mat descriptor;
+  Eigen::Vector3f pos, normal;
+  float min_dist = 0, max_dist = 1e30f;
+  std::set<const KeyFrame*> in_keyframes;
+  int added_to = -1;          // AddObservation(pKF, idx) / Replace() records, for the Fuse tests
+  MapPoint* replaced_by = nullptr;
+
+  bool isBad() { return bad; }
+  int Observations() { return observations; }
+  cv::Mat GetDescriptor() { return descriptor.clone(); }
+  Eigen::Vector3f GetWorldPos() { return pos; }
+  Eigen::Vector3f GetNormal() { return normal; }
+  float GetMinDistanceInvariance() { return min_dist; }
+  float GetMaxDistanceInvariance() { return max_dist; }
+  int PredictScale(const float&, KeyFrame*) { return predicted_level; }
+  int PredictScale(const float&, Frame*) { return predicted_level; }
+  bool IsInKeyFrame(KeyFrame* kf) { return in_keyframes.count(kf) != 0; }
+  std::map<const KeyFrame*, int> index_in;
+  std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* kf) {
+    auto it = index_in.find(kf);
+    return std::make_tuple(it == index_in.end() ? -1 : it->second, -1);
+  }
+  void AddObservation(KeyFrame*, int idx) { added_to = idx; }
+  void Replace(MapPoint* other) { replaced_by = other; }
+};
+
+// members shared by the Frame and KeyFrame stand-ins
+class FeatureHolder {
+ public:
+  int N = 0, Nleft = -1, NLeft = -1;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+  std::vector<float> mvuRight, mvDepth;
+  cv::Mat mDescriptors;
+  std::vector<float> mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+  DBoW2::FeatureVector mFeatVec;
+  GeometricCamera* mpCamera = nullptr;
+  GeometricCamera* mpCamera2 = nullptr;
+  float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0, mb = 0;
+  float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+  Sophus::SE3f pose;
+  const orbx_frame_view* view = nullptr;  // grid + keypoints for GetFeaturesInArea (the oracle's restatement of it)
+
+  std::vector<size_t> features_in_area(float x, float y, float r, int minLevel, int maxLevel) const {
+    std::vector<int32_t> idx(view->n + 1);
+    const int n = orbref_features_in_area(view, x, y, r, minLevel, maxLevel, idx.data());
+    return std::vector<size_t>(idx.begin(), idx.begin() + n);
+  }
+  bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
+  Sophus::SE3f GetPose() const { return pose; }
+  Sophus::SE3f GetPoseInverse() const { return pose.inverse(); }
+  Sophus::SE3f GetRightPose() const { return pose; }
+  Sophus::SE3f GetRightPoseInverse() const { return pose.inverse(); }
+  Eigen::Vector3f GetCameraCenter() const { return pose.inverse().translation(); }
+  Eigen::Vector3f GetRightCameraCenter() const { return pose.inverse().translation(); }
+  Sophus::SE3f GetRelativePoseTrl() const { return Sophus::SE3f(); }
+};
+
+class Frame : public FeatureHolder {
+ public:
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<bool> mvbOutlier;
+  std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
+                                        const int maxLevel = -1, const bool bRight = false) const {
+    return features_in_area(x, y, r, minLevel, maxLevel);
+  }
+};
+
+class KeyFrame : public FeatureHolder {
+ public:
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  std::set<MapPoint*> GetMapPoints() {
+    std::set<MapPoint*> s;
+    for (MapPoint* p : mvpMapPoints)
+      if (p) s.insert(p);
+    return s;
+  }
+  MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+  void AddMapPoint(MapPoint* p, const size_t& idx) { mvpMapPoints[idx] = p; }
+  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r,
+                                        const bool bRight = false) const {
+    return features_in_area(x, y, r, -1, -1);
+  }
+};
+}  // namespace ORB_SLAM3
+using namespace std;  // the reference's headers leak it; ORBmatcher.h relies on that
+#endif

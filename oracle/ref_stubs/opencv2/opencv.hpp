@@ -110,6 +110,10 @@ class Mat {
   const T& at(int y, int x) const { return data[(size_t)y * step + x]; }
   uchar* ptr(int y = 0) { return data + (size_t)y * step; }
   const uchar* ptr(int y = 0) const { return data + (size_t)y * step; }
+  template <typename T>
+  T* ptr(int y = 0) { return reinterpret_cast<T*>(data + (size_t)y * step); }
+  template <typename T>
+  const T* ptr(int y = 0) const { return reinterpret_cast<const T*>(data + (size_t)y * step); }
   Mat rowRange(int a, int b) const {
     Mat m = *this;
     m.data = data + (size_t)a * step;

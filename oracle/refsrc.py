@@ -74,3 +74,67 @@ class ReferenceExtractor:
         if n < 0:
             raise RuntimeError("capacity")
         return out[:n].copy()
+
+
+# ---- the reference's own src/ORBmatcher.cc (oracle/_ref/liborbref_matcher_src.so) ---------------------------------
+_MPATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liborbref_matcher_src.so")
+_mlib = None
+
+
+def matcher_available():
+    return os.path.exists(_MPATH)
+
+
+def mlib():
+    global _mlib
+    if _mlib is None:
+        _mlib = C.CDLL(_MPATH)
+        for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
+                     "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
+                     "orbrefsrc_search_for_initialization"):
+            getattr(_mlib, name).restype = C.c_int
+    return _mlib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def descriptor_distance(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return mlib().orbrefsrc_descriptor_distance(_p(a), _p(b))
+
+
+def search_by_projection_map(fv, mps, th, nnratio, far_points=False, th_far=0.0):
+    assign = np.empty(max(fv.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_projection_map(fv.ref(), mps.ref(), C.c_float(th), C.c_float(nnratio),
+                                                  int(far_points), C.c_float(th_far), _p(assign))
+    return n, assign[:fv.struct.n]
+
+
+def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False, check_orientation=True):
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    m = np.empty(max(kf1.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_for_triangulation(kf1.ref(), kf2.ref(), _p(F), C.c_float(ep[0]), C.c_float(ep[1]),
+                                                  int(only_stereo), int(coarse), int(check_orientation), _p(m))
+    return n, m[:kf1.struct.n]
+
+
+def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):
+    m = np.empty(max(frame.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_bow(kf.ref(), frame.ref(), C.c_float(nnratio), int(check_orientation), _p(m))
+    return n, m[:frame.struct.n]
+
+
+def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
+    m = np.empty(max(kf1.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_bow_kf(kf1.ref(), kf2.ref(), C.c_float(nnratio), int(check_orientation), _p(m))
+    return n, m[:kf1.struct.n]
+
+
+def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, check_orientation=True):
+    prev = np.ascontiguousarray(prev_xy, np.float32).reshape(-1, 2)
+    m = np.empty(max(f1.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_for_initialization(f1.ref(), f2.ref(), _p(prev), int(window_size), C.c_float(nnratio),
+                                                   int(check_orientation), _p(m))
+    return n, m[:f1.struct.n]

@@ -1,0 +1,127 @@
+"""The oracle's matcher restatements against the reference's OWN src/ORBmatcher.cc. oracle/_ref/liborbref_matcher_src.so
+is that file (all 1975 lines, plus Thirdparty/DBoW2/DBoW2/FeatureVector.cpp) compiled where it lies (oracle/Makefile,
+target `ref`) against a stand-in world (oracle/ref_stubs/matcher_world.h): Frame / KeyFrame / MapPoint as plain data with
+the members the matcher touches (their real headers need Eigen, Sophus, g2o and boost), Frame::GetFeaturesInArea served by
+the oracle's restatement of it, TBB run serially, an orthographic stand-in camera whose epipolarConstrain evaluates
+Pinhole.cpp:136-148 on a supplied F12. The matching loops, thresholds, ratio tests, rotation histograms and bookkeeping
+that run are the reference's code. CPU only; skipped where the reference tree was not available at build time."""
+import numpy as np
+import pytest
+
+from orb_slam3_fast_b200 import synth
+from oracle import orbref, refsrc
+from test_oracle_matchers import _keyframes, _view
+
+pytestmark = pytest.mark.skipif(not refsrc.matcher_available(),
+                                reason="oracle/_ref not built (no /root/reference at build time)")
+f32 = np.float32
+
+
+def test_descriptor_distance():
+    """ORBmatcher::DescriptorDistance, src/ORBmatcher.cc:1959-1973 (the SWAR popcount)."""
+    a, b = synth.descriptors(500, 1), synth.descriptors(500, 2)
+    b[:20] = a[:20]
+    b[20:40] = ~a[20:40]
+    for i in range(500):
+        assert refsrc.descriptor_distance(a[i], b[i]) == orbref.descriptor_distance(a[i], b[i])
+
+
+def _frame(n, w, h, seed, stereo, occupied_rate=0.1):
+    rng = np.random.default_rng(seed)
+    kps = np.zeros(n, synth.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(0, w, n).astype(f32), rng.uniform(0, h, n).astype(f32)
+    kps["octave"] = rng.integers(0, 8, n)
+    kps["angle"] = rng.uniform(0, 360, n).astype(f32)
+    desc = synth.descriptors(n, seed)
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    ur = np.where(rng.random(n) < 0.7, kps["x"] - rng.uniform(1, 40, n), -1).astype(f32) if stereo else None
+    occ = (rng.random(n) < occupied_rate).astype(np.uint8)
+    return kps, desc, sf, orbref.make_frame_view(kps, desc, ur, occ, g, keep, sf)
+
+
+@pytest.mark.parametrize("stereo,th,nnratio,far,seed", [(True, 1.0, 0.8, True, 3), (False, 3.0, 0.8, False, 4),
+                                                        (True, 5.0, 0.6, True, 5), (True, 15.0, 0.9, False, 6)])
+def test_search_by_projection_map(stereo, th, nnratio, far, seed):
+    """SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints), :42-221 — row a13."""
+    kps, desc, sf, fv = _frame(600, 640, 480, seed, stereo)
+    mp = synth.local_map(kps, desc, 2000, 640, 480, 8, seed)
+    mps = orbref.make_mappoints(**mp)
+    n_o, a_o = orbref.search_by_projection_map(fv, mps, th, nnratio, far, 15.0)
+    n_r, a_r = refsrc.search_by_projection_map(fv, mps, th, nnratio, far, 15.0)
+    assert n_o > 30
+    assert n_r == n_o and np.array_equal(a_r, a_o)
+
+
+def _triangulation_case(seed):
+    w, h = 640, 400
+    left, right, _ = synth.stereo_pair(h, w, seed, d_min=5, d_max=30)
+    e1, e2 = orbref.Extractor(1200), orbref.Extractor(1200)
+    _, k1, d1 = e1(left)
+    _, k2, d2 = e2(right)
+    rng = np.random.default_rng(seed)
+    views_ = []
+    for k, d in ((k1, d1), (k2, d2)):
+        node_of = (d[:, 0].astype(np.int64) >> 4) * 16 + (d[:, 1].astype(np.int64) >> 4)
+        ids, inv = np.unique(node_of, return_inverse=True)
+        order = np.argsort(inv, kind="stable")
+        off = np.zeros(len(ids) + 1, np.int32)
+        off[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+        ur = np.where(rng.random(len(k)) < 0.5, k["x"] - 10, -1).astype(f32)
+        hm = (rng.random(len(k)) < 0.2).astype(np.uint8)
+        views_.append(orbref.make_keyframe_view(k, d, ur, hm, ids.astype(np.uint32), off, order.astype(np.uint32),
+                                                e1.scale, e1.sigma2))
+    return views_
+
+
+@pytest.mark.parametrize("only_stereo,coarse,check,ep", [(False, False, True, (1e6, 200.0)), (True, False, True, (1e6, 200.0)),
+                                                         (False, True, False, (320.0, 200.0)),
+                                                         (False, False, False, (100.0, 150.0))])
+def test_search_for_triangulation(only_stereo, coarse, check, ep):
+    """SearchForTriangulation, :886-1106 — row a15 (epipole gate, epipolar test, best-per-idx1, rotation histogram)."""
+    v1, v2 = _triangulation_case(5)
+    F12 = np.array([[1e-7, 2e-6, -3e-4], [-2e-6, 1e-7, -1], [4e-4, 1, 2e-2]], f32)
+    n_o, m_o = orbref.search_for_triangulation(v1, v2, F12, ep, only_stereo, coarse, check)
+    n_r, m_r = refsrc.search_for_triangulation(v1, v2, F12, ep, only_stereo, coarse, check)
+    assert n_o > 20
+    assert n_r == n_o and np.array_equal(m_r, m_o)
+
+
+@pytest.mark.parametrize("seed,nnratio,check", [(1, 0.7, True), (2, 0.9, False), (3, 0.6, True)])
+def test_search_by_bow_both_overloads(seed, nnratio, check):
+    """SearchByBoW(KeyFrame*, Frame&, ...) :230-404 and SearchByBoW(KeyFrame*, KeyFrame*, ...) :766-884."""
+    k1, k2 = _keyframes(seed)
+    n_o, m_o = orbref.search_by_bow(_view(k1), _view(k2), nnratio, check)
+    n_r, m_r = refsrc.search_by_bow(_view(k1), _view(k2), nnratio, check)
+    assert n_o > 20 and n_r == n_o and np.array_equal(m_r, m_o)
+    n_o, m_o = orbref.search_by_bow_kf(_view(k1), _view(k2), nnratio, check)
+    n_r, m_r = refsrc.search_by_bow_kf(_view(k1), _view(k2), nnratio, check)
+    assert n_o > 20 and n_r == n_o and np.array_equal(m_r, m_o)
+
+
+@pytest.mark.parametrize("seed,window,nnratio,check", [(6, 30, 0.9, True), (7, 60, 0.9, False), (8, 100, 0.7, True)])
+def test_search_for_initialization(seed, window, nnratio, check):
+    """SearchForInitialization, :618-764, with the serial executor in place of its tbb::parallel_for."""
+    rng = np.random.default_rng(seed)
+    n, w, h = 500, 640, 480
+    k1, _, sf, _ = _frame(n, w, h, seed, False, 0.0)
+    k1["octave"] = (rng.random(n) < 0.3).astype(np.int32) * rng.integers(1, 8, n)
+    d1 = synth.flip_bits(synth.descriptors(n, seed, 40), rng.integers(0, 12, n), rng)
+    perm = rng.permutation(n)
+    k2 = k1[perm].copy()
+    k2["x"] += rng.normal(0, 3, n).astype(f32)
+    k2["y"] += rng.normal(0, 3, n).astype(f32)
+    k2["angle"] = ((k2["angle"] + rng.normal(0, 20, n)) % 360).astype(f32)
+    d2 = synth.flip_bits(d1[perm], rng.integers(0, 30, n), rng)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    fvs = []
+    for k, d in ((k1, d1), (k2, d2)):
+        off, items = orbref.build_grid(k, 0.0, 0.0, inv_w, inv_h)
+        g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+        fvs.append(orbref.make_frame_view(k, d, None, np.zeros(n, np.uint8), g, keep, sf))
+    prev = np.stack([k1["x"], k1["y"]], axis=1)
+    n_o, m_o = orbref.search_for_initialization(fvs[0], fvs[1], prev, window, nnratio, check)
+    n_r, m_r = refsrc.search_for_initialization(fvs[0], fvs[1], prev, window, nnratio, check)
+    assert n_o > 30 and n_r == n_o and np.array_equal(m_r, m_o)
