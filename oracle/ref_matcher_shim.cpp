@@ -149,4 +149,77 @@ int orbrefsrc_search_for_initialization(const orbx_frame_view* f1, const orbx_fr
   for (int i = 0; i < f1->n; i++) matches12[i] = m12[i];
   return n;
 }
+
+// SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono = false), :1594-1806. The points of the
+// last frame are placed at (u, v, z) in front of an identity-pose current frame with the orthographic stand-in camera,
+// so x3Dc = (u, v, z) and uv = (u, v) exactly; mode = +1 / -1 / 0 puts the last frame in front of / behind / beside the
+// current one (bForward / bBackward / neither). octave, angle = LastFrame.mvKeys[i]; has_obs = Observations() > 0.
+int orbrefsrc_search_by_projection_last_frame(const orbx_frame_view* fv, int m, const float* u, const float* v,
+                                              const float* z, const int32_t* octave, const float* angle,
+                                              const uint8_t* has_obs, const uint8_t* desc, float th, float mbf, float mb,
+                                              int mode, int check_orientation, int32_t* assign) {
+  FrameWorld W(fv);
+  W.f.mbf = mbf;
+  W.f.mb = mb;
+  W.f.mnMinX = W.f.mnMinY = -1e9f;
+  W.f.mnMaxX = W.f.mnMaxY = 1e9f;
+  Frame last;
+  last.N = m;
+  last.Nleft = -1;
+  last.mvKeys.resize(m);
+  last.mvKeysUn.resize(m);
+  last.mvbOutlier.assign(m, false);
+  std::vector<MapPoint> pts(m);
+  last.mvpMapPoints.resize(m);
+  for (int i = 0; i < m; i++) {
+    last.mvKeys[i].octave = last.mvKeysUn[i].octave = octave[i];
+    last.mvKeys[i].angle = last.mvKeysUn[i].angle = angle[i];
+    pts[i].pos = Eigen::Vector3f(u[i], v[i], z[i]);
+    pts[i].observations = has_obs[i] ? 1 : 0;
+    pts[i].descriptor = rows32(desc + (size_t)i * 32, 1);
+    last.mvpMapPoints[i] = &pts[i];
+  }
+  last.pose = Sophus::SE3f(Eigen::Matrix3f(), Eigen::Vector3f(0.f, 0.f, mode > 0 ? 1.f : (mode < 0 ? -1.f : 0.f)));
+  ORBmatcher matcher(0.9f, check_orientation != 0);
+  const int n = matcher.SearchByProjection(W.f, last, th, false);
+  for (int i = 0; i < fv->n; i++) {
+    const MapPoint* p = W.f.mvpMapPoints[i];
+    assign[i] = (p && p != &W.occupied) ? (int)(p - pts.data()) : -1;
+  }
+  return n;
+}
+
+// SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist), :1808-1918.
+// Same placement; level = what MapPoint::PredictScale returns; found[i] puts point i into sAlreadyFound. Every keypoint
+// flagged occupied in fv holds a MapPoint (here any MapPoint blocks, :1862).
+int orbrefsrc_search_by_projection_keyframe(const orbx_frame_view* fv, int m, const float* u, const float* v,
+                                            const int32_t* level, const float* angle, const uint8_t* found,
+                                            const uint8_t* desc, float th, int orb_dist, int check_orientation,
+                                            int32_t* assign) {
+  FrameWorld W(fv);
+  W.f.mnMinX = W.f.mnMinY = -1e9f;
+  W.f.mnMaxX = W.f.mnMaxY = 1e9f;
+  KeyFrame kf;
+  kf.N = m;
+  kf.mvKeysUn.resize(m);
+  std::vector<MapPoint> pts(m);
+  kf.mvpMapPoints.resize(m);
+  std::set<MapPoint*> already;
+  for (int i = 0; i < m; i++) {
+    kf.mvKeysUn[i].angle = angle[i];
+    pts[i].pos = Eigen::Vector3f(u[i], v[i], 1.f);
+    pts[i].predicted_level = level[i];
+    pts[i].observations = 1;
+    pts[i].descriptor = rows32(desc + (size_t)i * 32, 1);
+    kf.mvpMapPoints[i] = &pts[i];
+    if (found[i]) already.insert(&pts[i]);
+  }
+  ORBmatcher matcher(0.9f, check_orientation != 0);
+  const int n = matcher.SearchByProjection(W.f, &kf, already, th, orb_dist);
+  for (int i = 0; i < fv->n; i++) {
+    const MapPoint* p = W.f.mvpMapPoints[i];
+    assign[i] = (p && p != &W.occupied) ? (int)(p - pts.data()) : -1;
+  }
+  return n;
+}
 }

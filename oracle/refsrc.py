@@ -91,7 +91,8 @@ def mlib():
         _mlib = C.CDLL(_MPATH)
         for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
-                     "orbrefsrc_search_for_initialization"):
+                     "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
+                     "orbrefsrc_search_by_projection_keyframe"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -138,3 +139,22 @@ def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, che
     n = mlib().orbrefsrc_search_for_initialization(f1.ref(), f2.ref(), _p(prev), int(window_size), C.c_float(nnratio),
                                                    int(check_orientation), _p(m))
     return n, m[:f1.struct.n]
+
+
+def search_by_projection_last_frame(fv, u, v, z, octave, angle, has_obs, desc, th, mbf, mb, mode, check_orientation=True):
+    a = [np.ascontiguousarray(x, t) for x, t in ((u, np.float32), (v, np.float32), (z, np.float32), (octave, np.int32),
+                                                 (angle, np.float32), (has_obs, np.uint8), (desc, np.uint8))]
+    assign = np.empty(max(fv.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_projection_last_frame(fv.ref(), len(a[0]), *[_p(x) for x in a], C.c_float(th),
+                                                         C.c_float(mbf), C.c_float(mb), int(mode),
+                                                         int(check_orientation), _p(assign))
+    return n, assign[:fv.struct.n]
+
+
+def search_by_projection_keyframe(fv, u, v, level, angle, found, desc, th, orb_dist, check_orientation=True):
+    a = [np.ascontiguousarray(x, t) for x, t in ((u, np.float32), (v, np.float32), (level, np.int32),
+                                                 (angle, np.float32), (found, np.uint8), (desc, np.uint8))]
+    assign = np.empty(max(fv.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_projection_keyframe(fv.ref(), len(a[0]), *[_p(x) for x in a], C.c_float(th),
+                                                       int(orb_dist), int(check_orientation), _p(assign))
+    return n, assign[:fv.struct.n]

@@ -125,3 +125,55 @@ def test_search_for_initialization(seed, window, nnratio, check):
     n_o, m_o = orbref.search_for_initialization(fvs[0], fvs[1], prev, window, nnratio, check)
     n_r, m_r = refsrc.search_for_initialization(fvs[0], fvs[1], prev, window, nnratio, check)
     assert n_o > 30 and n_r == n_o and np.array_equal(m_r, m_o)
+
+
+def _projected_case(seed, m, th, stereo):
+    kps, desc, sf, fv = _frame(700, 640, 480, seed, stereo)
+    rng = np.random.default_rng(seed + 99)
+    n = len(kps)
+    src = rng.integers(0, n, m)
+    anchored = rng.random(m) < 0.8
+    u = np.where(anchored, kps["x"][src] + rng.normal(0, 2.0, m), rng.uniform(0, 640, m)).astype(f32)
+    v = np.where(anchored, kps["y"][src] + rng.normal(0, 2.0, m), rng.uniform(0, 480, m)).astype(f32)
+    octave = np.where(anchored, kps["octave"][src], rng.integers(0, 8, m)).astype(np.int32)
+    angle = (np.where(anchored, kps["angle"][src] + rng.normal(0, 8.0, m), rng.uniform(0, 360, m)) % 360.0).astype(f32)
+    d = synth.flip_bits(desc[src], rng.integers(0, 70, m), rng)
+    return fv, sf, u, v, octave, angle, d, rng
+
+
+@pytest.mark.parametrize("mode,stereo,th,check,seed", [(1, True, 7.0, True, 0), (-1, True, 7.0, True, 1),
+                                                       (0, True, 15.0, True, 2), (0, False, 15.0, False, 3)])
+def test_search_by_projection_last_frame(mode, stereo, th, check, seed):
+    """SearchByProjection(Frame&, const Frame&, th, bMono), :1594-1806 — row a14: forward / backward / neither level
+    windows, the uRight gate computed inside (uv(0) - mbf * invzc), already-matched rule, rotation histogram."""
+    m, mbf, mb = 900, f32(47.9), f32(0.11)
+    fv, sf, u, v, octave, angle, d, rng = _projected_case(seed, m, th, stereo)
+    z = rng.uniform(0.5, 20.0, m).astype(f32)
+    has_obs = (rng.random(m) < 0.9).astype(np.uint8)
+    invz = (1.0 / z.astype(np.float64)).astype(f32)                       # const float invzc = 1.0 / x3Dc(2)
+    ur = (u - (mbf * invz).astype(f32)).astype(f32) if stereo else None   # uv(0) - CurrentFrame.mbf * invzc
+    lo = octave if mode > 0 else (np.zeros(m, np.int32) if mode < 0 else octave - 1)
+    hi = np.full(m, -1, np.int32) if mode > 0 else (octave if mode < 0 else octave + 1)
+    pts = orbref.make_projected(u, v, ur, (f32(th) * sf[octave]).astype(f32), lo.astype(np.int32), hi.astype(np.int32),
+                                angle, has_obs, d)
+    n_o, a_o = orbref.search_by_projection_frame(fv, pts, 100, check)
+    n_r, a_r = refsrc.search_by_projection_last_frame(fv, u, v, z, octave, angle, has_obs, d, th, mbf, mb, mode, check)
+    assert n_o > 30
+    assert n_r == n_o and np.array_equal(a_r, a_o)
+
+
+@pytest.mark.parametrize("th,orb_dist,check,seed", [(10.0, 100, True, 4), (3.0, 64, True, 5), (10.0, 100, False, 6)])
+def test_search_by_projection_keyframe(th, orb_dist, check, seed):
+    """SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist), :1808-1918 (relocalisation): window
+    [L-1, L+1], any MapPoint on the keypoint blocks, ORBdist, points in sAlreadyFound are skipped."""
+    m = 900
+    fv, sf, u, v, level, angle, d, rng = _projected_case(seed, m, th, False)
+    found = (rng.random(m) < 0.15).astype(np.uint8)
+    keep = np.flatnonzero(found == 0)
+    pts = orbref.make_projected(u[keep], v[keep], None, (f32(th) * sf[level[keep]]).astype(f32),
+                                (level[keep] - 1).astype(np.int32), (level[keep] + 1).astype(np.int32), angle[keep],
+                                np.ones(len(keep), np.uint8), d[keep])
+    n_o, a_o = orbref.search_by_projection_frame(fv, pts, orb_dist, check)
+    n_r, a_r = refsrc.search_by_projection_keyframe(fv, u, v, level, angle, found, d, th, orb_dist, check)
+    assert n_o > 30
+    assert n_r == n_o and np.array_equal(a_r, np.where(a_o >= 0, keep[np.maximum(a_o, 0)], -1))
