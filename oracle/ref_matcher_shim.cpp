@@ -222,4 +222,44 @@ int orbrefsrc_search_by_projection_keyframe(const orbx_frame_view* fv, int m, co
   }
   return n;
 }
+
+// Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight = false), :1108-1281 (sim3 == 0) and
+// Fuse(KeyFrame*, Sophus::Sim3f&, const vector<MapPoint*>&, th, vpReplacePoint), :1283-1390 (sim3 != 0). The KeyFrame sits
+// at the origin with the orthographic stand-in camera and holds no MapPoints, point i is placed at (u, v, z) with its
+// normal along the viewing ray, PredictScale returns level[i]. best_idx[i] = the keypoint the point was fused into
+// (read off AddObservation) or -1 when the reference left it alone (bestDist > TH_LOW or no candidate).
+int orbrefsrc_fuse(const orbx_frame_view* kfv, const float* inv_level_sigma2, int m, const float* u, const float* v,
+                   const float* z, const int32_t* level, const uint8_t* desc, float th, float mbf, int sim3,
+                   int32_t* best_idx) {
+  KeyFrame kf;
+  fill_common(kf, kfv->kps, kfv->desc, kfv->u_right, kfv->n, kfv->scale_factors, nullptr, kfv->n_levels);
+  kf.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + kfv->n_levels);
+  kf.view = kfv;
+  kf.mbf = mbf;
+  kf.mnMinX = kf.mnMinY = -1e9f;
+  kf.mnMaxX = kf.mnMaxY = 1e9f;
+  kf.mvpMapPoints.assign(kfv->n, nullptr);
+  GeometricCamera camera;
+  kf.mpCamera = &camera;
+  std::vector<MapPoint> pts(m);
+  std::vector<MapPoint*> ptrs(m);
+  for (int i = 0; i < m; i++) {
+    pts[i].pos = Eigen::Vector3f(u[i], v[i], z[i]);
+    pts[i].normal = pts[i].pos * 10.f;
+    pts[i].predicted_level = level[i];
+    pts[i].descriptor = rows32(desc + (size_t)i * 32, 1);
+    ptrs[i] = &pts[i];
+  }
+  ORBmatcher matcher(0.6f, true);
+  int n;
+  if (sim3) {
+    Sophus::Sim3f Scw;
+    std::vector<MapPoint*> replace(m, nullptr);
+    n = matcher.Fuse(&kf, Scw, ptrs, th, replace);
+  } else {
+    n = matcher.Fuse(&kf, ptrs, th, false);
+  }
+  for (int i = 0; i < m; i++) best_idx[i] = pts[i].added_to;
+  return n;
+}
 }

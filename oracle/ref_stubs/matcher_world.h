@@ -218,7 +218,10 @@ class KeyFrame : public FeatureHolder {
     return s;
   }
   MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
-  void AddMapPoint(MapPoint* p, const size_t& idx) { mvpMapPoints[idx] = p; }
+  bool record_only = true;  // the Fuse tests read the match off MapPoint::added_to and leave the graph alone
+  void AddMapPoint(MapPoint* p, const size_t& idx) {
+    if (!record_only) mvpMapPoints[idx] = p;
+  }
   std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r,
                                         const bool bRight = false) const {
     return features_in_area(x, y, r, -1, -1);

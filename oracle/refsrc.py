@@ -92,7 +92,7 @@ def mlib():
         for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
-                     "orbrefsrc_search_by_projection_keyframe"):
+                     "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -158,3 +158,13 @@ def search_by_projection_keyframe(fv, u, v, level, angle, found, desc, th, orb_d
     n = mlib().orbrefsrc_search_by_projection_keyframe(fv.ref(), len(a[0]), *[_p(x) for x in a], C.c_float(th),
                                                        int(orb_dist), int(check_orientation), _p(assign))
     return n, assign[:fv.struct.n]
+
+
+def fuse(kfv, inv_level_sigma2, u, v, z, level, desc, th, mbf, sim3=False):
+    a = [np.ascontiguousarray(x, t) for x, t in ((u, np.float32), (v, np.float32), (z, np.float32), (level, np.int32),
+                                                 (desc, np.uint8))]
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    best = np.empty(max(len(a[0]), 1), np.int32)
+    n = mlib().orbrefsrc_fuse(kfv.ref(), _p(s2), len(a[0]), *[_p(x) for x in a], C.c_float(th), C.c_float(mbf),
+                              int(sim3), _p(best))
+    return n, best[:len(a[0])]

@@ -177,3 +177,41 @@ def test_search_by_projection_keyframe(th, orb_dist, check, seed):
     n_r, a_r = refsrc.search_by_projection_keyframe(fv, u, v, level, angle, found, d, th, orb_dist, check)
     assert n_o > 30
     assert n_r == n_o and np.array_equal(a_r, np.where(a_o >= 0, keep[np.maximum(a_o, 0)], -1))
+
+
+@pytest.mark.parametrize("sim3,th,seed", [(False, 3.0, 4), (True, 3.0, 5), (False, 2.5, 6), (True, 4.0, 7)])
+def test_fuse_both_overloads(sim3, th, seed):
+    """Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight) :1108-1281 (chi-square gate 7.8 / 5.99, level window
+    [L-1, L], TH_LOW) and Fuse(KeyFrame*, Sophus::Sim3f&, ...) :1283-1390 (no gate): the keypoint each point is fused
+    into, read off MapPoint::AddObservation, against the oracle's best_idx / best_dist."""
+    rng = np.random.default_rng(seed)
+    n, m, w, h = 600, 900, 640, 480
+    kps = np.zeros(n, synth.KP_DTYPE)
+    kps["x"], kps["y"] = rng.uniform(0, w, n).astype(f32), rng.uniform(0, h, n).astype(f32)
+    kps["octave"] = rng.integers(0, 8, n)
+    desc = synth.descriptors(n, seed)
+    mbf = f32(47.9)
+    ur_k = np.where(rng.random(n) < 0.5, kps["x"] - rng.uniform(1, 30, n), -1).astype(f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    kfv = orbref.make_frame_view(kps, desc, ur_k, np.zeros(n, np.uint8), g, keep, sf)
+    src = rng.integers(0, n, m)
+    u = (kps["x"][src] + rng.normal(0, 1.5, m)).astype(f32)
+    v = (kps["y"][src] + rng.normal(0, 1.5, m)).astype(f32)
+    # depth consistent with the source keypoint's disparity where it has one, so that the stereo gate lets some through
+    disp = np.where(ur_k[src] >= 0, kps["x"][src] - ur_k[src] + rng.normal(0, 1.0, m), rng.uniform(1, 30, m))
+    z = (mbf / np.maximum(disp, 0.5)).astype(f32)
+    lev = np.clip(kps["octave"][src] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    d = synth.flip_bits(desc[src], rng.integers(0, 60, m), rng)
+    invz = (f32(1) / z).astype(f32)                       # const float invz = 1 / p3Dc(2)
+    pur = (u - (mbf * invz).astype(f32)).astype(f32)      # const float ur = uv(0) - bf * invz
+    pts = orbref.make_projected(u, v, pur, (f32(th) * sf[lev]).astype(f32), lev - 1, lev, np.zeros(m, f32),
+                                np.zeros(m, np.uint8), d)
+    inv_s2 = (1.0 / (sf * sf)).astype(f32)
+    bi, bd = orbref.fuse_match(kfv, inv_s2, pts, not sim3)
+    n_r, best_r = refsrc.fuse(kfv, inv_s2, u, v, z, lev, d, th, mbf, sim3)
+    want = np.where(bd <= 50, bi, -1)
+    assert (want >= 0).sum() > 50
+    assert n_r == (want >= 0).sum() and np.array_equal(best_r, want)
