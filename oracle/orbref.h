@@ -18,11 +18,16 @@
  *     every primitive below byte-for-byte against the real OpenCV 4.13.0 kernels through cv2, and
  *     tests/test_oracle_pipeline.py checks the whole extractor against an independent Python pipeline that drives the
  *     real cv2 kernels (oracle/cv2_pipeline.py), from which tests/golden/ is frozen.
- *   - MATCHERS (src/ORBmatcher.cc, Frame::ComputeStereoMatches): their translation units pull in Eigen, Sophus, DBoW2
- *     and boost through Frame.h / KeyFrame.h / MapPoint.h and cannot be compiled here, so their ORCHESTRATION parity is
- *     UNPINNED by reference code; every matcher restatement is instead cross-checked against a second, independently
- *     written Python restatement of the same reference lines (tests/test_oracle_matchers.py), and knn2 against
- *     cv2.BFMatcher itself.
+ *   - MATCHERS of src/ORBmatcher.cc (rows a11, a13-a15 and the §8f searches): pinned by the reference's OWN source too.
+ *     oracle/_ref/liborbref_matcher_src.so is /root/reference/src/ORBmatcher.cc compiled where it lies against the
+ *     stand-in Frame / KeyFrame / MapPoint world of ref_stubs/matcher_world.h (their real headers need Eigen, Sophus,
+ *     g2o, boost); tests/test_oracle_matchers_vs_reference_source.py requires the restatements below to equal it word
+ *     for word (DescriptorDistance, SearchByProjection x3, SearchForTriangulation, SearchByBoW x2,
+ *     SearchForInitialization, Fuse x2).
+ *   - Frame::ComputeStereoMatches (src/Frame.cc), MapPoint::ComputeDistinctiveDescriptors and DBoW2's transform cannot
+ *     be compiled here (their class declarations cannot be replaced without copying them): their ORCHESTRATION parity
+ *     is UNPINNED by reference code; each is cross-checked against a second, independently written Python restatement
+ *     of the same reference lines (tests/test_oracle_matchers.py), and knn2 against cv2.BFMatcher itself.
  *
  * Build: oracle/Makefile (g++ -O2, no -march=native, -ffp-contract=off: the reference is built without FMA,
  * CMakeLists.txt:13-18).
