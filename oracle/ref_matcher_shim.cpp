@@ -262,4 +262,45 @@ int orbrefsrc_fuse(const orbx_frame_view* kfv, const float* inv_level_sigma2, in
   for (int i = 0; i < m; i++) best_idx[i] = pts[i].added_to;
   return n;
 }
+
+// SearchByProjection(KeyFrame*, Sophus::Sim3f& Scw, const vector<MapPoint*>&, vector<MapPoint*>& vpMatched, th,
+// ratioHamming), :406-506 (with_kfs == 0) and the overload that also records the source KeyFrames, :508-616
+// (with_kfs != 0). Identity Scw, same placement as orbrefsrc_fuse. matched_in[i] != 0: keypoint i already holds a match.
+// assign[i] = index of the point written to vpMatched[i] by this call, or -1.
+int orbrefsrc_search_by_projection_sim3(const orbx_frame_view* kfv, const uint8_t* matched_in, int m, const float* u,
+                                        const float* v, const int32_t* level, const uint8_t* desc, int th,
+                                        float ratio_hamming, int with_kfs, int32_t* assign) {
+  KeyFrame kf;
+  fill_common(kf, kfv->kps, kfv->desc, kfv->u_right, kfv->n, kfv->scale_factors, nullptr, kfv->n_levels);
+  kf.view = kfv;
+  kf.mnMinX = kf.mnMinY = -1e9f;
+  kf.mnMaxX = kf.mnMaxY = 1e9f;
+  kf.mvpMapPoints.assign(kfv->n, nullptr);
+  GeometricCamera camera;
+  kf.mpCamera = &camera;
+  MapPoint earlier;
+  std::vector<MapPoint> pts(m);
+  std::vector<MapPoint*> ptrs(m), matched(kfv->n, nullptr);
+  for (int i = 0; i < kfv->n; i++)
+    if (matched_in[i]) matched[i] = &earlier;
+  for (int i = 0; i < m; i++) {
+    pts[i].pos = Eigen::Vector3f(u[i], v[i], 1.f);
+    pts[i].normal = pts[i].pos * 10.f;
+    pts[i].predicted_level = level[i];
+    pts[i].descriptor = rows32(desc + (size_t)i * 32, 1);
+    ptrs[i] = &pts[i];
+  }
+  ORBmatcher matcher(0.75f, true);
+  Sophus::Sim3f Scw;
+  int n;
+  if (with_kfs) {
+    KeyFrame source;
+    std::vector<KeyFrame*> kfs(m, &source), matched_kf(kfv->n, nullptr);
+    n = matcher.SearchByProjection(&kf, Scw, ptrs, kfs, matched, matched_kf, th, ratio_hamming);
+  } else {
+    n = matcher.SearchByProjection(&kf, Scw, ptrs, matched, th, ratio_hamming);
+  }
+  for (int i = 0; i < kfv->n; i++) assign[i] = (matched[i] && matched[i] != &earlier) ? (int)(matched[i] - pts.data()) : -1;
+  return n;
+}
 }

@@ -92,7 +92,8 @@ def mlib():
         for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
-                     "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse"):
+                     "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
+                     "orbrefsrc_search_by_projection_sim3"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -168,3 +169,12 @@ def fuse(kfv, inv_level_sigma2, u, v, z, level, desc, th, mbf, sim3=False):
     n = mlib().orbrefsrc_fuse(kfv.ref(), _p(s2), len(a[0]), *[_p(x) for x in a], C.c_float(th), C.c_float(mbf),
                               int(sim3), _p(best))
     return n, best[:len(a[0])]
+
+
+def search_by_projection_sim3(kfv, matched_in, u, v, level, desc, th, ratio_hamming, with_kfs=False):
+    a = [np.ascontiguousarray(x, t) for x, t in ((u, np.float32), (v, np.float32), (level, np.int32), (desc, np.uint8))]
+    mi = np.ascontiguousarray(matched_in, np.uint8)
+    assign = np.empty(max(kfv.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_projection_sim3(kfv.ref(), _p(mi), len(a[0]), *[_p(x) for x in a], int(th),
+                                                   C.c_float(ratio_hamming), int(with_kfs), _p(assign))
+    return n, assign[:kfv.struct.n]

@@ -215,3 +215,31 @@ def test_fuse_both_overloads(sim3, th, seed):
     want = np.where(bd <= 50, bi, -1)
     assert (want >= 0).sum() > 50
     assert n_r == (want >= 0).sum() and np.array_equal(best_r, want)
+
+
+@pytest.mark.parametrize("with_kfs,th,ratio,seed", [(False, 8, 1.0, 8), (True, 8, 1.0, 9), (False, 4, 1.5, 10)])
+def test_sim3_search_by_projection_is_the_projected_form(with_kfs, th, ratio, seed):
+    """SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming) :406-506 and its :508-616 twin are
+    the projected search with window [L-1, L], max_dist = TH_LOW * ratioHamming, no rotation check, every already
+    matched keypoint closed and every written keypoint closing (the mapping INTEGRATION.md gives for them)."""
+    m = 900
+    fv, sf, u, v, level, angle, d, rng = _projected_case(seed, m, float(th), False)
+    kps_n = fv.struct.n
+    matched_in = (rng.random(kps_n) < 0.1).astype(np.uint8)
+    # (the reference ignores the frame view's own `occupied` here; the oracle gets matched_in in that role below)
+    n_r, a_r = refsrc.search_by_projection_sim3(fv, matched_in, u, v, level, d, th, ratio, with_kfs)
+    fv2 = _with_occupied(seed, matched_in)
+    pts = orbref.make_projected(u, v, None, (f32(th) * sf[level]).astype(f32), (level - 1).astype(np.int32), level,
+                                angle, np.ones(m, np.uint8), d)
+    n_o, a_o = orbref.search_by_projection_frame(fv2, pts, int(np.floor(50 * ratio)), False)
+    assert n_o > 30
+    assert n_r == n_o and np.array_equal(a_r, a_o)
+
+
+def _with_occupied(seed, occupied):
+    """The frame of _projected_case(seed, ...) with another occupied mask."""
+    kps, desc, sf, _ = _frame(700, 640, 480, seed, False)
+    inv_w, inv_h = f32(64) / f32(640), f32(48) / f32(480)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    return orbref.make_frame_view(kps, desc, None, np.ascontiguousarray(occupied, np.uint8), g, keep, sf)
