@@ -303,4 +303,44 @@ int orbrefsrc_search_by_projection_sim3(const orbx_frame_view* kfv, const uint8_
   for (int i = 0; i < kfv->n; i++) assign[i] = (matched[i] && matched[i] != &earlier) ? (int)(matched[i] - pts.data()) : -1;
   return n;
 }
+
+// SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12, const Sophus::Sim3f& S12, th),
+// :1392-1592. Identity poses and S12, fx = fy = 1, cx = cy = 0: the MapPoint of feature i of KeyFrame k sits at
+// (u_k[i], v_k[i], 1) and projects to exactly that in the other KeyFrame. has_k[i]: feature i holds a MapPoint;
+// level_k[i] = what PredictScale returns for it; desc_k = MapPoint::GetDescriptor(). matches12[i1] = idx2 or -1.
+int orbrefsrc_search_by_sim3(const orbx_frame_view* v1, const orbx_frame_view* v2, const uint8_t* has1, const float* u1,
+                             const float* vv1, const int32_t* level1, const uint8_t* desc1, const uint8_t* has2,
+                             const float* u2, const float* vv2, const int32_t* level2, const uint8_t* desc2, float th,
+                             int32_t* matches12) {
+  KeyFrame kf[2];
+  std::vector<MapPoint> pts[2];
+  const orbx_frame_view* views[2] = {v1, v2};
+  const uint8_t* has[2] = {has1, has2};
+  const float* us[2] = {u1, u2};
+  const float* vs[2] = {vv1, vv2};
+  const int32_t* levels[2] = {level1, level2};
+  const uint8_t* descs[2] = {desc1, desc2};
+  for (int k = 0; k < 2; k++) {
+    const orbx_frame_view* v = views[k];
+    fill_common(kf[k], v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
+    kf[k].view = v;
+    kf[k].mnMinX = kf[k].mnMinY = -1e9f;
+    kf[k].mnMaxX = kf[k].mnMaxY = 1e9f;
+    pts[k].resize(v->n);
+    kf[k].mvpMapPoints.assign(v->n, nullptr);
+    for (int i = 0; i < v->n; i++) {
+      if (!has[k][i]) continue;
+      pts[k][i].pos = Eigen::Vector3f(us[k][i], vs[k][i], 1.f);
+      pts[k][i].predicted_level = levels[k][i];
+      pts[k][i].descriptor = rows32(descs[k] + (size_t)i * 32, 1);
+      kf[k].mvpMapPoints[i] = &pts[k][i];
+    }
+  }
+  ORBmatcher matcher(0.75f, true);
+  std::vector<MapPoint*> m12(v1->n, nullptr);
+  Sophus::Sim3f S12;
+  const int n = matcher.SearchBySim3(&kf[0], &kf[1], m12, S12, th);
+  for (int i = 0; i < v1->n; i++) matches12[i] = m12[i] ? (int)(m12[i] - pts[1].data()) : -1;
+  return n;
+}
 }

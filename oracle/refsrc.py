@@ -93,7 +93,7 @@ def mlib():
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
-                     "orbrefsrc_search_by_projection_sim3"):
+                     "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -178,3 +178,15 @@ def search_by_projection_sim3(kfv, matched_in, u, v, level, desc, th, ratio_hamm
     n = mlib().orbrefsrc_search_by_projection_sim3(kfv.ref(), _p(mi), len(a[0]), *[_p(x) for x in a], int(th),
                                                    C.c_float(ratio_hamming), int(with_kfs), _p(assign))
     return n, assign[:kfv.struct.n]
+
+
+def search_by_sim3(v1, v2, side1, side2, th):
+    """side = (has_mappoint u8[n], u f32[n], v f32[n], level i32[n], desc u8[n, 32]) per KeyFrame."""
+    args = []
+    for has, u, v, level, desc in (side1, side2):
+        args += [np.ascontiguousarray(has, np.uint8), np.ascontiguousarray(u, np.float32),
+                 np.ascontiguousarray(v, np.float32), np.ascontiguousarray(level, np.int32),
+                 np.ascontiguousarray(desc, np.uint8)]
+    m = np.empty(max(v1.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_sim3(v1.ref(), v2.ref(), *[_p(x) for x in args], C.c_float(th), _p(m))
+    return n, m[:v1.struct.n]

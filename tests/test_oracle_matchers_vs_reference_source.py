@@ -243,3 +243,51 @@ def _with_occupied(seed, occupied):
     off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
     g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
     return orbref.make_frame_view(kps, desc, None, np.ascontiguousarray(occupied, np.uint8), g, keep, sf)
+
+
+@pytest.mark.parametrize("th,seed", [(7.5, 11), (4.0, 12)])
+def test_search_by_sim3_is_two_gate_free_fuse_matches_plus_agreement(th, seed):
+    """SearchBySim3, :1392-1592 = per direction the gate-free matching loop of orbref.fuse_match with
+    bestDist <= TH_HIGH, then the mutual-agreement pass of :1575-1588 (the mapping INTEGRATION.md gives for it)."""
+    rng = np.random.default_rng(seed)
+    n, w, h = 500, 640, 480
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    k1 = np.zeros(n, synth.KP_DTYPE)
+    k1["x"], k1["y"] = rng.uniform(0, w, n).astype(f32), rng.uniform(0, h, n).astype(f32)
+    k1["octave"] = rng.integers(0, 8, n)
+    d1 = synth.descriptors(n, seed)
+    perm = rng.permutation(n)
+    k2 = k1[perm].copy()
+    k2["x"] += rng.normal(0, 1.5, n).astype(f32)
+    k2["y"] += rng.normal(0, 1.5, n).astype(f32)
+    d2 = synth.flip_bits(d1[perm], rng.integers(0, 60, n), rng)
+    views_, sides = [], []
+    for k, d in ((k1, d1), (k2, d2)):
+        off, items = orbref.build_grid(k, 0.0, 0.0, inv_w, inv_h)
+        g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+        views_.append(orbref.make_frame_view(k, d, None, np.zeros(n, np.uint8), g, keep, sf))
+        has = (rng.random(n) < 0.8).astype(np.uint8)
+        u = (k["x"] + rng.normal(0, 1.0, n)).astype(f32)          # where the feature's MapPoint projects in the OTHER KeyFrame
+        v = (k["y"] + rng.normal(0, 1.0, n)).astype(f32)
+        level = np.clip(k["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
+        sides.append((has, u, v, level, synth.flip_bits(d, rng.integers(0, 20, n), rng)))
+    n_r, m_r = refsrc.search_by_sim3(views_[0], views_[1], sides[0], sides[1], th)
+
+    def direction(src, dst_view):
+        has, u, v, level, d = src
+        keep = np.flatnonzero(has)
+        pts = orbref.make_projected(u[keep], v[keep], None, (f32(th) * sf[level[keep]]).astype(f32),
+                                    (level[keep] - 1).astype(np.int32), level[keep], np.zeros(len(keep), f32),
+                                    np.zeros(len(keep), np.uint8), d[keep])
+        bi, bd = orbref.fuse_match(dst_view, (1.0 / (sf * sf)).astype(f32), pts, False)
+        out = np.full(n, -1, np.int32)
+        out[keep] = np.where(bd <= 100, bi, -1)
+        return out
+    match1, match2 = direction(sides[0], views_[1]), direction(sides[1], views_[0])
+    want = np.full(n, -1, np.int32)
+    for i1 in range(n):
+        if match1[i1] >= 0 and match2[match1[i1]] == i1:
+            want[i1] = match1[i1]
+    assert (want >= 0).sum() > 30
+    assert n_r == (want >= 0).sum() and np.array_equal(m_r, want)
