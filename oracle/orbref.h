@@ -24,7 +24,9 @@
  *     g2o, boost); tests/test_oracle_matchers_vs_reference_source.py requires the restatements below to equal it word
  *     for word (DescriptorDistance, SearchByProjection x3, SearchForTriangulation, SearchByBoW x2,
  *     SearchForInitialization, Fuse x2).
- *   - Frame::ComputeStereoMatches (src/Frame.cc), MapPoint::ComputeDistinctiveDescriptors and DBoW2's transform cannot
+ *   - DBoW2's transform (orbref_bow_transform): pinned by DBoW2's own TemplatedVocabulary / FORB code as vendored by the
+ *     reference, compiled in place into oracle/_ref/liborbref_dbow2_src.so (tests/test_oracle_vs_reference_source.py).
+ *   - Frame::ComputeStereoMatches (src/Frame.cc) and MapPoint::ComputeDistinctiveDescriptors cannot
  *     be compiled here (their class declarations cannot be replaced without copying them): their ORCHESTRATION parity
  *     is UNPINNED by reference code; each is cross-checked against a second, independently written Python restatement
  *     of the same reference lines (tests/test_oracle_matchers.py), and knn2 against cv2.BFMatcher itself.

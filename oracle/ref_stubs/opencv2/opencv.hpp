@@ -18,6 +18,10 @@
 #include <functional>
 #include <iterator>
 #include <memory>
+#include <string>
+#include <sstream>
+#include <fstream>
+#include <iostream>
 #include <vector>
 
 #include "orbref.h"
@@ -26,6 +30,7 @@ typedef unsigned char uchar;
 #define CV_PI 3.1415926535897932384626433832795
 #define CV_8U 0
 #define CV_8UC1 0
+#define CV_32F 5 /* named by FORB::toMat32F, which is never called here */
 
 static inline int cvRound(double v) { return (int)lrint(v); }
 static inline int cvRound(float v) { return (int)lrintf(v); }
@@ -101,6 +106,7 @@ class Mat {
     memset(m.data, 0, (size_t)r * c);
     return m;
   }
+  void release() { *this = Mat(); }
   int type() const { return CV_8UC1; }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   size_t step1() const { return step; }
@@ -192,6 +198,29 @@ static inline void copyMakeBorder(InputArray src, OutputArray dst, int top, int 
   Mat d = dst.getMat();
   orbref_border101(s.data, s.cols, s.rows, (int)s.step, d.data, (int)d.step, top);
 }
+
+
+// cv::FileStorage / FileNode: DBoW2's TemplatedVocabulary has virtual save() / load() members that name them; they are
+// never called here (the vocabulary is loaded with the reference's own loadFromTextFile), so these only have to parse.
+struct FileNode {
+  FileNode operator[](const char*) const { return FileNode(); }
+  FileNode operator[](const std::string&) const { return FileNode(); }
+  FileNode operator[](int) const { return FileNode(); }
+  template <typename T>
+  operator T() const { return T(); }
+  size_t size() const { return 0; }
+};
+struct FileStorage {
+  enum { READ = 0, WRITE = 1 };
+  FileStorage() {}
+  FileStorage(const std::string&, int) {}
+  bool isOpened() const { return false; }
+  void release() {}
+  FileNode operator[](const std::string&) const { return FileNode(); }
+  FileNode operator[](const char*) const { return FileNode(); }
+};
+template <typename T>
+static inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 
 }  // namespace cv
 #endif

@@ -190,3 +190,66 @@ def search_by_sim3(v1, v2, side1, side2, th):
     m = np.empty(max(v1.struct.n, 1), np.int32)
     n = mlib().orbrefsrc_search_by_sim3(v1.ref(), v2.ref(), *[_p(x) for x in args], C.c_float(th), _p(m))
     return n, m[:v1.struct.n]
+
+
+# ---- DBoW2's own TemplatedVocabulary<FORB> as vendored by the reference (oracle/_ref/liborbref_dbow2_src.so) --------
+_VPATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "liborbref_dbow2_src.so")
+_vlib = None
+
+
+def vocabulary_available():
+    return os.path.exists(_VPATH)
+
+
+def vlib():
+    global _vlib
+    if _vlib is None:
+        _vlib = C.CDLL(_VPATH)
+        _vlib.orbrefsrc_voc_load.restype = C.c_void_p
+        _vlib.orbrefsrc_voc_load.argtypes = [C.c_char_p]
+        _vlib.orbrefsrc_voc_destroy.argtypes = [C.c_void_p]
+        _vlib.orbrefsrc_voc_size.argtypes = [C.c_void_p]
+        _vlib.orbrefsrc_voc_transform.restype = C.c_int
+        _vlib.orbrefsrc_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+    return _vlib
+
+
+def write_vocabulary_text(voc, k, path):
+    """The flat tree of synth.vocabulary in the text format TemplatedVocabulary::loadFromTextFile reads: header
+    'k L scoring weighting' (L1_NORM, TF_IDF), then one line per node in id order: parent, is_leaf, 32 bytes, weight."""
+    off, children = voc["child_offsets"], voc["children"]
+    n = len(off) - 1
+    parent = np.zeros(n, np.int64)
+    for p in range(n):
+        parent[children[off[p]:off[p + 1]]] = p
+    lines = ["%d %d 0 0" % (k, voc["depth"])]
+    for i in range(1, n):
+        leaf = int(off[i + 1] == off[i])
+        lines.append("%d %d %s %s" % (parent[i], leaf, " ".join(str(int(b)) for b in voc["descriptors"][i]),
+                                      repr(float(voc["weight"][i]))))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))          # no trailing newline: the loader would read one more (empty) node
+
+
+class ReferenceVocabulary:
+    def __init__(self, path):
+        self._h = vlib().orbrefsrc_voc_load(path.encode())
+        if not self._h:
+            raise RuntimeError("loadFromTextFile failed")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            vlib().orbrefsrc_voc_destroy(self._h)
+            self._h = None
+
+    def words(self):
+        return vlib().orbrefsrc_voc_size(self._h)
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        word, weight, node = np.empty(n, np.uint32), np.empty(n, np.float64), np.empty(n, np.uint32)
+        bw, bvals = np.empty(n + 1, np.uint32), np.empty(n + 1, np.float64)
+        k = vlib().orbrefsrc_voc_transform(self._h, _p(desc), n, levelsup, _p(word), _p(weight), _p(node), _p(bw),
+                                           _p(bvals), n + 1)
+        return word, weight, node, bw[:k], bvals[:k]

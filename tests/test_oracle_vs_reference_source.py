@@ -82,3 +82,51 @@ def test_quadtree_of_the_reference_source_on_the_oracles_candidates():
         assert len(kept) == len(want) and len(kept) > 0
         assert np.array_equal(kept["x"] + 16, want["x"]) and np.array_equal(kept["y"] + 16, want["y"])
         assert np.array_equal(kept["response"], want["response"])
+
+
+@pytest.mark.skipif(not refsrc.vocabulary_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,depth,levelsup,ragged,seed", [(10, 4, 4, True, 0), (10, 4, 2, True, 1), (6, 5, 3, True, 2),
+                                                         (10, 3, 4, False, 3), (4, 6, 1, True, 4)])
+def test_bow_transform_equals_dbow2_itself(tmp_path, k, depth, levelsup, ragged, seed):
+    """Frame::ComputeBoW (src/Frame.cc:846-851) -> TemplatedVocabulary::transform(features, BowVector, FeatureVector,
+    levelsup): DBoW2's own template (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h + FORB.cpp, compiled in place), fed a
+    synthetic tree through its own loadFromTextFile, against orbref.bow_transform + the host-side accumulation the
+    shim keeps (addWeight / addFeature for weight > 0, L1 normalisation)."""
+    voc = synth.vocabulary(k, depth, seed, ragged)
+    path = str(tmp_path / "voc.txt")
+    refsrc.write_vocabulary_text(voc, k, path)
+    rv = refsrc.ReferenceVocabulary(path)
+    assert rv.words() == int((np.diff(voc["child_offsets"]) == 0).sum())
+    rng = np.random.default_rng(seed)
+    leaves = np.flatnonzero(np.diff(voc["child_offsets"]) == 0)
+    # features: perturbed leaf descriptors (meaningful descents, ties at the duplicated siblings) + pure noise
+    feats = np.concatenate([synth.flip_bits(voc["descriptors"][rng.choice(leaves, 600)], rng.integers(0, 40, 600), rng),
+                            synth.descriptors(200, seed + 50)])
+    word_r, weight_r, node_r, bow_w, bow_v = rv.transform(feats, levelsup)
+    word_o, weight_o, node_o = orbref.bow_transform(orbref.make_vocabulary(**voc), feats, levelsup)
+    assert np.array_equal(word_r, word_o)
+    assert np.array_equal(weight_r.view(np.uint64), weight_o.view(np.uint64))
+    filed = weight_o > 0                                      # stopped words are filed nowhere (:1154)
+    assert filed.sum() > 500 and (~filed).sum() > 0
+    # A leaf above level m_L - levelsup (possible only in a ragged tree; ORBvoc is complete) never assigns *nid, and
+    # DBoW2's caller passes an uninitialised NodeId (TemplatedVocabulary.h:1149): undefined there, 0 in the oracle.
+    off, children = voc["child_offsets"], voc["children"]
+    depth_of = np.zeros(len(off) - 1, np.int64)
+    for p in range(len(off) - 1):
+        depth_of[children[off[p]:off[p + 1]]] = depth_of[p] + 1
+    leaf_node = leaves[word_o.astype(np.int64)]               # word ids number the leaves in node order
+    reached = depth_of[leaf_node] >= depth - levelsup
+    assert np.array_equal(node_r[filed & reached], node_o[filed & reached]) and (node_r[~filed] == 0xffffffff).all()
+    assert (node_o[~reached] == 0).all()
+    # the BowVector: per word the sum of its features' weights in feature order, then divided by the L1 norm
+    acc = {}
+    for w, x in zip(word_o[filed], weight_o[filed]):
+        acc[int(w)] = acc.get(int(w), 0.0) + float(x)
+    norm = 0.0
+    for w in sorted(acc):
+        norm += abs(acc[w])
+    want_w = np.array(sorted(acc), np.uint32)
+    want_v = np.array([acc[w] / norm for w in sorted(acc)])
+    assert np.array_equal(bow_w, want_w)
+    assert np.array_equal(bow_v.view(np.uint64), want_v.view(np.uint64))
+
