@@ -10,6 +10,9 @@ namespace {
 struct Access : ORB_SLAM3::ORBextractor {
   using ORB_SLAM3::ORBextractor::ORBextractor;
   using ORB_SLAM3::ORBextractor::DistributeOctTree;
+  using ORB_SLAM3::ORBextractor::ComputePyramid;
+  using ORB_SLAM3::ORBextractor::ComputeKeyPointsOctTree;
+  using ORB_SLAM3::ORBextractor::ComputeKeyPointsOctTree_;
   using ORB_SLAM3::ORBextractor::mnFeaturesPerLevel;
   using ORB_SLAM3::ORBextractor::umax;
 };
@@ -68,5 +71,26 @@ int orbrefsrc_distribute(void* h, const void* kps_in, int n_in, int min_x, int m
   if ((int)out.size() > cap) return -1000;
   if (!out.empty()) memcpy(kps_out, out.data(), out.size() * sizeof(cv::KeyPoint));
   return (int)out.size();
+}
+
+// ComputePyramid + one of the two keypoint stages: serial_twin != 0 runs ComputeKeyPointsOctTree (:886-999), else the
+// TBB twin ComputeKeyPointsOctTree_ (:759-885, the one operator() calls) under the serial executor. Keypoints of all
+// levels, level by level (level coordinates, octave / size / angle set); counts[nlevels] = keypoints per level.
+int orbrefsrc_keypoints(void* h, const unsigned char* img, int w, int h_img, int stride, int serial_twin, void* kps,
+                        int cap, int* counts) {
+  Access* ex = static_cast<Access*>(h);
+  cv::Mat image(h_img, w, CV_8UC1, const_cast<unsigned char*>(img), (size_t)stride);
+  ex->ComputePyramid(image);
+  std::vector<std::vector<cv::KeyPoint>> all;
+  if (serial_twin) ex->ComputeKeyPointsOctTree(all);
+  else ex->ComputeKeyPointsOctTree_(all);
+  int n = 0;
+  for (size_t l = 0; l < all.size(); l++) {
+    counts[l] = (int)all[l].size();
+    if (n + counts[l] > cap) return -1000;
+    if (counts[l]) memcpy(static_cast<char*>(kps) + (size_t)n * sizeof(cv::KeyPoint), all[l].data(), all[l].size() * sizeof(cv::KeyPoint));
+    n += counts[l];
+  }
+  return n;
 }
 }

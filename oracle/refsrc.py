@@ -66,6 +66,19 @@ class ReferenceExtractor:
             raise RuntimeError("capacity")
         return mono, kps[:n.value].copy(), desc[:n.value].copy()
 
+    def keypoints(self, img, serial_twin):
+        """Per-level keypoints after ComputePyramid + ComputeKeyPointsOctTree (serial twin) or its TBB twin."""
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 8 * self.nlevels + 64
+        kps, counts = np.zeros(cap, KP_DTYPE), np.zeros(self.nlevels, np.int32)
+        fn = lib().orbrefsrc_keypoints
+        fn.restype = C.c_int
+        n = fn(C.c_void_p(self._h), C.c_void_p(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0],
+               int(serial_twin), C.c_void_p(kps.ctypes.data), cap, C.c_void_p(counts.ctypes.data))
+        if n < 0:
+            raise RuntimeError("capacity")
+        return kps[:n].copy(), counts
+
     def distribute(self, kps, min_x, max_x, min_y, max_y, n_want, level):
         kps = np.ascontiguousarray(kps, KP_DTYPE)
         out = np.zeros(len(kps) + 8, KP_DTYPE)

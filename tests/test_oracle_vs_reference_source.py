@@ -130,3 +130,25 @@ def test_bow_transform_equals_dbow2_itself(tmp_path, k, depth, levelsup, ragged,
     assert np.array_equal(bow_w, want_w)
     assert np.array_equal(bow_v.view(np.uint64), want_v.view(np.uint64))
 
+
+
+@pytest.mark.parametrize("kind,w,h,nfeat,seed", [("scene", 752, 480, 1200, 31), ("uniform_noise", 640, 480, 1000, 32)])
+def test_both_keypoint_stages_of_the_reference_agree_with_the_oracle(kind, w, h, nfeat, seed):
+    """The oracle follows the serial ComputeKeyPointsOctTree (:886-999); operator() calls its TBB twin (:759-885). Run
+    serially the two give the same per-level keypoints (positions, responses, octave, size, angle), and those are the
+    oracle's level keypoints."""
+    img = synth.make(kind, h, w, seed)
+    r = refsrc.ReferenceExtractor(nfeat)
+    k_serial, c_serial = r.keypoints(img, True)
+    k_tbb, c_tbb = r.keypoints(img, False)
+    assert np.array_equal(c_serial, c_tbb) and np.array_equal(k_serial, k_tbb)
+    o = orbref.Extractor(nfeat)
+    o(img, (0, 0))
+    at = 0
+    for level in range(8):
+        want = o.level_keypoints(level)
+        got = k_serial[at:at + c_serial[level]]
+        at += c_serial[level]
+        assert len(got) == len(want)
+        for f in ("x", "y", "response", "octave", "size", "angle"):
+            assert np.array_equal(got[f], want[f]), (level, f)
