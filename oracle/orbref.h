@@ -26,10 +26,14 @@
  *     SearchForInitialization, Fuse x2).
  *   - DBoW2's transform (orbref_bow_transform): pinned by DBoW2's own TemplatedVocabulary / FORB code as vendored by the
  *     reference, compiled in place into oracle/_ref/liborbref_dbow2_src.so (tests/test_oracle_vs_reference_source.py).
- *   - Frame::ComputeStereoMatches (src/Frame.cc) and MapPoint::ComputeDistinctiveDescriptors cannot
- *     be compiled here (their class declarations cannot be replaced without copying them): their ORCHESTRATION parity
- *     is UNPINNED by reference code; each is cross-checked against a second, independently written Python restatement
- *     of the same reference lines (tests/test_oracle_matchers.py), and knn2 against cv2.BFMatcher itself.
+ *   - Frame::ComputeStereoMatches (src/Frame.cc:921-1084, row a12): pinned by the reference's own text. Frame.cc cannot
+ *     be compiled as a whole, so oracle/Makefile cuts this one function out of the reference file by its signature and
+ *     pipes it to the compiler inside the stand-in world (nothing but the object file is written); the test runs the
+ *     reference's operator() on both images + its ComputeStereoMatches and requires mvuRight / mvDepth to equal
+ *     orbref_stereo_match bit for bit.
+ *   - MapPoint::ComputeDistinctiveDescriptors (orbref_distinctive_descriptor) is the one function left UNPINNED by
+ *     reference code; it is cross-checked against a Python restatement (tests/test_oracle_primitives.py). knn2 is pinned
+ *     to cv2.BFMatcher itself.
  *
  * Build: oracle/Makefile (g++ -O2, no -march=native, -ffp-contract=off: the reference is built without FMA,
  * CMakeLists.txt:13-18).

@@ -343,4 +343,43 @@ int orbrefsrc_search_by_sim3(const orbx_frame_view* v1, const orbx_frame_view* v
   for (int i = 0; i < v1->n; i++) matches12[i] = m12[i] ? (int)(m12[i] - pts[1].data()) : -1;
   return n;
 }
+
+// The stereo Frame constructor's hot path with the reference's own code end to end: ORBextractor::operator() on both
+// images (vLappingArea = {0, 0}, src/Frame.cc:200-203), then Frame::ComputeStereoMatches (:921-1084, its text piped into
+// this library at build time). Outputs: keypoints / descriptors of both eyes (cap rows), mvuRight / mvDepth [n_l].
+int orbrefsrc_stereo_frame(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                           const unsigned char* img_l, const unsigned char* img_r, int w, int h, int stride, float mbf,
+                           float mb, void* kps_l, unsigned char* desc_l, int* n_l, void* kps_r, unsigned char* desc_r,
+                           int* n_r, float* u_right, float* depth, int cap) {
+  ORBextractor left(nfeatures, scale_factor, nlevels, ini_th, min_th), right(nfeatures, scale_factor, nlevels, ini_th, min_th);
+  Frame F;
+  F.mpORBextractorLeft = &left;
+  F.mpORBextractorRight = &right;
+  std::vector<int> lapping = {0, 0};
+  cv::Mat mask;
+  cv::Mat il(h, w, CV_8UC1, const_cast<unsigned char*>(img_l), (size_t)stride);
+  cv::Mat ir(h, w, CV_8UC1, const_cast<unsigned char*>(img_r), (size_t)stride);
+  left(il, mask, F.mvKeys, F.mDescriptors, lapping);
+  right(ir, mask, F.mvKeysRight, F.mDescriptorsRight, lapping);
+  F.N = (int)F.mvKeys.size();
+  F.mvScaleFactors = left.GetScaleFactors();
+  F.mvInvScaleFactors = left.GetInverseScaleFactors();
+  F.mbf = mbf;
+  F.mb = mb;
+  *n_l = F.N;
+  *n_r = (int)F.mvKeysRight.size();
+  if (*n_l > cap || *n_r > cap) return -1000;
+  F.ComputeStereoMatches();
+  if (*n_l) memcpy(kps_l, F.mvKeys.data(), (size_t)*n_l * sizeof(cv::KeyPoint));
+  if (*n_r) memcpy(kps_r, F.mvKeysRight.data(), (size_t)*n_r * sizeof(cv::KeyPoint));
+  for (int i = 0; i < *n_l; i++) memcpy(desc_l + (size_t)i * 32, F.mDescriptors.ptr(i), 32);
+  for (int i = 0; i < *n_r; i++) memcpy(desc_r + (size_t)i * 32, F.mDescriptorsRight.ptr(i), 32);
+  int matched = 0;
+  for (int i = 0; i < *n_l; i++) {
+    u_right[i] = F.mvuRight[i];
+    depth[i] = F.mvDepth[i];
+    matched += F.mvuRight[i] >= 0;
+  }
+  return matched;
+}
 }

@@ -23,6 +23,7 @@
 #include <tbb/parallel_for.h>
 
 #include "Thirdparty/DBoW2/DBoW2/FeatureVector.h"
+#include "ORBextractor.h"  // the reference's own header: Frame::ComputeStereoMatches reads mvImagePyramid of both
 
 namespace Eigen {
 struct Vector2f {
@@ -198,6 +199,12 @@ class FeatureHolder {
 
 class Frame : public FeatureHolder {
  public:
+  // what Frame::ComputeStereoMatches (src/Frame.cc:921-1084) reads and writes besides the shared members
+  ORBextractor* mpORBextractorLeft = nullptr;
+  ORBextractor* mpORBextractorRight = nullptr;
+  cv::Mat mDescriptorsRight;
+  std::vector<float> mvInvScaleFactors;
+  void ComputeStereoMatches();  // defined by the reference's own text, piped in at build time (oracle/Makefile)
   std::vector<MapPoint*> mvpMapPoints;
   std::vector<bool> mvbOutlier;
   std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;

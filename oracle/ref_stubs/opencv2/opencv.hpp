@@ -163,6 +163,18 @@ class _OutputArray {
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
 
+enum { NORM_L1 = 2 };
+// cv::norm(a, b, NORM_L1) of two 8-bit views of one size: the sum of absolute differences (exact in a double)
+static inline double norm(InputArray a, InputArray b, int type) {
+  assert(type == NORM_L1);
+  const Mat x = a.getMat(), y = b.getMat();
+  assert(x.rows == y.rows && x.cols == y.cols);
+  long long acc = 0;
+  for (int r = 0; r < x.rows; r++)
+    for (int c = 0; c < x.cols; c++) acc += std::abs((int)x.data[(size_t)r * x.step + c] - (int)y.data[(size_t)r * y.step + c]);
+  return (double)acc;
+}
+
 static inline float fastAtan2(float y, float x) { return orbref_fast_atan2(y, x); }
 
 static inline void FAST(InputArray image, std::vector<KeyPoint>& keypoints, int threshold, bool nonmax = true) {

@@ -106,7 +106,7 @@ def mlib():
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
-                     "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3"):
+                     "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -266,3 +266,21 @@ class ReferenceVocabulary:
         k = vlib().orbrefsrc_voc_transform(self._h, _p(desc), n, levelsup, _p(word), _p(weight), _p(node), _p(bw),
                                            _p(bvals), n + 1)
         return word, weight, node, bw[:k], bvals[:k]
+
+
+def stereo_frame(left, right, mbf, mb, nfeatures=1200, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """Both ORBextractor::operator() calls + Frame::ComputeStereoMatches, all of it the reference's own code.
+    Returns (n_matched, kps_l, desc_l, kps_r, desc_r, u_right, depth)."""
+    left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+    cap = nfeatures + 8 * nlevels + 64
+    kl, kr = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    dl, dr = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    nl, nr = C.c_int(0), C.c_int(0)
+    n = mlib().orbrefsrc_stereo_frame(nfeatures, C.c_float(scale_factor), nlevels, ini_th, min_th, _p(left), _p(right),
+                                      left.shape[1], left.shape[0], left.strides[0], C.c_float(mbf), C.c_float(mb),
+                                      _p(kl), _p(dl), C.byref(nl), _p(kr), _p(dr), C.byref(nr), _p(ur), _p(dp), cap)
+    if n == -1000:
+        raise RuntimeError("capacity")
+    return (n, kl[:nl.value].copy(), dl[:nl.value].copy(), kr[:nr.value].copy(), dr[:nr.value].copy(),
+            ur[:nl.value].copy(), dp[:nl.value].copy())

@@ -291,3 +291,23 @@ def test_search_by_sim3_is_two_gate_free_fuse_matches_plus_agreement(th, seed):
             want[i1] = match1[i1]
     assert (want >= 0).sum() > 30
     assert n_r == (want >= 0).sum() and np.array_equal(m_r, want)
+
+
+@pytest.mark.parametrize("w,h,nfeat,seed,kind", [(752, 480, 1200, 1, "scene"), (640, 480, 1000, 2, "scene"),
+                                                 (752, 480, 1200, 3, "noise_blur"), (400, 300, 600, 8, "scene")])
+def test_stereo_frame_hot_path_equals_the_reference_source(w, h, nfeat, seed, kind):
+    """Row a12 and the headline path end to end: ORBextractor::operator() on both images + Frame::ComputeStereoMatches
+    (src/Frame.cc:921-1084: row table, Hamming search, 11x11 SAD slide on the raw pyramid levels, parabola, median
+    filter), every line of it the reference's own text, against the oracle's extract x2 + stereo_match."""
+    left, right, _ = synth.stereo_pair(h, w, seed, kind=kind)
+    mbf, mb = float(f32(435.2 * 0.11)), float(f32(0.11))
+    n_r, kl_r, dl_r, kr_r, dr_r, ur_r, dp_r = refsrc.stereo_frame(left, right, mbf, mb, nfeat)
+    ex_l, ex_r = orbref.Extractor(nfeat), orbref.Extractor(nfeat)
+    _, kl, dl = ex_l(left)
+    _, kr, dr = ex_r(right)
+    assert np.array_equal(kl, kl_r) and np.array_equal(dl, dl_r) and np.array_equal(kr, kr_r) and np.array_equal(dr, dr_r)
+    n_o, ur_o, dp_o = orbref.stereo_match(ex_l, ex_r, kl, dl, kr, dr, mbf, mb)
+    assert n_o > 50
+    assert n_r == n_o
+    assert np.array_equal(ur_r.view(np.uint32), ur_o.view(np.uint32))
+    assert np.array_equal(dp_r.view(np.uint32), dp_o.view(np.uint32))
