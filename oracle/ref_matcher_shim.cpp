@@ -35,6 +35,24 @@ void fill_featvec(DBoW2::FeatureVector& fv, const orbx_featvec& c) {
     fv[c.node_ids[a]] = std::vector<unsigned int>(c.indices + c.offsets[a], c.indices + c.offsets[a + 1]);
 }
 
+// Frame::mGrid built by the reference's AssignFeaturesToGrid from mvKeysUn and the view's bounds / cell sizes
+void build_grid(Frame& f, const orbx_frame_view* v) {
+  f.mnMinX = v->grid.min_x;
+  f.mnMinY = v->grid.min_y;
+  f.mfGridElementWidthInv = v->grid.inv_w;
+  f.mfGridElementHeightInv = v->grid.inv_h;
+  f.AssignFeaturesToGrid();
+}
+
+// a KeyFrame over a frame view: features from the view, grid copied from a Frame as KeyFrame::KeyFrame does
+void keyframe_from_view(KeyFrame& kf, const orbx_frame_view* v) {
+  fill_common(kf, v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
+  Frame tmp;
+  fill_common(tmp, v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
+  build_grid(tmp, v);
+  kf.take_grid(tmp);
+}
+
 // a KeyFrame whose feature i holds MapPoint &points[i] when has_mappoint[i]
 struct KeyFrameWorld {
   KeyFrame kf;
@@ -57,7 +75,7 @@ struct FrameWorld {
   GeometricCamera camera;
   explicit FrameWorld(const orbx_frame_view* v) {
     fill_common(f, v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
-    f.view = v;
+    build_grid(f, v);
     occupied.observations = 1;
     f.mvpMapPoints.assign(v->n, nullptr);
     for (int i = 0; i < v->n; i++)
@@ -161,8 +179,7 @@ int orbrefsrc_search_by_projection_last_frame(const orbx_frame_view* fv, int m, 
   FrameWorld W(fv);
   W.f.mbf = mbf;
   W.f.mb = mb;
-  W.f.mnMinX = W.f.mnMinY = -1e9f;
-  W.f.mnMaxX = W.f.mnMaxY = 1e9f;
+  W.f.mnMaxX = W.f.mnMaxY = 1e9f;  // (mnMinX / mnMinY stay the grid origin)
   Frame last;
   last.N = m;
   last.Nleft = -1;
@@ -197,8 +214,7 @@ int orbrefsrc_search_by_projection_keyframe(const orbx_frame_view* fv, int m, co
                                             const uint8_t* desc, float th, int orb_dist, int check_orientation,
                                             int32_t* assign) {
   FrameWorld W(fv);
-  W.f.mnMinX = W.f.mnMinY = -1e9f;
-  W.f.mnMaxX = W.f.mnMaxY = 1e9f;
+  W.f.mnMaxX = W.f.mnMaxY = 1e9f;  // (mnMinX / mnMinY stay the grid origin)
   KeyFrame kf;
   kf.N = m;
   kf.mvKeysUn.resize(m);
@@ -232,11 +248,9 @@ int orbrefsrc_fuse(const orbx_frame_view* kfv, const float* inv_level_sigma2, in
                    const float* z, const int32_t* level, const uint8_t* desc, float th, float mbf, int sim3,
                    int32_t* best_idx) {
   KeyFrame kf;
-  fill_common(kf, kfv->kps, kfv->desc, kfv->u_right, kfv->n, kfv->scale_factors, nullptr, kfv->n_levels);
+  keyframe_from_view(kf, kfv);
   kf.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + kfv->n_levels);
-  kf.view = kfv;
   kf.mbf = mbf;
-  kf.mnMinX = kf.mnMinY = -1e9f;
   kf.mnMaxX = kf.mnMaxY = 1e9f;
   kf.mvpMapPoints.assign(kfv->n, nullptr);
   GeometricCamera camera;
@@ -271,9 +285,7 @@ int orbrefsrc_search_by_projection_sim3(const orbx_frame_view* kfv, const uint8_
                                         const float* v, const int32_t* level, const uint8_t* desc, int th,
                                         float ratio_hamming, int with_kfs, int32_t* assign) {
   KeyFrame kf;
-  fill_common(kf, kfv->kps, kfv->desc, kfv->u_right, kfv->n, kfv->scale_factors, nullptr, kfv->n_levels);
-  kf.view = kfv;
-  kf.mnMinX = kf.mnMinY = -1e9f;
+  keyframe_from_view(kf, kfv);
   kf.mnMaxX = kf.mnMaxY = 1e9f;
   kf.mvpMapPoints.assign(kfv->n, nullptr);
   GeometricCamera camera;
@@ -322,9 +334,7 @@ int orbrefsrc_search_by_sim3(const orbx_frame_view* v1, const orbx_frame_view* v
   const uint8_t* descs[2] = {desc1, desc2};
   for (int k = 0; k < 2; k++) {
     const orbx_frame_view* v = views[k];
-    fill_common(kf[k], v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
-    kf[k].view = v;
-    kf[k].mnMinX = kf[k].mnMinY = -1e9f;
+    keyframe_from_view(kf[k], v);
     kf[k].mnMaxX = kf[k].mnMaxY = 1e9f;
     pts[k].resize(v->n);
     kf[k].mvpMapPoints.assign(v->n, nullptr);
@@ -381,5 +391,37 @@ int orbrefsrc_stereo_frame(int nfeatures, float scale_factor, int nlevels, int i
     matched += F.mvuRight[i] >= 0;
   }
   return matched;
+}
+
+// Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:520-547, 833-844) as CSR in the oracle's cell order
+// (cell = col * 48 + row): offsets[64 * 48 + 1], items[n].
+void orbrefsrc_build_grid(const orbx_frame_view* v, int32_t* offsets, int32_t* items) {
+  Frame f;
+  fill_common(f, v->kps, v->desc, v->u_right, v->n, v->scale_factors, nullptr, v->n_levels);
+  build_grid(f, v);
+  int at = 0;
+  for (int c = 0; c < FRAME_GRID_COLS; c++)
+    for (int r = 0; r < FRAME_GRID_ROWS; r++) {
+      offsets[c * FRAME_GRID_ROWS + r] = at;
+      for (size_t i : f.mGrid[c][r]) items[at++] = (int32_t)i;
+    }
+  offsets[FRAME_GRID_COLS * FRAME_GRID_ROWS] = at;
+}
+
+// Frame::GetFeaturesInArea (:765-831) and, with keyframe != 0, KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:705-749,
+// no level filter). Returns the count written to out.
+int orbrefsrc_features_in_area(const orbx_frame_view* v, float x, float y, float r, int min_level, int max_level,
+                               int keyframe, int32_t* out) {
+  std::vector<size_t> idx;
+  if (keyframe) {
+    KeyFrame kf;
+    keyframe_from_view(kf, v);
+    idx = kf.GetFeaturesInArea(x, y, r);
+  } else {
+    FrameWorld W(v);
+    idx = W.f.GetFeaturesInArea(x, y, r, min_level, max_level);
+  }
+  for (size_t i = 0; i < idx.size(); i++) out[i] = (int32_t)idx[i];
+  return (int)idx.size();
 }
 }

@@ -1,7 +1,7 @@
 // Stand-in world for compiling the reference's src/ORBmatcher.cc where it lies (oracle/Makefile, target `ref`): the
 // headers Frame.h / KeyFrame.h / MapPoint.h pull in Eigen, Sophus, DBoW2's vocabulary, g2o and boost and cannot be used
 // here, so their include guards are pre-defined and the classes below offer exactly the members ORBmatcher.cc touches,
-// as plain data the test shim fills in. The matcher code that runs against them is the reference's own. TEST
+// as plain data the test shim fills in (their grid functions are the reference's own text, piped in by the Makefile). The matcher code that runs against them is the reference's own. TEST
 // INFRASTRUCTURE. Geometry types are small value types; the tests drive the projecting overloads with identity poses
 // and an orthographic stand-in camera so that no result depends on how a 3x3 product is associated.
 #ifndef ORBREF_STUB_MATCHER_WORLD_H_
@@ -180,13 +180,6 @@ class FeatureHolder {
   float fx = 1, fy = 1, cx = 0, cy = 0, mbf = 0, mb = 0;
   float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
   Sophus::SE3f pose;
-  const orbx_frame_view* view = nullptr;  // grid + keypoints for GetFeaturesInArea (the oracle's restatement of it)
-
-  std::vector<size_t> features_in_area(float x, float y, float r, int minLevel, int maxLevel) const {
-    std::vector<int32_t> idx(view->n + 1);
-    const int n = orbref_features_in_area(view, x, y, r, minLevel, maxLevel, idx.data());
-    return std::vector<size_t>(idx.begin(), idx.begin() + n);
-  }
   bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
   Sophus::SE3f GetPose() const { return pose; }
   Sophus::SE3f GetPoseInverse() const { return pose.inverse(); }
@@ -208,10 +201,15 @@ class Frame : public FeatureHolder {
   std::vector<MapPoint*> mvpMapPoints;
   std::vector<bool> mvbOutlier;
   std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+  // the grid (include/Frame.h:279, 372-373; the reference keeps the bounds static): AssignFeaturesToGrid, PosInGrid and
+  // GetFeaturesInArea are the reference's own text, piped in at build time (src/Frame.cc:520-547, 833-844, 765-831)
+  std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  void AssignFeaturesToGrid();
+  bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
   std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
-                                        const int maxLevel = -1, const bool bRight = false) const {
-    return features_in_area(x, y, r, minLevel, maxLevel);
-  }
+                                        const int maxLevel = -1, const bool bRight = false) const;
 };
 
 class KeyFrame : public FeatureHolder {
@@ -229,9 +227,20 @@ class KeyFrame : public FeatureHolder {
   void AddMapPoint(MapPoint* p, const size_t& idx) {
     if (!record_only) mvpMapPoints[idx] = p;
   }
-  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r,
-                                        const bool bRight = false) const {
-    return features_in_area(x, y, r, -1, -1);
+  // KeyFrame::GetFeaturesInArea is the reference's own text too (src/KeyFrame.cc:705-749); the grid is the Frame's,
+  // copied as the KeyFrame constructor does (src/KeyFrame.cc:109-121)
+  int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+  float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
+  std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+  void take_grid(const Frame& F) {
+    mnMinX = F.mnMinX;
+    mnMinY = F.mnMinY;
+    mfGridElementWidthInv = F.mfGridElementWidthInv;
+    mfGridElementHeightInv = F.mfGridElementHeightInv;
+    mGrid.assign(mnGridCols, std::vector<std::vector<size_t>>(mnGridRows));
+    for (int i = 0; i < mnGridCols; i++)
+      for (int j = 0; j < mnGridRows; j++) mGrid[i][j] = F.mGrid[i][j];
   }
 };
 }  // namespace ORB_SLAM3

@@ -106,7 +106,8 @@ def mlib():
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
-                     "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame"):
+                     "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
+                     "orbrefsrc_features_in_area"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -284,3 +285,16 @@ def stereo_frame(left, right, mbf, mb, nfeatures=1200, scale_factor=1.2, nlevels
         raise RuntimeError("capacity")
     return (n, kl[:nl.value].copy(), dl[:nl.value].copy(), kr[:nr.value].copy(), dr[:nr.value].copy(),
             ur[:nl.value].copy(), dp[:nl.value].copy())
+
+
+def build_grid(fv):
+    off, items = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(fv.struct.n, 1), np.int32)
+    mlib().orbrefsrc_build_grid(fv.ref(), _p(off), _p(items))
+    return off, items[:off[-1]]
+
+
+def features_in_area(fv, x, y, r, min_level=-1, max_level=-1, keyframe=False):
+    out = np.empty(max(fv.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_features_in_area(fv.ref(), C.c_float(x), C.c_float(y), C.c_float(r), int(min_level),
+                                          int(max_level), int(keyframe), _p(out))
+    return out[:n].copy()

@@ -1,8 +1,9 @@
 """The oracle's matcher restatements against the reference's OWN src/ORBmatcher.cc. oracle/_ref/liborbref_matcher_src.so
 is that file (all 1975 lines, plus Thirdparty/DBoW2/DBoW2/FeatureVector.cpp) compiled where it lies (oracle/Makefile,
 target `ref`) against a stand-in world (oracle/ref_stubs/matcher_world.h): Frame / KeyFrame / MapPoint as plain data with
-the members the matcher touches (their real headers need Eigen, Sophus, g2o and boost), Frame::GetFeaturesInArea served by
-the oracle's restatement of it, TBB run serially, an orthographic stand-in camera whose epipolarConstrain evaluates
+the members the matcher touches (their real headers need Eigen, Sophus, g2o and boost); their grid functions
+(AssignFeaturesToGrid, PosInGrid, both GetFeaturesInArea) and Frame::ComputeStereoMatches are the reference's own text
+too, cut out of src/Frame.cc / src/KeyFrame.cc by signature and piped to the compiler; TBB run serially, an orthographic stand-in camera whose epipolarConstrain evaluates
 Pinhole.cpp:136-148 on a supplied F12. The matching loops, thresholds, ratio tests, rotation histograms and bookkeeping
 that run are the reference's code. CPU only; skipped where the reference tree was not available at build time."""
 import numpy as np
@@ -135,6 +136,8 @@ def _projected_case(seed, m, th, stereo):
     anchored = rng.random(m) < 0.8
     u = np.where(anchored, kps["x"][src] + rng.normal(0, 2.0, m), rng.uniform(0, 640, m)).astype(f32)
     v = np.where(anchored, kps["y"][src] + rng.normal(0, 2.0, m), rng.uniform(0, 480, m)).astype(f32)
+    # inside the image bounds: the reference tests uv against mnMinX.. itself (the caller-side filter of the projected form)
+    u, v = np.clip(u, 0.5, 639.5).astype(f32), np.clip(v, 0.5, 479.5).astype(f32)
     octave = np.where(anchored, kps["octave"][src], rng.integers(0, 8, m)).astype(np.int32)
     angle = (np.where(anchored, kps["angle"][src] + rng.normal(0, 8.0, m), rng.uniform(0, 360, m)) % 360.0).astype(f32)
     d = synth.flip_bits(desc[src], rng.integers(0, 70, m), rng)
@@ -198,8 +201,8 @@ def test_fuse_both_overloads(sim3, th, seed):
     sf = f32(1.2) ** np.arange(8, dtype=f32)
     kfv = orbref.make_frame_view(kps, desc, ur_k, np.zeros(n, np.uint8), g, keep, sf)
     src = rng.integers(0, n, m)
-    u = (kps["x"][src] + rng.normal(0, 1.5, m)).astype(f32)
-    v = (kps["y"][src] + rng.normal(0, 1.5, m)).astype(f32)
+    u = np.clip(kps["x"][src] + rng.normal(0, 1.5, m), 0.5, w - 0.5).astype(f32)   # IsInImage is the caller-side filter
+    v = np.clip(kps["y"][src] + rng.normal(0, 1.5, m), 0.5, h - 0.5).astype(f32)
     # depth consistent with the source keypoint's disparity where it has one, so that the stereo gate lets some through
     disp = np.where(ur_k[src] >= 0, kps["x"][src] - ur_k[src] + rng.normal(0, 1.0, m), rng.uniform(1, 30, m))
     z = (mbf / np.maximum(disp, 0.5)).astype(f32)
@@ -268,8 +271,9 @@ def test_search_by_sim3_is_two_gate_free_fuse_matches_plus_agreement(th, seed):
         g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
         views_.append(orbref.make_frame_view(k, d, None, np.zeros(n, np.uint8), g, keep, sf))
         has = (rng.random(n) < 0.8).astype(np.uint8)
-        u = (k["x"] + rng.normal(0, 1.0, n)).astype(f32)          # where the feature's MapPoint projects in the OTHER KeyFrame
-        v = (k["y"] + rng.normal(0, 1.0, n)).astype(f32)
+        # where the feature's MapPoint projects in the OTHER KeyFrame (inside its image: IsInImage)
+        u = np.clip(k["x"] + rng.normal(0, 1.0, n), 0.5, w - 0.5).astype(f32)
+        v = np.clip(k["y"] + rng.normal(0, 1.0, n), 0.5, h - 0.5).astype(f32)
         level = np.clip(k["octave"] + rng.integers(0, 2, n), 0, 7).astype(np.int32)
         sides.append((has, u, v, level, synth.flip_bits(d, rng.integers(0, 20, n), rng)))
     n_r, m_r = refsrc.search_by_sim3(views_[0], views_[1], sides[0], sides[1], th)
@@ -311,3 +315,30 @@ def test_stereo_frame_hot_path_equals_the_reference_source(w, h, nfeat, seed, ki
     assert n_r == n_o
     assert np.array_equal(ur_r.view(np.uint32), ur_o.view(np.uint32))
     assert np.array_equal(dp_r.view(np.uint32), dp_o.view(np.uint32))
+
+
+def test_grid_functions():
+    """Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:520-547, 833-844), Frame::GetFeaturesInArea (:765-831) and
+    KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:705-749) — §8(f) rank 1 — against orbref.build_grid / features_in_area."""
+    rng = np.random.default_rng(41)
+    n, w, h = 900, 640, 480
+    kps = np.zeros(n, synth.KP_DTYPE)
+    kps["x"] = rng.uniform(-15, w + 15, n).astype(f32)       # undistorted keypoints may leave the image (:838-842)
+    kps["y"] = rng.uniform(-15, h + 15, n).astype(f32)
+    kps["x"][:40] = (np.round(kps["x"][:40] / 10) * 10 + 5).astype(f32)   # on cell-rounding boundaries (w / 64 = 10)
+    kps["octave"] = rng.integers(0, 8, n)
+    desc = synth.descriptors(n, 41)
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    fv = orbref.make_frame_view(kps, desc, None, np.zeros(n, np.uint8), g, keep, sf)
+    off_r, items_r = refsrc.build_grid(fv)
+    assert np.array_equal(off_r, off) and np.array_equal(items_r, items[:off[-1]])
+    for _ in range(400):
+        x, y = float(rng.uniform(-30, w + 30)), float(rng.uniform(-30, h + 30))
+        r = float(rng.choice([2.5, 7.0, 15.0, 40.0, 100.0]))
+        lo, hi = [(-1, -1), (0, 0), (3, -1), (0, 4), (2, 3), (5, 6)][int(rng.integers(0, 6))]
+        want = orbref.features_in_area(fv, x, y, r, lo, hi)
+        assert np.array_equal(refsrc.features_in_area(fv, x, y, r, lo, hi), want)
+        assert np.array_equal(refsrc.features_in_area(fv, x, y, r, keyframe=True), orbref.features_in_area(fv, x, y, r, -1, -1))
