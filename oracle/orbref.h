@@ -31,9 +31,9 @@
  *     pipes it to the compiler inside the stand-in world (nothing but the object file is written); the test runs the
  *     reference's operator() on both images + its ComputeStereoMatches and requires mvuRight / mvDepth to equal
  *     orbref_stereo_match bit for bit.
- *   - MapPoint::ComputeDistinctiveDescriptors (orbref_distinctive_descriptor) is the one function left UNPINNED by
- *     reference code; it is cross-checked against a Python restatement (tests/test_oracle_primitives.py). knn2 is pinned
- *     to cv2.BFMatcher itself.
+ *   - Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea, KeyFrame::GetFeaturesInArea and
+ *     MapPoint::ComputeDistinctiveDescriptors: piped in the same way and checked directly. knn2 is pinned to
+ *     cv2.BFMatcher itself. No function below is left without a reference-source (or, for the OpenCV primitives, cv2) pin.
  *
  * Build: oracle/Makefile (g++ -O2, no -march=native, -ffp-contract=off: the reference is built without FMA,
  * CMakeLists.txt:13-18).

@@ -424,4 +424,20 @@ int orbrefsrc_features_in_area(const orbx_frame_view* v, float x, float y, float
   for (size_t i = 0; i < idx.size(); i++) out[i] = (int32_t)idx[i];
   return (int)idx.size();
 }
+
+// MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:372-441): one observing KeyFrame per descriptor row (the
+// KeyFrames sit in one array, so the std::map<KeyFrame*, ...> visits them in row order). out[32] = mDescriptor.
+// Returns 0 when the reference left mDescriptor empty (no observation).
+int orbrefsrc_distinctive_descriptor(const uint8_t* desc, int n, uint8_t* out) {
+  std::vector<KeyFrame> kfs(n);
+  MapPoint mp;
+  for (int i = 0; i < n; i++) {
+    kfs[i].mDescriptors = rows32(desc + (size_t)i * 32, 1);
+    mp.mObservations[&kfs[i]] = std::make_tuple(0, -1);
+  }
+  mp.ComputeDistinctiveDescriptors();
+  if (mp.mDescriptor.empty()) return 0;
+  memcpy(out, mp.mDescriptor.ptr(0), 32);
+  return 1;
+}
 }

@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <set>
 #include <tuple>
 #include <vector>
@@ -129,8 +130,21 @@ class GeometricCamera {
   }
 };
 
+// std::mutex members would make the stand-ins immovable; the tests are single threaded
+struct CopyableMutex : std::mutex {
+  CopyableMutex() {}
+  CopyableMutex(const CopyableMutex&) {}
+  CopyableMutex& operator=(const CopyableMutex&) { return *this; }
+};
+
 class MapPoint {
  public:
+  // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:372-441) is the reference's own text, piped in at build time
+  CopyableMutex mMutexFeatures;
+  bool mbBad = false;
+  std::map<KeyFrame*, std::tuple<int, int>> mObservations;
+  cv::Mat mDescriptor;
+  void ComputeDistinctiveDescriptors();
   // what Frame::isInFrustum leaves on the point (include/MapPoint.h:172-180)
   bool mbTrackInView = false, mbTrackInViewR = false;
   float mTrackProjX = 0, mTrackProjY = 0, mTrackProjXR = 0, mTrackProjYR = 0, mTrackDepth = 0, mTrackDepthR = 0;
@@ -215,6 +229,7 @@ class Frame : public FeatureHolder {
 class KeyFrame : public FeatureHolder {
  public:
   std::vector<MapPoint*> mvpMapPoints;
+  bool isBad() { return false; }
   std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
   std::set<MapPoint*> GetMapPoints() {
     std::set<MapPoint*> s;

@@ -107,7 +107,7 @@ def mlib():
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
                      "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
-                     "orbrefsrc_features_in_area"):
+                     "orbrefsrc_features_in_area", "orbrefsrc_distinctive_descriptor"):
             getattr(_mlib, name).restype = C.c_int
     return _mlib
 
@@ -298,3 +298,11 @@ def features_in_area(fv, x, y, r, min_level=-1, max_level=-1, keyframe=False):
     n = mlib().orbrefsrc_features_in_area(fv.ref(), C.c_float(x), C.c_float(y), C.c_float(r), int(min_level),
                                           int(max_level), int(keyframe), _p(out))
     return out[:n].copy()
+
+
+def distinctive_descriptor(desc):
+    """MapPoint::ComputeDistinctiveDescriptors over the rows of desc: the chosen descriptor (32 bytes) or None."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    out = np.zeros(32, np.uint8)
+    ok = mlib().orbrefsrc_distinctive_descriptor(_p(desc), len(desc), _p(out))
+    return out if ok else None

@@ -342,3 +342,19 @@ def test_grid_functions():
         want = orbref.features_in_area(fv, x, y, r, lo, hi)
         assert np.array_equal(refsrc.features_in_area(fv, x, y, r, lo, hi), want)
         assert np.array_equal(refsrc.features_in_area(fv, x, y, r, keyframe=True), orbref.features_in_area(fv, x, y, r, -1, -1))
+
+
+def test_compute_distinctive_descriptors():
+    """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:372-441): all-pairs distances, per row the element
+    [0.5 (N - 1)] of the sorted row, first row with the least such median."""
+    rng = np.random.default_rng(51)
+    assert refsrc.distinctive_descriptor(np.zeros((0, 32), np.uint8)) is None and orbref.distinctive_descriptor(np.zeros((0, 32), np.uint8)) == -1
+    for n in list(range(1, 12)) + [17, 30, 64, 101]:
+        for proto in (0, 3):
+            base = synth.descriptors(1, int(rng.integers(1 << 30)))[0]
+            d = synth.flip_bits(np.repeat(base[None], n, 0), rng.integers(0, 60, n), rng)
+            if proto:
+                d[rng.integers(0, n, max(1, n // 3))] = d[0]       # duplicates: equal medians, the first row must win
+            got = refsrc.distinctive_descriptor(d)
+            idx = orbref.distinctive_descriptor(d)
+            assert idx >= 0 and np.array_equal(got, d[idx]), (n, proto)
