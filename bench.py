@@ -9,7 +9,8 @@ collective is the gather of the per-pair result counts). A stereo pair counts as
   value  device-resident: images already in HBM, results left in HBM, CUDA events on the launching stream.
   e2e    the same batch through the host-facing C ABI call orbm_stereo_frames_batch (pinned host buffers in and out,
          H2D / D2H inside the timed region).
-  --impl reference: the CPU oracle port of the reference (oracle/liborbref.so) on all host cores, same workload.
+  --impl reference: the reference's own sources compiled in place (oracle/_ref; else the CPU oracle port,
+                    oracle/liborbref.so) on all host cores, same workload.
 """
 import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA starts: 2 streams per pipeline lane (see orbx_api.cu)
@@ -85,10 +86,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def reference_sources_available():
+    """oracle/_ref holds the reference's own extractor + ComputeStereoMatches sources compiled in place (oracle/Makefile,
+    target `ref`; built where /root/reference exists and shipped with the snapshot)."""
+    try:
+        from oracle import refsrc
+        return refsrc.matcher_available()
+    except Exception:
+        return False
+
+
 def cpu_reference_run(n_pairs, threads, seed0=1000):
-    """Times the oracle port (extract x2 + ComputeStereoMatches per pair) on `threads` host threads."""
-    from oracle import orbref
+    """Times the CPU implementation of the path (extract x2 + ComputeStereoMatches per pair) on `threads` host threads:
+    the reference's own sources from oracle/_ref when they are there (kind "reference": its orchestration code over the
+    oracle's scalar image primitives, one pair per thread), else the oracle port (kind "port")."""
     L, R = make_pairs(min(n_pairs, 8), seed0)
+    if reference_sources_available():
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import refsrc
+        refsrc.mlib()
+        order = [i % len(L) for i in range(n_pairs)]
+
+        def one(i):  # ctypes releases the GIL for the duration of the call
+            return refsrc.stereo_frame(L[i], R[i], MBF, MB, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)[0]
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(one, order))
+        dt = time.perf_counter() - t0
+        return 2.0 * n_pairs / dt, dt
+    from oracle import orbref
     reps = (n_pairs + len(L) - 1) // len(L)
     L = np.ascontiguousarray(np.tile(L, (reps, 1, 1))[:n_pairs])
     R = np.ascontiguousarray(np.tile(R, (reps, 1, 1))[:n_pairs])
@@ -97,6 +123,20 @@ def cpu_reference_run(n_pairs, threads, seed0=1000):
     orbref.stereo_many(L, R, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, MBF, MB, threads)
     dt = time.perf_counter() - t0
     return 2.0 * n_pairs / dt, dt
+
+
+def cpu_kind():
+    return "reference" if reference_sources_available() else "port"
+
+
+CPU_NOTES = {
+    "reference": "the reference's own src/ORBextractor.cc + Frame::ComputeStereoMatches compiled in place (oracle/_ref) "
+                 "against stand-in OpenCV / TBB headers: its orchestration code, serial inside a frame, over the oracle's "
+                 "scalar cv2-pinned image primitives; pair-parallel over the host threads. The full library cannot be "
+                 "built here (OpenCV / TBB / Eigen / Sophus C++ are not installed)",
+    "port": "CPU oracle port of the reference's serial path, pair-parallel over all host threads; the reference itself "
+            "needs OpenCV/TBB/Eigen C++ and cannot be built here",
+}
 
 
 def opencv_primitives_ms():
@@ -148,9 +188,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_step": per_step, "frames_per_step": 2 * per_step,
-                       "note": "CPU oracle port of the reference's serial path, pair-parallel over all host threads; "
-                               "the reference itself needs OpenCV/TBB/Eigen C++ and cannot be built here"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                       "note": CPU_NOTES[cpu_kind()]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu_kind(),
                              "sample": "%d stereo pairs per step x %d steps" % (per_step, args.steps)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -396,20 +435,19 @@ def main():
            "api": "orbm_stereo_frames_batch (host buffers, pinned)", "ms_per_step": 1e3 * dt / e2e_steps,
            "group_pairs": G, "timer": "host wall clock around the synchronous ABI calls, max over ranks"}
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample, rank 0 at N = 1 only ----
+    # ---- CPU baseline: oracle/_ref (or the oracle port) on the host cores, bounded sample, rank 0 at N = 1 only ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         _, dt1 = cpu_reference_run(cores, cores)
         n_pairs = int(min(max(cores, 15.0 / max(dt1, 1e-3) * cores), 8192))
         fps, dtc = cpu_reference_run(n_pairs, cores)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": "%d stereo pairs (752x480, 1200 feat/eye), oracle port pair-parallel on %d threads, %.1f s"
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu_kind(),
+               "sample": "%d stereo pairs (752x480, 1200 feat/eye), pair-parallel on %d threads, %.1f s"
                          % (n_pairs, cores, dtc),
                "opencv_simd_primitives_ms_per_frame_1thread": opencv_primitives_ms(),
-               "note": "the port is scalar C++ (the reference itself cannot be built here); the cv2 figure is the time "
-                       "of resize + FAST + blur alone in OpenCV's SIMD build, a lower bound of the reference's "
-                       "per-frame extraction cost on this host"}
+               "note": CPU_NOTES[cpu_kind()] + "; the cv2 figure is the time of resize + FAST + blur alone in OpenCV's "
+                       "SIMD build, a lower bound of the reference's per-frame extraction cost on this host"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
