@@ -64,6 +64,30 @@ struct Matrix3f {
       for (int j = 0; j < 3; j++) r.m[i][j] = m[i][0] * o.m[0][j] + m[i][1] * o.m[1][j] + m[i][2] * o.m[2][j];
     return r;
   }
+  // `m << a, b, c, ...;` (row major) and inverse(): used by the reference-side shim bodies (shim/*.cc), not by the matcher
+  struct CommaInit {
+    Matrix3f* m;
+    int at;
+    CommaInit& operator,(float x) {
+      m->m[at / 3][at % 3] = x;
+      at++;
+      return *this;
+    }
+  };
+  CommaInit operator<<(float x) {
+    m[0][0] = x;
+    return CommaInit{this, 1};
+  }
+  Matrix3f inverse() const {
+    const float a = m[0][0], b = m[0][1], c = m[0][2], d = m[1][0], e = m[1][1], f = m[1][2], g = m[2][0], h = m[2][1],
+                i = m[2][2];
+    const float det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    Matrix3f r;
+    r.m[0][0] = (e * i - f * h) / det; r.m[0][1] = (c * h - b * i) / det; r.m[0][2] = (b * f - c * e) / det;
+    r.m[1][0] = (f * g - d * i) / det; r.m[1][1] = (a * i - c * g) / det; r.m[1][2] = (c * d - a * f) / det;
+    r.m[2][0] = (d * h - e * g) / det; r.m[2][1] = (b * g - a * h) / det; r.m[2][2] = (a * e - b * d) / det;
+    return r;
+  }
   Matrix3f transpose() const {
     Matrix3f r;
     for (int i = 0; i < 3; i++)
@@ -115,6 +139,7 @@ class GeometricCamera {
   virtual ~GeometricCamera() {}
   // orthographic stand-in: the image point of (x, y, z) is (x, y); see the header comment
   virtual Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f(p(0), p(1)); }
+  virtual Eigen::Matrix3f toK_() { return Eigen::Matrix3f(); }
   // Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:122-149) with F12 supplied by the test
   float F12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
@@ -219,7 +244,9 @@ class Frame : public FeatureHolder {
   // GetFeaturesInArea are the reference's own text, piped in at build time (src/Frame.cc:520-547, 833-844, 765-831)
   std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
   std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
-  float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  // static like the reference's (include/Frame.h:372-378); they hide the per-object fields of the shared base
+  static inline float mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+  static inline float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   void AssignFeaturesToGrid();
   bool PosInGrid(const cv::KeyPoint& kp, int& posX, int& posY);
   std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const int minLevel = -1,
@@ -248,6 +275,8 @@ class KeyFrame : public FeatureHolder {
   float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   std::vector<std::vector<std::vector<size_t>>> mGrid, mGridRight;
   std::vector<size_t> GetFeaturesInArea(const float& x, const float& y, const float& r, const bool bRight = false) const;
+  // the accessor shim/ORBmatcher_next_orbx.cc asks a maintainer to add next to mGrid
+  const std::vector<size_t>& GetGridCell(int c, int r) const { return mGrid[c][r]; }
   void take_grid(const Frame& F) {
     mnMinX = F.mnMinX;
     mnMinY = F.mnMinY;

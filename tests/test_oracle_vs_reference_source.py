@@ -152,3 +152,40 @@ def test_both_keypoint_stages_of_the_reference_agree_with_the_oracle(kind, w, h,
         assert len(got) == len(want)
         for f in ("x", "y", "response", "octave", "size", "angle"):
             assert np.array_equal(got[f], want[f]), (level, f)
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/src/Frame.cc"), reason="no reference tree")
+def test_reference_caller_text_compiles_against_the_shim_header():
+    """shim/ORBextractor.h claims header compatibility with include/ORBextractor.h for its callers. The caller on the hot
+    path is Frame::ComputeStereoMatches (reads mpORBextractorLeft/Right->mvImagePyramid, src/Frame.cc:927-1029): its own
+    text, cut out of the reference file, must compile with the shim's header in place of the reference's."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = subprocess.check_output(
+        ["awk", r"/^void Frame::ComputeStereoMatches\(\) \{/{p=1} p{print} p&&/^}/{p=0}", "/root/reference/src/Frame.cc"],
+        text=True)
+    assert text.count("mvImagePyramid") >= 3
+    src = ('#include <climits>\n#include "ORBmatcher.h"\n'
+           "static_assert(sizeof(&ORB_SLAM3::ORBextractor::SetPyramidMirror) > 0, \"the shim header is the one in use\");\n"
+           "namespace ORB_SLAM3 {\n" + text + "}\n")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-include", "oracle/ref_stubs/matcher_world.h", "-Ishim",
+           "-Ioracle/ref_stubs", "-Ioracle", "-Iinclude", "-I/root/reference/include", "-I/root/reference", "-x", "c++", "-"]
+    r = subprocess.run(cmd, input=src, text=True, cwd=root, capture_output=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/include/ORBmatcher.h"), reason="no reference tree")
+@pytest.mark.parametrize("name", ["ORBmatcher_orbx.cc", "FrameStereo_orbx.cc", "ORBmatcher_next_orbx.cc"])
+def test_reference_side_shim_bodies_compile_against_the_reference_class(name):
+    """shim/*.cc are the bodies a maintainer drops in place of the reference's ORBmatcher / Frame methods. They need the
+    reference's headers, so they can only be type-checked where the tree exists: against the reference's own
+    include/ORBmatcher.h (the class declaration they must match) over the stand-in Frame / KeyFrame / MapPoint world."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-include", "oracle/ref_stubs/matcher_world.h", "-Ishim",
+           "-Ioracle/ref_stubs", "-Ioracle", "-Iinclude", "-I/root/reference/include", "-I/root/reference",
+           os.path.join("shim", name)]
+    r = subprocess.run(cmd, text=True, cwd=root, capture_output=True)
+    assert r.returncode == 0, r.stderr[-2000:]
