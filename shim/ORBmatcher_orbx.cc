@@ -108,8 +108,9 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
     lo.push_back(bForward ? nLastOctave : (bBackward ? 0 : nLastOctave - 1));
     hi.push_back(bForward ? -1 : (bBackward ? nLastOctave : nLastOctave + 1));
     angle.push_back(LastFrame.mvKeysUn[i].angle);
-    has_obs.push_back(1);
-    desc.insert(desc.end(), pMP->GetDescriptor().data, pMP->GetDescriptor().data + 32);
+    has_obs.push_back(pMP->Observations() > 0);  // temporal stereo points of UpdateLastFrame have none: they do not block (:1663)
+    const cv::Mat d = pMP->GetDescriptor();      // a clone per call: take the range from ONE of them
+    desc.insert(desc.end(), d.data, d.data + 32);
     src.push_back(i);
   }
   FrameFlat ff(CurrentFrame);

@@ -80,10 +80,11 @@ def _triangulation_case(seed):
 @pytest.mark.parametrize("only_stereo,coarse,check,ep", [(False, False, True, (1e6, 200.0)), (True, False, True, (1e6, 200.0)),
                                                          (False, True, False, (320.0, 200.0)),
                                                          (False, False, False, (100.0, 150.0))])
-def test_search_for_triangulation(only_stereo, coarse, check, ep):
+def test_search_for_triangulation(only_stereo, coarse, check, ep, F12=None):
     """SearchForTriangulation, :886-1106 — row a15 (epipole gate, epipolar test, best-per-idx1, rotation histogram)."""
     v1, v2 = _triangulation_case(5)
-    F12 = np.array([[1e-7, 2e-6, -3e-4], [-2e-6, 1e-7, -1], [4e-4, 1, 2e-2]], f32)
+    if F12 is None:
+        F12 = np.array([[1e-7, 2e-6, -3e-4], [-2e-6, 1e-7, -1], [4e-4, 1, 2e-2]], f32)
     n_o, m_o = orbref.search_for_triangulation(v1, v2, F12, ep, only_stereo, coarse, check)
     n_r, m_r = refsrc.search_for_triangulation(v1, v2, F12, ep, only_stereo, coarse, check)
     assert n_o > 20

@@ -1,0 +1,64 @@
+"""The reference-side drop-in bodies (shim/ORBmatcher_orbx.cc, shim/ORBmatcher_next_orbx.cc) against the reference's own
+ORBmatcher.cc, on the CPU: oracle/_ref/libshim_world.so links the shim bodies IN PLACE OF the reference's methods of the
+same name (they are listed first; the linker keeps the first definition), over the stand-in Frame / KeyFrame / MapPoint
+world, with the orbm C ABI answered by the oracle (tests/mock_orbm_oracle.cpp) instead of the CUDA library. What this
+exercises is the shim's glue: flattening the pointer graph into the views, the host-side projection, scattering the
+answers back. The same comparisons as tests/test_oracle_matchers_vs_reference_source.py are then run through it."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refsrc
+import test_oracle_matchers_vs_reference_source as T
+
+_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libshim_world.so")
+pytestmark = pytest.mark.skipif(not os.path.exists(_PATH), reason="oracle/_ref/libshim_world.so not built")
+
+
+@pytest.fixture()
+def shim_world(monkeypatch):
+    lib = C.CDLL(_PATH)
+    for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
+                 "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
+                 "orbrefsrc_features_in_area"):
+        getattr(lib, name).restype = C.c_int
+    refsrc.mlib()
+    monkeypatch.setattr(refsrc, "_mlib", lib)
+    return lib
+
+
+@pytest.mark.parametrize("args", [(True, 1.0, 0.8, True, 3), (False, 3.0, 0.8, False, 4), (True, 5.0, 0.6, True, 5)])
+def test_shim_search_by_projection_map(shim_world, args):
+    T.test_search_by_projection_map(*args)
+
+
+@pytest.mark.parametrize("args", [(1, True, 7.0, True, 0), (-1, True, 7.0, True, 1), (0, True, 15.0, True, 2),
+                                  (0, False, 15.0, False, 3)])
+def test_shim_search_by_projection_last_frame(shim_world, args):
+    T.test_search_by_projection_last_frame(*args)
+
+
+@pytest.mark.parametrize("args", [(False, False, True, (1e6, 200.0)), (True, False, True, (1e6, 200.0)),
+                                  (False, True, False, (320.0, 200.0)), (False, False, False, (-5000.0, 200.0))])
+def test_shim_search_for_triangulation(shim_world, args):
+    # the shim computes F12 itself (K1^-T [t12]x R12 K2^-1, src/CameraModels/Pinhole.cpp:130-133) from the KeyFrame poses:
+    # identity intrinsics and rotation in the stand-in world, t12 = (-ep_x, -ep_y, 0)  =>  F12 = [t12]x
+    ex, ey = args[3]
+    F12 = np.array([[0, 0, -ey], [0, 0, ex], [ey, -ex, 0]], np.float32)
+    T.test_search_for_triangulation(*args, F12=F12)
+
+
+@pytest.mark.parametrize("args", [(1, 0.7, True), (2, 0.9, False), (3, 0.6, True)])
+def test_shim_search_by_bow(shim_world, args):
+    T.test_search_by_bow_both_overloads(*args)
+
+
+@pytest.mark.parametrize("args", [(False, 3.0, 4), (False, 2.5, 6)])
+def test_shim_fuse(shim_world, args):
+    T.test_fuse_both_overloads(*args)
+
+
+def test_shim_assign_features_to_grid(shim_world):
+    T.test_grid_functions()
