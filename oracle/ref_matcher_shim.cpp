@@ -354,7 +354,6 @@ int orbrefsrc_search_by_sim3(const orbx_frame_view* v1, const orbx_frame_view* v
   return n;
 }
 
-#ifndef ORBREF_SHIM_WORLD  /* the shim-world build swaps in shim/ORBextractor.h, whose class needs the CUDA library */
 // The stereo Frame constructor's hot path with the reference's own code end to end: ORBextractor::operator() on both
 // images (vLappingArea = {0, 0}, src/Frame.cc:200-203), then Frame::ComputeStereoMatches (:921-1084, its text piped into
 // this library at build time). Outputs: keypoints / descriptors of both eyes (cap rows), mvuRight / mvDepth [n_l].
@@ -393,8 +392,6 @@ int orbrefsrc_stereo_frame(int nfeatures, float scale_factor, int nlevels, int i
   }
   return matched;
 }
-
-#endif
 
 // Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:520-547, 833-844) as CSR in the oracle's cell order
 // (cell = col * 48 + row): offsets[64 * 48 + 1], items[n].

@@ -5,9 +5,15 @@
 #include <cstring>
 
 #include "../include/orbm.h"
+#include "../include/orbx.h"
 #include "../oracle/orbref.h"
 
 struct orbm_matcher { int unused; };
+// the extractor handle of the mock: the oracle's extractor, whose last call holds the pyramid the stereo matcher reads
+struct orbx_extractor {
+  orbref_extractor* r;
+  int nfeatures, nlevels;
+};
 
 extern "C" {
 int orbm_create(orbm_matcher** out, int) {
@@ -62,6 +68,53 @@ int orbm_distinctive_descriptors(orbm_matcher*, const uint8_t* desc, const int32
                                  int32_t* best_idx) {
   for (int i = 0; i < n_points; i++)
     best_idx[i] = orbref_distinctive_descriptor(desc + (size_t)offsets[i] * 32, offsets[i + 1] - offsets[i]);
+  return ORBX_OK;
+}
+
+// ---- the part of include/orbx.h that shim/ORBextractor.cc calls, and orbm_stereo_match for shim/FrameStereo_orbx.cc ----
+int orbx_extractor_create(orbx_extractor** out, int, int nfeatures, float scale_factor, int nlevels, int ini_th_fast,
+                          int min_th_fast, int) {
+  *out = new orbx_extractor{orbref_extractor_create(nfeatures, scale_factor, nlevels, ini_th_fast, min_th_fast), nfeatures,
+                            nlevels};
+  return ORBX_OK;
+}
+void orbx_extractor_destroy(orbx_extractor* ex) {
+  if (!ex) return;
+  orbref_extractor_destroy(ex->r);
+  delete ex;
+}
+const char* orbx_last_error(const orbx_extractor*) { return "mock"; }
+int orbx_extractor_levels(const orbx_extractor* ex) { return ex->nlevels; }
+int orbx_extractor_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                          int32_t* features_per_level) {
+  orbref_extractor_tables(ex->r, scale, inv_scale, sigma2, inv_sigma2, features_per_level, nullptr);
+  return ORBX_OK;
+}
+int orbx_extractor_capacity(const orbx_extractor* ex) { return ex->nfeatures + 16 * ex->nlevels; }
+int orbx_extract(orbx_extractor* ex, const uint8_t* image, int width, int height, int stride, int lap0, int lap1,
+                 orbx_kp* kps, uint8_t* desc, int cap, int32_t* n_out, int32_t* mono_index) {
+  int n = 0, mono = 0;
+  const int rc = orbref_extract(ex->r, image, width, height, stride, lap0, lap1, kps, desc, cap, &n, &mono);
+  *n_out = n;
+  *mono_index = mono;
+  return rc == 0 ? ORBX_OK : (rc == -1 ? ORBX_E_EMPTY : ORBX_E_CAPACITY);
+}
+int orbx_level_size(const orbx_extractor* ex, int level, int* width, int* height) {
+  orbref_level_dims(ex->r, level, width, height);
+  return ORBX_OK;
+}
+int orbx_download_pyramid(orbx_extractor* ex, int, int level, uint8_t* dst, int dst_stride) {
+  int w = 0, h = 0, st = 0;
+  orbref_level_dims(ex->r, level, &w, &h);
+  const uint8_t* src = orbref_level_bordered(ex->r, level, &st);
+  for (int y = 0; y < h + 38; y++) memcpy(dst + (size_t)y * dst_stride, src + (size_t)y * st, (size_t)w + 38);
+  return ORBX_OK;
+}
+int orbm_stereo_match(orbm_matcher*, const orbx_extractor* left, const orbx_extractor* right, int, const orbx_kp* kps_l,
+                      const uint8_t* desc_l, int n_l, const orbx_kp* kps_r, const uint8_t* desc_r, int n_r, float mbf,
+                      float mb, float* u_right, float* depth, int32_t* n_matched) {
+  const int n = orbref_stereo_match(left->r, right->r, kps_l, desc_l, n_l, kps_r, desc_r, n_r, mbf, mb, u_right, depth);
+  if (n_matched) *n_matched = n;
   return ORBX_OK;
 }
 }

@@ -22,7 +22,7 @@ def shim_world(monkeypatch):
     lib = C.CDLL(_PATH)
     for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
                  "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
-                 "orbrefsrc_features_in_area"):
+                 "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame"):
         getattr(lib, name).restype = C.c_int
     refsrc.mlib()
     monkeypatch.setattr(refsrc, "_mlib", lib)
@@ -62,3 +62,11 @@ def test_shim_fuse(shim_world, args):
 
 def test_shim_assign_features_to_grid(shim_world):
     T.test_grid_functions()
+
+
+@pytest.mark.parametrize("args", [(752, 480, 1200, 1, "scene"), (400, 300, 600, 8, "scene")])
+def test_shim_extractor_class_and_compute_stereo_matches(shim_world, args):
+    """shim/ORBextractor.{h,cc} (constructor tables, operator(), the mvImagePyramid mirror) and the drop-in
+    Frame::ComputeStereoMatches of shim/FrameStereo_orbx.cc, driven exactly like the reference's stereo Frame constructor
+    drives the originals: keypoints, descriptors, mvuRight and mvDepth must come back as the oracle's."""
+    T.test_stereo_frame_hot_path_equals_the_reference_source(*args)
