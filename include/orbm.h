@@ -109,6 +109,49 @@ int orbm_search_by_projection_map_resident(orbm_matcher* m, const orbx_extractor
                                            float inv_w, float inv_h, const orbx_mappoints* mps, float th, float nnratio,
                                            int far_points, float th_far, int32_t* assign, int32_t* nmatches);
 
+/* bool Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (include/Frame.h:101, src/Frame.cc:632-699, Nleft == -1)
+ * with MapPoint::PredictScale (src/MapPoint.cc:559-573) for every point of local map `map_index`, as the loop of
+ * Tracking::SearchLocalPoints runs it (src/Tracking.cc:3288-3300) — SURVEY.md §8(f) rank 1. Host buffers. Outputs
+ * [map->m]: track_in_view = mbTrackInView (0 for skip[] points, which are not projected); proj_x / proj_y = mTrackProjX /
+ * mTrackProjY (-1 when the point falls outside the image, :635-636); proj_xr, level, view_cos, depth = mTrackProjXR,
+ * mnTrackScaleLevel, mTrackViewCos, mTrackDepth, meaningful only where track_in_view != 0 (the reference leaves them
+ * untouched otherwise). *n_in_view = nToMatch. The arrays are exactly what orbx_mappoints takes. */
+int orbm_is_in_frustum(orbm_matcher* m, const orbx_frustum* fr, const orbx_local_map* map, int map_index,
+                       float viewing_cos_limit, uint8_t* track_in_view, float* proj_x, float* proj_y, float* proj_xr,
+                       int32_t* level, float* view_cos, float* depth, int32_t* n_in_view);
+
+/* void Tracking::SearchLocalPoints() (src/Tracking.cc:3249-3330) for n_frames frames of ONE extract batch, everything
+ * resident in device memory and nothing synchronised (BASELINE.json configs[3] as a throughput path): per frame
+ * isInFrustum over its local map, Frame::AssignFeaturesToGrid (src/Frame.cc:520-547) and
+ * ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+ * (src/ORBmatcher.cc:42-221) in serial MapPoint order. Frame f = rows [f][cap] of d_kps / d_desc with count d_n[f]
+ * (what orbx_extract_batch_device wrote; mvKeysUn = mvKeys: undistorted camera, src/Frame.cc:562-571), d_u_right /
+ * d_occupied [f][cap] (mvuRight from orbm_stereo_match_batch_device; either may be NULL), pose d_frustums[f], local map
+ * d_map_index[f] (NULL: f % maps->n_maps) of *maps, whose array pointers are DEVICE pointers. `ex` supplies
+ * mvScaleFactors. Outputs: d_assign[f][cap] = index of the MapPoint written to mvpMapPoints[i] or -1, d_nmatches[f] =
+ * SearchByProjection's return value, d_n_in_view[f] = nToMatch, d_status[f] = 0 or ORBX_E_CAPACITY (candidate list,
+ * see orbx_track_params). cap < 65536. */
+int orbm_track_local_map_batch_device(orbm_matcher* m, const orbx_extractor* ex, int n_frames, const orbx_kp* d_kps,
+                                      const uint8_t* d_desc, const int32_t* d_n, int cap, const float* d_u_right,
+                                      const uint8_t* d_occupied, const orbx_frustum* d_frustums,
+                                      const orbx_local_map* maps, const int32_t* d_map_index,
+                                      const orbx_track_params* prm, int32_t* d_assign, int32_t* d_nmatches,
+                                      int32_t* d_n_in_view, int32_t* d_status, void* cuda_stream);
+
+/* orbm_stereo_frames_batch followed, per pair, by Tracking::SearchLocalPoints on the left frame (configs[3] end to end):
+ * host buffers in and out, pipelined over the lanes like orbm_stereo_frames_batch. Additional inputs (host):
+ * frustums[n_pairs], the local maps (*maps with HOST pointers; uploaded once per call), map_index[n_pairs] or NULL
+ * (pair p uses map p % n_maps), occupied[n_pairs][cap] or NULL. Additional outputs: assign[n_pairs][cap],
+ * nmatches[n_pairs], n_in_view[n_pairs]. Returns ORBX_E_CAPACITY if any frame overflowed an output or the candidate
+ * list. */
+int orbm_stereo_track_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                                   const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                                   int64_t frame_stride, float mbf, float mb, const orbx_frustum* frustums,
+                                   const orbx_local_map* maps, const int32_t* map_index, const uint8_t* occupied,
+                                   const orbx_track_params* prm, orbx_kp* kps_l, uint8_t* desc_l, int32_t* n_l,
+                                   orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right, float* depth,
+                                   int32_t* n_matched, int32_t* assign, int32_t* nmatches, int32_t* n_in_view);
+
 /* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
  * (src/ORBmatcher.cc:1594-1806) and (Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (:1808-1918), after the
  * caller-side SE3 projection (orbx_projected). max_dist = TH_HIGH or ORBdist; check_orientation = mbCheckOrientation.

@@ -67,6 +67,49 @@ typedef struct orbx_mappoints {
   const uint8_t* desc;          /* m x 32, MapPoint::GetDescriptor() */
 } orbx_mappoints;
 
+/* What bool Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (src/Frame.cc:632-699, Nleft == -1) reads from
+ * the Frame: the pose (mRcw row-major, mtcw, mOw; include/Frame.h:197-199), the pinhole intrinsics of mpCamera
+ * (src/CameraModels/Pinhole.cpp:47-53), mbf, the image bounds (include/Frame.h:372-375) and the scale pyramid
+ * (mfLogScaleFactor, mnScaleLevels; :305-307). 104 bytes, no padding; arrays of it cross the ABI for batched calls. */
+typedef struct orbx_frustum {
+  float Rcw[9];
+  float tcw[3];
+  float Ow[3];
+  float fx, fy, cx, cy;
+  float mbf;
+  float min_x, max_x, min_y, max_y; /* mnMinX, mnMaxX, mnMinY, mnMaxY */
+  float log_scale_factor;           /* mfLogScaleFactor = logf(mfScaleFactor) */
+  int32_t n_levels;                 /* mnScaleLevels */
+} orbx_frustum;
+
+/* mvpLocalMapPoints as the loop of Tracking::SearchLocalPoints (src/Tracking.cc:3288-3300) reads it, before the
+ * projection: one entry per MapPoint*. n_maps maps of m points each may be stored back to back ([n_maps][m] arrays);
+ * the single-frame calls use n_maps = 1. */
+typedef struct orbx_local_map {
+  int32_t m;
+  int32_t n_maps;
+  const float* pos;       /* [m][3] MapPoint::GetWorldPos() */
+  const float* normal;    /* [m][3] MapPoint::GetNormal() */
+  const float* min_dist;  /* mfMinDistance (GetMinDistanceInvariance() = 0.8f * it, src/MapPoint.cc:533-541) */
+  const float* max_dist;  /* mfMaxDistance (GetMaxDistanceInvariance() = 1.2f * it; PredictScale reads it raw, :559-573) */
+  const uint8_t* skip;    /* mnLastFrameSeen == mCurrentFrame.mnId || isBad() (src/Tracking.cc:3289) */
+  const uint8_t* has_obs; /* Observations() > 0 (src/ORBmatcher.cc:92-93) */
+  const uint8_t* desc;    /* [m][32] MapPoint::GetDescriptor() */
+} orbx_local_map;
+
+/* Scalars of one Tracking::SearchLocalPoints pass (src/Tracking.cc:3288-3330). */
+typedef struct orbx_track_params {
+  float viewing_cos_limit; /* isInFrustum(pMP, 0.5) */
+  float th;                /* SearchByProjection's th: 1, 3 (RGB-D), 2 / 6 / 10 (IMU states), 5, 15 (:3303-3322) */
+  float nnratio;           /* ORBmatcher matcher(0.8) */
+  int32_t far_points;      /* mpLocalMapper->mbFarPoints */
+  float th_far;            /* mpLocalMapper->mThFarPoints */
+  float min_x, min_y;      /* Frame::mnMinX, mnMinY */
+  float inv_w, inv_h;      /* Frame::mfGridElementWidthInv / HeightInv */
+  int32_t cand_per_frame;  /* capacity of the per-frame candidate list (keypoints that fall into some point's window);
+                              0 = 16 * m. A frame that needs more is reported with status ORBX_E_CAPACITY. */
+} orbx_track_params;
+
 /* Points of the last frame / a keyframe already projected into the current frame by the caller (the SE3 product and
  * camera projection stay on the host so Eigen's evaluation order is untouched): src/ORBmatcher.cc:1617-1660,
  * 1826-1853. One entry per candidate point that survived the caller-side tests. */

@@ -861,6 +861,55 @@ void orbref_build_grid(const orbx_kp* kps, int n, float min_x, float min_y, floa
   offsets[C * R] = o;
 }
 
+// Frame::isInFrustum (src/Frame.cc:632-699, the Nleft == -1 branch) with MapPoint::PredictScale (src/MapPoint.cc:559-573),
+// MapPoint::Get{Min,Max}DistanceInvariance (:533-541) and Pinhole::project (src/CameraModels/Pinhole.cpp:47-53), applied
+// to the points of one local map the way the loop of Tracking::SearchLocalPoints does (src/Tracking.cc:3288-3300).
+// Float expressions are written in the order Eigen evaluates them for fixed-size 3-vectors without packet access: a
+// 3-term reduction (dot, squaredNorm, a row of Matrix3f * Vector3f) is c0 + (c1 + c2) (redux_novec_unroller splits
+// the range in halves, Eigen/src/Core/Redux.h). log() is the host's glibc logf.
+void orbref_is_in_frustum(const orbx_frustum* fr, const orbx_local_map* map, int map_index, float viewing_cos_limit,
+                          uint8_t* track_in_view, float* proj_x, float* proj_y, float* proj_xr, int32_t* level,
+                          float* view_cos, float* depth) {
+  const size_t base = (size_t)map_index * (size_t)map->m;
+  auto dot3 = [](const float* a, const float* b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); };
+  for (int i = 0; i < map->m; i++) {
+    const size_t g = base + (size_t)i;
+    track_in_view[i] = 0;
+    if (map->skip && map->skip[g]) continue;  // Tracking.cc:3289: seen in this frame already, or bad
+    proj_x[i] = -1;                            // :635-636
+    proj_y[i] = -1;
+    const float* P = map->pos + 3 * g;
+    const float Pc[3] = {dot3(fr->Rcw + 0, P) + fr->tcw[0], dot3(fr->Rcw + 3, P) + fr->tcw[1],
+                         dot3(fr->Rcw + 6, P) + fr->tcw[2]};
+    const float Pc_dist = std::sqrt(dot3(Pc, Pc));
+    const float PcZ = Pc[2];
+    const float invz = 1.0f / PcZ;
+    if (PcZ < 0.0f) continue;
+    const float u = fr->fx * Pc[0] / Pc[2] + fr->cx;
+    const float v = fr->fy * Pc[1] / Pc[2] + fr->cy;
+    if (u < fr->min_x || u > fr->max_x) continue;
+    if (v < fr->min_y || v > fr->max_y) continue;
+    proj_x[i] = u;
+    proj_y[i] = v;
+    const float maxDistance = 1.2f * map->max_dist[g];
+    const float minDistance = 0.8f * map->min_dist[g];
+    const float PO[3] = {P[0] - fr->Ow[0], P[1] - fr->Ow[1], P[2] - fr->Ow[2]};
+    const float dist = std::sqrt(dot3(PO, PO));
+    if (dist < minDistance || dist > maxDistance) continue;
+    const float viewCos = dot3(PO, map->normal + 3 * g) / dist;
+    if (viewCos < viewing_cos_limit) continue;
+    const float ratio = map->max_dist[g] / dist;
+    int nScale = (int)std::ceil(std::log(ratio) / fr->log_scale_factor);  // float overloads: logf, ceilf
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= fr->n_levels) nScale = fr->n_levels - 1;
+    track_in_view[i] = 1;
+    proj_xr[i] = u - fr->mbf * invz;
+    depth[i] = Pc_dist;
+    level[i] = nScale;
+    view_cos[i] = viewCos;
+  }
+}
+
 // MapPoint::ComputeDistinctiveDescriptors — src/MapPoint.cc:407-435
 int orbref_distinctive_descriptor(const uint8_t* desc, int n) {
   if (n <= 0) return -1;

@@ -32,7 +32,11 @@
  *     reference's operator() on both images + its ComputeStereoMatches and requires mvuRight / mvDepth to equal
  *     orbref_stereo_match bit for bit.
  *   - Frame::AssignFeaturesToGrid / PosInGrid / GetFeaturesInArea, KeyFrame::GetFeaturesInArea and
- *     MapPoint::ComputeDistinctiveDescriptors: piped in the same way and checked directly. knn2 is pinned to
+ *     MapPoint::ComputeDistinctiveDescriptors: piped in the same way and checked directly.
+ *   - Frame::isInFrustum + MapPoint::PredictScale (orbref_is_in_frustum): the reference's own text piped in the same way,
+ *     against a stand-in Eigen whose 3-term reductions follow Eigen's own order c0 + (c1 + c2) (no Eigen headers exist in
+ *     this image, so THAT ORDER is this repository's reading of Eigen/src/Core/Redux.h, not something verified here) and
+ *     a stand-in Pinhole::project with the reference's expression. knn2 is pinned to
  *     cv2.BFMatcher itself. No function below is left without a reference-source (or, for the OpenCV primitives, cv2) pin.
  *
  * Build: oracle/Makefile (g++ -O2, no -march=native, -ffp-contract=off: the reference is built without FMA,
@@ -95,6 +99,14 @@ int orbref_stereo_match(const orbref_extractor* left, const orbref_extractor* ri
 /* Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:520-547,833-844). offsets[64*48+1], items[n]. */
 void orbref_build_grid(const orbx_kp* kps, int n, float min_x, float min_y, float inv_w, float inv_h,
                        int32_t* offsets, int32_t* items);
+/* bool Frame::isInFrustum(MapPoint*, viewingCosLimit) (src/Frame.cc:632-699, Nleft == -1) over the points of local map
+ * `map_index`, as the loop of Tracking::SearchLocalPoints runs it (src/Tracking.cc:3288-3300): a point with skip[] set is
+ * not projected (track_in_view = 0, nothing else written); for the others track_in_view = the return value, proj_x /
+ * proj_y = -1 or the projection (:635-636, :655-656), and the remaining MapPoint tracking fields (:676-685) are written
+ * only when the point is in view. Outputs have map->m entries. */
+void orbref_is_in_frustum(const orbx_frustum* fr, const orbx_local_map* map, int map_index, float viewing_cos_limit,
+                          uint8_t* track_in_view, float* proj_x, float* proj_y, float* proj_xr, int32_t* level,
+                          float* view_cos, float* depth);
 /* Frame::GetFeaturesInArea (src/Frame.cc:765-831), Nleft == -1. Returns the count written to out (cap >= n). */
 int orbref_features_in_area(const orbx_frame_view* f, float x, float y, float r, int min_level, int max_level,
                             int32_t* out);

@@ -63,6 +63,19 @@ class KeyFrameView(C.Structure):
                 ("level_sigma2", C.c_void_p), ("n_levels", C.c_int32)]
 
 
+class Frustum(C.Structure):
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("fx", C.c_float),
+                ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float), ("min_x", C.c_float),
+                ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float), ("log_scale_factor", C.c_float),
+                ("n_levels", C.c_int32)]
+
+
+class LocalMap(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n_maps", C.c_int32), ("pos", C.c_void_p), ("normal", C.c_void_p),
+                ("min_dist", C.c_void_p), ("max_dist", C.c_void_p), ("skip", C.c_void_p), ("has_obs", C.c_void_p),
+                ("desc", C.c_void_p)]
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -104,6 +117,54 @@ def make_mappoints(track_in_view, proj_x, proj_y, proj_xr, level, view_cos, dept
             _c(level, np.int32), _c(view_cos, np.float32), _c(depth, np.float32), _c(has_obs, np.uint8),
             _c(desc, np.uint8))
     return Holder(MapPoints(len(arrs[0]), *[_ptr(a) for a in arrs]), arrs)
+
+
+def make_local_map(pos, normal, min_dist, max_dist, skip, has_obs, desc):
+    pos = _c(pos, np.float32)
+    if pos.ndim == 2:
+        pos = pos[None]
+    n_maps, m = pos.shape[0], pos.shape[1]
+    arrs = (pos, _c(normal, np.float32).reshape(n_maps, m, 3), _c(min_dist, np.float32).reshape(n_maps, m),
+            _c(max_dist, np.float32).reshape(n_maps, m), None if skip is None else _c(skip, np.uint8).reshape(n_maps, m),
+            _c(has_obs, np.uint8).reshape(n_maps, m), _c(desc, np.uint8).reshape(n_maps, m, 32))
+    return Holder(LocalMap(m, n_maps, *[_ptr(a) for a in arrs]), arrs)
+
+
+def _frustum_out(m, out):
+    if out is None:
+        out = dict(track_in_view=np.zeros(m, np.uint8), proj_x=np.zeros(m, np.float32), proj_y=np.zeros(m, np.float32),
+                   proj_xr=np.zeros(m, np.float32), level=np.zeros(m, np.int32), view_cos=np.zeros(m, np.float32),
+                   depth=np.zeros(m, np.float32))
+    return out
+
+
+def is_in_frustum(frustum, local_map, map_index=0, viewing_cos_limit=0.5, out=None, fn=None):
+    """Frame::isInFrustum over local map `map_index` (orbref_is_in_frustum). frustum: a 104-byte record (numpy)."""
+    fr = np.ascontiguousarray(frustum).reshape(1)
+    assert fr.dtype.itemsize == 104
+    out = _frustum_out(local_map.struct.m, out)
+    fn = fn or lib().orbref_is_in_frustum
+    fn(_ptr(fr), local_map.ref(), C.c_int(map_index), C.c_float(viewing_cos_limit), _ptr(out["track_in_view"]),
+       _ptr(out["proj_x"]), _ptr(out["proj_y"]), _ptr(out["proj_xr"]), _ptr(out["level"]), _ptr(out["view_cos"]),
+       _ptr(out["depth"]))
+    return int(out["track_in_view"].sum()), out
+
+
+def track_local_map(frame_view, frustum, local_map, map_index, th, nnratio, far_points=False, th_far=0.0,
+                    viewing_cos_limit=0.5):
+    """Tracking::SearchLocalPoints (src/Tracking.cc:3288-3330): isInFrustum over the local map, then SearchByProjection.
+    Returns (nmatches, assign, n_in_view)."""
+    m = local_map.struct.m
+    nv, o = is_in_frustum(frustum, local_map, map_index, viewing_cos_limit)
+    base = map_index * m
+    has_obs = local_map.keep[5].reshape(-1)[base:base + m]
+    desc = local_map.keep[6].reshape(-1, 32)[base:base + m]
+    mps = make_mappoints(o["track_in_view"], o["proj_x"], o["proj_y"], o["proj_xr"], o["level"], o["view_cos"],
+                         o["depth"], has_obs, desc)
+    if nv == 0:
+        return 0, np.full(frame_view.struct.n, -1, np.int32), 0
+    nm, assign = search_by_projection_map(frame_view, mps, th, nnratio, far_points, th_far)
+    return nm, assign, nv
 
 
 def make_projected(u, v, u_right, radius, min_level, max_level, angle, has_obs, desc):
@@ -164,6 +225,8 @@ def lib():
         L.orbref_build_grid.argtypes = [vp, ci, cf, cf, cf, cf, vp, vp]
         L.orbref_features_in_area.argtypes = [vp, cf, cf, cf, ci, ci, vp]
         L.orbref_search_by_projection_map.argtypes = [vp, vp, cf, cf, ci, cf, vp]
+        L.orbref_is_in_frustum.argtypes = [vp, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp]
+        L.orbref_is_in_frustum.restype = None
         L.orbref_search_by_projection_frame.argtypes = [vp, vp, ci, ci, vp]
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]

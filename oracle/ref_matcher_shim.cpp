@@ -441,3 +441,47 @@ int orbrefsrc_distinctive_descriptor(const uint8_t* desc, int n, uint8_t* out) {
   return 1;
 }
 }
+
+// Frame::isInFrustum (src/Frame.cc:632-699) + MapPoint::PredictScale (src/MapPoint.cc:559-573): the reference's own text
+// on a stand-in Frame / MapPoint, driven like the loop of Tracking::SearchLocalPoints (src/Tracking.cc:3288-3300).
+// Outputs as orbref_is_in_frustum.
+extern "C" void orbrefsrc_is_in_frustum(const orbx_frustum* fr, const orbx_local_map* map, int map_index,
+                                        float viewing_cos_limit, uint8_t* track_in_view, float* proj_x, float* proj_y,
+                                        float* proj_xr, int32_t* level, float* view_cos, float* depth) {
+  Frame F;
+  PinholeStandIn cam;
+  cam.mvParameters[0] = fr->fx; cam.mvParameters[1] = fr->fy; cam.mvParameters[2] = fr->cx; cam.mvParameters[3] = fr->cy;
+  F.mpCamera = &cam;
+  F.Nleft = -1;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) F.mRcw(i, j) = fr->Rcw[3 * i + j];
+    F.mtcw(i) = fr->tcw[i];
+    F.mOw(i) = fr->Ow[i];
+  }
+  F.mbf = fr->mbf;
+  Frame::mnMinX = fr->min_x; Frame::mnMaxX = fr->max_x; Frame::mnMinY = fr->min_y; Frame::mnMaxY = fr->max_y;
+  F.mfLogScaleFactor = fr->log_scale_factor;
+  F.mnScaleLevels = fr->n_levels;
+  const size_t base = (size_t)map_index * (size_t)map->m;
+  for (int i = 0; i < map->m; i++) {
+    const size_t g = base + (size_t)i;
+    track_in_view[i] = 0;
+    if (map->skip && map->skip[g]) continue;
+    MapPoint p;
+    p.pos = Eigen::Vector3f(map->pos[3 * g], map->pos[3 * g + 1], map->pos[3 * g + 2]);
+    p.normal = Eigen::Vector3f(map->normal[3 * g], map->normal[3 * g + 1], map->normal[3 * g + 2]);
+    p.use_raw_distances = true;
+    p.mfMinDistance = map->min_dist[g];
+    p.mfMaxDistance = map->max_dist[g];
+    // every tracking field starts from the caller's value so that "left untouched" is observable
+    p.mTrackProjXR = proj_xr[i]; p.mTrackDepth = depth[i]; p.mnTrackScaleLevel = level[i]; p.mTrackViewCos = view_cos[i];
+    const bool in = F.isInFrustum(&p, viewing_cos_limit);
+    track_in_view[i] = (in && p.mbTrackInView) ? 1 : 0;
+    proj_x[i] = p.mTrackProjX;
+    proj_y[i] = p.mTrackProjY;
+    proj_xr[i] = p.mTrackProjXR;
+    depth[i] = p.mTrackDepth;
+    level[i] = p.mnTrackScaleLevel;
+    view_cos[i] = p.mTrackViewCos;
+  }
+}

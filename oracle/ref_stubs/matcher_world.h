@@ -45,7 +45,9 @@ struct Vector3f {
   Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
   Vector3f operator*(float s) const { return Vector3f(v[0] * s, v[1] * s, v[2] * s); }
   Vector3f operator-() const { return Vector3f(-v[0], -v[1], -v[2]); }
-  float dot(const Vector3f& o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+  // Eigen reduces a fixed-size 3-vector without packets as c0 + (c1 + c2) (redux_novec_unroller halves the range,
+  // Eigen/src/Core/Redux.h); Frame::isInFrustum's results depend on it (the other tests use identity poses)
+  float dot(const Vector3f& o) const { return v[0] * o.v[0] + (v[1] * o.v[1] + v[2] * o.v[2]); }
   float norm() const { return std::sqrt(dot(*this)); }
 };
 struct Matrix3f {
@@ -54,9 +56,9 @@ struct Matrix3f {
   float operator()(int i, int j) const { return m[i][j]; }
   float& operator()(int i, int j) { return m[i][j]; }
   Vector3f operator*(const Vector3f& p) const {
-    return Vector3f(m[0][0] * p.v[0] + m[0][1] * p.v[1] + m[0][2] * p.v[2],
-                    m[1][0] * p.v[0] + m[1][1] * p.v[1] + m[1][2] * p.v[2],
-                    m[2][0] * p.v[0] + m[2][1] * p.v[1] + m[2][2] * p.v[2]);
+    return Vector3f(m[0][0] * p.v[0] + (m[0][1] * p.v[1] + m[0][2] * p.v[2]),
+                    m[1][0] * p.v[0] + (m[1][1] * p.v[1] + m[1][2] * p.v[2]),
+                    m[2][0] * p.v[0] + (m[2][1] * p.v[1] + m[2][2] * p.v[2]));
   }
   Matrix3f operator*(const Matrix3f& o) const {
     Matrix3f r;
@@ -95,6 +97,11 @@ struct Matrix3f {
     return r;
   }
 };
+// Eigen::Matrix<float, 3, 1> / <float, 3, 3> as Frame::isInFrustum spells them
+template <int R, int C> struct MatSel;
+template <> struct MatSel<3, 1> { typedef Vector3f type; };
+template <> struct MatSel<3, 3> { typedef Matrix3f type; };
+template <typename T, int R, int C> using Matrix = typename MatSel<R, C>::type;
 }  // namespace Eigen
 
 namespace Sophus {
@@ -155,6 +162,19 @@ class GeometricCamera {
   }
 };
 
+// Pinhole::project(const Eigen::Vector3f&) (src/CameraModels/Pinhole.cpp:47-53) with the reference's expression; the
+// reference's Pinhole.cpp needs GeometricCamera.h (Eigen, boost serialization) and cannot be compiled here
+class PinholeStandIn : public GeometricCamera {
+ public:
+  float mvParameters[4] = {1, 1, 0, 0};
+  Eigen::Vector2f project(const Eigen::Vector3f& v3D) override {
+    Eigen::Vector2f res;
+    res(0) = mvParameters[0] * v3D(0) / v3D(2) + mvParameters[2];
+    res(1) = mvParameters[1] * v3D(1) / v3D(2) + mvParameters[3];
+    return res;
+  }
+};
+
 // std::mutex members would make the stand-ins immovable; the tests are single threaded
 struct CopyableMutex : std::mutex {
   CopyableMutex() {}
@@ -191,10 +211,16 @@ class MapPoint {
   cv::Mat GetDescriptor() { return descriptor.clone(); }
   Eigen::Vector3f GetWorldPos() { return pos; }
   Eigen::Vector3f GetNormal() { return normal; }
-  float GetMinDistanceInvariance() { return min_dist; }
-  float GetMaxDistanceInvariance() { return max_dist; }
+  bool use_raw_distances = false;  // isInFrustum test: the reference's accessors (src/MapPoint.cc:533-541)
+  float GetMinDistanceInvariance() { return use_raw_distances ? 0.8f * mfMinDistance : min_dist; }
+  float GetMaxDistanceInvariance() { return use_raw_distances ? 1.2f * mfMaxDistance : max_dist; }
   int PredictScale(const float&, KeyFrame*) { return predicted_level; }
   int PredictScale(const float&, Frame*) { return predicted_level; }
+  // MapPoint::PredictScale(const float&, Frame*) (src/MapPoint.cc:559-573) as the reference's own text, piped in under
+  // this name (the matcher tests above fix the predicted level instead); isInFrustum's call is renamed with it
+  int PredictScaleRef(const float& currentDist, Frame* pF);
+  CopyableMutex mMutexPos;
+  float mfMaxDistance = 0, mfMinDistance = 0;
   bool IsInKeyFrame(KeyFrame* kf) { return in_keyframes.count(kf) != 0; }
   std::map<const KeyFrame*, int> index_in;
   std::tuple<int, int> GetIndexInKeyFrame(KeyFrame* kf) {
@@ -236,6 +262,13 @@ class Frame : public FeatureHolder {
   ORBextractor* mpORBextractorRight = nullptr;
   cv::Mat mDescriptorsRight;
   std::vector<float> mvInvScaleFactors;
+  // Frame::isInFrustum (src/Frame.cc:632-699): the reference's own text, piped in at build time
+  Eigen::Matrix3f mRcw;
+  Eigen::Vector3f mtcw, mOw;
+  float mfLogScaleFactor = 0;
+  int mnScaleLevels = 0;
+  bool isInFrustum(MapPoint* pMP, float viewingCosLimit);
+  bool isInFrustumChecks(MapPoint*, float, bool = false) { return false; }
   void ComputeStereoMatches();  // defined by the reference's own text, piped in at build time (oracle/Makefile)
   std::vector<MapPoint*> mvpMapPoints;
   std::vector<bool> mvbOutlier;

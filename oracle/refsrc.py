@@ -128,6 +128,14 @@ def search_by_projection_map(fv, mps, th, nnratio, far_points=False, th_far=0.0)
     return n, assign[:fv.struct.n]
 
 
+def is_in_frustum(frustum, local_map, map_index=0, viewing_cos_limit=0.5, out=None):
+    """The reference's own Frame::isInFrustum + MapPoint::PredictScale text on the stand-in world."""
+    from . import orbref
+    fn = mlib().orbrefsrc_is_in_frustum
+    fn.restype = None
+    return orbref.is_in_frustum(frustum, local_map, map_index, viewing_cos_limit, out, fn=fn)
+
+
 def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False, check_orientation=True):
     F = np.ascontiguousarray(F12, np.float32).reshape(9)
     m = np.empty(max(kf1.struct.n, 1), np.int32)

@@ -11,137 +11,21 @@
 #include <vector>
 
 #include "../../include/orbm.h"
+#include "orbm_handle.h"
 #include "orbx_handle.h"
 #include "orbx_match.cuh"
 
 using namespace orbx;
 
-namespace {
-thread_local std::string g_m_create_error;
-
-// grow-only device buffer
-struct DevBuf {
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    const size_t want = std::max(bytes, (size_t)4096) * 5 / 4;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-enum { kBufs = 40 };
-}  // namespace
-
-struct orbm_matcher {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::string err;
-  DevBuf buf[kBufs];
-  int next_buf = 0;
-  // per-lane device outputs of orbm_stereo_frames_batch: u_right, depth, sad [B][cap], n_matched [B] (+ pinned copy)
-  DevBuf lane_buf[kLanes][4];
-  int32_t* lane_h_nm[kLanes] = {};
-  int lane_h_cap[kLanes] = {};
-  // small host arrays of one call are packed into one pinned block and cross PCIe in ONE copy (a frame / keyframe
-  // view is 8-10 arrays: 20 separate pageable copies cost more than the kernels of a guided search)
-  uint8_t* h_stage = nullptr;
-  uint8_t* d_stage = nullptr;
-  size_t stage_used = 0, stage_flushed = 0;
-  // the vocabulary tree of orbm_set_vocabulary (device resident across calls)
-  DevBuf voc_buf[5];
-  orbx::DevVocabulary voc{};
-  // +-1 byte expansions of the query / train descriptors for the tensor-core knn2 (256 B per row)
-  DevBuf tc_buf[2];
-};
+namespace orbm_detail {
+std::string& create_error() {
+  thread_local std::string e;
+  return e;
+}
+}  // namespace orbm_detail
+#define g_m_create_error (orbm_detail::create_error())
 
 namespace {
-
-// ORBM_KNN2_TC=0 keeps every knn2 call on the POPC kernel (A/B runs, and the parity test of one path against the other)
-bool knn2_tc_enabled() {
-  const char* v = getenv("ORBM_KNN2_TC");
-  return !(v && v[0] == '0');
-}
-
-int mfail(orbm_matcher* m, int code, const std::string& msg) {
-  if (m) m->err = msg;
-  else g_m_create_error = msg;
-  return code;
-}
-
-#define ORBM_CUDA(m, call)                                                                \
-  do {                                                                                    \
-    cudaError_t e_ = (call);                                                              \
-    if (e_ != cudaSuccess)                                                                \
-      return mfail(m, ORBX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
-  } while (0)
-
-// One call = a sequence of scratch allocations in fixed order; buffers are reused across calls by position.
-constexpr size_t kStageBytes = 8u << 20, kStageMaxItem = 512u << 10;
-
-struct Arena {
-  orbm_matcher* m;
-  cudaError_t err = cudaSuccess;
-  explicit Arena(orbm_matcher* mm) : m(mm) {
-    m->next_buf = 0;
-    m->stage_used = m->stage_flushed = 0;
-    if (!m->h_stage) {
-      if (cudaHostAlloc(reinterpret_cast<void**>(&m->h_stage), kStageBytes, cudaHostAllocDefault) != cudaSuccess ||
-          cudaMalloc(reinterpret_cast<void**>(&m->d_stage), kStageBytes) != cudaSuccess) {
-        if (m->h_stage) cudaFreeHost(m->h_stage);
-        m->h_stage = nullptr;  // staging is an optimisation: fall back to one copy per array
-        cudaGetLastError();
-      }
-    }
-  }
-  template <typename T>
-  T* alloc(size_t count) {
-    if (m->next_buf >= kBufs) {
-      err = cudaErrorMemoryAllocation;
-      return nullptr;
-    }
-    DevBuf& b = m->buf[m->next_buf++];
-    cudaError_t e = b.reserve(std::max(count, (size_t)1) * sizeof(T));
-    if (e != cudaSuccess) err = e;
-    return reinterpret_cast<T*>(b.p);
-  }
-  template <typename T>
-  T* upload(const T* host, size_t count) {
-    const size_t bytes = count * sizeof(T);
-    if (host && bytes && bytes <= kStageMaxItem && m->h_stage && m->stage_used + bytes <= kStageBytes) {
-      const size_t off = m->stage_used;
-      memcpy(m->h_stage + off, host, bytes);
-      m->stage_used = (off + bytes + 255) & ~(size_t)255;
-      return reinterpret_cast<T*>(m->d_stage + off);
-    }
-    T* d = alloc<T>(count);
-    if (d && host && count) {
-      cudaError_t e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, m->stream);
-      if (e != cudaSuccess) err = e;
-    }
-    return d;
-  }
-  // Sends what upload() packed since the last call (one H2D copy on the matcher's stream) and reports the first error
-  // of the arena. Every entry point calls it after its last upload and before its first kernel.
-  cudaError_t sync_uploads() {
-    if (m->stage_used > m->stage_flushed) {
-      cudaError_t e = cudaMemcpyAsync(m->d_stage + m->stage_flushed, m->h_stage + m->stage_flushed,
-                                      m->stage_used - m->stage_flushed, cudaMemcpyHostToDevice, m->stream);
-      if (e != cudaSuccess && err == cudaSuccess) err = e;
-      m->stage_flushed = m->stage_used;
-    }
-    return err;
-  }
-};
 
 void pyr_view(const orbx_extractor* ex, PyrView* v, int ln = -1) {
   memset(v, 0, sizeof(*v));
@@ -272,6 +156,12 @@ void orbm_destroy(orbm_matcher* m) {
     if (h) cudaFreeHost(h);
   for (auto& b : m->voc_buf) b.release();
   for (auto& b : m->tc_buf) b.release();
+  for (auto& lb : m->track_buf)
+    for (auto& b : lb) b.release();
+  for (auto& b : m->track_map) b.release();
+  for (auto& h : m->lane_h_track)
+    if (h) cudaFreeHost(h);
+  if (m->track_map_ready) cudaEventDestroy(m->track_map_ready);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -437,11 +327,24 @@ int orbm_stereo_match(orbm_matcher* m, const orbx_extractor* left, const orbx_ex
   return ORBX_OK;
 }
 
-int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
-                             const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
-                             int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
-                             int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
-                             float* depth, int32_t* n_matched) {
+}  // extern "C"
+
+namespace {
+// the optional Tracking::SearchLocalPoints stage of the pipelined stereo call (host pointers)
+struct TrackHost {
+  const orbx_frustum* frustums;
+  const orbx_local_map* maps;
+  const int32_t* map_index;
+  const uint8_t* occupied;
+  const orbx_track_params* prm;
+  int32_t *assign, *nmatches, *n_in_view;
+};
+
+int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                       const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                       int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
+                       int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
+                       float* depth, int32_t* n_matched, const TrackHost* trk) {
   if (!m || !left || !right || left == right) return mfail(m, ORBX_E_ARG, "bad argument");
   if (!imgs_l || !imgs_r || width <= 0 || height <= 0 || n_pairs <= 0) return mfail(m, ORBX_E_EMPTY, "empty image");
   if (stride < width || cap < 1 || !kps_l || !desc_l || !n_l || !kps_r || !desc_r || !n_r || !u_right || !depth ||
@@ -469,6 +372,55 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
     }
     if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
   }
+  // ---- the tracking stage: local maps go to the device once per call, on the matcher's stream ----
+  TrackArgs T0{};
+  orbx_local_map dmap{};
+  int32_t* d_map_index_all = nullptr;
+  if (trk) {
+    if (!trk->frustums || !trk->maps || !trk->prm || !trk->assign || !trk->nmatches || !trk->n_in_view)
+      return mfail(m, ORBX_E_ARG, "bad argument");
+    if ((rc = track_fill_params(m, left, trk->maps, trk->prm, left->lane[0].out_cap, &T0)) != 0) return rc;
+    const orbx_local_map& hm = *trk->maps;
+    const size_t tot = (size_t)hm.m * hm.n_maps;
+    const size_t bytes[8] = {tot * 12, tot * 12, tot * 4, tot * 4, hm.skip ? tot : 0, tot, tot * 32,
+                             trk->map_index ? (size_t)n_pairs * 4 : 0};
+    const void* host[8] = {hm.pos, hm.normal, hm.min_dist, hm.max_dist, hm.skip, hm.has_obs, hm.desc, trk->map_index};
+    if (!m->track_map_ready) ORBM_CUDA(m, cudaEventCreateWithFlags(&m->track_map_ready, cudaEventDisableTiming));
+    for (int k = 0; k < 8; k++) {
+      if (!bytes[k]) continue;
+      cudaError_t e = m->track_map[k].reserve(bytes[k]);
+      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+      ORBM_CUDA(m, cudaMemcpyAsync(m->track_map[k].p, host[k], bytes[k], cudaMemcpyHostToDevice, m->stream));
+    }
+    ORBM_CUDA(m, cudaEventRecord(m->track_map_ready, m->stream));
+    dmap.m = hm.m;
+    dmap.n_maps = hm.n_maps;
+    dmap.pos = static_cast<const float*>(m->track_map[0].p);
+    dmap.normal = static_cast<const float*>(m->track_map[1].p);
+    dmap.min_dist = static_cast<const float*>(m->track_map[2].p);
+    dmap.max_dist = static_cast<const float*>(m->track_map[3].p);
+    dmap.skip = hm.skip ? static_cast<const uint8_t*>(m->track_map[4].p) : nullptr;
+    dmap.has_obs = static_cast<const uint8_t*>(m->track_map[5].p);
+    dmap.desc = static_cast<const uint8_t*>(m->track_map[6].p);
+    d_map_index_all = trk->map_index ? static_cast<int32_t*>(m->track_map[7].p) : nullptr;
+    if (!trk->map_index && hm.n_maps > 1) {  // the default rule "pair p uses map p % n_maps", as an explicit array
+      std::vector<int32_t> idx(n_pairs);
+      for (int p = 0; p < n_pairs; p++) idx[p] = p % hm.n_maps;
+      cudaError_t e = m->track_map[7].reserve((size_t)n_pairs * 4);
+      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+      ORBM_CUDA(m, cudaMemcpy(m->track_map[7].p, idx.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
+    }
+    track_set_map(&dmap, &T0);
+    for (int ln = 0; ln < kLanes; ln++) {
+      if (m->lane_h_track_cap[ln] < B) {
+        if (m->lane_h_track[ln]) cudaFreeHost(m->lane_h_track[ln]);
+        m->lane_h_track[ln] = nullptr;
+        cudaError_t e = cudaHostAlloc(&m->lane_h_track[ln], (size_t)3 * B * 4, cudaHostAllocDefault);
+        m->lane_h_track_cap[ln] = e == cudaSuccess ? B : 0;
+        if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+      }
+    }
+  }
   int first_err = ORBX_OK;
   int pending_f0[kLanes], pending_nb[kLanes];
   for (int i = 0; i < kLanes; i++) pending_nb[i] = 0;
@@ -480,8 +432,13 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
       n_l[g] = left->lane[ln].h_small[f];
       n_r[g] = right->lane[ln].h_small[f];
       n_matched[g] = m->lane_h_nm[ln][f];
-      const bool bad = left->lane[ln].h_small[2 * B + f] != 0 || right->lane[ln].h_small[2 * B + f] != 0 ||
-                       n_l[g] > cap || n_r[g] > cap;
+      bool bad = left->lane[ln].h_small[2 * B + f] != 0 || right->lane[ln].h_small[2 * B + f] != 0 ||
+                 n_l[g] > cap || n_r[g] > cap;
+      if (trk) {
+        trk->nmatches[g] = m->lane_h_track[ln][f];
+        trk->n_in_view[g] = m->lane_h_track[ln][B + f];
+        bad = bad || m->lane_h_track[ln][2 * B + f] != 0;
+      }
       if (bad && first_err == ORBX_OK) first_err = ORBX_E_CAPACITY;
     }
     pending_nb[ln] = 0;
@@ -570,6 +527,66 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
                                      (size_t)rows * 4, nb, cudaMemcpyDeviceToHost, st));
     }
     ORBM_CUDA(m, cudaMemcpyAsync(m->lane_h_nm[ln], A.n_matched, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    if (trk) {
+      // Tracking::SearchLocalPoints on the left frames of the group, which are still resident in the lane
+      TrackArgs T = T0;
+      T.n_frames = nb;
+      T.kps = LL.d_kps;
+      T.desc = LL.d_desc;
+      T.n = LL.d_n;
+      T.u_right = A.u_right;
+      if ((rc = track_prepare(m, ln, &T)) != 0) return rc;
+      // per-group inputs / outputs live behind the scratch: frustums, occupied, assign, 3 result words per frame
+      DevBuf* tb = m->track_buf[ln];
+      cudaError_t e = tb[9].reserve((size_t)B * sizeof(orbx_frustum));
+      if (e == cudaSuccess) e = tb[10].reserve((size_t)B * dcap * 4 + (size_t)B * 3 * 4);
+      if (e == cudaSuccess && trk->occupied) e = tb[11].reserve((size_t)B * dcap);
+      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+      orbx_frustum* d_fr = static_cast<orbx_frustum*>(tb[9].p);
+      int32_t* d_assign = static_cast<int32_t*>(tb[10].p);
+      int32_t* d_words = d_assign + (size_t)B * dcap;  // nmatches[B] | n_in_view[B] | status[B]
+      ORBM_CUDA(m, cudaMemcpyAsync(d_fr, trk->frustums + f0, (size_t)nb * sizeof(orbx_frustum), cudaMemcpyHostToDevice, st));
+      T.frustums = d_fr;
+      T.map_index = nullptr;
+      if (d_map_index_all) T.map_index = d_map_index_all + f0;
+      else if (dmap.n_maps > 1) {
+        // pair p uses map p % n_maps: inside a group the kernel sees local frame numbers, so the rule needs the offset
+        // -> a per-call index array is built on the host once (below) when n_maps > 1 and no index was given
+        T.map_index = static_cast<int32_t*>(m->track_map[7].p) + f0;
+      }
+      T.occupied = nullptr;
+      if (trk->occupied) {
+        uint8_t* d_occ = static_cast<uint8_t*>(tb[11].p);
+        if (cap == dcap) {
+          ORBM_CUDA(m, cudaMemcpyAsync(d_occ, trk->occupied + (size_t)f0 * cap, (size_t)nb * cap, cudaMemcpyHostToDevice, st));
+        } else {
+          ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, (size_t)nb * dcap, st));
+          ORBM_CUDA(m, cudaMemcpy2DAsync(d_occ, dcap, trk->occupied + (size_t)f0 * cap, cap, std::min(cap, dcap), nb,
+                                         cudaMemcpyHostToDevice, st));
+        }
+        T.occupied = d_occ;
+      }
+      T.assign = d_assign;
+      T.nmatches = d_words;
+      T.n_in_view = d_words + B;
+      T.status = d_words + 2 * B;
+      ORBM_CUDA(m, cudaStreamWaitEvent(st, m->track_map_ready, 0));
+      if (!skip_kernels) {
+        launch_frustum_batch(T, st);
+        launch_track_search(T, st);
+      }
+      ORBM_CUDA(m, cudaGetLastError());
+      if (cap == dcap) {
+        ORBM_CUDA(m, cudaMemcpyAsync(trk->assign + (int64_t)f0 * cap, d_assign, (size_t)nb * cap * 4,
+                                     cudaMemcpyDeviceToHost, st));
+      } else {
+        ORBM_CUDA(m, cudaMemcpy2DAsync(trk->assign + (int64_t)f0 * cap, (size_t)cap * 4, d_assign, (size_t)dcap * 4,
+                                       (size_t)std::min(cap, dcap) * 4, nb, cudaMemcpyDeviceToHost, st));
+      }
+      for (int k = 0; k < 3; k++)
+        ORBM_CUDA(m, cudaMemcpyAsync(m->lane_h_track[ln] + (size_t)k * B, d_words + (size_t)k * B, (size_t)nb * 4,
+                                     cudaMemcpyDeviceToHost, st));
+    }
     ORBM_CUDA(m, cudaEventRecord(left->lane[ln].done, st));
     pending_f0[ln] = f0;
     pending_nb[ln] = nb;
@@ -580,8 +597,32 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
   if (trace)
     fprintf(stderr, "orbm_stereo_frames_batch: %zu groups, host issue %.2f ms, wait for lanes %.2f ms, drain %.2f ms\n",
             sizes.size(), 1e3 * t_issue, 1e3 * t_wait, 1e3 * (now() - td0));
-  if (first_err) return mfail(m, first_err, "output capacity too small for at least one frame");
+  if (first_err) return mfail(m, first_err, "output capacity (or the candidate list) too small for at least one frame");
   return ORBX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                             const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                             int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
+                             int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
+                             float* depth, int32_t* n_matched) {
+  return stereo_frames_impl(m, left, right, n_pairs, imgs_l, imgs_r, width, height, stride, frame_stride, mbf, mb, kps_l,
+                            desc_l, n_l, kps_r, desc_r, n_r, cap, u_right, depth, n_matched, nullptr);
+}
+
+int orbm_stereo_track_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                                   const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                                   int64_t frame_stride, float mbf, float mb, const orbx_frustum* frustums,
+                                   const orbx_local_map* maps, const int32_t* map_index, const uint8_t* occupied,
+                                   const orbx_track_params* prm, orbx_kp* kps_l, uint8_t* desc_l, int32_t* n_l,
+                                   orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right, float* depth,
+                                   int32_t* n_matched, int32_t* assign, int32_t* nmatches, int32_t* n_in_view) {
+  const TrackHost trk{frustums, maps, map_index, occupied, prm, assign, nmatches, n_in_view};
+  return stereo_frames_impl(m, left, right, n_pairs, imgs_l, imgs_r, width, height, stride, frame_stride, mbf, mb, kps_l,
+                            desc_l, n_l, kps_r, desc_r, n_r, cap, u_right, depth, n_matched, &trk);
 }
 
 namespace {

@@ -358,14 +358,16 @@ int orbx_extractor_levels(const orbx_extractor* ex) { return ex ? ex->nlevels : 
 int orbx_extractor_tables(const orbx_extractor* ex, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                           int32_t* features_per_level) {
   if (!ex) return ORBX_E_ARG;
-  Plan P;  // the tables do not depend on the image size; use a size every level count accepts
-  if (make_plan(4096, 4096, ex->nfeatures, ex->scale_factor, ex->nlevels, &P) != 0) return ORBX_E_ARG;
+  // the tables do not depend on the image size (and exist for level counts no image of <= 4096 px could carry)
+  float sf[kMaxLevels], s2[kMaxLevels];
+  int quota[kMaxLevels];
+  make_tables(ex->nfeatures, ex->scale_factor, ex->nlevels, sf, s2, quota);
   for (int l = 0; l < ex->nlevels; l++) {
-    if (scale) scale[l] = P.lv[l].scale;
-    if (inv_scale) inv_scale[l] = P.lv[l].inv_scale;
-    if (sigma2) sigma2[l] = P.lv[l].sigma2;
-    if (inv_sigma2) inv_sigma2[l] = P.lv[l].inv_sigma2;
-    if (features_per_level) features_per_level[l] = P.lv[l].quota;
+    if (scale) scale[l] = sf[l];
+    if (inv_scale) inv_scale[l] = 1.0f / sf[l];
+    if (sigma2) sigma2[l] = s2[l];
+    if (inv_sigma2) inv_sigma2[l] = 1.0f / s2[l];
+    if (features_per_level) features_per_level[l] = quota[l];
   }
   return ORBX_OK;
 }

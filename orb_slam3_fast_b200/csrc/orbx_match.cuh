@@ -118,6 +118,52 @@ struct ResolveArgs {
 void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchScratch& S, const ResolveArgs& R,
                            cudaStream_t st);
 
+// ---- batched local-map tracking search (k_track.cu): Tracking::SearchLocalPoints for the frames of one extract batch
+// Frame f: keypoints kps + f * cap (n[f] of them), descriptors desc + f * cap * 32, its pose frustums[f], its local map
+// map_index[f] (NULL: f % n_maps). Everything is device memory; nothing is synchronised.
+struct TrackArgs {
+  int n_frames, cap;
+  const orbx_kp* kps;
+  const uint8_t* desc;
+  const int32_t* n;
+  const float* u_right;     // [F][cap] mvuRight, or NULL (monocular)
+  const uint8_t* occupied;  // [F][cap] or NULL = no keypoint holds a MapPoint yet
+  float min_x, min_y, inv_w, inv_h;  // grid geometry (Frame::mnMinX / mnMinY / mfGridElement*Inv)
+  float scale_factors[kMaxLevels];
+  int n_levels;
+  // local maps: [n_maps][m]
+  int m, n_maps;
+  const float *pos, *normal, *min_dist, *max_dist;
+  const uint8_t *skip, *has_obs, *mdesc;
+  const int32_t* map_index;
+  const orbx_frustum* frustums;  // [F]
+  float viewing_cos_limit, th, nnratio, th_far;
+  int far_points;
+  // optional isInFrustum outputs, [F][m] each (any may be NULL)
+  uint8_t* o_in_view;
+  float *o_proj_x, *o_proj_y, *o_proj_xr, *o_view_cos, *o_depth;
+  int32_t* o_level;
+  // scratch
+  int32_t* grid_offsets;  // [F][64 * 48 + 1]
+  int32_t* grid_items;    // [F][cap]
+  float4* q;              // [F][m] projected query: (u, v, u_right, radius)
+  int32_t* q_level;       // [F][m] predicted level, -1 = not searched
+  int2* seg;              // [F][m] (first candidate, count) inside the frame's candidate slab
+  int4* pre;              // [F][m] unconstrained best / second best: (d1, pos1, d2, pos2), pos = -1 when absent
+  uint32_t* cand;         // [F][cand_cap] dist << 20 | octave << 16 | keypoint
+  int cand_cap;
+  int32_t* cand_total;    // [F] (zeroed by the launcher)
+  int32_t* dec;           // [F][m]
+  // results
+  int32_t* assign;        // [F][cap] index of the MapPoint written to mvpMapPoints[i], or -1
+  int32_t* nmatches;      // [F] SearchByProjection's return value
+  int32_t* n_in_view;     // [F] nToMatch (points isInFrustum accepted)
+  int32_t* status;        // [F] 0, or ORBX_E_CAPACITY when the candidate slab overflowed
+};
+void launch_frustum_batch(const TrackArgs& A, cudaStream_t st);
+void launch_track_search(const TrackArgs& A, cudaStream_t st);  // grid -> enumerate -> resolve
+size_t track_resolve_smem(int cap);
+
 struct DevKeyFrame {
   int n, n_levels;
   const orbx_kp* kps;

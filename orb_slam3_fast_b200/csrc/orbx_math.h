@@ -186,6 +186,112 @@ ORBX_HD void sincosf_glibc(float y, float* c_out, float* s_out) {
   *c_out = (float)sincosf_poly(xs, x2, n ^ 1, flip);
 }
 
+// ---- glibc logf (sysdeps/ieee754/flt-32/e_logf.c, the ARM optimized-routines version glibc ships since 2.27) ------
+// Called by MapPoint::PredictScale as log(ratio) on a float (src/MapPoint.cc:566; <cmath>'s float overload) and by the
+// Frame constructors for mfLogScaleFactor (src/Frame.cc:189). 16-entry table, order-3 polynomial in double, one final
+// rounding. tests/test_host_math.py compares this with the host's logf on every positive finite float pattern.
+ORBX_HD float logf_glibc(float x) {
+  const double T[16][2] = {
+      {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+      {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+      {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+      {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+      {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+      {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+      {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+      {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+  const double Ln2 = 0x1.62e42fefa39efp-1;
+  const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+  union { float f; uint32_t u; } v;
+  v.f = x;
+  uint32_t ix = v.u;
+  if (ix == 0x3f800000u) return 0.f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2 == 0) return -INFINITY;
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return NAN;
+    v.f = fmul(x, 0x1p23f);  // subnormal: normalise
+    ix = v.u - (23u << 23);
+  }
+  const uint32_t tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) % 16);
+  const int k = (int32_t)tmp >> 23;
+  v.u = ix - (tmp & 0xff800000u);
+  const double z = (double)v.f;
+  const double r = dsub(dmul(z, T[i][0]), 1.0);
+  const double y0 = dadd(T[i][1], dmul((double)k, Ln2));
+  const double r2 = dmul(r, r);
+  double y = dadd(dmul(A1, r), A2);
+  y = dadd(dmul(A0, r2), y);
+  y = dadd(dmul(y, r2), dadd(y0, r));
+  return (float)y;
+}
+
+// ---- Frame::isInFrustum (src/Frame.cc:632-699, Nleft == -1) for one MapPoint -------------------------------------
+// Eigen evaluates a fixed-size 3-vector reduction (dot, squaredNorm, a row of Matrix3f * Vector3f) without packets
+// (3 floats do not fill a Packet4f) through redux_novec_unroller, which splits the range in halves:
+// c0 + (c1 + c2) (Eigen/src/Core/Redux.h); the reference is built without FMA (CMakeLists.txt:13-18).
+ORBX_HD float eigen_dot3(float a0, float a1, float a2, float b0, float b1, float b2) {
+  return fadd(fmul(a0, b0), fadd(fmul(a1, b1), fmul(a2, b2)));
+}
+ORBX_HD float sqrtf_rn(float v) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(v);
+#else
+  return sqrtf(v);
+#endif
+}
+struct FrustumOut {
+  bool in_view;          // the return value = mbTrackInView
+  bool proj_valid;       // mTrackProjX / Y were set to uv (the bounds test passed); otherwise they are -1
+  float proj_x, proj_y, proj_xr, depth, view_cos;
+  int level;
+};
+// fr points at the 26 words of an orbx_frustum (include/orbx_types.h); pos / normal at 3 floats each.
+ORBX_HD FrustumOut is_in_frustum(const float* fr, int n_levels, const float* pos, const float* normal, float min_dist_raw,
+                                 float max_dist_raw, float viewing_cos_limit) {
+  FrustumOut o;
+  o.in_view = false;
+  o.proj_valid = false;
+  o.proj_x = o.proj_y = -1.f;
+  o.proj_xr = o.depth = o.view_cos = 0.f;
+  o.level = 0;
+  const float *R = fr, *t = fr + 9, *Ow = fr + 12;
+  const float fx = fr[15], fy = fr[16], cx = fr[17], cy = fr[18], mbf = fr[19];
+  const float min_x = fr[20], max_x = fr[21], min_y = fr[22], max_y = fr[23], log_sf = fr[24];
+  // Pc = mRcw * P + mtcw (:642)
+  const float pcx = fadd(eigen_dot3(R[0], R[1], R[2], pos[0], pos[1], pos[2]), t[0]);
+  const float pcy = fadd(eigen_dot3(R[3], R[4], R[5], pos[0], pos[1], pos[2]), t[1]);
+  const float pcz = fadd(eigen_dot3(R[6], R[7], R[8], pos[0], pos[1], pos[2]), t[2]);
+  const float pc_dist = sqrtf_rn(eigen_dot3(pcx, pcy, pcz, pcx, pcy, pcz));  // Pc.norm() (:643)
+  const float invz = fdiv(1.0f, pcz);                                         // :647
+  if (pcz < 0.0f) return o;                                                   // :648
+  const float u = fadd(fdiv(fmul(fx, pcx), pcz), cx);                         // Pinhole::project, Pinhole.cpp:47-53
+  const float v = fadd(fdiv(fmul(fy, pcy), pcz), cy);
+  if (u < min_x || u > max_x) return o;                                       // :652-653
+  if (v < min_y || v > max_y) return o;
+  o.proj_valid = true;
+  o.proj_x = u;
+  o.proj_y = v;
+  const float maxDistance = fmul(1.2f, max_dist_raw), minDistance = fmul(0.8f, min_dist_raw);  // MapPoint.cc:533-541
+  const float pox = fsub(pos[0], Ow[0]), poy = fsub(pos[1], Ow[1]), poz = fsub(pos[2], Ow[2]);
+  const float dist = sqrtf_rn(eigen_dot3(pox, poy, poz, pox, poy, poz));      // :662
+  if (dist < minDistance || dist > maxDistance) return o;                    // :664
+  const float viewCos = fdiv(eigen_dot3(pox, poy, poz, normal[0], normal[1], normal[2]), dist);  // :669
+  if (viewCos < viewing_cos_limit) return o;                                  // :671
+  // MapPoint::PredictScale(dist, this) (src/MapPoint.cc:559-573): ceil(logf(mfMaxDistance / dist) / mfLogScaleFactor)
+  const float ratio = fdiv(max_dist_raw, dist);
+  int nScale = (int)ceilf(fdiv(logf_glibc(ratio), log_sf));
+  if (nScale < 0) nScale = 0;
+  else if (nScale >= n_levels) nScale = n_levels - 1;
+  o.in_view = true;
+  o.proj_xr = fsub(u, fmul(mbf, invz));                                       // :680
+  o.depth = pc_dist;
+  o.level = nScale;
+  o.view_cos = viewCos;
+  return o;
+}
+
 // ---- libstdc++ std::sort (introsort + final insertion sort, _S_threshold = 16) ------------------------------------
 // The reference sorts vector<pair<int, ExtractorNode*>> with compareNodes (src/ORBextractor.cc:542-555, :686-688).
 // compareNodes orders by (size, UL.x); elements equal under it are permuted by the algorithm, and that permutation

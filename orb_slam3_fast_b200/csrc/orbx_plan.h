@@ -72,6 +72,27 @@ inline void axis_table(int ssize, int dsize, bool clamp, int16_t* ofs, int16_t* 
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// The image-size independent tables of the constructor (src/ORBextractor.cc:418-448): mvScaleFactor, mvLevelSigma2 and
+// mnFeaturesPerLevel. Valid for every constructor-legal (scaleFactor, nlevels).
+inline void make_tables(int nfeatures, float scale_factor_f, int nlevels, float* sf, float* s2, int* quota) {
+  const double scaleFactor = scale_factor_f;  // include/ORBextractor.h:106 — a double member set from a float
+  sf[0] = 1.0f;
+  s2[0] = 1.0f;
+  for (int i = 1; i < nlevels; i++) {
+    sf[i] = (float)(sf[i - 1] * scaleFactor);
+    s2[i] = sf[i] * sf[i];
+  }
+  const float factor = (float)(1.0f / scaleFactor);
+  float want = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+  int sum = 0;
+  for (int l = 0; l < nlevels - 1; l++) {
+    quota[l] = cv_round(want);
+    sum += quota[l];
+    want *= factor;
+  }
+  quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
+}
+
 // Returns 0, or a negative error: -1 bad arguments, -2 image too small for the level count, -3 too large.
 inline int make_plan(int w, int h, int nfeatures, float scale_factor_f, int nlevels, Plan* P) {
   memset(P, 0, sizeof(*P));
@@ -80,26 +101,9 @@ inline int make_plan(int w, int h, int nfeatures, float scale_factor_f, int nlev
   P->nlevels = nlevels;
   P->w = w;
   P->h = h;
-  const double scaleFactor = scale_factor_f;  // include/ORBextractor.h:106 — a double member set from a float
   float sf[kMaxLevels], s2[kMaxLevels];
-  sf[0] = 1.0f;
-  s2[0] = 1.0f;
-  for (int i = 1; i < nlevels; i++) {
-    sf[i] = (float)(sf[i - 1] * scaleFactor);
-    s2[i] = sf[i] * sf[i];
-  }
   int quota[kMaxLevels];
-  {
-    const float factor = (float)(1.0f / scaleFactor);
-    float want = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
-    int sum = 0;
-    for (int l = 0; l < nlevels - 1; l++) {
-      quota[l] = cv_round(want);
-      sum += quota[l];
-      want *= factor;
-    }
-    quota[nlevels - 1] = nfeatures - sum > 0 ? nfeatures - sum : 0;
-  }
+  make_tables(nfeatures, scale_factor_f, nlevels, sf, s2, quota);
   {  // umax :456-468
     int v, v0;
     const int vmax = (int)floorf(kHalfPatch * sqrtf(2.f) / 2 + 1);

@@ -41,6 +41,11 @@ def _bind(L):
     L.orbm_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     L.orbm_search_for_initialization.argtypes = [vp, vp, vp, vp, ci, cf, ci, vp, vp]
     L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
+    L.orbm_is_in_frustum.argtypes = [vp, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.orbm_track_local_map_batch_device.argtypes = [vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                                    vp]
+    L.orbm_stereo_track_frames_batch.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.c_int64, cf, cf, vp, vp, vp, vp,
+                                                 vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L._orbm_bound = True
 
 
@@ -144,6 +149,59 @@ class ORBmatcher:
             imgs_l.strides[0], mbf, mb, _l.ptr(out["kps_l"]), _l.ptr(out["desc_l"]), _l.ptr(out["n_l"]),
             _l.ptr(out["kps_r"]), _l.ptr(out["desc_r"]), _l.ptr(out["n_r"]), cap, _l.ptr(out["u_right"]),
             _l.ptr(out["depth"]), _l.ptr(out["n_matched"])))
+        return out
+
+    # bool Frame::isInFrustum(MapPoint*, viewingCosLimit) over a local map — src/Frame.cc:632-699, Tracking.cc:3288-3300
+    def IsInFrustum(self, frustum, local_map, map_index=0, viewingCosLimit=0.5, out=None):
+        """frustum: one views.FRUSTUM_DTYPE record; local_map: views.make_local_map(...). Returns (n_in_view, dict) with
+        the orbx_mappoints arrays track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth."""
+        m = local_map.struct.m
+        fr = np.ascontiguousarray(frustum).reshape(1)
+        if out is None:
+            out = dict(track_in_view=np.zeros(m, np.uint8), proj_x=np.zeros(m, np.float32),
+                       proj_y=np.zeros(m, np.float32), proj_xr=np.zeros(m, np.float32), level=np.zeros(m, np.int32),
+                       view_cos=np.zeros(m, np.float32), depth=np.zeros(m, np.float32))
+        nv = C.c_int32(0)
+        self._check(self._L.orbm_is_in_frustum(self._h, _l.ptr(fr), local_map.ref(), map_index, viewingCosLimit,
+                                               _l.ptr(out["track_in_view"]), _l.ptr(out["proj_x"]),
+                                               _l.ptr(out["proj_y"]), _l.ptr(out["proj_xr"]), _l.ptr(out["level"]),
+                                               _l.ptr(out["view_cos"]), _l.ptr(out["depth"]), C.byref(nv)))
+        return nv.value, out
+
+    # void Tracking::SearchLocalPoints() for the frames of one device-resident extract batch — src/Tracking.cc:3249-3330
+    def TrackLocalMapBatch_device(self, extractor, n_frames, d_kps, d_desc, d_n, cap, d_u_right, d_occupied, d_frustums,
+                                  local_map_device, d_map_index, params, d_assign, d_nmatches, d_n_in_view, d_status,
+                                  stream=0):
+        vp = C.c_void_p
+        self._check(self._L.orbm_track_local_map_batch_device(
+            self._h, extractor._h, n_frames, vp(d_kps), vp(d_desc), vp(d_n), cap, vp(d_u_right) if d_u_right else None,
+            vp(d_occupied) if d_occupied else None, vp(d_frustums), local_map_device.ref(),
+            vp(d_map_index) if d_map_index else None, C.byref(params), vp(d_assign), vp(d_nmatches), vp(d_n_in_view),
+            vp(d_status), vp(stream) if stream else None))
+
+    # the stereo Frame constructor's hot path + Tracking::SearchLocalPoints per pair, host buffers (configs[3] end to end)
+    @staticmethod
+    def alloc_track_outputs(n_pairs, cap, empty=np.empty):
+        out = ORBmatcher.alloc_stereo_outputs(n_pairs, cap, empty)
+        out.update(assign=empty((n_pairs, cap), np.int32), nmatches=empty((n_pairs,), np.int32),
+                   n_in_view=empty((n_pairs,), np.int32))
+        return out
+
+    def StereoTrackFramesBatch(self, ex_left, ex_right, imgs_l, imgs_r, mbf, mb, frustums, local_map, params,
+                               map_index=None, occupied=None, out=None):
+        assert imgs_l.shape == imgs_r.shape and imgs_l.strides == imgs_r.strides and imgs_l.strides[2] == 1
+        n, h, w = imgs_l.shape
+        cap = ex_left.capacity
+        if out is None:
+            out = self.alloc_track_outputs(n, cap)
+        assert frustums.dtype.itemsize == 104 and len(frustums) == n and frustums.flags.c_contiguous
+        self._check(self._L.orbm_stereo_track_frames_batch(
+            self._h, ex_left._h, ex_right._h, n, _l.ptr(imgs_l), _l.ptr(imgs_r), w, h, imgs_l.strides[1],
+            imgs_l.strides[0], mbf, mb, _l.ptr(frustums), local_map.ref(),
+            None if map_index is None else _l.ptr(map_index), None if occupied is None else _l.ptr(occupied),
+            C.byref(params), _l.ptr(out["kps_l"]), _l.ptr(out["desc_l"]), _l.ptr(out["n_l"]), _l.ptr(out["kps_r"]),
+            _l.ptr(out["desc_r"]), _l.ptr(out["n_r"]), cap, _l.ptr(out["u_right"]), _l.ptr(out["depth"]),
+            _l.ptr(out["n_matched"]), _l.ptr(out["assign"]), _l.ptr(out["nmatches"]), _l.ptr(out["n_in_view"])))
         return out
 
     # int SearchByProjection(Frame& F, const vector<MapPoint*>&, th, bFarPoints, thFarPoints) — src/ORBmatcher.cc:42

@@ -137,6 +137,84 @@ def local_map(kps, desc, m, w, h, n_levels, seed=0, bf=47.9):
                 has_obs=(rng.random(m) < 0.9).astype(np.uint8), desc=d)
 
 
+def camera_pose(seed=0):
+    """A seeded world-to-camera pose (Rcw, tcw) and the camera centre Ow = -Rcw^T tcw, float32 (Frame::SetPose /
+    UpdatePoseMatrices, src/Frame.cc:484-518)."""
+    rng = np.random.default_rng(seed + 7919)
+    a = rng.uniform(-0.6, 0.6, 3)
+    cx_, sx = np.cos(a[0]), np.sin(a[0])
+    cy_, sy = np.cos(a[1]), np.sin(a[1])
+    cz_, sz = np.cos(a[2]), np.sin(a[2])
+    R = (np.array([[cz_, -sz, 0], [sz, cz_, 0], [0, 0, 1]]) @ np.array([[cy_, 0, sy], [0, 1, 0], [-sy, 0, cy_]]) @
+         np.array([[1, 0, 0], [0, cx_, -sx], [0, sx, cx_]]))
+    t = rng.uniform(-2.0, 2.0, 3)
+    R32, t32 = R.astype(np.float32), t.astype(np.float32)
+    Ow = (-(R32.astype(np.float64).T @ t32.astype(np.float64))).astype(np.float32)
+    return R32, t32, Ow
+
+
+def frustum(w, h, seed=0, fx=435.2, fy=435.2, cx=None, cy=None, bf=47.9, scale_factor=1.2, n_levels=8):
+    """One orbx_frustum record (views.FRUSTUM_DTYPE) for an undistorted w x h pinhole camera at camera_pose(seed)."""
+    from .views import FRUSTUM_DTYPE
+    R, t, Ow = camera_pose(seed)
+    fr = np.zeros((), FRUSTUM_DTYPE)
+    fr["Rcw"], fr["tcw"], fr["Ow"] = R.reshape(9), t, Ow
+    fr["fx"], fr["fy"] = fx, fy
+    fr["cx"] = (w - 1) / 2.0 if cx is None else cx
+    fr["cy"] = (h - 1) / 2.0 if cy is None else cy
+    fr["mbf"] = bf
+    fr["min_x"], fr["max_x"], fr["min_y"], fr["max_y"] = 0.0, w, 0.0, h
+    fr["log_scale_factor"] = np.log(np.float32(scale_factor))   # float32 log, as logf(mfScaleFactor) (src/Frame.cc:189)
+    fr["n_levels"] = n_levels
+    return fr
+
+
+def local_map_world(kps, desc, m, fr, seed=0):
+    """Config 4 with the projection on the device: m world points of a synthetic local map seen from frustum `fr`
+    (SURVEY.md §8d): ~half are anchored on real keypoints of the frame (projection jittered by ~1.5 px, predicted level =
+    the keypoint's octave or one above, descriptor = the keypoint's with 0..80 flipped bits), the rest project uniformly
+    over (and slightly outside) the image; a few are behind the camera, out of their distance range or seen too
+    obliquely. Returns a dict in the orbx_local_map layout."""
+    rng = np.random.default_rng(seed + 611953)
+    n = len(kps)
+    w, h = float(fr["max_x"]), float(fr["max_y"])
+    n_levels = int(fr["n_levels"])
+    src = rng.integers(0, max(n, 1), m)
+    anchored = (rng.random(m) < 0.5) & (n > 0)
+    kx = kps["x"][src] if n else np.zeros(m)
+    ky = kps["y"][src] if n else np.zeros(m)
+    ko = kps["octave"][src] if n else np.zeros(m, np.int64)
+    px = np.where(anchored, kx + rng.normal(0, 1.5, m), rng.uniform(-20, w + 20, m))
+    py = np.where(anchored, ky + rng.normal(0, 1.5, m), rng.uniform(-20, h + 20, m))
+    level = np.where(anchored, np.clip(ko + rng.integers(0, 2, m), 0, n_levels - 1), rng.integers(0, n_levels, m))
+    z = rng.uniform(0.5, 20.0, m)
+    z = np.where(rng.random(m) < 0.02, -z, z)                                    # behind the camera
+    R = fr["Rcw"].reshape(3, 3).astype(np.float64)
+    t = fr["tcw"].astype(np.float64)
+    Pc = np.stack([(px - float(fr["cx"])) / float(fr["fx"]) * z, (py - float(fr["cy"])) / float(fr["fy"]) * z, z], 1)
+    P = (Pc - t) @ R                                                             # Rwc (Pc - tcw)
+    pos = P.astype(np.float32)
+    PO = pos.astype(np.float64) - fr["Ow"].astype(np.float64)
+    dist = np.linalg.norm(PO, axis=1)
+    # mean viewing direction: the ray to the camera centre tilted by up to ~70 degrees (cos limit 0.5 = 60 degrees)
+    tilt = rng.uniform(0, 1.2, m)
+    axis = np.cross(PO, rng.normal(size=(m, 3)))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True) + 1e-12
+    d0 = PO / (dist[:, None] + 1e-12)
+    nrm = d0 * np.cos(tilt)[:, None] + np.cross(axis, d0) * np.sin(tilt)[:, None]
+    # PredictScale = ceil(log(max_dist / dist) / log(scale)) -> aim at the middle of the level's interval
+    sf = float(np.exp(fr["log_scale_factor"]))
+    max_dist = dist * sf ** (level - 0.5)
+    min_dist = max_dist / sf ** (n_levels - 1)
+    bad_range = rng.random(m) < 0.05
+    max_dist = np.where(bad_range, dist * 0.5, max_dist)                         # dist > 1.2 * max_dist
+    flips = rng.integers(0, 81, m)
+    d = flip_bits(desc[src], flips, rng) if n else rng.integers(0, 256, (m, 32), dtype=np.uint8)
+    return dict(pos=pos, normal=nrm.astype(np.float32), min_dist=min_dist.astype(np.float32),
+                max_dist=max_dist.astype(np.float32), skip=(rng.random(m) < 0.08).astype(np.uint8),
+                has_obs=(rng.random(m) < 0.9).astype(np.uint8), desc=d)
+
+
 def projected_points(kps, desc, m, w, h, n_levels, scale_factors, seed=0, bf=47.9, th=7.0, stereo=True):
     """Points of a 'last frame' projected into the current one (input of SearchByProjection(Frame&, const Frame&)):
     most are real keypoints jittered by a small motion, the rest uniform. Returns a dict in the orbx_projected layout."""

@@ -48,6 +48,32 @@ class KeyFrameView(C.Structure):
                 ("level_sigma2", C.c_void_p), ("n_levels", C.c_int32)]
 
 
+class Frustum(C.Structure):
+    """orbx_frustum (include/orbx_types.h): what Frame::isInFrustum reads from the Frame; 104 bytes."""
+    _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("fx", C.c_float),
+                ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("mbf", C.c_float), ("min_x", C.c_float),
+                ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float), ("log_scale_factor", C.c_float),
+                ("n_levels", C.c_int32)]
+
+
+FRUSTUM_DTYPE = np.dtype([("Rcw", "<f4", 9), ("tcw", "<f4", 3), ("Ow", "<f4", 3), ("fx", "<f4"), ("fy", "<f4"),
+                          ("cx", "<f4"), ("cy", "<f4"), ("mbf", "<f4"), ("min_x", "<f4"), ("max_x", "<f4"),
+                          ("min_y", "<f4"), ("max_y", "<f4"), ("log_scale_factor", "<f4"), ("n_levels", "<i4")])
+assert FRUSTUM_DTYPE.itemsize == 104 and C.sizeof(Frustum) == 104
+
+
+class LocalMap(C.Structure):
+    _fields_ = [("m", C.c_int32), ("n_maps", C.c_int32), ("pos", C.c_void_p), ("normal", C.c_void_p),
+                ("min_dist", C.c_void_p), ("max_dist", C.c_void_p), ("skip", C.c_void_p), ("has_obs", C.c_void_p),
+                ("desc", C.c_void_p)]
+
+
+class TrackParams(C.Structure):
+    _fields_ = [("viewing_cos_limit", C.c_float), ("th", C.c_float), ("nnratio", C.c_float), ("far_points", C.c_int32),
+                ("th_far", C.c_float), ("min_x", C.c_float), ("min_y", C.c_float), ("inv_w", C.c_float),
+                ("inv_h", C.c_float), ("cand_per_frame", C.c_int32)]
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -145,3 +171,34 @@ def make_keyframe_view(kps, desc, u_right, has_mappoint, node_ids, offsets, indi
     fv = FeatVec(len(node_ids), _p(node_ids), _p(offsets), _p(indices))
     kv = KeyFrameView(len(kps), _p(kps), _p(desc), _p(u_right), _p(hm), fv, _p(sf), _p(s2), len(sf))
     return Holder(kv, (kps, desc, u_right, hm, node_ids, offsets, indices, sf, s2))
+
+
+def make_local_map(pos, normal, min_dist, max_dist, skip, has_obs, desc):
+    """orbx_local_map over host arrays: pos / normal [n_maps, m, 3], the others [n_maps, m] (desc [n_maps, m, 32]); a
+    single map may omit the leading axis."""
+    pos = _c(pos, np.float32)
+    if pos.ndim == 2:
+        pos = pos[None]
+    n_maps, m = pos.shape[0], pos.shape[1]
+    arrs = (pos, _c(normal, np.float32).reshape(n_maps, m, 3), _c(min_dist, np.float32).reshape(n_maps, m),
+            _c(max_dist, np.float32).reshape(n_maps, m), None if skip is None else _c(skip, np.uint8).reshape(n_maps, m),
+            _c(has_obs, np.uint8).reshape(n_maps, m), _c(desc, np.uint8).reshape(n_maps, m, 32))
+    return Holder(LocalMap(m, n_maps, *[_p(a) for a in arrs]), arrs)
+
+
+def make_local_map_device(m, n_maps, pos, normal, min_dist, max_dist, skip, has_obs, desc):
+    """orbx_local_map whose array pointers are device addresses (integers, e.g. torch data_ptr())."""
+    vp = C.c_void_p
+    return Holder(LocalMap(m, n_maps, vp(pos), vp(normal), vp(min_dist), vp(max_dist), vp(skip) if skip else None,
+                           vp(has_obs), vp(desc)), ())
+
+
+def make_track_params(width, height, th=1.0, nnratio=0.8, viewing_cos_limit=0.5, far_points=False, th_far=0.0,
+                      min_x=0.0, min_y=0.0, max_x=None, max_y=None, cand_per_frame=0):
+    """Tracking::SearchLocalPoints' scalars; the grid cell sizes as Frame computes them (src/Frame.cc:230-233)."""
+    max_x = float(width) if max_x is None else max_x
+    max_y = float(height) if max_y is None else max_y
+    inv_w = np.float32(GRID_COLS) / (np.float32(max_x) - np.float32(min_x))
+    inv_h = np.float32(GRID_ROWS) / (np.float32(max_y) - np.float32(min_y))
+    return TrackParams(viewing_cos_limit, th, nnratio, int(far_points), th_far, min_x, min_y, float(inv_w), float(inv_h),
+                       cand_per_frame)
