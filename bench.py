@@ -1,16 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — frames/s of the ORB front-end hot path on B200 (driver contract: see the task statement / DESIGN.md).
+"""bench.py — frames/s of the ORB tracking front-end hot path on B200 (driver contract: the task statement / DESIGN.md §5).
 
-Workload (BASELINE.json configs[1]): EuRoC-shaped 752x480 rectified stereo pairs, 1200 features per eye, 8 levels,
-scale 1.2, FAST 20/7: ORBextractor::operator() for both eyes + Frame::ComputeStereoMatches. One "step" = one batch of
-`--pairs` independent pairs per GPU (frames are independent: weak scaling, no data-path collective; the only
-collective is the gather of the per-pair result counts). A stereo pair counts as 2 frames (2 ORBextractor calls).
+Default workload = BASELINE.json configs[3], the configuration the metric is quoted on: rectified 640x480 stereo pairs,
+1200 features per eye, 8 levels, scale 1.2, FAST 20/7 — ORBextractor::operator() for both eyes +
+Frame::ComputeStereoMatches + Tracking::SearchLocalPoints (Frame::isInFrustum over a 10 000-point local map, then
+ORBmatcher::SearchByProjection, th = 1, nnratio = 0.8). Frames are independent: weak scaling, no data-path collective
+(the only collective is the gather of per-pair result counts). A "frame" is one ORBextractor call: a pair counts 2.
 
-  value  device-resident: images already in HBM, results left in HBM, CUDA events on the launching stream.
-  e2e    the same batch through the host-facing C ABI call orbm_stereo_frames_batch (pinned host buffers in and out,
-         H2D / D2H inside the timed region).
-  --impl reference: the reference's own sources compiled in place (oracle/_ref; else the CPU oracle port,
-                    oracle/liborbref.so) on all host cores, same workload.
+  step     `--reps` back-to-back batches of `--pairs` pairs per GPU (default 8 x 1024 pairs = 16 384 frames per step)
+  value    device-resident: images, poses and local maps already in HBM, results left in HBM; CUDA events on the
+           launching stream; per-batch durations give p10 / p50 / p90
+  e2e      the same batches through the host-facing C ABI call orbm_stereo_track_frames_batch: pinned host buffers in
+           and out, H2D (images, poses, occupancy, local maps) and D2H (keypoints, descriptors, uRight, depth, assign)
+           inside the timed region
+  --impl reference   the reference's own sources compiled in place (oracle/_ref; else the CPU oracle port) on all host
+                     cores, same workload
+  --config 1 | 2 | 4   the other BASELINE.json configurations as lines of their own (1: 752x480 stereo extract +
+                     ComputeStereoMatches; 2: 1280x720 mono, 64 frames sharded over the GPUs; 4: knn2 sweep); the
+                     default line also carries configs[1] as a second block.
 """
 import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA starts: 2 streams per pipeline lane (see orbx_api.cu)
@@ -28,21 +35,52 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 752, 480, 1200, 8, 1.2, 20, 7
+NLEVELS, SCALE, INI_TH, MIN_TH = 8, 1.2, 20, 7
 FX, BASELINE_M = 435.2, 0.11  # EuRoC-like rectified focal length / baseline
 MBF, MB = float(np.float32(FX * BASELINE_M)), float(np.float32(BASELINE_M))
-METRIC = "frames/sec ORB extract+match (752x480 stereo pairs, 1200 feat/eye, extract + ComputeStereoMatches)"
-WORKLOAD = "configs[1]: EuRoC-shaped 752x480 stereo pair, 1200 features/eye, extract + ComputeStereoMatches"
+try:
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+except Exception:
+    METRIC = "frames/sec ORB extract+match @640×480, 1/2/4/8 GPU; HBM GB/s vs roofline"
+
+CONFIGS = {
+    3: dict(w=640, h=480, nfeat=1200, track=True, map_points=10000, th=1.0, nnratio=0.8,
+            workload="configs[3]: stereo 640x480 extract (1200 features/eye) + ComputeStereoMatches + SearchLocalPoints "
+                     "(isInFrustum + SearchByProjection, th=1, nnratio=0.8) against a 10 000-MapPoint synthetic local map"),
+    1: dict(w=752, h=480, nfeat=1200, track=False, map_points=0, th=1.0, nnratio=0.8,
+            workload="configs[1]: EuRoC-shaped 752x480 stereo pair, 1200 features/eye, extract + ComputeStereoMatches"),
+}
+W, H, NFEAT = 752, 480, 1200  # configs[1] geometry: tools/ubench/make_hotpath_case.py and older tools import these
 
 
-def make_pairs(n_distinct, seed0):
+def make_pairs(n_distinct, seed0, w=W, h=H):
     from orb_slam3_fast_b200 import synth
     L, R = [], []
     for s in range(n_distinct):
-        l, r, _ = synth.stereo_pair(H, W, seed0 + s)
+        l, r, _ = synth.stereo_pair(h, w, seed0 + s)
         L.append(l)
         R.append(r)
     return np.stack(L), np.stack(R)
+
+
+def make_track_inputs(cfg, L, seed0, kps_desc=None):
+    """Per distinct pair: one pose (orbx_frustum) and one local map generated against the left frame's own keypoints
+    (~half of the points are anchored on real keypoints with 0..80 flipped descriptor bits), and a
+    per-keypoint occupancy array (25 % of the keypoints already hold a MapPoint). kps_desc: the left frames' (keypoints,
+    descriptors) if the caller has them (else the CPU oracle extracts them: test infrastructure used as a data generator
+    for the synthetic map, not as the thing measured)."""
+    from orb_slam3_fast_b200 import synth
+    n = len(L)
+    if kps_desc is None:
+        from oracle import orbref
+        ex = orbref.Extractor(cfg["nfeat"], SCALE, NLEVELS, INI_TH, MIN_TH)
+        kps_desc = [ex(L[i], (0, 0))[1:] for i in range(n)]
+    frs = np.stack([synth.frustum(cfg["w"], cfg["h"], seed=seed0 + i, fx=FX, fy=FX, bf=MBF, scale_factor=SCALE,
+                                  n_levels=NLEVELS) for i in range(n)])
+    maps = [synth.local_map_world(kps_desc[i][0], kps_desc[i][1], cfg["map_points"], frs[i], seed=seed0 + i)
+            for i in range(n)]
+    stacked = {k: np.ascontiguousarray(np.stack([mp[k] for mp in maps])) for k in maps[0]}
+    return frs, stacked
 
 
 class ClockSampler:
@@ -67,6 +105,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        return len(self.rows)
+
     def stop(self):
         if self.proc:
             self.proc.terminate()
@@ -76,6 +117,7 @@ class ClockSampler:
                 self.proc.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
             if len(r) >= 8:
@@ -83,12 +125,13 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": min(sm) if sm else None, "power_w_max": max(pw) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def reference_sources_available():
-    """oracle/_ref holds the reference's own extractor + ComputeStereoMatches sources compiled in place (oracle/Makefile,
-    target `ref`; built where /root/reference exists and shipped with the snapshot)."""
+    """oracle/_ref holds the reference's own extractor, matcher, ComputeStereoMatches and isInFrustum sources compiled in
+    place (oracle/Makefile, target `ref`; built where /root/reference exists and shipped with the snapshot)."""
     try:
         from oracle import refsrc
         return refsrc.matcher_available()
@@ -96,65 +139,115 @@ def reference_sources_available():
         return False
 
 
-def cpu_reference_run(n_pairs, threads, seed0=1000):
-    """Times the CPU implementation of the path (extract x2 + ComputeStereoMatches per pair) on `threads` host threads:
-    the reference's own sources from oracle/_ref when they are there (kind "reference": its orchestration code over the
-    oracle's scalar image primitives, one pair per thread), else the oracle port (kind "port")."""
-    L, R = make_pairs(min(n_pairs, 8), seed0)
-    if reference_sources_available():
-        from concurrent.futures import ThreadPoolExecutor
-        from oracle import refsrc
-        refsrc.mlib()
-        order = [i % len(L) for i in range(n_pairs)]
-
-        def one(i):  # ctypes releases the GIL for the duration of the call
-            return refsrc.stereo_frame(L[i], R[i], MBF, MB, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH)[0]
-        t0 = time.perf_counter()
-        with ThreadPoolExecutor(max_workers=threads) as pool:
-            list(pool.map(one, order))
-        dt = time.perf_counter() - t0
-        return 2.0 * n_pairs / dt, dt
-    from oracle import orbref
-    reps = (n_pairs + len(L) - 1) // len(L)
-    L = np.ascontiguousarray(np.tile(L, (reps, 1, 1))[:n_pairs])
-    R = np.ascontiguousarray(np.tile(R, (reps, 1, 1))[:n_pairs])
-    orbref.lib()
-    t0 = time.perf_counter()
-    orbref.stereo_many(L, R, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, MBF, MB, threads)
-    dt = time.perf_counter() - t0
-    return 2.0 * n_pairs / dt, dt
-
-
 def cpu_kind():
     return "reference" if reference_sources_available() else "port"
 
 
+_CPU_DATA = {}
+
+
+def cpu_data(cfg_id, n_distinct=8, seed0=1000):
+    """Inputs of the CPU arms: n_distinct pairs (+ poses / maps) of the workload, generated once."""
+    key = (cfg_id, n_distinct, seed0)
+    if key not in _CPU_DATA:
+        cfg = CONFIGS[cfg_id]
+        L, R = make_pairs(n_distinct, seed0, cfg["w"], cfg["h"])
+        d = dict(L=L, R=R)
+        if cfg["track"]:
+            from orb_slam3_fast_b200 import views
+            from oracle import orbref
+            frs, stacked = make_track_inputs(cfg, L, seed0)
+            d.update(frs=frs, lm=orbref.make_local_map(**stacked),
+                     prm=views.make_track_params(cfg["w"], cfg["h"], th=cfg["th"], nnratio=cfg["nnratio"]))
+            rng = np.random.default_rng(seed0)
+            d["occ"] = (rng.random((n_distinct, cfg["nfeat"] + 16 * NLEVELS + 64)) < 0.25).astype(np.uint8)
+        _CPU_DATA[key] = d
+    return _CPU_DATA[key]
+
+
+def cpu_reference_run(cfg_id, n_pairs, threads):
+    """Times the CPU implementation of the workload on `threads` host threads, one pair per thread at a time: the
+    reference's own sources from oracle/_ref when they are there (kind "reference"), else the oracle port (kind "port").
+    Returns (frames/s, seconds)."""
+    cfg = CONFIGS[cfg_id]
+    d = cpu_data(cfg_id)
+    L, R = d["L"], d["R"]
+    nd = len(L)
+    from concurrent.futures import ThreadPoolExecutor
+    if reference_sources_available():
+        from oracle import refsrc
+        refsrc.mlib()
+        if cfg["track"]:
+            def one(i):  # ctypes releases the GIL for the duration of the call
+                k = i % nd
+                return refsrc.stereo_track_frame(L[k], R[k], MBF, MB, d["frs"][k], d["lm"], k, d["occ"][k], d["prm"],
+                                                 cfg["nfeat"], SCALE, NLEVELS, INI_TH, MIN_TH)["nmatches"]
+        else:
+            def one(i):
+                k = i % nd
+                return refsrc.stereo_frame(L[k], R[k], MBF, MB, cfg["nfeat"], SCALE, NLEVELS, INI_TH, MIN_TH)[0]
+    else:
+        from oracle import orbref
+        orbref.lib()
+        tl = threading.local()
+
+        def one(i):
+            k = i % nd
+            if not hasattr(tl, "ex"):
+                tl.ex = (orbref.Extractor(cfg["nfeat"], SCALE, NLEVELS, INI_TH, MIN_TH),
+                         orbref.Extractor(cfg["nfeat"], SCALE, NLEVELS, INI_TH, MIN_TH))
+            rl, rr = tl.ex
+            _, kl, dl = rl(L[k], (0, 0))
+            _, kr, dr = rr(R[k], (0, 0))
+            nm, ur, dp = orbref.stereo_match(rl, rr, kl, dl, kr, dr, MBF, MB)
+            if cfg["track"]:
+                prm = d["prm"]
+                off, items = orbref.build_grid(kl, 0.0, 0.0, prm.inv_w, prm.inv_h)
+                g, keep = orbref.make_grid(off, items, 0.0, 0.0, prm.inv_w, prm.inv_h)
+                fv = orbref.make_frame_view(kl, dl, ur, d["occ"][k][:len(kl)], g, keep, rl.scale)
+                nm = orbref.track_local_map(fv, d["frs"][k], d["lm"], k, cfg["th"], cfg["nnratio"])[0]
+            return nm
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(one, range(n_pairs)))
+    dt = time.perf_counter() - t0
+    return 2.0 * n_pairs / dt, dt
+
+
 CPU_NOTES = {
-    "reference": "the reference's own src/ORBextractor.cc + Frame::ComputeStereoMatches compiled in place (oracle/_ref) "
-                 "against stand-in OpenCV / TBB headers: its orchestration code, serial inside a frame, over the oracle's "
-                 "scalar cv2-pinned image primitives; pair-parallel over the host threads. The full library cannot be "
-                 "built here (OpenCV / TBB / Eigen / Sophus C++ are not installed)",
-    "port": "CPU oracle port of the reference's serial path, pair-parallel over all host threads; the reference itself "
-            "needs OpenCV/TBB/Eigen C++ and cannot be built here",
+    "reference": "the reference's own src/ORBextractor.cc, src/ORBmatcher.cc and the text of Frame::ComputeStereoMatches / "
+                 "AssignFeaturesToGrid / isInFrustum compiled in place (oracle/_ref) against stand-in OpenCV / TBB / Eigen "
+                 "headers: its code, serial inside a frame, pair-parallel over the host threads; the image primitives "
+                 "(resize, FAST, GaussianBlur) are %s. The full library cannot be built here (OpenCV / TBB / Eigen / "
+                 "Sophus C++ are not installed)",
+    "port": "CPU oracle port of the reference's serial path, pair-parallel over all host threads (oracle/_ref is absent); "
+            "image primitives are %s",
 }
 
 
-def opencv_primitives_ms():
-    """Second opinion for the CPU baseline: the three OpenCV kernels the reference spends most of
-    its extraction time in — resize chain, FAST on the 8 whole levels, 7x7 blur — timed through cv2 (OpenCV's SIMD
-    builds) on one 752x480 frame, one thread. A lower bound of the reference's per-frame extraction cost on this host;
-    the oracle port is scalar C++ and slower than that. Returns None when cv2 is missing."""
+def cpu_primitives_note():
+    try:
+        from oracle import orbref
+        return orbref.primitives_kind()
+    except Exception:
+        return "the oracle's scalar cv2-pinned restatements"
+
+
+def opencv_primitives_ms(w, h):
+    """Second opinion for the CPU baseline: the three OpenCV kernels the reference spends most of its
+    extraction time in — resize chain, FAST on the 8 whole levels, 7x7 blur — timed through cv2 (OpenCV's own SIMD build)
+    on one frame, one thread. Returns None when cv2 is missing."""
     try:
         import cv2
     except Exception:
         return None
     from orb_slam3_fast_b200 import synth
     cv2.setNumThreads(1)
-    img = synth.stereo_pair(H, W, 1000)[0]
-    sizes = [(W, H)]
+    img = synth.stereo_pair(h, w, 1000)[0]
+    sizes = [(w, h)]
     for l in range(1, NLEVELS):
         s = 1.0 / (SCALE ** l)
-        sizes.append((int(round(W * s)), int(round(H * s))))
+        sizes.append((int(round(w * s)), int(round(h * s))))
     det = cv2.FastFeatureDetector_create(INI_TH, True)
     best = 1e9
     for _ in range(5):
@@ -169,28 +262,40 @@ def opencv_primitives_ms():
     return 1e3 * best
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cfg_id = args.config if args.config in CONFIGS else 3
+    cfg = CONFIGS[cfg_id]
+    cores = host_cores()
+    cpu_data(cfg_id)  # generate the inputs outside every timed region
     # bounded sample: calibrate on one pair per core, then size each step to ~4 s of wall time
-    fps1, dt1 = cpu_reference_run(cores, cores)
-    per_step = max(cores, int(4.0 / max(dt1, 1e-3) * cores))
-    per_step = min(per_step, 4096)
+    cpu_reference_run(cfg_id, cores, cores)  # also builds the per-thread MapPoint worlds
+    _, dt1 = cpu_reference_run(cfg_id, 2 * cores, cores)
+    per_step = int(min(max(cores, 4.0 / max(dt1, 1e-3) * 2 * cores), 4096))
     for _ in range(args.warmup):
-        cpu_reference_run(per_step, cores)
-    total = 0.0  # only the oracle calls are timed, not the synthetic image generation
+        cpu_reference_run(cfg_id, per_step, cores)
+    total = 0.0
     for _ in range(args.steps):
-        total += cpu_reference_run(per_step, cores)[1]
+        total += cpu_reference_run(cfg_id, per_step, cores)[1]
     fps = 2.0 * per_step * args.steps / total
+    _, dt_1t = cpu_reference_run(cfg_id, 4, 1)
+    kind = cpu_kind()
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_step": per_step, "frames_per_step": 2 * per_step,
-                       "note": CPU_NOTES[cpu_kind()]},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu_kind(),
-                             "sample": "%d stereo pairs per step x %d steps" % (per_step, args.steps)},
+            "config": {"workload": cfg["workload"], "pairs_per_step": per_step, "frames_per_step": 2 * per_step,
+                       "frame_definition": "one ORBextractor call (a stereo pair = 2 frames)",
+                       "note": CPU_NOTES[kind] % cpu_primitives_note()},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+                             "sample": "%d stereo pairs per step x %d steps" % (per_step, args.steps),
+                             "single_thread_frames_per_s": 8.0 / dt_1t,
+                             "opencv_simd_primitives_ms_per_frame_1thread": opencv_primitives_ms(cfg["w"], cfg["h"])},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
@@ -213,53 +318,133 @@ def emit(line):
     _REAL_STDOUT.flush()
 
 
-def main():
-    _claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="orbx")
-    ap.add_argument("--pairs", type=int, default=1024, help="stereo pairs per step per GPU")
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs tiled into a batch")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-group", type=int, default=0, help="pairs per pipelined group of the host-facing call")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
+def pctl(xs, q):
+    xs = sorted(xs)
+    if not xs:
+        return None
+    k = (len(xs) - 1) * q
+    lo, hi = int(np.floor(k)), int(np.ceil(k))
+    return xs[lo] + (xs[hi] - xs[lo]) * (k - lo)
 
-    import torch
-    import torch.distributed as dist
-    from orb_slam3_fast_b200 import ORBextractor, ORBmatcher
+
+class Ctx:
+    """torch / distributed plumbing shared by the workloads of one bench process."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        # a non-default torch stream: its handle is what the C ABI launches on, so torch.cuda.Event brackets the work
+        # (the legacy default stream's handle is 0, which the ABI reads as "use the handle's own stream")
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        self._keep = []
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def pinned(self, shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        tbuf = self.torch.empty(max(nbytes, 1), dtype=self.torch.uint8, pin_memory=True)
+        self._keep.append(tbuf)
+        return tbuf.numpy()[:nbytes].view(dtype).reshape(shape)
+
+    def h2d_ceiling_gbs(self, mb=256, reps=6):
+        """What the box gives this rank for pinned host -> device copies while EVERY rank copies at once (the ceiling
+        of the end-to-end leg's upload): a barrier, then `reps` copies of `mb` MB on this rank's stream."""
+        torch = self.torch
+        n = mb << 20
+        src = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        dst = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        dst.copy_(src, non_blocking=True)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return reps * n / (ms * 1e-3) / 1e9
+
+
+def run_stereo_workload(ctx, args, cfg_id, steps, warmup, reps, with_cpu, clock_sampler=None, latency=False):
+    """Device-resident and end-to-end legs of a stereo workload (configs[1] or configs[3]). Returns a dict."""
+    torch, dist = ctx.torch, ctx.dist
+    from orb_slam3_fast_b200 import ORBextractor, ORBmatcher, views
     from orb_slam3_fast_b200.lib import KP_DTYPE
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    P = args.pairs
-    exl = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=P)
-    exr = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=P)
-    mt = ORBmatcher(0.6, True, device=local)
+    cfg = CONFIGS[cfg_id]
+    w, h, nfeat, track = cfg["w"], cfg["h"], cfg["nfeat"], cfg["track"]
+    world, rank, local, dev = ctx.world, ctx.rank, ctx.local, ctx.dev
+    P, D = args.pairs, args.distinct
+    M = cfg["map_points"]
+    exl = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=P)
+    exr = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=P)
+    mt = ORBmatcher(cfg["nnratio"], True, device=local)
     cap = exl.capacity
+    prm = views.make_track_params(w, h, th=cfg["th"], nnratio=cfg["nnratio"]) if track else None
 
-    # ---- synthetic data: `distinct` seeded pairs per rank, tiled to a batch; two rotating batches in HBM ----
-    Ld, Rd = make_pairs(args.distinct, 100 * rank)
-    reps = (P + args.distinct - 1) // args.distinct
+    # ---- synthetic data: D seeded distinct pairs per rank (different on every rank), tiled to a batch; two rotating
+    #      batches; with tracking: one pose + one 10k-point local map + one occupancy array per distinct pair ----
+    Ld, Rd = make_pairs(D, 1000 * rank + 100 * cfg_id, w, h)
+    reps_tile = (P + D - 1) // D
     n_rot = 2
-    hostL = [np.ascontiguousarray(np.tile(np.roll(Ld, k, axis=0), (reps, 1, 1))[:P]) for k in range(n_rot)]
-    hostR = [np.ascontiguousarray(np.tile(np.roll(Rd, k, axis=0), (reps, 1, 1))[:P]) for k in range(n_rot)]
+    sel = [np.array([(p + k) % D for p in range(P)], np.int32) for k in range(n_rot)]  # pair p of batch k = distinct pair
+    hostL = [np.ascontiguousarray(Ld[s]) for s in sel]
+    hostR = [np.ascontiguousarray(Rd[s]) for s in sel]
     devL = [torch.from_numpy(a).to(dev) for a in hostL]
     devR = [torch.from_numpy(a).to(dev) for a in hostR]
+    del reps_tile
+
+    # the end-to-end extractors (small pipelined groups) also produce the keypoints the synthetic maps are anchored on
+    G = args.e2e_group or max(8, min(64, P // 8))
+    exl2 = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
+    exr2 = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
+    first = mt.StereoFramesBatch(exl2, exr2, Ld, Rd, MBF, MB)
+
+    frs_d = lm_host = occ_d = None
+    if track:
+        kd = [(first["kps_l"][i, :first["n_l"][i]], first["desc_l"][i, :first["n_l"][i]]) for i in range(D)]
+        frs_d, stacked = make_track_inputs(cfg, Ld, 1000 * rank + 100 * cfg_id, kd)
+        rng = np.random.default_rng(rank)
+        occ_d = (rng.random((D, cap)) < 0.25).astype(np.uint8)
+        lm_host = views.make_local_map(**stacked)
+        t_map = {k: torch.from_numpy(v).to(dev) for k, v in stacked.items()}
+        dmap = views.make_local_map_device(M, D, t_map["pos"].data_ptr(), t_map["normal"].data_ptr(),
+                                           t_map["min_dist"].data_ptr(), t_map["max_dist"].data_ptr(),
+                                           t_map["skip"].data_ptr(), t_map["has_obs"].data_ptr(),
+                                           t_map["desc"].data_ptr())
+        d_frs = [torch.from_numpy(np.ascontiguousarray(frs_d[s]).view(np.uint8).reshape(P, -1)).to(dev) for s in sel]
+        d_occ = [torch.from_numpy(np.ascontiguousarray(occ_d[s])).to(dev) for s in sel]
+        d_midx = [torch.from_numpy(s).to(dev) for s in sel]
+        d_assign = torch.empty((P, cap), dtype=torch.int32, device=dev)
+        d_tres = torch.empty((3, P), dtype=torch.int32, device=dev)  # nmatches, n_in_view, status
 
     def dev_out():
         return dict(kps=torch.empty((P, cap, 7), dtype=torch.int32, device=dev),
@@ -270,202 +455,355 @@ def main():
     d_ur = torch.empty((P, cap), dtype=torch.float32, device=dev)
     d_dp = torch.empty((P, cap), dtype=torch.float32, device=dev)
     d_nm = torch.empty(P, dtype=torch.int32, device=dev)
-    gathered = torch.empty((world, 3, P), dtype=torch.int32, device=dev) if world > 1 else None
+    n_counts = 5 if track else 3
+    gathered = torch.empty((world, n_counts, P), dtype=torch.int32, device=dev) if world > 1 else None
+    st = ctx.stream.cuda_stream
 
-    # a non-default torch stream: its handle is what the C ABI launches on, so torch.cuda.Event brackets the work
-    # (the legacy default stream's handle is 0, which the ABI reads as "use the extractor's own stream")
-    work_stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(work_stream)
-    assert work_stream.cuda_stream != 0
-
-    def step_device(k):
-        st = work_stream.cuda_stream
-        for ex, imgs, o in ((exl, devL[k % n_rot], oL), (exr, devR[k % n_rot], oR)):
-            ex.extract_batch_device(imgs.data_ptr(), P, W, H, W, W * H, (0, 0), o["kps"].data_ptr(),
+    def batch_device(k):
+        r = k % n_rot
+        for ex, imgs, o in ((exl, devL[r], oL), (exr, devR[r], oR)):
+            ex.extract_batch_device(imgs.data_ptr(), P, w, h, w, w * h, (0, 0), o["kps"].data_ptr(),
                                     o["desc"].data_ptr(), cap, o["n"].data_ptr(), o["mono"].data_ptr(),
                                     o["status"].data_ptr(), st)
         mt.ComputeStereoMatches_device(exl, exr, P, oL["kps"].data_ptr(), oL["desc"].data_ptr(), oL["n"].data_ptr(),
                                        oR["kps"].data_ptr(), oR["desc"].data_ptr(), oR["n"].data_ptr(), cap, MBF, MB,
                                        d_ur.data_ptr(), d_dp.data_ptr(), d_nm.data_ptr(), st)
+        if track:
+            mt.TrackLocalMapBatch_device(exl, P, oL["kps"].data_ptr(), oL["desc"].data_ptr(), oL["n"].data_ptr(), cap,
+                                         d_ur.data_ptr(), d_occ[r].data_ptr(), d_frs[r].data_ptr(), dmap,
+                                         d_midx[r].data_ptr(), prm, d_assign.data_ptr(), d_tres[0].data_ptr(),
+                                         d_tres[1].data_ptr(), d_tres[2].data_ptr(), st)
         if world > 1:  # the trivial result gather: per-pair counts of every rank
-            dist.all_gather_into_tensor(gathered, torch.stack((oL["n"], oR["n"], d_nm)))
+            rows = (oL["n"], oR["n"], d_nm) + ((d_tres[0], d_tres[1]) if track else ())
+            dist.all_gather_into_tensor(gathered, torch.stack(rows))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- pinned host buffers of the end-to-end leg ----
+    pinL = [ctx.pinned(a.shape, np.uint8) for a in hostL]
+    pinR = [ctx.pinned(a.shape, np.uint8) for a in hostR]
+    for k in range(n_rot):
+        pinL[k][...] = hostL[k]
+        pinR[k][...] = hostR[k]
+    if track:
+        pin_frs = [ctx.pinned((P,), views.FRUSTUM_DTYPE) for _ in range(n_rot)]
+        pin_occ = [ctx.pinned((P, cap), np.uint8) for _ in range(n_rot)]
+        for k in range(n_rot):
+            pin_frs[k][...] = frs_d[sel[k]]
+            pin_occ[k][...] = occ_d[sel[k]]
+        outs = ORBmatcher.alloc_track_outputs(P, cap, empty=ctx.pinned)
+    else:
+        outs = ORBmatcher.alloc_stereo_outputs(P, cap, empty=ctx.pinned)
 
-    # ---- parity gate on this configuration before any timing (rank 0, 2 pairs, CPU oracle as the checker) ----
+    def batch_e2e(k, ex_l=exl2, ex_r=exr2, n=None, out=None):
+        r = k % n_rot
+        n = P if n is None else n
+        out = outs if out is None else out
+        if track:
+            return mt.StereoTrackFramesBatch(ex_l, ex_r, pinL[r][:n], pinR[r][:n], MBF, MB, pin_frs[r][:n], lm_host, prm,
+                                             map_index=sel[r][:n], occupied=pin_occ[r][:n], out=out)
+        return mt.StereoFramesBatch(ex_l, ex_r, pinL[r][:n], pinR[r][:n], MBF, MB, out)
+
+    # ---- parity gate on this configuration before any timing: `--parity-pairs` distinct pairs (and their maps) of
+    #      rank 0 through the host-facing call against the CPU oracle, every output word ----
     parity = "skipped"
-    if rank == 0:
+    if rank == 0 and args.parity_pairs > 0:
         from oracle import orbref
-        out = mt.StereoFramesBatch(exl, exr, hostL[0][:2], hostR[0][:2], MBF, MB)
-        rl, rr = orbref.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH), orbref.Extractor(NFEAT, SCALE, NLEVELS,
-                                                                                           INI_TH, MIN_TH)
-        for i in range(2):
+        npar = min(args.parity_pairs, D, P)
+        out = batch_e2e(0, n=npar, out=(ORBmatcher.alloc_track_outputs if track else ORBmatcher.alloc_stereo_outputs)(npar, cap))
+        rl = orbref.Extractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH)
+        rr = orbref.Extractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH)
+        for i in range(npar):
             _, kl, dl = rl(hostL[0][i], (0, 0))
             _, kr, dr = rr(hostR[0][i], (0, 0))
             nm, ur, dp = orbref.stereo_match(rl, rr, kl, dl, kr, dr, MBF, MB)
             nl, nr = int(out["n_l"][i]), int(out["n_r"][i])
             ok = (nl == len(kl) and nr == len(kr) and np.array_equal(out["kps_l"][i, :nl], kl) and
-                  np.array_equal(out["desc_l"][i, :nl], dl) and np.array_equal(out["desc_r"][i, :nr], dr) and
-                  int(out["n_matched"][i]) == nm and np.array_equal(out["u_right"][i, :nl], ur) and
-                  np.array_equal(out["depth"][i, :nl], dp))
+                  np.array_equal(out["desc_l"][i, :nl], dl) and np.array_equal(out["kps_r"][i, :nr], kr) and
+                  np.array_equal(out["desc_r"][i, :nr], dr) and int(out["n_matched"][i]) == nm and
+                  out["u_right"][i, :nl].tobytes() == ur.tobytes() and out["depth"][i, :nl].tobytes() == dp.tobytes())
+            if ok and track:
+                off, items = orbref.build_grid(kl, 0.0, 0.0, prm.inv_w, prm.inv_h)
+                g, keep = orbref.make_grid(off, items, 0.0, 0.0, prm.inv_w, prm.inv_h)
+                fv = orbref.make_frame_view(kl, dl, ur, occ_d[sel[0][i]][:nl], g, keep, rl.scale)
+                lm1 = orbref.make_local_map(**{k2: v[sel[0][i]] for k2, v in stacked.items()})
+                tn, ta, tv = orbref.track_local_map(fv, frs_d[sel[0][i]], lm1, 0, cfg["th"], cfg["nnratio"])
+                ok = (int(out["nmatches"][i]) == tn and int(out["n_in_view"][i]) == tv and
+                      np.array_equal(out["assign"][i, :nl], ta))
             if not ok:
                 raise SystemExit("bench.py: parity check against the oracle FAILED on pair %d — not timing" % i)
-        parity = "bit-exact vs oracle on 2 pairs (keypoints, descriptors, uRight, depth)"
+        parity = ("bit-exact vs oracle on %d distinct pairs (keypoints, descriptors, uRight, depth%s)"
+                  % (npar, ", isInFrustum count, assign[], nmatches vs %d-point maps" % M if track else ""))
 
-    # ---- device-resident timing ----
-    for k in range(args.warmup):
-        step_device(k)
-    barrier()
+    # ---- device-resident timing: profiling OFF; one event per batch ----
+    for k in range(warmup * reps):
+        batch_device(k)
+    ctx.barrier()
+    nb = steps * reps
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(nb + 1)]
+    mark0 = clock_sampler.mark() if clock_sampler else 0
+    ctx.barrier()
+    evs[0].record()
+    for k in range(nb):
+        batch_device(k)
+        evs[k + 1].record()
+    ctx.barrier()
+    mark1 = clock_sampler.mark() if clock_sampler else 0
+    ms_total = ctx.max_over_ranks(evs[0].elapsed_time(evs[nb]))
+    per_batch = [evs[k].elapsed_time(evs[k + 1]) for k in range(nb)]
+    frames_per_step = 2 * P * reps * world
+    value = frames_per_step * steps / (ms_total * 1e-3)
+    status_ok = bool((oL["status"] == 0).all().item() and (oR["status"] == 0).all().item() and
+                     (not track or (d_tres[2] == 0).all().item()))
+    n_keypoints = float(oL["n"].float().mean().item())
+    matched = float(d_nm.float().mean().item())
+    track_stats = None
+    if track:
+        track_stats = {"map_points": M, "in_view_per_frame": float(d_tres[1].float().mean().item()),
+                       "matches_per_frame": float(d_tres[0].float().mean().item())}
+
+    # ---- stage pass: the same loop with per-stage CUDA events (orbx_profile_enable) — the roofline's kernel times ----
     exl.profile(True)
     exr.profile(True)
     exl.profile_read(True)
     exr.profile_read(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for k in range(args.steps):
-        step_device(k)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop() if rank == 0 else None
+    prof_batches = max(reps, min(nb, 4 * reps))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tr_ev = []
+    ctx.barrier()
+    e0.record()
+    for k in range(prof_batches):
+        if track:  # bracket the matcher's share: events around stereo + tracking are taken here
+            r = k % n_rot
+            for ex, imgs, o in ((exl, devL[r], oL), (exr, devR[r], oR)):
+                ex.extract_batch_device(imgs.data_ptr(), P, w, h, w, w * h, (0, 0), o["kps"].data_ptr(),
+                                        o["desc"].data_ptr(), cap, o["n"].data_ptr(), o["mono"].data_ptr(),
+                                        o["status"].data_ptr(), st)
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            mt.ComputeStereoMatches_device(exl, exr, P, oL["kps"].data_ptr(), oL["desc"].data_ptr(), oL["n"].data_ptr(),
+                                           oR["kps"].data_ptr(), oR["desc"].data_ptr(), oR["n"].data_ptr(), cap, MBF,
+                                           MB, d_ur.data_ptr(), d_dp.data_ptr(), d_nm.data_ptr(), st)
+            b.record()
+            mt.TrackLocalMapBatch_device(exl, P, oL["kps"].data_ptr(), oL["desc"].data_ptr(), oL["n"].data_ptr(), cap,
+                                         d_ur.data_ptr(), d_occ[r].data_ptr(), d_frs[r].data_ptr(), dmap,
+                                         d_midx[r].data_ptr(), prm, d_assign.data_ptr(), d_tres[0].data_ptr(),
+                                         d_tres[1].data_ptr(), d_tres[2].data_ptr(), st)
+            c.record()
+            tr_ev.append((a, b, c))
+        else:
+            batch_device(k)
+    e1.record()
+    ctx.barrier()
+    ms_prof = e0.elapsed_time(e1)
     stage_ms_l, stage_cnt = exl.profile_read(True)
     stage_ms_r, _ = exr.profile_read(True)
     exl.profile(False)
     exr.profile(False)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    frames_per_step = 2 * P * world
-    value = frames_per_step * args.steps / (ms * 1e-3)
-    status_ok = bool((oL["status"] == 0).all().item() and (oR["status"] == 0).all().item())
-    n_keypoints = float(oL["n"].float().mean().item())
-    matched = float(d_nm.float().mean().item())
+    stage_ms = {k: (stage_ms_l[k] + stage_ms_r[k]) / prof_batches for k in stage_ms_l}  # per batch (both eyes)
+    if tr_ev:
+        stage_ms["stereo"] = sum(a.elapsed_time(b) for a, b, _ in tr_ev) / len(tr_ev)
+        stage_ms["track"] = sum(b.elapsed_time(c) for _, b, c in tr_ev) / len(tr_ev)
 
-    # ---- roofline of the dominant kernel (stage times from CUDA events on the launching stream, timed region) ----
-    stage_ms = {k: stage_ms_l[k] + stage_ms_r[k] for k in stage_ms_l}
-    launches = stage_cnt["fast"] * 2  # one k_fast launch per extract call
-    dom = max(stage_ms, key=stage_ms.get)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     # candidates per frame (C) from a few frames of the last batch
     C = 0
     for f in range(4):
         C += sum(exl._check(exl._L.orbx_debug_candidates(exl._h, f, l, None, 0)) for l in range(NLEVELS))
     C /= 4.0
     sumP = sum(exl.level_size(l)[0] * exl.level_size(l)[1] for l in range(NLEVELS))
-    P0 = W * H
+    P0 = w * h
     Nk = n_keypoints
-    alg_bytes_per_frame = {
+    alg_bytes_per_frame = {  # SURVEY.md §8(d), per extractor call
         "pyramid": P0 + sumP, "fast": sumP + 8 * C, "blur": 2 * sumP, "describe": (749 + 1849 + 32 + 28) * Nk,
         "quadtree": 8 * C + 4 * Nk}
-    dur_ms = stage_ms[dom] / max(stage_cnt[dom] * 2, 1)   # per extract call (one batch of P frames)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    ext_stages = {k: v for k, v in stage_ms.items() if k in alg_bytes_per_frame}
+    dom = max(ext_stages, key=ext_stages.get)
+    launches_per_batch = max(stage_cnt[dom] * 2 // prof_batches, 1)  # both eyes
+    dur_ms = stage_ms[dom] / launches_per_batch                    # one launch group = one eye's batch of P frames
     achieved = alg_bytes_per_frame[dom] * P / (dur_ms * 1e-3) / 1e9
-    # measured DRAM traffic of that kernel (ncu --set full capture summarised by tools/profile_digest.py), per launch
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj["stages"][dom]["dram_bytes_per_frame"] * P
-        traffic_src = tj["source"]
+        tkey = "%dx%d" % (w, h)
+        tentry = tj.get(tkey, tj)["stages"][dom]
+        traffic = tentry["dram_bytes_per_frame"] * P
+        traffic_src = tj.get(tkey, tj).get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes_per_frame[dom] * P,
-                "peak_source": peak_src,
-                "ms_per_launch_group": dur_ms, "algorithmic_bytes_per_frame": alg_bytes_per_frame[dom],
-                "frames_per_launch": P,
-                "note": "FAST / quadtree are integer-ALU / latency bound, not HBM bound (SURVEY.md §8d); the HBM "
-                        "fraction is reported as the contract asks, the ALU analysis is in DESIGN.md",
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
-                # the same quotient for every stage: algorithmic GB/s (SURVEY §8d bytes) and its fraction of the peak
-                "stage_gbs": {k: round(alg_bytes_per_frame[k] * frames_per_step / world * args.steps / (v * 1e-3) / 1e9, 1)
+                "peak_source": peak_src, "ms_per_launch": dur_ms,
+                "algorithmic_bytes_per_frame": alg_bytes_per_frame[dom], "frames_per_launch": P,
+                "timed_with": "CUDA events around every stage on the launching stream (orbx_profile_enable), %d batches "
+                              "of the same loop right after the headline pass; that pass ran %.3f ms per batch against "
+                              "%.3f ms with the events off" % (prof_batches, ms_prof / prof_batches, ms_total / nb),
+                "note": "FAST / quadtree are integer-ALU / latency bound, not HBM bound (SURVEY.md §8d); the HBM fraction "
+                        "of the dominant kernel is reported as the contract asks, stage_frac gives every stage",
+                "stage_ms_per_batch": {k: round(v, 4) for k, v in stage_ms.items()},
+                "stage_gbs": {k: round(alg_bytes_per_frame[k] * 2 * P / (v * 1e-3) / 1e9, 1)
                               for k, v in stage_ms.items() if v > 0 and k in alg_bytes_per_frame},
-                "stage_frac": {k: round(alg_bytes_per_frame[k] * frames_per_step / world * args.steps / (v * 1e-3) / 1e9 / peak, 4)
+                "stage_frac": {k: round(alg_bytes_per_frame[k] * 2 * P / (v * 1e-3) / 1e9 / peak, 4)
                                for k, v in stage_ms.items() if v > 0 and k in alg_bytes_per_frame}}
 
     # ---- end to end through the host-facing ABI (pinned buffers; H2D + D2H inside the timed region) ----
-    def pinned(shape, dtype):
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        tbuf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
-        arr = tbuf.numpy()[:nbytes].view(dtype).reshape(shape)
-        pinned.keep.append(tbuf)
-        return arr
-    pinned.keep = []
-    pinL = [pinned(a.shape, np.uint8) for a in hostL]
-    pinR = [pinned(a.shape, np.uint8) for a in hostR]
-    for k in range(n_rot):
-        pinL[k][...] = hostL[k]
-        pinR[k][...] = hostR[k]
-    # the fused call pipelines groups of max_batch pairs over two lanes: use smaller groups than the resident batch
-    G = args.e2e_group or max(8, min(64, P // 8))
-    exl2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
-    exr2 = ORBextractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
-    outs = ORBmatcher.alloc_stereo_outputs(P, cap, empty=pinned)
-    e2e_steps = args.e2e_steps or args.steps
-    for k in range(max(3, args.warmup // 2)):
-        mt.StereoFramesBatch(exl2, exr2, pinL[k % n_rot], pinR[k % n_rot], MBF, MB, outs)
-    barrier()
+    e2e_steps = args.e2e_steps or steps
+    for k in range(max(3, warmup // 2)):
+        batch_e2e(k)
+    ctx.barrier()
+    per_call = []
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        mt.StereoFramesBatch(exl2, exr2, pinL[k % n_rot], pinR[k % n_rot], MBF, MB, outs)
+    for k in range(e2e_steps * reps):
+        tc = time.perf_counter()
+        batch_e2e(k)
+        per_call.append(1e3 * (time.perf_counter() - tc))
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
     e2e_val = frames_per_step * e2e_steps / dt
-    h2d = 2 * P * W * H
+    h2d = 2 * P * w * h
     d2h = P * (2 * cap * (KP_DTYPE.itemsize + 32) + 2 * cap * 4 + 3 * 4 * 3)
-    e2e = {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "orbm_stereo_frames_batch (host buffers, pinned)", "ms_per_step": 1e3 * dt / e2e_steps,
-           "group_pairs": G, "timer": "host wall clock around the synchronous ABI calls, max over ranks"}
+    if track:
+        h2d += P * (views.FRUSTUM_DTYPE.itemsize + cap + 4) + D * M * (12 + 12 + 4 + 4 + 1 + 1 + 32)
+        d2h += P * (cap * 4 + 3 * 4)
+    ceiling = ctx.h2d_ceiling_gbs()
+    e2e = {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d * reps, "d2h_bytes_per_step": d2h * reps,
+           "api": ("orbm_stereo_track_frames_batch" if track else "orbm_stereo_frames_batch") +
+                  " (host buffers, pinned); %d calls of %d pairs per step" % (reps, P),
+           "ms_per_step": 1e3 * dt / e2e_steps, "group_pairs": G,
+           "ms_per_call": {"p10": pctl(per_call, 0.1), "p50": pctl(per_call, 0.5), "p90": pctl(per_call, 0.9),
+                           "n": len(per_call)},
+           "h2d_gbs_per_rank": h2d * reps * e2e_steps / dt / 1e9,
+           "h2d_ceiling_gbs_per_rank": ceiling,
+           "frac_of_h2d_ceiling": h2d * reps * e2e_steps / dt / 1e9 / ceiling,
+           "h2d_ceiling_how": "pinned host -> device copies of 256 MB on every rank at once, right after the e2e leg",
+           "timer": "host wall clock around the synchronous ABI calls, max over ranks"}
+    if track:
+        e2e["local_maps"] = ("%d maps of %d points (%.1f MB) cross PCIe with EVERY call; a map is shared by the %d pairs "
+                             "of the batch that are copies of the same distinct pair" % (D, M, D * M * 66 / 1e6, P // D))
+
+    # ---- single-call latency: one pair through the host-facing call (what an online front-end lives on) ----
+    lat = None
+    if latency and rank == 0:
+        ex1l = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=1)
+        ex1r = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=1)
+        o1 = (ORBmatcher.alloc_track_outputs if track else ORBmatcher.alloc_stereo_outputs)(1, cap, empty=ctx.pinned)
+        ts = []
+        for k in range(220):
+            tc = time.perf_counter()
+            batch_e2e(0, ex1l, ex1r, n=1, out=o1)
+            ts.append(1e3 * (time.perf_counter() - tc))
+        ts = ts[20:]
+        lat = {"what": "ONE stereo pair through the same host-facing call (H2D, all kernels, D2H, synchronous), ms",
+               "p50": pctl(ts, 0.5), "p90": pctl(ts, 0.9), "p99": pctl(ts, 0.99), "n": len(ts),
+               "reference_published": "5.85 ms extraction + 2.75 ms stereo match per pair on the author's CPU "
+                                      "(README.md:5-25, other hardware, larger image)"}
 
     # ---- CPU baseline: oracle/_ref (or the oracle port) on the host cores, bounded sample, rank 0 at N = 1 only ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        _, dt1 = cpu_reference_run(cores, cores)
-        n_pairs = int(min(max(cores, 15.0 / max(dt1, 1e-3) * cores), 8192))
-        fps, dtc = cpu_reference_run(n_pairs, cores)
-        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": cpu_kind(),
-               "sample": "%d stereo pairs (752x480, 1200 feat/eye), pair-parallel on %d threads, %.1f s"
-                         % (n_pairs, cores, dtc),
-               "opencv_simd_primitives_ms_per_frame_1thread": opencv_primitives_ms(),
-               "note": CPU_NOTES[cpu_kind()] + "; the cv2 figure is the time of resize + FAST + blur alone in OpenCV's "
-                       "SIMD build, a lower bound of the reference's per-frame extraction cost on this host"}
+    if with_cpu and rank == 0 and world == 1:
+        cores = host_cores()
+        cpu_data(cfg_id)
+        cpu_reference_run(cfg_id, cores, cores)
+        _, dt1 = cpu_reference_run(cfg_id, 2 * cores, cores)
+        n_pairs = int(min(max(cores, 12.0 / max(dt1, 1e-3) * 2 * cores), 8192))
+        fps, dtc = cpu_reference_run(cfg_id, n_pairs, cores)
+        _, dt_1t = cpu_reference_run(cfg_id, 4, 1)
+        kind = cpu_kind()
+        cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
+               "sample": "%d stereo pairs of the workload, pair-parallel on %d threads, %.1f s" % (n_pairs, cores, dtc),
+               "single_thread_frames_per_s": 8.0 / dt_1t,
+               "opencv_simd_primitives_ms_per_frame_1thread": opencv_primitives_ms(w, h),
+               "note": CPU_NOTES[kind] % cpu_primitives_note() + "; the cv2 figure is the time of resize + FAST + blur "
+                       "alone in OpenCV's own SIMD build, a lower bound of the real library's per-frame extraction cost"}
 
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    launches_per_batch_all = 2 * int(exl._L.orbx_kernel_launches(exl._h)) + 2 + (4 if track else 0)
+    return dict(value=value, ms_total=ms_total, ms_per_step=ms_total / steps, frames_per_step=frames_per_step,
+                batch_ms={"p10": pctl(per_batch, 0.1), "p50": pctl(per_batch, 0.5), "p90": pctl(per_batch, 0.9),
+                          "n": len(per_batch), "unit": "ms per batch of %d pairs (this rank)" % P},
+                e2e=e2e, roofline=roofline, cpu=cpu, parity=parity, status_ok=status_ok, n_keypoints=n_keypoints, C=C,
+                matched=matched, track_stats=track_stats, latency=lat, gpu_launches=launches_per_batch_all * nb,
+                clock_marks=(mark0, mark1), cap=cap)
+
+
+def main():
+    _claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="orbx")
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs[] index: 3 (default), 1, 2 or 4")
+    ap.add_argument("--pairs", type=int, default=1024, help="stereo pairs per batch per GPU")
+    ap.add_argument("--reps", type=int, default=8, help="batches per step")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs (and local maps) per rank")
+    ap.add_argument("--parity-pairs", type=int, default=16, help="distinct pairs checked against the oracle before timing")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-second", action="store_true", help="skip the configs[1] block of the default line")
+    ap.add_argument("--e2e-group", type=int, default=0, help="pairs per pipelined group of the host-facing call")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.config in (2, 4):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        ctx = Ctx(args)
+        line = (bench_configs.run_config2 if args.config == 2 else bench_configs.run_config4)(ctx, args, METRIC)
+        if ctx.rank == 0:
+            emit(line)
+        if ctx.world > 1:
+            ctx.dist.destroy_process_group()
+        return 0
+
+    ctx = Ctx(args)
+    cfg_id = args.config if args.config in CONFIGS else 3
+    cfg = CONFIGS[cfg_id]
+    clocks = ClockSampler(ctx.local)
+    if ctx.rank == 0:
+        clocks.start()
+    res = run_stereo_workload(ctx, args, cfg_id, args.steps, args.warmup, args.reps, not args.no_cpu, clocks, latency=True)
+    second = None
+    if cfg_id == 3 and not args.no_second:
+        # configs[1] (round 1's headline) as a second block: fewer steps, no CPU arm, same protocol
+        r1 = run_stereo_workload(ctx, args, 1, max(2, args.steps // 4), 3, max(1, args.reps // 4), False)
+        second = {"workload": CONFIGS[1]["workload"], "value": r1["value"], "unit": "frames/s",
+                  "steps": max(2, args.steps // 4), "batches_per_step": max(1, args.reps // 4),
+                  "ms_per_batch": r1["batch_ms"], "e2e": {k: r1["e2e"][k] for k in
+                                                          ("value", "ms_per_step", "h2d_bytes_per_step",
+                                                           "d2h_bytes_per_step", "frac_of_h2d_ceiling")},
+                  "stage_ms_per_batch": r1["roofline"]["stage_ms_per_batch"],
+                  "stage_frac": r1["roofline"]["stage_frac"], "parity": r1["parity"],
+                  "keypoints_per_frame": r1["n_keypoints"], "all_frames_within_capacity": r1["status_ok"]}
+    clk = clocks.stop() if ctx.rank == 0 else None
+    if ctx.rank == 0:
+        P = args.pairs
+        line = {"metric": METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": ctx.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": P, "frames_per_step": frames_per_step,
-                           "frame_definition": "one ORBextractor call (a stereo pair = 2 frames)",
+                "config": {"workload": cfg["workload"], "pairs_per_batch_per_gpu": P, "batches_per_step": args.reps,
+                           "frames_per_step": res["frames_per_step"],
+                           "frame_definition": "one ORBextractor call (a stereo pair = 2 frames); pairs/s = value / 2",
                            "distinct_synthetic_pairs_per_rank": args.distinct,
-                           "l2": "per-step working set (%d frames x ~5.5 MB of pyramid/blur/candidate scratch) far "
-                                 "exceeds the 126 MB L2; two input batches alternate" % (2 * P),
-                           "keypoints_per_frame": n_keypoints, "candidates_per_frame": C,
-                           "stereo_matches_per_pair": matched, "all_frames_within_capacity": status_ok,
-                           "parity": parity, "parallelism": "frames sharded over GPUs, no data-path collective"},
-                "gpu_launches": (2 * int(exl._L.orbx_kernel_launches(exl._h)) + 2) * args.steps, "clocks": clk, "e2e": e2e, "roofline": roofline,
-                "cpu_baseline": cpu}
+                           "l2": "inputs larger than L2: a batch reads %d MB of images and streams ~%d MB of pyramid / "
+                                 "blur / candidate scratch per eye through HBM (126 MB L2); two input batches alternate"
+                                 % (2 * P * cfg["w"] * cfg["h"] >> 20, P * 5 * cfg["w"] * cfg["h"] >> 20),
+                           "timed_region_s": res["ms_total"] * 1e-3,
+                           "ms_per_batch": res["batch_ms"],
+                           "keypoints_per_frame": res["n_keypoints"], "candidates_per_frame": res["C"],
+                           "stereo_matches_per_pair": res["matched"], "tracking": res["track_stats"],
+                           "all_frames_within_capacity": res["status_ok"], "parity": res["parity"],
+                           "parallelism": "frames sharded over GPUs, no data-path collective"},
+                "gpu_launches": res["gpu_launches"], "clocks": clk, "e2e": res["e2e"], "roofline": res["roofline"],
+                "cpu_baseline": res["cpu"], "latency": res["latency"], "configs1_752x480": second}
         emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
     return 0
 
 

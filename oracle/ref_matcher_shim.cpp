@@ -485,3 +485,121 @@ extern "C" void orbrefsrc_is_in_frustum(const orbx_frustum* fr, const orbx_local
     view_cos[i] = p.mTrackViewCos;
   }
 }
+
+// BASELINE.json configs[3] on the CPU with the reference's own code end to end: both ORBextractor::operator() calls and
+// Frame::ComputeStereoMatches (as orbrefsrc_stereo_frame), then Tracking::SearchLocalPoints' work on the left frame
+// (src/Tracking.cc:3288-3330): Frame::AssignFeaturesToGrid, Frame::isInFrustum for every point of local map `map_index`
+// and ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints). The MapPoint objects of
+// a map are built once per thread and reused (in the reference they live in the Atlas), so that the timed work is the
+// reference's per-frame work only. Outputs as orbm_stereo_track_frames_batch for one pair.
+namespace {
+struct MapWorld {
+  std::vector<MapPoint> pts;
+  std::vector<MapPoint*> ptrs;
+  std::vector<uint8_t> skip;
+};
+MapWorld& map_world(const orbx_local_map* maps, int map_index) {
+  thread_local std::map<std::pair<const void*, int>, MapWorld> cache;
+  MapWorld& W = cache[{maps->pos, map_index}];
+  if ((int)W.pts.size() == maps->m && maps->m > 0) return W;
+  const size_t base = (size_t)map_index * maps->m;
+  W.pts.assign(maps->m, MapPoint());
+  W.ptrs.resize(maps->m);
+  W.skip.assign(maps->m, 0);
+  for (int i = 0; i < maps->m; i++) {
+    const size_t g = base + i;
+    MapPoint& p = W.pts[i];
+    p.pos = Eigen::Vector3f(maps->pos[3 * g], maps->pos[3 * g + 1], maps->pos[3 * g + 2]);
+    p.normal = Eigen::Vector3f(maps->normal[3 * g], maps->normal[3 * g + 1], maps->normal[3 * g + 2]);
+    p.use_raw_distances = true;
+    p.mfMinDistance = maps->min_dist[g];
+    p.mfMaxDistance = maps->max_dist[g];
+    p.observations = maps->has_obs[g] ? 1 : 0;
+    p.descriptor = rows32(maps->desc + g * 32, 1).clone();
+    W.skip[i] = maps->skip ? maps->skip[g] : 0;
+    W.ptrs[i] = &p;
+  }
+  return W;
+}
+}  // namespace
+
+extern "C" int orbrefsrc_stereo_track_frame(int nfeatures, float scale_factor, int nlevels, int ini_th, int min_th,
+                                            const unsigned char* img_l, const unsigned char* img_r, int w, int h,
+                                            int stride, float mbf, float mb, const orbx_frustum* fr,
+                                            const orbx_local_map* maps, int map_index, const uint8_t* occupied,
+                                            const orbx_track_params* prm, void* kps_l, unsigned char* desc_l, int* n_l,
+                                            void* kps_r, unsigned char* desc_r, int* n_r, float* u_right, float* depth,
+                                            int cap, int32_t* assign, int* nmatches, int* n_in_view) {
+  ORBextractor left(nfeatures, scale_factor, nlevels, ini_th, min_th), right(nfeatures, scale_factor, nlevels, ini_th, min_th);
+  Frame F;
+  PinholeStandIn cam;
+  F.mpORBextractorLeft = &left;
+  F.mpORBextractorRight = &right;
+  std::vector<int> lapping = {0, 0};
+  cv::Mat mask;
+  cv::Mat il(h, w, CV_8UC1, const_cast<unsigned char*>(img_l), (size_t)stride);
+  cv::Mat ir(h, w, CV_8UC1, const_cast<unsigned char*>(img_r), (size_t)stride);
+  left(il, mask, F.mvKeys, F.mDescriptors, lapping);
+  right(ir, mask, F.mvKeysRight, F.mDescriptorsRight, lapping);
+  F.N = (int)F.mvKeys.size();
+  F.Nleft = -1;
+  F.mvScaleFactors = left.GetScaleFactors();
+  F.mvInvScaleFactors = left.GetInverseScaleFactors();
+  F.mbf = mbf;
+  F.mb = mb;
+  *n_l = F.N;
+  *n_r = (int)F.mvKeysRight.size();
+  if (*n_l > cap || *n_r > cap) return -1000;
+  F.ComputeStereoMatches();
+  // the rest of the Frame constructor that the search reads: mvKeysUn (undistorted camera: a copy, src/Frame.cc:562-571),
+  // the grid (:235-236), the pose
+  F.mvKeysUn = F.mvKeys;
+  Frame::mnMinX = fr->min_x; Frame::mnMaxX = fr->max_x; Frame::mnMinY = fr->min_y; Frame::mnMaxY = fr->max_y;
+  Frame::mfGridElementWidthInv = prm->inv_w;
+  Frame::mfGridElementHeightInv = prm->inv_h;
+  F.AssignFeaturesToGrid();
+  cam.mvParameters[0] = fr->fx; cam.mvParameters[1] = fr->fy; cam.mvParameters[2] = fr->cx; cam.mvParameters[3] = fr->cy;
+  F.mpCamera = &cam;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) F.mRcw(i, j) = fr->Rcw[3 * i + j];
+    F.mtcw(i) = fr->tcw[i];
+    F.mOw(i) = fr->Ow[i];
+  }
+  F.mfLogScaleFactor = fr->log_scale_factor;
+  F.mnScaleLevels = fr->n_levels;
+  MapPoint occupied_point;
+  occupied_point.observations = 1;
+  F.mvpMapPoints.assign(F.N, nullptr);
+  if (occupied)
+    for (int i = 0; i < F.N; i++)
+      if (occupied[i]) F.mvpMapPoints[i] = &occupied_point;
+  MapWorld& W = map_world(maps, map_index);
+  int nToMatch = 0;
+  for (int i = 0; i < maps->m; i++) {  // src/Tracking.cc:3288-3300
+    MapPoint* pMP = W.ptrs[i];
+    pMP->mbTrackInView = false;
+    if (W.skip[i]) continue;
+    if (F.isInFrustum(pMP, prm->viewing_cos_limit)) nToMatch++;
+  }
+  *n_in_view = nToMatch;
+  *nmatches = 0;
+  if (nToMatch > 0) {
+    ORBmatcher matcher(prm->nnratio);
+    *nmatches = matcher.SearchByProjection(F, W.ptrs, prm->th, prm->far_points != 0, prm->th_far);
+  }
+  for (int i = 0; i < F.N; i++) {
+    const MapPoint* p = F.mvpMapPoints[i];
+    assign[i] = (p && p != &occupied_point) ? (int)(p - W.pts.data()) : -1;
+  }
+  if (*n_l) memcpy(kps_l, F.mvKeys.data(), (size_t)*n_l * sizeof(cv::KeyPoint));
+  if (*n_r) memcpy(kps_r, F.mvKeysRight.data(), (size_t)*n_r * sizeof(cv::KeyPoint));
+  for (int i = 0; i < *n_l; i++) memcpy(desc_l + (size_t)i * 32, F.mDescriptors.ptr(i), 32);
+  for (int i = 0; i < *n_r; i++) memcpy(desc_r + (size_t)i * 32, F.mDescriptorsRight.ptr(i), 32);
+  int matched = 0;
+  for (int i = 0; i < *n_l; i++) {
+    u_right[i] = F.mvuRight[i];
+    depth[i] = F.mvDepth[i];
+    matched += F.mvuRight[i] >= 0;
+  }
+  return matched;
+}

@@ -295,6 +295,39 @@ def stereo_frame(left, right, mbf, mb, nfeatures=1200, scale_factor=1.2, nlevels
             ur[:nl.value].copy(), dp[:nl.value].copy())
 
 
+class TrackParams(C.Structure):
+    _fields_ = [("viewing_cos_limit", C.c_float), ("th", C.c_float), ("nnratio", C.c_float), ("far_points", C.c_int32),
+                ("th_far", C.c_float), ("min_x", C.c_float), ("min_y", C.c_float), ("inv_w", C.c_float),
+                ("inv_h", C.c_float), ("cand_per_frame", C.c_int32)]
+
+
+def stereo_track_frame(left, right, mbf, mb, frustum, local_map, map_index, occupied, params, nfeatures=1200,
+                       scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    """configs[3] for one pair with the reference's own code: extract x2 + ComputeStereoMatches + AssignFeaturesToGrid +
+    isInFrustum over the local map + SearchByProjection. `params`: any ctypes struct with the orbx_track_params layout.
+    Returns dict(n_matched, kps_l, desc_l, kps_r, desc_r, u_right, depth, assign, nmatches, n_in_view)."""
+    left, right = np.ascontiguousarray(left, np.uint8), np.ascontiguousarray(right, np.uint8)
+    cap = nfeatures + 8 * nlevels + 64
+    kl, kr = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    dl, dr = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    assign = np.full(cap, -1, np.int32)
+    nl, nr, nm, nv = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    fr = np.ascontiguousarray(frustum).reshape(1)
+    occ = None if occupied is None else np.ascontiguousarray(occupied, np.uint8)
+    fn = mlib().orbrefsrc_stereo_track_frame
+    fn.restype = C.c_int
+    n = fn(nfeatures, C.c_float(scale_factor), nlevels, ini_th, min_th, _p(left), _p(right), left.shape[1], left.shape[0],
+           left.strides[0], C.c_float(mbf), C.c_float(mb), _p(fr), local_map.ref(), C.c_int(map_index),
+           None if occ is None else _p(occ), C.byref(params), _p(kl), _p(dl), C.byref(nl), _p(kr), _p(dr), C.byref(nr),
+           _p(ur), _p(dp), cap, _p(assign), C.byref(nm), C.byref(nv))
+    if n == -1000:
+        raise RuntimeError("capacity")
+    return dict(n_matched=n, kps_l=kl[:nl.value], desc_l=dl[:nl.value], kps_r=kr[:nr.value], desc_r=dr[:nr.value],
+                u_right=ur[:nl.value], depth=dp[:nl.value], assign=assign[:nl.value], nmatches=nm.value,
+                n_in_view=nv.value)
+
+
 def build_grid(fv):
     off, items = np.zeros(64 * 48 + 1, np.int32), np.zeros(max(fv.struct.n, 1), np.int32)
     mlib().orbrefsrc_build_grid(fv.ref(), _p(off), _p(items))

@@ -5,10 +5,12 @@
 //
 //   k_frustum        thread = (frame, point): the projection and the scalar prologue of the search loop (:55-74:
 //                    which points take part, r = RadiusByViewingCos(viewCos) * th * scale[level]) -> one float4 + level
-//   k_build_grid     (k_search.cu) one warp per frame
-//   k_track_enum     warp = (frame, point): lanes own the cells of the window, candidates come out in the reference's
-//                    order; ONE pass: the warp counts, takes its slice of the frame's candidate slab with one atomicAdd,
-//                    then writes (distance, octave, keypoint) words and the unconstrained top-2
+//   k_track_grid     one warp per frame: the 64x48 grid as u16 offsets + 16-byte search records in cell order
+//   k_track_enum     thread = (frame, point) over a frame staged in shared memory (grid, records, descriptors): counts,
+//                    the warp takes its slice of the frame's candidate slab with one atomicAdd, then writes (distance,
+//                    octave, keypoint) words in the reference's candidate order and the unconstrained top-2
+//                    (a warp per point spent 457 warp instructions per point on mostly idle lanes: 2.83 ms per 256
+//                    frames x 10 000 points)
 //   k_track_resolve  CTA = frame: the greedy order dependence (:92-93, :130) as the parallel fixed-point iteration of
 //                    k_search_resolve, T[] in shared memory
 #include "orbx_match.cuh"
@@ -73,120 +75,184 @@ void launch_frustum_batch(const TrackArgs& A, cudaStream_t st) {
   k_frustum<<<dim3((A.m + 255) / 256, A.n_frames), 256, 0, st>>>(A);
 }
 
-__device__ __forceinline__ DevFrame track_frame(const TrackArgs& A, int f) {
-  DevFrame F;
-  F.n = A.n[f];
-  F.n_levels = A.n_levels;
-  F.kps = A.kps + (size_t)f * A.cap;
-  F.desc = A.desc + (size_t)f * A.cap * 32;
-  F.u_right = A.u_right ? A.u_right + (size_t)f * A.cap : nullptr;
-  F.occupied = A.occupied ? A.occupied + (size_t)f * A.cap : nullptr;
-  F.cell_offsets = A.grid_offsets + (size_t)f * (ORBX_GRID_COLS * ORBX_GRID_ROWS + 1);
-  F.cell_items = A.grid_items + (size_t)f * A.cap;
-  F.min_x = A.min_x;
-  F.min_y = A.min_y;
-  F.inv_w = A.inv_w;
-  F.inv_h = A.inv_h;
-  F.scale_factors = nullptr;
-  return F;
+// ---- Frame::AssignFeaturesToGrid (src/Frame.cc:520-547, PosInGrid :833-844) in the form the enumeration wants: u16 cell
+// offsets and, IN CELL ORDER, one 16-byte search record per keypoint {x, y, u_right, keypoint | octave << 16 |
+// occupied << 31}, so that walking a cell is a run of consecutive LDS.128. One warp per frame (as k_build_grid).
+constexpr int kCells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
+constexpr int kOff16 = kTrackOff16;  // u16 offsets per frame: 64 * 48 + 1 used, padded so that a frame's array is 8-byte aligned
+
+__global__ void __launch_bounds__(32) k_track_grid(const TrackArgs A) {
+  constexpr int kPerLane = kCells / 32;
+  __shared__ int32_t cur[kCells];
+  const int lane = threadIdx.x, f = blockIdx.x;
+  const int n = min(A.n[f], A.cap);
+  const orbx_kp* kps = A.kps + (size_t)f * A.cap;
+  const float* ur = A.u_right ? A.u_right + (size_t)f * A.cap : nullptr;
+  const uint8_t* occ = A.occupied ? A.occupied + (size_t)f * A.cap : nullptr;
+  uint16_t* off16 = A.grid_off16 + (size_t)f * kOff16;
+  uint4* rec = A.grid_rec + (size_t)f * A.cap;
+  auto cell_of = [&](const orbx_kp& kp) {
+    const int px = (int)roundf(fmul(fsub(kp.x, A.min_x), A.inv_w));  // round(): half away from zero        :836-837
+    const int py = (int)roundf(fmul(fsub(kp.y, A.min_y), A.inv_h));
+    if (px < 0 || px >= ORBX_GRID_COLS || py < 0 || py >= ORBX_GRID_ROWS) return -1;  //                      :840-841
+    return px * ORBX_GRID_ROWS + py;
+  };
+  for (int c = lane; c < kCells; c += 32) cur[c] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int c = cell_of(kps[i]);
+    if (c >= 0) atomicAdd(&cur[c], 1);
+  }
+  __syncwarp();
+  int sum = 0;
+  for (int c = 0; c < kPerLane; c++) sum += cur[lane * kPerLane + c];
+  int incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  int run = incl - sum;
+  for (int c = 0; c < kPerLane; c++) {
+    const int k = lane * kPerLane + c, cnt = cur[k];
+    off16[k] = (uint16_t)run;
+    cur[k] = run;
+    run += cnt;
+  }
+  if (lane == 31) off16[kCells] = (uint16_t)run;
+  __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    orbx_kp kp;
+    int c = -1;
+    if (i < n) {
+      kp = kps[i];
+      c = cell_of(kp);
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, c);
+    int pos = 0;
+    if (c >= 0) pos = cur[c];
+    __syncwarp();
+    if (c >= 0) {
+      const uint32_t meta = (uint32_t)i | ((uint32_t)kp.octave << 16) | ((occ && occ[i]) ? 0x80000000u : 0u);
+      rec[pos + __popc(same & lt)] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y),
+                                                __float_as_uint(ur ? ur[i] : -1.f), meta);
+      if ((same & lt) == 0u) cur[c] = pos + __popc(same);
+    }
+    __syncwarp();
+  }
 }
 
-// cand_ok of orbx_search_dev.cuh with an optional occupancy array
-__device__ __forceinline__ bool track_cand_ok(const DevFrame& F, int idx, float x, float y, float r, int minLevel,
-                                              int maxLevel, bool has_ur, float ur, int* octave) {
-  const orbx_kp kp = F.kps[idx];
-  *octave = kp.octave;
-  if (kp.octave < minLevel || kp.octave > maxLevel) return false;               // Frame.cc:803-817 (maxLevel >= 0 here)
-  if (!(fabsf(fsub(kp.x, x)) < r && fabsf(fsub(kp.y, y)) < r)) return false;    // :823-826
-  if (F.occupied && F.occupied[idx]) return false;                              // ORBmatcher.cc:92-93 (static part)
-  if (has_ur && F.u_right[idx] > 0) {                                           // :95-98
-    const float er = fabsf(fsub(ur, F.u_right[idx]));
-    if (er > r) return false;
+// ---- enumeration: thread = (frame, point). The CTA stages its frame's grid (u16 offsets, records in cell order) and
+// descriptors into shared memory once and then serves kEnumPerThread points per thread from there; a thread walks its
+// point's window cell by cell (ix outer, iy inner, ascending keypoint index inside a cell = the reference's candidate
+// order, src/Frame.cc:803-829), first counting, then — after the warp has taken its slice of the frame's candidate slab
+// with ONE atomicAdd — writing (distance, octave, keypoint) words and keeping the unconstrained top-2.
+constexpr int kEnumThreads = 256, kEnumPerThread = 8;
+
+__device__ __forceinline__ bool rec_ok(const uint4 r, float x, float y, float rad, int minL, int maxL, bool has_ur,
+                                       float ur) {
+  const int oct = (int)((r.w >> 16) & 0x7fffu);
+  if (oct < minL || oct > maxL) return false;                                         // Frame.cc:803-817
+  const float kx = __uint_as_float(r.x), ky = __uint_as_float(r.y);
+  if (!(fabsf(fsub(kx, x)) < rad && fabsf(fsub(ky, y)) < rad)) return false;          // :823-826
+  if (r.w & 0x80000000u) return false;                                                // ORBmatcher.cc:92-93 (static part)
+  const float kur = __uint_as_float(r.z);
+  if (has_ur && kur > 0) {                                                            // :95-98
+    if (fabsf(fsub(ur, kur)) > rad) return false;
   }
   return true;
 }
 
-constexpr int kTrackWarps = 8;
-
-__global__ void __launch_bounds__(kTrackWarps * 32) k_track_enum(const TrackArgs A) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.y;
-  const int i = blockIdx.x * kTrackWarps + warp;
-  if (i >= A.m) return;
-  const size_t o = (size_t)f * A.m + i;
-  const int level = A.q_level[o];
-  int2 seg = make_int2(0, 0);
-  Top2 best{0, -1, 0, -1};
-  if (level >= 0) {
-    const DevFrame F = track_frame(A, f);
-    const float4 q = A.q[o];
-    const float x = q.x, y = q.y, ur = q.z, r = q.w;
-    // GetFeaturesInArea(x, y, r, level - 1, level): with minLevel = -1 (level 0) the octave test reduces to
-    // octave <= maxLevel, which octave >= -1 does not change
-    const int minL = level - 1, maxL = level;
-    const bool has_ur = F.u_right != nullptr;
-    const Window w = cell_window(F, x, y, r);
-    const int ny = w.y1 - w.y0 + 1;
-    const int ncell = w.x1 < w.x0 ? 0 : (w.x1 - w.x0 + 1) * ny;
-    int total = 0, oct;
-    for (int cb = 0; cb < ncell; cb += 32) {
-      const int c = cb + lane;
-      int n = 0;
-      if (c < ncell) {
-        const int cell = (w.x0 + c / ny) * ORBX_GRID_ROWS + w.y0 + c % ny;  // ix outer, iy inner
-        const int j0 = F.cell_offsets[cell], j1 = F.cell_offsets[cell + 1];
-        for (int j = j0; j < j1; j++) n += track_cand_ok(F, F.cell_items[j], x, y, r, minL, maxL, has_ur, ur, &oct) ? 1 : 0;
-      }
-      total += __reduce_add_sync(0xffffffffu, n);
-    }
-    if (total > 0) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&A.cand_total[f], total);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base + total > A.cand_cap) {
-        if (lane == 0) A.status[f] = ORBX_E_CAPACITY_I;  // reported, never silently truncated
-      } else {
-        uint32_t dq[8];
-        load_desc8(A.mdesc + ((size_t)(A.map_index ? A.map_index[f] : f % A.n_maps) * A.m + i) * 32, dq);
-        uint32_t* out = A.cand + (size_t)f * A.cand_cap + base;
-        int run = 0;
-        for (int cb = 0; cb < ncell; cb += 32) {
-          const int c = cb + lane;
-          int j0 = 0, j1 = 0;
-          if (c < ncell) {
-            const int cell = (w.x0 + c / ny) * ORBX_GRID_ROWS + w.y0 + c % ny;
-            j0 = F.cell_offsets[cell];
-            j1 = F.cell_offsets[cell + 1];
-          }
-          int n = 0;
-          for (int j = j0; j < j1; j++) n += track_cand_ok(F, F.cell_items[j], x, y, r, minL, maxL, has_ur, ur, &oct) ? 1 : 0;
-          int inc = n;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-          }
-          int pos = run + inc - n;
-          for (int j = j0; j < j1; j++) {
-            const int idx = F.cell_items[j];
-            if (!track_cand_ok(F, idx, x, y, r, minL, maxL, has_ur, ur, &oct)) continue;
-            const int dist = hamming8(dq, F.desc + (size_t)idx * 32);
-            out[pos] = ((uint32_t)dist << 20) | ((uint32_t)oct << 16) | (uint32_t)idx;
-            top2_insert(best, dist, pos);
-            pos++;
-          }
-          run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        seg = make_int2(base, total);
-      }
-    }
+__global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) {
+  extern __shared__ __align__(16) uint8_t en_smem[];  // uint4 rec[cap] | uint4 desc[2 * cap] | u16 off[kOff16]
+  const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int n = min(A.n[f], A.cap);
+  uint4* s_rec = reinterpret_cast<uint4*>(en_smem);
+  uint4* s_desc = s_rec + A.cap;
+  uint16_t* s_off = reinterpret_cast<uint16_t*>(s_desc + 2 * (size_t)A.cap);
+  {
+    const uint4* g_rec = A.grid_rec + (size_t)f * A.cap;
+    const uint4* g_desc = reinterpret_cast<const uint4*>(A.desc + (size_t)f * A.cap * 32);
+    const uint32_t* g_off = reinterpret_cast<const uint32_t*>(A.grid_off16 + (size_t)f * kOff16);
+    for (int i = tid; i < n; i += kEnumThreads) s_rec[i] = g_rec[i];
+    for (int i = tid; i < 2 * n; i += kEnumThreads) s_desc[i] = g_desc[i];
+    for (int i = tid; i < kOff16 / 2; i += kEnumThreads) reinterpret_cast<uint32_t*>(s_off)[i] = g_off[i];
   }
-  best = top2_warp(best);
-  if (lane == 0) {
+  __syncthreads();
+  const bool has_ur = A.u_right != nullptr;
+  const size_t map_base = (size_t)(A.map_index ? A.map_index[f] : f % A.n_maps) * A.m;
+  uint32_t* slab = A.cand + (size_t)f * A.cand_cap;
+  const int i0 = blockIdx.x * (kEnumThreads * kEnumPerThread);
+#pragma unroll 1
+  for (int k = 0; k < kEnumPerThread; k++) {
+    const int i = i0 + k * kEnumThreads + tid;
+    const bool valid = i < A.m;
+    const size_t o = (size_t)f * A.m + (valid ? i : 0);
+    const int level = valid ? A.q_level[o] : -1;
+    float x = 0, y = 0, ur = 0, rad = 0;
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+    const int minL = level - 1, maxL = level;  // GetFeaturesInArea(x, y, r, level - 1, level)
+    int cnt = 0;
+    if (level >= 0) {
+      const float4 q = A.q[o];
+      x = q.x; y = q.y; ur = q.z; rad = q.w;
+      // Frame::GetFeaturesInArea's cell range (src/Frame.cc:777-801)
+      x0 = max(0, (int)floorf(fmul(fsub(fsub(x, A.min_x), rad), A.inv_w)));
+      x1 = min(ORBX_GRID_COLS - 1, (int)ceilf(fmul(fadd(fsub(x, A.min_x), rad), A.inv_w)));
+      y0 = max(0, (int)floorf(fmul(fsub(fsub(y, A.min_y), rad), A.inv_h)));
+      y1 = min(ORBX_GRID_ROWS - 1, (int)ceilf(fmul(fadd(fsub(y, A.min_y), rad), A.inv_h)));
+      if (x0 >= ORBX_GRID_COLS || x1 < 0 || y0 >= ORBX_GRID_ROWS || y1 < 0) x1 = x0 - 1;
+      for (int ix = x0; ix <= x1; ix++) {
+        // the cells (ix, y0..y1) are consecutive: one run of records
+        const int j0 = s_off[ix * ORBX_GRID_ROWS + y0], j1 = s_off[ix * ORBX_GRID_ROWS + y1 + 1];
+        for (int j = j0; j < j1; j++) cnt += rec_ok(s_rec[j], x, y, rad, minL, maxL, has_ur, ur) ? 1 : 0;
+      }
+    }
+    // the warp takes its slice of the frame's slab
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const int wtotal = __shfl_sync(0xffffffffu, inc, 31);
+    int wbase = 0;
+    if (lane == 0 && wtotal > 0) wbase = atomicAdd(&A.cand_total[f], wtotal);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const bool overflow = wbase + wtotal > A.cand_cap;
+    if (overflow && lane == 0) A.status[f] = ORBX_E_CAPACITY_I;  // reported, never silently truncated
+    if (!valid) continue;
+    int2 seg = make_int2(0, 0);
+    Top2 best{0, -1, 0, -1};
+    if (cnt > 0 && !overflow) {
+      const int base = wbase + inc - cnt;
+      uint32_t dq[8];
+      load_desc8(A.mdesc + (map_base + i) * 32, dq);
+      int pos = 0;
+      for (int ix = x0; ix <= x1; ix++) {
+        const int j0 = s_off[ix * ORBX_GRID_ROWS + y0], j1 = s_off[ix * ORBX_GRID_ROWS + y1 + 1];
+        for (int j = j0; j < j1; j++) {
+          const uint4 r = s_rec[j];
+          if (!rec_ok(r, x, y, rad, minL, maxL, has_ur, ur)) continue;
+          const int idx = (int)(r.w & 0xffffu);
+          const uint4 da = s_desc[2 * idx], db = s_desc[2 * idx + 1];
+          const int dist = __popc(dq[0] ^ da.x) + __popc(dq[1] ^ da.y) + __popc(dq[2] ^ da.z) + __popc(dq[3] ^ da.w) +
+                           __popc(dq[4] ^ db.x) + __popc(dq[5] ^ db.y) + __popc(dq[6] ^ db.z) + __popc(dq[7] ^ db.w);
+          slab[base + pos] = ((uint32_t)dist << 20) | (r.w & 0x000fffffu);
+          top2_insert(best, dist, pos);
+          pos++;
+        }
+      }
+      seg = make_int2(base, cnt);
+    }
     A.seg[o] = seg;
     A.pre[o] = make_int4(best.d1, best.p1, best.d2, best.p2);
   }
 }
+
+size_t track_enum_smem(int cap) { return (size_t)cap * 48 + ((size_t)kOff16 * 2 + 15) / 16 * 16; }
 
 constexpr int kTrackResolveThreads = 1024;
 
@@ -287,11 +353,15 @@ __global__ void __launch_bounds__(kTrackResolveThreads) k_track_resolve(const Tr
 size_t track_resolve_smem(int cap) { return (size_t)cap * 4 + ((size_t)cap + 15) / 16 * 16; }
 
 void launch_track_search(const TrackArgs& A, cudaStream_t st) {
-  launch_build_grid(A.kps, A.n, 0, A.cap, A.n_frames, A.min_x, A.min_y, A.inv_w, A.inv_h, A.grid_offsets, A.grid_items,
-                    A.cap, st);
   cudaMemsetAsync(A.cand_total, 0, (size_t)A.n_frames * 4, st);
   cudaMemsetAsync(A.status, 0, (size_t)A.n_frames * 4, st);
-  if (A.m > 0) k_track_enum<<<dim3((A.m + kTrackWarps - 1) / kTrackWarps, A.n_frames), kTrackWarps * 32, 0, st>>>(A);
+  k_track_grid<<<A.n_frames, 32, 0, st>>>(A);
+  if (A.m > 0) {
+    const size_t es = track_enum_smem(A.cap);
+    if (es > 48 * 1024) cudaFuncSetAttribute(k_track_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);
+    const int per_cta = kEnumThreads * kEnumPerThread;
+    k_track_enum<<<dim3((A.m + per_cta - 1) / per_cta, A.n_frames), kEnumThreads, es, st>>>(A);
+  }
   const size_t smem = track_resolve_smem(A.cap);
   if (smem > 48 * 1024)  // per device: set on every launch that needs it
     cudaFuncSetAttribute(k_track_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -14,8 +14,8 @@ namespace orbm_detail {
 
 // Scratch of one batched tracking search in m->track_buf[slot]; fills the scratch pointers of A (n_frames, cap, m set).
 int track_prepare(orbm_matcher* m, int slot, TrackArgs* A) {
-  const size_t F = (size_t)A->n_frames, M = (size_t)std::max(A->m, 1), cells = ORBX_GRID_COLS * ORBX_GRID_ROWS + 1;
-  const size_t bytes[kTrackBufs] = {F * cells * 4,           F * A->cap * 4, F * M * sizeof(float4), F * M * 4,
+  const size_t F = (size_t)A->n_frames, M = (size_t)std::max(A->m, 1);
+  const size_t bytes[kTrackBufs] = {F * kTrackOff16 * 2,       F * A->cap * 16, F * M * sizeof(float4), F * M * 4,
                                     F * M * sizeof(int2),    F * M * sizeof(int4), F * (size_t)A->cand_cap * 4,
                                     F * 4,                   F * M * 4,      0, 0, 0};
   DevBuf* b = m->track_buf[slot];
@@ -24,8 +24,8 @@ int track_prepare(orbm_matcher* m, int slot, TrackArgs* A) {
     cudaError_t e = b[k].reserve(bytes[k]);
     if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, std::string("track scratch: ") + cudaGetErrorString(e));
   }
-  A->grid_offsets = static_cast<int32_t*>(b[0].p);
-  A->grid_items = static_cast<int32_t*>(b[1].p);
+  A->grid_off16 = static_cast<uint16_t*>(b[0].p);
+  A->grid_rec = static_cast<uint4*>(b[1].p);
   A->q = static_cast<float4*>(b[2].p);
   A->q_level = static_cast<int32_t*>(b[3].p);
   A->seg = static_cast<int2*>(b[4].p);

@@ -121,6 +121,7 @@ void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchS
 // ---- batched local-map tracking search (k_track.cu): Tracking::SearchLocalPoints for the frames of one extract batch
 // Frame f: keypoints kps + f * cap (n[f] of them), descriptors desc + f * cap * 32, its pose frustums[f], its local map
 // map_index[f] (NULL: f % n_maps). Everything is device memory; nothing is synchronised.
+constexpr int kTrackOff16 = ORBX_GRID_COLS * ORBX_GRID_ROWS + 4;  // u16 cell offsets per frame (3073 used)
 struct TrackArgs {
   int n_frames, cap;
   const orbx_kp* kps;
@@ -144,8 +145,8 @@ struct TrackArgs {
   float *o_proj_x, *o_proj_y, *o_proj_xr, *o_view_cos, *o_depth;
   int32_t* o_level;
   // scratch
-  int32_t* grid_offsets;  // [F][64 * 48 + 1]
-  int32_t* grid_items;    // [F][cap]
+  uint16_t* grid_off16;   // [F][kTrackOff16] cell offsets (cap < 65536)
+  uint4* grid_rec;        // [F][cap] per keypoint IN CELL ORDER: x, y, u_right (-1 = none), keypoint | octave << 16 | occupied << 31
   float4* q;              // [F][m] projected query: (u, v, u_right, radius)
   int32_t* q_level;       // [F][m] predicted level, -1 = not searched
   int2* seg;              // [F][m] (first candidate, count) inside the frame's candidate slab

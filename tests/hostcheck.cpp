@@ -51,6 +51,40 @@ long hc_sincosf_sweep(uint32_t lo, uint32_t hi) {
   }
   return bad;
 }
+// counts mismatches of logf_glibc vs the host's logf over all floats with bit patterns in [lo, hi) taking every step-th
+long hc_logf_sweep(uint32_t lo, uint32_t hi, uint32_t step) {
+  long bad = 0;
+  for (uint64_t u = lo; u < hi; u += step) {
+    const uint32_t b = (uint32_t)u;
+    float x;
+    memcpy(&x, &b, 4);
+    const float a = orbx::logf_glibc(x), r = logf(x);
+    if (memcmp(&a, &r, 4) && !(a != a && r != r)) bad++;
+  }
+  return bad;
+}
+// Frame::isInFrustum through the product's arithmetic for m points of one map; outputs as orbref_is_in_frustum
+void hc_is_in_frustum(const float* fr26, const float* pos, const float* normal, const float* min_dist,
+                      const float* max_dist, const uint8_t* skip, int m, float cos_limit, uint8_t* in_view, float* px,
+                      float* py, float* pxr, int32_t* level, float* vcos, float* depth) {
+  int32_t n_levels;
+  memcpy(&n_levels, fr26 + 25, 4);
+  for (int i = 0; i < m; i++) {
+    in_view[i] = 0;
+    if (skip && skip[i]) continue;
+    const orbx::FrustumOut o =
+        orbx::is_in_frustum(fr26, n_levels, pos + 3 * i, normal + 3 * i, min_dist[i], max_dist[i], cos_limit);
+    in_view[i] = o.in_view;
+    px[i] = o.proj_x;
+    py[i] = o.proj_y;
+    if (o.in_view) {
+      pxr[i] = o.proj_xr;
+      level[i] = o.level;
+      vcos[i] = o.view_cos;
+      depth[i] = o.depth;
+    }
+  }
+}
 int hc_plan(int w, int h, int nfeatures, float scale, int nlevels, orbx::Plan* out) {
   return orbx::make_plan(w, h, nfeatures, scale, nlevels, out);
 }

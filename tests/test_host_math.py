@@ -71,6 +71,46 @@ def test_sincosf_is_glibc_bit_exact(hc):
         assert np.float32(s.value).tobytes() == np.float32(libm.sinf(float(rad))).tobytes()
 
 
+def test_logf_is_glibc_bit_exact(hc):
+    """MapPoint::PredictScale's log(ratio) (src/MapPoint.cc:566) and mfLogScaleFactor (src/Frame.cc:189) are glibc logf; the
+    device restatement must equal the host's for every input (1 in 64 of all non-negative float patterns here, plus the
+    ranges PredictScale lives in exhaustively: ratio in [2^-8, 2^8])."""
+    hc.hc_logf_sweep.restype = C.c_long
+    hc.hc_logf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    assert hc.hc_logf_sweep(0, 0x7f800001, 64) == 0
+    lo = int(np.float32(2.0 ** -8).view(np.uint32))
+    hi = int(np.float32(2.0 ** 8).view(np.uint32))
+    assert hc.hc_logf_sweep(lo, hi, 1) == 0
+    assert hc.hc_logf_sweep(0x80000000, 0x80000010, 1) == 0 and hc.hc_logf_sweep(0x7f800000, 0x7f800010, 1) == 0
+
+
+def test_is_in_frustum_arithmetic_matches_oracle(hc):
+    """The product's Frame::isInFrustum arithmetic (orbx_math.h, what k_frustum runs) against the oracle's restatement on
+    the CPU: a GPU mismatch can then only come from data movement."""
+    from orb_slam3_fast_b200 import synth
+    img = synth.scene(480, 640, seed=11)
+    _, kps, desc = orbref.Extractor(1200)(img, (0, 0))
+    for seed in range(4):
+        fr = synth.frustum(640, 480, seed=seed)
+        mp = synth.local_map_world(kps, desc, 20000, fr, seed=seed)
+        nv, o = orbref.is_in_frustum(fr, orbref.make_local_map(**mp))
+        assert nv > 5000
+        m = 20000
+        got = dict(track_in_view=np.zeros(m, np.uint8), proj_x=np.zeros(m, np.float32), proj_y=np.zeros(m, np.float32),
+                   proj_xr=np.zeros(m, np.float32), level=np.zeros(m, np.int32), view_cos=np.zeros(m, np.float32),
+                   depth=np.zeros(m, np.float32))
+        frb = np.ascontiguousarray(fr).reshape(1).view(np.float32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        hc.hc_is_in_frustum.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_float] + [C.c_void_p] * 7
+        hc.hc_is_in_frustum.restype = None
+        arr = {k: np.ascontiguousarray(v) for k, v in mp.items()}
+        hc.hc_is_in_frustum(p(frb), p(arr["pos"]), p(arr["normal"]), p(arr["min_dist"]), p(arr["max_dist"]),
+                            p(arr["skip"]), m, 0.5, p(got["track_in_view"]), p(got["proj_x"]), p(got["proj_y"]),
+                            p(got["proj_xr"]), p(got["level"]), p(got["view_cos"]), p(got["depth"]))
+        for k in o:
+            assert got[k].tobytes() == o[k].tobytes(), k
+
+
 def test_cv_round_ties_to_even(hc):
     for v, r in ((0.5, 0), (1.5, 2), (2.5, 2), (-0.5, 0), (-1.5, -2), (-2.5, -2), (3.49, 3), (3.51, 4)):
         assert hc.hc_cv_round(v) == r

@@ -359,3 +359,30 @@ def test_compute_distinctive_descriptors():
             got = refsrc.distinctive_descriptor(d)
             idx = orbref.distinctive_descriptor(d)
             assert idx >= 0 and np.array_equal(got, d[idx]), (n, proto)
+
+
+@pytest.mark.parametrize("seed,m,cos_limit", [(0, 10000, 0.5), (1, 10000, 0.5), (2, 3000, 0.8), (3, 1, 0.5), (4, 500, -1.0)])
+def test_is_in_frustum(seed, m, cos_limit):
+    """Frame::isInFrustum (src/Frame.cc:632-699) + MapPoint::PredictScale (src/MapPoint.cc:559-573): the reference's own
+    text (cut out by signature, oracle/Makefile) on a general pose must leave exactly the oracle's words on every point:
+    mbTrackInView, mTrackProjX / Y (-1 outside the image), and — only when in view — mTrackProjXR, mnTrackScaleLevel,
+    mTrackViewCos, mTrackDepth. The stand-in Eigen reduces 3-vectors in Eigen's own order c0 + (c1 + c2)."""
+    from orb_slam3_fast_b200 import synth
+    img = synth.scene(480, 640, seed=20 + seed)
+    _, kps, desc = orbref.Extractor(1200)(img, (0, 0))
+    fr = synth.frustum(640, 480, seed=seed)
+    mp = synth.local_map_world(kps, desc, m, fr, seed=seed)
+    lm = orbref.make_local_map(**mp)
+    sentinel = lambda: dict(track_in_view=np.full(m, 7, np.uint8), proj_x=np.full(m, 3.5, np.float32),
+                            proj_y=np.full(m, 4.5, np.float32), proj_xr=np.full(m, 5.5, np.float32),
+                            level=np.full(m, -9, np.int32), view_cos=np.full(m, 6.5, np.float32),
+                            depth=np.full(m, 8.5, np.float32))
+    nv_r, o_r = refsrc.is_in_frustum(fr, lm, 0, cos_limit, sentinel())
+    nv, o = orbref.is_in_frustum(fr, lm, 0, cos_limit, sentinel())
+    assert nv == nv_r and (m < 100 or cos_limit > 0.6 or nv > m // 3)
+    for k in o:
+        assert o[k].tobytes() == o_r[k].tobytes(), k
+    # untouched fields really are untouched: points out of view keep the sentinel in the "only when in view" fields
+    out = o["track_in_view"] == 0
+    if out.any():
+        assert (o["level"][out] == -9).all() and (o["depth"][out] == 8.5).all()
