@@ -434,7 +434,14 @@ def run_stereo_workload(ctx, args, cfg_id, steps, warmup, reps, with_cpu, clock_
         frs_d, stacked = make_track_inputs(cfg, Ld, 1000 * rank + 100 * cfg_id, kd)
         rng = np.random.default_rng(rank)
         occ_d = (rng.random((D, cap)) < 0.25).astype(np.uint8)
-        lm_host = views.make_local_map(**stacked)
+        pinned_map = {}
+        for k2, v in stacked.items():  # pinned: a pageable 42 MB upload would block the call for milliseconds
+            pinned_map[k2] = ctx.pinned(v.shape, v.dtype)
+            pinned_map[k2][...] = v
+        lm_host = views.make_local_map(**pinned_map)
+        pin_sel = [ctx.pinned(s.shape, np.int32) for s in sel]
+        for k2 in range(n_rot):
+            pin_sel[k2][...] = sel[k2]
         t_map = {k: torch.from_numpy(v).to(dev) for k, v in stacked.items()}
         dmap = views.make_local_map_device(M, D, t_map["pos"].data_ptr(), t_map["normal"].data_ptr(),
                                            t_map["min_dist"].data_ptr(), t_map["max_dist"].data_ptr(),
@@ -499,7 +506,7 @@ def run_stereo_workload(ctx, args, cfg_id, steps, warmup, reps, with_cpu, clock_
         out = outs if out is None else out
         if track:
             return mt.StereoTrackFramesBatch(ex_l, ex_r, pinL[r][:n], pinR[r][:n], MBF, MB, pin_frs[r][:n], lm_host, prm,
-                                             map_index=sel[r][:n], occupied=pin_occ[r][:n], out=out)
+                                             map_index=pin_sel[r][:n], occupied=pin_occ[r][:n], out=out)
         return mt.StereoFramesBatch(ex_l, ex_r, pinL[r][:n], pinR[r][:n], MBF, MB, out)
 
     # ---- parity gate on this configuration before any timing: `--parity-pairs` distinct pairs (and their maps) of

@@ -479,6 +479,35 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     // (src/Frame.cc:200-203): the latency-bound stages of one eye (quadtree, small pyramid levels) overlap the
     // ALU-bound stages of the other, and with kLanes groups in flight the copy engines stay busy too.
     cudaStream_t st = left->lane[ln].stream, sr = right->lane[ln].stream;
+    // The tracking stage's small per-group inputs (poses, occupancy) cross PCIe FIRST: enqueued behind the stereo
+    // kernels they would sit in the copy engine's queue behind the next lanes' image uploads (measured: the call took
+    // 20.2 ms against 13.0 ms without the image uploads and 12.2 ms for the uploads alone)
+    orbx_frustum* d_fr = nullptr;
+    int32_t* d_assign = nullptr;
+    int32_t* d_words = nullptr;
+    uint8_t* d_occ = nullptr;
+    if (trk) {
+      const int dcap0 = left->lane[ln].out_cap;
+      DevBuf* tb = m->track_buf[ln];
+      cudaError_t e = tb[9].reserve((size_t)B * sizeof(orbx_frustum));
+      if (e == cudaSuccess) e = tb[10].reserve((size_t)B * dcap0 * 4 + (size_t)B * 3 * 4);
+      if (e == cudaSuccess && trk->occupied) e = tb[11].reserve((size_t)B * dcap0);
+      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
+      d_fr = static_cast<orbx_frustum*>(tb[9].p);
+      d_assign = static_cast<int32_t*>(tb[10].p);
+      d_words = d_assign + (size_t)B * dcap0;  // nmatches[B] | n_in_view[B] | status[B]
+      ORBM_CUDA(m, cudaMemcpyAsync(d_fr, trk->frustums + f0, (size_t)nb * sizeof(orbx_frustum), cudaMemcpyHostToDevice, st));
+      if (trk->occupied) {
+        d_occ = static_cast<uint8_t*>(tb[11].p);
+        if (cap == dcap0) {
+          ORBM_CUDA(m, cudaMemcpyAsync(d_occ, trk->occupied + (size_t)f0 * cap, (size_t)nb * cap, cudaMemcpyHostToDevice, st));
+        } else {
+          ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, (size_t)nb * dcap0, st));
+          ORBM_CUDA(m, cudaMemcpy2DAsync(d_occ, dcap0, trk->occupied + (size_t)f0 * cap, cap, std::min(cap, dcap0), nb,
+                                         cudaMemcpyHostToDevice, st));
+        }
+      }
+    }
     if ((rc = api_upload_and_run(left, ln, imgs_l + (int64_t)f0 * frame_stride, nb, width, height, stride,
                                  frame_stride, 0, 0, st)) != 0)
       return mfail(m, rc, orbx_last_error(left));
@@ -536,36 +565,11 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
       T.n = LL.d_n;
       T.u_right = A.u_right;
       if ((rc = track_prepare(m, ln, &T)) != 0) return rc;
-      // per-group inputs / outputs live behind the scratch: frustums, occupied, assign, 3 result words per frame
-      DevBuf* tb = m->track_buf[ln];
-      cudaError_t e = tb[9].reserve((size_t)B * sizeof(orbx_frustum));
-      if (e == cudaSuccess) e = tb[10].reserve((size_t)B * dcap * 4 + (size_t)B * 3 * 4);
-      if (e == cudaSuccess && trk->occupied) e = tb[11].reserve((size_t)B * dcap);
-      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
-      orbx_frustum* d_fr = static_cast<orbx_frustum*>(tb[9].p);
-      int32_t* d_assign = static_cast<int32_t*>(tb[10].p);
-      int32_t* d_words = d_assign + (size_t)B * dcap;  // nmatches[B] | n_in_view[B] | status[B]
-      ORBM_CUDA(m, cudaMemcpyAsync(d_fr, trk->frustums + f0, (size_t)nb * sizeof(orbx_frustum), cudaMemcpyHostToDevice, st));
       T.frustums = d_fr;
       T.map_index = nullptr;
       if (d_map_index_all) T.map_index = d_map_index_all + f0;
-      else if (dmap.n_maps > 1) {
-        // pair p uses map p % n_maps: inside a group the kernel sees local frame numbers, so the rule needs the offset
-        // -> a per-call index array is built on the host once (below) when n_maps > 1 and no index was given
-        T.map_index = static_cast<int32_t*>(m->track_map[7].p) + f0;
-      }
-      T.occupied = nullptr;
-      if (trk->occupied) {
-        uint8_t* d_occ = static_cast<uint8_t*>(tb[11].p);
-        if (cap == dcap) {
-          ORBM_CUDA(m, cudaMemcpyAsync(d_occ, trk->occupied + (size_t)f0 * cap, (size_t)nb * cap, cudaMemcpyHostToDevice, st));
-        } else {
-          ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, (size_t)nb * dcap, st));
-          ORBM_CUDA(m, cudaMemcpy2DAsync(d_occ, dcap, trk->occupied + (size_t)f0 * cap, cap, std::min(cap, dcap), nb,
-                                         cudaMemcpyHostToDevice, st));
-        }
-        T.occupied = d_occ;
-      }
+      else if (dmap.n_maps > 1) T.map_index = static_cast<int32_t*>(m->track_map[7].p) + f0;  // p % n_maps, see above
+      T.occupied = trk->occupied ? d_occ : nullptr;
       T.assign = d_assign;
       T.nmatches = d_words;
       T.n_in_view = d_words + B;

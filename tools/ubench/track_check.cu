@@ -1,0 +1,362 @@
+// track_check — bench.py's configs[3] hot path (extract x2 + ComputeStereoMatches + SearchLocalPoints) through the C ABI
+// without Python: (1) parity of every output word against the CPU oracle's outputs stored in data/track_case.bin
+// (tools/ubench/make_track_case.py writes it here, before gpurun), for the device-resident calls and for the host-facing
+// pipelined call; (2) device-resident timing with the matcher's share bracketed; (3) the end-to-end leg, with the
+// ORBX_DEBUG_SKIP_* toggles of the library available for pipeline accounting. Seconds of GPU box time per run.
+//
+//   ./track_check [pairs per batch = 1024] [batches = 10] [e2e batches = batches, 0 = skip] [group = 64] [case file]
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <string>
+#include <vector>
+
+#include "orbm.h"
+#include "orbx.h"
+
+#define CK(x)                                                                   \
+  do {                                                                          \
+    cudaError_t e_ = (x);                                                       \
+    if (e_ != cudaSuccess) {                                                    \
+      printf("%s:%d %s: %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+      return 1;                                                                 \
+    }                                                                           \
+  } while (0)
+#define OX(ex, x)                                                                        \
+  do {                                                                                   \
+    int rc_ = (x);                                                                       \
+    if (rc_ != 0) {                                                                      \
+      printf("%s:%d %s: rc %d: %s\n", __FILE__, __LINE__, #x, rc_, orbx_last_error(ex)); \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+#define OM(x)                                                                           \
+  do {                                                                                  \
+    int rc_ = (x);                                                                      \
+    if (rc_ != 0) {                                                                     \
+      printf("%s:%d %s: rc %d: %s\n", __FILE__, __LINE__, #x, rc_, orbm_last_error(mt)); \
+      return 1;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+struct Eye {
+  int32_t n, mono;
+  std::vector<uint8_t> kps, desc;
+};
+struct Pair {
+  Eye eye[2];
+  int32_t n_matched, nmatches, n_in_view;
+  std::vector<float> u_right, depth;
+  std::vector<int32_t> assign;
+};
+struct DevOut {
+  orbx_kp* kps;
+  uint8_t* desc;
+  int32_t *n, *mono, *status;
+};
+static bool rd(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
+template <typename T>
+static T* pin(size_t count) { return static_cast<T*>(orbx_host_alloc((int64_t)(count * sizeof(T)))); }
+
+int main(int argc, char** argv) {
+  const int P = argc > 1 ? atoi(argv[1]) : 1024, steps = argc > 2 ? atoi(argv[2]) : 10;
+  const int e2e_steps = argc > 3 ? atoi(argv[3]) : steps;
+  const int G = argc > 4 ? atoi(argv[4]) : 64;
+  std::string path = argc > 5 ? argv[5] : "";
+  if (path.empty()) {
+    path = argv[0];
+    const size_t s = path.find_last_of('/');
+    path = (s == std::string::npos ? std::string(".") : path.substr(0, s)) + "/data/track_case.bin";
+  }
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return printf("cannot open %s (run tools/ubench/make_track_case.py first)\n", path.c_str()), 1;
+  int32_t hdr[7];
+  float mbf, mb;
+  orbx_track_params prm;
+  if (!rd(f, hdr, 28) || hdr[0] != 0x4F524254 || !rd(f, &mbf, 4) || !rd(f, &mb, 4) || !rd(f, &prm, sizeof(prm)))
+    return printf("bad case file\n"), 1;
+  const int D = hdr[1], W = hdr[2], H = hdr[3], nfeat = hdr[4], M = hdr[5], ccap = hdr[6];
+  const size_t fbytes = (size_t)W * H, DM = (size_t)D * M;
+  std::vector<uint8_t> imgs[2] = {std::vector<uint8_t>(D * fbytes), std::vector<uint8_t>(D * fbytes)};
+  std::vector<orbx_frustum> frs(D);
+  std::vector<float> pos(DM * 3), nrm(DM * 3), mind(DM), maxd(DM);
+  std::vector<uint8_t> skip(DM), hobs(DM), mdesc(DM * 32), occ((size_t)D * ccap);
+  bool ok = rd(f, imgs[0].data(), D * fbytes) && rd(f, imgs[1].data(), D * fbytes) && rd(f, frs.data(), D * sizeof(orbx_frustum)) &&
+            rd(f, pos.data(), DM * 12) && rd(f, nrm.data(), DM * 12) && rd(f, mind.data(), DM * 4) && rd(f, maxd.data(), DM * 4) &&
+            rd(f, skip.data(), DM) && rd(f, hobs.data(), DM) && rd(f, mdesc.data(), DM * 32) && rd(f, occ.data(), occ.size());
+  std::vector<Pair> want(D);
+  for (int i = 0; ok && i < D; i++) {
+    for (int e = 0; ok && e < 2; e++) {
+      Eye& y = want[i].eye[e];
+      ok = rd(f, &y.n, 4) && rd(f, &y.mono, 4);
+      y.kps.resize((size_t)y.n * 28);
+      y.desc.resize((size_t)y.n * 32);
+      ok = ok && rd(f, y.kps.data(), y.kps.size()) && rd(f, y.desc.data(), y.desc.size());
+    }
+    const int nl = want[i].eye[0].n;
+    want[i].u_right.resize(nl);
+    want[i].depth.resize(nl);
+    want[i].assign.resize(nl);
+    ok = ok && rd(f, &want[i].n_matched, 4) && rd(f, want[i].u_right.data(), (size_t)nl * 4) &&
+         rd(f, want[i].depth.data(), (size_t)nl * 4) && rd(f, &want[i].nmatches, 4) && rd(f, &want[i].n_in_view, 4) &&
+         rd(f, want[i].assign.data(), (size_t)nl * 4);
+  }
+  fclose(f);
+  if (!ok) return printf("short case file\n"), 1;
+
+  orbx_extractor* ex[2] = {nullptr, nullptr};
+  orbm_matcher* mt = nullptr;
+  for (int e = 0; e < 2; e++) OX(nullptr, orbx_extractor_create(&ex[e], 0, nfeat, 1.2f, 8, 20, 7, P));
+  if (orbm_create(&mt, 0) != 0) return printf("orbm_create: %s\n", orbm_last_error(nullptr)), 1;
+  const int cap = orbx_extractor_capacity(ex[0]);
+  if (cap != ccap) return printf("capacity mismatch %d vs %d\n", cap, ccap), 1;
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+
+  // ---- device-resident inputs: two rotating batches (pair p of batch k = distinct pair (p + k) % D) ----
+  uint8_t* d_img[2][2];
+  orbx_frustum* d_fr[2];
+  uint8_t* d_occ[2];
+  int32_t* d_midx[2];
+  for (int k = 0; k < 2; k++) {
+    for (int e = 0; e < 2; e++) {
+      CK(cudaMalloc(&d_img[k][e], (size_t)P * fbytes));
+      for (int p = 0; p < P; p++)
+        CK(cudaMemcpyAsync(d_img[k][e] + (size_t)p * fbytes, imgs[e].data() + (size_t)((p + k) % D) * fbytes, fbytes,
+                           cudaMemcpyHostToDevice, st));
+    }
+    std::vector<orbx_frustum> hf(P);
+    std::vector<uint8_t> ho((size_t)P * cap);
+    std::vector<int32_t> hi(P);
+    for (int p = 0; p < P; p++) {
+      const int d = (p + k) % D;
+      hf[p] = frs[d];
+      memcpy(ho.data() + (size_t)p * cap, occ.data() + (size_t)d * cap, cap);
+      hi[p] = d;
+    }
+    CK(cudaMalloc(&d_fr[k], P * sizeof(orbx_frustum)));
+    CK(cudaMalloc(&d_occ[k], (size_t)P * cap));
+    CK(cudaMalloc(&d_midx[k], (size_t)P * 4));
+    CK(cudaMemcpy(d_fr[k], hf.data(), P * sizeof(orbx_frustum), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_occ[k], ho.data(), (size_t)P * cap, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_midx[k], hi.data(), (size_t)P * 4, cudaMemcpyHostToDevice));
+  }
+  orbx_local_map dmap{};
+  {
+    float *a, *b, *c, *d;
+    uint8_t *e, *g, *h;
+    CK(cudaMalloc(&a, DM * 12)); CK(cudaMalloc(&b, DM * 12)); CK(cudaMalloc(&c, DM * 4)); CK(cudaMalloc(&d, DM * 4));
+    CK(cudaMalloc(&e, DM)); CK(cudaMalloc(&g, DM)); CK(cudaMalloc(&h, DM * 32));
+    CK(cudaMemcpy(a, pos.data(), DM * 12, cudaMemcpyHostToDevice)); CK(cudaMemcpy(b, nrm.data(), DM * 12, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c, mind.data(), DM * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d, maxd.data(), DM * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e, skip.data(), DM, cudaMemcpyHostToDevice)); CK(cudaMemcpy(g, hobs.data(), DM, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h, mdesc.data(), DM * 32, cudaMemcpyHostToDevice));
+    dmap = orbx_local_map{M, D, a, b, c, d, e, g, h};
+  }
+  DevOut o[2];
+  for (int e = 0; e < 2; e++) {
+    CK(cudaMalloc(&o[e].kps, (size_t)P * cap * sizeof(orbx_kp)));
+    CK(cudaMalloc(&o[e].desc, (size_t)P * cap * 32));
+    CK(cudaMalloc(&o[e].n, (size_t)P * 4));
+    CK(cudaMalloc(&o[e].mono, (size_t)P * 4));
+    CK(cudaMalloc(&o[e].status, (size_t)P * 4));
+  }
+  float *d_ur, *d_dp;
+  int32_t *d_nm, *d_assign, *d_res;
+  CK(cudaMalloc(&d_ur, (size_t)P * cap * 4));
+  CK(cudaMalloc(&d_dp, (size_t)P * cap * 4));
+  CK(cudaMalloc(&d_nm, (size_t)P * 4));
+  CK(cudaMalloc(&d_assign, (size_t)P * cap * 4));
+  CK(cudaMalloc(&d_res, (size_t)3 * P * 4));
+  CK(cudaStreamSynchronize(st));
+
+  cudaEvent_t ea, eb, ec;
+  CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb)); CK(cudaEventCreate(&ec));
+  float ms_stereo = 0, ms_track = 0;
+  bool bracket = false;
+  auto step = [&](int k) -> int {
+    for (int e = 0; e < 2; e++)
+      OX(ex[e], orbx_extract_batch_device(ex[e], P, d_img[k & 1][e], W, H, W, (int64_t)fbytes, 0, 0, o[e].kps, o[e].desc,
+                                          cap, o[e].n, o[e].mono, o[e].status, st));
+    if (bracket) cudaEventRecord(ea, st);
+    OM(orbm_stereo_match_batch_device(mt, ex[0], ex[1], P, o[0].kps, o[0].desc, o[0].n, o[1].kps, o[1].desc, o[1].n, cap,
+                                      mbf, mb, d_ur, d_dp, d_nm, st));
+    if (bracket) cudaEventRecord(eb, st);
+    OM(orbm_track_local_map_batch_device(mt, ex[0], P, o[0].kps, o[0].desc, o[0].n, cap, d_ur, d_occ[k & 1], d_fr[k & 1],
+                                         &dmap, d_midx[k & 1], &prm, d_assign, d_res, d_res + P, d_res + 2 * P, st));
+    if (bracket) {
+      cudaEventRecord(ec, st);
+      cudaEventSynchronize(ec);
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, ea, eb);
+      cudaEventElapsedTime(&b, eb, ec);
+      ms_stereo += a;
+      ms_track += b;
+    }
+    return 0;
+  };
+
+  // ---- parity of the device-resident path: the first min(P, D) pairs of batch 0 are the case's pairs in order ----
+  if (step(0)) return 1;
+  CK(cudaStreamSynchronize(st));
+  const int nchk = P < D ? P : D;
+  long bad = 0;
+  {
+    std::vector<int32_t> res(3 * (size_t)P);
+    CK(cudaMemcpy(res.data(), d_res, res.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nchk; i++) {
+      const Pair& w = want[i];
+      for (int e = 0; e < 2; e++) {
+        int32_t n, mono, status;
+        CK(cudaMemcpy(&n, o[e].n + i, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&mono, o[e].mono + i, 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&status, o[e].status + i, 4, cudaMemcpyDeviceToHost));
+        const Eye& y = w.eye[e];
+        bool same = n == y.n && mono == y.mono && status == 0;
+        if (same) {
+          std::vector<uint8_t> k((size_t)y.n * 28), d((size_t)y.n * 32);
+          CK(cudaMemcpy(k.data(), o[e].kps + (size_t)i * cap, k.size(), cudaMemcpyDeviceToHost));
+          CK(cudaMemcpy(d.data(), o[e].desc + (size_t)i * cap * 32, d.size(), cudaMemcpyDeviceToHost));
+          same = memcmp(k.data(), y.kps.data(), k.size()) == 0 && memcmp(d.data(), y.desc.data(), d.size()) == 0;
+        }
+        if (!same && bad++ < 8) printf("pair %d eye %d differs (n %d vs %d, status %d)\n", i, e, n, y.n, status);
+      }
+      const int nl = w.eye[0].n;
+      int32_t nm;
+      std::vector<float> ur(nl), dp(nl);
+      std::vector<int32_t> as(nl);
+      CK(cudaMemcpy(&nm, d_nm + i, 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(ur.data(), d_ur + (size_t)i * cap, (size_t)nl * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(dp.data(), d_dp + (size_t)i * cap, (size_t)nl * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(as.data(), d_assign + (size_t)i * cap, (size_t)nl * 4, cudaMemcpyDeviceToHost));
+      if ((nm != w.n_matched || memcmp(ur.data(), w.u_right.data(), (size_t)nl * 4) || memcmp(dp.data(), w.depth.data(), (size_t)nl * 4)) && bad++ < 8)
+        printf("pair %d stereo differs (n_matched %d vs %d)\n", i, nm, w.n_matched);
+      if ((res[i] != w.nmatches || res[P + i] != w.n_in_view || res[2 * (size_t)P + i] != 0 ||
+           memcmp(as.data(), w.assign.data(), (size_t)nl * 4)) && bad++ < 8)
+        printf("pair %d tracking differs (nmatches %d vs %d, in view %d vs %d, status %d)\n", i, res[i], w.nmatches,
+               res[P + i], w.n_in_view, res[2 * (size_t)P + i]);
+    }
+  }
+  printf("parity vs oracle: %s (%d pairs: keypoints, descriptors, uRight, depth, isInFrustum count, assign[], nmatches)\n",
+         bad ? "FAILED" : "bit-exact", nchk);
+
+  // ---- device-resident timing ----
+  for (int k = 0; k < 3; k++)
+    if (step(k)) return 1;
+  CK(cudaStreamSynchronize(st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  for (int k = 0; k < steps; k++)
+    if (step(k)) return 1;
+  CK(cudaEventRecord(e1, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("%d pairs/batch x %d batches: %.3f ms/batch = %.0f frames/s device-resident\n", P, steps, ms / steps,
+         2.0 * P * steps / (ms * 1e-3));
+  for (int e = 0; e < 2; e++) {
+    orbx_profile_enable(ex[e], 1);
+    orbx_profile_read(ex[e], nullptr, nullptr, 1);
+  }
+  bracket = true;
+  const int psteps = steps < 4 ? steps : 4;
+  for (int k = 0; k < psteps; k++)
+    if (step(k)) return 1;
+  bracket = false;
+  float stage[5] = {0, 0, 0, 0, 0};
+  for (int e = 0; e < 2; e++) {
+    float s[5];
+    int32_t c[5];
+    if (orbx_profile_read(ex[e], s, c, 1) == 0)
+      for (int k = 0; k < 5; k++) stage[k] += s[k];
+    orbx_profile_enable(ex[e], 0);
+  }
+  printf("stage ms/batch: pyramid %.3f fast %.3f quadtree %.3f blur %.3f describe %.3f stereo %.3f track %.3f\n",
+         stage[0] / psteps, stage[1] / psteps, stage[2] / psteps, stage[3] / psteps, stage[4] / psteps, ms_stereo / psteps,
+         ms_track / psteps);
+
+  // ---- end to end: orbm_stereo_track_frames_batch, pinned host buffers in and out (bench.py's e2e leg) ----
+  if (e2e_steps > 0) {
+    orbx_extractor* ex2[2] = {nullptr, nullptr};
+    for (int e = 0; e < 2; e++) OX(nullptr, orbx_extractor_create(&ex2[e], 0, nfeat, 1.2f, 8, 20, 7, G));
+    uint8_t* h_img[2][2];
+    orbx_frustum* h_fr[2];
+    uint8_t* h_occ[2];
+    int32_t* h_midx[2];
+    for (int k = 0; k < 2; k++) {
+      for (int e = 0; e < 2; e++) {
+        h_img[k][e] = pin<uint8_t>((size_t)P * fbytes);
+        for (int p = 0; p < P; p++)
+          memcpy(h_img[k][e] + (size_t)p * fbytes, imgs[e].data() + (size_t)((p + k) % D) * fbytes, fbytes);
+      }
+      h_fr[k] = pin<orbx_frustum>(P);
+      h_occ[k] = pin<uint8_t>((size_t)P * cap);
+      h_midx[k] = pin<int32_t>(P);
+      for (int p = 0; p < P; p++) {
+        const int d = (p + k) % D;
+        h_fr[k][p] = frs[d];
+        memcpy(h_occ[k] + (size_t)p * cap, occ.data() + (size_t)d * cap, cap);
+        h_midx[k][p] = d;
+      }
+    }
+    float *pa = pin<float>(DM * 3), *pb = pin<float>(DM * 3), *pc = pin<float>(DM), *pd = pin<float>(DM);
+    uint8_t *pe = pin<uint8_t>(DM), *pg = pin<uint8_t>(DM), *ph = pin<uint8_t>(DM * 32);
+    memcpy(pa, pos.data(), DM * 12); memcpy(pb, nrm.data(), DM * 12); memcpy(pc, mind.data(), DM * 4);
+    memcpy(pd, maxd.data(), DM * 4); memcpy(pe, skip.data(), DM); memcpy(pg, hobs.data(), DM); memcpy(ph, mdesc.data(), DM * 32);
+    const orbx_local_map hmap{M, D, pa, pb, pc, pd, pe, pg, ph};
+    orbx_kp* h_kps[2];
+    uint8_t* h_desc[2];
+    int32_t* h_n[2];
+    for (int e = 0; e < 2; e++) {
+      h_kps[e] = pin<orbx_kp>((size_t)P * cap);
+      h_desc[e] = pin<uint8_t>((size_t)P * cap * 32);
+      h_n[e] = pin<int32_t>(P);
+    }
+    float *h_ur = pin<float>((size_t)P * cap), *h_dp = pin<float>((size_t)P * cap);
+    int32_t *h_nm = pin<int32_t>(P), *h_as = pin<int32_t>((size_t)P * cap), *h_tn = pin<int32_t>(P), *h_tv = pin<int32_t>(P);
+    auto e2e = [&](int k) -> int {
+      OM(orbm_stereo_track_frames_batch(mt, ex2[0], ex2[1], P, h_img[k & 1][0], h_img[k & 1][1], W, H, W, (int64_t)fbytes,
+                                        mbf, mb, h_fr[k & 1], &hmap, h_midx[k & 1], h_occ[k & 1], &prm, h_kps[0], h_desc[0],
+                                        h_n[0], h_kps[1], h_desc[1], h_n[1], cap, h_ur, h_dp, h_nm, h_as, h_tn, h_tv));
+      return 0;
+    };
+    for (int k = 0; k < 3; k++)
+      if (e2e(k)) return 1;
+    long bad2 = 0;
+    if (e2e(0)) return 1;
+    const bool garbage = getenv("ORBX_DEBUG_SKIP_H2D") || getenv("ORBX_DEBUG_SKIP_KERNELS");
+    for (int i = 0; i < nchk && !garbage; i++) {
+      const Pair& w = want[i];
+      const int nl = w.eye[0].n;
+      bool same = h_n[0][i] == nl && h_n[1][i] == w.eye[1].n && h_nm[i] == w.n_matched && h_tn[i] == w.nmatches &&
+                  h_tv[i] == w.n_in_view;
+      same = same && memcmp(h_kps[0] + (size_t)i * cap, w.eye[0].kps.data(), (size_t)nl * 28) == 0 &&
+             memcmp(h_desc[1] + (size_t)i * cap * 32, w.eye[1].desc.data(), (size_t)w.eye[1].n * 32) == 0 &&
+             memcmp(h_ur + (size_t)i * cap, w.u_right.data(), (size_t)nl * 4) == 0 &&
+             memcmp(h_dp + (size_t)i * cap, w.depth.data(), (size_t)nl * 4) == 0 &&
+             memcmp(h_as + (size_t)i * cap, w.assign.data(), (size_t)nl * 4) == 0;
+      if (!same && bad2++ < 8) printf("e2e pair %d differs\n", i);
+    }
+    printf("e2e parity vs oracle: %s\n", garbage ? "not checked (debug toggle set)" : bad2 ? "FAILED" : "bit-exact");
+    bad += bad2;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int k = 0; k < e2e_steps; k++)
+      if (e2e(k)) return 1;
+    CK(cudaDeviceSynchronize());
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double dt = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    printf("e2e (host buffers, groups of %d pairs): %.3f ms/call = %.0f frames/s\n", G, 1e3 * dt / e2e_steps,
+           2.0 * P * e2e_steps / dt);
+    for (int e = 0; e < 2; e++) orbx_extractor_destroy(ex2[e]);
+  }
+  orbm_destroy(mt);
+  for (int e = 0; e < 2; e++) orbx_extractor_destroy(ex[e]);
+  return bad ? 2 : 0;
+}
