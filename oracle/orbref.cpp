@@ -18,6 +18,19 @@
 #include <utility>
 #include <vector>
 
+// The hot loop of FAST uses SSE2 intrinsics (baseline x86-64: the reference is built without -march=native,
+// CMakeLists.txt:13-18, and an OpenCV binary runs its SSE2 / dispatched kernels either way) with OpenCV's own early exit
+// per 16-pixel block; integer arithmetic, same bytes as the plain loop it replaces (kept as the non-x86 fallback).
+// Measured dead end: GCC function multi-versioning (target_clones "avx2") of the three primitives made the extractor 37 %
+// SLOWER on the build host (per-cell calls through the resolver, AVX <-> SSE transitions), so there is no AVX2 variant.
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#define ORBREF_PRIMITIVES_KIND "the oracle's cv2-pinned restatements: SSE2 FAST with OpenCV's per-16-pixel early exit, compiler-vectorised (SSE2) resize / blur"
+#else
+#define ORBREF_PRIMITIVES_KIND "the oracle's cv2-pinned restatements (portable build, no SIMD intrinsics)"
+#endif
+#define ORBREF_SIMD_CLONES
+
 namespace {
 
 constexpr int kPatch = 31;      // PATCH_SIZE        src/ORBextractor.cc:71
@@ -73,9 +86,10 @@ AxisTab axis_table(int ssize, int dsize, bool clamp_like_x) {
   return t;
 }
 
-void resize_linear(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {
+ORBREF_SIMD_CLONES void resize_linear(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride) {
   AxisTab tx = axis_table(sw, dw, true), ty = axis_table(sh, dh, false);
   std::vector<int> r0(dw), r1(dw);
+  int have0 = -1000000, have1 = -1000000;  // source rows held by r0 / r1 (OpenCV keeps its horizontal rows the same way)
   auto hrow = [&](int sy, std::vector<int>& out) {
     sy = sy < 0 ? 0 : (sy >= sh ? sh - 1 : sy);  // rows are clipped, beta is kept (resizeGeneric_Invoker)
     const uint8_t* S = src + (size_t)sy * sstride;
@@ -86,8 +100,20 @@ void resize_linear(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst
     }
   };
   for (int y = 0; y < dh; y++) {
-    hrow(ty.ofs[y], r0);
-    hrow(ty.ofs[y] + 1, r1);
+    const int sy = ty.ofs[y];
+    if (sy == have1) {  // the lower row of the previous output row is this one's upper row
+      r0.swap(r1);
+      have0 = have1;
+      have1 = -1000000;
+    }
+    if (sy != have0) {
+      hrow(sy, r0);
+      have0 = sy;
+    }
+    if (sy + 1 != have1) {
+      hrow(sy + 1, r1);
+      have1 = sy + 1;
+    }
     const int b0 = ty.c0[y], b1 = ty.c1[y];
     uint8_t* D = dst + (size_t)y * dstride;
     for (int x = 0; x < dw; x++) {
@@ -101,7 +127,7 @@ void resize_linear(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst
 // cv::GaussianBlur(u8, Size(7,7), 2, 2, BORDER_REFLECT_101) — OpenCV smooth.dispatch.cpp fixed-point path:
 // Q0.8 kernel {18,34,48,56,48,34,18}, 16-bit horizontal sums, one rounding at the end. src/ORBextractor.cc:1075-1076.
 // ---------------------------------------------------------------------------------------------------------------
-void gauss7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
+ORBREF_SIMD_CLONES void gauss7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
   // same arithmetic as before (Q0.8 taps, 16-bit row sums, one rounding), arranged so that gcc vectorises both passes:
   // a reflect-padded copy of each row, then 7 shifted adds; the vertical pass walks 7 row pointers.
   std::vector<uint16_t> H((size_t)w * h);
@@ -181,13 +207,20 @@ inline bool has_arc9(unsigned mask) {
   return (r & (m2 >> 8)) != 0;
 }
 
-void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std::vector<FastPt>& out) {
+ORBREF_SIMD_CLONES void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std::vector<FastPt>& out) {
   out.clear();
   threshold = std::min(std::max(threshold, 0), 255);
   if (w < 7 || h < 7) return;
-  // three score rows are enough for the 3x3 non-max suppression (OpenCV keeps a rolling buffer the same way)
-  std::vector<int> rows((size_t)3 * w, 0);
-  std::vector<uint8_t> pass((size_t)w, 0), tmp((size_t)4 * w);
+  // Three score rows are enough for the 3x3 non-max suppression (OpenCV keeps a rolling buffer the same way). Each row
+  // also keeps the list of its corner columns (ascending): clearing a row and suppressing it then cost as much as the
+  // row has corners, not as it has pixels. thread_local: cv::FAST is called per 35 x 35 cell, ~600 times per frame.
+  thread_local std::vector<int> rows;
+  thread_local std::vector<int> cols[3];
+  thread_local std::vector<uint8_t> pass, tmp;
+  rows.assign((size_t)3 * w, 0);
+  pass.assign((size_t)w + 16, 0);
+  tmp.resize((size_t)4 * w);
+  for (auto& cvec : cols) cvec.clear();
   int off[16];
   for (int k = 0; k < 16; k++) off[k] = kRingDy[k] * stride + kRingDx[k];
   const int T = threshold;
@@ -195,7 +228,7 @@ void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std:
     const int* up = &rows[(size_t)((y - 1) % 3) * w];
     const int* c = &rows[(size_t)(y % 3) * w];
     const int* dn = &rows[(size_t)((y + 1) % 3) * w];
-    for (int x = 3; x < w - 3; x++) {
+    for (int x : cols[y % 3]) {
       const int s = c[x];
       if (s == 0) continue;  // OpenCV keeps scores in a buffer where 0 = "not a corner"; a 0-score corner never wins
       if (s > c[x - 1] && s > c[x + 1] && s > up[x - 1] && s > up[x] && s > up[x + 1] && s > dn[x - 1] && s > dn[x] &&
@@ -203,41 +236,18 @@ void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std:
         out.push_back({x, y, s});
     }
   };
+  auto clear_row = [&](int slot) {
+    int* sc = &rows[(size_t)slot * w];
+    for (int x : cols[slot]) sc[x] = 0;
+    cols[slot].clear();
+  };
   for (int y = 3; y < h - 3; y++) {
     const uint8_t* r = img + (size_t)y * stride;
     int* sc = &rows[(size_t)(y % 3) * w];
-    std::fill(sc, sc + w, 0);
-    // every arc of 9 ring pixels contains one end of each of the 8 diameters (k, k + 8): all 8 diameters must have a
-    // brighter end, or all 8 a darker end. Branch free over the row so that the compiler vectorises it (16 px / op).
-    uint8_t* __restrict__ ps = pass.data();
-    uint8_t* __restrict__ vb = tmp.data();
-    uint8_t* __restrict__ vd = tmp.data() + w;
-    uint8_t* __restrict__ br = tmp.data() + 2 * (size_t)w;
-    uint8_t* __restrict__ dk = tmp.data() + 3 * (size_t)w;
-    const int n = w - 6;
-    {
-      const uint8_t* __restrict__ c = r + 3;
-      for (int i = 0; i < n; i++) {
-        const int v = c[i];
-        vb[i] = (uint8_t)(v + T > 255 ? 255 : v + T);
-        vd[i] = (uint8_t)(v - T < 0 ? 0 : v - T);
-        br[i] = 1;
-        dk[i] = 1;
-      }
-    }
-    for (int k = 0; k < 8; k++) {
-      const uint8_t* __restrict__ qa = r + 3 + off[k];
-      const uint8_t* __restrict__ qb = r + 3 + off[k + 8];
-      for (int i = 0; i < n; i++) {
-        const uint8_t a = qa[i], b = qb[i];
-        const uint8_t hi = a > b ? a : b, lo = a < b ? a : b;
-        br[i] &= (uint8_t)(hi > vb[i]);
-        dk[i] &= (uint8_t)(lo < vd[i]);
-      }
-    }
-    for (int i = 0; i < n; i++) ps[i + 3] = br[i] | dk[i];
-    for (int x = 3; x < w - 3; x++) {
-      if (!ps[x]) continue;
+    clear_row(y % 3);
+    std::vector<int>& mine = cols[y % 3];
+    // the exact test + score of a pixel that passed the pre-test
+    auto candidate = [&](int x) {
       const uint8_t* p = r + x;
       const int v = p[0];
       unsigned ma = 0, mb = 0;
@@ -246,19 +256,81 @@ void fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, std:
         ma |= (unsigned)(d > T) << k;
         mb |= (unsigned)(d < -T) << k;
       }
-      if (!has_arc9(ma) && !has_arc9(mb)) continue;
+      if (!has_arc9(ma) && !has_arc9(mb)) return;
       sc[x] = fast_m(p, stride) - 1;  // m > T is guaranteed here
+      mine.push_back(x);
+    };
+    // pre-test: every arc of 9 ring pixels contains one end of each of the 8 diameters (k, k + 8): all 8 diameters must
+    // have a brighter end, or all 8 a darker end
+    const int n = w - 6;
+#if defined(__SSE2__)
+    if (n >= 16) {
+      // 16 pixels per step; a block where no pixel passes the first two diameters (the compass points) is skipped, as
+      // OpenCV's own SIMD loop does. The last block is re-aligned to end at n: only its new pixels are taken.
+      const __m128i sign = _mm_set1_epi8((char)0x80), tt = _mm_set1_epi8((char)T);
+      const uint8_t* c = r + 3;
+      static const int order[8] = {0, 4, 2, 6, 1, 3, 5, 7};
+      auto block = [&](int i, int first_new) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c + i));
+        const __m128i vbs = _mm_xor_si128(_mm_adds_epu8(v, tt), sign), vds = _mm_xor_si128(_mm_subs_epu8(v, tt), sign);
+        __m128i brm = _mm_set1_epi8((char)0xff), dkm = brm;
+        for (int q = 0; q < 8; q++) {
+          const int k = order[q];
+          const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c + i + off[k]));
+          const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(c + i + off[k + 8]));
+          const __m128i hi = _mm_xor_si128(_mm_max_epu8(a, b), sign), lo = _mm_xor_si128(_mm_min_epu8(a, b), sign);
+          brm = _mm_and_si128(brm, _mm_cmpgt_epi8(hi, vbs));
+          dkm = _mm_and_si128(dkm, _mm_cmpgt_epi8(vds, lo));
+          if (q == 1 && _mm_movemask_epi8(_mm_or_si128(brm, dkm)) == 0) return;
+        }
+        unsigned m = (unsigned)_mm_movemask_epi8(_mm_or_si128(brm, dkm));
+        m &= ~0u << first_new;
+        while (m) {
+          const int bit = __builtin_ctz(m);
+          m &= m - 1;
+          candidate(3 + i + bit);
+        }
+      };
+      int i = 0;
+      for (; i + 16 <= n; i += 16) block(i, 0);
+      if (i < n) block(n - 16, i - (n - 16));
+    } else
+#endif
+    {
+      uint8_t* __restrict__ ps = pass.data();
+      uint8_t* __restrict__ vb = tmp.data();
+      uint8_t* __restrict__ vd = tmp.data() + w;
+      uint8_t* __restrict__ br = tmp.data() + 2 * (size_t)w;
+      uint8_t* __restrict__ dk = tmp.data() + 3 * (size_t)w;
+      const uint8_t* __restrict__ c = r + 3;
+      for (int i = 0; i < n; i++) {
+        const int v = c[i];
+        vb[i] = (uint8_t)(v + T > 255 ? 255 : v + T);
+        vd[i] = (uint8_t)(v - T < 0 ? 0 : v - T);
+        br[i] = 1;
+        dk[i] = 1;
+      }
+      for (int k = 0; k < 8; k++) {
+        const uint8_t* __restrict__ qa = r + 3 + off[k];
+        const uint8_t* __restrict__ qb = r + 3 + off[k + 8];
+        for (int i = 0; i < n; i++) {
+          const uint8_t a = qa[i], b = qb[i];
+          const uint8_t hi = a > b ? a : b, lo = a < b ? a : b;
+          br[i] &= (uint8_t)(hi > vb[i]);
+          dk[i] &= (uint8_t)(lo < vd[i]);
+        }
+      }
+      for (int i = 0; i < n; i++) ps[i + 3] = br[i] | dk[i];
+      for (int x = 3; x < w - 3; x++)
+        if (ps[x]) candidate(x);
     }
     if (y >= 5) emit_row(y - 1);  // rows y - 2, y - 1, y are final (row 3's upper neighbour row 2 is all zeros)
     else if (y == 4) emit_row(3);
   }
   // last interior row: its lower neighbour (row h - 3) holds no corners
-  if (h - 4 >= 4) {
-    std::fill(&rows[(size_t)((h - 3) % 3) * w], &rows[(size_t)((h - 3) % 3) * w] + w, 0);
+  if (h - 4 >= 3) {
+    clear_row((h - 3) % 3);
     emit_row(h - 4);
-  } else if (h - 4 == 3) {
-    std::fill(&rows[(size_t)((h - 3) % 3) * w], &rows[(size_t)((h - 3) % 3) * w] + w, 0);
-    emit_row(3);
   }
 }
 
@@ -481,6 +553,7 @@ int orbref_fast9(const uint8_t* img, int w, int h, int stride, int threshold, in
   }
   return (int)pts.size();
 }
+const char* orbref_primitives_kind() { return ORBREF_PRIMITIVES_KIND; }
 float orbref_fast_atan2(float y, float x) { return fast_atan2(y, x); }
 int orbref_cv_round(float v) { return cv_round(v); }
 

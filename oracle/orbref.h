@@ -58,6 +58,8 @@ void orbref_border101(const uint8_t* src, int w, int h, int sstride, uint8_t* ds
 /* cv::FAST(img, kps, threshold, nonmaxSuppression=true), TYPE_9_16. Returns the count; fills up to cap entries. */
 int orbref_fast9(const uint8_t* img, int w, int h, int stride, int threshold, int* xs, int* ys, int* scores, int cap);
 float orbref_fast_atan2(float y, float x);
+/* How the image primitives above were built (reported by bench.py next to the CPU baseline). */
+const char* orbref_primitives_kind(void);
 int orbref_cv_round(float v);
 /* libstdc++ std::sort on (key0, key1) pairs with the reference's compareNodes ordering (src/ORBextractor.cc:542-555);
  * writes the resulting permutation (perm[i] = original index of the element now at position i). */

@@ -247,6 +247,12 @@ def lib():
 
 
 # ---- primitives -------------------------------------------------------------------------------------------------
+def primitives_kind():
+    L = lib()
+    L.orbref_primitives_kind.restype = C.c_char_p
+    return L.orbref_primitives_kind().decode()
+
+
 def resize_linear(src, dw, dh):
     src = _c(src, np.uint8)
     dst = np.empty((dh, dw), np.uint8)

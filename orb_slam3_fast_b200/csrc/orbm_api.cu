@@ -27,10 +27,10 @@ std::string& create_error() {
 
 namespace {
 
-void pyr_view(const orbx_extractor* ex, PyrView* v, int ln = -1) {
+void pyr_view(const orbx_extractor* ex, PyrView* v, int ln) {
   memset(v, 0, sizeof(*v));
   const Plan& P = ex->plan;
-  const FrameSet& fs = ex->lane[ln < 0 ? ex->last_lane : ln].last_fs;
+  const FrameSet& fs = ex->lane[ln].last_fs;
   for (int l = 0; l < P.nlevels; l++) {
     if (l == 0) {
       v->base[l] = fs.lvl0;
@@ -46,16 +46,17 @@ void pyr_view(const orbx_extractor* ex, PyrView* v, int ln = -1) {
   }
 }
 
+// lnl / lnr: the lanes of the two extractors that hold the pair(s)
 int stereo_args_common(orbm_matcher* m, const orbx_extractor* left, const orbx_extractor* right, StereoArgs* A,
-                       int ln = -1) {
-  if (!left || !right || !left->planned || !right->planned || left->lane[left->last_lane].last_frames < 1 || right->lane[right->last_lane].last_frames < 1)
+                       int lnl, int lnr) {
+  if (!left || !right || !left->planned || !right->planned || left->lane[lnl].last_frames < 1 || right->lane[lnr].last_frames < 1)
     return mfail(m, ORBX_E_ARG, "stereo match needs both extractors to have run");
   if (left->device != m->device || right->device != m->device)
     return mfail(m, ORBX_E_ARG, "extractors and matcher must live on the same device");
   if (left->nlevels != right->nlevels) return mfail(m, ORBX_E_ARG, "level count mismatch");
   memset(A, 0, sizeof(*A));
-  pyr_view(left, &A->left, ln);
-  pyr_view(right, &A->right, ln);
+  pyr_view(left, &A->left, lnl);
+  pyr_view(right, &A->right, lnr);
   A->nlevels = left->nlevels;
   for (int l = 0; l < left->nlevels; l++) {
     A->scale[l] = left->plan.lv[l].scale;
@@ -267,10 +268,14 @@ int orbm_stereo_match_batch_device(orbm_matcher* m, const orbx_extractor* left, 
     return mfail(m, ORBX_E_ARG, "bad argument");
   ORBM_CUDA(m, cudaSetDevice(m->device));
   StereoArgs A;
-  int rc = stereo_args_common(m, left, right, &A);
+  int lnl = 0, lnr = 0, ll = 0, lr = 0;
+  if (api_find_frame(left, 0, &lnl, &ll) != ORBX_OK || api_find_frame(right, 0, &lnr, &lr) != ORBX_OK || ll != 0 || lr != 0)
+    return mfail(m, ORBX_E_ARG, "stereo match needs both extractors to have run");
+  int rc = stereo_args_common(m, left, right, &A, lnl, lnr);
   if (rc) return rc;
-  if (n_pairs > left->lane[left->last_lane].last_frames || n_pairs > right->lane[right->last_lane].last_frames)
-    return mfail(m, ORBX_E_ARG, "n_pairs exceeds the frames of the extractors' last call");
+  // pairs 0 .. n_pairs - 1 must lie in ONE lane of each extractor (a device-resident call, or a host call of one group)
+  if (n_pairs > left->lane[lnl].last_frames || n_pairs > right->lane[lnr].last_frames)
+    return mfail(m, ORBX_E_ARG, "n_pairs exceeds the frames of the extractors' last call that are resident in one lane");
   DevBuf& sb = m->buf[kBufs - 2];
   cudaError_t e = sb.reserve((size_t)n_pairs * cap * 4);
   if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
@@ -295,15 +300,16 @@ int orbm_stereo_match(orbm_matcher* m, const orbx_extractor* left, const orbx_ex
   if (n_l == 0) return ORBX_OK;
   ORBM_CUDA(m, cudaSetDevice(m->device));
   StereoArgs A;
-  int rc = stereo_args_common(m, left, right, &A);
+  int lnl = 0, lnr = 0, ll = 0, lr = 0;
+  if (api_find_frame(left, frame, &lnl, &ll) != ORBX_OK || api_find_frame(right, frame, &lnr, &lr) != ORBX_OK || ll != lr)
+    return mfail(m, ORBX_E_ARG, "frame out of range, or no longer resident (only the last kLanes groups of a call are)");
+  int rc = stereo_args_common(m, left, right, &A, lnl, lnr);
   if (rc) return rc;
-  if (frame < 0 || frame >= left->lane[left->last_lane].last_frames || frame >= right->lane[right->last_lane].last_frames)
-    return mfail(m, ORBX_E_ARG, "frame out of range");
   // the extractors ran on their own streams
-  ORBM_CUDA(m, cudaStreamSynchronize(left->lane[left->last_lane].stream));
-  ORBM_CUDA(m, cudaStreamSynchronize(right->lane[right->last_lane].stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(left->lane[lnl].stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(right->lane[lnr].stream));
   Arena ar(m);
-  A.frame0 = frame;
+  A.frame0 = ll;
   A.kps_l = ar.upload(kps_l, n_l);
   A.desc_l = ar.upload(desc_l, (size_t)n_l * 32);
   A.kps_r = ar.upload(kps_r, n_r);  // n_r == 0: a 1-element dummy is allocated, the count gates every read
@@ -359,6 +365,8 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     if ((rc = api_ensure_plan(ex, width, height)) != 0 || (rc = api_ensure_out(ex, cap)) != 0)
       return mfail(m, rc, orbx_last_error(ex));
   }
+  api_begin_call(left);
+  api_begin_call(right);
   const int B = left->max_batch;
   for (int ln = 0; ln < kLanes; ln++) {
     cudaError_t e = cudaSuccess;
@@ -466,7 +474,8 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
   int group = 0, f0 = 0;
   for (size_t gi = 0; gi < sizes.size(); f0 += sizes[gi], gi++, group++) {
     const int nb = sizes[gi];
-    const int ln = group % kLanes;
+    static const int n_lanes = getenv("ORBX_LANES") ? std::max(1, std::min((int)kLanes, atoi(getenv("ORBX_LANES")))) : (int)kLanes;
+    const int ln = group % n_lanes;
     const double tw0 = trace ? now() : 0;
     if ((rc = retire(ln)) != 0) return rc;
     const double tw1 = trace ? now() : 0;
@@ -478,7 +487,8 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     // The two eyes run on their own streams, like the two std::threads of the reference's stereo constructor
     // (src/Frame.cc:200-203): the latency-bound stages of one eye (quadtree, small pyramid levels) overlap the
     // ALU-bound stages of the other, and with kLanes groups in flight the copy engines stay busy too.
-    cudaStream_t st = left->lane[ln].stream, sr = right->lane[ln].stream;
+    static const bool serial_eyes = getenv("ORBX_SERIAL_EYES") != nullptr;  // A/B experiment: both eyes on one stream
+    cudaStream_t st = left->lane[ln].stream, sr = serial_eyes ? st : right->lane[ln].stream;
     // The tracking stage's small per-group inputs (poses, occupancy) cross PCIe FIRST: enqueued behind the stereo
     // kernels they would sit in the copy engine's queue behind the next lanes' image uploads (measured: the call took
     // 20.2 ms against 13.0 ms without the image uploads and 12.2 ms for the uploads alone)
@@ -509,10 +519,10 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
       }
     }
     if ((rc = api_upload_and_run(left, ln, imgs_l + (int64_t)f0 * frame_stride, nb, width, height, stride,
-                                 frame_stride, 0, 0, st)) != 0)
+                                 frame_stride, 0, 0, st, f0)) != 0)
       return mfail(m, rc, orbx_last_error(left));
     if ((rc = api_upload_and_run(right, ln, imgs_r + (int64_t)f0 * frame_stride, nb, width, height, stride,
-                                 frame_stride, 0, 0, sr)) != 0)
+                                 frame_stride, 0, 0, sr, f0)) != 0)
       return mfail(m, rc, orbx_last_error(right));
     // the right eye's descriptors can go home while the stereo matcher runs
     if ((rc = api_download(right, ln, nb, kps_r + (int64_t)f0 * cap, desc_r + (int64_t)f0 * cap * 32, cap, sr)) != 0)
@@ -521,7 +531,7 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     ORBM_CUDA(m, cudaStreamWaitEvent(st, right->lane[ln].done, 0));
     // ... and ComputeStereoMatches (:223) on the outputs still resident in the lanes
     StereoArgs A;
-    if ((rc = stereo_args_common(m, left, right, &A, ln)) != 0) return rc;
+    if ((rc = stereo_args_common(m, left, right, &A, ln, ln)) != 0) return rc;
     const OrbxLane &LL = left->lane[ln], &RL = right->lane[ln];
     const int dcap = LL.out_cap;
     if (RL.out_cap != dcap) return mfail(m, ORBX_E_ARG, "extractor output capacities differ");
@@ -711,9 +721,12 @@ int resident_frame(orbm_matcher* m, Arena& ar, const orbx_extractor* ex, int fra
                    const uint8_t* occupied, float min_x, float min_y, float inv_w, float inv_h, DevFrame* out,
                    float* sf) {
   if (!ex->planned || ex->device != m->device) return mfail(m, ORBX_E_ARG, "extractor has not run on this device");
-  const OrbxLane& L = ex->lane[ex->last_lane];
-  if (frame < 0 || frame >= L.last_frames || !L.d_kps || n > L.out_cap)
-    return mfail(m, ORBX_E_ARG, "frame is not resident in the extractor's last batch");
+  int fl = 0, lf = 0;
+  if (api_find_frame(ex, frame, &fl, &lf) != ORBX_OK)
+    return mfail(m, ORBX_E_ARG, "frame is not resident in the extractor's last call (only its last kLanes groups are)");
+  const OrbxLane& L = ex->lane[fl];
+  frame = lf;
+  if (!L.d_kps || n > L.out_cap) return mfail(m, ORBX_E_ARG, "frame has no device outputs (host-facing calls only)");
   ORBM_CUDA(m, cudaSetDevice(m->device));
   const int cells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
   const Plan& P = ex->plan;

@@ -124,7 +124,7 @@ int alloc_lane_out(orbx_extractor* ex, OrbxLane& L, int cap) {
 
 // The whole extractor for `frames` frames whose level 0 is described by fs.{lvl0,pitch0,fstride0}, on lane ln.
 int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, int lap1, const OutSet& out,
-                 cudaStream_t st) {
+                 cudaStream_t st, int f0 = 0) {
   const Plan& P = ex->plan;
   OrbxLane& L = ex->lane[ln];
   int rc = alloc_lane(ex, L);
@@ -153,6 +153,8 @@ int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, 
   if (skip_kernels) {
     L.last_fs = fs;
     L.last_frames = frames;
+    L.last_f0 = f0;
+    L.last_call = ex->call_id;
     ex->last_lane = ln;
     return ORBX_OK;
   }
@@ -175,6 +177,8 @@ int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, 
   if (prof) ex->prof_used += 2 * kStages;
   L.last_fs = fs;
   L.last_frames = frames;
+  L.last_f0 = f0;
+  L.last_call = ex->call_id;
   ex->last_lane = ln;
   return ORBX_OK;
 }
@@ -187,6 +191,21 @@ int api_fail(orbx_extractor* ex, int code, const std::string& msg) {
   if (ex) ex->err = msg;
   else g_create_error = msg;
   return code;
+}
+
+void api_begin_call(orbx_extractor* ex) { ex->call_id++; }
+
+int api_find_frame(const orbx_extractor* ex, int frame, int* lane, int* local) {
+  if (!ex || !ex->planned || frame < 0) return ORBX_E_ARG;
+  for (int ln = 0; ln < kLanes; ln++) {
+    const OrbxLane& L = ex->lane[ln];
+    if (L.last_call == ex->call_id && L.last_frames > 0 && frame >= L.last_f0 && frame < L.last_f0 + L.last_frames) {
+      *lane = ln;
+      *local = frame - L.last_f0;
+      return ORBX_OK;
+    }
+  }
+  return ORBX_E_ARG;
 }
 
 int api_ensure_plan(orbx_extractor* ex, int w, int h) {
@@ -241,7 +260,7 @@ int api_ensure_out(orbx_extractor* ex, int cap) {
 }
 
 int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, int width, int height, int stride,
-                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st) {
+                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st, int f0) {
   OrbxLane& L = ex->lane[ln];
   int rc = alloc_lane(ex, L);
   if (rc) return rc;
@@ -265,7 +284,7 @@ int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, i
     fs.fstride0 = ex->in_fstride;
   }
   OutSet out{L.d_kps, L.d_desc, L.d_n, L.d_mono, L.d_status, L.out_cap};
-  return run_pipeline(ex, ln, fs, nb, lap0, lap1, out, st);
+  return run_pipeline(ex, ln, fs, nb, lap0, lap1, out, st, f0);
 }
 
 int api_download(orbx_extractor* ex, int ln, int nb, orbx_kp* kps, uint8_t* desc, int cap, cudaStream_t st) {
@@ -389,6 +408,7 @@ int orbx_extract_batch_device(orbx_extractor* ex, int n_frames, const uint8_t* d
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   int rc = api_ensure_plan(ex, width, height);
   if (rc) return rc;
+  api_begin_call(ex);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ex->lane[0].stream;
   FrameSet fs{};
   fs.lvl0 = d_images;
@@ -409,6 +429,7 @@ int orbx_extract_batch(orbx_extractor* ex, int n_frames, const uint8_t* images, 
   if (rc) return rc;
   rc = api_ensure_out(ex, cap);
   if (rc) return rc;
+  api_begin_call(ex);
   const int B = ex->max_batch;
   int first_err = ORBX_OK;
   int pending_f0[kLanes], pending_nb[kLanes];
@@ -434,7 +455,7 @@ int orbx_extract_batch(orbx_extractor* ex, int n_frames, const uint8_t* images, 
     OrbxLane& L = ex->lane[ln];
     if ((rc = retire(ln)) != 0) return rc;
     rc = api_upload_and_run(ex, ln, images + (int64_t)f0 * frame_stride, nb, width, height, stride, frame_stride,
-                            lap0, lap1, L.stream);
+                            lap0, lap1, L.stream, f0);
     if (rc) return rc;
     rc = api_download(ex, ln, nb, kps + (int64_t)f0 * cap, desc + (int64_t)f0 * cap * ORBX_DESC_BYTES, cap, L.stream);
     if (rc) return rc;
@@ -466,11 +487,13 @@ int orbx_level_size(const orbx_extractor* ex, int level, int* width, int* height
 }
 
 int orbx_debug_level(orbx_extractor* ex, int frame, int level, int which, uint8_t* dst, int dst_stride) {
-  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lane[ex->last_lane].last_frames || !dst)
-    return ORBX_E_ARG;
+  int fl = 0, lf = 0;
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || !dst || api_find_frame(ex, frame, &fl, &lf) != ORBX_OK)
+    return ex ? api_fail(ex, ORBX_E_ARG, "bad argument, or the frame is no longer resident (only the last kLanes groups of a call are)") : ORBX_E_ARG;
+  frame = lf;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   const LevelPlan& L = ex->plan.lv[level];
-  const FrameSet& fs = ex->lane[ex->last_lane].last_fs;
+  const FrameSet& fs = ex->lane[fl].last_fs;
   const uint8_t* src;
   int pitch;
   if (which == 1) {
@@ -523,15 +546,17 @@ static void unpack_kp(uint32_t cw, int add, int level, float size, orbx_kp* k) {
 }
 
 int orbx_debug_candidates(orbx_extractor* ex, int frame, int level, orbx_kp* out, int cap) {
-  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lane[ex->last_lane].last_frames)
+  int fl = 0, lf = 0;
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || api_find_frame(ex, frame, &fl, &lf) != ORBX_OK)
     return ORBX_E_ARG;
+  frame = lf;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   ORBX_CUDA(ex, cudaDeviceSynchronize());
   // the candidates of a level in the order the reference appends them (:905-958) = the per-cell slots written by
   // k_fast, cells in row-major order (pure data movement: the quadtree kernel builds the same array in shared memory)
   const Plan& P = ex->plan;
   const LevelPlan& L = P.lv[level];
-  const OrbxLane& ln = ex->lane[ex->last_lane];
+  const OrbxLane& ln = ex->lane[fl];
   const int ncell = L.nCols * L.nRows;
   std::vector<int32_t> cnt(ncell);
   std::vector<uint32_t> slots((size_t)ncell * L.slot_cap);
@@ -547,16 +572,18 @@ int orbx_debug_candidates(orbx_extractor* ex, int frame, int level, orbx_kp* out
 }
 
 int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp* out, int cap) {
-  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->lane[ex->last_lane].last_frames)
+  int fl = 0, lf = 0;
+  if (!ex || !ex->planned || level < 0 || level >= ex->nlevels || api_find_frame(ex, frame, &fl, &lf) != ORBX_OK)
     return ORBX_E_ARG;
+  frame = lf;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   ORBX_CUDA(ex, cudaDeviceSynchronize());
   const Plan& P = ex->plan;
   int32_t C = 0;
-  ORBX_CUDA(ex, cudaMemcpy(&C, ex->lane[ex->last_lane].ws.lvl_n + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
+  ORBX_CUDA(ex, cudaMemcpy(&C, ex->lane[fl].ws.lvl_n + frame * P.nlevels + level, 4, cudaMemcpyDeviceToHost));
   const int n = std::min(C, cap);
   std::vector<uint32_t> buf(std::max(n, 1));
-  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->lane[ex->last_lane].ws.lvl_kp + (int64_t)frame * P.kps_per_frame + P.lv[level].kp_base,
+  ORBX_CUDA(ex, cudaMemcpy(buf.data(), ex->lane[fl].ws.lvl_kp + (int64_t)frame * P.kps_per_frame + P.lv[level].kp_base,
                            (size_t)n * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n && out; i++) unpack_kp(buf[i], kMinBorder, level, (float)P.lv[level].patch, out + i);
   return C;
@@ -566,8 +593,11 @@ int orbx_debug_level_keypoints(orbx_extractor* ex, int frame, int level, orbx_kp
 // with -DORBX_QT_PROF; otherwise ORBX_E_ARG. Development aid, not part of the public header.
 int orbx_debug_qt_profile(orbx_extractor* ex, int frame, int level, long long* out) {
   if (!ex || !ex->planned || !out) return ORBX_E_ARG;
-  const OrbxLane& ln = ex->lane[ex->last_lane];
-  if (!ln.ws.qt_prof || frame < 0 || frame >= ln.last_frames || level < 0 || level >= ex->nlevels) return ORBX_E_ARG;
+  int fl = 0, lf = 0;
+  if (api_find_frame(ex, frame, &fl, &lf) != ORBX_OK) return ORBX_E_ARG;
+  frame = lf;
+  const OrbxLane& ln = ex->lane[fl];
+  if (!ln.ws.qt_prof || level < 0 || level >= ex->nlevels) return ORBX_E_ARG;
   ORBX_CUDA(ex, cudaSetDevice(ex->device));
   ORBX_CUDA(ex, cudaDeviceSynchronize());
   ORBX_CUDA(ex, cudaMemcpy(out, ln.ws.qt_prof + ((int64_t)frame * ex->nlevels + level) * 16, 16 * 8,

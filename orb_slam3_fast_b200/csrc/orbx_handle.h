@@ -31,6 +31,8 @@ struct OrbxLane {
   // what the lane holds since its last run (for downloads / stereo matching)
   orbx::FrameSet last_fs{};
   int last_frames = 0;
+  int last_f0 = 0;             // global index (inside the call) of the lane's first frame
+  unsigned long long last_call = 0;  // orbx_extractor::call_id of the call that filled the lane
 };
 
 struct orbx_extractor {
@@ -46,7 +48,9 @@ struct orbx_extractor {
   orbx::ResizeTab* d_tab = nullptr;
   int8_t* d_pattern = nullptr;
   OrbxLane lane[kLanes];
-  int last_lane = 0;  // lane of the most recent run: "frame f of the last call" lives there
+  int last_lane = 0;  // lane of the most recent run
+  unsigned long long call_id = 0;  // bumped by every public extract call; "frame f of the last call" = the lane whose
+                                   // last_call == call_id and last_f0 <= f < last_f0 + last_frames (api_find_frame)
   // profiling: event records around every stage, resolved lazily by orbx_profile_read (no sync inside a run)
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;  // pool, 2 * kStages per recorded run: (start, end) of every stage
@@ -60,9 +64,15 @@ namespace orbx {
 int api_fail(orbx_extractor* ex, int code, const std::string& msg);
 int api_ensure_plan(orbx_extractor* ex, int w, int h);
 int api_ensure_out(orbx_extractor* ex, int cap);
+// Where frame `frame` of the extractor's most recent call lives: lane + index inside the lane. A call of more than
+// kLanes * max_batch frames keeps only its last kLanes groups resident; ORBX_E_ARG for a frame that is gone (or never
+// existed).
+int api_find_frame(const orbx_extractor* ex, int frame, int* lane, int* local);
+// every public extract entry point calls this first: frames of earlier calls stop being addressable
+void api_begin_call(orbx_extractor* ex);
 // H2D of nb frames into lane `ln` and the whole extractor on stream st; results stay in the lane's device outputs
 int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, int width, int height, int stride,
-                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st);
+                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st, int f0 = 0);
 // D2H of the lane's outputs of nb frames into rows [0, nb) of the caller's arrays (counts go to the pinned h_small)
 int api_download(orbx_extractor* ex, int ln, int nb, orbx_kp* kps, uint8_t* desc, int cap, cudaStream_t st);
 }  // namespace orbx

@@ -124,6 +124,40 @@ def test_batch_matches_single_and_oracle(gpu):
         _compare_frame(ex_ref, kps[f, :n[f]], desc[f, :n[f]], mono[f], imgs[f], (0, 0), "batch frame %d" % f)
 
 
+def test_frame_index_addresses_the_whole_call_not_the_last_group(gpu):
+    """`frame` of orbx_download_pyramid / orbx_debug_* / orbm_stereo_match is the index inside the last call: with
+    n_frames > max_batch the frames of earlier groups stay addressable while their lane is resident (the last 4 groups),
+    and a frame that is gone is an error instead of another frame's data."""
+    from orb_slam3_fast_b200 import ORBmatcher
+    from orb_slam3_fast_b200.lib import OrbxError
+    n = 11
+    imgs = np.stack([synth.stereo_pair(480, 640, 70 + s)[0] for s in range(n)])
+    right = np.stack([synth.stereo_pair(480, 640, 70 + s)[1] for s in range(n)])
+    ex, exr = ORBextractor(1000, max_batch=2), ORBextractor(1000, max_batch=2)  # groups: 0-1 2-3 4-5 6-7 | 8-9 10
+    ex_ref, exr_ref = orbref.Extractor(1000), orbref.Extractor(1000)
+    nk, mono, kps, desc = ex.extract_batch(imgs, (0, 0))
+    nr, _, kr, dr = exr.extract_batch(right, (0, 0))
+    mt = ORBmatcher()
+    mbf, mb = float(np.float32(435.2 * 0.11)), float(np.float32(0.11))
+    for f in (4, 7, 8, 10):  # resident: lanes 2, 3, 0, 1
+        ex_ref(imgs[f], (0, 0))
+        exr_ref(right[f], (0, 0))
+        for l in (0, 5):
+            assert np.array_equal(ex.image_pyramid_bordered(l, f), ex_ref.level_bordered(l)), "frame %d level %d" % (f, l)
+            assert np.array_equal(ex.debug_level(l, True, f), ex_ref.level_blurred(l))
+            assert np.array_equal(ex.debug_level_keypoints(l, f)[["x", "y"]], ex_ref.level_keypoints(l)[["x", "y"]])
+        got = mt.ComputeStereoMatches(ex, exr, kps[f, :nk[f]], desc[f, :nk[f]], kr[f, :nr[f]], dr[f, :nr[f]], mbf, mb, frame=f)
+        ref = orbref.stereo_match(ex_ref, exr_ref, kps[f, :nk[f]], desc[f, :nk[f]], kr[f, :nr[f]], dr[f, :nr[f]], mbf, mb)
+        assert got[0] == ref[0] and got[1].tobytes() == ref[1].tobytes() and got[2].tobytes() == ref[2].tobytes(), f
+    for f in (0, 3, 11, -1):  # overwritten by the second round of groups / out of range
+        with pytest.raises(OrbxError):
+            ex.image_pyramid_bordered(0, f)
+    ex(imgs[0])  # a new call: the old indices are gone
+    with pytest.raises(OrbxError):
+        ex.image_pyramid_bordered(0, 8)
+    assert np.array_equal(ex.image_pyramid(0, 0), imgs[0])
+
+
 def test_host_pyramid_mirror_has_reference_border(gpu):
     img = synth.scene(480, 640, seed=9)
     ex, ex_ref = ORBextractor(1000), orbref.Extractor(1000)

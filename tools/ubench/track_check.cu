@@ -108,10 +108,22 @@ int main(int argc, char** argv) {
   fclose(f);
   if (!ok) return printf("short case file\n"), 1;
 
-  orbx_extractor* ex[2] = {nullptr, nullptr};
-  orbm_matcher* mt = nullptr;
-  for (int e = 0; e < 2; e++) OX(nullptr, orbx_extractor_create(&ex[e], 0, nfeat, 1.2f, 8, 20, 7, P));
-  if (orbm_create(&mt, 0) != 0) return printf("orbm_create: %s\n", orbm_last_error(nullptr)), 1;
+  // TRACK_LANES = n: the device-resident batch is cut into n sub-batches, each on its own stream with its own handles
+  // (a handle serves one stream at a time), forked from / joined to the timed stream by events — stages of different
+  // sub-batches then overlap (latency-bound quadtree under ALU-bound FAST), as in the library's pipelined host call
+  const int NL = getenv("TRACK_LANES") ? atoi(getenv("TRACK_LANES")) : 1;
+  if (NL < 1 || NL > 8 || P % NL) return printf("TRACK_LANES must divide the batch\n"), 1;
+  const int PL = P / NL;
+  orbx_extractor* exs[8][2] = {};
+  orbm_matcher* mts[8] = {};
+  cudaStream_t lane_st[8] = {};
+  for (int ln = 0; ln < NL; ln++) {
+    for (int e = 0; e < 2; e++) OX(nullptr, orbx_extractor_create(&exs[ln][e], 0, nfeat, 1.2f, 8, 20, 7, PL));
+    if (orbm_create(&mts[ln], 0) != 0) return printf("orbm_create: %s\n", orbm_last_error(nullptr)), 1;
+    if (ln) CK(cudaStreamCreateWithFlags(&lane_st[ln], cudaStreamNonBlocking));
+  }
+  orbx_extractor** ex = exs[0];
+  orbm_matcher* mt = mts[0];
   const int cap = orbx_extractor_capacity(ex[0]);
   if (cap != ccap) return printf("capacity mismatch %d vs %d\n", cap, ccap), 1;
   cudaStream_t st;
@@ -178,24 +190,45 @@ int main(int argc, char** argv) {
   CK(cudaEventCreate(&ea)); CK(cudaEventCreate(&eb)); CK(cudaEventCreate(&ec));
   float ms_stereo = 0, ms_track = 0;
   bool bracket = false;
+  cudaEvent_t fork, join[8];
+  CK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  for (int ln = 0; ln < 8; ln++) CK(cudaEventCreateWithFlags(&join[ln], cudaEventDisableTiming));
+  lane_st[0] = st;
   auto step = [&](int k) -> int {
-    for (int e = 0; e < 2; e++)
-      OX(ex[e], orbx_extract_batch_device(ex[e], P, d_img[k & 1][e], W, H, W, (int64_t)fbytes, 0, 0, o[e].kps, o[e].desc,
-                                          cap, o[e].n, o[e].mono, o[e].status, st));
-    if (bracket) cudaEventRecord(ea, st);
-    OM(orbm_stereo_match_batch_device(mt, ex[0], ex[1], P, o[0].kps, o[0].desc, o[0].n, o[1].kps, o[1].desc, o[1].n, cap,
-                                      mbf, mb, d_ur, d_dp, d_nm, st));
-    if (bracket) cudaEventRecord(eb, st);
-    OM(orbm_track_local_map_batch_device(mt, ex[0], P, o[0].kps, o[0].desc, o[0].n, cap, d_ur, d_occ[k & 1], d_fr[k & 1],
-                                         &dmap, d_midx[k & 1], &prm, d_assign, d_res, d_res + P, d_res + 2 * P, st));
-    if (bracket) {
-      cudaEventRecord(ec, st);
-      cudaEventSynchronize(ec);
-      float a = 0, b = 0;
-      cudaEventElapsedTime(&a, ea, eb);
-      cudaEventElapsedTime(&b, eb, ec);
-      ms_stereo += a;
-      ms_track += b;
+    if (NL > 1) {
+      cudaEventRecord(fork, st);
+      for (int ln = 1; ln < NL; ln++) cudaStreamWaitEvent(lane_st[ln], fork, 0);
+    }
+    for (int ln = 0; ln < NL; ln++) {
+      cudaStream_t s = lane_st[ln];
+      const size_t p0 = (size_t)ln * PL;
+      orbm_matcher* mt = mts[ln];
+      for (int e = 0; e < 2; e++)
+        OX(exs[ln][e], orbx_extract_batch_device(exs[ln][e], PL, d_img[k & 1][e] + p0 * fbytes, W, H, W, (int64_t)fbytes, 0, 0,
+                                                 o[e].kps + p0 * cap, o[e].desc + p0 * cap * 32, cap, o[e].n + p0,
+                                                 o[e].mono + p0, o[e].status + p0, s));
+      if (bracket) cudaEventRecord(ea, s);
+      OM(orbm_stereo_match_batch_device(mt, exs[ln][0], exs[ln][1], PL, o[0].kps + p0 * cap, o[0].desc + p0 * cap * 32,
+                                        o[0].n + p0, o[1].kps + p0 * cap, o[1].desc + p0 * cap * 32, o[1].n + p0, cap, mbf,
+                                        mb, d_ur + p0 * cap, d_dp + p0 * cap, d_nm + p0, s));
+      if (bracket) cudaEventRecord(eb, s);
+      OM(orbm_track_local_map_batch_device(mt, exs[ln][0], PL, o[0].kps + p0 * cap, o[0].desc + p0 * cap * 32, o[0].n + p0,
+                                           cap, d_ur + p0 * cap, d_occ[k & 1] + p0 * cap, d_fr[k & 1] + p0, &dmap,
+                                           d_midx[k & 1] + p0, &prm, d_assign + p0 * cap, d_res + p0, d_res + P + p0,
+                                           d_res + 2 * (size_t)P + p0, s));
+      if (bracket) {
+        cudaEventRecord(ec, s);
+        cudaEventSynchronize(ec);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ea, eb);
+        cudaEventElapsedTime(&b, eb, ec);
+        ms_stereo += a;
+        ms_track += b;
+      }
+      if (ln) {
+        cudaEventRecord(join[ln], s);
+        cudaStreamWaitEvent(st, join[ln], 0);
+      }
     }
     return 0;
   };
@@ -260,23 +293,25 @@ int main(int argc, char** argv) {
   CK(cudaEventElapsedTime(&ms, e0, e1));
   printf("%d pairs/batch x %d batches: %.3f ms/batch = %.0f frames/s device-resident\n", P, steps, ms / steps,
          2.0 * P * steps / (ms * 1e-3));
-  for (int e = 0; e < 2; e++) {
-    orbx_profile_enable(ex[e], 1);
-    orbx_profile_read(ex[e], nullptr, nullptr, 1);
-  }
+  for (int ln = 0; ln < NL; ln++)
+    for (int e = 0; e < 2; e++) {
+      orbx_profile_enable(exs[ln][e], 1);
+      orbx_profile_read(exs[ln][e], nullptr, nullptr, 1);
+    }
   bracket = true;
   const int psteps = steps < 4 ? steps : 4;
   for (int k = 0; k < psteps; k++)
     if (step(k)) return 1;
   bracket = false;
   float stage[5] = {0, 0, 0, 0, 0};
-  for (int e = 0; e < 2; e++) {
-    float s[5];
-    int32_t c[5];
-    if (orbx_profile_read(ex[e], s, c, 1) == 0)
-      for (int k = 0; k < 5; k++) stage[k] += s[k];
-    orbx_profile_enable(ex[e], 0);
-  }
+  for (int ln = 0; ln < NL; ln++)
+    for (int e = 0; e < 2; e++) {
+      float s[5];
+      int32_t c[5];
+      if (orbx_profile_read(exs[ln][e], s, c, 1) == 0)
+        for (int k = 0; k < 5; k++) stage[k] += s[k];
+      orbx_profile_enable(exs[ln][e], 0);
+    }
   printf("stage ms/batch: pyramid %.3f fast %.3f quadtree %.3f blur %.3f describe %.3f stereo %.3f track %.3f\n",
          stage[0] / psteps, stage[1] / psteps, stage[2] / psteps, stage[3] / psteps, stage[4] / psteps, ms_stereo / psteps,
          ms_track / psteps);
@@ -356,7 +391,9 @@ int main(int argc, char** argv) {
            2.0 * P * e2e_steps / dt);
     for (int e = 0; e < 2; e++) orbx_extractor_destroy(ex2[e]);
   }
-  orbm_destroy(mt);
-  for (int e = 0; e < 2; e++) orbx_extractor_destroy(ex[e]);
+  for (int ln = 0; ln < NL; ln++) {
+    orbm_destroy(mts[ln]);
+    for (int e = 0; e < 2; e++) orbx_extractor_destroy(exs[ln][e]);
+  }
   return bad ? 2 : 0;
 }
