@@ -9,17 +9,9 @@
 // off (ORBextractor::SetPyramidMirror(false)).
 #include "Frame.h"
 #include "orbm.h"
+#include "orbx_thread_matcher.h"
 
 namespace ORB_SLAM3 {
-
-namespace {
-// one matcher context per thread: Frame constructors run on the Tracking thread, but keep it re-entrant
-orbm_matcher* ThreadMatcher() {
-  thread_local orbm_matcher* m = nullptr;
-  if (!m && orbm_create(&m, 0) != ORBX_OK) throw std::runtime_error(orbm_last_error(nullptr));
-  return m;
-}
-}  // namespace
 
 void Frame::ComputeStereoMatches() {
   mvuRight = std::vector<float>(N, -1.0f);  // :922-923
@@ -27,11 +19,11 @@ void Frame::ComputeStereoMatches() {
   if (N == 0) return;
   int32_t n_matched = 0;
   const int rc = orbm_stereo_match(
-      ThreadMatcher(), mpORBextractorLeft->Handle(), mpORBextractorRight->Handle(), /*frame=*/0,
+      OrbxThreadMatcher(), mpORBextractorLeft->Handle(), mpORBextractorRight->Handle(), /*frame=*/0,
       reinterpret_cast<const orbx_kp*>(mvKeys.data()), mDescriptors.data, N,
       reinterpret_cast<const orbx_kp*>(mvKeysRight.data()), mDescriptorsRight.data, (int)mvKeysRight.size(), mbf, mb,
       mvuRight.data(), mvDepth.data(), &n_matched);
-  if (rc != ORBX_OK) throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+  if (rc != ORBX_OK) throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
 }
 
 }  // namespace ORB_SLAM3

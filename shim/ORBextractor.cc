@@ -2,6 +2,7 @@
 // src/ORBextractor.cc in libORB_SLAM3.so (CMakeLists.txt:69-75); link with -lorbx.
 #include "ORBextractor.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -11,11 +12,12 @@
 namespace ORB_SLAM3 {
 
 namespace {
-int g_device = 0;
+std::atomic<int> g_device{0};
 const int EDGE_THRESHOLD = 19;  // src/ORBextractor.cc:73
 }  // namespace
 
 void ORBextractor::SetDevice(int cuda_ordinal) { g_device = cuda_ordinal; }
+int ORBextractor::GetDevice() { return g_device; }
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST),
@@ -28,8 +30,9 @@ ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int
   mvLevelSigma2.resize(nlevels);
   mvInvLevelSigma2.resize(nlevels);
   mnFeaturesPerLevel.resize(nlevels);
-  orbx_extractor_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
-                        mvInvLevelSigma2.data(), mnFeaturesPerLevel.data());
+  if (orbx_extractor_tables(mpHandle, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                            mvInvLevelSigma2.data(), mnFeaturesPerLevel.data()) != ORBX_OK)
+    throw std::runtime_error("ORBextractor: orbx_extractor_tables failed");
   mvImagePyramid.resize(nlevels);  // :416
   mvBordered.resize(nlevels);
 }

@@ -49,6 +49,7 @@ class ORBextractor {
   void SetPyramidMirror(bool on) { mbMirrorPyramid = on; }
   orbx_extractor* Handle() const { return mpHandle; }  // for orbm_stereo_match (device-resident pyramid)
   static void SetDevice(int cuda_ordinal);             // device used by extractors constructed afterwards (default 0)
+  static int GetDevice();                              // ... and by the per-thread matcher contexts (orbx_thread_matcher.h)
 
  protected:
   int nfeatures;

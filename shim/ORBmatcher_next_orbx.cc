@@ -12,15 +12,11 @@
 // with the same non-fused FP32 operations.
 #include "ORBmatcher.h"
 #include "orbm.h"
+#include "orbx_thread_matcher.h"
 
 namespace ORB_SLAM3 {
 
 namespace {
-orbm_matcher* NextMatcher() {
-  thread_local orbm_matcher* m = nullptr;
-  if (!m && orbm_create(&m, 0) != ORBX_OK) throw std::runtime_error(orbm_last_error(nullptr));
-  return m;
-}
 
 // DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR, plus the per-feature flag the search reads
 struct BowFlat {
@@ -56,8 +52,8 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpM
   BowFlat fr(F.N, F.mvKeys, F.mDescriptors, F.mFeatVec, F.mvScaleFactors, F.mvLevelSigma2);          // angles: F.mvKeys
   std::vector<int32_t> mf(F.N, -1);
   int32_t nmatches = 0;
-  if (orbm_search_by_bow(NextMatcher(), &kf.v, &fr.v, mfNNratio, mbCheckOrientation, mf.data(), &nmatches) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  if (orbm_search_by_bow(OrbxThreadMatcher(), &kf.v, &fr.v, mfNNratio, mbCheckOrientation, mf.data(), &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   vpMapPointMatches.assign(F.N, static_cast<MapPoint*>(NULL));  // :235
   for (int i = 0; i < F.N; i++)
     if (mf[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[mf[i]];
@@ -72,8 +68,8 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
   for (int i = 0; i < pKF2->N; i++) k2.has_mp[i] = mp2[i] && !mp2[i]->isBad();  // :821-825
   std::vector<int32_t> m12(pKF1->N, -1);
   int32_t nmatches = 0;
-  if (orbm_search_by_bow_kf(NextMatcher(), &k1.v, &k2.v, mfNNratio, mbCheckOrientation, m12.data(), &nmatches) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  if (orbm_search_by_bow_kf(OrbxThreadMatcher(), &k1.v, &k2.v, mfNNratio, mbCheckOrientation, m12.data(), &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   vpMatches12.assign(mp1.size(), static_cast<MapPoint*>(NULL));  // :779-780
   for (int i = 0; i < pKF1->N; i++)
     if (m12[i] >= 0) vpMatches12[i] = mp2[m12[i]];
@@ -136,9 +132,9 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
   orbx_projected pts{(int32_t)src.size(), u.data(), v.data(), ur.data(), radius.data(), lmin.data(), lmax.data(),
                      angle.data(), has_obs.data(), desc.data()};
   std::vector<int32_t> best_idx(src.size(), -1), best_dist(src.size(), 256);
-  if (orbm_fuse_match(NextMatcher(), &kv, pKF->mvInvLevelSigma2.data(), &pts, /*chi2_gate*/ 1, best_idx.data(),
+  if (orbm_fuse_match(OrbxThreadMatcher(), &kv, pKF->mvInvLevelSigma2.data(), &pts, /*chi2_gate*/ 1, best_idx.data(),
                       best_dist.data()) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(NextMatcher()));
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   int nFused = 0;  // :1261-1273, in point order
   for (size_t k = 0; k < src.size(); k++) {
     if (best_dist[k] > TH_LOW) continue;
@@ -162,10 +158,10 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
 // Frame::AssignFeaturesToGrid() (src/Frame.cc:520-547), Nleft == -1
 void AssignFeaturesToGrid_orbx(Frame& F) {
   std::vector<int32_t> off(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1), items(F.N);
-  if (orbm_assign_features_to_grid(NextMatcher(), reinterpret_cast<const orbx_kp*>(F.mvKeysUn.data()), F.N, Frame::mnMinX,
+  if (orbm_assign_features_to_grid(OrbxThreadMatcher(), reinterpret_cast<const orbx_kp*>(F.mvKeysUn.data()), F.N, Frame::mnMinX,
                                    Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv,
                                    off.data(), items.data()) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(NextMatcher()));
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   for (int c = 0; c < FRAME_GRID_COLS; c++)
     for (int r = 0; r < FRAME_GRID_ROWS; r++)
       F.mGrid[c][r].assign(items.begin() + off[c * FRAME_GRID_ROWS + r], items.begin() + off[c * FRAME_GRID_ROWS + r + 1]);
@@ -181,8 +177,8 @@ std::vector<int32_t> DistinctiveDescriptors_orbx(const std::vector<std::vector<c
     off.push_back((int32_t)(all.size() / 32));
   }
   std::vector<int32_t> best(lists.size(), -1);
-  if (orbm_distinctive_descriptors(NextMatcher(), all.data(), off.data(), (int)lists.size(), best.data()) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(NextMatcher()));
+  if (orbm_distinctive_descriptors(OrbxThreadMatcher(), all.data(), off.data(), (int)lists.size(), best.data()) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   return best;  // mDescriptor = lists[p][best[p]].clone()                                                 :437-440
 }
 

@@ -11,15 +11,11 @@
 // (projection, radius) or by the device with the same non-fused FP32 operations.
 #include "ORBmatcher.h"
 #include "orbm.h"
+#include "orbx_thread_matcher.h"
 
 namespace ORB_SLAM3 {
 
 namespace {
-orbm_matcher* ThreadMatcher() {  // ORBmatcher objects are per-call temporaries on three threads: one context per thread
-  thread_local orbm_matcher* m = nullptr;
-  if (!m && orbm_create(&m, 0) != ORBX_OK) throw std::runtime_error(orbm_last_error(nullptr));
-  return m;
-}
 
 // Frame::mGrid[64][48] (std::vector<size_t> per cell, include/Frame.h:279) -> CSR; cell id = col * 48 + row
 struct GridCSR {
@@ -72,9 +68,9 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
                     has_obs.data(), desc.data()};
   std::vector<int32_t> assign(F.N, -1);
   int32_t nmatches = 0;
-  if (orbm_search_by_projection_map(ThreadMatcher(), &ff.v, &mp, th, mfNNratio, bFarPoints, thFarPoints, assign.data(),
+  if (orbm_search_by_projection_map(OrbxThreadMatcher(), &ff.v, &mp, th, mfNNratio, bFarPoints, thFarPoints, assign.data(),
                                     &nmatches) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   for (int i = 0; i < F.N; i++)
     if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assign[i]];  // :130
   return nmatches;
@@ -118,9 +114,9 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
                      radius.data(), lo.data(), hi.data(), angle.data(), has_obs.data(), desc.data()};
   std::vector<int32_t> assign(CurrentFrame.N, -1);
   int32_t nmatches = 0;
-  if (orbm_search_by_projection_frame(ThreadMatcher(), &ff.v, &pts, TH_HIGH, mbCheckOrientation, assign.data(),
+  if (orbm_search_by_projection_frame(OrbxThreadMatcher(), &ff.v, &pts, TH_HIGH, mbCheckOrientation, assign.data(),
                                       &nmatches) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   for (int i = 0; i < CurrentFrame.N; i++)
     if (assign[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[src[assign[i]]];
   return nmatches;
@@ -172,9 +168,9 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2,
   flatten(pKF2, hm2, ids2, off2, idx2, &v2);
   std::vector<int32_t> m12(pKF1->N, -1);
   int32_t nmatches = 0;
-  if (orbm_search_for_triangulation(ThreadMatcher(), &v1, &v2, F, ep(0), ep(1), bOnlyStereo, bCoarse,
+  if (orbm_search_for_triangulation(OrbxThreadMatcher(), &v1, &v2, F, ep(0), ep(1), bOnlyStereo, bCoarse,
                                     mbCheckOrientation, m12.data(), &nmatches) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(ThreadMatcher()));
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
   vMatchedPairs.clear();  // :1097-1103, ascending idx1
   vMatchedPairs.reserve(nmatches);
   for (size_t i = 0; i < m12.size(); i++)

@@ -37,3 +37,18 @@ def test_cpp_shim_matches_oracle(gpu, tmp_path, w, h, nf, lap):
     assert np.array_equal(kps, kps_r) and np.array_equal(desc, desc_r)
     assert np.array_equal(bordered, ex.level_bordered(3))
     assert "sf1=1.20000005" in txt   # GetScaleFactors()[1] = float(1.0 * double(1.2f))
+
+
+def test_threading_contract_two_extractor_threads_and_three_matcher_threads(gpu):
+    """SURVEY.md §8(b) threading: the reference runs its left / right extractor objects on two std::threads per frame
+    (src/Frame.cc:200-203) and ORBmatcher temporaries on three threads. tests/thread_check.cpp does both on the CUDA
+    library (per-thread matcher contexts as in shim/orbx_thread_matcher.h) and compares every output with the oracle's
+    stored words (tools/ubench/data/hotpath_case.bin, written by tools/ubench/make_hotpath_case.py)."""
+    root = os.path.dirname(HERE)
+    case = os.path.join(root, "tools", "ubench", "data", "hotpath_case.bin")
+    exe = os.path.join(HERE, "thread_check")
+    if not os.path.exists(case) or not os.path.exists(exe):
+        pytest.skip("thread_check / its case file are built in the build container (make -C tests; make -C tools/ubench)")
+    r = subprocess.run([exe, case, "2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "two extractor objects on two threads" in r.stdout and "FAILED" not in r.stdout

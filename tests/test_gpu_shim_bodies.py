@@ -1,0 +1,78 @@
+"""The reference-side drop-in bodies (shim/ORBmatcher_orbx.cc, shim/ORBmatcher_next_orbx.cc, shim/FrameStereo_orbx.cc,
+shim/ORBextractor.{h,cc}) ON THE CUDA LIBRARY: oracle/_ref/libshim_world_gpu.so is the stand-in Frame / KeyFrame /
+MapPoint world of tests/test_shim_bodies_vs_reference_source.py with the orbm / orbx C ABI answered by liborbx.so itself
+instead of the oracle mock. Every comparison of tests/test_oracle_matchers_vs_reference_source.py is re-run through it:
+the drop-in methods (C++ glue + CUDA kernels) must reproduce what the reference's own ORBmatcher.cc / Frame.cc text gives
+on the same stand-in frames (which the oracle equals, see the CPU tests)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refsrc
+import test_oracle_matchers_vs_reference_source as T
+
+_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libshim_world_gpu.so")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(_PATH), reason="oracle/_ref/libshim_world_gpu.so not built")]
+
+
+@pytest.fixture()
+def shim_world(gpu, monkeypatch):
+    lib = C.CDLL(_PATH)
+    for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
+                 "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
+                 "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame"):
+        getattr(lib, name).restype = C.c_int
+    refsrc.mlib()
+    monkeypatch.setattr(refsrc, "_mlib", lib)
+    return lib
+
+
+def test_the_world_is_linked_to_the_product_library(shim_world):
+    """The ABI symbols of this world must come from liborbx.so (not from a mock): ask the dynamic linker."""
+    import subprocess
+    out = subprocess.run(["ldd", _PATH], capture_output=True, text=True).stdout
+    assert "liborbx.so" in out and "not found" not in out
+    sym = subprocess.run(["nm", "-D", "--defined-only", _PATH], capture_output=True, text=True).stdout
+    assert " T orbm_search_by_projection_map" not in sym and " T orbx_extract" not in sym
+
+
+@pytest.mark.parametrize("args", [(True, 1.0, 0.8, True, 3), (False, 3.0, 0.8, False, 4), (True, 5.0, 0.6, True, 5)])
+def test_shim_search_by_projection_map(shim_world, args):
+    T.test_search_by_projection_map(*args)
+
+
+@pytest.mark.parametrize("args", [(1, True, 7.0, True, 0), (-1, True, 7.0, True, 1), (0, True, 15.0, True, 2),
+                                  (0, False, 15.0, False, 3)])
+def test_shim_search_by_projection_last_frame(shim_world, args):
+    T.test_search_by_projection_last_frame(*args)
+
+
+@pytest.mark.parametrize("args", [(False, False, True, (1e6, 200.0)), (True, False, True, (1e6, 200.0)),
+                                  (False, True, False, (320.0, 200.0)), (False, False, False, (-5000.0, 200.0))])
+def test_shim_search_for_triangulation(shim_world, args):
+    ex, ey = args[3]
+    F12 = np.array([[0, 0, -ey], [0, 0, ex], [ey, -ex, 0]], np.float32)
+    T.test_search_for_triangulation(*args, F12=F12)
+
+
+@pytest.mark.parametrize("args", [(1, 0.7, True), (2, 0.9, False), (3, 0.6, True)])
+def test_shim_search_by_bow(shim_world, args):
+    T.test_search_by_bow_both_overloads(*args)
+
+
+@pytest.mark.parametrize("args", [(False, 3.0, 4), (False, 2.5, 6)])
+def test_shim_fuse(shim_world, args):
+    T.test_fuse_both_overloads(*args)
+
+
+def test_shim_assign_features_to_grid(shim_world):
+    T.test_grid_functions()
+
+
+@pytest.mark.parametrize("args", [(752, 480, 1200, 1, "scene"), (400, 300, 600, 8, "scene"), (640, 480, 1200, 5, "noise_blur")])
+def test_shim_extractor_class_and_compute_stereo_matches(shim_world, args):
+    """shim/ORBextractor.{h,cc} and the drop-in Frame::ComputeStereoMatches driven like the reference's stereo Frame
+    constructor, on the GPU: keypoints, descriptors, mvuRight and mvDepth must come back as the oracle's."""
+    T.test_stereo_frame_hot_path_equals_the_reference_source(*args)
