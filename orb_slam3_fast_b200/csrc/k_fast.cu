@@ -475,6 +475,7 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
       total += __popc(b0) + __popc(b1);
     }
     if (total > 0 || min_th == ini_th) break;  // :946 — retry with minThFAST only when the cell came back empty
+    __syncwarp();  // the retry rewrites the score map and the list the suppression above has just read
   }
   if (lane == 0) *count_out = total;
 }
