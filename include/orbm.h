@@ -152,6 +152,20 @@ int orbm_stereo_track_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_e
                                    orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right, float* depth,
                                    int32_t* n_matched, int32_t* assign, int32_t* nmatches, int32_t* n_in_view);
 
+/* orbm_stereo_frames_batch / orbm_stereo_track_frames_batch over several GPUs of one box from ONE C/C++ caller: m[d],
+ * left[d], right[d] live on the same device d' (any ordinals). Pairs are independent: they are cut into n_devices
+ * contiguous blocks (as orbx_extract_batch_multi) and every block runs the single-device call on its own host thread;
+ * the eyes of a pair never split, so ComputeStereoMatches and the local-map search stay local; no inter-GPU traffic.
+ * The local maps (track form) are uploaded to every device. Pass frustums == NULL for the stereo-only form. */
+int orbm_stereo_track_frames_batch_multi(int n_devices, orbm_matcher* const* m, orbx_extractor* const* left,
+                                         orbx_extractor* const* right, int n_pairs, const uint8_t* imgs_l,
+                                         const uint8_t* imgs_r, int width, int height, int stride, int64_t frame_stride,
+                                         float mbf, float mb, const orbx_frustum* frustums, const orbx_local_map* maps,
+                                         const int32_t* map_index, const uint8_t* occupied, const orbx_track_params* prm,
+                                         orbx_kp* kps_l, uint8_t* desc_l, int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r,
+                                         int32_t* n_r, int cap, float* u_right, float* depth, int32_t* n_matched,
+                                         int32_t* assign, int32_t* nmatches, int32_t* n_in_view);
+
 /* int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
  * (src/ORBmatcher.cc:1594-1806) and (Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (:1808-1918), after the
  * caller-side SE3 projection (orbx_projected). max_dist = TH_HIGH or ORBdist; check_orientation = mbCheckOrientation.

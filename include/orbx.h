@@ -65,6 +65,15 @@ int orbx_extract_batch(orbx_extractor* ex, int n_frames, const uint8_t* images, 
                        int64_t frame_stride, int lap0, int lap1, orbx_kp* kps, uint8_t* desc, int cap,
                        int32_t* n_out, int32_t* mono_index);
 
+/* orbx_extract_batch over several GPUs of one box from ONE C/C++ caller ("frames sharded over
+ * visible GPUs"): ex[d] is an extractor created on device d' (any ordinals; same parameters), n_devices >= 1. Frames are
+ * independent, so they are cut into n_devices contiguous blocks (sizes differ by at most one, the first blocks take the
+ * extra) and every block runs orbx_extract_batch on its own host thread with its own handle; there is no inter-GPU
+ * traffic. Outputs land at the frames' global positions. Returns the first error. */
+int orbx_extract_batch_multi(int n_devices, orbx_extractor* const* ex, int n_frames, const uint8_t* images, int width,
+                             int height, int stride, int64_t frame_stride, int lap0, int lap1, orbx_kp* kps,
+                             uint8_t* desc, int cap, int32_t* n_out, int32_t* mono_index);
+
 /* Same, inputs and outputs resident in device memory; enqueued on `cuda_stream` (a cudaStream_t; NULL = the handle's
  * stream) and NOT synchronised. n_frames <= max_batch. d_status[n_frames] receives 0 or ORBX_E_CAPACITY per frame. */
 int orbx_extract_batch_device(orbx_extractor* ex, int n_frames, const uint8_t* d_images, int width, int height,

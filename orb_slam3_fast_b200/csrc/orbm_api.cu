@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/orbm.h"
@@ -637,6 +638,51 @@ int orbm_stereo_track_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_e
   const TrackHost trk{frustums, maps, map_index, occupied, prm, assign, nmatches, n_in_view};
   return stereo_frames_impl(m, left, right, n_pairs, imgs_l, imgs_r, width, height, stride, frame_stride, mbf, mb, kps_l,
                             desc_l, n_l, kps_r, desc_r, n_r, cap, u_right, depth, n_matched, &trk);
+}
+
+int orbm_stereo_track_frames_batch_multi(int n_devices, orbm_matcher* const* m, orbx_extractor* const* left,
+                                         orbx_extractor* const* right, int n_pairs, const uint8_t* imgs_l,
+                                         const uint8_t* imgs_r, int width, int height, int stride, int64_t frame_stride,
+                                         float mbf, float mb, const orbx_frustum* frustums, const orbx_local_map* maps,
+                                         const int32_t* map_index, const uint8_t* occupied, const orbx_track_params* prm,
+                                         orbx_kp* kps_l, uint8_t* desc_l, int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r,
+                                         int32_t* n_r, int cap, float* u_right, float* depth, int32_t* n_matched,
+                                         int32_t* assign, int32_t* nmatches, int32_t* n_in_view) {
+  if (n_devices < 1 || !m || !left || !right) return ORBX_E_ARG;
+  for (int d = 0; d < n_devices; d++)
+    if (!m[d] || !left[d] || !right[d]) return ORBX_E_ARG;
+  if (n_pairs <= 0) return mfail(m[0], ORBX_E_EMPTY, "empty image");
+  const bool track = frustums != nullptr;
+  // the default map rule "pair p uses map p % n_maps" is global: a block that does not start at 0 needs it spelled out
+  std::vector<int32_t> idx;
+  if (track && !map_index && maps && maps->n_maps > 1) {
+    idx.resize(n_pairs);
+    for (int p = 0; p < n_pairs; p++) idx[p] = p % maps->n_maps;
+    map_index = idx.data();
+  }
+  std::vector<int> rc(n_devices, ORBX_OK);
+  std::vector<std::thread> th;
+  const int base = n_pairs / n_devices, extra = n_pairs % n_devices;
+  int f0 = 0;
+  for (int d = 0; d < n_devices; d++) {
+    const int nb = base + (d < extra ? 1 : 0);
+    if (nb > 0)
+      th.emplace_back([=, &rc] {
+        const int64_t o = f0, oc = (int64_t)f0 * cap;
+        TrackHost trk{track ? frustums + o : nullptr, maps, map_index ? map_index + o : nullptr,
+                      occupied ? occupied + oc : nullptr, prm, assign ? assign + oc : nullptr,
+                      nmatches ? nmatches + o : nullptr, n_in_view ? n_in_view + o : nullptr};
+        rc[d] = stereo_frames_impl(m[d], left[d], right[d], nb, imgs_l + o * frame_stride, imgs_r + o * frame_stride, width,
+                                   height, stride, frame_stride, mbf, mb, kps_l + oc, desc_l + oc * 32, n_l + o, kps_r + oc,
+                                   desc_r + oc * 32, n_r + o, cap, u_right + oc, depth + oc, n_matched + o,
+                                   track ? &trk : nullptr);
+      });
+    f0 += nb;
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < n_devices; d++)
+    if (rc[d] != ORBX_OK) return rc[d];
+  return ORBX_OK;
 }
 
 namespace {

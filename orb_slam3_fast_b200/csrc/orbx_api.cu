@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/orbx.h"
@@ -466,6 +467,33 @@ int orbx_extract_batch(orbx_extractor* ex, int n_frames, const uint8_t* images, 
   for (int ln = 0; ln < kLanes; ln++)
     if ((rc = retire(ln)) != 0) return rc;
   if (first_err) return api_fail(ex, first_err, "output capacity too small for at least one frame");
+  return ORBX_OK;
+}
+
+int orbx_extract_batch_multi(int n_devices, orbx_extractor* const* ex, int n_frames, const uint8_t* images, int width,
+                             int height, int stride, int64_t frame_stride, int lap0, int lap1, orbx_kp* kps,
+                             uint8_t* desc, int cap, int32_t* n_out, int32_t* mono_index) {
+  if (n_devices < 1 || !ex) return ORBX_E_ARG;
+  for (int d = 0; d < n_devices; d++)
+    if (!ex[d]) return ORBX_E_ARG;
+  if (n_frames <= 0 || !images) return api_fail(ex[0], ORBX_E_EMPTY, "empty image");
+  std::vector<int> rc(n_devices, ORBX_OK);
+  std::vector<std::thread> th;
+  const int base = n_frames / n_devices, extra = n_frames % n_devices;
+  int f0 = 0;
+  for (int d = 0; d < n_devices; d++) {
+    const int nb = base + (d < extra ? 1 : 0);
+    if (nb > 0)
+      th.emplace_back([=, &rc] {
+        rc[d] = orbx_extract_batch(ex[d], nb, images + (int64_t)f0 * frame_stride, width, height, stride, frame_stride, lap0,
+                                   lap1, kps + (int64_t)f0 * cap, desc + (int64_t)f0 * cap * ORBX_DESC_BYTES, cap,
+                                   n_out + f0, mono_index ? mono_index + f0 : nullptr);
+      });
+    f0 += nb;
+  }
+  for (auto& t : th) t.join();
+  for (int d = 0; d < n_devices; d++)
+    if (rc[d] != ORBX_OK) return rc[d];
   return ORBX_OK;
 }
 

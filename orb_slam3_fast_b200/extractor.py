@@ -95,6 +95,29 @@ class ORBextractor:
                                                cap, _l.ptr(n_out), _l.ptr(mono)))
         return n_out, mono, kps, desc
 
+    @staticmethod
+    def extract_batch_multi(extractors, images, vLappingArea=(0, 0), out=None):
+        """orbx_extract_batch_multi: the frames are sharded over the given extractors (one per GPU) by the C library, one
+        host thread each. Returns (n_out[n], mono_index[n], kps[n, cap], desc[n, cap, 32])."""
+        images = np.ascontiguousarray(images, np.uint8)
+        nf, h, w = images.shape
+        cap = extractors[0].capacity
+        if out is None:
+            out = (np.empty(nf, np.int32), np.empty(nf, np.int32), np.empty((nf, cap), KP_DTYPE),
+                   np.empty((nf, cap, 32), np.uint8))
+        n_out, mono, kps, desc = out
+        L = extractors[0]._L
+        L.orbx_extract_batch_multi.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                               C.c_void_p]
+        hs = (C.c_void_p * len(extractors))(*[e._h for e in extractors])
+        rc = L.orbx_extract_batch_multi(len(extractors), hs, nf, _l.ptr(images), w, h, images.strides[1], images.strides[0],
+                                        int(vLappingArea[0]), int(vLappingArea[1]), _l.ptr(kps), _l.ptr(desc), cap,
+                                        _l.ptr(n_out), _l.ptr(mono))
+        if rc < 0:
+            raise OrbxError(rc, "; ".join(L.orbx_last_error(e._h).decode() for e in extractors))
+        return n_out, mono, kps, desc
+
     def extract_batch_device(self, d_images, n_frames, w, h, stride, frame_stride, vLappingArea, d_kps, d_desc, cap,
                              d_n, d_mono, d_status, stream=0):
         """All pointers are device addresses (ints). Enqueues on `stream` (a cudaStream_t value, 0 = handle stream)."""

@@ -46,6 +46,8 @@ def _bind(L):
                                                     vp]
     L.orbm_stereo_track_frames_batch.argtypes = [vp, vp, vp, ci, vp, vp, ci, ci, ci, C.c_int64, cf, cf, vp, vp, vp, vp,
                                                  vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
+    L.orbm_stereo_track_frames_batch_multi.argtypes = [ci, vp, vp, vp, ci, vp, vp, ci, ci, ci, C.c_int64, cf, cf, vp, vp, vp,
+                                                       vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L._orbm_bound = True
 
 
@@ -202,6 +204,32 @@ class ORBmatcher:
             C.byref(params), _l.ptr(out["kps_l"]), _l.ptr(out["desc_l"]), _l.ptr(out["n_l"]), _l.ptr(out["kps_r"]),
             _l.ptr(out["desc_r"]), _l.ptr(out["n_r"]), cap, _l.ptr(out["u_right"]), _l.ptr(out["depth"]),
             _l.ptr(out["n_matched"]), _l.ptr(out["assign"]), _l.ptr(out["nmatches"]), _l.ptr(out["n_in_view"])))
+        return out
+
+    @staticmethod
+    def StereoTrackFramesBatchMulti(matchers, ex_lefts, ex_rights, imgs_l, imgs_r, mbf, mb, frustums=None, local_map=None,
+                                    params=None, map_index=None, occupied=None, out=None):
+        """orbm_stereo_track_frames_batch_multi: the pairs are sharded over len(matchers) handle sets (one per GPU) by
+        the C library, one host thread per set. frustums = None gives the stereo-only form."""
+        assert imgs_l.shape == imgs_r.shape and imgs_l.strides == imgs_r.strides and imgs_l.strides[2] == 1
+        n, h, w = imgs_l.shape
+        nd = len(matchers)
+        cap = ex_lefts[0].capacity
+        track = frustums is not None
+        if out is None:
+            out = (ORBmatcher.alloc_track_outputs if track else ORBmatcher.alloc_stereo_outputs)(n, cap)
+        arr = lambda hs: (C.c_void_p * nd)(*[x._h for x in hs])
+        L = matchers[0]._L
+        rc = L.orbm_stereo_track_frames_batch_multi(
+            nd, arr(matchers), arr(ex_lefts), arr(ex_rights), n, _l.ptr(imgs_l), _l.ptr(imgs_r), w, h, imgs_l.strides[1],
+            imgs_l.strides[0], mbf, mb, _l.ptr(frustums) if track else None, local_map.ref() if track else None,
+            None if map_index is None else _l.ptr(map_index), None if occupied is None else _l.ptr(occupied),
+            C.byref(params) if track else None, _l.ptr(out["kps_l"]), _l.ptr(out["desc_l"]), _l.ptr(out["n_l"]),
+            _l.ptr(out["kps_r"]), _l.ptr(out["desc_r"]), _l.ptr(out["n_r"]), cap, _l.ptr(out["u_right"]),
+            _l.ptr(out["depth"]), _l.ptr(out["n_matched"]), _l.ptr(out["assign"]) if track else None,
+            _l.ptr(out["nmatches"]) if track else None, _l.ptr(out["n_in_view"]) if track else None)
+        if rc < 0:
+            raise OrbxError(rc, "; ".join(L.orbm_last_error(m._h).decode() for m in matchers))
         return out
 
     # int SearchByProjection(Frame& F, const vector<MapPoint*>&, th, bFarPoints, thFarPoints) — src/ORBmatcher.cc:42

@@ -176,3 +176,45 @@ def test_track_local_map_batch_device_equals_oracle(matcher):
     with pytest.raises(OrbxError):
         matcher.StereoTrackFramesBatch(ORBextractor(NF, max_batch=2), ORBextractor(NF, max_batch=2), L[:2], R[:2], MBF, MB,
                                        frs[:2], views.make_local_map(**{k: v.cpu().numpy() for k, v in t.items()}), small)
+
+
+def test_multi_gpu_c_entry_points_shard_and_equal_the_single_device_call(matcher):
+    """orbx_extract_batch_multi / orbm_stereo_track_frames_batch_multi (the C-level sharder over the GPUs of one box, one
+    host thread per device): with every visible device (and, on a one-GPU box, two handle sets on device 0, which
+    exercises the same threads and offsets) the outputs must equal the single-device call word for word — for an uneven
+    split, with the default map rule and with an explicit map_index."""
+    import torch
+    ndev = torch.cuda.device_count()
+    devs = list(range(ndev)) if ndev > 1 else [0, 0]
+    n = 7  # 7 pairs over 2+ handle sets: uneven blocks
+    L, R, ref = _frames(n, 80)
+    m = 1500
+    frs = np.stack([synth.frustum(W, H, seed=500 + i) for i in range(n)])
+    n_maps = 3
+    maps = [synth.local_map_world(ref[i]["kl"], ref[i]["dl"], m, frs[i], seed=600 + i) for i in range(n_maps)]
+    lm = views.make_local_map(**{k: np.stack([mp[k] for mp in maps]) for k in maps[0]})
+    prm = views.make_track_params(W, H, th=3.0, nnratio=0.8)
+    occ = (np.random.default_rng(2).random((n, NF + 16 * 8)) < 0.2).astype(np.uint8)
+    exl1, exr1 = ORBextractor(NF, max_batch=2), ORBextractor(NF, max_batch=2)
+    mts = [ORBmatcher(0.8, True, device=d) for d in devs]
+    exls = [ORBextractor(NF, max_batch=2, device=d) for d in devs]
+    exrs = [ORBextractor(NF, max_batch=2, device=d) for d in devs]
+    for mi in (None, np.array([2, 2, 0, 1, 1, 0, 2], np.int32)):
+        one = matcher.StereoTrackFramesBatch(exl1, exr1, L, R, MBF, MB, frs, lm, prm, map_index=mi, occupied=occ)
+        many = ORBmatcher.StereoTrackFramesBatchMulti(mts, exls, exrs, L, R, MBF, MB, frs, lm, prm, map_index=mi,
+                                                      occupied=occ)
+        for k in ("n_l", "n_r", "n_matched", "nmatches", "n_in_view"):
+            assert np.array_equal(one[k], many[k]), k
+        for i in range(n):
+            nl, nr = int(one["n_l"][i]), int(one["n_r"][i])
+            for k in ("kps_l", "desc_l", "u_right", "depth", "assign"):
+                assert one[k][i, :nl].tobytes() == many[k][i, :nl].tobytes(), (k, i)
+            assert one["desc_r"][i, :nr].tobytes() == many["desc_r"][i, :nr].tobytes()
+        assert int(one["nmatches"].sum()) > 40  # maps are anchored on frames 0..2 only: few but real matches
+    stereo = ORBmatcher.StereoTrackFramesBatchMulti(mts, exls, exrs, L, R, MBF, MB)
+    assert np.array_equal(stereo["n_matched"], one["n_matched"])
+    n1, mono1, k1, d1 = exl1.extract_batch(L, (0, 0))
+    n2, mono2, k2, d2 = ORBextractor.extract_batch_multi(exls, L, (0, 0))
+    assert np.array_equal(n1, n2) and np.array_equal(mono1, mono2)
+    assert all(k1[i, :n1[i]].tobytes() == k2[i, :n1[i]].tobytes() and d1[i, :n1[i]].tobytes() == d2[i, :n1[i]].tobytes()
+               for i in range(n))
