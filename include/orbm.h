@@ -212,7 +212,8 @@ int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, c
  * window and the chi-square gate (:1194-1257), -1 / 256 when none. The shim then applies bestDist <= TH_LOW and does
  * the Replace / AddObservation surgery in point order (:1261-1273). chi2_gate = 1 for this overload; 0 gives the loop
  * of Fuse(KeyFrame*, Sophus::Sim3f& Scw, const vector<MapPoint*>&, float th, vector<MapPoint*>& vpReplacePoint)
- * (:1277-1390), which has the same window and level test but no reprojection gate (:1356-1372). */
+ * (:1277-1390), which has the same window and level test but no reprojection gate (:1356-1372); inv_level_sigma2 is
+ * not read then and may be NULL. */
 int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
                     const orbx_projected* pts, int chi2_gate, int32_t* best_idx, int32_t* best_dist);
 

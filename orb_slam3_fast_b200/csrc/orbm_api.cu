@@ -1018,7 +1018,8 @@ int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, c
 
 int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
                     const orbx_projected* pts, int chi2_gate, int32_t* best_idx, int32_t* best_dist) {
-  if (!m || !kf || !pts || !inv_level_sigma2 || kf->n < 0 || pts->m < 0 || (pts->m > 0 && (!best_idx || !best_dist)))
+  if (!m || !kf || !pts || (chi2_gate && !inv_level_sigma2) || kf->n < 0 || pts->m < 0 ||
+      (pts->m > 0 && (!best_idx || !best_dist)))
     return mfail(m, ORBX_E_ARG, "bad argument");
   if (pts->m == 0) return ORBX_OK;
   ORBM_CUDA(m, cudaSetDevice(m->device));

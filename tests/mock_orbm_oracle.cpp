@@ -59,6 +59,13 @@ int orbm_fuse_match(orbm_matcher*, const orbx_frame_view* kf, const float* inv_l
   orbref_fuse_match(kf, inv_level_sigma2, pts, chi2_gate, best_idx, best_dist);
   return ORBX_OK;
 }
+int orbm_search_for_initialization(orbm_matcher*, const orbx_frame_view* f1, const orbx_frame_view* f2,
+                                   const float* prev_matched_xy, int window_size, float nnratio, int check_orientation,
+                                   int32_t* matches12, int32_t* nmatches) {
+  const int n = orbref_search_for_initialization(f1, f2, prev_matched_xy, window_size, nnratio, check_orientation, matches12);
+  if (nmatches) *nmatches = n;
+  return ORBX_OK;
+}
 int orbm_assign_features_to_grid(orbm_matcher*, const orbx_kp* kps, int n, float min_x, float min_y, float inv_w,
                                  float inv_h, int32_t* cell_offsets, int32_t* cell_items) {
   orbref_build_grid(kps, n, min_x, min_y, inv_w, inv_h, cell_offsets, cell_items);

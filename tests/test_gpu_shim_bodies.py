@@ -22,7 +22,9 @@ def shim_world(gpu, monkeypatch):
     lib = C.CDLL(_PATH)
     for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
                  "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
-                 "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame"):
+                 "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
+                 "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
+                 "orbrefsrc_distinctive_descriptor"):
         getattr(lib, name).restype = C.c_int
     refsrc.mlib()
     monkeypatch.setattr(refsrc, "_mlib", lib)
@@ -76,3 +78,33 @@ def test_shim_extractor_class_and_compute_stereo_matches(shim_world, args):
     """shim/ORBextractor.{h,cc} and the drop-in Frame::ComputeStereoMatches driven like the reference's stereo Frame
     constructor, on the GPU: keypoints, descriptors, mvuRight and mvDepth must come back as the oracle's."""
     T.test_stereo_frame_hot_path_equals_the_reference_source(*args)
+
+
+# ---- shim/ORBmatcher_sim3_orbx.cc: the Sim3 family, SearchForInitialization, the KeyFrame-set projection, distinctive descriptors ----
+@pytest.mark.parametrize("args", [(False, 8, 1.0, 8), (True, 8, 1.0, 9), (False, 4, 1.5, 10)])
+def test_shim_sim3_search_by_projection(shim_world, args):
+    T.test_sim3_search_by_projection_is_the_projected_form(*args)
+
+
+@pytest.mark.parametrize("args", [(7.5, 11), (4.0, 12)])
+def test_shim_search_by_sim3(shim_world, args):
+    T.test_search_by_sim3_is_two_gate_free_fuse_matches_plus_agreement(*args)
+
+
+@pytest.mark.parametrize("args", [(True, 3.0, 5), (True, 4.0, 7)])
+def test_shim_fuse_sim3(shim_world, args):
+    T.test_fuse_both_overloads(*args)
+
+
+@pytest.mark.parametrize("args", [(6, 30, 0.9, True), (7, 60, 0.9, False), (8, 100, 0.7, True)])
+def test_shim_search_for_initialization(shim_world, args):
+    T.test_search_for_initialization(*args)
+
+
+@pytest.mark.parametrize("args", [(10.0, 100, True, 4), (3.0, 64, True, 5), (10.0, 100, False, 6)])
+def test_shim_search_by_projection_keyframe(shim_world, args):
+    T.test_search_by_projection_keyframe(*args)
+
+
+def test_shim_compute_distinctive_descriptors(shim_world):
+    T.test_compute_distinctive_descriptors()
