@@ -15,9 +15,10 @@
 // issuer, warps 2..5 = epilogue (warp w may touch TMEM lanes 32 (w % 4) .. +31). blockIdx.y splits the train set;
 // the per-split (d1, i1, d2, i2) are merged by k_knn2_merge in split order like the POPC kernel's.
 //
-// Measured (profiles/r01_knn2_tc_prototype.log, the stand-alone form in tools/ubench/knn2_tc.cu): 100k x 100k in
-// 2.20 ms = 4.5 Tpair/s including expansion and merge (POPC kernel: 15.0 ms); 3.66 ms without the chunk filter
-// (epilogue bound); MMA-bound floor at the int8 peak ~1.1 ms.
+// Measured on B200 (bench.py --config 4, device-resident, expansion and merge included): 100k x 100k in 1.77 ms =
+// 5.66 Tpair/s = 2.9 Pop/s of s8 MACs, 64 % of the nominal 4.5 Pop/s dense int8 peak (POPC kernel: 15.0 ms). Round 1
+// stood at 2.20 ms (one tcgen05.wait::ld per 32-column load) and, through the library, 2.78 ms (7 train-set splits, see
+// knn2_tc_splits); 3.66 ms without the chunk filter (epilogue bound); MMA-bound floor ~1.15 ms.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -73,7 +74,7 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(sptr(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, int (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -82,8 +83,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -101,7 +102,9 @@ __global__ void k_expand_pm1(const uint8_t* __restrict__ desc, int n, int8_t* __
   reinterpret_cast<uint2*>(out)[i] = make_uint2(lo, hi);
 }
 
-template <bool kFilter>
+// kGroups = 32-column TMEM loads in flight per tcgen05.wait::ld (1 / 2 / 4 measured in tools/ubench/knn2_tc.cu: 2.20 /
+// 1.85 / 1.77 ms for 100k x 100k — one wait per load left the epilogue warps idle for the TMEM round trip 8 times a tile)
+template <bool kFilter, int kGroups>
 __global__ void __launch_bounds__(kThreads, 1)
 k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, int nq, int nt,
           int tiles_per_split, int4* __restrict__ partial) {
@@ -183,28 +186,35 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
       tc_fence_after();
       const int col0 = (tb + i) * kN;
 #pragma unroll 1
-      for (int c = 0; c < kN / 32; c++) {
-        int v[32];
-        tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + s * kN + c * 32, v);
-        bool hit = true;
-        if (kFilter) {
-          int mx = v[0];
+      for (int c0 = 0; c0 < kN / 32; c0 += kGroups) {
+        int v[kGroups][32];
 #pragma unroll
-          for (int j = 1; j < 31; j += 2) mx = max(mx, max(v[j], v[j + 1]));
-          mx = max(mx, v[31]);
-          hit = mx > thr;
-        }
-        if (hit) {
-          const uint32_t base = (256u << 21) | (uint32_t)(col0 + c * 32);
+        for (int g = 0; g < kGroups; g++)
+          tmem_ld32_issue(tmem + ((uint32_t)(quad * 32) << 16) + s * kN + (c0 + g) * 32, v[g]);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            if (col0 + c * 32 + j < nt) {  // rows past the end are TMA zero fill (accumulator 0 = distance 128)
-              const uint32_t key = base + j - ((uint32_t)v[j] << 21);  // ((256 - acc) / 2) << 22 | col
-              k2 = min(k2, max(k1, key));
-              k1 = min(k1, key);
-            }
+        for (int g = 0; g < kGroups; g++) {
+          const int c = c0 + g;
+          bool hit = true;
+          if (kFilter) {
+            int mx = v[g][0];
+#pragma unroll
+            for (int j = 1; j < 31; j += 2) mx = max(mx, max(v[g][j], v[g][j + 1]));
+            mx = max(mx, v[g][31]);
+            hit = mx > thr;
           }
-          thr = 256 - 2 * (int)(k2 >> 22);
+          if (hit) {
+            const uint32_t base = (256u << 21) | (uint32_t)(col0 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              if (col0 + c * 32 + j < nt) {  // rows past the end are TMA zero fill (accumulator 0 = distance 128)
+                const uint32_t key = base + j - ((uint32_t)v[g][j] << 21);  // ((256 - acc) / 2) << 22 | col
+                k2 = min(k2, max(k1, key));
+                k1 = min(k1, key);
+              }
+            }
+            thr = 256 - 2 * (int)(k2 >> 22);
+          }
         }
       }
       tc_fence_before();
@@ -259,26 +269,22 @@ bool knn2_tc_eligible(int nq, int nt) {
 
 size_t knn2_tc_expanded_bytes(int rows) { return (size_t)rows * kRowBytes; }
 
-// Splits of the train set: enough CTAs to fill 148 SMs twice for small query sets, and for large ones the count
-// (<= 8) that leaves the smallest idle tail in the last wave; every split keeps at least 4 tiles.
+// Splits of the train set. Measured on B200 (tools/ubench/knn2_tc.cu, round 2): a split costs more than it evens out —
+// every CTA reloads its query tile, and its chunk filter starts cold, so the first tiles of every split take the exact
+// insertion path (100k x 100k: 1.77 / 1.77 / 1.84 / 2.00 / 2.26 ms for 1 / 2 / 3 / 4 / 7 splits; 50k x 70k: 0.67 / 0.73 /
+// 0.72 / 0.78; 30k x 30k: 0.23 / 0.26 / 0.28 / 0.32). Splitting only pays while the query blocks alone leave SMs idle
+// (10k x 10k, 79 blocks: 0.074 / 0.070 / 0.072 / 0.078 ms for 2 / 4 / 8 / 14). So: one split once there is a CTA per SM,
+// otherwise enough to put ~2 CTAs on every SM; every split keeps at least 4 tiles.
 int knn2_tc_splits(int nq, int nt, int* tiles_per_split) {
   const int qblocks = (nq + kM - 1) / kM, total_tiles = (nt + kN - 1) / kN;
-  int smax = (2 * 148 + qblocks - 1) / qblocks;
-  if (smax < 8) smax = 8;
-  if (smax > total_tiles / 4) smax = total_tiles / 4;
-  int best = 1;
-  double best_cost = 1e30;
-  for (int s = 1; s <= smax; s++) {
-    const int tps = (total_tiles + s - 1) / s;
-    const int ctas = qblocks * ((total_tiles + tps - 1) / tps);
-    const double waves = (double)((ctas + 147) / 148);
-    const double cost = waves * (tps + 1.0);  // +1: the query tile load and the partial write of each CTA
-    if (cost < best_cost * 0.999) {
-      best_cost = cost;
-      best = s;
-    }
+  int s = 1;
+  if (qblocks < 148) {
+    s = (2 * 148 + qblocks - 1) / qblocks;
+    if (s > 16) s = 16;
+    if (s > total_tiles / 4) s = total_tiles / 4;
+    if (s < 1) s = 1;
   }
-  const int tps = (total_tiles + best - 1) / best;
+  const int tps = (total_tiles + s - 1) / s;
   *tiles_per_split = tps;
   return (total_tiles + tps - 1) / tps;  // no empty split
 }
@@ -287,11 +293,11 @@ cudaError_t launch_knn2_tc(const uint8_t* q, int nq, const uint8_t* t, int nt, i
                            int4* partial, int splits, int tiles_per_split, cudaStream_t st) {
   CUtensorMap mq, mt;
   if (!make_rows_map(&mq, expanded_q, nq, kM) || !make_rows_map(&mt, expanded_t, nt, kN)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(k_knn2_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+  cudaError_t e = cudaFuncSetAttribute(k_knn2_tc<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) return e;
   k_expand_pm1<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, nq, expanded_q);
   k_expand_pm1<<<(nt * 32 + 255) / 256, 256, 0, st>>>(t, nt, expanded_t);
-  k_knn2_tc<true><<<dim3((nq + kM - 1) / kM, splits), kThreads, kSmem, st>>>(mq, mt, nq, nt, tiles_per_split, partial);
+  k_knn2_tc<true, 4><<<dim3((nq + kM - 1) / kM, splits), kThreads, kSmem, st>>>(mq, mt, nq, nt, tiles_per_split, partial);
   return cudaGetLastError();
 }
 
