@@ -185,10 +185,43 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
   const size_t map_base = (size_t)(A.map_index ? A.map_index[f] : f % A.n_maps) * A.m;
   uint32_t* slab = A.cand + (size_t)f * A.cand_cap;
   const int i0 = blockIdx.x * (kEnumThreads * kEnumPerThread);
+  // The CTA's points are visited in the order of their predicted level (a counting sort of <= 2048 local indices): a
+  // level-7 window covers 13x the area of a level-0 one, and a warp whose lanes hold random levels runs every lane at
+  // the pace of its largest window. Points that are not searched (not in view, far, skipped) go last: whole warps
+  // then have nothing to do. The order of the points is free — every point owns its slice of the slab.
+  __shared__ int s_cnt[kMaxLevels + 1], s_base[kMaxLevels + 1];
+  __shared__ uint16_t s_order[kEnumThreads * kEnumPerThread];
+  if (tid <= kMaxLevels) s_cnt[tid] = 0;
+  __syncthreads();
+  {
+    int key[kEnumPerThread], rank[kEnumPerThread];
+#pragma unroll
+    for (int k = 0; k < kEnumPerThread; k++) {
+      const int i = i0 + k * kEnumThreads + tid;
+      const int lv = i < A.m ? A.q_level[(size_t)f * A.m + i] : -1;
+      key[k] = lv < 0 ? kMaxLevels : lv;
+      rank[k] = atomicAdd(&s_cnt[key[k]], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int b = 0; b <= kMaxLevels; b++) {
+        s_base[b] = run;
+        run += s_cnt[b];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kEnumPerThread; k++) s_order[s_base[key[k]] + rank[k]] = (uint16_t)(k * kEnumThreads + tid);
+  }
+  __syncthreads();
+  const int n_active = s_base[kMaxLevels];  // searched points of this CTA
 #pragma unroll 1
   for (int k = 0; k < kEnumPerThread; k++) {
-    const int i = i0 + k * kEnumThreads + tid;
-    const bool valid = i < A.m;
+    const int slot = k * kEnumThreads + tid;
+    if (k * kEnumThreads >= n_active) break;  // CTA-uniform: nothing but unsearched points from here on
+    const int i = i0 + (int)s_order[slot];
+    const bool valid = slot < n_active;
     const size_t o = (size_t)f * A.m + (valid ? i : 0);
     const int level = valid ? A.q_level[o] : -1;
     float x = 0, y = 0, ur = 0, rad = 0;
@@ -250,6 +283,11 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
     A.seg[o] = seg;
     A.pre[o] = make_int4(best.d1, best.p1, best.d2, best.p2);
   }
+  // unsearched points: an empty candidate list
+  for (int slot = n_active + tid; slot < kEnumThreads * kEnumPerThread; slot += kEnumThreads) {
+    const int i = i0 + (int)s_order[slot];
+    if (i < A.m) A.seg[(size_t)f * A.m + i] = make_int2(0, 0);
+  }
 }
 
 size_t track_enum_smem(int cap) { return (size_t)cap * 48 + ((size_t)kOff16 * 2 + 15) / 16 * 16; }
@@ -305,16 +343,32 @@ __global__ void __launch_bounds__(kTrackResolveThreads) k_track_resolve(const Tr
     occ0[k] = A.occupied ? A.occupied[(size_t)f * A.cap + k] : 0;
     assign[k] = -1;
   }
-  for (int i = tid; i < M; i += kTrackResolveThreads) dec[i] = -1;
+  // only points with candidates take part in the iteration: their indices are compacted into the (no longer needed)
+  // q_level slice of the frame; the order inside the list is irrelevant, a point's rank in the serial order is its index
+  int32_t* act = A.q_level + (size_t)f * M;
+  __shared__ int n_act_s;
+  if (tid == 0) n_act_s = 0;
   __syncthreads();
-  for (int round = 0; round <= M; round++) {
+  for (int base = 0; base < M; base += kTrackResolveThreads) {
+    const int i = base + tid;
+    const bool has = i < M && seg[i].y > 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, has);
+    int wbase = 0;
+    if ((tid & 31) == 0 && bal) wbase = atomicAdd(&n_act_s, __popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (i < M) dec[i] = -1;
+    __syncthreads();  // the reads of seg[] / q_level above precede the writes into act[] (same memory as q_level)
+    if (has) act[wbase + __popc(bal & ((1u << (tid & 31)) - 1u))] = i;
+  }
+  __syncthreads();
+  const int n_act = n_act_s;
+  for (int round = 0; round <= n_act; round++) {
     if (tid == 0) flag = 0;
     __syncthreads();
     bool changed = false;
-    for (int i = tid; i < M; i += kTrackResolveThreads) {
-      const int2 sg = seg[i];
-      if (sg.y == 0) continue;
-      const int d = track_resolve_point(A, cand, sg, pre[i], i, T, occ0);
+    for (int a = tid; a < n_act; a += kTrackResolveThreads) {
+      const int i = act[a];
+      const int d = track_resolve_point(A, cand, seg[i], pre[i], i, T, occ0);
       if (d != dec[i]) {
         dec[i] = d;
         changed = true;
@@ -325,7 +379,8 @@ __global__ void __launch_bounds__(kTrackResolveThreads) k_track_resolve(const Tr
     if (flag == 0) break;
     for (int k = tid; k < n; k += kTrackResolveThreads) T[k] = 0x7fffffff;
     __syncthreads();
-    for (int i = tid; i < M; i += kTrackResolveThreads) {
+    for (int a = tid; a < n_act; a += kTrackResolveThreads) {
+      const int i = act[a];
       const int d = dec[i];
       if (d >= 0 && has_obs[i]) atomicMin(&T[d], i);
     }
@@ -333,7 +388,8 @@ __global__ void __launch_bounds__(kTrackResolveThreads) k_track_resolve(const Tr
   }
   // F.mvpMapPoints[bestIdx] = pMP (:130): the last accepted point that chose a keypoint stays; every acceptance counts
   int mine = 0;
-  for (int i = tid; i < M; i += kTrackResolveThreads) {
+  for (int a = tid; a < n_act; a += kTrackResolveThreads) {
+    const int i = act[a];
     const int d = dec[i];
     if (d < 0) continue;
     atomicMax(&assign[d], i);
