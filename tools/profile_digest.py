@@ -6,7 +6,7 @@ the two files that are committed under profiles/:
   profiles/traffic.json                measured DRAM bytes per frame and launch time of every stage's kernels;
                                        bench.py reads it for `roofline.traffic` (per launch, like `achieved`)
 
-Usage: python tools/profile_digest.py <tag> [frames_per_launch=64]
+Usage: python tools/profile_digest.py <tag> [frames_per_launch=64] [round=r01] [geometry, e.g. 640x480] [how it was captured]
 """
 import csv
 import io
@@ -20,14 +20,16 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_summary  # noqa: E402
 
 STAGE = {"k_resize": "pyramid", "k_resize_tma": "pyramid", "k_fast": "fast", "k_quadtree": "quadtree", "k_blur7": "blur",
-         "k_describe": "describe", "k_stereo_match": "stereo", "k_stereo_median": "stereo"}
+         "k_describe": "describe", "k_stereo_match": "stereo", "k_stereo_median": "stereo", "k_frustum": "track",
+         "k_track_grid": "track", "k_track_enum": "track", "k_track_resolve": "track"}
+PAIR_STAGES = ("stereo", "track")  # launched once per pair batch, not per eye
 
 
 def num(v):
     return float(v.replace(",", ""))
 
 
-def main(tag, frames):
+def main(tag, frames, rnd="r01", geometry=None, how=None):
     raw = os.path.join(ROOT, "gpurun_out", "prof_%s_raw.csv" % tag)
     rows = list(csv.reader(open(raw)))
     h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
@@ -45,7 +47,7 @@ def main(tag, frames):
         st = STAGE.get(name)
         if st is None:
             continue
-        if seen_calls >= 1 and st != "stereo":
+        if seen_calls >= 1 and st not in PAIR_STAGES:
             continue  # one extract call (left eye) is enough; the second repeats it
         if name == "k_describe":
             seen_calls += 1  # k_describe is the last kernel of an extract call
@@ -54,25 +56,36 @@ def main(tag, frames):
         a["time_us"] += num(r[col["gpu__time_duration.sum"]]) * tscale
         a["dram_bytes"] += num(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]] + \
             num(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]]
-    out = {"source": "profiles/r01_%s_ncu_summary.txt (ncu --set full, %d frames per launch, cold cache, serialised)" % (tag, frames),
+    out = {"source": "profiles/%s_%s_ncu_summary.txt (ncu --set full --clock-control none, %d frames per launch, cold cache, "
+                     "serialised)" % (rnd, tag, frames),
            "frames_per_launch": frames, "stages": {}}
     for st, a in agg.items():
         per = frames if st != "stereo" else frames  # stereo: pairs per launch == frames per eye launch
         out["stages"][st] = {"kernel": a["kernel"], "launches_per_call": a["launches"], "time_us_per_call": round(a["time_us"], 2),
                              "dram_bytes_per_frame": round(a["dram_bytes"] / per, 1)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if geometry:  # keyed by geometry: bench.py looks up "<w>x<h>" first and falls back to the flat round-1 layout
+        try:
+            allj = json.load(open(tpath))
+        except Exception:
+            allj = {}
+        allj[geometry] = out
+        json.dump(allj, open(tpath, "w"), indent=1)
+    else:
+        json.dump(out, open(tpath, "w"), indent=1)
     buf = io.StringIO()
     with redirect_stdout(buf):
-        print("# ncu --set full --clock-control none, one bench step at %d pairs per step (tools/gpu_round.sh %s full)" % (frames, tag))
+        print("# ncu --set full --clock-control none, one step at %d pairs per launch (%s)" % (frames, how or "tools/gpu_round.sh %s full" % tag))
         print("# per-stage totals of one extract call (+ the stereo kernels of the pair batch):")
         for st, a in out["stages"].items():
             print("#   %-9s %-16s launches %d  %8.1f us  DRAM %10.0f B/frame" % (st, a["kernel"], a["launches_per_call"],
                                                                                a["time_us_per_call"], a["dram_bytes_per_frame"]))
         ncu_summary.main(raw)
-    open(os.path.join(ROOT, "profiles", "r01_%s_ncu_summary.txt" % tag), "w").write(buf.getvalue())
+    open(os.path.join(ROOT, "profiles", "%s_%s_ncu_summary.txt" % (rnd, tag)), "w").write(buf.getvalue())
     print(json.dumps(out["stages"], indent=1))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 64)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 64, sys.argv[3] if len(sys.argv) > 3 else "r01",
+         sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else None)
