@@ -90,6 +90,16 @@ int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extract
 int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, const orbx_mappoints* mps, float th,
                                   float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches);
 
+/* The same function on a two-camera Frame (Nleft != -1; KannalaBrandt8 rigs, src/ORBmatcher.cc:42-221 with its
+ * right-camera twin :148-217): per MapPoint the left search, then the right search on mGridRight / mvKeysRight, every
+ * accepted point also written to the stereo partner of its keypoint (mvLeftToRightMatch / mvRightToLeftMatch). The
+ * projections of both cameras come from the caller (Frame::isInFrustumChecks stays on the host: mpCamera2 is a
+ * KannalaBrandt8 model). assign[f->n_left + f->n_right] (host): index of the MapPoint each row of F.mvpMapPoints ends up
+ * with, or -1; *nmatches = the return value. Serial MapPoint order, exact. */
+int orbm_search_by_projection_map_fisheye(orbm_matcher* m, const orbx_fisheye_view* f, const orbx_mappoints* mps,
+                                          const orbx_mappoints_right* mr, float th, float nnratio, int far_points,
+                                          float th_far, int32_t* assign, int32_t* nmatches);
+
 /* void Frame::AssignFeaturesToGrid() with bool Frame::PosInGrid(const cv::KeyPoint&, int&, int&) (include/Frame.h:107,
  * 263; src/Frame.cc:520-547, 833-844), Nleft == -1: the 64x48 lookup grid of mvKeysUn as CSR (orbx_grid layout: cell
  * id = col * 48 + row, ascending keypoint indices inside a cell). SURVEY.md §8(f) rank 1 — the step immediately

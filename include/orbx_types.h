@@ -67,6 +67,36 @@ typedef struct orbx_mappoints {
   const uint8_t* desc;          /* m x 32, MapPoint::GetDescriptor() */
 } orbx_mappoints;
 
+/* A two-camera (fisheye rig) Frame as the guided searches read it (Nleft != -1, include/Frame.h:254-279, 345-357):
+ * mvKeys (left, n_left) and mvKeysRight (n_right) — NOT undistorted copies, Frame::GetFeaturesInArea reads mvKeys /
+ * mvKeysRight in this mode (src/Frame.cc:811-813) —, mDescriptors with the left rows first and the right rows after
+ * them (N = Nleft + Nright), one occupancy flag per row of mvpMapPoints[N], mGrid / mGridRight (same bounds and cell
+ * sizes, indices local to their camera), and the left <-> right stereo associations of
+ * Frame::ComputeStereoFishEyeMatches (mvLeftToRightMatch[Nleft], mvRightToLeftMatch[Nright], -1 = none). */
+typedef struct orbx_fisheye_view {
+  int32_t n_left, n_right;
+  const orbx_kp* kps_left;
+  const orbx_kp* kps_right;
+  const uint8_t* desc;          /* (n_left + n_right) x 32 */
+  const uint8_t* occupied;      /* [n_left + n_right]: mvpMapPoints[i] != NULL && Observations() > 0 */
+  orbx_grid grid_left;
+  orbx_grid grid_right;         /* min_x / min_y / inv_w / inv_h are read from grid_left */
+  const int32_t* left_to_right; /* [n_left] */
+  const int32_t* right_to_left; /* [n_right] */
+  const float* scale_factors;
+  int32_t n_levels;
+} orbx_fisheye_view;
+
+/* The right-camera tracking scratch of the local-map points (include/MapPoint.h:172-180), one entry per element of the
+ * orbx_mappoints it accompanies. */
+typedef struct orbx_mappoints_right {
+  const uint8_t* track_in_view_r; /* mbTrackInViewR && !isBad() */
+  const float* proj_x_r;          /* mTrackProjXR */
+  const float* proj_y_r;          /* mTrackProjYR */
+  const int32_t* level_r;         /* mnTrackScaleLevelR (-1: the right search is skipped, src/ORBmatcher.cc:150) */
+  const float* view_cos_r;        /* mTrackViewCosR */
+} orbx_mappoints_right;
+
 /* What bool Frame::isInFrustum(MapPoint* pMP, float viewingCosLimit) (src/Frame.cc:632-699, Nleft == -1) reads from
  * the Frame: the pose (mRcw row-major, mtcw, mOw; include/Frame.h:197-199), the pinhole intrinsics of mpCamera
  * (src/CameraModels/Pinhole.cpp:47-53), mbf, the image bounds (include/Frame.h:372-375) and the scale pyramid

@@ -1091,6 +1091,129 @@ int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoin
   return nmatches;
 }
 
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, ...) on a two-camera Frame — src/ORBmatcher.cc:42-221
+// with Nleft != -1, serial order
+int orbref_search_by_projection_map_fisheye(const orbx_fisheye_view* f, const orbx_mappoints* mps,
+                                            const orbx_mappoints_right* mr, float th, float nnratio, int far_points,
+                                            float th_far, int32_t* assign) {
+  const int TH_HIGH = 100;
+  const int NL = f->n_left, NR = f->n_right, N = NL + NR;
+  int nmatches = 0;
+  const bool bFactor = th != 1.0;
+  // slot state = F.mvpMapPoints: who sits there (-2 = the frame's own earlier occupant) and whether it has observations
+  std::vector<int32_t> who(N, -1);
+  std::vector<uint8_t> blocked(f->occupied, f->occupied + N);
+  // Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel, bRight) with Nleft != -1 (src/Frame.cc:765-831)
+  auto in_area = [&](float x, float y, float r, int minLevel, int maxLevel, bool right, std::vector<int>& out) {
+    out.clear();
+    const orbx_grid& g = right ? f->grid_right : f->grid_left;
+    const orbx_kp* kps = right ? f->kps_right : f->kps_left;
+    const float min_x = f->grid_left.min_x, min_y = f->grid_left.min_y, inv_w = f->grid_left.inv_w, inv_h = f->grid_left.inv_h;
+    const int C = ORBX_GRID_COLS, R = ORBX_GRID_ROWS;
+    const int x0 = std::max(0, (int)std::floor((x - min_x - r) * inv_w));
+    if (x0 >= C) return;
+    const int x1 = std::min(C - 1, (int)std::ceil((x - min_x + r) * inv_w));
+    if (x1 < 0) return;
+    const int y0 = std::max(0, (int)std::floor((y - min_y - r) * inv_h));
+    if (y0 >= R) return;
+    const int y1 = std::min(R - 1, (int)std::ceil((y - min_y + r) * inv_h));
+    if (y1 < 0) return;
+    const bool check = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = x0; ix <= x1; ix++)
+      for (int iy = y0; iy <= y1; iy++) {
+        const int c = ix * R + iy;
+        for (int j = g.cell_offsets[c]; j < g.cell_offsets[c + 1]; j++) {
+          const orbx_kp& kp = kps[g.cell_items[j]];
+          if (check) {
+            if (kp.octave < minLevel) continue;
+            if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+          }
+          if (std::fabs(kp.x - x) < r && std::fabs(kp.y - y) < r) out.push_back(g.cell_items[j]);
+        }
+      }
+  };
+  for (int i = 0; i < N; i++) assign[i] = -1;
+  std::vector<int> idxs;
+  for (int iMP = 0; iMP < mps->m; iMP++) {
+    const bool inL = mps->track_in_view[iMP] != 0, inR = mr->track_in_view_r[iMP] != 0;
+    if (!inL && !inR) continue;                                     // :55 (the isBad() test of :59 is folded into both flags)
+    if (far_points && mps->depth[iMP] > th_far) continue;           // :57
+    const uint8_t* dMP = mps->desc + (size_t)iMP * 32;
+    const uint8_t obs = mps->has_obs[iMP];
+    auto put = [&](int slot) {
+      who[slot] = iMP;
+      blocked[slot] = obs;
+    };
+    if (inL) {                                                      // :61-145
+      const int level = mps->level[iMP];
+      float r = ((double)mps->view_cos[iMP] > 0.998) ? 2.5f : 4.0f;
+      if (bFactor) r *= th;
+      in_area(mps->proj_x[iMP], mps->proj_y[iMP], r * f->scale_factors[level], level - 1, level, false, idxs);
+      if (!idxs.empty()) {
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : idxs) {
+          if (blocked[idx]) continue;
+          const int dist = orbref_descriptor_distance(dMP, f->desc + (size_t)idx * 32);
+          if (dist < bestDist) {
+            bestDist2 = bestDist;
+            bestDist = dist;
+            bestLevel2 = bestLevel;
+            bestLevel = f->kps_left[idx].octave;
+            bestIdx = idx;
+          } else if (dist < bestDist2) {
+            bestLevel2 = f->kps_left[idx].octave;
+            bestDist2 = dist;
+          }
+        }
+        if (bestDist <= TH_HIGH) {
+          // the reference `continue`s here (:125-126): the right-camera search of this point is skipped as well
+          if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+          put(bestIdx);
+          if (f->left_to_right[bestIdx] != -1) {                    // :131-137
+            put(f->left_to_right[bestIdx] + NL);
+            nmatches++;
+          }
+          nmatches++;
+        }
+      }
+    }
+    if (inR) {                                                      // :148-217
+      const int level = mr->level_r[iMP];
+      if (level != -1) {
+        const float r = ((double)mr->view_cos_r[iMP] > 0.998) ? 2.5f : 4.0f;  // no th factor here
+        in_area(mr->proj_x_r[iMP], mr->proj_y_r[iMP], r * f->scale_factors[level], level - 1, level, true, idxs);
+        if (idxs.empty()) continue;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : idxs) {
+          if (blocked[idx + NL]) continue;
+          const int dist = orbref_descriptor_distance(dMP, f->desc + (size_t)(idx + NL) * 32);
+          if (dist < bestDist) {
+            bestDist2 = bestDist;
+            bestDist = dist;
+            bestLevel2 = bestLevel;
+            bestLevel = f->kps_right[idx].octave;
+            bestIdx = idx;
+          } else if (dist < bestDist2) {
+            bestLevel2 = f->kps_right[idx].octave;
+            bestDist2 = dist;
+          }
+        }
+        if (bestDist <= TH_HIGH) {
+          if (bestLevel == bestLevel2 && (float)bestDist > nnratio * (float)bestDist2) continue;
+          if (f->right_to_left[bestIdx] != -1) {                    // :203-208
+            put(f->right_to_left[bestIdx]);
+            nmatches++;
+          }
+          put(bestIdx + NL);
+          nmatches++;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < N; i++) assign[i] = who[i];
+  return nmatches;
+}
+
 namespace {
 // ORBmatcher::ComputeThreeMaxima — src/ORBmatcher.cc:1920-1955
 void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {

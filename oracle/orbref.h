@@ -117,6 +117,16 @@ int orbref_features_in_area(const orbx_frame_view* f, float x, float y, float r,
  * (keypoints that were already occupied stay -1). Returns nmatches. */
 int orbref_search_by_projection_map(const orbx_frame_view* f, const orbx_mappoints* mps, float th, float nnratio,
                                     int far_points, float th_far, int32_t* assign);
+/* The same function on a two-camera Frame (Nleft != -1): per MapPoint, in vector order, the left search (:61-145 with
+ * the Nleft != -1 choices: no uRight gate, octave from mvKeys, the accepted point is also written to the stereo partner
+ * mvLeftToRightMatch[bestIdx] + Nleft, +1 match) and then the right-camera twin (:148-217: window on mTrackProjXR / YR at
+ * mnTrackScaleLevelR with NO th factor, mGridRight, rows idx + Nleft, the partner mvRightToLeftMatch[bestIdx]). A slot is
+ * closed for a later search while its CURRENT occupant has observations (:92-93, :183-185); partner writes are
+ * unconditional. mps->track_in_view / mr->track_in_view_r already include !isBad(); mps->proj_xr is not read.
+ * assign[n_left + n_right]: index of the MapPoint each slot ends up with, or -1. Returns nmatches. */
+int orbref_search_by_projection_map_fisheye(const orbx_fisheye_view* f, const orbx_mappoints* mps,
+                                            const orbx_mappoints_right* mr, float th, float nnratio, int far_points,
+                                            float th_far, int32_t* assign);
 /* ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) / (Frame&, KeyFrame*, set, th, ORBdist) after the
  * caller-side projection (src/ORBmatcher.cc:1594-1806, 1808-1918). block_any != 0 selects the keyframe variant's
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */

@@ -76,6 +76,18 @@ class LocalMap(C.Structure):
                 ("desc", C.c_void_p)]
 
 
+class FisheyeView(C.Structure):
+    _fields_ = [("n_left", C.c_int32), ("n_right", C.c_int32), ("kps_left", C.c_void_p), ("kps_right", C.c_void_p),
+                ("desc", C.c_void_p), ("occupied", C.c_void_p), ("grid_left", Grid), ("grid_right", Grid),
+                ("left_to_right", C.c_void_p), ("right_to_left", C.c_void_p), ("scale_factors", C.c_void_p),
+                ("n_levels", C.c_int32)]
+
+
+class MapPointsRight(C.Structure):
+    _fields_ = [("track_in_view_r", C.c_void_p), ("proj_x_r", C.c_void_p), ("proj_y_r", C.c_void_p),
+                ("level_r", C.c_void_p), ("view_cos_r", C.c_void_p)]
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -165,6 +177,36 @@ def track_local_map(frame_view, frustum, local_map, map_index, th, nnratio, far_
         return 0, np.full(frame_view.struct.n, -1, np.int32), 0
     nm, assign = search_by_projection_map(frame_view, mps, th, nnratio, far_points, th_far)
     return nm, assign, nv
+
+
+def make_fisheye_view(kps_left, kps_right, desc, occupied, min_x, min_y, inv_w, inv_h, left_to_right, right_to_left,
+                      scale_factors):
+    """orbx_fisheye_view; the two grids are built here with orbref_build_grid (Frame::AssignFeaturesToGrid)."""
+    kl, kr = _c(kps_left, KP_DTYPE), _c(kps_right, KP_DTYPE)
+    desc, occupied = _c(desc, np.uint8), _c(occupied, np.uint8)
+    l2r, r2l = _c(left_to_right, np.int32), _c(right_to_left, np.int32)
+    sf = _c(scale_factors, np.float32)
+    gl, keep_l = make_grid(*build_grid(kl, min_x, min_y, inv_w, inv_h), min_x, min_y, inv_w, inv_h)
+    gr, keep_r = make_grid(*build_grid(kr, min_x, min_y, inv_w, inv_h), min_x, min_y, inv_w, inv_h)
+    v = FisheyeView(len(kl), len(kr), _ptr(kl), _ptr(kr), _ptr(desc), _ptr(occupied), gl, gr, _ptr(l2r), _ptr(r2l),
+                    _ptr(sf), len(sf))
+    return Holder(v, (kl, kr, desc, occupied, keep_l, keep_r, l2r, r2l, sf))
+
+
+def make_mappoints_right(track_in_view_r, proj_x_r, proj_y_r, level_r, view_cos_r):
+    arrs = (_c(track_in_view_r, np.uint8), _c(proj_x_r, np.float32), _c(proj_y_r, np.float32), _c(level_r, np.int32),
+            _c(view_cos_r, np.float32))
+    return Holder(MapPointsRight(*[_ptr(a) for a in arrs]), arrs)
+
+
+def search_by_projection_map_fisheye(fv, mps, mr, th, nnratio, far_points=False, th_far=0.0, fn=None):
+    n_slots = fv.struct.n_left + fv.struct.n_right
+    assign = np.empty(max(n_slots, 1), np.int32)
+    fn = fn or lib().orbref_search_by_projection_map_fisheye
+    fn.restype = C.c_int
+    n = fn(fv.ref(), mps.ref(), mr.ref(), C.c_float(th), C.c_float(nnratio), C.c_int(int(far_points)), C.c_float(th_far),
+           _ptr(assign))
+    return n, assign[:n_slots]
 
 
 def make_projected(u, v, u_right, radius, min_level, max_level, angle, has_obs, desc):

@@ -603,3 +603,61 @@ extern "C" int orbrefsrc_stereo_track_frame(int nfeatures, float scale_factor, i
   }
   return matched;
 }
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, ...) on a two-camera Frame (Nleft != -1): the
+// reference's own method, fisheye branches included (src/ORBmatcher.cc:42-221), on a stand-in Frame whose grids are built
+// by the reference's own AssignFeaturesToGrid. Outputs as orbref_search_by_projection_map_fisheye.
+extern "C" int orbrefsrc_search_by_projection_map_fisheye(const orbx_fisheye_view* fv, const orbx_mappoints* mps,
+                                                          const orbx_mappoints_right* mr, float th, float nnratio,
+                                                          int far_points, float th_far, int32_t* assign) {
+  Frame F;
+  const int NL = fv->n_left, NR = fv->n_right, N = NL + NR;
+  F.N = N;
+  F.Nleft = NL;
+  F.mvKeys = keypoints(fv->kps_left, NL);
+  F.mvKeysRight = keypoints(fv->kps_right, NR);
+  F.mvKeysUn = F.mvKeys;
+  F.mDescriptors = rows32(fv->desc, N);
+  F.mvuRight.assign(N, -1.f);
+  F.mvScaleFactors.assign(fv->scale_factors, fv->scale_factors + fv->n_levels);
+  Frame::mnMinX = fv->grid_left.min_x;
+  Frame::mnMinY = fv->grid_left.min_y;
+  Frame::mfGridElementWidthInv = fv->grid_left.inv_w;
+  Frame::mfGridElementHeightInv = fv->grid_left.inv_h;
+  F.AssignFeaturesToGrid();
+  F.mvLeftToRightMatch.assign(fv->left_to_right, fv->left_to_right + NL);
+  F.mvRightToLeftMatch.assign(fv->right_to_left, fv->right_to_left + NR);
+  MapPoint occupied;
+  occupied.observations = 1;
+  F.mvpMapPoints.assign(N, nullptr);
+  for (int i = 0; i < N; i++)
+    if (fv->occupied && fv->occupied[i]) F.mvpMapPoints[i] = &occupied;
+  GeometricCamera camera;
+  F.mpCamera = F.mpCamera2 = &camera;
+  std::vector<MapPoint> pts(mps->m);
+  std::vector<MapPoint*> ptrs(mps->m);
+  for (int i = 0; i < mps->m; i++) {
+    MapPoint& p = pts[i];
+    p.mbTrackInView = mps->track_in_view[i] != 0;
+    p.mbTrackInViewR = mr->track_in_view_r[i] != 0;
+    p.mTrackProjX = mps->proj_x[i];
+    p.mTrackProjY = mps->proj_y[i];
+    p.mTrackProjXR = mr->proj_x_r[i];
+    p.mTrackProjYR = mr->proj_y_r[i];
+    p.mnTrackScaleLevel = mps->level[i];
+    p.mnTrackScaleLevelR = mr->level_r[i];
+    p.mTrackViewCos = mps->view_cos[i];
+    p.mTrackViewCosR = mr->view_cos_r[i];
+    p.mTrackDepth = mps->depth[i];
+    p.observations = mps->has_obs[i] ? 1 : 0;
+    p.descriptor = rows32(mps->desc + (size_t)i * 32, 1);
+    ptrs[i] = &p;
+  }
+  ORBmatcher matcher(nnratio, true);
+  const int n = matcher.SearchByProjection(F, ptrs, th, far_points != 0, th_far);
+  for (int i = 0; i < N; i++) {
+    const MapPoint* p = F.mvpMapPoints[i];
+    assign[i] = (p && p != &occupied) ? (int)(p - pts.data()) : -1;
+  }
+  return n;
+}

@@ -136,6 +136,13 @@ def is_in_frustum(frustum, local_map, map_index=0, viewing_cos_limit=0.5, out=No
     return orbref.is_in_frustum(frustum, local_map, map_index, viewing_cos_limit, out, fn=fn)
 
 
+def search_by_projection_map_fisheye(fv, mps, mr, th, nnratio, far_points=False, th_far=0.0):
+    """The reference's own SearchByProjection(Frame&, vector<MapPoint*>) on a two-camera stand-in Frame."""
+    from . import orbref
+    return orbref.search_by_projection_map_fisheye(fv, mps, mr, th, nnratio, far_points, th_far,
+                                                   fn=mlib().orbrefsrc_search_by_projection_map_fisheye)
+
+
 def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False, check_orientation=True):
     F = np.ascontiguousarray(F12, np.float32).reshape(9)
     m = np.empty(max(kf1.struct.n, 1), np.int32)

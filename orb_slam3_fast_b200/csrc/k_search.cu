@@ -400,6 +400,77 @@ void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchS
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The two-camera form of SearchByProjection(Frame&, vector<MapPoint*>) (Nleft != -1, src/ORBmatcher.cc:42-221). Per
+// MapPoint, in vector order: the left search, then — unless the left search left the loop body through its ratio-test
+// `continue` (:125-126) — the right-camera twin (:148-217). An accepted point is written to its keypoint AND,
+// unconditionally, to the keypoint's stereo partner (mvLeftToRightMatch / mvRightToLeftMatch); a slot is closed for a
+// later search while its CURRENT occupant has observations (:92-93, :183-185). Because a partner write can replace an
+// occupant that had observations by one that has none, a slot can re-open: "closed" is a function of the last writer, not
+// of the first, and the fixed-point iteration of k_search_resolve (which keeps one index per keypoint) does not apply.
+// This is the exact serial replay instead: ONE warp walks the points, its lanes share each point's candidate list
+// (enumerated and scored in parallel by k_search_enum), slot state lives in shared memory. ~1 ms for 10 000 points; the
+// fisheye branch is not on the headline path.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_search_resolve_fisheye(const FisheyeResolveArgs A) {
+  extern __shared__ __align__(16) uint8_t fs_smem[];  // int who[N] | u8 blocked[N]
+  const int lane = threadIdx.x, N = A.n_left + A.n_right, NL = A.n_left;
+  int* who = reinterpret_cast<int*>(fs_smem);
+  uint8_t* blocked = reinterpret_cast<uint8_t*>(who + N);
+  for (int k = lane; k < N; k += 32) {
+    who[k] = -1;
+    blocked[k] = A.occupied[k];
+  }
+  __syncwarp();
+  int nmatches = 0;
+  for (int i = 0; i < A.m; i++) {
+    const uint8_t obs = A.has_obs[i];
+    bool skip_right = false;
+#pragma unroll 1
+    for (int side = 0; side < 2; side++) {
+      if (side == 0 ? !A.in_left[i] : (!A.in_right[i] || skip_right)) continue;
+      const SearchScratch& S = side == 0 ? A.left : A.right;
+      const int base = side == 0 ? 0 : NL;
+      const int off = S.counts[i], cnt = S.counts[i + 1] - off;
+      if (cnt == 0) continue;
+      Top2 t{0, -1, 0, -1};
+      for (int c = lane; c < cnt; c += 32)
+        if (!blocked[base + S.cand_idx[off + c]]) top2_insert(t, S.cand_dist[off + c] & 0xffff, c);
+      t = top2_warp(t);
+      if (t.p1 < 0) continue;
+      const int bestDist = t.d1, bestLocal = S.cand_idx[off + t.p1], bestLevel = S.cand_dist[off + t.p1] >> 16;
+      const int bestDist2 = t.p2 >= 0 ? t.d2 : 256, bestLevel2 = t.p2 >= 0 ? (S.cand_dist[off + t.p2] >> 16) : -1;
+      if (bestDist > ORBM_TH_HIGH_I) continue;
+      if (bestLevel == bestLevel2 && (float)bestDist > fmul(A.nnratio, (float)bestDist2)) {
+        skip_right = side == 0;  // the reference `continue`s the MapPoint loop here
+        continue;
+      }
+      const int partner = side == 0 ? A.left_to_right[bestLocal] : A.right_to_left[bestLocal];
+      if (lane == 0) {
+        who[base + bestLocal] = i;
+        blocked[base + bestLocal] = obs;
+        if (partner != -1) {
+          const int ps = side == 0 ? partner + NL : partner;
+          who[ps] = i;
+          blocked[ps] = obs;
+        }
+      }
+      nmatches += 1 + (partner != -1);
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < N; k += 32) A.assign[k] = who[k];
+  if (lane == 0) *A.nmatches = nmatches;
+}
+
+void launch_search_resolve_fisheye(const FisheyeResolveArgs& A, cudaStream_t st) {
+  const size_t N = (size_t)A.n_left + A.n_right;
+  const size_t smem = N * 4 + (N + 15) / 16 * 16;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_search_resolve_fisheye, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_search_resolve_fisheye<<<1, 32, smem, st>>>(A);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // SearchForTriangulation. Rows of the result are independent (vbMatched2 is never written in the reference), so:
 //   k_tri_nodes   node a of kf1 -> position of the same vocabulary node in kf2 (binary search; both lists ascend)
 //   k_tri_match   one thread per shared node replays the reference's double loop for its features

@@ -742,6 +742,128 @@ int orbm_search_by_projection_map(orbm_matcher* m, const orbx_frame_view* f, con
                            th_far, f->n, assign, nmatches);
 }
 
+int orbm_search_by_projection_map_fisheye(orbm_matcher* m, const orbx_fisheye_view* f, const orbx_mappoints* mps,
+                                          const orbx_mappoints_right* mr, float th, float nnratio, int far_points,
+                                          float th_far, int32_t* assign, int32_t* nmatches) {
+  if (!m || !f || !mps || !mr || f->n_left < 0 || f->n_right < 0 || mps->m < 0 || (f->n_left + f->n_right > 0 && !assign) ||
+      !f->left_to_right || !f->right_to_left)
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (nmatches) *nmatches = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  const int NL = f->n_left, NR = f->n_right, N = NL + NR, M = mps->m, cells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
+  if (N == 0) return ORBX_OK;
+  Arena ar(m);
+  cudaStream_t st = m->stream;
+  // the enumeration must not drop occupied keypoints: a partner write can re-open a slot (see k_search_resolve_fisheye)
+  std::vector<uint8_t> zeros(std::max(N, 1), 0);
+  const uint8_t* d_zero = ar.upload(zeros.data(), N);
+  const uint8_t* d_desc = ar.upload(f->desc, (size_t)N * 32);
+  const float* d_sf = ar.upload(f->scale_factors, f->n_levels);
+  DevFrame F[2];
+  for (int side = 0; side < 2; side++) {
+    const orbx_grid& g = side ? f->grid_right : f->grid_left;
+    DevFrame& D = F[side];
+    D = DevFrame{};
+    D.n = side ? NR : NL;
+    D.n_levels = f->n_levels;
+    D.kps = ar.upload(side ? f->kps_right : f->kps_left, D.n);
+    D.desc = d_desc + (side ? (size_t)NL * 32 : 0);
+    D.u_right = nullptr;
+    D.occupied = d_zero;
+    D.cell_offsets = ar.upload(g.cell_offsets, cells + 1);
+    D.cell_items = ar.upload(g.cell_items, (size_t)g.cell_offsets[cells]);
+    D.min_x = f->grid_left.min_x;
+    D.min_y = f->grid_left.min_y;
+    D.inv_w = f->grid_left.inv_w;
+    D.inv_h = f->grid_left.inv_h;
+    D.scale_factors = d_sf;
+  }
+  // the scalar prologue of both loop bodies (:55-74, :148-160): who searches where, with which radius
+  std::vector<uint8_t> act[2] = {std::vector<uint8_t>(std::max(M, 1)), std::vector<uint8_t>(std::max(M, 1))};
+  std::vector<float> radius[2] = {std::vector<float>(std::max(M, 1)), std::vector<float>(std::max(M, 1))};
+  std::vector<int32_t> minl[2] = {std::vector<int32_t>(std::max(M, 1)), std::vector<int32_t>(std::max(M, 1))};
+  std::vector<int32_t> maxl[2] = {std::vector<int32_t>(std::max(M, 1)), std::vector<int32_t>(std::max(M, 1))};
+  const bool bFactor = th != 1.0;
+  for (int i = 0; i < M; i++) {
+    const bool inL = mps->track_in_view[i] != 0, inR = mr->track_in_view_r[i] != 0;
+    const bool gone = (!inL && !inR) || (far_points && mps->depth[i] > th_far);
+    for (int side = 0; side < 2; side++) {
+      const int level = side ? mr->level_r[i] : mps->level[i];
+      bool on = !gone && (side ? inR : inL);
+      if (on && side == 1 && level == -1) on = false;  // :150
+      if (on && (level < 0 || level >= f->n_levels)) on = false;
+      float r = ((double)(side ? mr->view_cos_r[i] : mps->view_cos[i]) > 0.998) ? 2.5f : 4.0f;
+      if (side == 0 && bFactor) r *= th;  // the right-camera twin has no th factor (:152)
+      act[side][i] = on;
+      radius[side][i] = on ? r * f->scale_factors[level] : 0.f;
+      minl[side][i] = level - 1;
+      maxl[side][i] = level;
+    }
+  }
+  const uint8_t* d_q_desc = ar.upload(mps->desc, (size_t)M * 32);
+  FisheyeResolveArgs R{};
+  R.m = M;
+  R.n_left = NL;
+  R.n_right = NR;
+  R.nnratio = nnratio;
+  R.has_obs = ar.upload(mps->has_obs, M);
+  R.occupied = f->occupied ? ar.upload(f->occupied, N) : d_zero;
+  R.left_to_right = ar.upload(f->left_to_right, NL);
+  R.right_to_left = ar.upload(f->right_to_left, NR);
+  R.assign = ar.alloc<int32_t>(N);
+  R.nmatches = ar.alloc<int32_t>(1);
+  DevQueries Q[2];
+  SearchScratch S[2];
+  int32_t* d_total[2];
+  for (int side = 0; side < 2; side++) {
+    Q[side] = DevQueries{};
+    Q[side].m = M;
+    Q[side].active = ar.upload(act[side].data(), M);
+    Q[side].u = ar.upload(side ? mr->proj_x_r : mps->proj_x, M);
+    Q[side].v = ar.upload(side ? mr->proj_y_r : mps->proj_y, M);
+    Q[side].radius = ar.upload(radius[side].data(), M);
+    Q[side].min_level = ar.upload(minl[side].data(), M);
+    Q[side].max_level = ar.upload(maxl[side].data(), M);
+    Q[side].u_right = nullptr;
+    Q[side].desc = d_q_desc;
+    S[side] = SearchScratch{};
+    S[side].counts = ar.alloc<int32_t>((size_t)M + 1);
+    S[side].pre = ar.alloc<int4>(M);
+    d_total[side] = ar.alloc<int32_t>(1);
+  }
+  R.in_left = Q[0].active;
+  R.in_right = Q[1].active;
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  int32_t total[2] = {0, 0};
+  for (int side = 0; side < 2; side++) {
+    if (M > 0) {
+      launch_search_count(F[side], Q[side], S[side].counts, st);
+      launch_scan(S[side].counts, M, d_total[side], st);
+      ORBM_CUDA(m, cudaMemcpyAsync(&total[side], d_total[side], 4, cudaMemcpyDeviceToHost, st));
+    } else {
+      ORBM_CUDA(m, cudaMemsetAsync(S[side].counts, 0, 4, st));
+    }
+  }
+  ORBM_CUDA(m, cudaStreamSynchronize(st));
+  for (int side = 0; side < 2; side++) {
+    S[side].cand_idx = ar.alloc<int32_t>(total[side]);
+    S[side].cand_dist = ar.alloc<int32_t>(total[side]);
+    S[side].cap_total = total[side];
+  }
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  for (int side = 0; side < 2; side++) launch_search_fill(F[side], Q[side], S[side], st);
+  R.left = S[0];
+  R.right = S[1];
+  launch_search_resolve_fisheye(R, st);
+  ORBM_CUDA(m, cudaGetLastError());
+  int32_t nm = 0;
+  ORBM_CUDA(m, cudaMemcpyAsync(assign, R.assign, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaMemcpyAsync(&nm, R.nmatches, 4, cudaMemcpyDeviceToHost, st));
+  ORBM_CUDA(m, cudaStreamSynchronize(st));
+  if (nmatches) *nmatches = nm;
+  return ORBX_OK;
+}
+
 int orbm_assign_features_to_grid(orbm_matcher* m, const orbx_kp* kps, int n, float min_x, float min_y, float inv_w,
                                  float inv_h, int32_t* cell_offsets, int32_t* cell_items) {
   if (!m || n < 0 || (n > 0 && (!kps || !cell_items)) || !cell_offsets) return mfail(m, ORBX_E_ARG, "bad argument");

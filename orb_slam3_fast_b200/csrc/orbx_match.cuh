@@ -165,6 +165,22 @@ void launch_frustum_batch(const TrackArgs& A, cudaStream_t st);
 void launch_track_search(const TrackArgs& A, cudaStream_t st);  // grid -> enumerate -> resolve
 size_t track_resolve_smem(int cap);
 
+// SearchByProjection(Frame&, vector<MapPoint*>) on a two-camera Frame (Nleft != -1, src/ORBmatcher.cc:42-221): the candidate
+// lists of the left and the right search come from the enumeration kernels above (one DevFrame / DevQueries /
+// SearchScratch per camera, WITHOUT the static occupancy filter); this replays the serial MapPoint order on them.
+struct FisheyeResolveArgs {
+  int m, n_left, n_right;
+  float nnratio;
+  const uint8_t *in_left, *in_right;  // [m] the two searches a point takes part in (view flags, far gate, level_r != -1)
+  const uint8_t* has_obs;            // [m]
+  const uint8_t* occupied;           // [n_left + n_right] initial slot state
+  const int32_t *left_to_right, *right_to_left;
+  SearchScratch left, right;
+  int32_t* assign;                   // [n_left + n_right]
+  int32_t* nmatches;
+};
+void launch_search_resolve_fisheye(const FisheyeResolveArgs& A, cudaStream_t st);
+
 struct DevKeyFrame {
   int n, n_levels;
   const orbx_kp* kps;

@@ -48,6 +48,7 @@ def _bind(L):
                                                  vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
     L.orbm_stereo_track_frames_batch_multi.argtypes = [ci, vp, vp, vp, ci, vp, vp, ci, ci, ci, C.c_int64, cf, cf, vp, vp, vp,
                                                        vp, vp, vp, vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp]
+    L.orbm_search_by_projection_map_fisheye.argtypes = [vp, vp, vp, vp, cf, cf, ci, cf, vp, vp]
     L._orbm_bound = True
 
 
@@ -240,6 +241,18 @@ class ORBmatcher:
         self._check(self._L.orbm_search_by_projection_map(self._h, frame_view.ref(), mappoints.ref(), th,
                                                           self.mfNNratio, int(bFarPoints), thFarPoints,
                                                           _l.ptr(assign), C.byref(nm)))
+        return nm.value, assign[:n]
+
+    # the same on a two-camera Frame (Nleft != -1): left search + right-camera twin + stereo partners — :42-221 incl. :148-217
+    def SearchByProjectionFisheye(self, fisheye_view, mappoints, mappoints_right, th=3.0, bFarPoints=False,
+                                  thFarPoints=50.0):
+        n = fisheye_view.struct.n_left + fisheye_view.struct.n_right
+        assign = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_by_projection_map_fisheye(self._h, fisheye_view.ref(), mappoints.ref(),
+                                                                  mappoints_right.ref(), th, self.mfNNratio,
+                                                                  int(bFarPoints), thFarPoints, _l.ptr(assign),
+                                                                  C.byref(nm)))
         return nm.value, assign[:n]
 
     # void Frame::AssignFeaturesToGrid() — src/Frame.cc:520-547 (PosInGrid :833-844), on the device

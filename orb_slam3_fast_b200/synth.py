@@ -215,6 +215,52 @@ def local_map_world(kps, desc, m, fr, seed=0):
                 has_obs=(rng.random(m) < 0.9).astype(np.uint8), desc=d)
 
 
+def fisheye_case(n_left=700, n_right=650, m=3000, w=640, h=480, n_levels=8, seed=0):
+    """A two-camera (Nleft != -1) frame and local-map points for SearchByProjection's fisheye branches: random left /
+    right keypoints, ~40 % of them associated left <-> right (mvLeftToRightMatch / mvRightToLeftMatch, a partial
+    bijection), points anchored on left and / or right keypoints with jittered projections and 0..70 flipped bits."""
+    rng = np.random.default_rng(seed + 271828)
+    def kps(n):
+        k = np.zeros(n, KP_DTYPE)
+        k["x"], k["y"] = rng.uniform(0, w, n).astype(np.float32), rng.uniform(0, h, n).astype(np.float32)
+        k["octave"] = rng.integers(0, n_levels, n)
+        k["size"], k["angle"], k["class_id"] = 31, rng.uniform(0, 360, n).astype(np.float32), -1
+        return k
+    kl, kr = kps(n_left), kps(n_right)
+    dl = descriptors(n_left, seed + 1)
+    dr = descriptors(n_right, seed + 2)
+    l2r = np.full(n_left, -1, np.int32)
+    r2l = np.full(n_right, -1, np.int32)
+    npair = int(0.4 * min(n_left, n_right))
+    pl, pr = rng.choice(n_left, npair, replace=False), rng.choice(n_right, npair, replace=False)
+    l2r[pl], r2l[pr] = pr, pl
+    dr[pr] = flip_bits(dl[pl], rng.integers(0, 25, npair), rng)      # associated keypoints look alike
+    kr["octave"][pr] = kl["octave"][pl]
+    desc = np.concatenate([dl, dr])
+    occupied = (rng.random(n_left + n_right) < 0.15).astype(np.uint8)
+    src_l, src_r = rng.integers(0, n_left, m), rng.integers(0, n_right, m)
+    kind = rng.integers(0, 4, m)                                       # 0 left only, 1 right only, 2 both, 3 neither
+    inL, inR = np.isin(kind, (0, 2)), np.isin(kind, (1, 2))
+    both = kind == 2
+    src_r = np.where(both & (l2r[src_l] >= 0), l2r[src_l], src_r)      # "both": the same physical point where possible
+    anch = rng.random(m) < 0.8
+    px = np.where(anch, kl["x"][src_l] + rng.normal(0, 1.5, m), rng.uniform(0, w, m)).astype(np.float32)
+    py = np.where(anch, kl["y"][src_l] + rng.normal(0, 1.5, m), rng.uniform(0, h, m)).astype(np.float32)
+    pxr = np.where(anch, kr["x"][src_r] + rng.normal(0, 1.5, m), rng.uniform(0, w, m)).astype(np.float32)
+    pyr = np.where(anch, kr["y"][src_r] + rng.normal(0, 1.5, m), rng.uniform(0, h, m)).astype(np.float32)
+    lvl = np.clip(kl["octave"][src_l] + rng.integers(0, 2, m), 0, n_levels - 1).astype(np.int32)
+    lvr = np.clip(kr["octave"][src_r] + rng.integers(0, 2, m), 0, n_levels - 1).astype(np.int32)
+    lvr = np.where(rng.random(m) < 0.05, -1, lvr).astype(np.int32)     # mnTrackScaleLevelR == -1: right search skipped
+    d = flip_bits(np.where(inL[:, None], dl[src_l], dr[src_r]), rng.integers(0, 71, m), rng)
+    frame = dict(kps_left=kl, kps_right=kr, desc=desc, occupied=occupied, left_to_right=l2r, right_to_left=r2l)
+    mp = dict(track_in_view=inL.astype(np.uint8), proj_x=px, proj_y=py, proj_xr=np.zeros(m, np.float32), level=lvl,
+              view_cos=rng.uniform(0.5, 1.0, m).astype(np.float32), depth=rng.uniform(0.5, 20.0, m).astype(np.float32),
+              has_obs=(rng.random(m) < 0.8).astype(np.uint8), desc=d)
+    mpr = dict(track_in_view_r=inR.astype(np.uint8), proj_x_r=pxr, proj_y_r=pyr, level_r=lvr,
+               view_cos_r=rng.uniform(0.5, 1.0, m).astype(np.float32))
+    return frame, mp, mpr
+
+
 def projected_points(kps, desc, m, w, h, n_levels, scale_factors, seed=0, bf=47.9, th=7.0, stereo=True):
     """Points of a 'last frame' projected into the current one (input of SearchByProjection(Frame&, const Frame&)):
     most are real keypoints jittered by a small motion, the rest uniform. Returns a dict in the orbx_projected layout."""

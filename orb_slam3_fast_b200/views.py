@@ -48,6 +48,18 @@ class KeyFrameView(C.Structure):
                 ("level_sigma2", C.c_void_p), ("n_levels", C.c_int32)]
 
 
+class FisheyeView(C.Structure):
+    _fields_ = [("n_left", C.c_int32), ("n_right", C.c_int32), ("kps_left", C.c_void_p), ("kps_right", C.c_void_p),
+                ("desc", C.c_void_p), ("occupied", C.c_void_p), ("grid_left", Grid), ("grid_right", Grid),
+                ("left_to_right", C.c_void_p), ("right_to_left", C.c_void_p), ("scale_factors", C.c_void_p),
+                ("n_levels", C.c_int32)]
+
+
+class MapPointsRight(C.Structure):
+    _fields_ = [("track_in_view_r", C.c_void_p), ("proj_x_r", C.c_void_p), ("proj_y_r", C.c_void_p),
+                ("level_r", C.c_void_p), ("view_cos_r", C.c_void_p)]
+
+
 class Frustum(C.Structure):
     """orbx_frustum (include/orbx_types.h): what Frame::isInFrustum reads from the Frame; 104 bytes."""
     _fields_ = [("Rcw", C.c_float * 9), ("tcw", C.c_float * 3), ("Ow", C.c_float * 3), ("fx", C.c_float),
@@ -202,3 +214,25 @@ def make_track_params(width, height, th=1.0, nnratio=0.8, viewing_cos_limit=0.5,
     inv_h = np.float32(GRID_ROWS) / (np.float32(max_y) - np.float32(min_y))
     return TrackParams(viewing_cos_limit, th, nnratio, int(far_points), th_far, min_x, min_y, float(inv_w), float(inv_h),
                        cand_per_frame)
+
+
+def make_fisheye_view(kps_left, kps_right, desc, occupied, min_x, min_y, inv_w, inv_h, left_to_right, right_to_left,
+                      scale_factors):
+    """orbx_fisheye_view of a two-camera Frame (Nleft != -1); both grids are built here (Frame::AssignFeaturesToGrid)."""
+    kl, kr = _c(kps_left, KP_DTYPE), _c(kps_right, KP_DTYPE)
+    desc, occupied = _c(desc, np.uint8), _c(occupied, np.uint8)
+    l2r, r2l = _c(left_to_right, np.int32), _c(right_to_left, np.int32)
+    sf = _c(scale_factors, np.float32)
+    ol, il = assign_features_to_grid(kl, min_x, min_y, inv_w, inv_h)
+    o_r, ir = assign_features_to_grid(kr, min_x, min_y, inv_w, inv_h)
+    ol, il, o_r, ir = _c(ol, np.int32), _c(il, np.int32), _c(o_r, np.int32), _c(ir, np.int32)
+    gl = Grid(_p(ol), _p(il), float(min_x), float(min_y), float(inv_w), float(inv_h))
+    gr = Grid(_p(o_r), _p(ir), float(min_x), float(min_y), float(inv_w), float(inv_h))
+    v = FisheyeView(len(kl), len(kr), _p(kl), _p(kr), _p(desc), _p(occupied), gl, gr, _p(l2r), _p(r2l), _p(sf), len(sf))
+    return Holder(v, (kl, kr, desc, occupied, ol, il, o_r, ir, l2r, r2l, sf))
+
+
+def make_mappoints_right(track_in_view_r, proj_x_r, proj_y_r, level_r, view_cos_r):
+    arrs = (_c(track_in_view_r, np.uint8), _c(proj_x_r, np.float32), _c(proj_y_r, np.float32), _c(level_r, np.int32),
+            _c(view_cos_r, np.float32))
+    return Holder(MapPointsRight(*[_p(a) for a in arrs]), arrs)

@@ -2,7 +2,7 @@
 //   ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)            src/ORBmatcher.cc:230-404
 //   ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)         :766-884
 //   ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight)         :1108-1275
-//   Frame::AssignFeaturesToGrid()                                             src/Frame.cc:520-547
+//   Frame::AssignFeaturesToGrid() (both rigs)                                 src/Frame.cc:520-547
 //   MapPoint::ComputeDistinctiveDescriptors() for a batch of points           src/MapPoint.cc:372-441
 //
 // COMPILES ONLY INSIDE THE REFERENCE TREE (needs the reference headers and their OpenCV / Eigen / Sophus / DBoW2
@@ -155,16 +155,25 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
   return nFused;
 }
 
-// Frame::AssignFeaturesToGrid() (src/Frame.cc:520-547), Nleft == -1
+// Frame::AssignFeaturesToGrid() (src/Frame.cc:520-547): mGrid from mvKeysUn (Nleft == -1), or — two-camera rigs — mGrid
+// from mvKeys and mGridRight from mvKeysRight with indices local to the right camera (:534-546)
 void AssignFeaturesToGrid_orbx(Frame& F) {
-  std::vector<int32_t> off(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1), items(F.N);
-  if (orbm_assign_features_to_grid(OrbxThreadMatcher(), reinterpret_cast<const orbx_kp*>(F.mvKeysUn.data()), F.N, Frame::mnMinX,
-                                   Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv,
-                                   off.data(), items.data()) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
-  for (int c = 0; c < FRAME_GRID_COLS; c++)
-    for (int r = 0; r < FRAME_GRID_ROWS; r++)
-      F.mGrid[c][r].assign(items.begin() + off[c * FRAME_GRID_ROWS + r], items.begin() + off[c * FRAME_GRID_ROWS + r + 1]);
+  auto build = [](const std::vector<cv::KeyPoint>& keys, int n, std::vector<std::size_t> (&grid)[FRAME_GRID_COLS][FRAME_GRID_ROWS]) {
+    std::vector<int32_t> off(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1), items(n > 0 ? n : 1);
+    if (orbm_assign_features_to_grid(OrbxThreadMatcher(), reinterpret_cast<const orbx_kp*>(keys.data()), n, Frame::mnMinX,
+                                     Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv,
+                                     off.data(), items.data()) != ORBX_OK)
+      throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+    for (int c = 0; c < FRAME_GRID_COLS; c++)
+      for (int r = 0; r < FRAME_GRID_ROWS; r++)
+        grid[c][r].assign(items.begin() + off[c * FRAME_GRID_ROWS + r], items.begin() + off[c * FRAME_GRID_ROWS + r + 1]);
+  };
+  if (F.Nleft == -1) {
+    build(F.mvKeysUn, F.N, F.mGrid);
+  } else {
+    build(F.mvKeys, F.Nleft, F.mGrid);
+    build(F.mvKeysRight, F.N - F.Nleft, F.mGridRight);
+  }
 }
 
 // MapPoint::ComputeDistinctiveDescriptors() (src/MapPoint.cc:372-441) for every point LocalMapping touched in one go:

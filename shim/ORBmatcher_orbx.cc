@@ -5,7 +5,8 @@
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   src/ORBmatcher.cc:42-221
 //   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)                                 :1594-1806
 //   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse)   :886-1106
-// with the ones below (pinhole rigs, Nleft == -1; keep the reference's code for the KannalaBrandt8 branches).
+// with the ones below. The local-map SearchByProjection covers both rigs (Nleft == -1 and the two-camera form with its
+// right-camera twin :148-217); the other two are the pinhole branches (keep the reference's code for KannalaBrandt8).
 // The shim's only job is flattening the pointer graph into the SoA / CSR views of include/orbx_types.h and scattering
 // the answers back; every float that decides a match is computed by the reference's own expressions on the host
 // (projection, radius) or by the device with the same non-fused FP32 operations.
@@ -49,8 +50,73 @@ struct FrameFlat {
 };
 }  // namespace
 
+namespace {
+// the two-camera form (F.Nleft != -1, KannalaBrandt8 rigs): both searches per point and the stereo partners,
+// src/ORBmatcher.cc:42-221 incl. :148-217 -> orbm_search_by_projection_map_fisheye
+int SearchByProjectionTwoCameras(Frame& F, const std::vector<MapPoint*>& vpMapPoints, float th, float nnratio,
+                                 bool bFarPoints, float thFarPoints) {
+  const int M = (int)vpMapPoints.size(), NL = F.Nleft, NR = F.N - F.Nleft;
+  std::vector<uint8_t> inL(M), inR(M), has_obs(M), desc((size_t)M * 32);
+  std::vector<float> px(M), py(M), pxr(M), pyr(M), vcos(M), vcosr(M), depth(M), unused(M, 0.f);
+  std::vector<int32_t> level(M), levelr(M);
+  for (int i = 0; i < M; i++) {  // MapPoint tracking scratch of both cameras, include/MapPoint.h:172-180
+    MapPoint* p = vpMapPoints[i];
+    const bool good = !p->isBad();
+    inL[i] = p->mbTrackInView && good;
+    inR[i] = p->mbTrackInViewR && good;
+    px[i] = p->mTrackProjX; py[i] = p->mTrackProjY; pxr[i] = p->mTrackProjXR; pyr[i] = p->mTrackProjYR;
+    level[i] = p->mnTrackScaleLevel; levelr[i] = p->mnTrackScaleLevelR;
+    vcos[i] = p->mTrackViewCos; vcosr[i] = p->mTrackViewCosR; depth[i] = p->mTrackDepth;
+    has_obs[i] = p->Observations() > 0;
+    if (inL[i] || inR[i]) memcpy(&desc[(size_t)i * 32], p->GetDescriptor().data, 32);
+  }
+  auto csr = [](const std::vector<std::size_t> (&grid)[FRAME_GRID_COLS][FRAME_GRID_ROWS], std::vector<int32_t>& off,
+                std::vector<int32_t>& items) {
+    off.assign(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0);
+    for (int c = 0; c < FRAME_GRID_COLS; c++)
+      for (int r = 0; r < FRAME_GRID_ROWS; r++) {
+        off[c * FRAME_GRID_ROWS + r + 1] = off[c * FRAME_GRID_ROWS + r] + (int32_t)grid[c][r].size();
+        for (std::size_t k : grid[c][r]) items.push_back((int32_t)k);
+      }
+  };
+  std::vector<int32_t> offL, itemsL, offR, itemsR;
+  csr(F.mGrid, offL, itemsL);
+  csr(F.mGridRight, offR, itemsR);
+  std::vector<uint8_t> occupied(F.N);
+  for (int i = 0; i < F.N; i++) occupied[i] = F.mvpMapPoints[i] && F.mvpMapPoints[i]->Observations() > 0;  // :92-93, :183-185
+  static_assert(sizeof(int) == sizeof(int32_t), "mvLeftToRightMatch crosses the ABI as int32");
+  orbx_fisheye_view fv;
+  fv.n_left = NL;
+  fv.n_right = NR;
+  fv.kps_left = reinterpret_cast<const orbx_kp*>(F.mvKeys.data());
+  fv.kps_right = reinterpret_cast<const orbx_kp*>(F.mvKeysRight.data());
+  fv.desc = F.mDescriptors.data;
+  fv.occupied = occupied.data();
+  fv.grid_left = orbx_grid{offL.data(), itemsL.data(), Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv,
+                           Frame::mfGridElementHeightInv};
+  fv.grid_right = orbx_grid{offR.data(), itemsR.data(), Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv,
+                            Frame::mfGridElementHeightInv};
+  fv.left_to_right = F.mvLeftToRightMatch.data();
+  fv.right_to_left = F.mvRightToLeftMatch.data();
+  fv.scale_factors = F.mvScaleFactors.data();
+  fv.n_levels = (int32_t)F.mvScaleFactors.size();
+  orbx_mappoints mp{M, inL.data(), px.data(), py.data(), unused.data(), level.data(), vcos.data(), depth.data(),
+                    has_obs.data(), desc.data()};
+  orbx_mappoints_right mr{inR.data(), pxr.data(), pyr.data(), levelr.data(), vcosr.data()};
+  std::vector<int32_t> assign(F.N, -1);
+  int32_t nmatches = 0;
+  if (orbm_search_by_projection_map_fisheye(OrbxThreadMatcher(), &fv, &mp, &mr, th, nnratio, bFarPoints, thFarPoints,
+                                            assign.data(), &nmatches) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  for (int i = 0; i < F.N; i++)
+    if (assign[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[assign[i]];  // :130-137, :203-211
+  return nmatches;
+}
+}  // namespace
+
 int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th,
                                    const bool bFarPoints, const float thFarPoints) {
+  if (F.Nleft != -1) return SearchByProjectionTwoCameras(F, vpMapPoints, th, mfNNratio, bFarPoints, thFarPoints);
   const int M = (int)vpMapPoints.size();
   std::vector<uint8_t> in_view(M), has_obs(M), desc((size_t)M * 32);
   std::vector<float> px(M), py(M), pxr(M), vcos(M), depth(M);

@@ -29,6 +29,13 @@ int orbm_search_by_projection_map(orbm_matcher*, const orbx_frame_view* f, const
   if (nmatches) *nmatches = n;
   return ORBX_OK;
 }
+int orbm_search_by_projection_map_fisheye(orbm_matcher*, const orbx_fisheye_view* f, const orbx_mappoints* mps,
+                                          const orbx_mappoints_right* mr, float th, float nnratio, int far_points,
+                                          float th_far, int32_t* assign, int32_t* nmatches) {
+  const int n = orbref_search_by_projection_map_fisheye(f, mps, mr, th, nnratio, far_points, th_far, assign);
+  if (nmatches) *nmatches = n;
+  return ORBX_OK;
+}
 int orbm_search_by_projection_frame(orbm_matcher*, const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                     int check_orientation, int32_t* assign, int32_t* nmatches) {
   const int n = orbref_search_by_projection_frame(f, pts, max_dist, check_orientation, assign);

@@ -393,3 +393,32 @@ def test_bow_transform(matcher, k, depth, levelsup, seed):
     assert abs(sum(bow.values()) - 1.0) < 1e-9 and sum(len(x) for x in fv.values()) == int((wt > 0).sum())
     if depth - levelsup <= 0:
         assert (nd == 0).all()
+
+
+@pytest.mark.parametrize("seed,th,far,sizes", [(0, 1.0, True, (700, 650, 3000)), (1, 3.0, False, (700, 650, 3000)),
+                                               (2, 6.0, True, (1200, 1100, 10000)), (3, 1.0, False, (40, 0, 200))])
+def test_search_by_projection_map_fisheye(matcher, seed, th, far, sizes):
+    """The two-camera form (Nleft != -1) of SearchByProjection(Frame&, vector<MapPoint*>), src/ORBmatcher.cc:42-221 with the
+    right-camera twin :148-217: left and right searches per point in serial order, stereo partners written
+    unconditionally, slots re-opening when a point without observations replaces one with. Every slot of mvpMapPoints
+    and the match count must equal the oracle's (which equals the reference's own method, CPU tests)."""
+    nl, nr, m = sizes
+    fr, mp, mpr = synth.fisheye_case(nl, nr, m, seed=seed) if nr else _left_only_case(nl, m, seed)
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    inv_w, inv_h = np.float32(64) / np.float32(640), np.float32(48) / np.float32(480)
+    args = (fr["kps_left"], fr["kps_right"], fr["desc"], fr["occupied"], 0.0, 0.0, inv_w, inv_h, fr["left_to_right"],
+            fr["right_to_left"], sf)
+    n_o, a_o = orbref.search_by_projection_map_fisheye(orbref.make_fisheye_view(*args), orbref.make_mappoints(**mp),
+                                                       orbref.make_mappoints_right(**mpr), th, 0.8, far, 15.0)
+    n_g, a_g = matcher.SearchByProjectionFisheye(views.make_fisheye_view(*args), views.make_mappoints(**mp),
+                                                 views.make_mappoints_right(**mpr), th, far, 15.0)
+    assert m < 1000 or n_o > 300, "degenerate test"
+    assert n_g == n_o and np.array_equal(a_g, a_o), np.nonzero(a_g != a_o)[0][:10]
+
+
+def _left_only_case(nl, m, seed):
+    fr, mp, mpr = synth.fisheye_case(nl, max(nl, 1), m, seed=seed)
+    fr["kps_right"], fr["right_to_left"] = fr["kps_right"][:0], fr["right_to_left"][:0]
+    fr["desc"], fr["occupied"] = fr["desc"][:nl], fr["occupied"][:nl]
+    fr["left_to_right"] = np.full(nl, -1, np.int32)
+    return fr, mp, mpr

@@ -386,3 +386,21 @@ def test_is_in_frustum(seed, m, cos_limit):
     out = o["track_in_view"] == 0
     if out.any():
         assert (o["level"][out] == -9).all() and (o["depth"][out] == 8.5).all()
+
+
+@pytest.mark.parametrize("seed,th,far,sizes", [(0, 1.0, True, (700, 650, 3000)), (1, 3.0, False, (700, 650, 3000)),
+                                               (2, 6.0, True, (1200, 1100, 10000)), (4, 15.0, False, (300, 280, 2000))])
+def test_search_by_projection_map_fisheye(seed, th, far, sizes):
+    """SearchByProjection(Frame&, vector<MapPoint*>) with Nleft != -1 (:42-221 incl. the right-camera twin :148-217): the
+    reference's own method on a two-camera stand-in Frame (grids from its own AssignFeaturesToGrid) against the oracle's
+    restatement — every slot of mvpMapPoints and the returned count, with stereo partners, overwrites and slots that
+    re-open when a point without observations replaces one with."""
+    fr, mp, mpr = synth.fisheye_case(*sizes, seed=seed)
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    fv = orbref.make_fisheye_view(fr["kps_left"], fr["kps_right"], fr["desc"], fr["occupied"], 0.0, 0.0, f32(64) / f32(640),
+                                  f32(48) / f32(480), fr["left_to_right"], fr["right_to_left"], sf)
+    mps, mr = orbref.make_mappoints(**mp), orbref.make_mappoints_right(**mpr)
+    n_o, a_o = orbref.search_by_projection_map_fisheye(fv, mps, mr, th, 0.8, far, 15.0)
+    n_r, a_r = refsrc.search_by_projection_map_fisheye(fv, mps, mr, th, 0.8, far, 15.0)
+    assert n_o > 300 and n_o > (a_o >= 0).sum(), "the case must contain partner writes"
+    assert n_r == n_o and np.array_equal(a_r, a_o)

@@ -24,7 +24,7 @@ def shim_world(monkeypatch):
                  "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
                  "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
                  "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
-                 "orbrefsrc_distinctive_descriptor"):
+                 "orbrefsrc_distinctive_descriptor", "orbrefsrc_search_by_projection_map_fisheye"):
         getattr(lib, name).restype = C.c_int
     refsrc.mlib()
     monkeypatch.setattr(refsrc, "_mlib", lib)
@@ -102,3 +102,9 @@ def test_shim_search_by_projection_keyframe(shim_world, args):
 
 def test_shim_compute_distinctive_descriptors(shim_world):
     T.test_compute_distinctive_descriptors()
+
+
+@pytest.mark.parametrize("args", [(0, 1.0, True, (700, 650, 3000)), (2, 6.0, True, (1200, 1100, 10000))])
+def test_shim_search_by_projection_two_cameras(shim_world, args):
+    """the fisheye (Nleft != -1) path of the drop-in SearchByProjection(Frame&, vector<MapPoint*>)"""
+    T.test_search_by_projection_map_fisheye(*args)
