@@ -236,6 +236,15 @@ int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv
 int orbm_search_by_bow(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
                        int check_orientation, int32_t* matches_f, int32_t* nmatches);
 
+/* The same function on a two-camera Frame (F.Nleft != -1, src/ORBmatcher.cc:274-365): rows [0, n_left_frame) of `frame`
+ * are the left camera's, the rest the right camera's; per KeyFrame feature the best two distances are kept apart for the
+ * two cameras, the left best is accepted by the ratio test and — inside "bestDist1 <= TH_LOW" (:319) — the right best
+ * whenever it is <= TH_LOW (its ratio test is switched off by "|| true", :347-350). kps of both views: left rows then
+ * right rows (mvKeys / mvKeysRight, :323-335; mvKeysUn for a one-camera KeyFrame). Outputs as orbm_search_by_bow. */
+int orbm_search_by_bow_fisheye(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame,
+                               int n_left_frame, float nnratio, int check_orientation, int32_t* matches_f,
+                               int32_t* nmatches);
+
 /* int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (include/ORBmatcher.h:67,
  * src/ORBmatcher.cc:766-884), NLeft == -1. has_mappoint[i] = vpMapPoints[i] != NULL && !isBad() on both sides;
  * matches12[kf1->n] (host) = index of the KeyFrame-2 feature whose MapPoint goes to vpMatches12[i], or -1. */

@@ -1345,6 +1345,84 @@ int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view*
   return nmatches;
 }
 
+// The same function on a two-camera Frame (F.Nleft != -1, src/ORBmatcher.cc:274-317, 319-365): per KeyFrame feature the
+// best two distances are kept separately over the frame's LEFT rows (realIdxF < Nleft) and RIGHT rows; the left best is
+// accepted by the ratio test, and — nested inside "bestDist1 <= TH_LOW" (:319) — the right best whenever
+// bestDist1R <= TH_LOW (its ratio test is disabled by "|| true", :347-350). kps of both views = left rows then right rows
+// (the keypoint selection of :323-335 / :352-362 flattened by the caller).
+int orbref_search_by_bow_fisheye(const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, int n_left_f,
+                                 float nnratio, int check_orientation, int32_t* matches_f) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  std::vector<int> rotHist[kHisto];
+  for (int i = 0; i < frame->n; i++) matches_f[i] = -1;
+  const orbx_featvec& vK = kf->featvec;
+  const orbx_featvec& vF = frame->featvec;
+  int a = 0, b = 0;
+  while (a < vK.n_nodes && b < vF.n_nodes) {
+    if (vK.node_ids[a] == vF.node_ids[b]) {
+      for (int pK = vK.offsets[a]; pK < vK.offsets[a + 1]; pK++) {
+        const int realIdxKF = (int)vK.indices[pK];
+        if (!kf->has_mappoint[realIdxKF]) continue;
+        const uint8_t* dKF = kf->desc + (size_t)realIdxKF * 32;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        int bestDist1R = 256, bestIdxFR = -1, bestDist2R = 256;
+        for (int pF = vF.offsets[b]; pF < vF.offsets[b + 1]; pF++) {
+          const int realIdxF = (int)vF.indices[pF];
+          if (matches_f[realIdxF] >= 0) continue;
+          const int dist = orbref_descriptor_distance(dKF, frame->desc + (size_t)realIdxF * 32);
+          if (realIdxF < n_left_f && dist < bestDist1) {
+            bestDist2 = bestDist1;
+            bestDist1 = dist;
+            bestIdxF = realIdxF;
+          } else if (realIdxF < n_left_f && dist < bestDist2) {
+            bestDist2 = dist;
+          }
+          if (realIdxF >= n_left_f && dist < bestDist1R) {
+            bestDist2R = bestDist1R;
+            bestDist1R = dist;
+            bestIdxFR = realIdxF;
+          } else if (realIdxF >= n_left_f && dist < bestDist2R) {
+            bestDist2R = dist;
+          }
+        }
+        if (bestDist1 <= TH_LOW) {
+          if ((float)bestDist1 < nnratio * (float)bestDist2) {
+            matches_f[bestIdxF] = realIdxKF;
+            if (check_orientation)
+              rotHist[rot_bin(kf->kps[realIdxKF].angle, frame->kps[bestIdxF].angle)].push_back(bestIdxF);
+            nmatches++;
+          }
+          if (bestDist1R <= TH_LOW) {
+            matches_f[bestIdxFR] = realIdxKF;
+            if (check_orientation)
+              rotHist[rot_bin(kf->kps[realIdxKF].angle, frame->kps[bestIdxFR].angle)].push_back(bestIdxFR);
+            nmatches++;
+          }
+        }
+      }
+      a++;
+      b++;
+    } else if (vK.node_ids[a] < vF.node_ids[b]) {
+      while (a < vK.n_nodes && vK.node_ids[a] < vF.node_ids[b]) a++;
+    } else {
+      while (b < vF.n_nodes && vF.node_ids[b] < vK.node_ids[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, kHisto, ind1, ind2, ind3);
+    for (int i = 0; i < kHisto; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idxF : rotHist[i]) {
+        matches_f[idxF] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
 // cv::remap(..., INTER_LINEAR), CV_8UC1 source, CV_32FC1 maps, BORDER_CONSTANT(0) (OpenCV imgproc/imgwarp.cpp:
 // remapBilinear with INTER_BITS = 5, INTER_REMAP_COEF_BITS = 15; the 32 x 32 weight table is exact: w = a * b * 32)
 void orbref_remap_linear(const uint8_t* src, int sw, int sh, int sstride, const float* mapx, const float* mapy, int dw,

@@ -176,6 +176,9 @@ int orbref_search_by_bow_kf(const orbx_keyframe_view* kf1, const orbx_keyframe_v
  * vpMapPointMatches[i], or -1. Returns nmatches. */
 int orbref_search_by_bow(const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
                          int check_orientation, int32_t* matches_f);
+/* ... on a two-camera Frame (Nleft != -1): left / right bests kept apart, :274-365. */
+int orbref_search_by_bow_fisheye(const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, int n_left_f,
+                                 float nnratio, int check_orientation, int32_t* matches_f);
 /* ORBmatcher::SearchForTriangulation, pinhole mono/stereo keyframes (src/ORBmatcher.cc:886-1106 +
  * src/CameraModels/Pinhole.cpp:122-149). F12 = K1^-T [t12]x R12 K2^-1 computed by the caller (row-major 3x3);
  * ep = projection of camera centre 1 into image 2. matches12[kf1->n] = idx2 or -1. Returns nmatches. */

@@ -273,6 +273,7 @@ def lib():
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_search_by_bow_fisheye.argtypes = [vp, vp, ci, cf, ci, vp]
         L.orbref_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp]
         L.orbref_bow_transform.restype = None
         L.orbref_search_for_initialization.argtypes = [vp, vp, vp, ci, cf, ci, vp]
@@ -479,6 +480,15 @@ def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False,
 def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):
     m = np.empty(max(frame.struct.n, 1), np.int32)
     n = lib().orbref_search_by_bow(kf.ref(), frame.ref(), float(nnratio), int(check_orientation), _ptr(m))
+    return n, m[:frame.struct.n]
+
+
+def search_by_bow_fisheye(kf, frame, n_left_f, nnratio=0.7, check_orientation=True):
+    """SearchByBoW(KeyFrame*, Frame&, ...) on a two-camera Frame: rows [0, n_left_f) of the frame view are the left
+    camera's, the rest the right camera's (src/ORBmatcher.cc:274-365)."""
+    m = np.empty(max(frame.struct.n, 1), np.int32)
+    n = lib().orbref_search_by_bow_fisheye(kf.ref(), frame.ref(), int(n_left_f), float(nnratio), int(check_orientation),
+                                           _ptr(m))
     return n, m[:frame.struct.n]
 
 

@@ -146,6 +146,32 @@ int orbrefsrc_search_by_bow(const orbx_keyframe_view* kfv, const orbx_keyframe_v
   return n;
 }
 
+// ... on a two-camera rig: rows >= NLeft of a view are the right camera's keypoints (mvKeysRight), both mpCamera2 set —
+// the fisheye branches of :274-365 run
+int orbrefsrc_search_by_bow_fisheye(const orbx_keyframe_view* kfv, int n_left_kf, const orbx_keyframe_view* frame,
+                                    int n_left_f, float nnratio, int check_orientation, int32_t* matches_f) {
+  KeyFrameWorld K(kfv);
+  GeometricCamera cam2;
+  auto split = [&](FeatureHolder& h, const orbx_keyframe_view* v, int nl) {
+    h.Nleft = h.NLeft = nl;
+    h.mvKeys = keypoints(v->kps, nl);
+    h.mvKeysRight = keypoints(v->kps + nl, v->n - nl);
+    h.mvKeysUn.clear();  // must not be read in this mode
+    h.mpCamera2 = &cam2;
+  };
+  split(K.kf, kfv, n_left_kf);
+  Frame F;
+  fill_common(F, frame->kps, frame->desc, frame->u_right, frame->n, frame->scale_factors, nullptr, frame->n_levels);
+  fill_featvec(F.mFeatVec, frame->featvec);
+  F.mpCamera = &cam2;
+  split(F, frame, n_left_f);
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> out;
+  const int n = matcher.SearchByBoW(&K.kf, F, out);
+  for (int i = 0; i < frame->n; i++) matches_f[i] = K.index_of(out[i]);
+  return n;
+}
+
 int orbrefsrc_search_by_bow_kf(const orbx_keyframe_view* v1, const orbx_keyframe_view* v2, float nnratio,
                                int check_orientation, int32_t* matches12) {
   KeyFrameWorld A(v1), B(v2);

@@ -104,6 +104,7 @@ def mlib():
         _mlib = C.CDLL(_MPATH)
         for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
+                     "orbrefsrc_search_by_bow_fisheye",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
                      "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
@@ -154,6 +155,15 @@ def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False,
 def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):
     m = np.empty(max(frame.struct.n, 1), np.int32)
     n = mlib().orbrefsrc_search_by_bow(kf.ref(), frame.ref(), C.c_float(nnratio), int(check_orientation), _p(m))
+    return n, m[:frame.struct.n]
+
+
+def search_by_bow_fisheye(kf, n_left_kf, frame, n_left_f, nnratio=0.7, check_orientation=True):
+    """The reference's own SearchByBoW(KeyFrame*, Frame&, ...) with pKF->NLeft = n_left_kf, F.Nleft = n_left_f and both
+    second cameras set (the keypoints of rows >= NLeft live in mvKeysRight)."""
+    m = np.empty(max(frame.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_bow_fisheye(kf.ref(), int(n_left_kf), frame.ref(), int(n_left_f), C.c_float(nnratio),
+                                               int(check_orientation), _p(m))
     return n, m[:frame.struct.n]
 
 

@@ -239,6 +239,7 @@ static bool make_blur_maps(const Plan& P, const FrameSet& fs, int frames, BlurMa
 }
 
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st) {
+  if (launch_blur_tc(P, fs, frames, st)) return;  // the tensor-core form (k_blur_tc.cu); below: the CUDA-core fallbacks
   int tasks = 0;
   for (int l = 0; l < P.nlevels; l++) tasks += ((P.lv[l].w + 127) / 128) * ((P.lv[l].h + kBlurRows - 1) / kBlurRows);
   dim3 grid((tasks + kBlurWarps - 1) / kBlurWarps, frames);

@@ -84,6 +84,11 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, int (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -116,7 +121,11 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
   uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = bars + 3, *acc_full = bars + 5, *acc_empty = bars + 7;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index and TMEM base are broadcast with shfl so that ptxas can prove them warp-uniform: the issue paths below
+  // run on the whole warp, only the asynchronous instructions sit under elect.sync. (Under `if (lane == 0)` every
+  // UTCIMMA / UTMALDG was wrapped in a uniformisation loop — R2UR.BROADCAST + BRA.U.ANY, ~13 instructions per MMA.)
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int q0 = blockIdx.x * kM;
   const int total_tiles = (nt + kN - 1) / kN;
   const int tb = blockIdx.y * tiles_per_split;
@@ -139,42 +148,48 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       bar_expect(a_full, kABytes);
       tma_rows(&map_q, sA, a_full, 0, q0);
       tma_rows(&map_q, sA + kM * kHalf, a_full, kHalf, q0);
-      for (int i = 0; i < ntile; i++) {
-        const int s = i & 1;
-        bar_wait(b_empty + s, ((i >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < ntile; i++) {
+      const int s = i & 1;
+      bar_wait(b_empty + s, ((i >> 1) & 1) ^ 1);
+      if (elect_one()) {
         bar_expect(b_full + s, kBBytes);
         tma_rows(&map_t, sB + s * kBBytes, b_full + s, 0, (tb + i) * kN);
         tma_rows(&map_t, sB + s * kBBytes + kN * kHalf, b_full + s, kHalf, (tb + i) * kN);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      bar_wait(a_full, 0);
-      for (int i = 0; i < ntile; i++) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        bar_wait(b_full + s, ph);
-        bar_wait(acc_empty + s, ph ^ 1);
-        tc_fence_after();
+    uint64_t da[8], db[2][8];
 #pragma unroll
-        for (int kk = 0; kk < 8; kk++) {  // 8 x (K = 32 bytes); 4 steps inside each 128-byte swizzle span
-          const uint64_t da = smem_desc(sA + (kk >> 2) * (kM * kHalf) + (kk & 3) * 32);
-          const uint64_t db = smem_desc(sB + s * kBBytes + (kk >> 2) * (kN * kHalf) + (kk & 3) * 32);
-          mma_i8(tmem + s * kN, da, db, kk > 0);
-        }
+    for (int kk = 0; kk < 8; kk++) {  // 8 x (K = 32 bytes); 4 steps inside each 128-byte swizzle span
+      da[kk] = smem_desc(sA + (kk >> 2) * (kM * kHalf) + (kk & 3) * 32);
+      db[0][kk] = smem_desc(sB + (kk >> 2) * (kN * kHalf) + (kk & 3) * 32);
+      db[1][kk] = smem_desc(sB + kBBytes + (kk >> 2) * (kN * kHalf) + (kk & 3) * 32);
+    }
+    bar_wait(a_full, 0);
+    for (int i = 0; i < ntile; i++) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      bar_wait(b_full + s, ph);
+      bar_wait(acc_empty + s, ph ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) mma_i8(tmem + s * kN, da[kk], s ? db[1][kk] : db[0][kk], kk > 0);
         mma_commit(b_empty + s);   // the stage may be refilled once these MMAs have read it
         mma_commit(acc_full + s);  // ... and the accumulator is complete
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int row = q0 + quad * 32 + lane;

@@ -59,7 +59,9 @@ size_t quadtree_smem_bytes(const Plan& P) { return qt_layout(P).total; }
 __global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P, const WorkSet ws, const QtSmem S,
                                                  int lap0, int lap1) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int l = blockIdx.x, f = blockIdx.y, lane = threadIdx.x;
+  // blockIdx.y = level: blocks are handed out level 0 first, so the long trees (level 0: ~100 us, level 7: ~8 us) start
+  // first and the tail of the launch is made of short ones (longest-processing-time-first)
+  const int l = blockIdx.y, f = blockIdx.x, lane = threadIdx.x;
   const LevelPlan& L = P.lv[l];
   const uint32_t* slots = ws.slots + (int64_t)f * P.slots_per_frame + L.slot_base;
   const int32_t* counts = ws.cell_count + (int64_t)f * P.cells_per_frame + L.cell_base;
@@ -190,7 +192,7 @@ void launch_quadtree(const Plan& P, const WorkSet& ws, int lap0, int lap1, int f
   const QtSmem S = qt_layout(P);
   cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(S.total > 48 * 1024 ? S.total : 48 * 1024));
-  dim3 grid(P.nlevels, frames);
+  dim3 grid(frames, P.nlevels);
   k_quadtree<<<grid, 32, S.total, st>>>(P, ws, S, lap0, lap1);
 }
 

@@ -700,14 +700,30 @@ __global__ void __launch_bounds__(kSearchWarps * 32) k_bow_match(const BowArgs A
     if (!K.has_mappoint[idxK]) continue;                                   // :262-264 / :802-804
     uint32_t dK[8];
     load_desc8(K.desc + (size_t)idxK * 32, dK);
-    Top2 t{0, -1, 0, -1};
+    Top2 t{0, -1, 0, -1}, tr{0, -1, 0, -1};  // tr: the right camera's rows of a two-camera Frame (:300-311)
     for (int c = lane; c < nf; c += 32) {
       const int idxF = (int)F.indices[f0 + c];
       // taken earlier — only ever by this warp: :280 / :821
       if (A.kf_kf ? (A.matched2[idxF] || !F.has_mappoint[idxF]) : (A.matches_f[idxF] >= 0)) continue;
-      top2_insert(t, hamming8(dK, F.desc + (size_t)idxF * 32), c);         // (distance, position) = the strict < scan
+      const int dist = hamming8(dK, F.desc + (size_t)idxF * 32);
+      if (A.n_left_f >= 0 && idxF >= A.n_left_f) top2_insert(tr, dist, c);
+      else top2_insert(t, dist, c);                                        // (distance, position) = the strict < scan
     }
     t = top2_warp(t);
+    if (A.n_left_f >= 0) {
+      // two-camera Frame: the left best passes the ratio test; the right best is taken whenever it is <= TH_LOW, but
+      // only inside the left one's "bestDist1 <= TH_LOW" (:319, :346-350 with its "|| true")
+      tr = top2_warp(tr);
+      if (t.p1 < 0 || t.d1 > ORBM_TH_LOW_I) continue;
+      const bool left_ok = (float)t.d1 < fmul(A.nnratio, (float)(t.p2 >= 0 ? t.d2 : 256));
+      const bool right_ok = tr.p1 >= 0 && tr.d1 <= ORBM_TH_LOW_I;
+      if (lane == 0) {
+        if (left_ok) A.matches_f[(int)F.indices[f0 + t.p1]] = idxK;
+        if (right_ok) A.matches_f[(int)F.indices[f0 + tr.p1]] = idxK;
+      }
+      if (left_ok || right_ok) __syncwarp();
+      continue;
+    }
     if (t.p1 < 0) continue;
     const int best1 = t.d1, best2 = t.p2 >= 0 ? t.d2 : 256;
     const bool low = A.kf_kf ? best1 < ORBM_TH_LOW_I : best1 <= ORBM_TH_LOW_I;  // :838 is strict, :319 is not

@@ -1183,7 +1183,7 @@ bool featvec_is_disjoint(const orbx_keyframe_view* k) {
 }
 
 int search_by_bow_common(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* second, float nnratio,
-                         int check_orientation, int kf_kf, int32_t* matches, int32_t* nmatches) {
+                         int check_orientation, int kf_kf, int32_t* matches, int32_t* nmatches, int n_left_f = -1) {
   const int n_out = kf_kf ? kf->n : second->n;
   if (!m || !kf || !second || kf->n < 0 || second->n < 0 || (n_out > 0 && !matches))
     return mfail(m, ORBX_E_ARG, "bad argument");
@@ -1197,6 +1197,7 @@ int search_by_bow_common(orbm_matcher* m, const orbx_keyframe_view* kf, const or
   A.nnratio = nnratio;
   A.check_orientation = check_orientation;
   A.kf_kf = kf_kf;
+  A.n_left_f = n_left_f;
   A.matches_f = ar.alloc<int32_t>(n_out);
   A.matched2 = ar.alloc<uint8_t>(second->n);
   A.nmatches = ar.alloc<int32_t>(1);
@@ -1217,6 +1218,13 @@ int search_by_bow_common(orbm_matcher* m, const orbx_keyframe_view* kf, const or
 int orbm_search_by_bow(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
                        int check_orientation, int32_t* matches_f, int32_t* nmatches) {
   return search_by_bow_common(m, kf, frame, nnratio, check_orientation, 0, matches_f, nmatches);
+}
+
+int orbm_search_by_bow_fisheye(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame,
+                               int n_left_frame, float nnratio, int check_orientation, int32_t* matches_f,
+                               int32_t* nmatches) {
+  if (!frame || n_left_frame < 0 || n_left_frame > frame->n) return mfail(m, ORBX_E_ARG, "bad argument");
+  return search_by_bow_common(m, kf, frame, nnratio, check_orientation, 0, matches_f, nmatches, n_left_frame);
 }
 
 int orbm_search_by_bow_kf(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,

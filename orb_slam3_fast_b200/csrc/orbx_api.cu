@@ -159,18 +159,26 @@ int run_pipeline(orbx_extractor* ex, int ln, FrameSet fs, int frames, int lap0, 
     ex->last_lane = ln;
     return ORBX_OK;
   }
+  static const bool blur_late = getenv("ORBX_BLUR_LATE") != nullptr;  // A/B experiment: blur after the quadtree
   begin(0, st);
   launch_pyramid(P, fs, ex->d_tab, frames, st);
   end(0, st);
-  begin(3, st);
-  launch_blur(P, fs, frames, st);
-  end(3, st);
+  if (!blur_late) {
+    begin(3, st);
+    launch_blur(P, fs, frames, st);
+    end(3, st);
+  }
   begin(1, st);
   launch_fast(P, fs, L.ws, ex->ini_th, ex->min_th, frames, st);
   end(1, st);
   begin(2, st);
   launch_quadtree(P, L.ws, lap0, lap1, frames, st);
   end(2, st);
+  if (blur_late) {
+    begin(3, st);
+    launch_blur(P, fs, frames, st);
+    end(3, st);
+  }
   begin(4, st);
   launch_describe(P, fs, L.ws, out, ex->d_pattern, frames, st);
   end(4, st);

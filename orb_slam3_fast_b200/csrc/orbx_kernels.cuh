@@ -67,6 +67,10 @@ void launch_fast(const Plan& P, const FrameSet& fs, const WorkSet& ws, int ini_t
                  cudaStream_t st);
 void launch_quadtree(const Plan& P, const WorkSet& ws, int lap0, int lap1, int frames, cudaStream_t st);
 void launch_blur(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st);
+// tensor-core form of the blur (k_blur_tc.cu); false = not applicable (launch_blur then takes k_blur7). ORBX_BLUR_TC=0
+// switches it off.
+bool launch_blur_tc(const Plan& P, const FrameSet& fs, int frames, cudaStream_t st);
+bool blur_tc_enabled();
 void launch_describe(const Plan& P, const FrameSet& fs, const WorkSet& ws, const OutSet& out, const int8_t* pattern,
                      int frames, cudaStream_t st);
 int launch_cvt_gray(const uint8_t* src, int w, int h, int sstride, int64_t sfstride, int channels, int rgb, uint8_t* dst,

@@ -223,6 +223,7 @@ struct BowArgs {
   DevKeyFrame kf, fr;
   float nnratio;
   int check_orientation;
+  int n_left_f;         // >= 0: fr is a two-camera Frame (rows < n_left_f = left camera): left / right bests, :274-365
   int kf_kf;            // 1: the KeyFrame-KeyFrame form (:766-884): matches indexed by kf, fr.has_mappoint read, < TH_LOW
   int32_t* matches_f;   // [fr.n] KeyFrame feature index or -1 (kf_kf: [kf.n] index into fr or -1)
   uint8_t* matched2;    // [fr.n] scratch (kf_kf): vbMatched2

@@ -41,6 +41,7 @@ def _bind(L):
     L.orbm_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     L.orbm_search_for_initialization.argtypes = [vp, vp, vp, vp, ci, cf, ci, vp, vp]
     L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
+    L.orbm_search_by_bow_fisheye.argtypes = [vp, vp, vp, ci, cf, ci, vp, vp]
     L.orbm_is_in_frustum.argtypes = [vp, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbm_track_local_map_batch_device.argtypes = [vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                     vp]
@@ -343,6 +344,15 @@ class ORBmatcher:
         nm = C.c_int32(0)
         self._check(self._L.orbm_search_by_bow(self._h, kf.ref(), frame.ref(), self.mfNNratio,
                                                int(self.mbCheckOrientation), _l.ptr(mf), C.byref(nm)))
+        return nm.value, mf[:n]
+
+    # the same on a two-camera Frame (F.Nleft = n_left_frame != -1): left / right bests kept apart, :274-365
+    def SearchByBoWTwoCameras(self, kf, frame, n_left_frame):
+        n = frame.struct.n
+        mf = np.empty(max(n, 1), np.int32)
+        nm = C.c_int32(0)
+        self._check(self._L.orbm_search_by_bow_fisheye(self._h, kf.ref(), frame.ref(), int(n_left_frame), self.mfNNratio,
+                                                       int(self.mbCheckOrientation), _l.ptr(mf), C.byref(nm)))
         return nm.value, mf[:n]
 
     # int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) — src/ORBmatcher.cc:766

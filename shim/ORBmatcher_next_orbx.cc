@@ -6,8 +6,8 @@
 //   MapPoint::ComputeDistinctiveDescriptors() for a batch of points           src/MapPoint.cc:372-441
 //
 // COMPILES ONLY INSIDE THE REFERENCE TREE (needs the reference headers and their OpenCV / Eigen / Sophus / DBoW2
-// dependencies); pinhole rigs (Nleft / NLeft == -1, bRight == false) — keep the reference's code for the fisheye
-// branches. As in ORBmatcher_orbx.cc the shim only flattens the pointer graph and scatters the answers back; every
+// dependencies). SearchByBoW(KeyFrame*, Frame&) and AssignFeaturesToGrid cover both rigs; the others are the pinhole
+// forms (NLeft == -1, bRight == false) — keep the reference's code for their fisheye branches. As in ORBmatcher_orbx.cc the shim only flattens the pointer graph and scatters the answers back; every
 // float that decides a match comes from the reference's own expressions on the host (projection) or from the device
 // with the same non-fused FP32 operations.
 #include "ORBmatcher.h"
@@ -49,11 +49,29 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpM
   const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
   BowFlat kf(pKF->N, pKF->mvKeysUn, pKF->mDescriptors, pKF->mFeatVec, pKF->mvScaleFactors, pKF->mvLevelSigma2);
   for (int i = 0; i < pKF->N; i++) kf.has_mp[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();  // :262-264
-  BowFlat fr(F.N, F.mvKeys, F.mDescriptors, F.mFeatVec, F.mvScaleFactors, F.mvLevelSigma2);          // angles: F.mvKeys
   std::vector<int32_t> mf(F.N, -1);
   int32_t nmatches = 0;
-  if (orbm_search_by_bow(OrbxThreadMatcher(), &kf.v, &fr.v, mfNNratio, mbCheckOrientation, mf.data(), &nmatches) != ORBX_OK)
-    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  if (F.Nleft == -1) {
+    BowFlat fr(F.N, F.mvKeys, F.mDescriptors, F.mFeatVec, F.mvScaleFactors, F.mvLevelSigma2);  // angles: F.mvKeys
+    if (orbm_search_by_bow(OrbxThreadMatcher(), &kf.v, &fr.v, mfNNratio, mbCheckOrientation, mf.data(), &nmatches) != ORBX_OK)
+      throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  } else {
+    // two-camera rig (:274-365): rows >= Nleft are the right camera's; the keypoint of a row is mvKeys[i] or
+    // mvKeysRight[i - Nleft] on both sides (:323-335, :352-362) — flattened here, left rows first
+    auto both = [](const std::vector<cv::KeyPoint>& l, const std::vector<cv::KeyPoint>& r, int nl) {
+      std::vector<cv::KeyPoint> k(l.begin(), l.begin() + nl);
+      k.insert(k.end(), r.begin(), r.end());
+      return k;
+    };
+    const std::vector<cv::KeyPoint> keysF = both(F.mvKeys, F.mvKeysRight, F.Nleft);
+    const std::vector<cv::KeyPoint> keysK =
+        pKF->mpCamera2 ? both(pKF->mvKeys, pKF->mvKeysRight, pKF->NLeft == -1 ? pKF->N : pKF->NLeft) : pKF->mvKeysUn;
+    kf.v.kps = reinterpret_cast<const orbx_kp*>(keysK.data());
+    BowFlat fr(F.N, keysF, F.mDescriptors, F.mFeatVec, F.mvScaleFactors, F.mvLevelSigma2);
+    if (orbm_search_by_bow_fisheye(OrbxThreadMatcher(), &kf.v, &fr.v, F.Nleft, mfNNratio, mbCheckOrientation, mf.data(),
+                                   &nmatches) != ORBX_OK)
+      throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  }
   vpMapPointMatches.assign(F.N, static_cast<MapPoint*>(NULL));  // :235
   for (int i = 0; i < F.N; i++)
     if (mf[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[mf[i]];

@@ -55,6 +55,13 @@ int orbm_search_by_bow(orbm_matcher*, const orbx_keyframe_view* kf, const orbx_k
   if (nmatches) *nmatches = n;
   return ORBX_OK;
 }
+int orbm_search_by_bow_fisheye(orbm_matcher*, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame,
+                               int n_left_frame, float nnratio, int check_orientation, int32_t* matches_f,
+                               int32_t* nmatches) {
+  const int n = orbref_search_by_bow_fisheye(kf, frame, n_left_frame, nnratio, check_orientation, matches_f);
+  if (nmatches) *nmatches = n;
+  return ORBX_OK;
+}
 int orbm_search_by_bow_kf(orbm_matcher*, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, float nnratio,
                           int check_orientation, int32_t* matches12, int32_t* nmatches) {
   const int n = orbref_search_by_bow_kf(kf1, kf2, nnratio, check_orientation, matches12);

@@ -310,6 +310,27 @@ def test_search_by_bow_keyframe_frame(gpu, nnratio, check, seed):
         assert n2 == n2_r and np.array_equal(m12, m12_r), np.nonzero(m12 != m12_r)[0][:10]
 
 
+@pytest.mark.parametrize("nnratio,check,seed", [(0.7, True, 1), (0.9, False, 2), (0.6, True, 3)])
+def test_search_by_bow_two_camera_frame(gpu, nnratio, check, seed):
+    """SearchByBoW(KeyFrame*, Frame&, ...) on a two-camera Frame (F.Nleft != -1, src/ORBmatcher.cc:274-365): left /
+    right bests kept apart, the right best accepted without a ratio test inside the left one's TH_LOW gate. The oracle
+    is pinned to the reference's own method (tests/test_oracle_matchers_vs_reference_source.py)."""
+    from test_oracle_matchers import _keyframes, _two_cameras
+    k1, k2 = _keyframes(seed, n=600, n_nodes=9)
+    k2, nl = _two_cameras(k2, seed, n_nodes=9)
+    sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
+    args = [(k["kps"], k["desc"], None, k["hm"], k["ids"], k["off"], k["idx"], sf, sf * sf) for k in (k1, k2)]
+    vg = [views.make_keyframe_view(*a) for a in args]
+    vr = [orbref.make_keyframe_view(*a) for a in args]
+    mt = ORBmatcher(nnratio, check)
+    for n_left in (nl, len(k2["kps"]), 0, nl // 2):
+        n, mf = mt.SearchByBoWTwoCameras(vg[0], vg[1], n_left)
+        n_r, mf_r = orbref.search_by_bow_fisheye(vr[0], vr[1], n_left, nnratio, check)
+        assert n == n_r and np.array_equal(mf, mf_r), (n_left, n, n_r, np.nonzero(mf != mf_r)[0][:10])
+        if n_left == nl:
+            assert (mf_r[:nl] >= 0).sum() > 20 and (mf_r[nl:] >= 0).sum() > 20, "degenerate test"
+
+
 @pytest.mark.parametrize("m,th,stereo,seed", [(3000, 3.0, True, 0), (1500, 2.5, False, 1), (6000, 4.0, True, 2)])
 def test_fuse_match(matcher, m, th, stereo, seed):
     """The matching loop of ORBmatcher::Fuse(KeyFrame*, vector<MapPoint*>, th) (src/ORBmatcher.cc:1194-1257): window

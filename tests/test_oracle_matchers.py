@@ -66,6 +66,30 @@ def _keyframes(seed, n=400, n_nodes=12):
     return out
 
 
+def _two_cameras(k, seed, n_nodes=12):
+    """A two-camera version of one _keyframes() entry: the rows as they are = the left camera, a noisy copy of every row
+    = the right camera (same vocabulary node: byte 0 kept), so that a KeyFrame feature usually has a close left AND a
+    close right candidate. Returns (dict, n_left)."""
+    rng = np.random.default_rng(seed + 1000)
+    n = len(k["kps"])
+    dr = k["desc"].copy()
+    flips = rng.integers(0, 40, n)
+    for i in range(n):
+        for bit in rng.choice(np.arange(8, 256), flips[i], replace=False):
+            dr[i, bit >> 3] ^= np.uint8(1 << (bit & 7))
+    kr = k["kps"].copy()
+    kr["angle"] = ((kr["angle"] + rng.normal(0, 25, n)) % 360).astype(np.float32)
+    kps = np.concatenate([k["kps"], kr])
+    d = np.concatenate([k["desc"], dr])
+    node_of = d[:, 0].astype(np.int64) % n_nodes * 5 + 2
+    ids, inv = np.unique(node_of, return_inverse=True)
+    order = np.argsort(inv, kind="stable")
+    off = np.zeros(len(ids) + 1, np.int32)
+    off[1:] = np.cumsum(np.bincount(inv, minlength=len(ids)))
+    hm = np.concatenate([k["hm"], (rng.random(n) < 0.7).astype(np.uint8)])
+    return dict(kps=kps, desc=d, hm=hm, ids=ids.astype(np.uint32), off=off, idx=order.astype(np.uint32)), n
+
+
 def _view(k):
     sf = np.float32(1.2) ** np.arange(8, dtype=np.float32)
     return orbref.make_keyframe_view(k["kps"], k["desc"], None, k["hm"], k["ids"], k["off"], k["idx"], sf, sf * sf)

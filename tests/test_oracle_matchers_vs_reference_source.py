@@ -11,7 +11,7 @@ import pytest
 
 from orb_slam3_fast_b200 import synth
 from oracle import orbref, refsrc
-from test_oracle_matchers import _keyframes, _view
+from test_oracle_matchers import _keyframes, _two_cameras, _view
 
 pytestmark = pytest.mark.skipif(not refsrc.matcher_available(),
                                 reason="oracle/_ref not built (no /root/reference at build time)")
@@ -101,6 +101,30 @@ def test_search_by_bow_both_overloads(seed, nnratio, check):
     n_o, m_o = orbref.search_by_bow_kf(_view(k1), _view(k2), nnratio, check)
     n_r, m_r = refsrc.search_by_bow_kf(_view(k1), _view(k2), nnratio, check)
     assert n_o > 20 and n_r == n_o and np.array_equal(m_r, m_o)
+
+
+@pytest.mark.parametrize("seed,nnratio,check,kf_two", [(1, 0.7, True, True), (2, 0.9, False, False), (3, 0.6, True, True),
+                                                       (4, 0.75, True, False)])
+def test_search_by_bow_two_camera_frame(seed, nnratio, check, kf_two):
+    """SearchByBoW(KeyFrame*, Frame&, ...) with F.Nleft != -1 (:274-365): left / right bests kept apart, the right one
+    accepted without a ratio test inside the left one's TH_LOW gate; keypoints of rows >= NLeft from mvKeysRight."""
+    k1, k2 = _keyframes(seed)
+    k2, nl_f = _two_cameras(k2, seed)
+    nl_kf = len(k1["kps"])
+    if kf_two:
+        k1, nl_kf = _two_cameras(k1, seed + 50)
+    v1, v2 = _view(k1), _view(k2)
+    n_o, m_o = orbref.search_by_bow_fisheye(v1, v2, nl_f, nnratio, check)
+    n_r, m_r = refsrc.search_by_bow_fisheye(v1, nl_kf, v2, nl_f, nnratio, check)
+    assert n_r == n_o and np.array_equal(m_r, m_o)
+    assert (m_o[:nl_f] >= 0).sum() > 20 and (m_o[nl_f:] >= 0).sum() > 20
+    # degenerate splits: everything left (== the one-camera function), everything right (no acceptance possible)
+    n_a, m_a = orbref.search_by_bow_fisheye(v1, v2, v2.struct.n, nnratio, check)
+    n_b, m_b = orbref.search_by_bow(v1, v2, nnratio, check)
+    assert n_a == n_b and np.array_equal(m_a, m_b)
+    n_c, m_c = refsrc.search_by_bow_fisheye(v1, nl_kf, v2, 0, nnratio, check)
+    n_d, m_d = orbref.search_by_bow_fisheye(v1, v2, 0, nnratio, check)
+    assert n_c == n_d == 0 and np.array_equal(m_c, m_d)
 
 
 @pytest.mark.parametrize("seed,window,nnratio,check", [(6, 30, 0.9, True), (7, 60, 0.9, False), (8, 100, 0.7, True)])
