@@ -85,6 +85,31 @@ struct FrameWorld {
 };
 }  // namespace
 
+// cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2) for the stand-in OpenCV: the oracle's knn2 (pinned to cv2.BFMatcher by
+// tests/test_oracle_primitives.py) reshaped into OpenCV's output — up to k matches per query, best first.
+void cv::BFMatcher::knnMatch(const cv::Mat& query, const cv::Mat& train, std::vector<std::vector<cv::DMatch>>& matches,
+                             int k) const {
+  const int nq = query.rows, nt = train.rows;
+  std::vector<uint8_t> q((size_t)std::max(nq, 1) * 32), t((size_t)std::max(nt, 1) * 32);
+  for (int i = 0; i < nq; i++) memcpy(&q[(size_t)i * 32], query.ptr(i), 32);
+  for (int i = 0; i < nt; i++) memcpy(&t[(size_t)i * 32], train.ptr(i), 32);
+  std::vector<int32_t> i1(std::max(nq, 1)), d1(std::max(nq, 1)), i2(std::max(nq, 1)), d2(std::max(nq, 1));
+  orbref_knn2(q.data(), nq, t.data(), nt, i1.data(), d1.data(), i2.data(), d2.data());
+  matches.assign(nq, std::vector<cv::DMatch>());
+  for (int i = 0; i < nq; i++) {
+    if (k >= 1 && i1[i] >= 0) {
+      cv::DMatch m;
+      m.queryIdx = i; m.trainIdx = i1[i]; m.distance = (float)d1[i];
+      matches[i].push_back(m);
+    }
+    if (k >= 2 && i2[i] >= 0) {
+      cv::DMatch m;
+      m.queryIdx = i; m.trainIdx = i2[i]; m.distance = (float)d2[i];
+      matches[i].push_back(m);
+    }
+  }
+}
+
 extern "C" {
 
 int orbrefsrc_descriptor_distance(const uint8_t* a, const uint8_t* b) {
@@ -416,6 +441,43 @@ int orbrefsrc_stereo_frame(int nfeatures, float scale_factor, int nlevels, int i
     depth[i] = F.mvDepth[i];
     matched += F.mvuRight[i] >= 0;
   }
+  return matched;
+}
+
+// Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331): the brute-force 2-NN of the lapping-area descriptors,
+// Lowe's ratio and the triangulation call, with the stand-in KannalaBrandt8 of matcher_world.h. In
+// liborbref_matcher_src.so the function is the reference's own text; in libshim_world*.so it is the drop-in body of
+// shim/FrameStereo_orbx.cc. Outputs: mvLeftToRightMatch[n_l], mvRightToLeftMatch[n_r], mvDepth[n_l],
+// mvStereo3Dpoints[n_l] (xyz; untouched rows read 0); returns the number of accepted pairs.
+int orbrefsrc_stereo_fisheye(const orbx_kp* kps_l, const unsigned char* desc_l, int n_l, const orbx_kp* kps_r,
+                             const unsigned char* desc_r, int n_r, int mono_left, int mono_right,
+                             const float* level_sigma2, int n_levels, const float* Rlr, const float* tlr,
+                             int32_t* left_to_right, int32_t* right_to_left, float* depth, float* p3d) {
+  Frame F;
+  KannalaBrandt8 cam1, cam2;
+  F.mpCamera = &cam1;
+  F.mpCamera2 = &cam2;
+  F.N = n_l + n_r;
+  F.Nleft = n_l;
+  F.Nright = n_r;
+  F.monoLeft = mono_left;
+  F.monoRight = mono_right;
+  F.mvKeys = keypoints(kps_l, n_l);
+  F.mvKeysRight = keypoints(kps_r, n_r);
+  F.mDescriptors = rows32(desc_l, n_l);
+  F.mDescriptorsRight = rows32(desc_r, n_r);
+  F.mvLevelSigma2.assign(level_sigma2, level_sigma2 + n_levels);
+  for (int i = 0; i < 9; i++) F.mRlr(i / 3, i % 3) = Rlr[i];
+  F.mtlr = Eigen::Vector3f(tlr[0], tlr[1], tlr[2]);
+  F.ComputeStereoFishEyeMatches();
+  int matched = 0;
+  for (int i = 0; i < n_l; i++) {
+    left_to_right[i] = F.mvLeftToRightMatch[i];
+    depth[i] = F.mvDepth[i];
+    for (int c = 0; c < 3; c++) p3d[3 * i + c] = F.mvStereo3Dpoints[i](c);
+    matched += F.mvLeftToRightMatch[i] >= 0;
+  }
+  for (int i = 0; i < n_r; i++) right_to_left[i] = F.mvRightToLeftMatch[i];
   return matched;
 }
 

@@ -175,6 +175,21 @@ class PinholeStandIn : public GeometricCamera {
   }
 };
 
+// KannalaBrandt8::TriangulateMatches (src/CameraModels/KannalaBrandt8.cpp) is camera-model code (out of scope, and it
+// needs Eigen's SVD): the stand-in returns a deterministic pseudo-depth of its inputs — positive for about two thirds of
+// the pairs — and a p3D that encodes both keypoints, so that Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331)
+// can be checked for WHICH pairs it triangulates, with which sigmas, and where it files the answers.
+class KannalaBrandt8 : public GeometricCamera {
+ public:
+  float TriangulateMatches(GeometricCamera* pCamera2, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
+                           const Eigen::Matrix3f& R12, const Eigen::Vector3f& t12, const float sigmaLevel, const float unc,
+                           Eigen::Vector3f& p3D) {
+    const float d = kp1.pt.x - kp2.pt.x + 0.25f * (kp1.pt.y - kp2.pt.y) + t12(0);
+    p3D = Eigen::Vector3f(kp1.pt.x * sigmaLevel, kp2.pt.y * unc, d * R12(0, 0));
+    return pCamera2 ? std::fmod(std::fabs(d), 3.0f) - 1.0f : -1.0f;
+  }
+};
+
 // std::mutex members would make the stand-ins immovable; the tests are single threaded
 struct CopyableMutex : std::mutex {
   CopyableMutex() {}
@@ -270,6 +285,13 @@ class Frame : public FeatureHolder {
   bool isInFrustum(MapPoint* pMP, float viewingCosLimit);
   bool isInFrustumChecks(MapPoint*, float, bool = false) { return false; }
   void ComputeStereoMatches();  // defined by the reference's own text, piped in at build time (oracle/Makefile)
+  // Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331): the reference's own text, piped in likewise
+  void ComputeStereoFishEyeMatches();
+  int Nright = 0, monoLeft = 0, monoRight = 0, mnCloseMPs = 0;
+  std::vector<Eigen::Vector3f> mvStereo3Dpoints;
+  Eigen::Matrix3f mRlr;
+  Eigen::Vector3f mtlr;
+  cv::BFMatcher BFmatcher;
   std::vector<MapPoint*> mvpMapPoints;
   std::vector<bool> mvbOutlier;
   std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;

@@ -222,6 +222,19 @@ struct FileNode {
   operator T() const { return T(); }
   size_t size() const { return 0; }
 };
+// cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2), the call of Frame::ComputeStereoFishEyeMatches
+// (src/Frame.cc:1293). Defined in oracle/ref_matcher_shim.cpp over the oracle's knn2, which the primitive tests pin to
+// the real cv2.BFMatcher.
+struct DMatch {
+  int queryIdx = -1, trainIdx = -1, imgIdx = -1;
+  float distance = 0;
+};
+enum { NORM_HAMMING = 6 };
+class BFMatcher {
+ public:
+  BFMatcher(int = NORM_HAMMING, bool = false) {}
+  void knnMatch(const Mat& query, const Mat& train, std::vector<std::vector<DMatch>>& matches, int k) const;
+};
 struct FileStorage {
   enum { READ = 0, WRITE = 1 };
   FileStorage() {}

@@ -104,7 +104,7 @@ def mlib():
         _mlib = C.CDLL(_MPATH)
         for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
-                     "orbrefsrc_search_by_bow_fisheye",
+                     "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
                      "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
@@ -171,6 +171,21 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.8, check_orientation=True):
     m = np.empty(max(kf1.struct.n, 1), np.int32)
     n = mlib().orbrefsrc_search_by_bow_kf(kf1.ref(), kf2.ref(), C.c_float(nnratio), int(check_orientation), _p(m))
     return n, m[:kf1.struct.n]
+
+
+def stereo_fisheye(kps_l, desc_l, kps_r, desc_r, mono_left, mono_right, level_sigma2, Rlr, tlr):
+    """Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331) with the stand-in KannalaBrandt8: returns
+    (n, mvLeftToRightMatch, mvRightToLeftMatch, mvDepth, mvStereo3Dpoints)."""
+    nl, nr = len(kps_l), len(kps_r)
+    kl, kr = np.ascontiguousarray(kps_l), np.ascontiguousarray(kps_r)
+    dl, dr = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+    s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    R, t = np.ascontiguousarray(Rlr, np.float32).reshape(9), np.ascontiguousarray(tlr, np.float32).reshape(3)
+    l2r, r2l = np.empty(max(nl, 1), np.int32), np.empty(max(nr, 1), np.int32)
+    depth, p3d = np.empty(max(nl, 1), np.float32), np.zeros((max(nl, 1), 3), np.float32)
+    n = mlib().orbrefsrc_stereo_fisheye(_p(kl), _p(dl), nl, _p(kr), _p(dr), nr, int(mono_left), int(mono_right), _p(s2),
+                                        len(s2), _p(R), _p(t), _p(l2r), _p(r2l), _p(depth), _p(p3d))
+    return n, l2r[:nl], r2l[:nr], depth[:nl], p3d[:nl]
 
 
 def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, check_orientation=True):

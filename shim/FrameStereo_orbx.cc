@@ -1,4 +1,5 @@
-// shim/FrameStereo_orbx.cc — body of Frame::ComputeStereoMatches (src/Frame.cc:921-1084) forwarding to orbm_stereo_match.
+// shim/FrameStereo_orbx.cc — bodies of Frame::ComputeStereoMatches (src/Frame.cc:921-1084) forwarding to
+// orbm_stereo_match, and of Frame::ComputeStereoFishEyeMatches (:1271-1331) forwarding to orbm_knn2.
 //
 // COMPILES ONLY INSIDE THE REFERENCE TREE (needs include/Frame.h and its OpenCV / Eigen / Sophus dependencies, none of
 // which exist in this repository's build image). Replace the reference's function body with this file's; everything
@@ -24,6 +25,40 @@ void Frame::ComputeStereoMatches() {
       reinterpret_cast<const orbx_kp*>(mvKeysRight.data()), mDescriptorsRight.data, (int)mvKeysRight.size(), mbf, mb,
       mvuRight.data(), mvDepth.data(), &n_matched);
   if (rc != ORBX_OK) throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+}
+
+// Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331): cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2) over the
+// lapping-area descriptors -> orbm_knn2 (POPC kernel at these sizes, the tensor-core form above ~6k x 6k); Lowe's ratio,
+// the triangulation call (the reference's own KannalaBrandt8 object — camera models are not rebuilt) and the
+// bookkeeping stay here, in the reference's statement order.
+void Frame::ComputeStereoFishEyeMatches() {
+  mvLeftToRightMatch = std::vector<int>(Nleft, -1);  // :1281-1286
+  mvRightToLeftMatch = std::vector<int>(Nright, -1);
+  mvDepth = std::vector<float>(Nleft, -1.0f);
+  mvuRight = std::vector<float>(Nleft, -1);
+  mvStereo3Dpoints = std::vector<Eigen::Vector3f>(Nleft);
+  mnCloseMPs = 0;
+  const int nq = mDescriptors.rows - monoLeft, nt = mDescriptorsRight.rows - monoRight;  // :1276-1278
+  if (nq <= 0) return;
+  std::vector<int32_t> i1(nq), d1(nq), i2(nq), d2(nq);
+  if (orbm_knn2(OrbxThreadMatcher(), mDescriptors.ptr(monoLeft), nq, nt > 0 ? mDescriptorsRight.ptr(monoRight) : nullptr,
+                nt > 0 ? nt : 0, i1.data(), d1.data(), i2.data(), d2.data()) != ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  for (int q = 0; q < nq; q++) {
+    // (*it).size() >= 2 && (*it)[0].distance < (*it)[1].distance * 0.7: float distances, the product in double  :1299
+    if (i2[q] < 0 || !((float)d1[q] < (float)d2[q] * 0.7)) continue;
+    const int il = q + monoLeft, ir = i1[q] + monoRight;
+    Eigen::Vector3f p3D;
+    const float sigma1 = mvLevelSigma2[mvKeys[il].octave], sigma2 = mvLevelSigma2[mvKeysRight[ir].octave];
+    const float depth = static_cast<KannalaBrandt8*>(mpCamera)->TriangulateMatches(mpCamera2, mvKeys[il], mvKeysRight[ir],
+                                                                                   mRlr, mtlr, sigma1, sigma2, p3D);
+    if (depth > 0.0001f) {  // :1317-1325
+      mvLeftToRightMatch[il] = ir;
+      mvRightToLeftMatch[ir] = il;
+      mvStereo3Dpoints[il] = p3D;
+      mvDepth[il] = depth;
+    }
+  }
 }
 
 }  // namespace ORB_SLAM3

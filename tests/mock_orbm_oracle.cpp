@@ -131,6 +131,11 @@ int orbx_download_pyramid(orbx_extractor* ex, int, int level, uint8_t* dst, int 
   for (int y = 0; y < h + 38; y++) memcpy(dst + (size_t)y * dst_stride, src + (size_t)y * st, (size_t)w + 38);
   return ORBX_OK;
 }
+int orbm_knn2(orbm_matcher*, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx1, int32_t* d1, int32_t* idx2,
+              int32_t* d2) {
+  orbref_knn2(q, nq, t, nt, idx1, d1, idx2, d2);
+  return ORBX_OK;
+}
 int orbm_stereo_match(orbm_matcher*, const orbx_extractor* left, const orbx_extractor* right, int, const orbx_kp* kps_l,
                       const uint8_t* desc_l, int n_l, const orbx_kp* kps_r, const uint8_t* desc_r, int n_r, float mbf,
                       float mb, float* u_right, float* depth, int32_t* n_matched) {

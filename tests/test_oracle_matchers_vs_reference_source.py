@@ -127,6 +127,53 @@ def test_search_by_bow_two_camera_frame(seed, nnratio, check, kf_two):
     assert n_c == n_d == 0 and np.array_equal(m_c, m_d)
 
 
+def _fisheye_stereo_python(kl, dl, kr, dr, mono_l, mono_r, s2, R, t):
+    """Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331) once more in numpy over the oracle's knn2, with the
+    pseudo-triangulation of the stand-in KannalaBrandt8 (oracle/ref_stubs/matcher_world.h) in float32."""
+    nl, nr = len(kl), len(kr)
+    l2r, r2l = np.full(nl, -1, np.int32), np.full(nr, -1, np.int32)
+    depth, p3d = np.full(nl, -1, f32), np.zeros((nl, 3), f32)
+    i1, d1, i2, d2 = orbref.knn2(dl[mono_l:], dr[mono_r:])
+    n = 0
+    for q in range(nl - mono_l):
+        if i2[q] < 0 or not (float(f32(d1[q])) < float(f32(d2[q])) * 0.7):
+            continue
+        a, b = q + mono_l, int(i1[q]) + mono_r
+        d = f32(f32(f32(kl["x"][a] - kr["x"][b]) + f32(f32(0.25) * f32(kl["y"][a] - kr["y"][b]))) + f32(t[0]))
+        z = f32(np.fmod(np.abs(d), f32(3.0)) - f32(1.0))
+        if z > f32(0.0001):
+            l2r[a], r2l[b], depth[a] = b, a, z
+            p3d[a] = (f32(kl["x"][a] * s2[kl["octave"][a]]), f32(kr["y"][b] * s2[kr["octave"][b]]), f32(d * f32(R[0])))
+            n += 1
+    return n, l2r, r2l, depth, p3d
+
+
+@pytest.mark.parametrize("seed,mono_l,mono_r", [(1, 0, 0), (2, 150, 90), (3, 399, 0), (4, 0, 398)])
+def test_compute_stereo_fisheye_matches(seed, mono_l, mono_r):
+    """Frame::ComputeStereoFishEyeMatches, src/Frame.cc:1271-1331 — the consumer of the brute-force 2-NN: Lowe's 0.7
+    ratio on float distances (product in double), the triangulation call with both level sigmas, the bookkeeping."""
+    rng = np.random.default_rng(seed)
+    n = 400
+    dl = synth.descriptors(n, seed)
+    perm = rng.permutation(n)
+    dr = synth.flip_bits(dl[perm], rng.integers(0, 60, n), rng)
+    dr[:40] = dr[40:80]                       # duplicates: ratio-test ties (d1 == d2)
+    kl, kr = np.zeros(n, synth.KP_DTYPE), np.zeros(n, synth.KP_DTYPE)
+    for k in (kl, kr):
+        k["x"], k["y"] = rng.uniform(0, 640, n).astype(f32), rng.uniform(0, 480, n).astype(f32)
+        k["octave"] = rng.integers(0, 8, n)
+    s2 = (f32(1.2) ** np.arange(8, dtype=f32)) ** 2
+    R = np.array([0.75, 0, 0, 0, 1, 0, 0, 0, 1], f32)
+    t = np.array([0.125, 0, 0], f32)
+    got = refsrc.stereo_fisheye(kl, dl, kr, dr, mono_l, mono_r, s2, R, t)
+    want = _fisheye_stereo_python(kl, dl, kr, dr, mono_l, mono_r, s2, R, t)
+    assert got[0] == want[0]
+    for g, w_ in zip(got[1:], want[1:]):
+        assert np.array_equal(g, w_)
+    if mono_l < 300 and mono_r < 300:
+        assert got[0] > 30 and (got[3] < 0).sum() > 30
+
+
 @pytest.mark.parametrize("seed,window,nnratio,check", [(6, 30, 0.9, True), (7, 60, 0.9, False), (8, 100, 0.7, True)])
 def test_search_for_initialization(seed, window, nnratio, check):
     """SearchForInitialization, :618-764, with the serial executor in place of its tbb::parallel_for."""

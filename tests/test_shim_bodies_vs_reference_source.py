@@ -25,7 +25,7 @@ def shim_world(monkeypatch):
                  "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
                  "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
                  "orbrefsrc_distinctive_descriptor", "orbrefsrc_search_by_projection_map_fisheye",
-                 "orbrefsrc_search_by_bow_fisheye"):
+                 "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye"):
         getattr(lib, name).restype = C.c_int
     refsrc.mlib()
     monkeypatch.setattr(refsrc, "_mlib", lib)
@@ -61,6 +61,11 @@ def test_shim_search_by_bow(shim_world, args):
 @pytest.mark.parametrize("args", [(1, 0.7, True, True), (2, 0.9, False, False), (3, 0.6, True, True)])
 def test_shim_search_by_bow_two_camera_frame(shim_world, args):
     T.test_search_by_bow_two_camera_frame(*args)
+
+
+@pytest.mark.parametrize("args", [(1, 0, 0), (2, 150, 90), (3, 399, 0), (4, 0, 398)])
+def test_shim_compute_stereo_fisheye_matches(shim_world, args):
+    T.test_compute_stereo_fisheye_matches(*args)
 
 
 @pytest.mark.parametrize("args", [(False, 3.0, 4), (False, 2.5, 6)])
