@@ -260,6 +260,16 @@ int orbm_search_for_triangulation(orbm_matcher* m, const orbx_keyframe_view* kf1
                                   const float* F12, float ep_x, float ep_y, int only_stereo, int coarse,
                                   int check_orientation, int32_t* matches12, int32_t* nmatches);
 
+/* The descriptor part of the same function for two-camera rigs (both KeyFrames with mpCamera2; src/ORBmatcher.cc:
+ * 973-988): the epipolar test of a KannalaBrandt8 pair is KannalaBrandt8::TriangulateMatches (camera models are the
+ * caller's), so the device enumerates, per kf1 feature without a MapPoint, the kf2 features without a MapPoint under
+ * the same vocabulary node whose descriptor distance is <= TH_LOW, in the reference's scan order, and the shim replays
+ * ":988-1052" over them with the reference's own camera objects (shim/ORBmatcher_orbx.cc). offsets[kf1->n + 1] (host):
+ * CSR offsets; cand_idx2 / cand_dist[cap] (host); *total = number of candidates. ORBX_E_CAPACITY when total > cap (the
+ * first cap are written; call again with a larger buffer). u_right of the views is not read. */
+int orbm_triangulation_candidates(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2,
+                                  int32_t* offsets, int32_t* cand_idx2, int32_t* cand_dist, int32_t cap, int32_t* total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1711,4 +1711,126 @@ int orbref_search_for_triangulation(const orbx_keyframe_view* kf1, const orbx_ke
   return nmatches;
 }
 
+// SearchForTriangulation on two-camera KeyFrames (both mpCamera2 set; src/ORBmatcher.cc:886-1106 with :960, :966-971,
+// :991-994, :1007-1043): no feature is "stereo" (bStereo1 / bStereo2 are false, so bOnlyStereo matches nothing), the epipole
+// gate is skipped (:996), and the epipolar test runs on the camera pair picked by which side of NLeft the two features lie
+// on — here in the Pinhole form on F12[pair], pair = 2 * right1 + right2 (the camera models themselves are not restated;
+// the product asks the caller's camera objects, see orbref_triangulation_candidates). kps: left rows then right rows.
+int orbref_search_for_triangulation_fisheye(const orbx_keyframe_view* kf1, int n_left1, const orbx_keyframe_view* kf2,
+                                            int n_left2, const float* F12x4, int only_stereo, int coarse,
+                                            int check_orientation, int32_t* matches12) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  std::vector<int> rotHist[kHisto];
+  for (int i = 0; i < kf1->n; i++) matches12[i] = -1;
+  const orbx_featvec& v1 = kf1->featvec;
+  const orbx_featvec& v2 = kf2->featvec;
+  int a = 0, b = 0;
+  while (a < v1.n_nodes && b < v2.n_nodes) {
+    if (v1.node_ids[a] == v2.node_ids[b]) {
+      for (int p1 = v1.offsets[a]; p1 < v1.offsets[a + 1]; p1++) {
+        const int idx1 = (int)v1.indices[p1];
+        if (kf1->has_mappoint[idx1]) continue;
+        if (only_stereo) continue;  // bStereo1 = (!mpCamera2 && ...) = false                                  :958-960
+        const orbx_kp& kp1 = kf1->kps[idx1];
+        const bool right1 = idx1 >= n_left1;
+        const uint8_t* d1 = kf1->desc + (size_t)idx1 * 32;
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int p2 = v2.offsets[b]; p2 < v2.offsets[b + 1]; p2++) {
+          const int idx2 = (int)v2.indices[p2];
+          if (kf2->has_mappoint[idx2]) continue;
+          const int dist = orbref_descriptor_distance(d1, kf2->desc + (size_t)idx2 * 32);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          const orbx_kp& kp2 = kf2->kps[idx2];
+          const bool right2 = idx2 >= n_left2;
+          bool ok = coarse != 0;
+          if (!ok) {
+            const float* F12 = F12x4 + 9 * (2 * (int)right1 + (int)right2);
+            const float ea = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+            const float eb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+            const float ec = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+            const float num = ea * kp2.x + eb * kp2.y + ec;
+            const float den = ea * ea + eb * eb;
+            if (den != 0) {
+              const float dsqr = num * num / den;
+              ok = (double)dsqr < 3.84 * (double)kf2->level_sigma2[kp2.octave];
+            }
+          }
+          if (ok) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) {
+          matches12[idx1] = bestIdx2;
+          nmatches++;
+          if (check_orientation) rotHist[rot_bin(kp1.angle, kf2->kps[bestIdx2].angle)].push_back(idx1);
+        }
+      }
+      a++;
+      b++;
+    } else if (v1.node_ids[a] < v2.node_ids[b]) {
+      while (a < v1.n_nodes && v1.node_ids[a] < v2.node_ids[b]) a++;
+    } else {
+      while (b < v2.n_nodes && v2.node_ids[b] < v1.node_ids[a]) b++;
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, kHisto, ind1, ind2, ind3);
+    for (int i = 0; i < kHisto; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) {
+        matches12[idx1] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
+// The descriptor part of SearchForTriangulation for rigs whose epipolar test the device cannot evaluate (KannalaBrandt8:
+// TriangulateMatches): for every kf1 feature without a MapPoint, the kf2 features without a MapPoint under the same
+// vocabulary node whose distance is <= TH_LOW, in the reference's scan order (:973-988). offsets[kf1->n + 1]; returns the
+// total (writes at most cap entries).
+int orbref_triangulation_candidates(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, int32_t* offsets,
+                                    int32_t* cand_idx2, int32_t* cand_dist, int cap) {
+  const int TH_LOW = 50;
+  std::vector<std::vector<std::pair<int, int>>> rows(kf1->n);
+  const orbx_featvec& v1 = kf1->featvec;
+  const orbx_featvec& v2 = kf2->featvec;
+  int a = 0, b = 0;
+  while (a < v1.n_nodes && b < v2.n_nodes) {
+    if (v1.node_ids[a] == v2.node_ids[b]) {
+      for (int p1 = v1.offsets[a]; p1 < v1.offsets[a + 1]; p1++) {
+        const int idx1 = (int)v1.indices[p1];
+        if (kf1->has_mappoint[idx1]) continue;
+        const uint8_t* d1 = kf1->desc + (size_t)idx1 * 32;
+        for (int p2 = v2.offsets[b]; p2 < v2.offsets[b + 1]; p2++) {
+          const int idx2 = (int)v2.indices[p2];
+          if (kf2->has_mappoint[idx2]) continue;
+          const int dist = orbref_descriptor_distance(d1, kf2->desc + (size_t)idx2 * 32);
+          if (dist <= TH_LOW) rows[idx1].push_back({idx2, dist});
+        }
+      }
+      a++;
+      b++;
+    } else if (v1.node_ids[a] < v2.node_ids[b]) {
+      while (a < v1.n_nodes && v1.node_ids[a] < v2.node_ids[b]) a++;
+    } else {
+      while (b < v2.n_nodes && v2.node_ids[b] < v1.node_ids[a]) b++;
+    }
+  }
+  int total = 0;
+  for (int i = 0; i < kf1->n; i++) {
+    offsets[i] = total;
+    for (const auto& c : rows[i]) {
+      if (total < cap) {
+        cand_idx2[total] = c.first;
+        cand_dist[total] = c.second;
+      }
+      total++;
+    }
+  }
+  offsets[kf1->n] = total;
+  return total;
+}
+
 }  // extern "C"

@@ -185,6 +185,15 @@ int orbref_search_by_bow_fisheye(const orbx_keyframe_view* kf, const orbx_keyfra
 int orbref_search_for_triangulation(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, const float* F12,
                                     float ep_x, float ep_y, int only_stereo, int coarse, int check_orientation,
                                     int32_t* matches12);
+/* ... on two-camera KeyFrames (src/ORBmatcher.cc:886-1106 with its NLeft / mpCamera2 branches): F12x4 = four row-major
+ * 3x3 matrices indexed 2 * right1 + right2, the Pinhole-form epipolar test of the selected camera pair. */
+int orbref_search_for_triangulation_fisheye(const orbx_keyframe_view* kf1, int n_left1, const orbx_keyframe_view* kf2,
+                                            int n_left2, const float* F12x4, int only_stereo, int coarse,
+                                            int check_orientation, int32_t* matches12);
+/* The descriptor part of SearchForTriangulation (:973-988): per kf1 feature the kf2 candidates with distance <= TH_LOW
+ * in scan order (CSR); returns the total, writes at most cap entries. */
+int orbref_triangulation_candidates(const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2, int32_t* offsets,
+                                    int32_t* cand_idx2, int32_t* cand_dist, int cap);
 
 #ifdef __cplusplus
 }

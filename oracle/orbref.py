@@ -272,6 +272,8 @@ def lib():
         L.orbref_search_by_projection_frame.argtypes = [vp, vp, ci, ci, vp]
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
+        L.orbref_search_for_triangulation_fisheye.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, vp]
+        L.orbref_triangulation_candidates.argtypes = [vp, vp, vp, vp, vp, ci]
         L.orbref_search_by_bow_kf.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_by_bow_fisheye.argtypes = [vp, vp, ci, cf, ci, vp]
         L.orbref_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp]
@@ -475,6 +477,27 @@ def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False,
     n = lib().orbref_search_for_triangulation(kf1.ref(), kf2.ref(), _ptr(F12), float(ep[0]), float(ep[1]),
                                               int(only_stereo), int(coarse), int(check_orientation), _ptr(m))
     return n, m[:kf1.struct.n]
+
+
+def search_for_triangulation_fisheye(kf1, n_left1, kf2, n_left2, F12x4, only_stereo=False, coarse=False,
+                                     check_orientation=True, fn=None):
+    """SearchForTriangulation on two-camera KeyFrames; F12x4[2 * right1 + right2] = the selected pair's matrix."""
+    F = np.ascontiguousarray(F12x4, np.float32).reshape(36)
+    m = np.empty(max(kf1.struct.n, 1), np.int32)
+    n = (fn or lib().orbref_search_for_triangulation_fisheye)(kf1.ref(), int(n_left1), kf2.ref(), int(n_left2), _ptr(F),
+                                                              int(only_stereo), int(coarse), int(check_orientation),
+                                                              _ptr(m))
+    return n, m[:kf1.struct.n]
+
+
+def triangulation_candidates(kf1, kf2):
+    """(offsets[n1 + 1], idx2[total], dist[total]): the descriptor part of SearchForTriangulation, :973-988."""
+    n1 = kf1.struct.n
+    off = np.zeros(n1 + 1, np.int32)
+    total = lib().orbref_triangulation_candidates(kf1.ref(), kf2.ref(), _ptr(off), None, None, 0)
+    idx, dist = np.empty(max(total, 1), np.int32), np.empty(max(total, 1), np.int32)
+    lib().orbref_triangulation_candidates(kf1.ref(), kf2.ref(), _ptr(off), _ptr(idx), _ptr(dist), total)
+    return off, idx[:total], dist[:total]
 
 
 def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):

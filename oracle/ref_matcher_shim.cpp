@@ -158,6 +158,35 @@ int orbrefsrc_search_for_triangulation(const orbx_keyframe_view* v1, const orbx_
   return n;
 }
 
+// ... on two-camera KeyFrames: NLeft set, rows >= NLeft in mvKeysRight, both cameras of both KeyFrames set. Camera 1 /
+// camera 2 of KeyFrame 1 carry (F12, F12b) = the matrices for a (left | right) second feature; see matcher_world.h.
+int orbrefsrc_search_for_triangulation_fisheye(const orbx_keyframe_view* v1, int n_left1, const orbx_keyframe_view* v2,
+                                               int n_left2, const float* F12x4, int only_stereo, int coarse,
+                                               int check_orientation, int32_t* matches12) {
+  KeyFrameWorld A(v1), B(v2);
+  GeometricCamera a2, b2;
+  auto split = [&](KeyFrame& kf, const orbx_keyframe_view* v, int nl, GeometricCamera* second) {
+    kf.Nleft = kf.NLeft = nl;
+    kf.mvKeys = keypoints(v->kps, nl);
+    kf.mvKeysRight = keypoints(v->kps + nl, v->n - nl);
+    kf.mvKeysUn.clear();
+    kf.mpCamera2 = second;
+    second->tag = 1;
+  };
+  split(A.kf, v1, n_left1, &a2);
+  split(B.kf, v2, n_left2, &b2);
+  memcpy(A.camera.F12, F12x4, 36);        // left1  x left2
+  memcpy(A.camera.F12b, F12x4 + 9, 36);   // left1  x right2
+  memcpy(a2.F12, F12x4 + 18, 36);         // right1 x left2
+  memcpy(a2.F12b, F12x4 + 27, 36);        // right1 x right2
+  ORBmatcher matcher(0.6f, check_orientation != 0);
+  std::vector<std::pair<size_t, size_t>> pairs;
+  const int n = matcher.SearchForTriangulation(&A.kf, &B.kf, pairs, only_stereo != 0, coarse != 0);
+  for (int i = 0; i < v1->n; i++) matches12[i] = -1;
+  for (const auto& pr : pairs) matches12[pr.first] = (int32_t)pr.second;
+  return n;
+}
+
 int orbrefsrc_search_by_bow(const orbx_keyframe_view* kfv, const orbx_keyframe_view* frame, float nnratio,
                             int check_orientation, int32_t* matches_f) {
   KeyFrameWorld K(kfv);
@@ -200,6 +229,22 @@ int orbrefsrc_search_by_bow_fisheye(const orbx_keyframe_view* kfv, int n_left_kf
 int orbrefsrc_search_by_bow_kf(const orbx_keyframe_view* v1, const orbx_keyframe_view* v2, float nnratio,
                                int check_orientation, int32_t* matches12) {
   KeyFrameWorld A(v1), B(v2);
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  std::vector<MapPoint*> out;
+  const int n = matcher.SearchByBoW(&A.kf, &B.kf, out);
+  for (int i = 0; i < v1->n; i++) matches12[i] = B.index_of(out[i]);
+  return n;
+}
+
+// ... on two-camera KeyFrames (:799-801, :816-818): NLeft != -1 and mvKeysUn holds the first n_un rows only — rows past
+// it (the right camera's) are skipped on both sides
+int orbrefsrc_search_by_bow_kf_fisheye(const orbx_keyframe_view* v1, int n_un1, const orbx_keyframe_view* v2, int n_un2,
+                                       float nnratio, int check_orientation, int32_t* matches12) {
+  KeyFrameWorld A(v1), B(v2);
+  A.kf.NLeft = A.kf.Nleft = n_un1;
+  A.kf.mvKeysUn.resize(n_un1);
+  B.kf.NLeft = B.kf.Nleft = n_un2;
+  B.kf.mvKeysUn.resize(n_un2);
   ORBmatcher matcher(nnratio, check_orientation != 0);
   std::vector<MapPoint*> out;
   const int n = matcher.SearchByBoW(&A.kf, &B.kf, out);

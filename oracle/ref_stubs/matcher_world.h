@@ -149,8 +149,13 @@ class GeometricCamera {
   virtual Eigen::Matrix3f toK_() { return Eigen::Matrix3f(); }
   // Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:122-149) with F12 supplied by the test
   float F12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  virtual bool epipolarConstrain(GeometricCamera*, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
+  // two-camera rigs: `tag` says which camera of its KeyFrame this is; against a second camera with tag 1 the test uses
+  // F12b, so a test can tell which of the four (left / right) x (left / right) pairs the matcher selected (:1007-1043)
+  int tag = 0;
+  float F12b[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  virtual bool epipolarConstrain(GeometricCamera* other, const cv::KeyPoint& kp1, const cv::KeyPoint& kp2,
                                  const Eigen::Matrix3f&, const Eigen::Vector3f&, const float, const float unc) {
+    const float* F12 = (other && other->tag) ? this->F12b : this->F12;
     const float a = kp1.pt.x * F12[0] + kp1.pt.y * F12[3] + F12[6];
     const float b = kp1.pt.x * F12[1] + kp1.pt.y * F12[4] + F12[7];
     const float c = kp1.pt.x * F12[2] + kp1.pt.y * F12[5] + F12[8];

@@ -104,7 +104,7 @@ def mlib():
         _mlib = C.CDLL(_MPATH)
         for name in ("orbrefsrc_descriptor_distance", "orbrefsrc_search_by_projection_map",
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
-                     "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye",
+                     "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye", "orbrefsrc_search_by_bow_kf_fisheye", "orbrefsrc_search_for_triangulation_fisheye",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
                      "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
@@ -152,6 +152,16 @@ def search_for_triangulation(kf1, kf2, F12, ep, only_stereo=False, coarse=False,
     return n, m[:kf1.struct.n]
 
 
+def search_for_triangulation_fisheye(kf1, n_left1, kf2, n_left2, F12x4, only_stereo=False, coarse=False,
+                                     check_orientation=True):
+    """The reference's own SearchForTriangulation on two-camera stand-in KeyFrames."""
+    from . import orbref
+    mlib().orbrefsrc_search_for_triangulation_fisheye.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                                  C.c_int, C.c_int, C.c_int, C.c_void_p]
+    return orbref.search_for_triangulation_fisheye(kf1, n_left1, kf2, n_left2, F12x4, only_stereo, coarse,
+                                                   check_orientation, fn=mlib().orbrefsrc_search_for_triangulation_fisheye)
+
+
 def search_by_bow(kf, frame, nnratio=0.7, check_orientation=True):
     m = np.empty(max(frame.struct.n, 1), np.int32)
     n = mlib().orbrefsrc_search_by_bow(kf.ref(), frame.ref(), C.c_float(nnratio), int(check_orientation), _p(m))
@@ -186,6 +196,14 @@ def stereo_fisheye(kps_l, desc_l, kps_r, desc_r, mono_left, mono_right, level_si
     n = mlib().orbrefsrc_stereo_fisheye(_p(kl), _p(dl), nl, _p(kr), _p(dr), nr, int(mono_left), int(mono_right), _p(s2),
                                         len(s2), _p(R), _p(t), _p(l2r), _p(r2l), _p(depth), _p(p3d))
     return n, l2r[:nl], r2l[:nr], depth[:nl], p3d[:nl]
+
+
+def search_by_bow_kf_fisheye(kf1, n_un1, kf2, n_un2, nnratio=0.8, check_orientation=True):
+    """The reference's own SearchByBoW(KeyFrame*, KeyFrame*, ...) with NLeft != -1 and mvKeysUn of n_un rows."""
+    m = np.empty(max(kf1.struct.n, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_bow_kf_fisheye(kf1.ref(), int(n_un1), kf2.ref(), int(n_un2), C.c_float(nnratio),
+                                                  int(check_orientation), _p(m))
+    return n, m[:kf1.struct.n]
 
 
 def search_for_initialization(f1, f2, prev_xy, window_size=100, nnratio=0.9, check_orientation=True):

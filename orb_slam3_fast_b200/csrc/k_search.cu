@@ -540,6 +540,54 @@ __global__ void k_tri_match(const TriArgs A) {
   }
 }
 
+// The descriptor part of SearchForTriangulation alone (:973-988), for rigs whose epipolar test is the caller's
+// (KannalaBrandt8::epipolarConstrain triangulates; camera models are not rebuilt): per kf1 feature without a MapPoint the
+// kf2 features without a MapPoint under the same vocabulary node with distance <= TH_LOW, in scan order. Pass 1 counts
+// (off[idx1] = count, 0 for features that take no part), k_scan turns the counts into offsets, pass 2 writes.
+template <bool kFill>
+__global__ void k_tri_cand(const TriArgs A, int32_t* off, int32_t* cand_idx2, int32_t* cand_dist, int cap) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.k1.n_nodes) return;
+  const int b = A.node_match[a];
+  if (b < 0) return;
+  const DevKeyFrame &K1 = A.k1, &K2 = A.k2;
+  for (int p1 = K1.offsets[a]; p1 < K1.offsets[a + 1]; p1++) {
+    const int idx1 = (int)K1.indices[p1];
+    if (K1.has_mappoint[idx1]) continue;
+    uint32_t d1[8];
+    load_desc8(K1.desc + (size_t)idx1 * 32, d1);
+    int n = 0;
+    const int base = kFill ? off[idx1] : 0;
+    for (int p2 = K2.offsets[b]; p2 < K2.offsets[b + 1]; p2++) {
+      const int idx2 = (int)K2.indices[p2];
+      if (K2.has_mappoint[idx2]) continue;
+      const int dist = hamming8(d1, K2.desc + (size_t)idx2 * 32);
+      if (dist > ORBM_TH_LOW_I) continue;
+      if (kFill && base + n < cap) {
+        cand_idx2[base + n] = idx2;
+        cand_dist[base + n] = dist;
+      }
+      n++;
+    }
+    if (!kFill) off[idx1] = n;
+  }
+}
+
+void launch_triangulation_candidates(const TriArgs& A, int32_t* off, int32_t* total, int32_t* cand_idx2,
+                                     int32_t* cand_dist, int cap, bool fill, cudaStream_t st) {
+  const int nb = (A.k1.n_nodes + 63) / 64;
+  if (!fill) {
+    cudaMemsetAsync(off, 0, (size_t)(A.k1.n + 1) * 4, st);
+    if (A.k1.n_nodes > 0) {
+      k_tri_nodes<<<(A.k1.n_nodes + 127) / 128, 128, 0, st>>>(A);
+      k_tri_cand<false><<<nb, 64, 0, st>>>(A, off, nullptr, nullptr, 0);
+    }
+    launch_scan(off, A.k1.n, total, st);
+  } else if (A.k1.n_nodes > 0) {
+    k_tri_cand<true><<<nb, 64, 0, st>>>(A, off, cand_idx2, cand_dist, cap);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_tri_rot(const TriArgs A) {
   __shared__ int histo[32];
   __shared__ int s_count, s_removed;

@@ -1264,4 +1264,37 @@ int orbm_search_for_triangulation(orbm_matcher* m, const orbx_keyframe_view* kf1
   return ORBX_OK;
 }
 
+int orbm_triangulation_candidates(orbm_matcher* m, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2,
+                                  int32_t* offsets, int32_t* cand_idx2, int32_t* cand_dist, int32_t cap, int32_t* total) {
+  if (!m || !kf1 || !kf2 || kf1->n < 0 || kf2->n < 0 || !offsets || !total || cap < 0 || (cap > 0 && (!cand_idx2 || !cand_dist)))
+    return mfail(m, ORBX_E_ARG, "bad argument");
+  *total = 0;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  TriArgs A{};
+  A.k1 = upload_keyframe(ar, kf1);
+  A.k2 = upload_keyframe(ar, kf2);
+  A.node_match = ar.alloc<int32_t>(A.k1.n_nodes);
+  int32_t* d_off = ar.alloc<int32_t>(kf1->n + 1);
+  int32_t* d_total = ar.alloc<int32_t>(1);
+  int32_t* d_idx = ar.alloc<int32_t>(cap);
+  int32_t* d_dist = ar.alloc<int32_t>(cap);
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  launch_triangulation_candidates(A, d_off, d_total, nullptr, nullptr, 0, false, m->stream);
+  launch_triangulation_candidates(A, d_off, d_total, d_idx, d_dist, cap, true, m->stream);
+  ORBM_CUDA(m, cudaGetLastError());
+  int32_t t = 0;
+  ORBM_CUDA(m, cudaMemcpyAsync(offsets, d_off, (size_t)(kf1->n + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaMemcpyAsync(&t, d_total, 4, cudaMemcpyDeviceToHost, m->stream));
+  ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  *total = t;
+  const int nw = t < cap ? t : cap;
+  if (nw > 0) {
+    ORBM_CUDA(m, cudaMemcpyAsync(cand_idx2, d_idx, (size_t)nw * 4, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaMemcpyAsync(cand_dist, d_dist, (size_t)nw * 4, cudaMemcpyDeviceToHost, m->stream));
+    ORBM_CUDA(m, cudaStreamSynchronize(m->stream));
+  }
+  return t > cap ? mfail(m, ORBX_E_CAPACITY, "candidate buffer too small: see *total") : ORBX_OK;
+}
+
 }  // extern "C"

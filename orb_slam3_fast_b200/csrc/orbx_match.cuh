@@ -204,6 +204,10 @@ struct TriArgs {
   int32_t* node_match; // [k1.n_nodes] scratch: index of the same node id in k2 or -1
 };
 void launch_triangulation(const TriArgs& A, cudaStream_t st);
+// fill == false: off[k1.n + 1] = exclusive offsets of the per-feature candidate counts, *total = their sum; fill == true:
+// the candidates themselves (at most cap)
+void launch_triangulation_candidates(const TriArgs& A, int32_t* off, int32_t* total, int32_t* cand_idx2,
+                                     int32_t* cand_dist, int cap, bool fill, cudaStream_t st);
 // SearchForInitialization: serial replay over the candidate lists of run_search (Q = the level-0 keypoints of F1)
 struct InitArgs {
   const orbx_kp* kps1;      // F1.mvKeysUn

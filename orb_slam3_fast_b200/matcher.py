@@ -42,6 +42,7 @@ def _bind(L):
     L.orbm_search_for_initialization.argtypes = [vp, vp, vp, vp, ci, cf, ci, vp, vp]
     L.orbm_search_by_bow_kf.argtypes = [vp, vp, vp, cf, ci, vp, vp]
     L.orbm_search_by_bow_fisheye.argtypes = [vp, vp, vp, ci, cf, ci, vp, vp]
+    L.orbm_triangulation_candidates.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
     L.orbm_is_in_frustum.argtypes = [vp, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp, vp]
     L.orbm_track_local_map_batch_device.argtypes = [vp, vp, ci, vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                                     vp]
@@ -363,6 +364,20 @@ class ORBmatcher:
         self._check(self._L.orbm_search_by_bow_kf(self._h, kf1.ref(), kf2.ref(), self.mfNNratio,
                                                   int(self.mbCheckOrientation), _l.ptr(m12), C.byref(nm)))
         return nm.value, m12[:n]
+
+    # the descriptor part of SearchForTriangulation for two-camera rigs (src/ORBmatcher.cc:973-988): CSR of candidates
+    def TriangulationCandidates(self, kf1, kf2, cap=None):
+        n1 = kf1.struct.n
+        off = np.zeros(n1 + 1, np.int32)
+        cap = int(cap if cap is not None else max(64 * n1, 1))
+        idx, dist = np.empty(max(cap, 1), np.int32), np.empty(max(cap, 1), np.int32)
+        total = C.c_int32(0)
+        rc = self._L.orbm_triangulation_candidates(self._h, kf1.ref(), kf2.ref(), _l.ptr(off), _l.ptr(idx), _l.ptr(dist),
+                                                   cap, C.byref(total))
+        if rc == -2 and total.value > cap:   # ORBX_E_CAPACITY: retry with the reported size
+            return self.TriangulationCandidates(kf1, kf2, total.value)
+        self._check(rc)
+        return off, idx[:total.value], dist[:total.value]
 
     def SearchForTriangulation(self, kf1, kf2, F12, ep, bOnlyStereo=False, bCoarse=False):
         F12 = np.ascontiguousarray(F12, np.float32).reshape(9)

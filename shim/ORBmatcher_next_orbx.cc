@@ -6,7 +6,7 @@
 //   MapPoint::ComputeDistinctiveDescriptors() for a batch of points           src/MapPoint.cc:372-441
 //
 // COMPILES ONLY INSIDE THE REFERENCE TREE (needs the reference headers and their OpenCV / Eigen / Sophus / DBoW2
-// dependencies). SearchByBoW(KeyFrame*, Frame&) and AssignFeaturesToGrid cover both rigs; the others are the pinhole
+// dependencies). Both SearchByBoW overloads and AssignFeaturesToGrid cover both rigs; the others are the pinhole
 // forms (NLeft == -1, bRight == false) — keep the reference's code for their fisheye branches. As in ORBmatcher_orbx.cc the shim only flattens the pointer graph and scatters the answers back; every
 // float that decides a match comes from the reference's own expressions on the host (projection) or from the device
 // with the same non-fused FP32 operations.
@@ -82,8 +82,23 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
   const std::vector<MapPoint*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
   BowFlat k1(pKF1->N, pKF1->mvKeysUn, pKF1->mDescriptors, pKF1->mFeatVec, pKF1->mvScaleFactors, pKF1->mvLevelSigma2);
   BowFlat k2(pKF2->N, pKF2->mvKeysUn, pKF2->mDescriptors, pKF2->mFeatVec, pKF2->mvScaleFactors, pKF2->mvLevelSigma2);
-  for (int i = 0; i < pKF1->N; i++) k1.has_mp[i] = mp1[i] && !mp1[i]->isBad();  // :802-804
-  for (int i = 0; i < pKF2->N; i++) k2.has_mp[i] = mp2[i] && !mp2[i]->isBad();  // :821-825
+  // two-camera KeyFrames: rows past mvKeysUn (the right camera's) are skipped on both sides (:799-801, :816-818) —
+  // the same effect as "no MapPoint"; the angle arrays are padded so that every row has an entry
+  const int un1 = pKF1->NLeft != -1 ? (int)pKF1->mvKeysUn.size() : pKF1->N;
+  const int un2 = pKF2->NLeft != -1 ? (int)pKF2->mvKeysUn.size() : pKF2->N;
+  std::vector<cv::KeyPoint> pad1, pad2;
+  if (un1 < pKF1->N) {
+    pad1 = pKF1->mvKeysUn;
+    pad1.resize(pKF1->N);
+    k1.v.kps = reinterpret_cast<const orbx_kp*>(pad1.data());
+  }
+  if (un2 < pKF2->N) {
+    pad2 = pKF2->mvKeysUn;
+    pad2.resize(pKF2->N);
+    k2.v.kps = reinterpret_cast<const orbx_kp*>(pad2.data());
+  }
+  for (int i = 0; i < pKF1->N; i++) k1.has_mp[i] = i < un1 && mp1[i] && !mp1[i]->isBad();  // :802-804
+  for (int i = 0; i < pKF2->N; i++) k2.has_mp[i] = i < un2 && mp2[i] && !mp2[i]->isBad();  // :821-825
   std::vector<int32_t> m12(pKF1->N, -1);
   int32_t nmatches = 0;
   if (orbm_search_by_bow_kf(OrbxThreadMatcher(), &k1.v, &k2.v, mfNNratio, mbCheckOrientation, m12.data(), &nmatches) != ORBX_OK)

@@ -5,8 +5,9 @@
 //   ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)   src/ORBmatcher.cc:42-221
 //   ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono)                                 :1594-1806
 //   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse)   :886-1106
-// with the ones below. The local-map SearchByProjection covers both rigs (Nleft == -1 and the two-camera form with its
-// right-camera twin :148-217); the other two are the pinhole branches (keep the reference's code for KannalaBrandt8).
+// with the ones below. The local-map SearchByProjection and SearchForTriangulation cover both rigs (the two-camera
+// forms: right-camera twin :148-217; camera-pair selection :1007-1043 with the epipolar test left to the reference's
+// KannalaBrandt8 object); the frame-to-frame SearchByProjection is the pinhole branch.
 // The shim's only job is flattening the pointer graph into the SoA / CSR views of include/orbx_types.h and scattering
 // the answers back; every float that decides a match is computed by the reference's own expressions on the host
 // (projection, radius) or by the device with the same non-fused FP32 operations.
@@ -188,9 +189,132 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
   return nmatches;
 }
 
+namespace {
+// DBoW2::FeatureVector + MapPoint flags of a KeyFrame -> orbx_keyframe_view (kps filled in by the caller)
+struct TriFlat {
+  std::vector<uint8_t> has_mp;
+  std::vector<uint32_t> ids, idx;
+  std::vector<int32_t> off{0};
+  orbx_keyframe_view v;
+  explicit TriFlat(KeyFrame* kf) : has_mp(kf->N) {
+    for (int i = 0; i < kf->N; i++) has_mp[i] = kf->GetMapPoint(i) != nullptr;
+    for (const auto& node : kf->mFeatVec) {
+      ids.push_back(node.first);
+      idx.insert(idx.end(), node.second.begin(), node.second.end());
+      off.push_back((int32_t)idx.size());
+    }
+    v.n = kf->N;
+    v.kps = nullptr;
+    v.desc = kf->mDescriptors.data;
+    v.u_right = nullptr;
+    v.has_mappoint = has_mp.data();
+    v.featvec = orbx_featvec{(int32_t)ids.size(), ids.data(), off.data(), idx.data()};
+    v.scale_factors = kf->mvScaleFactors.data();
+    v.level_sigma2 = kf->mvLevelSigma2.data();
+    v.n_levels = (int32_t)kf->mvScaleFactors.size();
+  }
+};
+
+// Both KeyFrames of a two-camera rig (:913-921, :958-971, :991-994, :1007-1052). The descriptor part — every pair under
+// a shared vocabulary node with distance <= TH_LOW, in scan order — comes from the device
+// (orbm_triangulation_candidates); the epipolar test is KannalaBrandt8::epipolarConstrain (= TriangulateMatches), which
+// stays the reference's own camera code, asked here candidate by candidate exactly where the reference asks it.
+template <class ThreeMaxima>  // ORBmatcher::ComputeThreeMaxima is a protected member: handed in by the caller
+int SearchForTriangulationTwoCameras(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<std::pair<size_t, size_t>>& vMatchedPairs,
+                                     bool bOnlyStereo, bool bCoarse, bool bCheckOrientation, ThreeMaxima three_maxima) {
+  const int TH_LOW = ORBmatcher::TH_LOW, HISTO_LENGTH = ORBmatcher::HISTO_LENGTH;
+  vMatchedPairs.clear();
+  if (bOnlyStereo) return 0;  // bStereo1 = (!mpCamera2 && ...) is false for every feature                   :958-960
+  const Sophus::SE3f T1w = pKF1->GetPose(), Tw2 = pKF2->GetPoseInverse();                           // :896-921
+  const Sophus::SE3f Tr1w = pKF1->GetRightPose(), Twr2 = pKF2->GetRightPoseInverse();
+  const Sophus::SE3f T[4] = {T1w * Tw2, T1w * Twr2, Tr1w * Tw2, Tr1w * Twr2};                       // ll, lr, rl, rr
+  Eigen::Matrix3f R[4];
+  Eigen::Vector3f t[4];
+  for (int k = 0; k < 4; k++) {
+    R[k] = T[k].rotationMatrix();
+    t[k] = T[k].translation();
+  }
+  TriFlat k1(pKF1), k2(pKF2);
+  auto key = [](KeyFrame* kf, int i) -> const cv::KeyPoint& {                                       // :966-969
+    return kf->NLeft == -1 ? kf->mvKeysUn[i] : (i < kf->NLeft ? kf->mvKeys[i] : kf->mvKeysRight[i - kf->NLeft]);
+  };
+  std::vector<cv::KeyPoint> keys1(pKF1->N), keys2(pKF2->N);
+  for (int i = 0; i < pKF1->N; i++) keys1[i] = key(pKF1, i);
+  for (int i = 0; i < pKF2->N; i++) keys2[i] = key(pKF2, i);
+  k1.v.kps = reinterpret_cast<const orbx_kp*>(keys1.data());
+  k2.v.kps = reinterpret_cast<const orbx_kp*>(keys2.data());
+  std::vector<int32_t> off(pKF1->N + 1), ci((size_t)16 * pKF1->N + 64), cd(ci.size());
+  int32_t total = 0;
+  int rc = orbm_triangulation_candidates(OrbxThreadMatcher(), &k1.v, &k2.v, off.data(), ci.data(), cd.data(),
+                                         (int32_t)ci.size(), &total);
+  if (rc == ORBX_E_CAPACITY) {
+    ci.resize(total);
+    cd.resize(total);
+    rc = orbm_triangulation_candidates(OrbxThreadMatcher(), &k1.v, &k2.v, off.data(), ci.data(), cd.data(), total, &total);
+  }
+  if (rc != ORBX_OK) throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  std::vector<int> vMatches12(pKF1->N, -1);
+  std::vector<std::vector<int>> rotHist(HISTO_LENGTH);
+  const float factor = 1.0f / HISTO_LENGTH;
+  int nmatches = 0;
+  // rows in the reference's order: vocabulary nodes ascending, features in the node's list order (only the rotation
+  // histogram's push order depends on it, and that order decides nothing)
+  for (int idx1 = 0; idx1 < pKF1->N; idx1++) {
+    if (off[idx1] == off[idx1 + 1]) continue;
+    const cv::KeyPoint& kp1 = keys1[idx1];
+    const bool bRight1 = !(pKF1->NLeft == -1 || idx1 < pKF1->NLeft);
+    int bestDist = TH_LOW, bestIdx2 = -1;
+    for (int c = off[idx1]; c < off[idx1 + 1]; c++) {
+      const int idx2 = ci[c], dist = cd[c];
+      if (dist > bestDist) continue;                                                                // :988
+      const cv::KeyPoint& kp2 = keys2[idx2];
+      const bool bRight2 = !(pKF2->NLeft == -1 || idx2 < pKF2->NLeft);
+      const int pair = 2 * (int)bRight1 + (int)bRight2;                                             // :1007-1043
+      GeometricCamera* pCamera1 = bRight1 ? pKF1->mpCamera2 : pKF1->mpCamera;
+      GeometricCamera* pCamera2 = bRight2 ? pKF2->mpCamera2 : pKF2->mpCamera;
+      if (bCoarse || pCamera1->epipolarConstrain(pCamera2, kp1, kp2, R[pair], t[pair], pKF1->mvLevelSigma2[kp1.octave],
+                                                 pKF2->mvLevelSigma2[kp2.octave])) {               // :1045-1052
+        bestIdx2 = idx2;
+        bestDist = dist;
+      }
+    }
+    if (bestIdx2 >= 0) {                                                                            // :1060-1076
+      vMatches12[idx1] = bestIdx2;
+      nmatches++;
+      if (bCheckOrientation) {
+        float rot = kp1.angle - keys2[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(idx1);
+      }
+    }
+  }
+  if (bCheckOrientation) {                                                                          // :1082-1095
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist.data(), HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+        vMatches12[rotHist[i][j]] = -1;
+        nmatches--;
+      }
+    }
+  }
+  vMatchedPairs.reserve(nmatches);
+  for (size_t i = 0, iend = vMatches12.size(); i < iend; i++)
+    if (vMatches12[i] >= 0) vMatchedPairs.push_back(std::make_pair(i, (size_t)vMatches12[i]));
+  return nmatches;
+}
+}  // namespace
+
 int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2,
                                        std::vector<std::pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo,
                                        const bool bCoarse) {
+  if (pKF1->mpCamera2 && pKF2->mpCamera2)
+    return SearchForTriangulationTwoCameras(
+        pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse, mbCheckOrientation,
+        [this](std::vector<int>* h, int L, int& a, int& b, int& c) { ComputeThreeMaxima(h, L, a, b, c); });
   // epipole and F12 exactly as the reference computes them (:893-911, src/CameraModels/Pinhole.cpp:122-149)
   const Sophus::SE3f T1w = pKF1->GetPose(), T2w = pKF2->GetPose(), Tw2 = pKF2->GetPoseInverse();
   const Eigen::Vector3f C2 = T2w * pKF1->GetCameraCenter();

@@ -49,6 +49,11 @@ int orbm_search_for_triangulation(orbm_matcher*, const orbx_keyframe_view* kf1, 
   if (nmatches) *nmatches = n;
   return ORBX_OK;
 }
+int orbm_triangulation_candidates(orbm_matcher*, const orbx_keyframe_view* kf1, const orbx_keyframe_view* kf2,
+                                  int32_t* offsets, int32_t* cand_idx2, int32_t* cand_dist, int32_t cap, int32_t* total) {
+  *total = orbref_triangulation_candidates(kf1, kf2, offsets, cand_idx2, cand_dist, cap);
+  return *total > cap ? ORBX_E_CAPACITY : ORBX_OK;
+}
 int orbm_search_by_bow(orbm_matcher*, const orbx_keyframe_view* kf, const orbx_keyframe_view* frame, float nnratio,
                        int check_orientation, int32_t* matches_f, int32_t* nmatches) {
   const int n = orbref_search_by_bow(kf, frame, nnratio, check_orientation, matches_f);

@@ -310,6 +310,22 @@ def test_search_by_bow_keyframe_frame(gpu, nnratio, check, seed):
         assert n2 == n2_r and np.array_equal(m12, m12_r), np.nonzero(m12 != m12_r)[0][:10]
 
 
+@pytest.mark.parametrize("seed", [5, 6])
+def test_triangulation_candidates(gpu, seed):
+    """orbm_triangulation_candidates: the descriptor part of SearchForTriangulation (src/ORBmatcher.cc:973-988) for rigs
+    whose epipolar test stays with the caller's camera objects — CSR of (idx2, distance <= TH_LOW) per kf1 feature in
+    scan order == oracle; a too small buffer is reported with the required size."""
+    from test_oracle_matchers_vs_reference_source import _triangulation_case
+    v1r, v2r = _triangulation_case(seed)   # the view structs are the ABI's: the oracle's holders serve both sides
+    off_r, idx_r, dist_r = orbref.triangulation_candidates(v1r, v2r)
+    mt = ORBmatcher(0.6, True)
+    off, idx, dist = mt.TriangulationCandidates(v1r, v2r)
+    assert len(idx_r) > 100
+    assert np.array_equal(off, off_r) and np.array_equal(idx, idx_r) and np.array_equal(dist, dist_r)
+    off2, idx2, dist2 = mt.TriangulationCandidates(v1r, v2r, cap=7)     # retried with the reported total
+    assert np.array_equal(off2, off_r) and np.array_equal(idx2, idx_r) and np.array_equal(dist2, dist_r)
+
+
 @pytest.mark.parametrize("nnratio,check,seed", [(0.7, True, 1), (0.9, False, 2), (0.6, True, 3)])
 def test_search_by_bow_two_camera_frame(gpu, nnratio, check, seed):
     """SearchByBoW(KeyFrame*, Frame&, ...) on a two-camera Frame (F.Nleft != -1, src/ORBmatcher.cc:274-365): left /

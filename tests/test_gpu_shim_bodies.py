@@ -25,7 +25,8 @@ def shim_world(gpu, monkeypatch):
                  "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
                  "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
                  "orbrefsrc_distinctive_descriptor", "orbrefsrc_search_by_projection_map_fisheye",
-                 "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye"):
+                 "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye",
+                 "orbrefsrc_search_by_bow_kf_fisheye", "orbrefsrc_search_for_triangulation_fisheye"):
         getattr(lib, name).restype = C.c_int
     refsrc.mlib()
     monkeypatch.setattr(refsrc, "_mlib", lib)
@@ -68,6 +69,17 @@ def test_shim_search_by_bow(shim_world, args):
 @pytest.mark.parametrize("args", [(1, 0.7, True, True), (2, 0.9, False, False), (3, 0.6, True, True)])
 def test_shim_search_by_bow_two_camera_frame(shim_world, args):
     T.test_search_by_bow_two_camera_frame(*args)
+
+
+@pytest.mark.parametrize("args", [(False, False, True, 0.5, 0.6), (False, False, False, 0.3, 1.0), (False, True, True, 0.5, 0.5),
+                                  (True, False, True, 0.5, 0.5), (False, False, True, 0.0, 0.4)])
+def test_shim_search_for_triangulation_two_camera_keyframes(shim_world, args):
+    T.test_search_for_triangulation_two_camera_keyframes(*args)
+
+
+@pytest.mark.parametrize("args", [(1, 0.7, True), (2, 0.9, False)])
+def test_shim_search_by_bow_two_camera_keyframes(shim_world, args):
+    T.test_search_by_bow_two_camera_keyframes(*args)
 
 
 @pytest.mark.parametrize("args", [(1, 0, 0), (2, 150, 90), (3, 399, 0), (4, 0, 398)])

@@ -91,6 +91,46 @@ def test_search_for_triangulation(only_stereo, coarse, check, ep, F12=None):
     assert n_r == n_o and np.array_equal(m_r, m_o)
 
 
+_F12X4 = np.array([[[1e-7, 2e-6, -3e-4], [-2e-6, 1e-7, -1], [4e-4, 1, 2e-2]],          # left  x left
+                   [[2e-7, 1e-6, -2e-4], [-1e-6, 2e-7, -1], [3e-4, 1, -3.0]],          # left  x right
+                   [[1e-7, -2e-6, 3e-4], [2e-6, 1e-7, -1], [-4e-4, 1, 2.5]],           # right x left
+                   [[3e-7, 2e-6, -1e-4], [-2e-6, 3e-7, -1], [1e-4, 1, -1.5]]], f32)     # right x right
+
+
+@pytest.mark.parametrize("only_stereo,coarse,check,fl1,fl2", [(False, False, True, 0.5, 0.6), (False, False, False, 0.3, 1.0),
+                                                              (False, True, True, 0.5, 0.5), (True, False, True, 0.5, 0.5),
+                                                              (False, False, True, 0.0, 0.4)])
+def test_search_for_triangulation_two_camera_keyframes(only_stereo, coarse, check, fl1, fl2):
+    """SearchForTriangulation with both mpCamera2 set (:958-960, :966-971, :991-994, :996, :1007-1043): nothing is
+    stereo, no epipole gate, the camera pair of the epipolar test follows the two features' sides of NLeft."""
+    v1, v2 = _triangulation_case(5)
+    nl1, nl2 = int(v1.struct.n * fl1), int(v2.struct.n * fl2)
+    n_o, m_o = orbref.search_for_triangulation_fisheye(v1, nl1, v2, nl2, _F12X4, only_stereo, coarse, check)
+    n_r, m_r = refsrc.search_for_triangulation_fisheye(v1, nl1, v2, nl2, _F12X4, only_stereo, coarse, check)
+    assert n_r == n_o and np.array_equal(m_r, m_o)
+    assert n_o == 0 if only_stereo else n_o > 20
+    if not only_stereo and not coarse and 0 < fl1 < 1 and fl2 < 1:
+        # the pair selection matters: one matrix for all four pairs gives a different answer
+        n_x, m_x = orbref.search_for_triangulation_fisheye(v1, nl1, v2, nl2, np.stack([_F12X4[0]] * 4), False, False, check)
+        assert not np.array_equal(m_x, m_o)
+
+
+def test_triangulation_candidates_replay_equals_the_search():
+    """orbref_triangulation_candidates + the host replay the drop-in body runs (bestDist = TH_LOW; a candidate at or
+    below the running best that passes the epipolar test takes over, :988-1052) == the one-piece search."""
+    v1, v2 = _triangulation_case(6)
+    off, idx2, dist = orbref.triangulation_candidates(v1, v2)
+    assert off[-1] == len(idx2) and len(idx2) > 100 and (dist <= 50).all()
+    n_o, m_o = orbref.search_for_triangulation_fisheye(v1, 0, v2, 0, np.stack([_F12X4[3]] * 4), False, True, False)
+    m = np.full(v1.struct.n, -1, np.int32)
+    for i in range(v1.struct.n):
+        best = 50
+        for c in range(off[i], off[i + 1]):
+            if dist[c] <= best:      # coarse: every candidate passes
+                best, m[i] = dist[c], idx2[c]
+    assert np.array_equal(m, m_o) and n_o == (m >= 0).sum()
+
+
 @pytest.mark.parametrize("seed,nnratio,check", [(1, 0.7, True), (2, 0.9, False), (3, 0.6, True)])
 def test_search_by_bow_both_overloads(seed, nnratio, check):
     """SearchByBoW(KeyFrame*, Frame&, ...) :230-404 and SearchByBoW(KeyFrame*, KeyFrame*, ...) :766-884."""
@@ -125,6 +165,21 @@ def test_search_by_bow_two_camera_frame(seed, nnratio, check, kf_two):
     n_c, m_c = refsrc.search_by_bow_fisheye(v1, nl_kf, v2, 0, nnratio, check)
     n_d, m_d = orbref.search_by_bow_fisheye(v1, v2, 0, nnratio, check)
     assert n_c == n_d == 0 and np.array_equal(m_c, m_d)
+
+
+@pytest.mark.parametrize("seed,nnratio,check", [(1, 0.7, True), (2, 0.9, False)])
+def test_search_by_bow_two_camera_keyframes(seed, nnratio, check):
+    """SearchByBoW(KeyFrame*, KeyFrame*, ...) with NLeft != -1 (:799-801, :816-818): rows past mvKeysUn are skipped on
+    both sides — the one-camera function on views whose MapPoint flags are cleared there."""
+    k1, k2 = _keyframes(seed)
+    un1, un2 = int(len(k1["kps"]) * 0.7), int(len(k2["kps"]) * 0.6)
+    n_r, m_r = refsrc.search_by_bow_kf_fisheye(_view(k1), un1, _view(k2), un2, nnratio, check)
+    c1, c2 = dict(k1), dict(k2)
+    c1["hm"], c2["hm"] = k1["hm"].copy(), k2["hm"].copy()
+    c1["hm"][un1:] = 0
+    c2["hm"][un2:] = 0
+    n_o, m_o = orbref.search_by_bow_kf(_view(c1), _view(c2), nnratio, check)
+    assert n_o > 10 and n_r == n_o and np.array_equal(m_r, m_o)
 
 
 def _fisheye_stereo_python(kl, dl, kr, dr, mono_l, mono_r, s2, R, t):
