@@ -467,7 +467,9 @@ def run_stereo_workload(ctx, args, cfg_id, steps, warmup, reps, with_cpu, clock_
     del reps_tile
 
     # the end-to-end extractors (small pipelined groups) also produce the keypoints the synthetic maps are anchored on
-    G = args.e2e_group or max(8, min(64, P // 8))
+    # pipelined group size: measured on B200 with the ordered upload stream (gpurun_out/exp_e2e_groups.log): 17.7 / 17.5 /
+    # 17.2 / 17.0 / 17.3 ms per 1024-pair call for groups of 64 / 96 / 128 / 192 / 256 pairs
+    G = args.e2e_group or max(8, min(128, P // 8))
     exl2 = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
     exr2 = ORBextractor(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_batch=G)
     first = mt.StereoFramesBatch(exl2, exr2, Ld, Rd, MBF, MB)

@@ -85,8 +85,8 @@ int orbx_extract_batch_device(orbx_extractor* ex, int n_frames, const uint8_t* d
  * the reference's layout — the (w + 38) x (h + 38) buffer with the 19-px BORDER_REFLECT_101 frame
  * (src/ORBextractor.cc:1114-1143); the cv::Mat the shim exposes is the ROI at (19, 19).
  * `frame` (here, in the orbx_debug_* calls and in the orbm_* calls that take an extractor + frame) is the index of the
- * frame inside the extractor's most recent extract call. A call keeps the device state of its last 4 groups of
- * max_batch frames: every frame of a call of <= 4 * max_batch frames is addressable, of a longer call only the tail;
+ * frame inside the extractor's most recent extract call. A call keeps the device state of its last 8 groups of
+ * max_batch frames: every frame of a call of <= 8 * max_batch frames is addressable, of a longer call only the tail;
  * a frame that is gone (or an index from an earlier call) gives ORBX_E_ARG, never another frame's data. */
 int orbx_level_size(const orbx_extractor* ex, int level, int* width, int* height);
 int orbx_download_pyramid(orbx_extractor* ex, int frame, int level, uint8_t* dst, int dst_stride);

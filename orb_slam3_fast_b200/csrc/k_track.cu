@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) k_frustum(const TrackArgs A) {
   __syncthreads();
   bool counted = false;
   if (i < A.m) {
-    const int mi = A.map_index ? A.map_index[f] : f % A.n_maps;
+    const int mi = A.map_index ? A.map_index[f] : (A.map_f0 + f) % A.n_maps;
     const size_t g = (size_t)mi * A.m + i, o = (size_t)f * A.m + i;
     float4 q = make_float4(-1.f, -1.f, 0.f, 0.f);
     int lvl = -1;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
   }
   __syncthreads();
   const bool has_ur = A.u_right != nullptr;
-  const size_t map_base = (size_t)(A.map_index ? A.map_index[f] : f % A.n_maps) * A.m;
+  const size_t map_base = (size_t)(A.map_index ? A.map_index[f] : (A.map_f0 + f) % A.n_maps) * A.m;
   uint32_t* slab = A.cand + (size_t)f * A.cand_cap;
   const int i0 = blockIdx.x * (kEnumThreads * kEnumPerThread);
   // The CTA's points are visited in the order of their predicted level (a counting sort of <= 2048 local indices): a
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(kTrackResolveThreads) k_track_resolve(const Tr
   const int2* seg = A.seg + (size_t)f * M;
   const int4* pre = A.pre + (size_t)f * M;
   const uint32_t* cand = A.cand + (size_t)f * A.cand_cap;
-  const uint8_t* has_obs = A.has_obs + (size_t)(A.map_index ? A.map_index[f] : f % A.n_maps) * M;
+  const uint8_t* has_obs = A.has_obs + (size_t)(A.map_index ? A.map_index[f] : (A.map_f0 + f) % A.n_maps) * M;
   for (int k = tid; k < n; k += kTrackResolveThreads) {
     T[k] = 0x7fffffff;
     occ0[k] = A.occupied ? A.occupied[(size_t)f * A.cap + k] : 0;

@@ -164,6 +164,9 @@ void orbm_destroy(orbm_matcher* m) {
   for (auto& h : m->lane_h_track)
     if (h) cudaFreeHost(h);
   if (m->track_map_ready) cudaEventDestroy(m->track_map_ready);
+  if (m->up_stream) cudaStreamDestroy(m->up_stream);
+  for (cudaEvent_t e : m->up_small)
+    if (e) cudaEventDestroy(e);
   if (m->h_stage) cudaFreeHost(m->h_stage);
   if (m->d_stage) cudaFree(m->d_stage);
   if (m->stream) cudaStreamDestroy(m->stream);
@@ -381,7 +384,10 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     }
     if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
   }
-  // ---- the tracking stage: local maps go to the device once per call, on the matcher's stream ----
+  if (!m->up_stream) ORBM_CUDA(m, cudaStreamCreateWithFlags(&m->up_stream, cudaStreamNonBlocking));
+  static const bool lane_uploads = getenv("ORBX_LANE_UPLOADS") != nullptr;  // A/B: uploads on the lanes' own streams
+  const cudaStream_t up = m->up_stream;
+  // ---- the tracking stage: local maps go to the device once per call, on the upload stream ----
   TrackArgs T0{};
   orbx_local_map dmap{};
   int32_t* d_map_index_all = nullptr;
@@ -399,9 +405,9 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
       if (!bytes[k]) continue;
       cudaError_t e = m->track_map[k].reserve(bytes[k]);
       if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
-      ORBM_CUDA(m, cudaMemcpyAsync(m->track_map[k].p, host[k], bytes[k], cudaMemcpyHostToDevice, m->stream));
+      ORBM_CUDA(m, cudaMemcpyAsync(m->track_map[k].p, host[k], bytes[k], cudaMemcpyHostToDevice, up));
     }
-    ORBM_CUDA(m, cudaEventRecord(m->track_map_ready, m->stream));
+    ORBM_CUDA(m, cudaEventRecord(m->track_map_ready, up));
     dmap.m = hm.m;
     dmap.n_maps = hm.n_maps;
     dmap.pos = static_cast<const float*>(m->track_map[0].p);
@@ -412,13 +418,7 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     dmap.has_obs = static_cast<const uint8_t*>(m->track_map[5].p);
     dmap.desc = static_cast<const uint8_t*>(m->track_map[6].p);
     d_map_index_all = trk->map_index ? static_cast<int32_t*>(m->track_map[7].p) : nullptr;
-    if (!trk->map_index && hm.n_maps > 1) {  // the default rule "pair p uses map p % n_maps", as an explicit array
-      std::vector<int32_t> idx(n_pairs);
-      for (int p = 0; p < n_pairs; p++) idx[p] = p % hm.n_maps;
-      cudaError_t e = m->track_map[7].reserve((size_t)n_pairs * 4);
-      if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
-      ORBM_CUDA(m, cudaMemcpy(m->track_map[7].p, idx.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice));
-    }
+    // without an explicit array pair p uses map p % n_maps: the kernels compute it from TrackArgs::map_f0
     track_set_map(&dmap, &T0);
     for (int ln = 0; ln < kLanes; ln++) {
       if (m->lane_h_track_cap[ln] < B) {
@@ -470,6 +470,23 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
   }
   // ORBX_TRACE=1: host time spent waiting for a lane vs issuing work, per call (stderr)
   static const bool trace = getenv("ORBX_TRACE") != nullptr;
+  static const bool timeline = trace && atoi(getenv("ORBX_TRACE")) >= 2;  // per-group GPU timeline (CUDA events)
+  std::vector<cudaEvent_t> tev;  // 9 per group, see the print below
+  auto tl = [&](int which, cudaStream_t s) {
+    if (!timeline) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    tev.push_back(e);
+    (void)which;
+    cudaEventRecord(e, s);
+  };
+  auto tl_slot = [&]() -> cudaEvent_t {
+    if (!timeline) return nullptr;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    tev.push_back(e);
+    return e;
+  };
   double t_wait = 0, t_issue = 0;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   int group = 0, f0 = 0;
@@ -507,27 +524,41 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
       d_fr = static_cast<orbx_frustum*>(tb[9].p);
       d_assign = static_cast<int32_t*>(tb[10].p);
       d_words = d_assign + (size_t)B * dcap0;  // nmatches[B] | n_in_view[B] | status[B]
-      ORBM_CUDA(m, cudaMemcpyAsync(d_fr, trk->frustums + f0, (size_t)nb * sizeof(orbx_frustum), cudaMemcpyHostToDevice, st));
+      const cudaStream_t cs = lane_uploads ? st : up;
+      ORBM_CUDA(m, cudaMemcpyAsync(d_fr, trk->frustums + f0, (size_t)nb * sizeof(orbx_frustum), cudaMemcpyHostToDevice, cs));
       if (trk->occupied) {
         d_occ = static_cast<uint8_t*>(tb[11].p);
         if (cap == dcap0) {
-          ORBM_CUDA(m, cudaMemcpyAsync(d_occ, trk->occupied + (size_t)f0 * cap, (size_t)nb * cap, cudaMemcpyHostToDevice, st));
+          ORBM_CUDA(m, cudaMemcpyAsync(d_occ, trk->occupied + (size_t)f0 * cap, (size_t)nb * cap, cudaMemcpyHostToDevice, cs));
         } else {
-          ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, (size_t)nb * dcap0, st));
+          ORBM_CUDA(m, cudaMemsetAsync(d_occ, 0, (size_t)nb * dcap0, cs));
           ORBM_CUDA(m, cudaMemcpy2DAsync(d_occ, dcap0, trk->occupied + (size_t)f0 * cap, cap, std::min(cap, dcap0), nb,
-                                         cudaMemcpyHostToDevice, st));
+                                         cudaMemcpyHostToDevice, cs));
         }
       }
+      if (!lane_uploads) {
+        if (!m->up_small[ln]) ORBM_CUDA(m, cudaEventCreateWithFlags(&m->up_small[ln], cudaEventDisableTiming));
+        ORBM_CUDA(m, cudaEventRecord(m->up_small[ln], up));
+        ORBM_CUDA(m, cudaStreamWaitEvent(st, m->up_small[ln], 0));
+      }
     }
+    tl(0, st);
+    orbx::g_trace_after_h2d = tl_slot();
     if ((rc = api_upload_and_run(left, ln, imgs_l + (int64_t)f0 * frame_stride, nb, width, height, stride,
-                                 frame_stride, 0, 0, st, f0)) != 0)
+                                 frame_stride, 0, 0, st, f0, lane_uploads ? nullptr : up)) != 0)
       return mfail(m, rc, orbx_last_error(left));
+    tl(2, st);
+    tl(5, sr);
+    orbx::g_trace_after_h2d = tl_slot();
     if ((rc = api_upload_and_run(right, ln, imgs_r + (int64_t)f0 * frame_stride, nb, width, height, stride,
-                                 frame_stride, 0, 0, sr, f0)) != 0)
+                                 frame_stride, 0, 0, sr, f0, lane_uploads ? nullptr : up)) != 0)
       return mfail(m, rc, orbx_last_error(right));
+    orbx::g_trace_after_h2d = nullptr;
+    tl(7, sr);
     // the right eye's descriptors can go home while the stereo matcher runs
     if ((rc = api_download(right, ln, nb, kps_r + (int64_t)f0 * cap, desc_r + (int64_t)f0 * cap * 32, cap, sr)) != 0)
       return mfail(m, rc, orbx_last_error(right));
+    tl(8, sr);
     ORBM_CUDA(m, cudaEventRecord(right->lane[ln].done, sr));
     ORBM_CUDA(m, cudaStreamWaitEvent(st, right->lane[ln].done, 0));
     // ... and ComputeStereoMatches (:223) on the outputs still resident in the lanes
@@ -552,6 +583,7 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     static const bool skip_kernels = getenv("ORBX_DEBUG_SKIP_KERNELS") != nullptr;  // timing experiment only
     if (!skip_kernels) launch_stereo(A, nb, dcap, st);
     ORBM_CUDA(m, cudaGetLastError());
+    tl(3, st);
     if ((rc = api_download(left, ln, nb, kps_l + (int64_t)f0 * cap, desc_l + (int64_t)f0 * cap * 32, cap, st)) != 0)
       return mfail(m, rc, orbx_last_error(left));
     if (cap == dcap) {
@@ -579,7 +611,7 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
       T.frustums = d_fr;
       T.map_index = nullptr;
       if (d_map_index_all) T.map_index = d_map_index_all + f0;
-      else if (dmap.n_maps > 1) T.map_index = static_cast<int32_t*>(m->track_map[7].p) + f0;  // p % n_maps, see above
+      T.map_f0 = f0;  // no explicit array: pair f0 + f uses map (f0 + f) % n_maps
       T.occupied = trk->occupied ? d_occ : nullptr;
       T.assign = d_assign;
       T.nmatches = d_words;
@@ -602,6 +634,7 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
         ORBM_CUDA(m, cudaMemcpyAsync(m->lane_h_track[ln] + (size_t)k * B, d_words + (size_t)k * B, (size_t)nb * 4,
                                      cudaMemcpyDeviceToHost, st));
     }
+    tl(4, st);
     ORBM_CUDA(m, cudaEventRecord(left->lane[ln].done, st));
     pending_f0[ln] = f0;
     pending_nb[ln] = nb;
@@ -612,6 +645,18 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
   if (trace)
     fprintf(stderr, "orbm_stereo_frames_batch: %zu groups, host issue %.2f ms, wait for lanes %.2f ms, drain %.2f ms\n",
             sizes.size(), 1e3 * t_issue, 1e3 * t_wait, 1e3 * (now() - td0));
+  if (timeline && tev.size() == 9 * sizes.size() && sizes.size() > 2) {
+    // per group, ms since the first event. Recording order: L.start, L.h2d (images up), L.extr (extractor done), R.start,
+    // R.h2d, R.extr, R.d2h (right results home), L.stereo (stereo matcher done), L.end (tracking + all results home)
+    fprintf(stderr, "group pairs |  L.start   L.h2d  L.extr L.stereo   L.end |  R.start   R.h2d  R.extr   R.d2h\n");
+    for (size_t g = 0; g < sizes.size(); g++) {
+      float t[9];
+      for (int k = 0; k < 9; k++) cudaEventElapsedTime(&t[k], tev[0], tev[9 * g + k]);
+      fprintf(stderr, "%5zu %5d | %8.2f %7.2f %7.2f %8.2f %7.2f | %8.2f %7.2f %7.2f %7.2f\n", g, sizes[g], t[0], t[1], t[2], t[7],
+              t[8], t[3], t[4], t[5], t[6]);
+    }
+  }
+  for (cudaEvent_t e : tev) cudaEventDestroy(e);
   if (first_err) return mfail(m, first_err, "output capacity (or the candidate list) too small for at least one frame");
   return ORBX_OK;
 }

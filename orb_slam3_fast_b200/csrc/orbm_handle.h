@@ -66,6 +66,11 @@ struct orbm_matcher {
   DevBuf track_buf[kLanes + 1][kTrackBufs];
   DevBuf track_map[8];
   cudaEvent_t track_map_ready = nullptr;
+  // every H2D copy of a pipelined stereo call goes through this one stream: the copy engine then serves them in issue
+  // order (with one stream per lane it served the channels round robin and the FIRST group's images arrived last, which
+  // kept its lane busy and the copy engine idle for ~2.8 ms per call; ORBX_TRACE=2 timeline)
+  cudaStream_t up_stream = nullptr;
+  cudaEvent_t up_small[8] = {};  // per lane: the tracking stage's small inputs are on the device
   int32_t* lane_h_track[kLanes] = {};
   int lane_h_track_cap[kLanes] = {};
 };

@@ -268,11 +268,14 @@ int api_ensure_out(orbx_extractor* ex, int cap) {
   return ORBX_OK;
 }
 
+thread_local cudaEvent_t g_trace_after_h2d = nullptr;
+
 int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, int width, int height, int stride,
-                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st, int f0) {
+                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st, int f0, cudaStream_t copy_stream) {
   OrbxLane& L = ex->lane[ln];
   int rc = alloc_lane(ex, L);
   if (rc) return rc;
+  const cudaStream_t cs = copy_stream ? copy_stream : st;
   FrameSet fs{};
   fs.lvl0 = L.d_in;
   if (frame_stride == (int64_t)stride * height && stride <= ex->in_pitch) {
@@ -282,15 +285,20 @@ int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, i
     // those of whatever the lane held before
     static const bool skip_h2d = getenv("ORBX_DEBUG_SKIP_H2D") != nullptr;
     if (!skip_h2d)
-      ORBX_CUDA(ex, cudaMemcpyAsync(L.d_in, src, (size_t)frame_stride * nb, cudaMemcpyHostToDevice, st));
+      ORBX_CUDA(ex, cudaMemcpyAsync(L.d_in, src, (size_t)frame_stride * nb, cudaMemcpyHostToDevice, cs));
+    if (g_trace_after_h2d) cudaEventRecord(g_trace_after_h2d, cs);  // ORBX_TRACE=2 timeline of the pipelined calls
     fs.pitch0 = stride;
     fs.fstride0 = frame_stride;
   } else {
     for (int f = 0; f < nb; f++)
       ORBX_CUDA(ex, cudaMemcpy2DAsync(L.d_in + f * ex->in_fstride, ex->in_pitch, src + f * frame_stride, stride,
-                                      width, height, cudaMemcpyHostToDevice, st));
+                                      width, height, cudaMemcpyHostToDevice, cs));
     fs.pitch0 = ex->in_pitch;
     fs.fstride0 = ex->in_fstride;
+  }
+  if (copy_stream) {
+    ORBX_CUDA(ex, cudaEventRecord(L.up, copy_stream));
+    ORBX_CUDA(ex, cudaStreamWaitEvent(st, L.up, 0));
   }
   OutSet out{L.d_kps, L.d_desc, L.d_n, L.d_mono, L.d_status, L.out_cap};
   return run_pipeline(ex, ln, fs, nb, lap0, lap1, out, st, f0);
@@ -352,6 +360,8 @@ int orbx_extractor_create(orbx_extractor** out, int device, int nfeatures, float
       return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
       return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&L.up, cudaEventDisableTiming)) != cudaSuccess)
+      return bail("cudaEventCreate", e);
     if ((e = cudaHostAlloc(&L.h_small, (size_t)3 * max_batch * 4, cudaHostAllocDefault)) != cudaSuccess)
       return bail("cudaHostAlloc", e);
   }
@@ -374,6 +384,7 @@ void orbx_extractor_destroy(orbx_extractor* ex) {
   for (OrbxLane& L : ex->lane) {
     if (L.h_small) cudaFreeHost(L.h_small);
     if (L.done) cudaEventDestroy(L.done);
+    if (L.up) cudaEventDestroy(L.up);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete ex;

@@ -14,11 +14,14 @@
 
 #include "orbx_kernels.cuh"
 
-enum { kStages = 5, kLanes = 4 };
+// 8 lanes: the pipelined host-facing calls are bound by the H2D copies once the kernels are fast enough, and with 4
+// lanes the copy engine idled ~1.8 ms per call while the host waited for the first group to retire (ORBX_TRACE=2 timeline)
+enum { kStages = 5, kLanes = 8 };
 
 struct OrbxLane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t up = nullptr;  // recorded on the caller's upload stream after the lane's H2D copy (api_upload_and_run)
   // geometry-dependent device state
   uint8_t *d_in = nullptr, *d_pyr = nullptr, *d_blur = nullptr;
   orbx::WorkSet ws{};
@@ -68,11 +71,16 @@ int api_ensure_out(orbx_extractor* ex, int cap);
 // kLanes * max_batch frames keeps only its last kLanes groups resident; ORBX_E_ARG for a frame that is gone (or never
 // existed).
 int api_find_frame(const orbx_extractor* ex, int frame, int* lane, int* local);
+// ORBX_TRACE=2: when set, api_upload_and_run records this event right after its H2D copy (timeline of the pipelined calls)
+extern thread_local cudaEvent_t g_trace_after_h2d;
 // every public extract entry point calls this first: frames of earlier calls stop being addressable
 void api_begin_call(orbx_extractor* ex);
 // H2D of nb frames into lane `ln` and the whole extractor on stream st; results stay in the lane's device outputs
+// copy_stream != nullptr: the H2D copy goes to that stream instead (the pipelined stereo calls keep ALL uploads of a call
+// on one stream, so that the copy engine serves them in issue order) and st waits for it through the lane's `up` event
 int api_upload_and_run(orbx_extractor* ex, int ln, const uint8_t* src, int nb, int width, int height, int stride,
-                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st, int f0 = 0);
+                       int64_t frame_stride, int lap0, int lap1, cudaStream_t st, int f0 = 0,
+                       cudaStream_t copy_stream = nullptr);
 // D2H of the lane's outputs of nb frames into rows [0, nb) of the caller's arrays (counts go to the pinned h_small)
 int api_download(orbx_extractor* ex, int ln, int nb, orbx_kp* kps, uint8_t* desc, int cap, cudaStream_t st);
 }  // namespace orbx

@@ -120,7 +120,7 @@ void launch_search_resolve(const DevFrame& F, const DevQueries& Q, const SearchS
 
 // ---- batched local-map tracking search (k_track.cu): Tracking::SearchLocalPoints for the frames of one extract batch
 // Frame f: keypoints kps + f * cap (n[f] of them), descriptors desc + f * cap * 32, its pose frustums[f], its local map
-// map_index[f] (NULL: f % n_maps). Everything is device memory; nothing is synchronised.
+// map_index[f] (NULL: (map_f0 + f) % n_maps). Everything is device memory; nothing is synchronised.
 constexpr int kTrackOff16 = ORBX_GRID_COLS * ORBX_GRID_ROWS + 4;  // u16 cell offsets per frame (3073 used)
 struct TrackArgs {
   int n_frames, cap;
@@ -137,6 +137,7 @@ struct TrackArgs {
   const float *pos, *normal, *min_dist, *max_dist;
   const uint8_t *skip, *has_obs, *mdesc;
   const int32_t* map_index;
+  int map_f0;  // map_index == NULL: frame f uses map (map_f0 + f) % n_maps
   const orbx_frustum* frustums;  // [F]
   float viewing_cos_limit, th, nnratio, th_far;
   int far_points;

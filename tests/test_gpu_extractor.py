@@ -126,20 +126,20 @@ def test_batch_matches_single_and_oracle(gpu):
 
 def test_frame_index_addresses_the_whole_call_not_the_last_group(gpu):
     """`frame` of orbx_download_pyramid / orbx_debug_* / orbm_stereo_match is the index inside the last call: with
-    n_frames > max_batch the frames of earlier groups stay addressable while their lane is resident (the last 4 groups),
+    n_frames > max_batch the frames of earlier groups stay addressable while their lane is resident (the last 8 groups),
     and a frame that is gone is an error instead of another frame's data."""
     from orb_slam3_fast_b200 import ORBmatcher
     from orb_slam3_fast_b200.lib import OrbxError
-    n = 11
+    n = 19
     imgs = np.stack([synth.stereo_pair(480, 640, 70 + s)[0] for s in range(n)])
     right = np.stack([synth.stereo_pair(480, 640, 70 + s)[1] for s in range(n)])
-    ex, exr = ORBextractor(1000, max_batch=2), ORBextractor(1000, max_batch=2)  # groups: 0-1 2-3 4-5 6-7 | 8-9 10
+    ex, exr = ORBextractor(1000, max_batch=2), ORBextractor(1000, max_batch=2)  # 10 groups of 2 (the last of 1) on 8 lanes: groups 0 and 1 are overwritten
     ex_ref, exr_ref = orbref.Extractor(1000), orbref.Extractor(1000)
     nk, mono, kps, desc = ex.extract_batch(imgs, (0, 0))
     nr, _, kr, dr = exr.extract_batch(right, (0, 0))
     mt = ORBmatcher()
     mbf, mb = float(np.float32(435.2 * 0.11)), float(np.float32(0.11))
-    for f in (4, 7, 8, 10):  # resident: lanes 2, 3, 0, 1
+    for f in (4, 7, 16, 18):  # resident: lanes 2, 3, 0, 1
         ex_ref(imgs[f], (0, 0))
         exr_ref(right[f], (0, 0))
         for l in (0, 5):
@@ -149,12 +149,12 @@ def test_frame_index_addresses_the_whole_call_not_the_last_group(gpu):
         got = mt.ComputeStereoMatches(ex, exr, kps[f, :nk[f]], desc[f, :nk[f]], kr[f, :nr[f]], dr[f, :nr[f]], mbf, mb, frame=f)
         ref = orbref.stereo_match(ex_ref, exr_ref, kps[f, :nk[f]], desc[f, :nk[f]], kr[f, :nr[f]], dr[f, :nr[f]], mbf, mb)
         assert got[0] == ref[0] and got[1].tobytes() == ref[1].tobytes() and got[2].tobytes() == ref[2].tobytes(), f
-    for f in (0, 3, 11, -1):  # overwritten by the second round of groups / out of range
+    for f in (0, 3, 19, -1):  # overwritten by the second round of groups / out of range
         with pytest.raises(OrbxError):
             ex.image_pyramid_bordered(0, f)
     ex(imgs[0])  # a new call: the old indices are gone
     with pytest.raises(OrbxError):
-        ex.image_pyramid_bordered(0, 8)
+        ex.image_pyramid_bordered(0, 16)
     assert np.array_equal(ex.image_pyramid(0, 0), imgs[0])
 
 
@@ -216,6 +216,41 @@ def test_device_resident_input_every_staging_variant(gpu, base_off, pad):
     for k in range(B):
         _compare_frame(ref, kps[k, :n[k]], desc[k, :n[k]], int(d_mono[k].item()), imgs[k], (0, 0),
                        "device input base+%d pitch+%d frame %d" % (base_off, pad, k))
+
+
+def test_blur_kernels_tensor_core_form_and_fallback(gpu):
+    """The Gaussian blur runs as banded u8 GEMMs on the tensor cores (k_blur_tc) whenever TMA can address the levels; the
+    CUDA-core kernel k_blur7<kBlurTma> is then only reached with ORBX_BLUR_TC=0 (read once per process, hence the
+    subprocess). Both must give the oracle's keypoints and descriptors — the descriptor bits are sign tests on the blurred
+    level, so a single wrong byte shows — on sizes whose levels have one tile column / row, ragged right / bottom tiles
+    and widths that are not multiples of 16."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+from orb_slam3_fast_b200 import ORBextractor, synth
+from oracle import orbref
+for (h, w, nf, nl) in ((480, 640, 1000, 8), (241, 333, 500, 5), (130, 517, 400, 3), (720, 1280, 1500, 8)):
+    img = synth.scene(h, w, seed=h + w)
+    ex, ref = ORBextractor(nf, 1.2, nl), orbref.Extractor(nf, 1.2, nl)
+    m, k, d = ex(img, (0, 0))
+    m_r, k_r, d_r = ref(img, (0, 0))
+    assert m == m_r and np.array_equal(k, k_r) and np.array_equal(d, d_r), (h, w)
+    imgs = np.stack([synth.scene(h, w, seed=h + w + s) for s in range(3)])
+    exb = ORBextractor(nf, 1.2, nl, max_batch=3)
+    n_out, _, kps, desc = exb.extract_batch(imgs)
+    for s in range(3):
+        _, k_r, d_r = ref(imgs[s], (0, 0))
+        n = int(n_out[s])
+        assert n == len(k_r) and np.array_equal(kps[s, :n], k_r) and np.array_equal(desc[s, :n], d_r), (h, w, s)
+print("ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for tc in ("1", "0"):
+        env = dict(os.environ, ORBX_BLUR_TC=tc)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "ok" in r.stdout, "ORBX_BLUR_TC=%s\n%s\n%s" % (tc, r.stdout[-2000:], r.stderr[-2000:])
 
 
 @pytest.mark.parametrize("channels,rgb", [(3, False), (3, True), (4, False), (4, True)])
