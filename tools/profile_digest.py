@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_summary  # noqa: E402
 
-STAGE = {"k_resize": "pyramid", "k_resize_tma": "pyramid", "k_fast": "fast", "k_quadtree": "quadtree", "k_blur7": "blur",
+STAGE = {"k_resize": "pyramid", "k_resize_tma": "pyramid", "k_fast": "fast", "k_quadtree": "quadtree", "k_blur7": "blur", "k_blur_tc": "blur",
          "k_describe": "describe", "k_stereo_match": "stereo", "k_stereo_median": "stereo", "k_frustum": "track",
          "k_track_grid": "track", "k_track_enum": "track", "k_track_resolve": "track"}
 PAIR_STAGES = ("stereo", "track")  # launched once per pair batch, not per eye
