@@ -682,9 +682,10 @@ def run_stereo_workload(ctx, args, cfg_id, steps, warmup, reps, with_cpu, clock_
 
     # candidates per frame (C) from a few frames of the last batch
     C = 0
-    for f in range(4):
+    n_probe = min(4, P)
+    for f in range(n_probe):
         C += sum(exl._check(exl._L.orbx_debug_candidates(exl._h, f, l, None, 0)) for l in range(NLEVELS))
-    C /= 4.0
+    C /= float(n_probe)
     sumP = sum(exl.level_size(l)[0] * exl.level_size(l)[1] for l in range(NLEVELS))
     P0 = w * h
     Nk = n_keypoints

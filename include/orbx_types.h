@@ -136,8 +136,10 @@ typedef struct orbx_track_params {
   float th_far;            /* mpLocalMapper->mThFarPoints */
   float min_x, min_y;      /* Frame::mnMinX, mnMinY */
   float inv_w, inv_h;      /* Frame::mfGridElementWidthInv / HeightInv */
-  int32_t cand_per_frame;  /* capacity of the per-frame candidate list (keypoints that fall into some point's window);
-                              0 = 16 * m. A frame that needs more is reported with status ORBX_E_CAPACITY. */
+  int32_t cand_per_frame;  /* capacity of the per-frame candidate list, counted in grid records: the keypoints of the
+                              cells every searched point's window touches (an upper bound of its candidates);
+                              0 = 16 * m * max(1, th^2 / 4), at most m * cap. A frame that needs more is reported
+                              with status ORBX_E_CAPACITY. */
 } orbx_track_params;
 
 /* Points of the last frame / a keyframe already projected into the current frame by the caller (the SE3 product and

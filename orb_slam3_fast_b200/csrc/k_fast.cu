@@ -161,7 +161,7 @@ template <bool kTma>
 __global__ void __launch_bounds__(kFastWarps * 32)
 k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, const FrameSet fs, const WorkSet ws,
        int ini_th, int min_th, int tp, int sp, int raw_bytes, int score_bytes, int per_warp, int box_w,
-       int box_bytes, int cell_begin, int cell_end) {
+       int box_bytes, int cell_begin, int cell_end, int pretest_mask) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = cell_begin + blockIdx.x * kFastWarps + warp;  // this launch covers the cells [cell_begin, cell_end)
@@ -330,7 +330,8 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
     const int T = pass == 0 ? ini_th : min_th;
     const int r_min = max(max(T - tlow + 1, 2 - tlow), 1);  // m > T and m - 1 > 0, in the r domain
     int n_score = ngroups;
-    if (pass == 0) {
+    const bool listed = (pretest_mask >> pass) & 1;
+    if (listed) {
       // -- compass pre-test, two adjacent groups (8 pixels) per lane step: rows r, r+3, r+6 of the tile are
       //    dy = -3, 0, +3; the step's tile words come in with 16-byte loads (tile rows and 8-pixel starts are 16-byte
       //    aligned) --
@@ -387,7 +388,7 @@ k_fast(const __grid_constant__ Plan P, const __grid_constant__ FastMaps maps, co
     for (int kbase = 0; kbase < n_score; kbase += 32) {
       const int k = kbase + lane;
       int r, g;
-      if (pass == 0) {
+      if (listed) {
         const uint32_t e = k < n_score ? list[k] : 0u;
         r = (int)(e >> 8);
         g = (int)(e & 255u);
@@ -530,18 +531,21 @@ static void launch_fast_levels(const Plan& P, const FrameSet& fs, const WorkSet&
   const int attr = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
   const int cell_begin = P.lv[l0].cell_base, cell_end = l1 < P.nlevels ? P.lv[l1].cell_base : P.cells_per_frame;
   dim3 grid((cell_end - cell_begin + kFastWarps - 1) / kFastWarps, frames);
+  // bit p: pass p (0 = iniThFAST, 1 = the minThFAST retry) runs the compass pre-test and scores listed groups only.
+  // Default: pass 0 only (DESIGN.md "measured decisions"); ORBX_FAST_PRETEST=3 is the A/B switch for the retry.
+  static const int pretest_mask = getenv("ORBX_FAST_PRETEST") ? atoi(getenv("ORBX_FAST_PRETEST")) & 3 : 1;
   FastMaps M;
   if (L.box_w <= 256 && L.box_h <= 256 && make_fast_maps(P, fs, L, frames, &M)) {
     cudaFuncSetAttribute(k_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     k_fast<true><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
                                                       L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h,
-                                                      cell_begin, cell_end);
+                                                      cell_begin, cell_end, pretest_mask);
   } else {
     memset(&M, 0, sizeof(M));
     cudaFuncSetAttribute(k_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attr);
     k_fast<false><<<grid, kFastWarps * 32, smem, st>>>(P, M, fs, ws, ini_th, min_th, L.tp, L.sp, L.raw_bytes,
                                                        L.score_bytes, L.per_warp, L.box_w, L.box_w * L.box_h,
-                                                       cell_begin, cell_end);
+                                                       cell_begin, cell_end, pretest_mask);
   }
 }
 

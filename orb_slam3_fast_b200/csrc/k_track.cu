@@ -6,9 +6,10 @@
 //   k_frustum        thread = (frame, point): the projection and the scalar prologue of the search loop (:55-74:
 //                    which points take part, r = RadiusByViewingCos(viewCos) * th * scale[level]) -> one float4 + level
 //   k_track_grid     one warp per frame: the 64x48 grid as u16 offsets + 16-byte search records in cell order
-//   k_track_enum     thread = (frame, point) over a frame staged in shared memory (grid, records, descriptors): counts,
-//                    the warp takes its slice of the frame's candidate slab with one atomicAdd, then writes (distance,
-//                    octave, keypoint) words in the reference's candidate order and the unconstrained top-2
+//   k_track_enum     thread = (frame, point) over a frame staged in shared memory (grid, records, descriptors): the
+//                    warp takes its points' slices of the frame's candidate slab (sized by the records of each window's
+//                    cells) with one atomicAdd, then every thread walks its window once: filter, (distance, octave,
+//                    keypoint) words in the reference's candidate order, unconstrained top-2
 //                    (a warp per point spent 457 warp instructions per point on mostly idle lanes: 2.83 ms per 256
 //                    frames x 10 000 points)
 //   k_track_resolve  CTA = frame: the greedy order dependence (:92-93, :130) as the parallel fixed-point iteration of
@@ -147,8 +148,10 @@ __global__ void __launch_bounds__(32) k_track_grid(const TrackArgs A) {
 // ---- enumeration: thread = (frame, point). The CTA stages its frame's grid (u16 offsets, records in cell order) and
 // descriptors into shared memory once and then serves kEnumPerThread points per thread from there; a thread walks its
 // point's window cell by cell (ix outer, iy inner, ascending keypoint index inside a cell = the reference's candidate
-// order, src/Frame.cc:803-829), first counting, then — after the warp has taken its slice of the frame's candidate slab
-// with ONE atomicAdd — writing (distance, octave, keypoint) words and keeping the unconstrained top-2.
+// order, src/Frame.cc:803-829) ONCE: the size of its slice of the frame's candidate slab is the number of records in the
+// window's cells (known from the offsets; the warp takes the slices of its 32 points with ONE atomicAdd), so the walk
+// filters, writes (distance, octave, keypoint) words and keeps the unconstrained top-2 in the same pass. The slab
+// capacity (orbx_track_params::cand_per_frame) therefore counts window records, not accepted candidates.
 constexpr int kEnumThreads = 256, kEnumPerThread = 8;
 
 __device__ __forceinline__ bool rec_ok(const uint4 r, float x, float y, float rad, int minL, int maxL, bool has_ur,
@@ -227,7 +230,10 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
     float x = 0, y = 0, ur = 0, rad = 0;
     int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
     const int minL = level - 1, maxL = level;  // GetFeaturesInArea(x, y, r, level - 1, level)
-    int cnt = 0;
+    // Upper bound of the point's candidate count = the records of its window's cells, from the offsets alone (no record
+    // is read): the point's slice of the slab is sized by it, so ONE walk over the records serves both the filter and
+    // the distances (a counting pass first, as round 2's first version did, read every record twice)
+    int wnd = 0;
     if (level >= 0) {
       const float4 q = A.q[o];
       x = q.x; y = q.y; ur = q.z; rad = q.w;
@@ -237,14 +243,13 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
       y0 = max(0, (int)floorf(fmul(fsub(fsub(y, A.min_y), rad), A.inv_h)));
       y1 = min(ORBX_GRID_ROWS - 1, (int)ceilf(fmul(fadd(fsub(y, A.min_y), rad), A.inv_h)));
       if (x0 >= ORBX_GRID_COLS || x1 < 0 || y0 >= ORBX_GRID_ROWS || y1 < 0) x1 = x0 - 1;
-      for (int ix = x0; ix <= x1; ix++) {
-        // the cells (ix, y0..y1) are consecutive: one run of records
-        const int j0 = s_off[ix * ORBX_GRID_ROWS + y0], j1 = s_off[ix * ORBX_GRID_ROWS + y1 + 1];
-        for (int j = j0; j < j1; j++) cnt += rec_ok(s_rec[j], x, y, rad, minL, maxL, has_ur, ur) ? 1 : 0;
-      }
+      // the cells (ix, y0..y1) are consecutive: one run of records per column
+      for (int ix = x0; ix <= x1; ix++) wnd += s_off[ix * ORBX_GRID_ROWS + y1 + 1] - s_off[ix * ORBX_GRID_ROWS + y0];
     }
+    uint32_t dq[8];
+    if (wnd > 0) load_desc8(A.mdesc + (map_base + i) * 32, dq);  // requested before the scan below hides its latency
     // the warp takes its slice of the frame's slab
-    int inc = cnt;
+    int inc = wnd;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -259,10 +264,8 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
     if (!valid) continue;
     int2 seg = make_int2(0, 0);
     Top2 best{0, -1, 0, -1};
-    if (cnt > 0 && !overflow) {
-      const int base = wbase + inc - cnt;
-      uint32_t dq[8];
-      load_desc8(A.mdesc + (map_base + i) * 32, dq);
+    if (wnd > 0 && !overflow) {
+      const int base = wbase + inc - wnd;
       int pos = 0;
       for (int ix = x0; ix <= x1; ix++) {
         const int j0 = s_off[ix * ORBX_GRID_ROWS + y0], j1 = s_off[ix * ORBX_GRID_ROWS + y1 + 1];
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kEnumThreads) k_track_enum(const TrackArgs A) 
           pos++;
         }
       }
-      seg = make_int2(base, cnt);
+      if (pos > 0) seg = make_int2(base, pos);
     }
     A.seg[o] = seg;
     A.pre[o] = make_int4(best.d1, best.p1, best.d2, best.p2);

@@ -61,7 +61,13 @@ int track_fill_params(orbm_matcher* m, const orbx_extractor* ex, const orbx_loca
   A->min_y = prm->min_y;
   A->inv_w = prm->inv_w;
   A->inv_h = prm->inv_h;
-  const long long cc = prm->cand_per_frame > 0 ? prm->cand_per_frame : std::max(16LL * maps->m, 65536LL);
+  // Default slab: 16 records per point at th <= 2 (a th = 1 window holds 1-6 records), growing with the window area
+  // (th^2), never more than every keypoint for every point
+  long long cc = prm->cand_per_frame;
+  if (cc <= 0) {
+    const double area = std::max(1.0, 0.25 * (double)prm->th * (double)prm->th);
+    cc = std::min(std::max((long long)(16.0 * area * maps->m), 65536LL), std::max((long long)maps->m * cap, 65536LL));
+  }
   if (cc > (1LL << 30)) return mfail(m, ORBX_E_ARG, "cand_per_frame too large");
   A->cand_cap = (int)cc;
   return ORBX_OK;
