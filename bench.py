@@ -730,6 +730,24 @@ def run_stereo_workload(ctx, args, cfg_id, steps, warmup, reps, with_cpu, clock_
                 "stage_frac": {k: round(alg_bytes_per_frame[k] * 2 * P / (v * 1e-3) / 1e9 / peak, 4)
                                for k, v in stage_ms.items() if v > 0 and k in alg_bytes_per_frame}}
 
+    # Second entry: the dominant kernel against the roof that actually binds it. k_fast is bound by the integer-ALU pipe
+    # (VIMNMX / PRMT / LOP3: 64 lanes per clock per SM, measured by tools/ubench/alu_tput.cu, profiles/r02_alu_tput.log);
+    # ALU-pipe warp instructions per frame come from the ncu capture at the benched launch size, the time is live.
+    try:
+        alu_wi = tentry.get("alu_pipe_warp_insts_per_frame")
+        if alu_wi:
+            sm_clk = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+            alu_peak = 148 * 64 * sm_clk / 1e12
+            alu_ach = alu_wi * 32 * P / (dur_ms * 1e-3) / 1e12
+            roofline["second"] = {"bound": "int-alu pipe", "kernel": dom, "achieved": alu_ach, "peak": alu_peak,
+                                  "unit": "T lane-slots/s", "frac": alu_ach / alu_peak,
+                                  "alu_pipe_warp_insts_per_launch": alu_wi * P,
+                                  "peak_source": "148 SMs x 64 lanes/clk (tools/ubench/alu_tput.cu on this GPU, "
+                                                 "profiles/r02_alu_tput.log) x %.0f MHz" % (sm_clk / 1e6),
+                                  "source": traffic_src}
+    except Exception:
+        pass
+
     # ---- end to end through the host-facing ABI (pinned buffers; H2D + D2H inside the timed region) ----
     e2e_steps = args.e2e_steps or steps
     for k in range(max(3, warmup // 2)):

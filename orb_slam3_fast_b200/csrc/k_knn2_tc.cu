@@ -15,13 +15,17 @@
 // issuer, warps 2..5 = epilogue (warp w may touch TMEM lanes 32 (w % 4) .. +31). blockIdx.y splits the train set;
 // the per-split (d1, i1, d2, i2) are merged by k_knn2_merge in split order like the POPC kernel's.
 //
-// Measured on B200 (bench.py --config 4, device-resident, expansion and merge included): 100k x 100k in 1.77 ms =
-// 5.66 Tpair/s = 2.9 Pop/s of s8 MACs, 64 % of the nominal 4.5 Pop/s dense int8 peak (POPC kernel: 15.0 ms). Round 1
-// stood at 2.20 ms (one tcgen05.wait::ld per 32-column load) and, through the library, 2.78 ms (7 train-set splits, see
-// knn2_tc_splits); 3.66 ms without the chunk filter (epilogue bound); MMA-bound floor ~1.15 ms.
+// Two forms live here. k_knn2_tc (this description) was round 2's first: 1.70 ms for 100k x 100k. k_knn2_tc_ts further
+// down (256 queries per CTA, both query tiles in tensor memory, N = 192, four train tiles in flight, two epilogue warps
+// per TMEM lane quarter) is the one that runs: 1.50 ms = 6.66 Tpair/s = 3.4 Pop/s of s8 MACs, 76 % of the nominal
+// 4.5 Pop/s dense int8 peak (bench.py --config 4, device-resident, expansion and merge included; POPC kernel: 15.0 ms).
+// History of the first form: 2.20 ms with one tcgen05.wait::ld per 32-column load, 1.77 ms with four in flight, 1.70 ms
+// with the lean issue path; 3.66 ms without the chunk filter; through the library in round 1: 2.78 ms (7 train-set
+// splits, see knn2_tc_splits). ORBM_KNN2_TS=0 selects it.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "orbx_match.cuh"
 
@@ -247,6 +251,225 @@ k_knn2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second form (the default): 256 queries per CTA, both query tiles in TENSOR MEMORY.
+//
+// What k_knn2_tc above is bound by is neither the tensor pipe nor the epilogue but the L2: every CTA streams the whole
+// expanded train set through its shared memory, 64 KB per 1024 clk of MMAs = 64 B/clk/SM, 9.5 KB/clk for 148 SMs against
+// the ~6.3 KB/clk the L2 slices deliver chip-wide (B300_MICROARCH.md "LTS throughput cap"; measured here: the query
+// tile in tensor memory, four train tiles in flight and a second set of epilogue warps moved 1.70 ms to 1.70 / 1.70 /
+// 1.61 ms). The bytes per MAC must come down, i.e. every train tile must meet more query rows:
+//  * the query rows never change during a CTA's life, so they live in tensor memory: the epilogue threads build TWO
+//    128-row tiles once, straight from the 32-byte descriptors (bit -> +-1 byte; no expanded query array in HBM, no TMA
+//    of A), tcgen05.st them into 2 x 64 columns, and every MMA takes A from there ("tcgen05.mma [d], [a], b-desc");
+//  * a train tile of N = 192 rows is multiplied with query tile 0 into accumulator 0 and with query tile 1 into
+//    accumulator 1 (2 x 192 + 2 x 64 = 512 columns): the two accumulators ARE the double buffer — the epilogue reads
+//    one while the tensor pipe fills the other — and a train byte now serves 256 query rows: 32 B/clk/SM;
+//  * shared memory holds nothing but train tiles: four of them in flight (4 x 48 KB);
+//  * two epilogue warps per TMEM lane quarter, each taking half of a tile's columns with its own best-two and filter
+//    threshold per query row (merged at the very end): the accumulator is released as soon as its values are in
+//    registers.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kM2 = 256;         // queries per CTA = two tcgen05 M = 128 tiles
+constexpr int kN2 = 192, kB2Bytes = kN2 * kRowBytes, kChunks2 = kN2 / 32, kACol = 2 * kN2;
+constexpr int kThreads2 = 320;   // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kChunksLo = kChunks2 / 2;  // chunks of a tile read by the first epilogue warp of a quarter; the rest by the second
+constexpr int kStages2 = 4;      // train tiles in flight
+constexpr int kSmem2 = kStages2 * kB2Bytes + 256 + 1024;
+constexpr uint32_t kIdesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN2 >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+static_assert(kN2 % 32 == 0 && kACol + 128 <= 512, "TMEM budget");
+static_assert(kSmem2 <= 227 * 1024, "shared memory");
+
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(kIdesc2), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// 4 bits -> 4 bytes of +-1, the order of k_expand_pm1 (bit j -> byte j)
+__device__ __forceinline__ uint32_t pm1_word(uint32_t nibble) {
+  const uint32_t spread = (nibble & 1u) | ((nibble & 2u) << 7) | ((nibble & 4u) << 14) | ((nibble & 8u) << 21);  // 0/1 per byte
+  return 0xffffffffu - spread * 0xfeu;  // byte = 0xff (bit clear: -1) or 0x01 (bit set: +1)
+}
+
+__global__ void __launch_bounds__(kThreads2, 1)
+k_knn2_tc_ts(const uint8_t* __restrict__ q, const __grid_constant__ CUtensorMap map_t, int nq, int nt, int tiles_per_split,
+             int4* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;  // [kStages2][2 halves][192 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kB2Bytes);
+  uint64_t *a_full = bars, *b_full = bars + 1, *b_empty = b_full + kStages2, *acc_full = b_empty + kStages2,
+           *acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int q0 = blockIdx.x * kM2;
+  const int total_tiles = (nt + kN2 - 1) / kN2;
+  const int tb = blockIdx.y * tiles_per_split;
+  const int ntile = max(0, min(total_tiles, tb + tiles_per_split) - tb);
+
+  if (threadIdx.x == 0) {
+    bar_init(a_full, 128);
+    for (int s = 0; s < kStages2; s++) {
+      bar_init(b_full + s, 1);
+      bar_init(b_empty + s, 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      bar_init(acc_full + s, 1);
+      bar_init(acc_empty + s, 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(sptr(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  // epilogue threads: best two keys of their two rows (query tile 0 / 1) over their half of the columns
+  uint32_t k1[2] = {0xffffffffu, 0xffffffffu}, k2[2] = {0xffffffffu, 0xffffffffu};
+  const int quad = warp & 3, half = (warp - 2) >> 2;  // warp w may touch TMEM lanes 32 (w % 4) .. +31
+  const int row0 = q0 + quad * 32 + lane;             // the thread's row of query tile 0; tile 1: + 128
+
+  if (warp == 0) {
+    for (int i = 0; i < ntile; i++) {
+      const int s = i % kStages2;
+      bar_wait(b_empty + s, ((i / kStages2) & 1) ^ 1);
+      if (elect_one()) {
+        bar_expect(b_full + s, kB2Bytes);
+        tma_rows(&map_t, sB + s * kB2Bytes, b_full + s, 0, (tb + i) * kN2);
+        tma_rows(&map_t, sB + s * kB2Bytes + kN2 * kHalf, b_full + s, kHalf, (tb + i) * kN2);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    uint64_t db[8];  // stage 0; stage s starts s * kB2Bytes further on (the address field counts 16-byte units)
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) db[kk] = smem_desc(sB + (kk >> 2) * (kN2 * kHalf) + (kk & 3) * 32);
+    bar_wait(a_full, 0);
+    for (int i = 0; i < ntile; i++) {
+      const int s = i % kStages2;
+      bar_wait(b_full + s, (i / kStages2) & 1);
+      const uint64_t soff = (uint64_t)(s * (kB2Bytes >> 4));
+#pragma unroll
+      for (int a = 0; a < 2; a++) {  // query tile a x train tile i -> accumulator a
+        bar_wait(acc_empty + a, (i & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++)  // K step kk = bytes 32 kk .. 32 kk + 31 of a row = A columns 8 kk .. 8 kk + 7
+            mma_i8_ts(tmem + a * kN2, tmem + kACol + 64 * a + 8 * kk, db[kk] + soff, kk > 0);
+          if (a == 1) mma_commit(b_empty + s);  // both query tiles have read the stage
+          mma_commit(acc_full + a);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    if (half == 0) {
+      // ---- the query tiles: lane = query row; descriptor byte b -> A columns 2 b (bits 0..3) and 2 b + 1 (bits 4..7),
+      //      i.e. element 8 b + j = bit j of byte b, exactly the layout k_expand_pm1 gives the train rows ----
+#pragma unroll 1
+      for (int a = 0; a < 2; a++) {
+        const int row = row0 + 128 * a;
+        uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+        if (row < nq) {
+          d0 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)row * 32));
+          d1 = __ldg(reinterpret_cast<const uint4*>(q + (size_t)row * 32) + 1);
+        }
+        const uint32_t w[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          uint32_t v[32];
+#pragma unroll
+          for (int c = 0; c < 32; c++) {
+            const int col = 32 * h + c;                     // column = 4 elements = one nibble of descriptor byte col / 2
+            const uint32_t byte = (w[col >> 3] >> (8 * ((col >> 1) & 3))) & 0xffu;
+            v[c] = pm1_word((col & 1) ? byte >> 4 : byte & 15u);
+          }
+          tmem_st32(lane_base + kACol + 64 * a + 32 * h, v);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      bar_arrive(a_full);
+    }
+    int thr[2] = {-100000, -100000};
+    const int cfirst = half == 0 ? 0 : kChunksLo;  // this warp's chunks of every tile: cfirst .. cfirst + kChunksLo - 1
+    for (int i = 0; i < ntile; i++) {
+      const int col0 = (tb + i) * kN2 + cfirst * 32;
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        bar_wait(acc_full + a, i & 1);
+        tc_fence_after();
+        int v[kChunksLo][32];
+#pragma unroll
+        for (int g = 0; g < kChunksLo; g++) tmem_ld32_issue(lane_base + a * kN2 + (cfirst + g) * 32, v[g]);
+        tmem_ld_wait();
+        tc_fence_before();
+        bar_arrive(acc_empty + a);  // the values are in registers: the accumulator may be overwritten
+#pragma unroll
+        for (int g = 0; g < kChunksLo; g++) {  // 32 accumulator columns = train rows cbase .. cbase + 31
+          const int cbase = col0 + g * 32;
+          int mx = v[g][0];
+#pragma unroll
+          for (int j = 1; j < 31; j += 2) mx = max(mx, max(v[g][j], v[g][j + 1]));
+          mx = max(mx, v[g][31]);
+          if (mx > thr[a]) {
+            // exact insertion, a serial k1 / k2 chain over the 32 elements. (A tournament — the chunk's own best two by
+            // independent pairwise merges, then one merge with the running pair — was measured SLOWER: 1.55 vs 1.52 ms
+            // for 100k x 100k; the path is bound by instruction issue, not by the chain's latency.)
+            const uint32_t base = (256u << 21) | (uint32_t)cbase;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              if (cbase + j < nt) {  // rows past the end are TMA zero fill (accumulator 0 = distance 128)
+                const uint32_t key = base + j - ((uint32_t)v[g][j] << 21);  // ((256 - acc) / 2) << 22 | col
+                k2[a] = min(k2[a], max(k1[a], key));
+                k1[a] = min(k1[a], key);
+              }
+            }
+            thr[a] = 256 - 2 * (int)(k2[a] >> 22);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  // ---- merge the two column halves of every row (shared memory is free: every train tile has been consumed) ----
+  uint4* xch = reinterpret_cast<uint4*>(smem);
+  if (warp >= 2 && half == 1) xch[quad * 32 + lane] = make_uint4(k1[0], k2[0], k1[1], k2[1]);
+  __syncthreads();
+  if (warp >= 2 && half == 0) {
+    const uint4 o = xch[quad * 32 + lane];
+    const uint32_t o1[2] = {o.x, o.z}, o2[2] = {o.y, o.w};
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      const int row = row0 + 128 * a;
+      if (row >= nq) continue;
+      const uint32_t m1 = min(k1[a], o1[a]), m2 = min(max(k1[a], o1[a]), min(k2[a], o2[a]));
+      const int i1 = m1 == 0xffffffffu ? -1 : (int)(m1 & 0x3fffff), i2 = m2 == 0xffffffffu ? -1 : (int)(m2 & 0x3fffff);
+      partial[(size_t)blockIdx.y * nq + row] =
+          make_int4(i1 < 0 ? 0x7fffffff : (int)(m1 >> 22), i1, i2 < 0 ? 0x7fffffff : (int)(m2 >> 22), i2);
+    }
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -283,6 +506,8 @@ bool knn2_tc_eligible(int nq, int nt) {
 }
 
 size_t knn2_tc_expanded_bytes(int rows) { return (size_t)rows * kRowBytes; }
+static bool knn2_ts();
+bool knn2_tc_expands_queries() { return !knn2_ts(); }
 
 // Splits of the train set. Measured on B200 (tools/ubench/knn2_tc.cu, round 2): a split costs more than it evens out —
 // every CTA reloads its query tile, and its chunk filter starts cold, so the first tiles of every split take the exact
@@ -290,7 +515,37 @@ size_t knn2_tc_expanded_bytes(int rows) { return (size_t)rows * kRowBytes; }
 // 0.72 / 0.78; 30k x 30k: 0.23 / 0.26 / 0.28 / 0.32). Splitting only pays while the query blocks alone leave SMs idle
 // (10k x 10k, 79 blocks: 0.074 / 0.070 / 0.072 / 0.078 ms for 2 / 4 / 8 / 14). So: one split once there is a CTA per SM,
 // otherwise enough to put ~2 CTAs on every SM; every split keeps at least 4 tiles.
+// ORBM_KNN2_TS=0 keeps the query tile in shared memory (k_knn2_tc); default: tensor memory (k_knn2_tc_ts)
+static bool knn2_ts() {
+  static const bool on = [] {
+    const char* e = getenv("ORBM_KNN2_TS");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 int knn2_tc_splits(int nq, int nt, int* tiles_per_split) {
+  if (knn2_ts()) {
+    // k_knn2_tc_ts: rounds of 148 CTAs x (tiles per CTA + a fixed cost per CTA: prologue, first TMA round trip and the
+    // cold chunk filter of its first tiles; measured ~42 tile times: 100k x 100k takes 1.52 ms in one split, 1.56 ms in
+    // three although three fill the last round of CTAs) — the split count with the least total wins
+    const int qblocks = (nq + kM2 - 1) / kM2, total_tiles = (nt + kN2 - 1) / kN2;
+    static const int c0 = getenv("ORBM_KNN2_C0") ? atoi(getenv("ORBM_KNN2_C0")) : 45;  // measured: ~42 (tuning aid)
+    int best_s = 1;
+    long long best = -1;
+    for (int s = 1; s <= 16 && (s == 1 || total_tiles / s >= 4); s++) {
+      const int tps = (total_tiles + s - 1) / s, real = (total_tiles + tps - 1) / tps;
+      const long long rounds = ((long long)qblocks * real + 147) / 148;
+      const long long cost = rounds * (tps + c0);
+      if (best < 0 || cost < best) {
+        best = cost;
+        best_s = s;
+      }
+    }
+    const int tps = (total_tiles + best_s - 1) / best_s;
+    *tiles_per_split = tps;
+    return (total_tiles + tps - 1) / tps;
+  }
   const int qblocks = (nq + kM - 1) / kM, total_tiles = (nt + kN - 1) / kN;
   int s = 1;
   if (qblocks < 148) {
@@ -307,6 +562,14 @@ int knn2_tc_splits(int nq, int nt, int* tiles_per_split) {
 cudaError_t launch_knn2_tc(const uint8_t* q, int nq, const uint8_t* t, int nt, int8_t* expanded_q, int8_t* expanded_t,
                            int4* partial, int splits, int tiles_per_split, cudaStream_t st) {
   CUtensorMap mq, mt;
+  if (knn2_ts()) {  // the query tile is built in tensor memory from the raw descriptors: no expanded query array
+    if (!make_rows_map(&mt, expanded_t, nt, kN2)) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_knn2_tc_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
+    k_expand_pm1<<<(nt * 32 + 255) / 256, 256, 0, st>>>(t, nt, expanded_t);
+    k_knn2_tc_ts<<<dim3((nq + kM2 - 1) / kM2, splits), kThreads2, kSmem2, st>>>(q, mt, nq, nt, tiles_per_split, partial);
+    return cudaGetLastError();
+  }
   if (!make_rows_map(&mq, expanded_q, nq, kM) || !make_rows_map(&mt, expanded_t, nt, kN)) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k_knn2_tc<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
   if (e != cudaSuccess) return e;

@@ -222,7 +222,7 @@ int orbm_knn2_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t*
     int tiles_per_split = 0;
     const int splits = knn2_tc_splits(nq, nt, &tiles_per_split);
     cudaError_t e = pb.reserve((size_t)splits * nq * sizeof(int4));
-    if (e == cudaSuccess) e = m->tc_buf[0].reserve(knn2_tc_expanded_bytes(nq));
+    if (e == cudaSuccess && knn2_tc_expands_queries()) e = m->tc_buf[0].reserve(knn2_tc_expanded_bytes(nq));
     if (e == cudaSuccess) e = m->tc_buf[1].reserve(knn2_tc_expanded_bytes(nt));
     if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
     ORBM_CUDA(m, launch_knn2_tc(d_q, nq, d_t, nt, static_cast<int8_t*>(m->tc_buf[0].p),

@@ -47,6 +47,7 @@ void launch_knn2_merge(const int4* partial, int nq, int splits, int32_t* idx1, i
 // k_knn2_tc.cu: the tcgen05 (s8 GEMM) form for large sets; partial = [splits][nq] like launch_knn2's
 bool knn2_tc_eligible(int nq, int nt);
 size_t knn2_tc_expanded_bytes(int rows);
+bool knn2_tc_expands_queries();  // false: the query tile is built in tensor memory from the raw descriptors
 int knn2_tc_splits(int nq, int nt, int* tiles_per_split);
 cudaError_t launch_knn2_tc(const uint8_t* q, int nq, const uint8_t* t, int nt, int8_t* expanded_q, int8_t* expanded_t,
                            int4* partial, int splits, int tiles_per_split, cudaStream_t st);

@@ -48,6 +48,31 @@ def test_knn2_tensor_core_path_equals_popc_path_and_oracle(matcher, monkeypatch,
         assert np.array_equal(b, r), "POPC %s differs at %s" % (name, np.nonzero(b != r)[0][:10])
 
 
+def test_knn2_tensor_core_fallback_form_equals_oracle():
+    """k_knn2_tc_ts (256 queries per CTA, query tiles in tensor memory) is the tensor-core form that normally runs; the
+    first form (k_knn2_tc: query tile in shared memory, 128 x 256 tiles) is kept behind ORBM_KNN2_TS=0. The switch is
+    read once per process, hence the subprocess. Both must give the oracle's words."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np\n"
+        "from orb_slam3_fast_b200 import ORBmatcher, synth\n"
+        "from oracle import orbref\n"
+        "m = ORBmatcher()\n"
+        "for nq, nt, proto in ((6000, 6000, 64), (8192, 4097, 16), (2000, 40000, 0)):\n"
+        "    q, t = synth.descriptors(nq, 21, proto), synth.descriptors(nt, 22, proto)\n"
+        "    q[: min(nq, nt) // 2] = t[: min(nq, nt) // 2]\n"
+        "    got, ref = m.knnMatch2(q, t), orbref.knn2(q, t)\n"
+        "    assert all(np.array_equal(g, r) for g, r in zip(got, ref)), (nq, nt, proto)\n"
+        "print('ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for ts in ("0", "1"):
+        env = dict(os.environ, ORBM_KNN2_TS=ts, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0 and "ok" in r.stdout, "ORBM_KNN2_TS=%s\n%s\n%s" % (ts, r.stdout[-2000:], r.stderr[-2000:])
+
+
 def test_knn2_agrees_with_cv2_bfmatcher(matcher):
     cv2 = pytest.importorskip("cv2")
     q, t = synth.descriptors(800, 5, 32), synth.descriptors(900, 6, 32)  # tie-heavy

@@ -36,6 +36,12 @@ def main(tag, frames, rnd="r01", geometry=None, how=None):
     hdr, units = rows[h], rows[h + 1]
     col = {k: hdr.index(k) for k in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum",
                                      "dram__bytes_write.sum", "Grid Size")}
+    # integer-ALU pipe occupancy (the roof that binds k_fast): a warp instruction holds its sub-partition's 16-lane ALU
+    # pipe for 2 cycles, so  ALU warp instructions = pipe-active fraction x active cycles x 4 sub-partitions x SMs / 2
+    c_alu = hdr.index("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active") \
+        if "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active" in hdr else None
+    c_act = hdr.index("sm__cycles_active.avg") if "sm__cycles_active.avg" in hdr else None
+    n_sm = 148
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}[units[col["gpu__time_duration.sum"]]]
     agg = {}
@@ -51,8 +57,10 @@ def main(tag, frames, rnd="r01", geometry=None, how=None):
             continue  # one extract call (left eye) is enough; the second repeats it
         if name == "k_describe":
             seen_calls += 1  # k_describe is the last kernel of an extract call
-        a = agg.setdefault(st, {"kernel": name, "launches": 0, "time_us": 0.0, "dram_bytes": 0.0})
+        a = agg.setdefault(st, {"kernel": name, "launches": 0, "time_us": 0.0, "dram_bytes": 0.0, "alu_warp_insts": 0.0})
         a["launches"] += 1
+        if c_alu is not None and c_act is not None:
+            a["alu_warp_insts"] += num(r[c_alu]) / 100.0 * num(r[c_act]) * 4 * n_sm / 2.0
         a["time_us"] += num(r[col["gpu__time_duration.sum"]]) * tscale
         a["dram_bytes"] += num(r[col["dram__bytes_read.sum"]]) * scale[units[col["dram__bytes_read.sum"]]] + \
             num(r[col["dram__bytes_write.sum"]]) * scale[units[col["dram__bytes_write.sum"]]]
@@ -63,6 +71,8 @@ def main(tag, frames, rnd="r01", geometry=None, how=None):
         per = frames if st != "stereo" else frames  # stereo: pairs per launch == frames per eye launch
         out["stages"][st] = {"kernel": a["kernel"], "launches_per_call": a["launches"], "time_us_per_call": round(a["time_us"], 2),
                              "dram_bytes_per_frame": round(a["dram_bytes"] / per, 1)}
+        if a["alu_warp_insts"] > 0:
+            out["stages"][st]["alu_pipe_warp_insts_per_frame"] = round(a["alu_warp_insts"] / per, 1)
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if geometry:  # keyed by geometry: bench.py looks up "<w>x<h>" first and falls back to the flat round-1 layout
