@@ -1,4 +1,5 @@
-// k_quadtree.cu — launches orbx::quadtree_run (orbx_quadtree.h) with one warp per (frame, level).
+// k_quadtree.cu — launches orbx::quadtree_run (orbx_quadtree.h): one CTA of kQtWarps warps per (frame, level); warp 0
+// runs the tree, the others help with everything that is per candidate (the gather below, the sweeps of the tree).
 // Before the tree: the per-cell candidate slots written by k_fast are compacted, cells in row-major order, into the
 // level's candidate array — the order ComputeKeyPointsOctTree appends them in (src/ORBextractor.cc:905-958). The
 // array (4 B per candidate) and the per-candidate node labels (2 B) live in shared memory when the level has at most
@@ -13,6 +14,7 @@
 namespace orbx {
 
 constexpr int kSmemCand = 2048;
+constexpr int kQtWarps = 4;  // tools/qt_prof.py: 70 % of a level-0 tree (125 us with one warp) is per-candidate work
 
 struct QtSmem {
   int cap;
@@ -56,12 +58,12 @@ static QtSmem qt_layout(const Plan& P) {
 
 size_t quadtree_smem_bytes(const Plan& P) { return qt_layout(P).total; }
 
-__global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P, const WorkSet ws, const QtSmem S,
+__global__ void __launch_bounds__(kQtWarps * 32) k_quadtree(const __grid_constant__ Plan P, const WorkSet ws, const QtSmem S,
                                                  int lap0, int lap1) {
   extern __shared__ __align__(16) uint8_t smem[];
   // blockIdx.y = level: blocks are handed out level 0 first, so the long trees (level 0: ~100 us, level 7: ~8 us) start
   // first and the tail of the launch is made of short ones (longest-processing-time-first)
-  const int l = blockIdx.y, f = blockIdx.x, lane = threadIdx.x;
+  const int l = blockIdx.y, f = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const LevelPlan& L = P.lv[l];
   const uint32_t* slots = ws.slots + (int64_t)f * P.slots_per_frame + L.slot_base;
   const int32_t* counts = ws.cell_count + (int64_t)f * P.cells_per_frame + L.cell_base;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P,
   T.prof = nullptr;
   T.prof_prev = 0;
 #ifdef ORBX_QT_PROF
-  if (ws.qt_prof) {
+  if (ws.qt_prof && warp == 0) {
     T.prof = ws.qt_prof + ((int64_t)f * P.nlevels + l) * kQtProfSlots;
     if (lane == 0)
       for (int k = 0; k < kQtProfSlots; k++) T.prof[k] = 0;
@@ -93,13 +95,19 @@ __global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P,
   //      output o belongs to the last cell whose prefix is <= o (binary search in shared memory). Every lane step is
   //      independent, 4 are in flight per lane. The prefix array borrows the tree's node arrays (not live yet). ----
   int* pref = reinterpret_cast<int*>(smem + S.off_box0);
+  int* vars = reinterpret_cast<int*>(smem + S.off_vars);
   const int kCellChunk = (int)((S.off_newpos - S.off_box0) / 4) - 1;
   int done = 0;
   for (int cb = 0; cb < ncell; cb += kCellChunk) {
     const int nc = min(kCellChunk, ncell - cb);
-    for (int i = lane; i < nc; i += 32) pref[i] = counts[cb + i];
-    __syncwarp();
-    const int total = excl_scan(pref, nc);
+    if (warp == 0) {
+      for (int i = lane; i < nc; i += 32) pref[i] = counts[cb + i];
+      __syncwarp();
+      const int t = excl_scan(pref, nc);
+      if (lane == 0) vars[kQtVarTotal] = t;
+    }
+    __syncthreads();
+    const int total = vars[kQtVarTotal];
     auto locate = [&](int o) {
       int lo = 0, hi = nc - 1;  // largest i with pref[i] <= o
       while (lo < hi) {
@@ -109,19 +117,20 @@ __global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P,
       }
       return slots + (int64_t)(cb + lo) * L.slot_cap + (o - pref[lo]);
     };
-    for (int o0 = lane; o0 < total; o0 += 4 * 32) {
+    const int tn = kQtWarps * 32;
+    for (int o0 = threadIdx.x; o0 < total; o0 += 4 * tn) {
       uint32_t v[4];
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (o0 + 32 * u < total) v[u] = *locate(o0 + 32 * u);
+        if (o0 + tn * u < total) v[u] = *locate(o0 + tn * u);
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (o0 + 32 * u < total) cand[done + o0 + 32 * u] = v[u];
+        if (o0 + tn * u < total) cand[done + o0 + tn * u] = v[u];
     }
     done += total;
-    __syncwarp();
+    __syncthreads();
   }
-  if (lane == 0) ws.lvl_c[f * P.nlevels + l] = C;
+  if (threadIdx.x == 0) ws.lvl_c[f * P.nlevels + l] = C;
   ORBX_QT_MARK(T, 1);
 
   T.cap = S.cap;
@@ -147,7 +156,12 @@ __global__ void __launch_bounds__(32) k_quadtree(const __grid_constant__ Plan P,
   uint32_t* out = reinterpret_cast<uint32_t*>(smem + S.off_sort);  // the sort buffer is free once the tree is built
 
   const int width = L.maxBX - kMinBorder, height = L.maxBY - kMinBorder;
+  if (warp != 0) {  // helper warps: their share of the candidate sweeps, until warp 0 releases them
+    quadtree_helper(T, L.hX);
+    return;
+  }
   const int n = quadtree_run(T, width, height, L.nIni, L.hX, L.quota, out);
+  quadtree_release(T);
 
   // ---- selected keypoints in list order + their rank among the level's mono / stereo keypoints ----
   uint32_t* kp = ws.lvl_kp + (int64_t)f * P.kps_per_frame + L.kp_base;
@@ -193,7 +207,7 @@ void launch_quadtree(const Plan& P, const WorkSet& ws, int lap0, int lap1, int f
   cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(S.total > 48 * 1024 ? S.total : 48 * 1024));
   dim3 grid(frames, P.nlevels);
-  k_quadtree<<<grid, 32, S.total, st>>>(P, ws, S, lap0, lap1);
+  k_quadtree<<<grid, kQtWarps * 32, S.total, st>>>(P, ws, S, lap0, lap1);
 }
 
 }  // namespace orbx

@@ -16,9 +16,14 @@
 //    final insertion sort is a stable rank inside a +-15 window. Lane 0 then walks from the back until the list holds
 //    >= N nodes (:729).
 //
+//  * The per-CANDIDATE sweeps (root labels, first histogram, one sweep per round: 55 % of a frame's tree time, 70 % of a
+//    level-0 tree, tools/qt_prof.py) are spread over the whole CTA ("team": the tree's warp 0 plus helper warps that
+//    wait at a barrier for a command); everything per NODE — list rebuild, sort, walk — stays on warp 0. The sweeps only
+//    touch their own candidate's label and shared-memory atomics, so the team needs no other coordination.
+//
 // The same source runs on the CPU (tests/hostcheck.cpp) with one "lane": ORBX_LANES loops cover every index, ballots
-// degenerate to serial counters. That is how the algorithm is checked against the oracle (and the sort against the
-// real std::sort) without a GPU.
+// degenerate to serial counters, the team is one thread. That is how the algorithm is checked against the oracle (and
+// the sort against the real std::sort) without a GPU.
 #ifndef ORBX_QUADTREE_H_
 #define ORBX_QUADTREE_H_
 
@@ -40,6 +45,16 @@ namespace orbx {
 #define ORBX_ATOMIC_MAX(p, v) (*(p) = *(p) > (v) ? *(p) : (v))
 #endif
 #define ORBX_LANES(i, n) for (int i = ORBX_LANE(); i < (n); i += ORBX_NLANES)
+// the team = every thread of the CTA (candidate sweeps); host: one thread
+#if defined(__CUDA_ARCH__)
+#define ORBX_TLANE() ((int)threadIdx.x)
+#define ORBX_TNLANES ((int)blockDim.x)
+#define ORBX_TSYNC() __syncthreads()
+#else
+#define ORBX_TLANE() 0
+#define ORBX_TNLANES 1
+#define ORBX_TSYNC() (void)0
+#endif
 
 // Shared-memory histogram / arg-max updates, predicated. (Warp-aggregating them with __match_any_sync was measured
 // 15 % SLOWER on B200 than letting the hardware serialise same-address shared atomics.)
@@ -306,6 +321,114 @@ ORBX_HD QBox child_box(const QBox& b, int q) {
 ORBX_HD int nonempty4(const int* h) { return (h[0] > 0) + (h[1] > 0) + (h[2] > 0) + (h[3] > 0); }
 ORBX_HD int multi4(const int* h) { return (h[0] > 1) + (h[1] > 1) + (h[2] > 1) + (h[3] > 1); }
 
+// ---- the candidate sweeps, executed by the whole team ----------------------------------------------------------
+enum { kQtCmdExit = 0, kQtCmdRoots = 1, kQtCmdFirst = 2, kQtCmdRound = 3 };
+enum { kQtVarCmd = 4, kQtVarNxt = 5, kQtVarFinish = 6, kQtVarTotal = 7 };  // T.vars slots of the team protocol
+
+// root of every candidate (:588-594) + root counts
+ORBX_HD void qt_sweep_roots(const QTree& T, float hX) {
+  for (int c = ORBX_TLANE(); c < T.C; c += ORBX_TNLANES) {
+    const int r = (int)fdiv((float)cand_x(T.cand[c]), hX);
+    T.lab[c] = (uint16_t)r;
+    ORBX_ATOMIC_ADD(&T.cnt[1][r], 1);
+  }
+}
+
+// compacted root position + quadrant inside it, first histogram
+ORBX_HD void qt_sweep_first(const QTree& T) {
+  for (int c = ORBX_TLANE(); c < T.C; c += ORBX_TNLANES) {
+    const int p = T.newpos[T.lab[c]];
+    uint32_t l = (uint32_t)p;
+    if (T.splittable[p]) {
+      const int q = quadrant_of(T.cand[c], T.box[0][p]);
+      l |= (uint32_t)q << 14;
+      ORBX_ATOMIC_ADD(&T.child[0][4 * p + q], 1);
+    }
+    T.lab[c] = (uint16_t)l;
+  }
+}
+
+// one round: move every candidate to its new node, then histogram (or, in the final round, arg-max). Stage-wise over 4
+// team steps so that the dependent shared-memory loads of different steps overlap:
+// label -> new position (one table for split parents and survivors) -> node word -> quadrant -> histogram.
+ORBX_HD void qt_sweep_round(const QTree& T, int nxt, bool finish) {
+  const int C = T.C;
+  int* child_nxt = T.child[nxt];
+  const int step = ORBX_TNLANES, me = ORBX_TLANE();
+  for (int c0 = 0; c0 < C; c0 += 4 * step) {
+    uint32_t lv[4], cv[4];
+    int np[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int c = c0 + u * step + me;
+      ok[u] = c < C;
+      lv[u] = ok[u] ? (uint32_t)T.lab[c] : 0u;
+      cv[u] = ok[u] ? T.cand[c] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) np[u] = T.childpos[4 * (int)(lv[u] & kLabPosMask) + (int)(lv[u] >> 14)];
+    if (finish) {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = c0 + u * step + me;
+        const uint32_t v = ((uint32_t)cand_s(cv[u]) << 24) | (0xffffffu - (uint32_t)c);
+        ORBX_AGG_MAX(child_nxt, np[u], v, ok[u]);
+        if (ok[u]) T.lab[c] = (uint16_t)np[u];
+      }
+    } else {
+      uint32_t info[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) info[u] = (uint32_t)T.scan[np[u]];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int c = c0 + u * step + me;
+        const bool split = ok[u] && (info[u] >> 31);
+        const int q = (cand_x(cv[u]) < (int)(info[u] & 0xfff) ? 0 : 1) + (cand_y(cv[u]) < (int)((info[u] >> 12) & 0xfff) ? 0 : 2);
+        ORBX_AGG_ADD(child_nxt, 4 * np[u] + q, split);
+        if (ok[u]) T.lab[c] = (uint16_t)((uint32_t)np[u] | (split ? (uint32_t)q << 14 : 0u));
+      }
+    }
+  }
+}
+
+ORBX_HD void qt_dispatch(const QTree& T, int cmd, int nxt, bool finish, float hX) {
+  if (cmd == kQtCmdRoots) qt_sweep_roots(T, hX);
+  else if (cmd == kQtCmdFirst) qt_sweep_first(T);
+  else if (cmd == kQtCmdRound) qt_sweep_round(T, nxt, finish);
+}
+
+// warp 0: publish the command, run it with the team, return when every member is done
+ORBX_HD void qt_team_run(const QTree& T, int cmd, int nxt, bool finish, float hX) {
+  if (ORBX_LANE() == 0) {
+    T.vars[kQtVarCmd] = cmd;
+    T.vars[kQtVarNxt] = nxt;
+    T.vars[kQtVarFinish] = finish ? 1 : 0;
+  }
+  ORBX_TSYNC();
+  qt_dispatch(T, cmd, nxt, finish, hX);
+  ORBX_TSYNC();
+}
+
+#if defined(__CUDACC__)
+// the helper warps of a tree: wait for a command, run their share of the sweep, until warp 0 says exit
+__device__ __forceinline__ void quadtree_helper(const QTree& T, float hX) {
+  for (;;) {
+    __syncthreads();
+    const int cmd = T.vars[kQtVarCmd], nxt = T.vars[kQtVarNxt], fin = T.vars[kQtVarFinish];
+    if (cmd == kQtCmdExit) return;
+    qt_dispatch(T, cmd, nxt, fin != 0, hX);
+    __syncthreads();
+  }
+}
+// warp 0, after quadtree_run: release the helpers
+__device__ __forceinline__ void quadtree_release(const QTree& T) {
+  __syncwarp();
+  if (ORBX_LANE() == 0) T.vars[kQtVarCmd] = kQtCmdExit;
+  __syncthreads();
+}
+#endif
+
 // Runs the whole culling for one level. Returns the number of selected keypoints; out[i] = candidate index of the
 // i-th keypoint in list order (front to back). `width`, `height` = maxBorder - minBorder of the level.
 ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, int N, uint32_t* out_cand_idx) {
@@ -323,13 +446,7 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     T.cnt[1][i] = 0;
   }
   ORBX_WSYNC();
-  ORBX_LANES_UNIFORM(c, C) {
-    const bool ok = c < C;
-    const int r = ok ? (int)fdiv((float)cand_x(T.cand[c]), hX) : 0;
-    if (ok) T.lab[c] = (uint16_t)r;
-    ORBX_AGG_ADD(T.cnt[1], r, ok);
-  }
-  ORBX_WSYNC();
+  qt_team_run(T, kQtCmdRoots, 0, false, hX);
   int S = warp_compact(nIni, T.rank2pos, [&](int i) { return T.cnt[1][i] > 0; });
   ORBX_LANES(p, S) {
     const int i = T.rank2pos[p];
@@ -343,20 +460,7 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     T.child[0][4 * p + 3] = 0;
   }
   ORBX_WSYNC();
-  ORBX_LANES_UNIFORM(c, C) {
-    const bool ok = c < C;
-    const int p = ok ? T.newpos[T.lab[c]] : 0;
-    uint32_t l = (uint32_t)p;
-    const bool split = ok && T.splittable[p];
-    int q = 0;
-    if (split) {
-      q = quadrant_of(T.cand[c], T.box[0][p]);
-      l |= (uint32_t)q << 14;
-    }
-    ORBX_AGG_ADD(T.child[0], 4 * p + q, split);
-    if (ok) T.lab[c] = (uint16_t)l;
-  }
-  ORBX_WSYNC();
+  qt_team_run(T, kQtCmdFirst, 0, false, hX);
   ORBX_QT_MARK(T, kQtInit);
 
   bool phase2 = false;
@@ -508,45 +612,8 @@ ORBX_HD int quadtree_run(QTree& T, int width, int height, int nIni, float hX, in
     }
     ORBX_WSYNC();
     ORBX_QT_MARK(T, kQtPrep);
-    // ---- one sweep over the candidates: move to the new node, then histogram / argmax. The loads of 4 lane steps
-    //      are issued before any of them is used ----
-    // Stage-wise over 4 lane steps so that the dependent shared-memory loads of different steps overlap:
-    // label -> new position (one table for split parents and survivors) -> node word -> quadrant -> histogram.
-    for (int c0 = 0; c0 < C; c0 += 4 * ORBX_NLANES) {
-      uint32_t lv[4], cv[4];
-      int np[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int c = c0 + u * ORBX_NLANES + ORBX_LANE();
-        ok[u] = c < C;
-        lv[u] = ok[u] ? (uint32_t)T.lab[c] : 0u;
-        cv[u] = ok[u] ? T.cand[c] : 0u;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) np[u] = T.childpos[4 * (int)(lv[u] & kLabPosMask) + (int)(lv[u] >> 14)];
-      if (finish) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int c = c0 + u * ORBX_NLANES + ORBX_LANE();
-          const uint32_t v = ((uint32_t)cand_s(cv[u]) << 24) | (0xffffffu - (uint32_t)c);
-          ORBX_AGG_MAX(child_nxt, np[u], v, ok[u]);
-          if (ok[u]) T.lab[c] = (uint16_t)np[u];
-        }
-      } else {
-        uint32_t info[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) info[u] = (uint32_t)T.scan[np[u]];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int c = c0 + u * ORBX_NLANES + ORBX_LANE();
-          const bool split = ok[u] && (info[u] >> 31);
-          const int q = (cand_x(cv[u]) < (int)(info[u] & 0xfff) ? 0 : 1) + (cand_y(cv[u]) < (int)((info[u] >> 12) & 0xfff) ? 0 : 2);
-          ORBX_AGG_ADD(child_nxt, 4 * np[u] + q, split);
-          if (ok[u]) T.lab[c] = (uint16_t)((uint32_t)np[u] | (split ? (uint32_t)q << 14 : 0u));
-        }
-      }
-    }
+    // ---- one sweep over the candidates (the whole team): move to the new node, then histogram / argmax ----
+    qt_team_run(T, kQtCmdRound, nxt, finish, hX);
     ORBX_WSYNC();
     ORBX_QT_MARK(T, kQtSweep);
 #if defined(ORBX_QT_PROF) && defined(__CUDA_ARCH__)

@@ -10,7 +10,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liborbx.so")
+SO_PATH = os.environ.get("ORBX_SO_PATH") or os.path.join(_HERE, "liborbx.so")  # the override is a development aid
+# (instrumented builds, e.g. -DORBX_QT_PROF); there is still no fallback: a missing file fails the import
 CSRC = os.path.join(_HERE, "csrc")
 
 KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),

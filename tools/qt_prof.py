@@ -5,7 +5,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from orb_slam3_fast_b200 import ORBextractor, synth
 ex = ORBextractor(1200, max_batch=8)
-imgs = np.stack([synth.stereo_pair(480, 752, s)[0] for s in range(8)])
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 752
+imgs = np.stack([synth.stereo_pair(480, W, s)[0] for s in range(8)])
 ex.extract_batch(imgs)
 ex.extract_batch(imgs)
 names = ["count", "gather", "init", "select", "sort", "walk", "children", "prep", "sweep", "tail", "rounds", "rounds2",
