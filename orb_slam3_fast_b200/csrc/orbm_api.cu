@@ -163,6 +163,9 @@ void orbm_destroy(orbm_matcher* m) {
   for (auto& b : m->track_map) b.release();
   for (auto& h : m->lane_h_track)
     if (h) cudaFreeHost(h);
+  for (auto& sl : m->sgraph)
+    if (sl.exec) cudaGraphExecDestroy(sl.exec);
+  if (m->sgraph_fork) cudaEventDestroy(m->sgraph_fork);
   if (m->track_map_ready) cudaEventDestroy(m->track_map_ready);
   if (m->up_stream) cudaStreamDestroy(m->up_stream);
   for (cudaEvent_t e : m->up_small)
@@ -350,11 +353,13 @@ struct TrackHost {
   int32_t *assign, *nmatches, *n_in_view;
 };
 
-int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+constexpr int kRetryDirect = 0x7e7e0001;  // internal: a graph recording failed, run the call again on the direct path
+
+int stereo_frames_body(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
                        const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
                        int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
                        int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
-                       float* depth, int32_t* n_matched, const TrackHost* trk) {
+                       float* depth, int32_t* n_matched, const TrackHost* trk, bool allow_graph) {
   if (!m || !left || !right || left == right) return mfail(m, ORBX_E_ARG, "bad argument");
   if (!imgs_l || !imgs_r || width <= 0 || height <= 0 || n_pairs <= 0) return mfail(m, ORBX_E_EMPTY, "empty image");
   if (stride < width || cap < 1 || !kps_l || !desc_l || !n_l || !kps_r || !desc_r || !n_r || !u_right || !depth ||
@@ -387,6 +392,86 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
   if (!m->up_stream) ORBM_CUDA(m, cudaStreamCreateWithFlags(&m->up_stream, cudaStreamNonBlocking));
   static const bool lane_uploads = getenv("ORBX_LANE_UPLOADS") != nullptr;  // A/B: uploads on the lanes' own streams
   const cudaStream_t up = m->up_stream;
+  // ---- a call of ONE group that comes back unchanged is recorded as a CUDA graph on its second run and replayed from
+  //      the third on (StereoGraphKey, orbm_handle.h): the single-pair call of an online front-end spends more host time
+  //      issuing ~60 launches and ~20 copies than the GPU spends executing them. ORBX_GRAPH=0 keeps the direct path. ----
+  enum { kDirect, kCapture, kReplay } mode = kDirect;
+  StereoGraphSlot* slot = nullptr;
+  static const bool graphs_on = [] {
+    const char* e = getenv("ORBX_GRAPH");
+    return !(e && e[0] == '0') && !getenv("ORBX_DEBUG_SKIP_KERNELS") && !getenv("ORBX_DEBUG_SKIP_H2D") &&
+           !getenv("ORBX_TRACE") && !getenv("ORBX_SERIAL_EYES") && !getenv("ORBX_LANE_UPLOADS");
+  }();
+  if (allow_graph && graphs_on && !m->sgraph_off && n_pairs <= B && !left->profile && !right->profile &&
+      (!trk || (trk->maps && trk->prm))) {
+    StereoGraphKey key;
+    memset(&key, 0, sizeof(key));
+    const void* ptrs[] = {left, right, imgs_l, imgs_r, kps_l, desc_l, kps_r, desc_r, u_right, depth,
+                          trk ? trk->frustums : nullptr, trk ? trk->maps->pos : nullptr, trk ? trk->maps->normal : nullptr,
+                          trk ? trk->maps->min_dist : nullptr, trk ? trk->maps->max_dist : nullptr,
+                          trk ? trk->maps->skip : nullptr, trk ? trk->maps->has_obs : nullptr,
+                          trk ? trk->maps->desc : nullptr, trk ? trk->map_index : nullptr, trk ? trk->occupied : nullptr,
+                          trk ? trk->assign : nullptr};
+    static_assert(sizeof(ptrs) <= sizeof(key.ptr), "key");
+    memcpy(key.ptr, ptrs, sizeof(ptrs));
+    const long long ints[] = {n_pairs, width, height, stride, (long long)frame_stride, cap, trk ? 1 : 0,
+                              trk ? trk->maps->m : 0, trk ? trk->maps->n_maps : 0, trk ? trk->prm->far_points : 0,
+                              trk ? trk->prm->cand_per_frame : 0};
+    static_assert(sizeof(ints) <= sizeof(key.iv), "key");
+    memcpy(key.iv, ints, sizeof(ints));
+    const float flts[] = {mbf, mb, trk ? trk->prm->viewing_cos_limit : 0.f, trk ? trk->prm->th : 0.f,
+                          trk ? trk->prm->nnratio : 0.f, trk ? trk->prm->th_far : 0.f, trk ? trk->prm->min_x : 0.f,
+                          trk ? trk->prm->min_y : 0.f, trk ? trk->prm->inv_w : 0.f, trk ? trk->prm->inv_h : 0.f};
+    static_assert(sizeof(flts) <= sizeof(key.fv), "key");
+    memcpy(key.fv, flts, sizeof(flts));
+    key.gen = orbx::alloc_generation().load();
+    StereoGraphSlot* victim = nullptr;  // a free slot, else the least recently used one
+    for (StereoGraphSlot& sl : m->sgraph) {
+      if (sl.used && memcmp(&sl.key, &key, sizeof(key)) == 0) slot = &sl;
+      if (!victim || (victim->used && (!sl.used || sl.stamp < victim->stamp))) victim = &sl;
+    }
+    if (slot) {
+      mode = slot->exec ? kReplay : kCapture;
+    } else {  // first sight: run directly (every buffer gets its final size), remember the call
+      if (victim->exec) cudaGraphExecDestroy(victim->exec);
+      victim->exec = nullptr;
+      victim->key = key;
+      victim->used = true;
+      slot = victim;
+    }
+    slot->stamp = ++m->sgraph_clock;
+  }
+  const cudaStream_t g_st = left->lane[0].stream, g_sr = right->lane[0].stream;
+  // Ends an open recording on every way out of this function; the caller (stereo_frames_impl) sees sgraph_recording
+  // still set, switches the handle to the direct path for good and runs the call again there.
+  struct RecordingGuard {
+    orbm_matcher* m;
+    cudaStream_t s;
+    ~RecordingGuard() {
+      if (!m->sgraph_recording) return;
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(s, &g);
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+    }
+  } recording_guard{m, g_st};
+  if (mode == kCapture) {
+    if (!m->sgraph_fork && cudaEventCreateWithFlags(&m->sgraph_fork, cudaEventDisableTiming) != cudaSuccess) mode = kDirect;
+  }
+  if (mode == kCapture) {
+    // the left lane's stream is the origin; the right eye's stream and the upload stream fork from it here and join it
+    // again through the events the direct path records anyway (lane.up, lane.done, track_map_ready)
+    if (cudaStreamBeginCapture(g_st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      m->sgraph_off = true;
+      mode = kDirect;
+    } else {
+      m->sgraph_recording = true;
+      ORBM_CUDA(m, cudaEventRecord(m->sgraph_fork, g_st));
+      ORBM_CUDA(m, cudaStreamWaitEvent(g_sr, m->sgraph_fork, 0));
+      ORBM_CUDA(m, cudaStreamWaitEvent(up, m->sgraph_fork, 0));
+    }
+  }
   // ---- the tracking stage: local maps go to the device once per call, on the upload stream ----
   TrackArgs T0{};
   orbx_local_map dmap{};
@@ -405,9 +490,10 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
       if (!bytes[k]) continue;
       cudaError_t e = m->track_map[k].reserve(bytes[k]);
       if (e != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(e));
-      ORBM_CUDA(m, cudaMemcpyAsync(m->track_map[k].p, host[k], bytes[k], cudaMemcpyHostToDevice, up));
+      if (mode != kReplay)  // a replayed call has these copies in its graph
+        ORBM_CUDA(m, cudaMemcpyAsync(m->track_map[k].p, host[k], bytes[k], cudaMemcpyHostToDevice, up));
     }
-    ORBM_CUDA(m, cudaEventRecord(m->track_map_ready, up));
+    if (mode != kReplay) ORBM_CUDA(m, cudaEventRecord(m->track_map_ready, up));
     dmap.m = hm.m;
     dmap.n_maps = hm.n_maps;
     dmap.pos = static_cast<const float*>(m->track_map[0].p);
@@ -433,9 +519,9 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
   int first_err = ORBX_OK;
   int pending_f0[kLanes], pending_nb[kLanes];
   for (int i = 0; i < kLanes; i++) pending_nb[i] = 0;
-  auto retire = [&](int ln) -> int {
+  auto retire = [&](int ln, bool synced = false) -> int {
     if (pending_nb[ln] == 0) return ORBX_OK;
-    ORBM_CUDA(m, cudaEventSynchronize(left->lane[ln].done));
+    if (!synced) ORBM_CUDA(m, cudaEventSynchronize(left->lane[ln].done));
     for (int f = 0; f < pending_nb[ln]; f++) {
       const int g = pending_f0[ln] + f;
       n_l[g] = left->lane[ln].h_small[f];
@@ -487,10 +573,29 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     tev.push_back(e);
     return e;
   };
+  auto finish_recorded = [&]() -> int {  // launch the recorded call, wait for it, hand out the pinned result words
+    ORBM_CUDA(m, cudaGraphLaunch(slot->exec, g_st));
+    ORBM_CUDA(m, cudaStreamSynchronize(g_st));
+    m->sgraph_launches++;
+    for (orbx_extractor* ex : {left, right}) {  // what run_pipeline leaves behind on the host side
+      OrbxLane& L = ex->lane[0];
+      L.last_fs = ex == left ? slot->fs_l : slot->fs_r;
+      L.last_frames = n_pairs;
+      L.last_f0 = 0;
+      L.last_call = ex->call_id;
+      ex->last_lane = 0;
+    }
+    pending_f0[0] = 0;
+    pending_nb[0] = n_pairs;
+    int r = retire(0, true);
+    if (r) return r;
+    if (first_err) return mfail(m, first_err, "output capacity (or the candidate list) too small for at least one frame");
+    return ORBX_OK;
+  };
+  if (mode == kReplay) return finish_recorded();
   double t_wait = 0, t_issue = 0;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  int group = 0, f0 = 0;
-  for (size_t gi = 0; gi < sizes.size(); f0 += sizes[gi], gi++, group++) {
+  auto issue_group = [&](size_t gi, int f0, int group) -> int {
     const int nb = sizes[gi];
     static const int n_lanes = getenv("ORBX_LANES") ? std::max(1, std::min((int)kLanes, atoi(getenv("ORBX_LANES")))) : (int)kLanes;
     const int ln = group % n_lanes;
@@ -638,6 +743,31 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
     ORBM_CUDA(m, cudaEventRecord(left->lane[ln].done, st));
     pending_f0[ln] = f0;
     pending_nb[ln] = nb;
+    return ORBX_OK;
+  };
+  {
+    int group = 0, f0 = 0;
+    for (size_t gi = 0; gi < sizes.size(); f0 += sizes[gi], gi++, group++)
+      if ((rc = issue_group(gi, f0, group)) != 0) return rc;  // (an open recording is ended by recording_guard)
+  }
+  if (mode == kCapture) {
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(g_st, &g);
+    cudaError_t ge = ce;
+    if (ce == cudaSuccess && g) ge = cudaGraphInstantiate(&slot->exec, g, 0);
+    if (g) cudaGraphDestroy(g);
+    if (ge != cudaSuccess || !slot->exec) {
+      slot->exec = nullptr;
+      cudaGetLastError();
+      m->sgraph_recording = false;  // the capture is closed; tell the caller to go direct
+      m->sgraph_off = true;
+      return kRetryDirect;
+    }
+    m->sgraph_recording = false;
+    slot->fs_l = left->lane[0].last_fs;
+    slot->fs_r = right->lane[0].last_fs;
+    pending_nb[0] = 0;  // nothing ran yet: the recorded work is launched now
+    return finish_recorded();
   }
   const double td0 = trace ? now() : 0;
   for (int ln = 0; ln < kLanes; ln++)
@@ -660,9 +790,30 @@ int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* ri
   if (first_err) return mfail(m, first_err, "output capacity (or the candidate list) too small for at least one frame");
   return ORBX_OK;
 }
+
+int stereo_frames_impl(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
+                       const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,
+                       int64_t frame_stride, float mbf, float mb, orbx_kp* kps_l, uint8_t* desc_l,
+                       int32_t* n_l, orbx_kp* kps_r, uint8_t* desc_r, int32_t* n_r, int cap, float* u_right,
+                       float* depth, int32_t* n_matched, const TrackHost* trk) {
+  int rc = stereo_frames_body(m, left, right, n_pairs, imgs_l, imgs_r, width, height, stride, frame_stride, mbf, mb, kps_l,
+                              desc_l, n_l, kps_r, desc_r, n_r, cap, u_right, depth, n_matched, trk, true);
+  if (m && m->sgraph_recording) {  // left early with a recording open (closed by its guard)
+    m->sgraph_recording = false;
+    m->sgraph_off = true;
+    rc = kRetryDirect;
+  }
+  if (rc == kRetryDirect)  // the recording met something a stream capture cannot hold: the handle stays direct from now on
+    rc = stereo_frames_body(m, left, right, n_pairs, imgs_l, imgs_r, width, height, stride, frame_stride, mbf, mb, kps_l,
+                            desc_l, n_l, kps_r, desc_r, n_r, cap, u_right, depth, n_matched, trk, false);
+  return rc;
+}
 }  // namespace
 
 extern "C" {
+
+/* Development aid (not in include/orbm.h): how many small stereo calls ran as a recorded CUDA graph on this handle. */
+int orbm_debug_graph_launches(const orbm_matcher* m) { return m ? (int)m->sgraph_launches : -1; }
 
 int orbm_stereo_frames_batch(orbm_matcher* m, orbx_extractor* left, orbx_extractor* right, int n_pairs,
                              const uint8_t* imgs_l, const uint8_t* imgs_r, int width, int height, int stride,

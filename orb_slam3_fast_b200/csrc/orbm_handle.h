@@ -21,6 +21,7 @@ struct DevBuf {
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    orbx::alloc_generation()++;  // recorded graphs that point into this buffer must not be replayed
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -30,12 +31,31 @@ struct DevBuf {
     return e;
   }
   void release() {
+    if (p) orbx::alloc_generation()++;
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
   }
 };
 enum { kBufs = 40, kTrackBufs = 12 };
+
+// A small stereo call (one pipeline group) issues ~60 kernels and ~20 copies / event operations whose host-side cost
+// (~0.8 ms) exceeds the GPU's (~0.5 ms for one 640x480 pair). When the SAME call comes back — same buffers, same sizes,
+// same parameters: the loop of an online front-end — its work is recorded once as a CUDA graph and replayed.
+struct StereoGraphKey {  // compared with memcmp: always memset before filling
+  const void* ptr[28];
+  long long iv[12];
+  float fv[12];
+  unsigned long long gen;  // orbx::alloc_generation() the call ran under
+};
+struct StereoGraphSlot {
+  StereoGraphKey key;
+  cudaGraphExec_t exec = nullptr;
+  bool used = false;
+  unsigned long long stamp = 0;
+  orbx::FrameSet fs_l{}, fs_r{};  // host-side bookkeeping of the recorded run (OrbxLane::last_fs)
+};
+enum { kStereoGraphSlots = 4 };
 }  // namespace orbm_detail
 using orbm_detail::DevBuf;
 using orbm_detail::kBufs;
@@ -73,6 +93,13 @@ struct orbm_matcher {
   cudaEvent_t up_small[8] = {};  // per lane: the tracking stage's small inputs are on the device
   int32_t* lane_h_track[kLanes] = {};
   int lane_h_track_cap[kLanes] = {};
+  // recorded small stereo calls (see StereoGraphKey)
+  orbm_detail::StereoGraphSlot sgraph[orbm_detail::kStereoGraphSlots];
+  unsigned long long sgraph_clock = 0;
+  bool sgraph_off = false;          // set when a recording failed: the handle stays on the direct path
+  bool sgraph_recording = false;    // a stream capture is open (stereo_frames_body)
+  cudaEvent_t sgraph_fork = nullptr;
+  unsigned long long sgraph_launches = 0;
 };
 
 namespace orbm_detail {

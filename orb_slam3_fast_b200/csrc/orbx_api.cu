@@ -37,6 +37,7 @@ thread_local std::string g_create_error;
   } while (0)
 
 void free_plan_buffers(orbx_extractor* ex) {
+  orbx::alloc_generation()++;
   for (OrbxLane& L : ex->lane) {
     cudaFree(L.d_in);
     cudaFree(L.d_pyr);
@@ -61,6 +62,7 @@ void free_plan_buffers(orbx_extractor* ex) {
 }
 
 void free_out_buffers(orbx_extractor* ex) {
+  orbx::alloc_generation()++;
   for (OrbxLane& L : ex->lane) {
     cudaFree(L.d_kps);
     cudaFree(L.d_desc);
@@ -83,6 +85,7 @@ int sync_all_lanes(orbx_extractor* ex) {
 // scratch of one lane; lanes beyond the first are only materialised when a call needs them
 int alloc_lane(orbx_extractor* ex, OrbxLane& L) {
   if (L.d_pyr) return ORBX_OK;
+  orbx::alloc_generation()++;
   const Plan& P = ex->plan;
   const size_t B = ex->max_batch;
   ORBX_CUDA(ex, cudaMalloc(&L.d_in, (size_t)ex->in_fstride * B));
@@ -106,6 +109,7 @@ int alloc_lane(orbx_extractor* ex, OrbxLane& L) {
 
 int alloc_lane_out(orbx_extractor* ex, OrbxLane& L, int cap) {
   if (L.out_cap >= cap && L.d_kps) return ORBX_OK;
+  orbx::alloc_generation()++;
   ORBX_CUDA(ex, cudaStreamSynchronize(L.stream));
   cudaFree(L.d_kps);
   cudaFree(L.d_desc);

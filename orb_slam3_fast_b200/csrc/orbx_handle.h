@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -63,6 +64,13 @@ struct orbx_extractor {
 };
 
 namespace orbx {
+// Bumped whenever the library frees or (re)allocates device memory that recorded work may point to (lane buffers, output
+// slabs, matcher scratch). A CUDA graph recorded by the matcher (orbm_api.cu: the small stereo calls) is only replayed
+// while the generation it was recorded under is still current.
+inline std::atomic<unsigned long long>& alloc_generation() {
+  static std::atomic<unsigned long long> g{1};
+  return g;
+}
 // internal entry points of orbx_api.cu used by the matcher's fused stereo call
 int api_fail(orbx_extractor* ex, int code, const std::string& msg);
 int api_ensure_plan(orbx_extractor* ex, int w, int h);

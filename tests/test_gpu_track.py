@@ -218,3 +218,81 @@ def test_multi_gpu_c_entry_points_shard_and_equal_the_single_device_call(matcher
     assert np.array_equal(n1, n2) and np.array_equal(mono1, mono2)
     assert all(k1[i, :n1[i]].tobytes() == k2[i, :n1[i]].tobytes() and d1[i, :n1[i]].tobytes() == d2[i, :n1[i]].tobytes()
                for i in range(n))
+
+
+def test_recorded_small_call_replays_with_the_callers_current_data():
+    """A one-group host call that comes back with the same buffers, sizes and parameters is recorded as a CUDA graph on
+    its second run and replayed from the third on (stereo_frames_body, orbm_api.cu). The replay must read what the
+    caller's buffers hold NOW (new images, poses, occupancy in the same pinned memory), a changed parameter must leave
+    the recorded path, and pageable buffers must keep working — every result against the oracle."""
+    import torch
+    mt = ORBmatcher(0.8, True)
+    n, m = 2, 1500
+    exl, exr = ORBextractor(NF, max_batch=2), ORBextractor(NF, max_batch=2)
+    cap = exl.capacity
+
+    def pinned(shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory().numpy()[:nbytes].view(dtype).reshape(shape)
+
+    imgs_l, imgs_r = pinned((n, H, W), np.uint8), pinned((n, H, W), np.uint8)
+    frs = pinned((n,), views.FRUSTUM_DTYPE)
+    occ = pinned((n, cap), np.uint8)
+    out = ORBmatcher.alloc_track_outputs(n, cap, empty=pinned)
+    sets = []
+    for seed0 in (1200, 1300):
+        L, R, ref = _frames(n, seed0)
+        f = np.stack([synth.frustum(W, H, seed=seed0 + 50 + i) for i in range(n)])
+        maps = [synth.local_map_world(ref[i]["kl"], ref[i]["dl"], m, f[i], seed=seed0 + 70 + i) for i in range(n)]
+        o = (np.random.default_rng(seed0).random((n, cap)) < 0.2).astype(np.uint8)
+        sets.append((L, R, ref, f, maps, o))
+    # the maps live in ONE set of pinned arrays whose contents are swapped with the scene
+    map_arrays = {k: pinned(np.stack([mp[k] for mp in sets[0][4]]).shape, sets[0][4][0][k].dtype) for k in sets[0][4][0]}
+    lm = views.make_local_map(**map_arrays)
+
+    def load(k):
+        L, R, ref, f, maps, o = sets[k]
+        imgs_l[:], imgs_r[:], frs[:], occ[:] = L, R, f, o
+        for key in map_arrays:
+            map_arrays[key][:] = np.stack([mp[key] for mp in maps])
+
+    def check(k, th):
+        L, R, ref, f, maps, o = sets[k]
+        for i in range(n):
+            r = ref[i]
+            nl = len(r["kl"])
+            assert int(out["n_l"][i]) == nl and _same(out["kps_l"][i, :nl], r["kl"]) and _same(out["desc_l"][i, :nl], r["dl"])
+            assert int(out["n_matched"][i]) == r["nm"] and _same(out["u_right"][i, :nl], r["ur"])
+            nm, assign, nv = _oracle_track(r, f[i], maps[i], o[i, :nl], th, 0.8, False, 0.0)
+            assert int(out["n_in_view"][i]) == nv and int(out["nmatches"][i]) == nm
+            assert np.array_equal(out["assign"][i, :nl], assign), "pair %d assign differs" % i
+
+    mt._L.orbm_debug_graph_launches.argtypes = [C.c_void_p]
+    launches = lambda: int(mt._L.orbm_debug_graph_launches(mt._h))
+    prm = views.make_track_params(W, H, th=1.0, nnratio=0.8)
+    load(0)
+    for rep in range(4):  # direct, (direct again if a buffer grew), recorded, replayed
+        for v in out.values():
+            v[...] = 0
+        mt.StereoTrackFramesBatch(exl, exr, imgs_l, imgs_r, MBF, MB, frs, lm, prm, occupied=occ, out=out)
+        check(0, 1.0)
+    assert launches() >= 1, "the repeated call never ran as a recorded graph"
+    before = launches()
+    load(1)  # same buffers, new contents
+    mt.StereoTrackFramesBatch(exl, exr, imgs_l, imgs_r, MBF, MB, frs, lm, prm, occupied=occ, out=out)
+    check(1, 1.0)
+    assert launches() == before + 1
+    prm3 = views.make_track_params(W, H, th=3.0, nnratio=0.8)  # another key: back on the direct path
+    mt.StereoTrackFramesBatch(exl, exr, imgs_l, imgs_r, MBF, MB, frs, lm, prm3, occupied=occ, out=out)
+    check(1, 3.0)
+    assert launches() == before + 1
+    # pageable buffers, repeated: whichever path the library takes, the words must be the oracle's
+    L, R, ref, f, maps, o = sets[0]
+    lm2 = views.make_local_map(**{k: np.stack([mp[k] for mp in maps]) for k in maps[0]})
+    out2 = ORBmatcher.alloc_track_outputs(n, cap)
+    Lc, Rc, fc, oc = L.copy(), R.copy(), f.copy(), o.copy()
+    for rep in range(4):
+        mt.StereoTrackFramesBatch(exl, exr, Lc, Rc, MBF, MB, fc, lm2, prm, occupied=oc, out=out2)
+        out, keep = out2, out
+        check(0, 1.0)
+        out = keep
