@@ -49,7 +49,11 @@ int orbm_distinctive_descriptors(orbm_matcher* m, const uint8_t* desc, const int
  * Host buffers: q[nq][32], t[nt][32], outputs [nq]. */
 int orbm_knn2(orbm_matcher* m, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx1, int32_t* d1,
               int32_t* idx2, int32_t* d2);
-/* Same with every pointer in device memory; enqueued on cuda_stream (NULL = the context's stream), not synchronised. */
+/* Same with every pointer in device memory; enqueued on cuda_stream (NULL = the context's stream), not synchronised.
+ * Stream contract of every *_device entry point of this header: the call uses the matcher context's scratch (partial
+ * results, expanded descriptors, candidate slabs), so one context serves ONE stream at a time — device calls of the same
+ * context on different streams must be ordered by the caller (see orbx_extract_batch_device in orbx.h). Contexts are
+ * cheap; give every concurrent stream its own, as every thread has its own (threading). */
 int orbm_knn2_device(orbm_matcher* m, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int32_t* d_idx1,
                      int32_t* d_d1, int32_t* d_idx2, int32_t* d_d2, void* cuda_stream);
 

@@ -75,7 +75,13 @@ int orbx_extract_batch_multi(int n_devices, orbx_extractor* const* ex, int n_fra
                              uint8_t* desc, int cap, int32_t* n_out, int32_t* mono_index);
 
 /* Same, inputs and outputs resident in device memory; enqueued on `cuda_stream` (a cudaStream_t; NULL = the handle's
- * stream) and NOT synchronised. n_frames <= max_batch. d_status[n_frames] receives 0 or ORBX_E_CAPACITY per frame. */
+ * stream) and NOT synchronised. n_frames <= max_batch. d_status[n_frames] receives 0 or ORBX_E_CAPACITY per frame.
+ * Stream contract: the call works in the handle's scratch (pyramid, blurred levels, candidate lists of lane 0), which
+ * the host-facing calls use on the handle's own stream. A handle therefore serves ONE stream at a time: two device
+ * calls on different streams, or a device call followed by a host-facing call (or by anything that reads the frame
+ * "of the last call": orbx_download_pyramid, orbm_stereo_match_batch_device, the *_resident searches), must be ordered
+ * by the caller — an event, or a synchronise — exactly like two kernels that share a buffer. The library adds no event
+ * of its own here, so that the call can sit inside a stream capture of the caller. */
 int orbx_extract_batch_device(orbx_extractor* ex, int n_frames, const uint8_t* d_images, int width, int height,
                               int stride, int64_t frame_stride, int lap0, int lap1, orbx_kp* d_kps, uint8_t* d_desc,
                               int cap, int32_t* d_n, int32_t* d_mono_index, int32_t* d_status, void* cuda_stream);

@@ -4,6 +4,8 @@
 //   k_stereo_match / _median     Frame::ComputeStereoMatches                                     src/Frame.cc:921-1084
 // All integer / bitwise work: descriptors are held in registers as 8 x u32, distances are __popc(a ^ b); warp-level
 // argmin keeps the reference's tie rules (first minimal element in visiting order wins because it compares with <).
+#include <stdlib.h>
+
 #include "orbx_match.cuh"
 
 namespace orbx {
@@ -282,7 +284,10 @@ void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_point
 // that ~7x. A second kernel (one CTA per pair) finds the median SAD by a two-level histogram select and removes
 // matches >= 1.5 * 1.4 * median (:1072-1083).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kStereoWarps = 4;
+// Warps per CTA: 4 for launches that fill the chip (1024 pairs: 1.21 ms; with 8 warps 1.40 ms), 8 for small ones, where
+// the CTA's list building (every thread scans 2 x 1200 keypoints / blockDim) and its ~40 left keypoints per band are
+// the latency of the launch (single pair: 68 -> 45 us).
+constexpr int kStereoWarpsBig = 4, kStereoWarpsSmall = 8;
 constexpr int kBandRows = 16;
 
 struct BandEntry {
@@ -291,6 +296,7 @@ struct BandEntry {
   int32_t idx;   // iR | octave << 16
 };
 
+template <int kStereoWarps>
 __global__ void __launch_bounds__(kStereoWarps * 32)
 k_stereo_match(const StereoArgs A) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -535,9 +541,19 @@ void launch_stereo(const StereoArgs& A, int n_pairs, int max_rows, cudaStream_t 
   if (n_pairs <= 0 || max_rows <= 0) return;
   const int bands = (A.left.h[0] + kBandRows - 1) / kBandRows;
   const size_t smem = (size_t)A.cap * (sizeof(BandEntry) + sizeof(uint16_t));
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_stereo_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(bands, n_pairs);
-  k_stereo_match<<<grid, kStereoWarps * 32, smem, st>>>(A);
+  // small launch = fewer than two CTAs per SM; ORBX_STEREO_WARPS=4|8 forces a form (parity test of one against the other)
+  bool small = (long long)bands * n_pairs < 2 * 148;
+  if (const char* e = getenv("ORBX_STEREO_WARPS")) small = e[0] == '8';
+  if (small) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_stereo_match<kStereoWarpsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_stereo_match<kStereoWarpsSmall><<<grid, kStereoWarpsSmall * 32, smem, st>>>(A);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_stereo_match<kStereoWarpsBig>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_stereo_match<kStereoWarpsBig><<<grid, kStereoWarpsBig * 32, smem, st>>>(A);
+  }
   k_stereo_median<<<n_pairs, 256, 0, st>>>(A);
 }
 

@@ -82,9 +82,14 @@ void launch_frustum_batch(const TrackArgs& A, cudaStream_t st) {
 constexpr int kCells = ORBX_GRID_COLS * ORBX_GRID_ROWS;
 constexpr int kOff16 = kTrackOff16;  // u16 offsets per frame: 64 * 48 + 1 used, padded so that a frame's array is 8-byte aligned
 
+// kStage: the frame's keypoints are first copied to shared memory (independent loads, all in flight at once): the two
+// passes over them below otherwise pay one dependent global round trip per 32 keypoints (2 x 38 for a 1200-keypoint
+// frame: 43 us for a single frame, the longest kernel of the single-pair tracking search).
+template <bool kStage>
 __global__ void __launch_bounds__(32) k_track_grid(const TrackArgs A) {
   constexpr int kPerLane = kCells / 32;
   __shared__ int32_t cur[kCells];
+  extern __shared__ __align__(16) uint8_t tg_smem[];  // kStage: float2 xy[cap] | uint32 meta[cap] | float ur[cap]
   const int lane = threadIdx.x, f = blockIdx.x;
   const int n = min(A.n[f], A.cap);
   const orbx_kp* kps = A.kps + (size_t)f * A.cap;
@@ -92,16 +97,28 @@ __global__ void __launch_bounds__(32) k_track_grid(const TrackArgs A) {
   const uint8_t* occ = A.occupied ? A.occupied + (size_t)f * A.cap : nullptr;
   uint16_t* off16 = A.grid_off16 + (size_t)f * kOff16;
   uint4* rec = A.grid_rec + (size_t)f * A.cap;
-  auto cell_of = [&](const orbx_kp& kp) {
-    const int px = (int)roundf(fmul(fsub(kp.x, A.min_x), A.inv_w));  // round(): half away from zero        :836-837
-    const int py = (int)roundf(fmul(fsub(kp.y, A.min_y), A.inv_h));
-    if (px < 0 || px >= ORBX_GRID_COLS || py < 0 || py >= ORBX_GRID_ROWS) return -1;  //                      :840-841
+  float2* s_xy = reinterpret_cast<float2*>(tg_smem);
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(tg_smem + (size_t)A.cap * 8);
+  float* s_ur = reinterpret_cast<float*>(tg_smem + (size_t)A.cap * 12);
+  auto cell_xy = [&](float x, float y) {
+    const int px = (int)roundf(fmul(fsub(x, A.min_x), A.inv_w));  // round(): half away from zero        :836-837
+    const int py = (int)roundf(fmul(fsub(y, A.min_y), A.inv_h));
+    if (px < 0 || px >= ORBX_GRID_COLS || py < 0 || py >= ORBX_GRID_ROWS) return -1;  //                  :840-841
     return px * ORBX_GRID_ROWS + py;
   };
   for (int c = lane; c < kCells; c += 32) cur[c] = 0;
+  if (kStage) {
+#pragma unroll 4
+    for (int i = lane; i < n; i += 32) {
+      const orbx_kp kp = kps[i];
+      s_xy[i] = make_float2(kp.x, kp.y);
+      s_meta[i] = (uint32_t)i | ((uint32_t)kp.octave << 16) | ((occ && occ[i]) ? 0x80000000u : 0u);
+      s_ur[i] = ur ? ur[i] : -1.f;
+    }
+  }
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
-    const int c = cell_of(kps[i]);
+    const int c = kStage ? cell_xy(s_xy[i].x, s_xy[i].y) : cell_xy(kps[i].x, kps[i].y);
     if (c >= 0) atomicAdd(&cur[c], 1);
   }
   __syncwarp();
@@ -125,20 +142,26 @@ __global__ void __launch_bounds__(32) k_track_grid(const TrackArgs A) {
   const unsigned lt = (1u << lane) - 1u;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
-    orbx_kp kp;
+    float x = 0, y = 0, u = -1.f;
+    uint32_t meta = 0;
     int c = -1;
     if (i < n) {
-      kp = kps[i];
-      c = cell_of(kp);
+      if (kStage) {
+        x = s_xy[i].x; y = s_xy[i].y; meta = s_meta[i]; u = s_ur[i];
+      } else {
+        const orbx_kp kp = kps[i];
+        x = kp.x; y = kp.y;
+        meta = (uint32_t)i | ((uint32_t)kp.octave << 16) | ((occ && occ[i]) ? 0x80000000u : 0u);
+        u = ur ? ur[i] : -1.f;
+      }
+      c = cell_xy(x, y);
     }
     const unsigned same = __match_any_sync(0xffffffffu, c);
     int pos = 0;
     if (c >= 0) pos = cur[c];
     __syncwarp();
     if (c >= 0) {
-      const uint32_t meta = (uint32_t)i | ((uint32_t)kp.octave << 16) | ((occ && occ[i]) ? 0x80000000u : 0u);
-      rec[pos + __popc(same & lt)] = make_uint4(__float_as_uint(kp.x), __float_as_uint(kp.y),
-                                                __float_as_uint(ur ? ur[i] : -1.f), meta);
+      rec[pos + __popc(same & lt)] = make_uint4(__float_as_uint(x), __float_as_uint(y), __float_as_uint(u), meta);
       if ((same & lt) == 0u) cur[c] = pos + __popc(same);
     }
     __syncwarp();
@@ -414,7 +437,15 @@ size_t track_resolve_smem(int cap) { return (size_t)cap * 4 + ((size_t)cap + 15)
 void launch_track_search(const TrackArgs& A, cudaStream_t st) {
   cudaMemsetAsync(A.cand_total, 0, (size_t)A.n_frames * 4, st);
   cudaMemsetAsync(A.status, 0, (size_t)A.n_frames * 4, st);
-  k_track_grid<<<A.n_frames, 32, 0, st>>>(A);
+  {
+    const size_t gs = (size_t)A.cap * 16;  // staged keypoints: xy, meta, u_right
+    if (gs <= 160 * 1024) {
+      if (gs > 36 * 1024) cudaFuncSetAttribute(k_track_grid<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs);
+      k_track_grid<true><<<A.n_frames, 32, gs, st>>>(A);
+    } else {
+      k_track_grid<false><<<A.n_frames, 32, 0, st>>>(A);
+    }
+  }
   if (A.m > 0) {
     const size_t es = track_enum_smem(A.cap);
     if (es > 48 * 1024) cudaFuncSetAttribute(k_track_enum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)es);

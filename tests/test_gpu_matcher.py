@@ -94,6 +94,18 @@ def _stereo_case(w, h, nf, seed, kind="scene"):
     return (exl, exr, rl, rr), (kl, dl, kr, dr)
 
 
+@pytest.mark.parametrize("warps", ["4", "8"])
+def test_stereo_match_both_cta_shapes_equal_oracle(matcher, monkeypatch, warps):
+    """k_stereo_match runs with 8 warps per CTA in small launches (latency) and with 4 in launches that fill the chip
+    (throughput); ORBX_STEREO_WARPS forces one form. Both must give the oracle's words on the same pair."""
+    monkeypatch.setenv("ORBX_STEREO_WARPS", warps)
+    (exl, exr, rl, rr), (kl, dl, kr, dr) = _stereo_case(640, 480, 1200, 7, kind="noise_blur")
+    mbf, mb = float(np.float32(435.2 * 0.11)), float(np.float32(0.11))
+    nm, ur, dp = matcher.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, mbf, mb)
+    nm_r, ur_r, dp_r = orbref.stereo_match(rl, rr, kl, dl, kr, dr, mbf, mb)
+    assert nm == nm_r and nm > 50 and ur.tobytes() == ur_r.tobytes() and dp.tobytes() == dp_r.tobytes()
+
+
 @pytest.mark.parametrize("w,h,nf,seed", [(752, 480, 1200, 0), (640, 480, 1000, 1), (1280, 720, 2000, 2)])
 def test_stereo_matches_oracle(matcher, w, h, nf, seed):
     (exl, exr, rl, rr), (kl, dl, kr, dr) = _stereo_case(w, h, nf, seed)
