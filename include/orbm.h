@@ -227,7 +227,11 @@ int orbm_search_for_initialization(orbm_matcher* m, const orbx_frame_view* f1, c
  * the Replace / AddObservation surgery in point order (:1261-1273). chi2_gate = 1 for this overload; 0 gives the loop
  * of Fuse(KeyFrame*, Sophus::Sim3f& Scw, const vector<MapPoint*>&, float th, vector<MapPoint*>& vpReplacePoint)
  * (:1277-1390), which has the same window and level test but no reprojection gate (:1356-1372); inv_level_sigma2 is
- * not read then and may be NULL. */
+ * not read then and may be NULL.
+ * Two-camera KeyFrames (NLeft != -1) and bRight (:1116-1124, :1200-1201, :1219-1221, :1247): the search runs on ONE
+ * camera, so kf is that camera's view — mvKeys / mGrid / descriptor rows [0, NLeft), or with bRight mvKeysRight /
+ * mGridRight / rows [NLeft, N) with u_right = mvuRight under the camera-local index — and the caller adds NLeft to
+ * best_idx (shim/ORBmatcher_next_orbx.cc; the projection stays with the reference's own mpCamera2 object). */
 int orbm_fuse_match(orbm_matcher* m, const orbx_frame_view* kf, const float* inv_level_sigma2,
                     const orbx_projected* pts, int chi2_gate, int32_t* best_idx, int32_t* best_dist);
 

@@ -373,6 +373,57 @@ int orbrefsrc_fuse(const orbx_frame_view* kfv, const float* inv_level_sigma2, in
   return n;
 }
 
+// Fuse(KeyFrame*, const vector<MapPoint*>&, th, bRight) on a two-camera KeyFrame (NLeft != -1), :1108-1281 with the
+// camera / pose / grid / keypoint selection of :1116-1124, :1200-1201, :1219-1221 and the "+ NLeft" of :1247: the left
+// search (b_right == 0: mvKeys, mGrid, rows [0, NLeft)) or the right one (b_right != 0: mvKeysRight, mGridRight, rows
+// [NLeft, N), pKF->mpCamera2, GetRightPose). Placement as orbrefsrc_fuse; both poses are the identity in the stand-in
+// world. mvuRight is all -1 on such KeyFrames (Frame::ComputeStereoFishEyeMatches, src/Frame.cc:1281-1286), so only the
+// 5.99 gate runs. best_idx[i] = the ROW of mDescriptors / mvpMapPoints point i was fused into, or -1.
+int orbrefsrc_fuse_two_camera(const orbx_fisheye_view* fv, const float* inv_level_sigma2, int m, const float* u,
+                              const float* v, const float* z, const int32_t* level, const uint8_t* desc, float th,
+                              float mbf, int b_right, int32_t* best_idx) {
+  const int NL = fv->n_left, NR = fv->n_right, N = NL + NR;
+  Frame F;
+  F.N = N;
+  F.Nleft = NL;
+  F.mvKeys = keypoints(fv->kps_left, NL);
+  F.mvKeysRight = keypoints(fv->kps_right, NR);
+  Frame::mnMinX = fv->grid_left.min_x;
+  Frame::mnMinY = fv->grid_left.min_y;
+  Frame::mfGridElementWidthInv = fv->grid_left.inv_w;
+  Frame::mfGridElementHeightInv = fv->grid_left.inv_h;
+  F.AssignFeaturesToGrid();
+  KeyFrame kf;
+  kf.N = N;
+  kf.Nleft = kf.NLeft = NL;
+  kf.mvKeys = F.mvKeys;
+  kf.mvKeysRight = F.mvKeysRight;
+  kf.mDescriptors = rows32(fv->desc, N);
+  kf.mvuRight.assign(N, -1.f);
+  kf.mvScaleFactors.assign(fv->scale_factors, fv->scale_factors + fv->n_levels);
+  kf.mvInvLevelSigma2.assign(inv_level_sigma2, inv_level_sigma2 + fv->n_levels);
+  kf.take_grid(F);
+  kf.mbf = mbf;
+  kf.mnMaxX = kf.mnMaxY = 1e9f;
+  kf.mvpMapPoints.assign(N, nullptr);
+  GeometricCamera camera, camera2;
+  kf.mpCamera = &camera;
+  kf.mpCamera2 = &camera2;
+  std::vector<MapPoint> pts(m);
+  std::vector<MapPoint*> ptrs(m);
+  for (int i = 0; i < m; i++) {
+    pts[i].pos = Eigen::Vector3f(u[i], v[i], z[i]);
+    pts[i].normal = pts[i].pos * 10.f;
+    pts[i].predicted_level = level[i];
+    pts[i].descriptor = rows32(desc + (size_t)i * 32, 1);
+    ptrs[i] = &pts[i];
+  }
+  ORBmatcher matcher(0.6f, true);
+  const int n = matcher.Fuse(&kf, ptrs, th, b_right != 0);
+  for (int i = 0; i < m; i++) best_idx[i] = pts[i].added_to;
+  return n;
+}
+
 // SearchByProjection(KeyFrame*, Sophus::Sim3f& Scw, const vector<MapPoint*>&, vector<MapPoint*>& vpMatched, th,
 // ratioHamming), :406-506 (with_kfs == 0) and the overload that also records the source KeyFrames, :508-616
 // (with_kfs != 0). Identity Scw, same placement as orbrefsrc_fuse. matched_in[i] != 0: keypoint i already holds a match.

@@ -343,9 +343,15 @@ class KeyFrame : public FeatureHolder {
     mfGridElementWidthInv = F.mfGridElementWidthInv;
     mfGridElementHeightInv = F.mfGridElementHeightInv;
     mGrid.assign(mnGridCols, std::vector<std::vector<size_t>>(mnGridRows));
+    mGridRight.assign(mnGridCols, std::vector<std::vector<size_t>>(mnGridRows));
     for (int i = 0; i < mnGridCols; i++)
-      for (int j = 0; j < mnGridRows; j++) mGrid[i][j] = F.mGrid[i][j];
+      for (int j = 0; j < mnGridRows; j++) {
+        mGrid[i][j] = F.mGrid[i][j];
+        mGridRight[i][j] = F.mGridRight[i][j];  // (src/KeyFrame.cc:109-121 copies both)
+      }
   }
+  // the right camera's cell, for the two-camera branch of shim Fuse (accessor to add next to mGridRight)
+  const std::vector<size_t>& GetGridCellRight(int c, int r) const { return mGridRight[c][r]; }
 };
 }  // namespace ORB_SLAM3
 using namespace std;  // the reference's headers leak it; ORBmatcher.h relies on that

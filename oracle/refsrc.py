@@ -106,7 +106,7 @@ def mlib():
                      "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow", "orbrefsrc_search_by_bow_kf",
                      "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye", "orbrefsrc_search_by_bow_kf_fisheye", "orbrefsrc_search_for_triangulation_fisheye",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
-                     "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse",
+                     "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse", "orbrefsrc_fuse_two_camera",
                      "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
                      "orbrefsrc_features_in_area", "orbrefsrc_distinctive_descriptor"):
             getattr(_mlib, name).restype = C.c_int
@@ -240,6 +240,17 @@ def fuse(kfv, inv_level_sigma2, u, v, z, level, desc, th, mbf, sim3=False):
     best = np.empty(max(len(a[0]), 1), np.int32)
     n = mlib().orbrefsrc_fuse(kfv.ref(), _p(s2), len(a[0]), *[_p(x) for x in a], C.c_float(th), C.c_float(mbf),
                               int(sim3), _p(best))
+    return n, best[:len(a[0])]
+
+
+def fuse_two_camera(fisheye_view, inv_level_sigma2, u, v, z, level, desc, th, mbf, b_right):
+    """ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight) on a two-camera KeyFrame; best[i] = row of mDescriptors or -1."""
+    a = [np.ascontiguousarray(x, t) for x, t in ((u, np.float32), (v, np.float32), (z, np.float32), (level, np.int32),
+                                                 (desc, np.uint8))]
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    best = np.empty(max(len(a[0]), 1), np.int32)
+    n = mlib().orbrefsrc_fuse_two_camera(fisheye_view.ref(), _p(s2), len(a[0]), *[_p(x) for x in a], C.c_float(th),
+                                         C.c_float(mbf), int(bool(b_right)), _p(best))
     return n, best[:len(a[0])]
 
 

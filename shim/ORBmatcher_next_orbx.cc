@@ -7,7 +7,7 @@
 //
 // COMPILES ONLY INSIDE THE REFERENCE TREE (needs the reference headers and their OpenCV / Eigen / Sophus / DBoW2
 // dependencies). Both SearchByBoW overloads and AssignFeaturesToGrid cover both rigs; the others are the pinhole
-// forms (NLeft == -1, bRight == false) — keep the reference's code for their fisheye branches. As in ORBmatcher_orbx.cc the shim only flattens the pointer graph and scatters the answers back; every
+// forms; Fuse(KeyFrame*, vpMapPoints, th, bRight) also covers two-camera KeyFrames and bRight. As in ORBmatcher_orbx.cc the shim only flattens the pointer graph and scatters the answers back; every
 // float that decides a match comes from the reference's own expressions on the host (projection) or from the device
 // with the same non-fused FP32 operations.
 #include "ORBmatcher.h"
@@ -110,9 +110,12 @@ int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint
 }
 
 int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th, const bool bRight) {
-  // (bRight == true: keep the reference body.) Host part = :1141-1192 verbatim: which points take part, uv, ur, level.
-  const Sophus::SE3f Tcw = pKF->GetPose();
-  const Eigen::Vector3f Ow = pKF->GetCameraCenter();
+  // Host part = :1116-1192 verbatim: camera, pose and centre of the searched camera (the right one with bRight), which
+  // points take part, uv, ur, level. The projection stays with the reference's own camera object (mpCamera2 is a
+  // KannalaBrandt8 model on two-camera rigs).
+  GeometricCamera* pCamera = bRight ? pKF->mpCamera2 : pKF->mpCamera;
+  const Sophus::SE3f Tcw = bRight ? pKF->GetRightPose() : pKF->GetPose();
+  const Eigen::Vector3f Ow = bRight ? pKF->GetRightCameraCenter() : pKF->GetCameraCenter();
   const float bf = pKF->mbf;
   std::vector<int> src;
   std::vector<float> u, v, ur, radius;
@@ -124,7 +127,7 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
     const Eigen::Vector3f p3Dw = pMP->GetWorldPos(), p3Dc = Tcw * p3Dw;
     if (p3Dc(2) < 0.0f) continue;
     const float invz = 1 / p3Dc(2);
-    const Eigen::Vector2f uv = pKF->mpCamera->project(p3Dc);
+    const Eigen::Vector2f uv = pCamera->project(p3Dc);
     if (!pKF->IsInImage(uv(0), uv(1))) continue;
     const Eigen::Vector3f PO = p3Dw - Ow;
     const float dist3D = PO.norm();
@@ -141,20 +144,28 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
     const cv::Mat d = pMP->GetDescriptor();
     desc.insert(desc.end(), d.data, d.data + 32);
   }
-  // KeyFrame view: mvKeysUn, mDescriptors, mvuRight, the KeyFrame's grid (mGrid, same layout as Frame's)
+  // KeyFrame view of the searched camera (:1200-1201, :1219-1221, :1247): pinhole rigs — mvKeysUn, mGrid, every row of
+  // mDescriptors; two-camera rigs — mvKeys / mGrid / rows [0, NLeft), or with bRight mvKeysRight / mGridRight / rows
+  // [NLeft, N), the fused row being the local index + NLeft. mvuRight is indexed with the LOCAL index (:1227).
+  const bool two = pKF->NLeft != -1;
+  const std::vector<cv::KeyPoint>& keys = !two ? pKF->mvKeysUn : (!bRight ? pKF->mvKeys : pKF->mvKeysRight);
+  const int row0 = two && bRight ? pKF->NLeft : 0, nk = (int)keys.size();
   std::vector<int32_t> off(pKF->mnGridCols * pKF->mnGridRows + 1, 0), items;
   for (int c = 0; c < pKF->mnGridCols; c++)
     for (int r = 0; r < pKF->mnGridRows; r++) {
-      const std::vector<size_t>& cell = pKF->GetGridCell(c, r);  // accessor to add next to mGrid (include/KeyFrame.h)
+      // accessors to add next to mGrid / mGridRight (include/KeyFrame.h)
+      const std::vector<size_t>& cell = two && bRight ? pKF->GetGridCellRight(c, r) : pKF->GetGridCell(c, r);
       off[c * pKF->mnGridRows + r + 1] = off[c * pKF->mnGridRows + r] + (int32_t)cell.size();
       for (size_t k : cell) items.push_back((int32_t)k);
     }
-  std::vector<uint8_t> occupied(pKF->N, 0);
+  std::vector<uint8_t> occupied(nk, 0);
+  std::vector<float> ur_local(nk, -1.f);
+  for (int k = 0; k < nk && k < (int)pKF->mvuRight.size(); k++) ur_local[k] = pKF->mvuRight[k];
   orbx_frame_view kv;
-  kv.n = pKF->N;
-  kv.kps = reinterpret_cast<const orbx_kp*>(pKF->mvKeysUn.data());
-  kv.desc = pKF->mDescriptors.data;
-  kv.u_right = pKF->mvuRight.data();
+  kv.n = nk;
+  kv.kps = reinterpret_cast<const orbx_kp*>(keys.data());
+  kv.desc = pKF->mDescriptors.data + (size_t)row0 * 32;
+  kv.u_right = ur_local.data();
   kv.occupied = occupied.data();
   kv.grid = orbx_grid{off.data(), items.data(), (float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv,
                       pKF->mfGridElementHeightInv};
@@ -173,15 +184,16 @@ int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, c
     if (best_dist[k] > TH_LOW) continue;
     MapPoint* pMP = vpMapPoints[src[k]];
     if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;  // an earlier Replace may have moved it in (:1141-1147)
-    MapPoint* pMPinKF = pKF->GetMapPoint(best_idx[k]);
+    const int bestIdx = best_idx[k] + row0;  // :1247
+    MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
     if (pMPinKF) {
       if (!pMPinKF->isBad()) {
         if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
         else pMPinKF->Replace(pMP);
       }
     } else {
-      pMP->AddObservation(pKF, best_idx[k]);
-      pKF->AddMapPoint(pMP, best_idx[k]);
+      pMP->AddObservation(pKF, bestIdx);
+      pKF->AddMapPoint(pMP, bestIdx);
     }
     nFused++;
   }

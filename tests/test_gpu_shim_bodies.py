@@ -22,6 +22,7 @@ def shim_world(gpu, monkeypatch):
     lib = C.CDLL(_PATH)
     for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
                  "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
+                 "orbrefsrc_fuse_two_camera",
                  "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
                  "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
                  "orbrefsrc_distinctive_descriptor", "orbrefsrc_search_by_projection_map_fisheye",
@@ -90,6 +91,11 @@ def test_shim_compute_stereo_fisheye_matches(shim_world, args):
 @pytest.mark.parametrize("args", [(False, 3.0, 4), (False, 2.5, 6)])
 def test_shim_fuse(shim_world, args):
     T.test_fuse_both_overloads(*args)
+
+
+@pytest.mark.parametrize("args", [(False, 3.0, 14), (True, 3.0, 15), (True, 2.5, 16)])
+def test_shim_fuse_two_camera_keyframe(shim_world, args):
+    T.test_fuse_two_camera_keyframe(*args)
 
 
 def test_shim_assign_features_to_grid(shim_world):

@@ -347,6 +347,49 @@ def test_fuse_both_overloads(sim3, th, seed):
     assert n_r == (want >= 0).sum() and np.array_equal(best_r, want)
 
 
+@pytest.mark.parametrize("b_right,th,seed", [(False, 3.0, 14), (True, 3.0, 15), (True, 2.5, 16)])
+def test_fuse_two_camera_keyframe(b_right, th, seed):
+    """Fuse(pKF, vpMapPoints, th, bRight) on a two-camera KeyFrame (NLeft != -1; :1116-1124, :1200-1201, :1219-1221,
+    :1247): the search runs on ONE camera's keypoints, grid and descriptor rows — the left ones, or with bRight the
+    right ones with the fused row offset by NLeft — so it is the oracle's fuse_match on that camera's view."""
+    rng = np.random.default_rng(seed)
+    nl, nr, m, w, h = 500, 430, 800, 640, 480
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+
+    def cam(n, s):
+        k = np.zeros(n, synth.KP_DTYPE)
+        k["x"], k["y"] = rng.uniform(0, w, n).astype(f32), rng.uniform(0, h, n).astype(f32)
+        k["octave"] = rng.integers(0, 8, n)
+        return k, synth.descriptors(n, s)
+
+    (kl, dl), (kr, dr) = cam(nl, seed), cam(nr, seed + 100)
+    desc = np.concatenate([dl, dr])
+    fv = orbref.make_fisheye_view(kl, kr, desc, np.zeros(nl + nr, np.uint8), 0.0, 0.0, inv_w, inv_h,
+                                  np.full(nl, -1, np.int32), np.full(nr, -1, np.int32), sf)
+    kc, dc, base = (kr, dr, nl) if b_right else (kl, dl, 0)
+    src = rng.integers(0, len(kc), m)
+    u = np.clip(kc["x"][src] + rng.normal(0, 1.5, m), 0.5, w - 0.5).astype(f32)
+    v = np.clip(kc["y"][src] + rng.normal(0, 1.5, m), 0.5, h - 0.5).astype(f32)
+    z = rng.uniform(1.0, 20.0, m).astype(f32)
+    lev = np.clip(kc["octave"][src] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    d = synth.flip_bits(dc[src], rng.integers(0, 60, m), rng)
+    mbf = f32(47.9)
+    pur = (u - (mbf * (f32(1) / z).astype(f32)).astype(f32)).astype(f32)
+    inv_s2 = (1.0 / (sf * sf)).astype(f32)
+    # the oracle on the searched camera's own view: mvuRight is all -1 on a two-camera KeyFrame (5.99 gate only)
+    off, items = orbref.build_grid(kc, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    view = orbref.make_frame_view(kc, dc, np.full(len(kc), -1, f32), np.zeros(len(kc), np.uint8), g, keep, sf)
+    pts = orbref.make_projected(u, v, pur, (f32(th) * sf[lev]).astype(f32), lev - 1, lev, np.zeros(m, f32),
+                                np.zeros(m, np.uint8), d)
+    bi, bd = orbref.fuse_match(view, inv_s2, pts, True)
+    want = np.where(bd <= 50, bi + base, -1)
+    n_r, best_r = refsrc.fuse_two_camera(fv, inv_s2, u, v, z, lev, d, th, mbf, b_right)
+    assert (want >= 0).sum() > 50
+    assert n_r == (want >= 0).sum() and np.array_equal(best_r, want)
+
+
 @pytest.mark.parametrize("with_kfs,th,ratio,seed", [(False, 8, 1.0, 8), (True, 8, 1.0, 9), (False, 4, 1.5, 10)])
 def test_sim3_search_by_projection_is_the_projected_form(with_kfs, th, ratio, seed):
     """SearchByProjection(KeyFrame*, Sim3f&, vpPoints, vpMatched, th, ratioHamming) :406-506 and its :508-616 twin are
