@@ -187,6 +187,17 @@ int orbm_stereo_track_frames_batch_multi(int n_devices, orbm_matcher* const* m, 
 int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
                                     int max_dist, int check_orientation, int32_t* assign, int32_t* nmatches);
 
+/* The candidate loop of the same function for ONE camera of a two-camera frame (CurrentFrame.Nleft != -1,
+ * src/ORBmatcher.cc:1649-1690 on mvKeys / mGrid / rows [0, Nleft) and its twin :1711-1755 on mvKeysRight / mGridRight /
+ * rows [Nleft, N)): f is that camera's view (u_right = NULL: the stereo gate of :1667 only exists for Nleft == -1).
+ * Both cameras share ONE rotation histogram (:1693-1706, :1757-1778, :1785-1803), so no orientation check happens
+ * here: decisions[pts->m] (host) = the camera-local keypoint each point is written to, or -1, under the serial order
+ * dependence of :1663-1665 (a keypoint is closed by an earlier point with observations); the caller bins and filters.
+ * window_count[pts->m] (host, may be NULL) = |GetFeaturesInArea(...)| of the point's window: the reference skips the
+ * right-camera search of a point whose LEFT window is empty (:1655). shim/ORBmatcher_orbx.cc shows the composition. */
+int orbm_search_by_projection_frame_decisions(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
+                                              int max_dist, int32_t* decisions, int32_t* window_count);
+
 /* orbm_search_by_projection_frame on a frame that never left the device (see orbm_search_by_projection_map_resident
  * for the conditions): SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, ...) right after ExtractORB,
  * src/Tracking.cc:2811. */

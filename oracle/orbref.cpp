@@ -1285,6 +1285,42 @@ int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_proje
   return nmatches;
 }
 
+// The candidate loop of SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, ...) for ONE camera of a
+// two-camera frame (src/ORBmatcher.cc:1649-1690 on mvKeys / mGrid, :1711-1755 on mvKeysRight / mGridRight), the
+// rotation histogram left to the caller because both cameras share it (:1693-1706, :1757-1778, :1785-1803).
+// decisions[i] = the keypoint point i is written to (-1: none), window[i] = |GetFeaturesInArea(...)| of its window (the
+// reference `continue`s past the right-camera search when the LEFT window is empty, :1655). Returns the acceptances.
+int orbref_search_by_projection_frame_decisions(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
+                                                int32_t* decisions, int32_t* window) {
+  int accepted = 0;
+  std::vector<uint8_t> occ(f->occupied, f->occupied + f->n);
+  std::vector<int32_t> idxs(f->n);
+  for (int i = 0; i < pts->m; i++) {
+    decisions[i] = -1;
+    const int nc = orbref_features_in_area(f, pts->u[i], pts->v[i], pts->radius[i], pts->min_level[i],
+                                           pts->max_level[i], idxs.data());
+    if (window) window[i] = nc;
+    const uint8_t* dMP = pts->desc + (size_t)i * 32;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int c = 0; c < nc; c++) {
+      const int i2 = idxs[c];
+      if (occ[i2]) continue;
+      if (f->u_right && pts->u_right && f->u_right[i2] > 0) {
+        const float er = std::fabs(pts->u_right[i] - f->u_right[i2]);
+        if (er > pts->radius[i]) continue;
+      }
+      const int dist = orbref_descriptor_distance(dMP, f->desc + (size_t)i2 * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= max_dist) {
+      decisions[i] = bestIdx2;
+      occ[bestIdx2] = pts->has_obs[i];  // a later point is blocked only by a MapPoint with observations (:1663-1665)
+      accepted++;
+    }
+  }
+  return accepted;
+}
+
 // ORBmatcher::SearchForTriangulation — src/ORBmatcher.cc:886-1106; Pinhole::epipolarConstrain —
 // src/CameraModels/Pinhole.cpp:122-149 (F12 supplied by the caller, row-major).
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) — src/ORBmatcher.cc:230-404, Nleft == -1

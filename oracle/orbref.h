@@ -132,6 +132,8 @@ int orbref_search_by_projection_map_fisheye(const orbx_fisheye_view* f, const or
  * "any MapPoint blocks" rule (:1862). assign[n] as above. Returns nmatches. */
 int orbref_search_by_projection_frame(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                       int check_orientation, int32_t* assign);
+int orbref_search_by_projection_frame_decisions(const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
+                                                int32_t* decisions, int32_t* window);
 /* cv::remap(src, dst, mapx, mapy, INTER_LINEAR) with CV_32FC1 maps, 8-bit single channel, BORDER_CONSTANT 0 — the stereo
  * rectification of System::TrackStereo (src/System.cc:293-294; maps from initUndistortRectifyMap(..., CV_32F, ...),
  * src/Settings.cc:557-572). OpenCV's fixed point: coordinates rounded to 1/32 px (cvRound(map * 32)), the four taps

@@ -270,6 +270,7 @@ def lib():
         L.orbref_is_in_frustum.argtypes = [vp, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp]
         L.orbref_is_in_frustum.restype = None
         L.orbref_search_by_projection_frame.argtypes = [vp, vp, ci, ci, vp]
+        L.orbref_search_by_projection_frame_decisions.argtypes = [vp, vp, ci, vp, vp]
         L.orbref_search_for_triangulation.argtypes = [vp, vp, vp, cf, cf, ci, ci, ci, vp]
         L.orbref_search_by_bow.argtypes = [vp, vp, cf, ci, vp]
         L.orbref_search_for_triangulation_fisheye.argtypes = [vp, ci, vp, ci, vp, ci, ci, ci, vp]
@@ -463,6 +464,16 @@ def search_by_projection_map(fv, mps, th, nnratio, far_points=False, th_far=0.0)
     assign = np.empty(max(fv.struct.n, 1), np.int32)
     n = lib().orbref_search_by_projection_map(fv.ref(), mps.ref(), th, nnratio, int(far_points), th_far, _ptr(assign))
     return n, assign[:fv.struct.n]
+
+
+def search_by_projection_frame_decisions(fv, pts, max_dist=100, fn=None):
+    """One camera's candidate loop of SearchByProjection(CurrentFrame, LastFrame): (decisions[m], window[m])."""
+    m = pts.struct.m
+    dec, win = np.empty(max(m, 1), np.int32), np.empty(max(m, 1), np.int32)
+    fn = fn or lib().orbref_search_by_projection_frame_decisions
+    fn.restype = C.c_int
+    fn(fv.ref(), pts.ref(), C.c_int(max_dist), _ptr(dec), _ptr(win))
+    return dec[:m], win[:m]
 
 
 def search_by_projection_frame(fv, pts, max_dist=100, check_orientation=True):

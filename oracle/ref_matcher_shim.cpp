@@ -302,6 +302,70 @@ int orbrefsrc_search_by_projection_last_frame(const orbx_frame_view* fv, int m, 
   return n;
 }
 
+// ... on a two-camera current frame (Nleft != -1): the left search (:1649-1706) and, for the points whose left window
+// held a feature, the right-camera twin (:1708-1780); GetRelativePoseTrl is the identity in the stand-in world, so the
+// right search runs at the same (u, v) on mvKeysRight / mGridRight. last_right[i] != 0 makes last-frame feature i a
+// right-camera one (rows >= LastFrame.Nleft). assign[n_left + n_right] = the point written to each row, or -1.
+int orbrefsrc_search_by_projection_last_frame_fisheye(const orbx_fisheye_view* fv, int m, const float* u, const float* v,
+                                                      const float* z, const int32_t* octave, const float* angle,
+                                                      const uint8_t* has_obs, const uint8_t* desc, float th, float mbf,
+                                                      float mb, int mode, int check_orientation, int32_t* assign) {
+  Frame F;
+  const int NL = fv->n_left, NR = fv->n_right, N = NL + NR;
+  F.N = N;
+  F.Nleft = NL;
+  F.mvKeys = keypoints(fv->kps_left, NL);
+  F.mvKeysRight = keypoints(fv->kps_right, NR);
+  F.mvKeysUn = F.mvKeys;
+  F.mDescriptors = rows32(fv->desc, N);
+  F.mvuRight.assign(N, -1.f);
+  F.mvScaleFactors.assign(fv->scale_factors, fv->scale_factors + fv->n_levels);
+  Frame::mnMinX = fv->grid_left.min_x;
+  Frame::mnMinY = fv->grid_left.min_y;
+  Frame::mfGridElementWidthInv = fv->grid_left.inv_w;
+  Frame::mfGridElementHeightInv = fv->grid_left.inv_h;
+  F.AssignFeaturesToGrid();
+  F.mbf = mbf;
+  F.mb = mb;
+  F.mnMaxX = F.mnMaxY = 1e9f;
+  MapPoint occupied;
+  occupied.observations = 1;
+  F.mvpMapPoints.assign(N, nullptr);
+  for (int i = 0; i < N; i++)
+    if (fv->occupied && fv->occupied[i]) F.mvpMapPoints[i] = &occupied;
+  GeometricCamera camera;
+  F.mpCamera = F.mpCamera2 = &camera;
+  // the last frame: the first half of its features are left-camera ones, the rest right-camera ones
+  Frame last;
+  last.N = m;
+  last.Nleft = m / 2;
+  last.mvKeys.resize(last.Nleft);
+  last.mvKeysRight.resize(m - last.Nleft);
+  last.mvKeysUn.resize(m);
+  last.mvbOutlier.assign(m, false);
+  std::vector<MapPoint> pts(m);
+  last.mvpMapPoints.resize(m);
+  for (int i = 0; i < m; i++) {
+    cv::KeyPoint& kp = i < last.Nleft ? last.mvKeys[i] : last.mvKeysRight[i - last.Nleft];
+    kp.octave = octave[i];
+    kp.angle = angle[i];
+    last.mvKeysUn[i].octave = -7;  // must not be read on a two-camera last frame
+    last.mvKeysUn[i].angle = -7.f;
+    pts[i].pos = Eigen::Vector3f(u[i], v[i], z[i]);
+    pts[i].observations = has_obs[i] ? 1 : 0;
+    pts[i].descriptor = rows32(desc + (size_t)i * 32, 1);
+    last.mvpMapPoints[i] = &pts[i];
+  }
+  last.pose = Sophus::SE3f(Eigen::Matrix3f(), Eigen::Vector3f(0.f, 0.f, mode > 0 ? 1.f : (mode < 0 ? -1.f : 0.f)));
+  ORBmatcher matcher(0.9f, check_orientation != 0);
+  const int n = matcher.SearchByProjection(F, last, th, false);
+  for (int i = 0; i < N; i++) {
+    const MapPoint* p = F.mvpMapPoints[i];
+    assign[i] = (p && p != &occupied) ? (int)(p - pts.data()) : -1;
+  }
+  return n;
+}
+
 // SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const set<MapPoint*>& sAlreadyFound, th, ORBdist), :1808-1918.
 // Same placement; level = what MapPoint::PredictScale returns; found[i] puts point i into sAlreadyFound. Every keypoint
 // flagged occupied in fv holds a MapPoint (here any MapPoint blocks, :1862).

@@ -107,6 +107,7 @@ def mlib():
                      "orbrefsrc_search_by_bow_fisheye", "orbrefsrc_stereo_fisheye", "orbrefsrc_search_by_bow_kf_fisheye", "orbrefsrc_search_for_triangulation_fisheye",
                      "orbrefsrc_search_for_initialization", "orbrefsrc_search_by_projection_last_frame",
                      "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_fuse", "orbrefsrc_fuse_two_camera",
+                     "orbrefsrc_search_by_projection_last_frame_fisheye",
                      "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3", "orbrefsrc_stereo_frame",
                      "orbrefsrc_features_in_area", "orbrefsrc_distinctive_descriptor"):
             getattr(_mlib, name).restype = C.c_int
@@ -222,6 +223,19 @@ def search_by_projection_last_frame(fv, u, v, z, octave, angle, has_obs, desc, t
                                                          C.c_float(mbf), C.c_float(mb), int(mode),
                                                          int(check_orientation), _p(assign))
     return n, assign[:fv.struct.n]
+
+
+def search_by_projection_last_frame_fisheye(fisheye_view, u, v, z, octave, angle, has_obs, desc, th, mbf, mb, mode,
+                                            check_orientation=True):
+    """SearchByProjection(CurrentFrame, LastFrame, th, false) on a two-camera current frame; assign[n_left + n_right]."""
+    a = [np.ascontiguousarray(x, t) for x, t in ((u, np.float32), (v, np.float32), (z, np.float32), (octave, np.int32),
+                                                 (angle, np.float32), (has_obs, np.uint8), (desc, np.uint8))]
+    n_rows = fisheye_view.struct.n_left + fisheye_view.struct.n_right
+    assign = np.empty(max(n_rows, 1), np.int32)
+    n = mlib().orbrefsrc_search_by_projection_last_frame_fisheye(fisheye_view.ref(), len(a[0]), *[_p(x) for x in a],
+                                                                 C.c_float(th), C.c_float(mbf), C.c_float(mb), int(mode),
+                                                                 int(check_orientation), _p(assign))
+    return n, assign[:n_rows]
 
 
 def search_by_projection_keyframe(fv, u, v, level, angle, found, desc, th, orb_dist, check_orientation=True):

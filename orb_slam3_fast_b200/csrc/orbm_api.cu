@@ -87,7 +87,7 @@ DevFrame upload_frame(Arena& ar, const orbx_frame_view* f) {
 
 // count -> scan -> (size scratch) -> fill -> resolve, then the results come back
 int run_search(orbm_matcher* m, Arena& ar, const DevFrame& F, const DevQueries& Q, ResolveArgs R, int n,
-               int32_t* assign, int32_t* nmatches) {
+               int32_t* assign, int32_t* nmatches, int32_t* decisions = nullptr) {
   cudaStream_t st = m->stream;
   SearchScratch S{};
   S.counts = ar.alloc<int32_t>((size_t)Q.m + 1);
@@ -115,7 +115,9 @@ int run_search(orbm_matcher* m, Arena& ar, const DevFrame& F, const DevQueries& 
   launch_search_fill(F, Q, S, st);
   launch_search_resolve(F, Q, S, R, st);
   ORBM_CUDA(m, cudaGetLastError());
-  if (n > 0) ORBM_CUDA(m, cudaMemcpyAsync(assign, R.assign, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (n > 0 && assign) ORBM_CUDA(m, cudaMemcpyAsync(assign, R.assign, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (decisions && Q.m > 0)  // the keypoint every point takes (mode 1), before any orientation filter
+    ORBM_CUDA(m, cudaMemcpyAsync(decisions, R.dec, (size_t)Q.m * 4, cudaMemcpyDeviceToHost, st));
   int32_t nm = 0;
   ORBM_CUDA(m, cudaMemcpyAsync(&nm, R.nmatches, 4, cudaMemcpyDeviceToHost, st));
   ORBM_CUDA(m, cudaStreamSynchronize(st));
@@ -1173,6 +1175,53 @@ int orbm_search_by_projection_frame(orbm_matcher* m, const orbx_frame_view* f, c
   Arena ar(m);
   const DevFrame F = upload_frame(ar, f);
   return search_frame_common(m, ar, F, f->u_right != nullptr, pts, max_dist, check_orientation, f->n, assign, nmatches);
+}
+
+int orbm_search_by_projection_frame_decisions(orbm_matcher* m, const orbx_frame_view* f, const orbx_projected* pts,
+                                              int max_dist, int32_t* decisions, int32_t* window_count) {
+  if (!m || !f || !pts || f->n < 0 || pts->m < 0 || (pts->m > 0 && !decisions)) return mfail(m, ORBX_E_ARG, "bad argument");
+  if (pts->m == 0) return ORBX_OK;
+  ORBM_CUDA(m, cudaSetDevice(m->device));
+  Arena ar(m);
+  const DevFrame F = upload_frame(ar, f);
+  const int M = pts->m;
+  DevQueries Q{};
+  Q.m = M;
+  Q.active = nullptr;
+  Q.u = ar.upload(pts->u, M);
+  Q.v = ar.upload(pts->v, M);
+  Q.radius = ar.upload(pts->radius, M);
+  Q.min_level = ar.upload(pts->min_level, M);
+  Q.max_level = ar.upload(pts->max_level, M);
+  Q.u_right = (f->u_right && pts->u_right) ? ar.upload(pts->u_right, M) : (ar.alloc<float>(1), nullptr);
+  Q.desc = ar.upload(pts->desc, (size_t)M * 32);
+  ResolveArgs R{};
+  R.mode = 1;
+  R.nnratio = 0.f;
+  R.max_dist = max_dist;
+  R.check_orientation = 0;
+  R.has_obs = ar.upload(pts->has_obs, M);
+  R.angle = ar.upload(pts->angle, M);
+  // |GetFeaturesInArea| per point: the candidate count with nothing occupied and no stereo gate
+  int32_t* d_win = nullptr;
+  uint8_t* d_zero = nullptr;
+  if (window_count) {
+    d_win = ar.alloc<int32_t>((size_t)M + 1);
+    d_zero = ar.alloc<uint8_t>((size_t)std::max(f->n, 1));
+  }
+  if (ar.sync_uploads() != cudaSuccess) return mfail(m, ORBX_E_CUDA, cudaGetErrorString(ar.err));
+  if (window_count) {
+    DevFrame F0 = F;
+    DevQueries Q0 = Q;
+    ORBM_CUDA(m, cudaMemsetAsync(d_zero, 0, (size_t)std::max(f->n, 1), m->stream));
+    F0.occupied = d_zero;
+    F0.u_right = nullptr;
+    Q0.u_right = nullptr;
+    launch_search_count(F0, Q0, d_win, m->stream);
+    ORBM_CUDA(m, cudaMemcpyAsync(window_count, d_win, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
+  }
+  std::vector<int32_t> assign_unused((size_t)std::max(f->n, 1));
+  return run_search(m, ar, F, Q, R, f->n, assign_unused.data(), nullptr, decisions);
 }
 
 int orbm_search_by_projection_frame_resident(orbm_matcher* m, const orbx_extractor* ex, int frame, int n,

@@ -30,6 +30,7 @@ def _bind(L):
                                            ci, vp, vp, vp]
     L.orbm_search_by_projection_map.argtypes = [vp, vp, vp, cf, cf, ci, cf, vp, vp]
     L.orbm_search_by_projection_frame.argtypes = [vp, vp, vp, ci, ci, vp, vp]
+    L.orbm_search_by_projection_frame_decisions.argtypes = [vp, vp, vp, ci, vp, vp]
     L.orbm_assign_features_to_grid.argtypes = [vp, vp, ci, cf, cf, cf, cf, vp, vp]
     L.orbm_search_by_projection_map_resident.argtypes = [vp, vp, ci, ci, vp, vp, cf, cf, cf, cf, vp, cf, cf, ci, cf, vp,
                                                          vp]
@@ -303,6 +304,15 @@ class ORBmatcher:
                                                             int(self.mbCheckOrientation), _l.ptr(assign),
                                                             C.byref(nm)))
         return nm.value, assign[:n]
+
+    # one camera's candidate loop of the same function on a two-camera frame (:1649-1690 / :1711-1755): which keypoint
+    # every point takes (orientation check left to the caller) and |GetFeaturesInArea| of its window
+    def SearchByProjectionProjectedDecisions(self, frame_view, projected, max_dist=TH_HIGH):
+        m = projected.struct.m
+        dec, win = np.empty(max(m, 1), np.int32), np.empty(max(m, 1), np.int32)
+        self._check(self._L.orbm_search_by_projection_frame_decisions(self._h, frame_view.ref(), projected.ref(),
+                                                                      max_dist, _l.ptr(dec), _l.ptr(win)))
+        return dec[:m], win[:m]
 
     # int SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse) — :886
     # Frame::ComputeBoW — src/Frame.cc:846-851: the vocabulary goes to the device once, then per-feature descents

@@ -7,7 +7,8 @@
 //   ORBmatcher::SearchForTriangulation(KeyFrame*, KeyFrame*, vMatchedPairs, bOnlyStereo, bCoarse)   :886-1106
 // with the ones below. The local-map SearchByProjection and SearchForTriangulation cover both rigs (the two-camera
 // forms: right-camera twin :148-217; camera-pair selection :1007-1043 with the epipolar test left to the reference's
-// KannalaBrandt8 object); the frame-to-frame SearchByProjection is the pinhole branch.
+// KannalaBrandt8 object); the frame-to-frame SearchByProjection covers both rigs too (two-camera frames: one
+// orbm_search_by_projection_frame_decisions call per camera + the shared rotation histogram here).
 // The shim's only job is flattening the pointer graph into the SoA / CSR views of include/orbx_types.h and scattering
 // the answers back; every float that decides a match is computed by the reference's own expressions on the host
 // (projection, radius) or by the device with the same non-fused FP32 operations.
@@ -143,7 +144,163 @@ int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMap
   return nmatches;
 }
 
+namespace {
+// One camera of a two-camera frame as an orbx_frame_view: its keypoints, its grid, its rows of mDescriptors and
+// mvpMapPoints (the skip rule of :1663-1665 / :1736-1740), no stereo gate (:1667 needs Nleft == -1).
+struct CameraFlat {
+  std::vector<int32_t> off, items;
+  std::vector<uint8_t> occupied;
+  orbx_frame_view v;
+  CameraFlat(const Frame& F, bool right) : off(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1, 0) {
+    const std::vector<cv::KeyPoint>& keys = right ? F.mvKeysRight : F.mvKeys;
+    const int row0 = right ? F.Nleft : 0, n = right ? F.N - F.Nleft : F.Nleft;
+    for (int c = 0; c < FRAME_GRID_COLS; c++)
+      for (int r = 0; r < FRAME_GRID_ROWS; r++) {
+        const std::vector<std::size_t>& cell = right ? F.mGridRight[c][r] : F.mGrid[c][r];
+        off[c * FRAME_GRID_ROWS + r + 1] = off[c * FRAME_GRID_ROWS + r] + (int32_t)cell.size();
+        for (std::size_t i : cell) items.push_back((int32_t)i);
+      }
+    occupied.resize(n);
+    for (int i = 0; i < n; i++)
+      occupied[i] = F.mvpMapPoints[row0 + i] && F.mvpMapPoints[row0 + i]->Observations() > 0;
+    v.n = n;
+    v.kps = reinterpret_cast<const orbx_kp*>(keys.data());
+    v.desc = F.mDescriptors.data + (size_t)row0 * 32;
+    v.u_right = nullptr;
+    v.occupied = occupied.data();
+    v.grid = orbx_grid{off.data(), items.data(), Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv,
+                       Frame::mfGridElementHeightInv};
+    v.scale_factors = F.mvScaleFactors.data();
+    v.n_levels = (int32_t)F.mvScaleFactors.size();
+  }
+};
+}  // namespace
+
+// The two-camera form (CurrentFrame.Nleft != -1, :1594-1806 with the right-camera block :1708-1780). The two cameras
+// write disjoint rows of mvpMapPoints, so each is one orbm_search_by_projection_frame_decisions call (the serial order
+// dependence of :1663-1665 is resolved on the device per camera); what they share — nmatches and ONE rotation
+// histogram — is put together here in the reference's point order with the reference's own expressions.
+namespace {
+int SearchByProjectionTwoCameraFrames(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono,
+                                      const bool mbCheckOrientation, std::vector<int>* rotHist /* [HISTO_LENGTH] */) {
+  const int TH_HIGH = ORBmatcher::TH_HIGH, HISTO_LENGTH = ORBmatcher::HISTO_LENGTH;
+  const Sophus::SE3f Tcw = CurrentFrame.GetPose();
+  const Eigen::Vector3f twc = Tcw.inverse().translation();
+  const Sophus::SE3f Tlw = LastFrame.GetPose();
+  const Eigen::Vector3f tlc = Tlw * twc;
+  const bool bForward = tlc(2) > CurrentFrame.mb && !bMono;
+  const bool bBackward = -tlc(2) > CurrentFrame.mb && !bMono;
+  const Sophus::SE3f Trl = CurrentFrame.GetRelativePoseTrl();
+  std::vector<float> u, v, ur2, vr2, radius, angle;
+  std::vector<int32_t> lo, hi, src;
+  std::vector<uint8_t> has_obs, desc;
+  for (int i = 0; i < LastFrame.N; i++) {
+    MapPoint* pMP = LastFrame.mvpMapPoints[i];
+    if (!pMP || LastFrame.mvbOutlier[i]) continue;
+    const Eigen::Vector3f x3Dc = Tcw * pMP->GetWorldPos();
+    const float invzc = 1.0 / x3Dc(2);
+    if (invzc < 0) continue;
+    const Eigen::Vector2f uv = CurrentFrame.mpCamera->project(x3Dc);
+    if (uv(0) < CurrentFrame.mnMinX || uv(0) > CurrentFrame.mnMaxX) continue;
+    if (uv(1) < CurrentFrame.mnMinY || uv(1) > CurrentFrame.mnMaxY) continue;
+    const int nLastOctave = (LastFrame.Nleft == -1 || i < LastFrame.Nleft)
+                                ? LastFrame.mvKeys[i].octave
+                                : LastFrame.mvKeysRight[i - LastFrame.Nleft].octave;
+    const Eigen::Vector3f x3Dr = Trl * x3Dc;                                   // :1709-1710 (mpCamera, as the reference)
+    const Eigen::Vector2f uvr = CurrentFrame.mpCamera->project(x3Dr);
+    u.push_back(uv(0)); v.push_back(uv(1));
+    ur2.push_back(uvr(0)); vr2.push_back(uvr(1));
+    radius.push_back(th * CurrentFrame.mvScaleFactors[nLastOctave]);
+    lo.push_back(bForward ? nLastOctave : (bBackward ? 0 : nLastOctave - 1));
+    hi.push_back(bForward ? -1 : (bBackward ? nLastOctave : nLastOctave + 1));
+    const cv::KeyPoint& kpLF = (LastFrame.Nleft == -1) ? LastFrame.mvKeysUn[i]
+                               : (i < LastFrame.Nleft) ? LastFrame.mvKeys[i]
+                                                       : LastFrame.mvKeysRight[i - LastFrame.Nleft];
+    angle.push_back(kpLF.angle);
+    has_obs.push_back(pMP->Observations() > 0);
+    const cv::Mat d = pMP->GetDescriptor();
+    desc.insert(desc.end(), d.data, d.data + 32);
+    src.push_back(i);
+  }
+  const int M = (int)src.size(), NL = CurrentFrame.Nleft;
+  // ---- left camera: every projected point ----
+  CameraFlat left(CurrentFrame, false);
+  orbx_projected ptsL{M, u.data(), v.data(), nullptr, radius.data(), lo.data(), hi.data(), angle.data(), has_obs.data(),
+                      desc.data()};
+  std::vector<int32_t> decL(M, -1), winL(M, 0);
+  if (orbm_search_by_projection_frame_decisions(OrbxThreadMatcher(), &left.v, &ptsL, TH_HIGH, decL.data(), winL.data()) !=
+      ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  // ---- right camera: the points whose LEFT window held a feature (`if (vIndices2.empty()) continue;`, :1655) ----
+  std::vector<int> keep;
+  for (int k = 0; k < M; k++)
+    if (winL[k] > 0) keep.push_back(k);
+  const int MR = (int)keep.size();
+  std::vector<float> uR(MR), vR(MR), radR(MR), angR(MR);
+  std::vector<int32_t> loR(MR), hiR(MR);
+  std::vector<uint8_t> obsR(MR), descR((size_t)MR * 32);
+  for (int j = 0; j < MR; j++) {
+    const int k = keep[j];
+    uR[j] = ur2[k]; vR[j] = vr2[k]; radR[j] = radius[k]; angR[j] = angle[k];
+    loR[j] = lo[k]; hiR[j] = hi[k]; obsR[j] = has_obs[k];
+    memcpy(&descR[(size_t)j * 32], &desc[(size_t)k * 32], 32);
+  }
+  CameraFlat right(CurrentFrame, true);
+  orbx_projected ptsR{MR, uR.data(), vR.data(), nullptr, radR.data(), loR.data(), hiR.data(), angR.data(), obsR.data(),
+                      descR.data()};
+  std::vector<int32_t> decR(MR, -1);
+  if (orbm_search_by_projection_frame_decisions(OrbxThreadMatcher(), &right.v, &ptsR, TH_HIGH, decR.data(), nullptr) !=
+      ORBX_OK)
+    throw std::runtime_error(orbm_last_error(OrbxThreadMatcher()));
+  // ---- the reference's bookkeeping in its own order: left then right of every point (:1692-1706, :1757-1778) ----
+  int nmatches = 0;
+  const float factor = 1.0f / HISTO_LENGTH;
+  auto bin_of = [&](float a_last, float a_cur) {
+    float rot = a_last - a_cur;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+  };
+  for (int k = 0, j = 0; k < M; k++) {
+    MapPoint* pMP = LastFrame.mvpMapPoints[src[k]];
+    if (decL[k] >= 0) {
+      CurrentFrame.mvpMapPoints[decL[k]] = pMP;
+      nmatches++;
+      if (mbCheckOrientation) rotHist[bin_of(angle[k], CurrentFrame.mvKeys[decL[k]].angle)].push_back(decL[k]);
+    }
+    if (j < MR && keep[j] == k) {
+      if (decR[j] >= 0) {
+        CurrentFrame.mvpMapPoints[decR[j] + NL] = pMP;
+        nmatches++;
+        if (mbCheckOrientation)
+          rotHist[bin_of(angle[k], CurrentFrame.mvKeysRight[decR[j]].angle)].push_back(decR[j] + NL);
+      }
+      j++;
+    }
+  }
+  return nmatches;
+}
+}  // namespace
+
 int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+  if (CurrentFrame.Nleft != -1) {
+    std::vector<int> rotHist[HISTO_LENGTH];
+    int nmatches = SearchByProjectionTwoCameraFrames(CurrentFrame, LastFrame, th, bMono, mbCheckOrientation, rotHist);
+    if (mbCheckOrientation) {  // :1785-1803
+      int ind1 = -1, ind2 = -1, ind3 = -1;
+      ComputeThreeMaxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+      for (int i = 0; i < HISTO_LENGTH; i++) {
+        if (i != ind1 && i != ind2 && i != ind3) {
+          for (size_t j = 0, jend = rotHist[i].size(); j < jend; j++) {
+            CurrentFrame.mvpMapPoints[rotHist[i][j]] = static_cast<MapPoint*>(NULL);
+            nmatches--;
+          }
+        }
+      }
+    }
+    return nmatches;
+  }
   // caller-side projection, exactly the reference's expressions (:1607-1690): Tcw, forward / backward, x3Dc, uv, level
   // window and radius are computed here on the host with Sophus / Eigen; only points that pass those tests are sent
   const Sophus::SE3f Tcw = CurrentFrame.GetPose();

@@ -36,6 +36,11 @@ int orbm_search_by_projection_map_fisheye(orbm_matcher*, const orbx_fisheye_view
   if (nmatches) *nmatches = n;
   return ORBX_OK;
 }
+int orbm_search_by_projection_frame_decisions(orbm_matcher*, const orbx_frame_view* f, const orbx_projected* pts,
+                                              int max_dist, int32_t* decisions, int32_t* window_count) {
+  orbref_search_by_projection_frame_decisions(f, pts, max_dist, decisions, window_count);
+  return 0;
+}
 int orbm_search_by_projection_frame(orbm_matcher*, const orbx_frame_view* f, const orbx_projected* pts, int max_dist,
                                     int check_orientation, int32_t* assign, int32_t* nmatches) {
   const int n = orbref_search_by_projection_frame(f, pts, max_dist, check_orientation, assign);

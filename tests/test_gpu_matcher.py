@@ -225,6 +225,31 @@ def test_search_by_projection_frame(gpu, m, th, stereo, check, seed):
     assert n2 == n_r and np.array_equal(assign2, assign_r)
 
 
+@pytest.mark.parametrize("m,th,seed", [(1200, 7.0, 3), (4000, 15.0, 4), (300, 1.0, 5)])
+def test_search_by_projection_frame_decisions(gpu, m, th, seed):
+    """orbm_search_by_projection_frame_decisions — one camera of SearchByProjection(CurrentFrame, LastFrame) on a
+    two-camera frame: the keypoint every point takes under the serial order dependence (occupied keypoints, points
+    without observations that do not block) and |GetFeaturesInArea| per window, against the oracle's serial loop."""
+    w, h = 752, 480
+    ex = ORBextractor(1200)
+    _, kps, desc = ex(synth.scene(h, w, seed))
+    rng = np.random.default_rng(seed)
+    occ = (rng.random(len(kps)) < 0.15).astype(np.uint8)
+    fv, fr = _frame_views(kps, desc, w, h, ex.GetScaleFactors(), None, occ)
+    pts = synth.projected_points(kps, desc, m, w, h, 8, ex.GetScaleFactors(), seed, th=th, stereo=False)
+    pts["has_obs"] = (rng.random(m) < 0.7).astype(np.uint8)
+    # a fifth of the windows far from every keypoint cluster
+    far = rng.random(m) < 0.2
+    pts["u"] = np.where(far, rng.uniform(0, w, m), pts["u"]).astype(np.float32)
+    pts["v"] = np.where(far, rng.uniform(0, h, m), pts["v"]).astype(np.float32)
+    mt = ORBmatcher(0.9, True)
+    dec, win = mt.SearchByProjectionProjectedDecisions(fv, views.make_projected(**pts), 100)
+    dec_r, win_r = orbref.search_by_projection_frame_decisions(fr, orbref.make_projected(**pts), 100)
+    assert (dec_r >= 0).sum() > min(100, m // 4) and (win_r == 0).any()
+    assert np.array_equal(win, win_r), np.nonzero(win != win_r)[0][:10]
+    assert np.array_equal(dec, dec_r), np.nonzero(dec != dec_r)[0][:10]
+
+
 @pytest.mark.parametrize("only_stereo,coarse,check,seed", [(False, False, True, 0), (True, False, True, 1),
                                                            (False, True, False, 2)])
 def test_search_for_triangulation(gpu, only_stereo, coarse, check, seed):

@@ -22,7 +22,7 @@ def shim_world(gpu, monkeypatch):
     lib = C.CDLL(_PATH)
     for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
                  "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
-                 "orbrefsrc_fuse_two_camera",
+                 "orbrefsrc_fuse_two_camera", "orbrefsrc_search_by_projection_last_frame_fisheye",
                  "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
                  "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
                  "orbrefsrc_distinctive_descriptor", "orbrefsrc_search_by_projection_map_fisheye",
@@ -91,6 +91,11 @@ def test_shim_compute_stereo_fisheye_matches(shim_world, args):
 @pytest.mark.parametrize("args", [(False, 3.0, 4), (False, 2.5, 6)])
 def test_shim_fuse(shim_world, args):
     T.test_fuse_both_overloads(*args)
+
+
+@pytest.mark.parametrize("args", [(0, 7.0, True, 20), (1, 7.0, True, 21), (-1, 10.0, True, 22), (0, 15.0, False, 23)])
+def test_shim_search_by_projection_last_frame_two_camera(shim_world, args):
+    T.test_search_by_projection_last_frame_two_camera(*args)
 
 
 @pytest.mark.parametrize("args", [(False, 3.0, 14), (True, 3.0, 15), (True, 2.5, 16)])

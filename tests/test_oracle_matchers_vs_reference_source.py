@@ -292,6 +292,116 @@ def test_search_by_projection_last_frame(mode, stereo, th, check, seed):
     assert n_r == n_o and np.array_equal(a_r, a_o)
 
 
+def _three_maxima(sizes):
+    """ORBmatcher::ComputeThreeMaxima (:1920-1955) on the bin sizes."""
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, s in enumerate(sizes):
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if max2 < f32(0.1) * f32(max1):
+        ind2 = ind3 = -1
+    elif max3 < f32(0.1) * f32(max1):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def _rot_bin(a_last, a_cur):
+    rot = f32(a_last) - f32(a_cur)            # float rot = kpLF.angle - kpCF.angle
+    if rot < 0.0:
+        rot = f32(rot + f32(360.0))
+    x = float(f32(rot * f32(1.0 / 30)))       # round(rot * factor): half away from zero
+    b = int(np.floor(x + 0.5)) if x >= 0 else int(np.ceil(x - 0.5))
+    return 0 if b == 30 else b
+
+
+@pytest.mark.parametrize("mode,th,check,seed", [(0, 7.0, True, 20), (1, 7.0, True, 21), (-1, 10.0, True, 22),
+                                                (0, 15.0, False, 23)])
+def test_search_by_projection_last_frame_two_camera(mode, th, check, seed):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono) with CurrentFrame.Nleft != -1 (:1594-1806 incl. the
+    right-camera block :1708-1780): per point the left search, then — unless the left window was empty (:1655) — the
+    right search on mvKeysRight / mGridRight; the cameras write disjoint rows and share nmatches and ONE rotation
+    histogram. The yardstick composes the oracle's one-camera loop (search_by_projection_frame_decisions) the way
+    shim/ORBmatcher_orbx.cc composes the device's."""
+    rng = np.random.default_rng(seed)
+    nl, nr, m, w, h = 520, 480, 800, 640, 480
+    sf = f32(1.2) ** np.arange(8, dtype=f32)
+    inv_w, inv_h = f32(64) / f32(w), f32(48) / f32(h)
+    kl = np.zeros(nl, synth.KP_DTYPE)
+    kl["x"], kl["y"] = rng.uniform(0, w, nl).astype(f32), rng.uniform(0, h, nl).astype(f32)
+    kl["octave"], kl["angle"] = rng.integers(0, 8, nl), rng.uniform(0, 360, nl).astype(f32)
+    # the right camera sees most of the left features a few pixels away (GetRelativePoseTrl is the identity here)
+    pick = rng.permutation(nl)[:nr]
+    kr = kl[pick].copy()
+    kr["x"] = np.clip(kr["x"] + rng.normal(0, 2.0, nr), 0, w - 1).astype(f32)
+    kr["y"] = np.clip(kr["y"] + rng.normal(0, 2.0, nr), 0, h - 1).astype(f32)
+    kr["angle"] = ((kr["angle"] + rng.normal(0, 4.0, nr)) % 360).astype(f32)
+    dl = synth.descriptors(nl, seed)
+    dr = synth.flip_bits(dl[pick], rng.integers(0, 25, nr), rng)
+    occ = (rng.random(nl + nr) < 0.1).astype(np.uint8)
+    fv = orbref.make_fisheye_view(kl, kr, np.concatenate([dl, dr]), occ, 0.0, 0.0, inv_w, inv_h,
+                                  np.full(nl, -1, np.int32), np.full(nr, -1, np.int32), sf)
+    src = rng.integers(0, nl, m)
+    # a fifth of the points far from every feature: empty left windows, whose right search the reference skips
+    far = rng.random(m) < 0.2
+    u = np.where(far, rng.uniform(0, w, m), np.clip(kl["x"][src] + rng.normal(0, 2.0, m), 0.5, w - 0.5)).astype(f32)
+    v = np.where(far, rng.uniform(0, h, m), np.clip(kl["y"][src] + rng.normal(0, 2.0, m), 0.5, h - 0.5)).astype(f32)
+    z = rng.uniform(0.5, 20.0, m).astype(f32)
+    octave = np.clip(kl["octave"][src] + rng.integers(-1, 2, m), 0, 7).astype(np.int32)
+    angle = ((kl["angle"][src] + np.where(rng.random(m) < 0.8, rng.normal(0, 5.0, m), rng.uniform(0, 360, m))) % 360).astype(f32)
+    has_obs = (rng.random(m) < 0.9).astype(np.uint8)
+    d = synth.flip_bits(dl[src], rng.integers(0, 70, m), rng)
+    mbf, mb = f32(47.9), f32(0.11)
+    lo = octave if mode > 0 else (np.zeros(m, np.int32) if mode < 0 else octave - 1)
+    hi = np.full(m, -1, np.int32) if mode > 0 else (octave if mode < 0 else octave + 1)
+    radius = (f32(th) * sf[octave]).astype(f32)
+
+    def view(k, dd, o):
+        off, items = orbref.build_grid(k, 0.0, 0.0, inv_w, inv_h)
+        g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+        return orbref.make_frame_view(k, dd, None, o, g, keep, sf)
+
+    ptsL = orbref.make_projected(u, v, None, radius, lo.astype(np.int32), hi.astype(np.int32), angle, has_obs, d)
+    decL, winL = orbref.search_by_projection_frame_decisions(view(kl, dl, occ[:nl]), ptsL, 100)
+    keep = np.flatnonzero(winL > 0)
+    assert 0 < len(keep) < m
+    ptsR = orbref.make_projected(u[keep], v[keep], None, radius[keep], lo[keep].astype(np.int32),
+                                 hi[keep].astype(np.int32), angle[keep], has_obs[keep], d[keep])
+    decR_k, _ = orbref.search_by_projection_frame_decisions(view(kr, dr, occ[nl:]), ptsR, 100)
+    decR = np.full(m, -1, np.int32)
+    decR[keep] = decR_k
+    want = np.full(nl + nr, -1, np.int32)
+    hist = [[] for _ in range(30)]
+    n_o = 0
+    for i in range(m):
+        if decL[i] >= 0:
+            want[decL[i]] = i
+            n_o += 1
+            if check:
+                hist[_rot_bin(angle[i], kl["angle"][decL[i]])].append(decL[i])
+        if decR[i] >= 0:
+            want[nl + decR[i]] = i
+            n_o += 1
+            if check:
+                hist[_rot_bin(angle[i], kr["angle"][decR[i]])].append(nl + decR[i])
+    if check:
+        keep_bins = _three_maxima([len(b) for b in hist])
+        for b in range(30):
+            if b not in keep_bins:
+                for row in hist[b]:
+                    want[row] = -1
+                    n_o -= 1
+    n_r, a_r = refsrc.search_by_projection_last_frame_fisheye(fv, u, v, z, octave, angle, has_obs, d, th, mbf, mb, mode, check)
+    assert n_o > 60 and (decR >= 0).sum() > 20
+    assert n_r == n_o and np.array_equal(a_r, want)
+
+
 @pytest.mark.parametrize("th,orb_dist,check,seed", [(10.0, 100, True, 4), (3.0, 64, True, 5), (10.0, 100, False, 6)])
 def test_search_by_projection_keyframe(th, orb_dist, check, seed):
     """SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist), :1808-1918 (relocalisation): window

@@ -22,7 +22,7 @@ def shim_world(monkeypatch):
     lib = C.CDLL(_PATH)
     for name in ("orbrefsrc_search_by_projection_map", "orbrefsrc_search_for_triangulation", "orbrefsrc_search_by_bow",
                  "orbrefsrc_search_by_bow_kf", "orbrefsrc_search_by_projection_last_frame", "orbrefsrc_fuse",
-                 "orbrefsrc_fuse_two_camera",
+                 "orbrefsrc_fuse_two_camera", "orbrefsrc_search_by_projection_last_frame_fisheye",
                  "orbrefsrc_features_in_area", "orbrefsrc_stereo_frame", "orbrefsrc_search_for_initialization",
                  "orbrefsrc_search_by_projection_keyframe", "orbrefsrc_search_by_projection_sim3", "orbrefsrc_search_by_sim3",
                  "orbrefsrc_distinctive_descriptor", "orbrefsrc_search_by_projection_map_fisheye",
@@ -74,6 +74,11 @@ def test_shim_search_for_triangulation_two_camera_keyframes(shim_world, args):
 @pytest.mark.parametrize("args", [(1, 0.7, True), (2, 0.9, False)])
 def test_shim_search_by_bow_two_camera_keyframes(shim_world, args):
     T.test_search_by_bow_two_camera_keyframes(*args)
+
+
+@pytest.mark.parametrize("args", [(0, 7.0, True, 20), (1, 7.0, True, 21), (-1, 10.0, True, 22), (0, 15.0, False, 23)])
+def test_shim_search_by_projection_last_frame_two_camera(shim_world, args):
+    T.test_search_by_projection_last_frame_two_camera(*args)
 
 
 @pytest.mark.parametrize("args", [(False, 3.0, 14), (True, 3.0, 15), (True, 2.5, 16)])
