@@ -245,7 +245,7 @@ def test_search_by_projection_frame_decisions(gpu, m, th, seed):
     mt = ORBmatcher(0.9, True)
     dec, win = mt.SearchByProjectionProjectedDecisions(fv, views.make_projected(**pts), 100)
     dec_r, win_r = orbref.search_by_projection_frame_decisions(fr, orbref.make_projected(**pts), 100)
-    assert (dec_r >= 0).sum() > min(100, m // 4) and (win_r == 0).any()
+    assert (dec_r >= 0).sum() > m // 8 and (win_r == 0).any()
     assert np.array_equal(win, win_r), np.nonzero(win != win_r)[0][:10]
     assert np.array_equal(dec, dec_r), np.nonzero(dec != dec_r)[0][:10]
 
