@@ -1,6 +1,7 @@
 // C entry points over the reference's own ORB_SLAM3::ORBmatcher (compiled from /root/reference/src/ORBmatcher.cc against
 // the stand-in world of oracle/ref_stubs/matcher_world.h). Same flat views and result conventions as the oracle's
 // functions of the same name (oracle/orbref.h), so a test compares the two outputs directly. TEST INFRASTRUCTURE.
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -732,6 +733,101 @@ extern "C" void orbrefsrc_is_in_frustum(const orbx_frustum* fr, const orbx_local
     level[i] = p.mnTrackScaleLevel;
     view_cos[i] = p.mTrackViewCos;
   }
+}
+
+// void Tracking::SearchLocalPoints() (src/Tracking.cc:3249-3330) on a stand-in Tracking object: in
+// liborbref_matcher_src.so the function is the reference's own text (cut out by its signature, oracle/Makefile), in the
+// shim worlds it is the drop-in body of shim/Tracking_orbx.cc. The frame comes from a frame view (grid by the
+// reference's AssignFeaturesToGrid), the pose from `fr`, mvpLocalMapPoints from local map `map_index`.
+//   held[fv->n]   what mCurrentFrame.mvpMapPoints[i] holds on entry: -1 nothing, k >= 0 local-map point k, -2 a point
+//                 with observations that is not in the local map
+//   bad[m]        MapPoint::isBad()
+//   ctl[8]        mSensor, isImuInitialized, GetIniertialBA2, mState, mCurrentFrame.mnId, mnLastRelocFrameId,
+//                 mbFarPoints, (unused)
+// In / out per local-map point (the caller's values are the state on entry, so "left untouched" is observable):
+// track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth, visible (mnVisible), last_seen (mnLastFrameSeen).
+// Out: assign[fv->n] = what mvpMapPoints[i] holds on return (same code as held), project_points[m][2] = the entry of
+// mCurrentFrame.mmProjectPoints under the point's mnId (NaN, NaN when there is none). Returns mmProjectPoints.size().
+extern "C" int orbrefsrc_search_local_points(const orbx_frame_view* fv, const orbx_frustum* fr, const orbx_local_map* map,
+                                             int map_index, const int32_t* held, const uint8_t* bad, const int32_t* ctl,
+                                             float th_far, int32_t* assign, uint8_t* track_in_view, float* proj_x,
+                                             float* proj_y, float* proj_xr, int32_t* level, float* view_cos, float* depth,
+                                             int32_t* visible, int32_t* last_seen, float* project_points) {
+  Tracking T;
+  Atlas atlas;
+  LocalMapping mapper;
+  PinholeStandIn cam;
+  T.mpAtlas = &atlas;
+  T.mpLocalMapper = &mapper;
+  T.mSensor = ctl[0];
+  atlas.imu_initialized = ctl[1] != 0;
+  atlas.map.inertial_ba2 = ctl[2] != 0;
+  T.mState = (Tracking::eTrackingState)ctl[3];
+  T.mnLastRelocFrameId = (unsigned int)ctl[5];
+  mapper.mbFarPoints = ctl[6] != 0;
+  mapper.mThFarPoints = th_far;
+  Frame& F = T.mCurrentFrame;
+  fill_common(F, fv->kps, fv->desc, fv->u_right, fv->n, fv->scale_factors, nullptr, fv->n_levels);
+  build_grid(F, fv);
+  F.mnId = (long unsigned int)ctl[4];
+  cam.mvParameters[0] = fr->fx; cam.mvParameters[1] = fr->fy; cam.mvParameters[2] = fr->cx; cam.mvParameters[3] = fr->cy;
+  F.mpCamera = &cam;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) F.mRcw(i, j) = fr->Rcw[3 * i + j];
+    F.mtcw(i) = fr->tcw[i];
+    F.mOw(i) = fr->Ow[i];
+  }
+  F.pose = Sophus::SE3f(F.mRcw, F.mtcw);  // Frame::GetPose(); mRcw / mtcw are its parts (Frame::UpdatePoseMatrices)
+  F.mbf = fr->mbf;
+  Frame::mnMinX = fr->min_x; Frame::mnMaxX = fr->max_x; Frame::mnMinY = fr->min_y; Frame::mnMaxY = fr->max_y;
+  F.mfLogScaleFactor = fr->log_scale_factor;
+  F.mnScaleLevels = fr->n_levels;
+  const int M = map->m;
+  const size_t base = (size_t)map_index * (size_t)M;
+  std::vector<MapPoint> pts(M);
+  T.mvpLocalMapPoints.resize(M);
+  for (int i = 0; i < M; i++) {
+    const size_t g = base + (size_t)i;
+    MapPoint& p = pts[i];
+    p.mnId = 1000 + (long unsigned int)i;
+    p.pos = Eigen::Vector3f(map->pos[3 * g], map->pos[3 * g + 1], map->pos[3 * g + 2]);
+    p.normal = Eigen::Vector3f(map->normal[3 * g], map->normal[3 * g + 1], map->normal[3 * g + 2]);
+    p.use_raw_distances = true;
+    p.mfMinDistance = map->min_dist[g];
+    p.mfMaxDistance = map->max_dist[g];
+    p.observations = map->has_obs[g] ? 1 : 0;
+    p.descriptor = rows32(map->desc + g * 32, 1).clone();
+    p.bad = bad && bad[i];
+    p.mbTrackInView = track_in_view[i] != 0;
+    p.mTrackProjX = proj_x[i]; p.mTrackProjY = proj_y[i]; p.mTrackProjXR = proj_xr[i];
+    p.mnTrackScaleLevel = level[i]; p.mTrackViewCos = view_cos[i]; p.mTrackDepth = depth[i];
+    p.visible = visible[i];
+    p.mnLastFrameSeen = (long unsigned int)last_seen[i];
+    T.mvpLocalMapPoints[i] = &p;
+  }
+  MapPoint outside;
+  outside.observations = 1;
+  outside.mnId = 999;
+  F.mvpMapPoints.assign(F.N, nullptr);
+  for (int i = 0; i < F.N; i++)
+    if (held && held[i] != -1) F.mvpMapPoints[i] = held[i] >= 0 ? &pts[held[i]] : &outside;
+  T.SearchLocalPoints();
+  for (int i = 0; i < F.N; i++) {
+    const MapPoint* p = F.mvpMapPoints[i];
+    assign[i] = !p ? -1 : (p == &outside ? -2 : (int)(p - pts.data()));
+  }
+  for (int i = 0; i < M; i++) {
+    const MapPoint& p = pts[i];
+    track_in_view[i] = p.mbTrackInView ? 1 : 0;
+    proj_x[i] = p.mTrackProjX; proj_y[i] = p.mTrackProjY; proj_xr[i] = p.mTrackProjXR;
+    level[i] = p.mnTrackScaleLevel; view_cos[i] = p.mTrackViewCos; depth[i] = p.mTrackDepth;
+    visible[i] = p.visible;
+    last_seen[i] = (int32_t)p.mnLastFrameSeen;
+    auto it = F.mmProjectPoints.find(p.mnId);
+    project_points[2 * i] = it == F.mmProjectPoints.end() ? NAN : it->second.x;
+    project_points[2 * i + 1] = it == F.mmProjectPoints.end() ? NAN : it->second.y;
+  }
+  return (int)F.mmProjectPoints.size();
 }
 
 // BASELINE.json configs[3] on the CPU with the reference's own code end to end: both ORBextractor::operator() calls and

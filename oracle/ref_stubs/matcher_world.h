@@ -9,6 +9,11 @@
 #define FRAME_H
 #define KEYFRAME_H
 #define MAPPOINT_H
+#define TRACKING_H
+#define ATLAS_H
+#define LOCALMAPPING_H
+#define SYSTEM_H
+#define MAP_H
 #define FRAME_GRID_ROWS 48
 #define FRAME_GRID_COLS 64
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
@@ -147,6 +152,8 @@ class GeometricCamera {
   // orthographic stand-in: the image point of (x, y, z) is (x, y); see the header comment
   virtual Eigen::Vector2f project(const Eigen::Vector3f& p) { return Eigen::Vector2f(p(0), p(1)); }
   virtual Eigen::Matrix3f toK_() { return Eigen::Matrix3f(); }
+  // GeometricCamera::getParameter (include/CameraModels/GeometricCamera.h:81): fx, fy, cx, cy of a pinhole model
+  virtual float getParameter(const int i) { return i < 2 ? 1.f : 0.f; }
   // Pinhole::epipolarConstrain (src/CameraModels/Pinhole.cpp:122-149) with F12 supplied by the test
   float F12[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // two-camera rigs: `tag` says which camera of its KeyFrame this is; against a second camera with tag 1 the test uses
@@ -172,6 +179,7 @@ class GeometricCamera {
 class PinholeStandIn : public GeometricCamera {
  public:
   float mvParameters[4] = {1, 1, 0, 0};
+  float getParameter(const int i) override { return mvParameters[i]; }
   Eigen::Vector2f project(const Eigen::Vector3f& v3D) override {
     Eigen::Vector2f res;
     res(0) = mvParameters[0] * v3D(0) / v3D(2) + mvParameters[2];
@@ -248,6 +256,14 @@ class MapPoint {
     return std::make_tuple(it == index_in.end() ? -1 : it->second, -1);
   }
   void AddObservation(KeyFrame*, int idx) { added_to = idx; }
+  // what Tracking::SearchLocalPoints (src/Tracking.cc:3249-3330) touches besides the tracking fields above
+  long unsigned int mnId = 0;
+  int visible = 0;  // mnVisible
+  void IncreaseVisible(int n = 1) { visible += n; }
+  // the two accessors shim/Tracking_orbx.cc asks a maintainer to add next to GetMinDistanceInvariance (mfMinDistance /
+  // mfMaxDistance are protected, include/MapPoint.h:241-242; PredictScale reads the raw value, src/MapPoint.cc:559-573)
+  float GetMinDistanceRaw() { return mfMinDistance; }
+  float GetMaxDistanceRaw() { return mfMaxDistance; }
   void Replace(MapPoint* other) { replaced_by = other; }
 };
 
@@ -288,6 +304,9 @@ class Frame : public FeatureHolder {
   float mfLogScaleFactor = 0;
   int mnScaleLevels = 0;
   bool isInFrustum(MapPoint* pMP, float viewingCosLimit);
+  Eigen::Vector3f GetOw() const { return mOw; }  // include/Frame.h:187
+  long unsigned int mnId = 0;
+  std::map<long unsigned int, cv::Point2f> mmProjectPoints;  // include/Frame.h:321
   bool isInFrustumChecks(MapPoint*, float, bool = false) { return false; }
   void ComputeStereoMatches();  // defined by the reference's own text, piped in at build time (oracle/Makefile)
   // Frame::ComputeStereoFishEyeMatches (src/Frame.cc:1271-1331): the reference's own text, piped in likewise
@@ -352,6 +371,45 @@ class KeyFrame : public FeatureHolder {
   }
   // the right camera's cell, for the two-camera branch of shim Fuse (accessor to add next to mGridRight)
   const std::vector<size_t>& GetGridCellRight(int c, int r) const { return mGridRight[c][r]; }
+};
+
+// The members Tracking::SearchLocalPoints (src/Tracking.cc:3249-3330) reads, as plain data: the reference's own text of
+// that function is piped in at build time (oracle/Makefile); shim/Tracking_orbx.cc is its drop-in body.
+class ORBmatcher;
+class System {
+ public:
+  enum eSensor { MONOCULAR = 0, STEREO = 1, RGBD = 2, IMU_MONOCULAR = 3, IMU_STEREO = 4, IMU_RGBD = 5 };  // include/System.h:87-94
+};
+class Map {
+ public:
+  bool inertial_ba2 = false;
+  bool GetIniertialBA2() { return inertial_ba2; }
+};
+class Atlas {
+ public:
+  Map map;
+  bool imu_initialized = false;
+  Map* GetCurrentMap() { return &map; }
+  bool isImuInitialized() { return imu_initialized; }
+};
+class LocalMapping {
+ public:
+  bool mbFarPoints = false;
+  float mThFarPoints = 0.f;
+};
+class Tracking {
+ public:
+  enum eTrackingState {  // include/Tracking.h:122-130
+    SYSTEM_NOT_READY = -1, NO_IMAGES_YET = 0, NOT_INITIALIZED = 1, OK = 2, RECENTLY_LOST = 3, LOST = 4, OK_KLT = 5
+  };
+  eTrackingState mState = OK;
+  int mSensor = System::STEREO;
+  Frame mCurrentFrame;
+  std::vector<MapPoint*> mvpLocalMapPoints;
+  Atlas* mpAtlas = nullptr;
+  LocalMapping* mpLocalMapper = nullptr;
+  unsigned int mnLastRelocFrameId = 0;
+  void SearchLocalPoints();
 };
 }  // namespace ORB_SLAM3
 using namespace std;  // the reference's headers leak it; ORBmatcher.h relies on that

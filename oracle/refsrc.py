@@ -138,6 +138,30 @@ def is_in_frustum(frustum, local_map, map_index=0, viewing_cos_limit=0.5, out=No
     return orbref.is_in_frustum(frustum, local_map, map_index, viewing_cos_limit, out, fn=fn)
 
 
+def search_local_points(fv, frustum, local_map, held, bad, ctl, th_far, state, map_index=0):
+    """Tracking::SearchLocalPoints (src/Tracking.cc:3249-3330) — the reference's own function text on a stand-in Tracking
+    object (in a shim world: the drop-in body of shim/Tracking_orbx.cc). held[n]: what mvpMapPoints[i] holds on entry
+    (-1 nothing, k >= 0 local-map point k, -2 a point outside the local map); bad[m]; ctl = (mSensor, isImuInitialized,
+    GetIniertialBA2, mState, frame id, mnLastRelocFrameId, mbFarPoints); state: dict of the per-point words on entry
+    (track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth, visible, last_seen). Returns (assign[n], state on
+    return, project_points[m][2] with NaN where mmProjectPoints has no entry, len(mmProjectPoints))."""
+    n, m = fv.struct.n, local_map.struct.m
+    fr = np.ascontiguousarray(frustum).reshape(1)
+    held = np.ascontiguousarray(held, np.int32)
+    bad = np.ascontiguousarray(bad, np.uint8)
+    c = np.zeros(8, np.int32)
+    c[:len(ctl)] = ctl
+    st = {k: np.ascontiguousarray(v).copy() for k, v in state.items()}
+    assign = np.full(max(n, 1), -7, np.int32)
+    pp = np.zeros((max(m, 1), 2), np.float32)
+    fn = mlib().orbrefsrc_search_local_points
+    fn.restype = C.c_int
+    k = fn(fv.ref(), _p(fr), local_map.ref(), C.c_int(map_index), _p(held), _p(bad), _p(c), C.c_float(th_far), _p(assign),
+           _p(st["track_in_view"]), _p(st["proj_x"]), _p(st["proj_y"]), _p(st["proj_xr"]), _p(st["level"]),
+           _p(st["view_cos"]), _p(st["depth"]), _p(st["visible"]), _p(st["last_seen"]), _p(pp))
+    return assign[:n], st, pp[:m], k
+
+
 def search_by_projection_map_fisheye(fv, mps, mr, th, nnratio, far_points=False, th_far=0.0):
     """The reference's own SearchByProjection(Frame&, vector<MapPoint*>) on a two-camera stand-in Frame."""
     from . import orbref

@@ -29,6 +29,15 @@ int orbm_search_by_projection_map(orbm_matcher*, const orbx_frame_view* f, const
   if (nmatches) *nmatches = n;
   return ORBX_OK;
 }
+int orbm_is_in_frustum(orbm_matcher*, const orbx_frustum* fr, const orbx_local_map* map, int map_index,
+                       float viewing_cos_limit, uint8_t* track_in_view, float* proj_x, float* proj_y, float* proj_xr,
+                       int32_t* level, float* view_cos, float* depth, int32_t* n_in_view) {
+  orbref_is_in_frustum(fr, map, map_index, viewing_cos_limit, track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth);
+  int n = 0;
+  for (int i = 0; i < map->m; i++) n += track_in_view[i] != 0;
+  if (n_in_view) *n_in_view = n;
+  return ORBX_OK;
+}
 int orbm_search_by_projection_map_fisheye(orbm_matcher*, const orbx_fisheye_view* f, const orbx_mappoints* mps,
                                           const orbx_mappoints_right* mr, float th, float nnratio, int far_points,
                                           float th_far, int32_t* assign, int32_t* nmatches) {

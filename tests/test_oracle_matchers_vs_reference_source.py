@@ -667,6 +667,95 @@ def test_is_in_frustum(seed, m, cos_limit):
         assert (o["level"][out] == -9).all() and (o["depth"][out] == 8.5).all()
 
 
+# (mSensor, isImuInitialized, GetIniertialBA2, mState, frame id, mnLastRelocFrameId, mbFarPoints) -> th of :3302-3322
+_SLP_CASES = [((1, 0, 0, 2, 40, 0, 1), 1), ((2, 0, 0, 2, 40, 0, 0), 3), ((4, 1, 1, 2, 40, 0, 1), 2), ((4, 1, 0, 2, 40, 0, 0), 6),
+              ((3, 0, 0, 2, 40, 0, 1), 10), ((1, 0, 0, 2, 40, 39, 0), 5), ((5, 1, 1, 3, 40, 39, 1), 15), ((0, 0, 0, 4, 7, 0, 0), 15)]
+
+
+@pytest.mark.parametrize("seed,m,case", [(0, 10000, 0), (1, 4000, 1), (2, 4000, 2), (3, 3000, 3), (4, 3000, 4), (5, 3000, 5),
+                                         (6, 2000, 6), (7, 2000, 7), (8, 1, 0), (9, 0, 0)])
+def test_search_local_points(seed, m, case):
+    """void Tracking::SearchLocalPoints() (src/Tracking.cc:3249-3330), the caller of a13 (SURVEY.md §8f rank 1): the
+    reference's own function text on a stand-in Tracking object (oracle/Makefile pipes it in) against the oracle's pieces
+    put together here — the bookkeeping loop over mCurrentFrame.mvpMapPoints (:3268-3285), isInFrustum over
+    mvpLocalMapPoints with the skip rule (:3288-3300), the search radius of the tracker's state (:3302-3322) and
+    SearchByProjection (:3324). Compared: every slot of mvpMapPoints, every tracking word of every MapPoint (incl. the ones
+    the reference leaves untouched, and stale mbTrackInView flags on bad points), mnVisible, mnLastFrameSeen and
+    mCurrentFrame.mmProjectPoints. The shim worlds run the same comparison on the drop-in body (shim/Tracking_orbx.cc)."""
+    ctl, th = _SLP_CASES[case]
+    rng = np.random.default_rng(900 + seed)
+    img = synth.scene(480, 640, seed=30 + seed)
+    ex = orbref.Extractor(1200)
+    _, kps, desc = ex(img, (0, 0))
+    n = len(kps)
+    fr = synth.frustum(640, 480, seed=seed)
+    mp = synth.local_map_world(kps, desc, max(m, 1), fr, seed=seed)
+    if m == 0:
+        mp = {k: v[:0] for k, v in mp.items()}
+    frame_id = ctl[4]
+    bad = (rng.random(m) < 0.04).astype(np.uint8)
+    held = np.full(n, -1, np.int32)
+    if m:
+        slots = rng.choice(n, min(n // 8, m), replace=False)
+        held[slots] = rng.choice(m, len(slots), replace=False)       # some of them bad, some without observations
+    held[rng.choice(n, n // 20, replace=False)] = -2
+    state = dict(track_in_view=(rng.random(m) < 0.3).astype(np.uint8), proj_x=np.full(m, 3.5, f32), proj_y=np.full(m, 4.5, f32),
+                 proj_xr=np.full(m, 5.5, f32), level=np.full(m, -9, np.int32), view_cos=np.full(m, 6.5, f32),
+                 depth=np.full(m, 8.5, f32), visible=rng.integers(0, 50, m).astype(np.int32),
+                 last_seen=np.where(rng.random(m) < 0.05, frame_id, frame_id - 1).astype(np.int32))
+    # mnLastFrameSeen == mnId is only ever written together with mbTrackInView = false (:3278-3280), so a live point seen
+    # in this frame cannot carry a stale flag (a bad point can: nothing touches it any more)
+    state["track_in_view"][(state["last_seen"] == frame_id) & (bad == 0)] = 0
+    inv_w, inv_h = f32(64) / f32(640), f32(48) / f32(480)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    ur = np.where(rng.random(n) < 0.6, kps["x"] - rng.uniform(1, 40, n), -1).astype(f32)
+    lm0 = orbref.make_local_map(**{**mp, "skip": None})
+    fv0 = orbref.make_frame_view(kps, desc, ur, np.zeros(n, np.uint8), g, keep, ex.scale)
+    a_r, s_r, pp_r, k_r = refsrc.search_local_points(fv0, fr, lm0, held, bad, ctl, 15.0, state)
+
+    # ---- the same pass from the oracle's pieces ----
+    st = {k: v.copy() for k, v in state.items()}
+    now = held.copy()
+    for i in np.flatnonzero(held >= 0):                            # :3268-3285
+        k = held[i]
+        if bad[k]:
+            now[i] = -1
+        else:
+            st["visible"][k] += 1
+            st["last_seen"][k] = frame_id
+            st["track_in_view"][k] = 0
+    skip = ((st["last_seen"] == frame_id) | (bad != 0)).astype(np.uint8)    # :3289
+    pp = np.full((m, 2), np.nan, f32)
+    nv = 0
+    if m:
+        lm = orbref.make_local_map(**{**mp, "skip": skip})
+        before = st["track_in_view"].copy()
+        nv, o = orbref.is_in_frustum(fr, lm, 0, 0.5, {k: st[k] for k in ("track_in_view", "proj_x", "proj_y", "proj_xr",
+                                                                         "level", "view_cos", "depth")})
+        for k in o:
+            st[k] = o[k]
+        st["track_in_view"] = np.where(skip != 0, before, st["track_in_view"])   # a skipped point is not touched at all
+        seen = (o["track_in_view"] != 0) & (skip == 0)
+        st["visible"][seen] += 1
+        pp[seen, 0], pp[seen, 1] = st["proj_x"][seen], st["proj_y"][seen]
+    want = now.copy()
+    if nv > 0:
+        occ = np.array([h == -2 or (h >= 0 and mp["has_obs"][h] != 0) for h in now], np.uint8)
+        fv = orbref.make_frame_view(kps, desc, ur, occ, g, keep, ex.scale)
+        mps = orbref.make_mappoints(st["track_in_view"] & (1 - bad), st["proj_x"], st["proj_y"], st["proj_xr"], st["level"],
+                                    st["view_cos"], st["depth"], mp["has_obs"], mp["desc"])
+        nm, assign = orbref.search_by_projection_map(fv, mps, float(th), 0.8, bool(ctl[6]), 15.0)
+        want = np.where(assign >= 0, assign, now)
+        assert m < 1000 or nm > 50, "the case must produce matches"
+    assert np.array_equal(a_r, want)
+    for k in st:
+        assert s_r[k].tobytes() == st[k].tobytes(), k
+    assert pp_r.tobytes() == pp.tobytes() and k_r == int(np.isfinite(pp[:, 0]).sum())
+    if m >= 1000:
+        assert nv > m // 4 and (skip != 0).sum() > 0 and (bad & state["track_in_view"]).sum() > 0
+
+
 @pytest.mark.parametrize("seed,th,far,sizes", [(0, 1.0, True, (700, 650, 3000)), (1, 3.0, False, (700, 650, 3000)),
                                                (2, 6.0, True, (1200, 1100, 10000)), (4, 15.0, False, (300, 280, 2000))])
 def test_search_by_projection_map_fisheye(seed, th, far, sizes):

@@ -142,3 +142,13 @@ def test_shim_compute_distinctive_descriptors(shim_world):
 def test_shim_search_by_projection_two_cameras(shim_world, args):
     """the fisheye (Nleft != -1) path of the drop-in SearchByProjection(Frame&, vector<MapPoint*>)"""
     T.test_search_by_projection_map_fisheye(*args)
+
+
+# ---- shim/Tracking_orbx.cc: the caller of the local-map search ----
+@pytest.mark.parametrize("args", [(0, 10000, 0), (1, 4000, 1), (2, 4000, 2), (3, 3000, 3), (4, 3000, 4), (5, 3000, 5),
+                                  (6, 2000, 6), (7, 2000, 7), (8, 1, 0), (9, 0, 0)])
+def test_shim_tracking_search_local_points(shim_world, args):
+    """the drop-in Tracking::SearchLocalPoints (one orbm_is_in_frustum call for the whole local map + the drop-in
+    SearchByProjection): mvpMapPoints, every MapPoint tracking word, mnVisible, mnLastFrameSeen and mmProjectPoints as the
+    reference's own function text leaves them"""
+    T.test_search_local_points(*args)
