@@ -51,4 +51,38 @@ int orbrefsrc_voc_transform(void* h, const unsigned char* desc, int n, int level
   }
   return k;
 }
+
+#ifdef ORBREF_BOW_WORLD
+// Frame::ComputeBoW() / KeyFrame::ComputeBoW() on the stand-in objects of ref_stubs/bow_world.h: in
+// liborbref_dbow2_src.so the two functions are the reference's own text (src/Frame.cc:846-851, src/KeyFrame.cc:98-107,
+// piped in), in the shim bow worlds they are the drop-in bodies of shim/FrameBoW_orbx.cc. which: 0 Frame, 1 KeyFrame,
+// 2 KeyFrame whose mBowVec is already filled but whose mFeatVec is empty (recomputed, :100), 3 Frame whose mBowVec is
+// already filled (left alone, :847). Outputs: the BowVector as (bow_words, bow_values)[cap], the FeatureVector as
+// node_id[n] per feature (0xffffffff = filed nowhere). Returns the BowVector's size.
+int orbrefsrc_compute_bow(void* h, const unsigned char* desc, int n, int which, unsigned* node_id, unsigned* bow_words,
+                          double* bow_values, int cap) {
+  ORB_SLAM3::Frame F;
+  ORB_SLAM3::KeyFrame K;
+  ORB_SLAM3::BowHolder& B = (which == 0 || which == 3) ? static_cast<ORB_SLAM3::BowHolder&>(F) : K;
+  B.mpORBvocabulary = static_cast<Vocabulary*>(h);
+  B.mDescriptors = cv::Mat(n, 32, CV_8U, const_cast<unsigned char*>(desc), 32).clone();
+  if (which >= 2) B.mBowVec.addWeight(7, 0.25);
+  if (which == 0 || which == 3)
+    F.ComputeBoW();
+  else
+    K.ComputeBoW();
+  for (int i = 0; i < n; i++) node_id[i] = 0xffffffffu;
+  for (const auto& kv : B.mFeatVec)
+    for (unsigned idx : kv.second) node_id[idx] = kv.first;
+  int k = 0;
+  for (const auto& kv : B.mBowVec) {
+    if (k < cap) {
+      bow_words[k] = kv.first;
+      bow_values[k] = kv.second;
+    }
+    k++;
+  }
+  return k;
+}
+#endif
 }

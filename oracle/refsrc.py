@@ -325,13 +325,7 @@ def vocabulary_available():
 def vlib():
     global _vlib
     if _vlib is None:
-        _vlib = C.CDLL(_VPATH)
-        _vlib.orbrefsrc_voc_load.restype = C.c_void_p
-        _vlib.orbrefsrc_voc_load.argtypes = [C.c_char_p]
-        _vlib.orbrefsrc_voc_destroy.argtypes = [C.c_void_p]
-        _vlib.orbrefsrc_voc_size.argtypes = [C.c_void_p]
-        _vlib.orbrefsrc_voc_transform.restype = C.c_int
-        _vlib.orbrefsrc_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+        _vlib = _vocabulary_lib(_VPATH)
     return _vlib
 
 
@@ -352,28 +346,56 @@ def write_vocabulary_text(voc, k, path):
         f.write("\n".join(lines))          # no trailing newline: the loader would read one more (empty) node
 
 
+def _vocabulary_lib(path):
+    lib = C.CDLL(path)
+    lib.orbrefsrc_voc_load.restype = C.c_void_p
+    lib.orbrefsrc_voc_load.argtypes = [C.c_char_p]
+    lib.orbrefsrc_voc_destroy.argtypes = [C.c_void_p]
+    lib.orbrefsrc_voc_size.argtypes = [C.c_void_p]
+    lib.orbrefsrc_voc_transform.restype = C.c_int
+    lib.orbrefsrc_voc_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_int]
+    lib.orbrefsrc_compute_bow.restype = C.c_int
+    lib.orbrefsrc_compute_bow.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int]
+    return lib
+
+
 class ReferenceVocabulary:
-    def __init__(self, path):
-        self._h = vlib().orbrefsrc_voc_load(path.encode())
+    """DBoW2's own vocabulary object. `world`: path of another library of the same world (a shim bow world, where
+    Frame / KeyFrame::ComputeBoW are the drop-in bodies of shim/FrameBoW_orbx.cc); the object is created, used and
+    destroyed by that one library."""
+
+    def __init__(self, path, world=None):
+        self._lib = vlib() if world is None else _vocabulary_lib(world)
+        self._h = self._lib.orbrefsrc_voc_load(path.encode())
         if not self._h:
             raise RuntimeError("loadFromTextFile failed")
 
     def __del__(self):
         if getattr(self, "_h", None):
-            vlib().orbrefsrc_voc_destroy(self._h)
+            self._lib.orbrefsrc_voc_destroy(self._h)
             self._h = None
 
     def words(self):
-        return vlib().orbrefsrc_voc_size(self._h)
+        return self._lib.orbrefsrc_voc_size(self._h)
 
     def transform(self, desc, levelsup=4):
         desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
         n = len(desc)
         word, weight, node = np.empty(n, np.uint32), np.empty(n, np.float64), np.empty(n, np.uint32)
         bw, bvals = np.empty(n + 1, np.uint32), np.empty(n + 1, np.float64)
-        k = vlib().orbrefsrc_voc_transform(self._h, _p(desc), n, levelsup, _p(word), _p(weight), _p(node), _p(bw),
-                                           _p(bvals), n + 1)
+        k = self._lib.orbrefsrc_voc_transform(self._h, _p(desc), n, levelsup, _p(word), _p(weight), _p(node), _p(bw),
+                                              _p(bvals), n + 1)
         return word, weight, node, bw[:k], bvals[:k]
+
+    def compute_bow(self, desc, which=0):
+        """Frame::ComputeBoW (which 0; 3: mBowVec already filled) / KeyFrame::ComputeBoW (1; 2: mBowVec filled, mFeatVec
+        empty) on a stand-in object holding `desc`: (node_id[n] of mFeatVec, words, values of mBowVec)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        node = np.empty(max(n, 1), np.uint32)
+        bw, bvals = np.empty(n + 2, np.uint32), np.empty(n + 2, np.float64)
+        k = self._lib.orbrefsrc_compute_bow(self._h, _p(desc), n, which, _p(node), _p(bw), _p(bvals), n + 2)
+        return node[:n], bw[:k], bvals[:k]
 
 
 def stereo_frame(left, right, mbf, mb, nfeatures=1200, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):

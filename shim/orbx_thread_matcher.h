@@ -1,5 +1,6 @@
 // shim/orbx_thread_matcher.h — the matcher context of the calling thread, shared by the reference-side bodies
-// (ORBmatcher_orbx.cc, ORBmatcher_next_orbx.cc, ORBmatcher_sim3_orbx.cc, FrameStereo_orbx.cc, FrameFisheye_orbx.cc).
+// (ORBmatcher_orbx.cc, ORBmatcher_next_orbx.cc, ORBmatcher_sim3_orbx.cc, FrameStereo_orbx.cc, Tracking_orbx.cc,
+// FrameBoW_orbx.cc).
 //
 // ORBmatcher objects are per-call stack temporaries used from the Tracking, LocalMapping and LoopClosing threads
 // (src/Tracking.cc:2784,3303, src/LocalMapping.cc:435, src/LoopClosing.cc:729), so the context cannot live in the

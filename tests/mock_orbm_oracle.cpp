@@ -8,7 +8,16 @@
 #include "../include/orbx.h"
 #include "../oracle/orbref.h"
 
-struct orbm_matcher { int unused; };
+#include <vector>
+
+// the mock context keeps its own copy of the vocabulary, as the library keeps one on the device
+struct orbm_matcher {
+  std::vector<int32_t> child_offsets;
+  std::vector<uint32_t> children, word_id;
+  std::vector<uint8_t> descriptors;
+  std::vector<double> weight;
+  orbx_vocabulary voc{};
+};
 // the extractor handle of the mock: the oracle's extractor, whose last call holds the pyramid the stereo matcher reads
 struct orbx_extractor {
   orbref_extractor* r;
@@ -27,6 +36,23 @@ int orbm_search_by_projection_map(orbm_matcher*, const orbx_frame_view* f, const
                                   float nnratio, int far_points, float th_far, int32_t* assign, int32_t* nmatches) {
   const int n = orbref_search_by_projection_map(f, mps, th, nnratio, far_points, th_far, assign);
   if (nmatches) *nmatches = n;
+  return ORBX_OK;
+}
+int orbm_set_vocabulary(orbm_matcher* m, const orbx_vocabulary* v) {
+  const int N = v->n_nodes, nc = v->child_offsets[N];
+  m->child_offsets.assign(v->child_offsets, v->child_offsets + N + 1);
+  m->children.assign(v->children, v->children + nc);
+  m->word_id.assign(v->word_id, v->word_id + N);
+  m->descriptors.assign(v->descriptors, v->descriptors + (size_t)N * 32);
+  m->weight.assign(v->weight, v->weight + N);
+  m->voc = orbx_vocabulary{N, v->depth, m->child_offsets.data(), m->children.data(), m->descriptors.data(),
+                           m->word_id.data(), m->weight.data()};
+  return ORBX_OK;
+}
+int orbm_bow_transform(orbm_matcher* m, const uint8_t* desc, int n, int levelsup, uint32_t* word_id, double* weight,
+                       uint32_t* node_id) {
+  if (m->voc.n_nodes < 1) return ORBX_E_ARG;
+  orbref_bow_transform(&m->voc, desc, n, levelsup, word_id, weight, node_id);
   return ORBX_OK;
 }
 int orbm_is_in_frustum(orbm_matcher*, const orbx_frustum* fr, const orbx_local_map* map, int map_index,
