@@ -1,6 +1,8 @@
 """Frame sharding across the GPUs of one box: frames are independent — the extractor keeps no state
-between frames (src/ORBextractor.cc:1116-1118 overwrites mvImagePyramid every call) — so frame i goes to rank
-i * world // n (contiguous blocks; the two eyes of a stereo pair are one unit and never split). There is no data-path
+between frames (src/ORBextractor.cc:1116-1118 overwrites mvImagePyramid every call) — so the n frames are cut
+into `world` contiguous blocks whose sizes differ by at most one, the first n % world ranks taking the extra frame
+(shard_range below; the C entry points orbx_extract_batch_multi / orbm_stereo_track_frames_batch_multi cut the same
+way); the two eyes of a stereo pair are one unit and never split. There is no data-path
 collective. The only communication is the gather of fixed-size result slabs (count + cap x 28 B keypoints + cap x 32 B
 descriptors per frame) to rank 0, done with torch.distributed on whatever backend the process group has (NCCL over
 NVLink on the GPU box, gloo in the CPU tests).
