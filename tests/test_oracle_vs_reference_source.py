@@ -189,3 +189,89 @@ def test_reference_side_shim_bodies_compile_against_the_reference_class(name):
            os.path.join("shim", name)]
     r = subprocess.run(cmd, text=True, cwd=root, capture_output=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+# What the drop-in bodies read through the stand-in classes (oracle/ref_stubs/matcher_world.h, bow_world.h) must exist,
+# under the same name and with a compatible declaration, in the reference's OWN headers — otherwise a body that compiles
+# and passes here would not compile in the reference tree. (ORBmatcher's methods are checked by the compiler itself: the
+# stand-in world includes the reference's real include/ORBmatcher.h.) One regular expression per member.
+_REAL_DECLARATIONS = [
+    # shim/Tracking_orbx.cc
+    ("include/Tracking.h", r"void\s+SearchLocalPoints\s*\(\s*\)\s*;"),
+    ("include/Tracking.h", r"Frame\s+mCurrentFrame\s*;"),
+    ("include/Tracking.h", r"std::vector<MapPoint\s*\*>\s+mvpLocalMapPoints\s*;"),
+    ("include/Tracking.h", r"eTrackingState\s+mState\s*;"),
+    ("include/Tracking.h", r"RECENTLY_LOST\s*=\s*3"),
+    ("include/Tracking.h", r"LOST\s*=\s*4"),
+    ("include/Tracking.h", r"int\s+mSensor\s*;"),
+    ("include/Tracking.h", r"Atlas\s*\*\s*mpAtlas\s*;"),
+    ("include/Tracking.h", r"LocalMapping\s*\*\s*mpLocalMapper\s*;"),
+    ("include/Tracking.h", r"unsigned int\s+mnLastRelocFrameId\s*;"),
+    ("include/System.h", r"RGBD\s*=\s*2"),
+    ("include/System.h", r"IMU_MONOCULAR\s*=\s*3"),
+    ("include/System.h", r"IMU_STEREO\s*=\s*4"),
+    ("include/System.h", r"IMU_RGBD\s*=\s*5"),
+    ("include/Atlas.h", r"bool\s+isImuInitialized\s*\(\s*\)\s*;"),
+    ("include/Atlas.h", r"Map\s*\*\s*GetCurrentMap\s*\(\s*\)\s*;"),
+    ("include/Map.h", r"bool\s+GetIniertialBA2\s*\(\s*\)\s*;"),
+    ("include/LocalMapping.h", r"bool\s+mbFarPoints\s*;"),
+    ("include/LocalMapping.h", r"float\s+mThFarPoints\s*;"),
+    ("include/Frame.h", r"bool\s+isInFrustum\s*\(\s*MapPoint\s*\*\s*pMP\s*,\s*float\s+viewingCosLimit\s*\)\s*;"),
+    ("include/Frame.h", r"GetPose\s*\(\s*\)\s*const"),
+    ("include/Frame.h", r"Eigen::Vector3f\s+GetOw\s*\(\s*\)\s*const"),
+    ("include/Frame.h", r"long unsigned int\s+mnId\s*;"),
+    ("include/Frame.h", r"map<long unsigned int,\s*cv::Point2f>\s+mmProjectPoints\s*;"),
+    ("include/Frame.h", r"std::vector<MapPoint\s*\*>\s+mvpMapPoints\s*;"),
+    ("include/Frame.h", r"float\s+mfLogScaleFactor\s*;"),
+    ("include/Frame.h", r"int\s+mnScaleLevels\s*;"),
+    ("include/Frame.h", r"float\s+mbf\s*;"),
+    ("include/Frame.h", r"static float\s+mnMinX\s*;"),
+    ("include/Frame.h", r"GeometricCamera\s*\*\s*mpCamera\s*,"),
+    ("include/Frame.h", r"int\s+Nleft\s*,"),
+    ("include/CameraModels/GeometricCamera.h", r"float\s+getParameter\s*\(\s*const int i\s*\)"),
+    ("include/MapPoint.h", r"void\s+IncreaseVisible\s*\(\s*int n\s*=\s*1\s*\)\s*;"),
+    ("include/MapPoint.h", r"long unsigned int\s+mnLastFrameSeen\s*;"),
+    ("include/MapPoint.h", r"long unsigned int\s+mnId\s*;"),
+    ("include/MapPoint.h", r"bool\s+mbTrackInView\s*,\s*mbTrackInViewR\s*;"),
+    ("include/MapPoint.h", r"float\s+mTrackProjX\s*;"),
+    ("include/MapPoint.h", r"float\s+mTrackProjXR\s*;"),
+    ("include/MapPoint.h", r"int\s+mnTrackScaleLevel\s*,"),
+    ("include/MapPoint.h", r"float\s+mTrackViewCos\s*,"),
+    ("include/MapPoint.h", r"float\s+mTrackDepth\s*;"),
+    ("include/MapPoint.h", r"Eigen::Vector3f\s+GetWorldPos\s*\(\s*\)\s*;"),
+    ("include/MapPoint.h", r"Eigen::Vector3f\s+GetNormal\s*\(\s*\)\s*;"),
+    ("include/MapPoint.h", r"float\s+mfMinDistance\s*;"),      # what the two accessors to add return
+    ("include/MapPoint.h", r"float\s+mfMaxDistance\s*;"),
+    # shim/FrameBoW_orbx.cc
+    ("include/Frame.h", r"void\s+ComputeBoW\s*\(\s*\)\s*;"),
+    ("include/KeyFrame.h", r"void\s+ComputeBoW\s*\(\s*\)\s*;"),
+    ("include/Frame.h", r"ORBVocabulary\s*\*\s*mpORBvocabulary\s*;"),
+    ("include/KeyFrame.h", r"ORBVocabulary\s*\*\s*mpORBvocabulary\s*;"),
+    ("include/Frame.h", r"DBoW2::BowVector\s+mBowVec\s*;"),
+    ("include/Frame.h", r"DBoW2::FeatureVector\s+mFeatVec\s*;"),
+    ("include/KeyFrame.h", r"DBoW2::BowVector\s+mBowVec\s*;"),
+    ("include/KeyFrame.h", r"DBoW2::FeatureVector\s+mFeatVec\s*;"),
+    ("include/Frame.h", r"cv::Mat\s+mDescriptors\s*,"),
+    ("include/KeyFrame.h", r"const cv::Mat\s+mDescriptors\s*;"),
+    ("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", r"std::vector<Node>\s+m_nodes\s*;"),
+    ("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", r"GeneralScoring\s*\*\s*m_scoring_object\s*;"),
+    ("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", r"inline int getDepthLevels\s*\(\s*\)\s*const"),
+    ("Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h", r"inline WeightingType getWeightingType\s*\(\s*\)\s*const"),
+    # shim/FrameStereo_orbx.cc, shim/ORBmatcher_next_orbx.cc
+    ("include/Frame.h", r"void\s+ComputeStereoMatches\s*\(\s*\)\s*;"),
+    ("include/Frame.h", r"void\s+ComputeStereoFishEyeMatches\s*\(\s*\)\s*;"),
+    ("include/Frame.h", r"void\s+AssignFeaturesToGrid\s*\(\s*\)\s*;"),
+    ("include/MapPoint.h", r"void\s+ComputeDistinctiveDescriptors\s*\(\s*\)\s*;"),
+]
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/include/Tracking.h"), reason="no reference tree")
+def test_members_the_drop_in_bodies_use_exist_in_the_reference_headers():
+    import re
+    cache, missing = {}, []
+    for rel, pattern in _REAL_DECLARATIONS:
+        if rel not in cache:
+            cache[rel] = open("/root/reference/" + rel, errors="replace").read()
+        if not re.search(pattern, cache[rel]):
+            missing.append((rel, pattern))
+    assert not missing, missing
