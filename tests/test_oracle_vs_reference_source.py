@@ -275,3 +275,29 @@ def test_members_the_drop_in_bodies_use_exist_in_the_reference_headers():
         if not re.search(pattern, cache[rel]):
             missing.append((rel, pattern))
     assert not missing, missing
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/include/Tracking.h"), reason="no reference tree")
+def test_every_member_name_the_shim_reaches_is_a_name_of_the_reference():
+    """Word-level net under the list above: every identifier the files of shim/ reach with `.` or `->` must occur in the
+    reference's headers (include/, CameraModels/, DBoW2), in this repository's C ABI headers, or be a standard-library /
+    OpenCV / Eigen method — except the accessors INTEGRATION.md asks a maintainer to add, which must be named there."""
+    import glob
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "".join(open(f, errors="replace").read() for pat in ("include/*.h", "include/CameraModels/*.h", "Thirdparty/DBoW2/DBoW2/*.h")
+                  for f in glob.glob("/root/reference/" + pat))
+    own = "".join(open(f).read() for f in glob.glob(os.path.join(root, "include", "*.h")))
+    known = set(re.findall(r"[A-Za-z_]\w*", ref)) | set(re.findall(r"[A-Za-z_]\w*", own))
+    library = {"getMat", "release", "dot"}                      # OpenCV / Eigen methods no reference header spells out
+    to_add = {"GetGridCell", "GetGridCellRight", "GetMinDistanceRaw", "GetMaxDistanceRaw"}   # accessors a maintainer adds
+    shim_own = {"Handle", "has_mp"}               # shim/ORBextractor.h's own accessor; a field of a struct local to a shim file
+    integration = open(os.path.join(root, "INTEGRATION.md")).read()
+    for name in to_add:
+        assert name in integration, name
+    for path in sorted(glob.glob(os.path.join(root, "shim", "*"))):
+        text = re.sub(r"//.*", "", open(path).read())
+        reached = set(re.findall(r"(?:->|\.)\s*([A-Za-z_]\w*)", text))
+        unknown = sorted(n for n in reached if n not in known and n not in library and n not in to_add and n not in shim_own)
+        assert not unknown, (os.path.basename(path), unknown)
