@@ -104,3 +104,35 @@ def test_gpu_shim_compute_bow(gpu, tmp_path, k, depth, ragged, seed):
     assert "liborbx.so" in out and "not found" not in out
     voc, path, feats = _case(tmp_path, k, depth, ragged, seed)
     _check(refsrc.ReferenceVocabulary(path, world=_GPU_WORLD), voc, feats)
+
+
+@pytest.mark.skipif(not os.path.exists(_CPU_WORLD), reason="oracle/_ref/libshim_bow_world.so not built")
+def test_shim_compute_bow_from_three_threads(tmp_path):
+    """Frame::ComputeBoW runs on the Tracking thread, KeyFrame::ComputeBoW on LocalMapping's and LoopClosing's: three
+    threads at once (ctypes releases the GIL during the call), each alternating between two vocabularies — the matcher
+    context and the record of which vocabulary it holds are per thread, so nobody may see another thread's tree."""
+    import threading
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    cases = []
+    for sub, (k, depth, seed) in (("a", (10, 4, 11)), ("b", (6, 5, 12))):
+        voc, path, feats = _case(tmp_path / sub, k, depth, False, seed, 400)
+        cases.append((refsrc.ReferenceVocabulary(path, world=_CPU_WORLD), _expected(voc, feats), feats))
+    errors = []
+
+    def worker(t):
+        try:
+            for it in range(6):
+                rv, (node_w, words_w, values_w), feats = cases[(t + it) % 2]
+                node, words, values = rv.compute_bow(feats, (t + it) % 3 if (t + it) % 3 < 2 else 1)
+                if not (np.array_equal(node, node_w) and np.array_equal(words, words_w) and values.tobytes() == values_w.tobytes()):
+                    errors.append((t, it))
+        except Exception as e:  # noqa: BLE001 - report whatever a thread died of
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
