@@ -152,3 +152,28 @@ def test_shim_tracking_search_local_points(shim_world, args):
     SearchByProjection): mvpMapPoints, every MapPoint tracking word, mnVisible, mnLastFrameSeen and mmProjectPoints as the
     reference's own function text leaves them"""
     T.test_search_local_points(*args)
+
+
+def test_shim_bodies_from_three_threads(shim_world):
+    """ORBmatcher temporaries live on the Tracking, LocalMapping and LoopClosing threads at once (src/Tracking.cc:3303,
+    src/LocalMapping.cc:435, src/LoopClosing.cc:729): three threads run drop-in bodies concurrently (ctypes releases the
+    GIL during the calls) — SearchLocalPoints + SearchByProjection on different frames and maps of one image size (the
+    stand-in Frame keeps the image bounds in statics, like the reference). Each thread's results must be the serial ones:
+    the matcher context is per thread (shim/orbx_thread_matcher.h) and the bodies keep no other state."""
+    import threading
+    errors = []
+
+    def worker(t):
+        try:
+            for seed, m, case in ((t, 3000, t % 3), (t + 3, 2000, 5 + t % 3)):
+                T.test_search_local_points(seed, m, case)
+            T.test_search_by_projection_map(True, 1.0 + 2 * t, 0.8, bool(t & 1), 3 + t)
+        except BaseException as e:  # noqa: BLE001 - an assertion of the comparison, or whatever the thread died of
+            errors.append((t, repr(e)[:300]))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(3)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
