@@ -36,12 +36,18 @@ void fill_featvec(DBoW2::FeatureVector& fv, const orbx_featvec& c) {
     fv[c.node_ids[a]] = std::vector<unsigned int>(c.indices + c.offsets[a], c.indices + c.offsets[a + 1]);
 }
 
+inline void set_static(float& s, float v) {
+  if (s != v) s = v;
+}
+
 // Frame::mGrid built by the reference's AssignFeaturesToGrid from mvKeysUn and the view's bounds / cell sizes
 void build_grid(Frame& f, const orbx_frame_view* v) {
-  f.mnMinX = v->grid.min_x;
-  f.mnMinY = v->grid.min_y;
-  f.mfGridElementWidthInv = v->grid.inv_w;
-  f.mfGridElementHeightInv = v->grid.inv_h;
+  // the image bounds / cell sizes are statics (as in the reference, include/Frame.h:372-378): written only when they
+  // change, so that threads working on frames of one geometry (the three-thread tests) only ever read them
+  set_static(Frame::mnMinX, v->grid.min_x);
+  set_static(Frame::mnMinY, v->grid.min_y);
+  set_static(Frame::mfGridElementWidthInv, v->grid.inv_w);
+  set_static(Frame::mfGridElementHeightInv, v->grid.inv_h);
   f.AssignFeaturesToGrid();
 }
 
@@ -779,7 +785,8 @@ extern "C" int orbrefsrc_search_local_points(const orbx_frame_view* fv, const or
   }
   F.pose = Sophus::SE3f(F.mRcw, F.mtcw);  // Frame::GetPose(); mRcw / mtcw are its parts (Frame::UpdatePoseMatrices)
   F.mbf = fr->mbf;
-  Frame::mnMinX = fr->min_x; Frame::mnMaxX = fr->max_x; Frame::mnMinY = fr->min_y; Frame::mnMaxY = fr->max_y;
+  set_static(Frame::mnMinX, fr->min_x); set_static(Frame::mnMaxX, fr->max_x); set_static(Frame::mnMinY, fr->min_y);
+  set_static(Frame::mnMaxY, fr->max_y);
   F.mfLogScaleFactor = fr->log_scale_factor;
   F.mnScaleLevels = fr->n_levels;
   const int M = map->m;

@@ -162,6 +162,7 @@ def test_shim_bodies_from_three_threads(shim_world):
     the matcher context is per thread (shim/orbx_thread_matcher.h) and the bodies keep no other state."""
     import threading
     errors = []
+    T.test_search_local_points(8, 1, 0)   # one serial call first: the stand-in Frame's static image bounds get their values
 
     def worker(t):
         try:
