@@ -1429,9 +1429,9 @@ bool featvec_is_disjoint(const orbx_keyframe_view* k) {
 
 int search_by_bow_common(orbm_matcher* m, const orbx_keyframe_view* kf, const orbx_keyframe_view* second, float nnratio,
                          int check_orientation, int kf_kf, int32_t* matches, int32_t* nmatches, int n_left_f = -1) {
+  if (!m || !kf || !second || kf->n < 0 || second->n < 0) return mfail(m, ORBX_E_ARG, "bad argument");
   const int n_out = kf_kf ? kf->n : second->n;
-  if (!m || !kf || !second || kf->n < 0 || second->n < 0 || (n_out > 0 && !matches))
-    return mfail(m, ORBX_E_ARG, "bad argument");
+  if (n_out > 0 && !matches) return mfail(m, ORBX_E_ARG, "bad argument");
   if (nmatches) *nmatches = 0;
   if (!featvec_is_disjoint(second)) return mfail(m, ORBX_E_ARG, "FeatureVector lists a feature twice");
   ORBM_CUDA(m, cudaSetDevice(m->device));

@@ -86,3 +86,44 @@ def test_package_never_imports_the_oracle():
                     "%s references the oracle" % os.path.join(dirpath, f)
     out = subprocess.check_output(["ldd", os.path.join(pkg, "liborbx.so")], text=True)
     assert "orbref" not in out
+
+
+def test_every_entry_point_answers_null_arguments_with_a_code():
+    """"Never throw, never exit, never crash" (include/orbx.h:8-11): every int-returning entry point of both headers,
+    called with a NULL handle, NULL pointers and zero sizes, must come back with a negative error code. The calls are
+    generated from the declarations and run in a child process, so that a crash is a test failure naming the entry point
+    (orbm_search_by_bow / _kf used to read their views before checking them)."""
+    import re
+    import sys
+    decls = []
+    for h in ("orbx.h", "orbm.h"):
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", h)).read(), flags=re.S)
+        for m in re.finditer(r"\bint\s+(orb[xm]_\w+)\s*\(([^;]*?)\)\s*;", text):
+            decls.append((m.group(1), [a.strip() for a in m.group(2).replace("\n", " ").split(",")]))
+    assert len(decls) >= 48
+    lines = ["import ctypes as C, sys", "sys.path.insert(0, %r)" % ROOT, "from orb_slam3_fast_b200 import lib", "L = lib.lib()"]
+    for name, args in decls:
+        vals = []
+        for a in args:
+            if a in ("void", ""):
+                continue
+            if "*" in a:
+                vals.append("None")
+            elif re.search(r"\bfloat\b", a):
+                vals.append("C.c_float(0)")
+            elif re.search(r"\bdouble\b", a):
+                vals.append("C.c_double(0)")
+            elif "int64_t" in a:
+                vals.append("C.c_int64(0)")
+            else:
+                vals.append("0")
+        lines.append("print(%r, L.%s(%s), flush=True)" % (name, name, ", ".join(vals)))
+    r = subprocess.run([sys.executable, "-c", "\n".join(lines)], capture_output=True, text=True)
+    answered = dict(l.split() for l in r.stdout.splitlines() if l.startswith("orb"))
+    assert r.returncode == 0, "crashed after %s: %s" % (list(answered)[-1:] or "nothing", r.stderr[-500:])
+    assert len(answered) == len(decls)
+    for name, rc in answered.items():
+        if name == "orbx_kernel_launches":       # a count, 0 for "no handle"
+            assert int(rc) == 0
+        else:
+            assert int(rc) < 0, (name, rc)
