@@ -127,3 +127,26 @@ def test_every_entry_point_answers_null_arguments_with_a_code():
             assert int(rc) == 0
         else:
             assert int(rc) < 0, (name, rc)
+
+
+def test_handle_less_entry_points_report_the_missing_device():
+    """The front-end entry points take a device ordinal instead of a handle: with valid host buffers and no CUDA device
+    they must answer ORBX_E_CUDA (-4) — no CPU fallback, no crash — and pinned allocation must answer NULL."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from orb_slam3_fast_b200 import lib
+    L = lib.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    src, dst = np.zeros((48, 64, 3), np.uint8), np.zeros((48, 64), np.uint8)
+    mx, my = np.zeros((48, 64), np.float32), np.zeros((48, 64), np.float32)
+    assert L.orbx_cvt_gray(0, p(src), 64, 48, 64 * 3, 3, 1, p(dst), 64) == -4
+    assert L.orbx_remap_linear(0, p(dst), 64, 48, 64, p(mx), p(my), 64, 48, p(dst), 64) == -4
+    assert L.orbx_cvt_gray_device(0, 1, p(src), 64, 48, 64 * 3, C.c_int64(64 * 48 * 3), 3, 1, p(dst), 64,
+                                  C.c_int64(64 * 48), None) == -4
+    L.orbx_host_alloc.restype = C.c_void_p
+    assert L.orbx_host_alloc(C.c_int64(4096)) is None
+    handles = (C.c_void_p * 2)(None, None)          # a device list with empty slots is an argument error, not a crash
+    assert L.orbx_extract_batch_multi(2, handles, 4, p(dst), 64, 48, 64, C.c_int64(64 * 48), 0, 0, None, None, 0, None,
+                                      None) == -3
