@@ -122,6 +122,13 @@ def test_every_entry_point_answers_null_arguments_with_a_code():
     answered = dict(l.split() for l in r.stdout.splitlines() if l.startswith("orb"))
     assert r.returncode == 0, "crashed after %s: %s" % (list(answered)[-1:] or "nothing", r.stderr[-500:])
     assert len(answered) == len(decls)
+    from orb_slam3_fast_b200 import lib                      # the entry points that return nothing / a string: NULL is a no-op
+    L = lib.lib()
+    L.orbm_last_error.restype = C.c_char_p
+    assert L.orbm_last_error(None) is not None
+    L.orbx_host_free(None)
+    L.orbm_destroy(None)
+    L.orbx_extractor_destroy(None)
     for name, rc in answered.items():
         if name == "orbx_kernel_launches":       # a count, 0 for "no handle"
             assert int(rc) == 0
