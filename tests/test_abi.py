@@ -157,3 +157,35 @@ def test_handle_less_entry_points_report_the_missing_device():
     handles = (C.c_void_p * 2)(None, None)          # a device list with empty slots is an argument error, not a crash
     assert L.orbx_extract_batch_multi(2, handles, 4, p(dst), 64, 48, 64, C.c_int64(64 * 48), 0, 0, None, None, 0, None,
                                       None) == -3
+
+
+def test_python_bindings_match_the_headers():
+    """The ctypes harness (orb_slam3_fast_b200/lib.py, matcher.py) declares argtypes by hand; most of those calls only run
+    on a GPU. Every declared signature must have the header's parameter count, pointers where the header has pointers,
+    c_float for float and a 64-bit integer for int64_t — a drifted binding would corrupt arguments silently."""
+    import re
+    from orb_slam3_fast_b200 import lib
+    import orb_slam3_fast_b200.matcher as matcher
+    L = lib.lib()
+    matcher._bind(L)
+    checked = 0
+    for h in ("orbx.h", "orbm.h"):
+        text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", h)).read(), flags=re.S)
+        for m in re.finditer(r"\b(?:int|void\*?|const char\*)\s*\*?\s*(orb[xm]_\w+)\s*\(([^;]*?)\)\s*;", text):
+            name = m.group(1)
+            params = [a.strip() for a in m.group(2).replace("\n", " ").split(",") if a.strip() not in ("void", "")]
+            argtypes = getattr(L, name).argtypes
+            if argtypes is None:
+                assert name == "orbx_extract_batch_multi", name      # bound at its only call site (extractor.py)
+                continue
+            assert len(argtypes) == len(params), (name, len(argtypes), len(params))
+            for i, (p, t) in enumerate(zip(params, argtypes)):
+                is_ptr = "*" in p
+                t_ptr = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents")
+                assert is_ptr == t_ptr, (name, i, p, t)
+                if not is_ptr and re.search(r"\bfloat\b", p):
+                    assert t is C.c_float, (name, i, p, t)
+                if not is_ptr and "int64_t" in p:
+                    assert C.sizeof(t) == 8, (name, i, p, t)
+            checked += 1
+    assert checked >= 53
