@@ -189,3 +189,58 @@ def test_python_bindings_match_the_headers():
                     assert C.sizeof(t) == 8, (name, i, p, t)
             checked += 1
     assert checked >= 53
+
+
+def test_python_structures_have_the_layout_of_the_c_header(tmp_path):
+    """include/orbx_types.h is mirrored by hand as ctypes Structures twice (orb_slam3_fast_b200/views.py for the product
+    harness, oracle/orbref.py for the oracle). A C program generated from the header prints sizeof and every field offset;
+    each mirror must have the same size and start every one of its fields on a field boundary of the C struct."""
+    import re
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "orbx_types.h")).read(), flags=re.S)
+    structs = {}
+    for m in re.finditer(r"typedef struct (\w+) \{(.*?)\} \1;", text, flags=re.S):
+        fields = []
+        for decl in m.group(2).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.split(",")
+            first = names[0].split()[-1]
+            fields += [re.sub(r"\[\d+\]|[\* ]", "", n) for n in [first] + [n.strip() for n in names[1:]]]
+        structs[m.group(1)] = fields
+    assert len(structs) >= 13 and structs["orbx_frustum"][:3] == ["Rcw", "tcw", "Ow"]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "orbx_types.h"', "int main(void) {"]
+    for name, fields in structs.items():
+        src.append('printf("%s %%zu", sizeof(%s));' % (name, name))
+        src += ['printf(" %%zu", offsetof(%s, %s));' % (name, f) for f in fields]
+        src.append('printf("\\n");')
+    src += ["return 0; }"]
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), "-o", exe, str(c)])
+    layout = {}
+    for line in subprocess.check_output([exe], text=True).splitlines():
+        parts = line.split()
+        layout[parts[0]] = (int(parts[1]), [int(x) for x in parts[2:]])
+    mirror = {"orbx_grid": "Grid", "orbx_frame_view": "FrameView", "orbx_mappoints": "MapPoints", "orbx_fisheye_view": "FisheyeView",
+              "orbx_mappoints_right": "MapPointsRight", "orbx_frustum": "Frustum", "orbx_local_map": "LocalMap",
+              "orbx_track_params": "TrackParams", "orbx_projected": "Projected", "orbx_featvec": "FeatVec",
+              "orbx_vocabulary": "Vocabulary", "orbx_keyframe_view": "KeyFrameView"}
+    from orb_slam3_fast_b200 import views
+    from oracle import orbref
+    compared = 0
+    for module in (views, orbref):
+        for cname, pyname in mirror.items():
+            cls = getattr(module, pyname, None)
+            if cls is None:
+                continue
+            size, offsets = layout[cname]
+            assert C.sizeof(cls) == size, (module.__name__, pyname, C.sizeof(cls), size)
+            for fname, _ in cls._fields_:
+                assert getattr(cls, fname).offset in offsets, (module.__name__, pyname, fname)
+            compared += 1
+    assert compared >= 22
+    from orb_slam3_fast_b200 import synth
+    assert synth.frustum(640, 480, seed=0).dtype.itemsize == layout["orbx_frustum"][0]
+    assert synth.KP_DTYPE.itemsize == layout["orbx_kp"][0] == 28
