@@ -749,7 +749,8 @@ extern "C" void orbrefsrc_is_in_frustum(const orbx_frustum* fr, const orbx_local
 //                 with observations that is not in the local map
 //   bad[m]        MapPoint::isBad()
 //   ctl[8]        mSensor, isImuInitialized, GetIniertialBA2, mState, mCurrentFrame.mnId, mnLastRelocFrameId,
-//                 mbFarPoints, (unused)
+//                 mbFarPoints, two-camera flag (Nleft = N: isInFrustum takes its Nleft != -1 branch, whose
+//                 isInFrustumChecks is a stand-in that sees nothing, so no point comes into view)
 // In / out per local-map point (the caller's values are the state on entry, so "left untouched" is observable):
 // track_in_view, proj_x, proj_y, proj_xr, level, view_cos, depth, visible (mnVisible), last_seen (mnLastFrameSeen).
 // Out: assign[fv->n] = what mvpMapPoints[i] holds on return (same code as held), project_points[m][2] = the entry of
@@ -776,6 +777,7 @@ extern "C" int orbrefsrc_search_local_points(const orbx_frame_view* fv, const or
   fill_common(F, fv->kps, fv->desc, fv->u_right, fv->n, fv->scale_factors, nullptr, fv->n_levels);
   build_grid(F, fv);
   F.mnId = (long unsigned int)ctl[4];
+  if (ctl[7]) F.Nleft = F.N;
   cam.mvParameters[0] = fr->fx; cam.mvParameters[1] = fr->fy; cam.mvParameters[2] = fr->cx; cam.mvParameters[3] = fr->cy;
   F.mpCamera = &cam;
   for (int i = 0; i < 3; i++) {

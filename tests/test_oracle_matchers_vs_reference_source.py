@@ -756,6 +756,52 @@ def test_search_local_points(seed, m, case):
         assert nv > m // 4 and (skip != 0).sum() > 0 and (bad & state["track_in_view"]).sum() > 0
 
 
+def test_search_local_points_two_camera_frame():
+    """The Nleft != -1 side of Tracking::SearchLocalPoints: Frame::isInFrustum (src/Frame.cc:687-698) resets
+    mbTrackInView / mnTrackScaleLevel of every point it is asked about and asks isInFrustumChecks, which in the stand-in
+    world sees nothing — so what is observable is the bookkeeping: the loop over the frame's own points, the skip rule, and
+    that skipped and bad points keep every word. (The drop-in body keeps the reference's per-point call on such frames.)"""
+    rng = np.random.default_rng(77)
+    img = synth.scene(480, 640, seed=41)
+    ex = orbref.Extractor(1200)
+    _, kps, desc = ex(img, (0, 0))
+    n, m, frame_id = len(kps), 1500, 40
+    fr = synth.frustum(640, 480, seed=3)
+    mp = synth.local_map_world(kps, desc, m, fr, seed=3)
+    bad = (rng.random(m) < 0.05).astype(np.uint8)
+    held = np.full(n, -1, np.int32)
+    slots = rng.choice(n, 100, replace=False)
+    held[slots] = rng.choice(m, 100, replace=False)
+    state = dict(track_in_view=(rng.random(m) < 0.3).astype(np.uint8), proj_x=np.full(m, 3.5, f32), proj_y=np.full(m, 4.5, f32),
+                 proj_xr=np.full(m, 5.5, f32), level=np.full(m, 2, np.int32), view_cos=np.full(m, 6.5, f32),
+                 depth=np.full(m, 8.5, f32), visible=rng.integers(0, 50, m).astype(np.int32),
+                 last_seen=np.where(rng.random(m) < 0.05, frame_id, frame_id - 1).astype(np.int32))
+    state["track_in_view"][(state["last_seen"] == frame_id) & (bad == 0)] = 0
+    inv_w, inv_h = f32(64) / f32(640), f32(48) / f32(480)
+    off, items = orbref.build_grid(kps, 0.0, 0.0, inv_w, inv_h)
+    g, keep = orbref.make_grid(off, items, 0.0, 0.0, inv_w, inv_h)
+    fv = orbref.make_frame_view(kps, desc, None, np.zeros(n, np.uint8), g, keep, ex.scale)
+    lm = orbref.make_local_map(**{**mp, "skip": None})
+    a_r, s_r, pp_r, k_r = refsrc.search_local_points(fv, fr, lm, held, bad, (1, 0, 0, 2, frame_id, 0, 0, 1), 15.0, state)
+    st = {k: v.copy() for k, v in state.items()}
+    now = held.copy()
+    for i in np.flatnonzero(held >= 0):
+        k = held[i]
+        if bad[k]:
+            now[i] = -1
+        else:
+            st["visible"][k] += 1
+            st["last_seen"][k] = frame_id
+            st["track_in_view"][k] = 0
+    asked = (st["last_seen"] != frame_id) & (bad == 0)
+    st["track_in_view"][asked] = 0
+    st["level"][asked] = -1
+    assert asked.sum() > m // 2 and (~asked).sum() > 100
+    assert np.array_equal(a_r, now) and k_r == 0 and np.isnan(pp_r).all()
+    for k in st:
+        assert s_r[k].tobytes() == st[k].tobytes(), k
+
+
 @pytest.mark.parametrize("seed,th,far,sizes", [(0, 1.0, True, (700, 650, 3000)), (1, 3.0, False, (700, 650, 3000)),
                                                (2, 6.0, True, (1200, 1100, 10000)), (4, 15.0, False, (300, 280, 2000))])
 def test_search_by_projection_map_fisheye(seed, th, far, sizes):

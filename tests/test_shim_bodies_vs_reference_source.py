@@ -178,3 +178,9 @@ def test_shim_bodies_from_three_threads(shim_world):
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+
+def test_shim_tracking_search_local_points_two_camera_frame(shim_world):
+    """the Nleft != -1 branch of the drop-in body (per-point Frame::isInFrustum kept on the host)"""
+    T.test_search_local_points_two_camera_frame()
